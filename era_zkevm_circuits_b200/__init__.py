@@ -1,0 +1,12 @@
+"""B200-native witness-generation / constraint-evaluation engine for the data-parallel hot path of
+the zkSync Era zkEVM circuits (reference: matter-labs/era-zkevm_circuits).  The compute lives in
+csrc/ (hand-written sm_100a CUDA behind the C ABI of include/zkc_b200.h); this package is the
+host-side mirror of the reference's entry points."""
+from . import abi  # noqa: F401
+from .engine import Engine, ZkcError  # noqa: F401
+from .ram_permutation import (  # noqa: F401
+    RamPermutationCircuitInstanceWitness,
+    RamPermutationResult,
+    ram_permutation_check_trace,
+    ram_permutation_entry_point,
+)

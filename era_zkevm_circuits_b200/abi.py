@@ -1,0 +1,120 @@
+"""ctypes view of include/zkc_b200.h (the C ABI of libzkc_b200.so) plus numpy record dtypes.
+
+Nothing here computes: it only marshals the reference's witness structures
+(/root/reference/src/ram_permutation/input.rs:27-116, src/fsm_input_output/mod.rs:32-48) into the
+`#[repr(C)]` records the sm_100a engine consumes.  Loading fails loudly when the CUDA library is
+missing -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzkc_b200.so")
+
+GL_P = 0xFFFFFFFF00000001
+
+ZKC_OK, ZKC_ERR_INVALID_ARGUMENT, ZKC_ERR_CUDA, ZKC_ERR_NO_DEVICE = 0, 1, 2, 3
+ZKC_ERR_UNSATISFIED, ZKC_ERR_FSM_OUTPUT_MISMATCH, ZKC_ERR_QUEUE_WITNESS_INCONSISTENT = 4, 5, 6
+CODE_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "CUDA", 3: "NO_DEVICE", 4: "UNSATISFIED",
+              5: "FSM_OUTPUT_MISMATCH", 6: "QUEUE_WITNESS_INCONSISTENT"}
+
+MEMORY_QUERY_DTYPE = np.dtype([
+    ("timestamp", "<u4"), ("memory_page", "<u4"), ("index", "<u4"), ("rw_flag", "<u4"), ("is_ptr", "<u4"),
+    ("value", "<u4", (8,)), ("_pad", "<u4", (3,)),
+])
+assert MEMORY_QUERY_DTYPE.itemsize == 64
+
+
+class Status(C.Structure):
+    _fields_ = [("code", C.c_int32), ("cuda_error", C.c_int32), ("first_bad_row", C.c_int64),
+                ("failed_checks", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class QueueState12(C.Structure):
+    _fields_ = [("head", C.c_uint64 * 12), ("tail", C.c_uint64 * 12), ("length", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class QueueState4(C.Structure):
+    _fields_ = [("head", C.c_uint64 * 4), ("tail", C.c_uint64 * 4), ("length", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class RamInputData(C.Structure):
+    _fields_ = [("unsorted_queue_initial_state", QueueState12), ("sorted_queue_initial_state", QueueState12),
+                ("non_deterministic_bootloader_memory_snapshot_length", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class RamFsm(C.Structure):
+    _fields_ = [("lhs_accumulator", C.c_uint64 * 2), ("rhs_accumulator", C.c_uint64 * 2),
+                ("current_unsorted_queue_state", QueueState12), ("current_sorted_queue_state", QueueState12),
+                ("previous_sorting_key", C.c_uint32 * 3), ("previous_full_key", C.c_uint32 * 2),
+                ("previous_value", C.c_uint32 * 8), ("previous_is_ptr", C.c_uint32),
+                ("num_nondeterministic_writes", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class RamClosedForm(C.Structure):
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("observable_input", RamInputData),
+                ("hidden_fsm_input", RamFsm), ("hidden_fsm_output", RamFsm)]
+
+
+class RamOptions(C.Structure):
+    _fields_ = [("bootloader_heap_page", C.c_uint32), ("compare_expected", C.c_uint32), ("_pad", C.c_uint32 * 2)]
+
+
+# trace columns, enum zkc_ram_col
+RAM_COLS = dict(
+    UNSORTED_IS_EMPTY=0, SORTED_IS_EMPTY=1, CAN_POP=2, UNSORTED_ITEM=3, UNSORTED_ENC=16, UNSORTED_HEAD=24,
+    UNSORTED_LEN=36, SORTED_ITEM=37, SORTED_ENC=50, SORTED_HEAD=58, SORTED_LEN=70, TS_IS_ZERO=71,
+    PAGE_IS_BOOTLOADER_HEAP=72, IS_NONDET_WRITE=73, NUM_NONDET_WRITES=74, CMP_DIFF=75, CMP_BORROW=78,
+    CMP_LIMB_EQ=81, KEYS_EQUAL=84, PREV_KEY_SMALLER=85, SAME_CELL=86, VALUE_EQUAL=87, VALUE_IS_ZERO=88,
+    IS_ZERO=89, PTR_EQUALITY=90, VALUE_AND_PTR_EQUAL=91, READ_UNINIT=92, CHECK_EQUALITY=93, GP_CHAIN=94,
+    GP_NEW=126, GP_ACC=130, NUM_COLS=134)
+
+RAM_CHK = dict(LENGTHS_EQUAL=1 << 0, EMPTY_SYNC=1 << 1, ASCENDING=1 << 2, UNINIT_READ_ZERO=1 << 3,
+               READ_CONSISTENT=1 << 4, QUEUE_CONSISTENCY=1 << 5, GRAND_PRODUCT=1 << 6, NONDET_COUNT=1 << 7,
+               TRIVIAL_HEAD=1 << 8, RANGE=1 << 9, QUEUE_HINT=1 << 10)
+
+_u64p = C.POINTER(C.c_uint64)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/zkc_b200.h declares
+SIGNATURES = {
+    "zkc_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "zkc_destroy": (None, [_vp]),
+    "zkc_set_stream": (C.c_int, [_vp, _vp]),
+    "zkc_version": (C.c_char_p, []),
+    "zkc_launch_count": (C.c_uint64, [_vp]),
+    "zkc_sm_count": (C.c_int, [_vp]),
+    "zkc_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "zkc_profile_query": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double), _u64p]),
+    "zkc_profile_reset": (C.c_int, [_vp]),
+    "zkc_host_alloc": (_vp, [C.c_size_t]),
+    "zkc_host_free": (None, [_vp]),
+    "zkc_poseidon2_permute": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int]),
+    "zkc_commit_encoding": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_int]),
+    "zkc_accumulate_grand_products": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "zkc_memory_queue_simulate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, C.c_int]),
+    "zkc_ram_permutation_entry_point": (C.c_int, [_vp, C.POINTER(RamClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,
+                                                  C.c_size_t, C.c_size_t, C.POINTER(RamOptions), C.c_int, _vp, _vp,
+                                                  C.POINTER(Status)]),
+    "zkc_ram_permutation_check_trace": (C.c_int, [_vp, C.POINTER(RamClosedForm), _vp, C.c_size_t, C.POINTER(RamOptions),
+                                                  C.c_uint32, C.c_int, _u64p, C.POINTER(Status)]),
+}
+
+GATES_GENERAL, GATES_ROUND_FUNCTION = 1, 2
+RAMV = dict(BOOLEAN=1 << 0, QUEUE_LEN=1 << 1, ENCODING=1 << 2, ROUND_FUNCTION=1 << 3, NONDET=1 << 4, COMPARISON=1 << 5,
+            FLAGS=1 << 6, ENFORCE=1 << 7, GP_CHAIN=1 << 8, GP_ACC=1 << 9)
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build the sm_100a engine first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library drift apart
+        fn.restype = res
+        fn.argtypes = args
+    return lib

@@ -1,0 +1,803 @@
+// RAM permutation circuit on sm_100a: witness generation (ram_permutation_entry_point,
+// /root/reference/src/ram_permutation/mod.rs:31-210) and constraint re-evaluation of the
+// finished trace.  One thread per loop iteration of partial_accumulate_inner (:246); the
+// sequential state the reference threads through the loop is recovered row-parallel:
+//   - queue heads: from the previous-state column of the raw queue witness
+//     (ram_permutation/input.rs:105-116), verified link by link;
+//   - previous key / value: the neighbouring row's sorted item;
+//   - running grand products and the non-deterministic write counter: one decoupled
+//     look-back scan (scan.cuh).
+#include "ctx.cuh"
+#include "poseidon2.cuh"
+#include "scan.cuh"
+
+namespace zkc {
+
+struct RamDev {
+    zkc_ram_closed_form io;       // in: H2D copy of the caller's struct; out: fsm output filled in
+    zkc_ram_options opt;
+    uint64_t n_unsorted, n_sorted, limit;
+    // prologue
+    uint64_t ch[2][9];
+    uint64_t acc0[4];             // rep*2 + side
+    uint32_t nnw0, start;
+    zkc_queue_state12 uq0, sq0;
+    uint64_t commit_obs_in[4], commit_fsm_in[4];
+    // row kernel
+    uint64_t acc_final[4];
+    uint32_t nnw_final, pad0;
+    uint64_t head_final[2][12];
+    zkc_memory_query last_sorted;
+    // status
+    unsigned long long first_bad;  // min over failing rows of (row << 16 | checks); ~0 = none
+    uint32_t failed_checks;
+    uint32_t hint_bad;
+    uint32_t prologue_checks, pad1;
+    // finalize
+    uint64_t commitment[4];
+    zkc_status status;
+    unsigned long long violations;
+};
+
+__device__ __forceinline__ void ram_encode(const zkc_memory_query &q, uint64_t (&e)[8]) {
+    // memory_query/mod.rs:103-221
+    const uint32_t *v = q.value;
+    e[0] = q.timestamp;
+    e[1] = q.memory_page;
+    e[2] = (uint64_t)q.index | ((uint64_t)(q.rw_flag & 1) << 32) | ((uint64_t)(q.is_ptr & 1) << 33);
+    e[3] = (uint64_t)v[0] | ((uint64_t)(v[5] & 0xFFFFFFu) << 32);
+    e[4] = (uint64_t)v[1] | ((uint64_t)(v[5] >> 24) << 32) | ((uint64_t)(v[6] & 0xFFFFu) << 40);
+    e[5] = (uint64_t)v[2] | ((uint64_t)(v[6] >> 16) << 32) | ((uint64_t)(v[7] & 0xFFu) << 48);
+    e[6] = (uint64_t)v[3] | ((uint64_t)(v[7] >> 8) << 32);
+    e[7] = v[4];
+}
+
+__device__ __forceinline__ zkc_memory_query ram_load_query(const zkc_memory_query *p) {
+    zkc_memory_query q;
+    const uint4 *s = reinterpret_cast<const uint4 *>(p);
+    uint4 *d = reinterpret_cast<uint4 *>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = __ldg(s + i);
+    return q;
+}
+__device__ __forceinline__ zkc_memory_query ram_zero_query() {
+    zkc_memory_query q;
+    uint4 *d = reinterpret_cast<uint4 *>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = make_uint4(0, 0, 0, 0);
+    return q;
+}
+
+__device__ int put_queue_state12(uint64_t *dst, const zkc_queue_state12 &s) {
+    for (int i = 0; i < 12; i++) dst[i] = s.head[i];
+    for (int i = 0; i < 12; i++) dst[12 + i] = s.tail[i];
+    dst[24] = s.length;
+    return 25;
+}
+// CSVarLengthEncodable order of RamPermutationFSMInputOutput, ram_permutation/input.rs:52-62
+__device__ int ram_encode_fsm(const zkc_ram_fsm &f, uint64_t *dst) {
+    int n = 0;
+    dst[n++] = f.lhs_accumulator[0]; dst[n++] = f.lhs_accumulator[1];
+    dst[n++] = f.rhs_accumulator[0]; dst[n++] = f.rhs_accumulator[1];
+    n += put_queue_state12(dst + n, f.current_unsorted_queue_state);
+    n += put_queue_state12(dst + n, f.current_sorted_queue_state);
+    for (int i = 0; i < 3; i++) dst[n++] = f.previous_sorting_key[i];
+    for (int i = 0; i < 2; i++) dst[n++] = f.previous_full_key[i];
+    for (int i = 0; i < 8; i++) dst[n++] = f.previous_value[i];
+    dst[n++] = f.previous_is_ptr;
+    dst[n++] = f.num_nondeterministic_writes;
+    return n;
+}
+
+// ---- prologue: FSM start selection, Fiat-Shamir challenges, input commitments ------------------
+__global__ void ram_prologue_kernel(RamDev *d) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane != 0) return;
+    const zkc_ram_closed_form &io = d->io;
+    const zkc_ram_input_data &obs = io.observable_input;
+    if (warp == 0) {
+        const bool start = io.start_flag != 0;
+        d->start = start;
+        d->uq0 = start ? obs.unsorted_queue_initial_state : io.hidden_fsm_input.current_unsorted_queue_state;
+        d->sq0 = start ? obs.sorted_queue_initial_state : io.hidden_fsm_input.current_sorted_queue_state;
+        for (int i = 0; i < 2; i++) {
+            d->acc0[i * 2 + 0] = start ? 1 : io.hidden_fsm_input.lhs_accumulator[i];
+            d->acc0[i * 2 + 1] = start ? 1 : io.hidden_fsm_input.rhs_accumulator[i];
+        }
+        d->nnw0 = start ? 0 : io.hidden_fsm_input.num_nondeterministic_writes;
+        uint32_t checks = 0;
+        for (int i = 0; i < 12; i++)
+            if (obs.unsorted_queue_initial_state.head[i] | obs.sorted_queue_initial_state.head[i])
+                checks |= ZKC_RAM_CHK_TRIVIAL_HEAD;
+        if (d->uq0.length != d->sq0.length) checks |= ZKC_RAM_CHK_LENGTHS_EQUAL;
+        d->prologue_checks = checks;
+        // produce_fs_challenges, utils.rs:12-78, over tail || len || tail || len (26 elements)
+        uint64_t in[26];
+        for (int i = 0; i < 12; i++) in[i] = obs.unsorted_queue_initial_state.tail[i];
+        in[12] = obs.unsorted_queue_initial_state.length;
+        for (int i = 0; i < 12; i++) in[13 + i] = obs.sorted_queue_initial_state.tail[i];
+        in[25] = obs.sorted_queue_initial_state.length;
+        uint64_t s[12];
+        sponge_init(s, 26);
+        for (int off = 0; off < 26; off += 8) {
+            for (int j = 0; j < 8; j++) s[j] = off + j < 26 ? in[off + j] : 0;
+            poseidon2_permute(s);
+        }
+        int can_take = 8;
+        for (int rep = 0; rep < 2; rep++) {
+            d->ch[rep][0] = 1;
+            for (int k = 1; k < 9; k++) {
+                if (can_take == 0) { poseidon2_permute(s); can_take = 8; }
+                uint64_t v = 0;
+                for (int j = 0; j < 8; j++) if (j == 8 - can_take) v = s[j];
+                d->ch[rep][k] = v;
+                can_take--;
+            }
+        }
+    } else if (warp == 1) {
+        uint64_t buf[51];
+        int n = put_queue_state12(buf, obs.unsorted_queue_initial_state);
+        n += put_queue_state12(buf + n, obs.sorted_queue_initial_state);
+        buf[n++] = obs.non_deterministic_bootloader_memory_snapshot_length;
+        commit_encoding_dev(buf, n, d->commit_obs_in);
+    } else if (warp == 2) {
+        uint64_t buf[69];
+        int n = ram_encode_fsm(io.hidden_fsm_input, buf);
+        commit_encoding_dev(buf, n, d->commit_fsm_in);
+    }
+}
+
+// sequential reconstruction of the previous-state column when the caller does not supply it
+// (2 threads, one hash chain each; only for callers without a raw queue witness)
+__global__ void ram_chain_kernel(RamDev *d, const zkc_memory_query *unsorted, const zkc_memory_query *sorted,
+                                 uint64_t *uprev, uint64_t *sprev, size_t rows) {
+    const int k = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) != 0 || k > 1) return;
+    const zkc_memory_query *q = k ? sorted : unsorted;
+    uint64_t *out = k ? sprev : uprev;
+    const zkc_queue_state12 &q0 = k ? d->sq0 : d->uq0;
+    uint64_t s[12];
+    for (int i = 0; i < 12; i++) s[i] = q0.head[i];
+    for (size_t r = 0; r < rows; r++) {
+        for (int i = 0; i < 12; i++) out[12 * r + i] = s[i];
+        zkc_memory_query it = q[r];
+        uint64_t e[8];
+        ram_encode(it, e);
+        for (int i = 0; i < 8; i++) s[i] = e[i];
+        poseidon2_permute(s);
+    }
+}
+
+__device__ __forceinline__ void ram_report(RamDev *d, size_t row, uint32_t checks) {
+    if (!checks) return;
+    atomicOr(&d->failed_checks, checks);
+    atomicMin(&d->first_bad, ((unsigned long long)row << 16) | checks);
+}
+
+// ---- the row kernel ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS)
+ram_rows_kernel(RamDev *d, const zkc_memory_query *__restrict__ unsorted, const uint64_t *__restrict__ uprev,
+                const zkc_memory_query *__restrict__ sorted, const uint64_t *__restrict__ sprev,
+                uint64_t *__restrict__ trace, ScanGlobal *sg, TileState *tiles) {
+    __shared__ ScanShared sh;
+    const unsigned int tile = scan_take_ticket(sg, sh);
+    const size_t limit = d->limit;
+    const size_t row = (size_t)tile * SCAN_THREADS + threadIdx.x;
+    const bool in_range = row < limit;
+    const uint32_t ulen0 = d->uq0.length, slen0 = d->sq0.length;
+    const bool u_empty = row >= ulen0, s_empty = row >= slen0;
+    const bool can_pop = in_range && !u_empty;
+    const size_t active_rows = limit < ulen0 ? limit : ulen0;  // rows that pop
+    const uint32_t heap_page = d->opt.bootloader_heap_page ? d->opt.bootloader_heap_page : ZKC_BOOTLOADER_HEAP_PAGE_DEFAULT;
+    uint32_t checks = 0;
+    if (in_range && u_empty != s_empty) checks |= ZKC_RAM_CHK_EMPTY_SYNC;
+
+#define TR(col) trace[(size_t)(col) * limit + row]
+    const bool wr = in_range && trace != nullptr;
+    zkc_memory_query si = ram_zero_query();
+    uint64_t contrib[4];  // rep*2 + side
+    // ---- two pops: item, encoding, head <- P(enc || head[8..12]) --------------------------------
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        const zkc_memory_query *recs = k ? sorted : unsorted;
+        const uint64_t *prev = k ? sprev : uprev;
+        const size_t n_rec = k ? d->n_sorted : d->n_unsorted;
+        const zkc_queue_state12 &q0 = k ? d->sq0 : d->uq0;
+        zkc_memory_query it = ram_zero_query();
+        if (can_pop && row < n_rec) it = ram_load_query(recs + row);
+        uint64_t e[8], s[12];
+        ram_encode(it, e);
+        if (can_pop) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) s[i] = e[i];
+            bool hint_ok = true;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const uint64_t h = __ldg(prev + 12 * row + i);
+                if (i >= 8) s[i] = h;
+                if (row == 0 && h != q0.head[i]) hint_ok = false;
+            }
+            poseidon2_permute(s);
+            if (row + 1 < active_rows) {
+#pragma unroll
+                for (int i = 0; i < 12; i++) hint_ok &= __ldg(prev + 12 * (row + 1) + i) == s[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; i++) d->head_final[k][i] = s[i];
+            }
+            if (!hint_ok) { checks |= ZKC_RAM_CHK_QUEUE_HINT; d->hint_bad = 1; }
+        } else {
+            // nothing popped: the head keeps its value.  Rows past the end of the queue see the
+            // fully drained queue, whose head equals its tail (enforce_consistency, :161-162)
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = ulen0 == 0 ? q0.head[i] : q0.tail[i];
+        }
+        if (wr) {
+            const int base = k ? ZKC_RAM_SORTED_ITEM : ZKC_RAM_UNSORTED_ITEM;
+            TR(base + 0) = it.timestamp; TR(base + 1) = it.memory_page; TR(base + 2) = it.index;
+            TR(base + 3) = it.rw_flag & 1; TR(base + 4) = it.is_ptr & 1;
+#pragma unroll
+            for (int i = 0; i < 8; i++) TR(base + 5 + i) = it.value[i];
+#pragma unroll
+            for (int i = 0; i < 8; i++) TR(base + 13 + i) = e[i];
+#pragma unroll
+            for (int i = 0; i < 12; i++) TR(base + 21 + i) = s[i];
+            const uint32_t len0 = k ? slen0 : ulen0;
+            const size_t popped_now = row + 1 < active_rows ? row + 1 : active_rows;
+            TR(base + 33) = len0 >= popped_now ? len0 - (uint32_t)popped_now : 0;
+        }
+        // utils.rs:104-129 contribution chains
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            uint64_t c = d->ch[rep][8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                c = gl_fma(e[i], d->ch[rep][i], c);
+                if (wr) TR(ZKC_RAM_GP_CHAIN + (rep * 2 + k) * 8 + i) = c;
+            }
+            contrib[rep * 2 + k] = c;
+        }
+        if (k == 1) si = it;
+    }
+
+    // ---- :260-290 non-deterministic writes ------------------------------------------------------
+    const bool ts_is_zero = si.timestamp == 0;
+    const bool page_is_heap = si.memory_page == heap_page;
+    const bool is_write = si.rw_flag & 1, is_ptr = si.is_ptr & 1;
+    const bool is_nondet = can_pop && ts_is_zero && page_is_heap && is_write && !is_ptr;
+
+    // ---- :296-362 ordering and read/write consistency against the previous row ------------------
+    uint32_t prev_sk[3], prev_fk[2], prev_val[8], prev_is_ptr;
+    if (row == 0) {
+        const zkc_ram_fsm &f = d->io.hidden_fsm_input;
+#pragma unroll
+        for (int i = 0; i < 3; i++) prev_sk[i] = f.previous_sorting_key[i];
+        prev_fk[0] = f.previous_full_key[0]; prev_fk[1] = f.previous_full_key[1];
+#pragma unroll
+        for (int i = 0; i < 8; i++) prev_val[i] = f.previous_value[i];
+        prev_is_ptr = f.previous_is_ptr & 1;
+    } else {
+        zkc_memory_query pq = ram_zero_query();
+        if (in_range && row - 1 < active_rows && row - 1 < d->n_sorted) pq = ram_load_query(sorted + row - 1);
+        prev_sk[0] = pq.timestamp; prev_sk[1] = pq.index; prev_sk[2] = pq.memory_page;
+        prev_fk[0] = pq.index; prev_fk[1] = pq.memory_page;
+#pragma unroll
+        for (int i = 0; i < 8; i++) prev_val[i] = pq.value[i];
+        prev_is_ptr = pq.is_ptr & 1;
+    }
+    const uint32_t sk[3] = {si.timestamp, si.index, si.memory_page};
+    uint32_t diff[3], bor[3];
+    uint32_t borrow = 0;
+    bool keys_equal = true;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {  // previous - current, least significant limb first
+        const uint64_t dd = (uint64_t)prev_sk[i] - sk[i] - borrow;
+        diff[i] = (uint32_t)dd;
+        borrow = (uint32_t)(dd >> 32) & 1u;
+        bor[i] = borrow;
+        keys_equal &= diff[i] == 0;
+    }
+    const bool prev_smaller = borrow;
+    const bool not_start = !d->start;
+    const bool first = row == 0;
+    if (can_pop && (!first || not_start) && !prev_smaller) checks |= ZKC_RAM_CHK_ASCENDING;
+    const bool same_cell = si.index == prev_fk[0] && si.memory_page == prev_fk[1];
+    bool value_equal = true, value_is_zero = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { value_equal &= si.value[i] == prev_val[i]; value_is_zero &= si.value[i] == 0; }
+    const bool not_rw = !is_write;
+    const bool is_zero = value_is_zero && !is_ptr;
+    const bool ptr_equality = prev_is_ptr == (uint32_t)is_ptr;
+    const bool value_and_ptr_equal = value_equal && ptr_equality;
+    bool read_uninit, check_equality;
+    if (!first) {
+        read_uninit = !same_cell && not_rw;
+        check_equality = same_cell && not_rw;
+    } else {
+        read_uninit = (not_start && !same_cell && not_rw) || (!not_start && not_rw);
+        check_equality = same_cell && not_rw && not_start;
+    }
+    if (in_range && read_uninit && !is_zero) checks |= ZKC_RAM_CHK_UNINIT_READ_ZERO;
+    if (in_range && check_equality && !value_and_ptr_equal) checks |= ZKC_RAM_CHK_READ_CONSISTENT;
+
+    // ---- running products + write counter ---------------------------------------------------------
+    ScanVal v = scan_identity();
+    if (can_pop) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) v.p[i] = contrib[i];
+    }
+    v.c = is_nondet;
+    ScanVal init;
+#pragma unroll
+    for (int i = 0; i < 4; i++) init.p[i] = d->acc0[i];
+    init.c = d->nnw0;
+    ScanVal incl;
+    const ScanVal excl = scan_tile(v, tile, init, tiles, sh, incl);
+
+    if (wr) {
+        TR(ZKC_RAM_UNSORTED_IS_EMPTY) = u_empty; TR(ZKC_RAM_SORTED_IS_EMPTY) = s_empty; TR(ZKC_RAM_CAN_POP) = can_pop;
+        TR(ZKC_RAM_TS_IS_ZERO) = ts_is_zero; TR(ZKC_RAM_PAGE_IS_BOOTLOADER_HEAP) = page_is_heap;
+        TR(ZKC_RAM_IS_NONDET_WRITE) = is_nondet; TR(ZKC_RAM_NUM_NONDET_WRITES) = incl.c;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            TR(ZKC_RAM_CMP_DIFF + i) = diff[i]; TR(ZKC_RAM_CMP_BORROW + i) = bor[i];
+            TR(ZKC_RAM_CMP_LIMB_EQ + i) = diff[i] == 0;
+        }
+        TR(ZKC_RAM_KEYS_EQUAL) = keys_equal; TR(ZKC_RAM_PREV_KEY_SMALLER) = prev_smaller;
+        TR(ZKC_RAM_SAME_CELL) = same_cell; TR(ZKC_RAM_VALUE_EQUAL) = value_equal;
+        TR(ZKC_RAM_VALUE_IS_ZERO) = value_is_zero; TR(ZKC_RAM_IS_ZERO) = is_zero;
+        TR(ZKC_RAM_PTR_EQUALITY) = ptr_equality; TR(ZKC_RAM_VALUE_AND_PTR_EQUAL) = value_and_ptr_equal;
+        TR(ZKC_RAM_READ_UNINIT) = read_uninit; TR(ZKC_RAM_CHECK_EQUALITY) = check_equality;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            TR(ZKC_RAM_GP_NEW + i) = can_pop ? incl.p[i] : gl_mul(excl.p[i], contrib[i]);
+            TR(ZKC_RAM_GP_ACC + i) = incl.p[i];
+        }
+    }
+    if (in_range && row == limit - 1) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) d->acc_final[i] = incl.p[i];
+        d->nnw_final = incl.c;
+        d->last_sorted = si;
+    }
+    if (in_range) ram_report(d, row, checks);
+#undef TR
+}
+
+// FullStateCircuitQueue::push of whole queues (the reference test builds its inputs this way,
+// ram_permutation/mod.rs:506-515): one thread per independent queue, each a sequential hash chain.
+__global__ void memory_queue_simulate_kernel(const zkc_memory_query *__restrict__ recs, size_t n_per_queue,
+                                             size_t n_queues, uint64_t *__restrict__ prev_states,
+                                             zkc_queue_state12 *__restrict__ final_states) {
+    const size_t qi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= n_queues) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    for (size_t r = 0; r < n_per_queue; r++) {
+        const size_t g = qi * n_per_queue + r;
+        if (prev_states) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) prev_states[12 * g + i] = s[i];
+        }
+        zkc_memory_query it = ram_load_query(recs + g);
+        uint64_t e[8];
+        ram_encode(it, e);
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = e[i];
+        poseidon2_permute(s);
+    }
+    zkc_queue_state12 &o = final_states[qi];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { o.head[i] = 0; o.tail[i] = s[i]; }
+    o.length = (uint32_t)n_per_queue;
+    o._pad = 0;
+}
+
+// ---- finalize: entry-point enforcements, FSM output, commitment ---------------------------------
+__global__ void ram_finalize_kernel(RamDev *d) {
+    if (threadIdx.x != 0) return;
+    zkc_ram_closed_form &io = d->io;
+    const size_t limit = d->limit;
+    const uint32_t len0 = d->uq0.length;
+    const size_t popped = limit < len0 ? limit : len0;
+    zkc_ram_fsm out;
+    memset(&out, 0, sizeof out);
+    out.current_unsorted_queue_state = d->uq0;
+    out.current_sorted_queue_state = d->sq0;
+    if (popped > 0) {
+        for (int i = 0; i < 12; i++) {
+            out.current_unsorted_queue_state.head[i] = d->head_final[0][i];
+            out.current_sorted_queue_state.head[i] = d->head_final[1][i];
+        }
+    }
+    out.current_unsorted_queue_state.length = len0 - (uint32_t)popped;
+    const size_t spopped = d->sq0.length < popped ? d->sq0.length : popped;
+    out.current_sorted_queue_state.length = d->sq0.length - (uint32_t)spopped;
+    if (limit > 0) {
+        for (int i = 0; i < 2; i++) {
+            out.lhs_accumulator[i] = d->acc_final[i * 2 + 0];
+            out.rhs_accumulator[i] = d->acc_final[i * 2 + 1];
+        }
+        out.num_nondeterministic_writes = d->nnw_final;
+        const zkc_memory_query &q = d->last_sorted;
+        out.previous_sorting_key[0] = q.timestamp; out.previous_sorting_key[1] = q.index; out.previous_sorting_key[2] = q.memory_page;
+        out.previous_full_key[0] = q.index; out.previous_full_key[1] = q.memory_page;
+        for (int i = 0; i < 8; i++) out.previous_value[i] = q.value[i];
+        out.previous_is_ptr = q.is_ptr & 1;
+    } else {
+        for (int i = 0; i < 2; i++) {
+            out.lhs_accumulator[i] = d->acc0[i * 2 + 0];
+            out.rhs_accumulator[i] = d->acc0[i * 2 + 1];
+        }
+        out.num_nondeterministic_writes = d->nnw0;
+        for (int i = 0; i < 3; i++) out.previous_sorting_key[i] = io.hidden_fsm_input.previous_sorting_key[i];
+        for (int i = 0; i < 2; i++) out.previous_full_key[i] = io.hidden_fsm_input.previous_full_key[i];
+        for (int i = 0; i < 8; i++) out.previous_value[i] = io.hidden_fsm_input.previous_value[i];
+        out.previous_is_ptr = io.hidden_fsm_input.previous_is_ptr;
+    }
+    uint32_t checks = 0;
+    // :161-162
+    const zkc_queue_state12 *qs[2] = {&out.current_unsorted_queue_state, &out.current_sorted_queue_state};
+    for (int k = 0; k < 2; k++)
+        if (qs[k]->length == 0)
+            for (int i = 0; i < 12; i++)
+                if (qs[k]->head[i] != qs[k]->tail[i]) checks |= ZKC_RAM_CHK_QUEUE_CONSISTENCY;
+    const bool completed = out.current_unsorted_queue_state.length == 0;  // :164
+    if (completed) {
+        for (int i = 0; i < 2; i++)
+            if (out.lhs_accumulator[i] != out.rhs_accumulator[i]) checks |= ZKC_RAM_CHK_GRAND_PRODUCT;  // :166-168
+        if (out.num_nondeterministic_writes != io.observable_input.non_deterministic_bootloader_memory_snapshot_length)
+            checks |= ZKC_RAM_CHK_NONDET_COUNT;  // :170-175
+    }
+    checks |= d->failed_checks | d->prologue_checks;
+    uint64_t e_out[69], e_exp[69];
+    const int n_out = ram_encode_fsm(out, e_out);
+    zkc_status st;
+    st.code = ZKC_OK; st.cuda_error = 0; st.first_bad_row = -1; st.failed_checks = checks; st.reserved = 0;
+    if (d->first_bad != ~0ull) st.first_bad_row = (int64_t)(d->first_bad >> 16);
+    if (checks) st.code = ZKC_ERR_UNSATISFIED;
+    if (d->hint_bad) st.code = ZKC_ERR_QUEUE_WITNESS_INCONSISTENT;
+    if (d->opt.compare_expected) {  // hook_compare_witness, fsm_input_output/mod.rs:102-133
+        ram_encode_fsm(io.hidden_fsm_output, e_exp);
+        bool same = (io.completion_flag != 0) == completed;
+        for (int i = 0; i < n_out; i++) same &= e_out[i] == e_exp[i];
+        if (!same && st.code == ZKC_OK) st.code = ZKC_ERR_FSM_OUTPUT_MISMATCH;
+    }
+    io.hidden_fsm_output = out;
+    io.completion_flag = completed;
+    // ClosedFormInputCompactForm::from_full_form + commitment, fsm_input_output/mod.rs:178-255
+    uint64_t compact[18];
+    compact[0] = d->start; compact[1] = completed;
+    for (int i = 0; i < 4; i++) {
+        compact[2 + i] = d->commit_obs_in[i];
+        compact[6 + i] = 0;  // observable output is `()`: commitment of the empty encoding is 0, and masked unless completed
+        compact[10 + i] = d->start ? 0 : d->commit_fsm_in[i];
+    }
+    uint64_t c_out[4];
+    commit_encoding_dev(e_out, n_out, c_out);
+    for (int i = 0; i < 4; i++) compact[14 + i] = completed ? 0 : c_out[i];
+    commit_encoding_dev(compact, 18, d->commitment);
+    d->status = st;
+}
+
+
+// ---- constraint evaluation of a finished trace --------------------------------------------------
+// One thread per row re-evaluates every relation the loop body of partial_accumulate_inner places
+// (boolean / range, queue length bookkeeping, MemoryQuery::encode packing, UIntXAddGate borrow
+// chain, zero-check / equality flags, conditional enforcements, the FMA chain and the accumulator
+// update; with ZKC_GATES_ROUND_FUNCTION also the Poseidon2 link of both queue heads).  Streaming
+// read of all ZKC_RAM_NUM_COLS columns (+ the previous row of the carried ones, an L1/L2 hit).
+enum : uint32_t {
+    RAMV_BOOLEAN = ZKC_RAMV_BOOLEAN, RAMV_QUEUE_LEN = ZKC_RAMV_QUEUE_LEN, RAMV_ENCODING = ZKC_RAMV_ENCODING,
+    RAMV_ROUND_FUNCTION = ZKC_RAMV_ROUND_FUNCTION, RAMV_NONDET = ZKC_RAMV_NONDET, RAMV_COMPARISON = ZKC_RAMV_COMPARISON,
+    RAMV_FLAGS = ZKC_RAMV_FLAGS, RAMV_ENFORCE = ZKC_RAMV_ENFORCE, RAMV_GP_CHAIN = ZKC_RAMV_GP_CHAIN, RAMV_GP_ACC = ZKC_RAMV_GP_ACC,
+};
+
+template <bool ROUND_FUNCTION>
+__global__ void __launch_bounds__(256)
+ram_check_kernel(RamDev *d, const uint64_t *__restrict__ trace) {
+    __shared__ uint64_t ch[2][9];
+    if (threadIdx.x < 18) ch[threadIdx.x / 9][threadIdx.x % 9] = d->ch[threadIdx.x / 9][threadIdx.x % 9];
+    __syncthreads();
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const bool first = row == 0;
+    const bool start = d->start;
+#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
+#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
+    uint32_t bad = 0;
+    const uint64_t u_empty = TR(ZKC_RAM_UNSORTED_IS_EMPTY), s_empty = TR(ZKC_RAM_SORTED_IS_EMPTY), can_pop = TR(ZKC_RAM_CAN_POP);
+    if ((u_empty | s_empty | can_pop) > 1 || u_empty != s_empty || can_pop != 1 - u_empty) bad |= RAMV_BOOLEAN;
+    const uint32_t heap_page = d->opt.bootloader_heap_page ? d->opt.bootloader_heap_page : ZKC_BOOTLOADER_HEAP_PAGE_DEFAULT;
+    uint64_t enc[2][8];
+    uint64_t it[13];  // the sorted item survives the loop
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int base = k ? ZKC_RAM_SORTED_ITEM : ZKC_RAM_UNSORTED_ITEM;
+        const zkc_queue_state12 &q0 = k ? d->sq0 : d->uq0;
+        uint64_t range = 0;
+#pragma unroll
+        for (int i = 0; i < 13; i++) { it[i] = TR(base + i); range |= it[i]; }
+        if ((range >> 32) || (it[3] | it[4]) > 1) bad |= RAMV_BOOLEAN;
+        // queue length: is_empty <=> previous length == 0, length decrements on a pop
+        const uint64_t len_prev = first ? q0.length : TP(base + 33);
+        const uint64_t len = TR(base + 33);
+        if ((k ? s_empty : u_empty) != (len_prev == 0) || len + can_pop != len_prev) bad |= RAMV_QUEUE_LEN;
+        // MemoryQuery::encode, memory_query/mod.rs:103-221
+        zkc_memory_query q;
+        q.timestamp = (uint32_t)it[0]; q.memory_page = (uint32_t)it[1]; q.index = (uint32_t)it[2];
+        q.rw_flag = (uint32_t)it[3]; q.is_ptr = (uint32_t)it[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) q.value[i] = (uint32_t)it[5 + i];
+        uint64_t e[8];
+        ram_encode(q, e);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { enc[k][i] = TR(base + 13 + i); if (enc[k][i] != e[i]) bad |= RAMV_ENCODING; }
+        // head' = can_pop ? P(enc || head[8..12]) : head
+        uint64_t s[12], hcur[12];
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            const uint64_t hp = first ? q0.head[i] : TP(base + 21 + i);
+            hcur[i] = TR(base + 21 + i);
+            same &= hp == hcur[i];
+            s[i] = i < 8 ? enc[k][i] : hp;
+        }
+        if (!can_pop && !same) bad |= RAMV_ROUND_FUNCTION;
+        if (ROUND_FUNCTION && can_pop) {
+            poseidon2_permute(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (s[i] != hcur[i]) bad |= RAMV_ROUND_FUNCTION;
+        }
+    }
+    // :260-290
+    const uint64_t ts_is_zero = TR(ZKC_RAM_TS_IS_ZERO), page_is_heap = TR(ZKC_RAM_PAGE_IS_BOOTLOADER_HEAP);
+    const uint64_t is_nondet = TR(ZKC_RAM_IS_NONDET_WRITE), nnw = TR(ZKC_RAM_NUM_NONDET_WRITES);
+    const uint64_t nnw_prev = first ? d->nnw0 : TP(ZKC_RAM_NUM_NONDET_WRITES);
+    const uint64_t rw = it[3], is_ptr = it[4];
+    if (ts_is_zero != (it[0] == 0) || page_is_heap != (it[1] == heap_page) ||
+        is_nondet != (can_pop & ts_is_zero & page_is_heap & rw & (1 - is_ptr)) || nnw != nnw_prev + is_nondet)
+        bad |= RAMV_NONDET;
+    // :296-304 borrow chain: prev - cur - borrow_in = diff - 2^32 * borrow_out
+    uint64_t prev_sk[3], prev_fk[2], prev_val[8], prev_is_ptr;
+    if (first) {
+        const zkc_ram_fsm &f = d->io.hidden_fsm_input;
+#pragma unroll
+        for (int i = 0; i < 3; i++) prev_sk[i] = f.previous_sorting_key[i];
+        prev_fk[0] = f.previous_full_key[0]; prev_fk[1] = f.previous_full_key[1];
+#pragma unroll
+        for (int i = 0; i < 8; i++) prev_val[i] = f.previous_value[i];
+        prev_is_ptr = f.previous_is_ptr & 1;
+    } else {
+        prev_sk[0] = TP(ZKC_RAM_SORTED_ITEM + 0); prev_sk[1] = TP(ZKC_RAM_SORTED_ITEM + 2); prev_sk[2] = TP(ZKC_RAM_SORTED_ITEM + 1);
+        prev_fk[0] = prev_sk[1]; prev_fk[1] = prev_sk[2];
+#pragma unroll
+        for (int i = 0; i < 8; i++) prev_val[i] = TP(ZKC_RAM_SORTED_ITEM + 5 + i);
+        prev_is_ptr = TP(ZKC_RAM_SORTED_ITEM + 4);
+    }
+    const uint64_t sk[3] = {it[0], it[2], it[1]};
+    uint64_t borrow = 0, all_eq = 1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const uint64_t diff = TR(ZKC_RAM_CMP_DIFF + i), bo = TR(ZKC_RAM_CMP_BORROW + i), leq = TR(ZKC_RAM_CMP_LIMB_EQ + i);
+        if ((diff >> 32) || bo > 1 || leq != (diff == 0) || prev_sk[i] + (bo << 32) != diff + sk[i] + borrow) bad |= RAMV_COMPARISON;
+        borrow = bo;
+        all_eq &= leq;
+    }
+    const uint64_t keys_equal = TR(ZKC_RAM_KEYS_EQUAL), prev_smaller = TR(ZKC_RAM_PREV_KEY_SMALLER);
+    if (keys_equal != all_eq || prev_smaller != borrow) bad |= RAMV_COMPARISON;
+    // :318-357 flags
+    const uint64_t same_cell = TR(ZKC_RAM_SAME_CELL), value_equal = TR(ZKC_RAM_VALUE_EQUAL), value_is_zero = TR(ZKC_RAM_VALUE_IS_ZERO);
+    const uint64_t is_zero = TR(ZKC_RAM_IS_ZERO), ptr_eq = TR(ZKC_RAM_PTR_EQUALITY), vpe = TR(ZKC_RAM_VALUE_AND_PTR_EQUAL);
+    const uint64_t read_uninit = TR(ZKC_RAM_READ_UNINIT), check_eq = TR(ZKC_RAM_CHECK_EQUALITY);
+    bool veq = true, vz = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { veq &= it[5 + i] == prev_val[i]; vz &= it[5 + i] == 0; }
+    const uint64_t not_rw = 1 - rw, not_start = start ? 0 : 1;
+    uint64_t ru, ce;
+    if (!first) { ru = (1 - same_cell) & not_rw; ce = same_cell & not_rw; }
+    else { ru = (not_start & (1 - same_cell) & not_rw) | ((1 - not_start) & not_rw); ce = same_cell & not_rw & not_start; }
+    if (same_cell != (uint64_t)(it[2] == prev_fk[0] && it[1] == prev_fk[1]) || value_equal != (uint64_t)veq ||
+        value_is_zero != (uint64_t)vz || is_zero != (value_is_zero & (1 - is_ptr)) || ptr_eq != (uint64_t)(prev_is_ptr == is_ptr) ||
+        vpe != (value_equal & ptr_eq) || read_uninit != ru || check_eq != ce)
+        bad |= RAMV_FLAGS;
+    // conditional enforcements :312-316, :336, :340, :351, :356
+    const uint64_t enforce_order = first ? (can_pop & not_start) : can_pop;
+    if ((enforce_order & (1 - prev_smaller)) | (read_uninit & (1 - is_zero)) | (check_eq & (1 - vpe))) bad |= RAMV_ENFORCE;
+    // utils.rs:104-135
+#pragma unroll
+    for (int rep = 0; rep < 2; rep++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int g = rep * 2 + k;
+            uint64_t c = ch[rep][8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint64_t cell = TR(ZKC_RAM_GP_CHAIN + g * 8 + i);
+                if (cell != gl_fma(enc[k][i], ch[rep][i], c)) bad |= RAMV_GP_CHAIN;
+                c = cell;
+            }
+            const uint64_t acc_prev = first ? d->acc0[g] : TP(ZKC_RAM_GP_ACC + g);
+            const uint64_t nw = TR(ZKC_RAM_GP_NEW + g), acc = TR(ZKC_RAM_GP_ACC + g);
+            if (nw != gl_mul(acc_prev, c) || acc != (can_pop ? nw : acc_prev)) bad |= RAMV_GP_ACC;
+        }
+    }
+#undef TR
+#undef TP
+    if (bad) {
+        atomicAdd(&d->violations, 1ull);
+        atomicOr(&d->failed_checks, bad);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+    }
+}
+
+}  // namespace zkc
+
+using namespace zkc;
+
+extern "C" int zkc_ram_permutation_entry_point(zkc_ctx *ctx, zkc_ram_closed_form *io, const zkc_memory_query *unsorted,
+                                               const uint64_t *unsorted_prev_states, size_t n_unsorted,
+                                               const zkc_memory_query *sorted, const uint64_t *sorted_prev_states,
+                                               size_t n_sorted, size_t limit, const zkc_ram_options *options,
+                                               int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN],
+                                               zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !commitment || (n_unsorted && !unsorted) || (n_sorted && !sorted) || limit > 0xFFFFFFFFull) {
+        status->code = ZKC_ERR_INVALID_ARGUMENT;
+        return ZKC_ERR_INVALID_ARGUMENT;
+    }
+    const zkc_queue_state12 &uq = io->start_flag ? io->observable_input.unsorted_queue_initial_state
+                                                 : io->hidden_fsm_input.current_unsorted_queue_state;
+    const size_t need = limit < uq.length ? limit : uq.length;
+    if (n_unsorted < need || n_sorted < need) {  // the reference would panic popping an exhausted witness deque
+        status->code = ZKC_ERR_INVALID_ARGUMENT;
+        return ZKC_ERR_INVALID_ARGUMENT;
+    }
+    const bool in_dev = on_device & ZKC_INPUTS_ON_DEVICE, trace_dev = on_device & ZKC_TRACE_ON_DEVICE;
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    const size_t tiles = (limit + SCAN_THREADS - 1) / SCAN_THREADS;
+    const bool need_chain = need && (!unsorted_prev_states || !sorted_prev_states);
+    size_t bytes = zkc_carver::bytes(1, sizeof(RamDev)) + zkc_carver::bytes(1, sizeof(ScanGlobal)) +
+                   zkc_carver::bytes(tiles + 1, sizeof(TileState));
+    if (!in_dev) bytes += 2 * zkc_carver::bytes(need, sizeof(zkc_memory_query)) + 2 * zkc_carver::bytes(need * 12, 8);
+    else if (need_chain) bytes += 2 * zkc_carver::bytes(need * 12, 8);
+    if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ZKC_RAM_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    RamDev *h = (RamDev *)ctx->pinned(sizeof(RamDev));
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    RamDev *d = cv.take<RamDev>(1);
+    ScanGlobal *sg = cv.take<ScanGlobal>(1);
+    TileState *ts = cv.take<TileState>(tiles + 1);
+    cudaStream_t s = ctx->stream;
+
+    memset(h, 0, sizeof(RamDev));
+    h->io = *io;
+    if (options) h->opt = *options;
+    h->n_unsorted = n_unsorted; h->n_sorted = n_sorted; h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(RamDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(sg, 0, (char *)(ts + tiles + 1) - (char *)sg, s));
+
+    const zkc_memory_query *du = unsorted, *dsq = sorted;
+    const uint64_t *dup = unsorted_prev_states, *dsp = sorted_prev_states;
+    uint64_t *dtrace = trace;
+    if (!in_dev) {
+        zkc_memory_query *bu = cv.take<zkc_memory_query>(need), *bs = cv.take<zkc_memory_query>(need);
+        uint64_t *bup = cv.take<uint64_t>(need * 12), *bsp = cv.take<uint64_t>(need * 12);
+        if (need) {
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(bu, unsorted, need * sizeof(zkc_memory_query), cudaMemcpyHostToDevice, s));
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(bs, sorted, need * sizeof(zkc_memory_query), cudaMemcpyHostToDevice, s));
+            if (!need_chain) {
+                ZKC_CUDA(ctx, status, cudaMemcpyAsync(bup, unsorted_prev_states, need * 96, cudaMemcpyHostToDevice, s));
+                ZKC_CUDA(ctx, status, cudaMemcpyAsync(bsp, sorted_prev_states, need * 96, cudaMemcpyHostToDevice, s));
+            }
+        }
+        du = bu; dsq = bs; dup = bup; dsp = bsp;
+    } else if (need_chain) {
+        dup = cv.take<uint64_t>(need * 12); dsp = cv.take<uint64_t>(need * 12);
+    }
+    if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ZKC_RAM_NUM_COLS * limit);
+
+    ZKC_LAUNCH(ctx, "ram_prologue", ram_prologue_kernel, 1, 96, 0, d);
+    if (need_chain) ZKC_LAUNCH(ctx, "ram_chain", ram_chain_kernel, 1, 64, 0, d, du, dsq, (uint64_t *)dup, (uint64_t *)dsp, need);
+    if (tiles) ZKC_LAUNCH(ctx, "ram_rows", ram_rows_kernel, (unsigned)tiles, SCAN_THREADS, 0, d, du, dup, dsq, dsp, dtrace, sg, ts);
+    ZKC_LAUNCH(ctx, "ram_finalize", ram_finalize_kernel, 1, 32, 0, d);
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(RamDev), cudaMemcpyDeviceToHost, s));
+    if (!trace_dev && trace && limit)
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(trace, dtrace, (size_t)ZKC_RAM_NUM_COLS * limit * 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    io->hidden_fsm_output = h->io.hidden_fsm_output;
+    io->completion_flag = h->io.completion_flag;
+    memcpy(commitment, h->commitment, 32);
+    *status = h->status;
+    return status->code;
+}
+
+extern "C" int zkc_memory_queue_simulate(zkc_ctx *ctx, const zkc_memory_query *records, size_t n_per_queue,
+                                         size_t n_queues, uint64_t *prev_states, zkc_queue_state12 *final_states,
+                                         int on_device) {
+    if (!ctx || !final_states || (n_per_queue && n_queues && !records)) return ZKC_ERR_INVALID_ARGUMENT;
+    if (!n_queues) return ZKC_OK;
+    zkc_status *st = nullptr;
+    ZKC_CUDA(ctx, st, cudaSetDevice(ctx->device));
+    const size_t n = n_per_queue * n_queues;
+    const zkc_memory_query *dr = records;
+    uint64_t *dp = prev_states;
+    zkc_queue_state12 *df = final_states;
+    cudaStream_t s = ctx->stream;
+    if (!on_device) {
+        size_t bytes = zkc_carver::bytes(n, sizeof(zkc_memory_query)) + zkc_carver::bytes(n * 12, 8) +
+                       zkc_carver::bytes(n_queues, sizeof(zkc_queue_state12));
+        void *blk = ctx->scratch(bytes);
+        if (!blk) return ZKC_ERR_CUDA;
+        zkc_carver cv(blk);
+        zkc_memory_query *br = cv.take<zkc_memory_query>(n);
+        dp = prev_states ? cv.take<uint64_t>(n * 12) : nullptr;
+        df = cv.take<zkc_queue_state12>(n_queues);
+        if (n) ZKC_CUDA(ctx, st, cudaMemcpyAsync(br, records, n * sizeof(zkc_memory_query), cudaMemcpyHostToDevice, s));
+        dr = br;
+    }
+    ZKC_LAUNCH(ctx, "memory_queue_simulate", memory_queue_simulate_kernel, (unsigned)((n_queues + 31) / 32), 32, 0, dr,
+               n_per_queue, n_queues, dp, df);
+    ZKC_CUDA(ctx, st, cudaGetLastError());
+    if (!on_device) {
+        if (prev_states && n) ZKC_CUDA(ctx, st, cudaMemcpyAsync(prev_states, dp, n * 96, cudaMemcpyDeviceToHost, s));
+        ZKC_CUDA(ctx, st, cudaMemcpyAsync(final_states, df, n_queues * sizeof(zkc_queue_state12), cudaMemcpyDeviceToHost, s));
+        ZKC_CUDA(ctx, st, cudaStreamSynchronize(s));
+    }
+    return ZKC_OK;
+}
+
+extern "C" int zkc_ram_permutation_check_trace(zkc_ctx *ctx, const zkc_ram_closed_form *io, const uint64_t *trace,
+                                               size_t limit, const zkc_ram_options *options, uint32_t gates,
+                                               int on_device, uint64_t *violations, zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !violations || (limit && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(RamDev));
+    if (!on_device) bytes += zkc_carver::bytes((size_t)ZKC_RAM_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    RamDev *h = (RamDev *)ctx->pinned(sizeof(RamDev));
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    RamDev *d = cv.take<RamDev>(1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(RamDev));
+    h->io = *io;
+    if (options) h->opt = *options;
+    h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(RamDev), cudaMemcpyHostToDevice, s));
+    const uint64_t *dt = trace;
+    if (!on_device && limit) {
+        uint64_t *b = cv.take<uint64_t>((size_t)ZKC_RAM_NUM_COLS * limit);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, (size_t)ZKC_RAM_NUM_COLS * limit * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    ZKC_LAUNCH(ctx, "ram_prologue", ram_prologue_kernel, 1, 96, 0, d);
+    if (limit) {
+        const unsigned grid = (unsigned)((limit + 255) / 256);
+        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION))
+            ZKC_LAUNCH(ctx, "ram_check_rf", ram_check_kernel<true>, grid, 256, 0, d, dt);
+        else
+            ZKC_LAUNCH(ctx, "ram_check", ram_check_kernel<false>, grid, 256, 0, d, dt);
+    }
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(RamDev), cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = h->violations;
+    status->failed_checks = h->failed_checks;
+    if (h->violations) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 16);
+    }
+    return status->code;
+}

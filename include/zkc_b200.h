@@ -1,0 +1,280 @@
+/* zkc_b200 -- C ABI of the B200-native witness-generation / constraint-evaluation engine for the
+ * zkSync Era zkEVM circuits' data-parallel hot path.
+ *
+ * The reference (matter-labs/era-zkevm_circuits, /root/reference) has no FFI of its own: its only
+ * seam is the generic `*_entry_point(cs, witness, round_function, limit) -> [Num<F>; 4]` function
+ * per circuit.  Each `zkc_*_entry_point` below replaces the body of the reference function cited
+ * next to it: the Rust shim marshals the `*CircuitInstanceWitness` into the
+ * `#[repr(C)]` records declared here, makes ONE call, and bulk-assigns the returned witness
+ * columns to its boojum variables.  Plain pointers and sizes only; no callbacks into the host
+ * during a call; failures are status codes (the reference panics / becomes unsatisfiable).
+ *
+ * Conventions
+ *  - field elements are canonical Goldilocks values (< p = 2^64 - 2^32 + 1) in uint64_t;
+ *  - "trace" outputs are COLUMN-MAJOR: cell (col, row) lives at trace[col * limit + row], one row per
+ *    iteration of the reference's `for _cycle in 0..limit` loop, one column per value the reference
+ *    names in that loop body, in the order the loop body allocates them;
+ *  - `on_device != 0` means every bulk pointer argument (records, prev states, trace) is a device
+ *    pointer already resident in HBM; otherwise they are host pointers and the call does the
+ *    H2D/D2H copies itself (pinned host memory makes them asynchronous).  The circuit entry points
+ *    take it as a bit mask: ZKC_INPUTS_ON_DEVICE | ZKC_TRACE_ON_DEVICE (e.g. host inputs, witness
+ *    left in HBM for a GPU prover = ZKC_TRACE_ON_DEVICE);
+ *  - small structs (closed-form inputs/outputs, status) are always host memory.
+ */
+#ifndef ZKC_B200_H
+#define ZKC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKC_GL_P 0xFFFFFFFF00000001ULL
+#define ZKC_INPUTS_ON_DEVICE 1
+#define ZKC_TRACE_ON_DEVICE 2
+#define ZKC_ALL_ON_DEVICE 3
+#define ZKC_NUM_REPETITIONS 2 /* DEFAULT_NUM_PERMUTATION_ARGUMENT_REPETITIONS, src/lib.rs:39 */
+#define ZKC_COMMITMENT_LEN 4  /* INPUT_OUTPUT_COMMITMENT_LENGTH, src/fsm_input_output/circuit_inputs/mod.rs:4 */
+#define ZKC_FULL_STATE 12     /* FULL_SPONGE_QUEUE_STATE_WIDTH, src/base_structures/vm_state/mod.rs:27-30 */
+#define ZKC_QUEUE_STATE 4     /* QUEUE_STATE_WIDTH */
+#define ZKC_BOOTLOADER_HEAP_PAGE_DEFAULT 10u /* zkevm_opcode_defs::BOOTLOADER_HEAP_PAGE (un-vendored; from memory) */
+
+/* ---- status ------------------------------------------------------------------------------ */
+enum zkc_code {
+    ZKC_OK = 0,
+    ZKC_ERR_INVALID_ARGUMENT = 1,
+    ZKC_ERR_CUDA = 2,
+    ZKC_ERR_NO_DEVICE = 3,
+    /* the reference would produce an unsatisfiable constraint system (an `enforce_*` fails) */
+    ZKC_ERR_UNSATISFIED = 4,
+    /* the reference would panic in hook_compare_witness (fsm_input_output/mod.rs:102-133) */
+    ZKC_ERR_FSM_OUTPUT_MISMATCH = 5,
+    /* raw queue witness is not a hash chain (previous-state column inconsistent) */
+    ZKC_ERR_QUEUE_WITNESS_INCONSISTENT = 6,
+};
+
+/* which enforcement failed first (row-ordered); bit set per failing check, circuit-specific */
+typedef struct zkc_status {
+    int32_t code;           /* enum zkc_code */
+    int32_t cuda_error;     /* cudaError_t when code == ZKC_ERR_CUDA */
+    int64_t first_bad_row;  /* loop iteration of the first failing enforcement, -1 if none/global */
+    uint32_t failed_checks; /* bit mask, see ZKC_*_CHK_* */
+    uint32_t reserved;
+} zkc_status;
+
+typedef struct zkc_ctx zkc_ctx;
+
+/* create an engine bound to one GPU (one process per GPU); uploads round constants */
+int zkc_create(int device, zkc_ctx **out);
+void zkc_destroy(zkc_ctx *ctx);
+/* all work of later calls is enqueued on `cuda_stream` (a cudaStream_t; NULL = legacy default) */
+int zkc_set_stream(zkc_ctx *ctx, void *cuda_stream);
+const char *zkc_version(void);
+/* kernels launched by this context since creation (the bench's `gpu_launches` claim) */
+uint64_t zkc_launch_count(const zkc_ctx *ctx);
+/* streaming multiprocessors of the bound device (grid sizing of callers that batch instances) */
+int zkc_sm_count(const zkc_ctx *ctx);
+/* per-kernel device timing (CUDA events on the context's stream). enable!=0 starts recording. */
+int zkc_profile_enable(zkc_ctx *ctx, int enable);
+/* sums elapsed ms / launches recorded for kernel `name` since the last reset; resolves events */
+int zkc_profile_query(zkc_ctx *ctx, const char *name, double *ms_total, uint64_t *launches);
+int zkc_profile_reset(zkc_ctx *ctx);
+/* pinned host allocations for asynchronous copies (cudaHostAlloc / cudaFreeHost) */
+void *zkc_host_alloc(size_t bytes);
+void zkc_host_free(void *p);
+
+/* ---- primitives (device buffers or host buffers per on_device) --------------------------------- */
+/* Poseidon2 permutation of n independent 12-element states, AoS [n][12].
+ * Replaces R::compute_round_function (boojum, called at src/main_vm/utils.rs:212, cycle.rs:952). */
+int zkc_poseidon2_permute(zkc_ctx *ctx, const uint64_t *states_in, uint64_t *states_out, size_t n,
+                          int on_device);
+/* commit_encoding, src/fsm_input_output/mod.rs:281-326, for `n_items` inputs of `len` elements
+ * each (AoS [n_items][len]); out AoS [n_items][4]. */
+int zkc_commit_encoding(zkc_ctx *ctx, const uint64_t *inputs, size_t len, size_t n_items,
+                        uint64_t *out, int on_device);
+
+/* accumulate_grand_products<ENC, ENC+1, 2>, src/utils.rs:81-137, over `rows` loop iterations.
+ *   lhs_enc/rhs_enc : column-major [enc_len][rows]
+ *   should_acc      : [rows] of 0/1 (NULL = all ones)
+ *   challenges      : host, [2][enc_len + 1] as returned by produce_fs_challenges
+ *   acc_in          : host, lhs[2] then rhs[2] (initial accumulators)
+ *   acc_out         : column-major [4][rows] = lhs rep0, lhs rep1, rhs rep0, rhs rep1 after each row
+ *   chain_out       : NULL, or column-major [4 * enc_len][rows]: the Num::fma partial sums
+ *                     (utils.rs:112-128), column (rep*2 + side) * enc_len + i, side 0 = lhs
+ *   acc_final       : host, the 4 accumulators after the last row */
+int zkc_accumulate_grand_products(zkc_ctx *ctx, const uint64_t *lhs_enc, const uint64_t *rhs_enc,
+                                  const uint8_t *should_acc, size_t enc_len, size_t rows,
+                                  const uint64_t *challenges, const uint64_t acc_in[4],
+                                  uint64_t *acc_out, uint64_t *chain_out, uint64_t acc_final[4],
+                                  int on_device);
+
+/* ---- records shared by circuits --------------------------------------------------------------- */
+/* MemoryQuery witness, src/base_structures/memory_query/mod.rs:30-37 (64-byte record) */
+typedef struct zkc_memory_query {
+    uint32_t timestamp;
+    uint32_t memory_page;
+    uint32_t index;
+    uint32_t rw_flag; /* 0/1 */
+    uint32_t is_ptr;  /* 0/1 */
+    uint32_t value[8]; /* little-endian u32 limbs of the U256 */
+    uint32_t _pad[3];
+} zkc_memory_query;
+
+/* QueueState<F, 12>: head, tail, length (src/ram_permutation/input.rs:28-29) */
+typedef struct zkc_queue_state12 {
+    uint64_t head[ZKC_FULL_STATE];
+    uint64_t tail[ZKC_FULL_STATE];
+    uint32_t length;
+    uint32_t _pad;
+} zkc_queue_state12;
+
+/* QueueState<F, 4> */
+typedef struct zkc_queue_state4 {
+    uint64_t head[ZKC_QUEUE_STATE];
+    uint64_t tail[ZKC_QUEUE_STATE];
+    uint32_t length;
+    uint32_t _pad;
+} zkc_queue_state4;
+
+/* FullStateCircuitQueue::push of `n_queues` independent, initially empty memory queues of
+ * `n_per_queue` records each (records laid out queue after queue): the way the reference builds
+ * its inputs (src/ram_permutation/mod.rs:506-515; the push rule is restated in-repo at
+ * src/main_vm/utils.rs:194-212).  prev_states (may be NULL): AoS [n_queues * n_per_queue][12], the
+ * tail before each push = the second element of each FullStateCircuitQueueRawWitness entry.
+ * final_states[n_queues]: head = 0, tail, length. */
+int zkc_memory_queue_simulate(zkc_ctx *ctx, const zkc_memory_query *records, size_t n_per_queue,
+                              size_t n_queues, uint64_t *prev_states, zkc_queue_state12 *final_states,
+                              int on_device);
+
+/* ---- ram_permutation (src/ram_permutation/mod.rs) ------------------------------------------- */
+/* RamPermutationInputData, input.rs:27-31 */
+typedef struct zkc_ram_input_data {
+    zkc_queue_state12 unsorted_queue_initial_state;
+    zkc_queue_state12 sorted_queue_initial_state;
+    uint32_t non_deterministic_bootloader_memory_snapshot_length;
+    uint32_t _pad;
+} zkc_ram_input_data;
+
+/* RamPermutationFSMInputOutput, input.rs:52-62 */
+typedef struct zkc_ram_fsm {
+    uint64_t lhs_accumulator[ZKC_NUM_REPETITIONS];
+    uint64_t rhs_accumulator[ZKC_NUM_REPETITIONS];
+    zkc_queue_state12 current_unsorted_queue_state;
+    zkc_queue_state12 current_sorted_queue_state;
+    uint32_t previous_sorting_key[3]; /* [timestamp, index, page] */
+    uint32_t previous_full_key[2];    /* [index, page] */
+    uint32_t previous_value[8];
+    uint32_t previous_is_ptr;
+    uint32_t num_nondeterministic_writes;
+    uint32_t _pad;
+} zkc_ram_fsm;
+
+/* ClosedFormInputWitness<F, RamPermutationFSMInputOutput, RamPermutationInputData, ()>,
+ * src/fsm_input_output/mod.rs:32-48 */
+typedef struct zkc_ram_closed_form {
+    uint32_t start_flag;
+    uint32_t completion_flag; /* output (ignored on input, alloc_ignoring_outputs) */
+    zkc_ram_input_data observable_input;
+    zkc_ram_fsm hidden_fsm_input;
+    zkc_ram_fsm hidden_fsm_output; /* output; on input: expected value if compare_expected != 0 */
+} zkc_ram_closed_form;
+
+/* trace columns of one loop iteration, in the order partial_accumulate_inner allocates them
+ * (src/ram_permutation/mod.rs:246-381) */
+enum zkc_ram_col {
+    ZKC_RAM_UNSORTED_IS_EMPTY = 0, /* :247 */
+    ZKC_RAM_SORTED_IS_EMPTY = 1,   /* :248 */
+    ZKC_RAM_CAN_POP = 2,           /* :253 */
+    ZKC_RAM_UNSORTED_ITEM = 3,     /* 13: ts, page, index, rw, is_ptr, value[8] (flatten order, memory_query/mod.rs:52-68) */
+    ZKC_RAM_UNSORTED_ENC = 16,     /* 8: MemoryQuery::encode */
+    ZKC_RAM_UNSORTED_HEAD = 24,    /* 12: queue head after the pop */
+    ZKC_RAM_UNSORTED_LEN = 36,     /* queue length after the pop */
+    ZKC_RAM_SORTED_ITEM = 37,      /* 13 */
+    ZKC_RAM_SORTED_ENC = 50,       /* 8 */
+    ZKC_RAM_SORTED_HEAD = 58,      /* 12 */
+    ZKC_RAM_SORTED_LEN = 70,
+    ZKC_RAM_TS_IS_ZERO = 71,              /* :261 */
+    ZKC_RAM_PAGE_IS_BOOTLOADER_HEAP = 72, /* :263 */
+    ZKC_RAM_IS_NONDET_WRITE = 73,         /* :270 */
+    ZKC_RAM_NUM_NONDET_WRITES = 74,       /* :284, after the select */
+    ZKC_RAM_CMP_DIFF = 75,                /* 3: limb differences of unpacked_long_comparison */
+    ZKC_RAM_CMP_BORROW = 78,              /* 3: borrow out of each limb */
+    ZKC_RAM_CMP_LIMB_EQ = 81,             /* 3: diff.is_zero() */
+    ZKC_RAM_KEYS_EQUAL = 84,              /* :304 */
+    ZKC_RAM_PREV_KEY_SMALLER = 85,        /* :304 */
+    ZKC_RAM_SAME_CELL = 86,               /* :318 */
+    ZKC_RAM_VALUE_EQUAL = 87,             /* :319 */
+    ZKC_RAM_VALUE_IS_ZERO = 88,           /* :326 */
+    ZKC_RAM_IS_ZERO = 89,                 /* :329 */
+    ZKC_RAM_PTR_EQUALITY = 90,            /* :330 */
+    ZKC_RAM_VALUE_AND_PTR_EQUAL = 91,     /* :331 */
+    ZKC_RAM_READ_UNINIT = 92,             /* :335 / :349 (the flag is_zero is enforced under) */
+    ZKC_RAM_CHECK_EQUALITY = 93,          /* :339 / :354 */
+    ZKC_RAM_GP_CHAIN = 94,  /* 32: fma partials, column (rep*2 + side)*8 + i, side 0 = lhs(unsorted); utils.rs:112-128 */
+    ZKC_RAM_GP_NEW = 126,   /* 4: lhs.mul / rhs.mul results, rep*2 + side; utils.rs:131-132 */
+    ZKC_RAM_GP_ACC = 130,   /* 4: accumulators after the select, rep*2 + side; utils.rs:134-135 */
+    ZKC_RAM_NUM_COLS = 134
+};
+
+/* failed_checks bits for ram_permutation */
+#define ZKC_RAM_CHK_LENGTHS_EQUAL (1u << 0)      /* :237 */
+#define ZKC_RAM_CHK_EMPTY_SYNC (1u << 1)         /* :252 */
+#define ZKC_RAM_CHK_ASCENDING (1u << 2)          /* :312 / :315 */
+#define ZKC_RAM_CHK_UNINIT_READ_ZERO (1u << 3)   /* :336 / :351 */
+#define ZKC_RAM_CHK_READ_CONSISTENT (1u << 4)    /* :340 / :356 */
+#define ZKC_RAM_CHK_QUEUE_CONSISTENCY (1u << 5)  /* :161-162 */
+#define ZKC_RAM_CHK_GRAND_PRODUCT (1u << 6)      /* :166-168 */
+#define ZKC_RAM_CHK_NONDET_COUNT (1u << 7)       /* :170-175 */
+#define ZKC_RAM_CHK_TRIVIAL_HEAD (1u << 8)       /* :58-60, :85-87 */
+#define ZKC_RAM_CHK_RANGE (1u << 9)              /* allocation range checks (booleans) */
+#define ZKC_RAM_CHK_QUEUE_HINT (1u << 10)        /* *_prev_states is not the hash chain of the records */
+
+typedef struct zkc_ram_options {
+    uint32_t bootloader_heap_page; /* 0 = ZKC_BOOTLOADER_HEAP_PAGE_DEFAULT */
+    uint32_t compare_expected;     /* !=0: hook_compare_witness against io->hidden_fsm_output */
+    uint32_t _pad[2];
+} zkc_ram_options;
+
+/* ram_permutation_entry_point, src/ram_permutation/mod.rs:31-210.
+ *   unsorted/sorted         : queue witnesses in pop order (FullStateCircuitQueueRawWitness elements,
+ *                             input.rs:105-116), n_* records
+ *   *_prev_states           : AoS [n][12], the previous-tail element of each raw witness entry; NULL =
+ *                             not supplied (the head chain is then recomputed sequentially on device)
+ *   trace                   : column-major [ZKC_RAM_NUM_COLS][limit] or NULL
+ *   io                      : in: start_flag, observable_input, hidden_fsm_input; out: completion_flag,
+ *                             hidden_fsm_output
+ *   commitment              : the 4 public inputs */
+int zkc_ram_permutation_entry_point(zkc_ctx *ctx, zkc_ram_closed_form *io,
+                                    const zkc_memory_query *unsorted, const uint64_t *unsorted_prev_states,
+                                    size_t n_unsorted, const zkc_memory_query *sorted,
+                                    const uint64_t *sorted_prev_states, size_t n_sorted, size_t limit,
+                                    const zkc_ram_options *options, int on_device, uint64_t *trace,
+                                    uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
+
+/* constraint evaluation of a finished ram_permutation trace: re-evaluates every relation of the
+ * loop body on every row (what the reference's test asserts through `check_if_satisfied`,
+ * src/ram_permutation/mod.rs:556) and returns the number of violating rows; status->first_bad_row /
+ * failed_checks (ZKC_RAMV_* bits) describe the first one.  `gates` selects the relation families:
+ * ZKC_GATES_GENERAL = the streaming (HBM-bound) relations, ZKC_GATES_ROUND_FUNCTION adds the
+ * Poseidon2 link of the two queue heads (integer-ALU bound); 0 = all. */
+#define ZKC_GATES_GENERAL 1u
+#define ZKC_GATES_ROUND_FUNCTION 2u
+#define ZKC_RAMV_BOOLEAN (1u << 0)
+#define ZKC_RAMV_QUEUE_LEN (1u << 1)
+#define ZKC_RAMV_ENCODING (1u << 2)
+#define ZKC_RAMV_ROUND_FUNCTION (1u << 3)
+#define ZKC_RAMV_NONDET (1u << 4)
+#define ZKC_RAMV_COMPARISON (1u << 5)
+#define ZKC_RAMV_FLAGS (1u << 6)
+#define ZKC_RAMV_ENFORCE (1u << 7)
+#define ZKC_RAMV_GP_CHAIN (1u << 8)
+#define ZKC_RAMV_GP_ACC (1u << 9)
+int zkc_ram_permutation_check_trace(zkc_ctx *ctx, const zkc_ram_closed_form *io, const uint64_t *trace,
+                                    size_t limit, const zkc_ram_options *options, uint32_t gates, int on_device,
+                                    uint64_t *violations, zkc_status *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

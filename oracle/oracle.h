@@ -1,0 +1,64 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C, sequential, one loop iteration at a time exactly like the reference)
+ * of the hot path of matter-labs/era-zkevm_circuits.  It is the parity checker for the CUDA engine
+ * and the `cpu_baseline` of bench.py.  The product (era_zkevm_circuits_b200/) never links, imports
+ * or executes anything in this directory.  It shares only the record/column declarations of the
+ * public ABI header (include/zkc_b200.h) so that both sides speak about the same cells.
+ *
+ * Pinning status (details in each file and DESIGN.md):
+ *   Goldilocks field         -- pinned by definition (Python big-int cross-check)
+ *   keccak-f / Keccak-256    -- pinned (reference tests compare against sha3::Keccak256)
+ *   SHA-256 compression      -- pinned against hashlib
+ *   Poseidon2                -- PARITY UNPINNED (un-vendored boojum; no reference KAT)
+ *   sorter / RAM loop logic  -- pinned to "the reference's own test vectors satisfy every
+ *                               enforcement"; accumulator values are unpinned (depend on Poseidon2)
+ */
+#ifndef ORC_ORACLE_H
+#define ORC_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#include "../include/zkc_b200.h"
+#include "gl.h"
+
+#define ORC_P2_NUM_CONSTANTS 360
+
+void orc_poseidon2_constants(uint64_t out[ORC_P2_NUM_CONSTANTS]);
+void orc_poseidon2_permutation(uint64_t s[12]);
+void orc_sponge_init(uint64_t s[12], uint64_t length);
+void orc_sponge_absorb8(uint64_t s[12], const uint64_t chunk[8]);
+void orc_commit_encoding(const uint64_t *input, size_t n, uint64_t out[4]);
+void orc_closed_form_commitment(int start_flag, int completion_flag, const uint64_t *obs_in, size_t n_obs_in,
+                                const uint64_t *obs_out, size_t n_obs_out, const uint64_t *fsm_in,
+                                size_t n_fsm_in, const uint64_t *fsm_out, size_t n_fsm_out, uint64_t out[4]);
+void orc_produce_fs_challenges(const uint64_t *unsorted_tail, uint32_t unsorted_len, const uint64_t *sorted_tail,
+                               uint32_t sorted_len, int tw, int num_challenges, uint64_t *result);
+
+/* field helpers exported for the Python tests */
+uint64_t orc_gl_mul(uint64_t a, uint64_t b);
+uint64_t orc_gl_add(uint64_t a, uint64_t b);
+uint64_t orc_gl_sub(uint64_t a, uint64_t b);
+uint64_t orc_gl_inv(uint64_t a);
+
+/* encodings */
+void orc_memory_query_encode(const zkc_memory_query *q, uint64_t out[8]);
+
+/* utils.rs:81-137 on column-major inputs; same contract as zkc_accumulate_grand_products */
+void orc_accumulate_grand_products(const uint64_t *lhs_enc, const uint64_t *rhs_enc, const uint8_t *should_acc,
+                                   size_t enc_len, size_t rows, const uint64_t *challenges,
+                                   const uint64_t acc_in[4], uint64_t *acc_out, uint64_t *chain_out,
+                                   uint64_t acc_final[4]);
+
+/* pushes `n` queries into an empty full-state queue (FullStateCircuitQueue::push), recording the
+ * tail BEFORE each push into prev_states[n][12] (the raw witness' second tuple element) and the
+ * final state. Used to build inputs exactly like the reference test does (:506-515). */
+void orc_memory_queue_simulate(const zkc_memory_query *q, size_t n, uint64_t *prev_states, zkc_queue_state12 *final_state);
+
+size_t orc_ram_encode_input_data(const zkc_ram_input_data *d, uint64_t *dst);
+size_t orc_ram_encode_fsm(const zkc_ram_fsm *f, uint64_t *dst);
+int orc_ram_permutation_entry_point(zkc_ram_closed_form *io, const zkc_memory_query *unsorted, size_t n_unsorted,
+                                    const zkc_memory_query *sorted, size_t n_sorted, size_t limit,
+                                    const zkc_ram_options *options, uint64_t *trace, uint64_t commitment[4],
+                                    zkc_status *status);
+
+#endif

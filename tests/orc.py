@@ -1,0 +1,104 @@
+"""ctypes loader of the CPU oracle (oracle/liborc.so) -- TEST INFRASTRUCTURE.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from era_zkevm_circuits_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+_vp = C.c_void_p
+
+
+def load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(ROOT, "oracle", "liborc.so")
+    srcs = [os.path.join(ROOT, "oracle", f) for f in os.listdir(os.path.join(ROOT, "oracle")) if f.endswith((".c", ".h"))]
+    if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = C.CDLL(path)
+    for name in ("orc_gl_mul", "orc_gl_add", "orc_gl_sub"):
+        getattr(lib, name).restype = C.c_uint64
+        getattr(lib, name).argtypes = [C.c_uint64, C.c_uint64]
+    lib.orc_gl_inv.restype = C.c_uint64
+    lib.orc_gl_inv.argtypes = [C.c_uint64]
+    lib.orc_poseidon2_constants.argtypes = [_vp]
+    lib.orc_poseidon2_permutation.argtypes = [_vp]
+    lib.orc_commit_encoding.argtypes = [_vp, C.c_size_t, _vp]
+    lib.orc_produce_fs_challenges.argtypes = [_vp, C.c_uint32, _vp, C.c_uint32, C.c_int, C.c_int, _vp]
+    lib.orc_memory_query_encode.argtypes = [_vp, _vp]
+    lib.orc_accumulate_grand_products.argtypes = [_vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp]
+    lib.orc_memory_queue_simulate.argtypes = [_vp, C.c_size_t, _vp, C.POINTER(abi.QueueState12)]
+    lib.orc_ram_permutation_entry_point.restype = C.c_int
+    lib.orc_ram_permutation_entry_point.argtypes = [C.POINTER(abi.RamClosedForm), _vp, C.c_size_t, _vp, C.c_size_t,
+                                                    C.c_size_t, C.POINTER(abi.RamOptions), _vp, _vp, C.POINTER(abi.Status)]
+    _LIB = lib
+    return lib
+
+
+def p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def poseidon2(lib, states):
+    out = np.array(states, dtype=np.uint64, copy=True).reshape(-1, 12)
+    for i in range(out.shape[0]):
+        lib.orc_poseidon2_permutation(C.c_void_p(out[i].ctypes.data))
+    return out
+
+
+def commit_encoding(lib, row):
+    row = np.ascontiguousarray(row, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    lib.orc_commit_encoding(p(row), len(row), p(out))
+    return out
+
+
+def memory_queue_simulate(lib, records):
+    records = np.ascontiguousarray(records)
+    prev = np.zeros((len(records), 12), dtype=np.uint64)
+    fin = abi.QueueState12()
+    lib.orc_memory_queue_simulate(p(records), len(records), p(prev), C.byref(fin))
+    return prev, fin
+
+
+def accumulate_grand_products(lib, lhs, rhs, ch, acc_in, flags=None, want_chain=False):
+    enc_len, rows = lhs.shape
+    lhs = np.ascontiguousarray(lhs, dtype=np.uint64); rhs = np.ascontiguousarray(rhs, dtype=np.uint64)
+    ch = np.ascontiguousarray(ch, dtype=np.uint64); acc_in = np.ascontiguousarray(acc_in, dtype=np.uint64)
+    acc = np.zeros((4, rows), dtype=np.uint64)
+    chain = np.zeros((4 * enc_len, rows), dtype=np.uint64) if want_chain else None
+    fin = np.zeros(4, dtype=np.uint64)
+    if flags is not None:
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    lib.orc_accumulate_grand_products(p(lhs), p(rhs), p(flags), enc_len, rows, p(ch), p(acc_in), p(acc), p(chain), p(fin))
+    return acc, chain, fin
+
+
+def ram_closed_form(unsorted_state, sorted_state, start=True, nondet_len=0, fsm_in=None):
+    io = abi.RamClosedForm()
+    io.start_flag = int(start)
+    io.observable_input.unsorted_queue_initial_state = unsorted_state
+    io.observable_input.sorted_queue_initial_state = sorted_state
+    io.observable_input.non_deterministic_bootloader_memory_snapshot_length = nondet_len
+    if fsm_in is not None:
+        io.hidden_fsm_input = fsm_in
+    return io
+
+
+def ram_entry_point(lib, io, unsorted, sorted_, limit, want_trace=True, compare_expected=False, heap_page=0):
+    """returns (rc, io_out, trace, commitment, status)"""
+    io2 = abi.RamClosedForm.from_buffer_copy(bytes(io))
+    unsorted = np.ascontiguousarray(unsorted); sorted_ = np.ascontiguousarray(sorted_)
+    trace = np.zeros((abi.RAM_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
+    com = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    opts = abi.RamOptions(heap_page, int(compare_expected))
+    rc = lib.orc_ram_permutation_entry_point(C.byref(io2), p(unsorted), len(unsorted), p(sorted_), len(sorted_), limit,
+                                             C.byref(opts), p(trace), p(com), C.byref(st))
+    return rc, io2, trace, com, st
