@@ -93,6 +93,7 @@ SIGNATURES = {
     "zkc_host_free": (None, [_vp]),
     "zkc_poseidon2_permute": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int]),
     "zkc_commit_encoding": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_int]),
+    "zkc_field_ops": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "zkc_accumulate_grand_products": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "zkc_memory_queue_simulate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, C.c_int]),
     "zkc_ram_permutation_entry_point": (C.c_int, [_vp, C.POINTER(RamClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,

@@ -136,6 +136,42 @@ extern "C" int zkc_commit_encoding(zkc_ctx *ctx, const uint64_t *inputs, size_t 
     return ZKC_OK;
 }
 
+// ---- element-wise field operations (diagnostic entry: pins the PTX carry chains of gl.cuh) ---------
+namespace zkc {
+__global__ void field_ops_kernel(const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n, uint64_t *mul,
+                                 uint64_t *add, uint64_t *sub, uint64_t *fma) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mul[i] = gl_mul(a[i], b[i]);
+    add[i] = gl_add(a[i], b[i]);
+    sub[i] = gl_sub(a[i], b[i]);
+    fma[i] = gl_fma(a[i], b[i], c[i]);
+}
+}  // namespace zkc
+
+extern "C" int zkc_field_ops(zkc_ctx *ctx, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n,
+                             uint64_t *out_mul, uint64_t *out_add, uint64_t *out_sub, uint64_t *out_fma) {
+    if (!ctx || !a || !b || !c || !out_mul || !out_add || !out_sub || !out_fma) return ZKC_ERR_INVALID_ARGUMENT;
+    if (!n) return ZKC_OK;
+    zkc_status *st = nullptr;
+    ZKC_CUDA(ctx, st, cudaSetDevice(ctx->device));
+    uint64_t *buf = (uint64_t *)ctx->scratch(7 * n * 8);
+    if (!buf) return ZKC_ERR_CUDA;
+    cudaStream_t s = ctx->stream;
+    ZKC_CUDA(ctx, st, cudaMemcpyAsync(buf, a, n * 8, cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, st, cudaMemcpyAsync(buf + n, b, n * 8, cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, st, cudaMemcpyAsync(buf + 2 * n, c, n * 8, cudaMemcpyHostToDevice, s));
+    ZKC_LAUNCH(ctx, "field_ops", field_ops_kernel, (unsigned)((n + 255) / 256), 256, 0, buf, buf + n, buf + 2 * n, n,
+               buf + 3 * n, buf + 4 * n, buf + 5 * n, buf + 6 * n);
+    ZKC_CUDA(ctx, st, cudaGetLastError());
+    ZKC_CUDA(ctx, st, cudaMemcpyAsync(out_mul, buf + 3 * n, n * 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, st, cudaMemcpyAsync(out_add, buf + 4 * n, n * 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, st, cudaMemcpyAsync(out_sub, buf + 5 * n, n * 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, st, cudaMemcpyAsync(out_fma, buf + 6 * n, n * 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, st, cudaStreamSynchronize(s));
+    return ZKC_OK;
+}
+
 // ---- stand-alone grand product ---------------------------------------------------------------
 namespace zkc {
 struct GpParams {

@@ -1,0 +1,624 @@
+// Events / L2->L1 message sorter on sm_100a: sort_and_deduplicate_events_entry_point
+// (/root/reference/src/log_sorter/mod.rs:34-232) and its loop
+// repack_and_prove_events_rollbacks_inner (:234-441), one thread per loop iteration.
+// Sequential state is recovered row-parallel exactly as in ram_permutation.cu; the additional
+// piece is the RESULT queue, whose tail is a hash chain over the executed pushes: rounds 0 and 1
+// of every push depend on the pushed item only and are computed per row, round 2 consumes the
+// previous tail and is either verified against host-supplied tails (`result_tails`) or rebuilt
+// by a sequential chain kernel (1 permutation per push).
+#include "ctx.cuh"
+#include "log_query.cuh"
+#include "scan.cuh"
+
+namespace zkc {
+
+struct EvDev {
+    zkc_events_closed_form io;
+    zkc_sorter_options opt;
+    uint64_t n_unsorted, n_sorted, n_result_tails, limit;
+    // prologue
+    uint64_t ch[2][21];
+    uint64_t acc0[4];  // rep*2 + side
+    uint32_t start, prev_trivial0, previous_key0, prologue_checks;
+    zkc_queue_state4 uq0, sq0, rq0;
+    zkc_log_query previous_item0;
+    uint64_t commit_obs_in[4], commit_fsm_in[4];
+    // rows
+    uint64_t acc_final[4];
+    uint32_t pushes_in_loop, pad0;
+    uint64_t head_final[2][4];
+    // status
+    unsigned long long first_bad;
+    uint32_t failed_checks, hint_bad;
+    // finalize
+    uint64_t commitment[4];
+    zkc_status status;
+};
+
+__device__ int ev_encode_fsm(const zkc_events_fsm &f, uint64_t *dst) {
+    int n = 0;
+    dst[n++] = f.lhs_accumulator[0]; dst[n++] = f.lhs_accumulator[1];
+    dst[n++] = f.rhs_accumulator[0]; dst[n++] = f.rhs_accumulator[1];
+    n += put_queue_state4(dst + n, f.initial_unsorted_queue_state);
+    n += put_queue_state4(dst + n, f.intermediate_sorted_queue_state);
+    n += put_queue_state4(dst + n, f.final_result_queue_state);
+    dst[n++] = f.previous_key;
+    for (int i = 0; i < 36; i++) dst[n++] = lq_flat(f.previous_item, i);
+    return n;  // 68
+}
+
+// query_to_add, log_sorter/mod.rs:381-393
+__device__ __forceinline__ zkc_log_query ev_cleaned_up(const zkc_log_query &p) {
+    zkc_log_query q = lq_zero();
+#pragma unroll
+    for (int i = 0; i < 5; i++) q.address[i] = p.address[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { q.key[i] = p.key[i]; q.written_value[i] = p.written_value[i]; }
+    q.tx_number_in_block = p.tx_number_in_block;
+    q.flags = ZKC_LQ_FLAGS(0, ZKC_LQ_SHARD(p.flags), 0, 0, ZKC_LQ_SERVICE(p.flags));
+    return q;
+}
+
+__global__ void ev_prologue_kernel(EvDev *d) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane != 0) return;
+    const zkc_events_closed_form &io = d->io;
+    if (warp == 0) {
+        const bool start = io.start_flag != 0;
+        d->start = start;
+        d->uq0 = start ? io.initial_log_queue_state : io.hidden_fsm_input.initial_unsorted_queue_state;
+        d->sq0 = start ? io.intermediate_sorted_queue_state : io.hidden_fsm_input.intermediate_sorted_queue_state;
+        zkc_queue_state4 empty;
+        for (int i = 0; i < 4; i++) empty.head[i] = empty.tail[i] = 0;
+        empty.length = 0; empty._pad = 0;
+        d->rq0 = start ? empty : io.hidden_fsm_input.final_result_queue_state;
+        for (int i = 0; i < 2; i++) {
+            d->acc0[i * 2 + 0] = start ? 1 : io.hidden_fsm_input.lhs_accumulator[i];
+            d->acc0[i * 2 + 1] = start ? 1 : io.hidden_fsm_input.rhs_accumulator[i];
+        }
+        d->previous_key0 = start ? 0 : io.hidden_fsm_input.previous_key;
+        d->previous_item0 = start ? lq_zero() : io.hidden_fsm_input.previous_item;
+        d->prev_trivial0 = (d->uq0.length == 0) || start;  // :266-267
+        uint32_t checks = 0;
+        for (int i = 0; i < 4; i++)
+            if (io.initial_log_queue_state.head[i] | io.intermediate_sorted_queue_state.head[i]) checks |= ZKC_EV_CHK_TRIVIAL_HEAD;
+        if (d->uq0.length != d->sq0.length) checks |= ZKC_EV_CHK_LENGTHS_EQUAL;
+        d->prologue_checks = checks;
+        fs_challenges_4(io.initial_log_queue_state, io.intermediate_sorted_queue_state, d->ch);
+    } else if (warp == 1) {
+        uint64_t buf[18];
+        int n = put_queue_state4(buf, io.initial_log_queue_state);
+        n += put_queue_state4(buf + n, io.intermediate_sorted_queue_state);
+        commit_encoding_dev(buf, n, d->commit_obs_in);
+    } else if (warp == 2) {
+        uint64_t buf[68];
+        const int n = ev_encode_fsm(io.hidden_fsm_input, buf);
+        commit_encoding_dev(buf, n, d->commit_fsm_in);
+    }
+}
+
+__device__ __forceinline__ void ev_report(EvDev *d, size_t row, uint32_t checks) {
+    if (!checks) return;
+    atomicOr(&d->failed_checks, checks);
+    atomicMin(&d->first_bad, ((unsigned long long)row << 16) | checks);
+}
+
+// ---- pass A: pops, grand product, ordering / rollback logic, rounds 0-1 of the result push ------
+__global__ void __launch_bounds__(SCAN_THREADS)
+ev_rows_kernel(EvDev *d, const zkc_log_query *__restrict__ unsorted, const uint64_t *__restrict__ uprev,
+               const zkc_log_query *__restrict__ sorted, const uint64_t *__restrict__ sprev,
+               uint64_t *__restrict__ trace, uint64_t *__restrict__ r2in, uint32_t *__restrict__ meta,
+               ScanGlobal *sg, TileState *tiles) {
+    __shared__ ScanShared sh;
+    __shared__ uint64_t ch[2][21];
+    if (threadIdx.x < 42) ch[threadIdx.x / 21][threadIdx.x % 21] = d->ch[threadIdx.x / 21][threadIdx.x % 21];
+    const unsigned int tile = scan_take_ticket(sg, sh);
+    const size_t limit = d->limit;
+    const size_t row = (size_t)tile * SCAN_THREADS + threadIdx.x;
+    const bool in_range = row < limit;
+    const uint32_t ulen0 = d->uq0.length, slen0 = d->sq0.length;
+    const bool o_empty = row >= ulen0, s_empty = row >= slen0;
+    const bool should_pop = in_range && !o_empty;
+    const size_t active_rows = limit < ulen0 ? limit : ulen0;
+    uint32_t checks = 0;
+    if (in_range && o_empty != s_empty) checks |= ZKC_EV_CHK_EMPTY_SYNC;
+#define TR(col) trace[(size_t)(col) * limit + row]
+    const bool wr = in_range && trace != nullptr;
+    zkc_log_query si = lq_zero();
+    uint64_t contrib[4];
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        const zkc_log_query *recs = k ? sorted : unsorted;
+        const uint64_t *prev = k ? sprev : uprev;
+        const size_t n_rec = k ? d->n_sorted : d->n_unsorted;
+        const zkc_queue_state4 &q0 = k ? d->sq0 : d->uq0;
+        zkc_log_query it = lq_zero();
+        if (should_pop && row < n_rec) it = lq_load(recs + row);
+        uint64_t e[20];
+        lq_encode(it, e);
+        uint64_t head[4];
+        if (should_pop) {
+            uint64_t s[12], chain[4];
+            bool hint_ok = true;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                chain[i] = __ldg(prev + 4 * row + i);
+                if (row == 0 && chain[i] != q0.head[i]) hint_ok = false;
+            }
+            lq_absorb_head(e, s);
+            lq_absorb_tail(e, chain, s);
+#pragma unroll
+            for (int i = 0; i < 4; i++) head[i] = s[i];
+            if (row + 1 < active_rows) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) hint_ok &= __ldg(prev + 4 * (row + 1) + i) == head[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) d->head_final[k][i] = head[i];
+            }
+            if (!hint_ok) { checks |= ZKC_EV_CHK_QUEUE_HINT; d->hint_bad = 1; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) head[i] = ulen0 == 0 ? q0.head[i] : q0.tail[i];
+        }
+        if (should_pop && !ZKC_LQ_RW(it.flags)) checks |= k ? ZKC_EV_CHK_SORTED_IS_WRITE : ZKC_EV_CHK_UNSORTED_IS_WRITE;
+        if (wr) {
+            const int base = k ? ZKC_EV_SORTED_ITEM : ZKC_EV_UNSORTED_ITEM;
+#pragma unroll
+            for (int i = 0; i < 36; i++) TR(base + i) = lq_flat(it, i);
+#pragma unroll
+            for (int i = 0; i < 20; i++) TR(base + 36 + i) = e[i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) TR(base + 56 + i) = head[i];
+            const uint32_t len0 = k ? slen0 : ulen0;
+            const size_t popped_now = row + 1 < active_rows ? row + 1 : active_rows;
+            TR(base + 60) = len0 >= popped_now ? len0 - (uint32_t)popped_now : 0;
+        }
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            uint64_t c = ch[rep][20];
+#pragma unroll
+            for (int i = 0; i < 20; i++) {
+                c = gl_fma(e[i], ch[rep][i], c);
+                if (wr) TR(ZKC_EV_GP_CHAIN + (rep * 2 + k) * 20 + i) = c;
+            }
+            contrib[rep * 2 + k] = c;
+        }
+        if (k == 1) si = it;
+    }
+
+    // ---- :315-400 ordering, rollback pairing, what to push ---------------------------------------------
+    zkc_log_query pq;
+    uint32_t previous_key;
+    bool previous_is_trivial;
+    if (row == 0) {
+        pq = d->previous_item0;
+        previous_key = d->previous_key0;
+        previous_is_trivial = d->prev_trivial0;
+    } else {
+        pq = lq_zero();
+        if (in_range && row - 1 < active_rows && row - 1 < d->n_sorted) pq = lq_load(sorted + row - 1);
+        previous_key = pq.timestamp;
+        previous_is_trivial = row - 1 >= ulen0;
+    }
+    const bool is_trivial = o_empty;
+    const uint32_t sorting_key = si.timestamp;
+    const uint64_t dd = (uint64_t)sorting_key - previous_key;  // b - a with a = previous, b = current
+    const uint32_t diff = (uint32_t)dd;
+    const bool new_key_is_smaller = (dd >> 32) & 1, keys_equal = diff == 0;
+    if (should_pop && new_key_is_smaller) checks |= ZKC_EV_CHK_ORDER;
+    const bool same_log = keys_equal;
+    const bool same_nontrivial = should_pop && same_log;
+    const bool maybe_different = !same_log;
+    const bool different_nontrivial = should_pop && maybe_different;
+    const bool rollback = ZKC_LQ_ROLLBACK(si.flags);
+    if (different_nontrivial && rollback) checks |= ZKC_EV_CHK_NOT_ROLLBACK;
+    if (same_nontrivial && !rollback) checks |= ZKC_EV_CHK_IS_ROLLBACK;
+    bool item_keys_equal = true, values_equal = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { item_keys_equal &= si.key[i] == pq.key[i]; values_equal &= si.written_value[i] == pq.written_value[i]; }
+    const bool same_body = item_keys_equal && values_equal;
+    const bool previous_non_trivial = !previous_is_trivial;
+    const bool should_enforce = same_log && previous_non_trivial;
+    if (in_range && should_enforce && !same_body) checks |= ZKC_EV_CHK_SAME_BODY;
+    const bool maybe_add = maybe_different || is_trivial;
+    const bool add = in_range && previous_non_trivial && maybe_add && !ZKC_LQ_ROLLBACK(pq.flags);
+
+    // rounds 0 and 1 of result_queue.push(query_to_add)
+    {
+        const zkc_log_query to_add = ev_cleaned_up(pq);
+        uint64_t pe[20], s[12];
+        lq_encode(to_add, pe);
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = i < 8 ? pe[i] : 0;
+        poseidon2_permute(s);
+        if (wr) {
+#pragma unroll
+            for (int i = 0; i < 20; i++) TR(ZKC_EV_PUSH_ENC + i) = pe[i];
+#pragma unroll
+            for (int i = 0; i < 12; i++) TR(ZKC_EV_PUSH_ROUND0 + i) = s[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = pe[8 + i];
+        poseidon2_permute(s);
+        if (wr) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) TR(ZKC_EV_PUSH_ROUND1 + i) = s[i];
+        }
+        if (in_range) {
+            ulonglong2 *o = reinterpret_cast<ulonglong2 *>(r2in + 8 * row);
+            o[0] = make_ulonglong2(pe[16], pe[17]); o[1] = make_ulonglong2(pe[18], pe[19]);
+            o[2] = make_ulonglong2(s[8], s[9]); o[3] = make_ulonglong2(s[10], s[11]);
+        }
+    }
+
+    ScanVal v = scan_identity();
+    if (should_pop) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) v.p[i] = contrib[i];
+    }
+    v.c = add;
+    ScanVal init;
+#pragma unroll
+    for (int i = 0; i < 4; i++) init.p[i] = d->acc0[i];
+    init.c = 0;
+    ScanVal incl;
+    const ScanVal excl = scan_tile(v, tile, init, tiles, sh, incl);
+    if (in_range) meta[row] = (excl.c << 1) | (uint32_t)add;
+
+    if (wr) {
+        TR(ZKC_EV_ORIGINAL_IS_EMPTY) = o_empty; TR(ZKC_EV_SORTED_IS_EMPTY) = s_empty; TR(ZKC_EV_SHOULD_POP) = should_pop;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            TR(ZKC_EV_GP_NEW + i) = should_pop ? incl.p[i] : gl_mul(excl.p[i], contrib[i]);
+            TR(ZKC_EV_GP_ACC + i) = incl.p[i];
+        }
+        TR(ZKC_EV_CMP_DIFF) = diff; TR(ZKC_EV_CMP_BORROW) = new_key_is_smaller; TR(ZKC_EV_KEYS_EQUAL) = keys_equal;
+        TR(ZKC_EV_SAME_NONTRIVIAL_LOG) = same_nontrivial; TR(ZKC_EV_DIFFERENT_NONTRIVIAL_LOG) = different_nontrivial;
+        TR(ZKC_EV_ITEM_KEYS_EQUAL) = item_keys_equal; TR(ZKC_EV_VALUES_EQUAL) = values_equal; TR(ZKC_EV_SAME_BODY) = same_body;
+        TR(ZKC_EV_PREVIOUS_IS_TRIVIAL) = previous_is_trivial; TR(ZKC_EV_SHOULD_ENFORCE) = should_enforce;
+        TR(ZKC_EV_MAYBE_ADD) = maybe_add; TR(ZKC_EV_ADD_TO_QUEUE) = add;
+        TR(ZKC_EV_RESULT_LEN) = d->rq0.length + incl.c;
+    }
+    if (in_range && row == limit - 1) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) d->acc_final[i] = incl.p[i];
+        d->pushes_in_loop = incl.c;
+    }
+    if (in_range) ev_report(d, row, checks);
+#undef TR
+}
+
+// ---- result-queue chain when the host supplies no tails: one permutation per executed push ------
+__global__ void ev_chain_kernel(const EvDev *d, const uint64_t *__restrict__ r2in, const uint32_t *__restrict__ meta,
+                                uint64_t *__restrict__ tails) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint64_t tail[4];
+    for (int i = 0; i < 4; i++) tail[i] = d->rq0.tail[i];
+    const size_t limit = d->limit;
+    size_t k = 0;
+    for (size_t row = 0; row < limit; row++) {
+        if (!(meta[row] & 1u)) continue;
+        uint64_t s[12];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { s[i] = r2in[8 * row + i]; s[4 + i] = tail[i]; s[8 + i] = r2in[8 * row + 4 + i]; }
+        poseidon2_permute(s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { tail[i] = s[i]; tails[4 * k + i] = s[i]; }
+        k++;
+    }
+}
+
+// ---- pass B: round 2 of the push against the chained tail -------------------------------------------
+__global__ void __launch_bounds__(256)
+ev_push_kernel(EvDev *d, const uint64_t *__restrict__ r2in, const uint32_t *__restrict__ meta,
+               const uint64_t *__restrict__ tails, size_t n_tails, uint64_t *__restrict__ trace) {
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const uint32_t m = meta[row];
+    const size_t k = m >> 1;
+    const bool add = m & 1u;
+    uint64_t before[4], s[12];
+    bool ok = true;
+    if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) before[i] = d->rq0.tail[i];
+    } else if (k - 1 < n_tails) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) before[i] = __ldg(tails + 4 * (k - 1) + i);
+    } else {
+        ok = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) before[i] = 0;
+    }
+    const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(r2in + 8 * row);
+    const ulonglong2 a = in[0], b = in[1], c = in[2], e = in[3];
+    s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
+#pragma unroll
+    for (int i = 0; i < 4; i++) s[4 + i] = before[i];
+    s[8] = c.x; s[9] = c.y; s[10] = e.x; s[11] = e.y;
+    poseidon2_permute(s);
+    if (add) {
+        if (k < n_tails) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) ok &= __ldg(tails + 4 * k + i) == s[i];
+        } else ok = false;
+    }
+    if (trace) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) trace[(size_t)(ZKC_EV_PUSH_ROUND2 + i) * limit + row] = s[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) trace[(size_t)(ZKC_EV_RESULT_TAIL + i) * limit + row] = add ? s[i] : before[i];
+    }
+    if (!ok) {
+        d->hint_bad = 1;
+        atomicOr(&d->failed_checks, (uint32_t)ZKC_EV_CHK_QUEUE_HINT);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | ZKC_EV_CHK_QUEUE_HINT);
+    }
+}
+
+// ---- finalize -----------------------------------------------------------------------------------------
+__global__ void ev_finalize_kernel(EvDev *d, const zkc_log_query *__restrict__ sorted, const uint64_t *__restrict__ tails,
+                                   size_t n_tails) {
+    if (threadIdx.x != 0) return;
+    zkc_events_closed_form &io = d->io;
+    const size_t limit = d->limit;
+    const uint32_t len0 = d->uq0.length;
+    const size_t popped = limit < len0 ? limit : len0;
+    zkc_events_fsm out;
+    memset(&out, 0, sizeof out);
+    out.initial_unsorted_queue_state = d->uq0;
+    out.intermediate_sorted_queue_state = d->sq0;
+    if (popped > 0)
+        for (int i = 0; i < 4; i++) {
+            out.initial_unsorted_queue_state.head[i] = d->head_final[0][i];
+            out.intermediate_sorted_queue_state.head[i] = d->head_final[1][i];
+        }
+    out.initial_unsorted_queue_state.length = len0 - (uint32_t)popped;
+    const size_t spopped = d->sq0.length < popped ? d->sq0.length : popped;
+    out.intermediate_sorted_queue_state.length = d->sq0.length - (uint32_t)spopped;
+    zkc_log_query previous_item = d->previous_item0;
+    uint32_t previous_key = d->previous_key0;
+    bool previous_is_trivial = d->prev_trivial0;
+    zkc_queue_state4 rq = d->rq0;
+    bool hint_bad = d->hint_bad;
+    if (limit > 0) {
+        for (int i = 0; i < 2; i++) { out.lhs_accumulator[i] = d->acc_final[2 * i]; out.rhs_accumulator[i] = d->acc_final[2 * i + 1]; }
+        previous_item = (limit - 1 < popped && limit - 1 < d->n_sorted) ? sorted[limit - 1] : lq_zero();
+        previous_key = previous_item.timestamp;
+        previous_is_trivial = limit - 1 >= len0;
+        const uint32_t pushes = d->pushes_in_loop;
+        if (pushes) {
+            if (pushes - 1 < n_tails) for (int i = 0; i < 4; i++) rq.tail[i] = tails[4 * (size_t)(pushes - 1) + i];
+            else hint_bad = true;
+        }
+        rq.length += pushes;
+    } else {
+        for (int i = 0; i < 2; i++) { out.lhs_accumulator[i] = d->acc0[2 * i]; out.rhs_accumulator[i] = d->acc0[2 * i + 1]; }
+    }
+    // finalisation push, :406-435
+    {
+        const bool now_empty = out.initial_unsorted_queue_state.length == 0;
+        const bool add = !previous_is_trivial && !ZKC_LQ_ROLLBACK(previous_item.flags) && now_empty;
+        if (add) {
+            const zkc_log_query to_add = ev_cleaned_up(previous_item);
+            uint64_t pe[20], s[12], chain[4];
+            lq_encode(to_add, pe);
+            for (int i = 0; i < 4; i++) chain[i] = rq.tail[i];
+            lq_absorb_head(pe, s);
+            lq_absorb_tail(pe, chain, s);
+            for (int i = 0; i < 4; i++) rq.tail[i] = s[i];
+            rq.length++;
+        }
+    }
+    out.previous_key = previous_key;
+    out.previous_item = previous_item;
+    out.final_result_queue_state = rq;
+    uint32_t checks = d->failed_checks | d->prologue_checks;
+    const zkc_queue_state4 *qs[2] = {&out.initial_unsorted_queue_state, &out.intermediate_sorted_queue_state};
+    for (int k = 0; k < 2; k++)
+        if (qs[k]->length == 0)
+            for (int i = 0; i < 4; i++)
+                if (qs[k]->head[i] != qs[k]->tail[i]) checks |= ZKC_EV_CHK_QUEUE_CONSISTENCY;
+    if ((qs[0]->length == 0) != (qs[1]->length == 0)) checks |= ZKC_EV_CHK_EMPTY_SYNC;
+    const bool completed = qs[0]->length == 0;
+    if (completed)
+        for (int i = 0; i < 2; i++)
+            if (out.lhs_accumulator[i] != out.rhs_accumulator[i]) checks |= ZKC_EV_CHK_GRAND_PRODUCT;
+    zkc_queue_state4 obs_out;
+    memset(&obs_out, 0, sizeof obs_out);
+    if (completed) obs_out = rq;
+
+    uint64_t e_out[68], e_exp[68], o_out[9], o_exp[9];
+    const int n_out = ev_encode_fsm(out, e_out);
+    put_queue_state4(o_out, obs_out);
+    zkc_status st;
+    st.code = ZKC_OK; st.cuda_error = 0; st.first_bad_row = -1; st.failed_checks = checks; st.reserved = 0;
+    if (d->first_bad != ~0ull) st.first_bad_row = (int64_t)(d->first_bad >> 16);
+    if (checks) st.code = ZKC_ERR_UNSATISFIED;
+    if (hint_bad) { st.code = ZKC_ERR_QUEUE_WITNESS_INCONSISTENT; st.failed_checks |= ZKC_EV_CHK_QUEUE_HINT; }
+    if (d->opt.compare_expected) {
+        ev_encode_fsm(io.hidden_fsm_output, e_exp);
+        put_queue_state4(o_exp, io.final_queue_state);
+        bool same = (io.completion_flag != 0) == completed;
+        for (int i = 0; i < n_out; i++) same &= e_out[i] == e_exp[i];
+        for (int i = 0; i < 9; i++) same &= o_out[i] == o_exp[i];
+        if (!same && st.code == ZKC_OK) st.code = ZKC_ERR_FSM_OUTPUT_MISMATCH;
+    }
+    io.hidden_fsm_output = out;
+    io.final_queue_state = obs_out;
+    io.completion_flag = completed;
+    uint64_t compact[18], c4[4];
+    compact[0] = d->start; compact[1] = completed;
+    commit_encoding_dev(o_out, 9, c4);
+    for (int i = 0; i < 4; i++) {
+        compact[2 + i] = d->commit_obs_in[i];
+        compact[6 + i] = completed ? c4[i] : 0;
+        compact[10 + i] = d->start ? 0 : d->commit_fsm_in[i];
+    }
+    commit_encoding_dev(e_out, n_out, c4);
+    for (int i = 0; i < 4; i++) compact[14 + i] = completed ? 0 : c4[i];
+    commit_encoding_dev(compact, 18, d->commitment);
+    d->status = st;
+}
+
+// CircuitQueue::push of whole queues: one thread per independent queue
+__global__ void log_queue_simulate_kernel(const zkc_log_query *__restrict__ recs, const uint32_t *__restrict__ extra_ts,
+                                          size_t n_per_queue, size_t n_queues, uint64_t *__restrict__ prev_tails,
+                                          zkc_queue_state4 *__restrict__ final_states) {
+    const size_t qi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= n_queues) return;
+    uint64_t tail[4] = {0, 0, 0, 0};
+    for (size_t r = 0; r < n_per_queue; r++) {
+        const size_t g = qi * n_per_queue + r;
+        if (prev_tails) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) prev_tails[4 * g + i] = tail[i];
+        }
+        const zkc_log_query it = lq_load(recs + g);
+        uint64_t e[20], s[12];
+        lq_encode(it, e);
+        if (extra_ts) e[19] += (uint64_t)extra_ts[g] << 8;  // storage_validity_by_grand_product/mod.rs:72-96
+        lq_absorb_head(e, s);
+        lq_absorb_tail(e, tail, s);
+#pragma unroll
+        for (int i = 0; i < 4; i++) tail[i] = s[i];
+    }
+    zkc_queue_state4 &o = final_states[qi];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { o.head[i] = 0; o.tail[i] = tail[i]; }
+    o.length = (uint32_t)n_per_queue;
+    o._pad = 0;
+}
+
+}  // namespace zkc
+
+using namespace zkc;
+
+extern "C" int zkc_log_queue_simulate(zkc_ctx *ctx, const zkc_log_query *records, const uint32_t *extra_timestamps,
+                                      size_t n_per_queue, size_t n_queues, uint64_t *prev_tails,
+                                      zkc_queue_state4 *final_states, int on_device) {
+    if (!ctx || !final_states || (n_per_queue && n_queues && !records)) return ZKC_ERR_INVALID_ARGUMENT;
+    if (!n_queues) return ZKC_OK;
+    zkc_status *st = nullptr;
+    ZKC_CUDA(ctx, st, cudaSetDevice(ctx->device));
+    const size_t n = n_per_queue * n_queues;
+    const zkc_log_query *dr = records;
+    const uint32_t *dt = extra_timestamps;
+    uint64_t *dp = prev_tails;
+    zkc_queue_state4 *df = final_states;
+    cudaStream_t s = ctx->stream;
+    if (!on_device) {
+        size_t bytes = zkc_carver::bytes(n, sizeof(zkc_log_query)) + zkc_carver::bytes(n, 4) + zkc_carver::bytes(n * 4, 8) +
+                       zkc_carver::bytes(n_queues, sizeof(zkc_queue_state4));
+        void *blk = ctx->scratch(bytes);
+        if (!blk) return ZKC_ERR_CUDA;
+        zkc_carver cv(blk);
+        zkc_log_query *br = cv.take<zkc_log_query>(n);
+        uint32_t *bt = cv.take<uint32_t>(n);
+        dp = prev_tails ? cv.take<uint64_t>(n * 4) : nullptr;
+        df = cv.take<zkc_queue_state4>(n_queues);
+        if (n) ZKC_CUDA(ctx, st, cudaMemcpyAsync(br, records, n * sizeof(zkc_log_query), cudaMemcpyHostToDevice, s));
+        if (n && extra_timestamps) ZKC_CUDA(ctx, st, cudaMemcpyAsync(bt, extra_timestamps, n * 4, cudaMemcpyHostToDevice, s));
+        dr = br; dt = extra_timestamps ? bt : nullptr;
+    }
+    ZKC_LAUNCH(ctx, "log_queue_simulate", log_queue_simulate_kernel, (unsigned)((n_queues + 31) / 32), 32, 0, dr, dt,
+               n_per_queue, n_queues, dp, df);
+    ZKC_CUDA(ctx, st, cudaGetLastError());
+    if (!on_device) {
+        if (prev_tails && n) ZKC_CUDA(ctx, st, cudaMemcpyAsync(prev_tails, dp, n * 32, cudaMemcpyDeviceToHost, s));
+        ZKC_CUDA(ctx, st, cudaMemcpyAsync(final_states, df, n_queues * sizeof(zkc_queue_state4), cudaMemcpyDeviceToHost, s));
+        ZKC_CUDA(ctx, st, cudaStreamSynchronize(s));
+    }
+    return ZKC_OK;
+}
+
+extern "C" int zkc_log_sorter_entry_point(zkc_ctx *ctx, zkc_events_closed_form *io, const zkc_log_query *unsorted,
+                                          const uint64_t *unsorted_prev_tails, size_t n_unsorted,
+                                          const zkc_log_query *sorted, const uint64_t *sorted_prev_tails, size_t n_sorted,
+                                          const uint64_t *result_tails, size_t n_result_tails, size_t limit,
+                                          const zkc_sorter_options *options, int on_device, uint64_t *trace,
+                                          uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !commitment || (n_unsorted && !unsorted) || (n_sorted && !sorted) || limit > 0x7FFFFFFFull) {
+        status->code = ZKC_ERR_INVALID_ARGUMENT;
+        return ZKC_ERR_INVALID_ARGUMENT;
+    }
+    const zkc_queue_state4 &uq = io->start_flag ? io->initial_log_queue_state : io->hidden_fsm_input.initial_unsorted_queue_state;
+    const size_t need = limit < uq.length ? limit : uq.length;
+    if (n_unsorted < need || n_sorted < need || (need && (!unsorted_prev_tails || !sorted_prev_tails))) {
+        status->code = ZKC_ERR_INVALID_ARGUMENT;
+        return ZKC_ERR_INVALID_ARGUMENT;
+    }
+    const bool in_dev = on_device & ZKC_INPUTS_ON_DEVICE, trace_dev = on_device & ZKC_TRACE_ON_DEVICE;
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    const size_t tiles = (limit + SCAN_THREADS - 1) / SCAN_THREADS;
+    const bool have_tails = result_tails != nullptr;
+    if (!have_tails) n_result_tails = limit + 1;
+    size_t bytes = zkc_carver::bytes(1, sizeof(EvDev)) + zkc_carver::bytes(1, sizeof(ScanGlobal)) +
+                   zkc_carver::bytes(tiles + 1, sizeof(TileState)) + zkc_carver::bytes(limit * 8 + 8, 8) +
+                   zkc_carver::bytes(limit + 1, 4);
+    if (!in_dev) bytes += 2 * zkc_carver::bytes(need + 1, sizeof(zkc_log_query)) + 2 * zkc_carver::bytes(need * 4 + 4, 8);
+    if (!in_dev || !have_tails) bytes += zkc_carver::bytes(n_result_tails * 4 + 4, 8);
+    if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ZKC_EV_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    EvDev *h = (EvDev *)ctx->pinned(sizeof(EvDev));
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    EvDev *d = cv.take<EvDev>(1);
+    ScanGlobal *sg = cv.take<ScanGlobal>(1);
+    TileState *ts = cv.take<TileState>(tiles + 1);
+    uint64_t *r2in = cv.take<uint64_t>(limit * 8 + 8);
+    uint32_t *meta = cv.take<uint32_t>(limit + 1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(EvDev));
+    h->io = *io;
+    if (options) h->opt = *options;
+    h->n_unsorted = n_unsorted; h->n_sorted = n_sorted; h->n_result_tails = n_result_tails; h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(EvDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(sg, 0, (char *)(ts + tiles + 1) - (char *)sg, s));
+    const zkc_log_query *du = unsorted, *dsq = sorted;
+    const uint64_t *dup = unsorted_prev_tails, *dsp = sorted_prev_tails, *dtails = result_tails;
+    uint64_t *dtrace = trace;
+    if (!in_dev) {
+        zkc_log_query *bu = cv.take<zkc_log_query>(need + 1), *bs = cv.take<zkc_log_query>(need + 1);
+        uint64_t *bup = cv.take<uint64_t>(need * 4 + 4), *bsp = cv.take<uint64_t>(need * 4 + 4);
+        if (need) {
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(bu, unsorted, need * sizeof(zkc_log_query), cudaMemcpyHostToDevice, s));
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(bs, sorted, need * sizeof(zkc_log_query), cudaMemcpyHostToDevice, s));
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(bup, unsorted_prev_tails, need * 32, cudaMemcpyHostToDevice, s));
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(bsp, sorted_prev_tails, need * 32, cudaMemcpyHostToDevice, s));
+        }
+        du = bu; dsq = bs; dup = bup; dsp = bsp;
+    }
+    if (!in_dev || !have_tails) {
+        uint64_t *bt = cv.take<uint64_t>(n_result_tails * 4 + 4);
+        if (have_tails && n_result_tails)
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(bt, result_tails, n_result_tails * 32, cudaMemcpyHostToDevice, s));
+        dtails = bt;
+    }
+    if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ZKC_EV_NUM_COLS * limit);
+
+    ZKC_LAUNCH(ctx, "ev_prologue", ev_prologue_kernel, 1, 96, 0, d);
+    if (tiles) {
+        ZKC_LAUNCH(ctx, "ev_rows", ev_rows_kernel, (unsigned)tiles, SCAN_THREADS, 0, d, du, dup, dsq, dsp, dtrace, r2in, meta, sg, ts);
+        if (!have_tails) ZKC_LAUNCH(ctx, "ev_chain", ev_chain_kernel, 1, 32, 0, d, r2in, meta, (uint64_t *)dtails);
+        ZKC_LAUNCH(ctx, "ev_push", ev_push_kernel, (unsigned)((limit + 255) / 256), 256, 0, d, r2in, meta, dtails, n_result_tails, dtrace);
+    }
+    ZKC_LAUNCH(ctx, "ev_finalize", ev_finalize_kernel, 1, 32, 0, d, dsq, dtails, n_result_tails);
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(EvDev), cudaMemcpyDeviceToHost, s));
+    if (!trace_dev && trace && limit)
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(trace, dtrace, (size_t)ZKC_EV_NUM_COLS * limit * 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    io->hidden_fsm_output = h->io.hidden_fsm_output;
+    io->final_queue_state = h->io.final_queue_state;
+    io->completion_flag = h->io.completion_flag;
+    memcpy(commitment, h->commitment, 32);
+    *status = h->status;
+    return status->code;
+}

@@ -104,6 +104,15 @@ class Engine:
             raise ZkcError(rc, what="zkc_poseidon2_permute")
         return out
 
+    def field_ops(self, a, b, c):
+        """element-wise (a*b, a+b, a-b, a*b+c) over Goldilocks; canonical uint64 numpy inputs"""
+        a, b, c = (np.ascontiguousarray(x, dtype=np.uint64) for x in (a, b, c))
+        outs = [np.empty_like(a) for _ in range(4)]
+        rc = self.lib.zkc_field_ops(self.h, ptr(a), ptr(b), ptr(c), a.size, *(ptr(o) for o in outs))
+        if rc:
+            raise ZkcError(rc, what="zkc_field_ops")
+        return outs
+
     def commit_encoding(self, inputs):
         """inputs [n_items, len] uint64 -> [n_items, 4]; fsm_input_output/mod.rs:281-326"""
         n, ln = inputs.shape
@@ -157,7 +166,8 @@ class Engine:
             rc = self.lib.zkc_memory_queue_simulate(self.h, ptr(records), n // n_queues, n_queues, ptr(prev), ptr(fin_d), 1)
             if rc:
                 raise ZkcError(rc, what="zkc_memory_queue_simulate")
-            C.memmove(final, fin_d.cpu().numpy().ctypes.data, C.sizeof(final))
+            host = fin_d.cpu().numpy()  # keep alive across the memmove
+            C.memmove(final, host.ctypes.data, C.sizeof(final))
         else:
             prev = np.empty((n, 12), dtype=np.uint64)
             rc = self.lib.zkc_memory_queue_simulate(self.h, ptr(records), n // n_queues, n_queues, ptr(prev),

@@ -94,6 +94,12 @@ int zkc_poseidon2_permute(zkc_ctx *ctx, const uint64_t *states_in, uint64_t *sta
 int zkc_commit_encoding(zkc_ctx *ctx, const uint64_t *inputs, size_t len, size_t n_items,
                         uint64_t *out, int on_device);
 
+/* element-wise Goldilocks a*b, a+b, a-b, a*b+c on canonical inputs (host buffers).  Diagnostic entry:
+ * lets the tests pin the register-level field arithmetic (Num::{mul,add,sub,fma} of boojum, call sites
+ * src/utils.rs:112-132) against big-integer arithmetic, edge values included. */
+int zkc_field_ops(zkc_ctx *ctx, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n,
+                  uint64_t *out_mul, uint64_t *out_add, uint64_t *out_sub, uint64_t *out_fma);
+
 /* accumulate_grand_products<ENC, ENC+1, 2>, src/utils.rs:81-137, over `rows` loop iterations.
  *   lhs_enc/rhs_enc : column-major [enc_len][rows]
  *   should_acc      : [rows] of 0/1 (NULL = all ones)
@@ -273,6 +279,129 @@ int zkc_ram_permutation_entry_point(zkc_ctx *ctx, zkc_ram_closed_form *io,
 int zkc_ram_permutation_check_trace(zkc_ctx *ctx, const zkc_ram_closed_form *io, const uint64_t *trace,
                                     size_t limit, const zkc_ram_options *options, uint32_t gates, int on_device,
                                     uint64_t *violations, zkc_status *status);
+
+
+/* ---- LogQuery circuits: log_sorter, storage_validity_by_grand_product ---------------------------- */
+/* LogQuery witness, src/base_structures/log_query/mod.rs:23-35 (128-byte record).
+ * flags = aux_byte | shard_id << 8 | rw_flag << 16 | rollback << 17 | is_service << 18 */
+typedef struct zkc_log_query {
+    uint32_t address[5];       /* UInt160, little-endian u32 limbs */
+    uint32_t key[8];           /* UInt256 */
+    uint32_t read_value[8];
+    uint32_t written_value[8];
+    uint32_t tx_number_in_block;
+    uint32_t timestamp;
+    uint32_t flags;
+} zkc_log_query;
+#define ZKC_LQ_AUX(f) ((f) & 0xFFu)
+#define ZKC_LQ_SHARD(f) (((f) >> 8) & 0xFFu)
+#define ZKC_LQ_RW(f) (((f) >> 16) & 1u)
+#define ZKC_LQ_ROLLBACK(f) (((f) >> 17) & 1u)
+#define ZKC_LQ_SERVICE(f) (((f) >> 18) & 1u)
+#define ZKC_LQ_FLAGS(aux, shard, rw, rollback, service) \
+    ((uint32_t)(aux) | (uint32_t)(shard) << 8 | (uint32_t)(rw) << 16 | (uint32_t)(rollback) << 17 | (uint32_t)(service) << 18)
+#define ZKC_LOG_QUERY_FLAT 36   /* FLATTENED_VARIABLE_LENGTH, log_query/mod.rs:42 */
+#define ZKC_LOG_QUERY_PACKED 20 /* LOG_QUERY_PACKED_WIDTH, log_query/mod.rs:38 */
+
+/* CircuitQueue<_, LogQuery, 8, 12, 4, 4, 20, R>::push of `n_queues` independent empty queues of
+ * `n_per_queue` records (StorageLogQueue, src/demux_log_queue/mod.rs:34; push rule restated in-repo at
+ * src/main_vm/opcodes/log.rs:469-600: empty sponge, absorb enc[0..8], enc[8..16], enc[16..20] || tail).
+ * extra_timestamps (may be NULL): per record, the TimestampedStorageLogRecord.timestamp folded into
+ * element 19 (storage_validity_by_grand_product/mod.rs:72-96).  prev_tails (may be NULL): AoS [n][4], the
+ * tail before each push = second element of each CircuitQueueRawWitness entry. */
+int zkc_log_queue_simulate(zkc_ctx *ctx, const zkc_log_query *records, const uint32_t *extra_timestamps,
+                           size_t n_per_queue, size_t n_queues, uint64_t *prev_tails,
+                           zkc_queue_state4 *final_states, int on_device);
+
+/* EventsDeduplicatorFSMInputOutput, src/log_sorter/input.rs:28-36 */
+typedef struct zkc_events_fsm {
+    uint64_t lhs_accumulator[ZKC_NUM_REPETITIONS];
+    uint64_t rhs_accumulator[ZKC_NUM_REPETITIONS];
+    zkc_queue_state4 initial_unsorted_queue_state;
+    zkc_queue_state4 intermediate_sorted_queue_state;
+    zkc_queue_state4 final_result_queue_state;
+    uint32_t previous_key;
+    uint32_t _pad;
+    zkc_log_query previous_item;
+} zkc_events_fsm;
+
+/* ClosedFormInputWitness<F, EventsDeduplicatorFSMInputOutput, EventsDeduplicatorInputData,
+ * EventsDeduplicatorOutputData>, src/log_sorter/input.rs:56-96 */
+typedef struct zkc_events_closed_form {
+    uint32_t start_flag;
+    uint32_t completion_flag;                          /* out */
+    zkc_queue_state4 initial_log_queue_state;          /* observable input */
+    zkc_queue_state4 intermediate_sorted_queue_state;  /* observable input */
+    zkc_queue_state4 final_queue_state;                /* observable output (out; expected if compared) */
+    zkc_events_fsm hidden_fsm_input;
+    zkc_events_fsm hidden_fsm_output;                  /* out; on input: expected value if compare_expected */
+} zkc_events_closed_form;
+
+/* trace columns of one iteration of repack_and_prove_events_rollbacks_inner (src/log_sorter/mod.rs:283-403) */
+enum zkc_events_col {
+    ZKC_EV_ORIGINAL_IS_EMPTY = 0, /* :284 */
+    ZKC_EV_SORTED_IS_EMPTY = 1,   /* :285 */
+    ZKC_EV_SHOULD_POP = 2,        /* :288 */
+    ZKC_EV_UNSORTED_ITEM = 3,     /* 36, flatten order log_query/mod.rs:62-101 */
+    ZKC_EV_UNSORTED_ENC = 39,     /* 20 */
+    ZKC_EV_UNSORTED_HEAD = 59,    /* 4: head after the pop */
+    ZKC_EV_UNSORTED_LEN = 63,
+    ZKC_EV_SORTED_ITEM = 64,      /* 36 */
+    ZKC_EV_SORTED_ENC = 100,      /* 20 */
+    ZKC_EV_SORTED_HEAD = 120,     /* 4 */
+    ZKC_EV_SORTED_LEN = 124,
+    ZKC_EV_GP_CHAIN = 125,        /* 80: (rep*2 + side)*20 + i */
+    ZKC_EV_GP_NEW = 205,          /* 4 */
+    ZKC_EV_GP_ACC = 209,          /* 4 */
+    ZKC_EV_CMP_DIFF = 213,        /* :327 unpacked_long_comparison([previous_key], [sorting_key]) */
+    ZKC_EV_CMP_BORROW = 214,      /* = new_key_is_smaller */
+    ZKC_EV_KEYS_EQUAL = 215,      /* same_log */
+    ZKC_EV_SAME_NONTRIVIAL_LOG = 216,      /* :335 */
+    ZKC_EV_DIFFERENT_NONTRIVIAL_LOG = 217, /* :337 */
+    ZKC_EV_ITEM_KEYS_EQUAL = 218,          /* :353 */
+    ZKC_EV_VALUES_EQUAL = 219,             /* :354 */
+    ZKC_EV_SAME_BODY = 220,                /* :356 */
+    ZKC_EV_PREVIOUS_IS_TRIVIAL = 221,      /* value on entry to the iteration */
+    ZKC_EV_SHOULD_ENFORCE = 222,           /* :360 */
+    ZKC_EV_MAYBE_ADD = 223,                /* :370 */
+    ZKC_EV_ADD_TO_QUEUE = 224,             /* :372 */
+    ZKC_EV_PUSH_ENC = 225,                 /* 20: encoding of query_to_add */
+    ZKC_EV_PUSH_ROUND0 = 245,              /* 12: sponge state after absorbing enc[0..8] */
+    ZKC_EV_PUSH_ROUND1 = 257,              /* 12 */
+    ZKC_EV_PUSH_ROUND2 = 269,              /* 12: after absorbing enc[16..20] || old tail */
+    ZKC_EV_RESULT_TAIL = 281,              /* 4: result queue tail after the conditional push */
+    ZKC_EV_RESULT_LEN = 285,
+    ZKC_EV_NUM_COLS = 286
+};
+
+#define ZKC_EV_CHK_LENGTHS_EQUAL (1u << 0)     /* :273-277 */
+#define ZKC_EV_CHK_EMPTY_SYNC (1u << 1)        /* :286 and entry point :186 */
+#define ZKC_EV_CHK_UNSORTED_IS_WRITE (1u << 2) /* :295-297 */
+#define ZKC_EV_CHK_SORTED_IS_WRITE (1u << 3)   /* :318-320 */
+#define ZKC_EV_CHK_ORDER (1u << 4)             /* :331 */
+#define ZKC_EV_CHK_NOT_ROLLBACK (1u << 5)      /* :342-343 */
+#define ZKC_EV_CHK_IS_ROLLBACK (1u << 6)       /* :347-349 */
+#define ZKC_EV_CHK_SAME_BODY (1u << 7)         /* :362 */
+#define ZKC_EV_CHK_QUEUE_CONSISTENCY (1u << 8) /* :437-438 */
+#define ZKC_EV_CHK_GRAND_PRODUCT (1u << 9)     /* :189-191 */
+#define ZKC_EV_CHK_TRIVIAL_HEAD (1u << 10)     /* :61, :87 */
+#define ZKC_EV_CHK_QUEUE_HINT (1u << 11)       /* *_prev_tails / result_tails is not the hash chain */
+
+typedef struct zkc_sorter_options {
+    uint32_t compare_expected; /* hook_compare_witness against the expected outputs in *io */
+    uint32_t _pad[3];
+} zkc_sorter_options;
+
+/* sort_and_deduplicate_events_entry_point, src/log_sorter/mod.rs:34-232.
+ *   unsorted / sorted, *_prev_tails : queue witnesses in pop order (CircuitQueueRawWitness, input.rs:98-106)
+ *   result_tails : NULL, or AoS [pushes][4]: the result-queue tail after each executed push (verified);
+ *                  when NULL the chain is rebuilt sequentially on the device (1 permutation per push)
+ *   trace        : column-major [ZKC_EV_NUM_COLS][limit] or NULL */
+int zkc_log_sorter_entry_point(zkc_ctx *ctx, zkc_events_closed_form *io, const zkc_log_query *unsorted,
+                               const uint64_t *unsorted_prev_tails, size_t n_unsorted, const zkc_log_query *sorted,
+                               const uint64_t *sorted_prev_tails, size_t n_sorted, const uint64_t *result_tails,
+                               size_t n_result_tails, size_t limit, const zkc_sorter_options *options, int on_device,
+                               uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
 #ifdef __cplusplus
 }

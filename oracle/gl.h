@@ -17,21 +17,25 @@
 
 typedef unsigned __int128 u128;
 
-static inline uint64_t gl_canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
+static inline uint64_t gl_canon(uint64_t x) { return x - (GL_P & (0 - (uint64_t)(x >= GL_P))); }
 
 static inline uint64_t gl_add(uint64_t a, uint64_t b) {
-    u128 s = (u128)a + b;
-    if (s >= GL_P) s -= GL_P;
-    return (uint64_t)s;
+    uint64_t s;
+    uint64_t c = __builtin_add_overflow(a, b, &s);
+    /* a, b < p: wrapped past 2^64 or landed in [p, 2^64) -> subtract p once */
+    return s - (GL_P & (0 - (c | (uint64_t)(s >= GL_P))));
 }
-static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return a >= b ? a - b : a + (GL_P - b); }
+static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return a - b + (GL_P & (0 - (uint64_t)(a < b))); }
 static inline uint64_t gl_neg(uint64_t a) { return a ? GL_P - a : 0; }
-/* 2^64 = eps, 2^96 = -1 (mod p): x = lo + eps*hi_lo - hi_hi */
+/* 2^64 = eps, 2^96 = -1 (mod p): x = lo + eps*hi_lo - hi_hi; branch-free (the carries are data
+ * dependent coin flips) */
 static inline uint64_t gl_reduce128(u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hh = hi >> 32, hl = hi & GL_EPS, t0, r;
-    if (__builtin_sub_overflow(lo, hh, &t0)) t0 -= GL_EPS;
-    if (__builtin_add_overflow(t0, hl * GL_EPS, &r)) r += GL_EPS;
+    uint64_t b = __builtin_sub_overflow(lo, hh, &t0);
+    t0 -= GL_EPS & (0 - b);
+    uint64_t c = __builtin_add_overflow(t0, hl * GL_EPS, &r);
+    r += GL_EPS & (0 - c);
     return gl_canon(r);
 }
 static inline uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128((u128)a * b); }

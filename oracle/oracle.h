@@ -61,4 +61,18 @@ int orc_ram_permutation_entry_point(zkc_ram_closed_form *io, const zkc_memory_qu
                                     const zkc_ram_options *options, uint64_t *trace, uint64_t commitment[4],
                                     zkc_status *status);
 
+
+/* log_query.c */
+void orc_log_query_encode(const zkc_log_query *q, uint64_t out[20]);
+void orc_log_query_flatten(const zkc_log_query *q, uint64_t out[36]);
+void orc_log_queue_absorb(uint64_t chain[4], const uint64_t enc[20], uint64_t *rounds);
+void orc_log_queue_simulate(const zkc_log_query *q, const uint32_t *extra_ts, size_t n, uint64_t *prev_tails,
+                            zkc_queue_state4 *final_state);
+size_t orc_put_queue_state4(uint64_t *dst, const zkc_queue_state4 *s);
+/* log_sorter.c; result_tails (optional out): tail after each executed push, n_result_tails their count */
+size_t orc_events_encode_fsm(const zkc_events_fsm *f, uint64_t *dst);
+int orc_log_sorter_entry_point(zkc_events_closed_form *io, const zkc_log_query *unsorted, size_t n_unsorted,
+                               const zkc_log_query *sorted, size_t n_sorted, size_t limit,
+                               const zkc_sorter_options *options, uint64_t *trace, uint64_t *result_tails,
+                               size_t *n_result_tails, uint64_t commitment[4], zkc_status *status);
 #endif

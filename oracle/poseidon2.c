@@ -71,26 +71,26 @@ static inline uint64_t sbox7(uint64_t x) {
     return gl_mul(x3, x4);
 }
 
-/* M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]] on each 4-block, then circ(2,1,1) over the blocks */
+/* M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]] on each 4-block, then circ(2,1,1) over the blocks.
+ * Coefficients are tiny, so everything is accumulated on 128-bit integers and reduced once per lane. */
 static void external_matrix(uint64_t s[12]) {
-    static const uint64_t M4[4][4] = {{5, 7, 1, 3}, {4, 6, 1, 1}, {1, 3, 5, 7}, {1, 1, 4, 6}};
-    uint64_t t[12];
-    for (int b = 0; b < 3; b++)
-        for (int i = 0; i < 4; i++) {
-            u128 acc = 0;
-            for (int j = 0; j < 4; j++) acc += (u128)M4[i][j] * s[4 * b + j];
-            t[4 * b + i] = gl_reduce128(acc);
-        }
+    u128 t[12];
+    for (int b = 0; b < 3; b++) {
+        const u128 x0 = s[4 * b], x1 = s[4 * b + 1], x2 = s[4 * b + 2], x3 = s[4 * b + 3];
+        t[4 * b + 0] = 5 * x0 + 7 * x1 + x2 + 3 * x3;
+        t[4 * b + 1] = 4 * x0 + 6 * x1 + x2 + x3;
+        t[4 * b + 2] = x0 + 3 * x1 + 5 * x2 + 7 * x3;
+        t[4 * b + 3] = x0 + x1 + 4 * x2 + 6 * x3;
+    }
     for (int i = 0; i < 4; i++) {
-        uint64_t sum = gl_add(gl_add(t[i], t[4 + i]), t[8 + i]);
-        for (int b = 0; b < 3; b++) s[4 * b + i] = gl_add(t[4 * b + i], sum);
+        const u128 sum = t[i] + t[4 + i] + t[8 + i];
+        for (int b = 0; b < 3; b++) s[4 * b + i] = gl_reduce128(t[4 * b + i] + sum);
     }
 }
 
 static void inner_matrix(uint64_t s[12]) {
-    u128 acc = 0;
-    for (int i = 0; i < 12; i++) acc += s[i];
-    uint64_t sum = gl_reduce128(acc);
+    u128 sum = 0;
+    for (int i = 0; i < 12; i++) sum += s[i];
     for (int i = 0; i < 12; i++) s[i] = gl_reduce128(((u128)s[i] << INNER_SHIFTS[i]) + sum);
 }
 

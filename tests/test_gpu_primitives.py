@@ -12,6 +12,22 @@ def rand_field(rng, shape):
     return (rng.integers(0, 1 << 63, size=shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=shape, dtype=np.uint64)) % np.uint64(P)
 
 
+def test_field_ops_edge_values_and_random(engine):
+    edge = [0, 1, 2, P - 1, P - 2, 0xFFFFFFFF, 0x100000000, 0xFFFFFFFE, 0xFFFFFFFF00000000, 0xFFFFFFFEFFFFFFFF,
+            0x8000000000000000, 0x7FFFFFFFFFFFFFFF, 0xFFFFFFFE00000001, 0x00000001FFFFFFFF, (1 << 63) % P]
+    rng = np.random.default_rng(5)
+    a = [x for x in edge for _ in edge] + rand_field(rng, (4000,)).tolist()
+    b = [y for _ in edge for y in edge] + rand_field(rng, (4000,)).tolist()
+    c = [edge[(i * 7) % len(edge)] for i in range(len(edge) ** 2)] + rand_field(rng, (4000,)).tolist()
+    mul, add, sub, fma = engine.field_ops(np.array(a, dtype=np.uint64), np.array(b, dtype=np.uint64), np.array(c, dtype=np.uint64))
+    for i, (x, y, z) in enumerate(zip(a, b, c)):
+        x, y, z = int(x), int(y), int(z)
+        assert int(mul[i]) == x * y % P, (hex(x), hex(y))
+        assert int(add[i]) == (x + y) % P, (hex(x), hex(y))
+        assert int(sub[i]) == (x - y) % P, (hex(x), hex(y))
+        assert int(fma[i]) == (x * y + z) % P, (hex(x), hex(y), hex(z))
+
+
 def test_poseidon2_batch(engine, orc):
     rng = np.random.default_rng(1)
     st = rand_field(rng, (1000, 12))

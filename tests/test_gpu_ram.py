@@ -54,7 +54,7 @@ def test_synthetic_bit_exact(engine, orc, n, limit):
 
 
 def test_empty_queue_and_zero_limit(engine, orc):
-    u, s = synthetic.ram_trace(0), synthetic.ram_trace(0)[1]
+    u, s = synthetic.ram_trace(0)
     io, up, sp = H.ram_instance(orc, u, s, 0)
     want, got = run_both(engine, orc, io, u, up, s, sp, 8)
     assert want[0] == abi.ZKC_OK
