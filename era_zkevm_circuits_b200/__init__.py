@@ -10,3 +10,8 @@ from .ram_permutation import (  # noqa: F401
     ram_permutation_check_trace,
     ram_permutation_entry_point,
 )
+from .log_sorter import (  # noqa: F401
+    EventsDeduplicatorInstanceWitness,
+    SorterResult,
+    sort_and_deduplicate_events_entry_point,
+)

@@ -40,6 +40,52 @@ class QueueState4(C.Structure):
     _fields_ = [("head", C.c_uint64 * 4), ("tail", C.c_uint64 * 4), ("length", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+LOG_QUERY_DTYPE = np.dtype([
+    ("address", "<u4", (5,)), ("key", "<u4", (8,)), ("read_value", "<u4", (8,)), ("written_value", "<u4", (8,)),
+    ("tx_number_in_block", "<u4"), ("timestamp", "<u4"), ("flags", "<u4"),
+])
+assert LOG_QUERY_DTYPE.itemsize == 128
+
+
+def lq_flags(aux=0, shard=0, rw=0, rollback=0, service=0):
+    return int(aux) | int(shard) << 8 | int(rw) << 16 | int(rollback) << 17 | int(service) << 18
+
+
+class LogQuery(C.Structure):
+    _fields_ = [("address", C.c_uint32 * 5), ("key", C.c_uint32 * 8), ("read_value", C.c_uint32 * 8),
+                ("written_value", C.c_uint32 * 8), ("tx_number_in_block", C.c_uint32), ("timestamp", C.c_uint32),
+                ("flags", C.c_uint32)]
+
+
+class EventsFsm(C.Structure):
+    _fields_ = [("lhs_accumulator", C.c_uint64 * 2), ("rhs_accumulator", C.c_uint64 * 2),
+                ("initial_unsorted_queue_state", QueueState4), ("intermediate_sorted_queue_state", QueueState4),
+                ("final_result_queue_state", QueueState4), ("previous_key", C.c_uint32), ("_pad", C.c_uint32),
+                ("previous_item", LogQuery)]
+
+
+class EventsClosedForm(C.Structure):
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("initial_log_queue_state", QueueState4),
+                ("intermediate_sorted_queue_state", QueueState4), ("final_queue_state", QueueState4),
+                ("hidden_fsm_input", EventsFsm), ("hidden_fsm_output", EventsFsm)]
+
+
+class SorterOptions(C.Structure):
+    _fields_ = [("compare_expected", C.c_uint32), ("_pad", C.c_uint32 * 3)]
+
+
+EV_COLS = dict(
+    ORIGINAL_IS_EMPTY=0, SORTED_IS_EMPTY=1, SHOULD_POP=2, UNSORTED_ITEM=3, UNSORTED_ENC=39, UNSORTED_HEAD=59,
+    UNSORTED_LEN=63, SORTED_ITEM=64, SORTED_ENC=100, SORTED_HEAD=120, SORTED_LEN=124, GP_CHAIN=125, GP_NEW=205,
+    GP_ACC=209, CMP_DIFF=213, CMP_BORROW=214, KEYS_EQUAL=215, SAME_NONTRIVIAL_LOG=216, DIFFERENT_NONTRIVIAL_LOG=217,
+    ITEM_KEYS_EQUAL=218, VALUES_EQUAL=219, SAME_BODY=220, PREVIOUS_IS_TRIVIAL=221, SHOULD_ENFORCE=222, MAYBE_ADD=223,
+    ADD_TO_QUEUE=224, PUSH_ENC=225, PUSH_ROUND0=245, PUSH_ROUND1=257, PUSH_ROUND2=269, RESULT_TAIL=281, RESULT_LEN=285,
+    NUM_COLS=286)
+EV_CHK = dict(LENGTHS_EQUAL=1 << 0, EMPTY_SYNC=1 << 1, UNSORTED_IS_WRITE=1 << 2, SORTED_IS_WRITE=1 << 3, ORDER=1 << 4,
+              NOT_ROLLBACK=1 << 5, IS_ROLLBACK=1 << 6, SAME_BODY=1 << 7, QUEUE_CONSISTENCY=1 << 8, GRAND_PRODUCT=1 << 9,
+              TRIVIAL_HEAD=1 << 10, QUEUE_HINT=1 << 11)
+
+
 class RamInputData(C.Structure):
     _fields_ = [("unsorted_queue_initial_state", QueueState12), ("sorted_queue_initial_state", QueueState12),
                 ("non_deterministic_bootloader_memory_snapshot_length", C.c_uint32), ("_pad", C.c_uint32)]
@@ -96,6 +142,10 @@ SIGNATURES = {
     "zkc_field_ops": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "zkc_accumulate_grand_products": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "zkc_memory_queue_simulate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, C.c_int]),
+    "zkc_log_queue_simulate": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, C.c_int]),
+    "zkc_log_sorter_entry_point": (C.c_int, [_vp, C.POINTER(EventsClosedForm), _vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t,
+                                             _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions), C.c_int, _vp, _vp,
+                                             C.POINTER(Status)]),
     "zkc_ram_permutation_entry_point": (C.c_int, [_vp, C.POINTER(RamClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,
                                                   C.c_size_t, C.c_size_t, C.POINTER(RamOptions), C.c_int, _vp, _vp,
                                                   C.POINTER(Status)]),

@@ -175,3 +175,29 @@ class Engine:
             if rc:
                 raise ZkcError(rc, what="zkc_memory_queue_simulate")
         return prev, final
+
+    def log_queue_simulate(self, records, extra_timestamps=None, n_queues=1):
+        """push every LogQuery record into `n_queues` empty 4-wide queues; returns (prev_tails [n, 4], final states)"""
+        n = len(records)
+        assert n % n_queues == 0
+        dev = on_device(records, extra_timestamps)
+        final = (abi.QueueState4 * n_queues)()
+        if dev:
+            import torch
+            prev = torch.empty((n, 4), dtype=torch.int64, device=records.device)
+            fin_d = torch.empty((n_queues, C.sizeof(abi.QueueState4)), dtype=torch.uint8, device=records.device)
+            rc = self.lib.zkc_log_queue_simulate(self.h, ptr(records), ptr(extra_timestamps), n // n_queues, n_queues,
+                                                 ptr(prev), ptr(fin_d), 1)
+            if rc:
+                raise ZkcError(rc, what="zkc_log_queue_simulate")
+            host = fin_d.cpu().numpy()
+            C.memmove(final, host.ctypes.data, C.sizeof(final))
+        else:
+            prev = np.empty((n, 4), dtype=np.uint64)
+            if extra_timestamps is not None:
+                extra_timestamps = np.ascontiguousarray(extra_timestamps, dtype=np.uint32)
+            rc = self.lib.zkc_log_queue_simulate(self.h, ptr(records), ptr(extra_timestamps), n // n_queues, n_queues,
+                                                 ptr(prev), C.cast(final, C.c_void_p), 0)
+            if rc:
+                raise ZkcError(rc, what="zkc_log_queue_simulate")
+        return prev, final

@@ -67,3 +67,42 @@ def ram_trace(n: int, seed: int = 0xC1, n_cells: int = 1 << 10, n_nondet: int = 
         head["value"] = splitmix64(seed, n_nondet * 4, 9).view("<u4").reshape(n_nondet, 8)
     srt = np.lexsort((q["timestamp"], q["index"], q["memory_page"]))
     return q, q[srt]
+
+
+def events_trace(n: int, seed: int = 0xC4, rollback_pct: int = 10):
+    """C4 (log_sorter): n event LogQuery records with unique timestamps, `rollback_pct` % of the forward
+    events followed LATER in the unsorted queue by their rollback twin (same timestamp, rollback = 1);
+    sorted order = by (timestamp, rollback), the order log_sorter/mod.rs:315-350 enforces.
+    Every record is a write (rw_flag = 1, :295-297).  Returns (unsorted, sorted)."""
+    q = np.zeros(n, dtype=abi.LOG_QUERY_DTYPE)
+    if n == 0:
+        return q, q.copy()
+    want_rb = (splitmix64(seed, n, 0) % np.uint64(100)) < np.uint64(rollback_pct)
+    # forward events take slots until n is reached together with their twins
+    n_fwd = n
+    while True:
+        n_rb = int(want_rb[:n_fwd].sum())
+        if n_fwd + n_rb <= n:
+            break
+        n_fwd -= max(1, (n_fwd + n_rb - n) // 2)
+    n_rb = n - n_fwd
+    rb_src = np.flatnonzero(want_rb[:n_fwd])[:n_rb]
+    if len(rb_src) < n_rb:  # top up so the total is exactly n
+        extra = np.setdiff1d(np.arange(n_fwd), rb_src)[:n_rb - len(rb_src)]
+        rb_src = np.sort(np.concatenate([rb_src, extra]))
+    fwd = q[:n_fwd]
+    fwd["timestamp"] = 1000 + 4 * np.arange(n_fwd, dtype=np.uint32)
+    fwd["address"] = splitmix64(seed, n_fwd * 3, 1).view("<u4").reshape(n_fwd, 6)[:, :5]
+    fwd["key"] = splitmix64(seed, n_fwd * 4, 2).view("<u4").reshape(n_fwd, 8)
+    fwd["written_value"] = splitmix64(seed, n_fwd * 4, 3).view("<u4").reshape(n_fwd, 8)
+    r = splitmix64(seed, n_fwd, 4)
+    fwd["tx_number_in_block"] = (r % np.uint64(1000)).astype(np.uint32)
+    service = ((r >> np.uint64(20)) & np.uint64(1)).astype(np.uint32)
+    aux = ((r >> np.uint64(24)) % np.uint64(3)).astype(np.uint32)
+    fwd["flags"] = aux | (1 << 16) | (service << 18)
+    q[n_fwd:] = fwd[rb_src]
+    q["flags"][n_fwd:] |= 1 << 17
+    # the unsorted queue is in execution order: rollbacks appear after all forward events (reverted frames)
+    rollback = (q["flags"] >> 17) & 1
+    srt = np.lexsort((rollback, q["timestamp"]))
+    return q, q[srt]

@@ -37,6 +37,12 @@ def load():
     lib.orc_ram_permutation_entry_point.restype = C.c_int
     lib.orc_ram_permutation_entry_point.argtypes = [C.POINTER(abi.RamClosedForm), _vp, C.c_size_t, _vp, C.c_size_t,
                                                     C.c_size_t, C.POINTER(abi.RamOptions), _vp, _vp, C.POINTER(abi.Status)]
+    lib.orc_log_query_encode.argtypes = [_vp, _vp]
+    lib.orc_log_queue_simulate.argtypes = [_vp, _vp, C.c_size_t, _vp, C.POINTER(abi.QueueState4)]
+    lib.orc_log_sorter_entry_point.restype = C.c_int
+    lib.orc_log_sorter_entry_point.argtypes = [C.POINTER(abi.EventsClosedForm), _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t,
+                                               C.POINTER(abi.SorterOptions), _vp, _vp, C.POINTER(C.c_size_t), _vp,
+                                               C.POINTER(abi.Status)]
     _LIB = lib
     return lib
 
@@ -102,3 +108,38 @@ def ram_entry_point(lib, io, unsorted, sorted_, limit, want_trace=True, compare_
     rc = lib.orc_ram_permutation_entry_point(C.byref(io2), p(unsorted), len(unsorted), p(sorted_), len(sorted_), limit,
                                              C.byref(opts), p(trace), p(com), C.byref(st))
     return rc, io2, trace, com, st
+
+
+def log_queue_simulate(lib, records, extra_ts=None):
+    records = np.ascontiguousarray(records)
+    prev = np.zeros((len(records), 4), dtype=np.uint64)
+    fin = abi.QueueState4()
+    if extra_ts is not None:
+        extra_ts = np.ascontiguousarray(extra_ts, dtype=np.uint32)
+    lib.orc_log_queue_simulate(p(records), p(extra_ts), len(records), p(prev), C.byref(fin))
+    return prev, fin
+
+
+def events_closed_form(unsorted_state, sorted_state, start=True, fsm_in=None):
+    io = abi.EventsClosedForm()
+    io.start_flag = int(start)
+    io.initial_log_queue_state = unsorted_state
+    io.intermediate_sorted_queue_state = sorted_state
+    if fsm_in is not None:
+        io.hidden_fsm_input = fsm_in
+    return io
+
+
+def log_sorter_entry_point(lib, io, unsorted, sorted_, limit, want_trace=True, compare_expected=False):
+    """returns (rc, io_out, trace, commitment, status, result_tails)"""
+    io2 = abi.EventsClosedForm.from_buffer_copy(bytes(io))
+    unsorted = np.ascontiguousarray(unsorted); sorted_ = np.ascontiguousarray(sorted_)
+    trace = np.zeros((abi.EV_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
+    tails = np.zeros((limit + 1, 4), dtype=np.uint64)
+    n_tails = C.c_size_t()
+    com = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    opts = abi.SorterOptions(int(compare_expected))
+    rc = lib.orc_log_sorter_entry_point(C.byref(io2), p(unsorted), len(unsorted), p(sorted_), len(sorted_), limit,
+                                        C.byref(opts), p(trace), p(tails), C.byref(n_tails), p(com), C.byref(st))
+    return rc, io2, trace, com, st, tails[:n_tails.value].copy()

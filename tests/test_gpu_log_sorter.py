@@ -1,0 +1,133 @@
+"""log_sorter: CUDA path through the C ABI vs the CPU oracle, bit-exact (trace, FSM output, observable
+output, commitment, status).  Mirrors /root/reference/src/log_sorter/mod.rs:494-635 and widens it."""
+import numpy as np
+import pytest
+
+import orc as O
+import vectors as V
+from era_zkevm_circuits_b200 import (EventsDeduplicatorInstanceWitness, abi, sort_and_deduplicate_events_entry_point,
+                                     synthetic)
+
+pytestmark = pytest.mark.gpu
+K = abi.EV_COLS
+CHK = abi.EV_CHK
+
+
+def instance(orc, u, s):
+    up, ufin = O.log_queue_simulate(orc, u)
+    sp, sfin = O.log_queue_simulate(orc, s)
+    return O.events_closed_form(ufin, sfin, True), up, sp
+
+
+def assert_same(want, got, check_trace=True):
+    rc, io, trace, com, st, tails = want
+    assert got.status.code == rc, (got.status.code, hex(got.status.failed_checks), got.status.first_bad_row)
+    assert got.status.failed_checks == st.failed_checks and got.status.first_bad_row == st.first_bad_row
+    assert got.closed_form_input.completion_flag == io.completion_flag
+    assert bytes(got.closed_form_input.hidden_fsm_output) == bytes(io.hidden_fsm_output)
+    assert bytes(got.closed_form_input.final_queue_state) == bytes(io.final_queue_state)
+    assert got.commitment.tolist() == com.tolist()
+    if check_trace:
+        bad = np.argwhere(got.trace != trace)
+        assert bad.size == 0, f"first differing (col,row): {bad[:5].tolist()}"
+
+
+def run_both(engine, orc, io, u, up, s, sp, limit, tails=None, **kw):
+    want = O.log_sorter_entry_point(orc, io, u, s, limit)
+    w = EventsDeduplicatorInstanceWitness(io, u, up, s, sp, tails)
+    got = sort_and_deduplicate_events_entry_point(engine, w, limit, raise_on_unsatisfied=False, **kw)
+    return want, got
+
+
+def test_reference_vector(engine, orc):
+    u, s = V.log_sorter_reference_vector()
+    io, up, sp = instance(orc, u, s)
+    want, got = run_both(engine, orc, io, u, up, s, sp, 16)
+    assert want[0] == abi.ZKC_OK
+    assert_same(want, got)
+    # with the host-supplied result-queue tails (verified, no sequential chain on the device)
+    want, got = run_both(engine, orc, io, u, up, s, sp, 16, tails=want[5])
+    assert_same(want, got)
+
+
+@pytest.mark.parametrize("n,limit,rb", [(1, 1, 0), (2, 2, 100), (255, 256, 10), (257, 257, 30), (1000, 1024, 10), (20000, 20000, 10)])
+def test_synthetic_bit_exact(engine, orc, n, limit, rb):
+    u, s = synthetic.events_trace(n, seed=n, rollback_pct=rb)
+    io, up, sp = instance(orc, u, s)
+    want, got = run_both(engine, orc, io, u, up, s, sp, limit)
+    assert want[0] == abi.ZKC_OK, (hex(want[4].failed_checks), want[4].first_bad_row)
+    assert_same(want, got)
+    want2, got2 = run_both(engine, orc, io, u, up, s, sp, limit, tails=want[5])
+    assert_same(want2, got2)
+
+
+def test_chained_instances_and_empty(engine, orc):
+    u, s = synthetic.events_trace(3000, seed=9, rollback_pct=15)
+    io, up, sp = instance(orc, u, s)
+    whole = sort_and_deduplicate_events_entry_point(engine, EventsDeduplicatorInstanceWitness(io, u, up, s, sp), 3000)
+    a = sort_and_deduplicate_events_entry_point(engine, EventsDeduplicatorInstanceWitness(io, u, up, s, sp), 1100)
+    assert a.closed_form_input.completion_flag == 0
+    nxt = abi.EventsClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+    want, got = run_both(engine, orc, nxt, u[1100:], up[1100:], s[1100:], sp[1100:], 1900)
+    assert_same(want, got)
+    assert bytes(got.closed_form_input.hidden_fsm_output) == bytes(whole.closed_form_input.hidden_fsm_output)
+    assert np.array_equal(np.concatenate([a.trace, got.trace], axis=1), whole.trace)
+    exp = abi.EventsClosedForm.from_buffer_copy(bytes(nxt))
+    exp.hidden_fsm_output = got.closed_form_input.hidden_fsm_output
+    exp.final_queue_state = got.closed_form_input.final_queue_state
+    exp.completion_flag = 1
+    ok = sort_and_deduplicate_events_entry_point(engine, EventsDeduplicatorInstanceWitness(exp, u[1100:], up[1100:], s[1100:], sp[1100:]),
+                                                 1900, compare_expected=True)
+    assert ok.status.code == 0
+    exp.final_queue_state.length += 1
+    bad = sort_and_deduplicate_events_entry_point(engine, EventsDeduplicatorInstanceWitness(exp, u[1100:], up[1100:], s[1100:], sp[1100:]),
+                                                  1900, compare_expected=True, raise_on_unsatisfied=False)
+    assert bad.status.code == abi.ZKC_ERR_FSM_OUTPUT_MISMATCH
+    # empty queues
+    e = np.zeros(0, dtype=abi.LOG_QUERY_DTYPE)
+    io0, up0, sp0 = instance(orc, e, e)
+    want, got = run_both(engine, orc, io0, e, up0, e, sp0, 8)
+    assert want[0] == abi.ZKC_OK
+    assert_same(want, got)
+
+
+def test_negative_cases_match_oracle(engine, orc):
+    u, s = synthetic.events_trace(1500, seed=4, rollback_pct=20)
+    cases = []
+    s2 = s.copy(); s2[[10, 60]] = s2[[60, 10]]; cases.append((u, s2))
+    rb = int(np.flatnonzero((s["flags"] >> 17) & 1)[3])
+    s3 = s.copy(); s3["key"][rb][5] ^= 1; cases.append((u, s3))
+    s4 = s.copy(); s4["flags"][700] ^= 1 << 17; cases.append((u, s4))
+    u5 = u.copy(); u5["flags"][9] ^= 1 << 16; cases.append((u5, s))
+    for uu, ss in cases:
+        io, up, sp = instance(orc, uu, ss)
+        want, got = run_both(engine, orc, io, uu, up, ss, sp, 1536)
+        assert want[0] == abi.ZKC_ERR_UNSATISFIED
+        assert_same(want, got)
+    # corrupted hints
+    io, up, sp = instance(orc, u, s)
+    want = O.log_sorter_entry_point(orc, io, u, s, 1536)
+    t = want[5].copy(); t[100, 2] ^= 1
+    r = sort_and_deduplicate_events_entry_point(engine, EventsDeduplicatorInstanceWitness(io, u, up, s, sp, t), 1536, raise_on_unsatisfied=False)
+    assert r.status.code == abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT
+    sp2 = sp.copy(); sp2[7, 0] ^= 1
+    r = sort_and_deduplicate_events_entry_point(engine, EventsDeduplicatorInstanceWitness(io, u, up, s, sp2), 1536, raise_on_unsatisfied=False)
+    assert r.status.code == abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT and r.status.first_bad_row in (6, 7)
+
+
+def test_device_resident_and_queue_simulate(engine, orc):
+    import torch
+    n = 5000
+    u, s = synthetic.events_trace(n, seed=13)
+    io, up, sp = instance(orc, u, s)
+    want = O.log_sorter_entry_point(orc, io, u, s, n)
+    prev, fin = engine.log_queue_simulate(u)
+    assert np.array_equal(prev, up) and bytes(fin[0]) == bytes(io.initial_log_queue_state)
+    tod = lambda a: torch.from_numpy(a.view(np.uint8).reshape(len(a), -1)).cuda()
+    t64 = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+    w = EventsDeduplicatorInstanceWitness(io, tod(u), t64(up), tod(s), t64(sp), t64(want[5]))
+    got = sort_and_deduplicate_events_entry_point(engine, w, n)
+    torch.cuda.synchronize()
+    assert got.commitment.tolist() == want[3].tolist()
+    assert np.array_equal(got.trace.cpu().numpy().view(np.uint64), want[2])

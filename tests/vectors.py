@@ -30,3 +30,37 @@ def ram_reference_vector():
         _mq(1025, 30, 0, 0, 0, 1125899906842626),
     ], dtype=abi.MEMORY_QUERY_DTYPE)
     return unsorted, sorted_
+
+
+def _limbs(v, n):
+    return [(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+
+
+def log_queries_from_fixture(items):
+    """tests/golden/*_vector.json (extracted from the reference by tools/extract_reference_vectors.py) -> records.
+    Address::from_low_u64_le(v) puts v's little-endian bytes into the LAST 8 bytes of the 20-byte big-endian address."""
+    out = np.zeros(len(items), dtype=abi.LOG_QUERY_DTYPE)
+    extra = np.zeros(len(items), dtype=np.uint32)
+    for i, q in enumerate(items):
+        addr_bytes = bytes(12) + int(q["address_low_u64_le"]).to_bytes(8, "little")
+        out[i]["address"] = _limbs(int.from_bytes(addr_bytes, "big"), 5)
+        out[i]["key"] = _limbs(int(q["key"]), 8)
+        out[i]["read_value"] = _limbs(int(q["read_value"]), 8)
+        out[i]["written_value"] = _limbs(int(q["written_value"]), 8)
+        out[i]["tx_number_in_block"] = q["tx_number_in_block"]
+        out[i]["timestamp"] = q["timestamp"]
+        out[i]["flags"] = abi.lq_flags(q["aux_byte"], q["shard_id"], q["rw_flag"], q["rollback"], q["is_service"])
+        extra[i] = q.get("extra_timestamp", 0)
+    return out, extra
+
+
+def _fixture(name):
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+
+
+def log_sorter_reference_vector():
+    """witness_input_unsorted / witness_input_sorted, /root/reference/src/log_sorter/mod.rs:637-816"""
+    f = _fixture("log_sorter_vector.json")
+    return log_queries_from_fixture(f["unsorted"])[0], log_queries_from_fixture(f["sorted"])[0]
