@@ -15,3 +15,7 @@ from .log_sorter import (  # noqa: F401
     SorterResult,
     sort_and_deduplicate_events_entry_point,
 )
+from .storage_validity import (  # noqa: F401
+    StorageDeduplicatorInstanceWitness,
+    sort_and_deduplicate_storage_access_entry_point,
+)

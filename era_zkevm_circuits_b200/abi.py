@@ -70,6 +70,40 @@ class EventsClosedForm(C.Structure):
                 ("hidden_fsm_input", EventsFsm), ("hidden_fsm_output", EventsFsm)]
 
 
+class StorageFsm(C.Structure):
+    _fields_ = [("lhs_accumulator", C.c_uint64 * 2), ("rhs_accumulator", C.c_uint64 * 2),
+                ("current_unsorted_queue_state", QueueState4), ("current_intermediate_sorted_queue_state", QueueState4),
+                ("current_final_sorted_queue_state", QueueState4), ("cycle_idx", C.c_uint32),
+                ("previous_packed_key", C.c_uint32 * 13), ("previous_key", C.c_uint32 * 8),
+                ("previous_address", C.c_uint32 * 5), ("previous_timestamp", C.c_uint32),
+                ("this_cell_has_explicit_read_and_rollback_depth_zero", C.c_uint32),
+                ("this_cell_base_value", C.c_uint32 * 8), ("this_cell_current_value", C.c_uint32 * 8),
+                ("this_cell_current_depth", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class StorageClosedForm(C.Structure):
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("shard_id_to_process", C.c_uint32),
+                ("_pad", C.c_uint32), ("unsorted_log_queue_state", QueueState4),
+                ("intermediate_sorted_queue_state", QueueState4), ("final_sorted_queue_state", QueueState4),
+                ("hidden_fsm_input", StorageFsm), ("hidden_fsm_output", StorageFsm)]
+
+
+ST_COLS = dict(
+    ORIGINAL_IS_EMPTY=0, SORTED_IS_EMPTY=1, SHOULD_POP=2, ORIGINAL_TIMESTAMP=3, UNSORTED_ITEM=4, UNSORTED_ENC=40,
+    UNSORTED_EXT19=60, UNSORTED_HEAD=61, UNSORTED_LEN=65, SORTED_ITEM=66, SORTED_ENC=103, SORTED_HEAD=123, SORTED_LEN=127,
+    SHARD_ID_IS_VALID=128, GP_CHAIN=129, GP_NEW=209, GP_ACC=213, CMP_DIFF=217, CMP_BORROW=230, CMP_LIMB_EQ=243,
+    KEYS_ARE_EQUAL=256, PREVIOUS_KEY_IS_GREATER=257, TS_DIFF=258, PREVIOUS_TIMESTAMP_IS_LESS=259, MUST_ENFORCE=260,
+    VALUE_IS_UNCHANGED=261, CURRENT_DEPTH_IS_ZERO=262, UNCHANGED_BUT_NOT_BY_ROLLBACK=263, ISSUE_PROTECTIVE_READ=264,
+    SHOULD_WRITE=265, SHOULD_UPDATE=266, SHOULD_PUSH=267, NEW_NON_TRIVIAL_CELL=268, PUSH_ENC=269, PUSH_ROUND0=289,
+    PUSH_ROUND1=301, PUSH_ROUND2=313, RESULT_TAIL=325, RESULT_LEN=329, CELL_BASE_VALUE=330, CELL_CURRENT_VALUE=338,
+    CELL_CURRENT_DEPTH=346, CELL_HAS_READ_AT_DEPTH_ZERO=347, NON_TRIVIAL_AND_SAME_CELL=348, READ_OF_SAME_CELL=349,
+    WRITE_OF_SAME_CELL=350, WRITE_NO_ROLLBACK=351, WRITE_ROLLBACK=352, READ_IS_EQUAL_TO_CURRENT=353,
+    CHECK_READ_CONSISTENCY=354, ROLLBACK_DEPTH_IS_ZERO=355, READ_AT_DEPTH_ZERO_OF_SAME_CELL=356, NUM_COLS=357)
+ST_CHK = dict(LENGTHS_EQUAL=1 << 0, EMPTY_SYNC=1 << 1, SHARD_ID=1 << 2, KEY_ORDER=1 << 3, TIMESTAMP_ORDER=1 << 4,
+              FIRST_KEY_NONZERO=1 << 5, READ_CONSISTENCY=1 << 6, QUEUE_CONSISTENCY=1 << 7, GRAND_PRODUCT=1 << 8,
+              TRIVIAL_HEAD=1 << 9, QUEUE_HINT=1 << 10, DEPTH_UNDERFLOW=1 << 11)
+
+
 class SorterOptions(C.Structure):
     _fields_ = [("compare_expected", C.c_uint32), ("_pad", C.c_uint32 * 3)]
 
@@ -146,6 +180,9 @@ SIGNATURES = {
     "zkc_log_sorter_entry_point": (C.c_int, [_vp, C.POINTER(EventsClosedForm), _vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t,
                                              _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions), C.c_int, _vp, _vp,
                                              C.POINTER(Status)]),
+    "zkc_storage_validity_entry_point": (C.c_int, [_vp, C.POINTER(StorageClosedForm), _vp, _vp, C.c_size_t, _vp, _vp, _vp,
+                                                   C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions),
+                                                   C.c_int, _vp, _vp, C.POINTER(Status)]),
     "zkc_ram_permutation_entry_point": (C.c_int, [_vp, C.POINTER(RamClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,
                                                   C.c_size_t, C.c_size_t, C.POINTER(RamOptions), C.c_int, _vp, _vp,
                                                   C.POINTER(Status)]),

@@ -8,6 +8,7 @@
 // by a sequential chain kernel (1 permutation per push).
 #include "ctx.cuh"
 #include "log_query.cuh"
+#include "result_queue.cuh"
 #include "scan.cuh"
 
 namespace zkc {
@@ -289,75 +290,6 @@ ev_rows_kernel(EvDev *d, const zkc_log_query *__restrict__ unsorted, const uint6
 #undef TR
 }
 
-// ---- result-queue chain when the host supplies no tails: one permutation per executed push ------
-__global__ void ev_chain_kernel(const EvDev *d, const uint64_t *__restrict__ r2in, const uint32_t *__restrict__ meta,
-                                uint64_t *__restrict__ tails) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t tail[4];
-    for (int i = 0; i < 4; i++) tail[i] = d->rq0.tail[i];
-    const size_t limit = d->limit;
-    size_t k = 0;
-    for (size_t row = 0; row < limit; row++) {
-        if (!(meta[row] & 1u)) continue;
-        uint64_t s[12];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { s[i] = r2in[8 * row + i]; s[4 + i] = tail[i]; s[8 + i] = r2in[8 * row + 4 + i]; }
-        poseidon2_permute(s);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { tail[i] = s[i]; tails[4 * k + i] = s[i]; }
-        k++;
-    }
-}
-
-// ---- pass B: round 2 of the push against the chained tail -------------------------------------------
-__global__ void __launch_bounds__(256)
-ev_push_kernel(EvDev *d, const uint64_t *__restrict__ r2in, const uint32_t *__restrict__ meta,
-               const uint64_t *__restrict__ tails, size_t n_tails, uint64_t *__restrict__ trace) {
-    const size_t limit = d->limit;
-    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= limit) return;
-    const uint32_t m = meta[row];
-    const size_t k = m >> 1;
-    const bool add = m & 1u;
-    uint64_t before[4], s[12];
-    bool ok = true;
-    if (k == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) before[i] = d->rq0.tail[i];
-    } else if (k - 1 < n_tails) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) before[i] = __ldg(tails + 4 * (k - 1) + i);
-    } else {
-        ok = false;
-#pragma unroll
-        for (int i = 0; i < 4; i++) before[i] = 0;
-    }
-    const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(r2in + 8 * row);
-    const ulonglong2 a = in[0], b = in[1], c = in[2], e = in[3];
-    s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
-#pragma unroll
-    for (int i = 0; i < 4; i++) s[4 + i] = before[i];
-    s[8] = c.x; s[9] = c.y; s[10] = e.x; s[11] = e.y;
-    poseidon2_permute(s);
-    if (add) {
-        if (k < n_tails) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) ok &= __ldg(tails + 4 * k + i) == s[i];
-        } else ok = false;
-    }
-    if (trace) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) trace[(size_t)(ZKC_EV_PUSH_ROUND2 + i) * limit + row] = s[i];
-#pragma unroll
-        for (int i = 0; i < 4; i++) trace[(size_t)(ZKC_EV_RESULT_TAIL + i) * limit + row] = add ? s[i] : before[i];
-    }
-    if (!ok) {
-        d->hint_bad = 1;
-        atomicOr(&d->failed_checks, (uint32_t)ZKC_EV_CHK_QUEUE_HINT);
-        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | ZKC_EV_CHK_QUEUE_HINT);
-    }
-}
-
 // ---- finalize -----------------------------------------------------------------------------------------
 __global__ void ev_finalize_kernel(EvDev *d, const zkc_log_query *__restrict__ sorted, const uint64_t *__restrict__ tails,
                                    size_t n_tails) {
@@ -606,8 +538,8 @@ extern "C" int zkc_log_sorter_entry_point(zkc_ctx *ctx, zkc_events_closed_form *
     ZKC_LAUNCH(ctx, "ev_prologue", ev_prologue_kernel, 1, 96, 0, d);
     if (tiles) {
         ZKC_LAUNCH(ctx, "ev_rows", ev_rows_kernel, (unsigned)tiles, SCAN_THREADS, 0, d, du, dup, dsq, dsp, dtrace, r2in, meta, sg, ts);
-        if (!have_tails) ZKC_LAUNCH(ctx, "ev_chain", ev_chain_kernel, 1, 32, 0, d, r2in, meta, (uint64_t *)dtails);
-        ZKC_LAUNCH(ctx, "ev_push", ev_push_kernel, (unsigned)((limit + 255) / 256), 256, 0, d, r2in, meta, dtails, n_result_tails, dtrace);
+        if (!have_tails) ZKC_LAUNCH(ctx, "ev_chain", rq_chain_kernel<EvDev>, 1, 32, 0, d, r2in, meta, (uint64_t *)dtails);
+        ZKC_LAUNCH(ctx, "ev_push", (rq_push_kernel<EvDev, ZKC_EV_PUSH_ROUND2, ZKC_EV_RESULT_TAIL, ZKC_EV_CHK_QUEUE_HINT>), (unsigned)((limit + 255) / 256), 256, 0, d, r2in, meta, dtails, n_result_tails, dtrace);
     }
     ZKC_LAUNCH(ctx, "ev_finalize", ev_finalize_kernel, 1, 32, 0, d, dsq, dtails, n_result_tails);
     ZKC_CUDA(ctx, status, cudaGetLastError());

@@ -106,3 +106,61 @@ def events_trace(n: int, seed: int = 0xC4, rollback_pct: int = 10):
     rollback = (q["flags"] >> 17) & 1
     srt = np.lexsort((rollback, q["timestamp"]))
     return q, q[srt]
+
+
+def storage_trace(n: int, seed: int = 0xC4, n_cells: int = 1 << 16, shard: int = 0, first_position: int = 0):
+    """C4 (storage_validity): n storage LogQuery records over n_cells (address, key) cells: 60 % reads,
+    30 % writes, 10 % write + rollback pairs (the rollback twin directly follows its write), shard 0.
+    Per cell the history is consistent: a read returns the current value, a write records the value it
+    replaces in read_value, a rollback restores it.  Returns (unsorted, sorted, sorted_timestamps) where
+    sorted is ordered by (address, key) as a 13-limb little-endian integer and then by queue position, and
+    sorted_timestamps = position of the record in the unsorted queue (the `cycle_idx` the circuit packs
+    into the unsorted encoding, storage_validity_by_grand_product/mod.rs:585-610)."""
+    q = np.zeros(n, dtype=abi.LOG_QUERY_DTYPE)
+    if n == 0:
+        return q, q.copy(), np.zeros(0, dtype=np.uint32)
+    n_cells = max(1, min(n_cells, n))
+    kind_r = splitmix64(seed, n, 0) % np.uint64(100)
+    # build the op list: 0 = read, 1 = write, 2 = write of a pair, 3 = rollback of the previous record
+    kind = np.where(kind_r < 60, 0, np.where(kind_r < 90, 1, 2)).astype(np.int8)
+    is_pair_w = kind == 2
+    is_pair_w[-1] = False
+    # a pair occupies positions i and i + 1; drop overlapping pair starts
+    nxt = np.zeros(n, dtype=bool); nxt[1:] = is_pair_w[:-1]
+    is_pair_w &= ~nxt
+    nxt = np.zeros(n, dtype=bool); nxt[1:] = is_pair_w[:-1]
+    kind = np.where(is_pair_w, 2, np.where(nxt, 3, np.where(kind == 2, 1, kind))).astype(np.int8)
+    cell = (splitmix64(seed, n, 1) % np.uint64(n_cells)).astype(np.int64)
+    cell[kind == 3] = cell[np.flatnonzero(kind == 3) - 1]
+    caddr = splitmix64(seed, n_cells * 3, 2).view("<u4").reshape(n_cells, 6)[:, :5].copy()
+    ckey = splitmix64(seed, n_cells * 4, 3).view("<u4").reshape(n_cells, 8).copy()
+    caddr[:, 0] |= 1  # never the all-zero key
+    cinit = splitmix64(seed, n_cells * 4, 4).view("<u4").reshape(n_cells, 8)
+    newval = splitmix64(seed, n * 4, 5).view("<u4").reshape(n, 8)
+    pos = np.arange(n)
+    order = np.lexsort((pos, cell))
+    sc, sk = cell[order], kind[order]
+    first = np.ones(n, dtype=bool); first[1:] = sc[1:] != sc[:-1]
+    # value before each record = written value of the last PLAIN write strictly before it in the cell, else the
+    # cell's initial value
+    is_plain_w = sk == 1
+    idx = np.where(is_plain_w, np.arange(n), -1)
+    seg_start = np.maximum.accumulate(np.where(first, np.arange(n), 0))
+    last_w_incl = np.maximum.accumulate(idx)
+    last_w_excl = np.empty(n, dtype=np.int64); last_w_excl[0] = -1; last_w_excl[1:] = last_w_incl[:-1]
+    has_w = last_w_excl >= seg_start
+    before = np.where(has_w[:, None], newval[order][np.maximum(last_w_excl, 0)], cinit[sc])
+    written = np.where((sk == 0)[:, None], before, newval[order])
+    rb_rows = np.flatnonzero(sk == 3)
+    written[rb_rows] = written[rb_rows - 1]
+    rec = np.zeros(n, dtype=abi.LOG_QUERY_DTYPE)
+    rec["address"], rec["key"] = caddr[sc], ckey[sc]
+    rec["read_value"], rec["written_value"] = before, written
+    rec["timestamp"] = 100 + order
+    rec["flags"] = (shard << 8) | ((sk != 0).astype(np.uint32) << 16) | ((sk == 3).astype(np.uint32) << 17)
+    q[order] = rec
+    # sorted: by the 13-limb packed key (address most significant) then by queue position
+    crank_order = np.lexsort(tuple(ckey[:, i] for i in range(8)) + tuple(caddr[:, i] for i in range(5)))
+    crank = np.empty(n_cells, dtype=np.int64); crank[crank_order] = np.arange(n_cells)
+    srt = np.lexsort((pos, crank[cell]))
+    return q, q[srt], (first_position + srt).astype(np.uint32)

@@ -403,6 +403,124 @@ int zkc_log_sorter_entry_point(zkc_ctx *ctx, zkc_events_closed_form *io, const z
                                size_t n_result_tails, size_t limit, const zkc_sorter_options *options, int on_device,
                                uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
+
+/* ---- storage_validity_by_grand_product (src/storage_validity_by_grand_product/mod.rs) ------------ */
+#define ZKC_PACKED_KEY_LENGTH 13 /* PACKED_KEY_LENGTH, input.rs:28 */
+
+/* StorageDeduplicatorFSMInputOutput, input.rs:37-52 */
+typedef struct zkc_storage_fsm {
+    uint64_t lhs_accumulator[ZKC_NUM_REPETITIONS];
+    uint64_t rhs_accumulator[ZKC_NUM_REPETITIONS];
+    zkc_queue_state4 current_unsorted_queue_state;
+    zkc_queue_state4 current_intermediate_sorted_queue_state;
+    zkc_queue_state4 current_final_sorted_queue_state;
+    uint32_t cycle_idx;
+    uint32_t previous_packed_key[ZKC_PACKED_KEY_LENGTH];
+    uint32_t previous_key[8];
+    uint32_t previous_address[5];
+    uint32_t previous_timestamp;
+    uint32_t this_cell_has_explicit_read_and_rollback_depth_zero;
+    uint32_t this_cell_base_value[8];
+    uint32_t this_cell_current_value[8];
+    uint32_t this_cell_current_depth;
+    uint32_t _pad;
+} zkc_storage_fsm;
+
+/* ClosedFormInputWitness<F, StorageDeduplicatorFSMInputOutput, StorageDeduplicatorInputData,
+ * StorageDeduplicatorOutputData>, input.rs:90-126 */
+typedef struct zkc_storage_closed_form {
+    uint32_t start_flag;
+    uint32_t completion_flag;                          /* out */
+    uint32_t shard_id_to_process;                      /* observable input */
+    uint32_t _pad;
+    zkc_queue_state4 unsorted_log_queue_state;         /* observable input */
+    zkc_queue_state4 intermediate_sorted_queue_state;  /* observable input */
+    zkc_queue_state4 final_sorted_queue_state;         /* observable output */
+    zkc_storage_fsm hidden_fsm_input;
+    zkc_storage_fsm hidden_fsm_output;
+} zkc_storage_closed_form;
+
+/* trace columns of one iteration of sort_and_deduplicate_storage_access_inner (mod.rs:584-833) */
+enum zkc_storage_col {
+    ZKC_ST_ORIGINAL_IS_EMPTY = 0,
+    ZKC_ST_SORTED_IS_EMPTY = 1,
+    ZKC_ST_SHOULD_POP = 2,
+    ZKC_ST_ORIGINAL_TIMESTAMP = 3, /* cycle_idx before the increment, :585 */
+    ZKC_ST_UNSORTED_ITEM = 4,      /* 36 */
+    ZKC_ST_UNSORTED_ENC = 40,      /* 20: LogQuery::encode */
+    ZKC_ST_UNSORTED_EXT19 = 60,    /* element 19 after append_timestamp_to_raw_query_encoding, :605-610 */
+    ZKC_ST_UNSORTED_HEAD = 61,     /* 4 */
+    ZKC_ST_UNSORTED_LEN = 65,
+    ZKC_ST_SORTED_ITEM = 66,       /* 37: record flatten + timestamp */
+    ZKC_ST_SORTED_ENC = 103,       /* 20: timestamped encoding */
+    ZKC_ST_SORTED_HEAD = 123,      /* 4 */
+    ZKC_ST_SORTED_LEN = 127,
+    ZKC_ST_SHARD_ID_IS_VALID = 128,
+    ZKC_ST_GP_CHAIN = 129,         /* 80 */
+    ZKC_ST_GP_NEW = 209,           /* 4 */
+    ZKC_ST_GP_ACC = 213,           /* 4 */
+    ZKC_ST_CMP_DIFF = 217,         /* 13: unpacked_long_comparison(previous_packed_key, packed_key), :635-636 */
+    ZKC_ST_CMP_BORROW = 230,       /* 13 */
+    ZKC_ST_CMP_LIMB_EQ = 243,      /* 13 */
+    ZKC_ST_KEYS_ARE_EQUAL = 256,
+    ZKC_ST_PREVIOUS_KEY_IS_GREATER = 257,
+    ZKC_ST_TS_DIFF = 258,          /* previous_timestamp - timestamp, :645 */
+    ZKC_ST_PREVIOUS_TIMESTAMP_IS_LESS = 259,
+    ZKC_ST_MUST_ENFORCE = 260,
+    ZKC_ST_VALUE_IS_UNCHANGED = 261,
+    ZKC_ST_CURRENT_DEPTH_IS_ZERO = 262,
+    ZKC_ST_UNCHANGED_BUT_NOT_BY_ROLLBACK = 263,
+    ZKC_ST_ISSUE_PROTECTIVE_READ = 264,
+    ZKC_ST_SHOULD_WRITE = 265,
+    ZKC_ST_SHOULD_UPDATE = 266,
+    ZKC_ST_SHOULD_PUSH = 267,
+    ZKC_ST_NEW_NON_TRIVIAL_CELL = 268,
+    ZKC_ST_PUSH_ENC = 269,         /* 20 */
+    ZKC_ST_PUSH_ROUND0 = 289,      /* 12 */
+    ZKC_ST_PUSH_ROUND1 = 301,      /* 12 */
+    ZKC_ST_PUSH_ROUND2 = 313,      /* 12 */
+    ZKC_ST_RESULT_TAIL = 325,      /* 4 */
+    ZKC_ST_RESULT_LEN = 329,
+    ZKC_ST_CELL_BASE_VALUE = 330,      /* 8: this_cell_base_value at the end of the iteration */
+    ZKC_ST_CELL_CURRENT_VALUE = 338,   /* 8 */
+    ZKC_ST_CELL_CURRENT_DEPTH = 346,
+    ZKC_ST_CELL_HAS_READ_AT_DEPTH_ZERO = 347,
+    ZKC_ST_NON_TRIVIAL_AND_SAME_CELL = 348,
+    ZKC_ST_READ_OF_SAME_CELL = 349,
+    ZKC_ST_WRITE_OF_SAME_CELL = 350,
+    ZKC_ST_WRITE_NO_ROLLBACK = 351,
+    ZKC_ST_WRITE_ROLLBACK = 352,
+    ZKC_ST_READ_IS_EQUAL_TO_CURRENT = 353,
+    ZKC_ST_CHECK_READ_CONSISTENCY = 354,
+    ZKC_ST_ROLLBACK_DEPTH_IS_ZERO = 355,
+    ZKC_ST_READ_AT_DEPTH_ZERO_OF_SAME_CELL = 356,
+    ZKC_ST_NUM_COLS = 357
+};
+
+#define ZKC_ST_CHK_LENGTHS_EQUAL (1u << 0)     /* :565-569 */
+#define ZKC_ST_CHK_EMPTY_SYNC (1u << 1)        /* :594 and entry point :431 */
+#define ZKC_ST_CHK_SHARD_ID (1u << 2)          /* :612-614 */
+#define ZKC_ST_CHK_KEY_ORDER (1u << 3)         /* :638-639 */
+#define ZKC_ST_CHK_TIMESTAMP_ORDER (1u << 4)   /* :645-648 */
+#define ZKC_ST_CHK_FIRST_KEY_NONZERO (1u << 5) /* :657-661 */
+#define ZKC_ST_CHK_READ_CONSISTENCY (1u << 6)  /* :787-792 */
+#define ZKC_ST_CHK_QUEUE_CONSISTENCY (1u << 7) /* :425-426 */
+#define ZKC_ST_CHK_GRAND_PRODUCT (1u << 8)     /* :434-437 */
+#define ZKC_ST_CHK_TRIVIAL_HEAD (1u << 9)      /* :213, :281 */
+#define ZKC_ST_CHK_QUEUE_HINT (1u << 10)
+#define ZKC_ST_CHK_DEPTH_UNDERFLOW (1u << 11)  /* a rollback at depth 0: decrement_unchecked (:774) would leave the u32
+                                                  range in the reference; such inputs are not legal traces */
+
+/* sort_and_deduplicate_storage_access_entry_point, mod.rs:166-507.  Arguments as zkc_log_sorter_entry_point;
+ * sorted_timestamps[n_sorted] = TimestampedStorageLogRecord.timestamp of each sorted record (mod.rs:63-66). */
+int zkc_storage_validity_entry_point(zkc_ctx *ctx, zkc_storage_closed_form *io, const zkc_log_query *unsorted,
+                                     const uint64_t *unsorted_prev_tails, size_t n_unsorted,
+                                     const zkc_log_query *sorted, const uint32_t *sorted_timestamps,
+                                     const uint64_t *sorted_prev_tails, size_t n_sorted, const uint64_t *result_tails,
+                                     size_t n_result_tails, size_t limit, const zkc_sorter_options *options,
+                                     int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN],
+                                     zkc_status *status);
+
 #ifdef __cplusplus
 }
 #endif

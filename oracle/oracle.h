@@ -75,4 +75,10 @@ int orc_log_sorter_entry_point(zkc_events_closed_form *io, const zkc_log_query *
                                const zkc_log_query *sorted, size_t n_sorted, size_t limit,
                                const zkc_sorter_options *options, uint64_t *trace, uint64_t *result_tails,
                                size_t *n_result_tails, uint64_t commitment[4], zkc_status *status);
+/* storage_validity.c */
+size_t orc_storage_encode_fsm(const zkc_storage_fsm *f, uint64_t *dst);
+int orc_storage_validity_entry_point(zkc_storage_closed_form *io, const zkc_log_query *unsorted, size_t n_unsorted,
+                                     const zkc_log_query *sorted, const uint32_t *sorted_ts, size_t n_sorted, size_t limit,
+                                     const zkc_sorter_options *options, uint64_t *trace, uint64_t *result_tails,
+                                     size_t *n_result_tails, uint64_t commitment[4], zkc_status *status);
 #endif

@@ -43,6 +43,10 @@ def load():
     lib.orc_log_sorter_entry_point.argtypes = [C.POINTER(abi.EventsClosedForm), _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t,
                                                C.POINTER(abi.SorterOptions), _vp, _vp, C.POINTER(C.c_size_t), _vp,
                                                C.POINTER(abi.Status)]
+    lib.orc_storage_validity_entry_point.restype = C.c_int
+    lib.orc_storage_validity_entry_point.argtypes = [C.POINTER(abi.StorageClosedForm), _vp, C.c_size_t, _vp, _vp, C.c_size_t,
+                                                     C.c_size_t, C.POINTER(abi.SorterOptions), _vp, _vp,
+                                                     C.POINTER(C.c_size_t), _vp, C.POINTER(abi.Status)]
     _LIB = lib
     return lib
 
@@ -142,4 +146,31 @@ def log_sorter_entry_point(lib, io, unsorted, sorted_, limit, want_trace=True, c
     opts = abi.SorterOptions(int(compare_expected))
     rc = lib.orc_log_sorter_entry_point(C.byref(io2), p(unsorted), len(unsorted), p(sorted_), len(sorted_), limit,
                                         C.byref(opts), p(trace), p(tails), C.byref(n_tails), p(com), C.byref(st))
+    return rc, io2, trace, com, st, tails[:n_tails.value].copy()
+
+
+def storage_closed_form(unsorted_state, sorted_state, shard=0, start=True, fsm_in=None):
+    io = abi.StorageClosedForm()
+    io.start_flag = int(start)
+    io.shard_id_to_process = shard
+    io.unsorted_log_queue_state = unsorted_state
+    io.intermediate_sorted_queue_state = sorted_state
+    if fsm_in is not None:
+        io.hidden_fsm_input = fsm_in
+    return io
+
+
+def storage_validity_entry_point(lib, io, unsorted, sorted_, sorted_ts, limit, want_trace=True, compare_expected=False):
+    """returns (rc, io_out, trace, commitment, status, result_tails)"""
+    io2 = abi.StorageClosedForm.from_buffer_copy(bytes(io))
+    unsorted = np.ascontiguousarray(unsorted); sorted_ = np.ascontiguousarray(sorted_)
+    sorted_ts = np.ascontiguousarray(sorted_ts, dtype=np.uint32)
+    trace = np.zeros((abi.ST_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
+    tails = np.zeros((limit + 1, 4), dtype=np.uint64)
+    n_tails = C.c_size_t()
+    com = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    opts = abi.SorterOptions(int(compare_expected))
+    rc = lib.orc_storage_validity_entry_point(C.byref(io2), p(unsorted), len(unsorted), p(sorted_), p(sorted_ts), len(sorted_),
+                                              limit, C.byref(opts), p(trace), p(tails), C.byref(n_tails), p(com), C.byref(st))
     return rc, io2, trace, com, st, tails[:n_tails.value].copy()

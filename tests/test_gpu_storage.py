@@ -1,0 +1,124 @@
+"""storage_validity_by_grand_product: CUDA path through the C ABI vs the CPU oracle, bit-exact.  Mirrors
+/root/reference/src/storage_validity_by_grand_product/mod.rs:1035-1160 (reference vectors) and widens it."""
+import numpy as np
+import pytest
+
+import orc as O
+import vectors as V
+from era_zkevm_circuits_b200 import (StorageDeduplicatorInstanceWitness, abi,
+                                     sort_and_deduplicate_storage_access_entry_point, synthetic)
+
+pytestmark = pytest.mark.gpu
+K = abi.ST_COLS
+CHK = abi.ST_CHK
+
+
+def instance(orc, u, s, ts, shard=0):
+    up, ufin = O.log_queue_simulate(orc, u)
+    sp, sfin = O.log_queue_simulate(orc, s, ts)
+    return O.storage_closed_form(ufin, sfin, shard, True), up, sp
+
+
+def assert_same(want, got, check_trace=True):
+    rc, io, trace, com, st, tails = want
+    assert got.status.code == rc, (got.status.code, hex(got.status.failed_checks), got.status.first_bad_row)
+    assert got.status.failed_checks == st.failed_checks and got.status.first_bad_row == st.first_bad_row
+    assert got.closed_form_input.completion_flag == io.completion_flag
+    assert bytes(got.closed_form_input.hidden_fsm_output) == bytes(io.hidden_fsm_output)
+    assert bytes(got.closed_form_input.final_sorted_queue_state) == bytes(io.final_sorted_queue_state)
+    assert got.commitment.tolist() == com.tolist()
+    if check_trace:
+        bad = np.argwhere(got.trace != trace)
+        assert bad.size == 0, f"first differing (col,row): {bad[:8].tolist()}"
+
+
+def run_both(engine, orc, io, u, up, s, ts, sp, limit, tails=None, **kw):
+    want = O.storage_validity_entry_point(orc, io, u, s, ts, limit)
+    w = StorageDeduplicatorInstanceWitness(io, u, up, s, ts, sp, tails)
+    got = sort_and_deduplicate_storage_access_entry_point(engine, w, limit, raise_on_unsatisfied=False, **kw)
+    return want, got
+
+
+def test_reference_vector(engine, orc):
+    u, s, ts = V.storage_reference_vector()
+    io, up, sp = instance(orc, u, s, ts)
+    want, got = run_both(engine, orc, io, u, up, s, ts, sp, 16)
+    assert want[4].failed_checks == CHK["GRAND_PRODUCT"]  # the reference's vector is not a permutation
+    assert_same(want, got)
+
+
+@pytest.mark.parametrize("n,limit,cells", [(1, 1, 1), (3, 4, 1), (255, 256, 7), (257, 257, 300), (1000, 1024, 20), (30000, 30000, 500)])
+def test_synthetic_bit_exact(engine, orc, n, limit, cells):
+    u, s, ts = synthetic.storage_trace(n, seed=n, n_cells=cells)
+    io, up, sp = instance(orc, u, s, ts)
+    want, got = run_both(engine, orc, io, u, up, s, ts, sp, limit)
+    assert want[0] == abi.ZKC_OK, (hex(want[4].failed_checks), want[4].first_bad_row)
+    assert_same(want, got)
+    want2, got2 = run_both(engine, orc, io, u, up, s, ts, sp, limit, tails=want[5])
+    assert_same(want2, got2)
+
+
+def test_chained_instances(engine, orc):
+    n = 4000
+    u, s, ts = synthetic.storage_trace(n, seed=9, n_cells=60)
+    io, up, sp = instance(orc, u, s, ts)
+    W = StorageDeduplicatorInstanceWitness
+    whole = sort_and_deduplicate_storage_access_entry_point(engine, W(io, u, up, s, ts, sp), n)
+    cut = 1777
+    a = sort_and_deduplicate_storage_access_entry_point(engine, W(io, u, up, s, ts, sp), cut)
+    assert a.closed_form_input.completion_flag == 0
+    nxt = abi.StorageClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+    want, got = run_both(engine, orc, nxt, u[cut:], up[cut:], s[cut:], ts[cut:], sp[cut:], n - cut)
+    assert_same(want, got)
+    assert bytes(got.closed_form_input.hidden_fsm_output) == bytes(whole.closed_form_input.hidden_fsm_output)
+    assert np.array_equal(np.concatenate([a.trace, got.trace], axis=1), whole.trace)
+    exp = abi.StorageClosedForm.from_buffer_copy(bytes(nxt))
+    exp.hidden_fsm_output = got.closed_form_input.hidden_fsm_output
+    exp.final_sorted_queue_state = got.closed_form_input.final_sorted_queue_state
+    exp.completion_flag = 1
+    ok = sort_and_deduplicate_storage_access_entry_point(engine, W(exp, u[cut:], up[cut:], s[cut:], ts[cut:], sp[cut:]), n - cut,
+                                                         compare_expected=True)
+    assert ok.status.code == 0
+    exp.hidden_fsm_output.this_cell_current_depth += 1
+    bad = sort_and_deduplicate_storage_access_entry_point(engine, W(exp, u[cut:], up[cut:], s[cut:], ts[cut:], sp[cut:]), n - cut,
+                                                          compare_expected=True, raise_on_unsatisfied=False)
+    assert bad.status.code == abi.ZKC_ERR_FSM_OUTPUT_MISMATCH
+
+
+def test_negative_cases_match_oracle(engine, orc):
+    u, s, ts = synthetic.storage_trace(2500, seed=8, n_cells=40)
+    cases = []
+    rd = int(np.flatnonzero(((s["flags"] >> 16) & 1) == 0)[200])
+    s2 = s.copy(); s2["read_value"][rd][1] ^= 1; u2 = u.copy(); u2["read_value"][ts[rd]][1] ^= 1
+    cases.append((u2, s2, ts, 0))
+    s3 = s.copy(); ts3 = ts.copy(); s3[[100, 1500]] = s3[[1500, 100]]; ts3[[100, 1500]] = ts3[[1500, 100]]
+    cases.append((u, s3, ts3, 0))
+    cases.append((u, s, ts, 1))
+    ts5 = ts.copy(); ts5[3] += 1
+    cases.append((u, s, ts5, 0))
+    rb = int(np.flatnonzero((s["flags"] >> 17) & 1)[0])
+    s6 = s.copy(); s6["flags"][rb - 1] ^= 1 << 17  # two rollbacks in a row: depth underflow
+    cases.append((u, s6, ts, 0))
+    for uu, ss, tt, shard in cases:
+        io, up, sp = instance(orc, uu, ss, tt, shard)
+        want, got = run_both(engine, orc, io, uu, up, ss, tt, sp, 2560)
+        assert want[0] == abi.ZKC_ERR_UNSATISFIED
+        assert_same(want, got)
+
+
+def test_device_resident(engine, orc):
+    import torch
+    n = 6000
+    u, s, ts = synthetic.storage_trace(n, seed=13, n_cells=100)
+    io, up, sp = instance(orc, u, s, ts)
+    want = O.storage_validity_entry_point(orc, io, u, s, ts, n)
+    prev, fin = engine.log_queue_simulate(s, ts)
+    assert np.array_equal(prev, sp) and bytes(fin[0]) == bytes(io.intermediate_sorted_queue_state)
+    tod = lambda a: torch.from_numpy(a.view(np.uint8).reshape(len(a), -1)).cuda()
+    t64 = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+    w = StorageDeduplicatorInstanceWitness(io, tod(u), t64(up), tod(s), torch.from_numpy(ts.view(np.int32)).cuda(), t64(sp), t64(want[5]))
+    got = sort_and_deduplicate_storage_access_entry_point(engine, w, n)
+    torch.cuda.synchronize()
+    assert got.commitment.tolist() == want[3].tolist()
+    assert np.array_equal(got.trace.cpu().numpy().view(np.uint64), want[2])

@@ -64,3 +64,11 @@ def log_sorter_reference_vector():
     """witness_input_unsorted / witness_input_sorted, /root/reference/src/log_sorter/mod.rs:637-816"""
     f = _fixture("log_sorter_vector.json")
     return log_queries_from_fixture(f["unsorted"])[0], log_queries_from_fixture(f["sorted"])[0]
+
+
+def storage_reference_vector():
+    """generate_test_input_unsorted / generate_test_input_sorted,
+    /root/reference/src/storage_validity_by_grand_product/test_input.rs; returns (unsorted, sorted, sorted_timestamps)"""
+    f = _fixture("storage_validity_vector.json")
+    s, ts = log_queries_from_fixture(f["sorted"])
+    return log_queries_from_fixture(f["unsorted"])[0], s, ts
