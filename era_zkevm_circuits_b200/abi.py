@@ -104,6 +104,37 @@ ST_CHK = dict(LENGTHS_EQUAL=1 << 0, EMPTY_SYNC=1 << 1, SHARD_ID=1 << 2, KEY_ORDE
               TRIVIAL_HEAD=1 << 9, QUEUE_HINT=1 << 10, DEPTH_UNDERFLOW=1 << 11)
 
 
+class KeccakFsm(C.Structure):
+    _fields_ = [("read_precompile_call", C.c_uint32), ("read_unaligned_words_for_round", C.c_uint32),
+                ("padding_round", C.c_uint32), ("completed", C.c_uint32), ("keccak_internal_state", C.c_uint8 * 200),
+                ("timestamp_to_use_for_read", C.c_uint32), ("timestamp_to_use_for_write", C.c_uint32),
+                ("input_page", C.c_uint32), ("input_memory_byte_offset", C.c_uint32), ("input_memory_byte_length", C.c_uint32),
+                ("output_page", C.c_uint32), ("output_word_offset", C.c_uint32), ("needs_full_padding_round", C.c_uint32),
+                ("buffer_bytes", C.c_uint8 * 192), ("buffer_filled", C.c_uint32), ("_pad", C.c_uint32),
+                ("log_queue_state", QueueState4), ("memory_queue_state", QueueState12)]
+
+
+class KeccakClosedForm(C.Structure):
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("initial_log_queue_state", QueueState4),
+                ("initial_memory_queue_state", QueueState12), ("final_memory_state", QueueState12),
+                ("hidden_fsm_input", KeccakFsm), ("hidden_fsm_output", KeccakFsm)]
+
+
+class PrecompileOptions(C.Structure):
+    _fields_ = [("compare_expected", C.c_uint32), ("precompile_address", C.c_uint32), ("aux_byte", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+KC_COLS = dict(FLAGS_IN=0, CALL_ITEM=4, REQ_HEAD=40, REQ_LEN=44, PARAMS=45, TS_READ=51, TS_WRITE=52, RESET_BUFFER=53,
+               READ_ZERO_LENGTH=54, READ_NON_ZERO_LENGTH=55, QUERY=56, QUERY_STRIDE=28, ZERO_BYTES_LEFT=224,
+               CURRENTLY_FILLED=225, DO_ONE_BYTE_OF_PADDING=226, BUFFER_NOW_EMPTY=227, APPLY_PADDING=228, INPUT=229,
+               STATE_OUT=365, WRITE_RESULT=565, RESULT=566, WRITE_TAIL=574, WRITE_LEN=586, FLAGS_OUT=587, BUFFER_OUT=591,
+               NUM_COLS=783)
+KC_CHK = dict(TRIVIAL_HEAD=1 << 0, AUX_BYTE=1 << 1, ADDRESS=1 << 2, BUFFER_OVERFLOW=1 << 3, QUEUE_CONSISTENCY=1 << 4,
+              QUEUE_HINT=1 << 5, WITNESS_EXHAUSTED=1 << 6)
+KECCAK256_PRECOMPILE_ADDRESS, SHA256_PRECOMPILE_ADDRESS, PRECOMPILE_AUX_BYTE = 0x8010, 0x02, 3
+
+
 class SorterOptions(C.Structure):
     _fields_ = [("compare_expected", C.c_uint32), ("_pad", C.c_uint32 * 3)]
 
@@ -183,6 +214,10 @@ SIGNATURES = {
     "zkc_storage_validity_entry_point": (C.c_int, [_vp, C.POINTER(StorageClosedForm), _vp, _vp, C.c_size_t, _vp, _vp, _vp,
                                                    C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions),
                                                    C.c_int, _vp, _vp, C.POINTER(Status)]),
+    "zkc_keccak256_round_function_entry_point": (C.c_int, [_vp, C.POINTER(KeccakClosedForm), _vp, _vp, C.c_size_t, _vp,
+                                                           C.c_size_t, _vp, C.c_size_t, C.c_size_t,
+                                                           C.POINTER(PrecompileOptions), C.c_int, _vp, _vp,
+                                                           C.POINTER(Status)]),
     "zkc_ram_permutation_entry_point": (C.c_int, [_vp, C.POINTER(RamClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,
                                                   C.c_size_t, C.c_size_t, C.POINTER(RamOptions), C.c_int, _vp, _vp,
                                                   C.POINTER(Status)]),

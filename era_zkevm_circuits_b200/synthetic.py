@@ -164,3 +164,49 @@ def storage_trace(n: int, seed: int = 0xC4, n_cells: int = 1 << 16, shard: int =
     crank = np.empty(n_cells, dtype=np.int64); crank[crank_order] = np.arange(n_cells)
     srt = np.lexsort((pos, crank[cell]))
     return q, q[srt], (first_position + srt).astype(np.uint32)
+
+
+def bytes_to_u256_words(data: bytes, unalignment: int) -> np.ndarray:
+    """memory words of a byte string that starts `unalignment` bytes into its first 32-byte word (big-endian words,
+    0xff filler before the data, zero fill after it) -- the reference test's helper,
+    keccak256_round_function/mod.rs:971-998.  Returns [n_words, 8] little-endian u32 limbs."""
+    stream = b"\xff" * unalignment + data
+    if len(stream) % 32:
+        stream += bytes(32 - len(stream) % 32)
+    words = np.frombuffer(stream, dtype=">u4").reshape(-1, 8)[:, ::-1]
+    return np.ascontiguousarray(words.astype("<u4"))
+
+
+def precompile_call(address: int, in_offset: int, in_length: int, out_offset: int, in_page: int, out_page: int,
+                    timestamp: int, extra: int = 0, aux_byte: int = abi.PRECOMPILE_AUX_BYTE):
+    """LogQuery of a precompile call; key = PrecompileCallABI::to_u256 (zkevm_opcode_defs, un-vendored): limbs
+    [0] input offset, [1] input length, [2] output offset, [3] output length, [4] page to read, [5] page to write,
+    [6..8] precompile_interpreted_data (keccak256_round_function/mod.rs:74-81, sha256_round_function/mod.rs:66-72)"""
+    q = np.zeros((), dtype=abi.LOG_QUERY_DTYPE)
+    q["address"][0] = address
+    q["key"] = [in_offset, in_length, out_offset, 1, in_page, out_page, extra & 0xFFFFFFFF, extra >> 32]
+    q["timestamp"] = timestamp
+    q["flags"] = abi.lq_flags(aux=aux_byte, rw=1)
+    return q
+
+
+def keccak_calls(n_calls: int, seed: int = 0xC3, max_len: int = 1024):
+    """C3 (keccak): back-to-back precompile calls with input lengths uniform in [0, max_len) bytes and unalignment
+    uniform in [0, 32).  Returns (requests [n_calls], memory_reads [n_words, 8], messages: list of bytes)."""
+    r = splitmix64(seed, 2 * n_calls, 0)
+    lengths = (r[:n_calls] % np.uint64(max(1, max_len))).astype(np.int64)
+    unal = (r[n_calls:] % np.uint64(32)).astype(np.int64)
+    blob = splitmix64(seed, int(lengths.sum()) // 8 + 1, 1).tobytes()
+    reqs = np.zeros(n_calls, dtype=abi.LOG_QUERY_DTYPE)
+    words, msgs, off = [], [], 0
+    for i in range(n_calls):
+        msg = blob[off:off + int(lengths[i])]
+        off += int(lengths[i])
+        msgs.append(msg)
+        base_word = 1000 * i
+        reqs[i] = precompile_call(abi.KECCAK256_PRECOMPILE_ADDRESS, base_word * 32 + int(unal[i]), len(msg), 7 + i,
+                                  100 + i, 200 + i, 10 + 4 * i)
+        if len(msg):
+            words.append(bytes_to_u256_words(msg, int(unal[i])))
+    reads = np.concatenate(words) if words else np.zeros((0, 8), dtype=np.uint32)
+    return reqs, reads, msgs

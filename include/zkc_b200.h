@@ -521,6 +521,112 @@ int zkc_storage_validity_entry_point(zkc_ctx *ctx, zkc_storage_closed_form *io, 
                                      int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN],
                                      zkc_status *status);
 
+
+/* ---- keccak256_round_function (src/keccak256_round_function/mod.rs) -------------------------------- */
+#define ZKC_KECCAK_RATE_BYTES 136            /* boojum KECCAK_RATE_BYTES */
+#define ZKC_KECCAK_BUFFER_SIZE 192           /* KECCAK_PRECOMPILE_BUFFER_SIZE, input.rs:24 */
+#define ZKC_KECCAK_MEMORY_QUERIES_PER_CYCLE 6 /* input.rs:23 */
+/* zkevm_opcode_defs::system_params (un-vendored; values from memory, overridable through zkc_precompile_options) */
+#define ZKC_KECCAK256_PRECOMPILE_ADDRESS_DEFAULT 0x8010u
+#define ZKC_SHA256_PRECOMPILE_ADDRESS_DEFAULT 0x02u
+#define ZKC_PRECOMPILE_AUX_BYTE_DEFAULT 3u
+
+/* Keccak256RoundFunctionFSMInputOutput, input.rs:29-39 + 56-61 */
+typedef struct zkc_keccak_fsm {
+    uint32_t read_precompile_call;
+    uint32_t read_unaligned_words_for_round;
+    uint32_t padding_round;
+    uint32_t completed;
+    uint8_t keccak_internal_state[200]; /* [i][j][byte]: (i * 5 + j) * 8 + b; lane (x = i, y = j), little-endian bytes */
+    uint32_t timestamp_to_use_for_read;
+    uint32_t timestamp_to_use_for_write;
+    /* Keccak256PrecompileCallParams, mod.rs:45-54 */
+    uint32_t input_page;
+    uint32_t input_memory_byte_offset;
+    uint32_t input_memory_byte_length;
+    uint32_t output_page;
+    uint32_t output_word_offset;
+    uint32_t needs_full_padding_round;
+    /* ByteBuffer<F, 192>, buffer/mod.rs:8-11 */
+    uint8_t buffer_bytes[ZKC_KECCAK_BUFFER_SIZE];
+    uint32_t buffer_filled;
+    uint32_t _pad;
+    zkc_queue_state4 log_queue_state;
+    zkc_queue_state12 memory_queue_state;
+} zkc_keccak_fsm;
+
+/* ClosedFormInputWitness<F, Keccak256RoundFunctionFSMInputOutput, PrecompileFunctionInputData,
+ * PrecompileFunctionOutputData>, input.rs:78-89, base_structures/precompile_input_outputs/mod.rs:23-46 */
+typedef struct zkc_keccak_closed_form {
+    uint32_t start_flag;
+    uint32_t completion_flag;                     /* out */
+    zkc_queue_state4 initial_log_queue_state;     /* observable input */
+    zkc_queue_state12 initial_memory_queue_state; /* observable input */
+    zkc_queue_state12 final_memory_state;         /* observable output */
+    zkc_keccak_fsm hidden_fsm_input;
+    zkc_keccak_fsm hidden_fsm_output;
+} zkc_keccak_closed_form;
+
+/* trace columns of one iteration of keccak256_precompile_inner's main work cycle (mod.rs:230-665) */
+enum zkc_keccak_col {
+    ZKC_KC_FLAGS_IN = 0,      /* 4: read_precompile_call, read_unaligned_words_for_round, padding_round, completed on entry */
+    ZKC_KC_CALL_ITEM = 4,     /* 36: popped precompile call (LogQuery flatten), :260 */
+    ZKC_KC_REQ_HEAD = 40,     /* 4: requests queue head after the pop */
+    ZKC_KC_REQ_LEN = 44,
+    ZKC_KC_PARAMS = 45,       /* 6: precompile_call_params after the select (:294-299): input_page, byte_offset, byte_length,
+                                 output_page, output_word_offset, needs_full_padding_round */
+    ZKC_KC_TS_READ = 51,
+    ZKC_KC_TS_WRITE = 52,
+    ZKC_KC_RESET_BUFFER = 53,           /* :321 */
+    ZKC_KC_READ_ZERO_LENGTH = 54,       /* have_read_zero_length_call, :325 */
+    ZKC_KC_READ_NON_ZERO_LENGTH = 55,   /* :331 */
+    ZKC_KC_QUERY = 56,        /* 6 x 28: aligned_index, unalignment, meaningful_bytes, should_read, value[8], memory tail[12],
+                                 memory length, byte_offset after, byte_length after, buffer filled after (:397-492) */
+    ZKC_KC_QUERY_STRIDE = 28,
+    ZKC_KC_ZERO_BYTES_LEFT = 224,       /* :497 */
+    ZKC_KC_CURRENTLY_FILLED = 225,      /* :502 */
+    ZKC_KC_DO_ONE_BYTE_OF_PADDING = 226,
+    ZKC_KC_BUFFER_NOW_EMPTY = 227,      /* :510 */
+    ZKC_KC_APPLY_PADDING = 228,         /* :515 */
+    ZKC_KC_INPUT = 229,       /* 136: the absorbed block after padding / full-padding select, :580 */
+    ZKC_KC_STATE_OUT = 365,   /* 200: keccak_internal_state after the permutation */
+    ZKC_KC_WRITE_RESULT = 565,
+    ZKC_KC_RESULT = 566,      /* 8: UInt256::from_be_bytes(squeezed) */
+    ZKC_KC_WRITE_TAIL = 574,  /* 12: memory queue tail after the conditional digest write */
+    ZKC_KC_WRITE_LEN = 586,
+    ZKC_KC_FLAGS_OUT = 587,   /* 4 */
+    ZKC_KC_BUFFER_OUT = 591,  /* 192: buffer bytes after the cycle */
+    ZKC_KC_NUM_COLS = 783
+};
+
+#define ZKC_KC_CHK_TRIVIAL_HEAD (1u << 0)      /* :705, :719 */
+#define ZKC_KC_CHK_AUX_BYTE (1u << 1)          /* :262-267 */
+#define ZKC_KC_CHK_ADDRESS (1u << 2)           /* :268-280 */
+#define ZKC_KC_CHK_BUFFER_OVERFLOW (1u << 3)   /* add_no_overflow / sub_no_overflow in the buffer, buffer/mod.rs:132-135 */
+#define ZKC_KC_CHK_QUEUE_CONSISTENCY (1u << 4) /* :667 */
+#define ZKC_KC_CHK_QUEUE_HINT (1u << 5)
+#define ZKC_KC_CHK_WITNESS_EXHAUSTED (1u << 6) /* `expect("not empty witness")`, storage_application/mod.rs:129-131 */
+
+typedef struct zkc_precompile_options {
+    uint32_t compare_expected;
+    uint32_t precompile_address; /* low 32 bits of the formal address (upper limbs 0); 0 = circuit default */
+    uint32_t aux_byte;           /* 0 = ZKC_PRECOMPILE_AUX_BYTE_DEFAULT */
+    uint32_t _pad;
+} zkc_precompile_options;
+
+/* keccak256_round_function_entry_point, mod.rs:673-794.
+ *   requests, requests_prev_tails : precompile calls queue witness in pop order (CircuitQueueRawWitness, input.rs:97)
+ *   memory_reads                  : memory_reads_witness (input.rs:98), n_reads x 8 little-endian u32 limbs, FIFO order
+ *   memory_states                 : NULL, or AoS [pushes][12]: memory queue tail after each executed push (verified);
+ *                                   when NULL the chain is rebuilt sequentially on the device
+ *   trace                         : column-major [ZKC_KC_NUM_COLS][limit] or NULL */
+int zkc_keccak256_round_function_entry_point(zkc_ctx *ctx, zkc_keccak_closed_form *io, const zkc_log_query *requests,
+                                             const uint64_t *requests_prev_tails, size_t n_requests,
+                                             const uint32_t *memory_reads, size_t n_reads, const uint64_t *memory_states,
+                                             size_t n_memory_states, size_t limit, const zkc_precompile_options *options,
+                                             int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN],
+                                             zkc_status *status);
+
 #ifdef __cplusplus
 }
 #endif

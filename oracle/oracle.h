@@ -81,4 +81,12 @@ int orc_storage_validity_entry_point(zkc_storage_closed_form *io, const zkc_log_
                                      const zkc_log_query *sorted, const uint32_t *sorted_ts, size_t n_sorted, size_t limit,
                                      const zkc_sorter_options *options, uint64_t *trace, uint64_t *result_tails,
                                      size_t *n_result_tails, uint64_t commitment[4], zkc_status *status);
+/* keccak256_round_function.c; memory_states (optional out): memory queue tail after each executed push */
+void orc_keccak_f1600(uint64_t A[25]);
+void orc_keccak256(const uint8_t *msg, size_t len, uint8_t digest[32]);
+size_t orc_keccak_encode_fsm(const zkc_keccak_fsm *f, uint64_t *dst);
+int orc_keccak256_entry_point(zkc_keccak_closed_form *io, const zkc_log_query *requests, size_t n_requests,
+                              const uint32_t *memory_reads, size_t n_reads, size_t limit,
+                              const zkc_precompile_options *options, uint64_t *trace, uint64_t *memory_states,
+                              size_t *n_memory_states, uint64_t commitment[4], zkc_status *status);
 #endif
