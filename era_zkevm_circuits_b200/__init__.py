@@ -23,3 +23,7 @@ from .keccak256_round_function import (  # noqa: F401
     Keccak256RoundFunctionCircuitInstanceWitness,
     keccak256_round_function_entry_point,
 )
+from .sha256_round_function import (  # noqa: F401
+    Sha256RoundFunctionCircuitInstanceWitness,
+    sha256_round_function_entry_point,
+)

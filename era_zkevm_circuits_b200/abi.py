@@ -120,6 +120,26 @@ class KeccakClosedForm(C.Structure):
                 ("hidden_fsm_input", KeccakFsm), ("hidden_fsm_output", KeccakFsm)]
 
 
+class Sha256Fsm(C.Structure):
+    _fields_ = [("read_precompile_call", C.c_uint32), ("read_words_for_round", C.c_uint32), ("completed", C.c_uint32),
+                ("sha256_inner_state", C.c_uint32 * 8), ("timestamp_to_use_for_read", C.c_uint32),
+                ("timestamp_to_use_for_write", C.c_uint32), ("input_page", C.c_uint32), ("input_offset", C.c_uint32),
+                ("output_page", C.c_uint32), ("output_offset", C.c_uint32), ("num_rounds", C.c_uint32), ("_pad", C.c_uint32),
+                ("log_queue_state", QueueState4), ("memory_queue_state", QueueState12)]
+
+
+class Sha256ClosedForm(C.Structure):
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("initial_log_queue_state", QueueState4),
+                ("initial_memory_queue_state", QueueState12), ("final_memory_state", QueueState12),
+                ("hidden_fsm_input", Sha256Fsm), ("hidden_fsm_output", Sha256Fsm)]
+
+
+SH_COLS = dict(FLAGS_IN=0, CALL_ITEM=3, REQ_HEAD=39, REQ_LEN=43, PARAMS=44, TS_READ=49, TS_WRITE=50, RESET_BUFFER=51,
+               SHOULD_READ=52, QUERY=53, QUERY_STRIDE=22, MESSAGE=97, NUM_ROUNDS=113, STATE_IN=114, STATE_OUT=122,
+               WRITE_RESULT=130, RESULT=131, WRITE_TAIL=139, WRITE_LEN=151, FLAGS_OUT=152, NUM_COLS=155)
+SH_CHK_ZERO_ROUNDS = 1 << 7
+
+
 class PrecompileOptions(C.Structure):
     _fields_ = [("compare_expected", C.c_uint32), ("precompile_address", C.c_uint32), ("aux_byte", C.c_uint32),
                 ("_pad", C.c_uint32)]
@@ -218,6 +238,9 @@ SIGNATURES = {
                                                            C.c_size_t, _vp, C.c_size_t, C.c_size_t,
                                                            C.POINTER(PrecompileOptions), C.c_int, _vp, _vp,
                                                            C.POINTER(Status)]),
+    "zkc_sha256_round_function_entry_point": (C.c_int, [_vp, C.POINTER(Sha256ClosedForm), _vp, _vp, C.c_size_t, _vp,
+                                                        C.c_size_t, _vp, C.c_size_t, C.c_size_t,
+                                                        C.POINTER(PrecompileOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
     "zkc_ram_permutation_entry_point": (C.c_int, [_vp, C.POINTER(RamClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,
                                                   C.c_size_t, C.c_size_t, C.POINTER(RamOptions), C.c_int, _vp, _vp,
                                                   C.POINTER(Status)]),

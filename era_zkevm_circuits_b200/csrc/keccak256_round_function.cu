@@ -15,6 +15,7 @@
 //   finalize  FSM output, observable output, commitment.
 #include "ctx.cuh"
 #include "log_query.cuh"
+#include "precompile_common.cuh"
 #include "scan.cuh"
 
 namespace zkc {
@@ -117,17 +118,6 @@ __device__ void kc_store_state(const KcState &s, zkc_keccak_fsm &f) {
     f.buffer_filled = s.filled; f._pad = 0;
     for (int i = 0; i < ZKC_KECCAK_BUFFER_SIZE; i++) f.buffer_bytes[i] = s.buffer[i];
     for (int i = 0; i < 200; i++) f.keccak_internal_state[i] = s.sponge[i];
-}
-
-__device__ __forceinline__ void mq_encode(uint32_t ts, uint32_t page, uint32_t index, uint32_t rw, const uint32_t *v, uint64_t *e) {
-    // MemoryQuery::encode, base_structures/memory_query/mod.rs:103-221 (is_ptr = false)
-    e[0] = ts; e[1] = page;
-    e[2] = (uint64_t)index | ((uint64_t)rw << 32);
-    e[3] = (uint64_t)v[0] | ((uint64_t)(v[5] & 0xFFFFFFu) << 32);
-    e[4] = (uint64_t)v[1] | ((uint64_t)(v[5] >> 24) << 32) | ((uint64_t)(v[6] & 0xFFFFu) << 40);
-    e[5] = (uint64_t)v[2] | ((uint64_t)(v[6] >> 16) << 32) | ((uint64_t)(v[7] & 0xFFu) << 48);
-    e[6] = (uint64_t)v[3] | ((uint64_t)(v[7] >> 8) << 32);
-    e[7] = v[4];
 }
 
 // what one cycle did to the outside world
@@ -506,76 +496,6 @@ kc_tail_kernel(KcDev *d, const KcPlan *__restrict__ starts, uint32_t *__restrict
     if (row == limit - 1) kc_store_state(s, d->s_final);
 }
 
-// ---- memory queue: chain (optional) + per-slot tails ----------------------------------------------------------------------
-__global__ void kc_mem_chain_kernel(const KcDev *d, const KcPlan *__restrict__ starts, const uint64_t *__restrict__ push_enc,
-                                    const uint32_t *__restrict__ slot_meta, uint64_t *__restrict__ states) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t s[12];
-    for (int i = 0; i < 12; i++) s[i] = d->mq0.tail[i];
-    const size_t limit = d->limit;
-    const uint32_t n = limit ? (slot_meta[7 * (limit - 1) + 6] & 0x7FFFFFFFu) : 0;
-    for (uint32_t k = 0; k < n; k++) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = push_enc[8 * (size_t)k + i];
-        poseidon2_permute(s);
-#pragma unroll
-        for (int i = 0; i < 12; i++) states[12 * (size_t)k + i] = s[i];
-    }
-    (void)starts;
-}
-
-__global__ void __launch_bounds__(256)
-kc_memq_kernel(KcDev *d, const uint64_t *__restrict__ push_enc, const uint32_t *__restrict__ slot_meta,
-               const uint64_t *__restrict__ states, size_t n_states, bool verify, uint64_t *__restrict__ trace) {
-    const size_t limit = d->limit;
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 7 * limit) return;
-    const size_t row = t / 7;
-    const int slot = (int)(t % 7);
-    const uint32_t m = slot_meta[t];
-    const uint32_t ord = m & 0x7FFFFFFFu;  // pushes executed up to and including this slot
-    const bool pushed = m >> 31;
-    uint64_t cur[12];
-    bool ok = true;
-    if (ord == 0) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) cur[i] = d->mq0.tail[i];
-    } else if (ord - 1 < n_states) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) cur[i] = __ldg(states + 12 * (size_t)(ord - 1) + i);
-    } else {
-        ok = false;
-#pragma unroll
-        for (int i = 0; i < 12; i++) cur[i] = 0;
-    }
-    if (pushed && verify && ok) {
-        uint64_t s[12];
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = push_enc[8 * (size_t)(ord - 1) + i];
-        if (ord == 1) {
-#pragma unroll
-            for (int i = 8; i < 12; i++) s[i] = d->mq0.tail[i];
-        } else {
-#pragma unroll
-            for (int i = 8; i < 12; i++) s[i] = __ldg(states + 12 * (size_t)(ord - 2) + i);
-        }
-        poseidon2_permute(s);
-#pragma unroll
-        for (int i = 0; i < 12; i++) ok &= s[i] == cur[i];
-    }
-    if (trace) {
-        const int base = slot < 6 ? ZKC_KC_QUERY + slot * ZKC_KC_QUERY_STRIDE + 12 : ZKC_KC_WRITE_TAIL;
-#pragma unroll
-        for (int i = 0; i < 12; i++) trace[(size_t)(base + i) * limit + row] = cur[i];
-        trace[(size_t)(base + 12) * limit + row] = d->mq0.length + ord;
-    }
-    if (!ok) {
-        d->hint_bad = 1;
-        atomicOr(&d->failed_checks, (uint32_t)ZKC_KC_CHK_QUEUE_HINT);
-        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | ZKC_KC_CHK_QUEUE_HINT);
-    }
-}
-
 // ---- finalize ----------------------------------------------------------------------------------------------------------------
 __global__ void kc_finalize_kernel(KcDev *d, const KcPlan *__restrict__ starts, const uint32_t *__restrict__ slot_meta,
                                    const uint64_t *__restrict__ states, size_t n_states) {
@@ -722,9 +642,9 @@ extern "C" int zkc_keccak256_round_function_entry_point(zkc_ctx *ctx, zkc_keccak
         ZKC_LAUNCH(ctx, "kc_calls", kc_calls_kernel, (unsigned)((max_units + 127) / 128), 128, 0, d, dreq, dprev, dreads, starts,
                    push_enc, slot_meta, dtrace);
         ZKC_LAUNCH(ctx, "kc_tail", kc_tail_kernel, (unsigned)((limit + 127) / 128), 128, 0, d, starts, slot_meta, dtrace);
-        if (!have_states) ZKC_LAUNCH(ctx, "kc_mem_chain", kc_mem_chain_kernel, 1, 32, 0, d, starts, push_enc, slot_meta, (uint64_t *)dstates);
-        ZKC_LAUNCH(ctx, "kc_memq", kc_memq_kernel, (unsigned)((7 * limit + 255) / 256), 256, 0, d, push_enc, slot_meta, dstates,
-                   n_memory_states, have_states, dtrace);
+        if (!have_states) ZKC_LAUNCH(ctx, "kc_mem_chain", (pc_mem_chain_kernel<KcDev, 7>), 1, 32, 0, d, push_enc, slot_meta, (uint64_t *)dstates);
+        ZKC_LAUNCH(ctx, "kc_memq", (pc_memq_kernel<KcDev, 7, ZKC_KC_QUERY + 12, ZKC_KC_QUERY_STRIDE, ZKC_KC_WRITE_TAIL, ZKC_KC_CHK_QUEUE_HINT>),
+                   (unsigned)((7 * limit + 255) / 256), 256, 0, d, push_enc, slot_meta, dstates, n_memory_states, have_states, dtrace);
     }
     ZKC_LAUNCH(ctx, "kc_finalize", kc_finalize_kernel, 1, 32, 0, d, starts, slot_meta, dstates, n_memory_states);
     ZKC_CUDA(ctx, status, cudaGetLastError());

@@ -1,0 +1,522 @@
+// sha256 precompile circuit on sm_100a: sha256_round_function_entry_point
+// (/root/reference/src/sha256_round_function/mod.rs:343-470) and its work cycle sha256_precompile_inner (:88-340).
+// Same decomposition as keccak256_round_function.cu: a call of `num_rounds` blocks takes exactly `num_rounds` cycles
+// (2 memory reads + one compression each, digest written at the last one), so the plan is a prefix sum of the
+// calls' round counts; one thread per call chains the compressions; the memory queue is handled by
+// precompile_common.cuh.
+#include "ctx.cuh"
+#include "log_query.cuh"
+#include "precompile_common.cuh"
+#include "scan.cuh"
+
+namespace zkc {
+
+__device__ __constant__ uint32_t SHA_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+    0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+    0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+    0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+    0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+    0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+__device__ __constant__ uint32_t SHA_IV[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+
+// FIPS 180-4 compression, message schedule kept as a 16-word ring in registers
+__device__ __forceinline__ void sha256_compress(uint32_t (&st)[8], uint32_t (&w)[16]) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            const uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+            const uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+            const uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+            w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+        }
+        const uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25), ch = (e & f) ^ (~e & g);
+        const uint32_t t1 = h + S1 + ch + SHA_K[i] + w[i & 15];
+        const uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22), maj = (a & b) ^ (a & c) ^ (b & c);
+        const uint32_t t2 = S0 + maj;
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+struct ShDev {
+    zkc_sha256_closed_form io;
+    zkc_precompile_options opt;
+    uint64_t n_requests, n_reads, n_memory_states, limit;
+    uint32_t start, prologue_checks, n_units, unit0_fresh;
+    zkc_sha256_fsm s0;
+    zkc_queue_state4 rq0;
+    zkc_queue_state12 mq0;
+    uint64_t commit_obs_in[4], commit_fsm_in[4];
+    zkc_sha256_fsm s_last, s_final;
+    uint32_t popped_requests, pad0;
+    uint64_t req_head_final[4];
+    unsigned long long first_bad;
+    uint32_t failed_checks, hint_bad;
+    uint64_t commitment[4];
+    zkc_status status;
+};
+
+struct ShPlan {
+    uint32_t cycles, reads, pushes, pad;
+};
+struct ShPlanOp {
+    static __device__ __forceinline__ ShPlan identity() { return ShPlan{0, 0, 0, 0}; }
+    static __device__ __forceinline__ ShPlan combine(const ShPlan &a, const ShPlan &b) {
+        return ShPlan{a.cycles + b.cycles, a.reads + b.reads, a.pushes + b.pushes, 0};
+    }
+};
+
+__device__ int sh_encode_fsm(const zkc_sha256_fsm &f, uint64_t *dst) {
+    int n = 0;
+    dst[n++] = f.read_precompile_call; dst[n++] = f.read_words_for_round; dst[n++] = f.completed;
+    for (int i = 0; i < 8; i++) dst[n++] = f.sha256_inner_state[i];
+    dst[n++] = f.timestamp_to_use_for_read; dst[n++] = f.timestamp_to_use_for_write;
+    dst[n++] = f.input_page; dst[n++] = f.input_offset; dst[n++] = f.output_page; dst[n++] = f.output_offset; dst[n++] = f.num_rounds;
+    n += put_queue_state4(dst + n, f.log_queue_state);
+    for (int i = 0; i < 12; i++) dst[n++] = f.memory_queue_state.head[i];
+    for (int i = 0; i < 12; i++) dst[n++] = f.memory_queue_state.tail[i];
+    dst[n++] = f.memory_queue_state.length;
+    return n;  // 52
+}
+__device__ int sh_put_q12(uint64_t *dst, const zkc_queue_state12 &s) {
+    for (int i = 0; i < 12; i++) dst[i] = s.head[i];
+    for (int i = 0; i < 12; i++) dst[12 + i] = s.tail[i];
+    dst[24] = s.length;
+    return 25;
+}
+
+__global__ void sh_prologue_kernel(ShDev *d) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane != 0) return;
+    const zkc_sha256_closed_form &io = d->io;
+    if (warp == 0) {
+        const bool start = io.start_flag != 0;
+        d->start = start;
+        d->rq0 = start ? io.initial_log_queue_state : io.hidden_fsm_input.log_queue_state;
+        d->mq0 = start ? io.initial_memory_queue_state : io.hidden_fsm_input.memory_queue_state;
+        zkc_sha256_fsm s;
+        if (start) {  // mod.rs:411-419; the placeholder FSM carries the IV (input.rs:36-50)
+            memset(&s, 0, sizeof s);
+            s.read_precompile_call = 1;
+            for (int i = 0; i < 8; i++) s.sha256_inner_state[i] = SHA_IV[i];
+        } else s = io.hidden_fsm_input;
+        const bool cfi = s.read_precompile_call && d->rq0.length == 0;  // :121-135
+        if (cfi) { s.read_precompile_call = 0; s.read_words_for_round = 0; s.completed = 1; }
+        d->s0 = s; d->s_last = s; d->s_final = s;
+        d->popped_requests = 0;
+        uint32_t checks = 0;
+        for (int i = 0; i < 4; i++) if (io.initial_log_queue_state.head[i]) checks |= ZKC_KC_CHK_TRIVIAL_HEAD;
+        for (int i = 0; i < 12; i++) if (io.initial_memory_queue_state.head[i]) checks |= ZKC_KC_CHK_TRIVIAL_HEAD;
+        d->prologue_checks = checks;
+        d->unit0_fresh = (s.read_precompile_call || s.completed) ? 1 : 0;
+        const uint64_t avail = d->rq0.length < d->n_requests ? d->rq0.length : d->n_requests;
+        d->n_units = 1 + (s.completed ? 0 : (uint32_t)avail);
+    } else if (warp == 1) {
+        uint64_t buf[34];
+        int n = put_queue_state4(buf, io.initial_log_queue_state);
+        n += sh_put_q12(buf + n, io.initial_memory_queue_state);
+        commit_encoding_dev(buf, n, d->commit_obs_in);
+    } else if (warp == 2) {
+        uint64_t buf[52];
+        const int n = sh_encode_fsm(io.hidden_fsm_input, buf);
+        commit_encoding_dev(buf, n, d->commit_fsm_in);
+    }
+}
+
+// cycles a call occupies: its round count (an illegal 0 never terminates: runs to the end of the instance)
+__device__ __forceinline__ uint32_t sh_cycles_of(uint32_t num_rounds, size_t limit) {
+    return num_rounds ? (num_rounds < limit ? num_rounds : (uint32_t)limit) : (uint32_t)limit;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+sh_plan_kernel(ShDev *d, const zkc_log_query *__restrict__ requests, ShPlan *__restrict__ starts, ScanGlobal *sg,
+               TileStateT<ShPlan> *tiles) {
+    __shared__ ScanSharedT<ShPlan> sh;
+    const unsigned int tile = scan_take_ticket(sg, sh);
+    const size_t u = (size_t)tile * SCAN_THREADS + threadIdx.x;
+    const uint32_t n_units = d->n_units;
+    ShPlan v = ShPlanOp::identity();
+    if (u < n_units) {
+        uint32_t rounds = 0;
+        bool run = true;
+        if (u == 0) { run = !d->unit0_fresh; rounds = d->s0.num_rounds; }
+        else rounds = __ldg(&requests[u - 1].key[6]);
+        if (run) {
+            v.cycles = sh_cycles_of(rounds, d->limit);
+            // reads happen while num_rounds != 0 at the start of the cycle
+            const uint32_t reading = rounds ? v.cycles : 0;
+            v.reads = 2 * reading;
+            v.pushes = 2 * reading + ((rounds && rounds == v.cycles) ? 1 : 0);
+        }
+    }
+    ShPlan incl;
+    const ShPlan excl = scan_tile_generic<ShPlan, ShPlanOp>(v, tile, ShPlanOp::identity(), tiles, sh, incl);
+    if (u < n_units) starts[u] = excl;
+    if (u + 1 == n_units) starts[n_units] = incl;
+}
+
+__device__ __forceinline__ void sh_report(ShDev *d, size_t row, uint32_t checks) {
+    if (!checks) return;
+    atomicOr(&d->failed_checks, checks);
+    atomicMin(&d->first_bad, ((unsigned long long)row << 16) | checks);
+}
+
+// one iteration of the main work cycle, mod.rs:146-330
+__device__ __forceinline__ void sh_cycle(zkc_sha256_fsm &s, const zkc_log_query &call, bool queue_empty_after,
+                                         const uint32_t *__restrict__ reads, size_t n_reads, size_t &read_cursor,
+                                         uint64_t *__restrict__ push_enc, uint32_t *__restrict__ slot_meta, uint32_t &push_ordinal,
+                                         uint64_t *__restrict__ trace, size_t limit, size_t row, uint32_t &checks) {
+#define TR(col) trace[(size_t)(col) * limit + row]
+    const bool wr = trace != nullptr;
+    const bool read_call = s.read_precompile_call;
+    if (wr) { TR(ZKC_SH_FLAGS_IN + 0) = s.read_precompile_call; TR(ZKC_SH_FLAGS_IN + 1) = s.read_words_for_round; TR(ZKC_SH_FLAGS_IN + 2) = s.completed; }
+    if (read_call) {
+        s.input_offset = call.key[0]; s.output_offset = call.key[2]; s.input_page = call.key[4]; s.output_page = call.key[5];
+        s.num_rounds = call.key[6];
+        s.timestamp_to_use_for_read = call.timestamp; s.timestamp_to_use_for_write = call.timestamp + 1;
+        if (s.num_rounds == 0) checks |= ZKC_SH_CHK_ZERO_ROUNDS;
+    }
+    const bool reset_buffer = read_call || s.completed;
+    s.read_words_for_round = read_call || s.read_words_for_round;
+    s.read_precompile_call = 0;
+    const bool should_read = s.num_rounds != 0;
+    if (wr) {
+        TR(ZKC_SH_PARAMS + 0) = s.input_page; TR(ZKC_SH_PARAMS + 1) = s.input_offset; TR(ZKC_SH_PARAMS + 2) = s.output_page;
+        TR(ZKC_SH_PARAMS + 3) = s.output_offset; TR(ZKC_SH_PARAMS + 4) = s.num_rounds;
+        TR(ZKC_SH_TS_READ) = s.timestamp_to_use_for_read; TR(ZKC_SH_TS_WRITE) = s.timestamp_to_use_for_write;
+        TR(ZKC_SH_RESET_BUFFER) = reset_buffer; TR(ZKC_SH_SHOULD_READ) = should_read;
+    }
+    uint32_t m[16];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        uint32_t value[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (should_read) {
+            if (read_cursor < n_reads) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) value[i] = __ldg(reads + 8 * read_cursor + i);
+            } else checks |= ZKC_KC_CHK_WITNESS_EXHAUSTED;
+            uint64_t e[8];
+            mq_encode(s.timestamp_to_use_for_read, s.input_page, s.input_offset, 0, value, e);
+#pragma unroll
+            for (int i = 0; i < 8; i++) push_enc[8 * (size_t)push_ordinal + i] = e[i];
+            read_cursor++; push_ordinal++;
+        }
+        if (s.read_words_for_round) s.input_offset++;
+        slot_meta[3 * row + q] = push_ordinal | (should_read ? 0x80000000u : 0u);
+#pragma unroll
+        for (int i = 0; i < 8; i++) m[8 * q + i] = value[7 - i];
+        if (wr) {
+            const int b = ZKC_SH_QUERY + q * ZKC_SH_QUERY_STRIDE;
+#pragma unroll
+            for (int i = 0; i < 8; i++) TR(b + i) = value[i];
+            TR(b + 21) = s.input_offset;
+        }
+    }
+    if (s.read_words_for_round) s.num_rounds--;
+    uint32_t cur[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) cur[i] = reset_buffer ? SHA_IV[i] : s.sha256_inner_state[i];
+    if (wr) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) TR(ZKC_SH_STATE_IN + i) = cur[i];
+#pragma unroll
+        for (int i = 0; i < 16; i++) TR(ZKC_SH_MESSAGE + i) = m[i];
+    }
+    sha256_compress(cur, m);
+#pragma unroll
+    for (int i = 0; i < 8; i++) s.sha256_inner_state[i] = cur[i];
+    const bool write_result = s.read_words_for_round && s.num_rounds == 0;
+    uint32_t result[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) result[7 - k] = cur[k];
+    if (write_result) {
+        uint64_t e[8];
+        mq_encode(s.timestamp_to_use_for_write, s.output_page, s.output_offset, 1, result, e);
+#pragma unroll
+        for (int i = 0; i < 8; i++) push_enc[8 * (size_t)push_ordinal + i] = e[i];
+        push_ordinal++;
+    }
+    slot_meta[3 * row + 2] = push_ordinal | (write_result ? 0x80000000u : 0u);
+    const bool nothing_left = write_result && queue_empty_after, process_next = write_result && !queue_empty_after;
+    s.read_precompile_call = process_next;
+    s.completed = s.completed || nothing_left;
+    s.read_words_for_round = !(s.read_precompile_call || s.completed);
+    if (wr) {
+        TR(ZKC_SH_NUM_ROUNDS) = s.num_rounds;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { TR(ZKC_SH_STATE_OUT + i) = cur[i]; TR(ZKC_SH_RESULT + i) = result[i]; }
+        TR(ZKC_SH_WRITE_RESULT) = write_result;
+        TR(ZKC_SH_FLAGS_OUT + 0) = s.read_precompile_call; TR(ZKC_SH_FLAGS_OUT + 1) = s.read_words_for_round; TR(ZKC_SH_FLAGS_OUT + 2) = s.completed;
+    }
+#undef TR
+}
+
+__global__ void __launch_bounds__(128)
+sh_calls_kernel(ShDev *d, const zkc_log_query *__restrict__ requests, const uint64_t *__restrict__ req_prev,
+                const uint32_t *__restrict__ reads, const ShPlan *__restrict__ starts, uint64_t *__restrict__ push_enc,
+                uint32_t *__restrict__ slot_meta, uint64_t *__restrict__ trace) {
+    const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_units = d->n_units;
+    if (u >= n_units) return;
+    const size_t limit = d->limit;
+    const ShPlan st = starts[u], en = starts[u + 1];
+    size_t row = st.cycles;
+    if (row >= limit || en.cycles == st.cycles) return;
+    zkc_sha256_fsm s = d->s0;
+    zkc_log_query call = lq_zero();
+    const uint32_t aux_byte = d->opt.aux_byte ? d->opt.aux_byte : ZKC_PRECOMPILE_AUX_BYTE_DEFAULT;
+    const uint32_t formal = d->opt.precompile_address ? d->opt.precompile_address : ZKC_SHA256_PRECOMPILE_ADDRESS_DEFAULT;
+    const uint32_t rq_len0 = d->rq0.length;
+    uint64_t head[4];
+    uint32_t len_after, checks = 0;
+    if (u == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) head[i] = d->rq0.head[i];
+        len_after = rq_len0;
+    } else {
+        call = lq_load(requests + (u - 1));
+        s.read_precompile_call = 1; s.read_words_for_round = 0; s.completed = 0;
+        uint64_t e[20], sp[12], chain[4];
+        bool hint_ok = true;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            chain[i] = __ldg(req_prev + 4 * (u - 1) + i);
+            if (u == 1 && chain[i] != d->rq0.head[i]) hint_ok = false;
+        }
+        lq_encode(call, e);
+        lq_absorb_head(e, sp);
+        lq_absorb_tail(e, chain, sp);
+#pragma unroll
+        for (int i = 0; i < 4; i++) head[i] = sp[i];
+        if (u + 1 < n_units && starts[u + 1].cycles < limit) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) hint_ok &= __ldg(req_prev + 4 * u + i) == head[i];
+        }
+        if (!hint_ok) { checks |= ZKC_KC_CHK_QUEUE_HINT; d->hint_bad = 1; }
+        len_after = rq_len0 - (uint32_t)u;
+        if (ZKC_LQ_AUX(call.flags) != aux_byte) checks |= ZKC_KC_CHK_AUX_BYTE;
+        if (call.address[0] != formal || call.address[1] || call.address[2] || call.address[3] || call.address[4]) checks |= ZKC_KC_CHK_ADDRESS;
+    }
+    size_t read_cursor = st.reads;
+    uint32_t push_ordinal = st.pushes;
+    bool first_cycle = true;
+    while (row < limit && row < en.cycles) {
+        uint32_t cyc_checks = first_cycle ? checks : 0;
+        if (trace) {
+            for (int i = 0; i < 36; i++) trace[(size_t)(ZKC_SH_CALL_ITEM + i) * limit + row] = first_cycle ? lq_flat(call, i) : 0;
+            for (int i = 0; i < 4; i++) trace[(size_t)(ZKC_SH_REQ_HEAD + i) * limit + row] = head[i];
+            trace[(size_t)ZKC_SH_REQ_LEN * limit + row] = len_after;
+        }
+        sh_cycle(s, first_cycle ? call : lq_zero(), len_after == 0, reads, d->n_reads, read_cursor, push_enc, slot_meta, push_ordinal,
+                 trace, limit, row, cyc_checks);
+        sh_report(d, row, cyc_checks);
+        first_cycle = false;
+        row++;
+    }
+    const size_t total = starts[n_units].cycles;
+    if (row == limit) d->s_final = s;
+    if (en.cycles == total && row == en.cycles) d->s_last = s;
+    if (u >= 1 && (u + 1 == n_units || starts[u + 1].cycles >= limit)) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) d->req_head_final[i] = head[i];
+        d->popped_requests = (uint32_t)u;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+sh_tail_kernel(ShDev *d, const ShPlan *__restrict__ starts, uint32_t *__restrict__ slot_meta, uint64_t *__restrict__ trace,
+               uint64_t *__restrict__ push_enc) {
+    const size_t limit = d->limit;
+    const size_t first = starts[d->n_units].cycles;
+    const size_t row = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    zkc_sha256_fsm s = d->s_last;
+    uint32_t checks = 0;
+    if (row > first) {
+        // state left by the previous tail row: compression of the zero block from the IV (the cycle resets first)
+        uint32_t st[8], w[16];
+        for (int i = 0; i < 8; i++) st[i] = SHA_IV[i];
+        for (int i = 0; i < 16; i++) w[i] = 0;
+        sha256_compress(st, w);
+        for (int i = 0; i < 8; i++) s.sha256_inner_state[i] = st[i];
+    }
+    const uint32_t popped = d->popped_requests;
+    const uint32_t len_now = d->rq0.length - popped;
+    if (s.read_precompile_call) checks |= ZKC_KC_CHK_WITNESS_EXHAUSTED;
+    if (trace) {
+        for (int i = 0; i < 36; i++) trace[(size_t)(ZKC_SH_CALL_ITEM + i) * limit + row] = 0;
+        for (int i = 0; i < 4; i++) trace[(size_t)(ZKC_SH_REQ_HEAD + i) * limit + row] = popped ? d->req_head_final[i] : d->rq0.head[i];
+        trace[(size_t)ZKC_SH_REQ_LEN * limit + row] = len_now;
+    }
+    size_t rc = 0;
+    uint32_t po = starts[d->n_units].pushes;
+    sh_cycle(s, lq_zero(), len_now == 0, nullptr, 0, rc, push_enc, slot_meta, po, trace, limit, row, checks);
+    sh_report(d, row, checks);
+    if (row == limit - 1) d->s_final = s;
+}
+
+__global__ void sh_finalize_kernel(ShDev *d, const uint32_t *__restrict__ slot_meta, const uint64_t *__restrict__ states, size_t n_states) {
+    if (threadIdx.x != 0) return;
+    zkc_sha256_closed_form &io = d->io;
+    const size_t limit = d->limit;
+    zkc_sha256_fsm out = limit ? d->s_final : d->s0;
+    zkc_queue_state4 rq = d->rq0;
+    const uint32_t popped = limit ? d->popped_requests : 0;
+    if (popped) for (int i = 0; i < 4; i++) rq.head[i] = d->req_head_final[i];
+    rq.length = d->rq0.length - popped;
+    zkc_queue_state12 mq = d->mq0;
+    bool hint_bad = d->hint_bad;
+    if (limit) {
+        const uint32_t pushes = slot_meta[3 * (limit - 1) + 2] & 0x7FFFFFFFu;
+        if (pushes) {
+            if (pushes - 1 < n_states) for (int i = 0; i < 12; i++) mq.tail[i] = states[12 * (size_t)(pushes - 1) + i];
+            else hint_bad = true;
+        }
+        mq.length += pushes;
+    }
+    out.log_queue_state = rq;
+    out.memory_queue_state = mq;
+    out._pad = 0;
+    uint32_t checks = d->failed_checks | d->prologue_checks;
+    if (rq.length == 0)
+        for (int i = 0; i < 4; i++) if (rq.head[i] != rq.tail[i]) checks |= ZKC_KC_CHK_QUEUE_CONSISTENCY;
+    const bool done = out.completed;
+    zkc_queue_state12 obs_out;
+    memset(&obs_out, 0, sizeof obs_out);
+    if (done) obs_out = mq;
+    uint64_t e_out[52], e_exp[52], o_out[25], o_exp[25];
+    const int n_out = sh_encode_fsm(out, e_out);
+    sh_put_q12(o_out, obs_out);
+    zkc_status st;
+    st.code = ZKC_OK; st.cuda_error = 0; st.first_bad_row = -1; st.failed_checks = checks; st.reserved = 0;
+    if (d->first_bad != ~0ull) st.first_bad_row = (int64_t)(d->first_bad >> 16);
+    if (checks) st.code = ZKC_ERR_UNSATISFIED;
+    if (hint_bad) { st.code = ZKC_ERR_QUEUE_WITNESS_INCONSISTENT; st.failed_checks |= ZKC_KC_CHK_QUEUE_HINT; }
+    if (d->opt.compare_expected) {
+        sh_encode_fsm(io.hidden_fsm_output, e_exp);
+        sh_put_q12(o_exp, io.final_memory_state);
+        bool same = (io.completion_flag != 0) == done;
+        for (int i = 0; i < n_out; i++) same &= e_out[i] == e_exp[i];
+        for (int i = 0; i < 25; i++) same &= o_out[i] == o_exp[i];
+        if (!same && st.code == ZKC_OK) st.code = ZKC_ERR_FSM_OUTPUT_MISMATCH;
+    }
+    io.hidden_fsm_output = out;
+    io.final_memory_state = obs_out;
+    io.completion_flag = done;
+    uint64_t compact[18], c4[4];
+    compact[0] = d->start; compact[1] = done;
+    commit_encoding_dev(o_out, 25, c4);
+    for (int i = 0; i < 4; i++) {
+        compact[2 + i] = d->commit_obs_in[i];
+        compact[6 + i] = done ? c4[i] : 0;
+        compact[10 + i] = d->start ? 0 : d->commit_fsm_in[i];
+    }
+    commit_encoding_dev(e_out, n_out, c4);
+    for (int i = 0; i < 4; i++) compact[14 + i] = done ? 0 : c4[i];
+    commit_encoding_dev(compact, 18, d->commitment);
+    d->status = st;
+}
+
+}  // namespace zkc
+
+using namespace zkc;
+
+extern "C" int zkc_sha256_round_function_entry_point(zkc_ctx *ctx, zkc_sha256_closed_form *io, const zkc_log_query *requests,
+                                                     const uint64_t *requests_prev_tails, size_t n_requests,
+                                                     const uint32_t *memory_reads, size_t n_reads, const uint64_t *memory_states,
+                                                     size_t n_memory_states, size_t limit, const zkc_precompile_options *options,
+                                                     int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN],
+                                                     zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !commitment || (n_requests && (!requests || !requests_prev_tails)) || (n_reads && !memory_reads) ||
+        limit > 0x0FFFFFFFull) {
+        status->code = ZKC_ERR_INVALID_ARGUMENT;
+        return ZKC_ERR_INVALID_ARGUMENT;
+    }
+    const bool in_dev = on_device & ZKC_INPUTS_ON_DEVICE, trace_dev = on_device & ZKC_TRACE_ON_DEVICE;
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    const size_t max_units = n_requests + 1;
+    const size_t tiles = (max_units + SCAN_THREADS - 1) / SCAN_THREADS;
+    const bool have_states = memory_states != nullptr;
+    const size_t max_pushes = 3 * limit + 1;
+    if (!have_states) n_memory_states = max_pushes;
+    size_t bytes = zkc_carver::bytes(1, sizeof(ShDev)) + zkc_carver::bytes(1, sizeof(ScanGlobal)) +
+                   zkc_carver::bytes(tiles + 1, sizeof(TileStateT<ShPlan>)) + zkc_carver::bytes(max_units + 2, sizeof(ShPlan)) +
+                   zkc_carver::bytes(max_pushes * 8, 8) + zkc_carver::bytes(3 * limit + 8, 4);
+    if (!in_dev) bytes += zkc_carver::bytes(n_requests + 1, sizeof(zkc_log_query)) + zkc_carver::bytes(n_requests * 4 + 4, 8) +
+                          zkc_carver::bytes(n_reads * 8 + 8, 4);
+    if (!in_dev || !have_states) bytes += zkc_carver::bytes(n_memory_states * 12 + 12, 8);
+    if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ZKC_SH_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    ShDev *h = (ShDev *)ctx->pinned(sizeof(ShDev));
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    ShDev *d = cv.take<ShDev>(1);
+    char *zero_begin = cv.base + cv.off;
+    ScanGlobal *sg = cv.take<ScanGlobal>(1);
+    TileStateT<ShPlan> *ts = cv.take<TileStateT<ShPlan>>(tiles + 1);
+    char *zero_end = cv.base + cv.off;
+    ShPlan *starts = cv.take<ShPlan>(max_units + 2);
+    uint64_t *push_enc = cv.take<uint64_t>(max_pushes * 8);
+    uint32_t *slot_meta = cv.take<uint32_t>(3 * limit + 8);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(ShDev));
+    h->io = *io;
+    if (options) h->opt = *options;
+    h->n_requests = n_requests; h->n_reads = n_reads; h->n_memory_states = n_memory_states; h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(ShDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(zero_begin, 0, zero_end - zero_begin, s));
+    const zkc_log_query *dreq = requests;
+    const uint64_t *dprev = requests_prev_tails, *dstates = memory_states;
+    const uint32_t *dreads = memory_reads;
+    uint64_t *dtrace = trace;
+    if (!in_dev) {
+        zkc_log_query *br = cv.take<zkc_log_query>(n_requests + 1);
+        uint64_t *bp = cv.take<uint64_t>(n_requests * 4 + 4);
+        uint32_t *bm = cv.take<uint32_t>(n_reads * 8 + 8);
+        if (n_requests) {
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(br, requests, n_requests * sizeof(zkc_log_query), cudaMemcpyHostToDevice, s));
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(bp, requests_prev_tails, n_requests * 32, cudaMemcpyHostToDevice, s));
+        }
+        if (n_reads) ZKC_CUDA(ctx, status, cudaMemcpyAsync(bm, memory_reads, n_reads * 32, cudaMemcpyHostToDevice, s));
+        dreq = br; dprev = bp; dreads = bm;
+    }
+    if (!in_dev || !have_states) {
+        uint64_t *bs = cv.take<uint64_t>(n_memory_states * 12 + 12);
+        if (have_states && n_memory_states)
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(bs, memory_states, n_memory_states * 96, cudaMemcpyHostToDevice, s));
+        dstates = bs;
+    }
+    if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ZKC_SH_NUM_COLS * limit);
+
+    ZKC_LAUNCH(ctx, "sh_prologue", sh_prologue_kernel, 1, 96, 0, d);
+    ZKC_LAUNCH(ctx, "sh_plan", sh_plan_kernel, (unsigned)tiles, SCAN_THREADS, 0, d, dreq, starts, sg, ts);
+    if (limit) {
+        ZKC_LAUNCH(ctx, "sh_calls", sh_calls_kernel, (unsigned)((max_units + 127) / 128), 128, 0, d, dreq, dprev, dreads, starts,
+                   push_enc, slot_meta, dtrace);
+        ZKC_LAUNCH(ctx, "sh_tail", sh_tail_kernel, (unsigned)((limit + 127) / 128), 128, 0, d, starts, slot_meta, dtrace, push_enc);
+        if (!have_states) ZKC_LAUNCH(ctx, "sh_mem_chain", (pc_mem_chain_kernel<ShDev, 3>), 1, 32, 0, d, push_enc, slot_meta, (uint64_t *)dstates);
+        ZKC_LAUNCH(ctx, "sh_memq", (pc_memq_kernel<ShDev, 3, ZKC_SH_QUERY + 8, ZKC_SH_QUERY_STRIDE, ZKC_SH_WRITE_TAIL, ZKC_KC_CHK_QUEUE_HINT>),
+                   (unsigned)((3 * limit + 255) / 256), 256, 0, d, push_enc, slot_meta, dstates, n_memory_states, have_states, dtrace);
+    }
+    ZKC_LAUNCH(ctx, "sh_finalize", sh_finalize_kernel, 1, 32, 0, d, slot_meta, dstates, n_memory_states);
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(ShDev), cudaMemcpyDeviceToHost, s));
+    if (!trace_dev && trace && limit)
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(trace, dtrace, (size_t)ZKC_SH_NUM_COLS * limit * 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    io->hidden_fsm_output = h->io.hidden_fsm_output;
+    io->final_memory_state = h->io.final_memory_state;
+    io->completion_flag = h->io.completion_flag;
+    memcpy(commitment, h->commitment, 32);
+    *status = h->status;
+    return status->code;
+}

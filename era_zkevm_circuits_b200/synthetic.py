@@ -210,3 +210,37 @@ def keccak_calls(n_calls: int, seed: int = 0xC3, max_len: int = 1024):
             words.append(bytes_to_u256_words(msg, int(unal[i])))
     reads = np.concatenate(words) if words else np.zeros((0, 8), dtype=np.uint32)
     return reqs, reads, msgs
+
+
+def sha256_pad(msg: bytes) -> bytes:
+    """FIPS 180-4 padding: the sha256 circuit consumes pre-padded blocks (sha256_round_function/mod.rs:72)"""
+    ml = len(msg) * 8
+    msg = msg + b"\x80"
+    msg += bytes((56 - len(msg) % 64) % 64)
+    return msg + ml.to_bytes(8, "big")
+
+
+def sha256_calls(n_calls: int, seed: int = 0xC3, max_rounds: int = 16):
+    """C3 (sha256): back-to-back precompile calls with num_rounds uniform in [1, max_rounds] (64-byte blocks of an
+    already padded message).  Returns (requests, memory_reads [2 * total_rounds, 8], messages)."""
+    r = splitmix64(seed, n_calls, 0)
+    rounds = (1 + r % np.uint64(max_rounds)).astype(np.int64)
+    reqs = np.zeros(n_calls, dtype=abi.LOG_QUERY_DTYPE)
+    words, msgs = [], []
+    rr = splitmix64(seed, n_calls, 1)
+    blob = splitmix64(seed, int(rounds.sum()) * 8 + 8, 2).tobytes()
+    off = 0
+    for i in range(n_calls):
+        # a message whose padded length is exactly rounds[i] blocks
+        max_len = int(rounds[i]) * 64 - 9
+        min_len = max(0, (int(rounds[i]) - 1) * 64 - 8)
+        ln = min_len + int(rr[i] % np.uint64(max_len - min_len + 1))
+        msg = blob[off:off + ln]
+        off += ln
+        padded = sha256_pad(msg)
+        assert len(padded) == int(rounds[i]) * 64
+        msgs.append(msg)
+        reqs[i] = precompile_call(abi.SHA256_PRECOMPILE_ADDRESS, 50 * i, 0, 9 + i, 300 + i, 400 + i, 20 + 4 * i,
+                                  extra=int(rounds[i]))
+        words.append(bytes_to_u256_words(padded, 0))
+    return reqs, np.concatenate(words), msgs

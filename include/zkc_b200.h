@@ -627,6 +627,72 @@ int zkc_keccak256_round_function_entry_point(zkc_ctx *ctx, zkc_keccak_closed_for
                                              int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN],
                                              zkc_status *status);
 
+
+/* ---- sha256_round_function (src/sha256_round_function/mod.rs) --------------------------------------- */
+/* Sha256RoundFunctionFSMInputOutput, input.rs:23-45 */
+typedef struct zkc_sha256_fsm {
+    uint32_t read_precompile_call;
+    uint32_t read_words_for_round;
+    uint32_t completed;
+    uint32_t sha256_inner_state[8];
+    uint32_t timestamp_to_use_for_read;
+    uint32_t timestamp_to_use_for_write;
+    /* Sha256PrecompileCallParams, mod.rs:44-50 */
+    uint32_t input_page;
+    uint32_t input_offset;
+    uint32_t output_page;
+    uint32_t output_offset;
+    uint32_t num_rounds;
+    uint32_t _pad;
+    zkc_queue_state4 log_queue_state;
+    zkc_queue_state12 memory_queue_state;
+} zkc_sha256_fsm;
+
+typedef struct zkc_sha256_closed_form {
+    uint32_t start_flag;
+    uint32_t completion_flag;                     /* out */
+    zkc_queue_state4 initial_log_queue_state;     /* observable input */
+    zkc_queue_state12 initial_memory_queue_state; /* observable input */
+    zkc_queue_state12 final_memory_state;         /* observable output */
+    zkc_sha256_fsm hidden_fsm_input;
+    zkc_sha256_fsm hidden_fsm_output;
+} zkc_sha256_closed_form;
+
+/* trace columns of one iteration of sha256_precompile_inner's main work cycle (mod.rs:146-330) */
+enum zkc_sha256_col {
+    ZKC_SH_FLAGS_IN = 0,     /* 3: read_precompile_call, read_words_for_round, completed on entry */
+    ZKC_SH_CALL_ITEM = 3,    /* 36 */
+    ZKC_SH_REQ_HEAD = 39,    /* 4 */
+    ZKC_SH_REQ_LEN = 43,
+    ZKC_SH_PARAMS = 44,      /* 5: after the select (:180-185): input_page, input_offset, output_page, output_offset, num_rounds */
+    ZKC_SH_TS_READ = 49,
+    ZKC_SH_TS_WRITE = 50,
+    ZKC_SH_RESET_BUFFER = 51, /* :204 */
+    ZKC_SH_SHOULD_READ = 52,  /* :215 */
+    ZKC_SH_QUERY = 53,        /* 2 x 22: value[8], memory tail[12], memory length, input_offset after (:219-247) */
+    ZKC_SH_QUERY_STRIDE = 22,
+    ZKC_SH_MESSAGE = 97,      /* 16 big-endian message words (:250-254) */
+    ZKC_SH_NUM_ROUNDS = 113,  /* after the conditional decrement, :257-268 */
+    ZKC_SH_STATE_IN = 114,    /* 8: state the compression starts from (IV on reset), :271-278 */
+    ZKC_SH_STATE_OUT = 122,   /* 8 */
+    ZKC_SH_WRITE_RESULT = 130,
+    ZKC_SH_RESULT = 131,      /* 8: write_word limbs (:290-299) */
+    ZKC_SH_WRITE_TAIL = 139,  /* 12 */
+    ZKC_SH_WRITE_LEN = 151,
+    ZKC_SH_FLAGS_OUT = 152,   /* 3 */
+    ZKC_SH_NUM_COLS = 155
+};
+#define ZKC_SH_CHK_ZERO_ROUNDS (1u << 7) /* a call with num_rounds = 0: decrement_unchecked (:257-262) would leave the u32
+                                            range in the reference; not a legal call (other bits as ZKC_KC_CHK_*) */
+
+/* sha256_round_function_entry_point, mod.rs:343-470.  Arguments as zkc_keccak256_round_function_entry_point. */
+int zkc_sha256_round_function_entry_point(zkc_ctx *ctx, zkc_sha256_closed_form *io, const zkc_log_query *requests,
+                                          const uint64_t *requests_prev_tails, size_t n_requests,
+                                          const uint32_t *memory_reads, size_t n_reads, const uint64_t *memory_states,
+                                          size_t n_memory_states, size_t limit, const zkc_precompile_options *options,
+                                          int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN],
+                                          zkc_status *status);
+
 #ifdef __cplusplus
 }
 #endif

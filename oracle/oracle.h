@@ -89,4 +89,11 @@ int orc_keccak256_entry_point(zkc_keccak_closed_form *io, const zkc_log_query *r
                               const uint32_t *memory_reads, size_t n_reads, size_t limit,
                               const zkc_precompile_options *options, uint64_t *trace, uint64_t *memory_states,
                               size_t *n_memory_states, uint64_t commitment[4], zkc_status *status);
+/* sha256_round_function.c */
+void orc_sha256_compress(uint32_t state[8], const uint32_t m[16]);
+size_t orc_sha256_encode_fsm(const zkc_sha256_fsm *f, uint64_t *dst);
+int orc_sha256_entry_point(zkc_sha256_closed_form *io, const zkc_log_query *requests, size_t n_requests,
+                           const uint32_t *memory_reads, size_t n_reads, size_t limit, const zkc_precompile_options *options,
+                           uint64_t *trace, uint64_t *memory_states, size_t *n_memory_states, uint64_t commitment[4],
+                           zkc_status *status);
 #endif

@@ -53,6 +53,11 @@ def load():
     lib.orc_keccak256_entry_point.argtypes = [C.POINTER(abi.KeccakClosedForm), _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t,
                                               C.POINTER(abi.PrecompileOptions), _vp, _vp, C.POINTER(C.c_size_t), _vp,
                                               C.POINTER(abi.Status)]
+    lib.orc_sha256_compress.argtypes = [_vp, _vp]
+    lib.orc_sha256_entry_point.restype = C.c_int
+    lib.orc_sha256_entry_point.argtypes = [C.POINTER(abi.Sha256ClosedForm), _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t,
+                                           C.POINTER(abi.PrecompileOptions), _vp, _vp, C.POINTER(C.c_size_t), _vp,
+                                           C.POINTER(abi.Status)]
     _LIB = lib
     return lib
 
@@ -206,4 +211,31 @@ def keccak_entry_point(lib, io, requests, memory_reads, limit, want_trace=True, 
     opts = abi.PrecompileOptions(int(compare_expected), 0, 0, 0)
     rc = lib.orc_keccak256_entry_point(C.byref(io2), p(requests), len(requests), p(memory_reads), len(memory_reads), limit,
                                        C.byref(opts), p(trace), p(states), C.byref(n_states), p(com), C.byref(st))
+    return rc, io2, trace, com, st, states[:n_states.value].copy()
+
+
+def sha256_closed_form(requests_state, memory_state=None, start=True, fsm_in=None):
+    io = abi.Sha256ClosedForm()
+    io.start_flag = int(start)
+    io.initial_log_queue_state = requests_state
+    if memory_state is not None:
+        io.initial_memory_queue_state = memory_state
+    if fsm_in is not None:
+        io.hidden_fsm_input = fsm_in
+    return io
+
+
+def sha256_entry_point(lib, io, requests, memory_reads, limit, want_trace=True, compare_expected=False):
+    """returns (rc, io_out, trace, commitment, status, memory_states)"""
+    io2 = abi.Sha256ClosedForm.from_buffer_copy(bytes(io))
+    requests = np.ascontiguousarray(requests)
+    memory_reads = np.ascontiguousarray(memory_reads, dtype=np.uint32).reshape(-1, 8)
+    trace = np.zeros((abi.SH_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
+    states = np.zeros((3 * limit + 1, 12), dtype=np.uint64)
+    n_states = C.c_size_t()
+    com = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    opts = abi.PrecompileOptions(int(compare_expected), 0, 0, 0)
+    rc = lib.orc_sha256_entry_point(C.byref(io2), p(requests), len(requests), p(memory_reads), len(memory_reads), limit,
+                                    C.byref(opts), p(trace), p(states), C.byref(n_states), p(com), C.byref(st))
     return rc, io2, trace, com, st, states[:n_states.value].copy()
