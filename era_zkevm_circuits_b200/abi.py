@@ -140,6 +140,76 @@ SH_COLS = dict(FLAGS_IN=0, CALL_ITEM=3, REQ_HEAD=39, REQ_LEN=43, PARAMS=44, TS_R
 SH_CHK_ZERO_ROUNDS = 1 << 7
 
 
+class VmIsa(C.Structure):
+    _fields_ = [("opcode_price", C.c_uint32 * 2048), ("opcode_props", C.c_uint64 * 2048), ("condition_table", (C.c_uint8 * 8) * 8),
+                ("nop_opcode_encoding", C.c_uint64), ("panic_opcode_encoding", C.c_uint64), ("nop_bitspread", C.c_uint64),
+                ("panic_bitspread", C.c_uint64), ("bootloader_base_page", C.c_uint32), ("bootloader_code_page", C.c_uint32),
+                ("bootloader_calldata_page", C.c_uint32), ("starting_timestamp", C.c_uint32), ("starting_base_page", C.c_uint32),
+                ("initial_frame_formal_eh_location", C.c_uint32), ("vm_initial_frame_ergs", C.c_uint32),
+                ("bootloader_formal_address_low", C.c_uint32), ("bootloader_max_memory", C.c_uint32),
+                ("vm_max_stack_depth", C.c_uint32), ("_pad", C.c_uint32 * 2)]
+
+
+class VmRegister(C.Structure):
+    _fields_ = [("is_pointer", C.c_uint32), ("value", C.c_uint32 * 8)]
+
+
+class VmContext(C.Structure):
+    _fields_ = [("this_address", C.c_uint32 * 5), ("caller", C.c_uint32 * 5), ("code_address", C.c_uint32 * 5),
+                ("code_page", C.c_uint32), ("base_page", C.c_uint32), ("heap_upper_bound", C.c_uint32),
+                ("aux_heap_upper_bound", C.c_uint32), ("reverted_queue_head", C.c_uint64 * 4),
+                ("reverted_queue_tail", C.c_uint64 * 4), ("reverted_queue_segment_len", C.c_uint32), ("pc", C.c_uint32),
+                ("sp", C.c_uint32), ("exception_handler_loc", C.c_uint32), ("ergs_remaining", C.c_uint32),
+                ("is_static_execution", C.c_uint32), ("is_kernel_mode", C.c_uint32), ("this_shard_id", C.c_uint32),
+                ("caller_shard_id", C.c_uint32), ("code_shard_id", C.c_uint32), ("context_u128_value_composite", C.c_uint32 * 4),
+                ("is_local_call", C.c_uint32), ("log_queue_forward_part_length", C.c_uint32),
+                ("log_queue_forward_tail", C.c_uint64 * 4)]
+
+
+class VmState(C.Structure):
+    _fields_ = [("previous_code_word", C.c_uint32 * 8), ("registers", VmRegister * 15), ("flags", C.c_uint32 * 3),
+                ("timestamp", C.c_uint32), ("memory_page_counter", C.c_uint32), ("tx_number_in_block", C.c_uint32),
+                ("previous_code_page", C.c_uint32), ("previous_super_pc", C.c_uint32), ("pending_exception", C.c_uint32),
+                ("ergs_per_pubdata_byte", C.c_uint32), ("context_stack_depth", C.c_uint32), ("memory_queue_length", C.c_uint32),
+                ("code_decommittment_queue_length", C.c_uint32), ("context_composite_u128", C.c_uint32 * 4), ("_pad", C.c_uint32),
+                ("current_context", VmContext), ("stack_sponge_state", C.c_uint64 * 12), ("memory_queue_state", C.c_uint64 * 12),
+                ("code_decommittment_queue_state", C.c_uint64 * 12)]
+
+
+class VmCycleWitness(C.Structure):
+    _fields_ = [("code_word", C.c_uint32 * 8), ("src0_is_pointer", C.c_uint32), ("src0_value", C.c_uint32 * 8), ("_pad", C.c_uint32 * 3)]
+
+
+class VmClosedForm(C.Structure):
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("rollback_queue_tail_for_block", C.c_uint64 * 4),
+                ("memory_queue_initial_tail", C.c_uint64 * 12), ("memory_queue_initial_length", C.c_uint32), ("_pad0", C.c_uint32),
+                ("decommitment_queue_initial_tail", C.c_uint64 * 12), ("decommitment_queue_initial_length", C.c_uint32),
+                ("zkporter_is_available", C.c_uint32), ("default_aa_code_hash", C.c_uint32 * 8),
+                ("log_queue_final_state", QueueState4), ("memory_queue_final_state", QueueState12),
+                ("decommitment_queue_final_state", QueueState12), ("hidden_fsm_input", VmState), ("hidden_fsm_output", VmState)]
+
+
+class VmOptions(C.Structure):
+    _fields_ = [("compare_expected", C.c_uint32), ("_pad", C.c_uint32 * 3)]
+
+
+assert C.sizeof(VmState) == 1176 and C.sizeof(VmContext) == 240 and C.sizeof(VmIsa) == 24720
+assert C.sizeof(VmClosedForm) == 3104 and C.sizeof(VmCycleWitness) == 80
+VM_STATE_DTYPE = np.dtype((np.void, 1176))
+VM_COLS = dict(
+    SHOULD_SKIP_CYCLE=0, PENDING_EXCEPTION_IN=1, SHOULD_READ_OPCODE=2, SUPER_PC=3, SUB_PC=4, CODE_WORD=5, MEMQ_AFTER_CODE=13,
+    OPCODE=26, VARIANT=28, CONDITION_IDX=29, CONDITION=30, ERGS_COST=31, OUT_OF_ERGS=32, KERNEL_MODE_EXCEPTION=33,
+    STATIC_EXCEPTION=34, CALLSTACK_IS_FULL=35, EXPLICIT_PANIC=36, MASK_INTO_PANIC=37, MASK_INTO_NOP=38, PROPS=39,
+    DIRTY_ERGS_LEFT=40, SRC0_REG=41, SRC1_REG=42, DST0_REG=43, DST1_REG=44, IMM0=45, IMM1=46, SRC0_PAGE=47, SRC0_INDEX=48,
+    SHOULD_READ_SRC0=49, SP_AFTER_SRC0=50, DST0_PAGE=51, DST0_INDEX=52, DST0_PERFORMS_MEMORY_ACCESS=53, NEW_SP=54,
+    SRC0_FROM_MEMORY=55, MEMQ_AFTER_SRC0=64, SWAP_OPERANDS=77, SRC0=78, SRC1=87, DST0=96, DST1=105,
+    PERFORM_DST0_MEMORY_WRITE=114, DST0_UPDATE_REGISTER=115, MEMQ_AFTER_DST0=116, FLAGS_OUT=129, PENDING_EXCEPTION_OUT=132,
+    PC_OUT=133, ERGS_OUT=134, NUM_COLS=135)
+VM_CHK = dict(INVALID_OPCODE=1, UNSUPPORTED_OPCODE=2, SNAPSHOT=4, DIV_RELATION=8, BOOTLOADER_EXIT=16)
+ZKC_ERR_UNSUPPORTED, ZKC_ERR_SNAPSHOT_MISMATCH = 7, 8
+CODE_NAMES.update({7: "UNSUPPORTED", 8: "SNAPSHOT_MISMATCH"})
+
+
 class PrecompileOptions(C.Structure):
     _fields_ = [("compare_expected", C.c_uint32), ("precompile_address", C.c_uint32), ("aux_byte", C.c_uint32),
                 ("_pad", C.c_uint32)]
@@ -241,6 +311,11 @@ SIGNATURES = {
     "zkc_sha256_round_function_entry_point": (C.c_int, [_vp, C.POINTER(Sha256ClosedForm), _vp, _vp, C.c_size_t, _vp,
                                                         C.c_size_t, _vp, C.c_size_t, C.c_size_t,
                                                         C.POINTER(PrecompileOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
+    "zkc_main_vm_entry_point": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), _vp, _vp, C.c_size_t,
+                                          C.POINTER(VmOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
+    "zkc_main_vm_initial_state": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), C.POINTER(VmState)]),
+    "zkc_main_vm_simulate": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp,
+                                       C.POINTER(Status)]),
     "zkc_ram_permutation_entry_point": (C.c_int, [_vp, C.POINTER(RamClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,
                                                   C.c_size_t, C.c_size_t, C.POINTER(RamOptions), C.c_int, _vp, _vp,
                                                   C.POINTER(Status)]),

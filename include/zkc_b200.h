@@ -693,6 +693,218 @@ int zkc_sha256_round_function_entry_point(zkc_ctx *ctx, zkc_sha256_closed_form *
                                           int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN],
                                           zkc_status *status);
 
+
+/* ---- main_vm (src/main_vm/) ------------------------------------------------------------------------- */
+/* The ISA tables (zkevm_opcode_defs, un-vendored) are INPUT DATA: opcode -> (price, 48-bit property bit spread +
+ * 3 aux bits), exactly the 3-column table of src/tables/opcodes_decoding.rs:14-38, plus the condition table of
+ * src/tables/conditional.rs:21-58 and the NOP / PANIC encodings the circuit masks with (main_vm/utils.rs:14-41,
+ * decoded_opcode.rs:120-157).  The LAYOUT of the 38 meaningful property bits is main_vm/opcode_bitmask.rs:83-127:
+ * [opcode type | 10 variant | 2 flags | 6 src addressing | 4 dst addressing]; the positions below are this
+ * engine's restatement of zkevm_opcode_defs' enumeration order (from memory -- the host shim passes the real
+ * tables, so only the enumeration order has to be confirmed against the crate). */
+#define ZKC_VM_OPCODES_TABLE_WIDTH 11
+#define ZKC_VM_NUM_OPCODES (1u << ZKC_VM_OPCODES_TABLE_WIDTH)
+#define ZKC_VM_OPCODE_TYPE_BITS 16
+#define ZKC_VM_VARIANT_BITS 10
+#define ZKC_VM_FLAG_BITS 2
+#define ZKC_VM_SRC_MODE_BITS 6
+#define ZKC_VM_DST_MODE_BITS 4
+#define ZKC_VM_DESCRIPTION_BITS 38
+#define ZKC_VM_DESCRIPTION_BITS_FLATTENED 48
+#define ZKC_VM_REGISTERS 15 /* REGISTERS_COUNT, base_structures/vm_state/mod.rs:30 */
+enum zkc_vm_opcode_type { /* zkevm_opcode_defs::Opcode variant order */
+    ZKC_OP_INVALID = 0, ZKC_OP_NOP, ZKC_OP_ADD, ZKC_OP_SUB, ZKC_OP_MUL, ZKC_OP_DIV, ZKC_OP_JUMP, ZKC_OP_CONTEXT,
+    ZKC_OP_SHIFT, ZKC_OP_BINOP, ZKC_OP_PTR, ZKC_OP_NEAR_CALL, ZKC_OP_LOG, ZKC_OP_FAR_CALL, ZKC_OP_RET, ZKC_OP_UMA
+};
+enum zkc_vm_variant { /* materialize_subvariant_idx of the multi-variant opcodes used by the built subset */
+    ZKC_VAR_CONTEXT_THIS = 0, ZKC_VAR_CONTEXT_CALLER, ZKC_VAR_CONTEXT_CODE_ADDRESS, ZKC_VAR_CONTEXT_META,
+    ZKC_VAR_CONTEXT_ERGS_LEFT, ZKC_VAR_CONTEXT_SP, ZKC_VAR_CONTEXT_GET_U128, ZKC_VAR_CONTEXT_SET_U128,
+    ZKC_VAR_CONTEXT_SET_ERGS_PER_PUBDATA, ZKC_VAR_CONTEXT_INC_TX_NUMBER,
+    ZKC_VAR_SHIFT_SHL = 0, ZKC_VAR_SHIFT_SHR, ZKC_VAR_SHIFT_ROL, ZKC_VAR_SHIFT_ROR,
+    ZKC_VAR_BINOP_XOR = 0, ZKC_VAR_BINOP_AND, ZKC_VAR_BINOP_OR,
+    ZKC_VAR_PTR_ADD = 0, ZKC_VAR_PTR_SUB, ZKC_VAR_PTR_PACK, ZKC_VAR_PTR_SHRINK
+};
+enum zkc_vm_src_mode { /* ImmMemHandlerFlags::variant_index */
+    ZKC_MODE_REG_ONLY = 0, ZKC_MODE_STACK_PUSH_POP, ZKC_MODE_STACK_OFFSET, ZKC_MODE_STACK_ABSOLUTE, ZKC_MODE_IMM16, ZKC_MODE_CODE_PAGE
+};
+#define ZKC_VM_SET_FLAGS_FLAG_IDX 0       /* SET_FLAGS_FLAG_IDX */
+#define ZKC_VM_SWAP_OPERANDS_FLAG_IDX 1   /* SWAP_OPERANDS_FLAG_IDX_FOR_ARITH_OPCODES */
+#define ZKC_VM_SWAP_OPERANDS_PTR_FLAG_IDX 0 /* SWAP_OPERANDS_FLAG_IDX_FOR_PTR_OPCODE */
+#define ZKC_VM_AUX_KERNEL_MODE 0          /* KERNER_MODE_FLAG_IDX */
+#define ZKC_VM_AUX_CAN_BE_USED_IN_STATIC 1
+#define ZKC_VM_AUX_EXPLICIT_PANIC 2
+/* bit position of a property inside the 38-bit description */
+#define ZKC_VM_BIT_TYPE(t) (t)
+#define ZKC_VM_BIT_VARIANT(v) (ZKC_VM_OPCODE_TYPE_BITS + (v))
+#define ZKC_VM_BIT_FLAG(f) (ZKC_VM_OPCODE_TYPE_BITS + ZKC_VM_VARIANT_BITS + (f))
+#define ZKC_VM_BIT_SRC_MODE(m) (ZKC_VM_OPCODE_TYPE_BITS + ZKC_VM_VARIANT_BITS + ZKC_VM_FLAG_BITS + (m))
+#define ZKC_VM_BIT_DST_MODE(m) (ZKC_VM_OPCODE_TYPE_BITS + ZKC_VM_VARIANT_BITS + ZKC_VM_FLAG_BITS + ZKC_VM_SRC_MODE_BITS + (m))
+
+typedef struct zkc_vm_isa {
+    uint32_t opcode_price[ZKC_VM_NUM_OPCODES];   /* OPCODES_PRICES */
+    uint64_t opcode_props[ZKC_VM_NUM_OPCODES];   /* OPCODES_PROPS_INTEGER_BITMASKS: 48 bits + 3 aux bits at bit 48 */
+    uint8_t condition_table[8][8];               /* [condition][of | eq << 1 | gt << 2] -> 0/1 */
+    uint64_t nop_opcode_encoding;                /* EncodingModeProduction::nop_encoding() */
+    uint64_t panic_opcode_encoding;              /* exception_revert_encoding() */
+    uint64_t nop_bitspread;                      /* NOP_BITSPREAD_U64 */
+    uint64_t panic_bitspread;                    /* PANIC_BITSPREAD_U64 */
+    /* zkevm_opcode_defs::system_params used by initial_bootloader_state (main_vm/loading.rs:13-226) and vm_cycle */
+    uint32_t bootloader_base_page, bootloader_code_page, bootloader_calldata_page;
+    uint32_t starting_timestamp, starting_base_page;
+    uint32_t initial_frame_formal_eh_location, vm_initial_frame_ergs, bootloader_formal_address_low;
+    uint32_t bootloader_max_memory, vm_max_stack_depth;
+    uint32_t _pad[2];
+} zkc_vm_isa;
+
+/* VMRegister, base_structures/register/mod.rs:21-24 */
+typedef struct zkc_vm_register {
+    uint32_t is_pointer;
+    uint32_t value[8];
+} zkc_vm_register;
+
+/* FullExecutionContext = ExecutionContextRecord + forward log tail, vm_state/saved_context.rs:36-59,
+ * vm_state/callstack.rs:45-49 (field order = declaration order = var-length encoding order) */
+typedef struct zkc_vm_context {
+    uint32_t this_address[5], caller[5], code_address[5];
+    uint32_t code_page, base_page, heap_upper_bound, aux_heap_upper_bound;
+    uint64_t reverted_queue_head[4], reverted_queue_tail[4];
+    uint32_t reverted_queue_segment_len;
+    uint32_t pc, sp, exception_handler_loc; /* u16 values */
+    uint32_t ergs_remaining;
+    uint32_t is_static_execution, is_kernel_mode;
+    uint32_t this_shard_id, caller_shard_id, code_shard_id; /* u8 values */
+    uint32_t context_u128_value_composite[4];
+    uint32_t is_local_call;
+    uint32_t log_queue_forward_part_length;
+    uint64_t log_queue_forward_tail[4];
+} zkc_vm_context;
+
+/* VmLocalState, vm_state/mod.rs:92-109: the per-cycle snapshot (243 field elements when flattened) */
+typedef struct zkc_vm_state {
+    uint32_t previous_code_word[8];
+    zkc_vm_register registers[ZKC_VM_REGISTERS];
+    uint32_t flags[3]; /* overflow_or_less_than, equal, greater_than */
+    uint32_t timestamp, memory_page_counter, tx_number_in_block, previous_code_page, previous_super_pc;
+    uint32_t pending_exception, ergs_per_pubdata_byte;
+    uint32_t context_stack_depth;
+    uint32_t memory_queue_length, code_decommittment_queue_length;
+    uint32_t context_composite_u128[4];
+    uint32_t _pad;
+    zkc_vm_context current_context;
+    uint64_t stack_sponge_state[12];
+    uint64_t memory_queue_state[12];
+    uint64_t code_decommittment_queue_state[12];
+} zkc_vm_state;
+#define ZKC_VM_STATE_FLAT 243
+
+/* answers of the WitnessOracle (main_vm/witness_oracle.rs:45-91) one cycle consumes, flattened by the host before
+ * the call.  The built opcode subset needs the two memory reads of create_prestate. */
+typedef struct zkc_vm_cycle_witness {
+    uint32_t code_word[8];       /* get_memory_witness_for_read of the opcode fetch (main_vm/utils.rs:158-181) */
+    uint32_t src0_is_pointer;    /* get_memory_witness_for_read of the src0 operand (main_vm/utils.rs:416-440) */
+    uint32_t src0_value[8];
+    uint32_t _pad[3];
+} zkc_vm_cycle_witness;
+
+/* ClosedFormInputWitness<F, VmLocalState, VmInputData, VmOutputData>, fsm_input_output/circuit_inputs/main_vm.rs:9-71 */
+typedef struct zkc_vm_closed_form {
+    uint32_t start_flag;
+    uint32_t completion_flag; /* out */
+    /* VmInputData */
+    uint64_t rollback_queue_tail_for_block[4];
+    uint64_t memory_queue_initial_tail[12];
+    uint32_t memory_queue_initial_length, _pad0;
+    uint64_t decommitment_queue_initial_tail[12];
+    uint32_t decommitment_queue_initial_length;
+    uint32_t zkporter_is_available;       /* GlobalContext, vm_state/mod.rs:159-162 */
+    uint32_t default_aa_code_hash[8];
+    /* VmOutputData (out; expected value if compare_expected) */
+    zkc_queue_state4 log_queue_final_state;
+    zkc_queue_state12 memory_queue_final_state;
+    zkc_queue_state12 decommitment_queue_final_state;
+    zkc_vm_state hidden_fsm_input;
+    zkc_vm_state hidden_fsm_output;
+} zkc_vm_closed_form;
+
+/* trace columns of one vm_cycle (main_vm/cycle.rs:28-795 and pre_state.rs:71-519) */
+enum zkc_vm_col {
+    ZKC_VM_SHOULD_SKIP_CYCLE = 0,    /* pre_state.rs:91-92 */
+    ZKC_VM_PENDING_EXCEPTION_IN = 1,
+    ZKC_VM_SHOULD_READ_OPCODE = 2,   /* :130-131 */
+    ZKC_VM_SUPER_PC = 3,
+    ZKC_VM_SUB_PC = 4,
+    ZKC_VM_CODE_WORD = 5,            /* 8: after the select with previous_code_word, :177-182 */
+    ZKC_VM_MEMQ_AFTER_CODE = 13,     /* 12 + length */
+    ZKC_VM_OPCODE = 26,              /* 2: after mask_into_nop / mask_into_panic, :216-221 */
+    ZKC_VM_VARIANT = 28,
+    ZKC_VM_CONDITION_IDX = 29,
+    ZKC_VM_CONDITION = 30,
+    ZKC_VM_ERGS_COST = 31,
+    ZKC_VM_OUT_OF_ERGS = 32,
+    ZKC_VM_KERNEL_MODE_EXCEPTION = 33,
+    ZKC_VM_STATIC_EXCEPTION = 34,
+    ZKC_VM_CALLSTACK_IS_FULL = 35,
+    ZKC_VM_EXPLICIT_PANIC = 36,
+    ZKC_VM_MASK_INTO_PANIC = 37,
+    ZKC_VM_MASK_INTO_NOP = 38,
+    ZKC_VM_PROPS = 39,               /* the 48-bit property bit spread after masking, as one integer */
+    ZKC_VM_DIRTY_ERGS_LEFT = 40,
+    ZKC_VM_SRC0_REG = 41, ZKC_VM_SRC1_REG = 42, ZKC_VM_DST0_REG = 43, ZKC_VM_DST1_REG = 44, /* 4-bit encodings after masking */
+    ZKC_VM_IMM0 = 45, ZKC_VM_IMM1 = 46,
+    ZKC_VM_SRC0_PAGE = 47, ZKC_VM_SRC0_INDEX = 48, ZKC_VM_SHOULD_READ_SRC0 = 49, ZKC_VM_SP_AFTER_SRC0 = 50,
+    ZKC_VM_DST0_PAGE = 51, ZKC_VM_DST0_INDEX = 52, ZKC_VM_DST0_PERFORMS_MEMORY_ACCESS = 53, ZKC_VM_NEW_SP = 54,
+    ZKC_VM_SRC0_FROM_MEMORY = 55,    /* 9: is_pointer, value */
+    ZKC_VM_MEMQ_AFTER_SRC0 = 64,     /* 12 + length */
+    ZKC_VM_SWAP_OPERANDS = 77,
+    ZKC_VM_SRC0 = 78,                /* 9: after swap and fat-pointer erasure, :418-472 */
+    ZKC_VM_SRC1 = 87,                /* 9 */
+    ZKC_VM_DST0 = 96,                /* 9: cycle.rs:200-230 */
+    ZKC_VM_DST1 = 105,               /* 9 */
+    ZKC_VM_PERFORM_DST0_MEMORY_WRITE = 114, /* :248-254 */
+    ZKC_VM_DST0_UPDATE_REGISTER = 115,      /* :312 */
+    ZKC_VM_MEMQ_AFTER_DST0 = 116,    /* 12 + length */
+    ZKC_VM_FLAGS_OUT = 129,          /* 3 */
+    ZKC_VM_PENDING_EXCEPTION_OUT = 132,
+    ZKC_VM_PC_OUT = 133,
+    ZKC_VM_ERGS_OUT = 134,
+    ZKC_VM_NUM_COLS = 135
+};
+
+#define ZKC_VM_CHK_INVALID_OPCODE (1u << 0)      /* pre_state.rs:291-299 */
+#define ZKC_VM_CHK_UNSUPPORTED_OPCODE (1u << 1)  /* log / near_call / far_call / ret / uma: not built in this engine yet */
+#define ZKC_VM_CHK_SNAPSHOT (1u << 2)            /* the host-supplied per-cycle VmLocalState is not what the previous cycle produces */
+#define ZKC_VM_CHK_DIV_RELATION (1u << 3)        /* mul_div.rs:321-324 (never fails on computed witnesses) */
+#define ZKC_VM_CHK_BOOTLOADER_EXIT (1u << 4)     /* main_vm/mod.rs:119-122 */
+#define ZKC_ERR_UNSUPPORTED 7
+#define ZKC_ERR_SNAPSHOT_MISMATCH 8
+
+typedef struct zkc_vm_options {
+    uint32_t compare_expected;
+    uint32_t _pad[3];
+} zkc_vm_options;
+
+/* main_vm_entry_point, main_vm/mod.rs:47-232.
+ *   snapshots : [limit + 1] VmLocalState before every cycle and after the last one (what makes one instance data
+ *               parallel).  snapshots[0] must be the start state the circuit selects (:85-97),
+ *               every snapshots[i + 1] is verified against the cycle's own result.
+ *   witness   : [limit] oracle answers
+ *   trace     : column-major [ZKC_VM_NUM_COLS][limit] or NULL */
+int zkc_main_vm_entry_point(zkc_ctx *ctx, zkc_vm_closed_form *io, const zkc_vm_isa *isa, const zkc_vm_state *snapshots,
+                            const zkc_vm_cycle_witness *witness, size_t limit, const zkc_vm_options *options,
+                            int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
+
+/* the state main_vm_entry_point starts from when start_flag is set: initial_bootloader_state, main_vm/loading.rs:13-226 */
+int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *out);
+
+/* Out-of-circuit run (the role of the external `zk_evm` crate + witness generation): executes `cycles` cycles of
+ * `n_instances` independent VMs from their initial states, answering memory reads from a per-instance memory model
+ * (code page and stack page of 2^16 words each, code pre-loaded from `code`, [n_instances][code_words][8] limbs), and
+ * records what the circuit needs: snapshots [n_instances][cycles + 1] and witness [n_instances][cycles].
+ * Device buffers only. */
+int zkc_main_vm_simulate(zkc_ctx *ctx, const zkc_vm_isa *isa, const zkc_vm_state *initial_states, const uint32_t *code,
+                         size_t code_words, size_t n_instances, size_t cycles, zkc_vm_state *snapshots_out,
+                         zkc_vm_cycle_witness *witness_out, zkc_status *status);
+
 #ifdef __cplusplus
 }
 #endif

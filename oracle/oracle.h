@@ -96,4 +96,13 @@ int orc_sha256_entry_point(zkc_sha256_closed_form *io, const zkc_log_query *requ
                            const uint32_t *memory_reads, size_t n_reads, size_t limit, const zkc_precompile_options *options,
                            uint64_t *trace, uint64_t *memory_states, size_t *n_memory_states, uint64_t commitment[4],
                            zkc_status *status);
+/* main_vm.c */
+size_t orc_vm_flatten_state(const zkc_vm_state *s, uint64_t *dst);
+void orc_vm_context_encode(const zkc_vm_context *c, uint64_t e[32]);
+void orc_vm_initial_bootloader_state(const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *st);
+int orc_main_vm_run(const zkc_vm_isa *isa, const zkc_vm_state *initial, const uint32_t *code, size_t code_words,
+                    size_t cycles, zkc_vm_state *snapshots, zkc_vm_cycle_witness *witness, zkc_status *status);
+int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const zkc_vm_state *snapshots,
+                            const zkc_vm_cycle_witness *witness, size_t limit, const zkc_vm_options *options,
+                            uint64_t *trace, uint64_t commitment[4], zkc_status *status);
 #endif

@@ -58,6 +58,15 @@ def load():
     lib.orc_sha256_entry_point.argtypes = [C.POINTER(abi.Sha256ClosedForm), _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t,
                                            C.POINTER(abi.PrecompileOptions), _vp, _vp, C.POINTER(C.c_size_t), _vp,
                                            C.POINTER(abi.Status)]
+    lib.orc_vm_initial_bootloader_state.argtypes = [C.POINTER(abi.VmClosedForm), C.POINTER(abi.VmIsa), C.POINTER(abi.VmState)]
+    lib.orc_main_vm_run.restype = C.c_int
+    lib.orc_main_vm_run.argtypes = [C.POINTER(abi.VmIsa), C.POINTER(abi.VmState), _vp, C.c_size_t, C.c_size_t, _vp, _vp,
+                                    C.POINTER(abi.Status)]
+    lib.orc_main_vm_entry_point.restype = C.c_int
+    lib.orc_main_vm_entry_point.argtypes = [C.POINTER(abi.VmClosedForm), C.POINTER(abi.VmIsa), _vp, _vp, C.c_size_t,
+                                            C.POINTER(abi.VmOptions), _vp, _vp, C.POINTER(abi.Status)]
+    lib.orc_vm_flatten_state.restype = C.c_size_t
+    lib.orc_vm_flatten_state.argtypes = [_vp, _vp]
     _LIB = lib
     return lib
 
@@ -239,3 +248,34 @@ def sha256_entry_point(lib, io, requests, memory_reads, limit, want_trace=True, 
     rc = lib.orc_sha256_entry_point(C.byref(io2), p(requests), len(requests), p(memory_reads), len(memory_reads), limit,
                                     C.byref(opts), p(trace), p(states), C.byref(n_states), p(com), C.byref(st))
     return rc, io2, trace, com, st, states[:n_states.value].copy()
+
+
+def vm_initial_state(lib, io, isa):
+    st = abi.VmState()
+    lib.orc_vm_initial_bootloader_state(C.byref(io), C.byref(isa), C.byref(st))
+    return st
+
+
+def vm_run(lib, isa, initial, code_words, cycles):
+    """out-of-circuit run: returns (rc, snapshots [cycles + 1] as a uint8 array [cycles + 1, 1176], witness [cycles, 80], status)"""
+    code_words = np.ascontiguousarray(code_words, dtype=np.uint32)
+    snaps = np.zeros((cycles + 1, C.sizeof(abi.VmState)), dtype=np.uint8)
+    wit = np.zeros((cycles, C.sizeof(abi.VmCycleWitness)), dtype=np.uint8)
+    st = abi.Status()
+    rc = lib.orc_main_vm_run(C.byref(isa), C.byref(initial), p(code_words), len(code_words), cycles, p(snaps), p(wit), C.byref(st))
+    return rc, snaps, wit, st
+
+
+def vm_state_at(snaps, i):
+    return abi.VmState.from_buffer_copy(snaps[i].tobytes())
+
+
+def vm_entry_point(lib, io, isa, snaps, wit, limit, want_trace=True, compare_expected=False):
+    io2 = abi.VmClosedForm.from_buffer_copy(bytes(io))
+    trace = np.zeros((abi.VM_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
+    com = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    opts = abi.VmOptions(int(compare_expected))
+    rc = lib.orc_main_vm_entry_point(C.byref(io2), C.byref(isa), p(np.ascontiguousarray(snaps)), p(np.ascontiguousarray(wit)), limit,
+                                     C.byref(opts), p(trace), p(com), C.byref(st))
+    return rc, io2, trace, com, st
