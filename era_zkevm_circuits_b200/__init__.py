@@ -27,3 +27,10 @@ from .sha256_round_function import (  # noqa: F401
     Sha256RoundFunctionCircuitInstanceWitness,
     sha256_round_function_entry_point,
 )
+from .main_vm import (  # noqa: F401
+    VmCircuitWitness,
+    main_vm_entry_point,
+    main_vm_entry_point_batch,
+    main_vm_initial_state,
+    main_vm_simulate,
+)

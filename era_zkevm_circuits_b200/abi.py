@@ -313,6 +313,8 @@ SIGNATURES = {
                                                         C.POINTER(PrecompileOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
     "zkc_main_vm_entry_point": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), _vp, _vp, C.c_size_t,
                                           C.POINTER(VmOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
+    "zkc_main_vm_entry_point_batch": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(VmIsa), _vp, _vp, C.c_size_t,
+                                                C.POINTER(VmOptions), C.c_int, _vp, _vp, _vp]),
     "zkc_main_vm_initial_state": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), C.POINTER(VmState)]),
     "zkc_main_vm_simulate": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp,
                                        C.POINTER(Status)]),

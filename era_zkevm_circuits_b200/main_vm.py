@@ -1,0 +1,97 @@
+"""Host-side mirror of `main_vm_entry_point` (/root/reference/src/main_vm/mod.rs:47-232) plus the out-of-circuit run
+that produces its witness (the role of the external zk_evm crate)."""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import abi
+from .engine import Engine, ZkcError, on_device, ptr
+from .log_sorter import SorterResult
+
+
+@dataclass
+class VmCircuitWitness:
+    """fsm_input_output/circuit_inputs/main_vm.rs:64-71.  The WitnessOracle is flattened into per-cycle answers, and
+    the per-cycle VmLocalState snapshots make the instance data parallel."""
+    closed_form_input: abi.VmClosedForm
+    isa: abi.VmIsa
+    snapshots: object  # [limit + 1, 1176] uint8 (numpy) or torch uint8 on the GPU: zkc_vm_state before each cycle + final
+    witness_oracle: object  # [limit, 80] uint8: zkc_vm_cycle_witness per cycle
+
+
+def main_vm_entry_point(engine: Engine, witness: VmCircuitWitness, limit: int, want_trace=True, compare_expected=False,
+                        raise_on_unsatisfied=True, trace_out=None) -> SorterResult:
+    w = witness
+    dev = on_device(w.snapshots, w.witness_oracle)
+    if trace_out is not None:
+        dev |= 2 * on_device(trace_out)
+    elif dev:
+        dev = 3
+    trace = trace_out
+    if want_trace and trace is None:
+        if dev & 2:
+            import torch
+            trace = torch.empty((abi.VM_COLS["NUM_COLS"], limit), dtype=torch.int64, device=w.snapshots.device)
+        else:
+            trace = np.empty((abi.VM_COLS["NUM_COLS"], limit), dtype=np.uint64)
+    io = abi.VmClosedForm.from_buffer_copy(bytes(w.closed_form_input))
+    opts = abi.VmOptions(int(compare_expected))
+    commitment = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    rc = engine.lib.zkc_main_vm_entry_point(engine.h, C.byref(io), C.byref(w.isa), ptr(w.snapshots), ptr(w.witness_oracle), limit,
+                                            C.byref(opts), dev, ptr(trace), ptr(commitment), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE) or (rc and raise_on_unsatisfied):
+        raise ZkcError(rc, st, "main_vm_entry_point")
+    return SorterResult(commitment, io, trace, st)
+
+
+def main_vm_initial_state(engine: Engine, closed_form_input: abi.VmClosedForm, isa: abi.VmIsa) -> abi.VmState:
+    """initial_bootloader_state, main_vm/loading.rs:13-226"""
+    out = abi.VmState()
+    rc = engine.lib.zkc_main_vm_initial_state(engine.h, C.byref(closed_form_input), C.byref(isa), C.byref(out))
+    if rc:
+        raise ZkcError(rc, what="zkc_main_vm_initial_state")
+    return out
+
+
+def main_vm_simulate(engine: Engine, isa: abi.VmIsa, initial_states, code, cycles: int):
+    """Out-of-circuit run of n independent VM instances on the GPU.  initial_states: list of abi.VmState;
+    code: [n, code_words, 8] uint32.  Returns torch CUDA tensors (snapshots [n, cycles + 1, 1176] uint8,
+    witness [n, cycles, 80] uint8) and the status."""
+    import torch
+    n = len(initial_states)
+    code = np.ascontiguousarray(code, dtype=np.uint32).reshape(n, -1, 8)
+    init = np.frombuffer(b"".join(bytes(s) for s in initial_states), dtype=np.uint8).reshape(n, -1)
+    d_init = torch.from_numpy(init.copy()).cuda()
+    d_code = torch.from_numpy(code.view(np.int32)).cuda()
+    snaps = torch.empty((n, cycles + 1, C.sizeof(abi.VmState)), dtype=torch.uint8, device="cuda")
+    wit = torch.empty((n, cycles, C.sizeof(abi.VmCycleWitness)), dtype=torch.uint8, device="cuda")
+    st = abi.Status()
+    rc = engine.lib.zkc_main_vm_simulate(engine.h, C.byref(isa), ptr(d_init), ptr(d_code), code.shape[1], n, cycles, ptr(snaps),
+                                         ptr(wit), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, st, "zkc_main_vm_simulate")
+    return snaps, wit, st
+
+
+def main_vm_entry_point_batch(engine: Engine, closed_form_inputs, isa: abi.VmIsa, snapshots, witness_oracle, limit: int,
+                              trace_out=None, compare_expected=False):
+    """n independent instances in one set of launches.  closed_form_inputs: list of abi.VmClosedForm;
+    snapshots [n, limit + 1, 1176], witness_oracle [n, limit, 80] (numpy or torch CUDA uint8); trace_out:
+    optional [n, NUM_COLS, limit] uint64.  Returns (commitments [n, 4], closed forms (updated), statuses, rc)."""
+    n = len(closed_form_inputs)
+    ios = (abi.VmClosedForm * n)(*[abi.VmClosedForm.from_buffer_copy(bytes(c)) for c in closed_form_inputs])
+    dev = on_device(snapshots, witness_oracle)
+    if trace_out is not None:
+        dev |= 2 * on_device(trace_out)
+    commitments = np.zeros((n, 4), dtype=np.uint64)
+    statuses = (abi.Status * n)()
+    opts = abi.VmOptions(int(compare_expected))
+    rc = engine.lib.zkc_main_vm_entry_point_batch(engine.h, C.cast(ios, C.c_void_p), n, C.byref(isa), ptr(snapshots),
+                                                  ptr(witness_oracle), limit, C.byref(opts), dev, ptr(trace_out),
+                                                  ptr(commitments), C.cast(statuses, C.c_void_p))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, statuses[0], "main_vm_entry_point_batch")
+    return commitments, ios, statuses, rc

@@ -893,6 +893,15 @@ int zkc_main_vm_entry_point(zkc_ctx *ctx, zkc_vm_closed_form *io, const zkc_vm_i
                             const zkc_vm_cycle_witness *witness, size_t limit, const zkc_vm_options *options,
                             int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
+/* The same over a batch of `n_instances` independent instances of equal `limit` in ONE set of launches (instances
+ * only communicate through their closed-form inputs): ios[n], snapshots [n][limit + 1],
+ * witness [n][limit], trace [n][ZKC_VM_NUM_COLS][limit] or NULL, commitments [n][4], statuses [n].  Returns the first
+ * non-OK status code. */
+int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa,
+                                  const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness, size_t limit,
+                                  const zkc_vm_options *options, int on_device, uint64_t *trace, uint64_t *commitments,
+                                  zkc_status *statuses);
+
 /* the state main_vm_entry_point starts from when start_flag is set: initial_bootloader_state, main_vm/loading.rs:13-226 */
 int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *out);
 

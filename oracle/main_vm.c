@@ -426,9 +426,12 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
     return checks;
 }
 
+/* status code = most specific aggregate: a broken snapshot chain outranks an unsupported opcode outranks a failed
+ * enforcement (an order-independent rule, so that the row-parallel engine reports the same code) */
 static void fail(zkc_status *st, int64_t row, uint32_t bits) {
-    if (st->code == ZKC_OK) st->code = (bits & ZKC_VM_CHK_UNSUPPORTED_OPCODE) ? ZKC_ERR_UNSUPPORTED : ZKC_ERR_UNSATISFIED;
     st->failed_checks |= bits;
+    st->code = (st->failed_checks & ZKC_VM_CHK_SNAPSHOT) ? ZKC_ERR_SNAPSHOT_MISMATCH
+             : (st->failed_checks & ZKC_VM_CHK_UNSUPPORTED_OPCODE) ? ZKC_ERR_UNSUPPORTED : ZKC_ERR_UNSATISFIED;
     if (row >= 0 && (st->first_bad_row < 0 || row < st->first_bad_row)) st->first_bad_row = row;
 }
 
@@ -465,7 +468,7 @@ int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const
     for (size_t c = 0; c < limit; c++) {
         /* the per-cycle snapshot is a hint: it must be the state the sequential run is in */
         orc_vm_flatten_state(&state, fa); orc_vm_flatten_state(&snapshots[c], fb);
-        if (memcmp(fa, fb, sizeof fa)) { fail(&st, (int64_t)c, ZKC_VM_CHK_SNAPSHOT); if (st.code == ZKC_ERR_UNSATISFIED) st.code = ZKC_ERR_SNAPSHOT_MISMATCH; }
+        if (memcmp(fa, fb, sizeof fa)) fail(&st, (int64_t)c, ZKC_VM_CHK_SNAPSHOT);
         zkc_vm_cycle_witness w = witness[c];
         zkc_vm_state next;
         const uint32_t chk = vm_cycle(isa, &snapshots[c], &w, NULL, &next, trace ? trace + c : NULL, limit);
@@ -473,7 +476,7 @@ int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const
         state = next;
     }
     orc_vm_flatten_state(&state, fa); orc_vm_flatten_state(&snapshots[limit], fb);
-    if (memcmp(fa, fb, sizeof fa)) { fail(&st, (int64_t)limit - 1, ZKC_VM_CHK_SNAPSHOT); if (st.code == ZKC_ERR_UNSATISFIED) st.code = ZKC_ERR_SNAPSHOT_MISMATCH; }
+    if (memcmp(fa, fb, sizeof fa)) fail(&st, (int64_t)limit - 1, ZKC_VM_CHK_SNAPSHOT);
     /* mod.rs:113-196 */
     const int done = state.context_stack_depth == 0;
     if (done && state.current_context.pc != 0) fail(&st, -1, ZKC_VM_CHK_BOOTLOADER_EXIT);
