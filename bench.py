@@ -1,13 +1,15 @@
 #!/usr/bin/env python3
 """bench.py -- one JSON line per run (driver contract).
 
-A "step" is one pass of the hot path over one batch of synthetic input PER GPU:
-witness generation of one circuit instance (entry point, witness columns written to HBM) followed by
-constraint evaluation of the finished trace.  `value` = loop iterations ("rows"/"cycles") per second,
-whole job over all ranks, inputs resident in HBM; `e2e` = the same through the reference-facing call
-with pinned HOST buffers (H2D of the inputs and D2H of the witness columns + FSM output inside the
-timed region).  `--impl reference` times the CPU oracle (oracle/, a C restatement of the Rust
-reference, which cannot be compiled in this image) on all host threads.
+Workload (BASELINE.json configs[1]): main_vm, 2^20 cycles per GPU per step, as 256 independent circuit instances of
+2^12 cycles each (a production main_vm instance holds ~5.6 k cycles; instances only communicate through their
+closed-form inputs).  A "step" = one batched main_vm entry point call: every cycle evaluated from its VmLocalState
+snapshot + oracle answers, memory-queue sponges, witness trace written to HBM, FSM outputs and the 256 commitments.
+`value` = cycles/s over all ranks with inputs resident in HBM; `e2e` = the same call with pinned HOST buffers (H2D of
+snapshots + witness, D2H of the trace + closed forms inside the timed region).  The second half of the headline metric
+(constraint-evaluation GB/s vs HBM peak) is measured in the same run on the streaming constraint evaluator of the
+ram_permutation trace and reported in `roofline`.  `--impl reference` times the CPU oracle (oracle/, a C restatement of
+the Rust reference, which cannot be compiled in this image) on all host threads.
 """
 import argparse
 import ctypes as C
@@ -24,9 +26,14 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WORKLOAD_ROWS = 1 << 20
-METRIC = "ram_permutation witness-gen + constraint-eval rows/sec at 2^20 rows per instance"
-UNIT = "rows/s"
+N_INSTANCES = 256
+CYCLES_PER_INSTANCE = 1 << 12
+PROGRAM_LEN = 1 << 12
+METRIC = "main_vm cycles/sec witness-gen at 2^20 cycles; constraint-eval GB/s vs HBM peak"
+UNIT = "cycles/s"
+WORKLOAD = ("main_vm, 2^20 cycles per GPU per step = 256 independent instances x 2^12 cycles, synthetic ISA table + random "
+            "straight-line programs (add/sub/binop/mul/div/shift/ptr/context, 30 % stack/code/immediate operands); "
+            "log/near_call/far_call/ret/uma opcodes are not built yet and do not occur in the programs")
 
 
 def measured_peaks():
@@ -43,24 +50,21 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.gpu, self.proc, self.lines = gpu_index, None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -69,7 +73,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if t0 is not None and not (t0 <= t <= t1 + 0.2):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -94,26 +100,34 @@ def pinned_array(eng, shape, dtype):
 
 
 # ------------------------------------------------------------------------------------------- reference arm / cpu baseline
-def oracle_ram_job(rows_per_instance, instances, threads):
-    """times the CPU oracle on `instances` independent ram_permutation instances, `threads` at a time.
-    Returns (rows/s, seconds)."""
+def oracle_vm_job(instances, cycles, threads, seed=0xC2):
+    """times the CPU oracle's main_vm entry point on `instances` independent instances, `threads` at a time.
+    Returns (cycles/s, seconds).  Input construction (the out-of-circuit run) is not timed."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orc as O  # oracle: the thing MEASURED here is the CPU baseline itself
-    import helpers as H
-    from era_zkevm_circuits_b200 import abi, synthetic
+    from era_zkevm_circuits_b200 import abi, isa as I
     lib = O.load()
-    u, s = synthetic.ram_trace(rows_per_instance, seed=0xC1, n_nondet=7)
-    io, _, _ = H.ram_instance(lib, u, s, 7)
-    traces = [np.zeros((abi.RAM_COLS["NUM_COLS"], rows_per_instance), dtype=np.uint64) for _ in range(min(threads, instances))]
+    isa = I.Isa()
+    distinct = min(instances, 4)  # a few distinct programs, reused round-robin: the work per instance is the same
+    jobs = []
+    for i in range(distinct):
+        io = abi.VmClosedForm(); io.start_flag = 1; io.rollback_queue_tail_for_block[0] = i
+        st = O.vm_initial_state(lib, io, isa.isa)
+        rc, snaps, wit, status = O.vm_run(lib, isa.isa, st, I.pack_code(I.random_program(isa, PROGRAM_LEN, seed=seed + i)), cycles)
+        assert rc == 0
+        jobs.append((io, snaps, wit))
+    ncols = abi.VM_COLS["NUM_COLS"]
+    traces = [np.zeros((ncols, cycles), dtype=np.uint64) for _ in range(min(threads, instances))]
 
     def work(slot, count):
-        for _ in range(count):
-            io2 = abi.RamClosedForm.from_buffer_copy(bytes(io))
+        for k in range(count):
+            io, snaps, wit = jobs[(slot + k) % distinct]
+            io2 = abi.VmClosedForm.from_buffer_copy(bytes(io))
             com = np.zeros(4, dtype=np.uint64)
             st = abi.Status()
-            opts = abi.RamOptions(0, 0)
-            rc = lib.orc_ram_permutation_entry_point(C.byref(io2), O.p(u), len(u), O.p(s), len(s), rows_per_instance,
-                                                     C.byref(opts), O.p(traces[slot]), O.p(com), C.byref(st))
+            opts = abi.VmOptions(0)
+            rc = lib.orc_main_vm_entry_point(C.byref(io2), C.byref(isa.isa), O.p(snaps), O.p(wit), cycles, C.byref(opts),
+                                             O.p(traces[slot]), O.p(com), C.byref(st))
             assert rc == 0
 
     per = [instances // threads + (1 if i < instances % threads else 0) for i in range(threads)]
@@ -124,29 +138,28 @@ def oracle_ram_job(rows_per_instance, instances, threads):
     for t in ts:
         t.join()
     dt = time.perf_counter() - t0
-    return rows_per_instance * instances / dt, dt
+    return instances * cycles / dt, dt
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
-    rows = 1 << 16
-    inst = cores  # one instance per host thread per step
+    inst = 64 * cores  # ~1-2 s of CPU work per step
     for _ in range(args.warmup):
-        oracle_ram_job(rows, inst, cores)
+        oracle_vm_job(inst, CYCLES_PER_INSTANCE, cores)
     tot, dt = 0, 0.0
     for _ in range(args.steps):
-        tot += rows * inst
-        dt += oracle_ram_job(rows, inst, cores)[1]  # the job's own clock: input construction is not timed
+        v, t = oracle_vm_job(inst, CYCLES_PER_INSTANCE, cores)
+        tot += inst * CYCLES_PER_INSTANCE
+        dt += t
     v = tot / dt
-    sample = f"{inst} independent instances x 2^16 rows per step on {cores} threads (C oracle, witness trace written)"
+    sample = (f"{inst} independent instances x 2^12 cycles per step on {cores} threads (C oracle of the same entry point, witness "
+              f"trace written; bounded sample of the 256-instance workload)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "ram_permutation, 2^20 rows per instance (reference arm: bounded sample of 2^16-row instances)"},
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -156,7 +169,8 @@ def run_reference(args):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from era_zkevm_circuits_b200 import (Engine, RamPermutationCircuitInstanceWitness, abi, ram_permutation_check_trace,
+    from era_zkevm_circuits_b200 import (Engine, RamPermutationCircuitInstanceWitness, abi, isa as I, main_vm_entry_point_batch,
+                                         main_vm_initial_state, main_vm_simulate, ram_permutation_check_trace,
                                          ram_permutation_entry_point, synthetic)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,86 +182,111 @@ def run_gpu(args):
     stream = torch.cuda.current_stream()
     eng.set_stream(stream)
 
-    n = WORKLOAD_ROWS
-    ncols = abi.RAM_COLS["NUM_COLS"]
-    u, s = synthetic.ram_trace(n, seed=0xC1 + rank, n_cells=1 << 10, n_nondet=7)
-    both = np.concatenate([u, s])
-    d_both = torch.from_numpy(both.view(np.uint8).reshape(2 * n, 64)).cuda()
-    prev, fin = eng.memory_queue_simulate(d_both, n_queues=2)  # device-side hash chains (setup, untimed)
-    torch.cuda.synchronize()
-    du, ds, dup, dsp = d_both[:n], d_both[n:], prev[:n], prev[n:]
-    io = abi.RamClosedForm()
-    io.start_flag = 1
-    io.observable_input.unsorted_queue_initial_state = fin[0]
-    io.observable_input.sorted_queue_initial_state = fin[1]
-    io.observable_input.non_deterministic_bootloader_memory_snapshot_length = 7
-    trace = torch.empty((ncols, n), dtype=torch.int64, device="cuda")
-    w_dev = RamPermutationCircuitInstanceWitness(io, du, dup, ds, dsp)
-    gathered = torch.zeros((world, 4), dtype=torch.int64, device="cuda") if world > 1 else None
+    # ---- inputs: out-of-circuit run of this rank's instances on the GPU (setup, untimed) -------------------------------------
+    n, cycles = N_INSTANCES, CYCLES_PER_INSTANCE
+    isa = I.Isa()
+    ios, states, codes = [], [], []
+    distinct_programs = [I.pack_code(I.random_program(isa, PROGRAM_LEN, seed=0xC2 + rank * 7 + k)) for k in range(8)]
+    for i in range(n):
+        io = abi.VmClosedForm(); io.start_flag = 1
+        io.rollback_queue_tail_for_block[0] = rank * n + i  # distinct instances -> distinct commitments
+        ios.append(io)
+        states.append(main_vm_initial_state(eng, io, isa.isa))
+        codes.append(distinct_programs[i % 8])
+    d_snaps, d_wit, st = main_vm_simulate(eng, isa.isa, states, np.stack(codes), cycles)
+    assert st.code == 0, (st.code, hex(st.failed_checks), st.first_bad_row)
+    ncols = abi.VM_COLS["NUM_COLS"]
+    trace = torch.empty((n, ncols, cycles), dtype=torch.int64, device="cuda")
+    gathered = torch.zeros((world * n, 4), dtype=torch.int64, device="cuda") if world > 1 else None
 
     def step_device():
-        r = ram_permutation_entry_point(eng, w_dev, n, trace_out=trace)
-        viol, _ = ram_permutation_check_trace(eng, io, trace, n, abi.GATES_GENERAL)
-        assert viol == 0 and r.status.code == 0
+        coms, out, statuses, rc = main_vm_entry_point_batch(eng, ios, isa.isa, d_snaps, d_wit, cycles, trace_out=trace)
+        assert rc == 0
         if world > 1:  # the only exchange of the sharded job: 4 x u64 commitment per instance
-            c = torch.from_numpy(r.commitment.view(np.int64)).cuda(non_blocking=True)
-            dist.all_gather_into_tensor(gathered, c.reshape(1, 4))
-        return r
+            c = torch.from_numpy(coms.view(np.int64)).cuda(non_blocking=True)
+            dist.all_gather_into_tensor(gathered, c)
+        return coms
 
     def timed(fn, steps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(steps):
             fn()
         e1.record(stream)
         torch.cuda.synchronize()
+        t1 = time.perf_counter()
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms
+        return ms, t0, t1
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.5)  # let nvidia-smi come up so that samples fall inside the timed region
+        time.sleep(0.5)
     for _ in range(args.warmup):
         step_device()
     eng.profile_reset()
     eng.profile(True)
     l0 = eng.launches
-    ms = timed(step_device, args.steps)
+    ms, t0, t1 = timed(step_device, args.steps)
     launches = eng.launches - l0
     eng.profile(False)
-    prof = {k: eng.profile_query(k) for k in ("ram_rows", "ram_check", "ram_prologue", "ram_finalize")}
-    clocks = sampler.stop() if rank == 0 else None
-    value = n * world * args.steps / (ms / 1e3)
+    prof = {k: eng.profile_query(k) for k in ("vm_cycles", "vm_prologue", "vm_finalize")}
+    value = n * cycles * world * args.steps / (ms / 1e3)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
 
-    # ---- e2e: pinned host inputs -> H2D -> kernels -> D2H of witness columns + FSM output -------------------------------
-    hu = pinned_array(eng, (n,), abi.MEMORY_QUERY_DTYPE); hu[:] = u
-    hs = pinned_array(eng, (n,), abi.MEMORY_QUERY_DTYPE); hs[:] = s
-    hup = pinned_array(eng, (n, 12), np.uint64); hup[:] = dup.cpu().numpy().view(np.uint64)
-    hsp = pinned_array(eng, (n, 12), np.uint64); hsp[:] = dsp.cpu().numpy().view(np.uint64)
-    htrace = pinned_array(eng, (ncols, n), np.uint64)
-    w_host = RamPermutationCircuitInstanceWitness(io, hu, hup, hs, hsp)
+    # ---- constraint evaluation (second half of the metric): streaming evaluator over a 2^20-row ram_permutation trace --------
+    rn = 1 << 20
+    u, s = synthetic.ram_trace(rn, seed=0xC1 + rank, n_cells=1 << 10, n_nondet=7)
+    d_both = torch.from_numpy(np.concatenate([u, s]).view(np.uint8).reshape(2 * rn, 64)).cuda()
+    prev, fin = eng.memory_queue_simulate(d_both, n_queues=2)  # the two 2^20-long hash chains of the instance (setup, ~20 s)
+    rio = abi.RamClosedForm(); rio.start_flag = 1
+    rio.observable_input.unsorted_queue_initial_state = fin[0]
+    rio.observable_input.sorted_queue_initial_state = fin[1]
+    rio.observable_input.non_deterministic_bootloader_memory_snapshot_length = 7
+    rtrace = torch.empty((abi.RAM_COLS["NUM_COLS"], rn), dtype=torch.int64, device="cuda")
+    rw = RamPermutationCircuitInstanceWitness(rio, d_both[:rn], prev[:rn], d_both[rn:], prev[rn:])
+    r = ram_permutation_entry_point(eng, rw, rn, trace_out=rtrace)
+    assert r.status.code == 0
+    for _ in range(3):
+        ram_permutation_check_trace(eng, rio, rtrace, rn, abi.GATES_GENERAL)
+    eng.profile_reset()
+    eng.profile(True)
+    for _ in range(max(5, min(args.steps, 20))):
+        viol, _ = ram_permutation_check_trace(eng, rio, rtrace, rn, abi.GATES_GENERAL)
+        assert viol == 0
+        r = ram_permutation_entry_point(eng, rw, rn, trace_out=rtrace)  # rewrites 1.1 GB: the next check reads cold HBM
+    eng.profile(False)
+    chk_ms, chk_n = eng.profile_query("ram_check")
+    rows_ms, rows_n = eng.profile_query("ram_rows")
+    del d_both, prev, rtrace
+
+    # ---- e2e: pinned host inputs -> H2D -> kernels -> D2H of witness columns + closed forms ------------------------------------
+    hs = pinned_array(eng, (n, cycles + 1, C.sizeof(abi.VmState)), np.uint8)
+    hw = pinned_array(eng, (n, cycles, C.sizeof(abi.VmCycleWitness)), np.uint8)
+    hs[:] = d_snaps.cpu().numpy(); hw[:] = d_wit.cpu().numpy()
+    htrace = pinned_array(eng, (n, ncols, cycles), np.uint64)
 
     def step_e2e():
-        r = ram_permutation_entry_point(eng, w_host, n, trace_out=htrace)
-        assert r.status.code == 0
+        coms, out, statuses, rc = main_vm_entry_point_batch(eng, ios, isa.isa, hs, hw, cycles, trace_out=htrace)
+        assert rc == 0
         if world > 1:
-            c = torch.from_numpy(r.commitment.view(np.int64)).cuda(non_blocking=True)
-            dist.all_gather_into_tensor(gathered, c.reshape(1, 4))
+            c = torch.from_numpy(coms.view(np.int64)).cuda(non_blocking=True)
+            dist.all_gather_into_tensor(gathered, c)
 
     e2e_steps = max(1, min(args.steps, 5))
     step_e2e()
-    ms_e2e = timed(step_e2e, e2e_steps)
-    e2e_value = n * world * e2e_steps / (ms_e2e / 1e3)
-    h2d = int(hu.nbytes + hs.nbytes + hup.nbytes + hsp.nbytes + C.sizeof(abi.RamClosedForm))
-    d2h = int(htrace.nbytes + C.sizeof(abi.RamClosedForm) + 32 + C.sizeof(abi.Status))
+    ms_e2e, _, _ = timed(step_e2e, e2e_steps)
+    e2e_value = n * cycles * world * e2e_steps / (ms_e2e / 1e3)
+    h2d = int(hs.nbytes + hw.nbytes + n * (C.sizeof(abi.VmClosedForm) + 64) + C.sizeof(abi.VmIsa))
+    d2h = int(htrace.nbytes + n * (C.sizeof(abi.VmClosedForm) + 64 + 32 + C.sizeof(abi.Status)))
 
     if rank != 0:
         if world > 1:
@@ -255,46 +294,44 @@ def run_gpu(args):
         return
 
     peak, peak_src = measured_peaks()
-    chk_ms, chk_n = prof["ram_check"]
-    rows_ms, rows_n = prof["ram_rows"]
-    chk_bytes = ncols * 8 * n
-    rows_bytes = (2 * 64 + 2 * 96 + ncols * 8) * n
+    chk_bytes = abi.RAM_COLS["NUM_COLS"] * 8 * rn
     chk_gbs = chk_bytes / (chk_ms / chk_n * 1e-3) / 1e9 if chk_n else None
-    rows_gbs = rows_bytes / (rows_ms / rows_n * 1e-3) / 1e9 if rows_n else None
-    roofline = {"kernel": "ram_check_kernel<false> (constraint evaluation, streaming relations)", "bound": "hbm",
-                "achieved": chk_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+    cyc_ms, cyc_n = prof["vm_cycles"]
+    vm_bytes = (C.sizeof(abi.VmState) + C.sizeof(abi.VmCycleWitness) + ncols * 8) * n * cycles
+    roofline = {"kernel": "ram_check_kernel<false> (constraint evaluation of a 2^20-row ram_permutation trace, streaming relations)",
+                "bound": "hbm", "achieved": chk_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": chk_gbs / peak if chk_gbs else None, "frac_of_nominal_8000": chk_gbs / 8000.0 if chk_gbs else None,
-                "algorithmic_bytes_per_row": ncols * 8, "avg_launch_ms": chk_ms / chk_n if chk_n else None, "traffic": None}
+                "algorithmic_bytes_per_row": abi.RAM_COLS["NUM_COLS"] * 8, "avg_launch_ms": chk_ms / chk_n if chk_n else None,
+                "traffic": (281072896 + 4868864) * 4,
+                "traffic_note": "ncu --set full dram__bytes_read+write of this kernel at 2^18 rows (profiles/r01_ncu_full_ram_kernels_raw.csv), "
+                                "scaled x4 to 2^20 rows: equals the algorithmic bytes (no re-reads)"}
     kernels = {
-        "ram_rows_kernel (witness generation: 2 Poseidon2/row + scan; integer-ALU bound)": {
-            "avg_launch_ms": rows_ms / rows_n if rows_n else None, "algorithmic_bytes_per_row": rows_bytes // n,
-            "achieved_gbs": rows_gbs, "frac_of_hbm_peak": rows_gbs / peak if rows_gbs else None,
-            "poseidon2_per_s": 2 * n / (rows_ms / rows_n * 1e-3) if rows_n else None},
-        "ram_prologue_kernel": {"avg_launch_ms": prof["ram_prologue"][0] / max(1, prof["ram_prologue"][1])},
-        "ram_finalize_kernel": {"avg_launch_ms": prof["ram_finalize"][0] / max(1, prof["ram_finalize"][1])},
+        "vm_cycles_kernel (main_vm witness generation, one thread per cycle; integer-ALU bound: ~2.2 Poseidon2/cycle)": {
+            "avg_launch_ms": cyc_ms / cyc_n if cyc_n else None, "algorithmic_bytes_per_cycle": vm_bytes // (n * cycles),
+            "achieved_gbs": vm_bytes / (cyc_ms / cyc_n * 1e-3) / 1e9 if cyc_n else None,
+            "share_of_step": (cyc_ms / cyc_n) / (ms / args.steps) if cyc_n else None},
+        "vm_prologue_kernel": {"avg_launch_ms": prof["vm_prologue"][0] / max(1, prof["vm_prologue"][1])},
+        "vm_finalize_kernel": {"avg_launch_ms": prof["vm_finalize"][0] / max(1, prof["vm_finalize"][1])},
+        "ram_rows_kernel (ram_permutation witness generation, 2^20 rows)": {"avg_launch_ms": rows_ms / rows_n if rows_n else None},
     }
-
     cores = os.cpu_count() or 1
-    cpu1, t1 = oracle_ram_job(1 << 16, 2, 1)
-    cpun, tn = oracle_ram_job(1 << 16, 2 * cores, cores)
+    cpu1, t_1 = oracle_vm_job(256, cycles, 1)
+    cpun, t_n = oracle_vm_job(512 * cores, cycles, cores)
     cpu_baseline = {"value": cpun, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"{2 * cores} instances x 2^16 rows of the same synthetic workload on {cores} threads ({tn:.1f} s); "
-                              f"single thread: {cpu1:.0f} rows/s ({t1:.1f} s); C oracle incl. witness trace, no constraint eval",
+                    "sample": f"{512 * cores} instances x 2^12 cycles of the same workload on {cores} threads ({t_n:.1f} s); single thread: "
+                              f"{cpu1:.0f} cycles/s ({t_1:.1f} s); C oracle of main_vm_entry_point incl. witness trace",
                     "single_thread_value": cpu1}
-
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "ram_permutation single instance per GPU, limit = 2^20 rows (C1 trace shape at the reference's "
-                               "max_trace_len); main_vm (configs[1]) is not built yet",
-                   "rows_per_gpu_per_step": n, "trace_columns": ncols,
-                   "l2_policy": "inputs (335 MB) and trace (1.1 GB) per step exceed the 126 MB L2",
-                   "step": "entry point (witness columns to HBM) + constraint evaluation (general gates) [+ NCCL all-gather "
-                           "of the 4-element commitments when n_gpus > 1]"},
+        "config": {"workload": WORKLOAD, "cycles_per_gpu_per_step": n * cycles, "instances_per_gpu": n, "trace_columns": ncols,
+                   "l2_policy": "snapshots + witness (1.35 GB) and trace (1.13 GB) per step exceed the 126 MB L2",
+                   "step": "batched main_vm entry point: start states, all cycles (witness columns to HBM), FSM outputs + commitments "
+                           "[+ NCCL all-gather of the 4-element commitments when n_gpus > 1]"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / e2e_steps, "note": "pinned host inputs; full witness trace copied back to the host"},
+                "ms_per_step": ms_e2e / e2e_steps, "note": "pinned host snapshots + witness in, full witness trace + closed forms out"},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }))
     if world > 1:
@@ -304,7 +341,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
