@@ -73,26 +73,64 @@ __device__ __forceinline__ bool u256_ge(const U256 &a, const U256 &b) {
     U256 t;
     return u256_sub(a, b, t) == 0;
 }
-// restoring binary division (b != 0)
+// q = a / b, r = a % b for b != 0: Knuth's algorithm D on 32-bit limbs (at most 8 quotient digits, each one 64/32
+// division + a multiply-subtract), instead of 256 shift-subtract steps that every lane of a warp would wait for
 __device__ void u256_divrem(const U256 &a, const U256 &b, U256 &q, U256 &r) {
 #pragma unroll
     for (int i = 0; i < 8; i++) { q.v[i] = 0; r.v[i] = 0; }
-#pragma unroll 1
-    for (int limb = 7; limb >= 0; limb--) {
-        const uint32_t aw = a.v[limb];
-        uint32_t qw = 0;
-#pragma unroll 1
-        for (int bit = 31; bit >= 0; bit--) {
-            const uint32_t top = r.v[7] >> 31;
-#pragma unroll
-            for (int i = 7; i > 0; i--) r.v[i] = (r.v[i] << 1) | (r.v[i - 1] >> 31);
-            r.v[0] = (r.v[0] << 1) | ((aw >> bit) & 1);
-            U256 t;
-            const uint32_t borrow = u256_sub(r, b, t);
-            if (top || !borrow) { r = t; qw |= 1u << bit; }
+    int n = 8;
+    while (n > 1 && b.v[n - 1] == 0) n--;
+    if (n == 1) {
+        uint64_t rem = 0;
+        const uint32_t d = b.v[0];
+        for (int i = 7; i >= 0; i--) {
+            const uint64_t cur = (rem << 32) | a.v[i];
+            q.v[i] = (uint32_t)(cur / d);
+            rem = cur % d;
         }
-        q.v[limb] = qw;
+        r.v[0] = (uint32_t)rem;
+        return;
     }
+    const int sh = __clz(b.v[n - 1]);
+    uint32_t v[8], u[9];
+    for (int i = n - 1; i > 0; i--) v[i] = sh ? (b.v[i] << sh) | (b.v[i - 1] >> (32 - sh)) : b.v[i];
+    v[0] = b.v[0] << sh;
+    u[8] = sh ? a.v[7] >> (32 - sh) : 0;
+    for (int i = 7; i > 0; i--) u[i] = sh ? (a.v[i] << sh) | (a.v[i - 1] >> (32 - sh)) : a.v[i];
+    u[0] = a.v[0] << sh;
+    for (int j = 8 - n; j >= 0; j--) {
+        const uint64_t num = ((uint64_t)u[j + n] << 32) | u[j + n - 1];
+        uint64_t qhat = num / v[n - 1], rhat = num % v[n - 1];
+        while (qhat >= (1ull << 32) || qhat * v[n - 2] > ((rhat << 32) | u[j + n - 2])) {
+            qhat--;
+            rhat += v[n - 1];
+            if (rhat >= (1ull << 32)) break;
+        }
+        // u[j .. j+n] -= qhat * v
+        int64_t borrow = 0;
+        uint64_t carry = 0;
+        for (int i = 0; i < n; i++) {
+            const uint64_t p = qhat * v[i] + carry;
+            carry = p >> 32;
+            const int64_t t = (int64_t)u[i + j] - (int64_t)(uint32_t)p + borrow;
+            u[i + j] = (uint32_t)t;
+            borrow = t >> 32;  // 0 or -1
+        }
+        const int64_t t = (int64_t)u[j + n] - (int64_t)carry + borrow;
+        u[j + n] = (uint32_t)t;
+        if (t < 0) {  // qhat was one too large: add the divisor back
+            qhat--;
+            uint64_t c = 0;
+            for (int i = 0; i < n; i++) {
+                const uint64_t x = (uint64_t)u[i + j] + v[i] + c;
+                u[i + j] = (uint32_t)x;
+                c = x >> 32;
+            }
+            u[j + n] += (uint32_t)c;
+        }
+        q.v[j] = (uint32_t)qhat;
+    }
+    for (int i = 0; i < n; i++) r.v[i] = sh ? (u[i] >> sh) | ((uint64_t)u[i + 1] << (32 - sh)) : u[i];
 }
 // (a << s) mod 2^256 and a >> (256 - s) for s in [0, 255]: the two halves of a * 2^s (shifts.rs:95-96)
 __device__ void u256_shl_wide(const U256 &a, uint32_t s, U256 &lo, U256 &hi) {
@@ -274,26 +312,81 @@ __device__ __forceinline__ U256 as_u256(const zkc_vm_register &r) {
     return x;
 }
 
-// One vm_cycle on `s` (in place).  SIM: memory reads are answered by `mem` and recorded into `w`; otherwise they
-// come from `w`.  trace / limit / row: where to put the row (trace may be null).  Returns the check bits.
+// what one cycle changes in a VmLocalState; every other word must carry over unchanged
+struct VmDelta {
+    uint32_t pending, pc, sp, ergs, prev_code_page, prev_super_pc, timestamp, memq_len;
+    uint32_t flags[3];
+    uint32_t cw[8];       // previous_code_word after the opcode fetch
+    uint32_t idx0, idx1;  // 1-based register written by dst0 / dst1, 0 = none (dst1 is applied after dst0)
+    zkc_vm_register val0, val1;
+    uint32_t set_u128, u128[4], set_pubdata, pubdata, inc_tx;
+    uint32_t push_mask;   // bit k: memory queue push k happens (0 opcode fetch, 1 src0 read, 2 dst0 write)
+};
+
+__device__ void vm_apply_delta(zkc_vm_state &t, const VmDelta &d) {
+    t.pending_exception = d.pending;
+    t.current_context.pc = d.pc; t.current_context.sp = d.sp; t.current_context.ergs_remaining = d.ergs;
+    t.previous_code_page = d.prev_code_page; t.previous_super_pc = d.prev_super_pc; t.timestamp = d.timestamp;
+    t.memory_queue_length = d.memq_len;
+    for (int i = 0; i < 3; i++) t.flags[i] = d.flags[i];
+    for (int i = 0; i < 8; i++) t.previous_code_word[i] = d.cw[i];
+    if (d.idx0) t.registers[d.idx0 - 1] = d.val0;
+    if (d.idx1) t.registers[d.idx1 - 1] = d.val1;
+    if (d.set_u128) for (int i = 0; i < 4; i++) t.context_composite_u128[i] = d.u128[i];
+    if (d.set_pubdata) t.ergs_per_pubdata_byte = d.pubdata;
+    if (d.inc_tx) t.tx_number_in_block += 1;
+}
+
+// memory queue push k of a cycle: tail' = P(enc || tail[8..12]) (main_vm/utils.rs:194-230, :442-515, cycle.rs:845-905).
+// SIM hashes at once into the running state `q`; the batched circuit only records the encoding -- the sponges of
+// all cycles run afterwards as dense launches (vm_memq_kernel), so that a warp never waits for a lane that hashes
 template <bool SIM>
-__device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_state &s, zkc_vm_cycle_witness &w, VmMemory *mem,
-                                 uint64_t *__restrict__ trace, size_t limit, size_t row) {
+__device__ __forceinline__ void vm_push(int k, bool execute, VmDelta &d, uint64_t *q, uint64_t *penc, uint32_t ts, uint32_t page,
+                                        uint32_t index, uint32_t rw, const zkc_vm_register &val) {
+    if (!execute) return;
+    uint64_t e[8];
+    vm_mq_encode(ts, page, index, rw, val, e);
+    d.push_mask |= 1u << k;
+    d.memq_len++;
+    if (SIM) {
+        uint64_t t[12];
+#pragma unroll
+        for (int i = 0; i < 8; i++) t[i] = e[i];
+#pragma unroll
+        for (int i = 8; i < 12; i++) t[i] = q[i];
+        poseidon2_permute(t);
+#pragma unroll
+        for (int i = 0; i < 12; i++) q[i] = t[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) penc[8 * k + i] = e[i];
+    }
+}
+
+// One vm_cycle from the state `s` (read only; only the words a cycle needs are touched): returns the check bits and
+// what changes in `d`.  SIM: memory reads are answered by `mem` and recorded into `w`; otherwise they come from `w`.
+// trace / limit / row: where to put the row (trace may be null; the MEMQ_AFTER_* columns are written by whoever runs
+// the sponges).
+template <bool SIM, typename W>
+__device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_vm_state &s, VmDelta &d, W &w, VmMemory *mem,
+                                 uint64_t *q, uint64_t *penc, uint64_t *__restrict__ trace, size_t limit, size_t row) {
 #define TR(col) trace[(size_t)(col) * limit + row]
     const bool wr = trace != nullptr;
     uint32_t checks = 0;
-    zkc_vm_context &ctx = s.current_context;
+    const zkc_vm_context &ctx = s.current_context;
+    d.push_mask = 0; d.set_u128 = 0; d.set_pubdata = 0; d.inc_tx = 0; d.idx0 = 0; d.idx1 = 0;
+    d.memq_len = s.memory_queue_length;
     // ---- create_prestate ---------------------------------------------------------------------------------------
     const bool should_skip = s.context_stack_depth == 0;
     const bool pending = s.pending_exception != 0;
     const bool should_try_read = !should_skip && !pending;
-    s.pending_exception = 0;
     const uint32_t pc = ctx.pc, super_pc = pc >> 2, sub_pc = pc & 3;
-    const bool should_read_opcode = should_try_read && !(s.previous_code_page == ctx.code_page && super_pc == s.previous_super_pc);
+    const uint32_t code_page = ctx.code_page;
+    const bool should_read_opcode = should_try_read && !(s.previous_code_page == code_page && super_pc == s.previous_super_pc);
     const uint32_t ts0 = s.timestamp;
     zkc_vm_register code_val = reg_zero();
     if (should_read_opcode) {
-        if (SIM) {
+        if constexpr (SIM) {
             code_val = mem->code[super_pc]; code_val.is_pointer = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) w.code_word[i] = code_val.value[i];
@@ -301,28 +394,29 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_stat
 #pragma unroll
             for (int i = 0; i < 8; i++) code_val.value[i] = w.code_word[i];
         }
-    } else if (SIM) {
+    } else if constexpr (SIM) {
 #pragma unroll
         for (int i = 0; i < 8; i++) w.code_word[i] = 0;
     }
-    vm_memq_push(s.memory_queue_state, s.memory_queue_length, ts0, ctx.code_page, super_pc, 0, code_val, should_read_opcode);
-    if (should_read_opcode) {
+    vm_push<SIM>(0, should_read_opcode, d, q, penc, ts0, code_page, super_pc, 0, code_val);
 #pragma unroll
-        for (int i = 0; i < 8; i++) s.previous_code_word[i] = code_val.value[i];
-    }
-    uint32_t op_lo = s.previous_code_word[6 - 2 * sub_pc], op_hi = s.previous_code_word[7 - 2 * sub_pc];
+    for (int i = 0; i < 8; i++) d.cw[i] = should_read_opcode ? code_val.value[i] : s.previous_code_word[i];
+    uint32_t op_lo = 0, op_hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) if ((int)sub_pc == i) { op_lo = d.cw[6 - 2 * i]; op_hi = d.cw[7 - 2 * i]; }
     if (should_skip) { op_lo = (uint32_t)isa->nop_opcode_encoding; op_hi = (uint32_t)(isa->nop_opcode_encoding >> 32); }
     if (pending) { op_lo = (uint32_t)isa->panic_opcode_encoding; op_hi = (uint32_t)(isa->panic_opcode_encoding >> 32); }
     if (wr) {
         TR(ZKC_VM_SHOULD_SKIP_CYCLE) = should_skip; TR(ZKC_VM_PENDING_EXCEPTION_IN) = pending; TR(ZKC_VM_SHOULD_READ_OPCODE) = should_read_opcode;
         TR(ZKC_VM_SUPER_PC) = super_pc; TR(ZKC_VM_SUB_PC) = sub_pc;
-        for (int i = 0; i < 8; i++) TR(ZKC_VM_CODE_WORD + i) = s.previous_code_word[i];
-        for (int i = 0; i < 12; i++) TR(ZKC_VM_MEMQ_AFTER_CODE + i) = s.memory_queue_state[i];
-        TR(ZKC_VM_MEMQ_AFTER_CODE + 12) = s.memory_queue_length;
+#pragma unroll
+        for (int i = 0; i < 8; i++) TR(ZKC_VM_CODE_WORD + i) = d.cw[i];
         TR(ZKC_VM_OPCODE) = op_lo; TR(ZKC_VM_OPCODE + 1) = op_hi;
     }
-    s.previous_code_page = ctx.code_page;
-    if (!should_skip) { ctx.pc = (pc + 1) & 0xFFFF; s.previous_super_pc = super_pc; s.timestamp = ts0 + 4; }
+    d.prev_code_page = code_page;
+    d.pc = should_skip ? pc : ((pc + 1) & 0xFFFF);
+    d.prev_super_pc = should_skip ? s.previous_super_pc : super_pc;
+    d.timestamp = should_skip ? ts0 : ts0 + 4;
     const bool is_kernel = ctx.is_kernel_mode != 0, is_static = ctx.is_static_execution != 0;
     const bool callstack_full = s.context_stack_depth == isa->vm_max_stack_depth;
     // ---- perform_initial_decoding ------------------------------------------------------------------------------
@@ -333,11 +427,13 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_stat
     constexpr uint64_t MASK48 = (1ull << ZKC_VM_DESCRIPTION_BITS_FLATTENED) - 1;
     uint64_t props = props_full & MASK48;
     const uint32_t aux = (uint32_t)(props_full >> ZKC_VM_DESCRIPTION_BITS_FLATTENED);
-    const uint32_t encoded_flags = (s.flags[0] & 1) | ((s.flags[1] & 1) << 1) | ((s.flags[2] & 1) << 2);
+    const uint32_t f0 = s.flags[0], f1 = s.flags[1], f2 = s.flags[2];
+    const uint32_t encoded_flags = (f0 & 1) | ((f1 & 1) << 1) | ((f2 & 1) << 2);
     const bool condition = isa->condition_table[cond_idx][encoded_flags] != 0;
     const uint32_t cost = should_skip ? 0 : isa->opcode_price[variant];
-    const bool out_of_ergs = ctx.ergs_remaining < cost;
-    const uint32_t ergs_left = out_of_ergs ? 0 : ctx.ergs_remaining - cost;
+    const uint32_t ergs_in = ctx.ergs_remaining;
+    const bool out_of_ergs = ergs_in < cost;
+    const uint32_t ergs_left = out_of_ergs ? 0 : ergs_in - cost;
     const bool explicit_panic = (aux >> ZKC_VM_AUX_EXPLICIT_PANIC) & 1;
     const bool kernel_exc = ((aux >> ZKC_VM_AUX_KERNEL_MODE) & 1) && !is_kernel;
     const bool static_exc = is_static && !((aux >> ZKC_VM_AUX_CAN_BE_USED_IN_STATIC) & 1);
@@ -347,7 +443,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_stat
     if (mask_into_nop) props = isa->nop_bitspread & MASK48;
     if (mask_into_nop || mask_into_panic) { src_regs = 0; dst_regs = 0; }
     const uint32_t src0_r = src_regs & 15, src1_r = src_regs >> 4, dst0_r = dst_regs & 15, dst1_r = dst_regs >> 4;
-    ctx.ergs_remaining = ergs_left;
+    d.ergs = ergs_left;
 #define TYPE(t) prop(props, ZKC_VM_BIT_TYPE(t))
 #define VAR(v) prop(props, ZKC_VM_BIT_VARIANT(v))
 #define FLAG(f) prop(props, ZKC_VM_BIT_FLAG(f))
@@ -377,7 +473,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_stat
         const uint32_t idx_abs = (src0_low + imm0) & 0xFFFF, idx_rel = (current_sp - idx_abs) & 0xFFFF;
         const bool use_stack = abs_ || rel || pp;
         should_read_src0 = (use_stack || use_code) && !is_nop;
-        src_page = use_stack ? stack_page : ctx.code_page;
+        src_page = use_stack ? stack_page : code_page;
         src_index = (use_code || abs_) ? idx_abs : idx_rel;
         sp_after_src0 = pp ? idx_rel : current_sp;
     }
@@ -390,10 +486,10 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_stat
         dst_index = abs_ ? idx_abs : (pp ? sp_after_src0 : ((sp_after_src0 - idx_abs) & 0xFFFF));
         new_sp = pp ? ((sp_after_src0 + idx_abs) & 0xFFFF) : sp_after_src0;
     }
-    ctx.sp = new_sp;
+    d.sp = new_sp;
     zkc_vm_register src0_mem = reg_zero();
     if (should_read_src0) {
-        if (SIM) {
+        if constexpr (SIM) {
             if (src_page == mem->code_page) { src0_mem = mem->code[src_index]; src0_mem.is_pointer = 0; }
             else if (src_page == mem->stack_page) src0_mem = mem->stack[src_index];
             w.src0_is_pointer = src0_mem.is_pointer;
@@ -404,20 +500,19 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_stat
 #pragma unroll
             for (int i = 0; i < 8; i++) src0_mem.value[i] = w.src0_value[i];
         }
-    } else if (SIM) {
+    } else if constexpr (SIM) {
         w.src0_is_pointer = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) w.src0_value[i] = 0;
     }
-    vm_memq_push(s.memory_queue_state, s.memory_queue_length, ts0, src_page, src_index, 0, src0_mem, should_read_src0);
+    vm_push<SIM>(1, should_read_src0, d, q, penc, ts0, src_page, src_index, 0, src0_mem);
     if (wr) {
         TR(ZKC_VM_SRC0_PAGE) = src_page; TR(ZKC_VM_SRC0_INDEX) = src_index; TR(ZKC_VM_SHOULD_READ_SRC0) = should_read_src0;
         TR(ZKC_VM_SP_AFTER_SRC0) = sp_after_src0; TR(ZKC_VM_DST0_PAGE) = stack_page; TR(ZKC_VM_DST0_INDEX) = dst_index;
         TR(ZKC_VM_DST0_PERFORMS_MEMORY_ACCESS) = dst0_mem; TR(ZKC_VM_NEW_SP) = new_sp;
         TR(ZKC_VM_SRC0_FROM_MEMORY) = src0_mem.is_pointer;
+#pragma unroll
         for (int i = 0; i < 8; i++) TR(ZKC_VM_SRC0_FROM_MEMORY + 1 + i) = src0_mem.value[i];
-        for (int i = 0; i < 12; i++) TR(ZKC_VM_MEMQ_AFTER_SRC0 + i) = s.memory_queue_state[i];
-        TR(ZKC_VM_MEMQ_AFTER_SRC0 + 12) = s.memory_queue_length;
     }
     zkc_vm_register src0 = SRCM(ZKC_MODE_REG_ONLY) ? draft_src0 : src0_mem;
     if (SRCM(ZKC_MODE_IMM16)) { src0 = reg_zero(); src0.value[0] = imm0; }
@@ -432,6 +527,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_stat
     }
     if (wr) {
         TR(ZKC_VM_SWAP_OPERANDS) = swap; TR(ZKC_VM_SRC0) = ra.is_pointer; TR(ZKC_VM_SRC1) = rb.is_pointer;
+#pragma unroll
         for (int i = 0; i < 8; i++) { TR(ZKC_VM_SRC0 + 1 + i) = ra.value[i]; TR(ZKC_VM_SRC1 + 1 + i) = rb.value[i]; }
     }
     // ---- the selected opcode ----------------------------------------------------------------------------------------
@@ -449,7 +545,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_stat
         nf0 = of; nf1 = z; nf2 = !(of || z);
         set_flags = sf; dst0_mem_capable = true;
     } else if (TYPE(ZKC_OP_JUMP)) {
-        ctx.pc = a.v[0] & 0xFFFF;
+        d.pc = a.v[0] & 0xFFFF;
     } else if (TYPE(ZKC_OP_BINOP)) {
         const bool is_or = VAR(ZKC_VAR_BINOP_OR), is_and = VAR(ZKC_VAR_BINOP_AND);
 #pragma unroll
@@ -507,31 +603,31 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, zkc_vm_stat
         }
         const bool set_u128 = VAR(ZKC_VAR_CONTEXT_SET_U128), set_pubdata = VAR(ZKC_VAR_CONTEXT_SET_ERGS_PER_PUBDATA), inc_tx = VAR(ZKC_VAR_CONTEXT_INC_TX_NUMBER);
         dst0_reg_only = !(set_u128 || set_pubdata || inc_tx);
-        if (set_u128) for (int i = 0; i < 4; i++) s.context_composite_u128[i] = a.v[i];
-        if (set_pubdata) s.ergs_per_pubdata_byte = a.v[0];
-        if (inc_tx) s.tx_number_in_block += 1;
+        d.set_u128 = set_u128; d.set_pubdata = set_pubdata; d.inc_tx = inc_tx;
+#pragma unroll
+        for (int i = 0; i < 4; i++) d.u128[i] = a.v[i];
+        d.pubdata = a.v[0];
     }
     // ---- state diffs ---------------------------------------------------------------------------------------------------
-    zkc_vm_register dst0, dst1;
-    dst0.is_pointer = d0_is_ptr; dst1.is_pointer = 0;
+    d.val0.is_pointer = d0_is_ptr; d.val1.is_pointer = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { dst0.value[i] = d0.v[i]; dst1.value[i] = d1.v[i]; }
+    for (int i = 0; i < 8; i++) { d.val0.value[i] = d0.v[i]; d.val1.value[i] = d1.v[i]; }
     const bool perform_mem_write = dst0_mem && dst0_mem_capable;
-    vm_memq_push(s.memory_queue_state, s.memory_queue_length, ts0 + 3, stack_page, dst_index, 1, dst0, perform_mem_write);
-    if (SIM && perform_mem_write && stack_page == mem->stack_page) mem->stack[dst_index] = dst0;
+    vm_push<SIM>(2, perform_mem_write, d, q, penc, ts0 + 3, stack_page, dst_index, 1, d.val0);
+    if constexpr (SIM) { if (perform_mem_write && stack_page == mem->stack_page) mem->stack[dst_index] = d.val0; }
     const bool dst0_update_register = dst0_reg_only || (!dst0_mem && dst0_mem_capable);
-    if (dst0_update_register && dst0_r) s.registers[dst0_r - 1] = dst0;
-    if (write_dst1 && dst1_r) s.registers[dst1_r - 1] = dst1;
-    if (set_flags) { s.flags[0] = nf0; s.flags[1] = nf1; s.flags[2] = nf2; }
-    s.pending_exception = new_pending;
+    if (dst0_update_register) d.idx0 = dst0_r;
+    if (write_dst1) d.idx1 = dst1_r;
+    d.flags[0] = set_flags ? nf0 : f0; d.flags[1] = set_flags ? nf1 : f1; d.flags[2] = set_flags ? nf2 : f2;
+    d.pending = new_pending;
     if (wr) {
-        TR(ZKC_VM_DST0) = dst0.is_pointer; TR(ZKC_VM_DST1) = 0;
-        for (int i = 0; i < 8; i++) { TR(ZKC_VM_DST0 + 1 + i) = dst0.value[i]; TR(ZKC_VM_DST1 + 1 + i) = dst1.value[i]; }
+        TR(ZKC_VM_DST0) = d.val0.is_pointer; TR(ZKC_VM_DST1) = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { TR(ZKC_VM_DST0 + 1 + i) = d.val0.value[i]; TR(ZKC_VM_DST1 + 1 + i) = d.val1.value[i]; }
         TR(ZKC_VM_PERFORM_DST0_MEMORY_WRITE) = perform_mem_write; TR(ZKC_VM_DST0_UPDATE_REGISTER) = dst0_update_register;
-        for (int i = 0; i < 12; i++) TR(ZKC_VM_MEMQ_AFTER_DST0 + i) = s.memory_queue_state[i];
-        TR(ZKC_VM_MEMQ_AFTER_DST0 + 12) = s.memory_queue_length;
-        for (int i = 0; i < 3; i++) TR(ZKC_VM_FLAGS_OUT + i) = s.flags[i];
-        TR(ZKC_VM_PENDING_EXCEPTION_OUT) = s.pending_exception; TR(ZKC_VM_PC_OUT) = ctx.pc; TR(ZKC_VM_ERGS_OUT) = ctx.ergs_remaining;
+#pragma unroll
+        for (int i = 0; i < 3; i++) TR(ZKC_VM_FLAGS_OUT + i) = d.flags[i];
+        TR(ZKC_VM_PENDING_EXCEPTION_OUT) = d.pending; TR(ZKC_VM_PC_OUT) = d.pc; TR(ZKC_VM_ERGS_OUT) = d.ergs;
     }
 #undef TR
 #undef TYPE
@@ -566,33 +662,246 @@ __device__ __forceinline__ void vm_report(VmDev *d, size_t row, uint32_t checks)
 }
 
 // ---- one thread per cycle (of any instance of the batch) -----------------------------------------------------------------
+constexpr int VM_WORDS = (int)(sizeof(zkc_vm_state) / 4);
+constexpr int VM_DIFF_WORDS = (VM_WORDS + 31) / 32;
+static_assert(sizeof(zkc_vm_state) == 1176 && VM_DIFF_WORDS == 10, "snapshot layout");
+#define VW(f) ((int)(offsetof(zkc_vm_state, f) / 4))
+#define VWC(f) ((int)((offsetof(zkc_vm_state, current_context) + offsetof(zkc_vm_context, f)) / 4))
+
+struct VmMask { uint32_t w[VM_DIFF_WORDS]; };
+__host__ __device__ constexpr VmMask vm_mask_clear(VmMask m, int lo, int n) {
+    for (int i = lo; i < lo + n; i++) m.w[i >> 5] &= ~(1u << (i & 31));
+    return m;
+}
+__host__ __device__ constexpr VmMask vm_mask_set(VmMask m, int lo, int n) {
+    for (int i = lo; i < lo + n; i++) m.w[i >> 5] |= 1u << (i & 31);
+    return m;
+}
+// words that may only change through an explicit flag of the delta: everything that is not padding, not a register,
+// not one of the per-cycle scalars (those are compared with their expected value) and not the memory queue state
+__host__ __device__ constexpr VmMask vm_keep_mask() {
+    VmMask m{};
+    m = vm_mask_set(m, 0, VM_WORDS);
+    m = vm_mask_clear(m, VW(_pad), VW(current_context) - VW(_pad));  // _pad + the alignment hole behind it
+    m = vm_mask_clear(m, VWC(aux_heap_upper_bound) + 1, 1);  // alignment hole in front of reverted_queue_head
+    m = vm_mask_clear(m, VW(previous_code_word), 8);
+    m = vm_mask_clear(m, VW(registers), 9 * ZKC_VM_REGISTERS);
+    m = vm_mask_clear(m, VW(flags), 3);
+    m = vm_mask_clear(m, VW(timestamp), 1);
+    m = vm_mask_clear(m, VW(previous_code_page), 1);
+    m = vm_mask_clear(m, VW(previous_super_pc), 1);
+    m = vm_mask_clear(m, VW(pending_exception), 1);
+    m = vm_mask_clear(m, VW(memory_queue_length), 1);
+    m = vm_mask_clear(m, VWC(pc), 1);
+    m = vm_mask_clear(m, VWC(sp), 1);
+    m = vm_mask_clear(m, VWC(ergs_remaining), 1);
+    m = vm_mask_clear(m, VW(memory_queue_state), 24);
+    return m;
+}
+__host__ __device__ constexpr VmMask vm_memq_mask() {
+    VmMask m{};
+    return vm_mask_set(m, VW(memory_queue_state), 24);
+}
+static_assert(offsetof(zkc_vm_context, reverted_queue_head) == offsetof(zkc_vm_context, aux_heap_upper_bound) + 8, "context hole");
+template <int K> struct VmKeepWord { static constexpr uint32_t value = vm_keep_mask().w[K]; };
+template <int K> struct VmMemqWord { static constexpr uint32_t value = vm_memq_mask().w[K]; };
+#define VM_FOR10(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
+
+__device__ __forceinline__ bool reg_equal(const zkc_vm_register &a, const zkc_vm_register &b) {
+    bool eq = a.is_pointer == b.is_pointer;
+#pragma unroll
+    for (int i = 0; i < 8; i++) eq &= a.value[i] == b.value[i];
+    return eq;
+}
+
+// scratch of one batch: what the cycle launch leaves for the sponge launches
+struct VmPushScratch {
+    uint32_t *counts;  // [3]
+    uint32_t *lists;   // [3][rows]: the rows whose push k happens, in no particular order
+    uint8_t *mask;     // [rows]
+    uint64_t *enc;     // [rows][3][8]
+    uint64_t *state;   // [rows][3][12]: memory queue state after push k
+};
+
+// Every thread evaluates its cycle from snapshot `row` and checks that snapshot `row + 1` is the result.  The check
+// has two parts.  (1) The warp walks its 32 consecutive snapshot pairs together: lane l compares words l, l+32, ...
+// of snapshot c with snapshot c+1 -- fully coalesced, each snapshot is fetched once -- and the ballots of iteration c
+// (a 294-bit "which words differ" mask) stay with lane c.  (2) The owner then demands that only words its cycle is
+// allowed to change differ, and compares the changed ones (a few scalars, at most two registers) with the values the
+// cycle produced.  The memory queue sponges are deferred: the cycle only emits their 8-word encodings.
 __global__ void __launch_bounds__(128)
 vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_state *__restrict__ snapshots,
-                 const zkc_vm_cycle_witness *__restrict__ witness, uint64_t *__restrict__ trace, size_t limit, size_t n_instances) {
+                 const zkc_vm_cycle_witness *__restrict__ witness, uint64_t *__restrict__ trace, size_t limit, size_t n_instances,
+                 VmPushScratch ps) {
+    const size_t total = limit * n_instances;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= limit * n_instances) return;
-    const size_t inst = g / limit, row = g - inst * limit;
-    VmDev *d = devs + inst;
-    const zkc_vm_state *snaps = snapshots + inst * (limit + 1);
-    zkc_vm_state s = snaps[row];
-    uint32_t checks = 0;
-    if (row == 0 && !vm_state_equal(s, d->s0)) checks |= ZKC_VM_CHK_SNAPSHOT;  // the hint chain starts at the circuit's own start state
-    zkc_vm_cycle_witness w = witness[inst * limit + row];
-    checks |= vm_cycle_dev<false>(isa, s, w, nullptr, trace ? trace + inst * (size_t)ZKC_VM_NUM_COLS * limit : nullptr, limit, row);
-    if (!vm_state_equal(s, snaps[row + 1])) {
-        // attribute the broken link to the cycle that would consume the wrong snapshot (what a sequential run sees)
-        if (row + 1 < limit) vm_report(d, row + 1, ZKC_VM_CHK_SNAPSHOT);
-        else checks |= ZKC_VM_CHK_SNAPSHOT;
+    const bool valid = g < total;
+    const unsigned lane = threadIdx.x & 31;
+    const size_t inst = valid ? g / limit : 0, row = valid ? g - inst * limit : 0;
+    const size_t idx = inst * (limit + 1) + row;
+    // ---- (1) cooperative word diff --------------------------------------------------------------------------------
+    uint32_t diff[VM_DIFF_WORDS];
+#pragma unroll
+    for (int k = 0; k < VM_DIFF_WORDS; k++) diff[k] = 0;
+    {
+        uint32_t cur[VM_DIFF_WORDS], nxt[VM_DIFF_WORDS];
+#pragma unroll
+        for (int k = 0; k < VM_DIFF_WORDS; k++) nxt[k] = 0;
+        unsigned long long prev_idx = ~0ull;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+#pragma unroll 1
+        for (int c = 0; c < 32; c++) {
+            if (!((vmask >> c) & 1)) break;  // valid lanes are a prefix
+            const unsigned long long ic = __shfl_sync(0xffffffffu, (unsigned long long)idx, c);
+            const uint32_t *pc = reinterpret_cast<const uint32_t *>(snapshots + ic), *pn = pc + VM_WORDS;
+            const bool chained = c > 0 && ic == prev_idx + 1;
+#pragma unroll
+            for (int k = 0; k < VM_DIFF_WORDS; k++) {
+                const int j = (int)lane + 32 * k;
+                const bool in = j < VM_WORDS;
+                cur[k] = chained ? nxt[k] : (in ? __ldg(pc + j) : 0u);
+                nxt[k] = in ? __ldg(pn + j) : 0u;
+                const unsigned m = __ballot_sync(0xffffffffu, cur[k] != nxt[k]);
+                if ((int)lane == c) diff[k] = m;
+            }
+            prev_idx = ic;
+        }
     }
-    if (row + 1 == limit) d->s_final = s;
-    vm_report(d, row, checks);
+    // ---- the cycle ------------------------------------------------------------------------------------------------------
+    VmDev *dev = devs + inst;
+    const zkc_vm_state &s = snapshots[idx], &next = snapshots[idx + 1];
+    uint32_t checks = 0, pmask = 0;
+    if (valid) {
+        if (row == 0 && !vm_state_equal(s, dev->s0)) checks |= ZKC_VM_CHK_SNAPSHOT;  // the hint chain starts at the circuit's own start state
+        VmDelta d;
+        checks |= vm_cycle_dev<false>(isa, s, d, witness[g], nullptr, nullptr, ps.enc + g * 24,
+                                      trace ? trace + inst * (size_t)ZKC_VM_NUM_COLS * limit : nullptr, limit, row);
+        pmask = d.push_mask;
+        ps.mask[g] = (uint8_t)pmask;
+        // ---- (2) is snapshot row + 1 what this cycle produces? ---------------------------------------------------------
+        bool bad = false;
+        if (d.set_u128) {
+            diff[VW(context_composite_u128) >> 5] &= ~(15u << (VW(context_composite_u128) & 31));
+            static_assert((VW(context_composite_u128) & 31) <= 28, "u128 words straddle a diff word");
+            for (int i = 0; i < 4; i++) bad |= next.context_composite_u128[i] != d.u128[i];
+        }
+        if (d.set_pubdata) {
+            diff[VW(ergs_per_pubdata_byte) >> 5] &= ~(1u << (VW(ergs_per_pubdata_byte) & 31));
+            bad |= next.ergs_per_pubdata_byte != d.pubdata;
+        }
+        if (d.inc_tx) {
+            diff[VW(tx_number_in_block) >> 5] &= ~(1u << (VW(tx_number_in_block) & 31));
+            bad |= next.tx_number_in_block != s.tx_number_in_block + 1;
+        }
+        uint32_t stray = 0, memq_diff = 0;
+#define X(K) stray |= diff[K] & VmKeepWord<K>::value; memq_diff |= diff[K] & VmMemqWord<K>::value;
+        VM_FOR10(X)
+#undef X
+        bad |= stray != 0;
+        if (!pmask) bad |= memq_diff != 0;  // otherwise the last sponge of the cycle compares (vm_memq_kernel)
+        uint32_t regdiff = 0;
+#pragma unroll
+        for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
+            const int lo = VW(registers) + 9 * r;
+            const uint32_t bits = __funnelshift_r(diff[lo >> 5], diff[(lo >> 5) + 1], lo & 31) & 0x1FFu;
+            regdiff |= (bits != 0) << r;
+        }
+        const uint32_t may = (d.idx0 ? 1u << (d.idx0 - 1) : 0u) | (d.idx1 ? 1u << (d.idx1 - 1) : 0u);
+        bad |= (regdiff & ~may) != 0;
+        if (d.idx1) bad |= !reg_equal(next.registers[d.idx1 - 1], d.val1);
+        if (d.idx0 && d.idx0 != d.idx1) bad |= !reg_equal(next.registers[d.idx0 - 1], d.val0);
+        bad |= next.pending_exception != d.pending || next.current_context.pc != d.pc || next.current_context.sp != d.sp ||
+               next.current_context.ergs_remaining != d.ergs || next.previous_code_page != d.prev_code_page ||
+               next.previous_super_pc != d.prev_super_pc || next.timestamp != d.timestamp || next.memory_queue_length != d.memq_len;
+#pragma unroll
+        for (int i = 0; i < 3; i++) bad |= next.flags[i] != d.flags[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) bad |= next.previous_code_word[i] != d.cw[i];
+        if (bad) {
+            // attribute the broken link to the cycle that would consume the wrong snapshot (what a sequential run sees)
+            if (row + 1 < limit) vm_report(dev, row + 1, ZKC_VM_CHK_SNAPSHOT);
+            else checks |= ZKC_VM_CHK_SNAPSHOT;
+        }
+        if (row + 1 == limit) {  // the state the circuit ends in, as computed (its memory queue state: vm_memq_kernel)
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&s);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&dev->s_final);
+            for (int i = 0; i < VM_WORDS; i++) dst[i] = src[i];
+            vm_apply_delta(dev->s_final, d);
+        }
+        vm_report(dev, row, checks);
+    }
+    // ---- rows whose push k happens, for the dense sponge launches ---------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const bool mine = (pmask >> k) & 1;
+        const unsigned b = __ballot_sync(0xffffffffu, mine);
+        if (!b) continue;
+        const int leader = __ffs(b) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(ps.counts + k, (uint32_t)__popc(b));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (mine) ps.lists[(size_t)k * total + base + __popc(b & ((1u << lane) - 1))] = (uint32_t)g;
+    }
+}
+
+// push k of every cycle that has one: tail' = P(enc || tail[8..12]), one thread per push, all lanes busy.  The state it
+// starts from is the cycle's previous push, or the snapshot; the last push of a cycle must land on the next snapshot.
+__global__ void __launch_bounds__(128)
+vm_memq_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, VmPushScratch ps, int k, size_t limit, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ps.counts[k]) return;
+    const size_t g = ps.lists[(size_t)k * total + i];
+    const size_t inst = g / limit, row = g - inst * limit, idx = inst * (limit + 1) + row;
+    const uint32_t m = ps.mask[g], before = m & ((1u << k) - 1);
+    const uint64_t *from = before ? ps.state + (g * 3 + (31 - __clz(before))) * 12 : snapshots[idx].memory_queue_state;
+    uint64_t q[12];
+#pragma unroll
+    for (int j = 0; j < 8; j++) q[j] = ps.enc[(g * 3 + k) * 8 + j];
+#pragma unroll
+    for (int j = 8; j < 12; j++) q[j] = from[j];
+    poseidon2_permute(q);
+    uint64_t *to = ps.state + (g * 3 + k) * 12;
+#pragma unroll
+    for (int j = 0; j < 12; j++) to[j] = q[j];
+    if (m >> (k + 1)) return;
+    VmDev *dev = devs + inst;
+    const uint64_t *want = snapshots[idx + 1].memory_queue_state;
+    bool same = true;
+#pragma unroll
+    for (int j = 0; j < 12; j++) same &= want[j] == q[j];
+    if (!same) vm_report(dev, row + 1 < limit ? row + 1 : row, ZKC_VM_CHK_SNAPSHOT);
+    if (row + 1 == limit)
+        for (int j = 0; j < 12; j++) dev->s_final.memory_queue_state[j] = q[j];
+}
+
+// the 3 x 13 MEMQ_AFTER_* columns of the trace
+__global__ void __launch_bounds__(256)
+vm_memq_trace_kernel(const zkc_vm_state *__restrict__ snapshots, VmPushScratch ps, uint64_t *__restrict__ trace, size_t limit, size_t total) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const size_t inst = g / limit, row = g - inst * limit, idx = inst * (limit + 1) + row;
+    uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit + row;
+    const uint32_t m = ps.mask[g];
+    const uint64_t *from = snapshots[idx].memory_queue_state;
+    uint64_t len = snapshots[idx].memory_queue_length;
+    constexpr int COL[3] = {ZKC_VM_MEMQ_AFTER_CODE, ZKC_VM_MEMQ_AFTER_SRC0, ZKC_VM_MEMQ_AFTER_DST0};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if ((m >> k) & 1) { from = ps.state + (g * 3 + k) * 12; len++; }
+#pragma unroll
+        for (int j = 0; j < 12; j++) t[(size_t)(COL[k] + j) * limit] = from[j];
+        t[(size_t)(COL[k] + 12) * limit] = len;
+    }
 }
 
 // 4 threads per instance: the four commitments of the closed form are independent sponges
-// (ClosedFormInputCompactForm::from_full_form, fsm_input_output/mod.rs:178-255); thread 0 then commits the compact form
+// (ClosedFormInputCompactForm::from_full_form, fsm_input_output/mod.rs:178-255); thread 0 then commits the compact form.
+// Each role flattens its encoding into its own global scratch row and absorbs from there (no 2 KB thread-local arrays),
+// and skips the sponge whose result the start / completion flags mask to zero anyway.
+constexpr int VM_FLAT_STRIDE = 248;
 __global__ void __launch_bounds__(128)
-vm_finalize_kernel(VmDev *devs, size_t n_instances) {
-    __shared__ uint64_t part[32][3][4];
+vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances) {
+    __shared__ uint64_t part[32][4][4];
     const size_t inst = (size_t)blockIdx.x * 32 + (threadIdx.x >> 2);
     const int role = threadIdx.x & 3, slot = threadIdx.x >> 2;
     const bool active = inst < n_instances;
@@ -600,24 +909,17 @@ vm_finalize_kernel(VmDev *devs, size_t n_instances) {
     zkc_vm_closed_form &io = d->io;
     const zkc_vm_state &state = d->s_final;
     const bool done = state.context_stack_depth == 0;  // mod.rs:113-122
-    zkc_queue_state4 log_out;
-    zkc_queue_state12 mem_out, dec_out;
-    memset(&log_out, 0, sizeof log_out); memset(&mem_out, 0, sizeof mem_out); memset(&dec_out, 0, sizeof dec_out);
-    if (done) {  // mod.rs:124-196
-        for (int i = 0; i < 12; i++) { mem_out.tail[i] = state.memory_queue_state[i]; dec_out.tail[i] = state.code_decommittment_queue_state[i]; }
-        mem_out.length = state.memory_queue_length; dec_out.length = state.code_decommittment_queue_length;
-        for (int i = 0; i < 4; i++) log_out.tail[i] = state.current_context.log_queue_forward_tail[i];
-        log_out.length = state.current_context.log_queue_forward_part_length;
-    }
+    const bool start = d->start != 0;
     uint64_t c4[4] = {0, 0, 0, 0};
-    uint64_t o_out[59];
     if (active) {
-        if (role == 1) {  // hidden FSM input
-            uint64_t buf[243];
+        uint64_t *buf = flat + (inst * 4 + role) * VM_FLAT_STRIDE;
+        if (role == 0 && !done) {  // hidden FSM output
+            vm_flatten_state(state, buf);
+            commit_encoding_call(buf, ZKC_VM_STATE_FLAT, c4);
+        } else if (role == 1 && !start) {  // hidden FSM input
             vm_flatten_state(io.hidden_fsm_input, buf);
-            commit_encoding_dev(buf, 243, c4);
+            commit_encoding_call(buf, ZKC_VM_STATE_FLAT, c4);
         } else if (role == 2) {  // observable input (VmInputData)
-            uint64_t buf[39];
             int n = 0;
             for (int i = 0; i < 4; i++) buf[n++] = io.rollback_queue_tail_for_block[i];
             for (int i = 0; i < 12; i++) buf[n++] = io.memory_queue_initial_tail[i];
@@ -626,25 +928,33 @@ vm_finalize_kernel(VmDev *devs, size_t n_instances) {
             buf[n++] = io.decommitment_queue_initial_length;
             buf[n++] = io.zkporter_is_available;
             for (int i = 0; i < 8; i++) buf[n++] = io.default_aa_code_hash[i];
-            commit_encoding_dev(buf, n, c4);
-        } else if (role == 3) {  // observable output (VmOutputData)
+            commit_encoding_call(buf, n, c4);
+        } else if (role == 3 && done) {  // observable output (VmOutputData, mod.rs:124-196): log queue, memory queue, decommitment queue
             int n = 0;
-            for (int i = 0; i < 4; i++) o_out[n++] = log_out.head[i];
-            for (int i = 0; i < 4; i++) o_out[n++] = log_out.tail[i];
-            o_out[n++] = log_out.length;
-            n += vm_put_q12(o_out + n, mem_out);
-            n += vm_put_q12(o_out + n, dec_out);
-            commit_encoding_dev(o_out, 59, c4);
+            for (int i = 0; i < 4; i++) buf[n++] = 0;
+            for (int i = 0; i < 4; i++) buf[n++] = state.current_context.log_queue_forward_tail[i];
+            buf[n++] = state.current_context.log_queue_forward_part_length;
+            for (int i = 0; i < 12; i++) buf[n++] = 0;
+            for (int i = 0; i < 12; i++) buf[n++] = state.memory_queue_state[i];
+            buf[n++] = state.memory_queue_length;
+            for (int i = 0; i < 12; i++) buf[n++] = 0;
+            for (int i = 0; i < 12; i++) buf[n++] = state.code_decommittment_queue_state[i];
+            buf[n++] = state.code_decommittment_queue_length;
+            commit_encoding_call(buf, n, c4);
         }
-        if (role > 0) for (int i = 0; i < 4; i++) part[slot][role - 1][i] = c4[i];
-    }
-    uint64_t e_out[243];
-    if (active && role == 0) {
-        vm_flatten_state(state, e_out);
-        commit_encoding_dev(e_out, 243, c4);
+        for (int i = 0; i < 4; i++) part[slot][role][i] = c4[i];
     }
     __syncthreads();
     if (!active || role != 0) return;
+    zkc_queue_state4 log_out;
+    zkc_queue_state12 mem_out, dec_out;
+    memset(&log_out, 0, sizeof log_out); memset(&mem_out, 0, sizeof mem_out); memset(&dec_out, 0, sizeof dec_out);
+    if (done) {
+        for (int i = 0; i < 12; i++) { mem_out.tail[i] = state.memory_queue_state[i]; dec_out.tail[i] = state.code_decommittment_queue_state[i]; }
+        mem_out.length = state.memory_queue_length; dec_out.length = state.code_decommittment_queue_length;
+        for (int i = 0; i < 4; i++) log_out.tail[i] = state.current_context.log_queue_forward_tail[i];
+        log_out.length = state.current_context.log_queue_forward_part_length;
+    }
     uint32_t checks = d->failed_checks;
     if (done && state.current_context.pc != 0) checks |= ZKC_VM_CHK_BOOTLOADER_EXIT;
     zkc_status st;
@@ -654,10 +964,7 @@ vm_finalize_kernel(VmDev *devs, size_t n_instances) {
     if (checks) st.code = (checks & ZKC_VM_CHK_SNAPSHOT) ? ZKC_ERR_SNAPSHOT_MISMATCH
                         : (checks & ZKC_VM_CHK_UNSUPPORTED_OPCODE) ? ZKC_ERR_UNSUPPORTED : ZKC_ERR_UNSATISFIED;
     if (d->opt.compare_expected) {
-        uint64_t e_exp[243];
-        vm_flatten_state(io.hidden_fsm_output, e_exp);
-        bool same = (io.completion_flag != 0) == done;
-        for (int i = 0; i < 243; i++) same &= e_out[i] == e_exp[i];
+        bool same = (io.completion_flag != 0) == done && vm_state_equal(io.hidden_fsm_output, state);
         for (int i = 0; i < 4; i++) same &= io.log_queue_final_state.head[i] == log_out.head[i] && io.log_queue_final_state.tail[i] == log_out.tail[i];
         same &= io.log_queue_final_state.length == log_out.length && io.memory_queue_final_state.length == mem_out.length &&
                 io.decommitment_queue_final_state.length == dec_out.length;
@@ -666,18 +973,22 @@ vm_finalize_kernel(VmDev *devs, size_t n_instances) {
                     io.decommitment_queue_final_state.head[i] == dec_out.head[i] && io.decommitment_queue_final_state.tail[i] == dec_out.tail[i];
         if (!same && st.code == ZKC_OK) st.code = ZKC_ERR_FSM_OUTPUT_MISMATCH;
     }
-    io.hidden_fsm_output = state;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&state);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&io.hidden_fsm_output);
+        for (int i = 0; i < (int)(sizeof(zkc_vm_state) / 4); i++) dst[i] = src[i];
+    }
     io.log_queue_final_state = log_out; io.memory_queue_final_state = mem_out; io.decommitment_queue_final_state = dec_out;
     io.completion_flag = done;
     uint64_t compact[18];
-    compact[0] = d->start; compact[1] = done;
+    compact[0] = start; compact[1] = done;
     for (int i = 0; i < 4; i++) {
-        compact[2 + i] = part[slot][1][i];
-        compact[6 + i] = done ? part[slot][2][i] : 0;
-        compact[10 + i] = d->start ? 0 : part[slot][0][i];
-        compact[14 + i] = done ? 0 : c4[i];
+        compact[2 + i] = part[slot][2][i];
+        compact[6 + i] = part[slot][3][i];   // zero unless done
+        compact[10 + i] = part[slot][1][i];  // zero if start
+        compact[14 + i] = part[slot][0][i];  // zero if done
     }
-    commit_encoding_dev(compact, 18, d->commitment);
+    commit_encoding_call(compact, 18, d->commitment);
     d->status = st;
 }
 
@@ -705,7 +1016,12 @@ vm_simulate_kernel(const zkc_vm_isa *__restrict__ isa, const zkc_vm_state *__res
     for (size_t c = 0; c < cycles; c++) {
         zkc_vm_cycle_witness w;
         memset(&w, 0, sizeof w);
-        const uint32_t checks = vm_cycle_dev<true>(isa, s, w, &mem, nullptr, 0, 0);
+        VmDelta d;
+        uint64_t q[12];
+        for (int i = 0; i < 12; i++) q[i] = s.memory_queue_state[i];
+        const uint32_t checks = vm_cycle_dev<true>(isa, s, d, w, &mem, q, nullptr, nullptr, 0, 0);
+        vm_apply_delta(s, d);
+        for (int i = 0; i < 12; i++) s.memory_queue_state[i] = q[i];
         wit[c] = w;
         snaps[c + 1] = s;
         if (checks) {
@@ -748,7 +1064,7 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
                                              const zkc_vm_options *options, int on_device, uint64_t *trace, uint64_t *commitments,
                                              zkc_status *statuses) {
     if (!ctx || !ios || !isa || !commitments || !statuses || (limit && n_instances && (!snapshots || !witness)) ||
-        limit > 0x0FFFFFFFull || n_instances > 0x00FFFFFFull)
+        limit > 0x0FFFFFFFull || n_instances > 0x00FFFFFFull || limit * n_instances > 0xFFFFFFFFull)
         return ZKC_ERR_INVALID_ARGUMENT;
     if (!n_instances) return ZKC_OK;
     zkc_status *status = statuses;
@@ -759,6 +1075,9 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     size_t bytes = zkc_carver::bytes(n_instances, sizeof(VmDev)) + zkc_carver::bytes(1, sizeof(zkc_vm_isa));
     if (!in_dev) bytes += zkc_carver::bytes(rows + n_instances, sizeof(zkc_vm_state)) + zkc_carver::bytes(rows + 1, sizeof(zkc_vm_cycle_witness));
     if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ZKC_VM_NUM_COLS * rows, 8);
+    bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
+    bytes += zkc_carver::bytes(4, 4) + zkc_carver::bytes(3 * rows, 4) + zkc_carver::bytes(rows, 1) + zkc_carver::bytes(rows * 24, 8) +
+             zkc_carver::bytes(rows * 36, 8);
     void *blk = ctx->scratch(bytes);
     VmDev *h = (VmDev *)ctx->pinned(n_instances * sizeof(VmDev));
     if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
@@ -786,9 +1105,23 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
         dsnap = bs; dwit = bw;
     }
     if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ZKC_VM_NUM_COLS * rows);
+    uint64_t *flat = cv.take<uint64_t>(n_instances * 4 * VM_FLAT_STRIDE);
+    VmPushScratch ps;
+    ps.counts = cv.take<uint32_t>(4);
+    ps.lists = cv.take<uint32_t>(3 * rows);
+    ps.mask = cv.take<uint8_t>(rows);
+    ps.enc = cv.take<uint64_t>(rows * 24);
+    ps.state = cv.take<uint64_t>(rows * 36);
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(ps.counts, 0, 16, s));
     ZKC_LAUNCH(ctx, "vm_prologue", vm_prologue_kernel, (unsigned)((n_instances + 31) / 32), 32, 0, d, disa, n_instances);
-    if (rows) ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, disa, dsnap, dwit, dtrace, limit, n_instances);
-    ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 31) / 32), 128, 0, d, n_instances);
+    if (rows) {
+        ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, disa, dsnap, dwit, dtrace, limit, n_instances, ps);
+        // the lists live on the device: size every sponge launch for the worst case, surplus threads leave at once
+        for (int k = 0; k < 3; k++)
+            ZKC_LAUNCH(ctx, "vm_memq", vm_memq_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, dsnap, ps, k, limit, rows);
+        if (dtrace) ZKC_LAUNCH(ctx, "vm_memq_trace", vm_memq_trace_kernel, (unsigned)((rows + 255) / 256), 256, 0, dsnap, ps, dtrace, limit, rows);
+    }
+    ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 31) / 32), 128, 0, d, flat, n_instances);
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, n_instances * sizeof(VmDev), cudaMemcpyDeviceToHost, s));
     if (!trace_dev && trace && rows)

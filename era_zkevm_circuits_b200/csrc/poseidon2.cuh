@@ -109,4 +109,13 @@ __device__ inline void commit_encoding_dev(const uint64_t *in, int n, uint64_t o
     for (int j = 0; j < 4; j++) out[j] = s[j];
 }
 
+// the same as one out-of-line copy, for kernels that commit at several places (finalize kernels): one instance of the
+// permutation in the kernel keeps the register allocation of the rest of it out of the spill range
+static __device__ __noinline__ void commit_encoding_call(const uint64_t *in, int n, uint64_t *out) {
+    uint64_t o[4];
+    commit_encoding_dev(in, n, o);
+#pragma unroll
+    for (int j = 0; j < 4; j++) out[j] = o[j];
+}
+
 }  // namespace zkc
