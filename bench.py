@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """bench.py -- one JSON line per run (driver contract).
 
-Workload (BASELINE.json configs[1]): main_vm, 2^20 cycles per GPU per step, as 256 independent circuit instances of
-2^12 cycles each (a production main_vm instance holds ~5.6 k cycles; instances only communicate through their
-closed-form inputs).  A "step" = one batched main_vm entry point call: every cycle evaluated from its VmLocalState
-snapshot + oracle answers, memory-queue sponges, witness trace written to HBM, FSM outputs and the 256 commitments.
+Workload (BASELINE.json configs[1]): main_vm, ONE instance of 2^20 cycles per GPU per step (--instances / --cycles
+reshape the same 2^20 cycles into a batch of shorter instances: a production main_vm instance holds ~5.6 k cycles and
+instances only communicate through their closed-form inputs).  A "step" = one main_vm entry point call: every cycle
+evaluated from its VmLocalState snapshot + oracle answers, memory-queue sponges, witness trace written to HBM, FSM
+output and the commitment.
 `value` = cycles/s over all ranks with inputs resident in HBM; `e2e` = the same call with pinned HOST buffers (H2D of
 snapshots + witness, D2H of the trace + closed forms inside the timed region).  The second half of the headline metric
 (constraint-evaluation GB/s vs HBM peak) is measured in the same run on the streaming constraint evaluator of the
@@ -26,14 +27,24 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-N_INSTANCES = 256
-CYCLES_PER_INSTANCE = 1 << 12
+N_INSTANCES = 1
+CYCLES_PER_INSTANCE = 1 << 20
 PROGRAM_LEN = 1 << 12
+CPU_CYCLES = 1 << 12  # the CPU legs run the same programs in instances of this many cycles (cost per cycle is the same)
 METRIC = "main_vm cycles/sec witness-gen at 2^20 cycles; constraint-eval GB/s vs HBM peak"
 UNIT = "cycles/s"
-WORKLOAD = ("main_vm, 2^20 cycles per GPU per step = 256 independent instances x 2^12 cycles, synthetic ISA table + random "
-            "straight-line programs (add/sub/binop/mul/div/shift/ptr/context, 30 % stack/code/immediate operands); "
+
+
+
+def workload(n, cycles):
+    return (f"main_vm, {n} instance(s) x {cycles} cycles per GPU per step, synthetic ISA table + random programs "
+            "(add/sub/binop/mul/div/shift/ptr/context/jump, 30 % stack/code/immediate operands); "
             "log/near_call/far_call/ret/uma opcodes are not built yet and do not occur in the programs")
+
+
+# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of vm_cycles_kernel per launch (profiles/README.md); None until captured
+VM_CYCLES_TRAFFIC = None
+VM_CYCLES_TRAFFIC_NOTE = "not captured yet for this kernel version"
 
 
 def measured_peaks():
@@ -147,19 +158,19 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     inst = 64 * cores  # ~1-2 s of CPU work per step
     for _ in range(args.warmup):
-        oracle_vm_job(inst, CYCLES_PER_INSTANCE, cores)
+        oracle_vm_job(inst, CPU_CYCLES, cores)
     tot, dt = 0, 0.0
     for _ in range(args.steps):
-        v, t = oracle_vm_job(inst, CYCLES_PER_INSTANCE, cores)
-        tot += inst * CYCLES_PER_INSTANCE
+        v, t = oracle_vm_job(inst, CPU_CYCLES, cores)
+        tot += inst * CPU_CYCLES
         dt += t
     v = tot / dt
     sample = (f"{inst} independent instances x 2^12 cycles per step on {cores} threads (C oracle of the same entry point, witness "
-              f"trace written; bounded sample of the 256-instance workload)")
+              f"trace written; bounded sample: the same programs cut into 2^12-cycle instances so that every host thread has work)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": {"workload": WORKLOAD},
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": {"workload": workload(args.instances, args.cycles)},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -183,7 +194,7 @@ def run_gpu(args):
     eng.set_stream(stream)
 
     # ---- inputs: out-of-circuit run of this rank's instances on the GPU (setup, untimed) -------------------------------------
-    n, cycles = N_INSTANCES, CYCLES_PER_INSTANCE
+    n, cycles = args.instances, args.cycles
     isa = I.Isa()
     ios, states, codes = [], [], []
     distinct_programs = [I.pack_code(I.random_program(isa, PROGRAM_LEN, seed=0xC2 + rank * 7 + k)) for k in range(8)]
@@ -238,7 +249,7 @@ def run_gpu(args):
     ms, t0, t1 = timed(step_device, args.steps)
     launches = eng.launches - l0
     eng.profile(False)
-    prof = {k: eng.profile_query(k) for k in ("vm_cycles", "vm_prologue", "vm_finalize")}
+    prof = {k: eng.profile_query(k) for k in ("vm_cycles", "vm_memq", "vm_memq_trace", "vm_prologue", "vm_finalize")}
     value = n * cycles * world * args.steps / (ms / 1e3)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
@@ -297,26 +308,30 @@ def run_gpu(args):
     chk_bytes = abi.RAM_COLS["NUM_COLS"] * 8 * rn
     chk_gbs = chk_bytes / (chk_ms / chk_n * 1e-3) / 1e9 if chk_n else None
     cyc_ms, cyc_n = prof["vm_cycles"]
-    vm_bytes = (C.sizeof(abi.VmState) + C.sizeof(abi.VmCycleWitness) + ncols * 8) * n * cycles
-    roofline = {"kernel": "ram_check_kernel<false> (constraint evaluation of a 2^20-row ram_permutation trace, streaming relations)",
-                "bound": "hbm", "achieved": chk_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": chk_gbs / peak if chk_gbs else None, "frac_of_nominal_8000": chk_gbs / 8000.0 if chk_gbs else None,
-                "algorithmic_bytes_per_row": abi.RAM_COLS["NUM_COLS"] * 8, "avg_launch_ms": chk_ms / chk_n if chk_n else None,
-                "traffic": (281072896 + 4868864) * 4,
-                "traffic_note": "ncu --set full dram__bytes_read+write of this kernel at 2^18 rows (profiles/r01_ncu_full_ram_kernels_raw.csv), "
-                                "scaled x4 to 2^20 rows: equals the algorithmic bytes (no re-reads)"}
-    kernels = {
-        "vm_cycles_kernel (main_vm witness generation, one thread per cycle; integer-ALU bound: ~2.2 Poseidon2/cycle)": {
-            "avg_launch_ms": cyc_ms / cyc_n if cyc_n else None, "algorithmic_bytes_per_cycle": vm_bytes // (n * cycles),
-            "achieved_gbs": vm_bytes / (cyc_ms / cyc_n * 1e-3) / 1e9 if cyc_n else None,
-            "share_of_step": (cyc_ms / cyc_n) / (ms / args.steps) if cyc_n else None},
-        "vm_prologue_kernel": {"avg_launch_ms": prof["vm_prologue"][0] / max(1, prof["vm_prologue"][1])},
-        "vm_finalize_kernel": {"avg_launch_ms": prof["vm_finalize"][0] / max(1, prof["vm_finalize"][1])},
-        "ram_rows_kernel (ram_permutation witness generation, 2^20 rows)": {"avg_launch_ms": rows_ms / rows_n if rows_n else None},
-    }
+    # algorithmic bytes of one cycle in vm_cycles_kernel: its snapshot (read once) + oracle answers in, the 96 trace columns it
+    # writes (the 39 MEMQ_AFTER_* columns belong to vm_memq_trace_kernel) -- DESIGN.md section 5
+    vm_cols = ncols - 39
+    vm_bytes_per_cycle = C.sizeof(abi.VmState) + C.sizeof(abi.VmCycleWitness) + vm_cols * 8
+    vm_gbs = vm_bytes_per_cycle * n * cycles / (cyc_ms / cyc_n * 1e-3) / 1e9 if cyc_n else None
+    roofline = {"kernel": "vm_cycles_kernel (main_vm witness generation: one thread per cycle, warp-cooperative snapshot diff)",
+                "bound": "hbm", "achieved": vm_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": vm_gbs / peak if vm_gbs else None, "frac_of_nominal_8000": vm_gbs / 8000.0 if vm_gbs else None,
+                "algorithmic_bytes_per_cycle": vm_bytes_per_cycle, "avg_launch_ms": cyc_ms / cyc_n if cyc_n else None,
+                "share_of_step": (cyc_ms / cyc_n) / (ms / args.steps) if cyc_n else None,
+                "traffic": VM_CYCLES_TRAFFIC, "traffic_note": VM_CYCLES_TRAFFIC_NOTE}
+    constraint_eval = {"kernel": "ram_check_kernel<false> (constraint evaluation of a 2^20-row ram_permutation trace, streaming relations)",
+                       "bound": "hbm", "achieved": chk_gbs, "peak": peak, "unit": "GB/s",
+                       "frac": chk_gbs / peak if chk_gbs else None, "frac_of_nominal_8000": chk_gbs / 8000.0 if chk_gbs else None,
+                       "algorithmic_bytes_per_row": abi.RAM_COLS["NUM_COLS"] * 8, "avg_launch_ms": chk_ms / chk_n if chk_n else None,
+                       "traffic": (281072896 + 4868864) * 4,
+                       "traffic_note": "ncu --set full dram__bytes_read+write of this kernel at 2^18 rows (profiles/r01_ncu_full_ram_kernels_raw.csv), "
+                                       "scaled x4 to 2^20 rows: equals the algorithmic bytes (no re-reads)"}
+    kernels = {k + "_kernel": {"avg_launch_ms": v[0] / v[1], "launches_per_step": v[1] / args.steps,
+                               "share_of_step": v[0] / ms} for k, v in prof.items() if v[1]}
+    kernels["ram_rows_kernel (ram_permutation witness generation, 2^20 rows)"] = {"avg_launch_ms": rows_ms / rows_n if rows_n else None}
     cores = os.cpu_count() or 1
-    cpu1, t_1 = oracle_vm_job(256, cycles, 1)
-    cpun, t_n = oracle_vm_job(512 * cores, cycles, cores)
+    cpu1, t_1 = oracle_vm_job(256, CPU_CYCLES, 1)
+    cpun, t_n = oracle_vm_job(512 * cores, CPU_CYCLES, cores)
     cpu_baseline = {"value": cpun, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{512 * cores} instances x 2^12 cycles of the same workload on {cores} threads ({t_n:.1f} s); single thread: "
                               f"{cpu1:.0f} cycles/s ({t_1:.1f} s); C oracle of main_vm_entry_point incl. witness trace",
@@ -325,14 +340,15 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cycles_per_gpu_per_step": n * cycles, "instances_per_gpu": n, "trace_columns": ncols,
-                   "l2_policy": "snapshots + witness (1.35 GB) and trace (1.13 GB) per step exceed the 126 MB L2",
-                   "step": "batched main_vm entry point: start states, all cycles (witness columns to HBM), FSM outputs + commitments "
-                           "[+ NCCL all-gather of the 4-element commitments when n_gpus > 1]"},
+        "config": {"workload": workload(n, cycles), "cycles_per_gpu_per_step": n * cycles, "instances_per_gpu": n, "trace_columns": ncols,
+                   "l2_policy": f"snapshots + witness ({(hs.nbytes + hw.nbytes) / 1e9:.2f} GB) and trace ({htrace.nbytes / 1e9:.2f} GB) "
+                                "per step exceed the 126 MB L2",
+                   "step": "main_vm entry point: start state, all cycles (witness columns to HBM), memory-queue sponges, FSM output + "
+                           "commitment [+ NCCL all-gather of the 4-element commitments when n_gpus > 1]"},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / e2e_steps, "note": "pinned host snapshots + witness in, full witness trace + closed forms out"},
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "constraint_eval": constraint_eval, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }))
     if world > 1:
         dist.destroy_process_group()
@@ -344,6 +360,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--instances", type=int, default=N_INSTANCES, help="main_vm instances per GPU per step")
+    ap.add_argument("--cycles", type=int, default=CYCLES_PER_INSTANCE, help="cycles per instance")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

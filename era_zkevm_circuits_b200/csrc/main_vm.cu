@@ -894,102 +894,113 @@ vm_memq_trace_kernel(const zkc_vm_state *__restrict__ snapshots, VmPushScratch p
     }
 }
 
-// 4 threads per instance: the four commitments of the closed form are independent sponges
-// (ClosedFormInputCompactForm::from_full_form, fsm_input_output/mod.rs:178-255); thread 0 then commits the compact form.
-// Each role flattens its encoding into its own global scratch row and absorbs from there (no 2 KB thread-local arrays),
-// and skips the sponge whose result the start / completion flags mask to zero anyway.
+// 64 threads per instance: the four commitments of the closed form are independent sponges
+// (ClosedFormInputCompactForm::from_full_form, fsm_input_output/mod.rs:178-255), each run by one 16-lane group with the
+// 12-lane permutation (poseidon2.cuh) -- the 31 dependent permutations over a VM state are the latency of this launch.
+// Each group flattens its encoding into its own global scratch row and absorbs from there, and skips the sponge whose
+// result the start / completion flags mask to zero anyway; group 0 then commits the compact form.
 constexpr int VM_FLAT_STRIDE = 248;
 __global__ void __launch_bounds__(128)
 vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances) {
-    __shared__ uint64_t part[32][4][4];
-    const size_t inst = (size_t)blockIdx.x * 32 + (threadIdx.x >> 2);
-    const int role = threadIdx.x & 3, slot = threadIdx.x >> 2;
+    __shared__ uint64_t part[2][4][4];
+    __shared__ uint64_t compact[2][24];
+    const int slot = threadIdx.x >> 6, role = (threadIdx.x >> 4) & 3, i = threadIdx.x & 15;
+    const unsigned gm = 0xFFFFu << (threadIdx.x & 16);
+    const size_t inst = (size_t)blockIdx.x * 2 + slot;
     const bool active = inst < n_instances;
     VmDev *d = devs + (active ? inst : 0);
     zkc_vm_closed_form &io = d->io;
     const zkc_vm_state &state = d->s_final;
     const bool done = state.context_stack_depth == 0;  // mod.rs:113-122
     const bool start = d->start != 0;
-    uint64_t c4[4] = {0, 0, 0, 0};
-    if (active) {
-        uint64_t *buf = flat + (inst * 4 + role) * VM_FLAT_STRIDE;
-        if (role == 0 && !done) {  // hidden FSM output
-            vm_flatten_state(state, buf);
-            commit_encoding_call(buf, ZKC_VM_STATE_FLAT, c4);
-        } else if (role == 1 && !start) {  // hidden FSM input
-            vm_flatten_state(io.hidden_fsm_input, buf);
-            commit_encoding_call(buf, ZKC_VM_STATE_FLAT, c4);
-        } else if (role == 2) {  // observable input (VmInputData)
-            int n = 0;
-            for (int i = 0; i < 4; i++) buf[n++] = io.rollback_queue_tail_for_block[i];
-            for (int i = 0; i < 12; i++) buf[n++] = io.memory_queue_initial_tail[i];
-            buf[n++] = io.memory_queue_initial_length;
-            for (int i = 0; i < 12; i++) buf[n++] = io.decommitment_queue_initial_tail[i];
-            buf[n++] = io.decommitment_queue_initial_length;
-            buf[n++] = io.zkporter_is_available;
-            for (int i = 0; i < 8; i++) buf[n++] = io.default_aa_code_hash[i];
-            commit_encoding_call(buf, n, c4);
-        } else if (role == 3 && done) {  // observable output (VmOutputData, mod.rs:124-196): log queue, memory queue, decommitment queue
-            int n = 0;
-            for (int i = 0; i < 4; i++) buf[n++] = 0;
-            for (int i = 0; i < 4; i++) buf[n++] = state.current_context.log_queue_forward_tail[i];
-            buf[n++] = state.current_context.log_queue_forward_part_length;
-            for (int i = 0; i < 12; i++) buf[n++] = 0;
-            for (int i = 0; i < 12; i++) buf[n++] = state.memory_queue_state[i];
-            buf[n++] = state.memory_queue_length;
-            for (int i = 0; i < 12; i++) buf[n++] = 0;
-            for (int i = 0; i < 12; i++) buf[n++] = state.code_decommittment_queue_state[i];
-            buf[n++] = state.code_decommittment_queue_length;
-            commit_encoding_call(buf, n, c4);
+    {
+        const uint64_t *buf = flat + (inst * 4 + role) * VM_FLAT_STRIDE;
+        int n = 0;
+        const bool need = active && (role == 0 ? !done : role == 1 ? !start : role == 2 ? true : done);
+        if (need) {
+            if (i == 0) {
+                uint64_t *w = flat + (inst * 4 + role) * VM_FLAT_STRIDE;
+                if (role == 0) vm_flatten_state(state, w);                      // hidden FSM output
+                else if (role == 1) vm_flatten_state(io.hidden_fsm_input, w);   // hidden FSM input
+                else if (role == 2) {                                           // observable input (VmInputData)
+                    int k = 0;
+                    for (int j = 0; j < 4; j++) w[k++] = io.rollback_queue_tail_for_block[j];
+                    for (int j = 0; j < 12; j++) w[k++] = io.memory_queue_initial_tail[j];
+                    w[k++] = io.memory_queue_initial_length;
+                    for (int j = 0; j < 12; j++) w[k++] = io.decommitment_queue_initial_tail[j];
+                    w[k++] = io.decommitment_queue_initial_length;
+                    w[k++] = io.zkporter_is_available;
+                    for (int j = 0; j < 8; j++) w[k++] = io.default_aa_code_hash[j];
+                } else {  // observable output (VmOutputData, mod.rs:124-196): log queue, memory queue, decommitment queue
+                    int k = 0;
+                    for (int j = 0; j < 4; j++) w[k++] = 0;
+                    for (int j = 0; j < 4; j++) w[k++] = state.current_context.log_queue_forward_tail[j];
+                    w[k++] = state.current_context.log_queue_forward_part_length;
+                    for (int j = 0; j < 12; j++) w[k++] = 0;
+                    for (int j = 0; j < 12; j++) w[k++] = state.memory_queue_state[j];
+                    w[k++] = state.memory_queue_length;
+                    for (int j = 0; j < 12; j++) w[k++] = 0;
+                    for (int j = 0; j < 12; j++) w[k++] = state.code_decommittment_queue_state[j];
+                    w[k++] = state.code_decommittment_queue_length;
+                }
+            }
+            n = role < 2 ? ZKC_VM_STATE_FLAT : (role == 2 ? 39 : 59);
+            __syncwarp(gm);
         }
-        for (int i = 0; i < 4; i++) part[slot][role][i] = c4[i];
+        const uint64_t c = commit_encoding_coop(gm, buf, n, i);  // n == 0: no permutation, zeros
+        if (i < 4) part[slot][role][i] = c;
     }
     __syncthreads();
-    if (!active || role != 0) return;
-    zkc_queue_state4 log_out;
-    zkc_queue_state12 mem_out, dec_out;
-    memset(&log_out, 0, sizeof log_out); memset(&mem_out, 0, sizeof mem_out); memset(&dec_out, 0, sizeof dec_out);
-    if (done) {
-        for (int i = 0; i < 12; i++) { mem_out.tail[i] = state.memory_queue_state[i]; dec_out.tail[i] = state.code_decommittment_queue_state[i]; }
-        mem_out.length = state.memory_queue_length; dec_out.length = state.code_decommittment_queue_length;
-        for (int i = 0; i < 4; i++) log_out.tail[i] = state.current_context.log_queue_forward_tail[i];
-        log_out.length = state.current_context.log_queue_forward_part_length;
+    if (active && role == 0 && i == 0) {
+        zkc_queue_state4 log_out;
+        zkc_queue_state12 mem_out, dec_out;
+        memset(&log_out, 0, sizeof log_out); memset(&mem_out, 0, sizeof mem_out); memset(&dec_out, 0, sizeof dec_out);
+        if (done) {
+            for (int j = 0; j < 12; j++) { mem_out.tail[j] = state.memory_queue_state[j]; dec_out.tail[j] = state.code_decommittment_queue_state[j]; }
+            mem_out.length = state.memory_queue_length; dec_out.length = state.code_decommittment_queue_length;
+            for (int j = 0; j < 4; j++) log_out.tail[j] = state.current_context.log_queue_forward_tail[j];
+            log_out.length = state.current_context.log_queue_forward_part_length;
+        }
+        uint32_t checks = d->failed_checks;
+        if (done && state.current_context.pc != 0) checks |= ZKC_VM_CHK_BOOTLOADER_EXIT;
+        zkc_status st;
+        st.code = ZKC_OK; st.cuda_error = 0; st.first_bad_row = -1; st.failed_checks = checks; st.reserved = 0;
+        if (d->first_bad != ~0ull) st.first_bad_row = (int64_t)(d->first_bad >> 16);
+        // most specific aggregate: broken snapshot chain > unsupported opcode > failed enforcement (order independent)
+        if (checks) st.code = (checks & ZKC_VM_CHK_SNAPSHOT) ? ZKC_ERR_SNAPSHOT_MISMATCH
+                            : (checks & ZKC_VM_CHK_UNSUPPORTED_OPCODE) ? ZKC_ERR_UNSUPPORTED : ZKC_ERR_UNSATISFIED;
+        if (d->opt.compare_expected) {
+            bool same = (io.completion_flag != 0) == done && vm_state_equal(io.hidden_fsm_output, state);
+            for (int j = 0; j < 4; j++) same &= io.log_queue_final_state.head[j] == log_out.head[j] && io.log_queue_final_state.tail[j] == log_out.tail[j];
+            same &= io.log_queue_final_state.length == log_out.length && io.memory_queue_final_state.length == mem_out.length &&
+                    io.decommitment_queue_final_state.length == dec_out.length;
+            for (int j = 0; j < 12; j++)
+                same &= io.memory_queue_final_state.head[j] == mem_out.head[j] && io.memory_queue_final_state.tail[j] == mem_out.tail[j] &&
+                        io.decommitment_queue_final_state.head[j] == dec_out.head[j] && io.decommitment_queue_final_state.tail[j] == dec_out.tail[j];
+            if (!same && st.code == ZKC_OK) st.code = ZKC_ERR_FSM_OUTPUT_MISMATCH;
+        }
+        io.log_queue_final_state = log_out; io.memory_queue_final_state = mem_out; io.decommitment_queue_final_state = dec_out;
+        io.completion_flag = done;
+        uint64_t *cf = compact[slot];
+        cf[0] = start; cf[1] = done;
+        for (int j = 0; j < 4; j++) {
+            cf[2 + j] = part[slot][2][j];
+            cf[6 + j] = part[slot][3][j];   // zero unless done
+            cf[10 + j] = part[slot][1][j];  // zero if start
+            cf[14 + j] = part[slot][0][j];  // zero if done
+        }
+        d->status = st;
     }
-    uint32_t checks = d->failed_checks;
-    if (done && state.current_context.pc != 0) checks |= ZKC_VM_CHK_BOOTLOADER_EXIT;
-    zkc_status st;
-    st.code = ZKC_OK; st.cuda_error = 0; st.first_bad_row = -1; st.failed_checks = checks; st.reserved = 0;
-    if (d->first_bad != ~0ull) st.first_bad_row = (int64_t)(d->first_bad >> 16);
-    // most specific aggregate: broken snapshot chain > unsupported opcode > failed enforcement (order independent)
-    if (checks) st.code = (checks & ZKC_VM_CHK_SNAPSHOT) ? ZKC_ERR_SNAPSHOT_MISMATCH
-                        : (checks & ZKC_VM_CHK_UNSUPPORTED_OPCODE) ? ZKC_ERR_UNSUPPORTED : ZKC_ERR_UNSATISFIED;
-    if (d->opt.compare_expected) {
-        bool same = (io.completion_flag != 0) == done && vm_state_equal(io.hidden_fsm_output, state);
-        for (int i = 0; i < 4; i++) same &= io.log_queue_final_state.head[i] == log_out.head[i] && io.log_queue_final_state.tail[i] == log_out.tail[i];
-        same &= io.log_queue_final_state.length == log_out.length && io.memory_queue_final_state.length == mem_out.length &&
-                io.decommitment_queue_final_state.length == dec_out.length;
-        for (int i = 0; i < 12; i++)
-            same &= io.memory_queue_final_state.head[i] == mem_out.head[i] && io.memory_queue_final_state.tail[i] == mem_out.tail[i] &&
-                    io.decommitment_queue_final_state.head[i] == dec_out.head[i] && io.decommitment_queue_final_state.tail[i] == dec_out.tail[i];
-        if (!same && st.code == ZKC_OK) st.code = ZKC_ERR_FSM_OUTPUT_MISMATCH;
-    }
-    {
+    __syncthreads();
+    if (active) {  // the 64 threads of the instance publish the state the circuit ended in
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&state);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&io.hidden_fsm_output);
-        for (int i = 0; i < (int)(sizeof(zkc_vm_state) / 4); i++) dst[i] = src[i];
+        for (int j = threadIdx.x & 63; j < (int)(sizeof(zkc_vm_state) / 4); j += 64) dst[j] = src[j];
     }
-    io.log_queue_final_state = log_out; io.memory_queue_final_state = mem_out; io.decommitment_queue_final_state = dec_out;
-    io.completion_flag = done;
-    uint64_t compact[18];
-    compact[0] = start; compact[1] = done;
-    for (int i = 0; i < 4; i++) {
-        compact[2 + i] = part[slot][2][i];
-        compact[6 + i] = part[slot][3][i];   // zero unless done
-        compact[10 + i] = part[slot][1][i];  // zero if start
-        compact[14 + i] = part[slot][0][i];  // zero if done
+    if (role == 0) {
+        const uint64_t c = commit_encoding_coop(gm, compact[slot], active ? 18 : 0, i);
+        if (active && i < 4) d->commitment[i] = c;
     }
-    commit_encoding_call(compact, 18, d->commitment);
-    d->status = st;
 }
 
 // ---- out-of-circuit run: one thread per independent VM instance ---------------------------------------------------------
@@ -1121,7 +1132,7 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
             ZKC_LAUNCH(ctx, "vm_memq", vm_memq_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, dsnap, ps, k, limit, rows);
         if (dtrace) ZKC_LAUNCH(ctx, "vm_memq_trace", vm_memq_trace_kernel, (unsigned)((rows + 255) / 256), 256, 0, dsnap, ps, dtrace, limit, rows);
     }
-    ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 31) / 32), 128, 0, d, flat, n_instances);
+    ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 1) / 2), 128, 0, d, flat, n_instances);
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, n_instances * sizeof(VmDev), cudaMemcpyDeviceToHost, s));
     if (!trace_dev && trace && rows)

@@ -109,6 +109,82 @@ __device__ inline void commit_encoding_dev(const uint64_t *in, int n, uint64_t o
     for (int j = 0; j < 4; j++) out[j] = s[j];
 }
 
+// ---- the same permutation spread over 12 lanes ------------------------------------------------------------------------
+// The sequential sponges (FSM commitments: 31 dependent permutations over a VM state; queue tail chains) are pure
+// latency with one thread per permutation: ~19 k instructions on one lane, ~25 us.  Here lane i of a 16-lane group
+// holds s[i] (i < 12; lanes 12..15 carry zeros and only take part in the shuffles): the S-boxes of a full round run
+// side by side and the linear layers are a handful of shuffles.  `gm` is the group's lane mask (0xFFFF or 0xFFFF0000);
+// the two groups of a warp are independent (different trip counts are fine), the 16 lanes of a group must stay together.
+static __device__ const uint64_t P2_RC_LANES[360] = {
+#include "poseidon2_rc.inc"
+};
+
+__device__ __forceinline__ Acc96 acc96_mul_small(uint64_t x, uint32_t c) {  // c < 2^32 really; used with c <= 7
+    const uint64_t lo = (uint64_t)(uint32_t)x * c;
+    const uint64_t hi = (uint64_t)(uint32_t)(x >> 32) * c + (lo >> 32);
+    return Acc96{(uint32_t)lo, (uint32_t)hi, (uint32_t)(hi >> 32)};
+}
+__device__ __forceinline__ uint64_t p2c_shfl(unsigned gm, uint64_t v, int src) { return __shfl_sync(gm, v, src, 16); }
+__device__ __forceinline__ Acc96 p2c_shfl(unsigned gm, const Acc96 &a, int src) {
+    return Acc96{__shfl_sync(gm, a.l0, src, 16), __shfl_sync(gm, a.l1, src, 16), __shfl_sync(gm, a.h, src, 16)};
+}
+__device__ __forceinline__ Acc96 p2c_shfl_xor(unsigned gm, const Acc96 &a, int m) {
+    return Acc96{__shfl_xor_sync(gm, a.l0, m, 16), __shfl_xor_sync(gm, a.l1, m, 16), __shfl_xor_sync(gm, a.h, m, 16)};
+}
+
+// circ(2*M4, M4, M4): row (i & 3) of M4 over the 4 lanes of the block, then t_i + (sum of the three blocks' t)
+__device__ __forceinline__ uint64_t p2c_external(unsigned gm, uint64_t x, int i) {
+    const uint32_t row = (uint32_t)(0x6411753111643175ull >> (16 * (i & 3))) & 0xFFFFu;  // nibble k = M4[i & 3][k]
+    Acc96 t = acc96_mul_small(p2c_shfl(gm, x, (i & 12) | 0), row & 15u);
+    t.add(acc96_mul_small(p2c_shfl(gm, x, (i & 12) | 1), (row >> 4) & 15u));
+    t.add(acc96_mul_small(p2c_shfl(gm, x, (i & 12) | 2), (row >> 8) & 15u));
+    t.add(acc96_mul_small(p2c_shfl(gm, x, (i & 12) | 3), row >> 12));
+    const int a = i < 8 ? i + 4 : (i < 12 ? i - 8 : i), b = i < 4 ? i + 8 : (i < 12 ? i - 4 : i);
+    const Acc96 ta = p2c_shfl(gm, t, a), tb = p2c_shfl(gm, t, b);
+    Acc96 o = t.shl(1);
+    o.add(ta);
+    o.add(tb);
+    return i < 12 ? o.reduce_nc() : 0ull;
+}
+
+// J + diag(2^shift_i): butterfly sum over the group (lanes 12..15 add zero)
+__device__ __forceinline__ uint64_t p2c_inner(unsigned gm, uint64_t x, int i) {
+    Acc96 sum = acc96(x);
+#pragma unroll
+    for (int m = 1; m < 16; m <<= 1) sum.add(p2c_shfl_xor(gm, sum, m));
+    const int sh = (int)((0xC36D92508BE4ull >> (4 * i)) & 15);  // nibble i = {4,14,11,8,0,5,2,9,13,6,3,12}[i]
+    Acc96 v = acc96(x).shl(sh);
+    v.add(sum);
+    return i < 12 ? v.reduce_nc() : 0ull;
+}
+
+// in: canonical or nc in lanes 0..11 of the group, zero in 12..15; out: canonical
+__device__ __forceinline__ uint64_t poseidon2_permute_coop(unsigned gm, uint64_t x, int i) {
+    const int ci = i < 12 ? i : 0;
+    x = p2c_external(gm, x, i);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) x = p2c_external(gm, p2_sbox_nc(gl_add_nc_canon(x, P2_RC_LANES[12 * r + ci])), i);
+#pragma unroll 1
+    for (int r = 4; r < 26; r++) {
+        if (i == 0) x = p2_sbox_nc(gl_add_nc_canon(x, P2_RC[12 * r]));
+        x = p2c_inner(gm, x, i);
+    }
+#pragma unroll 1
+    for (int r = 26; r < 30; r++) x = p2c_external(gm, p2_sbox_nc(gl_add_nc_canon(x, P2_RC_LANES[12 * r + ci])), i);
+    return i < 12 ? gl_canon(x) : 0ull;
+}
+
+// commit_encoding by one 16-lane group: `in` (global or shared, visible to every lane of the group), n the same in all
+// 16 lanes; lane j < 4 returns out[j]
+__device__ __forceinline__ uint64_t commit_encoding_coop(unsigned gm, const uint64_t *in, int n, int i) {
+    uint64_t x = i == 11 ? (uint64_t)n : 0ull;
+    for (int off = 0; off < n; off += 8) {
+        if (i < 8) x = off + i < n ? in[off + i] : 0ull;
+        x = poseidon2_permute_coop(gm, x, i);
+    }
+    return x;
+}
+
 // the same as one out-of-line copy, for kernels that commit at several places (finalize kernels): one instance of the
 // permutation in the kernel keeps the register allocation of the rest of it out of the spill range
 static __device__ __noinline__ void commit_encoding_call(const uint64_t *in, int n, uint64_t *out) {
