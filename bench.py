@@ -37,9 +37,9 @@ UNIT = "cycles/s"
 
 
 def workload(n, cycles):
-    return (f"main_vm, {n} instance(s) x {cycles} cycles per GPU per step, synthetic ISA table + random programs "
-            "(add/sub/binop/mul/div/shift/ptr/context/jump, 30 % stack/code/immediate operands); "
-            "log/near_call/far_call/ret/uma opcodes are not built yet and do not occur in the programs")
+    return (f"main_vm, {n} instance(s) x {cycles} cycles per GPU per step, synthetic ISA table + random programs with the C2 mix "
+            "of SURVEY 8d (40 % add/sub, 15 % binop, 10 % mul/div, 10 % shifts, 10 % UMA heap r/w, 5 % jumps, 5 % context/ptr, "
+            "3 % log, 2 % near_call/ret; 30 % stack/code/immediate operands); far_call is not built yet and does not occur")
 
 
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of vm_cycles_kernel per launch (profiles/README.md); None until captured
@@ -124,22 +124,24 @@ def oracle_vm_job(instances, cycles, threads, seed=0xC2):
     for i in range(distinct):
         io = abi.VmClosedForm(); io.start_flag = 1; io.rollback_queue_tail_for_block[0] = i
         st = O.vm_initial_state(lib, io, isa.isa)
-        rc, snaps, wit, status = O.vm_run(lib, isa.isa, st, I.pack_code(I.random_program(isa, PROGRAM_LEN, seed=seed + i)), cycles)
+        rc, snaps, wit, status, cw, tail = O.vm_run(lib, isa.isa, st, I.pack_code(I.random_program(isa, PROGRAM_LEN, seed=seed + i)), cycles, full=True)
         assert rc == 0
-        jobs.append((io, snaps, wit))
+        for k in range(4):
+            io.rollback_queue_tail_for_block[k] = int(tail[k])
+        jobs.append((io, snaps, wit, np.ascontiguousarray(cw)))
     ncols = abi.VM_COLS["NUM_COLS"]
     traces = [np.zeros((ncols, cycles), dtype=np.uint64) for _ in range(min(threads, instances))]
 
     def work(slot, count):
         for k in range(count):
-            io, snaps, wit = jobs[(slot + k) % distinct]
+            io, snaps, wit, cw = jobs[(slot + k) % distinct]
             io2 = abi.VmClosedForm.from_buffer_copy(bytes(io))
             com = np.zeros(4, dtype=np.uint64)
             st = abi.Status()
             opts = abi.VmOptions(0)
-            rc = lib.orc_main_vm_entry_point(C.byref(io2), C.byref(isa.isa), O.p(snaps), O.p(wit), cycles, C.byref(opts),
-                                             O.p(traces[slot]), O.p(com), C.byref(st))
-            assert rc == 0
+            rc = lib.orc_main_vm_entry_point(C.byref(io2), C.byref(isa.isa), O.p(snaps), O.p(wit), O.p(cw) if len(cw) else None, len(cw),
+                                             cycles, C.byref(opts), O.p(traces[slot]), O.p(com), C.byref(st))
+            assert rc == 0, (rc, hex(st.failed_checks), st.first_bad_row)
 
     per = [instances // threads + (1 if i < instances % threads else 0) for i in range(threads)]
     ts = [threading.Thread(target=work, args=(i, c)) for i, c in enumerate(per) if c]
@@ -204,15 +206,22 @@ def run_gpu(args):
         ios.append(io)
         states.append(main_vm_initial_state(eng, io, isa.isa))
         codes.append(distinct_programs[i % 8])
-    d_snaps, d_wit, st = main_vm_simulate(eng, isa.isa, states, np.stack(codes), cycles)
+    sim = main_vm_simulate(eng, isa.isa, states, np.stack(codes), cycles)
+    st = sim.status
     assert st.code == 0, (st.code, hex(st.failed_checks), st.first_bad_row)
+    d_snaps, d_wit = sim.snapshots, sim.witness
+    n_cw = max(1, int(sim.n_callstack.max()))
+    d_cw = sim.callstack_witness[:, :n_cw].contiguous()
+    for io, t in zip(ios, sim.rollback_tails):  # the block's rollback tail is an output of the out-of-circuit run
+        for k in range(4):
+            io.rollback_queue_tail_for_block[k] = int(t[k])
     ncols = abi.VM_COLS["NUM_COLS"]
     trace = torch.empty((n, ncols, cycles), dtype=torch.int64, device="cuda")
     gathered = torch.zeros((world * n, 4), dtype=torch.int64, device="cuda") if world > 1 else None
 
     def step_device():
-        coms, out, statuses, rc = main_vm_entry_point_batch(eng, ios, isa.isa, d_snaps, d_wit, cycles, trace_out=trace)
-        assert rc == 0
+        coms, out, statuses, rc = main_vm_entry_point_batch(eng, ios, isa.isa, d_snaps, d_wit, cycles, trace_out=trace, callstack_witness=d_cw)
+        assert rc == 0, [(x.code, hex(x.failed_checks), x.first_bad_row) for x in statuses][:4]
         if world > 1:  # the only exchange of the sharded job: 4 x u64 commitment per instance
             c = torch.from_numpy(coms.view(np.int64)).cuda(non_blocking=True)
             dist.all_gather_into_tensor(gathered, c)
@@ -249,7 +258,7 @@ def run_gpu(args):
     ms, t0, t1 = timed(step_device, args.steps)
     launches = eng.launches - l0
     eng.profile(False)
-    prof = {k: eng.profile_query(k) for k in ("vm_cycles", "vm_memq", "vm_memq_trace", "vm_prologue", "vm_finalize")}
+    prof = {k: eng.profile_query(k) for k in ("vm_cycles", "vm_sponge", "vm_sponge_trace", "vm_prologue", "vm_finalize")}
     value = n * cycles * world * args.steps / (ms / 1e3)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
@@ -282,11 +291,12 @@ def run_gpu(args):
     # ---- e2e: pinned host inputs -> H2D -> kernels -> D2H of witness columns + closed forms ------------------------------------
     hs = pinned_array(eng, (n, cycles + 1, C.sizeof(abi.VmState)), np.uint8)
     hw = pinned_array(eng, (n, cycles, C.sizeof(abi.VmCycleWitness)), np.uint8)
-    hs[:] = d_snaps.cpu().numpy(); hw[:] = d_wit.cpu().numpy()
+    hc = pinned_array(eng, (n, n_cw, C.sizeof(abi.VmCallstackWitness)), np.uint8)
+    hs[:] = d_snaps.cpu().numpy(); hw[:] = d_wit.cpu().numpy(); hc[:] = d_cw.cpu().numpy()
     htrace = pinned_array(eng, (n, ncols, cycles), np.uint64)
 
     def step_e2e():
-        coms, out, statuses, rc = main_vm_entry_point_batch(eng, ios, isa.isa, hs, hw, cycles, trace_out=htrace)
+        coms, out, statuses, rc = main_vm_entry_point_batch(eng, ios, isa.isa, hs, hw, cycles, trace_out=htrace, callstack_witness=hc)
         assert rc == 0
         if world > 1:
             c = torch.from_numpy(coms.view(np.int64)).cuda(non_blocking=True)
@@ -296,7 +306,7 @@ def run_gpu(args):
     step_e2e()
     ms_e2e, _, _ = timed(step_e2e, e2e_steps)
     e2e_value = n * cycles * world * e2e_steps / (ms_e2e / 1e3)
-    h2d = int(hs.nbytes + hw.nbytes + n * (C.sizeof(abi.VmClosedForm) + 64) + C.sizeof(abi.VmIsa))
+    h2d = int(hs.nbytes + hw.nbytes + hc.nbytes + n * (C.sizeof(abi.VmClosedForm) + 64) + C.sizeof(abi.VmIsa))
     d2h = int(htrace.nbytes + n * (C.sizeof(abi.VmClosedForm) + 64 + 32 + C.sizeof(abi.Status)))
 
     if rank != 0:
@@ -308,9 +318,9 @@ def run_gpu(args):
     chk_bytes = abi.RAM_COLS["NUM_COLS"] * 8 * rn
     chk_gbs = chk_bytes / (chk_ms / chk_n * 1e-3) / 1e9 if chk_n else None
     cyc_ms, cyc_n = prof["vm_cycles"]
-    # algorithmic bytes of one cycle in vm_cycles_kernel: its snapshot (read once) + oracle answers in, the 96 trace columns it
-    # writes (the 39 MEMQ_AFTER_* columns belong to vm_memq_trace_kernel) -- DESIGN.md section 5
-    vm_cols = ncols - 39
+    # algorithmic bytes of one cycle in vm_cycles_kernel: its snapshot (read once) + oracle answers in, the trace columns it
+    # writes (the 9 + 108 sponge columns belong to vm_sponge_trace_kernel) -- DESIGN.md section 5
+    vm_cols = ncols - 117
     vm_bytes_per_cycle = C.sizeof(abi.VmState) + C.sizeof(abi.VmCycleWitness) + vm_cols * 8
     vm_gbs = vm_bytes_per_cycle * n * cycles / (cyc_ms / cyc_n * 1e-3) / 1e9 if cyc_n else None
     roofline = {"kernel": "vm_cycles_kernel (main_vm witness generation: one thread per cycle, warp-cooperative snapshot diff)",
@@ -341,7 +351,7 @@ def run_gpu(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": workload(n, cycles), "cycles_per_gpu_per_step": n * cycles, "instances_per_gpu": n, "trace_columns": ncols,
-                   "l2_policy": f"snapshots + witness ({(hs.nbytes + hw.nbytes) / 1e9:.2f} GB) and trace ({htrace.nbytes / 1e9:.2f} GB) "
+                   "l2_policy": f"snapshots + witness ({(hs.nbytes + hw.nbytes + hc.nbytes) / 1e9:.2f} GB) and trace ({htrace.nbytes / 1e9:.2f} GB) "
                                 "per step exceed the 126 MB L2",
                    "step": "main_vm entry point: start state, all cycles (witness columns to HBM), memory-queue sponges, FSM output + "
                            "commitment [+ NCCL all-gather of the 4-element commitments when n_gpus > 1]"},

@@ -147,7 +147,8 @@ class VmIsa(C.Structure):
                 ("bootloader_calldata_page", C.c_uint32), ("starting_timestamp", C.c_uint32), ("starting_base_page", C.c_uint32),
                 ("initial_frame_formal_eh_location", C.c_uint32), ("vm_initial_frame_ergs", C.c_uint32),
                 ("bootloader_formal_address_low", C.c_uint32), ("bootloader_max_memory", C.c_uint32),
-                ("vm_max_stack_depth", C.c_uint32), ("_pad", C.c_uint32 * 2)]
+                ("vm_max_stack_depth", C.c_uint32), ("log_aux_bytes", C.c_uint32 * 4),
+                ("initial_storage_write_pubdata_bytes", C.c_uint32), ("l1_message_pubdata_bytes", C.c_uint32)]
 
 
 class VmRegister(C.Structure):
@@ -177,7 +178,13 @@ class VmState(C.Structure):
 
 
 class VmCycleWitness(C.Structure):
-    _fields_ = [("code_word", C.c_uint32 * 8), ("src0_is_pointer", C.c_uint32), ("src0_value", C.c_uint32 * 8), ("_pad", C.c_uint32 * 3)]
+    _fields_ = [("code_word", C.c_uint32 * 8), ("src0_is_pointer", C.c_uint32), ("src0_value", C.c_uint32 * 8),
+                ("callstack_index", C.c_uint32), ("refund", C.c_uint32), ("_pad", C.c_uint32), ("value_a", C.c_uint32 * 8),
+                ("value_b", C.c_uint32 * 8), ("rollback", C.c_uint64 * 4)]
+
+
+class VmCallstackWitness(C.Structure):
+    _fields_ = [("context", VmContext), ("previous_sponge_state", C.c_uint64 * 12)]
 
 
 class VmClosedForm(C.Structure):
@@ -193,19 +200,20 @@ class VmOptions(C.Structure):
     _fields_ = [("compare_expected", C.c_uint32), ("_pad", C.c_uint32 * 3)]
 
 
-assert C.sizeof(VmState) == 1176 and C.sizeof(VmContext) == 240 and C.sizeof(VmIsa) == 24720
-assert C.sizeof(VmClosedForm) == 3104 and C.sizeof(VmCycleWitness) == 80
+assert C.sizeof(VmState) == 1176 and C.sizeof(VmContext) == 240 and C.sizeof(VmIsa) == 24736
+assert C.sizeof(VmClosedForm) == 3104 and C.sizeof(VmCycleWitness) == 176 and C.sizeof(VmCallstackWitness) == 336
 VM_STATE_DTYPE = np.dtype((np.void, 1176))
 VM_COLS = dict(
-    SHOULD_SKIP_CYCLE=0, PENDING_EXCEPTION_IN=1, SHOULD_READ_OPCODE=2, SUPER_PC=3, SUB_PC=4, CODE_WORD=5, MEMQ_AFTER_CODE=13,
-    OPCODE=26, VARIANT=28, CONDITION_IDX=29, CONDITION=30, ERGS_COST=31, OUT_OF_ERGS=32, KERNEL_MODE_EXCEPTION=33,
-    STATIC_EXCEPTION=34, CALLSTACK_IS_FULL=35, EXPLICIT_PANIC=36, MASK_INTO_PANIC=37, MASK_INTO_NOP=38, PROPS=39,
-    DIRTY_ERGS_LEFT=40, SRC0_REG=41, SRC1_REG=42, DST0_REG=43, DST1_REG=44, IMM0=45, IMM1=46, SRC0_PAGE=47, SRC0_INDEX=48,
-    SHOULD_READ_SRC0=49, SP_AFTER_SRC0=50, DST0_PAGE=51, DST0_INDEX=52, DST0_PERFORMS_MEMORY_ACCESS=53, NEW_SP=54,
-    SRC0_FROM_MEMORY=55, MEMQ_AFTER_SRC0=64, SWAP_OPERANDS=77, SRC0=78, SRC1=87, DST0=96, DST1=105,
-    PERFORM_DST0_MEMORY_WRITE=114, DST0_UPDATE_REGISTER=115, MEMQ_AFTER_DST0=116, FLAGS_OUT=129, PENDING_EXCEPTION_OUT=132,
-    PC_OUT=133, ERGS_OUT=134, NUM_COLS=135)
-VM_CHK = dict(INVALID_OPCODE=1, UNSUPPORTED_OPCODE=2, SNAPSHOT=4, DIV_RELATION=8, BOOTLOADER_EXIT=16)
+    SHOULD_SKIP_CYCLE=0, PENDING_EXCEPTION_IN=1, SHOULD_READ_OPCODE=2, SUPER_PC=3, SUB_PC=4, CODE_WORD=5, OPCODE=13, VARIANT=15,
+    CONDITION_IDX=16, CONDITION=17, ERGS_COST=18, OUT_OF_ERGS=19, KERNEL_MODE_EXCEPTION=20, STATIC_EXCEPTION=21,
+    CALLSTACK_IS_FULL=22, EXPLICIT_PANIC=23, MASK_INTO_PANIC=24, MASK_INTO_NOP=25, PROPS=26, DIRTY_ERGS_LEFT=27, SRC0_REG=28,
+    SRC1_REG=29, DST0_REG=30, DST1_REG=31, IMM0=32, IMM1=33, SRC0_PAGE=34, SRC0_INDEX=35, SHOULD_READ_SRC0=36, SP_AFTER_SRC0=37,
+    DST0_PAGE=38, DST0_INDEX=39, DST0_PERFORMS_MEMORY_ACCESS=40, NEW_SP=41, SRC0_FROM_MEMORY=42, SWAP_OPERANDS=51, SRC0=52,
+    SRC1=61, DST0=70, DST1=79, PERFORM_DST0_MEMORY_WRITE=88, DST0_UPDATE_REGISTER=89, DST1_UPDATE_REGISTER=90, FLAGS_OUT=91,
+    PENDING_EXCEPTION_OUT=94, PC_OUT=95, ERGS_OUT=96, HEAP_BOUND_OUT=97, AUX_HEAP_BOUND_OUT=98, MEMQ_LENGTH_OUT=99, DEPTH_OUT=100,
+    FORWARD_TAIL_OUT=101, ROLLBACK_HEAD_OUT=106, SPONGE_ENFORCE=111, SPONGE_FINAL=120, OP_AUX=228, NUM_COLS=276)
+VM_CHK = dict(INVALID_OPCODE=1, UNSUPPORTED_OPCODE=2, SNAPSHOT=4, DIV_RELATION=8, BOOTLOADER_EXIT=16, ROLLBACK_QUEUE=32,
+              CALLSTACK=64, LOG_REFUND=128)
 ZKC_ERR_UNSUPPORTED, ZKC_ERR_SNAPSHOT_MISMATCH = 7, 8
 CODE_NAMES.update({7: "UNSUPPORTED", 8: "SNAPSHOT_MISMATCH"})
 
@@ -311,13 +319,13 @@ SIGNATURES = {
     "zkc_sha256_round_function_entry_point": (C.c_int, [_vp, C.POINTER(Sha256ClosedForm), _vp, _vp, C.c_size_t, _vp,
                                                         C.c_size_t, _vp, C.c_size_t, C.c_size_t,
                                                         C.POINTER(PrecompileOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
-    "zkc_main_vm_entry_point": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), _vp, _vp, C.c_size_t,
+    "zkc_main_vm_entry_point": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), _vp, _vp, _vp, C.c_size_t, C.c_size_t,
                                           C.POINTER(VmOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
-    "zkc_main_vm_entry_point_batch": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(VmIsa), _vp, _vp, C.c_size_t,
+    "zkc_main_vm_entry_point_batch": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(VmIsa), _vp, _vp, _vp, C.c_size_t, C.c_size_t,
                                                 C.POINTER(VmOptions), C.c_int, _vp, _vp, _vp]),
     "zkc_main_vm_initial_state": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), C.POINTER(VmState)]),
-    "zkc_main_vm_simulate": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp,
-                                       C.POINTER(Status)]),
+    "zkc_main_vm_simulate": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp,
+                                       C.c_size_t, _vp, _vp, C.POINTER(Status)]),
     "zkc_ram_permutation_entry_point": (C.c_int, [_vp, C.POINTER(RamClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,
                                                   C.c_size_t, C.c_size_t, C.POINTER(RamOptions), C.c_int, _vp, _vp,
                                                   C.POINTER(Status)]),

@@ -9,9 +9,13 @@
 // zkc_main_vm_simulate is the out-of-circuit run itself (one thread per independent VM instance, same cycle
 // function, memory reads answered by a per-instance memory model) -- the role of the external zk_evm crate.
 //
-// Built opcode subset: nop, add, sub, jump, binop, mul, div, shifts, ptr, context and every src0 / dst0 addressing
-// mode.  log / near_call / far_call / ret / uma (and therefore executed exceptions, which the circuit masks into
-// ret.panic) report ZKC_ERR_UNSUPPORTED.
+// Built opcodes: nop, add, sub, jump, binop, mul, div, shifts, ptr, context, uma, log, near_call, ret and every src0 / dst0
+// addressing mode (exceptions included: the circuit masks them into ret.panic).  far_call reports ZKC_ERR_UNSUPPORTED.
+//
+// Poseidon2 relations of a cycle (1 opcode fetch + up to 8, cycle.rs:620-795) are NOT run by the cycle's thread: the
+// cycle emits sponge JOBS (8 absorbed elements + where the capacity comes from + what the output must equal) and the
+// jobs of every cycle run afterwards as dense launches, one slot at a time (vm_sponge_kernel), so a warp never waits
+// for a lane that hashes.
 #include "ctx.cuh"
 #include "poseidon2.cuh"
 
@@ -291,14 +295,53 @@ __device__ void vm_initial_bootloader_state(const zkc_vm_closed_form &io, const 
     st.registers[0].value[1] = isa.bootloader_calldata_page;
 }
 
-// memory model of the out-of-circuit run: one code page and one stack page of 2^16 words
-struct VmMemory {
-    zkc_vm_register *code, *stack;
-    uint32_t code_page, stack_page;
+// ---- memory / storage model of the out-of-circuit run: code, stack, heap and aux heap pages of the root frame ---------
+constexpr uint32_t VM_PAGE_WORDS = 65536, VM_STORAGE_SLOTS = 4096, VM_SIM_MAX_DEPTH = 4096;
+struct VmSlot { uint32_t used, written, key[8], value[8]; };
+struct VmEntry {  // one rollback-queue event of a frame: its own call marker or a revertable log
+    long long prev;
+    uint32_t kind;   // 1 call marker, 2 log
+    int slot;        // storage slot a storage write touched, or -1
+    uint32_t prev_value[8], prev_written;
+    uint64_t enc16[4], cap[4];
 };
+struct VmSim {
+    zkc_vm_register *pages[4];
+    uint32_t page_ids[4];
+    VmSlot *storage;
+    zkc_vm_callstack_witness *stack;  // saved frames, [VM_SIM_MAX_DEPTH]
+    zkc_vm_callstack_witness *cw_out;
+    uint32_t cw_cap, n_cw;
+    int ev_kind;  // 0 none, 1 call, 2 ret ok, 3 ret revert / panic, 4 revertable log
+    VmEntry ev;
+    int overflow;
+};
+__device__ zkc_vm_register reg_zero();
+__device__ zkc_vm_register sim_read(const VmSim &m, uint32_t page, uint32_t index) {
+    if (index < VM_PAGE_WORDS)
+        for (int k = 0; k < 4; k++) if (page == m.page_ids[k]) return m.pages[k][index];
+    return reg_zero();
+}
+__device__ void sim_write(VmSim &m, uint32_t page, uint32_t index, const zkc_vm_register &v) {
+    if (index >= VM_PAGE_WORDS) return;
+    for (int k = 1; k < 4; k++) if (page == m.page_ids[k]) { m.pages[k][index] = v; return; }
+}
+__device__ int sim_slot(VmSim &m, const uint32_t *key) {
+    uint32_t h = 0x9E3779B9u;
+    for (int i = 0; i < 8; i++) h = (h ^ key[i]) * 0x85EBCA6Bu + (h >> 15);
+    for (uint32_t probe = 0; probe < VM_STORAGE_SLOTS; probe++) {
+        VmSlot &s = m.storage[(h + probe) % VM_STORAGE_SLOTS];
+        bool same = s.used != 0;
+        if (same) for (int i = 0; i < 8; i++) same &= s.key[i] == key[i];
+        if (!s.used) { s.used = 1; for (int i = 0; i < 8; i++) s.key[i] = key[i]; return (int)((h + probe) % VM_STORAGE_SLOTS); }
+        if (same) return (int)((h + probe) % VM_STORAGE_SLOTS);
+    }
+    m.overflow = 1;
+    return 0;
+}
 
 __device__ __forceinline__ bool prop(uint64_t props, int bit) { return (props >> bit) & 1; }
-__device__ __forceinline__ zkc_vm_register reg_zero() {
+__device__ zkc_vm_register reg_zero() {
     zkc_vm_register r;
     r.is_pointer = 0;
 #pragma unroll
@@ -312,6 +355,11 @@ __device__ __forceinline__ U256 as_u256(const zkc_vm_register &r) {
     return x;
 }
 
+// sponge slots in use (far calls would add 5..8) and where a job's capacity comes from / what its output must equal
+constexpr int VM_JOB_SLOTS = 5;
+enum : uint32_t { VM_CAP_ZERO = 9, VM_CAP_MEMQ = 10, VM_CAP_STACK = 11, VM_CAP_CALLSTACK_WITNESS = 12 };
+enum : uint32_t { VM_CHK_NONE = 0, VM_CHK_NEXT_MEMQ, VM_CHK_NEXT_STACK, VM_CHK_CUR_STACK, VM_CHK_NEXT_FWD_TAIL, VM_CHK_CUR_RB_HEAD };
+
 // what one cycle changes in a VmLocalState; every other word must carry over unchanged
 struct VmDelta {
     uint32_t pending, pc, sp, ergs, prev_code_page, prev_super_pc, timestamp, memq_len;
@@ -320,74 +368,171 @@ struct VmDelta {
     uint32_t idx0, idx1;  // 1-based register written by dst0 / dst1, 0 = none (dst1 is applied after dst0)
     zkc_vm_register val0, val1;
     uint32_t set_u128, u128[4], set_pubdata, pubdata, inc_tx;
-    uint32_t push_mask;   // bit k: memory queue push k happens (0 opcode fetch, 1 src0 read, 2 dst0 write)
+    uint32_t heap_bound, aux_bound, fwd_len, rb_len;
+    uint64_t rb_head[4];
+    uint32_t fwd_tail_kind;  // 0 unchanged, 1 output of the log's forward sponge (slot 3), 2 explicit (ret)
+    uint64_t fwd_tail[4];
+    uint32_t ctx_replaced;   // 0 no, 1 near call, 2 ret: the whole current context is nctx (forward tail / length apart)
+    uint32_t far_ret;        // r1 = r1_val, r2..r15 zeroed
+    zkc_vm_register r1_val;
+    uint32_t depth;
+    uint32_t cw_index;       // ret: the callstack witness used
+    uint32_t job_mask, cap_from, chk;  // sponge jobs: bit k / nibble k per slot
 };
+// sponge outputs of a cycle: known at once only to the out-of-circuit run
+struct VmSimOut { uint64_t memq[12], stack[12], fwd_tail[4]; };
 
-__device__ void vm_apply_delta(zkc_vm_state &t, const VmDelta &d) {
-    t.pending_exception = d.pending;
-    t.current_context.pc = d.pc; t.current_context.sp = d.sp; t.current_context.ergs_remaining = d.ergs;
-    t.previous_code_page = d.prev_code_page; t.previous_super_pc = d.prev_super_pc; t.timestamp = d.timestamp;
-    t.memory_queue_length = d.memq_len;
-    for (int i = 0; i < 3; i++) t.flags[i] = d.flags[i];
+__device__ void vm_apply_delta(zkc_vm_state &t, const VmDelta &d, const zkc_vm_context &nctx) {
     for (int i = 0; i < 8; i++) t.previous_code_word[i] = d.cw[i];
     if (d.idx0) t.registers[d.idx0 - 1] = d.val0;
+    if (d.far_ret) {
+        t.registers[0] = d.r1_val;
+        for (int r = 1; r < ZKC_VM_REGISTERS; r++) t.registers[r] = reg_zero();
+    }
     if (d.idx1) t.registers[d.idx1 - 1] = d.val1;
     if (d.set_u128) for (int i = 0; i < 4; i++) t.context_composite_u128[i] = d.u128[i];
     if (d.set_pubdata) t.ergs_per_pubdata_byte = d.pubdata;
     if (d.inc_tx) t.tx_number_in_block += 1;
+    if (d.ctx_replaced) {
+        const uint64_t t0 = t.current_context.log_queue_forward_tail[0], t1 = t.current_context.log_queue_forward_tail[1],
+                       t2 = t.current_context.log_queue_forward_tail[2], t3 = t.current_context.log_queue_forward_tail[3];
+        t.current_context = nctx;
+        t.current_context.log_queue_forward_tail[0] = t0; t.current_context.log_queue_forward_tail[1] = t1;
+        t.current_context.log_queue_forward_tail[2] = t2; t.current_context.log_queue_forward_tail[3] = t3;
+    } else {
+        t.current_context.pc = d.pc; t.current_context.sp = d.sp; t.current_context.ergs_remaining = d.ergs;
+        t.current_context.heap_upper_bound = d.heap_bound; t.current_context.aux_heap_upper_bound = d.aux_bound;
+        t.current_context.reverted_queue_segment_len = d.rb_len;
+        for (int i = 0; i < 4; i++) t.current_context.reverted_queue_head[i] = d.rb_head[i];
+    }
+    t.current_context.log_queue_forward_part_length = d.fwd_len;
+    if (d.fwd_tail_kind == 2) for (int i = 0; i < 4; i++) t.current_context.log_queue_forward_tail[i] = d.fwd_tail[i];
+    t.context_stack_depth = d.depth;
+    t.pending_exception = d.pending;
+    t.previous_code_page = d.prev_code_page; t.previous_super_pc = d.prev_super_pc; t.timestamp = d.timestamp;
+    t.memory_queue_length = d.memq_len;
+    for (int i = 0; i < 3; i++) t.flags[i] = d.flags[i];
 }
 
-// memory queue push k of a cycle: tail' = P(enc || tail[8..12]) (main_vm/utils.rs:194-230, :442-515, cycle.rs:845-905).
-// SIM hashes at once into the running state `q`; the batched circuit only records the encoding -- the sponges of
-// all cycles run afterwards as dense launches (vm_memq_kernel), so that a warp never waits for a lane that hashes
+// One Poseidon2 relation of the cycle: 8 absorbed elements over a capacity.  SIM runs it at once (cap = the 4 capacity
+// elements, out = the 12-element result); the circuit kernels record the job for the dense sponge launches.
 template <bool SIM>
-__device__ __forceinline__ void vm_push(int k, bool execute, VmDelta &d, uint64_t *q, uint64_t *penc, uint32_t ts, uint32_t page,
-                                        uint32_t index, uint32_t rw, const zkc_vm_register &val) {
-    if (!execute) return;
-    uint64_t e[8];
-    vm_mq_encode(ts, page, index, rw, val, e);
-    d.push_mask |= 1u << k;
-    d.memq_len++;
-    if (SIM) {
+__device__ __forceinline__ void vm_job(int slot, VmDelta &d, uint64_t *penc, const uint64_t (&in8)[8], const uint64_t *cap,
+                                       uint32_t cap_code, uint32_t chk, uint64_t *out) {
+    d.job_mask |= 1u << slot;
+    if constexpr (SIM) {
         uint64_t t[12];
 #pragma unroll
-        for (int i = 0; i < 8; i++) t[i] = e[i];
+        for (int i = 0; i < 8; i++) t[i] = in8[i];
 #pragma unroll
-        for (int i = 8; i < 12; i++) t[i] = q[i];
+        for (int i = 0; i < 4; i++) t[8 + i] = cap[i];
         poseidon2_permute(t);
 #pragma unroll
-        for (int i = 0; i < 12; i++) q[i] = t[i];
+        for (int i = 0; i < 12; i++) out[i] = t[i];
     } else {
+        d.cap_from |= cap_code << (4 * slot);
+        d.chk |= chk << (4 * slot);
 #pragma unroll
-        for (int i = 0; i < 8; i++) penc[8 * k + i] = e[i];
+        for (int i = 0; i < 8; i++) penc[8 * slot + i] = in8[i];
     }
 }
 
-// One vm_cycle from the state `s` (read only; only the words a cycle needs are touched): returns the check bits and
-// what changes in `d`.  SIM: memory reads are answered by `mem` and recorded into `w`; otherwise they come from `w`.
-// trace / limit / row: where to put the row (trace may be null; the MEMQ_AFTER_* columns are written by whoever runs
-// the sponges).
+// memory queue push: tail' = P(enc || tail[8..12]) (main_vm/utils.rs:194-230, :442-515, cycle.rs:845-905, uma.rs:362-812).
+// `last` = slot of the cycle's previous memory queue job (-1: none yet), updated.
+template <bool SIM>
+__device__ __forceinline__ void vm_push(int slot, bool execute, VmDelta &d, VmSimOut *so, uint64_t *penc, int &last, uint32_t ts,
+                                        uint32_t page, uint32_t index, uint32_t rw, const zkc_vm_register &val) {
+    if (!execute) return;
+    uint64_t e[8];
+    vm_mq_encode(ts, page, index, rw, val, e);
+    d.memq_len++;
+    if constexpr (SIM) vm_job<true>(slot, d, penc, e, so->memq + 8, 0, 0, so->memq);
+    else vm_job<false>(slot, d, penc, e, nullptr, last < 0 ? VM_CAP_MEMQ : (uint32_t)last, VM_CHK_NONE, nullptr);
+    last = slot;
+}
+
+// FatPtrInABI::parse_and_validate, call_ret_impl/far_call.rs:140-196
+struct VmFatPtr { uint32_t offset, page, start, length; };
+__device__ VmFatPtr vm_fat_ptr_parse(const U256 &v, bool as_fresh, uint32_t &upper_bound, bool &non_addressable) {
+    VmFatPtr p{v.v[0], v.v[1], v.v[2], v.v[3]};
+    const uint64_t end = (uint64_t)p.start + p.length;
+    const bool range_of = (end >> 32) != 0;
+    const bool invalid = (p.offset != 0 && as_fresh) || range_of || p.length < p.offset;
+    if (invalid) p = VmFatPtr{0, 0, 0, 0};
+    upper_bound = (uint32_t)end; non_addressable = range_of;
+    return p;
+}
+
+// ExecutionContextRecord in flatten (allocation) order: 42 elements
+__device__ void vm_flatten_record(const zkc_vm_context &c, uint64_t *dst) {
+    int n = 0;
+    for (int i = 0; i < 5; i++) dst[n++] = c.this_address[i];
+    for (int i = 0; i < 5; i++) dst[n++] = c.caller[i];
+    for (int i = 0; i < 5; i++) dst[n++] = c.code_address[i];
+    dst[n++] = c.code_page; dst[n++] = c.base_page; dst[n++] = c.heap_upper_bound; dst[n++] = c.aux_heap_upper_bound;
+    for (int i = 0; i < 4; i++) dst[n++] = c.reverted_queue_head[i];
+    for (int i = 0; i < 4; i++) dst[n++] = c.reverted_queue_tail[i];
+    dst[n++] = c.reverted_queue_segment_len;
+    dst[n++] = c.pc; dst[n++] = c.sp; dst[n++] = c.exception_handler_loc; dst[n++] = c.ergs_remaining;
+    dst[n++] = c.is_static_execution; dst[n++] = c.is_kernel_mode;
+    dst[n++] = c.this_shard_id; dst[n++] = c.caller_shard_id; dst[n++] = c.code_shard_id;
+    for (int i = 0; i < 4; i++) dst[n++] = c.context_u128_value_composite[i];
+    dst[n++] = c.is_local_call;
+}
+
+// LogQuery::encode, base_structures/log_query/mod.rs:121-517, from the pieces the log opcode has
+__device__ void vm_log_encode(const uint32_t *address, const uint32_t *key, const uint32_t *read_value, const uint32_t *written_value,
+                              uint32_t tx, uint32_t ts, uint32_t aux, uint32_t shard, uint32_t rw, uint32_t service, uint64_t *out) {
+    uint8_t b[52];
+    for (int l = 0; l < 8; l++)
+        for (int j = 0; j < 4; j++) b[4 * l + j] = (uint8_t)(key[l] >> (8 * j));
+    for (int l = 0; l < 5; l++)
+        for (int j = 0; j < 4; j++) b[32 + 4 * l + j] = (uint8_t)(address[l] >> (8 * j));
+    for (int i = 0; i < 16; i++) {
+        const uint64_t w = i < 8 ? read_value[i] : written_value[i - 8];
+        out[i] = w + ((uint64_t)b[3 * i] << 32) + ((uint64_t)b[3 * i + 1] << 40) + ((uint64_t)b[3 * i + 2] << 48);
+    }
+    out[16] = (uint64_t)ts + ((uint64_t)b[48] << 32) + ((uint64_t)b[49] << 40) + ((uint64_t)b[50] << 48);
+    out[17] = (uint64_t)tx + ((uint64_t)b[51] << 32) + ((uint64_t)aux << 40) + ((uint64_t)shard << 48);
+    out[18] = (uint64_t)rw + 2 * (uint64_t)service;
+    out[19] = 0;
+}
+
+// One vm_cycle from the state `s` (read only; only the words a cycle needs are touched): returns the check bits, what
+// changes in `d` (+ `nctx` when the callstack moves).  SIM: oracle answers come from `sim` and are recorded into `w` /
+// the callstack witness, sponges run at once into `so`; otherwise answers come from `w` / `cw` and the sponges are
+// emitted as jobs into `penc`.  trace / limit / row: where to put the row (trace may be null; the sponge columns are
+// written by whoever runs the sponges).  next: the following snapshot (circuit mode; forward tail column only).
 template <bool SIM, typename W>
-__device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_vm_state &s, VmDelta &d, W &w, VmMemory *mem,
-                                 uint64_t *q, uint64_t *penc, uint64_t *__restrict__ trace, size_t limit, size_t row) {
+__device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_vm_state &s, VmDelta &d, zkc_vm_context &nctx, W &w,
+                                 const zkc_vm_callstack_witness *__restrict__ cw, uint32_t n_cw, VmSim *sim, VmSimOut *so,
+                                 uint64_t *penc, const zkc_vm_state *next, uint64_t *__restrict__ trace, size_t limit, size_t row) {
 #define TR(col) trace[(size_t)(col) * limit + row]
     const bool wr = trace != nullptr;
     uint32_t checks = 0;
     const zkc_vm_context &ctx = s.current_context;
-    d.push_mask = 0; d.set_u128 = 0; d.set_pubdata = 0; d.inc_tx = 0; d.idx0 = 0; d.idx1 = 0;
+    d.set_u128 = 0; d.set_pubdata = 0; d.inc_tx = 0; d.idx0 = 0; d.idx1 = 0;
+    d.job_mask = 0; d.cap_from = 0; d.chk = 0; d.fwd_tail_kind = 0; d.ctx_replaced = 0; d.far_ret = 0; d.cw_index = 0;
     d.memq_len = s.memory_queue_length;
+    d.heap_bound = ctx.heap_upper_bound; d.aux_bound = ctx.aux_heap_upper_bound;
+    d.fwd_len = ctx.log_queue_forward_part_length; d.rb_len = ctx.reverted_queue_segment_len;
+#pragma unroll
+    for (int i = 0; i < 4; i++) d.rb_head[i] = ctx.reverted_queue_head[i];
+    d.depth = s.context_stack_depth;
+    int last_memq = -1;
+    if constexpr (SIM) sim->ev_kind = 0;
     // ---- create_prestate ---------------------------------------------------------------------------------------
     const bool should_skip = s.context_stack_depth == 0;
     const bool pending = s.pending_exception != 0;
     const bool should_try_read = !should_skip && !pending;
-    const uint32_t pc = ctx.pc, super_pc = pc >> 2, sub_pc = pc & 3;
+    const uint32_t pc = ctx.pc, super_pc = pc >> 2, sub_pc = pc & 3, pc_plus_one = (pc + 1) & 0xFFFF;
     const uint32_t code_page = ctx.code_page;
     const bool should_read_opcode = should_try_read && !(s.previous_code_page == code_page && super_pc == s.previous_super_pc);
     const uint32_t ts0 = s.timestamp;
     zkc_vm_register code_val = reg_zero();
     if (should_read_opcode) {
         if constexpr (SIM) {
-            code_val = mem->code[super_pc]; code_val.is_pointer = 0;
+            code_val = sim_read(*sim, code_page, super_pc); code_val.is_pointer = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) w.code_word[i] = code_val.value[i];
         } else {
@@ -398,7 +543,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
 #pragma unroll
         for (int i = 0; i < 8; i++) w.code_word[i] = 0;
     }
-    vm_push<SIM>(0, should_read_opcode, d, q, penc, ts0, code_page, super_pc, 0, code_val);
+    vm_push<SIM>(0, should_read_opcode, d, so, penc, last_memq, ts0, code_page, super_pc, 0, code_val);
 #pragma unroll
     for (int i = 0; i < 8; i++) d.cw[i] = should_read_opcode ? code_val.value[i] : s.previous_code_word[i];
     uint32_t op_lo = 0, op_hi = 0;
@@ -414,7 +559,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
         TR(ZKC_VM_OPCODE) = op_lo; TR(ZKC_VM_OPCODE + 1) = op_hi;
     }
     d.prev_code_page = code_page;
-    d.pc = should_skip ? pc : ((pc + 1) & 0xFFFF);
+    d.pc = should_skip ? pc : pc_plus_one;
     d.prev_super_pc = should_skip ? s.previous_super_pc : super_pc;
     d.timestamp = should_skip ? ts0 : ts0 + 4;
     const bool is_kernel = ctx.is_kernel_mode != 0, is_static = ctx.is_static_execution != 0;
@@ -450,7 +595,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
 #define SRCM(m) prop(props, ZKC_VM_BIT_SRC_MODE(m))
 #define DSTM(m) prop(props, ZKC_VM_BIT_DST_MODE(m))
     if (TYPE(ZKC_OP_INVALID)) checks |= ZKC_VM_CHK_INVALID_OPCODE;
-    if (TYPE(ZKC_OP_NEAR_CALL) || TYPE(ZKC_OP_LOG) || TYPE(ZKC_OP_FAR_CALL) || TYPE(ZKC_OP_RET) || TYPE(ZKC_OP_UMA)) checks |= ZKC_VM_CHK_UNSUPPORTED_OPCODE;
+    if (TYPE(ZKC_OP_FAR_CALL)) checks |= ZKC_VM_CHK_UNSUPPORTED_OPCODE;
     if (wr) {
         TR(ZKC_VM_VARIANT) = variant; TR(ZKC_VM_CONDITION_IDX) = cond_idx; TR(ZKC_VM_CONDITION) = condition; TR(ZKC_VM_ERGS_COST) = cost;
         TR(ZKC_VM_OUT_OF_ERGS) = out_of_ergs; TR(ZKC_VM_KERNEL_MODE_EXCEPTION) = kernel_exc; TR(ZKC_VM_STATIC_EXCEPTION) = static_exc;
@@ -464,7 +609,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
     const zkc_vm_register src1_register = src1_r ? s.registers[src1_r - 1] : reg_zero();
     const uint32_t src0_low = draft_src0.value[0] & 0xFFFF;
     const uint32_t dst0_low = (dst0_r ? s.registers[dst0_r - 1].value[0] : 0u) & 0xFFFF;
-    const uint32_t current_sp = ctx.sp, stack_page = ctx.base_page + 1;
+    const uint32_t current_sp = ctx.sp, stack_page = ctx.base_page + 1, heap_page = ctx.base_page + 2, aux_heap_page = ctx.base_page + 3;
     const bool is_nop = TYPE(ZKC_OP_NOP);
     uint32_t src_page, src_index, sp_after_src0;
     bool should_read_src0;
@@ -490,8 +635,8 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
     zkc_vm_register src0_mem = reg_zero();
     if (should_read_src0) {
         if constexpr (SIM) {
-            if (src_page == mem->code_page) { src0_mem = mem->code[src_index]; src0_mem.is_pointer = 0; }
-            else if (src_page == mem->stack_page) src0_mem = mem->stack[src_index];
+            src0_mem = sim_read(*sim, src_page, src_index);
+            if (src_page == code_page) src0_mem.is_pointer = 0;
             w.src0_is_pointer = src0_mem.is_pointer;
 #pragma unroll
             for (int i = 0; i < 8; i++) w.src0_value[i] = src0_mem.value[i];
@@ -505,7 +650,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
 #pragma unroll
         for (int i = 0; i < 8; i++) w.src0_value[i] = 0;
     }
-    vm_push<SIM>(1, should_read_src0, d, q, penc, ts0, src_page, src_index, 0, src0_mem);
+    vm_push<SIM>(1, should_read_src0, d, so, penc, last_memq, ts0, src_page, src_index, 0, src0_mem);
     if (wr) {
         TR(ZKC_VM_SRC0_PAGE) = src_page; TR(ZKC_VM_SRC0_INDEX) = src_index; TR(ZKC_VM_SHOULD_READ_SRC0) = should_read_src0;
         TR(ZKC_VM_SP_AFTER_SRC0) = sp_after_src0; TR(ZKC_VM_DST0_PAGE) = stack_page; TR(ZKC_VM_DST0_INDEX) = dst_index;
@@ -513,6 +658,8 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
         TR(ZKC_VM_SRC0_FROM_MEMORY) = src0_mem.is_pointer;
 #pragma unroll
         for (int i = 0; i < 8; i++) TR(ZKC_VM_SRC0_FROM_MEMORY + 1 + i) = src0_mem.value[i];
+#pragma unroll 1
+        for (int i = 0; i < ZKC_VM_OP_AUX_COLS; i++) TR(ZKC_VM_OP_AUX + i) = 0;  // the selected opcode family overwrites its part
     }
     zkc_vm_register src0 = SRCM(ZKC_MODE_REG_ONLY) ? draft_src0 : src0_mem;
     if (SRCM(ZKC_MODE_IMM16)) { src0 = reg_zero(); src0.value[0] = imm0; }
@@ -535,7 +682,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
     U256 d0, d1;
 #pragma unroll
     for (int i = 0; i < 8; i++) { d0.v[i] = 0; d1.v[i] = 0; }
-    uint32_t d0_is_ptr = 0;
+    uint32_t d0_is_ptr = 0, d1_is_ptr = 0;
     bool dst0_mem_capable = false, dst0_reg_only = false, write_dst1 = false, set_flags = false, new_pending = false;
     uint32_t nf0 = 0, nf1 = 0, nf2 = 0;
     const bool sf = FLAG(ZKC_VM_SET_FLAGS_FLAG_IDX);
@@ -607,27 +754,368 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
 #pragma unroll
         for (int i = 0; i < 4; i++) d.u128[i] = a.v[i];
         d.pubdata = a.v[0];
+    } else if (TYPE(ZKC_OP_UMA)) {  // uma.rs:18-1084
+        const bool heap_r = VAR(ZKC_VAR_UMA_HEAP_READ), heap_w = VAR(ZKC_VAR_UMA_HEAP_WRITE), aux_r = VAR(ZKC_VAR_UMA_AUX_HEAP_READ),
+                   aux_w = VAR(ZKC_VAR_UMA_AUX_HEAP_WRITE), ptr_r = VAR(ZKC_VAR_UMA_FAT_PTR_READ);
+        const bool increment = FLAG(ZKC_VM_UMA_INCREMENT_FLAG_IDX);
+        const bool access_heap = heap_r || heap_w, access_aux = aux_r || aux_w;
+        const bool not_a_ptr = ptr_r && !ra.is_pointer;
+        const uint32_t offset = a.v[0], page = a.v[1], start = a.v[2], length = a.v[3];
+        const bool skip_legit = !(offset < length) && ptr_r;
+        const uint32_t abs_addr = (ptr_r ? start : 0u) + offset;
+        const uint64_t inc64 = (uint64_t)offset + 32;
+        const uint32_t incremented = (uint32_t)inc64;
+        const bool non_addressable = (inc64 >> 32) != 0 || incremented == 0xFFFFFFFFu;
+        const bool qp_panic = not_a_ptr || non_addressable, qp_skip = not_a_ptr || skip_legit || non_addressable;
+        uint32_t bytes_oob = incremented - length;
+        if (qp_skip || incremented < length) bytes_oob = 0;
+        bytes_oob &= 31;
+        const uint32_t heap_bound = ctx.heap_upper_bound, aux_bound = ctx.aux_heap_upper_bound;
+        const uint32_t heap_max = access_heap ? incremented : 0u, aux_max = access_aux ? incremented : 0u;
+        const bool heap_uf = heap_max < heap_bound, aux_uf = aux_max < aux_bound;
+        uint32_t growth_cost = access_heap ? (heap_uf ? 0u : heap_max - heap_bound) : 0u;
+        if (access_aux) growth_cost = aux_uf ? 0u : aux_max - aux_bound;
+        const bool top_nz = (a.v[1] | a.v[2] | a.v[3] | a.v[4] | a.v[5] | a.v[6] | a.v[7]) != 0;
+        const bool exc_oob = (access_heap || access_aux) && (top_nz || non_addressable);
+        if (exc_oob) growth_cost = 0xFFFFFFFFu;
+        const bool uf = ergs_left < growth_cost;
+        const bool set_panic = qp_panic || uf || exc_oob;
+        const bool skip_mem = qp_skip || set_panic;
+        const bool is_read = heap_r || aux_r || ptr_r, is_write = heap_w || aux_w;
+        const uint32_t cell_idx = abs_addr >> 5, unalignment = abs_addr & 31;
+        const bool unaligned = unalignment != 0;
+        const uint32_t mem_page = access_aux ? aux_heap_page : (access_heap ? heap_page : page);
+        const uint32_t b_idx = cell_idx + 1;
+        const bool read_a = !skip_mem, read_b = unaligned && !skip_mem;
+        zkc_vm_register va = reg_zero(), vb = reg_zero();
+        if constexpr (SIM) {
+            if (read_a) va = sim_read(*sim, mem_page, cell_idx);
+            if (read_b) vb = sim_read(*sim, mem_page, b_idx);
+            va.is_pointer = 0; vb.is_pointer = 0;
+            for (int i = 0; i < 8; i++) { w.value_a[i] = va.value[i]; w.value_b[i] = vb.value[i]; }
+        } else {
+            if (read_a) for (int i = 0; i < 8; i++) va.value[i] = w.value_a[i];
+            if (read_b) for (int i = 0; i < 8; i++) vb.value[i] = w.value_b[i];
+        }
+        vm_push<SIM>(1, read_a, d, so, penc, last_memq, ts0, mem_page, cell_idx, 0, va);
+        vm_push<SIM>(2, read_b, d, so, penc, last_memq, ts0, mem_page, b_idx, 0, vb);
+        // 64-byte big-endian window over cells A, B (:533-560); byte i of a cell is bits of limb 7 - i / 4
+        uint8_t bytes[64], written[64];
+        for (int i = 0; i < 32; i++) {
+            bytes[i] = (uint8_t)(va.value[7 - i / 4] >> (8 * (3 - i % 4)));
+            bytes[32 + i] = (uint8_t)(vb.value[7 - i / 4] >> (8 * (3 - i % 4)));
+        }
+        for (int i = 0; i < 64; i++) written[i] = bytes[i];
+        for (int i = 0; i < 32; i++) written[unalignment + i] = (uint8_t)(b.v[7 - i / 4] >> (8 * (3 - i % 4)));
+        const uint32_t cleanup = ptr_r ? bytes_oob : 0u;
+        U256 rd, wa, wb;
+        for (int i = 0; i < 8; i++) { rd.v[i] = 0; wa.v[i] = 0; wb.v[i] = 0; }
+        for (int i = 0; i < 32; i++) {
+            const uint32_t byte = (uint32_t)i >= 32 - cleanup ? 0u : bytes[unalignment + i];
+            rd.v[7 - i / 4] |= byte << (8 * (3 - i % 4));
+            wa.v[7 - i / 4] |= (uint32_t)written[i] << (8 * (3 - i % 4));
+            wb.v[7 - i / 4] |= (uint32_t)written[32 + i] << (8 * (3 - i % 4));
+        }
+        const bool exec_write = is_write && !skip_mem, exec_write_b = exec_write && unaligned;
+        zkc_vm_register rwa = reg_zero(), rwb = reg_zero();
+        for (int i = 0; i < 8; i++) { rwa.value[i] = wa.v[i]; rwb.value[i] = wb.v[i]; }
+        vm_push<SIM>(3, exec_write, d, so, penc, last_memq, ts0 + 3, mem_page, cell_idx, 1, rwa);
+        vm_push<SIM>(4, exec_write_b, d, so, penc, last_memq, ts0 + 3, mem_page, b_idx, 1, rwb);
+        if constexpr (SIM) {
+            if (exec_write) sim_write(*sim, mem_page, cell_idx, rwa);
+            if (exec_write_b) sim_write(*sim, mem_page, b_idx, rwb);
+        }
+        const bool w_inc = is_write && increment, no_panic = !set_panic;
+        U256 inc_reg = a;
+        inc_reg.v[0] = incremented;
+        d0 = w_inc ? inc_reg : rd; d0_is_ptr = w_inc ? ra.is_pointer : 0u;
+        dst0_reg_only = no_panic && (is_read || w_inc);
+        write_dst1 = no_panic && is_read && increment;
+        d1 = inc_reg; d1_is_ptr = ra.is_pointer;
+        new_pending = set_panic;
+        if (access_heap) d.heap_bound = heap_uf ? heap_bound : heap_max;
+        if (access_aux) d.aux_bound = aux_uf ? aux_bound : aux_max;
+        d.ergs = uf ? 0u : ergs_left - growth_cost;
+        if (wr) {
+            TR(ZKC_VM_OP_AUX + 0) = abs_addr; TR(ZKC_VM_OP_AUX + 1) = cell_idx; TR(ZKC_VM_OP_AUX + 2) = unalignment; TR(ZKC_VM_OP_AUX + 3) = mem_page;
+            TR(ZKC_VM_OP_AUX + 4) = skip_mem; TR(ZKC_VM_OP_AUX + 5) = set_panic; TR(ZKC_VM_OP_AUX + 6) = growth_cost; TR(ZKC_VM_OP_AUX + 7) = incremented;
+            for (int i = 0; i < 8; i++) {
+                TR(ZKC_VM_OP_AUX + 8 + i) = va.value[i]; TR(ZKC_VM_OP_AUX + 16 + i) = vb.value[i];
+                TR(ZKC_VM_OP_AUX + 24 + i) = exec_write ? wa.v[i] : 0u; TR(ZKC_VM_OP_AUX + 32 + i) = exec_write_b ? wb.v[i] : 0u;
+            }
+        }
+    } else if (TYPE(ZKC_OP_LOG)) {  // log.rs:16-671
+        const bool st_read = VAR(ZKC_VAR_LOG_STORAGE_READ), st_write = VAR(ZKC_VAR_LOG_STORAGE_WRITE), is_event = VAR(ZKC_VAR_LOG_EVENT),
+                   is_l1 = VAR(ZKC_VAR_LOG_TO_L1_MESSAGE), is_precompile = VAR(ZKC_VAR_LOG_PRECOMPILE_CALL);
+        uint32_t key[8];
+        for (int i = 0; i < 8; i++) key[i] = a.v[i];
+        if (is_precompile && key[4] == 0) key[4] = heap_page;
+        if (is_precompile && key[5] == 0) key[5] = heap_page;
+        const bool write_to_rollup = ctx.this_shard_id == 0 && st_write;
+        const bool is_storage = st_read || st_write, revertable = !(st_read || is_precompile);
+        const uint32_t aux_byte = (is_storage ? isa->log_aux_bytes[0] : 0u) + (is_event ? isa->log_aux_bytes[1] : 0u) +
+                                  (is_l1 ? isa->log_aux_bytes[2] : 0u) + (is_precompile ? isa->log_aux_bytes[3] : 0u);
+        const uint32_t is_service = FLAG(ZKC_VM_FIRST_MESSAGE_FLAG_IDX);
+        int slot = -1;
+        if constexpr (SIM) {
+            w.refund = 0;
+            if (st_write) { slot = sim_slot(*sim, key); w.refund = sim->storage[slot].written ? isa->initial_storage_write_pubdata_bytes : 0u; }
+        }
+        const uint32_t refund = w.refund;
+        if (refund > isa->initial_storage_write_pubdata_bytes) checks |= ZKC_VM_CHK_LOG_REFUND;
+        const uint32_t net_cost = isa->initial_storage_write_pubdata_bytes - refund;
+        uint32_t burn = write_to_rollup ? s.ergs_per_pubdata_byte * net_cost : 0u;
+        if (is_precompile) burn = b.v[0];
+        if (is_l1) burn = s.ergs_per_pubdata_byte * isa->l1_message_pubdata_bytes;
+        const bool not_enough = ergs_left < burn;
+        const bool execute = !not_enough, execute_rollback = execute && revertable;
+        uint32_t read_value[8], written_value[8];
+        if constexpr (SIM) {
+            for (int i = 0; i < 8; i++) w.value_a[i] = 0;
+            if (is_storage && execute) {
+                if (slot < 0) slot = sim_slot(*sim, key);
+                for (int i = 0; i < 8; i++) w.value_a[i] = sim->storage[slot].value[i];
+            }
+        }
+        for (int i = 0; i < 8; i++) { read_value[i] = is_storage ? w.value_a[i] : 0u; written_value[i] = revertable ? b.v[i] : read_value[i]; }
+        uint64_t enc[20];
+        vm_log_encode(ctx.this_address, key, read_value, written_value, s.tx_number_in_block, ts0 + 1, aux_byte, ctx.this_shard_id, revertable,
+                      is_service, enc);
+        uint64_t fin[12], in8[8];
+        const uint64_t zero4[4] = {0, 0, 0, 0};
+        if (execute) {
+            for (int i = 0; i < 8; i++) in8[i] = enc[i];
+            vm_job<SIM>(1, d, penc, in8, zero4, VM_CAP_ZERO, VM_CHK_NONE, fin);
+            for (int i = 0; i < 8; i++) in8[i] = enc[8 + i];
+            vm_job<SIM>(2, d, penc, in8, fin + 8, 1, VM_CHK_NONE, fin);
+            for (int i = 0; i < 4; i++) { in8[i] = enc[16 + i]; in8[4 + i] = ctx.log_queue_forward_tail[i]; }
+            uint64_t fwd[12];
+            vm_job<SIM>(3, d, penc, in8, fin + 8, 2, VM_CHK_NEXT_FWD_TAIL, fwd);
+            d.fwd_tail_kind = 1; d.fwd_len++;
+            if constexpr (SIM) for (int i = 0; i < 4; i++) so->fwd_tail[i] = fwd[i];
+        }
+        if constexpr (SIM) {
+            if (execute_rollback) {
+                sim->ev_kind = 4; sim->ev.kind = 2; sim->ev.slot = -1;
+                for (int i = 0; i < 4; i++) { sim->ev.enc16[i] = enc[16 + i]; sim->ev.cap[i] = fin[8 + i]; }
+                sim->ev.enc16[3] = 1;
+            }
+            if (st_write && execute) {
+                VmSlot &sl = sim->storage[slot];
+                sim->ev.slot = slot; sim->ev.prev_written = sl.written;
+                for (int i = 0; i < 8; i++) { sim->ev.prev_value[i] = sl.value[i]; sl.value[i] = b.v[i]; }
+                sl.written = 1;
+            }
+        }
+        if (execute_rollback) {
+            for (int i = 0; i < 4; i++) { in8[i] = enc[16 + i]; in8[4 + i] = w.rollback[i]; }
+            in8[3] = 1;  // update_packing_for_rollback, log_query/mod.rs:52-58
+            uint64_t rb[12];
+            vm_job<SIM>(4, d, penc, in8, fin + 8, 2, VM_CHK_CUR_RB_HEAD, rb);
+            if constexpr (SIM) {
+                bool same = true;
+                for (int i = 0; i < 4; i++) same &= rb[i] == ctx.reverted_queue_head[i];
+                if (!same) checks |= ZKC_VM_CHK_ROLLBACK_QUEUE;
+            }
+            for (int i = 0; i < 4; i++) d.rb_head[i] = w.rollback[i];
+            d.rb_len++;
+        }
+        if (st_read) for (int i = 0; i < 8; i++) d0.v[i] = read_value[i];
+        else d0.v[0] = execute;
+        dst0_reg_only = st_read || is_precompile;
+        d.ergs = not_enough ? 0u : ergs_left - burn;
+        if (wr) {
+            for (int i = 0; i < 20; i++) TR(ZKC_VM_OP_AUX + i) = enc[i];
+            for (int i = 0; i < 8; i++) TR(ZKC_VM_OP_AUX + 20 + i) = read_value[i];
+            TR(ZKC_VM_OP_AUX + 28) = execute; TR(ZKC_VM_OP_AUX + 29) = execute_rollback; TR(ZKC_VM_OP_AUX + 30) = burn;
+        }
+    } else if (TYPE(ZKC_OP_NEAR_CALL) || TYPE(ZKC_OP_RET)) {  // call_ret.rs:24-512
+        const bool apply_near = TYPE(ZKC_OP_NEAR_CALL), apply_ret = !apply_near;
+        const uint32_t fwd_byte = (a.v[ZKC_VM_ABI_FORWARDING_MODE_BYTE_IDX / 4] >> (8 * (ZKC_VM_ABI_FORWARDING_MODE_BYTE_IDX % 4))) & 0xFF;
+        const bool use_aux = fwd_byte == ZKC_VM_FORWARD_USE_AUX_HEAP, fwd_ptr = fwd_byte == ZKC_VM_FORWARD_FAT_POINTER;
+        const bool use_heap = !(use_aux || fwd_ptr);
+        uint32_t upper_bound;
+        bool non_addressable;
+        const VmFatPtr fp = vm_fat_ptr_parse(a, !fwd_ptr, upper_bound, non_addressable);
+        zkc_vm_context old_entry;
+        bool is_panic_out = false, perform_revert = false;
+        // the draft context: what create_prestate leaves (pc, sp, ergs updated)
+        zkc_vm_context cur_e = ctx;
+        cur_e.pc = d.pc; cur_e.sp = new_sp; cur_e.ergs_remaining = ergs_left;
+        uint32_t cap_code;
+        const uint64_t *cap_sim = nullptr;
+        uint64_t prev_sponge[12];
+        if (apply_near) {  // near_call.rs:34-184
+            cur_e.pc = pc_plus_one;
+            nctx = cur_e;
+            for (int i = 0; i < 4; i++) { nctx.reverted_queue_tail[i] = w.rollback[i]; nctx.reverted_queue_head[i] = w.rollback[i]; }
+            nctx.reverted_queue_segment_len = 0;
+            const uint32_t ergs_passed = a.v[0];
+            const uint32_t to_pass = ergs_passed == 0 ? ergs_left : ergs_passed;
+            const bool uf = ergs_left < to_pass;
+            cur_e.ergs_remaining = uf ? 0u : ergs_left - to_pass;
+            nctx.ergs_remaining = uf ? ergs_left : to_pass;
+            nctx.pc = imm0; nctx.exception_handler_loc = imm1; nctx.is_local_call = 1;
+            old_entry = cur_e;
+            d.depth = s.context_stack_depth + 1;
+            cap_code = VM_CAP_STACK;
+            if constexpr (SIM) {
+                cap_sim = so->stack + 8;
+                if (s.context_stack_depth >= VM_SIM_MAX_DEPTH) sim->overflow = 1;
+                else {
+                    sim->stack[s.context_stack_depth].context = old_entry;
+                    for (int i = 0; i < 12; i++) sim->stack[s.context_stack_depth].previous_sponge_state[i] = s.stack_sponge_state[i];
+                }
+                sim->ev_kind = 1; sim->ev.kind = 1; sim->ev.slot = -1;
+            }
+        } else {  // ret.rs:29-479
+            const bool is_ok = VAR(ZKC_VAR_RET_OK), is_revert = VAR(ZKC_VAR_RET_REVERT), is_ret_panic = VAR(ZKC_VAR_RET_PANIC);
+            const bool is_local = ctx.is_local_call != 0, is_far_return = !is_local;
+            const bool src0_is_ptr = ra.is_pointer && !is_ret_panic;
+            const bool is_to_label = FLAG(ZKC_VM_RET_TO_LABEL_FLAG_IDX);
+            bool have = false;
+            uint32_t cwi = 0;
+            if constexpr (SIM) {
+                if (s.context_stack_depth >= 1 && s.context_stack_depth - 1 < VM_SIM_MAX_DEPTH) {
+                    const zkc_vm_callstack_witness &top = sim->stack[s.context_stack_depth - 1];
+                    if (sim->n_cw < sim->cw_cap) { cwi = sim->n_cw; sim->cw_out[sim->n_cw++] = top; w.callstack_index = cwi; have = true; }
+                    else sim->overflow = 1;
+                    nctx = top.context;
+                    for (int i = 0; i < 12; i++) prev_sponge[i] = top.previous_sponge_state[i];
+                }
+            } else {
+                cwi = w.callstack_index;
+                have = cwi < n_cw;
+                if (have) {
+                    nctx = cw[cwi].context;
+                    for (int i = 0; i < 12; i++) prev_sponge[i] = cw[cwi].previous_sponge_state[i];
+                } else checks |= ZKC_VM_CHK_CALLSTACK;
+            }
+            if (!have) {
+                memset(&nctx, 0, sizeof nctx);
+                for (int i = 0; i < 12; i++) prev_sponge[i] = 0;
+            }
+            d.cw_index = cwi;
+            old_entry = nctx;
+            const uint32_t popped_seg_len = nctx.reverted_queue_segment_len;
+            const bool exc1 = fwd_ptr && !src0_is_ptr && is_far_return;
+            const bool exc2 = fwd_ptr && fp.page < cur_e.base_page;
+            const bool exceptions_collapsed = exc1 || exc2 || is_ret_panic;
+            VmFatPtr p = exceptions_collapsed ? VmFatPtr{0, 0, 0, 0} : fp;
+            p = fwd_ptr ? VmFatPtr{0, p.page, p.start + p.offset, p.length - p.offset} : VmFatPtr{0, use_heap ? heap_page : aux_heap_page, p.start, p.length};
+            uint32_t ub = exceptions_collapsed ? 0u : upper_bound;
+            if (non_addressable && !fwd_ptr) ub = 0xFFFFFFFFu;
+            const uint32_t heap_max = use_heap ? ub : 0u, aux_max = use_aux ? ub : 0u;
+            const uint32_t heap_growth = heap_max < cur_e.heap_upper_bound ? 0u : heap_max - cur_e.heap_upper_bound;
+            const uint32_t aux_growth = aux_max < cur_e.aux_heap_upper_bound ? 0u : aux_max - cur_e.aux_heap_upper_bound;
+            uint32_t growth_cost = (use_heap && is_far_return) ? heap_growth : 0u;
+            if (use_aux && is_far_return) growth_cost = aux_growth;
+            const bool uf = ergs_left < growth_cost;
+            uint32_t ergs_after = uf ? 0u : ergs_left - growth_cost;
+            if (is_local) ergs_after = ergs_left;
+            const bool non_local_panic = (exceptions_collapsed || uf || is_ret_panic) && is_far_return;
+            if (non_local_panic) p = VmFatPtr{0, 0, 0, 0};
+            const uint64_t ergs_sum = (uint64_t)ergs_after + nctx.ergs_remaining;
+            if (ergs_sum >> 32) checks |= ZKC_VM_CHK_CALLSTACK;
+            nctx.ergs_remaining = (uint32_t)ergs_sum;
+            if (is_local) { nctx.heap_upper_bound = cur_e.heap_upper_bound; nctx.aux_heap_upper_bound = cur_e.aux_heap_upper_bound; }
+            const bool should_revert = is_revert || is_ret_panic || non_local_panic;
+            perform_revert = should_revert;
+            bool head_is_fwd_tail = true, head_is_tail = true;
+            for (int i = 0; i < 4; i++) {
+                head_is_fwd_tail &= cur_e.reverted_queue_head[i] == cur_e.log_queue_forward_tail[i];
+                head_is_tail &= nctx.reverted_queue_head[i] == cur_e.reverted_queue_tail[i];
+            }
+            const bool ret_ok = is_ok && !non_local_panic;
+            if ((should_revert && !head_is_fwd_tail) || (ret_ok && !head_is_tail)) checks |= ZKC_VM_CHK_ROLLBACK_QUEUE;
+            if (should_revert) {
+                d.fwd_tail_kind = 2;
+                for (int i = 0; i < 4; i++) d.fwd_tail[i] = cur_e.reverted_queue_tail[i];
+                d.fwd_len = cur_e.log_queue_forward_part_length + cur_e.reverted_queue_segment_len;
+            }
+            if (ret_ok) {
+                for (int i = 0; i < 4; i++) nctx.reverted_queue_head[i] = cur_e.reverted_queue_head[i];
+                nctx.reverted_queue_segment_len = popped_seg_len + cur_e.reverted_queue_segment_len;
+            }
+            const bool use_label = is_to_label && is_local;
+            const uint32_t ok_pc = use_label ? imm0 : nctx.pc, eh_pc = use_label ? imm0 : cur_e.exception_handler_loc;
+            nctx.pc = should_revert ? eh_pc : ok_pc;
+            d.far_ret = is_far_return;
+            d.r1_val = reg_zero();
+            d.r1_val.is_pointer = 1;
+            d.r1_val.value[0] = p.offset; d.r1_val.value[1] = p.page; d.r1_val.value[2] = p.start; d.r1_val.value[3] = p.length;
+            is_panic_out = is_ret_panic || non_local_panic;
+            if (is_far_return) { d.set_u128 = 1; for (int i = 0; i < 4; i++) d.u128[i] = 0; }
+            if (s.context_stack_depth == 0) checks |= ZKC_VM_CHK_CALLSTACK;
+            d.depth = s.context_stack_depth - 1;
+            cap_code = VM_CAP_CALLSTACK_WITNESS;
+            if constexpr (SIM) { cap_sim = prev_sponge + 8; sim->ev_kind = should_revert ? 3 : 2; }
+        }
+        // the callstack sponge: 4 absorptions of the saved frame's encoding (call_ret.rs:176-284)
+        uint64_t enc[32], st12[12], in8[8];
+        vm_context_encode(old_entry, enc);
+        for (int r = 0; r < 4; r++) {
+            for (int i = 0; i < 8; i++) in8[i] = enc[8 * r + i];
+            vm_job<SIM>(1 + r, d, penc, in8, r == 0 ? cap_sim : st12 + 8, r == 0 ? cap_code : (uint32_t)r,
+                        r == 3 ? (apply_ret ? VM_CHK_CUR_STACK : VM_CHK_NEXT_STACK) : VM_CHK_NONE, st12);
+        }
+        if constexpr (SIM) {
+            if (apply_ret) {
+                bool same = true;
+                for (int i = 0; i < 12; i++) same &= st12[i] == s.stack_sponge_state[i];
+                if (!same) checks |= ZKC_VM_CHK_CALLSTACK;
+                for (int i = 0; i < 12; i++) so->stack[i] = prev_sponge[i];
+            } else for (int i = 0; i < 12; i++) so->stack[i] = st12[i];
+        }
+        d.ctx_replaced = apply_near ? 1u : 2u;
+        set_flags = true; nf0 = is_panic_out && apply_ret; nf1 = 0; nf2 = 0;
+        if (wr) {
+            uint64_t f[42];
+            vm_flatten_record(nctx, f);
+            for (int i = 0; i < 42; i++) TR(ZKC_VM_OP_AUX + i) = f[i];
+            TR(ZKC_VM_OP_AUX + 42) = apply_near; TR(ZKC_VM_OP_AUX + 43) = apply_ret; TR(ZKC_VM_OP_AUX + 44) = is_panic_out;
+            TR(ZKC_VM_OP_AUX + 45) = perform_revert;
+        }
     }
     // ---- state diffs ---------------------------------------------------------------------------------------------------
-    d.val0.is_pointer = d0_is_ptr; d.val1.is_pointer = 0;
+    // dst0 / dst1 are dot products of (flag, candidate) pairs (cycle.rs:199-246): zero when no candidate's flag is set
+    const bool dst0_any = dst0_mem_capable || dst0_reg_only;
+    d.val0.is_pointer = dst0_any ? d0_is_ptr : 0u; d.val1.is_pointer = write_dst1 ? d1_is_ptr : 0u;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { d.val0.value[i] = d0.v[i]; d.val1.value[i] = d1.v[i]; }
+    for (int i = 0; i < 8; i++) { d.val0.value[i] = dst0_any ? d0.v[i] : 0u; d.val1.value[i] = write_dst1 ? d1.v[i] : 0u; }
     const bool perform_mem_write = dst0_mem && dst0_mem_capable;
-    vm_push<SIM>(2, perform_mem_write, d, q, penc, ts0 + 3, stack_page, dst_index, 1, d.val0);
-    if constexpr (SIM) { if (perform_mem_write && stack_page == mem->stack_page) mem->stack[dst_index] = d.val0; }
+    vm_push<SIM>(2, perform_mem_write, d, so, penc, last_memq, ts0 + 3, stack_page, dst_index, 1, d.val0);
+    if constexpr (SIM) { if (perform_mem_write) sim_write(*sim, stack_page, dst_index, d.val0); }
+    if constexpr (!SIM) { if (last_memq >= 0) d.chk |= VM_CHK_NEXT_MEMQ << (4 * last_memq); }
     const bool dst0_update_register = dst0_reg_only || (!dst0_mem && dst0_mem_capable);
     if (dst0_update_register) d.idx0 = dst0_r;
     if (write_dst1) d.idx1 = dst1_r;
     d.flags[0] = set_flags ? nf0 : f0; d.flags[1] = set_flags ? nf1 : f1; d.flags[2] = set_flags ? nf2 : f2;
     d.pending = new_pending;
     if (wr) {
-        TR(ZKC_VM_DST0) = d.val0.is_pointer; TR(ZKC_VM_DST1) = 0;
+        TR(ZKC_VM_DST0) = d.val0.is_pointer; TR(ZKC_VM_DST1) = d.val1.is_pointer;
 #pragma unroll
         for (int i = 0; i < 8; i++) { TR(ZKC_VM_DST0 + 1 + i) = d.val0.value[i]; TR(ZKC_VM_DST1 + 1 + i) = d.val1.value[i]; }
         TR(ZKC_VM_PERFORM_DST0_MEMORY_WRITE) = perform_mem_write; TR(ZKC_VM_DST0_UPDATE_REGISTER) = dst0_update_register;
+        TR(ZKC_VM_DST1_UPDATE_REGISTER) = write_dst1;
 #pragma unroll
         for (int i = 0; i < 3; i++) TR(ZKC_VM_FLAGS_OUT + i) = d.flags[i];
-        TR(ZKC_VM_PENDING_EXCEPTION_OUT) = d.pending; TR(ZKC_VM_PC_OUT) = d.pc; TR(ZKC_VM_ERGS_OUT) = d.ergs;
+        const bool rep = d.ctx_replaced != 0;
+        TR(ZKC_VM_PENDING_EXCEPTION_OUT) = d.pending; TR(ZKC_VM_PC_OUT) = rep ? nctx.pc : d.pc; TR(ZKC_VM_ERGS_OUT) = rep ? nctx.ergs_remaining : d.ergs;
+        TR(ZKC_VM_HEAP_BOUND_OUT) = rep ? nctx.heap_upper_bound : d.heap_bound; TR(ZKC_VM_AUX_HEAP_BOUND_OUT) = rep ? nctx.aux_heap_upper_bound : d.aux_bound;
+        TR(ZKC_VM_MEMQ_LENGTH_OUT) = d.memq_len; TR(ZKC_VM_DEPTH_OUT) = d.depth;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            // the forward tail a log produces is a sponge output: taken from the following snapshot (verified by the sponge launch)
+            uint64_t ft = d.fwd_tail_kind == 2 ? d.fwd_tail[i] : ctx.log_queue_forward_tail[i];
+            if (d.fwd_tail_kind == 1) {
+                if constexpr (SIM) ft = so->fwd_tail[i];
+                else ft = next->current_context.log_queue_forward_tail[i];
+            }
+            TR(ZKC_VM_FORWARD_TAIL_OUT + i) = ft;
+            TR(ZKC_VM_ROLLBACK_HEAD_OUT + i) = rep ? nctx.reverted_queue_head[i] : d.rb_head[i];
+        }
+        TR(ZKC_VM_FORWARD_TAIL_OUT + 4) = d.fwd_len; TR(ZKC_VM_ROLLBACK_HEAD_OUT + 4) = rep ? nctx.reverted_queue_segment_len : d.rb_len;
     }
 #undef TR
 #undef TYPE
@@ -677,13 +1165,29 @@ __host__ __device__ constexpr VmMask vm_mask_set(VmMask m, int lo, int n) {
     for (int i = lo; i < lo + n; i++) m.w[i >> 5] |= 1u << (i & 31);
     return m;
 }
-// words that may only change through an explicit flag of the delta: everything that is not padding, not a register,
-// not one of the per-cycle scalars (those are compared with their expected value) and not the memory queue state
+// the words of the current context a cycle that keeps its frame may NOT change: everything except the alignment hole
+// and the scalars / queue ends that are compared with their expected values
+__host__ __device__ constexpr VmMask vm_ctx_keep_mask() {
+    VmMask m{};
+    m = vm_mask_set(m, VW(current_context), (int)(sizeof(zkc_vm_context) / 4));
+    m = vm_mask_clear(m, VWC(aux_heap_upper_bound) + 1, 1);  // alignment hole in front of reverted_queue_head
+    m = vm_mask_clear(m, VWC(pc), 1);
+    m = vm_mask_clear(m, VWC(sp), 1);
+    m = vm_mask_clear(m, VWC(ergs_remaining), 1);
+    m = vm_mask_clear(m, VWC(heap_upper_bound), 2);
+    m = vm_mask_clear(m, VWC(reverted_queue_head), 8);
+    m = vm_mask_clear(m, VWC(reverted_queue_segment_len), 1);
+    m = vm_mask_clear(m, VWC(log_queue_forward_part_length), 1);
+    m = vm_mask_clear(m, VWC(log_queue_forward_tail), 8);
+    return m;
+}
+// words outside the context that may only change through an explicit flag of the delta: not padding, not a register,
+// not one of the per-cycle scalars (compared with their expected value), not a sponge-derived queue state
 __host__ __device__ constexpr VmMask vm_keep_mask() {
     VmMask m{};
     m = vm_mask_set(m, 0, VM_WORDS);
     m = vm_mask_clear(m, VW(_pad), VW(current_context) - VW(_pad));  // _pad + the alignment hole behind it
-    m = vm_mask_clear(m, VWC(aux_heap_upper_bound) + 1, 1);  // alignment hole in front of reverted_queue_head
+    m = vm_mask_clear(m, VW(current_context), (int)(sizeof(zkc_vm_context) / 4));
     m = vm_mask_clear(m, VW(previous_code_word), 8);
     m = vm_mask_clear(m, VW(registers), 9 * ZKC_VM_REGISTERS);
     m = vm_mask_clear(m, VW(flags), 3);
@@ -692,19 +1196,20 @@ __host__ __device__ constexpr VmMask vm_keep_mask() {
     m = vm_mask_clear(m, VW(previous_super_pc), 1);
     m = vm_mask_clear(m, VW(pending_exception), 1);
     m = vm_mask_clear(m, VW(memory_queue_length), 1);
-    m = vm_mask_clear(m, VWC(pc), 1);
-    m = vm_mask_clear(m, VWC(sp), 1);
-    m = vm_mask_clear(m, VWC(ergs_remaining), 1);
+    m = vm_mask_clear(m, VW(context_stack_depth), 1);
     m = vm_mask_clear(m, VW(memory_queue_state), 24);
+    m = vm_mask_clear(m, VW(stack_sponge_state), 24);
     return m;
 }
-__host__ __device__ constexpr VmMask vm_memq_mask() {
-    VmMask m{};
-    return vm_mask_set(m, VW(memory_queue_state), 24);
-}
+__host__ __device__ constexpr VmMask vm_memq_mask() { return vm_mask_set(VmMask{}, VW(memory_queue_state), 24); }
+__host__ __device__ constexpr VmMask vm_stack_mask() { return vm_mask_set(VmMask{}, VW(stack_sponge_state), 24); }
+__host__ __device__ constexpr VmMask vm_fwd_tail_mask() { return vm_mask_set(VmMask{}, VWC(log_queue_forward_tail), 8); }
 static_assert(offsetof(zkc_vm_context, reverted_queue_head) == offsetof(zkc_vm_context, aux_heap_upper_bound) + 8, "context hole");
 template <int K> struct VmKeepWord { static constexpr uint32_t value = vm_keep_mask().w[K]; };
+template <int K> struct VmCtxKeepWord { static constexpr uint32_t value = vm_ctx_keep_mask().w[K]; };
 template <int K> struct VmMemqWord { static constexpr uint32_t value = vm_memq_mask().w[K]; };
+template <int K> struct VmStackWord { static constexpr uint32_t value = vm_stack_mask().w[K]; };
+template <int K> struct VmFwdTailWord { static constexpr uint32_t value = vm_fwd_tail_mask().w[K]; };
 #define VM_FOR10(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 
 __device__ __forceinline__ bool reg_equal(const zkc_vm_register &a, const zkc_vm_register &b) {
@@ -713,26 +1218,40 @@ __device__ __forceinline__ bool reg_equal(const zkc_vm_register &a, const zkc_vm
     for (int i = 0; i < 8; i++) eq &= a.value[i] == b.value[i];
     return eq;
 }
+// ExecutionContextRecord equality (the forward-log fields are not part of the record)
+__device__ bool vm_record_equal(const zkc_vm_context &c, const zkc_vm_context &e) {
+    bool eq = true;
+    for (int i = 0; i < 5; i++) eq &= c.this_address[i] == e.this_address[i] && c.caller[i] == e.caller[i] && c.code_address[i] == e.code_address[i];
+    eq &= c.code_page == e.code_page && c.base_page == e.base_page && c.heap_upper_bound == e.heap_upper_bound &&
+          c.aux_heap_upper_bound == e.aux_heap_upper_bound && c.reverted_queue_segment_len == e.reverted_queue_segment_len &&
+          c.pc == e.pc && c.sp == e.sp && c.exception_handler_loc == e.exception_handler_loc && c.ergs_remaining == e.ergs_remaining &&
+          c.is_static_execution == e.is_static_execution && c.is_kernel_mode == e.is_kernel_mode && c.this_shard_id == e.this_shard_id &&
+          c.caller_shard_id == e.caller_shard_id && c.code_shard_id == e.code_shard_id && c.is_local_call == e.is_local_call;
+    for (int i = 0; i < 4; i++)
+        eq &= c.reverted_queue_head[i] == e.reverted_queue_head[i] && c.reverted_queue_tail[i] == e.reverted_queue_tail[i] &&
+              c.context_u128_value_composite[i] == e.context_u128_value_composite[i];
+    return eq;
+}
 
 // scratch of one batch: what the cycle launch leaves for the sponge launches
 struct VmPushScratch {
-    uint32_t *counts;  // [3]
-    uint32_t *lists;   // [3][rows]: the rows whose push k happens, in no particular order
-    uint8_t *mask;     // [rows]
-    uint64_t *enc;     // [rows][3][8]
-    uint64_t *state;   // [rows][3][12]: memory queue state after push k
+    uint32_t *counts;  // [VM_JOB_SLOTS]
+    uint32_t *lists;   // [VM_JOB_SLOTS][rows]: the rows whose slot-k job runs, in no particular order
+    uint32_t *meta;    // [rows][3]: job mask, capacity sources (nibble per slot), checks (nibble per slot)
+    uint64_t *enc;     // [rows][VM_JOB_SLOTS][8]
+    uint64_t *state;   // [rows][VM_JOB_SLOTS][12]: permutation outputs
 };
 
 // Every thread evaluates its cycle from snapshot `row` and checks that snapshot `row + 1` is the result.  The check
 // has two parts.  (1) The warp walks its 32 consecutive snapshot pairs together: lane l compares words l, l+32, ...
 // of snapshot c with snapshot c+1 -- fully coalesced, each snapshot is fetched once -- and the ballots of iteration c
 // (a 294-bit "which words differ" mask) stay with lane c.  (2) The owner then demands that only words its cycle is
-// allowed to change differ, and compares the changed ones (a few scalars, at most two registers) with the values the
-// cycle produced.  The memory queue sponges are deferred: the cycle only emits their 8-word encodings.
+// allowed to change differ, and compares the changed ones (a few scalars, at most two registers, rarely the whole
+// frame) with the values the cycle produced.  The Poseidon2 relations are deferred: the cycle only emits their jobs.
 __global__ void __launch_bounds__(128)
 vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_state *__restrict__ snapshots,
-                 const zkc_vm_cycle_witness *__restrict__ witness, uint64_t *__restrict__ trace, size_t limit, size_t n_instances,
-                 VmPushScratch ps) {
+                 const zkc_vm_cycle_witness *__restrict__ witness, const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw,
+                 uint64_t *__restrict__ trace, size_t limit, size_t n_instances, VmPushScratch ps) {
     const size_t total = limit * n_instances;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = g < total;
@@ -770,14 +1289,16 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
     // ---- the cycle ------------------------------------------------------------------------------------------------------
     VmDev *dev = devs + inst;
     const zkc_vm_state &s = snapshots[idx], &next = snapshots[idx + 1];
-    uint32_t checks = 0, pmask = 0;
+    uint32_t checks = 0, jmask = 0;
     if (valid) {
         if (row == 0 && !vm_state_equal(s, dev->s0)) checks |= ZKC_VM_CHK_SNAPSHOT;  // the hint chain starts at the circuit's own start state
         VmDelta d;
-        checks |= vm_cycle_dev<false>(isa, s, d, witness[g], nullptr, nullptr, ps.enc + g * 24,
+        zkc_vm_context nctx;
+        checks |= vm_cycle_dev<false>(isa, s, d, nctx, witness[g], cws + inst * (size_t)n_cw, n_cw, nullptr, nullptr,
+                                      ps.enc + g * (VM_JOB_SLOTS * 8), &next,
                                       trace ? trace + inst * (size_t)ZKC_VM_NUM_COLS * limit : nullptr, limit, row);
-        pmask = d.push_mask;
-        ps.mask[g] = (uint8_t)pmask;
+        jmask = d.job_mask;
+        ps.meta[g * 3] = jmask; ps.meta[g * 3 + 1] = d.cap_from; ps.meta[g * 3 + 2] = d.chk;
         // ---- (2) is snapshot row + 1 what this cycle produces? ---------------------------------------------------------
         bool bad = false;
         if (d.set_u128) {
@@ -793,26 +1314,57 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
             diff[VW(tx_number_in_block) >> 5] &= ~(1u << (VW(tx_number_in_block) & 31));
             bad |= next.tx_number_in_block != s.tx_number_in_block + 1;
         }
-        uint32_t stray = 0, memq_diff = 0;
-#define X(K) stray |= diff[K] & VmKeepWord<K>::value; memq_diff |= diff[K] & VmMemqWord<K>::value;
+        // which sponge-derived words this cycle's jobs vouch for
+        bool memq_job = false, stack_job = false;
+#pragma unroll
+        for (int k = 0; k < VM_JOB_SLOTS; k++) {
+            const uint32_t c = (d.chk >> (4 * k)) & 15;
+            memq_job |= c == VM_CHK_NEXT_MEMQ; stack_job |= c == VM_CHK_NEXT_STACK;
+        }
+        uint32_t stray = 0, memq_diff = 0, stack_diff = 0, ctx_diff = 0, fwd_diff = 0;
+#define X(K) stray |= diff[K] & VmKeepWord<K>::value; memq_diff |= diff[K] & VmMemqWord<K>::value; \
+             stack_diff |= diff[K] & VmStackWord<K>::value; ctx_diff |= diff[K] & VmCtxKeepWord<K>::value; \
+             fwd_diff |= diff[K] & VmFwdTailWord<K>::value;
         VM_FOR10(X)
 #undef X
         bad |= stray != 0;
-        if (!pmask) bad |= memq_diff != 0;  // otherwise the last sponge of the cycle compares (vm_memq_kernel)
-        uint32_t regdiff = 0;
+        if (!memq_job) bad |= memq_diff != 0;  // otherwise the last memory queue job of the cycle compares (vm_sponge_kernel)
+        const zkc_vm_context &nc = next.current_context;
+        if (!d.ctx_replaced) {
+            bad |= ctx_diff != 0 || stack_diff != 0;
+            bad |= nc.pc != d.pc || nc.sp != d.sp || nc.ergs_remaining != d.ergs || nc.heap_upper_bound != d.heap_bound ||
+                   nc.aux_heap_upper_bound != d.aux_bound || nc.reverted_queue_segment_len != d.rb_len;
 #pragma unroll
-        for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
-            const int lo = VW(registers) + 9 * r;
-            const uint32_t bits = __funnelshift_r(diff[lo >> 5], diff[(lo >> 5) + 1], lo & 31) & 0x1FFu;
-            regdiff |= (bits != 0) << r;
+            for (int i = 0; i < 4; i++) bad |= nc.reverted_queue_head[i] != d.rb_head[i];
+        } else {
+            bad |= !vm_record_equal(nc, nctx);
+            if (d.ctx_replaced == 2) {  // ret: the stack state below the popped frame is the witness'
+                const uint64_t *p = cws[inst * (size_t)n_cw + (d.cw_index < n_cw ? d.cw_index : 0)].previous_sponge_state;
+                for (int i = 0; i < 12; i++) bad |= next.stack_sponge_state[i] != (d.cw_index < n_cw ? p[i] : 0ull);
+            } else if (!stack_job) bad |= stack_diff != 0;
         }
-        const uint32_t may = (d.idx0 ? 1u << (d.idx0 - 1) : 0u) | (d.idx1 ? 1u << (d.idx1 - 1) : 0u);
-        bad |= (regdiff & ~may) != 0;
-        if (d.idx1) bad |= !reg_equal(next.registers[d.idx1 - 1], d.val1);
-        if (d.idx0 && d.idx0 != d.idx1) bad |= !reg_equal(next.registers[d.idx0 - 1], d.val0);
-        bad |= next.pending_exception != d.pending || next.current_context.pc != d.pc || next.current_context.sp != d.sp ||
-               next.current_context.ergs_remaining != d.ergs || next.previous_code_page != d.prev_code_page ||
-               next.previous_super_pc != d.prev_super_pc || next.timestamp != d.timestamp || next.memory_queue_length != d.memq_len;
+        bad |= nc.log_queue_forward_part_length != d.fwd_len;
+        if (d.fwd_tail_kind == 0) bad |= fwd_diff != 0;
+        else if (d.fwd_tail_kind == 2) for (int i = 0; i < 4; i++) bad |= nc.log_queue_forward_tail[i] != d.fwd_tail[i];
+        if (d.far_ret) {
+            bad |= !reg_equal(next.registers[0], d.r1_val);
+            for (int r = 1; r < ZKC_VM_REGISTERS; r++) bad |= !reg_equal(next.registers[r], reg_zero());
+        } else {
+            uint32_t regdiff = 0;
+#pragma unroll
+            for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
+                const int lo = VW(registers) + 9 * r;
+                const uint32_t bits = __funnelshift_r(diff[lo >> 5], diff[(lo >> 5) + 1], lo & 31) & 0x1FFu;
+                regdiff |= (bits != 0) << r;
+            }
+            const uint32_t may = (d.idx0 ? 1u << (d.idx0 - 1) : 0u) | (d.idx1 ? 1u << (d.idx1 - 1) : 0u);
+            bad |= (regdiff & ~may) != 0;
+            if (d.idx1) bad |= !reg_equal(next.registers[d.idx1 - 1], d.val1);
+            if (d.idx0 && d.idx0 != d.idx1) bad |= !reg_equal(next.registers[d.idx0 - 1], d.val0);
+        }
+        bad |= next.pending_exception != d.pending || next.previous_code_page != d.prev_code_page ||
+               next.previous_super_pc != d.prev_super_pc || next.timestamp != d.timestamp || next.memory_queue_length != d.memq_len ||
+               next.context_stack_depth != d.depth;
 #pragma unroll
         for (int i = 0; i < 3; i++) bad |= next.flags[i] != d.flags[i];
 #pragma unroll
@@ -822,18 +1374,20 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
             if (row + 1 < limit) vm_report(dev, row + 1, ZKC_VM_CHK_SNAPSHOT);
             else checks |= ZKC_VM_CHK_SNAPSHOT;
         }
-        if (row + 1 == limit) {  // the state the circuit ends in, as computed (its memory queue state: vm_memq_kernel)
+        if (row + 1 == limit) {  // the state the circuit ends in, as computed (its sponge-derived parts: vm_sponge_kernel)
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&s);
             uint32_t *dst = reinterpret_cast<uint32_t *>(&dev->s_final);
             for (int i = 0; i < VM_WORDS; i++) dst[i] = src[i];
-            vm_apply_delta(dev->s_final, d);
+            vm_apply_delta(dev->s_final, d, nctx);
+            if (d.ctx_replaced == 2 && d.cw_index < n_cw)
+                for (int i = 0; i < 12; i++) dev->s_final.stack_sponge_state[i] = cws[inst * (size_t)n_cw + d.cw_index].previous_sponge_state[i];
         }
         vm_report(dev, row, checks);
     }
-    // ---- rows whose push k happens, for the dense sponge launches ---------------------------------------------------------
+    // ---- rows whose slot-k job runs, for the dense sponge launches ---------------------------------------------------------
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const bool mine = (pmask >> k) & 1;
+    for (int k = 0; k < VM_JOB_SLOTS; k++) {
+        const bool mine = (jmask >> k) & 1;
         const unsigned b = __ballot_sync(0xffffffffu, mine);
         if (!b) continue;
         const int leader = __ffs(b) - 1;
@@ -844,53 +1398,79 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
     }
 }
 
-// push k of every cycle that has one: tail' = P(enc || tail[8..12]), one thread per push, all lanes busy.  The state it
-// starts from is the cycle's previous push, or the snapshot; the last push of a cycle must land on the next snapshot.
+// slot k of every cycle that has one: out = P(enc || capacity), one thread per job, all lanes busy.  The capacity is a
+// previous job's output of the same cycle, zeros, or a queue state of the snapshot / the callstack witness; the output
+// of the last job of a chain must land on the next snapshot (or, for the joins the circuit enforces, on the current one).
 __global__ void __launch_bounds__(128)
-vm_memq_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, VmPushScratch ps, int k, size_t limit, size_t total) {
+vm_sponge_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
+                 const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, VmPushScratch ps, int k, size_t limit, size_t total) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ps.counts[k]) return;
     const size_t g = ps.lists[(size_t)k * total + i];
     const size_t inst = g / limit, row = g - inst * limit, idx = inst * (limit + 1) + row;
-    const uint32_t m = ps.mask[g], before = m & ((1u << k) - 1);
-    const uint64_t *from = before ? ps.state + (g * 3 + (31 - __clz(before))) * 12 : snapshots[idx].memory_queue_state;
+    const uint32_t cap_from = (ps.meta[g * 3 + 1] >> (4 * k)) & 15, chk = (ps.meta[g * 3 + 2] >> (4 * k)) & 15;
+    const zkc_vm_state &s = snapshots[idx];
     uint64_t q[12];
 #pragma unroll
-    for (int j = 0; j < 8; j++) q[j] = ps.enc[(g * 3 + k) * 8 + j];
+    for (int j = 0; j < 8; j++) q[j] = ps.enc[(g * VM_JOB_SLOTS + k) * 8 + j];
+    if (cap_from == VM_CAP_ZERO) {
 #pragma unroll
-    for (int j = 8; j < 12; j++) q[j] = from[j];
+        for (int j = 8; j < 12; j++) q[j] = 0;
+    } else {
+        const uint64_t *from;
+        if (cap_from < VM_JOB_SLOTS) from = ps.state + (g * VM_JOB_SLOTS + cap_from) * 12;
+        else if (cap_from == VM_CAP_MEMQ) from = s.memory_queue_state;
+        else if (cap_from == VM_CAP_STACK) from = s.stack_sponge_state;
+        else {
+            const uint32_t cwi = witness[g].callstack_index;
+            from = cws[inst * (size_t)n_cw + (cwi < n_cw ? cwi : 0)].previous_sponge_state;
+        }
+#pragma unroll
+        for (int j = 8; j < 12; j++) q[j] = from[j];
+    }
     poseidon2_permute(q);
-    uint64_t *to = ps.state + (g * 3 + k) * 12;
+    uint64_t *to = ps.state + (g * VM_JOB_SLOTS + k) * 12;
 #pragma unroll
     for (int j = 0; j < 12; j++) to[j] = q[j];
-    if (m >> (k + 1)) return;
+    if (chk == VM_CHK_NONE) return;
     VmDev *dev = devs + inst;
-    const uint64_t *want = snapshots[idx + 1].memory_queue_state;
+    const zkc_vm_state &next = snapshots[idx + 1];
+    const bool last_row = row + 1 == limit;
+    const uint64_t *want;
+    int n = 12;
+    if (chk == VM_CHK_NEXT_MEMQ) want = next.memory_queue_state;
+    else if (chk == VM_CHK_NEXT_STACK) want = next.stack_sponge_state;
+    else if (chk == VM_CHK_CUR_STACK) want = s.stack_sponge_state;
+    else if (chk == VM_CHK_NEXT_FWD_TAIL) { want = next.current_context.log_queue_forward_tail; n = 4; }
+    else { want = s.current_context.reverted_queue_head; n = 4; }
     bool same = true;
 #pragma unroll
-    for (int j = 0; j < 12; j++) same &= want[j] == q[j];
-    if (!same) vm_report(dev, row + 1 < limit ? row + 1 : row, ZKC_VM_CHK_SNAPSHOT);
-    if (row + 1 == limit)
-        for (int j = 0; j < 12; j++) dev->s_final.memory_queue_state[j] = q[j];
+    for (int j = 0; j < 12; j++) same &= j >= n || want[j] == q[j];
+    if (chk == VM_CHK_CUR_STACK) { if (!same) vm_report(dev, row, ZKC_VM_CHK_CALLSTACK); return; }
+    if (chk == VM_CHK_CUR_RB_HEAD) { if (!same) vm_report(dev, row, ZKC_VM_CHK_ROLLBACK_QUEUE); return; }
+    if (!same) vm_report(dev, last_row ? row : row + 1, ZKC_VM_CHK_SNAPSHOT);
+    if (last_row) {
+        uint64_t *dst = chk == VM_CHK_NEXT_MEMQ ? dev->s_final.memory_queue_state
+                      : chk == VM_CHK_NEXT_STACK ? dev->s_final.stack_sponge_state : dev->s_final.current_context.log_queue_forward_tail;
+        for (int j = 0; j < n; j++) dst[j] = q[j];
+    }
 }
 
-// the 3 x 13 MEMQ_AFTER_* columns of the trace
+// the sponge columns of the trace: 9 enforce flags + 9 x 12 permutation outputs (zeros where a relation is not enforced)
 __global__ void __launch_bounds__(256)
-vm_memq_trace_kernel(const zkc_vm_state *__restrict__ snapshots, VmPushScratch ps, uint64_t *__restrict__ trace, size_t limit, size_t total) {
+vm_sponge_trace_kernel(VmPushScratch ps, uint64_t *__restrict__ trace, size_t limit, size_t total) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total) return;
-    const size_t inst = g / limit, row = g - inst * limit, idx = inst * (limit + 1) + row;
+    const size_t inst = g / limit, row = g - inst * limit;
     uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit + row;
-    const uint32_t m = ps.mask[g];
-    const uint64_t *from = snapshots[idx].memory_queue_state;
-    uint64_t len = snapshots[idx].memory_queue_length;
-    constexpr int COL[3] = {ZKC_VM_MEMQ_AFTER_CODE, ZKC_VM_MEMQ_AFTER_SRC0, ZKC_VM_MEMQ_AFTER_DST0};
+    const uint32_t m = ps.meta[g * 3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        if ((m >> k) & 1) { from = ps.state + (g * 3 + k) * 12; len++; }
+    for (int k = 0; k < ZKC_VM_NUM_SPONGES; k++) {
+        const bool on = k < VM_JOB_SLOTS && ((m >> k) & 1);
+        t[(size_t)(ZKC_VM_SPONGE_ENFORCE + k) * limit] = on;
+        const uint64_t *from = ps.state + (g * VM_JOB_SLOTS + (k < VM_JOB_SLOTS ? k : 0)) * 12;
 #pragma unroll
-        for (int j = 0; j < 12; j++) t[(size_t)(COL[k] + j) * limit] = from[j];
-        t[(size_t)(COL[k] + 12) * limit] = len;
+        for (int j = 0; j < 12; j++) t[(size_t)(ZKC_VM_SPONGE_FINAL + 12 * k + j) * limit] = on ? from[j] : 0ull;
     }
 }
 
@@ -1004,41 +1584,148 @@ vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances)
 }
 
 // ---- out-of-circuit run: one thread per independent VM instance ---------------------------------------------------------
+// Rollback-queue resolution.  A frame's rollback segment is hash-chained BACKWARDS: every revertable log claims a new head
+// h' with H(rollback item, h') == current head (log.rs:351-371, :583-632), a frame that returns ok hands its segment to
+// its parent (the parent's saved head must be the child's tail, ret.rs:396-404) and a frame that reverts must have its
+// head where the forward queue ends (ret.rs:373-383), its tail becoming the new forward tail.  The claimed heads / frame
+// tails are therefore only known once a frame's fate is: its events (own call marker, logs, merged children) are walked
+// from the most recent one back, starting from the required final head.  Pass 1 (resolve) does that and patches the
+// witness; pass 2 replays with the witness given and records the snapshots.
+struct VmLists { VmEntry *entries; long long *first, *last; };
+__device__ void vm_list_merge_into_parent(VmLists &L, size_t child) {
+    if (L.first[child] < 0) return;
+    L.entries[L.first[child]].prev = L.last[child - 1];
+    if (L.first[child - 1] < 0) L.first[child - 1] = L.first[child];
+    L.last[child - 1] = L.last[child];
+    L.first[child] = L.last[child] = -1;
+}
+__device__ void vm_list_walk(VmLists &L, size_t depth, uint64_t (&cur)[4], zkc_vm_cycle_witness *witness, bool resolve, VmSim &sim, bool restore) {
+    for (long long e = L.last[depth]; e >= 0; e = L.entries[e].prev) {
+        VmEntry &en = L.entries[e];
+        if (resolve) for (int i = 0; i < 4; i++) witness[e].rollback[i] = cur[i];
+        if (en.kind == 2) {
+            uint64_t st[12];
+            for (int i = 0; i < 4; i++) { st[i] = en.enc16[i]; st[4 + i] = cur[i]; st[8 + i] = en.cap[i]; }
+            poseidon2_permute(st);
+            for (int i = 0; i < 4; i++) cur[i] = st[i];
+            if (restore && en.slot >= 0) {
+                for (int i = 0; i < 8; i++) sim.storage[en.slot].value[i] = en.prev_value[i];
+                sim.storage[en.slot].written = en.prev_written;
+            }
+        }
+    }
+    L.first[depth] = L.last[depth] = -1;
+}
+
+struct VmSimScratch {
+    zkc_vm_register *pages;            // [n][4][VM_PAGE_WORDS]
+    VmSlot *storage;                   // [n][VM_STORAGE_SLOTS]
+    zkc_vm_callstack_witness *stack;   // [n][VM_SIM_MAX_DEPTH]
+    VmEntry *entries;                  // [n][cycles]
+    long long *first, *last;           // [n][VM_SIM_MAX_DEPTH + 2]
+    uint64_t *root_tails;              // [n][4] in / out
+    uint32_t *n_cw;                    // [n] out
+};
+
 __global__ void __launch_bounds__(32)
 vm_simulate_kernel(const zkc_vm_isa *__restrict__ isa, const zkc_vm_state *__restrict__ initial, const uint32_t *__restrict__ code,
-                   size_t code_words, size_t n_instances, size_t cycles, zkc_vm_register *__restrict__ pages,
-                   zkc_vm_state *__restrict__ snapshots, zkc_vm_cycle_witness *__restrict__ witness, unsigned long long *first_bad,
-                   uint32_t *failed_checks) {
+                   size_t code_words, size_t n_instances, size_t cycles, VmSimScratch sc, zkc_vm_state *__restrict__ snapshots,
+                   zkc_vm_cycle_witness *__restrict__ witness, zkc_vm_callstack_witness *__restrict__ cw_out, uint32_t cw_cap, int resolve,
+                   unsigned long long *first_bad, uint32_t *failed_checks) {
     const size_t inst = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= n_instances) return;
-    VmMemory mem;
-    mem.code = pages + inst * 2 * 65536;
-    mem.stack = mem.code + 65536;
-    for (size_t i = 0; i < code_words && i < 65536; i++) {
-        mem.code[i].is_pointer = 0;
-        for (int j = 0; j < 8; j++) mem.code[i].value[j] = code[(inst * code_words + i) * 8 + j];
-    }
+    VmSim sim;
+    for (int k = 0; k < 4; k++) sim.pages[k] = sc.pages + (inst * 4 + k) * VM_PAGE_WORDS;
+    sim.storage = sc.storage + inst * VM_STORAGE_SLOTS;
+    sim.stack = sc.stack + inst * VM_SIM_MAX_DEPTH;
+    sim.cw_out = cw_out + inst * (size_t)cw_cap; sim.cw_cap = cw_cap; sim.n_cw = 0;
+    sim.ev_kind = 0; sim.overflow = 0;
+    VmLists L;
+    L.entries = sc.entries + inst * cycles;
+    L.first = sc.first + inst * (VM_SIM_MAX_DEPTH + 2); L.last = sc.last + inst * (VM_SIM_MAX_DEPTH + 2);
+    for (uint32_t i = 0; i < VM_SIM_MAX_DEPTH + 2; i++) { L.first[i] = -1; L.last[i] = -1; }
+    for (size_t i = 0; i < (size_t)4 * VM_PAGE_WORDS; i++) sim.pages[0][i] = reg_zero();
+    for (uint32_t i = 0; i < VM_STORAGE_SLOTS; i++) { sim.storage[i].used = 0; sim.storage[i].written = 0; for (int j = 0; j < 8; j++) sim.storage[i].value[j] = 0; }
+    for (size_t i = 0; i < code_words && i < VM_PAGE_WORDS; i++)
+        for (int j = 0; j < 8; j++) sim.pages[0][i].value[j] = code[(inst * code_words + i) * 8 + j];
     zkc_vm_state s = initial[inst];
-    mem.code_page = s.current_context.code_page;
-    mem.stack_page = s.current_context.base_page + 1;
+    sim.page_ids[0] = s.current_context.code_page;
+    sim.page_ids[1] = s.current_context.base_page + 1; sim.page_ids[2] = s.current_context.base_page + 2; sim.page_ids[3] = s.current_context.base_page + 3;
+    uint64_t root_tail[4];
+    for (int i = 0; i < 4; i++) root_tail[i] = sc.root_tails[inst * 4 + i];
+    {   // the frame below the root: the empty context initial_bootloader_state hashes into the stack sponge (loading.rs:96-186)
+        for (int i = 0; i < 4; i++) { s.current_context.reverted_queue_head[i] = root_tail[i]; s.current_context.reverted_queue_tail[i] = root_tail[i]; }
+        zkc_vm_context empty;
+        memset(&empty, 0, sizeof empty);
+        for (int i = 0; i < 4; i++) { empty.reverted_queue_tail[i] = root_tail[i]; empty.reverted_queue_head[i] = root_tail[i]; }
+        empty.is_kernel_mode = 1;
+        sim.stack[0].context = empty;
+        uint64_t enc[32], sp12[12];
+        vm_context_encode(empty, enc);
+        for (int i = 0; i < 12; i++) { sp12[i] = 0; sim.stack[0].previous_sponge_state[i] = 0; }
+        for (int r = 0; r < 4; r++) {
+            for (int i = 0; i < 8; i++) sp12[i] = enc[8 * r + i];
+            poseidon2_permute(sp12);
+        }
+        for (int i = 0; i < 12; i++) s.stack_sponge_state[i] = sp12[i];
+    }
     zkc_vm_state *snaps = snapshots + inst * (cycles + 1);
     zkc_vm_cycle_witness *wit = witness + inst * cycles;
-    snaps[0] = s;
+    if (!resolve) snaps[0] = s;
+    const uint32_t ignore = resolve ? ZKC_VM_CHK_ROLLBACK_QUEUE : 0u;  // the joins cannot hold before the witness is resolved
     for (size_t c = 0; c < cycles; c++) {
         zkc_vm_cycle_witness w;
         memset(&w, 0, sizeof w);
+        if (!resolve) for (int i = 0; i < 4; i++) w.rollback[i] = wit[c].rollback[i];
         VmDelta d;
-        uint64_t q[12];
-        for (int i = 0; i < 12; i++) q[i] = s.memory_queue_state[i];
-        const uint32_t checks = vm_cycle_dev<true>(isa, s, d, w, &mem, q, nullptr, nullptr, 0, 0);
-        vm_apply_delta(s, d);
-        for (int i = 0; i < 12; i++) s.memory_queue_state[i] = q[i];
-        wit[c] = w;
-        snaps[c + 1] = s;
+        zkc_vm_context nctx;
+        VmSimOut so;
+        for (int i = 0; i < 12; i++) { so.memq[i] = s.memory_queue_state[i]; so.stack[i] = s.stack_sponge_state[i]; }
+        const size_t depth = s.context_stack_depth;
+        uint64_t fwd_before[4];
+        for (int i = 0; i < 4; i++) fwd_before[i] = s.current_context.log_queue_forward_tail[i];
+        const uint32_t checks = vm_cycle_dev<true>(isa, s, d, nctx, w, nullptr, 0, &sim, &so, nullptr, nullptr, nullptr, 0, 0) & ~ignore;
+        vm_apply_delta(s, d, nctx);
+        for (int i = 0; i < 12; i++) s.memory_queue_state[i] = so.memq[i];
+        if (d.ctx_replaced) for (int i = 0; i < 12; i++) s.stack_sponge_state[i] = so.stack[i];
+        if (d.fwd_tail_kind == 1) for (int i = 0; i < 4; i++) s.current_context.log_queue_forward_tail[i] = so.fwd_tail[i];
+        if (sim.ev_kind == 1 && depth + 1 < VM_SIM_MAX_DEPTH + 2) {
+            VmEntry &en = L.entries[c];
+            en.kind = 1; en.slot = -1; en.prev = L.last[depth + 1];
+            L.last[depth + 1] = (long long)c;
+            if (L.first[depth + 1] < 0) L.first[depth + 1] = (long long)c;
+        } else if (sim.ev_kind == 4) {
+            L.entries[c] = sim.ev;
+            L.entries[c].prev = L.last[depth];
+            L.last[depth] = (long long)c;
+            if (L.first[depth] < 0) L.first[depth] = (long long)c;
+        } else if (sim.ev_kind == 2 && depth >= 2) vm_list_merge_into_parent(L, depth);
+        else if (sim.ev_kind == 3) {
+            // the reverting frame's final head is the forward tail at this point; its tail becomes the forward tail
+            vm_list_walk(L, depth, fwd_before, wit, resolve != 0, sim, true);
+            if (resolve) {
+                for (int i = 0; i < 4; i++) s.current_context.log_queue_forward_tail[i] = fwd_before[i];
+                if (depth == 1) for (int i = 0; i < 4; i++) root_tail[i] = fwd_before[i];
+            }
+        }
+        if (!resolve) { wit[c] = w; snaps[c + 1] = s; }  // pass 1 writes the witness only through the walks (rollback fields)
         if (checks) {
             atomicOr(failed_checks, checks);
             atomicMin(first_bad, ((unsigned long long)(inst * cycles + c) << 16) | checks);
         }
+    }
+    if (resolve) {
+        // frames still open (and the root after an ok exit): as if they all returned ok, chained from the given tail
+        size_t top = s.context_stack_depth;
+        if (top > VM_SIM_MAX_DEPTH) top = VM_SIM_MAX_DEPTH;
+        for (size_t dd = top; dd >= 2; dd--) vm_list_merge_into_parent(L, dd);
+        if (L.last[1] >= 0) vm_list_walk(L, 1, root_tail, wit, true, sim, false);
+        for (int i = 0; i < 4; i++) sc.root_tails[inst * 4 + i] = root_tail[i];
+    }
+    sc.n_cw[inst] = sim.n_cw;
+    if (sim.overflow) {
+        atomicOr(failed_checks, (uint32_t)ZKC_VM_CHK_UNSUPPORTED_OPCODE);
+        atomicMin(first_bad, ((unsigned long long)(inst * cycles) << 16) | ZKC_VM_CHK_UNSUPPORTED_OPCODE);
     }
 }
 
@@ -1071,10 +1758,12 @@ extern "C" int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form 
 }
 
 extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa,
-                                             const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness, size_t limit,
+                                             const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness,
+                                             const zkc_vm_callstack_witness *callstack_witness, size_t n_callstack_witness, size_t limit,
                                              const zkc_vm_options *options, int on_device, uint64_t *trace, uint64_t *commitments,
                                              zkc_status *statuses) {
     if (!ctx || !ios || !isa || !commitments || !statuses || (limit && n_instances && (!snapshots || !witness)) ||
+        (n_callstack_witness && !callstack_witness) || n_callstack_witness > 0xFFFFFFFFull ||
         limit > 0x0FFFFFFFull || n_instances > 0x00FFFFFFull || limit * n_instances > 0xFFFFFFFFull)
         return ZKC_ERR_INVALID_ARGUMENT;
     if (!n_instances) return ZKC_OK;
@@ -1082,13 +1771,14 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     for (size_t i = 0; i < n_instances; i++) statuses[i] = zkc_status{ZKC_OK, 0, -1, 0, 0};
     const bool in_dev = on_device & ZKC_INPUTS_ON_DEVICE, trace_dev = on_device & ZKC_TRACE_ON_DEVICE;
     ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
-    const size_t rows = limit * n_instances;
+    const size_t rows = limit * n_instances, n_cw = n_callstack_witness * n_instances;
     size_t bytes = zkc_carver::bytes(n_instances, sizeof(VmDev)) + zkc_carver::bytes(1, sizeof(zkc_vm_isa));
-    if (!in_dev) bytes += zkc_carver::bytes(rows + n_instances, sizeof(zkc_vm_state)) + zkc_carver::bytes(rows + 1, sizeof(zkc_vm_cycle_witness));
+    if (!in_dev) bytes += zkc_carver::bytes(rows + n_instances, sizeof(zkc_vm_state)) + zkc_carver::bytes(rows + 1, sizeof(zkc_vm_cycle_witness)) +
+                          zkc_carver::bytes(n_cw + 1, sizeof(zkc_vm_callstack_witness));
     if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ZKC_VM_NUM_COLS * rows, 8);
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
-    bytes += zkc_carver::bytes(4, 4) + zkc_carver::bytes(3 * rows, 4) + zkc_carver::bytes(rows, 1) + zkc_carver::bytes(rows * 24, 8) +
-             zkc_carver::bytes(rows * 36, 8);
+    bytes += zkc_carver::bytes(8, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 3, 4) +
+             zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8);
     void *blk = ctx->scratch(bytes);
     VmDev *h = (VmDev *)ctx->pinned(n_instances * sizeof(VmDev));
     if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
@@ -1107,30 +1797,35 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(disa, isa, sizeof(zkc_vm_isa), cudaMemcpyHostToDevice, s));  // the ISA tables are always host data
     const zkc_vm_state *dsnap = snapshots;
     const zkc_vm_cycle_witness *dwit = witness;
+    const zkc_vm_callstack_witness *dcw = callstack_witness;
     uint64_t *dtrace = trace;
     if (!in_dev && limit) {
         zkc_vm_state *bs = cv.take<zkc_vm_state>(rows + n_instances);
         zkc_vm_cycle_witness *bw = cv.take<zkc_vm_cycle_witness>(rows + 1);
+        zkc_vm_callstack_witness *bc = cv.take<zkc_vm_callstack_witness>(n_cw + 1);
         ZKC_CUDA(ctx, status, cudaMemcpyAsync(bs, snapshots, (rows + n_instances) * sizeof(zkc_vm_state), cudaMemcpyHostToDevice, s));
         ZKC_CUDA(ctx, status, cudaMemcpyAsync(bw, witness, rows * sizeof(zkc_vm_cycle_witness), cudaMemcpyHostToDevice, s));
-        dsnap = bs; dwit = bw;
+        if (n_cw) ZKC_CUDA(ctx, status, cudaMemcpyAsync(bc, callstack_witness, n_cw * sizeof(zkc_vm_callstack_witness), cudaMemcpyHostToDevice, s));
+        dsnap = bs; dwit = bw; dcw = bc;
     }
     if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ZKC_VM_NUM_COLS * rows);
     uint64_t *flat = cv.take<uint64_t>(n_instances * 4 * VM_FLAT_STRIDE);
     VmPushScratch ps;
-    ps.counts = cv.take<uint32_t>(4);
-    ps.lists = cv.take<uint32_t>(3 * rows);
-    ps.mask = cv.take<uint8_t>(rows);
-    ps.enc = cv.take<uint64_t>(rows * 24);
-    ps.state = cv.take<uint64_t>(rows * 36);
-    ZKC_CUDA(ctx, status, cudaMemsetAsync(ps.counts, 0, 16, s));
+    ps.counts = cv.take<uint32_t>(8);
+    ps.lists = cv.take<uint32_t>(VM_JOB_SLOTS * rows);
+    ps.meta = cv.take<uint32_t>(rows * 3);
+    ps.enc = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 8);
+    ps.state = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 12);
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(ps.counts, 0, 32, s));
     ZKC_LAUNCH(ctx, "vm_prologue", vm_prologue_kernel, (unsigned)((n_instances + 31) / 32), 32, 0, d, disa, n_instances);
     if (rows) {
-        ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, disa, dsnap, dwit, dtrace, limit, n_instances, ps);
+        ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, disa, dsnap, dwit, dcw,
+                   (uint32_t)n_callstack_witness, dtrace, limit, n_instances, ps);
         // the lists live on the device: size every sponge launch for the worst case, surplus threads leave at once
-        for (int k = 0; k < 3; k++)
-            ZKC_LAUNCH(ctx, "vm_memq", vm_memq_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, dsnap, ps, k, limit, rows);
-        if (dtrace) ZKC_LAUNCH(ctx, "vm_memq_trace", vm_memq_trace_kernel, (unsigned)((rows + 255) / 256), 256, 0, dsnap, ps, dtrace, limit, rows);
+        for (int k = 0; k < VM_JOB_SLOTS; k++)
+            ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, dsnap, dwit, dcw,
+                       (uint32_t)n_callstack_witness, ps, k, limit, rows);
+        if (dtrace) ZKC_LAUNCH(ctx, "vm_sponge_trace", vm_sponge_trace_kernel, (unsigned)((rows + 255) / 256), 256, 0, ps, dtrace, limit, rows);
     }
     ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 1) / 2), 128, 0, d, flat, n_instances);
     ZKC_CUDA(ctx, status, cudaGetLastError());
@@ -1153,48 +1848,78 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
 }
 
 extern "C" int zkc_main_vm_entry_point(zkc_ctx *ctx, zkc_vm_closed_form *io, const zkc_vm_isa *isa, const zkc_vm_state *snapshots,
-                                       const zkc_vm_cycle_witness *witness, size_t limit, const zkc_vm_options *options,
+                                       const zkc_vm_cycle_witness *witness, const zkc_vm_callstack_witness *callstack_witness,
+                                       size_t n_callstack_witness, size_t limit, const zkc_vm_options *options,
                                        int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status) {
     zkc_status local;
     if (!status) status = &local;
     *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
     if (!io || !commitment) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
-    const int rc = zkc_main_vm_entry_point_batch(ctx, io, 1, isa, snapshots, witness, limit, options, on_device, trace, commitment, status);
+    const int rc = zkc_main_vm_entry_point_batch(ctx, io, 1, isa, snapshots, witness, callstack_witness, n_callstack_witness, limit, options,
+                                                 on_device, trace, commitment, status);
     if (rc == ZKC_ERR_INVALID_ARGUMENT) status->code = rc;
     return rc;
 }
 
 extern "C" int zkc_main_vm_simulate(zkc_ctx *ctx, const zkc_vm_isa *isa, const zkc_vm_state *initial_states, const uint32_t *code,
                                     size_t code_words, size_t n_instances, size_t cycles, zkc_vm_state *snapshots_out,
-                                    zkc_vm_cycle_witness *witness_out, zkc_status *status) {
+                                    zkc_vm_cycle_witness *witness_out, zkc_vm_callstack_witness *callstack_witness_out,
+                                    size_t callstack_capacity, uint32_t *n_callstack_out, uint64_t *rollback_tails_out,
+                                    zkc_status *status) {
     zkc_status local;
     if (!status) status = &local;
     *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
-    if (!ctx || !isa || !initial_states || !code || !snapshots_out || !witness_out || code_words > 65536) {
+    if (!ctx || !isa || !initial_states || !code || !snapshots_out || !witness_out || code_words > 65536 ||
+        (callstack_capacity && !callstack_witness_out) || callstack_capacity > 0xFFFFFFFFull) {
         status->code = ZKC_ERR_INVALID_ARGUMENT;
         return ZKC_ERR_INVALID_ARGUMENT;
     }
     if (!n_instances) return ZKC_OK;
     ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    const size_t n = n_instances;
     const size_t bytes = zkc_carver::bytes(1, sizeof(zkc_vm_isa)) + zkc_carver::bytes(4, 8) +
-                         zkc_carver::bytes(n_instances * 2 * 65536, sizeof(zkc_vm_register));
+                         zkc_carver::bytes(n * 4 * VM_PAGE_WORDS, sizeof(zkc_vm_register)) + zkc_carver::bytes(n * VM_STORAGE_SLOTS, sizeof(VmSlot)) +
+                         zkc_carver::bytes(n * VM_SIM_MAX_DEPTH, sizeof(zkc_vm_callstack_witness)) + zkc_carver::bytes(n * (cycles + 1), sizeof(VmEntry)) +
+                         2 * zkc_carver::bytes(n * (VM_SIM_MAX_DEPTH + 2), 8) + zkc_carver::bytes(n * 4, 8) + zkc_carver::bytes(n, 4) +
+                         zkc_carver::bytes(1, sizeof(zkc_vm_callstack_witness));
     void *blk = ctx->scratch(bytes);
-    unsigned long long *hres = (unsigned long long *)ctx->pinned(32);
+    const size_t hbytes = 32 + n * 32 + n * 4;
+    unsigned long long *hres = (unsigned long long *)ctx->pinned(hbytes);
     if (!blk || !hres) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
+    uint64_t *htails = (uint64_t *)(hres + 4);
+    uint32_t *hncw = (uint32_t *)(htails + 4 * n);
     zkc_carver cv(blk);
     zkc_vm_isa *disa = cv.take<zkc_vm_isa>(1);
     unsigned long long *dres = cv.take<unsigned long long>(4);
-    zkc_vm_register *pages = cv.take<zkc_vm_register>(n_instances * 2 * 65536);
+    VmSimScratch sc;
+    sc.pages = cv.take<zkc_vm_register>(n * 4 * VM_PAGE_WORDS);
+    sc.storage = cv.take<VmSlot>(n * VM_STORAGE_SLOTS);
+    sc.stack = cv.take<zkc_vm_callstack_witness>(n * VM_SIM_MAX_DEPTH);
+    sc.entries = cv.take<VmEntry>(n * (cycles + 1));
+    sc.first = cv.take<long long>(n * (VM_SIM_MAX_DEPTH + 2));
+    sc.last = cv.take<long long>(n * (VM_SIM_MAX_DEPTH + 2));
+    sc.root_tails = cv.take<uint64_t>(n * 4);
+    sc.n_cw = cv.take<uint32_t>(n);
+    zkc_vm_callstack_witness *dummy_cw = cv.take<zkc_vm_callstack_witness>(1);
     cudaStream_t s = ctx->stream;
     hres[0] = ~0ull; hres[1] = 0;
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(disa, isa, sizeof(zkc_vm_isa), cudaMemcpyHostToDevice, s));
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(dres, hres, 16, cudaMemcpyHostToDevice, s));
-    ZKC_CUDA(ctx, status, cudaMemsetAsync(pages, 0, n_instances * 2 * 65536 * sizeof(zkc_vm_register), s));
-    ZKC_LAUNCH(ctx, "vm_simulate", vm_simulate_kernel, (unsigned)((n_instances + 31) / 32), 32, 0, disa, initial_states, code, code_words,
-               n_instances, cycles, pages, snapshots_out, witness_out, dres, (uint32_t *)(dres + 1));
+    // the block's rollback tail each run starts from: the start state's own (resolved by pass 1)
+    ZKC_CUDA(ctx, status, cudaMemcpy2DAsync(sc.root_tails, 32, (const char *)initial_states + offsetof(zkc_vm_state, current_context) +
+                                            offsetof(zkc_vm_context, reverted_queue_tail), sizeof(zkc_vm_state), 32, n, cudaMemcpyDeviceToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(witness_out, 0, n * cycles * sizeof(zkc_vm_cycle_witness), s));
+    zkc_vm_callstack_witness *cwo = callstack_capacity ? callstack_witness_out : dummy_cw;
+    for (int resolve = 1; resolve >= 0; resolve--)
+        ZKC_LAUNCH(ctx, "vm_simulate", vm_simulate_kernel, (unsigned)((n + 31) / 32), 32, 0, disa, initial_states, code, code_words, n, cycles,
+                   sc, snapshots_out, witness_out, cwo, (uint32_t)callstack_capacity, resolve, dres, (uint32_t *)(dres + 1));
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(hres, dres, 16, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(htails, sc.root_tails, n * 32, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(hncw, sc.n_cw, n * 4, cudaMemcpyDeviceToHost, s));
     ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    if (rollback_tails_out) memcpy(rollback_tails_out, htails, n * 32);
+    if (n_callstack_out) memcpy(n_callstack_out, hncw, n * 4);
     const uint32_t checks = (uint32_t)hres[1];
     if (checks) {
         status->failed_checks = checks;

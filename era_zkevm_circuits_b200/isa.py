@@ -18,6 +18,10 @@ COND_ALWAYS, COND_GT, COND_LT, COND_EQ, COND_GE, COND_LE, COND_NE, COND_GT_OR_LT
 TYPE_BITS, VARIANT_BITS, FLAG_BITS, SRC_BITS, DST_BITS = 16, 10, 2, 6, 4
 FULL_DST = (OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_SHIFT, OP_BINOP, OP_PTR)  # can_write_dst0_into_memory
 N_VARIANTS = {OP_CONTEXT: 10, OP_SHIFT: 4, OP_BINOP: 3, OP_PTR: 4}
+LOG_STORAGE_READ, LOG_STORAGE_WRITE, LOG_TO_L1, LOG_EVENT, LOG_PRECOMPILE = range(5)
+RET_OK, RET_REVERT, RET_PANIC = range(3)
+UMA_HEAP_READ, UMA_HEAP_WRITE, UMA_AUX_READ, UMA_AUX_WRITE, UMA_PTR_READ = range(5)
+FORWARD_HEAP, FORWARD_PTR, FORWARD_AUX = 0, 1, 2
 
 
 def props_bits(op, variant=0, flags=0, src=MODE_REG, dst=MODE_REG):
@@ -57,9 +61,19 @@ class Isa:
             add(OP_JUMP, 0, 0, src, MODE_REG, 2)
         for variant in range(10):
             add(OP_CONTEXT, variant, 0, MODE_REG, MODE_REG, 2, kernel=int(variant >= 7), static_ok=int(variant < 7))
-        ret_panic = add(OP_RET, 2, 0, MODE_REG, MODE_REG, 1)
-        for op in (OP_NEAR_CALL, OP_LOG, OP_FAR_CALL, OP_UMA):
-            add(op, 0, 0, MODE_REG, MODE_REG, 5, static_ok=0)
+        for variant in (RET_OK, RET_REVERT, RET_PANIC):
+            for flags in (0, 1):  # to-label
+                add(OP_RET, variant, flags, MODE_REG, MODE_REG, 5)
+        ret_panic = self.index[(OP_RET, RET_PANIC, 0, MODE_REG, MODE_REG)]
+        add(OP_NEAR_CALL, 0, 0, MODE_REG, MODE_REG, 25)
+        for variant in range(5):
+            for flags in (0, 1):  # increment (reads) / increment (writes)
+                add(OP_UMA, variant, flags, MODE_REG, MODE_REG, 6, static_ok=int(variant in (UMA_HEAP_READ, UMA_AUX_READ, UMA_PTR_READ)))
+        for variant in range(5):
+            for flags in (0, 1):  # first message
+                add(OP_LOG, variant, flags, MODE_REG, MODE_REG, 40, kernel=int(variant in (LOG_TO_L1, LOG_PRECOMPILE)),
+                    static_ok=int(variant == LOG_STORAGE_READ))
+        add(OP_FAR_CALL, 0, 0, MODE_REG, MODE_REG, 100, static_ok=1)
         assert nxt[0] <= 2048
         for i in range(nxt[0], 2048):  # unused opcode numbers decode to Invalid with the explicit-panic aux bit
             self.isa.opcode_props[i] = self.isa.opcode_props[0]
@@ -77,6 +91,9 @@ class Isa:
         self.isa.initial_frame_formal_eh_location, self.isa.vm_initial_frame_ergs = 0xFFFF, 0xFFFFFFFF
         self.isa.bootloader_formal_address_low, self.isa.bootloader_max_memory = 0x8001, 1 << 24
         self.isa.vm_max_stack_depth = 1 << 16
+        for i, v in enumerate((0, 1, 2, 3)):  # STORAGE / EVENT / L1_MESSAGE / PRECOMPILE aux bytes
+            self.isa.log_aux_bytes[i] = v
+        self.isa.initial_storage_write_pubdata_bytes, self.isa.l1_message_pubdata_bytes = 64, 88
 
     def encode(self, op, variant=0, flags=0, src=MODE_REG, dst=MODE_REG, cond=COND_ALWAYS, src0=0, src1=0, dst0=0, dst1=0,
                imm0=0, imm1=0):
@@ -98,19 +115,28 @@ def pack_code(opcodes):
     return words
 
 
-def random_program(isa: Isa, n: int, seed: int = 0xC2, with_memory=True):
-    """straight-line mix (restricted to the built opcode subset): 45 % add/sub, 17 % binop, 12 % mul/div,
-    12 % shifts, 6 % ptr, 6 % context, 2 % nop/conditional; 30 % of the arithmetic uses stack / code-page / immediate
-    operands.  The last instruction jumps back to 0, so the program runs for any number of cycles."""
+def random_program(isa: Isa, n: int, seed: int = 0xC2, with_memory=True, full=True):
+    """the C2 instruction mix of SURVEY 8d: 40 % add/sub, 15 % binop, 10 % mul/div, 10 % shifts, 10 % UMA heap / aux heap
+    reads and writes, 5 % jumps, 5 % context / ptr, 3 % log (storage reads / writes, events, L1 messages, precompile calls),
+    2 % near calls into small subroutines that return ok / revert / panic; 30 % of the arithmetic uses stack / code-page /
+    immediate operands, 10 % of the instructions are conditional.  `n` instructions: a main body that ends with a jump
+    back to 0 (so the program runs for any number of cycles) followed by the subroutines.  r14 / r15 are reserved for
+    storage keys and heap offsets (each UMA / log is preceded by the immediate load of its address, counted as an add).
+    full=False restricts the mix to the arithmetic / addressing subset (no uma / log / calls)."""
     r = splitmix64(seed, 8 * n, 0).reshape(n, 8)
+    n_subs = max(1, n // 64) if full else 0
+    sub_len = 6
+    n_main = n - n_subs * sub_len
+    assert n_main >= 8
     ops = []
-    for i in range(n - 1):
-        k = int(r[i, 0] % 100)
-        src0, src1, dst0, dst1 = (int(r[i, j] % 14) + 2 for j in (1, 2, 3, 4))  # r2..r15: r1 keeps the calldata pointer
+
+    def arith(i, k, allow_mem=True):
+        src0, src1 = (int(r[i, j] % 14) + 2 for j in (1, 2))
+        dst0, dst1 = (int(r[i, j] % 12) + 2 for j in (3, 4))  # r2..r13: r1 keeps the calldata pointer, r14 / r15 are reserved
         flags = int(r[i, 5] % 4)
         cond = COND_ALWAYS if int(r[i, 6] % 10) else int(r[i, 6] >> 8) % 8
         src, dst, imm0, imm1 = MODE_REG, MODE_REG, 0, 0
-        if with_memory and int(r[i, 7] % 10) < 3:
+        if with_memory and allow_mem and int(r[i, 7] % 10) < 3:
             m = int(r[i, 7] >> 8) % 5
             if m == 0:
                 src, imm0 = MODE_IMM16, int(r[i, 7] >> 16) & 0xFFFF
@@ -122,19 +148,57 @@ def random_program(isa: Isa, n: int, seed: int = 0xC2, with_memory=True):
                 dst, dst0, imm1 = MODE_STACK_ABS, 0, int(r[i, 7] >> 16) % 64
             else:
                 src, src0, imm0, dst, dst0, imm1 = MODE_STACK_OFFSET, 0, int(r[i, 7] >> 16) % 16, MODE_PUSH_POP, 0, 1
-        if k < 45:
-            ops.append(isa.encode(OP_ADD if k % 2 else OP_SUB, 0, flags, src, dst, cond, src0, src1, dst0, imm0=imm0, imm1=imm1))
-        elif k < 62:
-            ops.append(isa.encode(OP_BINOP, k % 3, flags, src, dst, cond, src0, src1, dst0, imm0=imm0, imm1=imm1))
-        elif k < 74:
-            ops.append(isa.encode(OP_MUL if k % 2 else OP_DIV, 0, flags, src, dst, cond, src0, src1, dst0, dst1, imm0, imm1))
-        elif k < 86:
-            ops.append(isa.encode(OP_SHIFT, k % 4, flags, src, dst, cond, src0, src1, dst0, imm0=imm0, imm1=imm1))
-        elif k < 92:  # ptr.add / ptr.shrink of the calldata pointer by a small immediate never panics
-            ops.append(isa.encode(OP_PTR, 0, 1, MODE_IMM16, MODE_REG, COND_ALWAYS, src1=1, dst0=dst0, imm0=int(r[i, 7] % 7)))
-        elif k < 98:
-            ops.append(isa.encode(OP_CONTEXT, int(r[i, 7] % 10), 0, MODE_REG, MODE_REG, COND_ALWAYS, src0=src0, dst0=dst0))
+        if k < 40:
+            return isa.encode(OP_ADD if k % 2 else OP_SUB, 0, flags, src, dst, cond, src0, src1, dst0, imm0=imm0, imm1=imm1)
+        if k < 55:
+            return isa.encode(OP_BINOP, k % 3, flags, src, dst, cond, src0, src1, dst0, imm0=imm0, imm1=imm1)
+        if k < 65:
+            return isa.encode(OP_MUL if k % 2 else OP_DIV, 0, flags, src, dst, cond, src0, src1, dst0, dst1, imm0, imm1)
+        return isa.encode(OP_SHIFT, k % 4, flags, src, dst, cond, src0, src1, dst0, imm0=imm0, imm1=imm1)
+
+    i = 0
+    while len(ops) < n_main - 1:
+        room = n_main - 1 - len(ops)
+        k = int(r[i, 0] % 100) if full else int(r[i, 0] % 75) if int(r[i, 0] % 100) < 92 else 80 + int(r[i, 0] % 6)
+        x = int(r[i, 7])
+        dst0 = int(r[i, 3] % 12) + 2
+        if k < 75:
+            ops.append(arith(i, k))
+        elif k < 80:  # short forward jump
+            ops.append(isa.encode(OP_JUMP, 0, 0, MODE_IMM16, imm0=min(len(ops) + 1 + x % 3, n_main - 1)))
+        elif k < 83:  # ptr.add of the calldata pointer by a small immediate never panics
+            ops.append(isa.encode(OP_PTR, 0, 1, MODE_IMM16, MODE_REG, COND_ALWAYS, src1=1, dst0=dst0, imm0=x % 7))
+        elif k < 85:
+            ops.append(isa.encode(OP_CONTEXT, x % 10, 0, MODE_REG, MODE_REG, COND_ALWAYS, src0=int(r[i, 1] % 14) + 2, dst0=dst0))
+        elif k < 95 and room >= 2:  # UMA: offset -> r15, then the access
+            variant = (UMA_HEAP_READ, UMA_HEAP_WRITE, UMA_HEAP_READ, UMA_HEAP_WRITE, UMA_AUX_READ, UMA_AUX_WRITE, UMA_PTR_READ)[x % 7]
+            inc = (x >> 3) & 1
+            off = (x >> 8) % 4096 if (x >> 4) & 1 else ((x >> 8) % 128) * 32  # half of the accesses are aligned
+            if variant == UMA_PTR_READ:  # through the (empty) calldata pointer: a legitimate read beyond the slice
+                ops.append(isa.encode(OP_UMA, variant, inc, src0=1, dst0=dst0, dst1=13))
+            else:
+                ops.append(isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=15, imm0=off))
+                ops.append(isa.encode(OP_UMA, variant, inc, src0=15, src1=int(r[i, 2] % 14) + 2, dst0=dst0, dst1=15))
+        elif k < 98 and room >= 2:  # log: key -> r14, then the query
+            variant = (LOG_STORAGE_READ, LOG_STORAGE_WRITE, LOG_STORAGE_WRITE, LOG_EVENT, LOG_TO_L1, LOG_PRECOMPILE)[x % 6]
+            ops.append(isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=14, imm0=(x >> 8) % 48))
+            src1 = 14 if variant == LOG_PRECOMPILE else int(r[i, 2] % 14) + 2  # a precompile call burns src1[0] ergs
+            ops.append(isa.encode(OP_LOG, variant, (x >> 3) & 1 if variant in (LOG_EVENT, LOG_TO_L1) else 0, src0=14, src1=src1, dst0=dst0))
+        elif k >= 98 and n_subs:
+            sub = n_main + (x % n_subs) * sub_len
+            ops.append(isa.encode(OP_NEAR_CALL, src0=0, imm0=sub, imm1=len(ops) + 1))
         else:
-            ops.append(isa.encode(OP_NOP, cond=cond))
+            ops.append(isa.encode(OP_NOP, cond=int(r[i, 6] >> 8) % 8))
+        i += 1
     ops.append(isa.encode(OP_JUMP, 0, 0, MODE_IMM16, imm0=0))
+    for sidx in range(n_subs):
+        j = n_main + sidx * sub_len
+        x = int(r[j, 7])
+        body = [arith(j + t, int(r[j + t, 0] % 75), allow_mem=False) for t in range(sub_len - 3)]
+        body.append(isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=14, imm0=(x >> 8) % 48))
+        body.append(isa.encode(OP_LOG, (LOG_STORAGE_WRITE, LOG_EVENT)[x % 2], 0, src0=14, src1=int(r[j, 2] % 14) + 2))
+        kind = x % 10
+        body.append(isa.encode(OP_RET, RET_OK if kind < 6 else RET_REVERT if kind < 9 else RET_PANIC))
+        ops += body
+    assert len(ops) == n
     return ops

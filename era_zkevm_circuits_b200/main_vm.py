@@ -13,18 +13,25 @@ from .log_sorter import SorterResult
 
 @dataclass
 class VmCircuitWitness:
-    """fsm_input_output/circuit_inputs/main_vm.rs:64-71.  The WitnessOracle is flattened into per-cycle answers, and
-    the per-cycle VmLocalState snapshots make the instance data parallel."""
+    """fsm_input_output/circuit_inputs/main_vm.rs:64-71.  The WitnessOracle is flattened into per-cycle answers (+ the
+    frames its rets pop, out of line), and the per-cycle VmLocalState snapshots make the instance data parallel."""
     closed_form_input: abi.VmClosedForm
     isa: abi.VmIsa
     snapshots: object  # [limit + 1, 1176] uint8 (numpy) or torch uint8 on the GPU: zkc_vm_state before each cycle + final
-    witness_oracle: object  # [limit, 80] uint8: zkc_vm_cycle_witness per cycle
+    witness_oracle: object  # [limit, 176] uint8: zkc_vm_cycle_witness per cycle
+    callstack_witness: object = None  # [n, 336] uint8: zkc_vm_callstack_witness, indexed by witness.callstack_index
+
+
+def _n_cw(cw):
+    return 0 if cw is None else int(cw.shape[-2])
 
 
 def main_vm_entry_point(engine: Engine, witness: VmCircuitWitness, limit: int, want_trace=True, compare_expected=False,
                         raise_on_unsatisfied=True, trace_out=None) -> SorterResult:
     w = witness
     dev = on_device(w.snapshots, w.witness_oracle)
+    if w.callstack_witness is not None and _n_cw(w.callstack_witness):
+        assert on_device(w.callstack_witness) == dev, "snapshots / witness / callstack witness must live on the same side"
     if trace_out is not None:
         dev |= 2 * on_device(trace_out)
     elif dev:
@@ -40,7 +47,9 @@ def main_vm_entry_point(engine: Engine, witness: VmCircuitWitness, limit: int, w
     opts = abi.VmOptions(int(compare_expected))
     commitment = np.zeros(4, dtype=np.uint64)
     st = abi.Status()
-    rc = engine.lib.zkc_main_vm_entry_point(engine.h, C.byref(io), C.byref(w.isa), ptr(w.snapshots), ptr(w.witness_oracle), limit,
+    n_cw = _n_cw(w.callstack_witness)
+    rc = engine.lib.zkc_main_vm_entry_point(engine.h, C.byref(io), C.byref(w.isa), ptr(w.snapshots), ptr(w.witness_oracle),
+                                            ptr(w.callstack_witness) if n_cw else None, n_cw, limit,
                                             C.byref(opts), dev, ptr(trace), ptr(commitment), C.byref(st))
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE) or (rc and raise_on_unsatisfied):
         raise ZkcError(rc, st, "main_vm_entry_point")
@@ -56,31 +65,45 @@ def main_vm_initial_state(engine: Engine, closed_form_input: abi.VmClosedForm, i
     return out
 
 
-def main_vm_simulate(engine: Engine, isa: abi.VmIsa, initial_states, code, cycles: int):
-    """Out-of-circuit run of n independent VM instances on the GPU.  initial_states: list of abi.VmState;
-    code: [n, code_words, 8] uint32.  Returns torch CUDA tensors (snapshots [n, cycles + 1, 1176] uint8,
-    witness [n, cycles, 80] uint8) and the status."""
+@dataclass
+class VmSimulation:
+    snapshots: object          # torch uint8 [n, cycles + 1, 1176]
+    witness: object            # torch uint8 [n, cycles, 176]
+    callstack_witness: object  # torch uint8 [n, capacity, 336]
+    n_callstack: np.ndarray    # [n] frames popped per instance
+    rollback_tails: np.ndarray  # [n, 4] resolved rollback_queue_tail_for_block per instance
+    status: abi.Status
+
+
+def main_vm_simulate(engine: Engine, isa: abi.VmIsa, initial_states, code, cycles: int, callstack_capacity=None) -> VmSimulation:
+    """Out-of-circuit run of n independent VM instances on the GPU (two passes: the rollback queue is resolved first).
+    initial_states: list of abi.VmState (bootloader start states); code: [n, code_words, 8] uint32."""
     import torch
     n = len(initial_states)
     code = np.ascontiguousarray(code, dtype=np.uint32).reshape(n, -1, 8)
     init = np.frombuffer(b"".join(bytes(s) for s in initial_states), dtype=np.uint8).reshape(n, -1)
     d_init = torch.from_numpy(init.copy()).cuda()
     d_code = torch.from_numpy(code.view(np.int32)).cuda()
+    cap = callstack_capacity if callstack_capacity is not None else max(16, cycles // 16)
     snaps = torch.empty((n, cycles + 1, C.sizeof(abi.VmState)), dtype=torch.uint8, device="cuda")
     wit = torch.empty((n, cycles, C.sizeof(abi.VmCycleWitness)), dtype=torch.uint8, device="cuda")
+    cw = torch.zeros((n, cap, C.sizeof(abi.VmCallstackWitness)), dtype=torch.uint8, device="cuda")
+    n_cw = np.zeros(n, dtype=np.uint32)
+    tails = np.zeros((n, 4), dtype=np.uint64)
     st = abi.Status()
     rc = engine.lib.zkc_main_vm_simulate(engine.h, C.byref(isa), ptr(d_init), ptr(d_code), code.shape[1], n, cycles, ptr(snaps),
-                                         ptr(wit), C.byref(st))
+                                         ptr(wit), ptr(cw), cap, ptr(n_cw), ptr(tails), C.byref(st))
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
         raise ZkcError(rc, st, "zkc_main_vm_simulate")
-    return snaps, wit, st
+    return VmSimulation(snaps, wit, cw, n_cw, tails, st)
 
 
 def main_vm_entry_point_batch(engine: Engine, closed_form_inputs, isa: abi.VmIsa, snapshots, witness_oracle, limit: int,
-                              trace_out=None, compare_expected=False):
+                              trace_out=None, compare_expected=False, callstack_witness=None):
     """n independent instances in one set of launches.  closed_form_inputs: list of abi.VmClosedForm;
-    snapshots [n, limit + 1, 1176], witness_oracle [n, limit, 80] (numpy or torch CUDA uint8); trace_out:
-    optional [n, NUM_COLS, limit] uint64.  Returns (commitments [n, 4], closed forms (updated), statuses, rc)."""
+    snapshots [n, limit + 1, 1176], witness_oracle [n, limit, 176], callstack_witness [n, capacity, 336] (numpy or torch
+    CUDA uint8); trace_out: optional [n, NUM_COLS, limit] uint64.  Returns (commitments [n, 4], closed forms (updated),
+    statuses, rc)."""
     n = len(closed_form_inputs)
     ios = (abi.VmClosedForm * n)(*[abi.VmClosedForm.from_buffer_copy(bytes(c)) for c in closed_form_inputs])
     dev = on_device(snapshots, witness_oracle)
@@ -89,9 +112,10 @@ def main_vm_entry_point_batch(engine: Engine, closed_form_inputs, isa: abi.VmIsa
     commitments = np.zeros((n, 4), dtype=np.uint64)
     statuses = (abi.Status * n)()
     opts = abi.VmOptions(int(compare_expected))
+    n_cw = _n_cw(callstack_witness)
     rc = engine.lib.zkc_main_vm_entry_point_batch(engine.h, C.cast(ios, C.c_void_p), n, C.byref(isa), ptr(snapshots),
-                                                  ptr(witness_oracle), limit, C.byref(opts), dev, ptr(trace_out),
-                                                  ptr(commitments), C.cast(statuses, C.c_void_p))
+                                                  ptr(witness_oracle), ptr(callstack_witness) if n_cw else None, n_cw, limit,
+                                                  C.byref(opts), dev, ptr(trace_out), ptr(commitments), C.cast(statuses, C.c_void_p))
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
         raise ZkcError(rc, statuses[0], "main_vm_entry_point_batch")
     return commitments, ios, statuses, rc

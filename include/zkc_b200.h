@@ -716,13 +716,17 @@ enum zkc_vm_opcode_type { /* zkevm_opcode_defs::Opcode variant order */
     ZKC_OP_INVALID = 0, ZKC_OP_NOP, ZKC_OP_ADD, ZKC_OP_SUB, ZKC_OP_MUL, ZKC_OP_DIV, ZKC_OP_JUMP, ZKC_OP_CONTEXT,
     ZKC_OP_SHIFT, ZKC_OP_BINOP, ZKC_OP_PTR, ZKC_OP_NEAR_CALL, ZKC_OP_LOG, ZKC_OP_FAR_CALL, ZKC_OP_RET, ZKC_OP_UMA
 };
-enum zkc_vm_variant { /* materialize_subvariant_idx of the multi-variant opcodes used by the built subset */
+enum zkc_vm_variant { /* materialize_subvariant_idx of the multi-variant opcodes */
     ZKC_VAR_CONTEXT_THIS = 0, ZKC_VAR_CONTEXT_CALLER, ZKC_VAR_CONTEXT_CODE_ADDRESS, ZKC_VAR_CONTEXT_META,
     ZKC_VAR_CONTEXT_ERGS_LEFT, ZKC_VAR_CONTEXT_SP, ZKC_VAR_CONTEXT_GET_U128, ZKC_VAR_CONTEXT_SET_U128,
     ZKC_VAR_CONTEXT_SET_ERGS_PER_PUBDATA, ZKC_VAR_CONTEXT_INC_TX_NUMBER,
     ZKC_VAR_SHIFT_SHL = 0, ZKC_VAR_SHIFT_SHR, ZKC_VAR_SHIFT_ROL, ZKC_VAR_SHIFT_ROR,
     ZKC_VAR_BINOP_XOR = 0, ZKC_VAR_BINOP_AND, ZKC_VAR_BINOP_OR,
-    ZKC_VAR_PTR_ADD = 0, ZKC_VAR_PTR_SUB, ZKC_VAR_PTR_PACK, ZKC_VAR_PTR_SHRINK
+    ZKC_VAR_PTR_ADD = 0, ZKC_VAR_PTR_SUB, ZKC_VAR_PTR_PACK, ZKC_VAR_PTR_SHRINK,
+    ZKC_VAR_LOG_STORAGE_READ = 0, ZKC_VAR_LOG_STORAGE_WRITE, ZKC_VAR_LOG_TO_L1_MESSAGE, ZKC_VAR_LOG_EVENT, ZKC_VAR_LOG_PRECOMPILE_CALL,
+    ZKC_VAR_RET_OK = 0, ZKC_VAR_RET_REVERT, ZKC_VAR_RET_PANIC,
+    ZKC_VAR_UMA_HEAP_READ = 0, ZKC_VAR_UMA_HEAP_WRITE, ZKC_VAR_UMA_AUX_HEAP_READ, ZKC_VAR_UMA_AUX_HEAP_WRITE, ZKC_VAR_UMA_FAT_PTR_READ,
+    ZKC_VAR_FAR_CALL_NORMAL = 0, ZKC_VAR_FAR_CALL_DELEGATE, ZKC_VAR_FAR_CALL_MIMIC
 };
 enum zkc_vm_src_mode { /* ImmMemHandlerFlags::variant_index */
     ZKC_MODE_REG_ONLY = 0, ZKC_MODE_STACK_PUSH_POP, ZKC_MODE_STACK_OFFSET, ZKC_MODE_STACK_ABSOLUTE, ZKC_MODE_IMM16, ZKC_MODE_CODE_PAGE
@@ -730,6 +734,15 @@ enum zkc_vm_src_mode { /* ImmMemHandlerFlags::variant_index */
 #define ZKC_VM_SET_FLAGS_FLAG_IDX 0       /* SET_FLAGS_FLAG_IDX */
 #define ZKC_VM_SWAP_OPERANDS_FLAG_IDX 1   /* SWAP_OPERANDS_FLAG_IDX_FOR_ARITH_OPCODES */
 #define ZKC_VM_SWAP_OPERANDS_PTR_FLAG_IDX 0 /* SWAP_OPERANDS_FLAG_IDX_FOR_PTR_OPCODE */
+#define ZKC_VM_RET_TO_LABEL_FLAG_IDX 0    /* zkevm_opcode_defs::ret::RET_TO_LABEL_BIT_IDX */
+#define ZKC_VM_UMA_INCREMENT_FLAG_IDX 0   /* UMA_INCREMENT_FLAG_IDX */
+#define ZKC_VM_FIRST_MESSAGE_FLAG_IDX 0   /* FIRST_MESSAGE_FLAG_IDX (log.event / log.to_l1) */
+/* call / ret ABI (zkevm_opcode_defs::definitions::abi, from memory of v1.4.1): the top 64 bits of src0 are
+ * [ergs_passed u32 | forwarding mode byte | shard id byte | constructor call byte | system call byte] */
+#define ZKC_VM_ABI_FORWARDING_MODE_BYTE_IDX 28 /* FAR_CALL_FORWARDING_MODE_BYTE_IDX; ret uses the same byte */
+#define ZKC_VM_FORWARD_USE_HEAP 0              /* FarCallForwardPageType::UseHeap */
+#define ZKC_VM_FORWARD_FAT_POINTER 1           /* ForwardFatPointer */
+#define ZKC_VM_FORWARD_USE_AUX_HEAP 2          /* UseAuxHeap */
 #define ZKC_VM_AUX_KERNEL_MODE 0          /* KERNER_MODE_FLAG_IDX */
 #define ZKC_VM_AUX_CAN_BE_USED_IN_STATIC 1
 #define ZKC_VM_AUX_EXPLICIT_PANIC 2
@@ -753,7 +766,10 @@ typedef struct zkc_vm_isa {
     uint32_t starting_timestamp, starting_base_page;
     uint32_t initial_frame_formal_eh_location, vm_initial_frame_ergs, bootloader_formal_address_low;
     uint32_t bootloader_max_memory, vm_max_stack_depth;
-    uint32_t _pad[2];
+    /* log opcode constants (main_vm/opcodes/log.rs:128-167): aux bytes of storage / event / L1 message / precompile
+     * queries and the pubdata byte counts a rollup storage write / an L1 message pay for */
+    uint32_t log_aux_bytes[4];
+    uint32_t initial_storage_write_pubdata_bytes, l1_message_pubdata_bytes;
 } zkc_vm_isa;
 
 /* VMRegister, base_structures/register/mod.rs:21-24 */
@@ -798,13 +814,28 @@ typedef struct zkc_vm_state {
 #define ZKC_VM_STATE_FLAT 243
 
 /* answers of the WitnessOracle (main_vm/witness_oracle.rs:45-91) one cycle consumes, flattened by the host before
- * the call.  The built opcode subset needs the two memory reads of create_prestate. */
+ * the call.  Only one opcode executes per cycle, so the opcode-specific answers share fields. */
 typedef struct zkc_vm_cycle_witness {
     uint32_t code_word[8];       /* get_memory_witness_for_read of the opcode fetch (main_vm/utils.rs:158-181) */
     uint32_t src0_is_pointer;    /* get_memory_witness_for_read of the src0 operand (main_vm/utils.rs:416-440) */
     uint32_t src0_value[8];
-    uint32_t _pad[3];
+    uint32_t callstack_index;    /* ret: which zkc_vm_callstack_witness answers get_callstack_witness (ret.rs:118-160) */
+    uint32_t refund;             /* log: get_refunds (log.rs:232-252) */
+    uint32_t _pad;
+    uint32_t value_a[8];         /* uma: get_memory_witness_for_read of cell A (uma.rs:277-312);
+                                    log: get_storage_read_witness (log.rs:300-323) */
+    uint32_t value_b[8];         /* uma: cell B (uma.rs:315-356) */
+    uint64_t rollback[4];        /* near_call: get_rollback_queue_tail_witness_for_call (near_call.rs:70-91);
+                                    log: get_rollback_queue_witness (log.rs:351-371) */
 } zkc_vm_cycle_witness;
+
+/* get_callstack_witness (witness_oracle.rs:80-84): the ExecutionContextRecord a ret pops and the callstack sponge
+ * state below it.  Out of line (rets are rare): [n_callstack_witness] per instance, indexed by
+ * zkc_vm_cycle_witness.callstack_index.  The forward-log fields of `context` are not part of the record (ignored). */
+typedef struct zkc_vm_callstack_witness {
+    zkc_vm_context context;
+    uint64_t previous_sponge_state[12];
+} zkc_vm_callstack_witness;
 
 /* ClosedFormInputWitness<F, VmLocalState, VmInputData, VmOutputData>, fsm_input_output/circuit_inputs/main_vm.rs:9-71 */
 typedef struct zkc_vm_closed_form {
@@ -826,7 +857,20 @@ typedef struct zkc_vm_closed_form {
     zkc_vm_state hidden_fsm_output;
 } zkc_vm_closed_form;
 
-/* trace columns of one vm_cycle (main_vm/cycle.rs:28-795 and pre_state.rs:71-519) */
+/* trace columns of one vm_cycle (main_vm/cycle.rs:28-795 and pre_state.rs:71-519): the values of the path the
+ * cycle takes (the reference evaluates every opcode gadget obliviously and selects; the selected values are the
+ * ones that reach the next state).  The nine Poseidon2 relations of a cycle (1 opcode fetch + MAX_SPONGES_PER_CYCLE = 8,
+ * state_diffs.rs:15, cycle.rs:937-957) are columns too: slot k holds the permutation OUTPUT when the relation is
+ * enforced, zeros otherwise.  Slot use:
+ *   0 opcode fetch | 1 src0 read, uma read A, log round 0, callstack round 0 | 2 dst0 write, uma read B, log round 1,
+ *   callstack round 1 | 3 uma write A, log round 2 (forward), callstack round 2 | 4 uma write B, log round 2 (rollback),
+ *   callstack round 3 | 5-7 far call code-hash read | 8 far call decommit (far calls are not built yet).
+ * OP_AUX is one block shared by the opcode families (zero for every other opcode):
+ *   uma       +0 absolute address, +1 cell index, +2 unalignment, +3 page, +4 skip memory access, +5 set panic,
+ *             +6 growth cost, +7 incremented offset, +8 read A (8), +16 read B (8), +24 written A (8), +32 written B (8)
+ *   log       +0 packed forward encoding (20), +20 read value (8), +28 execute, +29 execute rollback, +30 ergs to burn
+ *   near_call / ret   +0 new ExecutionContextRecord (42, flatten order), +42 apply near call, +43 apply ret,
+ *             +44 ret is panic (after the non-local-frame exceptions), +45 perform revert */
 enum zkc_vm_col {
     ZKC_VM_SHOULD_SKIP_CYCLE = 0,    /* pre_state.rs:91-92 */
     ZKC_VM_PENDING_EXCEPTION_IN = 1,
@@ -834,47 +878,59 @@ enum zkc_vm_col {
     ZKC_VM_SUPER_PC = 3,
     ZKC_VM_SUB_PC = 4,
     ZKC_VM_CODE_WORD = 5,            /* 8: after the select with previous_code_word, :177-182 */
-    ZKC_VM_MEMQ_AFTER_CODE = 13,     /* 12 + length */
-    ZKC_VM_OPCODE = 26,              /* 2: after mask_into_nop / mask_into_panic, :216-221 */
-    ZKC_VM_VARIANT = 28,
-    ZKC_VM_CONDITION_IDX = 29,
-    ZKC_VM_CONDITION = 30,
-    ZKC_VM_ERGS_COST = 31,
-    ZKC_VM_OUT_OF_ERGS = 32,
-    ZKC_VM_KERNEL_MODE_EXCEPTION = 33,
-    ZKC_VM_STATIC_EXCEPTION = 34,
-    ZKC_VM_CALLSTACK_IS_FULL = 35,
-    ZKC_VM_EXPLICIT_PANIC = 36,
-    ZKC_VM_MASK_INTO_PANIC = 37,
-    ZKC_VM_MASK_INTO_NOP = 38,
-    ZKC_VM_PROPS = 39,               /* the 48-bit property bit spread after masking, as one integer */
-    ZKC_VM_DIRTY_ERGS_LEFT = 40,
-    ZKC_VM_SRC0_REG = 41, ZKC_VM_SRC1_REG = 42, ZKC_VM_DST0_REG = 43, ZKC_VM_DST1_REG = 44, /* 4-bit encodings after masking */
-    ZKC_VM_IMM0 = 45, ZKC_VM_IMM1 = 46,
-    ZKC_VM_SRC0_PAGE = 47, ZKC_VM_SRC0_INDEX = 48, ZKC_VM_SHOULD_READ_SRC0 = 49, ZKC_VM_SP_AFTER_SRC0 = 50,
-    ZKC_VM_DST0_PAGE = 51, ZKC_VM_DST0_INDEX = 52, ZKC_VM_DST0_PERFORMS_MEMORY_ACCESS = 53, ZKC_VM_NEW_SP = 54,
-    ZKC_VM_SRC0_FROM_MEMORY = 55,    /* 9: is_pointer, value */
-    ZKC_VM_MEMQ_AFTER_SRC0 = 64,     /* 12 + length */
-    ZKC_VM_SWAP_OPERANDS = 77,
-    ZKC_VM_SRC0 = 78,                /* 9: after swap and fat-pointer erasure, :418-472 */
-    ZKC_VM_SRC1 = 87,                /* 9 */
-    ZKC_VM_DST0 = 96,                /* 9: cycle.rs:200-230 */
-    ZKC_VM_DST1 = 105,               /* 9 */
-    ZKC_VM_PERFORM_DST0_MEMORY_WRITE = 114, /* :248-254 */
-    ZKC_VM_DST0_UPDATE_REGISTER = 115,      /* :312 */
-    ZKC_VM_MEMQ_AFTER_DST0 = 116,    /* 12 + length */
-    ZKC_VM_FLAGS_OUT = 129,          /* 3 */
-    ZKC_VM_PENDING_EXCEPTION_OUT = 132,
-    ZKC_VM_PC_OUT = 133,
-    ZKC_VM_ERGS_OUT = 134,
-    ZKC_VM_NUM_COLS = 135
+    ZKC_VM_OPCODE = 13,              /* 2: after mask_into_nop / mask_into_panic, :216-221 */
+    ZKC_VM_VARIANT = 15,
+    ZKC_VM_CONDITION_IDX = 16,
+    ZKC_VM_CONDITION = 17,
+    ZKC_VM_ERGS_COST = 18,
+    ZKC_VM_OUT_OF_ERGS = 19,
+    ZKC_VM_KERNEL_MODE_EXCEPTION = 20,
+    ZKC_VM_STATIC_EXCEPTION = 21,
+    ZKC_VM_CALLSTACK_IS_FULL = 22,
+    ZKC_VM_EXPLICIT_PANIC = 23,
+    ZKC_VM_MASK_INTO_PANIC = 24,
+    ZKC_VM_MASK_INTO_NOP = 25,
+    ZKC_VM_PROPS = 26,               /* the 48-bit property bit spread after masking, as one integer */
+    ZKC_VM_DIRTY_ERGS_LEFT = 27,
+    ZKC_VM_SRC0_REG = 28, ZKC_VM_SRC1_REG = 29, ZKC_VM_DST0_REG = 30, ZKC_VM_DST1_REG = 31, /* 4-bit encodings after masking */
+    ZKC_VM_IMM0 = 32, ZKC_VM_IMM1 = 33,
+    ZKC_VM_SRC0_PAGE = 34, ZKC_VM_SRC0_INDEX = 35, ZKC_VM_SHOULD_READ_SRC0 = 36, ZKC_VM_SP_AFTER_SRC0 = 37,
+    ZKC_VM_DST0_PAGE = 38, ZKC_VM_DST0_INDEX = 39, ZKC_VM_DST0_PERFORMS_MEMORY_ACCESS = 40, ZKC_VM_NEW_SP = 41,
+    ZKC_VM_SRC0_FROM_MEMORY = 42,    /* 9: is_pointer, value */
+    ZKC_VM_SWAP_OPERANDS = 51,
+    ZKC_VM_SRC0 = 52,                /* 9: after swap and fat-pointer erasure, :418-472 */
+    ZKC_VM_SRC1 = 61,                /* 9 */
+    ZKC_VM_DST0 = 70,                /* 9: cycle.rs:200-230 */
+    ZKC_VM_DST1 = 79,                /* 9 */
+    ZKC_VM_PERFORM_DST0_MEMORY_WRITE = 88, /* :248-254 */
+    ZKC_VM_DST0_UPDATE_REGISTER = 89,      /* :312 */
+    ZKC_VM_DST1_UPDATE_REGISTER = 90,
+    ZKC_VM_FLAGS_OUT = 91,           /* 3 */
+    ZKC_VM_PENDING_EXCEPTION_OUT = 94,
+    ZKC_VM_PC_OUT = 95,
+    ZKC_VM_ERGS_OUT = 96,
+    ZKC_VM_HEAP_BOUND_OUT = 97, ZKC_VM_AUX_HEAP_BOUND_OUT = 98,   /* cycle.rs:489-520 */
+    ZKC_VM_MEMQ_LENGTH_OUT = 99,
+    ZKC_VM_DEPTH_OUT = 100,          /* callstack depth after the cycle */
+    ZKC_VM_FORWARD_TAIL_OUT = 101,   /* 4 + length: forward log queue after the cycle, cycle.rs:556-577 */
+    ZKC_VM_ROLLBACK_HEAD_OUT = 106,  /* 4 + segment length: rollback queue head of the current frame, cycle.rs:580-607 */
+    ZKC_VM_SPONGE_ENFORCE = 111,     /* 9 */
+    ZKC_VM_SPONGE_FINAL = 120,       /* 9 x 12 */
+    ZKC_VM_OP_AUX = 228,             /* 48 */
+    ZKC_VM_NUM_COLS = 276
 };
+#define ZKC_VM_NUM_SPONGES 9
+#define ZKC_VM_OP_AUX_COLS 48
 
 #define ZKC_VM_CHK_INVALID_OPCODE (1u << 0)      /* pre_state.rs:291-299 */
-#define ZKC_VM_CHK_UNSUPPORTED_OPCODE (1u << 1)  /* log / near_call / far_call / ret / uma: not built in this engine yet */
+#define ZKC_VM_CHK_UNSUPPORTED_OPCODE (1u << 1)  /* far_call: not built in this engine yet */
 #define ZKC_VM_CHK_SNAPSHOT (1u << 2)            /* the host-supplied per-cycle VmLocalState is not what the previous cycle produces */
 #define ZKC_VM_CHK_DIV_RELATION (1u << 3)        /* mul_div.rs:321-324 (never fails on computed witnesses) */
 #define ZKC_VM_CHK_BOOTLOADER_EXIT (1u << 4)     /* main_vm/mod.rs:119-122 */
+#define ZKC_VM_CHK_ROLLBACK_QUEUE (1u << 5)      /* ret.rs:373-404 (head / tail joins), log.rs:627-632 (claimed rollback head) */
+#define ZKC_VM_CHK_CALLSTACK (1u << 6)           /* call_ret.rs:279-284 (popped frame does not hash to the stack state), :300 (depth
+                                                    underflow), ret.rs:310-311 (ergs overflow), bad callstack_index */
+#define ZKC_VM_CHK_LOG_REFUND (1u << 7)          /* log.rs:256 (refund above the pubdata bytes of an initial write) */
 #define ZKC_ERR_UNSUPPORTED 7
 #define ZKC_ERR_SNAPSHOT_MISMATCH 8
 
@@ -888,17 +944,20 @@ typedef struct zkc_vm_options {
  *               parallel).  snapshots[0] must be the start state the circuit selects (:85-97),
  *               every snapshots[i + 1] is verified against the cycle's own result.
  *   witness   : [limit] oracle answers
+ *   callstack_witness : [n_callstack_witness] frames popped by the rets of the instance (may be NULL when 0)
  *   trace     : column-major [ZKC_VM_NUM_COLS][limit] or NULL */
 int zkc_main_vm_entry_point(zkc_ctx *ctx, zkc_vm_closed_form *io, const zkc_vm_isa *isa, const zkc_vm_state *snapshots,
-                            const zkc_vm_cycle_witness *witness, size_t limit, const zkc_vm_options *options,
-                            int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
+                            const zkc_vm_cycle_witness *witness, const zkc_vm_callstack_witness *callstack_witness,
+                            size_t n_callstack_witness, size_t limit, const zkc_vm_options *options, int on_device,
+                            uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
 /* The same over a batch of `n_instances` independent instances of equal `limit` in ONE set of launches (instances
  * only communicate through their closed-form inputs): ios[n], snapshots [n][limit + 1],
- * witness [n][limit], trace [n][ZKC_VM_NUM_COLS][limit] or NULL, commitments [n][4], statuses [n].  Returns the first
- * non-OK status code. */
+ * witness [n][limit], callstack_witness [n][n_callstack_witness] (equal capacity per instance), trace
+ * [n][ZKC_VM_NUM_COLS][limit] or NULL, commitments [n][4], statuses [n].  Returns the first non-OK status code. */
 int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa,
-                                  const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness, size_t limit,
+                                  const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness,
+                                  const zkc_vm_callstack_witness *callstack_witness, size_t n_callstack_witness, size_t limit,
                                   const zkc_vm_options *options, int on_device, uint64_t *trace, uint64_t *commitments,
                                   zkc_status *statuses);
 
@@ -906,13 +965,22 @@ int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t 
 int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *out);
 
 /* Out-of-circuit run (the role of the external `zk_evm` crate + witness generation): executes `cycles` cycles of
- * `n_instances` independent VMs from their initial states, answering memory reads from a per-instance memory model
- * (code page and stack page of 2^16 words each, code pre-loaded from `code`, [n_instances][code_words][8] limbs), and
- * records what the circuit needs: snapshots [n_instances][cycles + 1] and witness [n_instances][cycles].
- * Device buffers only. */
+ * `n_instances` independent VMs from bootloader start states (registers / flags may be preset), answering memory reads
+ * from a per-instance memory model (code, stack, heap and aux heap pages of the root frame, 2^16 words each, code
+ * pre-loaded from `code`, [n_instances][code_words][8] limbs; storage slots start at zero), and records what the
+ * circuit needs: snapshots [n_instances][cycles + 1], witness [n_instances][cycles] and the popped frames
+ * callstack_witness_out [n_instances][callstack_capacity] (n_callstack_out[n_instances] = how many were used).
+ * The rollback queue is hash-chained BACKWARDS (every revertable log prepends to its frame's segment, log.rs:351-371,
+ * and a reverting frame's segment must start where the forward queue ends, ret.rs:373-383), so the run takes two
+ * passes: the first resolves every claimed rollback head / frame tail, the second records.  The resolved
+ * rollback_queue_tail_for_block of each instance is written to rollback_tails_out [n_instances][4] (equal to the
+ * start state's own tail when the root frame logs nothing) and snapshots[0] carries it.
+ * Device buffers only (rollback_tails_out and n_callstack_out are host memory). */
 int zkc_main_vm_simulate(zkc_ctx *ctx, const zkc_vm_isa *isa, const zkc_vm_state *initial_states, const uint32_t *code,
                          size_t code_words, size_t n_instances, size_t cycles, zkc_vm_state *snapshots_out,
-                         zkc_vm_cycle_witness *witness_out, zkc_status *status);
+                         zkc_vm_cycle_witness *witness_out, zkc_vm_callstack_witness *callstack_witness_out,
+                         size_t callstack_capacity, uint32_t *n_callstack_out, uint64_t *rollback_tails_out,
+                         zkc_status *status);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,7 @@
 /* ORACLE -- TEST INFRASTRUCTURE ONLY (see gl.h header).
  *
- * Sequential CPU restatement of the main VM circuit, value level, for the opcode subset the engine builds
- * (nop, add, sub, jump, binop, mul, div, shifts, ptr, context + every addressing mode of src0 / dst0):
+ * Sequential CPU restatement of the main VM circuit, value level (nop, add, sub, jump, binop, mul, div, shifts, ptr,
+ * context, uma, log, near_call, ret + every addressing mode of src0 / dst0; far_call is not restated yet):
  *   main_vm_entry_point            /root/reference/src/main_vm/mod.rs:47-232
  *   initial_bootloader_state       /root/reference/src/main_vm/loading.rs:13-226
  *   vm_cycle                       /root/reference/src/main_vm/cycle.rs:28-795
@@ -9,9 +9,12 @@
  *   perform_initial_decoding       /root/reference/src/main_vm/decoded_opcode.rs:42-220, :395-527
  *   memory helpers                 /root/reference/src/main_vm/utils.rs:14-522, cycle.rs:799-935
  *   opcodes                        /root/reference/src/main_vm/opcodes/{nop,add_sub,jump,binop,mul_div,shifts,ptr,context}.rs
+ *   uma                            /root/reference/src/main_vm/opcodes/uma.rs:18-1103
+ *   log                            /root/reference/src/main_vm/opcodes/log.rs:16-671
+ *   near_call / ret / callstack    /root/reference/src/main_vm/opcodes/call_ret.rs:24-512, call_ret_impl/{near_call.rs:34-184,
+ *                                  ret.rs:29-479, mod.rs:38-86, far_call.rs:140-262 (FatPtrInABI)}
  *   ExecutionContextRecord::encode /root/reference/src/base_structures/vm_state/saved_context.rs:111-270
- * log / near_call / far_call / ret / uma are NOT restated yet: a cycle that decodes to one of them (this includes
- * every exception, which the circuit masks into ret.panic) reports ZKC_VM_CHK_UNSUPPORTED_OPCODE.
+ * far_call is NOT restated yet: a cycle that decodes to it reports ZKC_VM_CHK_UNSUPPORTED_OPCODE.
  * PARITY UNPINNED: the reference has no main_vm test and the ISA tables (zkevm_opcode_defs) are un-vendored; the
  * tables are input data (zkc_vm_isa) and the bit layout follows main_vm/opcode_bitmask.rs:83-127.
  */
@@ -144,38 +147,117 @@ void orc_vm_initial_bootloader_state(const zkc_vm_closed_form *io, const zkc_vm_
     st->registers[0].value[1] = isa->bootloader_calldata_page;
 }
 
-/* ---- memory model of the out-of-circuit run ------------------------------------------------------------- */
-typedef struct orc_vm_memory {
-    zkc_vm_register *code;  /* 2^16 words */
-    zkc_vm_register *stack; /* 2^16 words */
-    uint32_t code_page, stack_page;
-} orc_vm_memory;
+/* ---- memory / storage model and bookkeeping of the out-of-circuit run ------------------------------------------ */
+#define ORC_VM_PAGE_WORDS 65536
+#define ORC_VM_STORAGE_SLOTS 4096
+typedef struct orc_vm_slot { uint32_t used, written; uint32_t key[8]; uint32_t value[8]; } orc_vm_slot;
+/* one rollback-queue event of a frame: its own call marker or a revertable log */
+typedef struct orc_vm_entry {
+    int64_t prev;
+    uint32_t kind;              /* 1 call marker, 2 log */
+    int32_t slot;               /* storage slot a storage write touched, or -1 */
+    uint32_t prev_value[8];     /* its value (and written marker) before the write */
+    uint32_t prev_written;
+    uint64_t enc16[4], cap[4];  /* rollback packing elements 16..19 and the sponge capacity after round 1 */
+} orc_vm_entry;
+typedef struct orc_vm_sim {
+    zkc_vm_register *pages[4];  /* code, stack, heap, aux heap of the root frame (near calls share them) */
+    uint32_t page_ids[4];
+    orc_vm_slot *storage;
+    zkc_vm_callstack_witness *stack; /* saved frames, [max_depth] */
+    size_t max_depth;
+    zkc_vm_callstack_witness *cw_out; size_t cw_cap, n_cw;
+    /* what the cycle reports to the driver (rollback bookkeeping) */
+    int ev_kind;                /* 0 none, 1 call, 2 ret ok, 3 ret revert / panic, 4 revertable log */
+    orc_vm_entry ev;
+    int overflow;               /* a model limit was hit (depth, storage slots, callstack witness capacity) */
+} orc_vm_sim;
 
-static void memq_push(uint64_t state[12], uint32_t *len, uint32_t ts, uint32_t page, uint32_t index, uint32_t rw,
-                      const zkc_vm_register *v, int execute) {
-    if (!execute) return;
+static zkc_vm_register sim_read(const orc_vm_sim *m, uint32_t page, uint32_t index) {
+    zkc_vm_register z;
+    memset(&z, 0, sizeof z);
+    if (index >= ORC_VM_PAGE_WORDS) return z;
+    for (int k = 0; k < 4; k++) if (page == m->page_ids[k]) return m->pages[k][index];
+    return z;
+}
+static void sim_write(orc_vm_sim *m, uint32_t page, uint32_t index, const zkc_vm_register *v) {
+    if (index >= ORC_VM_PAGE_WORDS) return;
+    for (int k = 1; k < 4; k++) if (page == m->page_ids[k]) { m->pages[k][index] = *v; return; }
+}
+static int sim_slot(orc_vm_sim *m, const uint32_t key[8]) {
+    uint32_t h = 0x9E3779B9u;
+    for (int i = 0; i < 8; i++) h = (h ^ key[i]) * 0x85EBCA6Bu + (h >> 15);
+    for (uint32_t probe = 0; probe < ORC_VM_STORAGE_SLOTS; probe++) {
+        orc_vm_slot *s = &m->storage[(h + probe) % ORC_VM_STORAGE_SLOTS];
+        if (!s->used) { s->used = 1; memcpy(s->key, key, 32); return (int)((h + probe) % ORC_VM_STORAGE_SLOTS); }
+        if (!memcmp(s->key, key, 32)) return (int)((h + probe) % ORC_VM_STORAGE_SLOTS);
+    }
+    m->overflow = 1;
+    return 0;
+}
+
+static void mq_encode(uint32_t ts, uint32_t page, uint32_t index, uint32_t rw, const zkc_vm_register *v, uint64_t enc[8]) {
     zkc_memory_query q;
     memset(&q, 0, sizeof q);
     q.timestamp = ts; q.memory_page = page; q.index = index; q.rw_flag = rw; q.is_ptr = v->is_pointer & 1;
     memcpy(q.value, v->value, 32);
-    uint64_t enc[8];
     orc_memory_query_encode(&q, enc);
-    memcpy(state, enc, 64);
-    orc_poseidon2_permutation(state);
-    (*len)++;
 }
 
 static int prop(uint64_t props, int bit) { return (int)((props >> bit) & 1); }
 
+/* the nine Poseidon2 relations of a cycle (cycle.rs:620-795): slot -> enforced flag + permutation output */
+typedef struct vm_sponges { int enf[ZKC_VM_NUM_SPONGES]; uint64_t fin[ZKC_VM_NUM_SPONGES][12]; } vm_sponges;
+/* absorb-with-replacement of 8 elements over the capacity cap[4] */
+static void sponge_run(vm_sponges *sp, int slot, const uint64_t in8[8], const uint64_t cap[4]) {
+    uint64_t s[12];
+    memcpy(s, in8, 64); memcpy(s + 8, cap, 32);
+    orc_poseidon2_permutation(s);
+    sp->enf[slot] = 1; memcpy(sp->fin[slot], s, 96);
+}
+/* memory queue push (main_vm/utils.rs:194-230, :442-515, cycle.rs:845-905, uma.rs:362-520, :682-812) */
+static void memq_push(vm_sponges *sp, int slot, uint64_t state[12], uint32_t *len, uint32_t ts, uint32_t page, uint32_t index,
+                      uint32_t rw, const zkc_vm_register *v, int execute) {
+    if (!execute) return;
+    uint64_t enc[8];
+    mq_encode(ts, page, index, rw, v, enc);
+    sponge_run(sp, slot, enc, state + 8);
+    memcpy(state, sp->fin[slot], 96);
+    (*len)++;
+}
+
+/* FatPtrInABI::parse_and_validate, far_call.rs:140-196 */
+typedef struct vm_fat_ptr { uint32_t offset, page, start, length; } vm_fat_ptr;
+static vm_fat_ptr fat_ptr_parse(const uint32_t v[8], int as_fresh, uint32_t *upper_bound, int *generally_invalid, int *non_addressable) {
+    vm_fat_ptr p = {v[0], v[1], v[2], v[3]};
+    const uint64_t end = (uint64_t)p.start + p.length;
+    const int range_of = (int)(end >> 32), invalid_slice = p.length < p.offset;
+    const int invalid = (p.offset != 0 && as_fresh) || range_of || invalid_slice;
+    if (invalid) { p.offset = 0; p.page = 0; p.start = 0; p.length = 0; }
+    *upper_bound = (uint32_t)end; *generally_invalid = invalid; *non_addressable = range_of;
+    return p;
+}
+
+static void flatten_record_cols(const zkc_vm_context *c, uint64_t *row, size_t stride, int col) {
+    uint64_t f[42];
+    orc_vm_flatten_context_record(c, f);
+    for (int i = 0; i < 42; i++) row[(size_t)(col + i) * stride] = f[i];
+}
+
 #define T(col) row[(size_t)(col) * stride]
 
-/* one vm_cycle.  mem != NULL: out-of-circuit run (memory reads answered by the model and RECORDED into *w);
- * mem == NULL: witness-driven (reads answered from *w).  row/stride: trace row or NULL.  Returns check bits. */
-static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_cycle_witness *w, orc_vm_memory *mem,
-                         zkc_vm_state *out, uint64_t *row, size_t stride) {
+/* one vm_cycle.  sim != NULL: out-of-circuit run (oracle answers come from the model and are RECORDED into *w / the
+ * callstack witness); sim == NULL: witness-driven (answers come from *w / cw).  row/stride: trace row or NULL.
+ * Returns check bits. */
+static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_cycle_witness *w, const zkc_vm_callstack_witness *cw,
+                         size_t n_cw, orc_vm_sim *sim, zkc_vm_state *out, uint64_t *row, size_t stride) {
     uint32_t checks = 0;
     zkc_vm_state s = *cur;
     zkc_vm_context *ctx = &s.current_context;
+    vm_sponges sp;
+    memset(&sp, 0, sizeof sp);
+    if (sim) sim->ev_kind = 0;
+    if (row) for (int c = 0; c < ZKC_VM_NUM_COLS; c++) T(c) = 0;
     /* ---------------- create_prestate, pre_state.rs:71-519 ---------------- */
     const int should_skip = s.context_stack_depth == 0;
     const int pending = (int)s.pending_exception;
@@ -184,15 +266,15 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
     const uint32_t pc = ctx->pc, pc_plus_one = (pc + 1) & 0xFFFF, super_pc = pc >> 2, sub_pc = pc & 3;
     const int should_read_new = !(s.previous_code_page == ctx->code_page && super_pc == s.previous_super_pc);
     const int should_read_opcode = should_try_read && should_read_new;
-    const uint32_t ts0 = s.timestamp, ts_dst = ts0 + 3;
+    const uint32_t ts0 = s.timestamp, ts_log = ts0 + 1, ts_dst = ts0 + 3;
     const uint32_t next_ts = should_skip ? ts0 : ts0 + 4;
     zkc_vm_register code_val;
     memset(&code_val, 0, sizeof code_val);
     if (should_read_opcode) {
-        if (mem) { code_val = mem->code[super_pc]; code_val.is_pointer = 0; memcpy(w->code_word, code_val.value, 32); }
+        if (sim) { code_val = sim_read(sim, ctx->code_page, super_pc); code_val.is_pointer = 0; memcpy(w->code_word, code_val.value, 32); }
         else memcpy(code_val.value, w->code_word, 32);
-    } else if (mem) memset(w->code_word, 0, 32);
-    memq_push(s.memory_queue_state, &s.memory_queue_length, ts0, ctx->code_page, super_pc, 0, &code_val, should_read_opcode);
+    } else if (sim) memset(w->code_word, 0, 32);
+    memq_push(&sp, 0, s.memory_queue_state, &s.memory_queue_length, ts0, ctx->code_page, super_pc, 0, &code_val, should_read_opcode);
     uint32_t code_word[8];
     memcpy(code_word, should_read_opcode ? code_val.value : s.previous_code_word, 32);
     uint32_t op_lo = code_word[6 - 2 * sub_pc], op_hi = code_word[7 - 2 * sub_pc]; /* :185-206 */
@@ -202,8 +284,6 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
         T(ZKC_VM_SHOULD_SKIP_CYCLE) = (uint64_t)should_skip; T(ZKC_VM_PENDING_EXCEPTION_IN) = (uint64_t)pending;
         T(ZKC_VM_SHOULD_READ_OPCODE) = (uint64_t)should_read_opcode; T(ZKC_VM_SUPER_PC) = super_pc; T(ZKC_VM_SUB_PC) = sub_pc;
         for (int i = 0; i < 8; i++) T(ZKC_VM_CODE_WORD + i) = code_word[i];
-        for (int i = 0; i < 12; i++) T(ZKC_VM_MEMQ_AFTER_CODE + i) = s.memory_queue_state[i];
-        T(ZKC_VM_MEMQ_AFTER_CODE + 12) = s.memory_queue_length;
         T(ZKC_VM_OPCODE) = op_lo; T(ZKC_VM_OPCODE + 1) = op_hi;
     }
     memcpy(s.previous_code_word, code_word, 32);
@@ -259,7 +339,6 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
     const uint32_t dst0_reg_lowest = (dst0_r ? s.registers[dst0_r - 1].value[0] : 0) & 0xFFFF;
     const uint32_t current_sp = ctx->sp, code_page = ctx->code_page;
     const uint32_t stack_page = ctx->base_page + 1, heap_page = ctx->base_page + 2, aux_heap_page = ctx->base_page + 3;
-    (void)heap_page; (void)aux_heap_page;
     const int is_nop = TYPE(ZKC_OP_NOP);
     /* resolve_memory_region_and_index_for_source, utils.rs:237-305 */
     uint32_t src_page, src_index, sp_after_src0;
@@ -290,20 +369,18 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
     zkc_vm_register src0_mem;
     memset(&src0_mem, 0, sizeof src0_mem);
     if (should_read_src0) {
-        if (mem) {
-            if (src_page == mem->code_page) { src0_mem = mem->code[src_index]; src0_mem.is_pointer = 0; }
-            else if (src_page == mem->stack_page) src0_mem = mem->stack[src_index];
+        if (sim) {
+            src0_mem = sim_read(sim, src_page, src_index);
+            if (src_page == code_page) src0_mem.is_pointer = 0;
             w->src0_is_pointer = src0_mem.is_pointer; memcpy(w->src0_value, src0_mem.value, 32);
         } else { src0_mem.is_pointer = w->src0_is_pointer & 1; memcpy(src0_mem.value, w->src0_value, 32); }
-    } else if (mem) { w->src0_is_pointer = 0; memset(w->src0_value, 0, 32); }
-    memq_push(s.memory_queue_state, &s.memory_queue_length, ts0, src_page, src_index, 0, &src0_mem, should_read_src0);
+    } else if (sim) { w->src0_is_pointer = 0; memset(w->src0_value, 0, 32); }
+    memq_push(&sp, 1, s.memory_queue_state, &s.memory_queue_length, ts0, src_page, src_index, 0, &src0_mem, should_read_src0);
     if (row) {
         T(ZKC_VM_SRC0_PAGE) = src_page; T(ZKC_VM_SRC0_INDEX) = src_index; T(ZKC_VM_SHOULD_READ_SRC0) = (uint64_t)should_read_src0;
         T(ZKC_VM_SP_AFTER_SRC0) = sp_after_src0; T(ZKC_VM_DST0_PAGE) = dst_page; T(ZKC_VM_DST0_INDEX) = dst_index;
         T(ZKC_VM_DST0_PERFORMS_MEMORY_ACCESS) = (uint64_t)dst0_mem; T(ZKC_VM_NEW_SP) = new_sp;
         T(ZKC_VM_SRC0_FROM_MEMORY) = src0_mem.is_pointer; for (int i = 0; i < 8; i++) T(ZKC_VM_SRC0_FROM_MEMORY + 1 + i) = src0_mem.value[i];
-        for (int i = 0; i < 12; i++) T(ZKC_VM_MEMQ_AFTER_SRC0 + i) = s.memory_queue_state[i];
-        T(ZKC_VM_MEMQ_AFTER_SRC0 + 12) = s.memory_queue_length;
     }
     zkc_vm_register src0 = SRCM(ZKC_MODE_REG_ONLY) ? draft_src0 : src0_mem;
     if (SRCM(ZKC_MODE_IMM16)) { src0 = zero_reg; src0.value[0] = imm0; }
@@ -328,7 +405,7 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
     int set_flags = 0;
     uint32_t nf[3] = {0, 0, 0};
     int new_pending = 0;
-    if (TYPE(ZKC_OP_NEAR_CALL) || TYPE(ZKC_OP_LOG) || TYPE(ZKC_OP_FAR_CALL) || TYPE(ZKC_OP_RET) || TYPE(ZKC_OP_UMA)) checks |= ZKC_VM_CHK_UNSUPPORTED_OPCODE;
+    if (TYPE(ZKC_OP_FAR_CALL)) checks |= ZKC_VM_CHK_UNSUPPORTED_OPCODE;
     const int sf = FLAG(ZKC_VM_SET_FLAGS_FLAG_IDX);
     if (TYPE(ZKC_OP_ADD) || TYPE(ZKC_OP_SUB)) { /* add_sub.rs:8-166 */
         const int of = TYPE(ZKC_OP_ADD) ? u256_add(a.value, b.value, dst0.value) : u256_sub(a.value, b.value, dst0.value);
@@ -403,24 +480,369 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
         if (set_pubdata) s.ergs_per_pubdata_byte = a.value[0];
         if (inc_tx) s.tx_number_in_block = s.tx_number_in_block + 1;
     }
+    /* state the selected opcode may replace later (cycle.rs:435-610 applies them in this order) */
+    uint32_t ergs_candidate = ergs_left;           /* new_ergs_left_candidates */
+    int replace_callstack = 0;
+    zkc_vm_context new_ctx;                        /* callstacks: the full new current context */
+    uint64_t new_stack_sponge[12];
+    uint32_t new_depth = s.context_stack_depth;
+    int far_return_registers = 0;
+    zkc_vm_register far_return_r1 = zero_reg;
+    int reset_context_u128 = 0;
+    uint64_t draft_memq[12];
+    memcpy(draft_memq, s.memory_queue_state, 96);  /* memory queue after the prestate reads; UMA continues from here */
+    uint32_t draft_memq_len = s.memory_queue_length;
+    int uma_applies = 0;
+    uint64_t uma_memq[12]; uint32_t uma_memq_len = 0;
+    if (TYPE(ZKC_OP_UMA)) { /* uma.rs:18-1002 */
+        const int heap_r = VAR(ZKC_VAR_UMA_HEAP_READ), heap_w = VAR(ZKC_VAR_UMA_HEAP_WRITE), aux_r = VAR(ZKC_VAR_UMA_AUX_HEAP_READ),
+                  aux_w = VAR(ZKC_VAR_UMA_AUX_HEAP_WRITE), ptr_r = VAR(ZKC_VAR_UMA_FAT_PTR_READ);
+        const int increment = FLAG(ZKC_VM_UMA_INCREMENT_FLAG_IDX);
+        const int access_heap = heap_r || heap_w, access_aux = aux_r || aux_w;
+        const int not_a_ptr = ptr_r && !a.is_pointer;
+        /* QuasiFatPtrInUMA::parse_and_validate, :1004-1084 */
+        const uint32_t offset = a.value[0], page = a.value[1], start = a.value[2], length = a.value[3];
+        const int beyond = !(offset < length), skip_legit = beyond && ptr_r;
+        const uint32_t abs_addr = (ptr_r ? start : 0) + offset;
+        const uint64_t inc64 = (uint64_t)offset + 32;
+        const uint32_t incremented = (uint32_t)inc64;
+        const int non_addressable = (int)(inc64 >> 32) || incremented == 0xFFFFFFFFu;
+        const int qp_panic = not_a_ptr || non_addressable;
+        const int qp_skip = not_a_ptr || skip_legit || non_addressable;
+        uint32_t bytes_oob = incremented - length;
+        if (qp_skip || incremented < length) bytes_oob = 0;
+        bytes_oob &= 31;
+        /* heap growth, :110-142 */
+        const uint32_t heap_bound = ctx->heap_upper_bound, aux_bound = ctx->aux_heap_upper_bound;
+        const uint32_t heap_max = access_heap ? incremented : 0, aux_max = access_aux ? incremented : 0;
+        const int heap_uf = heap_max < heap_bound, aux_uf = aux_max < aux_bound;
+        const uint32_t heap_growth = heap_uf ? 0 : heap_max - heap_bound, aux_growth = aux_uf ? 0 : aux_max - aux_bound;
+        const uint32_t new_heap_bound = heap_uf ? heap_bound : heap_max, new_aux_bound = aux_uf ? aux_bound : aux_max;
+        uint32_t growth_cost = access_heap ? heap_growth : 0;
+        if (access_aux) growth_cost = aux_growth;
+        int top_nz = 0;
+        for (int i = 1; i < 8; i++) top_nz |= a.value[i] != 0;
+        const int exc_oob = (access_heap || access_aux) && (top_nz || non_addressable);
+        if (exc_oob) growth_cost = 0xFFFFFFFFu;
+        const int uf = ergs_left < growth_cost;
+        const int set_panic = qp_panic || uf || exc_oob;
+        const uint32_t ergs_after = uf ? 0 : ergs_left - growth_cost;
+        const int skip_mem = qp_skip || set_panic;
+        const int is_read = heap_r || aux_r || ptr_r, is_write = heap_w || aux_w;
+        const uint32_t cell_idx = abs_addr / 32, unalignment = abs_addr % 32;
+        const int unaligned = unalignment != 0;
+        uint32_t mem_page = page;
+        if (access_heap) mem_page = heap_page;
+        if (access_aux) mem_page = aux_heap_page;
+        const uint32_t b_idx = cell_idx + 1; /* wraps */
+        const int read_a = !skip_mem, read_b = unaligned && !skip_mem;
+        zkc_vm_register va = zero_reg, vb = zero_reg;
+        if (sim) {
+            if (read_a) va = sim_read(sim, mem_page, cell_idx);
+            if (read_b) vb = sim_read(sim, mem_page, b_idx);
+            va.is_pointer = 0; vb.is_pointer = 0;
+            memcpy(w->value_a, va.value, 32); memcpy(w->value_b, vb.value, 32);
+        } else {
+            if (read_a) memcpy(va.value, w->value_a, 32); /* masked to zero when not read, :313, :357 */
+            if (read_b) memcpy(vb.value, w->value_b, 32);
+        }
+        uma_applies = 1;
+        memcpy(uma_memq, draft_memq, 96); uma_memq_len = draft_memq_len;
+        /* the sponges run when the opcode applies without panic (apply_any, :955-985); skip_mem covers set_panic */
+        memq_push(&sp, 1, uma_memq, &uma_memq_len, ts0, mem_page, cell_idx, 0, &va, read_a);
+        memq_push(&sp, 2, uma_memq, &uma_memq_len, ts0, mem_page, b_idx, 0, &vb, read_b);
+        /* 64-byte big-endian window over cells A, B (:533-560) */
+        uint8_t bytes[64], word[32], written[64], wbytes[32];
+        for (int i = 0; i < 32; i++) {
+            bytes[i] = (uint8_t)(va.value[7 - i / 4] >> (8 * (3 - i % 4)));
+            bytes[32 + i] = (uint8_t)(vb.value[7 - i / 4] >> (8 * (3 - i % 4)));
+            wbytes[i] = (uint8_t)(b.value[7 - i / 4] >> (8 * (3 - i % 4)));
+        }
+        memcpy(word, bytes + unalignment, 32);
+        /* fat-pointer reads beyond the slice end are zeroed (:562-585): the last bytes_oob bytes */
+        const uint32_t cleanup = ptr_r ? bytes_oob : 0;
+        for (uint32_t i = 0; i < cleanup; i++) word[31 - i] = 0;
+        memcpy(written, bytes, 64);
+        memcpy(written + unalignment, wbytes, 32);
+        const int exec_write = is_write && !skip_mem, exec_write_b = exec_write && unaligned;
+        zkc_vm_register wa = zero_reg, wb = zero_reg;
+        for (int i = 0; i < 32; i++) {
+            wa.value[7 - i / 4] |= (uint32_t)written[i] << (8 * (3 - i % 4));
+            wb.value[7 - i / 4] |= (uint32_t)written[32 + i] << (8 * (3 - i % 4));
+        }
+        memq_push(&sp, 3, uma_memq, &uma_memq_len, ts_dst, mem_page, cell_idx, 1, &wa, exec_write);
+        memq_push(&sp, 4, uma_memq, &uma_memq_len, ts_dst, mem_page, b_idx, 1, &wb, exec_write_b);
+        if (sim) {
+            if (exec_write) sim_write(sim, mem_page, cell_idx, &wa);
+            if (exec_write_b) sim_write(sim, mem_page, b_idx, &wb);
+        }
+        zkc_vm_register read_reg = zero_reg, inc_reg = a;
+        for (int i = 0; i < 32; i++) read_reg.value[7 - i / 4] |= (uint32_t)word[i] << (8 * (3 - i % 4));
+        inc_reg.value[0] = incremented;
+        const int w_inc = is_write && increment;
+        const int no_panic = !set_panic;
+        dst0 = w_inc ? inc_reg : read_reg;
+        dst0_reg_only = no_panic && (is_read || w_inc);
+        write_dst1 = no_panic && is_read && increment;
+        dst1 = inc_reg;
+        new_pending = set_panic;
+        if (access_heap) ctx->heap_upper_bound = new_heap_bound;
+        if (access_aux) ctx->aux_heap_upper_bound = new_aux_bound;
+        ergs_candidate = ergs_after;
+        if (row) {
+            uint64_t *x = &T(ZKC_VM_OP_AUX);
+            x[0] = abs_addr; x[stride] = cell_idx; x[2 * stride] = unalignment; x[3 * stride] = mem_page; x[4 * stride] = (uint64_t)skip_mem;
+            x[5 * stride] = (uint64_t)set_panic; x[6 * stride] = growth_cost; x[7 * stride] = incremented;
+            for (int i = 0; i < 8; i++) {
+                x[(8 + i) * stride] = va.value[i]; x[(16 + i) * stride] = vb.value[i];
+                x[(24 + i) * stride] = exec_write ? wa.value[i] : 0; x[(32 + i) * stride] = exec_write_b ? wb.value[i] : 0;
+            }
+        }
+    }
+    if (TYPE(ZKC_OP_LOG)) { /* log.rs:16-467 */
+        const int st_read = VAR(ZKC_VAR_LOG_STORAGE_READ), st_write = VAR(ZKC_VAR_LOG_STORAGE_WRITE), is_event = VAR(ZKC_VAR_LOG_EVENT),
+                  is_l1 = VAR(ZKC_VAR_LOG_TO_L1_MESSAGE), is_precompile = VAR(ZKC_VAR_LOG_PRECOMPILE_CALL);
+        zkc_log_query q;
+        memset(&q, 0, sizeof q);
+        memcpy(q.address, ctx->this_address, 20);
+        memcpy(q.key, a.value, 32);
+        if (is_precompile && q.key[4] == 0) q.key[4] = heap_page;
+        if (is_precompile && q.key[5] == 0) q.key[5] = heap_page;
+        const int is_rollup = ctx->this_shard_id == 0, write_to_rollup = is_rollup && st_write;
+        const int is_storage = st_read || st_write, nonrevertable = st_read || is_precompile, revertable = !nonrevertable;
+        const uint32_t aux_byte = (is_storage ? isa->log_aux_bytes[0] : 0) + (is_event ? isa->log_aux_bytes[1] : 0) +
+                                  (is_l1 ? isa->log_aux_bytes[2] : 0) + (is_precompile ? isa->log_aux_bytes[3] : 0);
+        const int is_service = FLAG(ZKC_VM_FIRST_MESSAGE_FLAG_IDX);
+        q.tx_number_in_block = s.tx_number_in_block; q.timestamp = ts_log;
+        q.flags = ZKC_LQ_FLAGS(aux_byte, ctx->this_shard_id, revertable, 0, is_service);
+        memcpy(q.written_value, b.value, 32);
+        int slot = -1;
+        if (sim) {
+            w->refund = 0;
+            if (st_write) { slot = sim_slot(sim, q.key); w->refund = sim->storage[slot].written ? isa->initial_storage_write_pubdata_bytes : 0; }
+        }
+        const uint32_t refund = w->refund;
+        if (refund > isa->initial_storage_write_pubdata_bytes) checks |= ZKC_VM_CHK_LOG_REFUND; /* sub_no_overflow, :256 */
+        const uint32_t net_cost = isa->initial_storage_write_pubdata_bytes - refund;
+        uint32_t burn = write_to_rollup ? s.ergs_per_pubdata_byte * net_cost : 0;
+        if (is_precompile) burn = b.value[0];
+        if (is_l1) burn = s.ergs_per_pubdata_byte * isa->l1_message_pubdata_bytes;
+        const int not_enough = ergs_left < burn;
+        const uint32_t ergs_after = not_enough ? 0 : ergs_left - burn;
+        const int execute = !not_enough, execute_rollback = execute && revertable;
+        uint32_t read_value[8] = {0};
+        if (sim) {
+            memset(w->value_a, 0, 32);
+            if (is_storage && execute) {
+                if (slot < 0) slot = sim_slot(sim, q.key);
+                memcpy(w->value_a, sim->storage[slot].value, 32);
+            }
+        }
+        if (is_storage) memcpy(read_value, w->value_a, 32);
+        memcpy(q.read_value, read_value, 32);
+        if (!revertable) memcpy(q.written_value, read_value, 32); /* convention for reads, :328-330 */
+        uint64_t enc[20], cap[4] = {0, 0, 0, 0};
+        orc_log_query_encode(&q, enc);
+        /* construct_hash_relations_for_log_and_new_queue_states, :469-671 */
+        uint64_t in8[8];
+        if (execute) {
+            sponge_run(&sp, 1, enc, cap);
+            sponge_run(&sp, 2, enc + 8, sp.fin[1] + 8);
+            memcpy(in8, enc + 16, 32); memcpy(in8 + 4, ctx->log_queue_forward_tail, 32);
+            sponge_run(&sp, 3, in8, sp.fin[2] + 8);
+        }
+        if (sim) {
+            if (execute_rollback) {
+                sim->ev_kind = 4; sim->ev.kind = 2; sim->ev.slot = -1;
+                memcpy(sim->ev.enc16, enc + 16, 32); sim->ev.enc16[3] = 1; memcpy(sim->ev.cap, sp.fin[2] + 8, 32);
+            }
+            if (st_write && execute) {
+                orc_vm_slot *sl = &sim->storage[slot];
+                sim->ev.slot = slot; memcpy(sim->ev.prev_value, sl->value, 32); sim->ev.prev_written = sl->written;
+                memcpy(sl->value, b.value, 32); sl->written = 1;
+            }
+        }
+        if (execute_rollback) {
+            memcpy(in8, enc + 16, 32); in8[3] = 1; /* update_packing_for_rollback, log_query/mod.rs:52-58 */
+            memcpy(in8 + 4, w->rollback, 32);
+            sponge_run(&sp, 4, in8, sp.fin[2] + 8);
+            if (memcmp(sp.fin[4], ctx->reverted_queue_head, 32)) checks |= ZKC_VM_CHK_ROLLBACK_QUEUE; /* :627-632 */
+            memcpy(ctx->reverted_queue_head, w->rollback, 32);
+            ctx->reverted_queue_segment_len++;
+        }
+        if (execute) { memcpy(ctx->log_queue_forward_tail, sp.fin[3], 32); ctx->log_queue_forward_part_length++; }
+        if (st_read) memcpy(dst0.value, read_value, 32);
+        else dst0.value[0] = (uint32_t)execute; /* precompile call result; selected for every non-read variant, :396-412 */
+        dst0_reg_only = st_read || is_precompile;
+        ergs_candidate = ergs_after;
+        if (row) {
+            uint64_t *x = &T(ZKC_VM_OP_AUX);
+            for (int i = 0; i < 20; i++) x[i * stride] = enc[i];
+            for (int i = 0; i < 8; i++) x[(20 + i) * stride] = read_value[i];
+            x[28 * stride] = (uint64_t)execute; x[29 * stride] = (uint64_t)execute_rollback; x[30 * stride] = burn;
+        }
+    }
+    if (TYPE(ZKC_OP_NEAR_CALL) || TYPE(ZKC_OP_RET)) { /* call_ret.rs:24-512 */
+        const int apply_near = TYPE(ZKC_OP_NEAR_CALL), apply_ret = TYPE(ZKC_OP_RET);
+        /* compute_shared_abi_parts, call_ret_impl/mod.rs:38-86 */
+        const uint32_t fwd_byte = a.value[ZKC_VM_ABI_FORWARDING_MODE_BYTE_IDX / 4] >> (8 * (ZKC_VM_ABI_FORWARDING_MODE_BYTE_IDX % 4)) & 0xFF;
+        const int use_aux = fwd_byte == ZKC_VM_FORWARD_USE_AUX_HEAP, fwd_ptr = fwd_byte == ZKC_VM_FORWARD_FAT_POINTER;
+        const int use_heap = !(use_aux || fwd_ptr);
+        uint32_t upper_bound; int generally_invalid, non_addressable;
+        vm_fat_ptr fp = fat_ptr_parse(a.value, !fwd_ptr, &upper_bound, &generally_invalid, &non_addressable);
+        (void)generally_invalid;
+        zkc_vm_context old_entry, new_entry;
+        uint64_t sponge_from[12];
+        int is_panic_out = 0, perform_revert = 0;
+        uint64_t new_fwd_tail[4]; uint32_t new_fwd_len = ctx->log_queue_forward_part_length;
+        memcpy(new_fwd_tail, ctx->log_queue_forward_tail, 32);
+        if (apply_near) { /* near_call.rs:34-184 */
+            zkc_vm_context cur_e = *ctx;
+            cur_e.pc = pc_plus_one;
+            new_entry = cur_e;
+            memcpy(new_entry.reverted_queue_tail, w->rollback, 32);
+            memcpy(new_entry.reverted_queue_head, w->rollback, 32);
+            new_entry.reverted_queue_segment_len = 0;
+            const uint32_t ergs_passed = a.value[0];
+            const uint32_t to_pass = ergs_passed == 0 ? ergs_left : ergs_passed;
+            const int uf = ergs_left < to_pass;
+            cur_e.ergs_remaining = uf ? 0 : ergs_left - to_pass;
+            new_entry.ergs_remaining = uf ? ergs_left : to_pass;
+            new_entry.pc = imm0; new_entry.exception_handler_loc = imm1; new_entry.is_local_call = 1;
+            old_entry = cur_e;
+            memcpy(sponge_from, s.stack_sponge_state, 96);
+            new_depth = s.context_stack_depth + 1;
+            if (sim) {
+                if (s.context_stack_depth >= sim->max_depth) sim->overflow = 1;
+                else { sim->stack[s.context_stack_depth].context = old_entry; memcpy(sim->stack[s.context_stack_depth].previous_sponge_state, s.stack_sponge_state, 96); }
+                sim->ev_kind = 1; sim->ev.kind = 1; sim->ev.slot = -1;
+            }
+        } else { /* ret.rs:29-479 */
+            const int is_ok = VAR(ZKC_VAR_RET_OK), is_revert = VAR(ZKC_VAR_RET_REVERT), is_ret_panic = VAR(ZKC_VAR_RET_PANIC);
+            const int is_local = (int)ctx->is_local_call, is_far_return = !is_local;
+            zkc_vm_register src0r = a;
+            if (is_ret_panic) src0r = zero_reg;
+            const int is_to_label = FLAG(ZKC_VM_RET_TO_LABEL_FLAG_IDX);
+            zkc_vm_callstack_witness popped;
+            memset(&popped, 0, sizeof popped);
+            if (sim) {
+                if (s.context_stack_depth >= 1 && s.context_stack_depth - 1 < sim->max_depth) popped = sim->stack[s.context_stack_depth - 1];
+                if (sim->n_cw < sim->cw_cap) { w->callstack_index = (uint32_t)sim->n_cw; sim->cw_out[sim->n_cw++] = popped; }
+                else sim->overflow = 1;
+            } else if (w->callstack_index < n_cw) popped = cw[w->callstack_index];
+            else checks |= ZKC_VM_CHK_CALLSTACK;
+            new_entry = popped.context;
+            const zkc_vm_context cur_e = *ctx;
+            const int exc1 = fwd_ptr && !src0r.is_pointer && is_far_return;
+            const int exc2 = fwd_ptr && fp.page < cur_e.base_page;
+            const int exceptions_collapsed = exc1 || exc2 || is_ret_panic;
+            vm_fat_ptr p = fp;
+            if (exceptions_collapsed) memset(&p, 0, sizeof p);
+            vm_fat_ptr adjusted = {0, p.page, p.start + p.offset, p.length - p.offset};
+            vm_fat_ptr for_heaps = {0, use_heap ? heap_page : aux_heap_page, p.start, p.length};
+            p = fwd_ptr ? adjusted : for_heaps;
+            uint32_t ub = exceptions_collapsed ? 0 : upper_bound;
+            if (non_addressable && !fwd_ptr) ub = 0xFFFFFFFFu;
+            const uint32_t heap_max = use_heap ? ub : 0, aux_max = use_aux ? ub : 0;
+            const uint32_t heap_growth = heap_max < cur_e.heap_upper_bound ? 0 : heap_max - cur_e.heap_upper_bound;
+            const uint32_t aux_growth = aux_max < cur_e.aux_heap_upper_bound ? 0 : aux_max - cur_e.aux_heap_upper_bound;
+            uint32_t growth_cost = (use_heap && is_far_return) ? heap_growth : 0;
+            if (use_aux && is_far_return) growth_cost = aux_growth;
+            const int uf = ergs_left < growth_cost;
+            uint32_t ergs_after = uf ? 0 : ergs_left - growth_cost;
+            if (is_local) ergs_after = ergs_left;
+            const int non_local_panic = (exceptions_collapsed || uf || is_ret_panic) && is_far_return;
+            if (non_local_panic) memset(&p, 0, sizeof p);
+            const uint64_t ergs_sum = (uint64_t)ergs_after + new_entry.ergs_remaining;
+            if (ergs_sum >> 32) checks |= ZKC_VM_CHK_CALLSTACK; /* add_no_overflow, :310-311 */
+            new_entry.ergs_remaining = (uint32_t)ergs_sum;
+            if (is_local) { new_entry.heap_upper_bound = cur_e.heap_upper_bound; new_entry.aux_heap_upper_bound = cur_e.aux_heap_upper_bound; }
+            const int should_revert = is_revert || is_ret_panic || non_local_panic;
+            perform_revert = should_revert;
+            if (should_revert && memcmp(cur_e.reverted_queue_head, cur_e.log_queue_forward_tail, 32)) checks |= ZKC_VM_CHK_ROLLBACK_QUEUE; /* :373-383 */
+            const int ret_ok = is_ok && !non_local_panic;
+            if (ret_ok && memcmp(new_entry.reverted_queue_head, cur_e.reverted_queue_tail, 32)) checks |= ZKC_VM_CHK_ROLLBACK_QUEUE; /* :396-404 */
+            if (should_revert) { memcpy(new_fwd_tail, cur_e.reverted_queue_tail, 32); new_fwd_len = cur_e.log_queue_forward_part_length + cur_e.reverted_queue_segment_len; }
+            if (ret_ok) {
+                memcpy(new_entry.reverted_queue_head, cur_e.reverted_queue_head, 32);
+                new_entry.reverted_queue_segment_len = popped.context.reverted_queue_segment_len + cur_e.reverted_queue_segment_len;
+            }
+            const int use_label = is_to_label && is_local;
+            const uint32_t ok_pc = use_label ? imm0 : new_entry.pc, eh_pc = use_label ? imm0 : cur_e.exception_handler_loc;
+            new_entry.pc = should_revert ? eh_pc : ok_pc;
+            far_return_registers = is_far_return;
+            far_return_r1.is_pointer = 1;
+            far_return_r1.value[0] = p.offset; far_return_r1.value[1] = p.page; far_return_r1.value[2] = p.start; far_return_r1.value[3] = p.length;
+            is_panic_out = is_ret_panic || non_local_panic;
+            reset_context_u128 = is_far_return;
+            old_entry = popped.context;
+            memcpy(sponge_from, popped.previous_sponge_state, 96);
+            if (s.context_stack_depth == 0) checks |= ZKC_VM_CHK_CALLSTACK; /* :300 */
+            new_depth = s.context_stack_depth - 1;
+            if (sim) sim->ev_kind = should_revert ? 3 : 2;
+        }
+        /* the callstack sponge: 4 absorptions of the saved frame's encoding (call_ret.rs:176-284) */
+        uint64_t enc[32], st12[12];
+        orc_vm_context_encode(&old_entry, enc);
+        memcpy(st12, sponge_from, 96);
+        for (int r = 0; r < 4; r++) { sponge_run(&sp, 1 + r, enc + 8 * r, st12 + 8); memcpy(st12, sp.fin[1 + r], 96); }
+        if (apply_ret) {
+            if (memcmp(st12, s.stack_sponge_state, 96)) checks |= ZKC_VM_CHK_CALLSTACK;
+            memcpy(new_stack_sponge, sponge_from, 96);
+        } else memcpy(new_stack_sponge, st12, 96);
+        replace_callstack = 1;
+        new_ctx = new_entry;
+        memcpy(new_ctx.log_queue_forward_tail, new_fwd_tail, 32);
+        new_ctx.log_queue_forward_part_length = new_fwd_len;
+        set_flags = 1; nf[0] = (uint32_t)(is_panic_out && apply_ret); nf[1] = 0; nf[2] = 0;
+        if (row) {
+            flatten_record_cols(&new_entry, row, stride, ZKC_VM_OP_AUX);
+            uint64_t *x = &T(ZKC_VM_OP_AUX);
+            x[42 * stride] = (uint64_t)apply_near; x[43 * stride] = (uint64_t)apply_ret; x[44 * stride] = (uint64_t)is_panic_out;
+            x[45 * stride] = (uint64_t)perform_revert;
+        }
+    }
     /* ---------------- state diffs, cycle.rs:158-616 ---------------- */
+    /* dst0 / dst1 are dot products of (flag, candidate) pairs (:199-246): zero when no candidate's flag is set */
+    if (!(dst0_to_mem_capable || dst0_reg_only)) dst0 = zero_reg;
+    if (!write_dst1) dst1 = zero_reg;
     const int perform_mem_write = dst0_mem && dst0_to_mem_capable;
-    memq_push(s.memory_queue_state, &s.memory_queue_length, ts_dst, dst_page, dst_index, 1, &dst0, perform_mem_write);
-    if (mem && perform_mem_write && dst_page == mem->stack_page) mem->stack[dst_index] = dst0;
+    memq_push(&sp, 2, s.memory_queue_state, &s.memory_queue_length, ts_dst, dst_page, dst_index, 1, &dst0, perform_mem_write);
+    if (sim && perform_mem_write) sim_write(sim, dst_page, dst_index, &dst0);
     const int dst0_update_register = dst0_reg_only || (!dst0_mem && dst0_to_mem_capable);
     if (dst0_update_register && dst0_r) s.registers[dst0_r - 1] = dst0;
+    if (far_return_registers) { /* specific updates, zeroing and pointer-marker removal ride on the dst0 slot, :352-384 */
+        s.registers[0] = far_return_r1;
+        for (int r = 1; r < 15; r++) s.registers[r] = zero_reg;
+    }
     if (write_dst1 && dst1_r) s.registers[dst1_r - 1] = dst1; /* dst1 applied after dst0, cycle.rs:421-433 */
+    ctx->ergs_remaining = ergs_candidate;
+    if (reset_context_u128) memset(s.context_composite_u128, 0, 16);
+    if (uma_applies) { memcpy(s.memory_queue_state, uma_memq, 96); s.memory_queue_length = uma_memq_len; }
     if (set_flags) memcpy(s.flags, nf, sizeof nf);
+    if (replace_callstack) {
+        s.current_context = new_ctx;
+        s.context_stack_depth = new_depth;
+        memcpy(s.stack_sponge_state, new_stack_sponge, 96);
+    }
     s.pending_exception = (uint32_t)new_pending;
     s.memory_page_counter = cur->memory_page_counter; /* only far calls move it */
     if (row) {
         T(ZKC_VM_DST0) = dst0.is_pointer; T(ZKC_VM_DST1) = dst1.is_pointer;
         for (int i = 0; i < 8; i++) { T(ZKC_VM_DST0 + 1 + i) = dst0.value[i]; T(ZKC_VM_DST1 + 1 + i) = dst1.value[i]; }
         T(ZKC_VM_PERFORM_DST0_MEMORY_WRITE) = (uint64_t)perform_mem_write; T(ZKC_VM_DST0_UPDATE_REGISTER) = (uint64_t)dst0_update_register;
-        for (int i = 0; i < 12; i++) T(ZKC_VM_MEMQ_AFTER_DST0 + i) = s.memory_queue_state[i];
-        T(ZKC_VM_MEMQ_AFTER_DST0 + 12) = s.memory_queue_length;
+        T(ZKC_VM_DST1_UPDATE_REGISTER) = (uint64_t)write_dst1;
         for (int i = 0; i < 3; i++) T(ZKC_VM_FLAGS_OUT + i) = s.flags[i];
-        T(ZKC_VM_PENDING_EXCEPTION_OUT) = s.pending_exception; T(ZKC_VM_PC_OUT) = ctx->pc; T(ZKC_VM_ERGS_OUT) = ctx->ergs_remaining;
+        const zkc_vm_context *c = &s.current_context;
+        T(ZKC_VM_PENDING_EXCEPTION_OUT) = s.pending_exception; T(ZKC_VM_PC_OUT) = c->pc; T(ZKC_VM_ERGS_OUT) = c->ergs_remaining;
+        T(ZKC_VM_HEAP_BOUND_OUT) = c->heap_upper_bound; T(ZKC_VM_AUX_HEAP_BOUND_OUT) = c->aux_heap_upper_bound;
+        T(ZKC_VM_MEMQ_LENGTH_OUT) = s.memory_queue_length; T(ZKC_VM_DEPTH_OUT) = s.context_stack_depth;
+        for (int i = 0; i < 4; i++) { T(ZKC_VM_FORWARD_TAIL_OUT + i) = c->log_queue_forward_tail[i]; T(ZKC_VM_ROLLBACK_HEAD_OUT + i) = c->reverted_queue_head[i]; }
+        T(ZKC_VM_FORWARD_TAIL_OUT + 4) = c->log_queue_forward_part_length; T(ZKC_VM_ROLLBACK_HEAD_OUT + 4) = c->reverted_queue_segment_len;
+        for (int k = 0; k < ZKC_VM_NUM_SPONGES; k++) {
+            T(ZKC_VM_SPONGE_ENFORCE + k) = (uint64_t)sp.enf[k];
+            for (int i = 0; i < 12; i++) T(ZKC_VM_SPONGE_FINAL + 12 * k + i) = sp.enf[k] ? sp.fin[k][i] : 0;
+        }
     }
     *out = s;
     return checks;
@@ -435,29 +857,143 @@ static void fail(zkc_status *st, int64_t row, uint32_t bits) {
     if (row >= 0 && (st->first_bad_row < 0 || row < st->first_bad_row)) st->first_bad_row = row;
 }
 
-/* out-of-circuit run: fills snapshots[cycles + 1] and witness[cycles]; code: [code_words][8] */
-int orc_main_vm_run(const zkc_vm_isa *isa, const zkc_vm_state *initial, const uint32_t *code, size_t code_words,
-                    size_t cycles, zkc_vm_state *snapshots, zkc_vm_cycle_witness *witness, zkc_status *status) {
-    zkc_status st = {ZKC_OK, 0, -1, 0, 0};
-    orc_vm_memory mem;
-    mem.code = calloc(65536, sizeof(zkc_vm_register));
-    mem.stack = calloc(65536, sizeof(zkc_vm_register));
-    mem.code_page = initial->current_context.code_page;
-    mem.stack_page = initial->current_context.base_page + 1;
-    for (size_t i = 0; i < code_words && i < 65536; i++) memcpy(mem.code[i].value, code + 8 * i, 32);
-    snapshots[0] = *initial;
-    for (size_t c = 0; c < cycles; c++) {
-        memset(&witness[c], 0, sizeof witness[c]);
-        const uint32_t chk = vm_cycle(isa, &snapshots[c], &witness[c], &mem, &snapshots[c + 1], NULL, 0);
-        if (chk) fail(&st, (int64_t)c, chk);
+/* Rollback-queue resolution of the out-of-circuit run.  A frame's rollback segment is hash-chained BACKWARDS: every
+ * revertable log claims a new head h' with H(rollback item, h') == current head (log.rs:351-371, :583-632), a frame
+ * that returns ok hands its segment to its parent (the parent's saved head must be the child's tail, ret.rs:396-404)
+ * and a frame that reverts must have its head where the forward queue ends (ret.rs:373-383), its tail becoming the
+ * new forward tail.  So the claimed heads / frame tails are only known once a frame's fate is: walk its events
+ * (own call marker, logs, merged children) from the most recent one back, starting from the required final head. */
+typedef struct orc_vm_lists { orc_vm_entry *entries; int64_t *first, *last; } orc_vm_lists;
+static void list_append(orc_vm_lists *L, size_t depth, int64_t e) {
+    L->entries[e].prev = L->last[depth];
+    L->last[depth] = e;
+    if (L->first[depth] < 0) L->first[depth] = e;
+}
+static void list_merge_into_parent(orc_vm_lists *L, size_t child) {
+    if (L->first[child] < 0) return;
+    L->entries[L->first[child]].prev = L->last[child - 1];
+    if (L->first[child - 1] < 0) L->first[child - 1] = L->first[child];
+    L->last[child - 1] = L->last[child];
+    L->first[child] = L->last[child] = -1;
+}
+/* walks the list of `depth` backwards from head value `cur`; resolve: writes the claimed heads / tails into the
+ * witness; restore: undoes the storage writes (a reverted frame).  Returns the segment tail in cur. */
+static void list_walk(orc_vm_lists *L, size_t depth, uint64_t cur[4], zkc_vm_cycle_witness *witness, int resolve, orc_vm_sim *sim, int restore) {
+    for (int64_t e = L->last[depth]; e >= 0; e = L->entries[e].prev) {
+        orc_vm_entry *en = &L->entries[e];
+        if (resolve) memcpy(witness[e].rollback, cur, 32);
+        if (en->kind == 2) {
+            uint64_t st[12];
+            memcpy(st, en->enc16, 32); memcpy(st + 4, cur, 32); memcpy(st + 8, en->cap, 32);
+            orc_poseidon2_permutation(st);
+            memcpy(cur, st, 32);
+            if (restore && en->slot >= 0) { memcpy(sim->storage[en->slot].value, en->prev_value, 32); sim->storage[en->slot].written = en->prev_written; }
+        }
     }
-    free(mem.code); free(mem.stack);
+    L->first[depth] = L->last[depth] = -1;
+}
+
+/* one pass of the run.  resolve: pass 1 (rollback witness unknown: computed here and patched into `witness`, the
+ * states it produces carry unresolved rollback heads and are discarded); otherwise witness[].rollback is input. */
+static int vm_run_pass(const zkc_vm_isa *isa, const zkc_vm_state *initial, const uint32_t *code, size_t code_words, size_t cycles,
+                       zkc_vm_state *snapshots, zkc_vm_cycle_witness *witness, zkc_vm_callstack_witness *cw_out, size_t cw_cap,
+                       size_t *n_cw, uint64_t root_tail[4], int resolve, zkc_status *status) {
+    zkc_status st = {ZKC_OK, 0, -1, 0, 0};
+    orc_vm_sim sim;
+    memset(&sim, 0, sizeof sim);
+    for (int k = 0; k < 4; k++) sim.pages[k] = calloc(ORC_VM_PAGE_WORDS, sizeof(zkc_vm_register));
+    sim.storage = calloc(ORC_VM_STORAGE_SLOTS, sizeof(orc_vm_slot));
+    sim.max_depth = cycles + 2;
+    sim.stack = calloc(sim.max_depth, sizeof(zkc_vm_callstack_witness));
+    sim.cw_out = cw_out; sim.cw_cap = cw_cap;
+    orc_vm_lists L;
+    L.entries = calloc(cycles ? cycles : 1, sizeof(orc_vm_entry));
+    L.first = malloc(sim.max_depth * sizeof(int64_t)); L.last = malloc(sim.max_depth * sizeof(int64_t));
+    for (size_t i = 0; i < sim.max_depth; i++) L.first[i] = L.last[i] = -1;
+    sim.page_ids[0] = initial->current_context.code_page;
+    sim.page_ids[1] = initial->current_context.base_page + 1;
+    sim.page_ids[2] = initial->current_context.base_page + 2;
+    sim.page_ids[3] = initial->current_context.base_page + 3;
+    for (size_t i = 0; i < code_words && i < ORC_VM_PAGE_WORDS; i++) memcpy(sim.pages[0][i].value, code + 8 * i, 32);
+    /* the frame below the root: the empty context initial_bootloader_state hashes into the stack sponge */
+    zkc_vm_state s0 = *initial;
+    memcpy(s0.current_context.reverted_queue_head, root_tail, 32);
+    memcpy(s0.current_context.reverted_queue_tail, root_tail, 32);
+    {
+        zkc_vm_context empty;
+        memset(&empty, 0, sizeof empty);
+        memcpy(empty.reverted_queue_tail, root_tail, 32); memcpy(empty.reverted_queue_head, root_tail, 32);
+        empty.is_kernel_mode = 1;
+        sim.stack[0].context = empty;
+        uint64_t enc[32], sp12[12] = {0};
+        orc_vm_context_encode(&empty, enc);
+        for (int r = 0; r < 4; r++) { memcpy(sp12, enc + 8 * r, 64); orc_poseidon2_permutation(sp12); }
+        memcpy(s0.stack_sponge_state, sp12, 96);
+    }
+    zkc_vm_state cur = s0, next;
+    if (snapshots) snapshots[0] = cur;
+    for (size_t c = 0; c < cycles; c++) {
+        uint64_t keep[4];
+        memcpy(keep, witness[c].rollback, 32);
+        memset(&witness[c], 0, sizeof witness[c]);
+        if (!resolve) memcpy(witness[c].rollback, keep, 32);
+        const size_t depth = cur.context_stack_depth;
+        const uint32_t chk = vm_cycle(isa, &cur, &witness[c], NULL, 0, &sim, &next, NULL, 0);
+        /* the joins of the rollback queue cannot hold before the witness is resolved */
+        const uint32_t ignore = resolve ? ZKC_VM_CHK_ROLLBACK_QUEUE : 0;
+        if (chk & ~ignore) fail(&st, (int64_t)c, chk & ~ignore);
+        if (sim.ev_kind == 1) { list_append(&L, depth + 1, (int64_t)c); L.entries[c] = (orc_vm_entry){L.entries[c].prev, 1, -1, {0}, 0, {0}, {0}}; }
+        else if (sim.ev_kind == 4) { const int64_t prev = L.last[depth]; L.entries[c] = sim.ev; L.entries[c].prev = prev; L.last[depth] = (int64_t)c; if (L.first[depth] < 0) L.first[depth] = (int64_t)c; }
+        else if (sim.ev_kind == 2 && depth >= 2) list_merge_into_parent(&L, depth);
+        else if (sim.ev_kind == 3) {
+            /* the reverting frame's final head is the forward tail at this point; its tail becomes the forward tail */
+            uint64_t h[4];
+            memcpy(h, cur.current_context.log_queue_forward_tail, 32);
+            list_walk(&L, depth, h, witness, resolve, &sim, 1);
+            if (resolve) {
+                memcpy(next.current_context.log_queue_forward_tail, h, 32);
+                if (depth == 1) memcpy(root_tail, h, 32);
+            }
+        }
+        cur = next;
+        if (snapshots) snapshots[c + 1] = cur;
+    }
+    if (resolve) {
+        /* frames still open (and the root after an ok exit): as if they all returned ok, chained from the given tail */
+        size_t top = cur.context_stack_depth;
+        for (size_t d = top; d >= 2; d--) list_merge_into_parent(&L, d);
+        if (L.last[1] >= 0 || top >= 1) {
+            uint64_t h[4];
+            memcpy(h, root_tail, 32);
+            if (L.last[1] >= 0) { list_walk(&L, 1, h, witness, 1, &sim, 0); memcpy(root_tail, h, 32); }
+        }
+    }
+    if (sim.overflow) fail(&st, -1, ZKC_VM_CHK_UNSUPPORTED_OPCODE);
+    if (n_cw) *n_cw = sim.n_cw;
+    for (int k = 0; k < 4; k++) free(sim.pages[k]);
+    free(sim.storage); free(sim.stack); free(L.entries); free(L.first); free(L.last);
     if (status) *status = st;
     return st.code;
 }
 
+/* out-of-circuit run: fills snapshots[cycles + 1], witness[cycles] and the popped frames; code: [code_words][8].
+ * rollback_tail_out: the resolved rollback_queue_tail_for_block (snapshots[0] carries it). */
+int orc_main_vm_run(const zkc_vm_isa *isa, const zkc_vm_state *initial, const uint32_t *code, size_t code_words,
+                    size_t cycles, zkc_vm_state *snapshots, zkc_vm_cycle_witness *witness, zkc_vm_callstack_witness *cw_out,
+                    size_t cw_cap, size_t *n_cw, uint64_t rollback_tail_out[4], zkc_status *status) {
+    uint64_t root_tail[4];
+    memcpy(root_tail, initial->current_context.reverted_queue_tail, 32);
+    memset(witness, 0, cycles * sizeof *witness);
+    int rc = vm_run_pass(isa, initial, code, code_words, cycles, NULL, witness, cw_out, cw_cap, n_cw, root_tail, 1, status);
+    if (rc == ZKC_OK || rc == ZKC_ERR_UNSATISFIED)
+        rc = vm_run_pass(isa, initial, code, code_words, cycles, snapshots, witness, cw_out, cw_cap, n_cw, root_tail, 0, status);
+    if (rollback_tail_out) memcpy(rollback_tail_out, root_tail, 32);
+    return rc;
+}
+
 int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const zkc_vm_state *snapshots,
-                            const zkc_vm_cycle_witness *witness, size_t limit, const zkc_vm_options *options,
+                            const zkc_vm_cycle_witness *witness, const zkc_vm_callstack_witness *callstack_witness,
+                            size_t n_callstack_witness, size_t limit, const zkc_vm_options *options,
                             uint64_t *trace, uint64_t commitment[4], zkc_status *status) {
     zkc_status st = {ZKC_OK, 0, -1, 0, 0};
     const int start = io->start_flag != 0;
@@ -471,7 +1007,7 @@ int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const
         if (memcmp(fa, fb, sizeof fa)) fail(&st, (int64_t)c, ZKC_VM_CHK_SNAPSHOT);
         zkc_vm_cycle_witness w = witness[c];
         zkc_vm_state next;
-        const uint32_t chk = vm_cycle(isa, &snapshots[c], &w, NULL, &next, trace ? trace + c : NULL, limit);
+        const uint32_t chk = vm_cycle(isa, &snapshots[c], &w, callstack_witness, n_callstack_witness, NULL, &next, trace ? trace + c : NULL, limit);
         if (chk) fail(&st, (int64_t)c, chk);
         state = next;
     }

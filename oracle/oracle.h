@@ -101,8 +101,10 @@ size_t orc_vm_flatten_state(const zkc_vm_state *s, uint64_t *dst);
 void orc_vm_context_encode(const zkc_vm_context *c, uint64_t e[32]);
 void orc_vm_initial_bootloader_state(const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *st);
 int orc_main_vm_run(const zkc_vm_isa *isa, const zkc_vm_state *initial, const uint32_t *code, size_t code_words,
-                    size_t cycles, zkc_vm_state *snapshots, zkc_vm_cycle_witness *witness, zkc_status *status);
+                    size_t cycles, zkc_vm_state *snapshots, zkc_vm_cycle_witness *witness, zkc_vm_callstack_witness *cw_out,
+                    size_t cw_cap, size_t *n_cw, uint64_t rollback_tail_out[4], zkc_status *status);
 int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const zkc_vm_state *snapshots,
-                            const zkc_vm_cycle_witness *witness, size_t limit, const zkc_vm_options *options,
+                            const zkc_vm_cycle_witness *witness, const zkc_vm_callstack_witness *callstack_witness,
+                            size_t n_callstack_witness, size_t limit, const zkc_vm_options *options,
                             uint64_t *trace, uint64_t commitment[4], zkc_status *status);
 #endif

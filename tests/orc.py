@@ -60,10 +60,10 @@ def load():
                                            C.POINTER(abi.Status)]
     lib.orc_vm_initial_bootloader_state.argtypes = [C.POINTER(abi.VmClosedForm), C.POINTER(abi.VmIsa), C.POINTER(abi.VmState)]
     lib.orc_main_vm_run.restype = C.c_int
-    lib.orc_main_vm_run.argtypes = [C.POINTER(abi.VmIsa), C.POINTER(abi.VmState), _vp, C.c_size_t, C.c_size_t, _vp, _vp,
-                                    C.POINTER(abi.Status)]
+    lib.orc_main_vm_run.argtypes = [C.POINTER(abi.VmIsa), C.POINTER(abi.VmState), _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp,
+                                    C.c_size_t, C.POINTER(C.c_size_t), _vp, C.POINTER(abi.Status)]
     lib.orc_main_vm_entry_point.restype = C.c_int
-    lib.orc_main_vm_entry_point.argtypes = [C.POINTER(abi.VmClosedForm), C.POINTER(abi.VmIsa), _vp, _vp, C.c_size_t,
+    lib.orc_main_vm_entry_point.argtypes = [C.POINTER(abi.VmClosedForm), C.POINTER(abi.VmIsa), _vp, _vp, _vp, C.c_size_t, C.c_size_t,
                                             C.POINTER(abi.VmOptions), _vp, _vp, C.POINTER(abi.Status)]
     lib.orc_vm_flatten_state.restype = C.c_size_t
     lib.orc_vm_flatten_state.argtypes = [_vp, _vp]
@@ -256,13 +256,20 @@ def vm_initial_state(lib, io, isa):
     return st
 
 
-def vm_run(lib, isa, initial, code_words, cycles):
-    """out-of-circuit run: returns (rc, snapshots [cycles + 1] as a uint8 array [cycles + 1, 1176], witness [cycles, 80], status)"""
+def vm_run(lib, isa, initial, code_words, cycles, full=False):
+    """out-of-circuit run: returns (rc, snapshots [cycles + 1, 1176] uint8, witness [cycles, 176] uint8, status); full=True
+    appends (callstack witness [n, 336] uint8, resolved rollback_queue_tail_for_block [4])"""
     code_words = np.ascontiguousarray(code_words, dtype=np.uint32)
     snaps = np.zeros((cycles + 1, C.sizeof(abi.VmState)), dtype=np.uint8)
     wit = np.zeros((cycles, C.sizeof(abi.VmCycleWitness)), dtype=np.uint8)
+    cw = np.zeros((cycles + 1, C.sizeof(abi.VmCallstackWitness)), dtype=np.uint8)
+    n_cw = C.c_size_t()
+    tail = np.zeros(4, dtype=np.uint64)
     st = abi.Status()
-    rc = lib.orc_main_vm_run(C.byref(isa), C.byref(initial), p(code_words), len(code_words), cycles, p(snaps), p(wit), C.byref(st))
+    rc = lib.orc_main_vm_run(C.byref(isa), C.byref(initial), p(code_words), len(code_words), cycles, p(snaps), p(wit), p(cw),
+                             len(cw), C.byref(n_cw), p(tail), C.byref(st))
+    if full:
+        return rc, snaps, wit, st, cw[:n_cw.value].copy(), tail
     return rc, snaps, wit, st
 
 
@@ -270,12 +277,14 @@ def vm_state_at(snaps, i):
     return abi.VmState.from_buffer_copy(snaps[i].tobytes())
 
 
-def vm_entry_point(lib, io, isa, snaps, wit, limit, want_trace=True, compare_expected=False):
+def vm_entry_point(lib, io, isa, snaps, wit, limit, want_trace=True, compare_expected=False, cw=None):
     io2 = abi.VmClosedForm.from_buffer_copy(bytes(io))
     trace = np.zeros((abi.VM_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
     com = np.zeros(4, dtype=np.uint64)
     st = abi.Status()
     opts = abi.VmOptions(int(compare_expected))
-    rc = lib.orc_main_vm_entry_point(C.byref(io2), C.byref(isa), p(np.ascontiguousarray(snaps)), p(np.ascontiguousarray(wit)), limit,
+    n_cw = 0 if cw is None else len(cw)
+    rc = lib.orc_main_vm_entry_point(C.byref(io2), C.byref(isa), p(np.ascontiguousarray(snaps)), p(np.ascontiguousarray(wit)),
+                                     p(np.ascontiguousarray(cw)) if n_cw else None, n_cw, limit,
                                      C.byref(opts), p(trace), p(com), C.byref(st))
     return rc, io2, trace, com, st

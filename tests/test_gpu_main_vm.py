@@ -1,6 +1,6 @@
-"""main_vm: CUDA path (one thread per cycle from host-supplied snapshots) through the C ABI vs the sequential CPU
-oracle: trace, every per-cycle state, FSM output, commitment and status bit-exact; plus the GPU out-of-circuit run
-against the oracle's."""
+"""main_vm: CUDA path (one thread per cycle from host-supplied snapshots, sponges as dense job launches) through the C
+ABI vs the sequential CPU oracle: trace, every per-cycle state, FSM output, commitment and status bit-exact; plus the GPU
+out-of-circuit run (two passes: rollback-queue resolution, then recording) against the oracle's."""
 import ctypes as C
 
 import numpy as np
@@ -24,16 +24,27 @@ def fresh(orc):
     return isa, io, O.vm_initial_state(orc, io, isa.isa)
 
 
+def with_tail(io, tail):
+    io2 = abi.VmClosedForm.from_buffer_copy(bytes(io))
+    for i in range(4):
+        io2.rollback_queue_tail_for_block[i] = int(tail[i])
+    return io2
+
+
+def flat(lib, state_bytes):
+    a = np.zeros(243, dtype=np.uint64)
+    buf = np.ascontiguousarray(np.frombuffer(bytes(state_bytes), dtype=np.uint8))
+    lib.orc_vm_flatten_state(O.p(buf), O.p(a))
+    return a
+
+
 def assert_same(want, got, check_trace=True):
     rc, io, trace, com, st = want
-    assert got.status.code == rc, (got.status.code, hex(got.status.failed_checks), got.status.first_bad_row)
+    assert got.status.code == rc, (got.status.code, hex(got.status.failed_checks), got.status.first_bad_row, rc, hex(st.failed_checks), st.first_bad_row)
     assert got.status.failed_checks == st.failed_checks and got.status.first_bad_row == st.first_bad_row
     assert got.closed_form_input.completion_flag == io.completion_flag
-    a, b = np.zeros(243, dtype=np.uint64), np.zeros(243, dtype=np.uint64)
     lib = O.load()
-    lib.orc_vm_flatten_state(C.byref(got.closed_form_input.hidden_fsm_output), O.p(a))
-    lib.orc_vm_flatten_state(C.byref(io.hidden_fsm_output), O.p(b))
-    assert np.array_equal(a, b)
+    assert np.array_equal(flat(lib, got.closed_form_input.hidden_fsm_output), flat(lib, io.hidden_fsm_output))
     assert got.commitment.tolist() == com.tolist()
     if check_trace:
         bad = np.argwhere(got.trace != trace)
@@ -46,51 +57,125 @@ def test_initial_state_matches_oracle(engine, orc):
     assert bytes(got) == bytes(st)
 
 
-@pytest.mark.parametrize("n_ops,cycles,seed", [(8, 1, 1), (64, 127, 2), (256, 700, 3), (1024, 5000, 4), (4096, 20000, 5)])
-def test_random_programs_bit_exact(engine, orc, n_ops, cycles, seed):
+@pytest.mark.parametrize("n_ops,cycles,seed,full", [(8, 1, 1, False), (64, 127, 2, False), (256, 700, 3, True), (1024, 5000, 4, True),
+                                                    (4096, 20000, 5, True), (512, 3000, 6, True)])
+def test_random_programs_bit_exact(engine, orc, n_ops, cycles, seed, full):
     isa, io, st = fresh(orc)
-    ops = I.random_program(isa, n_ops, seed=seed)
-    rc, snaps, wit, status = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles)
+    ops = I.random_program(isa, n_ops, seed=seed, full=full)
+    rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
     assert rc == 0, (hex(status.failed_checks), status.first_bad_row)
-    want = O.vm_entry_point(orc, io, isa.isa, snaps, wit, cycles)
-    assert want[0] == 0
-    got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps, wit), cycles)
+    io = with_tail(io, tail)
+    want = O.vm_entry_point(orc, io, isa.isa, snaps, wit, cycles, cw=cw)
+    assert want[0] == 0, (want[0], hex(want[4].failed_checks), want[4].first_bad_row)
+    got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps, wit, cw), cycles)
     assert_same(want, got)
-    # the GPU out-of-circuit run reproduces the oracle's snapshots and witness
-    d_snaps, d_wit, st2 = main_vm_simulate(engine, isa.isa, [st], I.pack_code(ops)[None], cycles)
-    assert st2.code == 0
-    hs, hw = d_snaps.cpu().numpy()[0], d_wit.cpu().numpy()[0]
+    if full:
+        props = got.trace[K["PROPS"]]
+        for op in (I.OP_UMA, I.OP_LOG, I.OP_NEAR_CALL, I.OP_RET):
+            assert ((props >> np.uint64(op)) & np.uint64(1)).sum() > 0, op
+    # the GPU out-of-circuit run reproduces the oracle's snapshots, witness, popped frames and resolved rollback tail
+    sim = main_vm_simulate(engine, isa.isa, [st], I.pack_code(ops)[None], cycles)
+    assert sim.status.code == 0, (sim.status.code, hex(sim.status.failed_checks), sim.status.first_bad_row)
+    hs, hw = sim.snapshots.cpu().numpy()[0], sim.witness.cpu().numpy()[0]
     lib = O.load()
     for i in (0, 1, cycles // 2, cycles):
-        a, b = np.zeros(243, dtype=np.uint64), np.zeros(243, dtype=np.uint64)
-        lib.orc_vm_flatten_state(O.p(np.ascontiguousarray(hs[i])), O.p(a)); lib.orc_vm_flatten_state(O.p(np.ascontiguousarray(snaps[i])), O.p(b))
-        assert np.array_equal(a, b), i
-    assert np.array_equal(hw[:, :68], wit[:, :68])
+        assert np.array_equal(flat(lib, hs[i].tobytes()), flat(lib, snaps[i].tobytes())), i
+    assert np.array_equal(hw, wit)
+    assert sim.rollback_tails[0].tolist() == tail.tolist() and int(sim.n_callstack[0]) == len(cw)
+    assert np.array_equal(sim.callstack_witness.cpu().numpy()[0, :len(cw)], cw)
     # device-resident inputs straight from the simulator
-    got2 = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, d_snaps[0], d_wit[0]), cycles)
+    got2 = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, sim.snapshots[0], sim.witness[0], sim.callstack_witness[0]), cycles)
     assert got2.commitment.tolist() == want[3].tolist() and got2.status.code == 0
     assert np.array_equal(got2.trace.cpu().numpy().view(np.uint64), want[2])
+
+
+def test_hand_written_calls_logs_uma(engine, orc):
+    """the programs of tests/test_oracle_main_vm_ops.py (every branch of near_call / ret / log / uma) on the GPU"""
+    import test_oracle_main_vm_ops as T
+    isa, io, st = T.fresh(orc, tail=4242)
+    A, B, Cv = 0x1111 << 200 | 5, 0x2222 << 100 | 6, 0x3333
+    T.set_reg(st, 2, 7); T.set_reg(st, 3, A); T.set_reg(st, 4, B); T.set_reg(st, 5, Cv); T.set_reg(st, 6, 9)
+    T.set_reg(st, 7, 70); T.set_reg(st, 8, (3 | (10 << 32) | (64 << 64) | (10 << 96)), is_ptr=1)
+    ops = [
+        isa.encode(I.OP_LOG, I.LOG_STORAGE_WRITE, src0=2, src1=3),
+        isa.encode(I.OP_LOG, I.LOG_STORAGE_READ, src0=2, dst0=10),
+        isa.encode(I.OP_NEAR_CALL, src0=0, imm0=8, imm1=12),
+        isa.encode(I.OP_LOG, I.LOG_STORAGE_READ, src0=2, dst0=11),
+        isa.encode(I.OP_NEAR_CALL, src0=0, imm0=14, imm1=12),
+        isa.encode(I.OP_LOG, I.LOG_STORAGE_READ, src0=6, dst0=12),
+        isa.encode(I.OP_LOG, I.LOG_EVENT, 1, src0=2, src1=5),
+        isa.encode(I.OP_JUMP, 0, 0, src=I.MODE_IMM16, imm0=20),
+        isa.encode(I.OP_LOG, I.LOG_STORAGE_WRITE, src0=2, src1=4),
+        isa.encode(I.OP_UMA, I.UMA_HEAP_WRITE, 1, src0=7, src1=3, dst0=9),
+        isa.encode(I.OP_LOG, I.LOG_EVENT, 0, src0=3, src1=4),
+        isa.encode(I.OP_RET, I.RET_REVERT),
+        isa.encode(I.OP_JUMP, 0, 0, src=I.MODE_IMM16, imm0=3),
+        isa.encode(I.OP_NOP),
+        isa.encode(I.OP_LOG, I.LOG_STORAGE_WRITE, src0=6, src1=5),
+        isa.encode(I.OP_RET, I.RET_OK),
+    ] + [isa.encode(I.OP_NOP)] * 4 + [
+        isa.encode(I.OP_LOG, I.LOG_PRECOMPILE, src0=2, src1=6, dst0=14),
+        isa.encode(I.OP_UMA, I.UMA_HEAP_READ, 1, src0=7, dst0=13, dst1=7),
+        isa.encode(I.OP_UMA, I.UMA_PTR_READ, 0, src0=8, dst0=15),
+        isa.encode(I.OP_UMA, I.UMA_AUX_WRITE, 0, src0=2, src1=4),
+        isa.encode(I.OP_PTR, 0, 1, src=I.MODE_IMM16, src1=2, dst0=11, imm0=1),  # exception -> the root frame panics
+        isa.encode(I.OP_NOP),
+    ]
+    cycles = 26
+    rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+    assert rc == 0
+    io2 = with_tail(io, tail); io2.start_flag = 0; io2.hidden_fsm_input = O.vm_state_at(snaps, 0)
+    want = O.vm_entry_point(orc, io2, isa.isa, snaps, wit, cycles, cw=cw)
+    assert want[0] == abi.ZKC_ERR_UNSATISFIED and want[4].failed_checks == abi.VM_CHK["BOOTLOADER_EXIT"] and want[1].completion_flag == 1
+    got = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, snaps, wit, cw), cycles, raise_on_unsatisfied=False)
+    assert_same(want, got)
+    # the same on the GPU simulator
+    sim = main_vm_simulate(engine, isa.isa, [st], I.pack_code(ops)[None], cycles)
+    assert sim.status.code == 0 and np.array_equal(sim.witness.cpu().numpy()[0], wit)
+    assert sim.rollback_tails[0].tolist() == tail.tolist()
+    assert np.array_equal(flat(O.load(), sim.snapshots.cpu().numpy()[0, cycles].tobytes()), flat(O.load(), snaps[cycles].tobytes()))
+    # circuit enforcement failures are reported like the oracle reports them: a wrong claimed rollback head, a wrong popped frame
+    for what, (row, byte) in {"rollback": (0, 144), "value": (1, 80)}.items():
+        w2 = wit.copy(); w2[row, byte] ^= 1
+        want = O.vm_entry_point(orc, io2, isa.isa, snaps, w2, cycles, cw=cw)
+        got = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, snaps, w2, cw), cycles, raise_on_unsatisfied=False)
+        assert want[0] != 0
+        assert_same(want, got, check_trace=False)
+    for byte in (0, 100, 250, 300):  # context fields / previous sponge state of the first popped frame
+        cw2 = cw.copy(); cw2[0, byte] ^= 1
+        want = O.vm_entry_point(orc, io2, isa.isa, snaps, wit, cycles, cw=cw2)
+        got = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, snaps, wit, cw2), cycles, raise_on_unsatisfied=False)
+        assert want[0] != 0, byte
+        assert_same(want, got, check_trace=False)
+    # a callstack index out of range
+    ret_row = int(np.flatnonzero(want[2][K["OP_AUX"] + 43])[0]) if want[2] is not None else 0
+    w2 = wit.copy(); w2[ret_row, 68:72] = np.frombuffer(np.uint32(1000).tobytes(), dtype=np.uint8)
+    want = O.vm_entry_point(orc, io2, isa.isa, snaps, w2, cycles, cw=cw)
+    got = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, snaps, w2, cw), cycles, raise_on_unsatisfied=False)
+    assert want[4].failed_checks & abi.VM_CHK["CALLSTACK"]
+    assert_same(want, got, check_trace=False)
 
 
 def test_chained_instances_and_expected_output(engine, orc):
     isa, io, st = fresh(orc)
     ops = I.random_program(isa, 512, seed=9)
     cycles, cut = 3000, 1234
-    rc, snaps, wit, _ = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles)
-    whole = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps, wit), cycles)
-    a = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps[:cut + 1], wit[:cut]), cut)
+    rc, snaps, wit, _, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+    io = with_tail(io, tail)
+    whole = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps, wit, cw), cycles)
+    a = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps[:cut + 1], wit[:cut], cw), cut)
     nxt = abi.VmClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
     nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
-    want = O.vm_entry_point(orc, nxt, isa.isa, snaps[cut:], wit[cut:], cycles - cut)
-    b = main_vm_entry_point(engine, VmCircuitWitness(nxt, isa.isa, snaps[cut:], wit[cut:]), cycles - cut)
+    want = O.vm_entry_point(orc, nxt, isa.isa, snaps[cut:], wit[cut:], cycles - cut, cw=cw)
+    b = main_vm_entry_point(engine, VmCircuitWitness(nxt, isa.isa, snaps[cut:], wit[cut:], cw), cycles - cut)
     assert_same(want, b)
     assert np.array_equal(np.concatenate([a.trace, b.trace], axis=1), whole.trace)
     exp = abi.VmClosedForm.from_buffer_copy(bytes(nxt))
     exp.hidden_fsm_output = b.closed_form_input.hidden_fsm_output
-    ok = main_vm_entry_point(engine, VmCircuitWitness(exp, isa.isa, snaps[cut:], wit[cut:]), cycles - cut, compare_expected=True)
+    ok = main_vm_entry_point(engine, VmCircuitWitness(exp, isa.isa, snaps[cut:], wit[cut:], cw), cycles - cut, compare_expected=True)
     assert ok.status.code == 0
     exp.hidden_fsm_output.flags[1] ^= 1
-    bad = main_vm_entry_point(engine, VmCircuitWitness(exp, isa.isa, snaps[cut:], wit[cut:]), cycles - cut, compare_expected=True,
+    bad = main_vm_entry_point(engine, VmCircuitWitness(exp, isa.isa, snaps[cut:], wit[cut:], cw), cycles - cut, compare_expected=True,
                               raise_on_unsatisfied=False)
     assert bad.status.code == abi.ZKC_ERR_FSM_OUTPUT_MISMATCH
 
@@ -99,26 +184,26 @@ def test_error_cases_match_oracle(engine, orc):
     isa, io, st = fresh(orc)
     ops = I.random_program(isa, 256, seed=13)
     cycles = 900
-    rc, snaps, wit, _ = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles)
-    # corrupted snapshot: a register limb, then a queue state element
-    for idx, byte in ((123, 40), (500, 1100), (0, 36), (cycles, 44)):
+    rc, snaps, wit, _, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+    io = with_tail(io, tail)
+    # corrupted snapshot: a register limb, a queue state element, context words, the stack sponge
+    for idx, byte in ((123, 40), (500, 1100), (0, 36), (cycles, 44), (300, 700), (301, 760), (640, 900), (77, 1000), (10, 812)):
         bad = snaps.copy(); bad[idx, byte] ^= 1
-        want = O.vm_entry_point(orc, io, isa.isa, bad, wit, cycles)
-        got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, bad, wit), cycles, raise_on_unsatisfied=False)
-        assert want[0] == abi.ZKC_ERR_SNAPSHOT_MISMATCH
+        want = O.vm_entry_point(orc, io, isa.isa, bad, wit, cycles, cw=cw)
+        got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, bad, wit, cw), cycles, raise_on_unsatisfied=False)
+        assert want[0] == abi.ZKC_ERR_SNAPSHOT_MISMATCH, (idx, byte)
         assert_same(want, got, check_trace=False)
     # corrupted oracle answer (a memory read value): the next state no longer matches
-    r = int(np.flatnonzero(O.vm_entry_point(orc, io, isa.isa, snaps, wit, cycles)[2][K["SHOULD_READ_SRC0"]])[7])
+    r = int(np.flatnonzero(O.vm_entry_point(orc, io, isa.isa, snaps, wit, cycles, cw=cw)[2][K["SHOULD_READ_SRC0"]])[7])
     w2 = wit.copy(); w2[r, 36] ^= 1
-    want = O.vm_entry_point(orc, io, isa.isa, snaps, w2, cycles)
-    got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps, w2), cycles, raise_on_unsatisfied=False)
+    want = O.vm_entry_point(orc, io, isa.isa, snaps, w2, cycles, cw=cw)
+    got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps, w2, cw), cycles, raise_on_unsatisfied=False)
     assert want[0] == abi.ZKC_ERR_SNAPSHOT_MISMATCH and want[4].first_bad_row == r + 1
     assert_same(want, got, check_trace=False)
-    # a program that raises an exception (ptr.add on a non-pointer): the panic cycle is reported as unsupported
-    ops2 = [isa.encode(I.OP_ADD, 0, 0, src0=2, src1=3, dst0=4)] * 5 + [isa.encode(I.OP_PTR, 0, 1, src=I.MODE_IMM16, src1=2, dst0=5, imm0=1)]
-    ops2 += [isa.encode(I.OP_NOP)] * 4
+    # a far call is reported as unsupported
+    ops2 = [isa.encode(I.OP_ADD, 0, 0, src0=2, src1=3, dst0=4)] * 5 + [isa.encode(I.OP_FAR_CALL)] + [isa.encode(I.OP_NOP)] * 4
     rc, s2, w3, status = O.vm_run(orc, isa.isa, st, I.pack_code(ops2), 8)
-    assert rc == abi.ZKC_ERR_UNSUPPORTED and status.first_bad_row == 6
+    assert rc == abi.ZKC_ERR_UNSUPPORTED and status.first_bad_row == 5
     want = O.vm_entry_point(orc, io, isa.isa, s2, w3, 8)
     got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, s2, w3), 8, raise_on_unsatisfied=False)
     assert want[0] == abi.ZKC_ERR_UNSUPPORTED
@@ -134,21 +219,24 @@ def test_batch_of_instances(engine, orc):
         io = abi.VmClosedForm(); io.start_flag = 1; io.rollback_queue_tail_for_block[1] = 100 + i
         ios.append(io); states.append(O.vm_initial_state(orc, io, isa.isa))
         codes.append(I.pack_code(I.random_program(isa, 128, seed=50 + i)))
-    d_snaps, d_wit, st = main_vm_simulate(engine, isa.isa, states, np.stack(codes), cycles)
-    assert st.code == 0
+    sim = main_vm_simulate(engine, isa.isa, states, np.stack(codes), cycles)
+    assert sim.status.code == 0
+    ios = [with_tail(io, t) for io, t in zip(ios, sim.rollback_tails)]
     import torch
     trace = torch.empty((n, K["NUM_COLS"], cycles), dtype=torch.int64, device="cuda")
-    coms, out, statuses, rc = main_vm_entry_point_batch(engine, ios, isa.isa, d_snaps, d_wit, cycles, trace_out=trace)
-    assert rc == 0
-    hs, hw, ht = d_snaps.cpu().numpy(), d_wit.cpu().numpy(), trace.cpu().numpy().view(np.uint64)
+    coms, out, statuses, rc = main_vm_entry_point_batch(engine, ios, isa.isa, sim.snapshots, sim.witness, cycles, trace_out=trace,
+                                                        callstack_witness=sim.callstack_witness)
+    assert rc == 0, [(s.code, hex(s.failed_checks), s.first_bad_row) for s in statuses]
+    hs, hw, hc, ht = sim.snapshots.cpu().numpy(), sim.witness.cpu().numpy(), sim.callstack_witness.cpu().numpy(), trace.cpu().numpy().view(np.uint64)
     for i in range(n):
-        want = O.vm_entry_point(orc, ios[i], isa.isa, hs[i], hw[i], cycles)
+        want = O.vm_entry_point(orc, ios[i], isa.isa, hs[i], hw[i], cycles, cw=hc[i])
         assert want[0] == 0 and coms[i].tolist() == want[3].tolist()
         assert np.array_equal(ht[i], want[2])
     assert len({tuple(c) for c in coms.tolist()}) == n
     # one bad instance does not disturb the others
     hs2 = hs.copy(); hs2[3, 77, 40] ^= 1
-    coms2, out2, statuses2, rc2 = main_vm_entry_point_batch(engine, ios, isa.isa, np.ascontiguousarray(hs2), np.ascontiguousarray(hw), cycles)
+    coms2, out2, statuses2, rc2 = main_vm_entry_point_batch(engine, ios, isa.isa, np.ascontiguousarray(hs2), np.ascontiguousarray(hw), cycles,
+                                                            callstack_witness=np.ascontiguousarray(hc))
     assert rc2 == abi.ZKC_ERR_SNAPSHOT_MISMATCH and statuses2[3].first_bad_row == 77
     assert [s.code for s in statuses2] == [0, 0, 0, abi.ZKC_ERR_SNAPSHOT_MISMATCH, 0, 0]
     assert coms2[[0, 1, 2, 4, 5]].tolist() == coms[[0, 1, 2, 4, 5]].tolist()

@@ -1,4 +1,5 @@
-"""main_vm oracle (value-level restatement of vm_cycle for the built opcode subset).  PARITY UNPINNED against the
+"""main_vm oracle (value-level restatement of vm_cycle): arithmetic / addressing subset; uma / log / calls are in
+test_oracle_main_vm_ops.py.  PARITY UNPINNED against the
 reference (no main_vm test, un-vendored ISA tables): the semantics are pinned here against Python big-int arithmetic
 on hand-written programs, instruction by instruction."""
 import ctypes as C
@@ -137,14 +138,17 @@ def test_conditions_jump_context_ptr(orc):
     assert reg(s(6), 9) == 0x8001 and list(s(7).context_composite_u128) == [5, 0, 0, 0]
     assert reg(s(8), 10) == (7 << 32) + 9 and s(8).registers[9].is_pointer == 1 and reg(s(8), 7) == 0
     assert s(9).pending_exception == 1 and reg(s(9), 11) == 0
-    # the pending exception is masked into ret.panic next cycle: not built -> reported, not mis-executed
+    # the pending exception is masked into ret.panic next cycle: the root frame is left
     rc, snaps, wit, status = run(orc, isa, st, ops, cycles=10)
-    assert rc == abi.ZKC_ERR_UNSUPPORTED and status.first_bad_row == 9 and status.failed_checks == abi.VM_CHK["UNSUPPORTED_OPCODE"]
+    assert rc == 0 and O.vm_state_at(snaps, 10).context_stack_depth == 0
+    # far calls are not built: reported, not mis-executed
+    rc, snaps, wit, status = run(orc, isa, st, [isa.encode(I.OP_NOP), isa.encode(I.OP_FAR_CALL)], cycles=2)
+    assert rc == abi.ZKC_ERR_UNSUPPORTED and status.first_bad_row == 1 and status.failed_checks == abi.VM_CHK["UNSUPPORTED_OPCODE"]
 
 
 def test_entry_point_on_random_program(orc):
     isa, io, st = fresh(orc)
-    ops = I.random_program(isa, 256, seed=11)
+    ops = I.random_program(isa, 256, seed=11, full=False)
     cycles = 700
     rc, snaps, wit, status = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles)
     assert rc == 0, (hex(status.failed_checks), status.first_bad_row)
