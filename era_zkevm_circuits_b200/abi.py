@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkc_b200.so")
+LIB_PATH = os.environ.get("ZKC_B200_LIB") or os.path.join(_HERE, "libzkc_b200.so")  # the env override selects another BUILD of the same engine
 
 GL_P = 0xFFFFFFFF00000001
 

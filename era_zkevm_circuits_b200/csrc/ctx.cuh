@@ -31,6 +31,13 @@ struct zkc_ctx {
     size_t h_pinned_bytes = 0;
     int sm_count = 148;
     int last_cuda_error = 0;
+    // copy streams of the pipelined host paths (H2D of chunk i+1 | kernels of chunk i | D2H of chunk i-1)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    bool copy_streams() {
+        if (!copy_in && cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (!copy_out && cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking) != cudaSuccess) return false;
+        return true;
+    }
 
     void *scratch(size_t bytes) {
         if (bytes > d_scratch_bytes) {

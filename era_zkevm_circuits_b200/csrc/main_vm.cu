@@ -16,6 +16,7 @@
 // cycle emits sponge JOBS (8 absorbed elements + where the capacity comes from + what the output must equal) and the
 // jobs of every cycle run afterwards as dense launches, one slot at a time (vm_sponge_kernel), so a warp never waits
 // for a lane that hashes.
+#include <algorithm>
 #include "ctx.cuh"
 #include "poseidon2.cuh"
 
@@ -1248,42 +1249,73 @@ struct VmPushScratch {
 // (a 294-bit "which words differ" mask) stay with lane c.  (2) The owner then demands that only words its cycle is
 // allowed to change differ, and compares the changed ones (a few scalars, at most two registers, rarely the whole
 // frame) with the values the cycle produced.  The Poseidon2 relations are deferred: the cycle only emits their jobs.
-__global__ void __launch_bounds__(128)
+#ifndef VM_DIFF_GROUP
+#define VM_DIFF_GROUP 8
+#endif
+#ifndef VM_CYCLES_MIN_BLOCKS
+#define VM_CYCLES_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, VM_CYCLES_MIN_BLOCKS)
 vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_state *__restrict__ snapshots,
                  const zkc_vm_cycle_witness *__restrict__ witness, const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw,
-                 uint64_t *__restrict__ trace, size_t limit, size_t n_instances, VmPushScratch ps) {
+                 uint64_t *__restrict__ trace, size_t limit, size_t n_instances, size_t row0, size_t row_count, VmPushScratch ps) {
+    // this launch covers rows [row0, row0 + row_count) of every instance (one chunk of the pipelined host path, or all)
     const size_t total = limit * n_instances;
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = g < total;
+    const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = l < row_count * n_instances;
     const unsigned lane = threadIdx.x & 31;
-    const size_t inst = valid ? g / limit : 0, row = valid ? g - inst * limit : 0;
+    const size_t inst = valid ? l / row_count : 0, row = valid ? row0 + (l - inst * row_count) : 0;
+    const size_t g = inst * limit + row;
     const size_t idx = inst * (limit + 1) + row;
     // ---- (1) cooperative word diff --------------------------------------------------------------------------------
+    // Groups of VM_DIFF_GROUP consecutive cycles: the group's VM_DIFF_GROUP + 1 snapshots are contiguous in memory (one
+    // instance), so every lane first issues all of its loads for the group -- (G + 1) x 10 independent coalesced words
+    // in flight per lane -- and only then ballots; the memory latency is paid once per group, not once per cycle.
     uint32_t diff[VM_DIFF_WORDS];
 #pragma unroll
     for (int k = 0; k < VM_DIFF_WORDS; k++) diff[k] = 0;
     {
-        uint32_t cur[VM_DIFF_WORDS], nxt[VM_DIFF_WORDS];
-#pragma unroll
-        for (int k = 0; k < VM_DIFF_WORDS; k++) nxt[k] = 0;
-        unsigned long long prev_idx = ~0ull;
+        constexpr int G = VM_DIFF_GROUP;
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
 #pragma unroll 1
-        for (int c = 0; c < 32; c++) {
-            if (!((vmask >> c) & 1)) break;  // valid lanes are a prefix
-            const unsigned long long ic = __shfl_sync(0xffffffffu, (unsigned long long)idx, c);
-            const uint32_t *pc = reinterpret_cast<const uint32_t *>(snapshots + ic), *pn = pc + VM_WORDS;
-            const bool chained = c > 0 && ic == prev_idx + 1;
+        for (int c0 = 0; c0 < 32; c0 += G) {
+            if (!((vmask >> c0) & 1)) break;  // valid lanes are a prefix
+            const unsigned long long i0 = __shfl_sync(0xffffffffu, (unsigned long long)idx, c0);
+            // is the whole group valid and contiguous (same instance)?
+            const bool mine_ok = (int)lane < c0 || (int)lane >= c0 + G || (valid && (unsigned long long)idx == i0 + (lane - c0));
+            if (__all_sync(0xffffffffu, mine_ok)) {
+                const uint32_t *p0 = reinterpret_cast<const uint32_t *>(snapshots + i0);
+                uint32_t w[G + 1][VM_DIFF_WORDS];
 #pragma unroll
-            for (int k = 0; k < VM_DIFF_WORDS; k++) {
-                const int j = (int)lane + 32 * k;
-                const bool in = j < VM_WORDS;
-                cur[k] = chained ? nxt[k] : (in ? __ldg(pc + j) : 0u);
-                nxt[k] = in ? __ldg(pn + j) : 0u;
-                const unsigned m = __ballot_sync(0xffffffffu, cur[k] != nxt[k]);
-                if ((int)lane == c) diff[k] = m;
+                for (int j = 0; j <= G; j++)
+#pragma unroll
+                    for (int k = 0; k < VM_DIFF_WORDS; k++) {
+                        const int o = (int)lane + 32 * k;
+                        w[j][k] = o < VM_WORDS ? __ldg(p0 + (size_t)j * VM_WORDS + o) : 0u;
+                    }
+#pragma unroll
+                for (int j = 0; j < G; j++)
+#pragma unroll
+                    for (int k = 0; k < VM_DIFF_WORDS; k++) {
+                        const unsigned m = __ballot_sync(0xffffffffu, w[j][k] != w[j + 1][k]);
+                        if ((int)lane == c0 + j) diff[k] = m;
+                    }
+            } else {  // a group that straddles instances or the end of the launch: one cycle at a time
+#pragma unroll 1
+                for (int c = c0; c < c0 + G; c++) {
+                    if (!((vmask >> c) & 1)) break;
+                    const unsigned long long ic = __shfl_sync(0xffffffffu, (unsigned long long)idx, c);
+                    const uint32_t *pc = reinterpret_cast<const uint32_t *>(snapshots + ic), *pn = pc + VM_WORDS;
+#pragma unroll
+                    for (int k = 0; k < VM_DIFF_WORDS; k++) {
+                        const int o = (int)lane + 32 * k;
+                        const bool in = o < VM_WORDS;
+                        const uint32_t a = in ? __ldg(pc + o) : 0u, b = in ? __ldg(pn + o) : 0u;
+                        const unsigned m = __ballot_sync(0xffffffffu, a != b);
+                        if ((int)lane == c) diff[k] = m;
+                    }
+                }
             }
-            prev_idx = ic;
         }
     }
     // ---- the cycle ------------------------------------------------------------------------------------------------------
@@ -1458,10 +1490,10 @@ vm_sponge_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const 
 
 // the sponge columns of the trace: 9 enforce flags + 9 x 12 permutation outputs (zeros where a relation is not enforced)
 __global__ void __launch_bounds__(256)
-vm_sponge_trace_kernel(VmPushScratch ps, uint64_t *__restrict__ trace, size_t limit, size_t total) {
-    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total) return;
-    const size_t inst = g / limit, row = g - inst * limit;
+vm_sponge_trace_kernel(VmPushScratch ps, uint64_t *__restrict__ trace, size_t limit, size_t n_instances, size_t row0, size_t row_count) {
+    const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= row_count * n_instances) return;
+    const size_t inst = l / row_count, row = row0 + (l - inst * row_count), g = inst * limit + row;
     uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit + row;
     const uint32_t m = ps.meta[g * 3];
 #pragma unroll
@@ -1777,7 +1809,7 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
                           zkc_carver::bytes(n_cw + 1, sizeof(zkc_vm_callstack_witness));
     if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ZKC_VM_NUM_COLS * rows, 8);
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
-    bytes += zkc_carver::bytes(8, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 3, 4) +
+    bytes += zkc_carver::bytes(8 * 16, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 3, 4) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8);
     void *blk = ctx->scratch(bytes);
     VmDev *h = (VmDev *)ctx->pinned(n_instances * sizeof(VmDev));
@@ -1799,40 +1831,92 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     const zkc_vm_cycle_witness *dwit = witness;
     const zkc_vm_callstack_witness *dcw = callstack_witness;
     uint64_t *dtrace = trace;
-    if (!in_dev && limit) {
-        zkc_vm_state *bs = cv.take<zkc_vm_state>(rows + n_instances);
-        zkc_vm_cycle_witness *bw = cv.take<zkc_vm_cycle_witness>(rows + 1);
-        zkc_vm_callstack_witness *bc = cv.take<zkc_vm_callstack_witness>(n_cw + 1);
-        ZKC_CUDA(ctx, status, cudaMemcpyAsync(bs, snapshots, (rows + n_instances) * sizeof(zkc_vm_state), cudaMemcpyHostToDevice, s));
-        ZKC_CUDA(ctx, status, cudaMemcpyAsync(bw, witness, rows * sizeof(zkc_vm_cycle_witness), cudaMemcpyHostToDevice, s));
-        if (n_cw) ZKC_CUDA(ctx, status, cudaMemcpyAsync(bc, callstack_witness, n_cw * sizeof(zkc_vm_callstack_witness), cudaMemcpyHostToDevice, s));
-        dsnap = bs; dwit = bw; dcw = bc;
-    }
-    if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ZKC_VM_NUM_COLS * rows);
     uint64_t *flat = cv.take<uint64_t>(n_instances * 4 * VM_FLAT_STRIDE);
+    // Host buffers: the rows are cut into chunks and pipelined over three streams -- H2D of chunk i+1 | kernels of chunk i |
+    // D2H of chunk i-1 -- so that a step costs max(H2D, D2H) instead of their sum (PCIe is full duplex).
+    size_t n_chunks = 1;
+    if ((!in_dev || (trace && !trace_dev)) && limit >= 8192 && rows >= (1u << 16)) n_chunks = limit >= (1u << 18) ? 16 : 4;
+    if (n_chunks > 1 && !ctx->copy_streams()) n_chunks = 1;
+    const size_t chunk_rows = (limit + n_chunks - 1) / n_chunks;
+    cudaStream_t s_in = n_chunks > 1 ? ctx->copy_in : s, s_out = n_chunks > 1 ? ctx->copy_out : s;
+    uint32_t *counts = cv.take<uint32_t>(8 * n_chunks);
+    uint32_t *lists = cv.take<uint32_t>(VM_JOB_SLOTS * rows);
     VmPushScratch ps;
-    ps.counts = cv.take<uint32_t>(8);
-    ps.lists = cv.take<uint32_t>(VM_JOB_SLOTS * rows);
     ps.meta = cv.take<uint32_t>(rows * 3);
     ps.enc = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 8);
     ps.state = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 12);
-    ZKC_CUDA(ctx, status, cudaMemsetAsync(ps.counts, 0, 32, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(counts, 0, 32 * n_chunks, s));
     ZKC_LAUNCH(ctx, "vm_prologue", vm_prologue_kernel, (unsigned)((n_instances + 31) / 32), 32, 0, d, disa, n_instances);
-    if (rows) {
-        ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, disa, dsnap, dwit, dcw,
-                   (uint32_t)n_callstack_witness, dtrace, limit, n_instances, ps);
+    // [n] lines of `width` bytes, `pitch` apart on both sides
+    auto copy_lines = [&](void *dst, const void *src, size_t pitch, size_t width, size_t lines, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
+        if (lines == 1 || width == pitch) return cudaMemcpyAsync(dst, src, width * (width == pitch ? lines : 1), kind, st);
+        if (pitch < (1ull << 31)) return cudaMemcpy2DAsync(dst, pitch, src, pitch, width, lines, kind, st);
+        for (size_t i = 0; i < lines; i++) {
+            const cudaError_t e = cudaMemcpyAsync((char *)dst + i * pitch, (const char *)src + i * pitch, width, kind, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    std::vector<cudaEvent_t> used_events;
+    auto event = [&]() { cudaEvent_t e = ctx->get_event(); used_events.push_back(e); return e; };
+    if (n_chunks > 1) {  // the copy streams start after what the main stream has queued so far (scratch reuse, VmDev upload)
+        cudaEvent_t e0 = event();
+        ZKC_CUDA(ctx, status, cudaEventRecord(e0, s));
+        ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_in, e0, 0));
+        ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_out, e0, 0));
+    }
+    zkc_vm_state *bs = nullptr;
+    zkc_vm_cycle_witness *bw = nullptr;
+    if (!in_dev && limit) {
+        bs = cv.take<zkc_vm_state>(rows + n_instances);
+        bw = cv.take<zkc_vm_cycle_witness>(rows + 1);
+        zkc_vm_callstack_witness *bc = cv.take<zkc_vm_callstack_witness>(n_cw + 1);
+        if (n_cw) ZKC_CUDA(ctx, status, cudaMemcpyAsync(bc, callstack_witness, n_cw * sizeof(zkc_vm_callstack_witness), cudaMemcpyHostToDevice, s_in));
+        dsnap = bs; dwit = bw; dcw = bc;
+    }
+    if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ZKC_VM_NUM_COLS * rows);
+    for (size_t c = 0; c < n_chunks && limit; c++) {
+        const size_t r0 = c * chunk_rows;
+        if (r0 >= limit) break;
+        const size_t cnt = std::min(chunk_rows, limit - r0), n_thr = cnt * n_instances;
+        if (!in_dev) {
+            ZKC_CUDA(ctx, status, copy_lines(bs + r0, snapshots + r0, (limit + 1) * sizeof(zkc_vm_state), (cnt + 1) * sizeof(zkc_vm_state), n_instances,
+                                             cudaMemcpyHostToDevice, s_in));
+            ZKC_CUDA(ctx, status, copy_lines(bw + r0, witness + r0, limit * sizeof(zkc_vm_cycle_witness), cnt * sizeof(zkc_vm_cycle_witness), n_instances,
+                                             cudaMemcpyHostToDevice, s_in));
+            if (n_chunks > 1) {
+                cudaEvent_t e = event();
+                ZKC_CUDA(ctx, status, cudaEventRecord(e, s_in));
+                ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e, 0));
+            }
+        }
+        ps.counts = counts + 8 * c;
+        ps.lists = lists + n_instances * r0;
+        ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, dsnap, dwit, dcw,
+                   (uint32_t)n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps);
         // the lists live on the device: size every sponge launch for the worst case, surplus threads leave at once
         for (int k = 0; k < VM_JOB_SLOTS; k++)
-            ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_kernel, (unsigned)((rows + 127) / 128), 128, 0, d, dsnap, dwit, dcw,
+            ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, dsnap, dwit, dcw,
                        (uint32_t)n_callstack_witness, ps, k, limit, rows);
-        if (dtrace) ZKC_LAUNCH(ctx, "vm_sponge_trace", vm_sponge_trace_kernel, (unsigned)((rows + 255) / 256), 256, 0, ps, dtrace, limit, rows);
+        if (dtrace) ZKC_LAUNCH(ctx, "vm_sponge_trace", vm_sponge_trace_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, ps, dtrace, limit, n_instances, r0, cnt);
+        if (trace && !trace_dev) {
+            if (n_chunks > 1) {
+                cudaEvent_t e = event();
+                ZKC_CUDA(ctx, status, cudaEventRecord(e, s));
+                ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_out, e, 0));
+            }
+            ZKC_CUDA(ctx, status, copy_lines(trace + r0, dtrace + r0, limit * 8, cnt * 8, n_instances * (size_t)ZKC_VM_NUM_COLS, cudaMemcpyDeviceToHost, s_out));
+        }
     }
     ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 1) / 2), 128, 0, d, flat, n_instances);
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, n_instances * sizeof(VmDev), cudaMemcpyDeviceToHost, s));
-    if (!trace_dev && trace && rows)
-        ZKC_CUDA(ctx, status, cudaMemcpyAsync(trace, dtrace, (size_t)ZKC_VM_NUM_COLS * rows * 8, cudaMemcpyDeviceToHost, s));
     ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    if (n_chunks > 1) {
+        ZKC_CUDA(ctx, status, cudaStreamSynchronize(s_in));
+        ZKC_CUDA(ctx, status, cudaStreamSynchronize(s_out));
+    }
+    for (cudaEvent_t e : used_events) ctx->event_pool.push_back(e);
     int worst = ZKC_OK;
     for (size_t i = 0; i < n_instances; i++) {
         ios[i].hidden_fsm_output = h[i].io.hidden_fsm_output;

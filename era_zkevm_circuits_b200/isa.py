@@ -169,7 +169,9 @@ def random_program(isa: Isa, n: int, seed: int = 0xC2, with_memory=True, full=Tr
         elif k < 83:  # ptr.add of the calldata pointer by a small immediate never panics
             ops.append(isa.encode(OP_PTR, 0, 1, MODE_IMM16, MODE_REG, COND_ALWAYS, src1=1, dst0=dst0, imm0=x % 7))
         elif k < 85:
-            ops.append(isa.encode(OP_CONTEXT, x % 10, 0, MODE_REG, MODE_REG, COND_ALWAYS, src0=int(r[i, 1] % 14) + 2, dst0=dst0))
+            # set_ergs_per_pubdata takes the (small) key register: a random 256-bit price would burn every erg at the next write
+            variant = x % 10
+            ops.append(isa.encode(OP_CONTEXT, variant, 0, MODE_REG, MODE_REG, COND_ALWAYS, src0=14 if variant == 8 else int(r[i, 1] % 14) + 2, dst0=dst0))
         elif k < 95 and room >= 2:  # UMA: offset -> r15, then the access
             variant = (UMA_HEAP_READ, UMA_HEAP_WRITE, UMA_HEAP_READ, UMA_HEAP_WRITE, UMA_AUX_READ, UMA_AUX_WRITE, UMA_PTR_READ)[x % 7]
             inc = (x >> 3) & 1

@@ -984,9 +984,8 @@ int orc_main_vm_run(const zkc_vm_isa *isa, const zkc_vm_state *initial, const ui
     uint64_t root_tail[4];
     memcpy(root_tail, initial->current_context.reverted_queue_tail, 32);
     memset(witness, 0, cycles * sizeof *witness);
-    int rc = vm_run_pass(isa, initial, code, code_words, cycles, NULL, witness, cw_out, cw_cap, n_cw, root_tail, 1, status);
-    if (rc == ZKC_OK || rc == ZKC_ERR_UNSATISFIED)
-        rc = vm_run_pass(isa, initial, code, code_words, cycles, snapshots, witness, cw_out, cw_cap, n_cw, root_tail, 0, status);
+    vm_run_pass(isa, initial, code, code_words, cycles, NULL, witness, cw_out, cw_cap, n_cw, root_tail, 1, status);
+    const int rc = vm_run_pass(isa, initial, code, code_words, cycles, snapshots, witness, cw_out, cw_cap, n_cw, root_tail, 0, status);
     if (rollback_tail_out) memcpy(rollback_tail_out, root_tail, 32);
     return rc;
 }

@@ -185,6 +185,7 @@ def test_error_cases_match_oracle(engine, orc):
     ops = I.random_program(isa, 256, seed=13)
     cycles = 900
     rc, snaps, wit, _, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+    io0 = io
     io = with_tail(io, tail)
     # corrupted snapshot: a register limb, a queue state element, context words, the stack sponge
     for idx, byte in ((123, 40), (500, 1100), (0, 36), (cycles, 44), (300, 700), (301, 760), (640, 900), (77, 1000), (10, 812)):
@@ -204,8 +205,8 @@ def test_error_cases_match_oracle(engine, orc):
     ops2 = [isa.encode(I.OP_ADD, 0, 0, src0=2, src1=3, dst0=4)] * 5 + [isa.encode(I.OP_FAR_CALL)] + [isa.encode(I.OP_NOP)] * 4
     rc, s2, w3, status = O.vm_run(orc, isa.isa, st, I.pack_code(ops2), 8)
     assert rc == abi.ZKC_ERR_UNSUPPORTED and status.first_bad_row == 5
-    want = O.vm_entry_point(orc, io, isa.isa, s2, w3, 8)
-    got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, s2, w3), 8, raise_on_unsatisfied=False)
+    want = O.vm_entry_point(orc, io0, isa.isa, s2, w3, 8)
+    got = main_vm_entry_point(engine, VmCircuitWitness(io0, isa.isa, s2, w3), 8, raise_on_unsatisfied=False)
     assert want[0] == abi.ZKC_ERR_UNSUPPORTED
     assert_same(want, got, check_trace=False)
 

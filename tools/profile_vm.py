@@ -19,11 +19,16 @@ progs = [I.pack_code(I.random_program(isa, 4096, seed=0xC2 + k)) for k in range(
 for i in range(n):
     io = abi.VmClosedForm(); io.start_flag = 1; io.rollback_queue_tail_for_block[0] = i
     ios.append(io); states.append(main_vm_initial_state(eng, io, isa.isa)); codes.append(progs[i % 4])
-snaps, wit, st = main_vm_simulate(eng, isa.isa, states, np.stack(codes), cycles)
-assert st.code == 0
+sim = main_vm_simulate(eng, isa.isa, states, np.stack(codes), cycles)
+assert sim.status.code == 0
+for io, t in zip(ios, sim.rollback_tails):
+    for k in range(4):
+        io.rollback_queue_tail_for_block[k] = int(t[k])
+cw = sim.callstack_witness[:, :max(1, int(sim.n_callstack.max()))].contiguous()
 trace = torch.empty((n, abi.VM_COLS["NUM_COLS"], cycles), dtype=torch.int64, device="cuda")
 for _ in range(3):
-    coms, out, statuses, rc = main_vm_entry_point_batch(eng, ios, isa.isa, snaps, wit, cycles, trace_out=trace)
+    coms, out, statuses, rc = main_vm_entry_point_batch(eng, ios, isa.isa, sim.snapshots, sim.witness, cycles, trace_out=trace,
+                                                        callstack_witness=cw)
     assert rc == 0
 torch.cuda.synchronize()
 print("ok")
