@@ -29,6 +29,7 @@ extern "C" void zkc_destroy(zkc_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->prof_resolve();
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);

@@ -33,6 +33,16 @@ struct zkc_ctx {
     int last_cuda_error = 0;
     // copy streams of the pipelined host paths (H2D of chunk i+1 | kernels of chunk i | D2H of chunk i-1)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // high-priority side stream for small latency-bound kernels that can run beside the main launches
+    cudaStream_t aux = nullptr;
+    cudaStream_t aux_stream() {
+        if (!aux) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, hi) != cudaSuccess) aux = nullptr;
+        }
+        return aux;
+    }
     bool copy_streams() {
         if (!copy_in && cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking) != cudaSuccess) return false;
         if (!copy_out && cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking) != cudaSuccess) return false;

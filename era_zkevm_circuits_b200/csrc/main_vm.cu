@@ -33,6 +33,8 @@ struct VmDev {
     uint32_t failed_checks, pad1;
     uint64_t commitment[4];
     zkc_status status;
+    uint64_t hint_commitment[4];  // commitment computed ahead of time from the host's final snapshot (vm_finalize_kernel, mode 0)
+    uint32_t hint_ok, pad2;
 };
 
 // ---- 256-bit helpers on little-endian u32 limbs -------------------------------------------------------------
@@ -1323,7 +1325,6 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
     const zkc_vm_state &s = snapshots[idx], &next = snapshots[idx + 1];
     uint32_t checks = 0, jmask = 0;
     if (valid) {
-        if (row == 0 && !vm_state_equal(s, dev->s0)) checks |= ZKC_VM_CHK_SNAPSHOT;  // the hint chain starts at the circuit's own start state
         VmDelta d;
         zkc_vm_context nctx;
         checks |= vm_cycle_dev<false>(isa, s, d, nctx, witness[g], cws + inst * (size_t)n_cw, n_cw, nullptr, nullptr,
@@ -1433,18 +1434,22 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
 // slot k of every cycle that has one: out = P(enc || capacity), one thread per job, all lanes busy.  The capacity is a
 // previous job's output of the same cycle, zeros, or a queue state of the snapshot / the callstack witness; the output
 // of the last job of a chain must land on the next snapshot (or, for the joins the circuit enforces, on the current one).
-__global__ void __launch_bounds__(128)
-vm_sponge_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
-                 const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, VmPushScratch ps, int k, size_t limit, size_t total) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ps.counts[k]) return;
-    const size_t g = ps.lists[(size_t)k * total + i];
+// One job: slot k of cycle g.  `flags` (persistent launch): per-job completion flags -- a job whose capacity is another
+// job's output waits for it, and publishes its own output when done.
+__device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
+                                              const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, const VmPushScratch &ps, int k, size_t g,
+                                              size_t limit, uint32_t *flags) {
     const size_t inst = g / limit, row = g - inst * limit, idx = inst * (limit + 1) + row;
     const uint32_t cap_from = (ps.meta[g * 3 + 1] >> (4 * k)) & 15, chk = (ps.meta[g * 3 + 2] >> (4 * k)) & 15;
     const zkc_vm_state &s = snapshots[idx];
     uint64_t q[12];
 #pragma unroll
     for (int j = 0; j < 8; j++) q[j] = ps.enc[(g * VM_JOB_SLOTS + k) * 8 + j];
+    if (flags && cap_from < VM_JOB_SLOTS) {
+        const volatile uint32_t *f = flags + g * VM_JOB_SLOTS + cap_from;
+        while (*f == 0) __nanosleep(64);
+        __threadfence();
+    }
     if (cap_from == VM_CAP_ZERO) {
 #pragma unroll
         for (int j = 8; j < 12; j++) q[j] = 0;
@@ -1464,6 +1469,10 @@ vm_sponge_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const 
     uint64_t *to = ps.state + (g * VM_JOB_SLOTS + k) * 12;
 #pragma unroll
     for (int j = 0; j < 12; j++) to[j] = q[j];
+    if (flags) {
+        __threadfence();
+        *(volatile uint32_t *)(flags + g * VM_JOB_SLOTS + k) = 1u;
+    }
     if (chk == VM_CHK_NONE) return;
     VmDev *dev = devs + inst;
     const zkc_vm_state &next = snapshots[idx + 1];
@@ -1485,6 +1494,42 @@ vm_sponge_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const 
         uint64_t *dst = chk == VM_CHK_NEXT_MEMQ ? dev->s_final.memory_queue_state
                       : chk == VM_CHK_NEXT_STACK ? dev->s_final.stack_sponge_state : dev->s_final.current_context.log_queue_forward_tail;
         for (int j = 0; j < n; j++) dst[j] = q[j];
+    }
+}
+
+// slot k of every cycle that has one, one thread per job (one launch per slot)
+__global__ void __launch_bounds__(128)
+vm_sponge_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
+                 const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, VmPushScratch ps, int k, size_t limit, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ps.counts[k]) return;
+    vm_sponge_job(devs, snapshots, witness, cws, n_cw, ps, k, ps.lists[(size_t)k * total + i], limit, nullptr);
+}
+
+// All slots in ONE persistent launch (grid = what is resident at once).  The jobs are numbered slot by slot (every
+// slot's range padded to a multiple of 32) and handed out in that order, a warp at a time, by an atomic ticket; a job
+// that continues another slot's output spins on that job's flag.  Its dependency has a smaller number, so it was handed
+// out earlier to a warp that is resident and never waits on a larger number: no deadlock, and no launch boundary --
+// the tail of slot k overlaps the head of slot k + 1 instead of draining the machine five times.
+__global__ void __launch_bounds__(128)
+vm_sponge_persistent_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
+                            const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, VmPushScratch ps, unsigned long long *ticket,
+                            uint32_t *flags, size_t limit, size_t total) {
+    const unsigned lane = threadIdx.x & 31;
+    unsigned long long start[VM_JOB_SLOTS + 1];
+    start[0] = 0;
+#pragma unroll
+    for (int k = 0; k < VM_JOB_SLOTS; k++) start[k + 1] = start[k] + (((unsigned long long)ps.counts[k] + 31) & ~31ull);
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 32ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= start[VM_JOB_SLOTS]) return;
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < VM_JOB_SLOTS; j++) k += t >= start[j];
+        const unsigned long long i = t - start[k] + lane;
+        if (i < ps.counts[k]) vm_sponge_job(devs, snapshots, witness, cws, n_cw, ps, k, ps.lists[(size_t)k * total + i], limit, flags);
     }
 }
 
@@ -1511,9 +1556,14 @@ vm_sponge_trace_kernel(VmPushScratch ps, uint64_t *__restrict__ trace, size_t li
 // 12-lane permutation (poseidon2.cuh) -- the 31 dependent permutations over a VM state are the latency of this launch.
 // Each group flattens its encoding into its own global scratch row and absorbs from there, and skips the sponge whose
 // result the start / completion flags mask to zero anyway; group 0 then commits the compact form.
+// Two modes.  HINT (mode 0) runs on a side stream concurrently with the cycle launches and commits the closed form from
+// the HOST's final snapshot; FINAL (mode 1) runs last: when every snapshot link verified, the state the circuit ends in
+// IS that snapshot and the hinted commitment is taken (the 31 dependent permutations are off the critical path),
+// otherwise everything is recomputed from the computed final state.  FINAL also owns the check that the hint chain
+// starts at the circuit's own start state (snapshot 0 == s0), so that the cycle launch does not wait for the prologue.
 constexpr int VM_FLAT_STRIDE = 248;
 __global__ void __launch_bounds__(128)
-vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances) {
+vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances, const zkc_vm_state *__restrict__ snapshots, size_t limit, int mode) {
     __shared__ uint64_t part[2][4][4];
     __shared__ uint64_t compact[2][24];
     const int slot = threadIdx.x >> 6, role = (threadIdx.x >> 4) & 3, i = threadIdx.x & 15;
@@ -1522,13 +1572,21 @@ vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances)
     const bool active = inst < n_instances;
     VmDev *d = devs + (active ? inst : 0);
     zkc_vm_closed_form &io = d->io;
-    const zkc_vm_state &state = d->s_final;
+    const bool hint_mode = mode == 0;
+    const zkc_vm_state &state = hint_mode ? snapshots[(active ? inst : 0) * (limit + 1) + limit] : d->s_final;
     const bool done = state.context_stack_depth == 0;  // mod.rs:113-122
-    const bool start = d->start != 0;
+    const bool start = hint_mode ? io.start_flag != 0 : d->start != 0;
+    bool use_hint = false;
+    if (!hint_mode && active) {
+        const bool chain_starts_right = limit == 0 || vm_state_equal(snapshots[inst * (limit + 1)], d->s0);
+        if (!chain_starts_right && threadIdx.x % 64 == 0) vm_report(d, 0, ZKC_VM_CHK_SNAPSHOT);
+        use_hint = limit != 0 && chain_starts_right && d->hint_ok && !(d->failed_checks & ZKC_VM_CHK_SNAPSHOT);
+    }
+    __syncthreads();  // the report above is read below
     {
         const uint64_t *buf = flat + (inst * 4 + role) * VM_FLAT_STRIDE;
         int n = 0;
-        const bool need = active && (role == 0 ? !done : role == 1 ? !start : role == 2 ? true : done);
+        const bool need = active && !use_hint && (role == 0 ? !done : role == 1 ? !start : role == 2 ? true : done);
         if (need) {
             if (i == 0) {
                 uint64_t *w = flat + (inst * 4 + role) * VM_FLAT_STRIDE;
@@ -1564,6 +1622,16 @@ vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances)
     }
     __syncthreads();
     if (active && role == 0 && i == 0) {
+        uint64_t *cf = compact[slot];
+        cf[0] = start; cf[1] = done;
+        for (int j = 0; j < 4; j++) {
+            cf[2 + j] = part[slot][2][j];
+            cf[6 + j] = part[slot][3][j];   // zero unless done
+            cf[10 + j] = part[slot][1][j];  // zero if start
+            cf[14 + j] = part[slot][0][j];  // zero if done
+        }
+    }
+    if (active && role == 0 && i == 0 && !hint_mode) {
         zkc_queue_state4 log_out;
         zkc_queue_state12 mem_out, dec_out;
         memset(&log_out, 0, sizeof log_out); memset(&mem_out, 0, sizeof mem_out); memset(&dec_out, 0, sizeof dec_out);
@@ -1593,25 +1661,21 @@ vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances)
         }
         io.log_queue_final_state = log_out; io.memory_queue_final_state = mem_out; io.decommitment_queue_final_state = dec_out;
         io.completion_flag = done;
-        uint64_t *cf = compact[slot];
-        cf[0] = start; cf[1] = done;
-        for (int j = 0; j < 4; j++) {
-            cf[2 + j] = part[slot][2][j];
-            cf[6 + j] = part[slot][3][j];   // zero unless done
-            cf[10 + j] = part[slot][1][j];  // zero if start
-            cf[14 + j] = part[slot][0][j];  // zero if done
-        }
         d->status = st;
     }
     __syncthreads();
-    if (active) {  // the 64 threads of the instance publish the state the circuit ended in
+    if (active && !hint_mode) {  // the 64 threads of the instance publish the state the circuit ended in
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&state);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&io.hidden_fsm_output);
         for (int j = threadIdx.x & 63; j < (int)(sizeof(zkc_vm_state) / 4); j += 64) dst[j] = src[j];
     }
     if (role == 0) {
-        const uint64_t c = commit_encoding_coop(gm, compact[slot], active ? 18 : 0, i);
-        if (active && i < 4) d->commitment[i] = c;
+        const uint64_t c = commit_encoding_coop(gm, compact[slot], active && !use_hint ? 18 : 0, i);
+        if (active && i < 4) {
+            if (hint_mode) d->hint_commitment[i] = c;
+            else d->commitment[i] = use_hint ? d->hint_commitment[i] : c;
+        }
+        if (active && hint_mode && i == 0) d->hint_ok = 1;
     }
 }
 
@@ -1810,7 +1874,8 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ZKC_VM_NUM_COLS * rows, 8);
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
     bytes += zkc_carver::bytes(8 * 16, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 3, 4) +
-             zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8);
+             zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8) +
+             zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(16, 8);
     void *blk = ctx->scratch(bytes);
     VmDev *h = (VmDev *)ctx->pinned(n_instances * sizeof(VmDev));
     if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
@@ -1845,8 +1910,16 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     ps.meta = cv.take<uint32_t>(rows * 3);
     ps.enc = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 8);
     ps.state = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 12);
+    uint32_t *job_flags = cv.take<uint32_t>(rows * VM_JOB_SLOTS);
+    unsigned long long *tickets = cv.take<unsigned long long>(16);
     ZKC_CUDA(ctx, status, cudaMemsetAsync(counts, 0, 32 * n_chunks, s));
-    ZKC_LAUNCH(ctx, "vm_prologue", vm_prologue_kernel, (unsigned)((n_instances + 31) / 32), 32, 0, d, disa, n_instances);
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(job_flags, 0, rows * VM_JOB_SLOTS * 4, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(tickets, 0, 16 * 8, s));
+    static int sponge_blocks_per_sm = 0;
+    if (!sponge_blocks_per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sponge_blocks_per_sm, vm_sponge_persistent_kernel, 128, 0) != cudaSuccess || sponge_blocks_per_sm < 1)
+            sponge_blocks_per_sm = 1;
+    }
     // [n] lines of `width` bytes, `pitch` apart on both sides
     auto copy_lines = [&](void *dst, const void *src, size_t pitch, size_t width, size_t lines, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
         if (lines == 1 || width == pitch) return cudaMemcpyAsync(dst, src, width * (width == pitch ? lines : 1), kind, st);
@@ -1875,13 +1948,44 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
         dsnap = bs; dwit = bw; dcw = bc;
     }
     if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ZKC_VM_NUM_COLS * rows);
+    // Side stream: the start state (4 dependent permutations) and the closed-form commitments from the host's final
+    // snapshot (31 dependent permutations) run beside the cycle launches; the FINAL pass below takes them when every link
+    // verified.  Host inputs: the final snapshots are copied first (the chunk copies then leave them alone).
+    cudaStream_t s_aux = ctx->aux_stream();
+    if (!s_aux) s_aux = s;
+    cudaEvent_t e_final_snapshot = nullptr, e_hint = nullptr;
+    {
+        if (s_aux != s) {
+            cudaEvent_t e = event();
+            ZKC_CUDA(ctx, status, cudaEventRecord(e, s));
+            ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_aux, e, 0));
+        }
+        ctx->launches++;
+        vm_prologue_kernel<<<(unsigned)((n_instances + 31) / 32), 32, 0, s_aux>>>(d, disa, n_instances);
+        if (limit) {
+            if (!in_dev) {
+                ZKC_CUDA(ctx, status, copy_lines(bs + limit, snapshots + limit, (limit + 1) * sizeof(zkc_vm_state), sizeof(zkc_vm_state), n_instances,
+                                                 cudaMemcpyHostToDevice, s_aux));
+                e_final_snapshot = event();
+                ZKC_CUDA(ctx, status, cudaEventRecord(e_final_snapshot, s_aux));
+            }
+            ctx->launches++;
+            vm_finalize_kernel<<<(unsigned)((n_instances + 1) / 2), 128, 0, s_aux>>>(d, flat, n_instances, dsnap, limit, 0);
+        }
+        if (s_aux != s) {
+            e_hint = event();
+            ZKC_CUDA(ctx, status, cudaEventRecord(e_hint, s_aux));
+        }
+    }
     for (size_t c = 0; c < n_chunks && limit; c++) {
         const size_t r0 = c * chunk_rows;
         if (r0 >= limit) break;
         const size_t cnt = std::min(chunk_rows, limit - r0), n_thr = cnt * n_instances;
         if (!in_dev) {
-            ZKC_CUDA(ctx, status, copy_lines(bs + r0, snapshots + r0, (limit + 1) * sizeof(zkc_vm_state), (cnt + 1) * sizeof(zkc_vm_state), n_instances,
-                                             cudaMemcpyHostToDevice, s_in));
+            const bool last_chunk = r0 + cnt == limit;  // its final snapshot came with the side stream
+            ZKC_CUDA(ctx, status, copy_lines(bs + r0, snapshots + r0, (limit + 1) * sizeof(zkc_vm_state), (cnt + (last_chunk ? 0 : 1)) * sizeof(zkc_vm_state),
+                                             n_instances, cudaMemcpyHostToDevice, s_in));
+            if (last_chunk && e_final_snapshot && s_aux != s) ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e_final_snapshot, 0));
             ZKC_CUDA(ctx, status, copy_lines(bw + r0, witness + r0, limit * sizeof(zkc_vm_cycle_witness), cnt * sizeof(zkc_vm_cycle_witness), n_instances,
                                              cudaMemcpyHostToDevice, s_in));
             if (n_chunks > 1) {
@@ -1894,10 +1998,12 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
         ps.lists = lists + n_instances * r0;
         ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, dsnap, dwit, dcw,
                    (uint32_t)n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps);
-        // the lists live on the device: size every sponge launch for the worst case, surplus threads leave at once
-        for (int k = 0; k < VM_JOB_SLOTS; k++)
-            ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, dsnap, dwit, dcw,
-                       (uint32_t)n_callstack_witness, ps, k, limit, rows);
+        // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists
+        {
+            const size_t max_blocks = (size_t)ctx->sm_count * sponge_blocks_per_sm, need_blocks = (n_thr * VM_JOB_SLOTS + 127) / 128;
+            ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_persistent_kernel, (unsigned)std::min(max_blocks, std::max<size_t>(need_blocks, 1)), 128, 0, d, dsnap,
+                       dwit, dcw, (uint32_t)n_callstack_witness, ps, tickets + c, job_flags, limit, rows);
+        }
         if (dtrace) ZKC_LAUNCH(ctx, "vm_sponge_trace", vm_sponge_trace_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, ps, dtrace, limit, n_instances, r0, cnt);
         if (trace && !trace_dev) {
             if (n_chunks > 1) {
@@ -1908,7 +2014,8 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
             ZKC_CUDA(ctx, status, copy_lines(trace + r0, dtrace + r0, limit * 8, cnt * 8, n_instances * (size_t)ZKC_VM_NUM_COLS, cudaMemcpyDeviceToHost, s_out));
         }
     }
-    ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 1) / 2), 128, 0, d, flat, n_instances);
+    if (e_hint) ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e_hint, 0));
+    ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 1) / 2), 128, 0, d, flat, n_instances, dsnap, limit, 1);
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, n_instances * sizeof(VmDev), cudaMemcpyDeviceToHost, s));
     ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
