@@ -197,7 +197,13 @@ class VmClosedForm(C.Structure):
 
 
 class VmOptions(C.Structure):
-    _fields_ = [("compare_expected", C.c_uint32), ("_pad", C.c_uint32 * 3)]
+    _fields_ = [("compare_expected", C.c_uint32), ("trace_layout", C.c_uint32), ("sponge_records_capacity", C.c_uint64),
+                ("sponge_records", C.c_void_p)]
+
+
+VM_SPONGE_RECORD_DTYPE = np.dtype([("row", "<u4"), ("slot", "<u4"), ("out", "<u8", (12,))])
+assert VM_SPONGE_RECORD_DTYPE.itemsize == 104
+VM_TRACE_DENSE, VM_TRACE_COMPACT = 0, 1
 
 
 assert C.sizeof(VmState) == 1176 and C.sizeof(VmContext) == 240 and C.sizeof(VmIsa) == 24736
@@ -212,6 +218,25 @@ VM_COLS = dict(
     SRC1=61, DST0=70, DST1=79, PERFORM_DST0_MEMORY_WRITE=88, DST0_UPDATE_REGISTER=89, DST1_UPDATE_REGISTER=90, FLAGS_OUT=91,
     PENDING_EXCEPTION_OUT=94, PC_OUT=95, ERGS_OUT=96, HEAP_BOUND_OUT=97, AUX_HEAP_BOUND_OUT=98, MEMQ_LENGTH_OUT=99, DEPTH_OUT=100,
     FORWARD_TAIL_OUT=101, ROLLBACK_HEAD_OUT=106, SPONGE_ENFORCE=111, SPONGE_FINAL=120, OP_AUX=228, NUM_COLS=276)
+VM_COMPACT_COLS, VM_COMPACT_OP_AUX = 276 - 117, 228 - 117
+
+
+def vm_expand_compact_trace(compact, records, limit):
+    """dense [.., 276, limit] trace from the COMPACT layout (159 columns + sponge records); compact: [159, limit] or
+    [n, 159, limit]"""
+    compact = np.asarray(compact)
+    batched = compact.ndim == 3
+    c3 = compact if batched else compact[None]
+    n = c3.shape[0]
+    dense = np.zeros((n, VM_COLS["NUM_COLS"], limit), dtype=np.uint64)
+    dense[:, :VM_COLS["SPONGE_ENFORCE"]] = c3[:, :VM_COLS["SPONGE_ENFORCE"]]
+    dense[:, VM_COLS["OP_AUX"]:] = c3[:, VM_COMPACT_OP_AUX:]
+    rec = np.asarray(records)
+    inst, row, slot = rec["row"] // limit, rec["row"] % limit, rec["slot"].astype(np.int64)
+    dense[inst, VM_COLS["SPONGE_ENFORCE"] + slot, row] = 1
+    for j in range(12):
+        dense[inst, VM_COLS["SPONGE_FINAL"] + 12 * slot + j, row] = rec["out"][:, j]
+    return dense if batched else dense[0]
 VM_CHK = dict(INVALID_OPCODE=1, UNSUPPORTED_OPCODE=2, SNAPSHOT=4, DIV_RELATION=8, BOOTLOADER_EXIT=16, ROLLBACK_QUEUE=32,
               CALLSTACK=64, LOG_REFUND=128)
 ZKC_ERR_UNSUPPORTED, ZKC_ERR_SNAPSHOT_MISMATCH = 7, 8

@@ -17,6 +17,7 @@
 // jobs of every cycle run afterwards as dense launches, one slot at a time (vm_sponge_kernel), so a warp never waits
 // for a lane that hashes.
 #include <algorithm>
+#include <cstdlib>
 #include "ctx.cuh"
 #include "poseidon2.cuh"
 
@@ -509,7 +510,8 @@ __device__ void vm_log_encode(const uint32_t *address, const uint32_t *key, cons
 template <bool SIM, typename W>
 __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_vm_state &s, VmDelta &d, zkc_vm_context &nctx, W &w,
                                  const zkc_vm_callstack_witness *__restrict__ cw, uint32_t n_cw, VmSim *sim, VmSimOut *so,
-                                 uint64_t *penc, const zkc_vm_state *next, uint64_t *__restrict__ trace, size_t limit, size_t row) {
+                                 uint64_t *penc, const zkc_vm_state *next, uint64_t *__restrict__ trace, size_t limit, size_t row,
+                                 int aux_base = ZKC_VM_OP_AUX) {
 #define TR(col) trace[(size_t)(col) * limit + row]
     const bool wr = trace != nullptr;
     uint32_t checks = 0;
@@ -662,7 +664,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
 #pragma unroll
         for (int i = 0; i < 8; i++) TR(ZKC_VM_SRC0_FROM_MEMORY + 1 + i) = src0_mem.value[i];
 #pragma unroll 1
-        for (int i = 0; i < ZKC_VM_OP_AUX_COLS; i++) TR(ZKC_VM_OP_AUX + i) = 0;  // the selected opcode family overwrites its part
+        for (int i = 0; i < ZKC_VM_OP_AUX_COLS; i++) TR(aux_base + i) = 0;  // the selected opcode family overwrites its part
     }
     zkc_vm_register src0 = SRCM(ZKC_MODE_REG_ONLY) ? draft_src0 : src0_mem;
     if (SRCM(ZKC_MODE_IMM16)) { src0 = reg_zero(); src0.value[0] = imm0; }
@@ -840,11 +842,11 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
         if (access_aux) d.aux_bound = aux_uf ? aux_bound : aux_max;
         d.ergs = uf ? 0u : ergs_left - growth_cost;
         if (wr) {
-            TR(ZKC_VM_OP_AUX + 0) = abs_addr; TR(ZKC_VM_OP_AUX + 1) = cell_idx; TR(ZKC_VM_OP_AUX + 2) = unalignment; TR(ZKC_VM_OP_AUX + 3) = mem_page;
-            TR(ZKC_VM_OP_AUX + 4) = skip_mem; TR(ZKC_VM_OP_AUX + 5) = set_panic; TR(ZKC_VM_OP_AUX + 6) = growth_cost; TR(ZKC_VM_OP_AUX + 7) = incremented;
+            TR(aux_base + 0) = abs_addr; TR(aux_base + 1) = cell_idx; TR(aux_base + 2) = unalignment; TR(aux_base + 3) = mem_page;
+            TR(aux_base + 4) = skip_mem; TR(aux_base + 5) = set_panic; TR(aux_base + 6) = growth_cost; TR(aux_base + 7) = incremented;
             for (int i = 0; i < 8; i++) {
-                TR(ZKC_VM_OP_AUX + 8 + i) = va.value[i]; TR(ZKC_VM_OP_AUX + 16 + i) = vb.value[i];
-                TR(ZKC_VM_OP_AUX + 24 + i) = exec_write ? wa.v[i] : 0u; TR(ZKC_VM_OP_AUX + 32 + i) = exec_write_b ? wb.v[i] : 0u;
+                TR(aux_base + 8 + i) = va.value[i]; TR(aux_base + 16 + i) = vb.value[i];
+                TR(aux_base + 24 + i) = exec_write ? wa.v[i] : 0u; TR(aux_base + 32 + i) = exec_write_b ? wb.v[i] : 0u;
             }
         }
     } else if (TYPE(ZKC_OP_LOG)) {  // log.rs:16-671
@@ -928,9 +930,9 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
         dst0_reg_only = st_read || is_precompile;
         d.ergs = not_enough ? 0u : ergs_left - burn;
         if (wr) {
-            for (int i = 0; i < 20; i++) TR(ZKC_VM_OP_AUX + i) = enc[i];
-            for (int i = 0; i < 8; i++) TR(ZKC_VM_OP_AUX + 20 + i) = read_value[i];
-            TR(ZKC_VM_OP_AUX + 28) = execute; TR(ZKC_VM_OP_AUX + 29) = execute_rollback; TR(ZKC_VM_OP_AUX + 30) = burn;
+            for (int i = 0; i < 20; i++) TR(aux_base + i) = enc[i];
+            for (int i = 0; i < 8; i++) TR(aux_base + 20 + i) = read_value[i];
+            TR(aux_base + 28) = execute; TR(aux_base + 29) = execute_rollback; TR(aux_base + 30) = burn;
         }
     } else if (TYPE(ZKC_OP_NEAR_CALL) || TYPE(ZKC_OP_RET)) {  // call_ret.rs:24-512
         const bool apply_near = TYPE(ZKC_OP_NEAR_CALL), apply_ret = !apply_near;
@@ -1075,9 +1077,9 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
         if (wr) {
             uint64_t f[42];
             vm_flatten_record(nctx, f);
-            for (int i = 0; i < 42; i++) TR(ZKC_VM_OP_AUX + i) = f[i];
-            TR(ZKC_VM_OP_AUX + 42) = apply_near; TR(ZKC_VM_OP_AUX + 43) = apply_ret; TR(ZKC_VM_OP_AUX + 44) = is_panic_out;
-            TR(ZKC_VM_OP_AUX + 45) = perform_revert;
+            for (int i = 0; i < 42; i++) TR(aux_base + i) = f[i];
+            TR(aux_base + 42) = apply_near; TR(aux_base + 43) = apply_ret; TR(aux_base + 44) = is_panic_out;
+            TR(aux_base + 45) = perform_revert;
         }
     }
     // ---- state diffs ---------------------------------------------------------------------------------------------------
@@ -1243,6 +1245,10 @@ struct VmPushScratch {
     uint32_t *meta;    // [rows][3]: job mask, capacity sources (nibble per slot), checks (nibble per slot)
     uint64_t *enc;     // [rows][VM_JOB_SLOTS][8]
     uint64_t *state;   // [rows][VM_JOB_SLOTS][12]: permutation outputs
+    // COMPACT trace layout: every executed job also appends a record (null otherwise)
+    zkc_vm_sponge_record *records;
+    unsigned long long *n_records;
+    unsigned long long records_capacity;
 };
 
 // Every thread evaluates its cycle from snapshot `row` and checks that snapshot `row + 1` is the result.  The check
@@ -1260,7 +1266,8 @@ struct VmPushScratch {
 __global__ void __launch_bounds__(128, VM_CYCLES_MIN_BLOCKS)
 vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_state *__restrict__ snapshots,
                  const zkc_vm_cycle_witness *__restrict__ witness, const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw,
-                 uint64_t *__restrict__ trace, size_t limit, size_t n_instances, size_t row0, size_t row_count, VmPushScratch ps) {
+                 uint64_t *__restrict__ trace, size_t limit, size_t n_instances, size_t row0, size_t row_count, VmPushScratch ps,
+                 int ncols, int aux_base) {
     // this launch covers rows [row0, row0 + row_count) of every instance (one chunk of the pipelined host path, or all)
     const size_t total = limit * n_instances;
     const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1329,7 +1336,7 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
         zkc_vm_context nctx;
         checks |= vm_cycle_dev<false>(isa, s, d, nctx, witness[g], cws + inst * (size_t)n_cw, n_cw, nullptr, nullptr,
                                       ps.enc + g * (VM_JOB_SLOTS * 8), &next,
-                                      trace ? trace + inst * (size_t)ZKC_VM_NUM_COLS * limit : nullptr, limit, row);
+                                      trace ? trace + inst * (size_t)ncols * limit : nullptr, limit, row, aux_base);
         jmask = d.job_mask;
         ps.meta[g * 3] = jmask; ps.meta[g * 3 + 1] = d.cap_from; ps.meta[g * 3 + 2] = d.chk;
         // ---- (2) is snapshot row + 1 what this cycle produces? ---------------------------------------------------------
@@ -1445,11 +1452,16 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
     uint64_t q[12];
 #pragma unroll
     for (int j = 0; j < 8; j++) q[j] = ps.enc[(g * VM_JOB_SLOTS + k) * 8 + j];
-    if (flags && cap_from < VM_JOB_SLOTS) {
-        const volatile uint32_t *f = flags + g * VM_JOB_SLOTS + cap_from;
-        while (*f == 0) __nanosleep(64);
-        __threadfence();
+    if (flags && cap_from < VM_JOB_SLOTS) {  // acquire the producer's output
+        const uint32_t *f = flags + g * VM_JOB_SLOTS + cap_from;
+        uint32_t v;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v) break;
+            __nanosleep(100);
+        }
     }
+    if (flags) __syncwarp(__activemask());  // lanes that had to wait rejoin before the permutation
     if (cap_from == VM_CAP_ZERO) {
 #pragma unroll
         for (int j = 8; j < 12; j++) q[j] = 0;
@@ -1469,9 +1481,20 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
     uint64_t *to = ps.state + (g * VM_JOB_SLOTS + k) * 12;
 #pragma unroll
     for (int j = 0; j < 12; j++) to[j] = q[j];
-    if (flags) {
-        __threadfence();
-        *(volatile uint32_t *)(flags + g * VM_JOB_SLOTS + k) = 1u;
+    if (flags) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + g * VM_JOB_SLOTS + k), "r"(1u) : "memory");
+    if (ps.records) {  // one allocation per warp
+        const unsigned act = __activemask();
+        const int leader = __ffs(act) - 1;
+        unsigned long long base = 0;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(ps.n_records, (unsigned long long)__popc(act));
+        base = __shfl_sync(act, base, leader);
+        const unsigned long long pos = base + __popc(act & ((1u << (threadIdx.x & 31)) - 1));
+        if (pos < ps.records_capacity) {
+            zkc_vm_sponge_record &r = ps.records[pos];
+            r.row = (uint32_t)g; r.slot = (uint32_t)k;
+#pragma unroll
+            for (int j = 0; j < 12; j++) r.out[j] = q[j];
+        }
     }
     if (chk == VM_CHK_NONE) return;
     VmDev *dev = devs + inst;
@@ -1871,11 +1894,16 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     size_t bytes = zkc_carver::bytes(n_instances, sizeof(VmDev)) + zkc_carver::bytes(1, sizeof(zkc_vm_isa));
     if (!in_dev) bytes += zkc_carver::bytes(rows + n_instances, sizeof(zkc_vm_state)) + zkc_carver::bytes(rows + 1, sizeof(zkc_vm_cycle_witness)) +
                           zkc_carver::bytes(n_cw + 1, sizeof(zkc_vm_callstack_witness));
-    if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ZKC_VM_NUM_COLS * rows, 8);
+    const bool compact = options && options->trace_layout == ZKC_VM_TRACE_COMPACT && trace;
+    if (options && options->trace_layout > ZKC_VM_TRACE_COMPACT) return ZKC_ERR_INVALID_ARGUMENT;
+    if (compact && options->sponge_records_capacity && !options->sponge_records) return ZKC_ERR_INVALID_ARGUMENT;
+    const int ncols = compact ? ZKC_VM_COMPACT_COLS : ZKC_VM_NUM_COLS, aux_base = compact ? ZKC_VM_COMPACT_OP_AUX : ZKC_VM_OP_AUX;
+    const size_t rec_cap = compact ? (size_t)options->sponge_records_capacity : 0;
+    if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ncols * rows, 8) + zkc_carver::bytes(rec_cap + 1, sizeof(zkc_vm_sponge_record));
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
     bytes += zkc_carver::bytes(8 * 16, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 3, 4) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8) +
-             zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(16, 8);
+             zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(32, 8);
     void *blk = ctx->scratch(bytes);
     VmDev *h = (VmDev *)ctx->pinned(n_instances * sizeof(VmDev));
     if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
@@ -1911,10 +1939,10 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     ps.enc = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 8);
     ps.state = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 12);
     uint32_t *job_flags = cv.take<uint32_t>(rows * VM_JOB_SLOTS);
-    unsigned long long *tickets = cv.take<unsigned long long>(16);
+    unsigned long long *tickets = cv.take<unsigned long long>(32);  // [0..15] chunk tickets, [31] record count
     ZKC_CUDA(ctx, status, cudaMemsetAsync(counts, 0, 32 * n_chunks, s));
     ZKC_CUDA(ctx, status, cudaMemsetAsync(job_flags, 0, rows * VM_JOB_SLOTS * 4, s));
-    ZKC_CUDA(ctx, status, cudaMemsetAsync(tickets, 0, 16 * 8, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(tickets, 0, 32 * 8, s));
     static int sponge_blocks_per_sm = 0;
     if (!sponge_blocks_per_sm) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sponge_blocks_per_sm, vm_sponge_persistent_kernel, 128, 0) != cudaSuccess || sponge_blocks_per_sm < 1)
@@ -1947,7 +1975,10 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
         if (n_cw) ZKC_CUDA(ctx, status, cudaMemcpyAsync(bc, callstack_witness, n_cw * sizeof(zkc_vm_callstack_witness), cudaMemcpyHostToDevice, s_in));
         dsnap = bs; dwit = bw; dcw = bc;
     }
-    if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ZKC_VM_NUM_COLS * rows);
+    if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ncols * rows);
+    ps.records = nullptr; ps.n_records = tickets + 31; ps.records_capacity = rec_cap;
+    if (compact) ps.records = (trace_dev || !rec_cap) ? options->sponge_records : cv.take<zkc_vm_sponge_record>(rec_cap + 1);
+    if (compact && !ps.records) ps.records = (zkc_vm_sponge_record *)(tickets + 30);  // capacity 0: count only (never written)
     // Side stream: the start state (4 dependent permutations) and the closed-form commitments from the host's final
     // snapshot (31 dependent permutations) run beside the cycle launches; the FINAL pass below takes them when every link
     // verified.  Host inputs: the final snapshots are copied first (the chunk copies then leave them alone).
@@ -1997,28 +2028,40 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
         ps.counts = counts + 8 * c;
         ps.lists = lists + n_instances * r0;
         ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, dsnap, dwit, dcw,
-                   (uint32_t)n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps);
-        // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists
-        {
+                   (uint32_t)n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base);
+        // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists, or one launch per slot
+        static const int sponge_mode = getenv("ZKC_VM_SPONGE_MODE") ? atoi(getenv("ZKC_VM_SPONGE_MODE")) : 0;
+        if (sponge_mode == 0) {
+            for (int k = 0; k < VM_JOB_SLOTS; k++)
+                ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, dsnap, dwit, dcw,
+                           (uint32_t)n_callstack_witness, ps, k, limit, rows);
+        } else {
             const size_t max_blocks = (size_t)ctx->sm_count * sponge_blocks_per_sm, need_blocks = (n_thr * VM_JOB_SLOTS + 127) / 128;
             ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_persistent_kernel, (unsigned)std::min(max_blocks, std::max<size_t>(need_blocks, 1)), 128, 0, d, dsnap,
                        dwit, dcw, (uint32_t)n_callstack_witness, ps, tickets + c, job_flags, limit, rows);
         }
-        if (dtrace) ZKC_LAUNCH(ctx, "vm_sponge_trace", vm_sponge_trace_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, ps, dtrace, limit, n_instances, r0, cnt);
+        if (dtrace && !compact)
+            ZKC_LAUNCH(ctx, "vm_sponge_trace", vm_sponge_trace_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, ps, dtrace, limit, n_instances, r0, cnt);
         if (trace && !trace_dev) {
             if (n_chunks > 1) {
                 cudaEvent_t e = event();
                 ZKC_CUDA(ctx, status, cudaEventRecord(e, s));
                 ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_out, e, 0));
             }
-            ZKC_CUDA(ctx, status, copy_lines(trace + r0, dtrace + r0, limit * 8, cnt * 8, n_instances * (size_t)ZKC_VM_NUM_COLS, cudaMemcpyDeviceToHost, s_out));
+            ZKC_CUDA(ctx, status, copy_lines(trace + r0, dtrace + r0, limit * 8, cnt * 8, n_instances * (size_t)ncols, cudaMemcpyDeviceToHost, s_out));
         }
     }
     if (e_hint) ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e_hint, 0));
     ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 1) / 2), 128, 0, d, flat, n_instances, dsnap, limit, 1);
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, n_instances * sizeof(VmDev), cudaMemcpyDeviceToHost, s));
+    unsigned long long n_records = 0;
+    if (compact) ZKC_CUDA(ctx, status, cudaMemcpyAsync(&n_records, ps.n_records, 8, cudaMemcpyDeviceToHost, s));
     ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    if (compact && !trace_dev && rec_cap && n_records)  // the records of the whole call, one copy (they are ~4 % of the dense sponge columns)
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(options->sponge_records, ps.records, std::min<size_t>(n_records, rec_cap) * sizeof(zkc_vm_sponge_record),
+                                              cudaMemcpyDeviceToHost, s));
+    if (compact) ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
     if (n_chunks > 1) {
         ZKC_CUDA(ctx, status, cudaStreamSynchronize(s_in));
         ZKC_CUDA(ctx, status, cudaStreamSynchronize(s_out));
@@ -2035,6 +2078,7 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
         statuses[i] = h[i].status;
         if (statuses[i].code != ZKC_OK && worst == ZKC_OK) worst = statuses[i].code;
     }
+    if (compact) statuses[0].reserved = (uint32_t)std::min<unsigned long long>(n_records, 0xFFFFFFFFull);
     return worst;
 }
 

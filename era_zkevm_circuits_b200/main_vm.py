@@ -99,7 +99,7 @@ def main_vm_simulate(engine: Engine, isa: abi.VmIsa, initial_states, code, cycle
 
 
 def main_vm_entry_point_batch(engine: Engine, closed_form_inputs, isa: abi.VmIsa, snapshots, witness_oracle, limit: int,
-                              trace_out=None, compare_expected=False, callstack_witness=None):
+                              trace_out=None, compare_expected=False, callstack_witness=None, sponge_records_out=None):
     """n independent instances in one set of launches.  closed_form_inputs: list of abi.VmClosedForm;
     snapshots [n, limit + 1, 1176], witness_oracle [n, limit, 176], callstack_witness [n, capacity, 336] (numpy or torch
     CUDA uint8); trace_out: optional [n, NUM_COLS, limit] uint64.  Returns (commitments [n, 4], closed forms (updated),
@@ -112,6 +112,13 @@ def main_vm_entry_point_batch(engine: Engine, closed_form_inputs, isa: abi.VmIsa
     commitments = np.zeros((n, 4), dtype=np.uint64)
     statuses = (abi.Status * n)()
     opts = abi.VmOptions(int(compare_expected))
+    if sponge_records_out is not None:
+        # COMPACT layout: trace_out is [n, VM_COMPACT_COLS, limit]; the sponge columns come back as records
+        # (abi.VM_SPONGE_RECORD_DTYPE array or torch uint8 [capacity, 104]); statuses[0].reserved = how many
+        assert trace_out is not None and on_device(sponge_records_out) == on_device(trace_out)
+        opts.trace_layout = abi.VM_TRACE_COMPACT
+        opts.sponge_records_capacity = len(sponge_records_out)
+        opts.sponge_records = ptr(sponge_records_out)
     n_cw = _n_cw(callstack_witness)
     rc = engine.lib.zkc_main_vm_entry_point_batch(engine.h, C.cast(ios, C.c_void_p), n, C.byref(isa), ptr(snapshots),
                                                   ptr(witness_oracle), ptr(callstack_witness) if n_cw else None, n_cw, limit,

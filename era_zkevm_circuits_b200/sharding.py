@@ -31,3 +31,46 @@ def gather_commitments(local_commitments: np.ndarray, n_total: int, rank: int, w
         idx = shard_instances(n_total, r, world)
         result[idx] = out[r, : len(idx)]
     return result
+
+
+GL_P = 0xFFFFFFFF00000001
+
+
+def row_range(n_rows: int, rank: int, world: int):
+    """contiguous row range [lo, hi) of rank `rank` when one long loop is cut over `world` ranks"""
+    per = (n_rows + world - 1) // world
+    return min(rank * per, n_rows), min((rank + 1) * per, n_rows)
+
+
+def distributed_grand_products(local_fn, rank: int, world: int, acc_in=(1, 1, 1, 1), device=None):
+    """ONE long grand product (utils.rs:81-137: the running lhs / rhs accumulators of a sorter circuit) over `world`
+    ranks, each owning a contiguous row range.  The accumulators are running PRODUCTS, so a
+    rank's rows only need the product of everything before them: every rank first accumulates its own rows from the
+    neutral element, the 4 local totals are exchanged in the path's ONE collective (an all-gather of 4 x u64 per
+    rank), and each rank re-runs its range seeded with acc_in * (the exclusive prefix of the lower ranks' totals) --
+    exactly the reference's own instance chaining (hidden_fsm_output of part k = hidden_fsm_input of part k + 1,
+    ram_permutation/input.rs:52-62) with the chain resolved in one exchange instead of sequentially.
+
+    local_fn(acc_in [4] uint64) -> (acc_out, acc_final [4] uint64) runs the rank's rows (zkc_accumulate_grand_products
+    on its shard).  Returns (acc_out, acc_final of this rank, grand totals [4] over all ranks)."""
+    import torch
+    import torch.distributed as dist
+    ones = np.ones(4, dtype=np.uint64)
+    _, local_total = local_fn(ones)
+    mine = torch.from_numpy(np.ascontiguousarray(local_total, dtype=np.uint64).view(np.int64).copy())
+    if device is not None:
+        mine = mine.to(device)
+    allt = torch.zeros((world, 4), dtype=torch.int64, device=mine.device)
+    if world > 1:
+        dist.all_gather_into_tensor(allt, mine.reshape(1, 4))
+    else:
+        allt.copy_(mine.reshape(1, 4))
+    totals = allt.cpu().numpy().view(np.uint64)
+    seed = [int(a) % GL_P for a in acc_in]
+    for r in range(rank):
+        seed = [s * int(t) % GL_P for s, t in zip(seed, totals[r])]
+    acc_out, acc_final = local_fn(np.array(seed, dtype=np.uint64))
+    grand = [int(a) % GL_P for a in acc_in]
+    for r in range(world):
+        grand = [g * int(t) % GL_P for g, t in zip(grand, totals[r])]
+    return acc_out, acc_final, np.array(grand, dtype=np.uint64)

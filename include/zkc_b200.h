@@ -934,9 +934,27 @@ enum zkc_vm_col {
 #define ZKC_ERR_UNSUPPORTED 7
 #define ZKC_ERR_SNAPSHOT_MISMATCH 8
 
+/* Trace layouts.  DENSE: [ZKC_VM_NUM_COLS][limit].  COMPACT: the 117 sponge columns are zero except where a relation is
+ * enforced (~1 of 9 slots per cycle), so they travel as a list instead: `trace` is [ZKC_VM_COMPACT_COLS][limit] -- the dense
+ * columns below ZKC_VM_SPONGE_ENFORCE keep their index, the OP_AUX block moves down to ZKC_VM_COMPACT_OP_AUX -- and every
+ * enforced relation is one zkc_vm_sponge_record in options->sponge_records (host or device memory like `trace`; in no
+ * particular order; their number is returned in statuses[0].reserved; ZKC_ERR_INVALID_ARGUMENT-free overflow: records
+ * beyond the capacity are dropped and the count still reports how many there were).  Same values, 38 % fewer bytes. */
+#define ZKC_VM_TRACE_DENSE 0
+#define ZKC_VM_TRACE_COMPACT 1
+#define ZKC_VM_COMPACT_COLS (ZKC_VM_NUM_COLS - 9 - 9 * 12)
+#define ZKC_VM_COMPACT_OP_AUX (ZKC_VM_OP_AUX - 9 - 9 * 12)
+typedef struct zkc_vm_sponge_record {
+    uint32_t row;   /* instance * limit + cycle */
+    uint32_t slot;  /* 0..8: column block ZKC_VM_SPONGE_FINAL + 12 * slot (and ZKC_VM_SPONGE_ENFORCE + slot = 1) */
+    uint64_t out[12];
+} zkc_vm_sponge_record;
+
 typedef struct zkc_vm_options {
     uint32_t compare_expected;
-    uint32_t _pad[3];
+    uint32_t trace_layout;                 /* ZKC_VM_TRACE_DENSE / ZKC_VM_TRACE_COMPACT */
+    uint64_t sponge_records_capacity;      /* COMPACT: records the buffer below holds */
+    zkc_vm_sponge_record *sponge_records;  /* COMPACT: out */
 } zkc_vm_options;
 
 /* main_vm_entry_point, main_vm/mod.rs:47-232.

@@ -41,3 +41,16 @@ def test_create_without_gpu_fails_loudly():
     h = C.c_void_p()
     assert lib.zkc_create(0, C.byref(h)) == abi.ZKC_ERR_NO_DEVICE
     assert lib.zkc_version().startswith(b"zkc_b200")
+
+
+def test_vm_columns_mirror_header():
+    """abi.VM_COLS / VM_CHK are hand-written mirrors of the header's enum zkc_vm_col and ZKC_VM_CHK_* defines"""
+    text = open(os.path.join(ROOT, "include", "zkc_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", text[text.index("enum zkc_vm_col {"):], flags=re.S)
+    body = body[:body.index("};")]
+    cols = {m.group(1): int(m.group(2)) for m in re.finditer(r"ZKC_VM_([A-Z0-9_]+)\s*=\s*(\d+)", body)}
+    assert cols == abi.VM_COLS
+    chk = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"#define ZKC_VM_CHK_([A-Z_]+) \(1u << (\d+)\)", text)}
+    assert chk == abi.VM_CHK
+    assert abi.VM_COMPACT_COLS == abi.VM_COLS["NUM_COLS"] - 117 and abi.VM_COMPACT_OP_AUX == abi.VM_COLS["OP_AUX"] - 117
+    assert C.sizeof(abi.VmOptions) == 24 and C.sizeof(abi.VmCycleWitness) == 176 and C.sizeof(abi.VmCallstackWitness) == 336

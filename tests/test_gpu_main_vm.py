@@ -241,3 +241,50 @@ def test_batch_of_instances(engine, orc):
     assert rc2 == abi.ZKC_ERR_SNAPSHOT_MISMATCH and statuses2[3].first_bad_row == 77
     assert [s.code for s in statuses2] == [0, 0, 0, abi.ZKC_ERR_SNAPSHOT_MISMATCH, 0, 0]
     assert coms2[[0, 1, 2, 4, 5]].tolist() == coms[[0, 1, 2, 4, 5]].tolist()
+
+
+def test_compact_trace_layout(engine, orc):
+    """COMPACT layout (159 dense columns + one record per enforced sponge relation) carries exactly the dense trace"""
+    from era_zkevm_circuits_b200 import main_vm_entry_point_batch
+    import torch
+    n, cycles = 3, 9000  # 9000 rows x 3 instances: the chunked host pipeline is taken
+    isa = I.Isa()
+    ios, states, codes = [], [], []
+    for i in range(n):
+        io = abi.VmClosedForm(); io.start_flag = 1; io.rollback_queue_tail_for_block[2] = 7 + i
+        ios.append(io); states.append(O.vm_initial_state(orc, io, isa.isa))
+        codes.append(I.pack_code(I.random_program(isa, 512, seed=90 + i)))
+    sim = main_vm_simulate(engine, isa.isa, states, np.stack(codes), cycles)
+    assert sim.status.code == 0
+    ios = [with_tail(io, t) for io, t in zip(ios, sim.rollback_tails)]
+    dense = torch.empty((n, K["NUM_COLS"], cycles), dtype=torch.int64, device="cuda")
+    coms, _, _, rc = main_vm_entry_point_batch(engine, ios, isa.isa, sim.snapshots, sim.witness, cycles, trace_out=dense,
+                                               callstack_witness=sim.callstack_witness)
+    assert rc == 0
+    want = dense.cpu().numpy().view(np.uint64)
+    n_jobs = int(want[:, K["SPONGE_ENFORCE"]:K["SPONGE_ENFORCE"] + 9].sum())
+    # device-resident compact output
+    comp = torch.empty((n, abi.VM_COMPACT_COLS, cycles), dtype=torch.int64, device="cuda")
+    rec = torch.zeros((n_jobs + 10, 104), dtype=torch.uint8, device="cuda")
+    coms2, _, st2, rc = main_vm_entry_point_batch(engine, ios, isa.isa, sim.snapshots, sim.witness, cycles, trace_out=comp,
+                                                  callstack_witness=sim.callstack_witness, sponge_records_out=rec)
+    assert rc == 0 and coms2.tolist() == coms.tolist() and st2[0].reserved == n_jobs
+    records = rec.cpu().numpy().view(abi.VM_SPONGE_RECORD_DTYPE).reshape(-1)[:n_jobs]
+    got = abi.vm_expand_compact_trace(comp.cpu().numpy().view(np.uint64), records, cycles)
+    assert np.array_equal(got, want)
+    # host buffers (the chunked H2D | kernels | D2H pipeline), dense and compact
+    hs, hw, hc = (np.ascontiguousarray(x.cpu().numpy()) for x in (sim.snapshots, sim.witness, sim.callstack_witness))
+    hdense = np.zeros((n, K["NUM_COLS"], cycles), dtype=np.uint64)
+    coms3, _, _, rc = main_vm_entry_point_batch(engine, ios, isa.isa, hs, hw, cycles, trace_out=hdense, callstack_witness=hc)
+    assert rc == 0 and coms3.tolist() == coms.tolist() and np.array_equal(hdense, want)
+    hcomp = np.zeros((n, abi.VM_COMPACT_COLS, cycles), dtype=np.uint64)
+    hrec = np.zeros(n_jobs, dtype=abi.VM_SPONGE_RECORD_DTYPE)
+    coms4, _, st4, rc = main_vm_entry_point_batch(engine, ios, isa.isa, hs, hw, cycles, trace_out=hcomp, callstack_witness=hc,
+                                                  sponge_records_out=hrec)
+    assert rc == 0 and coms4.tolist() == coms.tolist() and st4[0].reserved == n_jobs
+    assert np.array_equal(abi.vm_expand_compact_trace(hcomp, hrec, cycles), want)
+    # too small a record buffer: the count still tells how many there were
+    small = np.zeros(5, dtype=abi.VM_SPONGE_RECORD_DTYPE)
+    _, _, st5, rc = main_vm_entry_point_batch(engine, ios, isa.isa, hs, hw, cycles, trace_out=hcomp, callstack_witness=hc,
+                                              sponge_records_out=small)
+    assert rc == 0 and st5[0].reserved == n_jobs

@@ -57,3 +57,54 @@ def test_shard_assignment():
         owned = sorted(i for r in range(world) for i in sharding.shard_instances(64, r, world))
         assert owned == list(range(64))
         assert all(len(sharding.shard_instances(64, r, world)) == 64 // world for r in range(world))
+
+
+# ---- one long grand product cut over the ranks by row ranges ----------------------------------
+GP_ROWS, GP_ENC = 1000, 20
+
+
+def _gp_inputs():
+    rng = np.random.default_rng(44)
+    P = 0xFFFFFFFF00000001
+    lhs = rng.integers(0, P, size=(GP_ENC, GP_ROWS), dtype=np.uint64)
+    rhs = rng.integers(0, P, size=(GP_ENC, GP_ROWS), dtype=np.uint64)
+    ch = rng.integers(0, P, size=(2, GP_ENC + 1), dtype=np.uint64)
+    flags = (rng.integers(0, 10, size=GP_ROWS) != 0).astype(np.uint8)
+    return lhs, rhs, ch, flags
+
+
+def _gp_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+    import orc as O
+    from era_zkevm_circuits_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = O.load()
+    lhs, rhs, ch, flags = _gp_inputs()
+    lo, hi = sharding.row_range(GP_ROWS, rank, world)
+
+    def local(acc_in):  # the CPU oracle stands in for zkc_accumulate_grand_products on this rank's rows
+        acc, _, fin = O.accumulate_grand_products(lib, lhs[:, lo:hi], rhs[:, lo:hi], ch, acc_in, flags[lo:hi])
+        return acc, fin
+
+    acc, fin, grand = sharding.distributed_grand_products(local, rank, world, acc_in=(3, 5, 7, 11))
+    np.save(os.path.join(out_dir, f"gp{rank}.npy"), acc)
+    np.save(os.path.join(out_dir, f"gpt{rank}.npy"), grand)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grand_product_over_row_ranges(tmp_path):
+    sys.path.insert(0, HERE)
+    import orc as O
+    world = 3
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_gp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    lhs, rhs, ch, flags = _gp_inputs()
+    want, _, fin = O.accumulate_grand_products(O.load(), lhs, rhs, ch, np.array([3, 5, 7, 11], dtype=np.uint64), flags)
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), f"gp{r}.npy")) for r in range(world)], axis=1)
+    assert np.array_equal(got, want)
+    for r in range(world):
+        assert np.load(os.path.join(str(tmp_path), f"gpt{r}.npy")).tolist() == fin.tolist()
