@@ -148,7 +148,12 @@ class VmIsa(C.Structure):
                 ("initial_frame_formal_eh_location", C.c_uint32), ("vm_initial_frame_ergs", C.c_uint32),
                 ("bootloader_formal_address_low", C.c_uint32), ("bootloader_max_memory", C.c_uint32),
                 ("vm_max_stack_depth", C.c_uint32), ("log_aux_bytes", C.c_uint32 * 4),
-                ("initial_storage_write_pubdata_bytes", C.c_uint32), ("l1_message_pubdata_bytes", C.c_uint32)]
+                ("initial_storage_write_pubdata_bytes", C.c_uint32), ("l1_message_pubdata_bytes", C.c_uint32),
+                ("new_frame_memory_stipend", C.c_uint32), ("new_memory_pages_per_far_call", C.c_uint32),
+                ("deployer_system_contract_address_low", C.c_uint32), ("ergs_per_code_word_decommittment", C.c_uint32),
+                ("code_hash_version_byte", C.c_uint32), ("code_hash_yet_constructed_marker", C.c_uint32),
+                ("code_hash_at_rest_marker", C.c_uint32), ("call_system_abi_registers", C.c_uint32 * 2),
+                ("call_reserved_range", C.c_uint32 * 2), ("call_implicit_parameter_reg_idx", C.c_uint32)]
 
 
 class VmRegister(C.Structure):
@@ -179,7 +184,7 @@ class VmState(C.Structure):
 
 class VmCycleWitness(C.Structure):
     _fields_ = [("code_word", C.c_uint32 * 8), ("src0_is_pointer", C.c_uint32), ("src0_value", C.c_uint32 * 8),
-                ("callstack_index", C.c_uint32), ("refund", C.c_uint32), ("_pad", C.c_uint32), ("value_a", C.c_uint32 * 8),
+                ("callstack_index", C.c_uint32), ("refund", C.c_uint32), ("suggested_page", C.c_uint32), ("value_a", C.c_uint32 * 8),
                 ("value_b", C.c_uint32 * 8), ("rollback", C.c_uint64 * 4)]
 
 
@@ -206,7 +211,7 @@ assert VM_SPONGE_RECORD_DTYPE.itemsize == 104
 VM_TRACE_DENSE, VM_TRACE_COMPACT = 0, 1
 
 
-assert C.sizeof(VmState) == 1176 and C.sizeof(VmContext) == 240 and C.sizeof(VmIsa) == 24736
+assert C.sizeof(VmState) == 1176 and C.sizeof(VmContext) == 240 and C.sizeof(VmIsa) == 24784
 assert C.sizeof(VmClosedForm) == 3104 and C.sizeof(VmCycleWitness) == 176 and C.sizeof(VmCallstackWitness) == 336
 VM_STATE_DTYPE = np.dtype((np.void, 1176))
 VM_COLS = dict(

@@ -360,9 +360,10 @@ __device__ __forceinline__ U256 as_u256(const zkc_vm_register &r) {
 }
 
 // sponge slots in use (far calls would add 5..8) and where a job's capacity comes from / what its output must equal
-constexpr int VM_JOB_SLOTS = 5;
-enum : uint32_t { VM_CAP_ZERO = 9, VM_CAP_MEMQ = 10, VM_CAP_STACK = 11, VM_CAP_CALLSTACK_WITNESS = 12 };
-enum : uint32_t { VM_CHK_NONE = 0, VM_CHK_NEXT_MEMQ, VM_CHK_NEXT_STACK, VM_CHK_CUR_STACK, VM_CHK_NEXT_FWD_TAIL, VM_CHK_CUR_RB_HEAD };
+constexpr int VM_JOB_SLOTS = ZKC_VM_NUM_SPONGES;
+enum : uint32_t { VM_CAP_ZERO = 9, VM_CAP_MEMQ = 10, VM_CAP_STACK = 11, VM_CAP_CALLSTACK_WITNESS = 12, VM_CAP_DECOMMIT = 13 };
+enum : uint32_t { VM_CHK_NONE = 0, VM_CHK_NEXT_MEMQ, VM_CHK_NEXT_STACK, VM_CHK_CUR_STACK, VM_CHK_NEXT_FWD_TAIL, VM_CHK_CUR_RB_HEAD,
+                  VM_CHK_NEXT_DECOMMIT };
 
 // what one cycle changes in a VmLocalState; every other word must carry over unchanged
 struct VmDelta {
@@ -376,23 +377,43 @@ struct VmDelta {
     uint64_t rb_head[4];
     uint32_t fwd_tail_kind;  // 0 unchanged, 1 output of the log's forward sponge (slot 3), 2 explicit (ret)
     uint64_t fwd_tail[4];
-    uint32_t ctx_replaced;   // 0 no, 1 near call, 2 ret: the whole current context is nctx (forward tail / length apart)
+    uint32_t ctx_replaced;   // 0 no, 1 near call, 2 ret, 3 far call: the whole current context is nctx (forward tail / length apart)
     uint32_t far_ret;        // r1 = r1_val, r2..r15 zeroed
+    uint32_t far_call;       // r1 = r1_val, r2 = r2_low, ABI / reserved / implicit registers cleaned (far_call_system: ABI values kept)
+    uint32_t far_call_system, r2_low;
     zkc_vm_register r1_val;
     uint32_t depth;
+    uint32_t page_counter, decommit_len;
     uint32_t cw_index;       // ret: the callstack witness used
-    uint32_t job_mask, cap_from, chk;  // sponge jobs: bit k / nibble k per slot
+    uint32_t job_mask;       // sponge jobs: bit k per slot
+    uint64_t cap_from, chk;  // nibble k per slot
 };
+// register r (0-based) after a far call (far_call.rs:1018-1066)
+__device__ __forceinline__ zkc_vm_register vm_far_call_register(const zkc_vm_isa *isa, const VmDelta &d, int r, const zkc_vm_register &old) {
+    if (r == 0) return d.r1_val;
+    zkc_vm_register v = reg_zero();
+    if (r == 1) { v.value[0] = d.r2_low; return v; }
+    if ((uint32_t)r >= isa->call_system_abi_registers[0] && (uint32_t)r < isa->call_system_abi_registers[1]) {
+        if (d.far_call_system) { v = old; v.is_pointer = 0; }
+        return v;
+    }
+    if (((uint32_t)r >= isa->call_reserved_range[0] && (uint32_t)r < isa->call_reserved_range[1]) || (uint32_t)r == isa->call_implicit_parameter_reg_idx) return v;
+    return old;
+}
 // sponge outputs of a cycle: known at once only to the out-of-circuit run
 struct VmSimOut { uint64_t memq[12], stack[12], fwd_tail[4]; };
 
-__device__ void vm_apply_delta(zkc_vm_state &t, const VmDelta &d, const zkc_vm_context &nctx) {
+__device__ void vm_apply_delta(zkc_vm_state &t, const VmDelta &d, const zkc_vm_context &nctx, const zkc_vm_isa *isa) {
     for (int i = 0; i < 8; i++) t.previous_code_word[i] = d.cw[i];
     if (d.idx0) t.registers[d.idx0 - 1] = d.val0;
     if (d.far_ret) {
         t.registers[0] = d.r1_val;
         for (int r = 1; r < ZKC_VM_REGISTERS; r++) t.registers[r] = reg_zero();
     }
+    if (d.far_call)
+        for (int r = 0; r < ZKC_VM_REGISTERS; r++) t.registers[r] = vm_far_call_register(isa, d, r, t.registers[r]);
+    t.memory_page_counter = d.page_counter;
+    t.code_decommittment_queue_length = d.decommit_len;
     if (d.idx1) t.registers[d.idx1 - 1] = d.val1;
     if (d.set_u128) for (int i = 0; i < 4; i++) t.context_composite_u128[i] = d.u128[i];
     if (d.set_pubdata) t.ergs_per_pubdata_byte = d.pubdata;
@@ -434,8 +455,8 @@ __device__ __forceinline__ void vm_job(int slot, VmDelta &d, uint64_t *penc, con
 #pragma unroll
         for (int i = 0; i < 12; i++) out[i] = t[i];
     } else {
-        d.cap_from |= cap_code << (4 * slot);
-        d.chk |= chk << (4 * slot);
+        d.cap_from |= (uint64_t)cap_code << (4 * slot);
+        d.chk |= (uint64_t)chk << (4 * slot);
 #pragma unroll
         for (int i = 0; i < 8; i++) penc[8 * slot + i] = in8[i];
     }
@@ -508,7 +529,7 @@ __device__ void vm_log_encode(const uint32_t *address, const uint32_t *key, cons
 // emitted as jobs into `penc`.  trace / limit / row: where to put the row (trace may be null; the sponge columns are
 // written by whoever runs the sponges).  next: the following snapshot (circuit mode; forward tail column only).
 template <bool SIM, typename W>
-__device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_vm_state &s, VmDelta &d, zkc_vm_context &nctx, W &w,
+__device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_vm_closed_form *gc, const zkc_vm_state &s, VmDelta &d, zkc_vm_context &nctx, W &w,
                                  const zkc_vm_callstack_witness *__restrict__ cw, uint32_t n_cw, VmSim *sim, VmSimOut *so,
                                  uint64_t *penc, const zkc_vm_state *next, uint64_t *__restrict__ trace, size_t limit, size_t row,
                                  int aux_base = ZKC_VM_OP_AUX) {
@@ -518,6 +539,8 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
     const zkc_vm_context &ctx = s.current_context;
     d.set_u128 = 0; d.set_pubdata = 0; d.inc_tx = 0; d.idx0 = 0; d.idx1 = 0;
     d.job_mask = 0; d.cap_from = 0; d.chk = 0; d.fwd_tail_kind = 0; d.ctx_replaced = 0; d.far_ret = 0; d.cw_index = 0;
+    d.far_call = 0; d.far_call_system = 0; d.r2_low = 0;
+    d.page_counter = s.memory_page_counter; d.decommit_len = s.code_decommittment_queue_length;
     d.memq_len = s.memory_queue_length;
     d.heap_bound = ctx.heap_upper_bound; d.aux_bound = ctx.aux_heap_upper_bound;
     d.fwd_len = ctx.log_queue_forward_part_length; d.rb_len = ctx.reverted_queue_segment_len;
@@ -600,7 +623,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
 #define SRCM(m) prop(props, ZKC_VM_BIT_SRC_MODE(m))
 #define DSTM(m) prop(props, ZKC_VM_BIT_DST_MODE(m))
     if (TYPE(ZKC_OP_INVALID)) checks |= ZKC_VM_CHK_INVALID_OPCODE;
-    if (TYPE(ZKC_OP_FAR_CALL)) checks |= ZKC_VM_CHK_UNSUPPORTED_OPCODE;
+    if constexpr (SIM) { if (TYPE(ZKC_OP_FAR_CALL)) checks |= ZKC_VM_CHK_UNSUPPORTED_OPCODE; }  // the GPU run's memory model has one frame's pages
     if (wr) {
         TR(ZKC_VM_VARIANT) = variant; TR(ZKC_VM_CONDITION_IDX) = cond_idx; TR(ZKC_VM_CONDITION) = condition; TR(ZKC_VM_ERGS_COST) = cost;
         TR(ZKC_VM_OUT_OF_ERGS) = out_of_ergs; TR(ZKC_VM_KERNEL_MODE_EXCEPTION) = kernel_exc; TR(ZKC_VM_STATIC_EXCEPTION) = static_exc;
@@ -934,14 +957,16 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
             for (int i = 0; i < 8; i++) TR(aux_base + 20 + i) = read_value[i];
             TR(aux_base + 28) = execute; TR(aux_base + 29) = execute_rollback; TR(aux_base + 30) = burn;
         }
-    } else if (TYPE(ZKC_OP_NEAR_CALL) || TYPE(ZKC_OP_RET)) {  // call_ret.rs:24-512
-        const bool apply_near = TYPE(ZKC_OP_NEAR_CALL), apply_ret = !apply_near;
+    } else if (TYPE(ZKC_OP_NEAR_CALL) || TYPE(ZKC_OP_RET) || (!SIM && TYPE(ZKC_OP_FAR_CALL))) {  // call_ret.rs:24-512
+        const bool apply_near = TYPE(ZKC_OP_NEAR_CALL), apply_far = TYPE(ZKC_OP_FAR_CALL), apply_ret = !apply_near && !apply_far;
+        bool far_exception = false;
         const uint32_t fwd_byte = (a.v[ZKC_VM_ABI_FORWARDING_MODE_BYTE_IDX / 4] >> (8 * (ZKC_VM_ABI_FORWARDING_MODE_BYTE_IDX % 4))) & 0xFF;
         const bool use_aux = fwd_byte == ZKC_VM_FORWARD_USE_AUX_HEAP, fwd_ptr = fwd_byte == ZKC_VM_FORWARD_FAT_POINTER;
         const bool use_heap = !(use_aux || fwd_ptr);
         uint32_t upper_bound;
         bool non_addressable;
         const VmFatPtr fp = vm_fat_ptr_parse(a, !fwd_ptr, upper_bound, non_addressable);
+        const bool generally_invalid = (a.v[0] != 0 && !fwd_ptr) || non_addressable || a.v[3] < a.v[0];
         zkc_vm_context old_entry;
         bool is_panic_out = false, perform_revert = false;
         // the draft context: what create_prestate leaves (pc, sp, ergs updated)
@@ -973,6 +998,117 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
                 }
                 sim->ev_kind = 1; sim->ev.kind = 1; sim->ev.slot = -1;
             }
+        } else if (apply_far) {  // far_call.rs:268-1098 (circuit side only: the GPU out-of-circuit run has no far calls)
+            const bool is_delegated = VAR(ZKC_VAR_FAR_CALL_DELEGATE), is_mimic = VAR(ZKC_VAR_FAR_CALL_MIMIC);
+            cur_e.pc = pc_plus_one;
+            memset(&nctx, 0, sizeof nctx);
+            nctx.heap_upper_bound = isa->new_frame_memory_stipend; nctx.aux_heap_upper_bound = isa->new_frame_memory_stipend;
+            const bool is_static_call = FLAG(ZKC_VM_FAR_CALL_STATIC_FLAG_IDX), is_call_shard = FLAG(ZKC_VM_FAR_CALL_SHARD_FLAG_IDX);
+#define ABI_BYTE(k) ((a.v[(k) / 4] >> (8 * ((k) % 4))) & 0xFF)
+            const uint32_t abi_ergs_passed = a.v[6], abi_shard = ABI_BYTE(ZKC_VM_ABI_SHARD_ID_BYTE_IDX);
+            bool abi_constructor = ABI_BYTE(ZKC_VM_ABI_CONSTRUCTOR_CALL_BYTE_IDX) != 0, abi_system = ABI_BYTE(ZKC_VM_ABI_SYSTEM_CALL_BYTE_IDX) != 0;
+#undef ABI_BYTE
+            const uint32_t caller_shard = cur_e.this_shard_id;
+            const uint32_t dest_shard = is_call_shard ? abi_shard : caller_shard;
+            const bool target_is_zkporter = dest_shard != 0;
+            const bool target_is_kernel = (b.v[0] >> 16) == 0 && (b.v[1] | b.v[2] | b.v[3] | b.v[4]) == 0;
+            abi_constructor = abi_constructor && is_kernel; abi_system = abi_system && target_is_kernel;
+            const uint32_t new_base_page = s.memory_page_counter;
+            d.page_counter = s.memory_page_counter + isa->new_memory_pages_per_far_call;
+            // may_be_read_code_hash, :1104-1272
+            const bool zkporter_available = gc->zkporter_is_available != 0;
+            const bool should_read = !target_is_zkporter || zkporter_available, needs_porter_mask = target_is_zkporter && !zkporter_available;
+            uint32_t hash[8], dep_addr[5] = {isa->deployer_system_contract_address_low, 0, 0, 0, 0}, key[8] = {b.v[0], b.v[1], b.v[2], b.v[3], b.v[4], 0, 0, 0};
+            for (int i = 0; i < 8; i++) hash[i] = w.value_a[i];
+            bool empty = true;
+            for (int i = 0; i < 8; i++) empty &= hash[i] == 0;
+            if (should_read) {  // construct_hash_relations_code_hash_read, :1274-1411
+                uint64_t enc[20], in8[8], f[12];
+                const uint64_t zero4[4] = {0, 0, 0, 0};
+                vm_log_encode(dep_addr, key, hash, hash, s.tx_number_in_block, ts0 + 1, isa->log_aux_bytes[0], dest_shard, 0, 0, enc);
+                for (int i = 0; i < 8; i++) in8[i] = enc[i];
+                vm_job<SIM>(5, d, penc, in8, zero4, VM_CAP_ZERO, VM_CHK_NONE, f);
+                for (int i = 0; i < 8; i++) in8[i] = enc[8 + i];
+                vm_job<SIM>(6, d, penc, in8, f + 8, 5, VM_CHK_NONE, f);
+                for (int i = 0; i < 4; i++) { in8[i] = enc[16 + i]; in8[4 + i] = ctx.log_queue_forward_tail[i]; }
+                vm_job<SIM>(7, d, penc, in8, f + 8, 6, VM_CHK_NEXT_FWD_TAIL, f);
+                d.fwd_tail_kind = 1; d.fwd_len++;
+            }
+            const bool mask_default_aa = should_read && empty && !target_is_kernel;
+            if (mask_default_aa) for (int i = 0; i < 8; i++) hash[i] = gc->default_aa_code_hash[i];
+            if (needs_porter_mask) for (int i = 0; i < 8; i++) hash[i] = 0;
+            const bool hash_is_trivial = (empty && !mask_default_aa) || needs_porter_mask || !should_read;
+            uint32_t target_code_page = hash_is_trivial ? 0u : s.memory_page_counter;
+            const uint32_t top = hash[7], version_byte = top >> 24, marker = (top >> 16) & 0xFF;
+            const bool normal_marker = marker == 0, constructor_marker = marker == isa->code_hash_yet_constructed_marker;
+            const bool code_format_exception = version_byte != isa->code_hash_version_byte || !(normal_marker || constructor_marker);
+            const bool can_call_code = (normal_marker && !abi_constructor) || (constructor_marker && abi_constructor);
+            uint32_t masked_hash[8];
+            for (int i = 0; i < 8; i++) masked_hash[i] = can_call_code ? hash[i] : (target_is_kernel ? 0u : gc->default_aa_code_hash[i]);
+            if (can_call_code) masked_hash[7] = (top & 0xFFFF) | (isa->code_hash_at_rest_marker << 16) | (isa->code_hash_version_byte << 24);
+            const uint32_t code_len_words = code_format_exception ? 0u : (masked_hash[7] & 0xFFFF);
+            const bool exceptions_collapsed = code_format_exception || (!can_call_code && target_is_kernel) || (fwd_ptr && !ra.is_pointer) ||
+                                              generally_invalid || non_addressable;
+            VmFatPtr p = fwd_ptr ? VmFatPtr{0, fp.page, fp.start + fp.offset, fp.length - fp.offset} : VmFatPtr{0, use_heap ? heap_page : aux_heap_page, fp.start, fp.length};
+            if (exceptions_collapsed) p = VmFatPtr{0, 0, 0, 0};
+            uint32_t ub = exceptions_collapsed ? 0u : upper_bound;
+            if (non_addressable && !fwd_ptr) ub = 0xFFFFFFFFu;
+            const uint32_t heap_max = use_heap ? ub : 0u, aux_max = use_aux ? ub : 0u;
+            const bool heap_uf = heap_max < cur_e.heap_upper_bound, aux_uf = aux_max < cur_e.aux_heap_upper_bound;
+            uint32_t growth_cost = use_heap ? (heap_uf ? 0u : heap_max - cur_e.heap_upper_bound) : 0u;
+            if (use_aux) growth_cost = aux_uf ? 0u : aux_max - cur_e.aux_heap_upper_bound;
+            const bool growth_uf = ergs_left < growth_cost;
+            const uint32_t ergs_after_growth = growth_uf ? 0u : ergs_left - growth_cost;
+            if (use_heap && !heap_uf) cur_e.heap_upper_bound = heap_max;
+            if (use_aux && !aux_uf) cur_e.aux_heap_upper_bound = aux_max;
+            bool exception = exceptions_collapsed || growth_uf;
+            bool should_decommit = !exception;
+            if (!should_decommit) target_code_page = 0;
+            // add_to_decommittment_queue, :1418-1603
+            const uint32_t decommit_cost = isa->ergs_per_code_word_decommittment * code_len_words;
+            const bool not_enough_for_decommit = ergs_after_growth < decommit_cost;
+            should_decommit = should_decommit && !not_enough_for_decommit;
+            uint32_t ergs_after_decommit = should_decommit ? ergs_after_growth - decommit_cost : ergs_after_growth;
+            const uint32_t suggested_page = w.suggested_page;
+            const bool is_first = target_code_page == suggested_page;
+            if (should_decommit && !is_first) ergs_after_decommit = ergs_after_growth;
+            if (should_decommit) {
+                uint64_t e8[8], f[12];
+                const uint32_t tsd = ts0 + 1;
+                e8[0] = (uint64_t)masked_hash[0] + ((uint64_t)(suggested_page & 0xFFFFFF) << 32);
+                e8[1] = (uint64_t)masked_hash[1] + ((uint64_t)(suggested_page >> 24) << 32) + ((uint64_t)(tsd & 0xFFFF) << 40);
+                e8[2] = (uint64_t)masked_hash[2] + ((uint64_t)(tsd >> 16) << 32) + ((uint64_t)is_first << 48);
+                for (int i = 3; i < 8; i++) e8[i] = masked_hash[i];
+                vm_job<SIM>(8, d, penc, e8, nullptr, VM_CAP_DECOMMIT, VM_CHK_NEXT_DECOMMIT, f);
+                d.decommit_len = s.code_decommittment_queue_length + 1;
+            }
+            const uint32_t code_memory_page = should_decommit ? suggested_page : 0u;
+            exception = exception || not_enough_for_decommit;
+            const uint32_t max_passable = (ergs_after_decommit / 64) * 63, leftover = ergs_after_decommit - max_passable;
+            const bool pass_uf = max_passable < abi_ergs_passed;
+            cur_e.ergs_remaining = pass_uf ? leftover : leftover + (max_passable - abi_ergs_passed);
+            for (int i = 0; i < 4; i++) { nctx.reverted_queue_tail[i] = w.rollback[i]; nctx.reverted_queue_head[i] = w.rollback[i]; }
+            nctx.ergs_remaining = pass_uf ? max_passable : abi_ergs_passed; nctx.pc = 0; nctx.exception_handler_loc = imm0;
+            nctx.is_static_execution = is_static_call || cur_e.is_static_execution;
+            nctx.is_kernel_mode = is_delegated ? cur_e.is_kernel_mode : (uint32_t)target_is_kernel;
+            nctx.code_shard_id = dest_shard; nctx.this_shard_id = is_delegated ? caller_shard : dest_shard; nctx.caller_shard_id = caller_shard;
+            const zkc_vm_register &mimic_reg = s.registers[isa->call_implicit_parameter_reg_idx < ZKC_VM_REGISTERS ? isa->call_implicit_parameter_reg_idx : 0];
+            for (int i = 0; i < 5; i++) {
+                nctx.code_address[i] = b.v[i];
+                nctx.this_address[i] = is_delegated ? cur_e.this_address[i] : b.v[i];
+                nctx.caller[i] = is_mimic ? mimic_reg.value[i] : (is_delegated ? cur_e.caller[i] : cur_e.this_address[i]);
+            }
+            nctx.code_page = code_memory_page; nctx.base_page = new_base_page;
+            for (int i = 0; i < 4; i++) nctx.context_u128_value_composite[i] = is_delegated ? cur_e.context_u128_value_composite[i] : s.context_composite_u128[i];
+            d.far_call = 1; d.far_call_system = abi_system; d.r2_low = (uint32_t)abi_constructor + 2u * (uint32_t)abi_system;
+            d.r1_val = reg_zero(); d.r1_val.is_pointer = 1;
+            d.r1_val.value[0] = p.offset; d.r1_val.value[1] = p.page; d.r1_val.value[2] = p.start; d.r1_val.value[3] = p.length;
+            far_exception = exception;
+            d.set_u128 = 1;
+            for (int i = 0; i < 4; i++) d.u128[i] = 0;
+            old_entry = cur_e;
+            d.depth = s.context_stack_depth + 1;
+            cap_code = VM_CAP_STACK;
         } else {  // ret.rs:29-479
             const bool is_ok = VAR(ZKC_VAR_RET_OK), is_revert = VAR(ZKC_VAR_RET_REVERT), is_ret_panic = VAR(ZKC_VAR_RET_PANIC);
             const bool is_local = ctx.is_local_call != 0, is_far_return = !is_local;
@@ -1072,14 +1208,15 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
                 for (int i = 0; i < 12; i++) so->stack[i] = prev_sponge[i];
             } else for (int i = 0; i < 12; i++) so->stack[i] = st12[i];
         }
-        d.ctx_replaced = apply_near ? 1u : 2u;
+        d.ctx_replaced = apply_near ? 1u : (apply_far ? 3u : 2u);
         set_flags = true; nf0 = is_panic_out && apply_ret; nf1 = 0; nf2 = 0;
+        new_pending = far_exception;
         if (wr) {
             uint64_t f[42];
             vm_flatten_record(nctx, f);
             for (int i = 0; i < 42; i++) TR(aux_base + i) = f[i];
             TR(aux_base + 42) = apply_near; TR(aux_base + 43) = apply_ret; TR(aux_base + 44) = is_panic_out;
-            TR(aux_base + 45) = perform_revert;
+            TR(aux_base + 45) = perform_revert; TR(aux_base + 46) = apply_far; TR(aux_base + 47) = far_exception;
         }
     }
     // ---- state diffs ---------------------------------------------------------------------------------------------------
@@ -1091,7 +1228,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
     const bool perform_mem_write = dst0_mem && dst0_mem_capable;
     vm_push<SIM>(2, perform_mem_write, d, so, penc, last_memq, ts0 + 3, stack_page, dst_index, 1, d.val0);
     if constexpr (SIM) { if (perform_mem_write) sim_write(*sim, stack_page, dst_index, d.val0); }
-    if constexpr (!SIM) { if (last_memq >= 0) d.chk |= VM_CHK_NEXT_MEMQ << (4 * last_memq); }
+    if constexpr (!SIM) { if (last_memq >= 0) d.chk |= (uint64_t)VM_CHK_NEXT_MEMQ << (4 * last_memq); }
     const bool dst0_update_register = dst0_reg_only || (!dst0_mem && dst0_mem_capable);
     if (dst0_update_register) d.idx0 = dst0_r;
     if (write_dst1) d.idx1 = dst1_r;
@@ -1204,8 +1341,12 @@ __host__ __device__ constexpr VmMask vm_keep_mask() {
     m = vm_mask_clear(m, VW(context_stack_depth), 1);
     m = vm_mask_clear(m, VW(memory_queue_state), 24);
     m = vm_mask_clear(m, VW(stack_sponge_state), 24);
+    m = vm_mask_clear(m, VW(code_decommittment_queue_state), 24);
+    m = vm_mask_clear(m, VW(code_decommittment_queue_length), 1);
+    m = vm_mask_clear(m, VW(memory_page_counter), 1);
     return m;
 }
+__host__ __device__ constexpr VmMask vm_decommit_mask() { return vm_mask_set(VmMask{}, VW(code_decommittment_queue_state), 24); }
 __host__ __device__ constexpr VmMask vm_memq_mask() { return vm_mask_set(VmMask{}, VW(memory_queue_state), 24); }
 __host__ __device__ constexpr VmMask vm_stack_mask() { return vm_mask_set(VmMask{}, VW(stack_sponge_state), 24); }
 __host__ __device__ constexpr VmMask vm_fwd_tail_mask() { return vm_mask_set(VmMask{}, VWC(log_queue_forward_tail), 8); }
@@ -1215,6 +1356,7 @@ template <int K> struct VmCtxKeepWord { static constexpr uint32_t value = vm_ctx
 template <int K> struct VmMemqWord { static constexpr uint32_t value = vm_memq_mask().w[K]; };
 template <int K> struct VmStackWord { static constexpr uint32_t value = vm_stack_mask().w[K]; };
 template <int K> struct VmFwdTailWord { static constexpr uint32_t value = vm_fwd_tail_mask().w[K]; };
+template <int K> struct VmDecommitWord { static constexpr uint32_t value = vm_decommit_mask().w[K]; };
 #define VM_FOR10(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 
 __device__ __forceinline__ bool reg_equal(const zkc_vm_register &a, const zkc_vm_register &b) {
@@ -1240,9 +1382,9 @@ __device__ bool vm_record_equal(const zkc_vm_context &c, const zkc_vm_context &e
 
 // scratch of one batch: what the cycle launch leaves for the sponge launches
 struct VmPushScratch {
-    uint32_t *counts;  // [VM_JOB_SLOTS]
+    uint32_t *counts;  // [16] (VM_JOB_SLOTS used)
     uint32_t *lists;   // [VM_JOB_SLOTS][rows]: the rows whose slot-k job runs, in no particular order
-    uint32_t *meta;    // [rows][3]: job mask, capacity sources (nibble per slot), checks (nibble per slot)
+    uint64_t *meta;    // [rows][2]: job mask | capacity sources << 16 (nibble per slot), checks (nibble per slot)
     uint64_t *enc;     // [rows][VM_JOB_SLOTS][8]
     uint64_t *state;   // [rows][VM_JOB_SLOTS][12]: permutation outputs
     // COMPACT trace layout: every executed job also appends a record (null otherwise)
@@ -1334,11 +1476,11 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
     if (valid) {
         VmDelta d;
         zkc_vm_context nctx;
-        checks |= vm_cycle_dev<false>(isa, s, d, nctx, witness[g], cws + inst * (size_t)n_cw, n_cw, nullptr, nullptr,
+        checks |= vm_cycle_dev<false>(isa, &dev->io, s, d, nctx, witness[g], cws + inst * (size_t)n_cw, n_cw, nullptr, nullptr,
                                       ps.enc + g * (VM_JOB_SLOTS * 8), &next,
                                       trace ? trace + inst * (size_t)ncols * limit : nullptr, limit, row, aux_base);
         jmask = d.job_mask;
-        ps.meta[g * 3] = jmask; ps.meta[g * 3 + 1] = d.cap_from; ps.meta[g * 3 + 2] = d.chk;
+        ps.meta[g * 2] = (uint64_t)jmask | (d.cap_from << 16); ps.meta[g * 2 + 1] = d.chk;
         // ---- (2) is snapshot row + 1 what this cycle produces? ---------------------------------------------------------
         bool bad = false;
         if (d.set_u128) {
@@ -1355,20 +1497,22 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
             bad |= next.tx_number_in_block != s.tx_number_in_block + 1;
         }
         // which sponge-derived words this cycle's jobs vouch for
-        bool memq_job = false, stack_job = false;
+        bool memq_job = false, stack_job = false, decommit_job = false;
 #pragma unroll
         for (int k = 0; k < VM_JOB_SLOTS; k++) {
-            const uint32_t c = (d.chk >> (4 * k)) & 15;
-            memq_job |= c == VM_CHK_NEXT_MEMQ; stack_job |= c == VM_CHK_NEXT_STACK;
+            const uint32_t c = (uint32_t)(d.chk >> (4 * k)) & 15;
+            memq_job |= c == VM_CHK_NEXT_MEMQ; stack_job |= c == VM_CHK_NEXT_STACK; decommit_job |= c == VM_CHK_NEXT_DECOMMIT;
         }
-        uint32_t stray = 0, memq_diff = 0, stack_diff = 0, ctx_diff = 0, fwd_diff = 0;
+        uint32_t stray = 0, memq_diff = 0, stack_diff = 0, ctx_diff = 0, fwd_diff = 0, decommit_diff = 0;
 #define X(K) stray |= diff[K] & VmKeepWord<K>::value; memq_diff |= diff[K] & VmMemqWord<K>::value; \
              stack_diff |= diff[K] & VmStackWord<K>::value; ctx_diff |= diff[K] & VmCtxKeepWord<K>::value; \
-             fwd_diff |= diff[K] & VmFwdTailWord<K>::value;
+             fwd_diff |= diff[K] & VmFwdTailWord<K>::value; decommit_diff |= diff[K] & VmDecommitWord<K>::value;
         VM_FOR10(X)
 #undef X
         bad |= stray != 0;
         if (!memq_job) bad |= memq_diff != 0;  // otherwise the last memory queue job of the cycle compares (vm_sponge_kernel)
+        if (!decommit_job) bad |= decommit_diff != 0;
+        bad |= next.memory_page_counter != d.page_counter || next.code_decommittment_queue_length != d.decommit_len;
         const zkc_vm_context &nc = next.current_context;
         if (!d.ctx_replaced) {
             bad |= ctx_diff != 0 || stack_diff != 0;
@@ -1389,6 +1533,8 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
         if (d.far_ret) {
             bad |= !reg_equal(next.registers[0], d.r1_val);
             for (int r = 1; r < ZKC_VM_REGISTERS; r++) bad |= !reg_equal(next.registers[r], reg_zero());
+        } else if (d.far_call) {
+            for (int r = 0; r < ZKC_VM_REGISTERS; r++) bad |= !reg_equal(next.registers[r], vm_far_call_register(isa, d, r, s.registers[r]));
         } else {
             uint32_t regdiff = 0;
 #pragma unroll
@@ -1418,7 +1564,7 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&s);
             uint32_t *dst = reinterpret_cast<uint32_t *>(&dev->s_final);
             for (int i = 0; i < VM_WORDS; i++) dst[i] = src[i];
-            vm_apply_delta(dev->s_final, d, nctx);
+            vm_apply_delta(dev->s_final, d, nctx, isa);
             if (d.ctx_replaced == 2 && d.cw_index < n_cw)
                 for (int i = 0; i < 12; i++) dev->s_final.stack_sponge_state[i] = cws[inst * (size_t)n_cw + d.cw_index].previous_sponge_state[i];
         }
@@ -1447,7 +1593,7 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
                                               const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, const VmPushScratch &ps, int k, size_t g,
                                               size_t limit, uint32_t *flags) {
     const size_t inst = g / limit, row = g - inst * limit, idx = inst * (limit + 1) + row;
-    const uint32_t cap_from = (ps.meta[g * 3 + 1] >> (4 * k)) & 15, chk = (ps.meta[g * 3 + 2] >> (4 * k)) & 15;
+    const uint32_t cap_from = (uint32_t)(ps.meta[g * 2] >> (16 + 4 * k)) & 15, chk = (uint32_t)(ps.meta[g * 2 + 1] >> (4 * k)) & 15;
     const zkc_vm_state &s = snapshots[idx];
     uint64_t q[12];
 #pragma unroll
@@ -1470,6 +1616,7 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
         if (cap_from < VM_JOB_SLOTS) from = ps.state + (g * VM_JOB_SLOTS + cap_from) * 12;
         else if (cap_from == VM_CAP_MEMQ) from = s.memory_queue_state;
         else if (cap_from == VM_CAP_STACK) from = s.stack_sponge_state;
+        else if (cap_from == VM_CAP_DECOMMIT) from = s.code_decommittment_queue_state;
         else {
             const uint32_t cwi = witness[g].callstack_index;
             from = cws[inst * (size_t)n_cw + (cwi < n_cw ? cwi : 0)].previous_sponge_state;
@@ -1506,6 +1653,7 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
     else if (chk == VM_CHK_NEXT_STACK) want = next.stack_sponge_state;
     else if (chk == VM_CHK_CUR_STACK) want = s.stack_sponge_state;
     else if (chk == VM_CHK_NEXT_FWD_TAIL) { want = next.current_context.log_queue_forward_tail; n = 4; }
+    else if (chk == VM_CHK_NEXT_DECOMMIT) want = next.code_decommittment_queue_state;
     else { want = s.current_context.reverted_queue_head; n = 4; }
     bool same = true;
 #pragma unroll
@@ -1515,7 +1663,8 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
     if (!same) vm_report(dev, last_row ? row : row + 1, ZKC_VM_CHK_SNAPSHOT);
     if (last_row) {
         uint64_t *dst = chk == VM_CHK_NEXT_MEMQ ? dev->s_final.memory_queue_state
-                      : chk == VM_CHK_NEXT_STACK ? dev->s_final.stack_sponge_state : dev->s_final.current_context.log_queue_forward_tail;
+                      : chk == VM_CHK_NEXT_STACK ? dev->s_final.stack_sponge_state
+                      : chk == VM_CHK_NEXT_DECOMMIT ? dev->s_final.code_decommittment_queue_state : dev->s_final.current_context.log_queue_forward_tail;
         for (int j = 0; j < n; j++) dst[j] = q[j];
     }
 }
@@ -1563,7 +1712,7 @@ vm_sponge_trace_kernel(VmPushScratch ps, uint64_t *__restrict__ trace, size_t li
     if (l >= row_count * n_instances) return;
     const size_t inst = l / row_count, row = row0 + (l - inst * row_count), g = inst * limit + row;
     uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit + row;
-    const uint32_t m = ps.meta[g * 3];
+    const uint32_t m = (uint32_t)ps.meta[g * 2] & 0xFFFFu;
 #pragma unroll
     for (int k = 0; k < ZKC_VM_NUM_SPONGES; k++) {
         const bool on = k < VM_JOB_SLOTS && ((m >> k) & 1);
@@ -1803,8 +1952,8 @@ vm_simulate_kernel(const zkc_vm_isa *__restrict__ isa, const zkc_vm_state *__res
         const size_t depth = s.context_stack_depth;
         uint64_t fwd_before[4];
         for (int i = 0; i < 4; i++) fwd_before[i] = s.current_context.log_queue_forward_tail[i];
-        const uint32_t checks = vm_cycle_dev<true>(isa, s, d, nctx, w, nullptr, 0, &sim, &so, nullptr, nullptr, nullptr, 0, 0) & ~ignore;
-        vm_apply_delta(s, d, nctx);
+        const uint32_t checks = vm_cycle_dev<true>(isa, nullptr, s, d, nctx, w, nullptr, 0, &sim, &so, nullptr, nullptr, nullptr, 0, 0) & ~ignore;
+        vm_apply_delta(s, d, nctx, isa);
         for (int i = 0; i < 12; i++) s.memory_queue_state[i] = so.memq[i];
         if (d.ctx_replaced) for (int i = 0; i < 12; i++) s.stack_sponge_state[i] = so.stack[i];
         if (d.fwd_tail_kind == 1) for (int i = 0; i < 4; i++) s.current_context.log_queue_forward_tail[i] = so.fwd_tail[i];
@@ -1901,7 +2050,7 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     const size_t rec_cap = compact ? (size_t)options->sponge_records_capacity : 0;
     if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ncols * rows, 8) + zkc_carver::bytes(rec_cap + 1, sizeof(zkc_vm_sponge_record));
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
-    bytes += zkc_carver::bytes(8 * 16, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 3, 4) +
+    bytes += zkc_carver::bytes(16 * 16, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 2, 8) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(32, 8);
     void *blk = ctx->scratch(bytes);
@@ -1932,15 +2081,15 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     if (n_chunks > 1 && !ctx->copy_streams()) n_chunks = 1;
     const size_t chunk_rows = (limit + n_chunks - 1) / n_chunks;
     cudaStream_t s_in = n_chunks > 1 ? ctx->copy_in : s, s_out = n_chunks > 1 ? ctx->copy_out : s;
-    uint32_t *counts = cv.take<uint32_t>(8 * n_chunks);
+    uint32_t *counts = cv.take<uint32_t>(16 * n_chunks);
     uint32_t *lists = cv.take<uint32_t>(VM_JOB_SLOTS * rows);
     VmPushScratch ps;
-    ps.meta = cv.take<uint32_t>(rows * 3);
+    ps.meta = cv.take<uint64_t>(rows * 2);
     ps.enc = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 8);
     ps.state = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 12);
     uint32_t *job_flags = cv.take<uint32_t>(rows * VM_JOB_SLOTS);
     unsigned long long *tickets = cv.take<unsigned long long>(32);  // [0..15] chunk tickets, [31] record count
-    ZKC_CUDA(ctx, status, cudaMemsetAsync(counts, 0, 32 * n_chunks, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(counts, 0, 64 * n_chunks, s));
     ZKC_CUDA(ctx, status, cudaMemsetAsync(job_flags, 0, rows * VM_JOB_SLOTS * 4, s));
     ZKC_CUDA(ctx, status, cudaMemsetAsync(tickets, 0, 32 * 8, s));
     static int sponge_blocks_per_sm = 0;
@@ -2025,7 +2174,7 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
                 ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e, 0));
             }
         }
-        ps.counts = counts + 8 * c;
+        ps.counts = counts + 16 * c;
         ps.lists = lists + n_instances * r0;
         ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, dsnap, dwit, dcw,
                    (uint32_t)n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base);

@@ -22,6 +22,7 @@ LOG_STORAGE_READ, LOG_STORAGE_WRITE, LOG_TO_L1, LOG_EVENT, LOG_PRECOMPILE = rang
 RET_OK, RET_REVERT, RET_PANIC = range(3)
 UMA_HEAP_READ, UMA_HEAP_WRITE, UMA_AUX_READ, UMA_AUX_WRITE, UMA_PTR_READ = range(5)
 FORWARD_HEAP, FORWARD_PTR, FORWARD_AUX = 0, 1, 2
+FAR_CALL_NORMAL, FAR_CALL_DELEGATE, FAR_CALL_MIMIC = range(3)
 
 
 def props_bits(op, variant=0, flags=0, src=MODE_REG, dst=MODE_REG):
@@ -73,7 +74,9 @@ class Isa:
             for flags in (0, 1):  # first message
                 add(OP_LOG, variant, flags, MODE_REG, MODE_REG, 40, kernel=int(variant in (LOG_TO_L1, LOG_PRECOMPILE)),
                     static_ok=int(variant == LOG_STORAGE_READ))
-        add(OP_FAR_CALL, 0, 0, MODE_REG, MODE_REG, 100, static_ok=1)
+        for variant in range(3):      # normal / delegate / mimic
+            for flags in range(4):    # static | shard << 1
+                add(OP_FAR_CALL, variant, flags, MODE_REG, MODE_REG, 100, static_ok=1)
         assert nxt[0] <= 2048
         for i in range(nxt[0], 2048):  # unused opcode numbers decode to Invalid with the explicit-panic aux bit
             self.isa.opcode_props[i] = self.isa.opcode_props[0]
@@ -87,13 +90,20 @@ class Isa:
         self.isa.panic_bitspread = self.isa.opcode_props[ret_panic] & ((1 << 48) - 1)
         # zkevm_opcode_defs::system_params (from memory; data, not logic)
         self.isa.bootloader_base_page, self.isa.bootloader_code_page, self.isa.bootloader_calldata_page = 8, 8, 7
-        self.isa.starting_timestamp, self.isa.starting_base_page = 1024, 8
+        self.isa.starting_timestamp, self.isa.starting_base_page = 1024, 16  # far calls take pages from here (bootloader: 8..11)
         self.isa.initial_frame_formal_eh_location, self.isa.vm_initial_frame_ergs = 0xFFFF, 0xFFFFFFFF
         self.isa.bootloader_formal_address_low, self.isa.bootloader_max_memory = 0x8001, 1 << 24
         self.isa.vm_max_stack_depth = 1 << 16
         for i, v in enumerate((0, 1, 2, 3)):  # STORAGE / EVENT / L1_MESSAGE / PRECOMPILE aux bytes
             self.isa.log_aux_bytes[i] = v
         self.isa.initial_storage_write_pubdata_bytes, self.isa.l1_message_pubdata_bytes = 64, 88
+        # far call parameters (zkevm_opcode_defs, from memory; data, not logic)
+        self.isa.new_frame_memory_stipend, self.isa.new_memory_pages_per_far_call = 1 << 12, 8
+        self.isa.deployer_system_contract_address_low, self.isa.ergs_per_code_word_decommittment = 0x8006, 4
+        self.isa.code_hash_version_byte, self.isa.code_hash_yet_constructed_marker, self.isa.code_hash_at_rest_marker = 1, 1, 0
+        self.isa.call_system_abi_registers[0], self.isa.call_system_abi_registers[1] = 2, 12   # r3..r12
+        self.isa.call_reserved_range[0], self.isa.call_reserved_range[1] = 12, 14              # r13, r14
+        self.isa.call_implicit_parameter_reg_idx = 14                                         # r15
 
     def encode(self, op, variant=0, flags=0, src=MODE_REG, dst=MODE_REG, cond=COND_ALWAYS, src0=0, src1=0, dst0=0, dst1=0,
                imm0=0, imm1=0):
@@ -115,20 +125,28 @@ def pack_code(opcodes):
     return words
 
 
-def random_program(isa: Isa, n: int, seed: int = 0xC2, with_memory=True, full=True):
+def random_program(isa: Isa, n: int, seed: int = 0xC2, with_memory=True, full=True, far_calls=False):
     """the C2 instruction mix of SURVEY 8d: 40 % add/sub, 15 % binop, 10 % mul/div, 10 % shifts, 10 % UMA heap / aux heap
     reads and writes, 5 % jumps, 5 % context / ptr, 3 % log (storage reads / writes, events, L1 messages, precompile calls),
     2 % near calls into small subroutines that return ok / revert / panic; 30 % of the arithmetic uses stack / code-page /
     immediate operands, 10 % of the instructions are conditional.  `n` instructions: a main body that ends with a jump
     back to 0 (so the program runs for any number of cycles) followed by the subroutines.  r14 / r15 are reserved for
     storage keys and heap offsets (each UMA / log is preceded by the immediate load of its address, counted as an add).
-    full=False restricts the mix to the arithmetic / addressing subset (no uma / log / calls)."""
+    full=False restricts the mix to the arithmetic / addressing subset (no uma / log / calls).  far_calls=True (not part
+    of the C2 mix) turns a quarter of the calls into far calls of a deployed address: every frame runs this same program
+    from pc 0, so it opens with a 3-instruction dispatch (caller == 0: the root's main body; otherwise the callee body,
+    which logs, touches its own heap and returns)."""
     r = splitmix64(seed, 8 * n, 0).reshape(n, 8)
     n_subs = max(1, n // 64) if full else 0
     sub_len = 6
-    n_main = n - n_subs * sub_len
-    assert n_main >= 8
+    callee_len = 8 if far_calls else 0
+    n_main = n - n_subs * sub_len - callee_len
+    assert n_main >= 16
     ops = []
+    if far_calls:
+        ops += [isa.encode(OP_CONTEXT, 1, 0, dst0=13),                                   # r13 = caller
+                isa.encode(OP_SUB, 0, 1, src0=13, src1=0, dst0=13),                      # EQ iff the root frame
+                isa.encode(OP_JUMP, 0, 0, MODE_IMM16, cond=COND_NE, imm0=n_main)]        # a callee: its body sits behind the main body
 
     def arith(i, k, allow_mem=True):
         src0, src1 = (int(r[i, j] % 14) + 2 for j in (1, 2))
@@ -186,15 +204,31 @@ def random_program(isa: Isa, n: int, seed: int = 0xC2, with_memory=True, full=Tr
             ops.append(isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=14, imm0=(x >> 8) % 48))
             src1 = 14 if variant == LOG_PRECOMPILE else int(r[i, 2] % 14) + 2  # a precompile call burns src1[0] ergs
             ops.append(isa.encode(OP_LOG, variant, (x >> 3) & 1 if variant in (LOG_EVENT, LOG_TO_L1) else 0, src0=14, src1=src1, dst0=dst0))
+        elif k >= 98 and far_calls and (x >> 20) % 4 == 0 and room >= 5:
+            # ABI register: ergs in bits 192..224 (forwarding mode 0, normal call); every odd address is deployed
+            ops.append(isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=13, imm0=20000 + x % 30000))
+            ops.append(isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=15, imm0=192))
+            ops.append(isa.encode(OP_SHIFT, 0, 0, src0=13, src1=15, dst0=13))
+            ops.append(isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=14, imm0=0x9000 | ((x >> 8) % 64) | ((x >> 16) & 1)))
+            ops.append(isa.encode(OP_FAR_CALL, (x >> 24) % 3, (x >> 28) % 4 & 1, src0=13, src1=14, imm0=len(ops) + 1))
         elif k >= 98 and n_subs:
-            sub = n_main + (x % n_subs) * sub_len
+            sub = n_main + callee_len + (x % n_subs) * sub_len
             ops.append(isa.encode(OP_NEAR_CALL, src0=0, imm0=sub, imm1=len(ops) + 1))
         else:
             ops.append(isa.encode(OP_NOP, cond=int(r[i, 6] >> 8) % 8))
         i += 1
     ops.append(isa.encode(OP_JUMP, 0, 0, MODE_IMM16, imm0=0))
+    if far_calls:  # the callee body: registers were cleaned by the call, r0-based operands only
+        ops += [isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=2, imm0=int(r[0, 1] % 1000)),
+                isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=14, imm0=int(r[0, 2] % 48)),
+                isa.encode(OP_LOG, LOG_STORAGE_WRITE, 0, src0=14, src1=2),
+                isa.encode(OP_UMA, UMA_HEAP_WRITE, 1, src0=14, src1=2, dst0=15),
+                isa.encode(OP_UMA, UMA_HEAP_READ, 0, src0=14, dst0=3),
+                isa.encode(OP_MUL, 0, 0, src0=2, src1=3, dst0=4, dst1=5),
+                isa.encode(OP_LOG, LOG_EVENT, 0, src0=14, src1=4),
+                isa.encode(OP_RET, RET_OK if int(r[0, 3] % 4) else RET_REVERT)]
     for sidx in range(n_subs):
-        j = n_main + sidx * sub_len
+        j = n_main + callee_len + sidx * sub_len
         x = int(r[j, 7])
         body = [arith(j + t, int(r[j + t, 0] % 75), allow_mem=False) for t in range(sub_len - 3)]
         body.append(isa.encode(OP_ADD, 0, 0, MODE_IMM16, src1=0, dst0=14, imm0=(x >> 8) % 48))

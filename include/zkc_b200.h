@@ -743,6 +743,11 @@ enum zkc_vm_src_mode { /* ImmMemHandlerFlags::variant_index */
 #define ZKC_VM_FORWARD_USE_HEAP 0              /* FarCallForwardPageType::UseHeap */
 #define ZKC_VM_FORWARD_FAT_POINTER 1           /* ForwardFatPointer */
 #define ZKC_VM_FORWARD_USE_AUX_HEAP 2          /* UseAuxHeap */
+#define ZKC_VM_ABI_SHARD_ID_BYTE_IDX 29         /* FAR_CALL_SHARD_ID_BYTE_IDX */
+#define ZKC_VM_ABI_CONSTRUCTOR_CALL_BYTE_IDX 30 /* FAR_CALL_CONSTRUCTOR_CALL_BYTE_IDX */
+#define ZKC_VM_ABI_SYSTEM_CALL_BYTE_IDX 31      /* FAR_CALL_SYSTEM_CALL_BYTE_IDX */
+#define ZKC_VM_FAR_CALL_STATIC_FLAG_IDX 0       /* FAR_CALL_STATIC_FLAG_IDX */
+#define ZKC_VM_FAR_CALL_SHARD_FLAG_IDX 1        /* FAR_CALL_SHARD_FLAG_IDX */
 #define ZKC_VM_AUX_KERNEL_MODE 0          /* KERNER_MODE_FLAG_IDX */
 #define ZKC_VM_AUX_CAN_BE_USED_IN_STATIC 1
 #define ZKC_VM_AUX_EXPLICIT_PANIC 2
@@ -770,6 +775,15 @@ typedef struct zkc_vm_isa {
      * queries and the pubdata byte counts a rollup storage write / an L1 message pay for */
     uint32_t log_aux_bytes[4];
     uint32_t initial_storage_write_pubdata_bytes, l1_message_pubdata_bytes;
+    /* far call constants (call_ret_impl/far_call.rs): NEW_FRAME_MEMORY_STIPEND :343-351, NEW_MEMORY_PAGES_PER_FAR_CALL :447,
+     * DEPLOYER_SYSTEM_CONTRACT_ADDRESS_LOW :1166, ERGS_PER_CODE_WORD_DECOMMITTMENT :1446, ContractCodeSha256 VERSION_BYTE /
+     * YET_CONSTRUCTED_MARKER / CODE_AT_REST_MARKER :513-557, and the register conventions of
+     * zkevm_opcode_defs::definitions::far_call (:1041-1066): CALL_SYSTEM_ABI_REGISTERS [lo, hi), CALL_RESERVED_RANGE [lo, hi),
+     * CALL_IMPLICIT_PARAMETER_REG_IDX (0-based register indices) */
+    uint32_t new_frame_memory_stipend, new_memory_pages_per_far_call, deployer_system_contract_address_low;
+    uint32_t ergs_per_code_word_decommittment;
+    uint32_t code_hash_version_byte, code_hash_yet_constructed_marker, code_hash_at_rest_marker;
+    uint32_t call_system_abi_registers[2], call_reserved_range[2], call_implicit_parameter_reg_idx;
 } zkc_vm_isa;
 
 /* VMRegister, base_structures/register/mod.rs:21-24 */
@@ -821,11 +835,11 @@ typedef struct zkc_vm_cycle_witness {
     uint32_t src0_value[8];
     uint32_t callstack_index;    /* ret: which zkc_vm_callstack_witness answers get_callstack_witness (ret.rs:118-160) */
     uint32_t refund;             /* log: get_refunds (log.rs:232-252) */
-    uint32_t _pad;
+    uint32_t suggested_page;     /* far_call: get_decommittment_request_suggested_page (far_call.rs:1484-1504) */
     uint32_t value_a[8];         /* uma: get_memory_witness_for_read of cell A (uma.rs:277-312);
-                                    log: get_storage_read_witness (log.rs:300-323) */
+                                    log: get_storage_read_witness (log.rs:300-323); far_call: the code hash read (far_call.rs:1203-1223) */
     uint32_t value_b[8];         /* uma: cell B (uma.rs:315-356) */
-    uint64_t rollback[4];        /* near_call: get_rollback_queue_tail_witness_for_call (near_call.rs:70-91);
+    uint64_t rollback[4];        /* near_call / far_call: get_rollback_queue_tail_witness_for_call (near_call.rs:70-91, far_call.rs:830-848);
                                     log: get_rollback_queue_witness (log.rs:351-371) */
 } zkc_vm_cycle_witness;
 
@@ -864,13 +878,14 @@ typedef struct zkc_vm_closed_form {
  * enforced, zeros otherwise.  Slot use:
  *   0 opcode fetch | 1 src0 read, uma read A, log round 0, callstack round 0 | 2 dst0 write, uma read B, log round 1,
  *   callstack round 1 | 3 uma write A, log round 2 (forward), callstack round 2 | 4 uma write B, log round 2 (rollback),
- *   callstack round 3 | 5-7 far call code-hash read | 8 far call decommit (far calls are not built yet).
+ *   callstack round 3 | 5-7 far call code-hash read (forward log queue) | 8 far call decommitment queue push.
  * OP_AUX is one block shared by the opcode families (zero for every other opcode):
  *   uma       +0 absolute address, +1 cell index, +2 unalignment, +3 page, +4 skip memory access, +5 set panic,
  *             +6 growth cost, +7 incremented offset, +8 read A (8), +16 read B (8), +24 written A (8), +32 written B (8)
  *   log       +0 packed forward encoding (20), +20 read value (8), +28 execute, +29 execute rollback, +30 ergs to burn
- *   near_call / ret   +0 new ExecutionContextRecord (42, flatten order), +42 apply near call, +43 apply ret,
- *             +44 ret is panic (after the non-local-frame exceptions), +45 perform revert */
+ *   near_call / far_call / ret   +0 new ExecutionContextRecord (42, flatten order), +42 apply near call, +43 apply ret,
+ *             +44 ret is panic (after the non-local-frame exceptions), +45 perform revert, +46 apply far call,
+ *             +47 far call exception (becomes the pending exception) */
 enum zkc_vm_col {
     ZKC_VM_SHOULD_SKIP_CYCLE = 0,    /* pre_state.rs:91-92 */
     ZKC_VM_PENDING_EXCEPTION_IN = 1,
@@ -923,7 +938,7 @@ enum zkc_vm_col {
 #define ZKC_VM_OP_AUX_COLS 48
 
 #define ZKC_VM_CHK_INVALID_OPCODE (1u << 0)      /* pre_state.rs:291-299 */
-#define ZKC_VM_CHK_UNSUPPORTED_OPCODE (1u << 1)  /* far_call: not built in this engine yet */
+#define ZKC_VM_CHK_UNSUPPORTED_OPCODE (1u << 1)  /* a limit of the out-of-circuit run's memory model (zkc_main_vm_simulate) */
 #define ZKC_VM_CHK_SNAPSHOT (1u << 2)            /* the host-supplied per-cycle VmLocalState is not what the previous cycle produces */
 #define ZKC_VM_CHK_DIV_RELATION (1u << 3)        /* mul_div.rs:321-324 (never fails on computed witnesses) */
 #define ZKC_VM_CHK_BOOTLOADER_EXIT (1u << 4)     /* main_vm/mod.rs:119-122 */

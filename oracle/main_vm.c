@@ -150,7 +150,9 @@ void orc_vm_initial_bootloader_state(const zkc_vm_closed_form *io, const zkc_vm_
 /* ---- memory / storage model and bookkeeping of the out-of-circuit run ------------------------------------------ */
 #define ORC_VM_PAGE_WORDS 65536
 #define ORC_VM_STORAGE_SLOTS 4096
-typedef struct orc_vm_slot { uint32_t used, written; uint32_t key[8]; uint32_t value[8]; } orc_vm_slot;
+#define ORC_VM_MEM_CELLS (1u << 20)
+typedef struct orc_vm_slot { uint32_t used, written, addr0; uint32_t key[8]; uint32_t value[8]; } orc_vm_slot;
+typedef struct orc_vm_cell { uint32_t used, page, index; zkc_vm_register v; } orc_vm_cell;
 /* one rollback-queue event of a frame: its own call marker or a revertable log */
 typedef struct orc_vm_entry {
     int64_t prev;
@@ -161,36 +163,59 @@ typedef struct orc_vm_entry {
     uint64_t enc16[4], cap[4];  /* rollback packing elements 16..19 and the sponge capacity after round 1 */
 } orc_vm_entry;
 typedef struct orc_vm_sim {
-    zkc_vm_register *pages[4];  /* code, stack, heap, aux heap of the root frame (near calls share them) */
-    uint32_t page_ids[4];
+    orc_vm_cell *cells;         /* memory: (page, index) -> word, every page of every frame (index < 2^16) */
     orc_vm_slot *storage;
+    const uint32_t *code; size_t code_words;  /* the one program of this world: every deployed address runs it */
+    uint32_t code_hash[8];      /* its versioned hash */
+    uint32_t decommitted_page;  /* page the program was first decommitted to (0: not yet) */
     zkc_vm_callstack_witness *stack; /* saved frames, [max_depth] */
     size_t max_depth;
     zkc_vm_callstack_witness *cw_out; size_t cw_cap, n_cw;
     /* what the cycle reports to the driver (rollback bookkeeping) */
     int ev_kind;                /* 0 none, 1 call, 2 ret ok, 3 ret revert / panic, 4 revertable log */
     orc_vm_entry ev;
-    int overflow;               /* a model limit was hit (depth, storage slots, callstack witness capacity) */
+    int overflow;               /* a model limit was hit (depth, storage slots, memory cells, callstack witness capacity) */
 } orc_vm_sim;
 
-static zkc_vm_register sim_read(const orc_vm_sim *m, uint32_t page, uint32_t index) {
+static orc_vm_cell *sim_cell(orc_vm_sim *m, uint32_t page, uint32_t index, int create) {
+    uint32_t h = (page * 0x9E3779B1u) ^ (index * 0x85EBCA77u);
+    h ^= h >> 15;
+    for (uint32_t probe = 0; probe < ORC_VM_MEM_CELLS; probe++) {
+        orc_vm_cell *c = &m->cells[(h + probe) & (ORC_VM_MEM_CELLS - 1)];
+        if (!c->used) {
+            if (!create) return NULL;
+            c->used = 1; c->page = page; c->index = index;
+            return c;
+        }
+        if (c->page == page && c->index == index) return c;
+    }
+    m->overflow = 1;
+    return NULL;
+}
+static zkc_vm_register sim_read(orc_vm_sim *m, uint32_t page, uint32_t index) {
     zkc_vm_register z;
     memset(&z, 0, sizeof z);
     if (index >= ORC_VM_PAGE_WORDS) return z;
-    for (int k = 0; k < 4; k++) if (page == m->page_ids[k]) return m->pages[k][index];
-    return z;
+    const orc_vm_cell *c = sim_cell(m, page, index, 0);
+    return c ? c->v : z;
 }
 static void sim_write(orc_vm_sim *m, uint32_t page, uint32_t index, const zkc_vm_register *v) {
     if (index >= ORC_VM_PAGE_WORDS) return;
-    for (int k = 1; k < 4; k++) if (page == m->page_ids[k]) { m->pages[k][index] = *v; return; }
+    orc_vm_cell *c = sim_cell(m, page, index, 1);
+    if (c) c->v = *v;
 }
-static int sim_slot(orc_vm_sim *m, const uint32_t key[8]) {
-    uint32_t h = 0x9E3779B9u;
+static void sim_load_code(orc_vm_sim *m, uint32_t page) {
+    zkc_vm_register r;
+    memset(&r, 0, sizeof r);
+    for (size_t i = 0; i < m->code_words && i < ORC_VM_PAGE_WORDS; i++) { memcpy(r.value, m->code + 8 * i, 32); sim_write(m, page, (uint32_t)i, &r); }
+}
+static int sim_slot(orc_vm_sim *m, uint32_t addr0, const uint32_t key[8]) {
+    uint32_t h = 0x9E3779B9u ^ (addr0 * 0x27D4EB2Fu);
     for (int i = 0; i < 8; i++) h = (h ^ key[i]) * 0x85EBCA6Bu + (h >> 15);
     for (uint32_t probe = 0; probe < ORC_VM_STORAGE_SLOTS; probe++) {
         orc_vm_slot *s = &m->storage[(h + probe) % ORC_VM_STORAGE_SLOTS];
-        if (!s->used) { s->used = 1; memcpy(s->key, key, 32); return (int)((h + probe) % ORC_VM_STORAGE_SLOTS); }
-        if (!memcmp(s->key, key, 32)) return (int)((h + probe) % ORC_VM_STORAGE_SLOTS);
+        if (!s->used) { s->used = 1; s->addr0 = addr0; memcpy(s->key, key, 32); return (int)((h + probe) % ORC_VM_STORAGE_SLOTS); }
+        if (s->addr0 == addr0 && !memcmp(s->key, key, 32)) return (int)((h + probe) % ORC_VM_STORAGE_SLOTS);
     }
     m->overflow = 1;
     return 0;
@@ -249,8 +274,8 @@ static void flatten_record_cols(const zkc_vm_context *c, uint64_t *row, size_t s
 /* one vm_cycle.  sim != NULL: out-of-circuit run (oracle answers come from the model and are RECORDED into *w / the
  * callstack witness); sim == NULL: witness-driven (answers come from *w / cw).  row/stride: trace row or NULL.
  * Returns check bits. */
-static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_cycle_witness *w, const zkc_vm_callstack_witness *cw,
-                         size_t n_cw, orc_vm_sim *sim, zkc_vm_state *out, uint64_t *row, size_t stride) {
+static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_closed_form *gc, const zkc_vm_state *cur, zkc_vm_cycle_witness *w,
+                         const zkc_vm_callstack_witness *cw, size_t n_cw, orc_vm_sim *sim, zkc_vm_state *out, uint64_t *row, size_t stride) {
     uint32_t checks = 0;
     zkc_vm_state s = *cur;
     zkc_vm_context *ctx = &s.current_context;
@@ -405,7 +430,6 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
     int set_flags = 0;
     uint32_t nf[3] = {0, 0, 0};
     int new_pending = 0;
-    if (TYPE(ZKC_OP_FAR_CALL)) checks |= ZKC_VM_CHK_UNSUPPORTED_OPCODE;
     const int sf = FLAG(ZKC_VM_SET_FLAGS_FLAG_IDX);
     if (TYPE(ZKC_OP_ADD) || TYPE(ZKC_OP_SUB)) { /* add_sub.rs:8-166 */
         const int of = TYPE(ZKC_OP_ADD) ? u256_add(a.value, b.value, dst0.value) : u256_sub(a.value, b.value, dst0.value);
@@ -488,6 +512,12 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
     uint32_t new_depth = s.context_stack_depth;
     int far_return_registers = 0;
     zkc_vm_register far_return_r1 = zero_reg;
+    int far_call_registers = 0, far_call_system = 0;   /* far call: r1 / r2 set, ABI / reserved / implicit registers cleaned */
+    zkc_vm_register far_call_r2 = zero_reg;
+    uint32_t new_memory_page_counter = s.memory_page_counter;
+    int decommit_applies = 0;
+    uint64_t new_decommit_state[12]; uint32_t new_decommit_len = s.code_decommittment_queue_length;
+    memcpy(new_decommit_state, s.code_decommittment_queue_state, 96);
     int reset_context_u128 = 0;
     uint64_t draft_memq[12];
     memcpy(draft_memq, s.memory_queue_state, 96);  /* memory queue after the prestate reads; UMA continues from here */
@@ -619,7 +649,7 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
         int slot = -1;
         if (sim) {
             w->refund = 0;
-            if (st_write) { slot = sim_slot(sim, q.key); w->refund = sim->storage[slot].written ? isa->initial_storage_write_pubdata_bytes : 0; }
+            if (st_write) { slot = sim_slot(sim, q.address[0], q.key); w->refund = sim->storage[slot].written ? isa->initial_storage_write_pubdata_bytes : 0; }
         }
         const uint32_t refund = w->refund;
         if (refund > isa->initial_storage_write_pubdata_bytes) checks |= ZKC_VM_CHK_LOG_REFUND; /* sub_no_overflow, :256 */
@@ -634,7 +664,7 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
         if (sim) {
             memset(w->value_a, 0, 32);
             if (is_storage && execute) {
-                if (slot < 0) slot = sim_slot(sim, q.key);
+                if (slot < 0) slot = sim_slot(sim, q.address[0], q.key);
                 memcpy(w->value_a, sim->storage[slot].value, 32);
             }
         }
@@ -682,8 +712,9 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
             x[28 * stride] = (uint64_t)execute; x[29 * stride] = (uint64_t)execute_rollback; x[30 * stride] = burn;
         }
     }
-    if (TYPE(ZKC_OP_NEAR_CALL) || TYPE(ZKC_OP_RET)) { /* call_ret.rs:24-512 */
-        const int apply_near = TYPE(ZKC_OP_NEAR_CALL), apply_ret = TYPE(ZKC_OP_RET);
+    if (TYPE(ZKC_OP_NEAR_CALL) || TYPE(ZKC_OP_RET) || TYPE(ZKC_OP_FAR_CALL)) { /* call_ret.rs:24-512 */
+        const int apply_near = TYPE(ZKC_OP_NEAR_CALL), apply_ret = TYPE(ZKC_OP_RET), apply_far = TYPE(ZKC_OP_FAR_CALL);
+        int far_exception = 0;
         /* compute_shared_abi_parts, call_ret_impl/mod.rs:38-86 */
         const uint32_t fwd_byte = a.value[ZKC_VM_ABI_FORWARDING_MODE_BYTE_IDX / 4] >> (8 * (ZKC_VM_ABI_FORWARDING_MODE_BYTE_IDX % 4)) & 0xFF;
         const int use_aux = fwd_byte == ZKC_VM_FORWARD_USE_AUX_HEAP, fwd_ptr = fwd_byte == ZKC_VM_FORWARD_FAT_POINTER;
@@ -709,6 +740,149 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
             cur_e.ergs_remaining = uf ? 0 : ergs_left - to_pass;
             new_entry.ergs_remaining = uf ? ergs_left : to_pass;
             new_entry.pc = imm0; new_entry.exception_handler_loc = imm1; new_entry.is_local_call = 1;
+            old_entry = cur_e;
+            memcpy(sponge_from, s.stack_sponge_state, 96);
+            new_depth = s.context_stack_depth + 1;
+            if (sim) {
+                if (s.context_stack_depth >= sim->max_depth) sim->overflow = 1;
+                else { sim->stack[s.context_stack_depth].context = old_entry; memcpy(sim->stack[s.context_stack_depth].previous_sponge_state, s.stack_sponge_state, 96); }
+                sim->ev_kind = 1; sim->ev.kind = 1; sim->ev.slot = -1;
+            }
+        } else if (apply_far) { /* far_call.rs:268-1098 */
+            const int is_delegated = VAR(ZKC_VAR_FAR_CALL_DELEGATE), is_mimic = VAR(ZKC_VAR_FAR_CALL_MIMIC);
+            zkc_vm_context cur_e = *ctx;
+            cur_e.pc = pc_plus_one;
+            memset(&new_entry, 0, sizeof new_entry);
+            new_entry.heap_upper_bound = isa->new_frame_memory_stipend; new_entry.aux_heap_upper_bound = isa->new_frame_memory_stipend;
+            const zkc_vm_register *mimic_reg = &s.registers[isa->call_implicit_parameter_reg_idx];
+            const uint32_t *dest = b.value; /* src1: the target address */
+            const int is_static_call = FLAG(ZKC_VM_FAR_CALL_STATIC_FLAG_IDX), is_call_shard = FLAG(ZKC_VM_FAR_CALL_SHARD_FLAG_IDX);
+            /* FarCallPartialABI::from_register_view, :69-98 */
+#define ABI_BYTE(k) ((a.value[(k) / 4] >> (8 * ((k) % 4))) & 0xFF)
+            const uint32_t abi_ergs_passed = a.value[6], abi_shard = ABI_BYTE(ZKC_VM_ABI_SHARD_ID_BYTE_IDX);
+            int abi_constructor = ABI_BYTE(ZKC_VM_ABI_CONSTRUCTOR_CALL_BYTE_IDX) != 0, abi_system = ABI_BYTE(ZKC_VM_ABI_SYSTEM_CALL_BYTE_IDX) != 0;
+#undef ABI_BYTE
+            const uint32_t caller_shard = cur_e.this_shard_id;
+            const uint32_t dest_shard = is_call_shard ? abi_shard : caller_shard;
+            const int target_is_zkporter = dest_shard != 0;
+            const int target_is_kernel = (dest[0] >> 16) == 0 && dest[1] == 0 && dest[2] == 0 && dest[3] == 0 && dest[4] == 0; /* :396-423 */
+            abi_constructor = abi_constructor && is_kernel; abi_system = abi_system && target_is_kernel;
+            const uint32_t new_base_page = s.memory_page_counter;
+            new_memory_page_counter = s.memory_page_counter + isa->new_memory_pages_per_far_call;
+            /* may_be_read_code_hash, :1104-1272 */
+            const int zkporter_available = gc->zkporter_is_available != 0;
+            const int can_read = !target_is_zkporter || zkporter_available, should_read = can_read, needs_porter_mask = target_is_zkporter && !zkporter_available;
+            zkc_log_query q;
+            memset(&q, 0, sizeof q);
+            q.address[0] = isa->deployer_system_contract_address_low;
+            memcpy(q.key, dest, 20);
+            q.tx_number_in_block = s.tx_number_in_block; q.timestamp = ts_log;
+            q.flags = ZKC_LQ_FLAGS(isa->log_aux_bytes[0], dest_shard, 0, 0, 0);
+            if (sim) { /* every address with an odd low word is deployed and runs the world's one program */
+                memset(w->value_a, 0, 32);
+                if (should_read && (dest[0] & 1)) memcpy(w->value_a, sim->code_hash, 32);
+            }
+            uint32_t hash[8];
+            memcpy(hash, w->value_a, 32);
+            memcpy(q.read_value, hash, 32); memcpy(q.written_value, hash, 32);
+            const int empty = u256_is_zero(hash);
+            const int mask_default_aa = should_read && empty && !target_is_kernel;
+            if (mask_default_aa) memcpy(hash, gc->default_aa_code_hash, 32);
+            if (needs_porter_mask) memset(hash, 0, 32);
+            const int hash_is_trivial = (empty && !mask_default_aa) || needs_porter_mask || !should_read;
+            if (should_read) { /* construct_hash_relations_code_hash_read, :1274-1411 */
+                uint64_t enc[20], in8[8], cap0[4] = {0, 0, 0, 0};
+                orc_log_query_encode(&q, enc);
+                sponge_run(&sp, 5, enc, cap0);
+                sponge_run(&sp, 6, enc + 8, sp.fin[5] + 8);
+                memcpy(in8, enc + 16, 32); memcpy(in8 + 4, ctx->log_queue_forward_tail, 32);
+                sponge_run(&sp, 7, in8, sp.fin[6] + 8);
+                memcpy(new_fwd_tail, sp.fin[7], 32); new_fwd_len++;
+            }
+            uint32_t target_code_page = hash_is_trivial ? 0 : s.memory_page_counter;
+            /* code hash format, :503-585 */
+            const uint32_t top = hash[7], version_byte = top >> 24, marker = (top >> 16) & 0xFF;
+            const int normal_marker = marker == 0, constructor_marker = marker == isa->code_hash_yet_constructed_marker;
+            const int code_format_exception = version_byte != isa->code_hash_version_byte || !(normal_marker || constructor_marker);
+            const int can_call_code = (normal_marker && !abi_constructor) || (constructor_marker && abi_constructor);
+            uint32_t masked_hash[8];
+            if (can_call_code) { memcpy(masked_hash, hash, 32); masked_hash[7] = (top & 0xFFFF) | (isa->code_hash_at_rest_marker << 16) | (isa->code_hash_version_byte << 24); }
+            else if (target_is_kernel) memset(masked_hash, 0, 32);
+            else memcpy(masked_hash, gc->default_aa_code_hash, 32);
+            const uint32_t code_len_words = code_format_exception ? 0 : (masked_hash[7] & 0xFFFF);
+            const int call_now_in_construction_kernel = !can_call_code && target_is_kernel;
+            const int exceptions_collapsed = code_format_exception || call_now_in_construction_kernel || (fwd_ptr && !a.is_pointer) ||
+                                             generally_invalid || non_addressable;
+            vm_fat_ptr p = fp;
+            vm_fat_ptr adjusted = {0, p.page, p.start + p.offset, p.length - p.offset};
+            vm_fat_ptr for_heaps = {0, use_heap ? heap_page : aux_heap_page, p.start, p.length};
+            p = fwd_ptr ? adjusted : for_heaps;
+            if (exceptions_collapsed) memset(&p, 0, sizeof p);
+            uint32_t ub = exceptions_collapsed ? 0 : upper_bound;
+            if (non_addressable && !fwd_ptr) ub = 0xFFFFFFFFu;
+            const uint32_t heap_max = use_heap ? ub : 0, aux_max = use_aux ? ub : 0;
+            const int heap_uf = heap_max < cur_e.heap_upper_bound, aux_uf = aux_max < cur_e.aux_heap_upper_bound;
+            uint32_t growth_cost = use_heap ? (heap_uf ? 0 : heap_max - cur_e.heap_upper_bound) : 0;
+            if (use_aux) growth_cost = aux_uf ? 0 : aux_max - cur_e.aux_heap_upper_bound;
+            const int growth_uf = ergs_left < growth_cost;
+            const uint32_t ergs_after_growth = growth_uf ? 0 : ergs_left - growth_cost;
+            if (use_heap) cur_e.heap_upper_bound = heap_uf ? cur_e.heap_upper_bound : heap_max;
+            if (use_aux) cur_e.aux_heap_upper_bound = aux_uf ? cur_e.aux_heap_upper_bound : aux_max;
+            int exception = exceptions_collapsed || growth_uf; /* callee stipend: FORCED_ERGS_FOR_MSG_VALUE_SIMUALTOR == false */
+            int should_decommit = !exception;
+            if (!should_decommit) target_code_page = 0;
+            /* add_to_decommittment_queue, :1418-1603 */
+            const uint32_t decommit_cost = isa->ergs_per_code_word_decommittment * code_len_words;
+            const int not_enough_for_decommit = ergs_after_growth < decommit_cost;
+            should_decommit = should_decommit && !not_enough_for_decommit;
+            uint32_t ergs_after_decommit = should_decommit ? ergs_after_growth - decommit_cost : ergs_after_growth;
+            if (sim) {
+                w->suggested_page = 0;
+                if (should_decommit) {
+                    if (!memcmp(masked_hash, sim->code_hash, 32)) {
+                        if (!sim->decommitted_page) { sim->decommitted_page = target_code_page; sim_load_code(sim, target_code_page); }
+                        w->suggested_page = sim->decommitted_page;
+                    } else w->suggested_page = target_code_page; /* unknown code: a fresh, empty page */
+                }
+            }
+            const uint32_t suggested_page = w->suggested_page;
+            const int is_first = target_code_page == suggested_page;
+            if (should_decommit && !is_first) ergs_after_decommit = ergs_after_growth; /* refund: already decommitted */
+            if (should_decommit) {
+                uint64_t e8[8];
+                e8[0] = (uint64_t)masked_hash[0] + ((uint64_t)(suggested_page & 0xFFFFFF) << 32);
+                e8[1] = (uint64_t)masked_hash[1] + ((uint64_t)(suggested_page >> 24) << 32) + ((uint64_t)(ts_log & 0xFFFF) << 40);
+                e8[2] = (uint64_t)masked_hash[2] + ((uint64_t)(ts_log >> 16) << 32) + ((uint64_t)is_first << 48);
+                for (int i = 3; i < 8; i++) e8[i] = masked_hash[i];
+                sponge_run(&sp, 8, e8, s.code_decommittment_queue_state + 8);
+                decommit_applies = 1; memcpy(new_decommit_state, sp.fin[8], 96); new_decommit_len = s.code_decommittment_queue_length + 1;
+            }
+            const uint32_t code_memory_page = should_decommit ? suggested_page : 0; /* UNMAPPED_PAGE */
+            exception = exception || not_enough_for_decommit;
+            /* the 63 / 64 rule, :870-905 */
+            const uint32_t max_passable = (ergs_after_decommit / 64) * 63, leftover = ergs_after_decommit - max_passable;
+            const int pass_uf = max_passable < abi_ergs_passed;
+            const uint32_t to_pass = pass_uf ? max_passable : abi_ergs_passed;
+            cur_e.ergs_remaining = pass_uf ? leftover : leftover + (max_passable - abi_ergs_passed);
+            memcpy(new_entry.reverted_queue_tail, w->rollback, 32); memcpy(new_entry.reverted_queue_head, w->rollback, 32);
+            new_entry.ergs_remaining = to_pass; new_entry.pc = 0; new_entry.exception_handler_loc = imm0;
+            new_entry.is_static_execution = is_static_call || cur_e.is_static_execution;
+            new_entry.is_kernel_mode = is_delegated ? cur_e.is_kernel_mode : (uint32_t)target_is_kernel;
+            new_entry.code_shard_id = dest_shard; memcpy(new_entry.code_address, dest, 20);
+            new_entry.this_shard_id = is_delegated ? caller_shard : dest_shard;
+            memcpy(new_entry.this_address, is_delegated ? cur_e.this_address : dest, 20);
+            memcpy(new_entry.caller, is_delegated ? cur_e.caller : cur_e.this_address, 20);
+            if (is_mimic) memcpy(new_entry.caller, mimic_reg->value, 20);
+            new_entry.caller_shard_id = caller_shard;
+            new_entry.code_page = code_memory_page; new_entry.base_page = new_base_page;
+            memcpy(new_entry.context_u128_value_composite, is_delegated ? cur_e.context_u128_value_composite : s.context_composite_u128, 16);
+            new_entry.is_local_call = 0;
+            far_call_registers = 1; far_call_system = abi_system;
+            far_return_r1 = zero_reg; far_return_r1.is_pointer = 1;
+            far_return_r1.value[0] = p.offset; far_return_r1.value[1] = p.page; far_return_r1.value[2] = p.start; far_return_r1.value[3] = p.length;
+            far_call_r2.value[0] = (uint32_t)abi_constructor + 2 * (uint32_t)abi_system;
+            far_exception = exception;
+            reset_context_u128 = 1;
             old_entry = cur_e;
             memcpy(sponge_from, s.stack_sponge_state, 96);
             new_depth = s.context_stack_depth + 1;
@@ -795,11 +969,12 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
         memcpy(new_ctx.log_queue_forward_tail, new_fwd_tail, 32);
         new_ctx.log_queue_forward_part_length = new_fwd_len;
         set_flags = 1; nf[0] = (uint32_t)(is_panic_out && apply_ret); nf[1] = 0; nf[2] = 0;
+        new_pending = far_exception; /* pending_exception_if_far_call, call_ret.rs:131-132 */
         if (row) {
             flatten_record_cols(&new_entry, row, stride, ZKC_VM_OP_AUX);
             uint64_t *x = &T(ZKC_VM_OP_AUX);
             x[42 * stride] = (uint64_t)apply_near; x[43 * stride] = (uint64_t)apply_ret; x[44 * stride] = (uint64_t)is_panic_out;
-            x[45 * stride] = (uint64_t)perform_revert;
+            x[45 * stride] = (uint64_t)perform_revert; x[46 * stride] = (uint64_t)apply_far; x[47 * stride] = (uint64_t)far_exception;
         }
     }
     /* ---------------- state diffs, cycle.rs:158-616 ---------------- */
@@ -815,6 +990,16 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
         s.registers[0] = far_return_r1;
         for (int r = 1; r < 15; r++) s.registers[r] = zero_reg;
     }
+    if (far_call_registers) { /* far_call.rs:1018-1066: r1 = calldata pointer, r2 = call flags, the rest per the calling convention */
+        s.registers[0] = far_return_r1;
+        s.registers[1] = far_call_r2;
+        for (uint32_t r = isa->call_system_abi_registers[0]; r < isa->call_system_abi_registers[1] && r < 15; r++) {
+            s.registers[r].is_pointer = 0;
+            if (!far_call_system) memset(s.registers[r].value, 0, 32);
+        }
+        for (uint32_t r = isa->call_reserved_range[0]; r < isa->call_reserved_range[1] && r < 15; r++) s.registers[r] = zero_reg;
+        if (isa->call_implicit_parameter_reg_idx < 15) s.registers[isa->call_implicit_parameter_reg_idx] = zero_reg;
+    }
     if (write_dst1 && dst1_r) s.registers[dst1_r - 1] = dst1; /* dst1 applied after dst0, cycle.rs:421-433 */
     ctx->ergs_remaining = ergs_candidate;
     if (reset_context_u128) memset(s.context_composite_u128, 0, 16);
@@ -826,7 +1011,8 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_state *cur, zkc_vm_
         memcpy(s.stack_sponge_state, new_stack_sponge, 96);
     }
     s.pending_exception = (uint32_t)new_pending;
-    s.memory_page_counter = cur->memory_page_counter; /* only far calls move it */
+    s.memory_page_counter = new_memory_page_counter;
+    if (decommit_applies) { memcpy(s.code_decommittment_queue_state, new_decommit_state, 96); s.code_decommittment_queue_length = new_decommit_len; }
     if (row) {
         T(ZKC_VM_DST0) = dst0.is_pointer; T(ZKC_VM_DST1) = dst1.is_pointer;
         for (int i = 0; i < 8; i++) { T(ZKC_VM_DST0 + 1 + i) = dst0.value[i]; T(ZKC_VM_DST1 + 1 + i) = dst1.value[i]; }
@@ -895,13 +1081,13 @@ static void list_walk(orc_vm_lists *L, size_t depth, uint64_t cur[4], zkc_vm_cyc
 
 /* one pass of the run.  resolve: pass 1 (rollback witness unknown: computed here and patched into `witness`, the
  * states it produces carry unresolved rollback heads and are discarded); otherwise witness[].rollback is input. */
-static int vm_run_pass(const zkc_vm_isa *isa, const zkc_vm_state *initial, const uint32_t *code, size_t code_words, size_t cycles,
+static int vm_run_pass(const zkc_vm_isa *isa, const zkc_vm_closed_form *gc, const zkc_vm_state *initial, const uint32_t *code, size_t code_words, size_t cycles,
                        zkc_vm_state *snapshots, zkc_vm_cycle_witness *witness, zkc_vm_callstack_witness *cw_out, size_t cw_cap,
                        size_t *n_cw, uint64_t root_tail[4], int resolve, zkc_status *status) {
     zkc_status st = {ZKC_OK, 0, -1, 0, 0};
     orc_vm_sim sim;
     memset(&sim, 0, sizeof sim);
-    for (int k = 0; k < 4; k++) sim.pages[k] = calloc(ORC_VM_PAGE_WORDS, sizeof(zkc_vm_register));
+    sim.cells = calloc(ORC_VM_MEM_CELLS, sizeof(orc_vm_cell));
     sim.storage = calloc(ORC_VM_STORAGE_SLOTS, sizeof(orc_vm_slot));
     sim.max_depth = cycles + 2;
     sim.stack = calloc(sim.max_depth, sizeof(zkc_vm_callstack_witness));
@@ -910,11 +1096,11 @@ static int vm_run_pass(const zkc_vm_isa *isa, const zkc_vm_state *initial, const
     L.entries = calloc(cycles ? cycles : 1, sizeof(orc_vm_entry));
     L.first = malloc(sim.max_depth * sizeof(int64_t)); L.last = malloc(sim.max_depth * sizeof(int64_t));
     for (size_t i = 0; i < sim.max_depth; i++) L.first[i] = L.last[i] = -1;
-    sim.page_ids[0] = initial->current_context.code_page;
-    sim.page_ids[1] = initial->current_context.base_page + 1;
-    sim.page_ids[2] = initial->current_context.base_page + 2;
-    sim.page_ids[3] = initial->current_context.base_page + 3;
-    for (size_t i = 0; i < code_words && i < ORC_VM_PAGE_WORDS; i++) memcpy(sim.pages[0][i].value, code + 8 * i, 32);
+    sim.code = code; sim.code_words = code_words;
+    sim_load_code(&sim, initial->current_context.code_page);
+    /* the versioned hash every deployed address answers with: [version byte | marker 0 | length in words] on top */
+    for (int i = 0; i < 7; i++) sim.code_hash[i] = 0xC0DE0000u + (uint32_t)i;
+    sim.code_hash[7] = (isa->code_hash_version_byte << 24) | (uint32_t)(code_words & 0xFFFF);
     /* the frame below the root: the empty context initial_bootloader_state hashes into the stack sponge */
     zkc_vm_state s0 = *initial;
     memcpy(s0.current_context.reverted_queue_head, root_tail, 32);
@@ -938,7 +1124,7 @@ static int vm_run_pass(const zkc_vm_isa *isa, const zkc_vm_state *initial, const
         memset(&witness[c], 0, sizeof witness[c]);
         if (!resolve) memcpy(witness[c].rollback, keep, 32);
         const size_t depth = cur.context_stack_depth;
-        const uint32_t chk = vm_cycle(isa, &cur, &witness[c], NULL, 0, &sim, &next, NULL, 0);
+        const uint32_t chk = vm_cycle(isa, gc, &cur, &witness[c], NULL, 0, &sim, &next, NULL, 0);
         /* the joins of the rollback queue cannot hold before the witness is resolved */
         const uint32_t ignore = resolve ? ZKC_VM_CHK_ROLLBACK_QUEUE : 0;
         if (chk & ~ignore) fail(&st, (int64_t)c, chk & ~ignore);
@@ -970,7 +1156,7 @@ static int vm_run_pass(const zkc_vm_isa *isa, const zkc_vm_state *initial, const
     }
     if (sim.overflow) fail(&st, -1, ZKC_VM_CHK_UNSUPPORTED_OPCODE);
     if (n_cw) *n_cw = sim.n_cw;
-    for (int k = 0; k < 4; k++) free(sim.pages[k]);
+    free(sim.cells);
     free(sim.storage); free(sim.stack); free(L.entries); free(L.first); free(L.last);
     if (status) *status = st;
     return st.code;
@@ -978,14 +1164,16 @@ static int vm_run_pass(const zkc_vm_isa *isa, const zkc_vm_state *initial, const
 
 /* out-of-circuit run: fills snapshots[cycles + 1], witness[cycles] and the popped frames; code: [code_words][8].
  * rollback_tail_out: the resolved rollback_queue_tail_for_block (snapshots[0] carries it). */
-int orc_main_vm_run(const zkc_vm_isa *isa, const zkc_vm_state *initial, const uint32_t *code, size_t code_words,
+int orc_main_vm_run(const zkc_vm_isa *isa, const zkc_vm_closed_form *gc, const zkc_vm_state *initial, const uint32_t *code, size_t code_words,
                     size_t cycles, zkc_vm_state *snapshots, zkc_vm_cycle_witness *witness, zkc_vm_callstack_witness *cw_out,
                     size_t cw_cap, size_t *n_cw, uint64_t rollback_tail_out[4], zkc_status *status) {
     uint64_t root_tail[4];
     memcpy(root_tail, initial->current_context.reverted_queue_tail, 32);
     memset(witness, 0, cycles * sizeof *witness);
-    vm_run_pass(isa, initial, code, code_words, cycles, NULL, witness, cw_out, cw_cap, n_cw, root_tail, 1, status);
-    const int rc = vm_run_pass(isa, initial, code, code_words, cycles, snapshots, witness, cw_out, cw_cap, n_cw, root_tail, 0, status);
+    zkc_vm_closed_form none;
+    if (!gc) { memset(&none, 0, sizeof none); gc = &none; }  /* GlobalContext: zkporter_is_available, default_aa_code_hash */
+    vm_run_pass(isa, gc, initial, code, code_words, cycles, NULL, witness, cw_out, cw_cap, n_cw, root_tail, 1, status);
+    const int rc = vm_run_pass(isa, gc, initial, code, code_words, cycles, snapshots, witness, cw_out, cw_cap, n_cw, root_tail, 0, status);
     if (rollback_tail_out) memcpy(rollback_tail_out, root_tail, 32);
     return rc;
 }
@@ -1006,7 +1194,7 @@ int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const
         if (memcmp(fa, fb, sizeof fa)) fail(&st, (int64_t)c, ZKC_VM_CHK_SNAPSHOT);
         zkc_vm_cycle_witness w = witness[c];
         zkc_vm_state next;
-        const uint32_t chk = vm_cycle(isa, &snapshots[c], &w, callstack_witness, n_callstack_witness, NULL, &next, trace ? trace + c : NULL, limit);
+        const uint32_t chk = vm_cycle(isa, io, &snapshots[c], &w, callstack_witness, n_callstack_witness, NULL, &next, trace ? trace + c : NULL, limit);
         if (chk) fail(&st, (int64_t)c, chk);
         state = next;
     }

@@ -100,7 +100,7 @@ int orc_sha256_entry_point(zkc_sha256_closed_form *io, const zkc_log_query *requ
 size_t orc_vm_flatten_state(const zkc_vm_state *s, uint64_t *dst);
 void orc_vm_context_encode(const zkc_vm_context *c, uint64_t e[32]);
 void orc_vm_initial_bootloader_state(const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *st);
-int orc_main_vm_run(const zkc_vm_isa *isa, const zkc_vm_state *initial, const uint32_t *code, size_t code_words,
+int orc_main_vm_run(const zkc_vm_isa *isa, const zkc_vm_closed_form *gc, const zkc_vm_state *initial, const uint32_t *code, size_t code_words,
                     size_t cycles, zkc_vm_state *snapshots, zkc_vm_cycle_witness *witness, zkc_vm_callstack_witness *cw_out,
                     size_t cw_cap, size_t *n_cw, uint64_t rollback_tail_out[4], zkc_status *status);
 int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const zkc_vm_state *snapshots,

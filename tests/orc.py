@@ -60,7 +60,7 @@ def load():
                                            C.POINTER(abi.Status)]
     lib.orc_vm_initial_bootloader_state.argtypes = [C.POINTER(abi.VmClosedForm), C.POINTER(abi.VmIsa), C.POINTER(abi.VmState)]
     lib.orc_main_vm_run.restype = C.c_int
-    lib.orc_main_vm_run.argtypes = [C.POINTER(abi.VmIsa), C.POINTER(abi.VmState), _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp,
+    lib.orc_main_vm_run.argtypes = [C.POINTER(abi.VmIsa), C.POINTER(abi.VmClosedForm), C.POINTER(abi.VmState), _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp,
                                     C.c_size_t, C.POINTER(C.c_size_t), _vp, C.POINTER(abi.Status)]
     lib.orc_main_vm_entry_point.restype = C.c_int
     lib.orc_main_vm_entry_point.argtypes = [C.POINTER(abi.VmClosedForm), C.POINTER(abi.VmIsa), _vp, _vp, _vp, C.c_size_t, C.c_size_t,
@@ -256,7 +256,7 @@ def vm_initial_state(lib, io, isa):
     return st
 
 
-def vm_run(lib, isa, initial, code_words, cycles, full=False):
+def vm_run(lib, isa, initial, code_words, cycles, full=False, gc=None):
     """out-of-circuit run: returns (rc, snapshots [cycles + 1, 1176] uint8, witness [cycles, 176] uint8, status); full=True
     appends (callstack witness [n, 336] uint8, resolved rollback_queue_tail_for_block [4])"""
     code_words = np.ascontiguousarray(code_words, dtype=np.uint32)
@@ -266,7 +266,7 @@ def vm_run(lib, isa, initial, code_words, cycles, full=False):
     n_cw = C.c_size_t()
     tail = np.zeros(4, dtype=np.uint64)
     st = abi.Status()
-    rc = lib.orc_main_vm_run(C.byref(isa), C.byref(initial), p(code_words), len(code_words), cycles, p(snaps), p(wit), p(cw),
+    rc = lib.orc_main_vm_run(C.byref(isa), C.byref(gc) if gc is not None else None, C.byref(initial), p(code_words), len(code_words), cycles, p(snaps), p(wit), p(cw),
                              len(cw), C.byref(n_cw), p(tail), C.byref(st))
     if full:
         return rc, snaps, wit, st, cw[:n_cw.value].copy(), tail

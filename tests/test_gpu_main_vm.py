@@ -201,14 +201,6 @@ def test_error_cases_match_oracle(engine, orc):
     got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps, w2, cw), cycles, raise_on_unsatisfied=False)
     assert want[0] == abi.ZKC_ERR_SNAPSHOT_MISMATCH and want[4].first_bad_row == r + 1
     assert_same(want, got, check_trace=False)
-    # a far call is reported as unsupported
-    ops2 = [isa.encode(I.OP_ADD, 0, 0, src0=2, src1=3, dst0=4)] * 5 + [isa.encode(I.OP_FAR_CALL)] + [isa.encode(I.OP_NOP)] * 4
-    rc, s2, w3, status = O.vm_run(orc, isa.isa, st, I.pack_code(ops2), 8)
-    assert rc == abi.ZKC_ERR_UNSUPPORTED and status.first_bad_row == 5
-    want = O.vm_entry_point(orc, io0, isa.isa, s2, w3, 8)
-    got = main_vm_entry_point(engine, VmCircuitWitness(io0, isa.isa, s2, w3), 8, raise_on_unsatisfied=False)
-    assert want[0] == abi.ZKC_ERR_UNSUPPORTED
-    assert_same(want, got, check_trace=False)
 
 
 def test_batch_of_instances(engine, orc):
@@ -288,3 +280,56 @@ def test_compact_trace_layout(engine, orc):
     _, _, st5, rc = main_vm_entry_point_batch(engine, ios, isa.isa, hs, hw, cycles, trace_out=hcomp, callstack_witness=hc,
                                               sponge_records_out=small)
     assert rc == 0 and st5[0].reserved == n_jobs
+
+
+@pytest.mark.parametrize("n_ops,cycles,seed", [(1024, 20000, 1), (1024, 20000, 3), (512, 6000, 8)])
+def test_far_calls_bit_exact(engine, orc, n_ops, cycles, seed):
+    """far calls (normal / delegate / mimic, static, to deployed, undeployed and kernel addresses, with exceptions) in the
+    random mix: the witness comes from the oracle's out-of-circuit run (the GPU run models one frame's pages)"""
+    isa, io, st = fresh(orc)
+    io.default_aa_code_hash[7] = (1 << 24) | 5; io.default_aa_code_hash[2] = 0xA1
+    ops = I.random_program(isa, n_ops, seed=seed, far_calls=True)
+    rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True, gc=io)
+    assert rc == 0, (hex(status.failed_checks), status.first_bad_row)
+    io = with_tail(io, tail)
+    want = O.vm_entry_point(orc, io, isa.isa, snaps, wit, cycles, cw=cw)
+    assert want[0] == 0, (want[0], hex(want[4].failed_checks), want[4].first_bad_row)
+    assert want[2][K["OP_AUX"] + 46].sum() > 10
+    got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps, wit, cw), cycles)
+    assert_same(want, got)
+    # corrupted far-call witnesses: the code hash read, the suggested decommit page
+    row = int(np.flatnonzero((want[2][K["OP_AUX"] + 46] == 1) & (want[2][K["SPONGE_ENFORCE"] + 8] == 1))[0])
+    for byte in (80, 76):
+        w2 = wit.copy(); w2[row, byte] ^= 1
+        want2 = O.vm_entry_point(orc, io, isa.isa, snaps, w2, cycles, cw=cw)
+        got2 = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, snaps, w2, cw), cycles, raise_on_unsatisfied=False)
+        assert want2[0] != 0
+        assert_same(want2, got2, check_trace=False)
+    # the GPU out-of-circuit run refuses far calls loudly
+    sim = main_vm_simulate(engine, isa.isa, [st], I.pack_code(ops)[None], 2000)
+    assert sim.status.code == abi.ZKC_ERR_UNSUPPORTED
+
+
+def test_far_call_hand_written(engine, orc):
+    import test_oracle_main_vm_ops as T
+    isa, io, st = T.fresh(orc, tail=31)
+    abi_reg = 100000 << 192
+    T.set_reg(st, 2, abi_reg); T.set_reg(st, 3, 0x9001); T.set_reg(st, 4, 0x9002)
+    ops = T.far_call_program(isa)
+    cycles = 20
+    rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+    assert rc == 0
+    io2 = with_tail(io, tail); io2.start_flag = 0; io2.hidden_fsm_input = O.vm_state_at(snaps, 0)
+    want = O.vm_entry_point(orc, io2, isa.isa, snaps, wit, cycles, cw=cw)
+    assert want[0] == 0
+    got = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, snaps, wit, cw), cycles)
+    assert_same(want, got)
+    # instance boundary right behind the far call: the computed final state carries the new frame + decommit queue
+    want4 = O.vm_entry_point(orc, io2, isa.isa, snaps[:5], wit[:4], 4, cw=cw)
+    got4 = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, snaps[:5], wit[:4], cw), 4)
+    assert_same(want4, got4)
+    bad = snaps.copy(); bad[4, 1176 - 96 + 8] ^= 1  # decommitment queue state of the snapshot behind the far call
+    want5 = O.vm_entry_point(orc, io2, isa.isa, bad[:5], wit[:4], 4, cw=cw)
+    got5 = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, bad[:5], wit[:4], cw), 4, raise_on_unsatisfied=False)
+    assert want5[0] == abi.ZKC_ERR_SNAPSHOT_MISMATCH
+    assert_same(want5, got5, check_trace=False)

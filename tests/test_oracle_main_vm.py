@@ -141,9 +141,6 @@ def test_conditions_jump_context_ptr(orc):
     # the pending exception is masked into ret.panic next cycle: the root frame is left
     rc, snaps, wit, status = run(orc, isa, st, ops, cycles=10)
     assert rc == 0 and O.vm_state_at(snaps, 10).context_stack_depth == 0
-    # far calls are not built: reported, not mis-executed
-    rc, snaps, wit, status = run(orc, isa, st, [isa.encode(I.OP_NOP), isa.encode(I.OP_FAR_CALL)], cycles=2)
-    assert rc == abi.ZKC_ERR_UNSUPPORTED and status.first_bad_row == 1 and status.failed_checks == abi.VM_CHK["UNSUPPORTED_OPCODE"]
 
 
 def test_entry_point_on_random_program(orc):

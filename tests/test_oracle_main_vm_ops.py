@@ -333,3 +333,87 @@ def test_random_programs_with_every_opcode(orc):
         rc, b, tb, com_b, _ = O.vm_entry_point(orc, nxt, isa.isa, snaps[cut:], wit[cut:], cycles - cut, cw=cw)
         assert rc == 0 and bytes(b.hidden_fsm_output) == bytes(out.hidden_fsm_output)
         assert np.array_equal(np.concatenate([ta, tb], axis=1), trace)
+
+
+def far_call_program(isa):
+    return [
+        isa.encode(I.OP_CONTEXT, 1, 0, dst0=10),                                   # 0: r10 = caller
+        isa.encode(I.OP_SUB, 0, 1, src0=10, src1=0, dst0=11),                      # 1: EQ iff caller == 0 (the root frame)
+        isa.encode(I.OP_JUMP, 0, 0, src=I.MODE_IMM16, cond=I.COND_NE, imm0=12),    # 2: callee -> 12
+        isa.encode(I.OP_FAR_CALL, I.FAR_CALL_NORMAL, 0, src0=2, src1=3, imm0=10),  # 3: call r3 with ABI r2, eh 10
+        isa.encode(I.OP_ADD, 0, 0, src=I.MODE_IMM16, dst0=6, imm0=77),             # 4: after the ok return
+        isa.encode(I.OP_FAR_CALL, I.FAR_CALL_NORMAL, 0, src0=2, src1=4, imm0=10),  # 5: registers were cleaned: address 0, no code
+        isa.encode(I.OP_NOP), isa.encode(I.OP_NOP), isa.encode(I.OP_NOP), isa.encode(I.OP_NOP),
+        isa.encode(I.OP_ADD, 0, 0, src=I.MODE_IMM16, dst0=7, imm0=99),             # 10: exception handler
+        isa.encode(I.OP_JUMP, 0, 0, src=I.MODE_IMM16, imm0=20),                    # 11
+        isa.encode(I.OP_ADD, 0, 0, src=I.MODE_IMM16, dst0=8, imm0=5),              # 12: callee body
+        isa.encode(I.OP_LOG, I.LOG_STORAGE_WRITE, src0=5, src1=8),                 # 13: [0] = 5 in the callee's storage
+        isa.encode(I.OP_UMA, I.UMA_HEAP_WRITE, 0, src0=5, src1=8),                 # 14: heap[0] = 5 on the callee's own heap page
+        isa.encode(I.OP_RET, I.RET_OK),                                            # 15
+    ] + [isa.encode(I.OP_NOP)] * 8
+
+
+def test_far_call_decommit_and_return(orc):
+    isa, io, st = fresh(orc, tail=31)
+    abi_reg = 100000 << 192                     # ergs_passed in bits 192..224, forwarding mode 0 (use heap), normal call
+    set_reg(st, 2, abi_reg); set_reg(st, 3, 0x9001); set_reg(st, 4, 0x9002); set_reg(st, 9, 0xABCDEF)
+    ops = far_call_program(isa)
+    cycles = 20
+    snaps, wit, cw, tail, res = run_full(orc, isa, io, st, ops, cycles)
+    assert res[0] == 0, (res[0], hex(res[4].failed_checks), res[4].first_bad_row)
+    s = lambda i: O.vm_state_at(snaps, i)
+    c = lambda i: s(i).current_context
+    words = len(I.pack_code(ops))
+    # cycle 3: the far call
+    callee = c(4)
+    assert s(4).context_stack_depth == 2 and s(4).memory_page_counter == 16 + 8 and s(4).pending_exception == 0
+    assert (callee.this_address[0], callee.caller[0], callee.code_address[0]) == (0x9001, 0x8001, 0x9001)
+    assert (callee.base_page, callee.code_page, callee.pc, callee.exception_handler_loc) == (16, 16, 0, 10)
+    assert (callee.is_kernel_mode, callee.is_local_call, callee.is_static_execution) == (1, 0, 0)
+    assert (callee.heap_upper_bound, callee.aux_heap_upper_bound, callee.ergs_remaining) == (4096, 4096, 100000)
+    assert s(4).code_decommittment_queue_length == 1 and callee.log_queue_forward_part_length == 1
+    # r1 = (empty) calldata pointer into the caller's heap, r2 = flags, r3..r15 cleaned for a non-system call
+    r1 = s(4).registers[0]
+    assert r1.is_pointer == 1 and list(r1.value[:4]) == [0, 8 + 2, 0, 0]
+    assert all(reg(s(4), r) == 0 for r in range(2, 16))
+    # caller frame: 63/64 rule after the decommit cost
+    e_before = c(3).ergs_remaining
+    after_decommit = e_before - 100 - 4 * words
+    assert len(cw) == 2
+    saved = abi.VmCallstackWitness.from_buffer_copy(cw[0].tobytes()).context
+    assert saved.ergs_remaining == after_decommit - 100000 and saved.pc == 4
+    # the callee runs the same program from 0: caller != 0 -> body at 12, writes its own storage + heap, returns
+    assert c(7).pc == 12 and reg(s(8), 8) == 5
+    ret_state = s(11)
+    assert ret_state.context_stack_depth == 1 and ret_state.current_context.pc == 4 and list(ret_state.flags) == [0, 0, 0]
+    assert ret_state.registers[0].is_pointer == 1 and list(ret_state.registers[0].value[:4]) == [0, 16 + 2, 0, 0]
+    assert all(reg(ret_state, r) == 0 for r in range(2, 16)) and list(ret_state.context_composite_u128) == [0, 0, 0, 0]
+    assert ret_state.current_context.reverted_queue_segment_len == 1  # the callee's storage write, handed to the root
+    # cycle 11: add; cycle 12: far call to address 0 (kernel space, no code): exception, frame with the unmapped page
+    assert reg(s(12), 6) == 77
+    bad = s(13)
+    assert bad.context_stack_depth == 2 and bad.pending_exception == 1 and bad.current_context.code_page == 0
+    assert bad.memory_page_counter == 16 + 16 and bad.code_decommittment_queue_length == 1
+    # next cycle: the pending exception is a ret.panic out of the callee: back in the root at its handler
+    back = s(14)
+    assert back.context_stack_depth == 1 and back.current_context.pc == 10 and list(back.flags) == [1, 0, 0]
+    assert reg(s(15), 7) == 99
+    t = res[2]
+    assert t[K["OP_AUX"] + 46].sum() == 2 and t[K["OP_AUX"] + 47].tolist()[12] == 1
+    assert t[K["SPONGE_ENFORCE"] + 5:K["SPONGE_ENFORCE"] + 9, 3].tolist() == [1, 1, 1, 1]
+    assert t[K["SPONGE_ENFORCE"] + 5:K["SPONGE_ENFORCE"] + 9, 12].tolist() == [1, 1, 1, 0]  # the code hash is read, nothing is decommitted
+    # delegate / mimic calls keep / forge the caller
+    for variant, want_this, want_caller in ((I.FAR_CALL_DELEGATE, 0x8001, 0), (I.FAR_CALL_MIMIC, 0x9001, 0x7777)):
+        isa, io, st = fresh(orc)
+        set_reg(st, 2, abi_reg); set_reg(st, 3, 0x9001); set_reg(st, 15, 0x7777)
+        rc, sn, _, _ = O.vm_run(orc, isa.isa, st, I.pack_code([isa.encode(I.OP_FAR_CALL, variant, 1, src0=2, src1=3, imm0=3)]), 1)
+        cc = O.vm_state_at(sn, 1).current_context
+        assert rc == 0 and (cc.this_address[0], cc.caller[0], cc.code_address[0], cc.is_static_execution) == (want_this, want_caller, 0x9001, 1)
+    # a user-space address without code runs the default account code hash of the block
+    isa, io, st = fresh(orc)
+    io.default_aa_code_hash[7] = (1 << 24) | 3; io.default_aa_code_hash[0] = 0xAA
+    set_reg(st, 2, abi_reg); set_reg(st, 3, 0x12340002)
+    rc, sn, wt, _ = O.vm_run(orc, isa.isa, st, I.pack_code([isa.encode(I.OP_FAR_CALL, 0, 0, src0=2, src1=3, imm0=3)]), 1, gc=io)
+    s1 = O.vm_state_at(sn, 1)
+    assert rc == 0 and s1.pending_exception == 0 and s1.current_context.is_kernel_mode == 0 and s1.code_decommittment_queue_length == 1
+    assert s1.current_context.code_page == 16  # unknown code: a fresh page
