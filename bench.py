@@ -39,7 +39,7 @@ UNIT = "cycles/s"
 def workload(n, cycles):
     return (f"main_vm, {n} instance(s) x {cycles} cycles per GPU per step, synthetic ISA table + random programs with the C2 mix "
             "of SURVEY 8d (40 % add/sub, 15 % binop, 10 % mul/div, 10 % shifts, 10 % UMA heap r/w, 5 % jumps, 5 % context/ptr, "
-            "3 % log, 2 % near_call/ret; 30 % stack/code/immediate operands); far_call is not built yet and does not occur")
+            "3 % log, 2 % near_call/ret; 30 % stack/code/immediate operands; far calls are not part of that mix)")
 
 
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of vm_cycles_kernel per launch (profiles/README.md); None until captured
@@ -258,7 +258,7 @@ def run_gpu(args):
     ms, t0, t1 = timed(step_device, args.steps)
     launches = eng.launches - l0
     eng.profile(False)
-    prof = {k: eng.profile_query(k) for k in ("vm_cycles", "vm_sponge", "vm_sponge_trace", "vm_prologue", "vm_finalize")}
+    prof = {k: eng.profile_query(k) for k in ("vm_cycles", "vm_sponge", "vm_sponge_far", "vm_sponge_trace", "vm_finalize")}
     value = n * cycles * world * args.steps / (ms / 1e3)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 

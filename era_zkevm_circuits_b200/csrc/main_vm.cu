@@ -361,6 +361,9 @@ __device__ __forceinline__ U256 as_u256(const zkc_vm_register &r) {
 
 // sponge slots in use (far calls would add 5..8) and where a job's capacity comes from / what its output must equal
 constexpr int VM_JOB_SLOTS = ZKC_VM_NUM_SPONGES;
+// slots 0..4 are the common ones; the far call's 5..8 live in their own (sparsely touched) scratch arrays so that the common
+// slots keep their dense per-row stride
+constexpr int VM_JOB_SLOTS_LO = 5, VM_JOB_SLOTS_HI = VM_JOB_SLOTS - VM_JOB_SLOTS_LO;
 enum : uint32_t { VM_CAP_ZERO = 9, VM_CAP_MEMQ = 10, VM_CAP_STACK = 11, VM_CAP_CALLSTACK_WITNESS = 12, VM_CAP_DECOMMIT = 13 };
 enum : uint32_t { VM_CHK_NONE = 0, VM_CHK_NEXT_MEMQ, VM_CHK_NEXT_STACK, VM_CHK_CUR_STACK, VM_CHK_NEXT_FWD_TAIL, VM_CHK_CUR_RB_HEAD,
                   VM_CHK_NEXT_DECOMMIT };
@@ -387,6 +390,7 @@ struct VmDelta {
     uint32_t cw_index;       // ret: the callstack witness used
     uint32_t job_mask;       // sponge jobs: bit k per slot
     uint64_t cap_from, chk;  // nibble k per slot
+    uint64_t *penc_hi;       // circuit mode: where the encodings of slots 5..8 go (set by the caller)
 };
 // register r (0-based) after a far call (far_call.rs:1018-1066)
 __device__ __forceinline__ zkc_vm_register vm_far_call_register(const zkc_vm_isa *isa, const VmDelta &d, int r, const zkc_vm_register &old) {
@@ -457,8 +461,9 @@ __device__ __forceinline__ void vm_job(int slot, VmDelta &d, uint64_t *penc, con
     } else {
         d.cap_from |= (uint64_t)cap_code << (4 * slot);
         d.chk |= (uint64_t)chk << (4 * slot);
+        uint64_t *dst = slot < VM_JOB_SLOTS_LO ? penc + 8 * slot : d.penc_hi + 8 * (slot - VM_JOB_SLOTS_LO);
 #pragma unroll
-        for (int i = 0; i < 8; i++) penc[8 * slot + i] = in8[i];
+        for (int i = 0; i < 8; i++) dst[i] = in8[i];
     }
 }
 
@@ -1385,8 +1390,14 @@ struct VmPushScratch {
     uint32_t *counts;  // [16] (VM_JOB_SLOTS used)
     uint32_t *lists;   // [VM_JOB_SLOTS][rows]: the rows whose slot-k job runs, in no particular order
     uint64_t *meta;    // [rows][2]: job mask | capacity sources << 16 (nibble per slot), checks (nibble per slot)
-    uint64_t *enc;     // [rows][VM_JOB_SLOTS][8]
-    uint64_t *state;   // [rows][VM_JOB_SLOTS][12]: permutation outputs
+    uint64_t *enc, *enc_hi;      // [rows][5][8], [rows][4][8]
+    uint64_t *state, *state_hi;  // [rows][5][12], [rows][4][12]: permutation outputs
+    __device__ __forceinline__ uint64_t *enc_of(size_t g, int k) const {
+        return k < VM_JOB_SLOTS_LO ? enc + (g * VM_JOB_SLOTS_LO + k) * 8 : enc_hi + (g * VM_JOB_SLOTS_HI + (k - VM_JOB_SLOTS_LO)) * 8;
+    }
+    __device__ __forceinline__ uint64_t *state_of(size_t g, int k) const {
+        return k < VM_JOB_SLOTS_LO ? state + (g * VM_JOB_SLOTS_LO + k) * 12 : state_hi + (g * VM_JOB_SLOTS_HI + (k - VM_JOB_SLOTS_LO)) * 12;
+    }
     // COMPACT trace layout: every executed job also appends a record (null otherwise)
     zkc_vm_sponge_record *records;
     unsigned long long *n_records;
@@ -1476,8 +1487,9 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
     if (valid) {
         VmDelta d;
         zkc_vm_context nctx;
+        d.penc_hi = ps.enc_hi + g * (VM_JOB_SLOTS_HI * 8);
         checks |= vm_cycle_dev<false>(isa, &dev->io, s, d, nctx, witness[g], cws + inst * (size_t)n_cw, n_cw, nullptr, nullptr,
-                                      ps.enc + g * (VM_JOB_SLOTS * 8), &next,
+                                      ps.enc + g * (VM_JOB_SLOTS_LO * 8), &next,
                                       trace ? trace + inst * (size_t)ncols * limit : nullptr, limit, row, aux_base);
         jmask = d.job_mask;
         ps.meta[g * 2] = (uint64_t)jmask | (d.cap_from << 16); ps.meta[g * 2 + 1] = d.chk;
@@ -1572,8 +1584,8 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
     }
     // ---- rows whose slot-k job runs, for the dense sponge launches ---------------------------------------------------------
 #pragma unroll
-    for (int k = 0; k < VM_JOB_SLOTS; k++) {
-        const bool mine = (jmask >> k) & 1;
+    for (int k = 0; k <= VM_JOB_SLOTS_LO; k++) {  // slots 0..4 + 5 (a far call: its thread also runs 6, 7, 8)
+        const bool mine = k < VM_JOB_SLOTS_LO ? (jmask >> k) & 1 : (jmask >> VM_JOB_SLOTS_LO) != 0;
         const unsigned b = __ballot_sync(0xffffffffu, mine);
         if (!b) continue;
         const int leader = __ffs(b) - 1;
@@ -1597,7 +1609,7 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
     const zkc_vm_state &s = snapshots[idx];
     uint64_t q[12];
 #pragma unroll
-    for (int j = 0; j < 8; j++) q[j] = ps.enc[(g * VM_JOB_SLOTS + k) * 8 + j];
+    for (int j = 0; j < 8; j++) q[j] = ps.enc_of(g, k)[j];
     if (flags && cap_from < VM_JOB_SLOTS) {  // acquire the producer's output
         const uint32_t *f = flags + g * VM_JOB_SLOTS + cap_from;
         uint32_t v;
@@ -1613,7 +1625,7 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
         for (int j = 8; j < 12; j++) q[j] = 0;
     } else {
         const uint64_t *from;
-        if (cap_from < VM_JOB_SLOTS) from = ps.state + (g * VM_JOB_SLOTS + cap_from) * 12;
+        if (cap_from < VM_JOB_SLOTS) from = ps.state_of(g, (int)cap_from);
         else if (cap_from == VM_CAP_MEMQ) from = s.memory_queue_state;
         else if (cap_from == VM_CAP_STACK) from = s.stack_sponge_state;
         else if (cap_from == VM_CAP_DECOMMIT) from = s.code_decommittment_queue_state;
@@ -1625,7 +1637,7 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
         for (int j = 8; j < 12; j++) q[j] = from[j];
     }
     poseidon2_permute(q);
-    uint64_t *to = ps.state + (g * VM_JOB_SLOTS + k) * 12;
+    uint64_t *to = ps.state_of(g, k);
 #pragma unroll
     for (int j = 0; j < 12; j++) to[j] = q[j];
     if (flags) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + g * VM_JOB_SLOTS + k), "r"(1u) : "memory");
@@ -1678,6 +1690,18 @@ vm_sponge_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const 
     vm_sponge_job(devs, snapshots, witness, cws, n_cw, ps, k, ps.lists[(size_t)k * total + i], limit, nullptr);
 }
 
+// the far calls of the launch: slots 5, 6, 7 (code-hash read: a chain) and 8 (decommitment queue) of a cycle by one thread
+__global__ void __launch_bounds__(128)
+vm_sponge_far_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
+                     const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, VmPushScratch ps, size_t limit, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ps.counts[VM_JOB_SLOTS_LO]) return;
+    const size_t g = ps.lists[(size_t)VM_JOB_SLOTS_LO * total + i];
+    const uint32_t m = (uint32_t)ps.meta[g * 2] & 0xFFFFu;
+    for (int k = VM_JOB_SLOTS_LO; k < VM_JOB_SLOTS; k++)
+        if ((m >> k) & 1) vm_sponge_job(devs, snapshots, witness, cws, n_cw, ps, k, g, limit, nullptr);
+}
+
 // All slots in ONE persistent launch (grid = what is resident at once).  The jobs are numbered slot by slot (every
 // slot's range padded to a multiple of 32) and handed out in that order, a warp at a time, by an atomic ticket; a job
 // that continues another slot's output spins on that job's flag.  Its dependency has a smaller number, so it was handed
@@ -1688,18 +1712,18 @@ vm_sponge_persistent_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapsh
                             const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, VmPushScratch ps, unsigned long long *ticket,
                             uint32_t *flags, size_t limit, size_t total) {
     const unsigned lane = threadIdx.x & 31;
-    unsigned long long start[VM_JOB_SLOTS + 1];
+    unsigned long long start[VM_JOB_SLOTS_LO + 1];
     start[0] = 0;
 #pragma unroll
-    for (int k = 0; k < VM_JOB_SLOTS; k++) start[k + 1] = start[k] + (((unsigned long long)ps.counts[k] + 31) & ~31ull);
+    for (int k = 0; k < VM_JOB_SLOTS_LO; k++) start[k + 1] = start[k] + (((unsigned long long)ps.counts[k] + 31) & ~31ull);
     for (;;) {
         unsigned long long t = 0;
         if (lane == 0) t = atomicAdd(ticket, 32ull);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= start[VM_JOB_SLOTS]) return;
+        if (t >= start[VM_JOB_SLOTS_LO]) return;
         int k = 0;
 #pragma unroll
-        for (int j = 1; j < VM_JOB_SLOTS; j++) k += t >= start[j];
+        for (int j = 1; j < VM_JOB_SLOTS_LO; j++) k += t >= start[j];
         const unsigned long long i = t - start[k] + lane;
         if (i < ps.counts[k]) vm_sponge_job(devs, snapshots, witness, cws, n_cw, ps, k, ps.lists[(size_t)k * total + i], limit, flags);
     }
@@ -1715,9 +1739,9 @@ vm_sponge_trace_kernel(VmPushScratch ps, uint64_t *__restrict__ trace, size_t li
     const uint32_t m = (uint32_t)ps.meta[g * 2] & 0xFFFFu;
 #pragma unroll
     for (int k = 0; k < ZKC_VM_NUM_SPONGES; k++) {
-        const bool on = k < VM_JOB_SLOTS && ((m >> k) & 1);
+        const bool on = (m >> k) & 1;
         t[(size_t)(ZKC_VM_SPONGE_ENFORCE + k) * limit] = on;
-        const uint64_t *from = ps.state + (g * VM_JOB_SLOTS + (k < VM_JOB_SLOTS ? k : 0)) * 12;
+        const uint64_t *from = ps.state_of(g, k);
 #pragma unroll
         for (int j = 0; j < 12; j++) t[(size_t)(ZKC_VM_SPONGE_FINAL + 12 * k + j) * limit] = on ? from[j] : 0ull;
     }
@@ -2052,7 +2076,7 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
     bytes += zkc_carver::bytes(16 * 16, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 2, 8) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8) +
-             zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(32, 8);
+             zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(32, 8) + 4096;  // + slack: the slot arrays are carved in two parts
     void *blk = ctx->scratch(bytes);
     VmDev *h = (VmDev *)ctx->pinned(n_instances * sizeof(VmDev));
     if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
@@ -2085,8 +2109,10 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     uint32_t *lists = cv.take<uint32_t>(VM_JOB_SLOTS * rows);
     VmPushScratch ps;
     ps.meta = cv.take<uint64_t>(rows * 2);
-    ps.enc = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 8);
-    ps.state = cv.take<uint64_t>(rows * VM_JOB_SLOTS * 12);
+    ps.enc = cv.take<uint64_t>(rows * VM_JOB_SLOTS_LO * 8);
+    ps.state = cv.take<uint64_t>(rows * VM_JOB_SLOTS_LO * 12);
+    ps.enc_hi = cv.take<uint64_t>(rows * VM_JOB_SLOTS_HI * 8);
+    ps.state_hi = cv.take<uint64_t>(rows * VM_JOB_SLOTS_HI * 12);
     uint32_t *job_flags = cv.take<uint32_t>(rows * VM_JOB_SLOTS);
     unsigned long long *tickets = cv.take<unsigned long long>(32);  // [0..15] chunk tickets, [31] record count
     ZKC_CUDA(ctx, status, cudaMemsetAsync(counts, 0, 64 * n_chunks, s));
@@ -2181,7 +2207,7 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
         // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists, or one launch per slot
         static const int sponge_mode = getenv("ZKC_VM_SPONGE_MODE") ? atoi(getenv("ZKC_VM_SPONGE_MODE")) : 0;
         if (sponge_mode == 0) {
-            for (int k = 0; k < VM_JOB_SLOTS; k++)
+            for (int k = 0; k < VM_JOB_SLOTS_LO; k++)
                 ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, dsnap, dwit, dcw,
                            (uint32_t)n_callstack_witness, ps, k, limit, rows);
         } else {
@@ -2189,6 +2215,8 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
             ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_persistent_kernel, (unsigned)std::min(max_blocks, std::max<size_t>(need_blocks, 1)), 128, 0, d, dsnap,
                        dwit, dcw, (uint32_t)n_callstack_witness, ps, tickets + c, job_flags, limit, rows);
         }
+        ZKC_LAUNCH(ctx, "vm_sponge_far", vm_sponge_far_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, dsnap, dwit, dcw,
+                   (uint32_t)n_callstack_witness, ps, limit, rows);
         if (dtrace && !compact)
             ZKC_LAUNCH(ctx, "vm_sponge_trace", vm_sponge_trace_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, ps, dtrace, limit, n_instances, r0, cnt);
         if (trace && !trace_dev) {

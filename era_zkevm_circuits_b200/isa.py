@@ -141,7 +141,7 @@ def random_program(isa: Isa, n: int, seed: int = 0xC2, with_memory=True, full=Tr
     sub_len = 6
     callee_len = 8 if far_calls else 0
     n_main = n - n_subs * sub_len - callee_len
-    assert n_main >= 16
+    assert n_main >= (16 if far_calls else 8)
     ops = []
     if far_calls:
         ops += [isa.encode(OP_CONTEXT, 1, 0, dst0=13),                                   # r13 = caller

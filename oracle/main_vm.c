@@ -1,7 +1,7 @@
 /* ORACLE -- TEST INFRASTRUCTURE ONLY (see gl.h header).
  *
- * Sequential CPU restatement of the main VM circuit, value level (nop, add, sub, jump, binop, mul, div, shifts, ptr,
- * context, uma, log, near_call, ret + every addressing mode of src0 / dst0; far_call is not restated yet):
+ * Sequential CPU restatement of the main VM circuit, value level (every opcode gadget: nop, add, sub, jump, binop, mul,
+ * div, shifts, ptr, context, uma, log, near_call, far_call, ret + every addressing mode of src0 / dst0):
  *   main_vm_entry_point            /root/reference/src/main_vm/mod.rs:47-232
  *   initial_bootloader_state       /root/reference/src/main_vm/loading.rs:13-226
  *   vm_cycle                       /root/reference/src/main_vm/cycle.rs:28-795
@@ -14,7 +14,8 @@
  *   near_call / ret / callstack    /root/reference/src/main_vm/opcodes/call_ret.rs:24-512, call_ret_impl/{near_call.rs:34-184,
  *                                  ret.rs:29-479, mod.rs:38-86, far_call.rs:140-262 (FatPtrInABI)}
  *   ExecutionContextRecord::encode /root/reference/src/base_structures/vm_state/saved_context.rs:111-270
- * far_call is NOT restated yet: a cycle that decodes to it reports ZKC_VM_CHK_UNSUPPORTED_OPCODE.
+ *   far_call                       /root/reference/src/main_vm/opcodes/call_ret_impl/far_call.rs:268-1603
+ *   DecommitQuery::encode          /root/reference/src/base_structures/decommit_query/mod.rs:31-107
  * PARITY UNPINNED: the reference has no main_vm test and the ISA tables (zkevm_opcode_defs) are un-vendored; the
  * tables are input data (zkc_vm_isa) and the bit layout follows main_vm/opcode_bitmask.rs:83-127.
  */

@@ -333,3 +333,65 @@ def test_far_call_hand_written(engine, orc):
     got5 = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, bad[:5], wit[:4], cw), 4, raise_on_unsatisfied=False)
     assert want5[0] == abi.ZKC_ERR_SNAPSHOT_MISMATCH
     assert_same(want5, got5, check_trace=False)
+
+
+def test_full_size_instance_properties(engine, orc):
+    """BASELINE.json configs[1] size (one instance of 2^20 cycles, the C2 instruction mix): the oracle is too slow to
+    replay it here, so parity rests on size-independent properties -- every snapshot link, sponge chain and queue join
+    verifies (status OK); the instance cut in two chained instances (hidden_fsm_output -> hidden_fsm_input) reproduces
+    the same trace and final state; the host-buffer path (chunked H2D | kernels | D2H pipeline, COMPACT layout) returns
+    the same witness as the device-resident one; and a 2^12-cycle prefix of the same run is bit-exact against the oracle."""
+    import torch
+    from era_zkevm_circuits_b200 import main_vm_entry_point_batch
+    cycles = 1 << 20
+    isa = I.Isa()
+    io = abi.VmClosedForm(); io.start_flag = 1; io.rollback_queue_tail_for_block[0] = 0xC2
+    st = O.vm_initial_state(orc, io, isa.isa)
+    code = I.pack_code(I.random_program(isa, 4096, seed=0xC2))
+    sim = main_vm_simulate(engine, isa.isa, [st], code[None], cycles)
+    assert sim.status.code == 0
+    io = with_tail(io, sim.rollback_tails[0])
+    n_cw = int(sim.n_callstack[0])
+    cw = sim.callstack_witness[:, :max(1, n_cw)].contiguous()
+    trace = torch.empty((1, K["NUM_COLS"], cycles), dtype=torch.int64, device="cuda")
+    coms, out, sts, rc = main_vm_entry_point_batch(engine, [io], isa.isa, sim.snapshots, sim.witness, cycles, trace_out=trace, callstack_witness=cw)
+    assert rc == 0 and sts[0].code == 0 and sts[0].failed_checks == 0
+    # the instruction mix is what the bench claims
+    props = trace[0, K["PROPS"]]
+    share = {op: float(((props >> op) & 1).sum()) / cycles for op in range(16)}
+    assert 0.30 < share[I.OP_ADD] + share[I.OP_SUB] < 0.60 and 0.05 < share[I.OP_UMA] < 0.15 and 0.01 < share[I.OP_LOG] < 0.05
+    assert 0.005 < share[I.OP_NEAR_CALL] < 0.03 and share[I.OP_RET] > 0.005 and share[I.OP_FAR_CALL] == 0
+    # queue bookkeeping: the memory queue grew by exactly the enforced memory relations
+    fin = out[0].hidden_fsm_output
+    assert fin.memory_queue_length == int(trace[0, K["MEMQ_LENGTH_OUT"], -1])
+    # two chained instances == the whole
+    cut = 333333
+    ta = torch.empty((1, K["NUM_COLS"], cut), dtype=torch.int64, device="cuda")
+    ca, oa, sa, rc = main_vm_entry_point_batch(engine, [io], isa.isa, sim.snapshots[:, :cut + 1].contiguous(), sim.witness[:, :cut].contiguous(), cut,
+                                               trace_out=ta, callstack_witness=cw)
+    assert rc == 0
+    nxt = abi.VmClosedForm.from_buffer_copy(bytes(oa[0])); nxt.start_flag = 0; nxt.hidden_fsm_input = oa[0].hidden_fsm_output
+    tb = torch.empty((1, K["NUM_COLS"], cycles - cut), dtype=torch.int64, device="cuda")
+    cb, ob, sb, rc = main_vm_entry_point_batch(engine, [nxt], isa.isa, sim.snapshots[:, cut:].contiguous(), sim.witness[:, cut:].contiguous(), cycles - cut,
+                                               trace_out=tb, callstack_witness=cw)
+    assert rc == 0
+    lib = O.load()
+    assert np.array_equal(flat(lib, ob[0].hidden_fsm_output), flat(lib, fin))
+    assert torch.equal(torch.cat([ta, tb], dim=2), trace)
+    del ta, tb
+    # host buffers, COMPACT layout
+    hs, hw, hc = (np.ascontiguousarray(x.cpu().numpy()) for x in (sim.snapshots, sim.witness, cw))
+    hcomp = np.zeros((1, abi.VM_COMPACT_COLS, cycles), dtype=np.uint64)
+    hrec = np.zeros(int(cycles * 1.25), dtype=abi.VM_SPONGE_RECORD_DTYPE)
+    c2, o2, s2, rc = main_vm_entry_point_batch(engine, [io], isa.isa, hs, hw, cycles, trace_out=hcomp, callstack_witness=hc, sponge_records_out=hrec)
+    assert rc == 0 and c2.tolist() == coms.tolist()
+    n_rec = s2[0].reserved
+    assert n_rec == int(trace[0, K["SPONGE_ENFORCE"]:K["SPONGE_ENFORCE"] + 9].sum())
+    dense = trace.cpu().numpy().view(np.uint64)
+    assert np.array_equal(hcomp[0, :K["SPONGE_ENFORCE"]], dense[0, :K["SPONGE_ENFORCE"]]) and np.array_equal(hcomp[0, abi.VM_COMPACT_OP_AUX:], dense[0, K["OP_AUX"]:])
+    rec = hrec[:n_rec]
+    assert np.array_equal(dense[0, K["SPONGE_FINAL"] + 12 * rec["slot"].astype(np.int64) + 3, rec["row"]], rec["out"][:, 3])
+    # a prefix of the same run against the oracle
+    pre = 1 << 12
+    want = O.vm_entry_point(orc, io, isa.isa, hs[0, :pre + 1], hw[0, :pre], pre, cw=hc[0])
+    assert want[0] == 0 and np.array_equal(want[2], dense[0, :, :pre])
