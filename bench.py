@@ -263,6 +263,19 @@ def run_gpu(args):
     value = n * cycles * world * args.steps / (ms / 1e3)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
+    # ---- constraint evaluation of the main_vm trace itself: the row-local relations of vm_cycle, one stream over 276 columns -----
+    from era_zkevm_circuits_b200 import main_vm_check_trace
+    for _ in range(3):
+        vviol, _ = main_vm_check_trace(eng, isa.isa, trace, cycles, n)
+    assert vviol == 0
+    eng.profile_reset()
+    eng.profile(True)
+    for _ in range(max(5, min(args.steps, 20))):
+        step_device()  # rewrites the 2.3 GB trace: the next check reads cold HBM
+        vviol, _ = main_vm_check_trace(eng, isa.isa, trace, cycles, n)
+    eng.profile(False)
+    vchk_ms, vchk_n = eng.profile_query("vm_check")
+
     # ---- constraint evaluation (second half of the metric): streaming evaluator over a 2^20-row ram_permutation trace --------
     rn = 1 << 20
     u, s = synthetic.ram_trace(rn, seed=0xC1 + rank, n_cells=1 << 10, n_nondet=7)
@@ -344,6 +357,12 @@ def run_gpu(args):
                        "traffic": (281072896 + 4868864) * 4,
                        "traffic_note": "ncu --set full dram__bytes_read+write of this kernel at 2^18 rows (profiles/r01_ncu_full_ram_kernels_raw.csv), "
                                        "scaled x4 to 2^20 rows: equals the algorithmic bytes (no re-reads)"}
+    vchk_gbs = ncols * 8 * n * cycles / (vchk_ms / vchk_n * 1e-3) / 1e9 if vchk_n else None
+    constraint_eval_vm = {"kernel": "vm_check_kernel (constraint evaluation of the main_vm trace: decoding, exception masks, add/sub, mul/div, "
+                                    "bitwise relations, selection, sponge columns; every cell read once)",
+                          "bound": "hbm", "achieved": vchk_gbs, "peak": peak, "unit": "GB/s", "frac": vchk_gbs / peak if vchk_gbs else None,
+                          "frac_of_nominal_8000": vchk_gbs / 8000.0 if vchk_gbs else None, "algorithmic_bytes_per_row": ncols * 8,
+                          "avg_launch_ms": vchk_ms / vchk_n if vchk_n else None, "traffic": None}
     kernels = {k + "_kernel": {"avg_launch_ms": v[0] / v[1], "launches_per_step": v[1] / args.steps,
                                "share_of_step": v[0] / ms} for k, v in prof.items() if v[1]}
     kernels["ram_rows_kernel (ram_permutation witness generation, 2^20 rows)"] = {"avg_launch_ms": rows_ms / rows_n if rows_n else None}
@@ -367,7 +386,7 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / e2e_steps, "note": "pinned host snapshots + witness in; full witness out in the COMPACT layout (159 dense columns + sponge records) + closed forms; "
                         "H2D | kernels | D2H pipelined over 16 row chunks", "sponge_records_per_step": n_records[0]},
-        "roofline": roofline, "constraint_eval": constraint_eval, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "constraint_eval": constraint_eval, "constraint_eval_main_vm": constraint_eval_vm, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }))
     if world > 1:
         dist.destroy_process_group()

@@ -224,6 +224,7 @@ VM_COLS = dict(
     PENDING_EXCEPTION_OUT=94, PC_OUT=95, ERGS_OUT=96, HEAP_BOUND_OUT=97, AUX_HEAP_BOUND_OUT=98, MEMQ_LENGTH_OUT=99, DEPTH_OUT=100,
     FORWARD_TAIL_OUT=101, ROLLBACK_HEAD_OUT=106, SPONGE_ENFORCE=111, SPONGE_FINAL=120, OP_AUX=228, NUM_COLS=276)
 VM_COMPACT_COLS, VM_COMPACT_OP_AUX = 276 - 117, 228 - 117
+VMV = dict(BOOLEAN=1, RANGE=2, DECODE=4, EXCEPTION_MASKS=8, ADD_SUB=16, MUL_DIV=32, BINOP=64, FLAGS=128, SELECTION=256, SPONGE=512)
 
 
 def vm_expand_compact_trace(compact, records, limit):
@@ -353,6 +354,7 @@ SIGNATURES = {
                                           C.POINTER(VmOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
     "zkc_main_vm_entry_point_batch": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(VmIsa), _vp, _vp, _vp, C.c_size_t, C.c_size_t,
                                                 C.POINTER(VmOptions), C.c_int, _vp, _vp, _vp]),
+    "zkc_main_vm_check_trace": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, C.c_size_t, C.c_size_t, C.c_int, _u64p, C.POINTER(Status)]),
     "zkc_main_vm_initial_state": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), C.POINTER(VmState)]),
     "zkc_main_vm_simulate": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp,
                                        C.c_size_t, _vp, _vp, C.POINTER(Status)]),

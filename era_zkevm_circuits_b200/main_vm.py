@@ -126,3 +126,14 @@ def main_vm_entry_point_batch(engine: Engine, closed_form_inputs, isa: abi.VmIsa
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
         raise ZkcError(rc, statuses[0], "main_vm_entry_point_batch")
     return commitments, ios, statuses, rc
+
+
+def main_vm_check_trace(engine: Engine, isa: abi.VmIsa, trace, limit: int, n_instances: int = 1):
+    """Constraint evaluation of finished main_vm traces (DENSE layout): the row-local relations of vm_cycle.  trace:
+    [NUM_COLS, limit] or [n, NUM_COLS, limit] uint64 (numpy: host, torch CUDA: device).  Returns (violating rows, status)."""
+    st = abi.Status()
+    viol = C.c_uint64()
+    rc = engine.lib.zkc_main_vm_check_trace(engine.h, C.byref(isa), ptr(trace), limit, n_instances, on_device(trace), C.byref(viol), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, st, "main_vm_check_trace")
+    return viol.value, st

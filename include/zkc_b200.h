@@ -994,6 +994,26 @@ int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t 
                                   const zkc_vm_options *options, int on_device, uint64_t *trace, uint64_t *commitments,
                                   zkc_status *statuses);
 
+/* Constraint evaluation of finished main_vm traces (DENSE layout, [n_instances][ZKC_VM_NUM_COLS][limit]): every relation
+ * that is local to a row -- booleanity / ranges of the allocated cells, opcode decoding against the ISA tables
+ * (decoded_opcode.rs:395-527) and the exception masks (:120-157), AddSubRelation / MulDivRelation / bitwise relations of the
+ * arithmetic opcodes (opcodes/mod.rs:101-180, binop.rs), the dot-product selection of dst0 / dst1 (cycle.rs:199-246), zero
+ * sponge columns where nothing is enforced.  violations = number of rows with at least one failing relation;
+ * status->failed_checks = which families (ZKC_VMV_*), status->first_bad_row = instance * limit + row.  A pure stream over
+ * the trace: 2 208 bytes per row, HBM-bound. */
+#define ZKC_VMV_BOOLEAN (1u << 0)
+#define ZKC_VMV_RANGE (1u << 1)
+#define ZKC_VMV_DECODE (1u << 2)
+#define ZKC_VMV_EXCEPTION_MASKS (1u << 3)
+#define ZKC_VMV_ADD_SUB (1u << 4)
+#define ZKC_VMV_MUL_DIV (1u << 5)
+#define ZKC_VMV_BINOP (1u << 6)
+#define ZKC_VMV_FLAGS (1u << 7)
+#define ZKC_VMV_SELECTION (1u << 8)
+#define ZKC_VMV_SPONGE (1u << 9)
+int zkc_main_vm_check_trace(zkc_ctx *ctx, const zkc_vm_isa *isa, const uint64_t *trace, size_t limit, size_t n_instances,
+                            int on_device, uint64_t *violations, zkc_status *status);
+
 /* the state main_vm_entry_point starts from when start_flag is set: initial_bootloader_state, main_vm/loading.rs:13-226 */
 int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *out);
 

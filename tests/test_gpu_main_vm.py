@@ -395,3 +395,54 @@ def test_full_size_instance_properties(engine, orc):
     pre = 1 << 12
     want = O.vm_entry_point(orc, io, isa.isa, hs[0, :pre + 1], hw[0, :pre], pre, cw=hc[0])
     assert want[0] == 0 and np.array_equal(want[2], dense[0, :, :pre])
+
+
+def test_check_trace_constraint_evaluation(engine, orc):
+    """zkc_main_vm_check_trace: valid traces (the ORACLE's own, and the engine's, far calls included) satisfy every
+    row-local relation; a fault injected into any relation family is found, at its row, with its family bit"""
+    import torch
+    from era_zkevm_circuits_b200 import main_vm_check_trace
+    V = abi.VMV
+    isa, io, st = fresh(orc)
+    cycles = 6000
+    ops = I.random_program(isa, 1024, seed=21, far_calls=True)
+    rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+    assert rc == 0
+    io = with_tail(io, tail)
+    want = O.vm_entry_point(orc, io, isa.isa, snaps, wit, cycles, cw=cw)
+    assert want[0] == 0
+    trace = want[2]
+    viol, stt = main_vm_check_trace(engine, isa.isa, trace, cycles)       # the oracle's trace, host memory
+    assert viol == 0 and stt.code == 0, (viol, hex(stt.failed_checks), stt.first_bad_row)
+    got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, torch.from_numpy(snaps).cuda(), torch.from_numpy(wit).cuda(),
+                                                       torch.from_numpy(np.ascontiguousarray(cw)).cuda()), cycles)
+    viol, stt = main_vm_check_trace(engine, isa.isa, got.trace, cycles)   # the engine's trace, device memory
+    assert viol == 0
+    props = trace[K["PROPS"]]
+    is_op = lambda op: np.flatnonzero((props >> np.uint64(op)) & np.uint64(1))
+    faults = [
+        (K["CONDITION"], 17, 2, V["BOOLEAN"]),
+        (K["SUB_PC"], 40, 5, V["RANGE"]),
+        (K["VARIANT"], 99, None, V["DECODE"]),
+        (K["PROPS"], 123, None, V["DECODE"]),
+        (K["ERGS_COST"], 200, None, V["DECODE"]),
+        (K["MASK_INTO_NOP"], int(np.flatnonzero(trace[K["MASK_INTO_NOP"]] == 0)[5]), 1, V["EXCEPTION_MASKS"]),
+        (K["DST0"] + 3, int(is_op(I.OP_ADD)[3]), None, V["ADD_SUB"]),
+        (K["DST0"] + 1, int(is_op(I.OP_SUB)[2]), None, V["ADD_SUB"]),
+        (K["DST1"] + 2, int(is_op(I.OP_MUL)[1]), None, V["MUL_DIV"]),
+        (K["DST0"] + 1, int(is_op(I.OP_DIV)[1]), None, V["MUL_DIV"]),
+        (K["DST0"] + 8, int(is_op(I.OP_BINOP)[4]), None, V["BINOP"]),
+        (K["SPONGE_FINAL"] + 12 * 6 + 2, int(np.flatnonzero(trace[K["SPONGE_ENFORCE"] + 6] == 0)[0]), 77, V["SPONGE"]),
+        (K["OP_AUX"] + 5, int(is_op(I.OP_ADD)[0]), 9, V["SELECTION"]),
+        (K["DST1"] + 1, int(is_op(I.OP_ADD)[7]), 9, V["SELECTION"]),
+    ]
+    for col, row, val, bit in faults:
+        bad = trace.copy()
+        bad[col, row] = np.uint64(val) if val is not None else bad[col, row] ^ np.uint64(1)
+        viol, stt = main_vm_check_trace(engine, isa.isa, bad, cycles)
+        assert viol == 1 and stt.first_bad_row == row and stt.failed_checks & bit, (col, row, viol, stt.first_bad_row, hex(stt.failed_checks))
+    # a batch of instances
+    two = np.ascontiguousarray(np.stack([trace, trace]))
+    two[1, K["CONDITION"], 5] = 3
+    viol, stt = main_vm_check_trace(engine, isa.isa, two, cycles, n_instances=2)
+    assert viol == 1 and stt.first_bad_row == cycles + 5
