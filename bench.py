@@ -43,9 +43,9 @@ def workload(n, cycles):
 
 
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of vm_cycles_kernel per launch (profiles/README.md); None until captured
-VM_CYCLES_TRAFFIC = (385296384 + 358972416) * 4
+VM_CYCLES_TRAFFIC = (416582912 + 368345600) * 4
 VM_CYCLES_TRAFFIC_NOTE = ("ncu --set full dram__bytes_read+write of vm_cycles_kernel at 2^18 cycles (profiles/r01_ncu_full_vm_kernels_raw.csv, "
-                          "captured before the grouped-prefetch diff; same loads and stores), scaled x4 to 2^20 cycles: 1.08x the algorithmic bytes")
+                          "final kernel of the round), scaled x4 to 2^20 cycles: 1.14x the algorithmic bytes")
 
 
 def measured_peaks():

@@ -21,7 +21,13 @@ struct VmCheckDev {
 
 __device__ __forceinline__ bool prop_bit(uint64_t props, int bit) { return (props >> bit) & 1; }
 
-__global__ void __launch_bounds__(256)
+#ifndef VM_CHECK_THREADS
+#define VM_CHECK_THREADS 128
+#endif
+#ifndef VM_CHECK_MIN_BLOCKS
+#define VM_CHECK_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(VM_CHECK_THREADS, VM_CHECK_MIN_BLOCKS)
 vm_check_kernel(VmCheckDev *out, const zkc_vm_isa *__restrict__ isa, const uint64_t *__restrict__ trace, size_t limit, size_t n_instances) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= limit * n_instances) return;
@@ -239,7 +245,8 @@ extern "C" int zkc_main_vm_check_trace(zkc_ctx *ctx, const zkc_vm_isa *isa, cons
         ZKC_CUDA(ctx, status, cudaMemcpyAsync(buf, trace, rows * ZKC_VM_NUM_COLS * 8, cudaMemcpyHostToDevice, s));
         dt = buf;
     }
-    ZKC_LAUNCH(ctx, "vm_check", vm_check_kernel, (unsigned)((rows + 255) / 256), 256, 0, d, disa, dt, limit, n_instances);
+    ZKC_LAUNCH(ctx, "vm_check", vm_check_kernel, (unsigned)((rows + VM_CHECK_THREADS - 1) / VM_CHECK_THREADS), VM_CHECK_THREADS, 0, d, disa, dt, limit,
+               n_instances);
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof *h, cudaMemcpyDeviceToHost, s));
     ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));

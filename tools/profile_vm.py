@@ -30,5 +30,8 @@ for _ in range(3):
     coms, out, statuses, rc = main_vm_entry_point_batch(eng, ios, isa.isa, sim.snapshots, sim.witness, cycles, trace_out=trace,
                                                         callstack_witness=cw)
     assert rc == 0
+from era_zkevm_circuits_b200 import main_vm_check_trace  # noqa: E402
+viol, _ = main_vm_check_trace(eng, isa.isa, trace, cycles, n)
+assert viol == 0
 torch.cuda.synchronize()
 print("ok")
