@@ -19,6 +19,10 @@ from .storage_validity import (  # noqa: F401
     StorageDeduplicatorInstanceWitness,
     sort_and_deduplicate_storage_access_entry_point,
 )
+from .sort_decommittment_requests import (  # noqa: F401
+    CodeDecommittmentsDeduplicatorInstanceWitness,
+    sort_and_deduplicate_code_decommittments_entry_point,
+)
 from .keccak256_round_function import (  # noqa: F401
     Keccak256RoundFunctionCircuitInstanceWitness,
     keccak256_round_function_entry_point,

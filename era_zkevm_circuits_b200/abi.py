@@ -280,6 +280,39 @@ EV_CHK = dict(LENGTHS_EQUAL=1 << 0, EMPTY_SYNC=1 << 1, UNSORTED_IS_WRITE=1 << 2,
               TRIVIAL_HEAD=1 << 10, QUEUE_HINT=1 << 11)
 
 
+DECOMMIT_QUERY_DTYPE = np.dtype([("code_hash", "<u4", (8,)), ("page", "<u4"), ("is_first", "<u4"), ("timestamp", "<u4"),
+                                 ("_pad", "<u4")])
+assert DECOMMIT_QUERY_DTYPE.itemsize == 48
+
+
+class DecommitQuery(C.Structure):
+    _fields_ = [("code_hash", C.c_uint32 * 8), ("page", C.c_uint32), ("is_first", C.c_uint32), ("timestamp", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+class DecommitSorterFsm(C.Structure):
+    _fields_ = [("initial_queue_state", QueueState12), ("sorted_queue_state", QueueState12), ("final_queue_state", QueueState12),
+                ("lhs_accumulator", C.c_uint64 * 2), ("rhs_accumulator", C.c_uint64 * 2),
+                ("previous_packed_key", C.c_uint32 * 9), ("first_encountered_timestamp", C.c_uint32),
+                ("previous_record", DecommitQuery)]
+
+
+class DecommitSorterClosedForm(C.Structure):
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("initial_queue_state", QueueState12),
+                ("sorted_queue_initial_state", QueueState12), ("final_queue_state", QueueState12),
+                ("hidden_fsm_input", DecommitSorterFsm), ("hidden_fsm_output", DecommitSorterFsm)]
+
+
+DQ_COLS = dict(
+    ORIGINAL_IS_EMPTY=0, SORTED_IS_EMPTY=1, SHOULD_POP=2, UNSORTED_ITEM=3, UNSORTED_ENC=14, UNSORTED_HEAD=22, UNSORTED_LEN=34,
+    SORTED_ITEM=35, SORTED_ENC=46, SORTED_HEAD=54, SORTED_LEN=66, GP_CHAIN=67, GP_NEW=99, GP_ACC=103, CMP_DIFF=107,
+    CMP_BORROW=116, CMP_LIMB_EQ=125, KEYS_ARE_EQUAL=134, SAME_HASH=135, ENFORCE_MUST_BE_FIRST=136, PREVIOUS_IS_TRIVIAL=137,
+    ENFORCE_SAME_MEMORY_PAGE=138, ADD_TO_QUEUE=139, PUSH_ITEM=140, PUSH_ENC=151, RESULT_TAIL=159, RESULT_LEN=171,
+    FIRST_TIMESTAMP=172, NUM_COLS=173)
+DQ_CHK = dict(LENGTHS_EQUAL=1 << 0, EMPTY_SYNC=1 << 1, ORDER=1 << 2, MUST_BE_FIRST=1 << 3, SAME_MEMORY_PAGE=1 << 4,
+              QUEUE_CONSISTENCY=1 << 5, GRAND_PRODUCT=1 << 6, TRIVIAL_HEAD=1 << 7, QUEUE_HINT=1 << 8)
+
+
 class RamInputData(C.Structure):
     _fields_ = [("unsorted_queue_initial_state", QueueState12), ("sorted_queue_initial_state", QueueState12),
                 ("non_deterministic_bootloader_memory_snapshot_length", C.c_uint32), ("_pad", C.c_uint32)]
@@ -340,6 +373,10 @@ SIGNATURES = {
     "zkc_log_sorter_entry_point": (C.c_int, [_vp, C.POINTER(EventsClosedForm), _vp, _vp, C.c_size_t, _vp, _vp, C.c_size_t,
                                              _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions), C.c_int, _vp, _vp,
                                              C.POINTER(Status)]),
+    "zkc_decommit_queue_simulate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, C.c_int]),
+    "zkc_sort_decommittments_entry_point": (C.c_int, [_vp, C.POINTER(DecommitSorterClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,
+                                                      C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions),
+                                                      C.c_int, _vp, _vp, C.POINTER(Status)]),
     "zkc_storage_validity_entry_point": (C.c_int, [_vp, C.POINTER(StorageClosedForm), _vp, _vp, C.c_size_t, _vp, _vp, _vp,
                                                    C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions),
                                                    C.c_int, _vp, _vp, C.POINTER(Status)]),

@@ -1630,11 +1630,13 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
         else if (cap_from == VM_CAP_STACK) from = s.stack_sponge_state;
         else if (cap_from == VM_CAP_DECOMMIT) from = s.code_decommittment_queue_state;
         else {
+            // an index outside the table was already reported by the cycle kernel (ZKC_VM_CHK_CALLSTACK);
+            // the job then runs from the all-zero capacity like the oracle does
             const uint32_t cwi = witness[g].callstack_index;
-            from = cws[inst * (size_t)n_cw + (cwi < n_cw ? cwi : 0)].previous_sponge_state;
+            from = cwi < n_cw ? cws[inst * (size_t)n_cw + cwi].previous_sponge_state : nullptr;
         }
 #pragma unroll
-        for (int j = 8; j < 12; j++) q[j] = from[j];
+        for (int j = 8; j < 12; j++) q[j] = from ? from[j] : 0ull;
     }
     poseidon2_permute(q);
     uint64_t *to = ps.state_of(g, k);

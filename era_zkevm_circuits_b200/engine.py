@@ -176,6 +176,30 @@ class Engine:
                 raise ZkcError(rc, what="zkc_memory_queue_simulate")
         return prev, final
 
+    def decommit_queue_simulate(self, records, n_queues=1):
+        """push every DecommitQuery record into `n_queues` empty full-state queues (records split evenly, in order).
+        Returns (prev_states [n, 12] uint64, final_states: array of QueueState12)."""
+        n = len(records)
+        assert n % n_queues == 0
+        dev = on_device(records)
+        final = (abi.QueueState12 * n_queues)()
+        if dev:
+            import torch
+            prev = torch.empty((n, 12), dtype=torch.int64, device=records.device)
+            fin_d = torch.empty((n_queues, C.sizeof(abi.QueueState12)), dtype=torch.uint8, device=records.device)
+            rc = self.lib.zkc_decommit_queue_simulate(self.h, ptr(records), n // n_queues, n_queues, ptr(prev), ptr(fin_d), 1)
+            if rc:
+                raise ZkcError(rc, what="zkc_decommit_queue_simulate")
+            host = fin_d.cpu().numpy()
+            C.memmove(final, host.ctypes.data, C.sizeof(final))
+        else:
+            prev = np.empty((n, 12), dtype=np.uint64)
+            rc = self.lib.zkc_decommit_queue_simulate(self.h, ptr(records), n // n_queues, n_queues, ptr(prev),
+                                                      C.cast(final, C.c_void_p), 0)
+            if rc:
+                raise ZkcError(rc, what="zkc_decommit_queue_simulate")
+        return prev, final
+
     def log_queue_simulate(self, records, extra_timestamps=None, n_queues=1):
         """push every LogQuery record into `n_queues` empty 4-wide queues; returns (prev_tails [n, 4], final states)"""
         n = len(records)

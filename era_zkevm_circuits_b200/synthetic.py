@@ -108,6 +108,29 @@ def events_trace(n: int, seed: int = 0xC4, rollback_pct: int = 10):
     return q, q[srt]
 
 
+def decommit_requests_trace(n: int, seed: int = 0xC4, n_hashes: int = 1 << 10):
+    """(f)1 (sort_decommittment_requests): n DecommitQuery records over n_hashes distinct code hashes in execution
+    order: unique ascending timestamps, the first request of a hash carries is_first = 1 and fixes the page every later
+    request of that hash repeats (what add_to_decommittment_queue of the VM produces).  sorted order = by
+    (code_hash as a 256-bit integer, timestamp): concatenate_key, sort_decommittment_requests/mod.rs:383-401.
+    Returns (unsorted, sorted)."""
+    q = np.zeros(n, dtype=abi.DECOMMIT_QUERY_DTYPE)
+    if n == 0:
+        return q, q.copy()
+    n_hashes = max(1, min(n_hashes, n))
+    hashes = splitmix64(seed, n_hashes * 4, 1).view("<u4").reshape(n_hashes, 8).copy()
+    hashes[:, 7] |= 1  # never the all-zero placeholder hash
+    which = (splitmix64(seed, n, 2) % np.uint64(n_hashes)).astype(np.int64)
+    q["code_hash"] = hashes[which]
+    q["timestamp"] = 1000 + 4 * np.arange(n, dtype=np.uint32)
+    first_pos = np.full(n_hashes, n, dtype=np.int64)
+    np.minimum.at(first_pos, which, np.arange(n))
+    q["is_first"] = (first_pos[which] == np.arange(n)).astype(np.uint32)
+    q["page"] = (2048 + 8 * first_pos[which]).astype(np.uint32)
+    keys = [q["timestamp"]] + [q["code_hash"][:, i] for i in range(8)]
+    return q, q[np.lexsort(keys)]
+
+
 def storage_trace(n: int, seed: int = 0xC4, n_cells: int = 1 << 16, shard: int = 0, first_position: int = 0):
     """C4 (storage_validity): n storage LogQuery records over n_cells (address, key) cells: 60 % reads,
     30 % writes, 10 % write + rollback pairs (the rollback twin directly follows its write), shard 0.

@@ -522,6 +522,106 @@ int zkc_storage_validity_entry_point(zkc_ctx *ctx, zkc_storage_closed_form *io, 
                                      zkc_status *status);
 
 
+/* ---- sort_decommittment_requests (src/sort_decommittment_requests/mod.rs) ------------------------ */
+/* DecommitQuery witness, src/base_structures/decommit_query/mod.rs:20-27 (48-byte record) */
+typedef struct zkc_decommit_query {
+    uint32_t code_hash[8]; /* UInt256, little-endian u32 limbs */
+    uint32_t page;
+    uint32_t is_first;     /* Boolean */
+    uint32_t timestamp;
+    uint32_t _pad;
+} zkc_decommit_query;
+#define ZKC_DECOMMIT_QUERY_FLAT 11   /* INTERNAL_STRUCT_LEN, decommit_query/mod.rs:116 */
+#define ZKC_DECOMMIT_QUERY_PACKED 8  /* DECOMMIT_QUERY_PACKED_WIDTH, decommit_query/mod.rs:29 */
+#define ZKC_DQ_PACKED_KEY_LENGTH 9   /* PACKED_KEY_LENGTH, sort_decommittment_requests/input.rs:21 */
+
+/* FullStateCircuitQueue::push of `n_queues` independent, initially empty DecommitQueues (DecommitQueue,
+ * decommit_query/mod.rs:174-182; the way the reference test builds its inputs, mod.rs:506-517).
+ * prev_states (may be NULL): AoS [n][12], the tail before each push. */
+int zkc_decommit_queue_simulate(zkc_ctx *ctx, const zkc_decommit_query *records, size_t n_per_queue, size_t n_queues,
+                                uint64_t *prev_states, zkc_queue_state12 *final_states, int on_device);
+
+/* CodeDecommittmentsDeduplicatorFSMInputOutput, input.rs:26-38 */
+typedef struct zkc_decommit_sorter_fsm {
+    zkc_queue_state12 initial_queue_state;
+    zkc_queue_state12 sorted_queue_state;
+    zkc_queue_state12 final_queue_state;
+    uint64_t lhs_accumulator[ZKC_NUM_REPETITIONS];
+    uint64_t rhs_accumulator[ZKC_NUM_REPETITIONS];
+    uint32_t previous_packed_key[ZKC_DQ_PACKED_KEY_LENGTH]; /* [timestamp, code_hash limbs 0..7] */
+    uint32_t first_encountered_timestamp;
+    zkc_decommit_query previous_record;
+} zkc_decommit_sorter_fsm;
+
+/* ClosedFormInputWitness<F, CodeDecommittmentsDeduplicatorFSMInputOutput, ...InputData, ...OutputData>,
+ * input.rs:63-112 */
+typedef struct zkc_decommit_sorter_closed_form {
+    uint32_t start_flag;
+    uint32_t completion_flag;                     /* out */
+    zkc_queue_state12 initial_queue_state;        /* observable input */
+    zkc_queue_state12 sorted_queue_initial_state; /* observable input */
+    zkc_queue_state12 final_queue_state;          /* observable output (out; expected if compared) */
+    zkc_decommit_sorter_fsm hidden_fsm_input;
+    zkc_decommit_sorter_fsm hidden_fsm_output;    /* out; on input: expected value if compare_expected */
+} zkc_decommit_sorter_closed_form;
+
+/* trace columns of one iteration of sort_and_deduplicate_code_decommittments_inner (mod.rs:277-355) */
+enum zkc_decommit_sorter_col {
+    ZKC_DQ_ORIGINAL_IS_EMPTY = 0, /* :278 */
+    ZKC_DQ_SORTED_IS_EMPTY = 1,   /* :279 */
+    ZKC_DQ_SHOULD_POP = 2,        /* :282 */
+    ZKC_DQ_UNSORTED_ITEM = 3,     /* 11, flatten order decommit_query/mod.rs:136-152 */
+    ZKC_DQ_UNSORTED_ENC = 14,     /* 8 */
+    ZKC_DQ_UNSORTED_HEAD = 22,    /* 12: head after the pop */
+    ZKC_DQ_UNSORTED_LEN = 34,
+    ZKC_DQ_SORTED_ITEM = 35,      /* 11 */
+    ZKC_DQ_SORTED_ENC = 46,       /* 8 */
+    ZKC_DQ_SORTED_HEAD = 54,      /* 12 */
+    ZKC_DQ_SORTED_LEN = 66,
+    ZKC_DQ_GP_CHAIN = 67,         /* 32: (rep*2 + side)*8 + i */
+    ZKC_DQ_GP_NEW = 99,           /* 4 */
+    ZKC_DQ_GP_ACC = 103,          /* 4 */
+    ZKC_DQ_CMP_DIFF = 107,        /* 9: unpacked_long_comparison(packed_key, previous_packed_key), :309-310 */
+    ZKC_DQ_CMP_BORROW = 116,      /* 9; the last one = new_key_is_greater */
+    ZKC_DQ_CMP_LIMB_EQ = 125,     /* 9 */
+    ZKC_DQ_KEYS_ARE_EQUAL = 134,
+    ZKC_DQ_SAME_HASH = 135,               /* :314 */
+    ZKC_DQ_ENFORCE_MUST_BE_FIRST = 136,   /* :318 */
+    ZKC_DQ_PREVIOUS_IS_TRIVIAL = 137,     /* value on entry to the iteration */
+    ZKC_DQ_ENFORCE_SAME_MEMORY_PAGE = 138,/* :325-326 */
+    ZKC_DQ_ADD_TO_QUEUE = 139,            /* :336 */
+    ZKC_DQ_PUSH_ITEM = 140,               /* 11: record_to_add, :338-340 */
+    ZKC_DQ_PUSH_ENC = 151,                /* 8 */
+    ZKC_DQ_RESULT_TAIL = 159,             /* 12: result queue tail after the conditional push */
+    ZKC_DQ_RESULT_LEN = 171,
+    ZKC_DQ_FIRST_TIMESTAMP = 172,         /* first_encountered_timestamp after the update, :345-350 */
+    ZKC_DQ_NUM_COLS = 173
+};
+
+#define ZKC_DQ_CHK_LENGTHS_EQUAL (1u << 0)     /* :265-269 */
+#define ZKC_DQ_CHK_EMPTY_SYNC (1u << 1)        /* :280 and :360-362 */
+#define ZKC_DQ_CHK_ORDER (1u << 2)             /* :312 */
+#define ZKC_DQ_CHK_MUST_BE_FIRST (1u << 3)     /* :319-321 */
+#define ZKC_DQ_CHK_SAME_MEMORY_PAGE (1u << 4)  /* :328-333 */
+#define ZKC_DQ_CHK_QUEUE_CONSISTENCY (1u << 5) /* :377-378 */
+#define ZKC_DQ_CHK_GRAND_PRODUCT (1u << 6)     /* :183-185 */
+#define ZKC_DQ_CHK_TRIVIAL_HEAD (1u << 7)      /* :78, :93 */
+#define ZKC_DQ_CHK_QUEUE_HINT (1u << 8)        /* *_prev_states / result_states is not the hash chain */
+
+/* sort_and_deduplicate_code_decommittments_entry_point, src/sort_decommittment_requests/mod.rs:40-233.
+ *   unsorted / sorted, *_prev_states : queue witnesses in pop order (FullStateCircuitQueueRawWitness, input.rs:114-131):
+ *                   record + the 12-element queue state before it was pushed
+ *   result_states : NULL, or AoS [pushes][12]: the result-queue tail after each executed push (verified);
+ *                   when NULL the chain is rebuilt sequentially on the device (1 permutation per push)
+ *   trace         : column-major [ZKC_DQ_NUM_COLS][limit] or NULL */
+int zkc_sort_decommittments_entry_point(zkc_ctx *ctx, zkc_decommit_sorter_closed_form *io, const zkc_decommit_query *unsorted,
+                                        const uint64_t *unsorted_prev_states, size_t n_unsorted,
+                                        const zkc_decommit_query *sorted, const uint64_t *sorted_prev_states,
+                                        size_t n_sorted, const uint64_t *result_states, size_t n_result_states,
+                                        size_t limit, const zkc_sorter_options *options, int on_device, uint64_t *trace,
+                                        uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
+
+
 /* ---- keccak256_round_function (src/keccak256_round_function/mod.rs) -------------------------------- */
 #define ZKC_KECCAK_RATE_BYTES 136            /* boojum KECCAK_RATE_BYTES */
 #define ZKC_KECCAK_BUFFER_SIZE 192           /* KECCAK_PRECOMPILE_BUFFER_SIZE, input.rs:24 */

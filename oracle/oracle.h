@@ -81,6 +81,15 @@ int orc_storage_validity_entry_point(zkc_storage_closed_form *io, const zkc_log_
                                      const zkc_log_query *sorted, const uint32_t *sorted_ts, size_t n_sorted, size_t limit,
                                      const zkc_sorter_options *options, uint64_t *trace, uint64_t *result_tails,
                                      size_t *n_result_tails, uint64_t commitment[4], zkc_status *status);
+/* sort_decommittments.c; result_states (optional out): result-queue tail [12] after each executed push */
+void orc_decommit_query_encode(const zkc_decommit_query *q, uint64_t out[8]);
+void orc_decommit_query_flatten(const zkc_decommit_query *q, uint64_t out[11]);
+void orc_decommit_queue_simulate(const zkc_decommit_query *q, size_t n, uint64_t *prev_states, zkc_queue_state12 *final_state);
+size_t orc_decommit_sorter_encode_fsm(const zkc_decommit_sorter_fsm *f, uint64_t *dst);
+int orc_sort_decommittments_entry_point(zkc_decommit_sorter_closed_form *io, const zkc_decommit_query *unsorted, size_t n_unsorted,
+                                        const zkc_decommit_query *sorted, size_t n_sorted, size_t limit,
+                                        const zkc_sorter_options *options, uint64_t *trace, uint64_t *result_states,
+                                        size_t *n_result_states, uint64_t commitment[4], zkc_status *status);
 /* keccak256_round_function.c; memory_states (optional out): memory queue tail after each executed push */
 void orc_keccak_f1600(uint64_t A[25]);
 void orc_keccak256(const uint8_t *msg, size_t len, uint8_t digest[32]);

@@ -47,6 +47,12 @@ def load():
     lib.orc_storage_validity_entry_point.argtypes = [C.POINTER(abi.StorageClosedForm), _vp, C.c_size_t, _vp, _vp, C.c_size_t,
                                                      C.c_size_t, C.POINTER(abi.SorterOptions), _vp, _vp,
                                                      C.POINTER(C.c_size_t), _vp, C.POINTER(abi.Status)]
+    lib.orc_decommit_query_encode.argtypes = [_vp, _vp]
+    lib.orc_decommit_queue_simulate.argtypes = [_vp, C.c_size_t, _vp, C.POINTER(abi.QueueState12)]
+    lib.orc_sort_decommittments_entry_point.restype = C.c_int
+    lib.orc_sort_decommittments_entry_point.argtypes = [C.POINTER(abi.DecommitSorterClosedForm), _vp, C.c_size_t, _vp, C.c_size_t,
+                                                        C.c_size_t, C.POINTER(abi.SorterOptions), _vp, _vp,
+                                                        C.POINTER(C.c_size_t), _vp, C.POINTER(abi.Status)]
     lib.orc_keccak_f1600.argtypes = [_vp]
     lib.orc_keccak256.argtypes = [_vp, C.c_size_t, _vp]
     lib.orc_keccak256_entry_point.restype = C.c_int
@@ -167,6 +173,40 @@ def log_sorter_entry_point(lib, io, unsorted, sorted_, limit, want_trace=True, c
     rc = lib.orc_log_sorter_entry_point(C.byref(io2), p(unsorted), len(unsorted), p(sorted_), len(sorted_), limit,
                                         C.byref(opts), p(trace), p(tails), C.byref(n_tails), p(com), C.byref(st))
     return rc, io2, trace, com, st, tails[:n_tails.value].copy()
+
+
+def decommit_queue_simulate(lib, records):
+    """returns (prev_states [n, 12], final QueueState12)"""
+    records = np.ascontiguousarray(records)
+    prev = np.zeros((len(records), 12), dtype=np.uint64)
+    fin = abi.QueueState12()
+    lib.orc_decommit_queue_simulate(p(records), len(records), p(prev), C.byref(fin))
+    return prev, fin
+
+
+def decommit_sorter_closed_form(unsorted_state, sorted_state, start=True, fsm_in=None):
+    io = abi.DecommitSorterClosedForm()
+    io.start_flag = int(start)
+    io.initial_queue_state = unsorted_state
+    io.sorted_queue_initial_state = sorted_state
+    if fsm_in is not None:
+        io.hidden_fsm_input = fsm_in
+    return io
+
+
+def sort_decommittments_entry_point(lib, io, unsorted, sorted_, limit, want_trace=True, compare_expected=False):
+    """returns (rc, io_out, trace, commitment, status, result_states)"""
+    io2 = abi.DecommitSorterClosedForm.from_buffer_copy(bytes(io))
+    unsorted = np.ascontiguousarray(unsorted); sorted_ = np.ascontiguousarray(sorted_)
+    trace = np.zeros((abi.DQ_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
+    states = np.zeros((limit + 1, 12), dtype=np.uint64)
+    n_states = C.c_size_t()
+    com = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    opts = abi.SorterOptions(int(compare_expected))
+    rc = lib.orc_sort_decommittments_entry_point(C.byref(io2), p(unsorted), len(unsorted), p(sorted_), len(sorted_), limit,
+                                                 C.byref(opts), p(trace), p(states), C.byref(n_states), p(com), C.byref(st))
+    return rc, io2, trace, com, st, states[:n_states.value].copy()
 
 
 def storage_closed_form(unsorted_state, sorted_state, shard=0, start=True, fsm_in=None):

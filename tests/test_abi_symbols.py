@@ -54,3 +54,26 @@ def test_vm_columns_mirror_header():
     assert chk == abi.VM_CHK
     assert abi.VM_COMPACT_COLS == abi.VM_COLS["NUM_COLS"] - 117 and abi.VM_COMPACT_OP_AUX == abi.VM_COLS["OP_AUX"] - 117
     assert C.sizeof(abi.VmOptions) == 24 and C.sizeof(abi.VmCycleWitness) == 176 and C.sizeof(abi.VmCallstackWitness) == 336
+
+
+def test_decommit_sorter_mirrors_header():
+    """abi.DQ_COLS / DQ_CHK / struct sizes against the header (gcc computes the sizes)"""
+    import subprocess
+    import tempfile
+    text = open(os.path.join(ROOT, "include", "zkc_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", text[text.index("enum zkc_decommit_sorter_col {"):], flags=re.S)
+    body = body[:body.index("};")]
+    cols = {m.group(1): int(m.group(2)) for m in re.finditer(r"ZKC_DQ_([A-Z0-9_]+)\s*=\s*(\d+)", body)}
+    assert cols == abi.DQ_COLS
+    chk = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"#define ZKC_DQ_CHK_([A-Z_]+) \(1u << (\d+)\)", text)}
+    assert chk == abi.DQ_CHK
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s.c")
+        open(src, "w").write('#include <stdio.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu\\n", sizeof(zkc_decommit_query), '
+                             'sizeof(zkc_decommit_sorter_fsm), sizeof(zkc_decommit_sorter_closed_form));return 0;}\n'
+                             % os.path.join(ROOT, "include", "zkc_b200.h"))
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-o", exe, src])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [abi.DECOMMIT_QUERY_DTYPE.itemsize, C.sizeof(abi.DecommitSorterFsm), C.sizeof(abi.DecommitSorterClosedForm)]
+    assert C.sizeof(abi.DecommitQuery) == 48

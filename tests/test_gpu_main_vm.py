@@ -154,6 +154,11 @@ def test_hand_written_calls_logs_uma(engine, orc):
     got = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, snaps, w2, cw), cycles, raise_on_unsatisfied=False)
     assert want[4].failed_checks & abi.VM_CHK["CALLSTACK"]
     assert_same(want, got, check_trace=False)
+    # no popped-frame table at all: every ret is reported, nothing is dereferenced
+    want = O.vm_entry_point(orc, io2, isa.isa, snaps, wit, cycles, cw=None)
+    got = main_vm_entry_point(engine, VmCircuitWitness(io2, isa.isa, snaps, wit, None), cycles, raise_on_unsatisfied=False)
+    assert want[4].failed_checks & abi.VM_CHK["CALLSTACK"]
+    assert_same(want, got, check_trace=False)
 
 
 def test_chained_instances_and_expected_output(engine, orc):

@@ -1,0 +1,177 @@
+"""sort_decommittment_requests: CUDA path through the C ABI vs the CPU oracle, bit-exact (trace, FSM output, observable
+output, commitment, status).  Mirrors /root/reference/src/sort_decommittment_requests/mod.rs:420-563 and widens it."""
+import numpy as np
+import pytest
+
+import orc as O
+import vectors as V
+from era_zkevm_circuits_b200 import (CodeDecommittmentsDeduplicatorInstanceWitness as Witness, abi,
+                                     sort_and_deduplicate_code_decommittments_entry_point as entry_point, synthetic)
+
+pytestmark = pytest.mark.gpu
+K = abi.DQ_COLS
+CHK = abi.DQ_CHK
+
+
+def instance(orc, u, s):
+    up, ufin = O.decommit_queue_simulate(orc, u)
+    sp, sfin = O.decommit_queue_simulate(orc, s)
+    return O.decommit_sorter_closed_form(ufin, sfin, True), up, sp
+
+
+def assert_same(want, got, check_trace=True):
+    rc, io, trace, com, st, states = want
+    assert got.status.code == rc, (got.status.code, hex(got.status.failed_checks), got.status.first_bad_row, rc, hex(st.failed_checks))
+    assert got.status.failed_checks == st.failed_checks and got.status.first_bad_row == st.first_bad_row
+    assert got.closed_form_input.completion_flag == io.completion_flag
+    assert bytes(got.closed_form_input.hidden_fsm_output) == bytes(io.hidden_fsm_output)
+    assert bytes(got.closed_form_input.final_queue_state) == bytes(io.final_queue_state)
+    assert got.commitment.tolist() == com.tolist()
+    if check_trace:
+        bad = np.argwhere(got.trace != trace)
+        assert bad.size == 0, f"first differing (col,row): {bad[:5].tolist()}"
+
+
+def run_both(engine, orc, io, u, up, s, sp, limit, states=None, **kw):
+    want = O.sort_decommittments_entry_point(orc, io, u, s, limit)
+    got = entry_point(engine, Witness(io, u, up, s, sp, states), limit, raise_on_unsatisfied=False, **kw)
+    return want, got
+
+
+def test_reference_vector(engine, orc):
+    u, s = V.sort_decommittments_reference_vector()
+    io, up, sp = instance(orc, u, s)
+    want, got = run_both(engine, orc, io, u, up, s, sp, 16)
+    assert want[0] == abi.ZKC_OK
+    assert_same(want, got)
+    # with the host-supplied result-queue states (verified, no sequential chain on the device)
+    want, got = run_both(engine, orc, io, u, up, s, sp, 16, states=want[5])
+    assert_same(want, got)
+
+
+@pytest.mark.parametrize("n,limit,hashes", [(1, 1, 1), (2, 2, 1), (2, 3, 2), (255, 256, 7), (257, 257, 300), (1000, 1024, 50),
+                                            (20000, 20000, 1000), (5000, 6000, 1)])
+def test_synthetic_bit_exact(engine, orc, n, limit, hashes):
+    u, s = synthetic.decommit_requests_trace(n, seed=n, n_hashes=hashes)
+    io, up, sp = instance(orc, u, s)
+    want, got = run_both(engine, orc, io, u, up, s, sp, limit)
+    assert want[0] == abi.ZKC_OK, (hex(want[4].failed_checks), want[4].first_bad_row)
+    assert want[1].final_queue_state.length == int(u["is_first"].sum()) <= min(hashes, n)
+    assert_same(want, got)
+    want2, got2 = run_both(engine, orc, io, u, up, s, sp, limit, states=want[5])
+    assert_same(want2, got2)
+
+
+def test_chained_instances_and_empty(engine, orc):
+    u, s = synthetic.decommit_requests_trace(3000, seed=9, n_hashes=64)
+    io, up, sp = instance(orc, u, s)
+    whole = entry_point(engine, Witness(io, u, up, s, sp), 3000)
+    assert whole.closed_form_input.completion_flag == 1 and whole.closed_form_input.final_queue_state.length == 64
+    # cut inside a run of equal hashes and at a run boundary
+    for cut in (1100, int(np.flatnonzero(s["is_first"])[20])):
+        a = entry_point(engine, Witness(io, u, up, s, sp), cut)
+        assert a.closed_form_input.completion_flag == 0
+        nxt = abi.DecommitSorterClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+        nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+        want, got = run_both(engine, orc, nxt, u[cut:], up[cut:], s[cut:], sp[cut:], 3000 - cut)
+        assert_same(want, got)
+        assert bytes(got.closed_form_input.hidden_fsm_output) == bytes(whole.closed_form_input.hidden_fsm_output)
+        assert np.array_equal(np.concatenate([a.trace, got.trace], axis=1), whole.trace)
+    exp = abi.DecommitSorterClosedForm.from_buffer_copy(bytes(nxt))
+    exp.hidden_fsm_output = got.closed_form_input.hidden_fsm_output
+    exp.final_queue_state = got.closed_form_input.final_queue_state
+    exp.completion_flag = 1
+    ok = entry_point(engine, Witness(exp, u[cut:], up[cut:], s[cut:], sp[cut:]), 3000 - cut, compare_expected=True)
+    assert ok.status.code == 0
+    exp.final_queue_state.length += 1
+    bad = entry_point(engine, Witness(exp, u[cut:], up[cut:], s[cut:], sp[cut:]), 3000 - cut, compare_expected=True,
+                      raise_on_unsatisfied=False)
+    assert bad.status.code == abi.ZKC_ERR_FSM_OUTPUT_MISMATCH
+    # empty queues, limit 0
+    e = np.zeros(0, dtype=abi.DECOMMIT_QUERY_DTYPE)
+    io0, up0, sp0 = instance(orc, e, e)
+    want, got = run_both(engine, orc, io0, e, up0, e, sp0, 8)
+    assert want[0] == abi.ZKC_OK
+    assert_same(want, got)
+    want, got = run_both(engine, orc, io, u, up, s, sp, 0)
+    assert_same(want, got)
+
+
+def test_negative_cases_match_oracle(engine, orc):
+    u, s = synthetic.decommit_requests_trace(1500, seed=4, n_hashes=32)
+    cases = []
+    s2 = s.copy(); s2[[10, 60]] = s2[[60, 10]]; cases.append((u, s2))
+    first = int(np.flatnonzero(s["is_first"])[3])
+    s3 = s.copy(); s3["is_first"][first] = 0; cases.append((u, s3))
+    rep = int(np.flatnonzero(s["is_first"] == 0)[700])
+    s4 = s.copy(); s4["page"][rep] += 8; cases.append((u, s4))
+    cases.append((u, s[:-1]))
+    for uu, ss in cases:
+        io, up, sp = instance(orc, uu, ss)
+        want, got = run_both(engine, orc, io, uu, up, ss, sp, 1536)
+        assert want[0] == abi.ZKC_ERR_UNSATISFIED
+        assert_same(want, got)
+    io, up, sp = instance(orc, u, s)
+    io.sorted_queue_initial_state.head[11] = 5
+    want, got = run_both(engine, orc, io, u, up, s, sp, 1536)
+    assert want[4].failed_checks & CHK["TRIVIAL_HEAD"]
+    assert_same(want, got)
+    # corrupted hints
+    io, up, sp = instance(orc, u, s)
+    want = O.sort_decommittments_entry_point(orc, io, u, s, 1536)
+    t = want[5].copy(); t[10, 9] ^= 1
+    r = entry_point(engine, Witness(io, u, up, s, sp, t), 1536, raise_on_unsatisfied=False)
+    assert r.status.code == abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT
+    r = entry_point(engine, Witness(io, u, up, s, sp, want[5][:-2]), 1536, raise_on_unsatisfied=False)
+    assert r.status.code == abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT
+    sp2 = sp.copy(); sp2[7, 10] ^= 1
+    r = entry_point(engine, Witness(io, u, up, s, sp2), 1536, raise_on_unsatisfied=False)
+    assert r.status.code == abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT and r.status.first_bad_row in (6, 7)
+
+
+def test_device_resident_and_queue_simulate(engine, orc):
+    import torch
+    n = 5000
+    u, s = synthetic.decommit_requests_trace(n, seed=13, n_hashes=200)
+    io, up, sp = instance(orc, u, s)
+    want = O.sort_decommittments_entry_point(orc, io, u, s, n)
+    prev, fin = engine.decommit_queue_simulate(u)
+    assert np.array_equal(prev, up) and bytes(fin[0]) == bytes(io.initial_queue_state)
+    tod = lambda a: torch.from_numpy(a.view(np.uint8).reshape(len(a), -1)).cuda()
+    t64 = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+    prev_d, fin_d = engine.decommit_queue_simulate(tod(np.concatenate([u, s])), n_queues=2)
+    assert np.array_equal(prev_d.cpu().numpy().view(np.uint64), np.concatenate([up, sp]))
+    assert bytes(fin_d[1]) == bytes(io.sorted_queue_initial_state)
+    got = entry_point(engine, Witness(io, tod(u), t64(up), tod(s), t64(sp), t64(want[5])), n)
+    torch.cuda.synchronize()
+    assert got.commitment.tolist() == want[3].tolist()
+    assert np.array_equal(got.trace.cpu().numpy().view(np.uint64), want[2])
+
+
+def test_full_size_properties(engine, orc):
+    """2^20 requests over 2^14 hashes, device resident, no oracle: the sorted queue is a permutation of the original one
+    (grand products meet), one output record per hash, chained halves == whole"""
+    import torch
+    n = 1 << 20
+    u, s = synthetic.decommit_requests_trace(n, seed=77, n_hashes=1 << 14)
+    tod = lambda a: torch.from_numpy(a.view(np.uint8).reshape(len(a), -1)).cuda()
+    du, ds = tod(u), tod(s)
+    prev, fin = engine.decommit_queue_simulate(torch.cat([du, ds]), n_queues=2)
+    io = O.decommit_sorter_closed_form(fin[0], fin[1], True)
+    whole = entry_point(engine, Witness(io, du, prev[:n], ds, prev[n:]), n, want_trace=False)
+    out = whole.closed_form_input
+    assert whole.status.code == 0 and out.completion_flag == 1
+    assert list(out.hidden_fsm_output.lhs_accumulator) == list(out.hidden_fsm_output.rhs_accumulator)
+    assert out.final_queue_state.length == 1 << 14
+    half = n // 2 + 12345
+    a = entry_point(engine, Witness(io, du, prev[:n], ds, prev[n:]), half, want_trace=False)
+    nxt = abi.DecommitSorterClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+    b = entry_point(engine, Witness(nxt, du[half:], prev[half:n], ds[half:], prev[n + half:]), n - half, want_trace=False)
+    assert bytes(b.closed_form_input.hidden_fsm_output) == bytes(out.hidden_fsm_output)
+    assert bytes(b.closed_form_input.final_queue_state) == bytes(out.final_queue_state)
+    # the result queue is the queue of the deduplicated records (first timestamp, is_first = 1)
+    firsts = s[np.flatnonzero(np.r_[True, (s["code_hash"][1:] != s["code_hash"][:-1]).any(axis=1)])].copy()
+    firsts["is_first"] = 1
+    _, fin2 = engine.decommit_queue_simulate(tod(firsts))
+    assert list(fin2[0].tail) == list(out.final_queue_state.tail)

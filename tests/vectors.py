@@ -72,3 +72,17 @@ def storage_reference_vector():
     f = _fixture("storage_validity_vector.json")
     s, ts = log_queries_from_fixture(f["sorted"])
     return log_queries_from_fixture(f["unsorted"])[0], s, ts
+
+
+def decommit_queries_from_fixture(items):
+    out = np.zeros(len(items), dtype=abi.DECOMMIT_QUERY_DTYPE)
+    for i, q in enumerate(items):
+        out[i]["code_hash"] = _limbs(int(q["code_hash"]), 8)
+        out[i]["page"], out[i]["is_first"], out[i]["timestamp"] = q["page"], q["is_first"], q["timestamp"]
+    return out
+
+
+def sort_decommittments_reference_vector():
+    """witness_input_unsorted / witness_input_sorted, /root/reference/src/sort_decommittment_requests/mod.rs:565-1390"""
+    f = _fixture("sort_decommittments_vector.json")
+    return decommit_queries_from_fixture(f["unsorted"]), decommit_queries_from_fixture(f["sorted"])

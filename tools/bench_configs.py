@@ -23,7 +23,8 @@ from era_zkevm_circuits_b200 import (Engine, EventsDeduplicatorInstanceWitness, 
                                      RamPermutationCircuitInstanceWitness, Sha256RoundFunctionCircuitInstanceWitness,
                                      StorageDeduplicatorInstanceWitness, abi, keccak256_round_function_entry_point,
                                      ram_permutation_entry_point, sha256_round_function_entry_point, sharding,
-                                     sort_and_deduplicate_events_entry_point, sort_and_deduplicate_storage_access_entry_point, synthetic)
+                                     sort_and_deduplicate_events_entry_point, sort_and_deduplicate_storage_access_entry_point, synthetic,
+                                     CodeDecommittmentsDeduplicatorInstanceWitness, sort_and_deduplicate_code_decommittments_entry_point)
 
 
 def timed(fn, steps=5, warmup=2):
@@ -163,6 +164,37 @@ def c4(eng, log2rows):
                       "trace_GB": trace.numel() * 8 / 1e9}))
 
 
+def dq(eng, log2rows):
+    """sort_decommittment_requests, 2^log2rows requests over 2^14 code hashes, device resident"""
+    n = 1 << log2rows
+    u, s = synthetic.decommit_requests_trace(n, seed=0xC4, n_hashes=1 << 14)
+    prev, fin = eng.decommit_queue_simulate(dev(np.concatenate([u, s])), n_queues=2)
+    io = abi.DecommitSorterClosedForm(); io.start_flag = 1
+    io.initial_queue_state = fin[0]; io.sorted_queue_initial_state = fin[1]
+    w = CodeDecommittmentsDeduplicatorInstanceWitness(io, dev(u), prev[:n], dev(s), prev[n:], None)
+    trace = torch.empty((abi.DQ_COLS["NUM_COLS"], n), dtype=torch.int64, device="cuda")
+    K = abi.DQ_COLS
+    run = lambda: sort_and_deduplicate_code_decommittments_entry_point(eng, w, n, trace_out=trace, raise_on_unsatisfied=False)
+    ms0, got = once(run)
+    states = pushes_from_trace(trace, None, [K["ADD_TO_QUEUE"]], [K["RESULT_TAIL"]], 12)
+    fin_tail = torch.tensor(np.array(list(got.closed_form_input.final_queue_state.tail), dtype=np.uint64).view(np.int64), device="cuda").reshape(1, 12)
+    if int(got.closed_form_input.final_queue_state.length) == len(states) + 1:
+        states = torch.cat([states, fin_tail])
+    w.result_queue_states = states.contiguous()
+    ms, got = timed(run, steps=5, warmup=2)
+    eng.profile(True)
+    run()
+    prof = {k: eng.profile_query(k)[0] for k in ("dq_rows", "dq_push", "dq_finalize", "dq_prologue")}
+    eng.profile(False)
+    # algorithmic bytes per row: 2 records (48 B) + 2 previous states (96 B) read, 173 trace columns written
+    alg = n * (2 * 48 + 2 * 96 + 8 * abi.DQ_COLS["NUM_COLS"])
+    print(json.dumps({"config": f"sort_decommittment_requests, 2^{log2rows} rows, 2^14 hashes", "gpu_ms_with_result_states": ms,
+                      "rows_per_s": n / ms * 1e3, "algorithmic_GB_per_s": alg / ms / 1e6,
+                      "gpu_ms_without_result_states_sequential_chain": ms0, "result_pushes": len(states), "status": got.status.code,
+                      "failed_checks": got.status.failed_checks, "completed": int(got.closed_form_input.completion_flag),
+                      "kernel_ms": prof, "trace_GB": trace.numel() * 8 / 1e9}))
+
+
 def gp(eng, log2rows):
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,5 +248,7 @@ if __name__ == "__main__":
         c3(eng)
     elif what == "c4":
         c4(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 20)
+    elif what == "dq":
+        dq(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 20)
     elif what == "gp":
         gp(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 22)

@@ -2,6 +2,7 @@
 """Extracts the reference's own in-repo LogQuery test vectors into JSON fixtures (tests/golden/):
   /root/reference/src/log_sorter/mod.rs:637-816                       -> log_sorter_vector.json
   /root/reference/src/storage_validity_by_grand_product/test_input.rs -> storage_validity_vector.json
+  /root/reference/src/sort_decommittment_requests/mod.rs:565-1390      -> sort_decommittments_vector.json
 Run in the build container (the reference is not present on the GPU box); only the extracted DATA is
 committed, no reference source.  Values are kept as decimal strings / ints exactly as written there."""
 import json
@@ -42,6 +43,19 @@ def parse_queries(text):
     return out
 
 
+def parse_decommit_queries(text):
+    """every `DecommitQuery::<F> { ... }` literal, in order"""
+    out = []
+    for m in re.finditer(r"DecommitQuery::<F>\s*\{(.*?)\n\s*\};", text, re.S):
+        body = m.group(1)
+        q = {"code_hash": re.search(r"from_dec_str\(\s*\"(\d+)\"", body, re.S).group(1),
+             "page": int(re.search(r"page:\s*UInt32::allocated_constant\(cs,\s*(\d+)\)", body).group(1)),
+             "is_first": BOOL[re.search(r"is_first:\s*(\w+)", body).group(1)],
+             "timestamp": int(re.search(r"timestamp:\s*UInt32::allocated_constant\(cs,\s*(\d+)\)", body).group(1))}
+        out.append(q)
+    return out
+
+
 def split_fn(text, name):
     i = text.index("fn " + name)
     j = text.find("\n    fn ", i + 1)
@@ -64,6 +78,12 @@ def main():
     assert len(fixture["unsorted"]) == len(fixture["sorted"]) == 16, (len(fixture["unsorted"]), len(fixture["sorted"]))
     assert all("extra_timestamp" in q for q in fixture["sorted"])
     json.dump(fixture, open(os.path.join(OUT, "storage_validity_vector.json"), "w"), indent=1)
+    sd = open(os.path.join(REF, "sort_decommittment_requests", "mod.rs")).read()
+    fixture = {"source": "reference src/sort_decommittment_requests/mod.rs witness_input_unsorted / witness_input_sorted (test :420, limit 16)",
+               "unsorted": parse_decommit_queries(split_fn(sd, "witness_input_unsorted")),
+               "sorted": parse_decommit_queries(split_fn(sd, "witness_input_sorted"))}
+    assert len(fixture["unsorted"]) == len(fixture["sorted"]) == 29, (len(fixture["unsorted"]), len(fixture["sorted"]))
+    json.dump(fixture, open(os.path.join(OUT, "sort_decommittments_vector.json"), "w"), indent=1)
     print("ok")
 
 
