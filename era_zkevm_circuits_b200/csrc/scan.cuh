@@ -148,9 +148,10 @@ __device__ __forceinline__ V scan_tile_generic(const V &v, unsigned int tile, co
                 const int first = incl_mask ? __ffs(incl_mask) - 1 : 32;
                 V c = Op::identity();
                 if (look >= 0 && lane <= first) c = lane == first ? v_load_cg(&states[look].inc) : v_load_cg(&states[look].agg);
-                // ordered butterfly: higher lanes hold EARLIER tiles
+                // ordered butterfly: higher lanes hold EARLIER tiles.  Neighbours first (d = 1, 2, 4, ...), so that every
+                // step joins two ADJACENT runs of tiles: required for operators that are not commutative
 #pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) {
+                for (int d = 1; d <= 16; d <<= 1) {
                     const V o = v_shfl_xor(c, d);
                     c = (lane & d) ? Op::combine(c, o) : Op::combine(o, c);
                 }

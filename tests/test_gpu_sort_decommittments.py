@@ -50,7 +50,7 @@ def test_reference_vector(engine, orc):
 
 
 @pytest.mark.parametrize("n,limit,hashes", [(1, 1, 1), (2, 2, 1), (2, 3, 2), (255, 256, 7), (257, 257, 300), (1000, 1024, 50),
-                                            (20000, 20000, 1000), (5000, 6000, 1)])
+                                            (20000, 20000, 1000), (5000, 6000, 1), (20000, 60000, 3), (300, 100000, 2)])
 def test_synthetic_bit_exact(engine, orc, n, limit, hashes):
     u, s = synthetic.decommit_requests_trace(n, seed=n, n_hashes=hashes)
     io, up, sp = instance(orc, u, s)
