@@ -23,6 +23,10 @@ from .sort_decommittment_requests import (  # noqa: F401
     CodeDecommittmentsDeduplicatorInstanceWitness,
     sort_and_deduplicate_code_decommittments_entry_point,
 )
+from .demux_log_queue import (  # noqa: F401
+    LogDemuxerCircuitInstanceWitness,
+    demultiplex_storage_logs_enty_point,
+)
 from .keccak256_round_function import (  # noqa: F401
     Keccak256RoundFunctionCircuitInstanceWitness,
     keccak256_round_function_entry_point,

@@ -313,6 +313,30 @@ DQ_CHK = dict(LENGTHS_EQUAL=1 << 0, EMPTY_SYNC=1 << 1, ORDER=1 << 2, MUST_BE_FIR
               QUEUE_CONSISTENCY=1 << 5, GRAND_PRODUCT=1 << 6, TRIVIAL_HEAD=1 << 7, QUEUE_HINT=1 << 8)
 
 
+class DemuxFsm(C.Structure):
+    _fields_ = [("initial_log_queue_state", QueueState4), ("output_queue_states", QueueState4 * 6)]
+
+
+class DemuxClosedForm(C.Structure):
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("initial_log_queue_state", QueueState4),
+                ("output_queue_states", QueueState4 * 6), ("hidden_fsm_input", DemuxFsm), ("hidden_fsm_output", DemuxFsm)]
+
+
+class DemuxOptions(C.Structure):
+    _fields_ = [("compare_expected", C.c_uint32), ("custom_constants", C.c_uint32), ("aux_bytes", C.c_uint32 * 4),
+                ("precompile_addresses", C.c_uint32 * 3), ("_pad", C.c_uint32 * 3)]
+
+
+DEMUX_QUEUES = ("storage", "events", "l1messages", "keccak256", "sha256", "ecrecover")  # enum LogType, demux_log_queue/mod.rs:224-232
+STORAGE_AUX_BYTE, EVENT_AUX_BYTE, L1_MESSAGE_AUX_BYTE = 0, 1, 2
+ECRECOVER_PRECOMPILE_ADDRESS = 0x01
+DMX_COLS = dict(
+    QUEUE_IS_EMPTY=0, EXECUTE=1, ITEM=2, ENC=38, HEAD=58, LEN=62, IS_AUX=63, IS_ADDRESS=67, IS_ROLLUP_SHARD=70,
+    EXECUTE_PORTER_STORAGE=71, BITMASK=72, IS_BITMASK=78, EXEC_TAIL=79, EXEC_LEN=83, PUSH_ROUND0=84, PUSH_ROUND1=96,
+    PUSH_ROUND2=108, QUEUE_TAILS=120, QUEUE_LENS=144, NUM_COLS=150)
+DMX_CHK = dict(TRIVIAL_HEAD=1 << 0, PORTER_STORAGE=1 << 1, BITMASK=1 << 2, QUEUE_CONSISTENCY=1 << 3, QUEUE_HINT=1 << 4)
+
+
 class RamInputData(C.Structure):
     _fields_ = [("unsorted_queue_initial_state", QueueState12), ("sorted_queue_initial_state", QueueState12),
                 ("non_deterministic_bootloader_memory_snapshot_length", C.c_uint32), ("_pad", C.c_uint32)]
@@ -377,6 +401,9 @@ SIGNATURES = {
     "zkc_sort_decommittments_entry_point": (C.c_int, [_vp, C.POINTER(DecommitSorterClosedForm), _vp, _vp, C.c_size_t, _vp, _vp,
                                                       C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions),
                                                       C.c_int, _vp, _vp, C.POINTER(Status)]),
+    "zkc_demux_log_queue_entry_point": (C.c_int, [_vp, C.POINTER(DemuxClosedForm), _vp, _vp, C.c_size_t, _vp,
+                                                  C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(DemuxOptions), C.c_int, _vp, _vp,
+                                                  C.POINTER(Status)]),
     "zkc_storage_validity_entry_point": (C.c_int, [_vp, C.POINTER(StorageClosedForm), _vp, _vp, C.c_size_t, _vp, _vp, _vp,
                                                    C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions),
                                                    C.c_int, _vp, _vp, C.POINTER(Status)]),

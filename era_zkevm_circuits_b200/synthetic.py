@@ -131,6 +131,34 @@ def decommit_requests_trace(n: int, seed: int = 0xC4, n_hashes: int = 1 << 10):
     return q, q[np.lexsort(keys)]
 
 
+def vm_log_queue_trace(n: int, seed: int = 0xC4, mix=(50, 25, 10, 6, 6, 3)):
+    """(f)2 (demux_log_queue): n LogQuery records as the VM's log opcode emits them, in execution order, `mix` = per cent
+    of rollup-storage accesses, events, L2->L1 messages, keccak256 / sha256 / ecrecover precompile calls (aux byte and
+    formal address as demux_log_queue/mod.rs:285-330 tests them).  Returns the records."""
+    q = np.zeros(n, dtype=abi.LOG_QUERY_DTYPE)
+    if n == 0:
+        return q
+    r = splitmix64(seed, n, 0) % np.uint64(100)
+    edges = np.cumsum(mix)
+    kind = np.searchsorted(edges, r.astype(np.int64), side="right").clip(0, 5)
+    q["address"] = splitmix64(seed, n * 3, 1).view("<u4").reshape(n, 6)[:, :5]
+    q["key"] = splitmix64(seed, n * 4, 2).view("<u4").reshape(n, 8)
+    q["read_value"] = splitmix64(seed, n * 4, 3).view("<u4").reshape(n, 8)
+    q["written_value"] = splitmix64(seed, n * 4, 4).view("<u4").reshape(n, 8)
+    q["timestamp"] = 1000 + 4 * np.arange(n, dtype=np.uint32)
+    t = splitmix64(seed, n, 5)
+    q["tx_number_in_block"] = (t % np.uint64(1000)).astype(np.uint32)
+    rw = ((t >> np.uint64(20)) & np.uint64(1)).astype(np.uint32)
+    aux = np.array([abi.STORAGE_AUX_BYTE, abi.EVENT_AUX_BYTE, abi.L1_MESSAGE_AUX_BYTE, abi.PRECOMPILE_AUX_BYTE,
+                    abi.PRECOMPILE_AUX_BYTE, abi.PRECOMPILE_AUX_BYTE], dtype=np.uint32)[kind]
+    q["flags"] = aux | (np.where(kind == 0, rw, 1).astype(np.uint32) << 16)
+    for k, addr in ((3, abi.KECCAK256_PRECOMPILE_ADDRESS), (4, abi.SHA256_PRECOMPILE_ADDRESS), (5, abi.ECRECOVER_PRECOMPILE_ADDRESS)):
+        sel = kind == k
+        q["address"][sel] = 0
+        q["address"][sel, 0] = addr
+    return q
+
+
 def storage_trace(n: int, seed: int = 0xC4, n_cells: int = 1 << 16, shard: int = 0, first_position: int = 0):
     """C4 (storage_validity): n storage LogQuery records over n_cells (address, key) cells: 60 % reads,
     30 % writes, 10 % write + rollback pairs (the rollback twin directly follows its write), shard 0.

@@ -622,6 +622,80 @@ int zkc_sort_decommittments_entry_point(zkc_ctx *ctx, zkc_decommit_sorter_closed
                                         uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
 
+/* ---- demux_log_queue (src/demux_log_queue/mod.rs) ------------------------------------------------- */
+#define ZKC_DEMUX_NUM_QUEUES 6 /* NUM_SEPARATE_QUEUES, mod.rs:221; queue order = enum LogType, mod.rs:224-232:
+                                  rollup storage, events, L1 messages, keccak256, sha256, ecrecover */
+
+/* LogDemuxerFSMInputOutput, demux_log_queue/input.rs:24-32 */
+typedef struct zkc_demux_fsm {
+    zkc_queue_state4 initial_log_queue_state;
+    zkc_queue_state4 output_queue_states[ZKC_DEMUX_NUM_QUEUES];
+} zkc_demux_fsm;
+
+/* ClosedFormInputWitness<F, LogDemuxerFSMInputOutput, LogDemuxerInputData, LogDemuxerOutputData>, input.rs:50-122 */
+typedef struct zkc_demux_closed_form {
+    uint32_t start_flag;
+    uint32_t completion_flag;                                    /* out */
+    zkc_queue_state4 initial_log_queue_state;                    /* observable input */
+    zkc_queue_state4 output_queue_states[ZKC_DEMUX_NUM_QUEUES];  /* observable output (out; expected if compared) */
+    zkc_demux_fsm hidden_fsm_input;
+    zkc_demux_fsm hidden_fsm_output;                             /* out; on input: expected value if compare_expected */
+} zkc_demux_closed_form;
+
+/* the constants the loop compares with come from the un-vendored zkevm_opcode_defs (system_params): the defaults are
+ * its v1.4.1 values; custom_constants != 0 replaces them (all four aux bytes distinct, all three addresses distinct) */
+typedef struct zkc_demux_options {
+    uint32_t compare_expected;
+    uint32_t custom_constants;
+    uint32_t aux_bytes[4];            /* STORAGE_AUX_BYTE 0, EVENT_AUX_BYTE 1, L1_MESSAGE_AUX_BYTE 2, PRECOMPILE_AUX_BYTE 3 */
+    uint32_t precompile_addresses[3]; /* formal addresses (low limb, upper limbs zero): keccak256 0x8010, sha256 0x02, ecrecover 0x01 */
+    uint32_t _pad[3];
+} zkc_demux_options;
+
+/* trace columns of one iteration of demultiplex_storage_logs_inner (mod.rs:268-393) */
+enum zkc_demux_col {
+    ZKC_DMX_QUEUE_IS_EMPTY = 0,  /* :271 */
+    ZKC_DMX_EXECUTE = 1,         /* :272 */
+    ZKC_DMX_ITEM = 2,            /* 36: popped record, flatten order log_query/mod.rs:62-101 */
+    ZKC_DMX_ENC = 38,            /* 20 */
+    ZKC_DMX_HEAD = 58,           /* 4: head after the pop */
+    ZKC_DMX_LEN = 62,
+    ZKC_DMX_IS_AUX = 63,         /* 4: is_storage / is_event / is_l1_message / is_precompile aux byte, :285-290 */
+    ZKC_DMX_IS_ADDRESS = 67,     /* 3: is_keccak / is_sha256 / is_ecrecover address, :292-295 */
+    ZKC_DMX_IS_ROLLUP_SHARD = 70,        /* :297 */
+    ZKC_DMX_EXECUTE_PORTER_STORAGE = 71, /* :300-302, enforced false */
+    ZKC_DMX_BITMASK = 72,        /* 6: execute_* per output queue, :353-360 */
+    ZKC_DMX_IS_BITMASK = 78,     /* check_if_bitmask_and_if_empty, :383-384 */
+    ZKC_DMX_EXEC_TAIL = 79,      /* 4: tail of the state push_with_optimize selects (:419-425) */
+    ZKC_DMX_EXEC_LEN = 83,
+    ZKC_DMX_PUSH_ROUND0 = 84,    /* 12: sponge state after absorbing enc[0..8] (the pop's first round has the same value) */
+    ZKC_DMX_PUSH_ROUND1 = 96,    /* 12 */
+    ZKC_DMX_PUSH_ROUND2 = 108,   /* 12: after absorbing enc[16..20] || selected tail: exec_queue.tail = first 4 */
+    ZKC_DMX_QUEUE_TAILS = 120,   /* 24: the six output queues' tails after the iteration, :437-442 */
+    ZKC_DMX_QUEUE_LENS = 144,    /* 6 */
+    ZKC_DMX_NUM_COLS = 150
+};
+
+#define ZKC_DMX_CHK_TRIVIAL_HEAD (1u << 0)      /* :66-69 */
+#define ZKC_DMX_CHK_PORTER_STORAGE (1u << 1)    /* :304-305 */
+#define ZKC_DMX_CHK_BITMASK (1u << 2)           /* :383-384 */
+#define ZKC_DMX_CHK_QUEUE_CONSISTENCY (1u << 3) /* :395 */
+#define ZKC_DMX_CHK_QUEUE_HINT (1u << 4)        /* prev_tails / output_tails is not the hash chain */
+
+/* demultiplex_storage_logs_enty_point, src/demux_log_queue/mod.rs:38-217.
+ *   records, prev_tails : the log queue's witness in pop order (CircuitQueueRawWitness, input.rs:124-129)
+ *   output_tails : NULL, or AoS [sum n_output_tails][4] grouped by output queue: queue q's tail after each of its
+ *                  executed pushes (what the out-of-circuit demultiplexer produced; together with the initial tail these
+ *                  are the `prev_tails` the six downstream circuits consume).  Verified; when NULL the six chains are
+ *                  rebuilt sequentially on the device (1 permutation per push, the six queues side by side)
+ *   trace        : column-major [ZKC_DMX_NUM_COLS][limit] or NULL */
+int zkc_demux_log_queue_entry_point(zkc_ctx *ctx, zkc_demux_closed_form *io, const zkc_log_query *records,
+                                    const uint64_t *prev_tails, size_t n_records, const uint64_t *output_tails,
+                                    const size_t n_output_tails[ZKC_DEMUX_NUM_QUEUES], size_t limit,
+                                    const zkc_demux_options *options, int on_device, uint64_t *trace,
+                                    uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
+
+
 /* ---- keccak256_round_function (src/keccak256_round_function/mod.rs) -------------------------------- */
 #define ZKC_KECCAK_RATE_BYTES 136            /* boojum KECCAK_RATE_BYTES */
 #define ZKC_KECCAK_BUFFER_SIZE 192           /* KECCAK_PRECOMPILE_BUFFER_SIZE, input.rs:24 */

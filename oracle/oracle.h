@@ -90,6 +90,11 @@ int orc_sort_decommittments_entry_point(zkc_decommit_sorter_closed_form *io, con
                                         const zkc_decommit_query *sorted, size_t n_sorted, size_t limit,
                                         const zkc_sorter_options *options, uint64_t *trace, uint64_t *result_states,
                                         size_t *n_result_states, uint64_t commitment[4], zkc_status *status);
+/* demux_log_queue.c; output_tails (optional out): [6][limit][4], queue q's tail after each of its executed pushes */
+size_t orc_demux_encode_fsm(const zkc_demux_fsm *f, uint64_t *dst);
+int orc_demux_log_queue_entry_point(zkc_demux_closed_form *io, const zkc_log_query *records, size_t n_records, size_t limit,
+                                    const zkc_demux_options *options, uint64_t *trace, uint64_t *output_tails,
+                                    size_t n_output_tails[6], uint64_t commitment[4], zkc_status *status);
 /* keccak256_round_function.c; memory_states (optional out): memory queue tail after each executed push */
 void orc_keccak_f1600(uint64_t A[25]);
 void orc_keccak256(const uint8_t *msg, size_t len, uint8_t digest[32]);

@@ -53,6 +53,10 @@ def load():
     lib.orc_sort_decommittments_entry_point.argtypes = [C.POINTER(abi.DecommitSorterClosedForm), _vp, C.c_size_t, _vp, C.c_size_t,
                                                         C.c_size_t, C.POINTER(abi.SorterOptions), _vp, _vp,
                                                         C.POINTER(C.c_size_t), _vp, C.POINTER(abi.Status)]
+    lib.orc_demux_log_queue_entry_point.restype = C.c_int
+    lib.orc_demux_log_queue_entry_point.argtypes = [C.POINTER(abi.DemuxClosedForm), _vp, C.c_size_t, C.c_size_t,
+                                                    C.POINTER(abi.DemuxOptions), _vp, _vp, C.POINTER(C.c_size_t), _vp,
+                                                    C.POINTER(abi.Status)]
     lib.orc_keccak_f1600.argtypes = [_vp]
     lib.orc_keccak256.argtypes = [_vp, C.c_size_t, _vp]
     lib.orc_keccak256_entry_point.restype = C.c_int
@@ -207,6 +211,31 @@ def sort_decommittments_entry_point(lib, io, unsorted, sorted_, limit, want_trac
     rc = lib.orc_sort_decommittments_entry_point(C.byref(io2), p(unsorted), len(unsorted), p(sorted_), len(sorted_), limit,
                                                  C.byref(opts), p(trace), p(states), C.byref(n_states), p(com), C.byref(st))
     return rc, io2, trace, com, st, states[:n_states.value].copy()
+
+
+def demux_closed_form(queue_state, start=True, fsm_in=None):
+    io = abi.DemuxClosedForm()
+    io.start_flag = int(start)
+    io.initial_log_queue_state = queue_state
+    if fsm_in is not None:
+        io.hidden_fsm_input = fsm_in
+    return io
+
+
+def demux_entry_point(lib, io, records, limit, want_trace=True, compare_expected=False, options=None):
+    """returns (rc, io_out, trace, commitment, status, tails): tails = list of 6 arrays [n_q, 4] (tail after each push)"""
+    io2 = abi.DemuxClosedForm.from_buffer_copy(bytes(io))
+    records = np.ascontiguousarray(records)
+    trace = np.zeros((abi.DMX_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
+    tails = np.zeros((6, max(limit, 1), 4), dtype=np.uint64)
+    n_tails = (C.c_size_t * 6)()
+    com = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    opts = options if options is not None else abi.DemuxOptions()
+    opts.compare_expected = int(compare_expected)
+    rc = lib.orc_demux_log_queue_entry_point(C.byref(io2), p(records), len(records), limit, C.byref(opts), p(trace), p(tails),
+                                             n_tails, p(com), C.byref(st))
+    return rc, io2, trace, com, st, [tails[q, :n_tails[q]].copy() for q in range(6)]
 
 
 def storage_closed_form(unsorted_state, sorted_state, shard=0, start=True, fsm_in=None):

@@ -77,3 +77,24 @@ def test_decommit_sorter_mirrors_header():
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [abi.DECOMMIT_QUERY_DTYPE.itemsize, C.sizeof(abi.DecommitSorterFsm), C.sizeof(abi.DecommitSorterClosedForm)]
     assert C.sizeof(abi.DecommitQuery) == 48
+
+
+def test_demux_mirrors_header():
+    import subprocess
+    import tempfile
+    text = open(os.path.join(ROOT, "include", "zkc_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", text[text.index("enum zkc_demux_col {"):], flags=re.S)
+    body = body[:body.index("};")]
+    cols = {m.group(1): int(m.group(2)) for m in re.finditer(r"ZKC_DMX_([A-Z0-9_]+)\s*=\s*(\d+)", body)}
+    assert cols == abi.DMX_COLS
+    chk = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"#define ZKC_DMX_CHK_([A-Z_]+) \(1u << (\d+)\)", text)}
+    assert chk == abi.DMX_CHK
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s.c")
+        open(src, "w").write('#include <stdio.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu\\n", sizeof(zkc_demux_fsm), '
+                             'sizeof(zkc_demux_closed_form), sizeof(zkc_demux_options));return 0;}\n'
+                             % os.path.join(ROOT, "include", "zkc_b200.h"))
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-o", exe, src])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(abi.DemuxFsm), C.sizeof(abi.DemuxClosedForm), C.sizeof(abi.DemuxOptions)]

@@ -86,3 +86,8 @@ def sort_decommittments_reference_vector():
     """witness_input_unsorted / witness_input_sorted, /root/reference/src/sort_decommittment_requests/mod.rs:565-1390"""
     f = _fixture("sort_decommittments_vector.json")
     return decommit_queries_from_fixture(f["unsorted"]), decommit_queries_from_fixture(f["sorted"])
+
+
+def demux_reference_vector():
+    """witness_input_unsorted, /root/reference/src/demux_log_queue/mod.rs:602-923"""
+    return log_queries_from_fixture(_fixture("demux_log_queue_vector.json")["records"])[0]

@@ -24,7 +24,8 @@ from era_zkevm_circuits_b200 import (Engine, EventsDeduplicatorInstanceWitness, 
                                      StorageDeduplicatorInstanceWitness, abi, keccak256_round_function_entry_point,
                                      ram_permutation_entry_point, sha256_round_function_entry_point, sharding,
                                      sort_and_deduplicate_events_entry_point, sort_and_deduplicate_storage_access_entry_point, synthetic,
-                                     CodeDecommittmentsDeduplicatorInstanceWitness, sort_and_deduplicate_code_decommittments_entry_point)
+                                     CodeDecommittmentsDeduplicatorInstanceWitness, sort_and_deduplicate_code_decommittments_entry_point,
+                                     LogDemuxerCircuitInstanceWitness, demultiplex_storage_logs_enty_point)
 
 
 def timed(fn, steps=5, warmup=2):
@@ -195,6 +196,38 @@ def dq(eng, log2rows):
                       "kernel_ms": prof, "trace_GB": trace.numel() * 8 / 1e9}))
 
 
+def dmx(eng, log2rows):
+    """demux_log_queue, 2^log2rows VM log records, device resident"""
+    n = 1 << log2rows
+    recs = synthetic.vm_log_queue_trace(n, seed=0xC4)
+    t0 = time.perf_counter()
+    prev, fin = eng.log_queue_simulate(dev(recs))
+    setup = time.perf_counter() - t0
+    io = abi.DemuxClosedForm(); io.start_flag = 1
+    io.initial_log_queue_state = fin[0]
+    w = LogDemuxerCircuitInstanceWitness(io, dev(recs), prev, None, None)
+    trace = torch.empty((abi.DMX_COLS["NUM_COLS"], n), dtype=torch.int64, device="cuda")
+    K = abi.DMX_COLS
+    run = lambda: demultiplex_storage_logs_enty_point(eng, w, n, trace_out=trace, raise_on_unsatisfied=False)
+    ms0, got = once(run)
+    # per queue: the tail after each of its pushes, from the trace of the un-hinted run
+    tails, counts = [], []
+    for q in range(6):
+        rows = torch.nonzero(trace[K["BITMASK"] + q]).flatten()
+        tails.append(trace[K["QUEUE_TAILS"] + 4 * q:K["QUEUE_TAILS"] + 4 * q + 4].t()[rows])
+        counts.append(len(rows))
+    w.output_queue_tails = torch.cat(tails).contiguous(); w.output_queue_counts = counts
+    ms, got = timed(run, steps=5, warmup=2)
+    eng.profile(True)
+    run()
+    prof = {k: eng.profile_query(k)[0] for k in ("dmx_rows", "dmx_push", "dmx_finalize", "dmx_prologue")}
+    eng.profile(False)
+    print(json.dumps({"config": f"demux_log_queue, 2^{log2rows} rows", "gpu_ms_with_output_tails": ms, "rows_per_s": n / ms * 1e3,
+                      "gpu_ms_without_output_tails_sequential_chains": ms0, "pushes_per_queue": counts, "status": got.status.code,
+                      "failed_checks": got.status.failed_checks, "completed": int(got.closed_form_input.completion_flag),
+                      "kernel_ms": prof, "queue_setup_s": setup, "trace_GB": trace.numel() * 8 / 1e9}))
+
+
 def gp(eng, log2rows):
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,5 +283,7 @@ if __name__ == "__main__":
         c4(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 20)
     elif what == "dq":
         dq(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 20)
+    elif what == "dmx":
+        dmx(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 18)
     elif what == "gp":
         gp(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 22)

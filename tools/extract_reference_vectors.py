@@ -3,6 +3,7 @@
   /root/reference/src/log_sorter/mod.rs:637-816                       -> log_sorter_vector.json
   /root/reference/src/storage_validity_by_grand_product/test_input.rs -> storage_validity_vector.json
   /root/reference/src/sort_decommittment_requests/mod.rs:565-1390      -> sort_decommittments_vector.json
+  /root/reference/src/demux_log_queue/mod.rs:602-923                   -> demux_log_queue_vector.json
 Run in the build container (the reference is not present on the GPU box); only the extracted DATA is
 committed, no reference source.  Values are kept as decimal strings / ints exactly as written there."""
 import json
@@ -84,6 +85,11 @@ def main():
                "sorted": parse_decommit_queries(split_fn(sd, "witness_input_sorted"))}
     assert len(fixture["unsorted"]) == len(fixture["sorted"]) == 29, (len(fixture["unsorted"]), len(fixture["sorted"]))
     json.dump(fixture, open(os.path.join(OUT, "sort_decommittments_vector.json"), "w"), indent=1)
+    dm = open(os.path.join(REF, "demux_log_queue", "mod.rs")).read()
+    fixture = {"source": "reference src/demux_log_queue/mod.rs witness_input_unsorted (test :482, limit 16)",
+               "records": parse_queries(split_fn(dm, "witness_input_unsorted"))}
+    assert len(fixture["records"]) >= 8, len(fixture["records"])
+    json.dump(fixture, open(os.path.join(OUT, "demux_log_queue_vector.json"), "w"), indent=1)
     print("ok")
 
 
