@@ -60,41 +60,57 @@ __device__ __forceinline__ zkc_log_query ev_cleaned_up(const zkc_log_query &p) {
     return q;
 }
 
+// three warps, one 16-lane group each, every permutation spread over 12 lanes (poseidon2_permute_coop)
 __global__ void ev_prologue_kernel(EvDev *d) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane != 0) return;
+    __shared__ uint64_t buf[3][80];
+    const int warp = threadIdx.x >> 5, i = threadIdx.x & 31;
+    if (i >= 16) return;
+    const unsigned gm = 0xFFFFu;
     const zkc_events_closed_form &io = d->io;
     if (warp == 0) {
-        const bool start = io.start_flag != 0;
-        d->start = start;
-        d->uq0 = start ? io.initial_log_queue_state : io.hidden_fsm_input.initial_unsorted_queue_state;
-        d->sq0 = start ? io.intermediate_sorted_queue_state : io.hidden_fsm_input.intermediate_sorted_queue_state;
-        zkc_queue_state4 empty;
-        for (int i = 0; i < 4; i++) empty.head[i] = empty.tail[i] = 0;
-        empty.length = 0; empty._pad = 0;
-        d->rq0 = start ? empty : io.hidden_fsm_input.final_result_queue_state;
-        for (int i = 0; i < 2; i++) {
-            d->acc0[i * 2 + 0] = start ? 1 : io.hidden_fsm_input.lhs_accumulator[i];
-            d->acc0[i * 2 + 1] = start ? 1 : io.hidden_fsm_input.rhs_accumulator[i];
+        if (i == 0) {
+            const bool start = io.start_flag != 0;
+            d->start = start;
+            d->uq0 = start ? io.initial_log_queue_state : io.hidden_fsm_input.initial_unsorted_queue_state;
+            d->sq0 = start ? io.intermediate_sorted_queue_state : io.hidden_fsm_input.intermediate_sorted_queue_state;
+            zkc_queue_state4 empty;
+            for (int i = 0; i < 4; i++) empty.head[i] = empty.tail[i] = 0;
+            empty.length = 0; empty._pad = 0;
+            d->rq0 = start ? empty : io.hidden_fsm_input.final_result_queue_state;
+            for (int i = 0; i < 2; i++) {
+                d->acc0[i * 2 + 0] = start ? 1 : io.hidden_fsm_input.lhs_accumulator[i];
+                d->acc0[i * 2 + 1] = start ? 1 : io.hidden_fsm_input.rhs_accumulator[i];
+            }
+            d->previous_key0 = start ? 0 : io.hidden_fsm_input.previous_key;
+            d->previous_item0 = start ? lq_zero() : io.hidden_fsm_input.previous_item;
+            d->prev_trivial0 = (d->uq0.length == 0) || start;  // :266-267
+            uint32_t checks = 0;
+            for (int i = 0; i < 4; i++)
+                if (io.initial_log_queue_state.head[i] | io.intermediate_sorted_queue_state.head[i]) checks |= ZKC_EV_CHK_TRIVIAL_HEAD;
+            if (d->uq0.length != d->sq0.length) checks |= ZKC_EV_CHK_LENGTHS_EQUAL;
+            d->prologue_checks = checks;
+            // produce_fs_challenges over tail || len || tail || len (10 elements), 2 x 20 challenges
+            uint64_t *in = buf[0];
+            for (int k = 0; k < 4; k++) { in[k] = io.initial_log_queue_state.tail[k]; in[5 + k] = io.intermediate_sorted_queue_state.tail[k]; }
+            in[4] = io.initial_log_queue_state.length; in[9] = io.intermediate_sorted_queue_state.length;
         }
-        d->previous_key0 = start ? 0 : io.hidden_fsm_input.previous_key;
-        d->previous_item0 = start ? lq_zero() : io.hidden_fsm_input.previous_item;
-        d->prev_trivial0 = (d->uq0.length == 0) || start;  // :266-267
-        uint32_t checks = 0;
-        for (int i = 0; i < 4; i++)
-            if (io.initial_log_queue_state.head[i] | io.intermediate_sorted_queue_state.head[i]) checks |= ZKC_EV_CHK_TRIVIAL_HEAD;
-        if (d->uq0.length != d->sq0.length) checks |= ZKC_EV_CHK_LENGTHS_EQUAL;
-        d->prologue_checks = checks;
-        fs_challenges_4(io.initial_log_queue_state, io.intermediate_sorted_queue_state, d->ch);
-    } else if (warp == 1) {
-        uint64_t buf[18];
-        int n = put_queue_state4(buf, io.initial_log_queue_state);
-        n += put_queue_state4(buf + n, io.intermediate_sorted_queue_state);
-        commit_encoding_dev(buf, n, d->commit_obs_in);
-    } else if (warp == 2) {
-        uint64_t buf[68];
-        const int n = ev_encode_fsm(io.hidden_fsm_input, buf);
-        commit_encoding_dev(buf, n, d->commit_fsm_in);
+        __syncwarp(gm);
+        fs_challenges_coop(gm, buf[0], 10, 21, &d->ch[0][0], i);
+    } else {
+        uint64_t *b = buf[warp];
+        int n = 0;
+        if (i == 0) {
+            if (warp == 1) {
+                n = put_queue_state4(b, io.initial_log_queue_state);
+                n += put_queue_state4(b + n, io.intermediate_sorted_queue_state);
+            } else {
+                n = ev_encode_fsm(io.hidden_fsm_input, b);
+            }
+        }
+        __syncwarp(gm);
+        n = __shfl_sync(gm, n, 0, 16);
+        const uint64_t c = commit_encoding_coop(gm, b, n, i);
+        if (i < 4) (warp == 1 ? d->commit_obs_in : d->commit_fsm_in)[i] = c;
     }
 }
 
@@ -293,7 +309,12 @@ ev_rows_kernel(EvDev *d, const zkc_log_query *__restrict__ unsorted, const uint6
 // ---- finalize -----------------------------------------------------------------------------------------
 __global__ void ev_finalize_kernel(EvDev *d, const zkc_log_query *__restrict__ sorted, const uint64_t *__restrict__ tails,
                                    size_t n_tails) {
-    if (threadIdx.x != 0) return;
+    // lane 0 does the scalar bookkeeping; the commitments' permutations run on the two 16-lane groups, 12 lanes each
+    __shared__ uint64_t e_out[80], o_out[16], compact[24];
+    __shared__ uint32_t sh_completed, sh_n_out;
+    const int lane = threadIdx.x & 31, li = lane & 15;
+    const unsigned gm = lane < 16 ? 0xFFFFu : 0xFFFF0000u;
+    if (lane == 0) {
     zkc_events_closed_form &io = d->io;
     const size_t limit = d->limit;
     const uint32_t len0 = d->uq0.length;
@@ -362,7 +383,7 @@ __global__ void ev_finalize_kernel(EvDev *d, const zkc_log_query *__restrict__ s
     memset(&obs_out, 0, sizeof obs_out);
     if (completed) obs_out = rq;
 
-    uint64_t e_out[68], e_exp[68], o_out[9], o_exp[9];
+    uint64_t e_exp[68], o_exp[9];
     const int n_out = ev_encode_fsm(out, e_out);
     put_queue_state4(o_out, obs_out);
     zkc_status st;
@@ -381,18 +402,24 @@ __global__ void ev_finalize_kernel(EvDev *d, const zkc_log_query *__restrict__ s
     io.hidden_fsm_output = out;
     io.final_queue_state = obs_out;
     io.completion_flag = completed;
-    uint64_t compact[18], c4[4];
     compact[0] = d->start; compact[1] = completed;
-    commit_encoding_dev(o_out, 9, c4);
     for (int i = 0; i < 4; i++) {
         compact[2 + i] = d->commit_obs_in[i];
-        compact[6 + i] = completed ? c4[i] : 0;
         compact[10 + i] = d->start ? 0 : d->commit_fsm_in[i];
     }
-    commit_encoding_dev(e_out, n_out, c4);
-    for (int i = 0; i < 4; i++) compact[14 + i] = completed ? 0 : c4[i];
-    commit_encoding_dev(compact, 18, d->commitment);
     d->status = st;
+    sh_completed = completed; sh_n_out = n_out;
+    }
+    __syncwarp();
+    const bool completed = sh_completed;
+    const uint64_t c = commit_encoding_coop(gm, lane < 16 ? e_out : o_out, lane < 16 ? (int)sh_n_out : 9, li);
+    if (lane < 4) compact[14 + lane] = completed ? 0 : c;
+    if (lane >= 16 && lane < 20) compact[6 + lane - 16] = completed ? c : 0;
+    __syncwarp();
+    if (lane < 16) {
+        const uint64_t f = commit_encoding_coop(gm, compact, 18, li);
+        if (li < 4) d->commitment[li] = f;
+    }
 }
 
 // CircuitQueue::push of whole queues: one thread per independent queue

@@ -185,6 +185,20 @@ __device__ __forceinline__ uint64_t commit_encoding_coop(unsigned gm, const uint
     return x;
 }
 
+// produce_fs_challenges (/root/reference/src/utils.rs:12-78) by one 16-lane group: `in` holds the n absorbed elements
+// (visible to the whole group).  Two repetitions of `per_rep` challenges each, ch[rep * per_rep] = 1 and the rest taken
+// from ONE stream of squeezed rate elements, 8 per permutation, that runs on across the repetitions.
+__device__ __forceinline__ void fs_challenges_coop(unsigned gm, const uint64_t *in, int n, int per_rep, uint64_t *ch, int i) {
+    uint64_t x = commit_encoding_coop(gm, in, n, i);  // the same sponge: length in the capacity, zero-padded 8-chunks
+    const int per = per_rep - 1, total = 2 * per;
+    for (int t = 0; 8 * t < total; t++) {
+        if (t) x = poseidon2_permute_coop(gm, x, i);
+        const int idx = 8 * t + i;
+        if (i < 8 && idx < total) ch[(idx / per) * per_rep + 1 + idx % per] = x;
+    }
+    if (i < 2) ch[i * per_rep] = 1;
+}
+
 // the same as one out-of-line copy, for kernels that commit at several places (finalize kernels): one instance of the
 // permutation in the kernel keeps the register allocation of the rest of it out of the spill range
 static __device__ __noinline__ void commit_encoding_call(const uint64_t *in, int n, uint64_t *out) {

@@ -90,60 +90,56 @@ __device__ int ram_encode_fsm(const zkc_ram_fsm &f, uint64_t *dst) {
 }
 
 // ---- prologue: FSM start selection, Fiat-Shamir challenges, input commitments ------------------
+// three warps, one 16-lane group each, every permutation spread over 12 lanes (poseidon2_permute_coop)
 __global__ void ram_prologue_kernel(RamDev *d) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane != 0) return;
+    __shared__ uint64_t buf[3][72];
+    const int warp = threadIdx.x >> 5, i = threadIdx.x & 31;
+    if (i >= 16) return;
+    const unsigned gm = 0xFFFFu;
     const zkc_ram_closed_form &io = d->io;
     const zkc_ram_input_data &obs = io.observable_input;
     if (warp == 0) {
-        const bool start = io.start_flag != 0;
-        d->start = start;
-        d->uq0 = start ? obs.unsorted_queue_initial_state : io.hidden_fsm_input.current_unsorted_queue_state;
-        d->sq0 = start ? obs.sorted_queue_initial_state : io.hidden_fsm_input.current_sorted_queue_state;
-        for (int i = 0; i < 2; i++) {
-            d->acc0[i * 2 + 0] = start ? 1 : io.hidden_fsm_input.lhs_accumulator[i];
-            d->acc0[i * 2 + 1] = start ? 1 : io.hidden_fsm_input.rhs_accumulator[i];
+        if (i == 0) {
+            const bool start = io.start_flag != 0;
+            d->start = start;
+            d->uq0 = start ? obs.unsorted_queue_initial_state : io.hidden_fsm_input.current_unsorted_queue_state;
+            d->sq0 = start ? obs.sorted_queue_initial_state : io.hidden_fsm_input.current_sorted_queue_state;
+            for (int k = 0; k < 2; k++) {
+                d->acc0[k * 2 + 0] = start ? 1 : io.hidden_fsm_input.lhs_accumulator[k];
+                d->acc0[k * 2 + 1] = start ? 1 : io.hidden_fsm_input.rhs_accumulator[k];
+            }
+            d->nnw0 = start ? 0 : io.hidden_fsm_input.num_nondeterministic_writes;
+            uint32_t checks = 0;
+            for (int k = 0; k < 12; k++)
+                if (obs.unsorted_queue_initial_state.head[k] | obs.sorted_queue_initial_state.head[k])
+                    checks |= ZKC_RAM_CHK_TRIVIAL_HEAD;
+            if (d->uq0.length != d->sq0.length) checks |= ZKC_RAM_CHK_LENGTHS_EQUAL;
+            d->prologue_checks = checks;
+            // produce_fs_challenges, utils.rs:12-78, over tail || len || tail || len (26 elements)
+            uint64_t *in = buf[0];
+            for (int k = 0; k < 12; k++) in[k] = obs.unsorted_queue_initial_state.tail[k];
+            in[12] = obs.unsorted_queue_initial_state.length;
+            for (int k = 0; k < 12; k++) in[13 + k] = obs.sorted_queue_initial_state.tail[k];
+            in[25] = obs.sorted_queue_initial_state.length;
         }
-        d->nnw0 = start ? 0 : io.hidden_fsm_input.num_nondeterministic_writes;
-        uint32_t checks = 0;
-        for (int i = 0; i < 12; i++)
-            if (obs.unsorted_queue_initial_state.head[i] | obs.sorted_queue_initial_state.head[i])
-                checks |= ZKC_RAM_CHK_TRIVIAL_HEAD;
-        if (d->uq0.length != d->sq0.length) checks |= ZKC_RAM_CHK_LENGTHS_EQUAL;
-        d->prologue_checks = checks;
-        // produce_fs_challenges, utils.rs:12-78, over tail || len || tail || len (26 elements)
-        uint64_t in[26];
-        for (int i = 0; i < 12; i++) in[i] = obs.unsorted_queue_initial_state.tail[i];
-        in[12] = obs.unsorted_queue_initial_state.length;
-        for (int i = 0; i < 12; i++) in[13 + i] = obs.sorted_queue_initial_state.tail[i];
-        in[25] = obs.sorted_queue_initial_state.length;
-        uint64_t s[12];
-        sponge_init(s, 26);
-        for (int off = 0; off < 26; off += 8) {
-            for (int j = 0; j < 8; j++) s[j] = off + j < 26 ? in[off + j] : 0;
-            poseidon2_permute(s);
-        }
-        int can_take = 8;
-        for (int rep = 0; rep < 2; rep++) {
-            d->ch[rep][0] = 1;
-            for (int k = 1; k < 9; k++) {
-                if (can_take == 0) { poseidon2_permute(s); can_take = 8; }
-                uint64_t v = 0;
-                for (int j = 0; j < 8; j++) if (j == 8 - can_take) v = s[j];
-                d->ch[rep][k] = v;
-                can_take--;
+        __syncwarp(gm);
+        fs_challenges_coop(gm, buf[0], 26, 9, &d->ch[0][0], i);
+    } else {
+        uint64_t *b = buf[warp];
+        int n = 0;
+        if (i == 0) {
+            if (warp == 1) {
+                n = put_queue_state12(b, obs.unsorted_queue_initial_state);
+                n += put_queue_state12(b + n, obs.sorted_queue_initial_state);
+                b[n++] = obs.non_deterministic_bootloader_memory_snapshot_length;
+            } else {
+                n = ram_encode_fsm(io.hidden_fsm_input, b);
             }
         }
-    } else if (warp == 1) {
-        uint64_t buf[51];
-        int n = put_queue_state12(buf, obs.unsorted_queue_initial_state);
-        n += put_queue_state12(buf + n, obs.sorted_queue_initial_state);
-        buf[n++] = obs.non_deterministic_bootloader_memory_snapshot_length;
-        commit_encoding_dev(buf, n, d->commit_obs_in);
-    } else if (warp == 2) {
-        uint64_t buf[69];
-        int n = ram_encode_fsm(io.hidden_fsm_input, buf);
-        commit_encoding_dev(buf, n, d->commit_fsm_in);
+        __syncwarp(gm);
+        n = __shfl_sync(gm, n, 0, 16);
+        const uint64_t c = commit_encoding_coop(gm, b, n, i);
+        if (i < 4) (warp == 1 ? d->commit_obs_in : d->commit_fsm_in)[i] = c;
     }
 }
 
@@ -396,7 +392,13 @@ __global__ void memory_queue_simulate_kernel(const zkc_memory_query *__restrict_
 
 // ---- finalize: entry-point enforcements, FSM output, commitment ---------------------------------
 __global__ void ram_finalize_kernel(RamDev *d) {
-    if (threadIdx.x != 0) return;
+    // lane 0 does the scalar bookkeeping, the permutations of the two commitments run on 12 lanes
+    __shared__ uint64_t e_out[72], compact[24];
+    __shared__ uint32_t sh_completed;
+    const int lane = threadIdx.x & 31;
+    if (lane >= 16) return;
+    const unsigned gm = 0xFFFFu;
+    if (lane == 0) {
     zkc_ram_closed_form &io = d->io;
     const size_t limit = d->limit;
     const uint32_t len0 = d->uq0.length;
@@ -451,7 +453,7 @@ __global__ void ram_finalize_kernel(RamDev *d) {
             checks |= ZKC_RAM_CHK_NONDET_COUNT;  // :170-175
     }
     checks |= d->failed_checks | d->prologue_checks;
-    uint64_t e_out[69], e_exp[69];
+    uint64_t e_exp[69];
     const int n_out = ram_encode_fsm(out, e_out);
     zkc_status st;
     st.code = ZKC_OK; st.cuda_error = 0; st.first_bad_row = -1; st.failed_checks = checks; st.reserved = 0;
@@ -467,18 +469,21 @@ __global__ void ram_finalize_kernel(RamDev *d) {
     io.hidden_fsm_output = out;
     io.completion_flag = completed;
     // ClosedFormInputCompactForm::from_full_form + commitment, fsm_input_output/mod.rs:178-255
-    uint64_t compact[18];
     compact[0] = d->start; compact[1] = completed;
     for (int i = 0; i < 4; i++) {
         compact[2 + i] = d->commit_obs_in[i];
         compact[6 + i] = 0;  // observable output is `()`: commitment of the empty encoding is 0, and masked unless completed
         compact[10 + i] = d->start ? 0 : d->commit_fsm_in[i];
     }
-    uint64_t c_out[4];
-    commit_encoding_dev(e_out, n_out, c_out);
-    for (int i = 0; i < 4; i++) compact[14 + i] = completed ? 0 : c_out[i];
-    commit_encoding_dev(compact, 18, d->commitment);
     d->status = st;
+    sh_completed = completed;
+    }
+    __syncwarp(gm);
+    const uint64_t c_out = commit_encoding_coop(gm, e_out, 69, lane);
+    if (lane < 4) compact[14 + lane] = sh_completed ? 0 : c_out;
+    __syncwarp(gm);
+    const uint64_t f = commit_encoding_coop(gm, compact, 18, lane);
+    if (lane < 4) d->commitment[lane] = f;
 }
 
 

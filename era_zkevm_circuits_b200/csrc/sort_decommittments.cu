@@ -151,12 +151,7 @@ __global__ void dq_prologue_kernel(DqDev *d) {
             in[25] = io.sorted_queue_initial_state.length;
         }
         __syncwarp(gm);
-        // absorb 26 elements (the same sponge as commit_encoding), then squeeze 8 + 8 rate elements
-        uint64_t x = commit_encoding_coop(gm, buf[0], 26, i);
-        if (i < 8) d->ch[0][1 + i] = x;
-        x = poseidon2_permute_coop(gm, x, i);
-        if (i < 8) d->ch[1][1 + i] = x;
-        if (i == 0) d->ch[0][0] = d->ch[1][0] = 1;
+        fs_challenges_coop(gm, buf[0], 26, 9, &d->ch[0][0], i);
     } else if (warp == 1) {
         int n = 0;
         if (i == 0) {

@@ -114,44 +114,59 @@ __device__ int st_encode_fsm(const zkc_storage_fsm &f, uint64_t *dst) {
     return n;  // 77
 }
 
+// three warps, one 16-lane group each, every permutation spread over 12 lanes (poseidon2_permute_coop)
 __global__ void st_prologue_kernel(StDev *d) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane != 0) return;
+    __shared__ uint64_t buf[3][80];
+    const int warp = threadIdx.x >> 5, i = threadIdx.x & 31;
+    if (i >= 16) return;
+    const unsigned gm = 0xFFFFu;
     const zkc_storage_closed_form &io = d->io;
     if (warp == 0) {
-        const bool start = io.start_flag != 0;
-        d->start = start;
-        d->shard = io.shard_id_to_process & 0xFF;
-        d->uq0 = start ? io.unsorted_log_queue_state : io.hidden_fsm_input.current_unsorted_queue_state;
-        d->sq0 = start ? io.intermediate_sorted_queue_state : io.hidden_fsm_input.current_intermediate_sorted_queue_state;
-        zkc_queue_state4 empty;
-        for (int i = 0; i < 4; i++) empty.head[i] = empty.tail[i] = 0;
-        empty.length = 0; empty._pad = 0;
-        d->rq0 = start ? empty : io.hidden_fsm_input.current_final_sorted_queue_state;
-        for (int i = 0; i < 2; i++) {
-            d->acc0[i * 2 + 0] = start ? 1 : io.hidden_fsm_input.lhs_accumulator[i];
-            d->acc0[i * 2 + 1] = start ? 1 : io.hidden_fsm_input.rhs_accumulator[i];
+        if (i == 0) {
+            const bool start = io.start_flag != 0;
+            d->start = start;
+            d->shard = io.shard_id_to_process & 0xFF;
+            d->uq0 = start ? io.unsorted_log_queue_state : io.hidden_fsm_input.current_unsorted_queue_state;
+            d->sq0 = start ? io.intermediate_sorted_queue_state : io.hidden_fsm_input.current_intermediate_sorted_queue_state;
+            zkc_queue_state4 empty;
+            for (int i = 0; i < 4; i++) empty.head[i] = empty.tail[i] = 0;
+            empty.length = 0; empty._pad = 0;
+            d->rq0 = start ? empty : io.hidden_fsm_input.current_final_sorted_queue_state;
+            for (int i = 0; i < 2; i++) {
+                d->acc0[i * 2 + 0] = start ? 1 : io.hidden_fsm_input.lhs_accumulator[i];
+                d->acc0[i * 2 + 1] = start ? 1 : io.hidden_fsm_input.rhs_accumulator[i];
+            }
+            for (int i = 0; i < 13; i++) d->packed_key0[i] = start ? 0 : io.hidden_fsm_input.previous_packed_key[i];  // :382-387
+            d->cycle0 = start ? 0 : io.hidden_fsm_input.cycle_idx;                                                       // :389-394
+            d->prev_trivial0 = (d->uq0.length == 0) || start;                                                            // :574-575
+            uint32_t checks = 0;
+            for (int i = 0; i < 4; i++)
+                if (io.unsorted_log_queue_state.head[i] | io.intermediate_sorted_queue_state.head[i]) checks |= ZKC_ST_CHK_TRIVIAL_HEAD;
+            if (d->uq0.length != d->sq0.length) checks |= ZKC_ST_CHK_LENGTHS_EQUAL;
+            d->prologue_checks = checks;
+            // produce_fs_challenges over tail || len || tail || len (10 elements), 2 x 20 challenges
+            uint64_t *in = buf[0];
+            for (int k = 0; k < 4; k++) { in[k] = io.unsorted_log_queue_state.tail[k]; in[5 + k] = io.intermediate_sorted_queue_state.tail[k]; }
+            in[4] = io.unsorted_log_queue_state.length; in[9] = io.intermediate_sorted_queue_state.length;
         }
-        for (int i = 0; i < 13; i++) d->packed_key0[i] = start ? 0 : io.hidden_fsm_input.previous_packed_key[i];  // :382-387
-        d->cycle0 = start ? 0 : io.hidden_fsm_input.cycle_idx;                                                       // :389-394
-        d->prev_trivial0 = (d->uq0.length == 0) || start;                                                            // :574-575
-        uint32_t checks = 0;
-        for (int i = 0; i < 4; i++)
-            if (io.unsorted_log_queue_state.head[i] | io.intermediate_sorted_queue_state.head[i]) checks |= ZKC_ST_CHK_TRIVIAL_HEAD;
-        if (d->uq0.length != d->sq0.length) checks |= ZKC_ST_CHK_LENGTHS_EQUAL;
-        d->prologue_checks = checks;
-        fs_challenges_4(io.unsorted_log_queue_state, io.intermediate_sorted_queue_state, d->ch);
-    } else if (warp == 1) {
-        uint64_t buf[19];
+        __syncwarp(gm);
+        fs_challenges_coop(gm, buf[0], 10, 21, &d->ch[0][0], i);
+    } else {
+        uint64_t *b = buf[warp];
         int n = 0;
-        buf[n++] = io.shard_id_to_process & 0xFF;
-        n += put_queue_state4(buf + n, io.unsorted_log_queue_state);
-        n += put_queue_state4(buf + n, io.intermediate_sorted_queue_state);
-        commit_encoding_dev(buf, n, d->commit_obs_in);
-    } else if (warp == 2) {
-        uint64_t buf[77];
-        const int n = st_encode_fsm(io.hidden_fsm_input, buf);
-        commit_encoding_dev(buf, n, d->commit_fsm_in);
+        if (i == 0) {
+            if (warp == 1) {
+                b[n++] = io.shard_id_to_process & 0xFF;
+                n += put_queue_state4(b + n, io.unsorted_log_queue_state);
+                n += put_queue_state4(b + n, io.intermediate_sorted_queue_state);
+            } else {
+                n = st_encode_fsm(io.hidden_fsm_input, b);
+            }
+        }
+        __syncwarp(gm);
+        n = __shfl_sync(gm, n, 0, 16);
+        const uint64_t c = commit_encoding_coop(gm, b, n, i);
+        if (i < 4) (warp == 1 ? d->commit_obs_in : d->commit_fsm_in)[i] = c;
     }
 }
 
@@ -561,7 +576,12 @@ st_push_rows_kernel(StDev *d, const zkc_log_query *__restrict__ sorted, const St
 // ---- finalize ---------------------------------------------------------------------------------------------
 __global__ void st_finalize_kernel(StDev *d, const zkc_log_query *__restrict__ sorted, const StMeta1 *__restrict__ meta1,
                                    const StMeta2 *__restrict__ meta2, const uint64_t *__restrict__ tails, size_t n_tails) {
-    if (threadIdx.x != 0) return;
+    // lane 0 does the scalar bookkeeping; the commitments' permutations run on the two 16-lane groups, 12 lanes each
+    __shared__ uint64_t e_out[80], o_out[16], compact[24];
+    __shared__ uint32_t sh_completed, sh_n_out;
+    const int lane = threadIdx.x & 31, li = lane & 15;
+    const unsigned gm = lane < 16 ? 0xFFFFu : 0xFFFF0000u;
+    if (lane == 0) {
     zkc_storage_closed_form &io = d->io;
     const zkc_storage_fsm &fin = io.hidden_fsm_input;
     const size_t limit = d->limit;
@@ -641,7 +661,7 @@ __global__ void st_finalize_kernel(StDev *d, const zkc_log_query *__restrict__ s
     zkc_queue_state4 obs_out;
     memset(&obs_out, 0, sizeof obs_out);
     if (completed) obs_out = rq;
-    uint64_t e_out[77], e_exp[77], o_out[9], o_exp[9];
+    uint64_t e_exp[77], o_exp[9];
     const int n_out = st_encode_fsm(out, e_out);
     put_queue_state4(o_out, obs_out);
     zkc_status st;
@@ -660,18 +680,24 @@ __global__ void st_finalize_kernel(StDev *d, const zkc_log_query *__restrict__ s
     io.hidden_fsm_output = out;
     io.final_sorted_queue_state = obs_out;
     io.completion_flag = completed;
-    uint64_t compact[18], c4[4];
     compact[0] = d->start; compact[1] = completed;
-    commit_encoding_dev(o_out, 9, c4);
     for (int i = 0; i < 4; i++) {
         compact[2 + i] = d->commit_obs_in[i];
-        compact[6 + i] = completed ? c4[i] : 0;
         compact[10 + i] = d->start ? 0 : d->commit_fsm_in[i];
     }
-    commit_encoding_dev(e_out, n_out, c4);
-    for (int i = 0; i < 4; i++) compact[14 + i] = completed ? 0 : c4[i];
-    commit_encoding_dev(compact, 18, d->commitment);
     d->status = st;
+    sh_completed = completed; sh_n_out = n_out;
+    }
+    __syncwarp();
+    const bool completed = sh_completed;
+    const uint64_t c = commit_encoding_coop(gm, lane < 16 ? e_out : o_out, lane < 16 ? (int)sh_n_out : 9, li);
+    if (lane < 4) compact[14 + lane] = completed ? 0 : c;
+    if (lane >= 16 && lane < 20) compact[6 + lane - 16] = completed ? c : 0;
+    __syncwarp();
+    if (lane < 16) {
+        const uint64_t f = commit_encoding_coop(gm, compact, 18, li);
+        if (li < 4) d->commitment[li] = f;
+    }
 }
 
 }  // namespace zkc
