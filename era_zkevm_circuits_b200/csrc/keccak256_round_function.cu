@@ -310,8 +310,11 @@ __device__ int put_q12(uint64_t *dst, const zkc_queue_state12 &s) {
 }
 
 __global__ void kc_prologue_kernel(KcDev *d) {
+    // warp 0: scalar start selection; warps 1 / 2: the two input commitments, every permutation on 12 cooperating lanes
+    __shared__ uint64_t buf[2][440];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane != 0) return;
+    if (lane >= 16 || (warp == 0 && lane != 0)) return;
+    const unsigned gm = 0xFFFFu;
     const zkc_keccak_closed_form &io = d->io;
     if (warp == 0) {
         const bool start = io.start_flag != 0;
@@ -335,15 +338,21 @@ __global__ void kc_prologue_kernel(KcDev *d) {
         d->unit0_fresh = (s.read_precompile_call || s.completed) ? 1 : 0;
         const uint64_t avail = d->rq0.length < d->n_requests ? d->rq0.length : d->n_requests;
         d->n_units = 1 + (s.completed ? 0 : (uint32_t)avail);
-    } else if (warp == 1) {
-        uint64_t buf[34];
-        int n = put_queue_state4(buf, io.initial_log_queue_state);
-        n += put_q12(buf + n, io.initial_memory_queue_state);
-        commit_encoding_dev(buf, n, d->commit_obs_in);
-    } else if (warp == 2) {
-        uint64_t buf[439];
-        const int n = kc_encode_fsm(io.hidden_fsm_input, buf);
-        commit_encoding_dev(buf, n, d->commit_fsm_in);
+    } else {
+        uint64_t *b = buf[warp - 1];
+        int n = 0;
+        if (lane == 0) {
+            if (warp == 1) {
+                n = put_queue_state4(b, io.initial_log_queue_state);
+                n += put_q12(b + n, io.initial_memory_queue_state);
+            } else {
+                n = kc_encode_fsm(io.hidden_fsm_input, b);
+            }
+        }
+        __syncwarp(gm);
+        n = __shfl_sync(gm, n, 0, 16);
+        const uint64_t c = commit_encoding_coop(gm, b, n, lane);
+        if (lane < 4) (warp == 1 ? d->commit_obs_in : d->commit_fsm_in)[lane] = c;
     }
 }
 
@@ -499,7 +508,12 @@ kc_tail_kernel(KcDev *d, const KcPlan *__restrict__ starts, uint32_t *__restrict
 // ---- finalize ----------------------------------------------------------------------------------------------------------------
 __global__ void kc_finalize_kernel(KcDev *d, const KcPlan *__restrict__ starts, const uint32_t *__restrict__ slot_meta,
                                    const uint64_t *__restrict__ states, size_t n_states) {
-    if (threadIdx.x != 0) return;
+    // lane 0 does the scalar bookkeeping; the commitments' permutations run on the two 16-lane groups, 12 lanes each
+    __shared__ uint64_t e_out[440], o_out[32], compact[24];
+    __shared__ uint32_t sh_done, sh_n_out;
+    const int lane = threadIdx.x & 31, li = lane & 15;
+    const unsigned gm = lane < 16 ? 0xFFFFu : 0xFFFF0000u;
+    if (lane == 0) {
     zkc_keccak_closed_form &io = d->io;
     const size_t limit = d->limit;
     zkc_keccak_fsm out = limit ? d->s_final : d->s0;
@@ -528,7 +542,7 @@ __global__ void kc_finalize_kernel(KcDev *d, const KcPlan *__restrict__ starts, 
     zkc_queue_state12 obs_out;
     memset(&obs_out, 0, sizeof obs_out);
     if (done) obs_out = mq;
-    uint64_t e_out[439], e_exp[439], o_out[25], o_exp[25];
+    uint64_t e_exp[439], o_exp[25];
     const int n_out = kc_encode_fsm(out, e_out);
     put_q12(o_out, obs_out);
     zkc_status st;
@@ -547,18 +561,24 @@ __global__ void kc_finalize_kernel(KcDev *d, const KcPlan *__restrict__ starts, 
     io.hidden_fsm_output = out;
     io.final_memory_state = obs_out;
     io.completion_flag = done;
-    uint64_t compact[18], c4[4];
     compact[0] = d->start; compact[1] = done;
-    commit_encoding_dev(o_out, 25, c4);
     for (int i = 0; i < 4; i++) {
         compact[2 + i] = d->commit_obs_in[i];
-        compact[6 + i] = done ? c4[i] : 0;
         compact[10 + i] = d->start ? 0 : d->commit_fsm_in[i];
     }
-    commit_encoding_dev(e_out, n_out, c4);
-    for (int i = 0; i < 4; i++) compact[14 + i] = done ? 0 : c4[i];
-    commit_encoding_dev(compact, 18, d->commitment);
     d->status = st;
+    sh_done = done; sh_n_out = n_out;
+    }
+    __syncwarp();
+    const bool done = sh_done;
+    const uint64_t c = commit_encoding_coop(gm, lane < 16 ? e_out : o_out, lane < 16 ? (int)sh_n_out : 25, li);
+    if (lane < 4) compact[14 + lane] = done ? 0 : c;
+    if (lane >= 16 && lane < 20) compact[6 + lane - 16] = done ? c : 0;
+    __syncwarp();
+    if (lane < 16) {
+        const uint64_t f = commit_encoding_coop(gm, compact, 18, li);
+        if (li < 4) d->commitment[li] = f;
+    }
 }
 
 }  // namespace zkc

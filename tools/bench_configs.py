@@ -79,8 +79,8 @@ def c1(eng):
                       "cpu_rows_per_s": n / cpu_s, "bit_exact_vs_oracle": same, "status": got.status.code}))
 
 
-def c3(eng):
-    cycles = 1 << 18
+def c3(eng, log2cycles=18):
+    cycles = 1 << log2cycles
     reqs, reads, msgs = synthetic.keccak_calls(cycles // 4, seed=0xC3)  # ~4.3 cycles per call at lengths < 1024
     prev, fin = eng.log_queue_simulate(dev(reqs))
     io = abi.KeccakClosedForm(); io.start_flag = 1; io.initial_log_queue_state = fin[0]
@@ -95,7 +95,7 @@ def c3(eng):
     w.memory_queue_states = pushes_from_trace(trace, None, fc, sc, 12)
     ref = trace.clone()
     ms, got = timed(lambda: keccak256_round_function_entry_point(eng, w, cycles, trace_out=trace, raise_on_unsatisfied=False))
-    print(json.dumps({"config": "C3 keccak256_round_function, 2^18 cycles", "gpu_ms_with_queue_states": ms, "cycles_per_s": cycles / ms * 1e3,
+    print(json.dumps({"config": f"C3 keccak256_round_function, 2^{log2cycles} cycles", "gpu_ms_with_queue_states": ms, "cycles_per_s": cycles / ms * 1e3,
                       "gpu_ms_without_queue_states_sequential_chain": ms0, "calls": len(reqs), "memory_pushes": len(w.memory_queue_states),
                       "status": got.status.code, "completed": int(got.closed_form_input.completion_flag), "trace_columns": K["NUM_COLS"],
                       "same_trace_both_ways": bool(torch.equal(ref, trace))}))
@@ -112,7 +112,7 @@ def c3(eng):
                                               [K["QUERY"] + 8, K["QUERY"] + K["QUERY_STRIDE"] + 8, K["WRITE_TAIL"]], 12)
     ref = trace.clone()
     ms, got = timed(lambda: sha256_round_function_entry_point(eng, w, cycles, trace_out=trace, raise_on_unsatisfied=False))
-    print(json.dumps({"config": "C3 sha256_round_function, 2^18 cycles", "gpu_ms_with_queue_states": ms, "cycles_per_s": cycles / ms * 1e3,
+    print(json.dumps({"config": f"C3 sha256_round_function, 2^{log2cycles} cycles", "gpu_ms_with_queue_states": ms, "cycles_per_s": cycles / ms * 1e3,
                       "gpu_ms_without_queue_states_sequential_chain": ms0, "calls": len(reqs), "memory_pushes": len(w.memory_queue_states),
                       "status": got.status.code, "completed": int(got.closed_form_input.completion_flag), "trace_columns": K["NUM_COLS"],
                       "same_trace_both_ways": bool(torch.equal(ref, trace))}))
@@ -278,7 +278,7 @@ if __name__ == "__main__":
     if what == "c1":
         c1(eng)
     elif what == "c3":
-        c3(eng)
+        c3(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 18)
     elif what == "c4":
         c4(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 20)
     elif what == "dq":
