@@ -4,6 +4,8 @@ import ctypes as C
 import os
 import re
 
+import pytest
+
 from era_zkevm_circuits_b200 import abi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -98,3 +100,25 @@ def test_demux_mirrors_header():
         subprocess.check_call(["gcc", "-o", exe, src])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(abi.DemuxFsm), C.sizeof(abi.DemuxClosedForm), C.sizeof(abi.DemuxOptions)]
+
+
+@pytest.mark.parametrize("enum,prefix,cols,chk", [
+    ("zkc_ram_col", "RAM", "RAM_COLS", "RAM_CHK"), ("zkc_events_col", "EV", "EV_COLS", "EV_CHK"),
+    ("zkc_storage_col", "ST", "ST_COLS", "ST_CHK"), ("zkc_keccak_col", "KC", "KC_COLS", "KC_CHK"),
+    ("zkc_sha256_col", "SH", "SH_COLS", None)])
+def test_column_enums_mirror_header(enum, prefix, cols, chk):
+    """every name the Python mirror uses has the header's value (the mirrors may name a subset of the columns)"""
+    text = open(os.path.join(ROOT, "include", "zkc_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", text[text.index("enum %s {" % enum):], flags=re.S)
+    body = body[:body.index("};")]
+    header = {m.group(1): int(m.group(2)) for m in re.finditer(r"ZKC_%s_([A-Z0-9_]+)\s*=\s*(\d+)" % prefix, body)}
+    mirror = getattr(abi, cols)
+    assert mirror["NUM_COLS"] == header["NUM_COLS"]
+    for name, value in mirror.items():
+        if name in header:
+            assert header[name] == value, name
+    assert len(set(mirror) & set(header)) >= min(len(mirror), 8)
+    if chk:
+        hchk = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"#define ZKC_%s_CHK_([A-Z_0-9]+) \(1u << (\d+)\)" % prefix, text)}
+        for name, value in getattr(abi, chk).items():
+            assert hchk[name] == value, name
