@@ -1,0 +1,216 @@
+// C++ host mirror (include/zkc_b200.hpp) against the CPU oracle, written the way the reference's own tests are
+// (/root/reference/src/ram_permutation/mod.rs:395-557, sort_decommittment_requests/mod.rs:420-563, demux_log_queue/mod.rs:482-600):
+// push the inputs into fresh queues, run the entry point, check the outcome.  TEST INFRASTRUCTURE: links oracle/liborc.so as
+// the checker.
+//   host_mirror_test nodevice   no GPU required: the engine must refuse to start (no CPU fallback) and say why
+//   host_mirror_test parity     on a GPU: ram_permutation, sort_decommittment_requests, demux_log_queue bit-exact vs the oracle
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "zkc_b200.hpp"
+extern "C" {
+#include "oracle.h"
+}
+
+using namespace zkc_b200;
+
+static uint64_t sm64(uint64_t &s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static int failures = 0;
+#define CHECK(cond)                                                                  \
+    do {                                                                             \
+        if (!(cond)) { std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond); failures++; } \
+    } while (0)
+
+template <class T>
+static bool same_bytes(const T &a, const T &b) { return std::memcmp(&a, &b, sizeof(T)) == 0; }
+
+static void ram_parity(Engine &e) {
+    const size_t n = 1000, limit = 1024;
+    uint64_t seed = 0xC1;
+    std::vector<zkc_memory_query> u(n);
+    uint32_t cur[64][8] = {};
+    for (size_t i = 0; i < n; i++) {
+        zkc_memory_query q;
+        std::memset(&q, 0, sizeof q);
+        const uint32_t cell = (uint32_t)(sm64(seed) % 64);
+        q.timestamp = 1000 + 4 * (uint32_t)i; q.memory_page = 20 + cell / 16; q.index = cell % 16;
+        q.rw_flag = sm64(seed) % 100 < 60;
+        if (q.rw_flag) for (int k = 0; k < 8; k++) cur[cell][k] = (uint32_t)sm64(seed);
+        std::memcpy(q.value, cur[cell], 32);
+        u[i] = q;
+    }
+    std::vector<zkc_memory_query> s = u;
+    std::stable_sort(s.begin(), s.end(), [](const zkc_memory_query &a, const zkc_memory_query &b) {
+        if (a.memory_page != b.memory_page) return a.memory_page < b.memory_page;
+        if (a.index != b.index) return a.index < b.index;
+        return a.timestamp < b.timestamp;
+    });
+    RamPermutationCircuitInstanceWitness w;
+    w.unsorted_queue_witness = u; w.sorted_queue_witness = s;
+    w.closed_form_input.start_flag = 1;
+    w.closed_form_input.observable_input.unsorted_queue_initial_state = memory_queue_simulate(e, u, w.unsorted_queue_prev_states);
+    w.closed_form_input.observable_input.sorted_queue_initial_state = memory_queue_simulate(e, s, w.sorted_queue_prev_states);
+    // the engine's queue simulation against the oracle's
+    std::vector<uint64_t> prev(12 * n);
+    zkc_queue_state12 fin;
+    orc_memory_queue_simulate(u.data(), n, prev.data(), &fin);
+    CHECK(same_bytes(fin, w.closed_form_input.observable_input.unsorted_queue_initial_state));
+    CHECK(std::memcmp(prev.data(), w.unsorted_queue_prev_states.data(), prev.size() * 8) == 0);
+
+    const auto got = ram_permutation_entry_point(e, w, limit);
+    zkc_ram_closed_form io = w.closed_form_input;
+    std::vector<uint64_t> trace((size_t)ZKC_RAM_NUM_COLS * limit);
+    uint64_t com[4];
+    zkc_status st;
+    const int rc = orc_ram_permutation_entry_point(&io, u.data(), n, s.data(), n, limit, nullptr, trace.data(), com, &st);
+    CHECK(rc == ZKC_OK && got.status.code == ZKC_OK);
+    CHECK(std::memcmp(com, got.commitment.data(), 32) == 0);
+    CHECK(same_bytes(io.hidden_fsm_output, got.closed_form_input.hidden_fsm_output));
+    CHECK(io.completion_flag == 1 && got.closed_form_input.completion_flag == 1);
+    CHECK(std::memcmp(trace.data(), got.trace.data(), trace.size() * 8) == 0);
+    // an unsatisfiable witness is a status, a broken queue witness a panic
+    auto bad = w;
+    std::swap(bad.sorted_queue_witness[10], bad.sorted_queue_witness[500]);
+    bool threw = false;
+    try { ram_permutation_entry_point(e, bad, limit); } catch (const Error &err) { threw = err.code == ZKC_ERR_QUEUE_WITNESS_INCONSISTENT; }
+    CHECK(threw);
+    std::printf("ram_permutation: %zu queries, commitment %016llx, launches so far %llu\n", n, (unsigned long long)got.commitment[0],
+                (unsigned long long)e.launch_count());
+}
+
+static void decommit_parity(Engine &e) {
+    const size_t n = 500, limit = 512, hashes = 20;
+    uint64_t seed = 0xF1;
+    uint32_t hash[hashes][8];
+    for (auto &h : hash) { for (auto &l : h) l = (uint32_t)sm64(seed); h[7] |= 1; }
+    std::vector<zkc_decommit_query> u(n);
+    size_t first[hashes];
+    std::fill(first, first + hashes, n);
+    for (size_t i = 0; i < n; i++) {
+        const size_t k = sm64(seed) % hashes;
+        zkc_decommit_query q;
+        std::memset(&q, 0, sizeof q);
+        std::memcpy(q.code_hash, hash[k], 32);
+        if (first[k] == n) first[k] = i;
+        q.is_first = first[k] == i; q.page = 2048 + 8 * (uint32_t)first[k]; q.timestamp = 1000 + 4 * (uint32_t)i;
+        u[i] = q;
+    }
+    std::vector<zkc_decommit_query> s = u;
+    std::stable_sort(s.begin(), s.end(), [](const zkc_decommit_query &a, const zkc_decommit_query &b) {
+        for (int l = 7; l >= 0; l--) if (a.code_hash[l] != b.code_hash[l]) return a.code_hash[l] < b.code_hash[l];
+        return a.timestamp < b.timestamp;
+    });
+    CodeDecommittmentsDeduplicatorInstanceWitness w;
+    w.initial_queue_witness = u; w.sorted_queue_witness = s;
+    w.closed_form_input.start_flag = 1;
+    w.closed_form_input.initial_queue_state = decommit_queue_simulate(e, u, w.initial_queue_prev_states);
+    w.closed_form_input.sorted_queue_initial_state = decommit_queue_simulate(e, s, w.sorted_queue_prev_states);
+    zkc_decommit_sorter_closed_form io = w.closed_form_input;
+    std::vector<uint64_t> trace((size_t)ZKC_DQ_NUM_COLS * limit), states(12 * (limit + 1));
+    size_t n_states = 0;
+    uint64_t com[4];
+    zkc_status st;
+    const int rc = orc_sort_decommittments_entry_point(&io, u.data(), n, s.data(), n, limit, nullptr, trace.data(), states.data(), &n_states, com, &st);
+    CHECK(rc == ZKC_OK && n_states == hashes && io.final_queue_state.length == hashes);
+    for (int pass = 0; pass < 2; pass++) {  // without and with the result-queue hints
+        if (pass) {
+            w.result_queue_states.resize(n_states);
+            std::memcpy(w.result_queue_states.data(), states.data(), n_states * 96);
+        }
+        const auto got = sort_and_deduplicate_code_decommittments_entry_point(e, w, limit);
+        CHECK(got.status.code == ZKC_OK);
+        CHECK(std::memcmp(com, got.commitment.data(), 32) == 0);
+        CHECK(same_bytes(io.hidden_fsm_output, got.closed_form_input.hidden_fsm_output));
+        CHECK(same_bytes(io.final_queue_state, got.closed_form_input.final_queue_state));
+        CHECK(std::memcmp(trace.data(), got.trace.data(), trace.size() * 8) == 0);
+    }
+    std::printf("sort_decommittment_requests: %zu requests -> %zu records\n", n, n_states);
+}
+
+static void demux_parity(Engine &e) {
+    const size_t n = 600, limit = 640;
+    uint64_t seed = 0xD3;
+    std::vector<zkc_log_query> recs(n);
+    for (size_t i = 0; i < n; i++) {
+        zkc_log_query q;
+        std::memset(&q, 0, sizeof q);
+        for (auto &l : q.address) l = (uint32_t)sm64(seed);
+        for (auto &l : q.key) l = (uint32_t)sm64(seed);
+        for (auto &l : q.read_value) l = (uint32_t)sm64(seed);
+        for (auto &l : q.written_value) l = (uint32_t)sm64(seed);
+        q.timestamp = 1000 + 4 * (uint32_t)i; q.tx_number_in_block = (uint32_t)(sm64(seed) % 1000);
+        const uint32_t r = (uint32_t)(sm64(seed) % 100);
+        const uint32_t kind = r < 50 ? 0 : r < 75 ? 1 : r < 85 ? 2 : r < 91 ? 3 : r < 97 ? 4 : 5;
+        const uint32_t aux = kind < 3 ? kind : 3;
+        q.flags = ZKC_LQ_FLAGS(aux, 0, 1, 0, 0);
+        if (kind >= 3) {
+            std::memset(q.address, 0, sizeof q.address);
+            q.address[0] = kind == 3 ? 0x8010u : kind == 4 ? 0x02u : 0x01u;
+        }
+        recs[i] = q;
+    }
+    LogDemuxerCircuitInstanceWitness w;
+    w.initial_queue_witness = recs;
+    w.closed_form_input.start_flag = 1;
+    w.closed_form_input.initial_log_queue_state = log_queue_simulate(e, recs, w.initial_queue_prev_tails);
+    zkc_demux_closed_form io = w.closed_form_input;
+    std::vector<uint64_t> trace((size_t)ZKC_DMX_NUM_COLS * limit), tails((size_t)6 * limit * 4);
+    size_t counts[6];
+    uint64_t com[4];
+    zkc_status st;
+    const int rc = orc_demux_log_queue_entry_point(&io, recs.data(), n, limit, nullptr, trace.data(), tails.data(), counts, com, &st);
+    CHECK(rc == ZKC_OK && std::accumulate(counts, counts + 6, (size_t)0) == n);
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass) {
+            w.have_output_queue_tails = true;
+            for (int q = 0; q < 6; q++) {
+                w.output_queue_tails[q].resize(counts[q]);
+                std::memcpy(w.output_queue_tails[q].data(), tails.data() + (size_t)q * limit * 4, counts[q] * 32);
+            }
+        }
+        const auto got = demultiplex_storage_logs_enty_point(e, w, limit);
+        CHECK(got.status.code == ZKC_OK);
+        CHECK(std::memcmp(com, got.commitment.data(), 32) == 0);
+        CHECK(same_bytes(io.hidden_fsm_output, got.closed_form_input.hidden_fsm_output));
+        CHECK(std::memcmp(io.output_queue_states, got.closed_form_input.output_queue_states, sizeof io.output_queue_states) == 0);
+        CHECK(std::memcmp(trace.data(), got.trace.data(), trace.size() * 8) == 0);
+    }
+    std::printf("demux_log_queue: %zu records -> %zu / %zu / %zu / %zu / %zu / %zu\n", n, counts[0], counts[1], counts[2], counts[3],
+                counts[4], counts[5]);
+}
+
+int main(int argc, char **argv) {
+    const std::string mode = argc > 1 ? argv[1] : "nodevice";
+    std::printf("%s\n", Engine::version().c_str());
+    // every entry point of the mirror instantiates (the header is header-only: this is its compile check)
+    void *instantiated[] = {(void *)&ram_permutation_entry_point, (void *)&sort_and_deduplicate_events_entry_point,
+                            (void *)&sort_and_deduplicate_storage_access_entry_point,
+                            (void *)&sort_and_deduplicate_code_decommittments_entry_point, (void *)&demultiplex_storage_logs_enty_point,
+                            (void *)&keccak256_round_function_entry_point, (void *)&sha256_round_function_entry_point,
+                            (void *)&main_vm_entry_point, (void *)&main_vm_initial_state};
+    std::printf("%zu entry points\n", sizeof instantiated / sizeof instantiated[0]);
+    if (mode == "nodevice") {
+        try {
+            Engine e(0);
+            std::printf("a device is present: nothing to check in this mode\n");
+        } catch (const Error &err) {
+            if (err.code != ZKC_ERR_NO_DEVICE) { std::printf("unexpected error: %s\n", err.what()); return 1; }
+            std::printf("refused without a device: %s\n", err.what());
+        }
+        return 0;
+    }
+    Engine e(0);
+    ram_parity(e);
+    decommit_parity(e);
+    demux_parity(e);
+    std::printf(failures ? "%d check(s) FAILED\n" : "all checks passed\n", failures);
+    return failures ? 1 : 0;
+}
