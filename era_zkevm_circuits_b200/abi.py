@@ -337,6 +337,33 @@ DMX_COLS = dict(
 DMX_CHK = dict(TRIVIAL_HEAD=1 << 0, PORTER_STORAGE=1 << 1, BITMASK=1 << 2, QUEUE_CONSISTENCY=1 << 3, QUEUE_HINT=1 << 4)
 
 
+class CodeDecommittmentFsm(C.Structure):
+    _fields_ = [("sha256_inner_state", C.c_uint32 * 8), ("hash_to_compare_against", C.c_uint32 * 8), ("current_index", C.c_uint32),
+                ("current_page", C.c_uint32), ("timestamp", C.c_uint32), ("num_rounds_left", C.c_uint32),
+                ("length_in_bits", C.c_uint32), ("state_get_from_queue", C.c_uint32), ("state_decommit", C.c_uint32),
+                ("finished", C.c_uint32)]
+
+
+class CodeUnpackerFsm(C.Structure):
+    _fields_ = [("internal_fsm", CodeDecommittmentFsm), ("decommittment_requests_queue_state", QueueState12),
+                ("memory_queue_state", QueueState12)]
+
+
+class CodeUnpackerClosedForm(C.Structure):
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("memory_queue_initial_state", QueueState12),
+                ("sorted_requests_queue_initial_state", QueueState12), ("memory_queue_final_state", QueueState12),
+                ("hidden_fsm_input", CodeUnpackerFsm), ("hidden_fsm_output", CodeUnpackerFsm)]
+
+
+CODE_HASH_VERSION_TOP16 = 0x0100
+CU_COLS = dict(
+    FLAGS_IN=0, REQUEST=3, REQ_HEAD=14, REQ_LEN=26, VERSION_MATCHES=27, LENGTH_IN_WORDS=28, LENGTH_IN_ROUNDS=29, LENGTH_IN_BITS=30,
+    TIMESTAMP=31, PAGE=32, HASH_TO_COMPARE=33, DECOMMIT=41, NUM_ROUNDS_LEFT=42, LAST_ROUND=43, FINALIZE=44, PROCESS_SECOND_WORD=45,
+    WORD0=46, WORD1=54, INDEX0=62, INDEX1=63, INDEX_OUT=64, MEM_TAIL0=65, MEM_TAIL1=78, MESSAGE=91, STATE_IN=107, STATE_NEW=115,
+    STATE_OUT=123, FLAGS_OUT=131, NUM_COLS=134)
+CU_CHK = dict(VERSION=1 << 0, LENGTH=1 << 1, HASH=1 << 2, QUEUE_CONSISTENCY=1 << 3, QUEUE_HINT=1 << 4, WITNESS_EXHAUSTED=1 << 5)
+
+
 class RamInputData(C.Structure):
     _fields_ = [("unsorted_queue_initial_state", QueueState12), ("sorted_queue_initial_state", QueueState12),
                 ("non_deterministic_bootloader_memory_snapshot_length", C.c_uint32), ("_pad", C.c_uint32)]
@@ -404,6 +431,8 @@ SIGNATURES = {
     "zkc_demux_log_queue_entry_point": (C.c_int, [_vp, C.POINTER(DemuxClosedForm), _vp, _vp, C.c_size_t, _vp,
                                                   C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(DemuxOptions), C.c_int, _vp, _vp,
                                                   C.POINTER(Status)]),
+    "zkc_code_unpacker_entry_point": (C.c_int, [_vp, C.POINTER(CodeUnpackerClosedForm), _vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp,
+                                                C.c_size_t, C.c_size_t, C.POINTER(SorterOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
     "zkc_storage_validity_entry_point": (C.c_int, [_vp, C.POINTER(StorageClosedForm), _vp, _vp, C.c_size_t, _vp, _vp, _vp,
                                                    C.c_size_t, _vp, C.c_size_t, C.c_size_t, C.POINTER(SorterOptions),
                                                    C.c_int, _vp, _vp, C.POINTER(Status)]),

@@ -159,6 +159,28 @@ def vm_log_queue_trace(n: int, seed: int = 0xC4, mix=(50, 25, 10, 6, 6, 3)):
     return q
 
 
+def code_decommit_requests(n: int, seed: int = 0xC4, max_words: int = 63):
+    """(f)3 (code_unpacker_sha256): n deduplicated decommitment requests (what sort_decommittment_requests leaves) with their
+    bytecodes: an odd number of 32-byte words each (the padding block then completes the last SHA-256 round,
+    code_unpacker_sha256/mod.rs:215-221), code_hash = SHA-256 of the code with the top 4 bytes replaced by the version byte
+    and the length in words (versioned hash, mod.rs:187-213).  Returns (requests, code_words [total_words, 8] uint32 limbs)."""
+    import hashlib
+    q = np.zeros(n, dtype=abi.DECOMMIT_QUERY_DTYPE)
+    words = []
+    lens = 1 + 2 * (splitmix64(seed, max(n, 1), 0) % np.uint64((max_words + 1) // 2)).astype(np.int64)
+    for i in range(n):
+        code = splitmix64(seed + 1 + i, int(lens[i]) * 4, 1).tobytes()
+        digest = int.from_bytes(hashlib.sha256(code).digest(), "big")
+        q["code_hash"][i] = [(digest >> (32 * k)) & 0xFFFFFFFF for k in range(7)] + [(abi.CODE_HASH_VERSION_TOP16 << 16) | int(lens[i])]
+        for wi in range(int(lens[i])):
+            v = int.from_bytes(code[32 * wi:32 * wi + 32], "big")
+            words.append([(v >> (32 * k)) & 0xFFFFFFFF for k in range(8)])
+    q["page"] = 2048 + 8 * np.arange(n, dtype=np.uint32)
+    q["timestamp"] = 1000 + 4 * np.arange(n, dtype=np.uint32)
+    q["is_first"] = 1
+    return q, np.array(words, dtype=np.uint32).reshape(-1, 8)
+
+
 def storage_trace(n: int, seed: int = 0xC4, n_cells: int = 1 << 16, shard: int = 0, first_position: int = 0):
     """C4 (storage_validity): n storage LogQuery records over n_cells (address, key) cells: 60 % reads,
     30 % writes, 10 % write + rollback pairs (the rollback twin directly follows its write), shard 0.

@@ -868,6 +868,96 @@ int zkc_sha256_round_function_entry_point(zkc_ctx *ctx, zkc_sha256_closed_form *
                                           zkc_status *status);
 
 
+/* ---- code_unpacker_sha256 (src/code_unpacker_sha256/mod.rs) --------------------------------------------- */
+/* CodeDecommittmentFSM, code_unpacker_sha256/input.rs:27-38 */
+typedef struct zkc_code_decommittment_fsm {
+    uint32_t sha256_inner_state[8];
+    uint32_t hash_to_compare_against[8]; /* UInt256, little-endian u32 limbs (limb 7 cleared) */
+    uint32_t current_index;
+    uint32_t current_page;
+    uint32_t timestamp;
+    uint32_t num_rounds_left;            /* UInt16 */
+    uint32_t length_in_bits;
+    uint32_t state_get_from_queue;
+    uint32_t state_decommit;
+    uint32_t finished;
+} zkc_code_decommittment_fsm;
+
+/* CodeDecommitterFSMInputOutput, input.rs:70-74 */
+typedef struct zkc_code_unpacker_fsm {
+    zkc_code_decommittment_fsm internal_fsm;
+    zkc_queue_state12 decommittment_requests_queue_state;
+    zkc_queue_state12 memory_queue_state;
+} zkc_code_unpacker_fsm;
+
+/* ClosedFormInputWitness<F, CodeDecommitterFSMInputOutput, CodeDecommitterInputData, CodeDecommitterOutputData>,
+ * input.rs:92-150 */
+typedef struct zkc_code_unpacker_closed_form {
+    uint32_t start_flag;
+    uint32_t completion_flag;                              /* out */
+    zkc_queue_state12 memory_queue_initial_state;          /* observable input */
+    zkc_queue_state12 sorted_requests_queue_initial_state; /* observable input */
+    zkc_queue_state12 memory_queue_final_state;            /* observable output (out; expected if compared) */
+    zkc_code_unpacker_fsm hidden_fsm_input;
+    zkc_code_unpacker_fsm hidden_fsm_output;               /* out; on input: expected value if compare_expected */
+} zkc_code_unpacker_closed_form;
+
+#define ZKC_CODE_HASH_VERSION_TOP16 0x0100u /* ContractCodeSha256::VERSION_BYTE << 8 (zkevm_opcode_defs, un-vendored), mod.rs:187-189 */
+
+/* trace columns of one iteration of unpack_code_into_memory_inner (mod.rs:191-447) */
+enum zkc_code_unpacker_col {
+    ZKC_CU_FLAGS_IN = 0,          /* 3: state_get_from_queue, state_decommit, finished on entry */
+    ZKC_CU_REQUEST = 3,           /* 11: popped DecommitQuery (zero if nothing popped), :195-196 */
+    ZKC_CU_REQ_HEAD = 14,         /* 12: requests queue head after the pop */
+    ZKC_CU_REQ_LEN = 26,
+    ZKC_CU_VERSION_MATCHES = 27,  /* :202 */
+    ZKC_CU_LENGTH_IN_WORDS = 28,  /* :207-213 */
+    ZKC_CU_LENGTH_IN_ROUNDS = 29, /* :215-221 */
+    ZKC_CU_LENGTH_IN_BITS = 30,   /* state.length_in_bits after the selection, :240-245 */
+    ZKC_CU_TIMESTAMP = 31,
+    ZKC_CU_PAGE = 32,
+    ZKC_CU_HASH_TO_COMPARE = 33,  /* 8 */
+    ZKC_CU_DECOMMIT = 41,         /* state_decommit || state_get_from_queue, :277 */
+    ZKC_CU_NUM_ROUNDS_LEFT = 42,  /* after the conditional decrement, :281-287 */
+    ZKC_CU_LAST_ROUND = 43,
+    ZKC_CU_FINALIZE = 44,
+    ZKC_CU_PROCESS_SECOND_WORD = 45,
+    ZKC_CU_WORD0 = 46,            /* 8: code_word_0, little-endian u32 limbs */
+    ZKC_CU_WORD1 = 54,            /* 8 */
+    ZKC_CU_INDEX0 = 62,           /* index of mem_query_0 */
+    ZKC_CU_INDEX1 = 63,           /* index of mem_query_1 */
+    ZKC_CU_INDEX_OUT = 64,        /* state.current_index after the cycle */
+    ZKC_CU_MEM_TAIL0 = 65,        /* 12 + length: memory queue after the first conditional push, :351 */
+    ZKC_CU_MEM_TAIL1 = 78,        /* 12 + length: after the second, :352 */
+    ZKC_CU_MESSAGE = 91,          /* 16: sha256 block as big-endian words, padding selected in on finalize, :354-381 */
+    ZKC_CU_STATE_IN = 107,        /* 8 */
+    ZKC_CU_STATE_NEW = 115,       /* 8: round function output, :383-384 */
+    ZKC_CU_STATE_OUT = 123,       /* 8: state.sha256_inner_state after the selection, :386-391 */
+    ZKC_CU_FLAGS_OUT = 131,       /* 3 */
+    ZKC_CU_NUM_COLS = 134
+};
+
+#define ZKC_CU_CHK_VERSION (1u << 0)           /* :202-204 */
+#define ZKC_CU_CHK_LENGTH (1u << 1)            /* (length_in_words + 1) / 2 is not a UInt16, :215-221 */
+#define ZKC_CU_CHK_HASH (1u << 2)              /* :409-420 */
+#define ZKC_CU_CHK_QUEUE_CONSISTENCY (1u << 3) /* :449 */
+#define ZKC_CU_CHK_QUEUE_HINT (1u << 4)        /* requests_prev_states / memory_states is not the hash chain */
+#define ZKC_CU_CHK_WITNESS_EXHAUSTED (1u << 5) /* a pop from the empty requests queue / code_words ran dry */
+
+/* unpack_code_into_memory_entry_point, src/code_unpacker_sha256/mod.rs:33-148.
+ *   requests, requests_prev_states : sorted_requests_queue_witness (FullStateCircuitQueueRawWitness, input.rs:157-158)
+ *   code_words    : `code_words` flattened (input.rs:159), n_code_words x 8 little-endian u32 limbs, in pop order
+ *   memory_states : NULL, or AoS [pushes][12]: the memory queue's tail after each executed push (verified);
+ *                   when NULL the chain is rebuilt sequentially on the device (1 permutation per push)
+ *   trace         : column-major [ZKC_CU_NUM_COLS][limit] or NULL
+ * One thread per decommitment request chains its SHA-256 rounds; requests run side by side. */
+int zkc_code_unpacker_entry_point(zkc_ctx *ctx, zkc_code_unpacker_closed_form *io, const zkc_decommit_query *requests,
+                                  const uint64_t *requests_prev_states, size_t n_requests, const uint32_t *code_words,
+                                  size_t n_code_words, const uint64_t *memory_states, size_t n_memory_states, size_t limit,
+                                  const zkc_sorter_options *options, int on_device, uint64_t *trace,
+                                  uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
+
+
 /* ---- main_vm (src/main_vm/) ------------------------------------------------------------------------- */
 /* The ISA tables (zkevm_opcode_defs, un-vendored) are INPUT DATA: opcode -> (price, 48-bit property bit spread +
  * 3 aux bits), exactly the 3-column table of src/tables/opcodes_decoding.rs:14-38, plus the condition table of

@@ -95,6 +95,12 @@ size_t orc_demux_encode_fsm(const zkc_demux_fsm *f, uint64_t *dst);
 int orc_demux_log_queue_entry_point(zkc_demux_closed_form *io, const zkc_log_query *records, size_t n_records, size_t limit,
                                     const zkc_demux_options *options, uint64_t *trace, uint64_t *output_tails,
                                     size_t n_output_tails[6], uint64_t commitment[4], zkc_status *status);
+/* code_unpacker_sha256.c; memory_states (optional out): memory queue tail [12] after each executed push */
+size_t orc_code_unpacker_encode_fsm(const zkc_code_unpacker_fsm *f, uint64_t *dst);
+int orc_code_unpacker_entry_point(zkc_code_unpacker_closed_form *io, const zkc_decommit_query *requests, size_t n_requests,
+                                  const uint32_t *code_words, size_t n_code_words, size_t limit, const zkc_sorter_options *options,
+                                  uint64_t *trace, uint64_t *memory_states, size_t *n_memory_states, uint64_t commitment[4],
+                                  zkc_status *status);
 /* keccak256_round_function.c; memory_states (optional out): memory queue tail after each executed push */
 void orc_keccak_f1600(uint64_t A[25]);
 void orc_keccak256(const uint8_t *msg, size_t len, uint8_t digest[32]);

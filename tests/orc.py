@@ -57,6 +57,10 @@ def load():
     lib.orc_demux_log_queue_entry_point.argtypes = [C.POINTER(abi.DemuxClosedForm), _vp, C.c_size_t, C.c_size_t,
                                                     C.POINTER(abi.DemuxOptions), _vp, _vp, C.POINTER(C.c_size_t), _vp,
                                                     C.POINTER(abi.Status)]
+    lib.orc_code_unpacker_entry_point.restype = C.c_int
+    lib.orc_code_unpacker_entry_point.argtypes = [C.POINTER(abi.CodeUnpackerClosedForm), _vp, C.c_size_t, _vp, C.c_size_t, C.c_size_t,
+                                                  C.POINTER(abi.SorterOptions), _vp, _vp, C.POINTER(C.c_size_t), _vp,
+                                                  C.POINTER(abi.Status)]
     lib.orc_keccak_f1600.argtypes = [_vp]
     lib.orc_keccak256.argtypes = [_vp, C.c_size_t, _vp]
     lib.orc_keccak256_entry_point.restype = C.c_int
@@ -236,6 +240,33 @@ def demux_entry_point(lib, io, records, limit, want_trace=True, compare_expected
     rc = lib.orc_demux_log_queue_entry_point(C.byref(io2), p(records), len(records), limit, C.byref(opts), p(trace), p(tails),
                                              n_tails, p(com), C.byref(st))
     return rc, io2, trace, com, st, [tails[q, :n_tails[q]].copy() for q in range(6)]
+
+
+def code_unpacker_closed_form(requests_state, memory_state=None, start=True, fsm_in=None):
+    io = abi.CodeUnpackerClosedForm()
+    io.start_flag = int(start)
+    io.sorted_requests_queue_initial_state = requests_state
+    if memory_state is not None:
+        io.memory_queue_initial_state = memory_state
+    if fsm_in is not None:
+        io.hidden_fsm_input = fsm_in
+    return io
+
+
+def code_unpacker_entry_point(lib, io, requests, code_words, limit, want_trace=True, compare_expected=False):
+    """returns (rc, io_out, trace, commitment, status, memory_states)"""
+    io2 = abi.CodeUnpackerClosedForm.from_buffer_copy(bytes(io))
+    requests = np.ascontiguousarray(requests)
+    code_words = np.ascontiguousarray(code_words, dtype=np.uint32).reshape(-1, 8)
+    trace = np.zeros((abi.CU_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
+    states = np.zeros((2 * limit + 1, 12), dtype=np.uint64)
+    n_states = C.c_size_t()
+    com = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    opts = abi.SorterOptions(int(compare_expected))
+    rc = lib.orc_code_unpacker_entry_point(C.byref(io2), p(requests), len(requests), p(code_words), len(code_words), limit,
+                                           C.byref(opts), p(trace), p(states), C.byref(n_states), p(com), C.byref(st))
+    return rc, io2, trace, com, st, states[:n_states.value].copy()
 
 
 def storage_closed_form(unsorted_state, sorted_state, shard=0, start=True, fsm_in=None):

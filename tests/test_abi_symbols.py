@@ -122,3 +122,24 @@ def test_column_enums_mirror_header(enum, prefix, cols, chk):
         hchk = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"#define ZKC_%s_CHK_([A-Z_0-9]+) \(1u << (\d+)\)" % prefix, text)}
         for name, value in getattr(abi, chk).items():
             assert hchk[name] == value, name
+
+
+def test_code_unpacker_mirrors_header():
+    import subprocess
+    import tempfile
+    text = open(os.path.join(ROOT, "include", "zkc_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", text[text.index("enum zkc_code_unpacker_col {"):], flags=re.S)
+    body = body[:body.index("};")]
+    cols = {m.group(1): int(m.group(2)) for m in re.finditer(r"ZKC_CU_([A-Z0-9_]+)\s*=\s*(\d+)", body)}
+    assert cols == abi.CU_COLS
+    chk = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"#define ZKC_CU_CHK_([A-Z_]+) \(1u << (\d+)\)", text)}
+    assert chk == abi.CU_CHK
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s.c")
+        open(src, "w").write('#include <stdio.h>\n#include "%s"\nint main(void){printf("%%zu %%zu %%zu\\n", sizeof(zkc_code_decommittment_fsm), '
+                             'sizeof(zkc_code_unpacker_fsm), sizeof(zkc_code_unpacker_closed_form));return 0;}\n'
+                             % os.path.join(ROOT, "include", "zkc_b200.h"))
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-o", exe, src])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(abi.CodeDecommittmentFsm), C.sizeof(abi.CodeUnpackerFsm), C.sizeof(abi.CodeUnpackerClosedForm)]

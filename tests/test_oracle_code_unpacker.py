@@ -1,0 +1,97 @@
+"""code_unpacker_sha256 oracle: the FSM's SHA-256 over the unpacked words against hashlib (a request is satisfiable exactly
+when its versioned hash is the SHA-256 of its code), memory writes, chaining over instances, negative cases.  The reference's
+own test (/root/reference/src/code_unpacker_sha256/mod.rs:480-...) builds one request the same way."""
+import hashlib
+
+import numpy as np
+
+import orc as O
+from era_zkevm_circuits_b200 import abi, synthetic
+
+K = abi.CU_COLS
+CHK = abi.CU_CHK
+
+
+def instance(orc, reqs):
+    prev, fin = O.decommit_queue_simulate(orc, reqs)
+    return O.code_unpacker_closed_form(fin, None, True), prev
+
+
+def test_single_request_sha256_and_memory_writes(orc):
+    reqs, words = synthetic.code_decommit_requests(1, seed=1, max_words=9)
+    n_words = int(reqs["code_hash"][0][7]) & 0xFFFF
+    assert n_words % 2 == 1 and len(words) == n_words
+    rounds = (n_words + 1) // 2
+    io, _ = instance(orc, reqs)
+    rc, out, trace, com, st, states = O.code_unpacker_entry_point(orc, io, reqs, words, rounds + 2)
+    assert rc == abi.ZKC_OK, (hex(st.failed_checks), st.first_bad_row)
+    assert out.completion_flag == 1 and out.hidden_fsm_output.internal_fsm.finished == 1
+    # one memory write per word, indices 0 .. n_words-1 on the request's page at its timestamp
+    assert len(states) == n_words == out.memory_queue_final_state.length
+    idx = np.concatenate([np.stack([trace[K["INDEX0"]][:rounds], trace[K["INDEX1"]][:rounds]], axis=1).reshape(-1)[:n_words]])
+    assert idx.tolist() == list(range(n_words))
+    assert set(trace[K["PAGE"]][:rounds].tolist()) == {int(reqs["page"][0])}
+    # the state after the finalizing round is the SHA-256 of the code
+    code = b"".join(int(sum(int(l) << (32 * k) for k, l in enumerate(w))).to_bytes(32, "big") for w in words)
+    digest = hashlib.sha256(code).digest()
+    got = b"".join(int(trace[K["STATE_NEW"] + i][rounds - 1]).to_bytes(4, "big") for i in range(8))
+    assert got == digest
+    assert trace[K["FINALIZE"]].tolist() == [0] * (rounds - 1) + [1, 0, 0]
+    # idle afterwards
+    assert trace[K["FLAGS_OUT"] + 2][rounds - 1:].tolist() == [1, 1, 1] and trace[K["DECOMMIT"]][rounds:].sum() == 0
+
+
+def test_many_requests_chain_and_compare(orc):
+    reqs, words = synthetic.code_decommit_requests(40, seed=7, max_words=31)
+    total_rounds = int((((reqs["code_hash"][:, 7] & 0xFFFF) + 1) // 2).sum())
+    io, _ = instance(orc, reqs)
+    rc, out, trace, com, st, states = O.code_unpacker_entry_point(orc, io, reqs, words, total_rounds + 5)
+    assert rc == abi.ZKC_OK, (hex(st.failed_checks), st.first_bad_row)
+    assert out.completion_flag == 1 and len(states) == len(words)
+    assert trace[K["FINALIZE"]].sum() == 40 and trace[K["FLAGS_IN"]].sum() == 40
+    # chained instances == whole (cut inside a request)
+    cut = total_rounds // 2 + 1
+    rc, a, ta, _, st, s1 = O.code_unpacker_entry_point(orc, io, reqs, words, cut)
+    assert rc == abi.ZKC_OK and a.completion_flag == 0
+    popped = len(reqs) - a.hidden_fsm_output.decommittment_requests_queue_state.length
+    nxt = abi.CodeUnpackerClosedForm.from_buffer_copy(bytes(a)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.hidden_fsm_output
+    rc, b, tb, _, st, s2 = O.code_unpacker_entry_point(orc, nxt, reqs[popped:], words[len(s1):], total_rounds + 5 - cut)
+    assert rc == abi.ZKC_OK, (hex(st.failed_checks), st.first_bad_row)
+    assert bytes(b.hidden_fsm_output) == bytes(out.hidden_fsm_output) and bytes(b.memory_queue_final_state) == bytes(out.memory_queue_final_state)
+    assert np.array_equal(np.concatenate([ta, tb], axis=1), trace) and np.array_equal(np.concatenate([s1, s2]), states)
+    exp = abi.CodeUnpackerClosedForm.from_buffer_copy(bytes(b)); exp.start_flag = 0; exp.hidden_fsm_input = a.hidden_fsm_output
+    rc, *_ = O.code_unpacker_entry_point(orc, exp, reqs[popped:], words[len(s1):], total_rounds + 5 - cut, compare_expected=True)
+    assert rc == abi.ZKC_OK
+    exp.hidden_fsm_output.internal_fsm.current_index ^= 1
+    rc, *_ = O.code_unpacker_entry_point(orc, exp, reqs[popped:], words[len(s1):], total_rounds + 5 - cut, compare_expected=True)
+    assert rc == abi.ZKC_ERR_FSM_OUTPUT_MISMATCH
+
+
+def test_negative_cases(orc):
+    reqs, words = synthetic.code_decommit_requests(6, seed=3, max_words=15)
+    rounds = ((reqs["code_hash"][:, 7] & 0xFFFF) + 1) // 2
+    limit = int(rounds.sum()) + 2
+    # a flipped code bit: the hash of request 2 no longer matches, at its finalizing round
+    w2 = words.copy(); w2[int((reqs["code_hash"][:2, 7] & 0xFFFF).sum()) + 1, 3] ^= 4
+    io, _ = instance(orc, reqs)
+    rc, _, _, _, st, _ = O.code_unpacker_entry_point(orc, io, reqs, w2, limit)
+    assert st.failed_checks == CHK["HASH"] and st.first_bad_row == int(rounds[:3].sum()) - 1
+    # wrong version byte
+    r3 = reqs.copy(); r3["code_hash"][1][7] ^= 1 << 24
+    io3, _ = instance(orc, r3)
+    rc, _, _, _, st, _ = O.code_unpacker_entry_point(orc, io3, r3, words, limit)
+    assert st.failed_checks & CHK["VERSION"] and st.first_bad_row == int(rounds[0])
+    # an even number of words
+    r4 = reqs.copy(); r4["code_hash"][0][7] += 1
+    io4, _ = instance(orc, r4)
+    rc, _, _, _, st, _ = O.code_unpacker_entry_point(orc, io4, r4, words, limit)
+    assert st.failed_checks & CHK["LENGTH"] and st.first_bad_row == 0
+    # the code words run dry
+    rc, _, _, _, st, _ = O.code_unpacker_entry_point(orc, io, reqs, words[:-3], limit)
+    assert st.failed_checks & CHK["WITNESS_EXHAUSTED"]
+    # empty requests queue at the start: the first cycle pops from an empty queue
+    e = np.zeros(0, dtype=abi.DECOMMIT_QUERY_DTYPE)
+    io0, _ = instance(orc, e)
+    rc, out, _, _, st, _ = O.code_unpacker_entry_point(orc, io0, e, words[:0], 4)
+    assert st.failed_checks & CHK["WITNESS_EXHAUSTED"] and st.first_bad_row == 0
