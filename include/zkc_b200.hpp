@@ -335,6 +335,33 @@ inline Result<zkc_sha256_closed_form> sha256_round_function_entry_point(Engine &
     return r;
 }
 
+// ---- code_unpacker_sha256 -----------------------------------------------------------------------------------------------------
+// CodeDecommitterCircuitInstanceWitness, /root/reference/src/code_unpacker_sha256/input.rs:152-160
+struct CodeDecommitterCircuitInstanceWitness {
+    zkc_code_unpacker_closed_form closed_form_input{};
+    std::vector<zkc_decommit_query> sorted_requests_queue_witness;
+    std::vector<State12> sorted_requests_queue_prev_states;
+    std::vector<std::array<uint32_t, 8>> code_words;  // flattened over the requests, little-endian u32 limbs per 256-bit word
+    std::vector<State12> memory_queue_states;         // optional hint: memory-queue state after every executed write
+};
+
+// unpack_code_into_memory_entry_point, /root/reference/src/code_unpacker_sha256/mod.rs:33-148
+inline Result<zkc_code_unpacker_closed_form> unpack_code_into_memory_entry_point(Engine &e, const CodeDecommitterCircuitInstanceWitness &w,
+                                                                                 size_t limit, bool want_trace = true,
+                                                                                 const zkc_sorter_options *options = nullptr,
+                                                                                 bool throw_if_unsatisfied = false) {
+    detail::same_length("unpack_code_into_memory_entry_point", w.sorted_requests_queue_witness.size(), w.sorted_requests_queue_prev_states.size());
+    Result<zkc_code_unpacker_closed_form> r;
+    r.closed_form_input = w.closed_form_input;
+    uint64_t *trace = detail::make_trace(r, ZKC_CU_NUM_COLS, limit, want_trace);
+    const int rc = zkc_code_unpacker_entry_point(
+        e.handle(), &r.closed_form_input, detail::ptr(w.sorted_requests_queue_witness), detail::flat(w.sorted_requests_queue_prev_states),
+        w.sorted_requests_queue_witness.size(), w.code_words.empty() ? nullptr : w.code_words.front().data(), w.code_words.size(),
+        detail::flat(w.memory_queue_states), w.memory_queue_states.size(), limit, options, 0, trace, r.commitment.data(), &r.status);
+    detail::finish("unpack_code_into_memory_entry_point", rc, r, throw_if_unsatisfied);
+    return r;
+}
+
 // ---- main_vm ---------------------------------------------------------------------------------------------------------------
 // VmCircuitWitness, /root/reference/src/fsm_input_output/circuit_inputs/main_vm.rs:64-71, with the WitnessOracle flattened
 // per cycle: `snapshots` = the VmLocalState before every cycle + the final one (limit + 1),

@@ -194,7 +194,7 @@ int main(int argc, char **argv) {
     void *instantiated[] = {(void *)&ram_permutation_entry_point, (void *)&sort_and_deduplicate_events_entry_point,
                             (void *)&sort_and_deduplicate_storage_access_entry_point,
                             (void *)&sort_and_deduplicate_code_decommittments_entry_point, (void *)&demultiplex_storage_logs_enty_point,
-                            (void *)&keccak256_round_function_entry_point, (void *)&sha256_round_function_entry_point,
+                            (void *)&unpack_code_into_memory_entry_point, (void *)&keccak256_round_function_entry_point, (void *)&sha256_round_function_entry_point,
                             (void *)&main_vm_entry_point, (void *)&main_vm_initial_state};
     std::printf("%zu entry points\n", sizeof instantiated / sizeof instantiated[0]);
     if (mode == "nodevice") {

@@ -25,7 +25,8 @@ from era_zkevm_circuits_b200 import (Engine, EventsDeduplicatorInstanceWitness, 
                                      ram_permutation_entry_point, sha256_round_function_entry_point, sharding,
                                      sort_and_deduplicate_events_entry_point, sort_and_deduplicate_storage_access_entry_point, synthetic,
                                      CodeDecommittmentsDeduplicatorInstanceWitness, sort_and_deduplicate_code_decommittments_entry_point,
-                                     LogDemuxerCircuitInstanceWitness, demultiplex_storage_logs_enty_point)
+                                     LogDemuxerCircuitInstanceWitness, demultiplex_storage_logs_enty_point,
+                                     CodeDecommitterCircuitInstanceWitness, unpack_code_into_memory_entry_point)
 
 
 def timed(fn, steps=5, warmup=2):
@@ -228,6 +229,34 @@ def dmx(eng, log2rows):
                       "kernel_ms": prof, "queue_setup_s": setup, "trace_GB": trace.numel() * 8 / 1e9}))
 
 
+def cu(eng):
+    """code_unpacker_sha256, ~2^17 cycles, device resident: many short bytecodes vs few long ones (one thread per request)"""
+    for n, max_words in ((4096, 127), (512, 1023)):
+        reqs, words = synthetic.code_decommit_requests(n, seed=0xC4, max_words=max_words)
+        cycles = int((((reqs["code_hash"][:, 7] & 0xFFFF).astype(np.int64) + 1) // 2).sum())
+        d_reqs = dev(reqs)
+        prev, fin = eng.decommit_queue_simulate(d_reqs)
+        io = abi.CodeUnpackerClosedForm(); io.start_flag = 1
+        io.sorted_requests_queue_initial_state = fin[0]
+        w = CodeDecommitterCircuitInstanceWitness(io, d_reqs, prev, torch.from_numpy(words.view(np.int32)).cuda(), None)
+        trace = torch.empty((abi.CU_COLS["NUM_COLS"], cycles), dtype=torch.int64, device="cuda")
+        K = abi.CU_COLS
+        run = lambda: unpack_code_into_memory_entry_point(eng, w, cycles, trace_out=trace, raise_on_unsatisfied=False)
+        ms0, got = once(run)
+        states = pushes_from_trace(trace, None, [K["DECOMMIT"], K["PROCESS_SECOND_WORD"]], [K["MEM_TAIL0"], K["MEM_TAIL1"]], 12)
+        w.memory_queue_states = states.contiguous()
+        ms, got = timed(run, steps=5, warmup=2)
+        eng.profile(True)
+        run()
+        prof = {k: eng.profile_query(k)[0] for k in ("cu_requests", "cu_memq", "cu_tail", "cu_plan", "cu_prologue", "cu_finalize")}
+        eng.profile(False)
+        print(json.dumps({"config": f"code_unpacker_sha256, {n} requests, {len(words)} words, {cycles} cycles", "gpu_ms_with_memory_states": ms,
+                          "cycles_per_s": cycles / ms * 1e3, "MB_of_code_per_s": len(words) * 32 / ms / 1e3,
+                          "gpu_ms_without_memory_states_sequential_chain": ms0, "memory_pushes": len(states), "status": got.status.code,
+                          "failed_checks": got.status.failed_checks, "completed": int(got.closed_form_input.completion_flag), "kernel_ms": prof}))
+        del trace, w
+
+
 def gp(eng, log2rows):
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -285,5 +314,7 @@ if __name__ == "__main__":
         dq(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 20)
     elif what == "dmx":
         dmx(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 18)
+    elif what == "cu":
+        cu(eng)
     elif what == "gp":
         gp(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 22)
