@@ -1,10 +1,13 @@
 // Code decommitter on sm_100a: unpack_code_into_memory_entry_point (/root/reference/src/code_unpacker_sha256/mod.rs:33-148)
 // and its work cycle unpack_code_into_memory_inner (:150-453): every deduplicated decommitment request is popped, its
 // bytecode written to memory two words per cycle, and the SHA-256 of the code compared with the versioned hash.
-// Same decomposition as sha256_round_function.cu: a request of w words takes exactly (w + 1) / 2 cycles, so the plan is a
-// prefix sum over the requests' round counts; ONE THREAD PER REQUEST chains its SHA-256 rounds (a hash chain no witness
-// breaks), requests run side by side; the rows after the last request idle and are row-parallel; the memory queue's
-// conditional pushes (2 slots per cycle) are handled by precompile_common.cuh against host-supplied states or rebuilt.
+// A request of w words takes exactly (w + 1) / 2 cycles, so the plan is a prefix sum over the requests' round counts.  The only
+// state a cycle inherits that no witness supplies is the SHA-256 state (a hash chain): pass 1 runs ONE THREAD PER REQUEST
+// over nothing but that chain (pop of the request, 2 code words in, one compression, 32 bytes of state out per round);
+// pass 2 is ONE THREAD PER CYCLE: it rebuilds the FSM state of its cycle in closed form from (request, round index, chained
+// SHA-256 state), evaluates the cycle and writes its 134 witness cells, coalesced.  The rows after the last request idle and
+// are row-parallel too; the memory queue's conditional pushes (2 slots per cycle) are handled by precompile_common.cuh
+// against host-supplied states or rebuilt.
 #include "ctx.cuh"
 #include "poseidon2.cuh"
 #include "precompile_common.cuh"
@@ -273,31 +276,29 @@ __device__ __forceinline__ void cu_cycle(zkc_code_decommittment_fsm &s, const zk
 #undef TR
 }
 
-// one thread per request: pop (verified against the queue witness), then its rounds in order
+// pass 1, one thread per request: pop (verified against the queue witness), then ONLY the SHA-256 chain of its rounds:
+// sha_in[row] = the state before the round of that row.  The next round's code words are in flight while this one compresses.
 __global__ void __launch_bounds__(128)
-cu_requests_kernel(CuDev *d, const zkc_decommit_query *__restrict__ requests, const uint64_t *__restrict__ req_prev,
-                   const uint32_t *__restrict__ words, const CuPlan *__restrict__ starts, uint64_t *__restrict__ push_enc,
-                   uint32_t *__restrict__ slot_meta, uint64_t *__restrict__ trace) {
+cu_chain_kernel(CuDev *d, const zkc_decommit_query *__restrict__ requests, const uint64_t *__restrict__ req_prev,
+                const uint32_t *__restrict__ words, const CuPlan *__restrict__ starts, uint32_t *__restrict__ sha_in,
+                uint64_t *__restrict__ heads) {
     const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_units = d->n_units;
     if (u >= n_units) return;
-    const size_t limit = d->limit;
+    const size_t limit = d->limit, n_words = d->n_code_words;
     const CuPlan st = starts[u], en = starts[u + 1];
     size_t row = st.cycles;
     if (row >= limit || en.cycles == st.cycles) return;
-    zkc_code_decommittment_fsm s = d->s0;
-    zkc_decommit_query req = cu_zero_request();
-    const uint32_t rq_len0 = d->rq0.length;
-    uint64_t head[12];
-    uint32_t len_after, checks = 0;
+    uint32_t sha[8], rounds_left, length_in_bits;
     if (u == 0) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) head[i] = d->rq0.head[i];
-        len_after = rq_len0;
+        for (int i = 0; i < 8; i++) sha[i] = d->s0.sha256_inner_state[i];
+        rounds_left = d->s0.num_rounds_left;
+        length_in_bits = d->s0.length_in_bits;
+#pragma unroll
+        for (int i = 0; i < 12; i++) heads[i] = d->rq0.head[i];
     } else {
-        req = cu_load_request(requests + (u - 1));
-        s.state_get_from_queue = 1;
-        if (u > 1 || !d->unit0_fresh) s.state_decommit = 0;  // the previous request ended with its finalizing round
+        const zkc_decommit_query req = cu_load_request(requests + (u - 1));
         uint64_t e[8], sp[12];
         bool hint_ok = true;
         cu_encode_request(req, e);
@@ -309,38 +310,119 @@ cu_requests_kernel(CuDev *d, const zkc_decommit_query *__restrict__ requests, co
         }
         poseidon2_permute(sp);
 #pragma unroll
-        for (int i = 0; i < 12; i++) head[i] = sp[i];
+        for (int i = 0; i < 12; i++) heads[12 * u + i] = sp[i];
         if (u + 1 < n_units && starts[u + 1].cycles < limit) {
 #pragma unroll
-            for (int i = 0; i < 12; i++) hint_ok &= __ldg(req_prev + 12 * u + i) == head[i];
+            for (int i = 0; i < 12; i++) hint_ok &= __ldg(req_prev + 12 * u + i) == sp[i];
         }
-        if (!hint_ok) { checks |= ZKC_CU_CHK_QUEUE_HINT; d->hint_bad = 1; }
-        len_after = rq_len0 - (uint32_t)u;
-    }
-    size_t word_cursor = st.words;
-    uint32_t push_ordinal = st.words;
-    bool first_cycle = true;
-    while (row < limit && row < en.cycles) {
-        uint32_t cyc_checks = first_cycle ? checks : 0;
-        if (trace) {
-            for (int i = 0; i < 11; i++) trace[(size_t)(ZKC_CU_REQUEST + i) * limit + row] = first_cycle ? cu_flat_request(req, i) : 0;
-            for (int i = 0; i < 12; i++) trace[(size_t)(ZKC_CU_REQ_HEAD + i) * limit + row] = head[i];
-            trace[(size_t)ZKC_CU_REQ_LEN * limit + row] = len_after;
-        }
-        cu_cycle(s, first_cycle ? req : cu_zero_request(), true, len_after == 0, words, d->n_code_words, word_cursor, push_enc, slot_meta,
-                 push_ordinal, trace, limit, row, cyc_checks);
-        cu_report(d, row, cyc_checks);
-        first_cycle = false;
-        row++;
-    }
-    const size_t total = starts[n_units].cycles;
-    if (row == limit) d->s_final = s;
-    if (en.cycles == total && row == en.cycles) d->s_last = s;
-    if (u >= 1 && (u + 1 == n_units || starts[u + 1].cycles >= limit)) {
+        if (!hint_ok) { d->hint_bad = 1; cu_report(d, row, ZKC_CU_CHK_QUEUE_HINT); }
+        if (u + 1 == n_units || starts[u + 1].cycles >= limit) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) d->req_head_final[i] = head[i];
-        d->popped_requests = (uint32_t)u;
+            for (int i = 0; i < 12; i++) d->req_head_final[i] = sp[i];
+            d->popped_requests = (uint32_t)u;
+        }
+        const uint32_t length_in_words = req.code_hash[7] & 0xFFFFu;
+        rounds_left = (length_in_words + 1) >> 1;
+        length_in_bits = length_in_words * 256u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) sha[i] = SHA_IV[i];
     }
+    size_t wc = st.words;
+    uint32_t nxt[16];
+    auto fetch = [&](size_t cursor, bool second) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const bool take = (q == 0 || second) && cursor + q < n_words;
+#pragma unroll
+            for (int i = 0; i < 8; i++) nxt[8 * q + i] = take ? __ldg(words + 8 * (cursor + q) + 7 - i) : 0u;
+        }
+    };
+    fetch(wc, ((rounds_left - 1) & 0xFFFFu) != 0);
+    while (row < limit && row < en.cycles) {
+        uint4 *o = reinterpret_cast<uint4 *>(sha_in + 8 * row);
+        o[0] = make_uint4(sha[0], sha[1], sha[2], sha[3]);
+        o[1] = make_uint4(sha[4], sha[5], sha[6], sha[7]);
+        rounds_left = (rounds_left - 1) & 0xFFFFu;
+        const bool last_round = rounds_left == 0;
+        uint32_t m[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) m[i] = nxt[i];
+        if (last_round) {  // :366-377
+            m[8] = 0x80000000u;
+#pragma unroll
+            for (int i = 9; i < 15; i++) m[i] = 0;
+            m[15] = length_in_bits;
+        }
+        wc += last_round ? 1 : 2;
+        row++;
+        if (row < limit && row < en.cycles) fetch(wc, ((rounds_left - 1) & 0xFFFFu) != 0);
+        sha256_compress(sha, m);
+    }
+}
+
+// pass 2, one thread per cycle of a request: the FSM state on entry in closed form, then the cycle itself
+__global__ void __launch_bounds__(128)
+cu_rows_kernel(CuDev *d, const zkc_decommit_query *__restrict__ requests, const uint32_t *__restrict__ words,
+               const CuPlan *__restrict__ starts, const uint32_t *__restrict__ sha_in, const uint64_t *__restrict__ heads,
+               uint64_t *__restrict__ push_enc, uint32_t *__restrict__ slot_meta, uint64_t *__restrict__ trace) {
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t limit = d->limit;
+    const uint32_t n_units = d->n_units;
+    const size_t total = starts[n_units].cycles;
+    if (row >= limit || row >= total) return;
+    // the request this cycle belongs to: the last unit that starts at or before it
+    uint32_t lo = 0, hi = n_units - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (starts[mid].cycles <= row) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t u = lo;
+    const CuPlan st = starts[u];
+    const uint32_t idx = (uint32_t)(row - st.cycles);
+    zkc_code_decommittment_fsm s = d->s0;
+    zkc_decommit_query req = cu_zero_request();
+    if (u >= 1) {
+        req = cu_load_request(requests + (u - 1));
+        if (idx == 0) {
+            s.state_get_from_queue = 1;
+            if (u > 1 || !d->unit0_fresh) s.state_decommit = 0;  // the previous request ended with its finalizing round
+        } else {
+            const uint32_t length_in_words = req.code_hash[7] & 0xFFFFu;
+            s.state_get_from_queue = 0; s.state_decommit = 1;
+            s.num_rounds_left = (((length_in_words + 1) >> 1) - idx) & 0xFFFFu;
+            s.length_in_bits = length_in_words * 256u;
+            s.timestamp = req.timestamp;
+            s.current_page = req.page;
+#pragma unroll
+            for (int i = 0; i < 7; i++) s.hash_to_compare_against[i] = req.code_hash[i];
+            s.hash_to_compare_against[7] = 0;
+            s.current_index = 2 * idx;
+        }
+    } else if (idx > 0) {
+        s.state_get_from_queue = 0; s.state_decommit = 1;
+        s.num_rounds_left = (d->s0.num_rounds_left - idx) & 0xFFFFu;
+        s.current_index = d->s0.current_index + 2 * idx;
+    }
+    if (idx > 0 || u == 0) {
+        const uint4 *in = reinterpret_cast<const uint4 *>(sha_in + 8 * row);
+        const uint4 a = in[0], b = in[1];
+        s.sha256_inner_state[0] = a.x; s.sha256_inner_state[1] = a.y; s.sha256_inner_state[2] = a.z; s.sha256_inner_state[3] = a.w;
+        s.sha256_inner_state[4] = b.x; s.sha256_inner_state[5] = b.y; s.sha256_inner_state[6] = b.z; s.sha256_inner_state[7] = b.w;
+    }
+    const uint32_t len_after = d->rq0.length - u;
+    if (trace) {
+        for (int i = 0; i < 11; i++) trace[(size_t)(ZKC_CU_REQUEST + i) * limit + row] = (idx == 0 && u >= 1) ? cu_flat_request(req, i) : 0;
+        for (int i = 0; i < 12; i++) trace[(size_t)(ZKC_CU_REQ_HEAD + i) * limit + row] = heads[12 * (size_t)u + i];
+        trace[(size_t)ZKC_CU_REQ_LEN * limit + row] = len_after;
+    }
+    size_t word_cursor = (size_t)st.words + 2 * (size_t)idx;
+    uint32_t push_ordinal = st.words + 2 * idx;
+    uint32_t checks = 0;
+    cu_cycle(s, (idx == 0 && u >= 1) ? req : cu_zero_request(), true, len_after == 0, words, d->n_code_words, word_cursor, push_enc,
+             slot_meta, push_ordinal, trace, limit, row, checks);
+    cu_report(d, row, checks);
+    if (row == limit - 1) d->s_final = s;
+    if (row == total - 1) d->s_last = s;
 }
 
 // the rows after the last request: the FSM idles (or reports that it wanted a request nobody supplied), row-parallel
@@ -468,7 +550,8 @@ extern "C" int zkc_code_unpacker_entry_point(zkc_ctx *ctx, zkc_code_unpacker_clo
     if (!have_states) n_memory_states = max_pushes;
     size_t bytes = zkc_carver::bytes(1, sizeof(CuDev)) + zkc_carver::bytes(1, sizeof(ScanGlobal)) +
                    zkc_carver::bytes(tiles + 1, sizeof(TileStateT<CuPlan>)) + zkc_carver::bytes(max_units + 2, sizeof(CuPlan)) +
-                   zkc_carver::bytes(max_pushes * 8, 8) + zkc_carver::bytes(2 * limit + 8, 4);
+                   zkc_carver::bytes(max_pushes * 8, 8) + zkc_carver::bytes(2 * limit + 8, 4) + zkc_carver::bytes(8 * limit + 8, 4) +
+                   zkc_carver::bytes(12 * (max_units + 1), 8);
     if (!in_dev) bytes += zkc_carver::bytes(n_requests + 1, sizeof(zkc_decommit_query)) + zkc_carver::bytes(n_requests * 12 + 12, 8) +
                           zkc_carver::bytes(n_code_words * 8 + 8, 4);
     if (!in_dev || !have_states) bytes += zkc_carver::bytes(n_memory_states * 12 + 12, 8);
@@ -485,6 +568,8 @@ extern "C" int zkc_code_unpacker_entry_point(zkc_ctx *ctx, zkc_code_unpacker_clo
     CuPlan *starts = cv.take<CuPlan>(max_units + 2);
     uint64_t *push_enc = cv.take<uint64_t>(max_pushes * 8);
     uint32_t *slot_meta = cv.take<uint32_t>(2 * limit + 8);
+    uint32_t *sha_in = cv.take<uint32_t>(8 * limit + 8);
+    uint64_t *heads = cv.take<uint64_t>(12 * (max_units + 1));
     cudaStream_t s = ctx->stream;
     memset(h, 0, sizeof(CuDev));
     h->io = *io;
@@ -519,7 +604,9 @@ extern "C" int zkc_code_unpacker_entry_point(zkc_ctx *ctx, zkc_code_unpacker_clo
     ZKC_LAUNCH(ctx, "cu_prologue", cu_prologue_kernel, 1, 96, 0, d);
     ZKC_LAUNCH(ctx, "cu_plan", cu_plan_kernel, (unsigned)tiles, SCAN_THREADS, 0, d, dreq, starts, sg, ts);
     if (limit) {
-        ZKC_LAUNCH(ctx, "cu_requests", cu_requests_kernel, (unsigned)((max_units + 127) / 128), 128, 0, d, dreq, dprev, dwords, starts,
+        ZKC_LAUNCH(ctx, "cu_chain", cu_chain_kernel, (unsigned)((max_units + 127) / 128), 128, 0, d, dreq, dprev, dwords, starts, sha_in,
+                   heads);
+        ZKC_LAUNCH(ctx, "cu_rows", cu_rows_kernel, (unsigned)((limit + 127) / 128), 128, 0, d, dreq, dwords, starts, sha_in, heads,
                    push_enc, slot_meta, dtrace);
         ZKC_LAUNCH(ctx, "cu_tail", cu_tail_kernel, (unsigned)((limit + 127) / 128), 128, 0, d, starts, slot_meta, dtrace, push_enc);
         if (!have_states) ZKC_LAUNCH(ctx, "cu_mem_chain", (pc_mem_chain_kernel<CuDev, 2>), 1, 32, 0, d, push_enc, slot_meta, (uint64_t *)dstates);

@@ -248,7 +248,7 @@ def cu(eng):
         ms, got = timed(run, steps=5, warmup=2)
         eng.profile(True)
         run()
-        prof = {k: eng.profile_query(k)[0] for k in ("cu_requests", "cu_memq", "cu_tail", "cu_plan", "cu_prologue", "cu_finalize")}
+        prof = {k: eng.profile_query(k)[0] for k in ("cu_chain", "cu_rows", "cu_memq", "cu_tail", "cu_plan", "cu_prologue", "cu_finalize")}
         eng.profile(False)
         print(json.dumps({"config": f"code_unpacker_sha256, {n} requests, {len(words)} words, {cycles} cycles", "gpu_ms_with_memory_states": ms,
                           "cycles_per_s": cycles / ms * 1e3, "MB_of_code_per_s": len(words) * 32 / ms / 1e3,
