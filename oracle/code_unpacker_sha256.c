@@ -6,8 +6,10 @@
  *   CodeDecommittmentFSM                  /root/reference/src/code_unpacker_sha256/input.rs:27-38
  *   ConditionalWitnessAllocator           /root/reference/src/storage_application/mod.rs:95-229
  * ContractCodeSha256::VERSION_BYTE (= 1) is from the un-vendored zkevm_opcode_defs.
- * Pinning: the SHA-256 the FSM computes over the unpacked words is pinned against hashlib (tests/test_oracle_code_unpacker.py:
- * a request is satisfiable exactly when its hash is the SHA-256 of its code); queue states / commitments PARITY UNPINNED
+ * Pinning: pinned by the reference's own vector (test_code_unpacker_inner, mod.rs:472-700: one request, 33 words, limit 40,
+ * extracted to tests/golden/code_unpacker_vector.json): every enforcement holds -- the versioned-hash format, word order,
+ * padding and the hash comparison among them -- the requests queue ends empty and the memory queue equals the queue of the 33
+ * writes the test rebuilds; the SHA-256 is additionally pinned against hashlib.  Queue-state / commitment VALUES: PARITY UNPINNED
  * (Poseidon2, see poseidon2.c).
  */
 #include "oracle.h"

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import orc as O
+import vectors as V
 from era_zkevm_circuits_b200 import (CodeDecommitterCircuitInstanceWitness as Witness, abi, synthetic,
                                      unpack_code_into_memory_entry_point as entry_point)
 
@@ -38,6 +39,17 @@ def run_both(engine, orc, io, reqs, prev, words, limit, states=None, **kw):
     want = O.code_unpacker_entry_point(orc, io, reqs, words, limit)
     got = entry_point(engine, Witness(io, reqs, prev, words, states), limit, raise_on_unsatisfied=False, **kw)
     return want, got
+
+
+def test_reference_vector(engine, orc):
+    """/root/reference/src/code_unpacker_sha256/mod.rs:472-700: 1 request, 33 words, limit 40"""
+    reqs, words = V.code_unpacker_reference_vector()
+    io, prev = instance(orc, reqs)
+    want, got = run_both(engine, orc, io, reqs, prev, words, 40)
+    assert want[0] == abi.ZKC_OK and want[1].completion_flag == 1
+    assert_same(want, got)
+    want, got = run_both(engine, orc, io, reqs, prev, words, 40, states=want[5])
+    assert_same(want, got)
 
 
 @pytest.mark.parametrize("n,max_words,extra", [(1, 1, 0), (1, 9, 3), (5, 15, 0), (40, 31, 7), (300, 63, 100), (3, 1001, 1)])

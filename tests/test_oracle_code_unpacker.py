@@ -6,6 +6,7 @@ import hashlib
 import numpy as np
 
 import orc as O
+import vectors as V
 from era_zkevm_circuits_b200 import abi, synthetic
 
 K = abi.CU_COLS
@@ -15,6 +16,28 @@ CHK = abi.CU_CHK
 def instance(orc, reqs):
     prev, fin = O.decommit_queue_simulate(orc, reqs)
     return O.code_unpacker_closed_form(fin, None, True), prev
+
+
+def test_reference_vector_is_satisfied(orc):
+    """the reference's own test: 1 request, 33 words, limit 40; every enforcement holds (the hash check among them), the requests
+    queue ends empty and the memory queue equals the queue of the 33 writes (mod.rs:600-615)"""
+    reqs, words = V.code_unpacker_reference_vector()
+    assert int(reqs["code_hash"][0][7]) == (abi.CODE_HASH_VERSION_TOP16 << 16) | 33
+    io, _ = instance(orc, reqs)
+    rc, out, trace, com, st, states = O.code_unpacker_entry_point(orc, io, reqs, words, 40)
+    assert rc == abi.ZKC_OK and st.failed_checks == 0
+    assert out.completion_flag == 1 and out.hidden_fsm_output.decommittment_requests_queue_state.length == 0
+    assert trace[K["FINALIZE"]].tolist() == [0] * 16 + [1] + [0] * 23
+    mq = np.zeros(33, dtype=abi.MEMORY_QUERY_DTYPE)
+    mq["timestamp"], mq["memory_page"], mq["index"], mq["rw_flag"], mq["value"] = 40973, 2368, np.arange(33), 1, words
+    prev = np.zeros((33, 12), dtype=np.uint64)
+    fin = abi.QueueState12()
+    orc.orc_memory_queue_simulate(O.p(mq), 33, O.p(prev), O.C.byref(fin))
+    assert list(fin.tail) == list(out.memory_queue_final_state.tail) and out.memory_queue_final_state.length == 33
+    # a flipped bit of the code is caught by the hash comparison of the finalizing round
+    w2 = words.copy(); w2[20, 2] ^= 1
+    rc, _, _, _, st, _ = O.code_unpacker_entry_point(orc, io, reqs, w2, 40)
+    assert st.failed_checks == CHK["HASH"] and st.first_bad_row == 16
 
 
 def test_single_request_sha256_and_memory_writes(orc):

@@ -91,3 +91,14 @@ def sort_decommittments_reference_vector():
 def demux_reference_vector():
     """witness_input_unsorted, /root/reference/src/demux_log_queue/mod.rs:602-923"""
     return log_queries_from_fixture(_fixture("demux_log_queue_vector.json")["records"])[0]
+
+
+def code_unpacker_reference_vector():
+    """test_code_unpacker_inner, /root/reference/src/code_unpacker_sha256/mod.rs:472-700: one request (versioned code hash,
+    page 2368, timestamp 40973) and its 33 bytecode words.  Returns (requests [1], code_words [33, 8] uint32 limbs)."""
+    f = _fixture("code_unpacker_vector.json")
+    req = np.zeros(1, dtype=abi.DECOMMIT_QUERY_DTYPE)
+    req["code_hash"][0] = _limbs(int(f["code_hash"]), 8)
+    req["page"], req["is_first"], req["timestamp"] = f["page"], f["is_first"], f["timestamp"]
+    words = np.array([_limbs(int(w), 8) for w in f["code_words"]], dtype=np.uint32)
+    return req, words

@@ -4,6 +4,7 @@
   /root/reference/src/storage_validity_by_grand_product/test_input.rs -> storage_validity_vector.json
   /root/reference/src/sort_decommittment_requests/mod.rs:565-1390      -> sort_decommittments_vector.json
   /root/reference/src/demux_log_queue/mod.rs:602-923                   -> demux_log_queue_vector.json
+  /root/reference/src/code_unpacker_sha256/mod.rs:632-700              -> code_unpacker_vector.json
 Run in the build container (the reference is not present on the GPU box); only the extracted DATA is
 committed, no reference source.  Values are kept as decimal strings / ints exactly as written there."""
 import json
@@ -90,6 +91,15 @@ def main():
                "records": parse_queries(split_fn(dm, "witness_input_unsorted"))}
     assert len(fixture["records"]) >= 8, len(fixture["records"])
     json.dump(fixture, open(os.path.join(OUT, "demux_log_queue_vector.json"), "w"), indent=1)
+    cu = open(os.path.join(REF, "code_unpacker_sha256", "mod.rs")).read()
+    req = re.search(r"page:\s*(\d+),\s*is_first:\s*(true|false),\s*timestamp:\s*(\d+)", split_fn(cu, "create_request_queue_witness"))
+    fixture = {"source": "reference src/code_unpacker_sha256/mod.rs test_code_unpacker_inner (:472, limit 40): get_code_hash_witness, "
+                         "get_byte_code_witness, create_request_queue_witness",
+               "code_hash": re.search(r'from_dec_str\(\s*"(\d+)"', split_fn(cu, "get_code_hash_witness"), re.S).group(1),
+               "page": int(req.group(1)), "is_first": int(req.group(2) == "true"), "timestamp": int(req.group(3)),
+               "code_words": re.findall(r'"(\d+)"', split_fn(cu, "get_byte_code_witness"))}
+    assert len(fixture["code_words"]) == 33, len(fixture["code_words"])
+    json.dump(fixture, open(os.path.join(OUT, "code_unpacker_vector.json"), "w"), indent=1)
     print("ok")
 
 
