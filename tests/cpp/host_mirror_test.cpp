@@ -3,7 +3,8 @@
 // push the inputs into fresh queues, run the entry point, check the outcome.  TEST INFRASTRUCTURE: links oracle/liborc.so as
 // the checker.
 //   host_mirror_test nodevice   no GPU required: the engine must refuse to start (no CPU fallback) and say why
-//   host_mirror_test parity     on a GPU: ram_permutation, sort_decommittment_requests, demux_log_queue bit-exact vs the oracle
+//   host_mirror_test parity     on a GPU: ram_permutation, sort_decommittment_requests, demux_log_queue, code_unpacker_sha256
+//                               bit-exact vs the oracle
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -187,6 +188,54 @@ static void demux_parity(Engine &e) {
                 counts[4], counts[5]);
 }
 
+static void code_unpacker_parity(Engine &e) {
+    // three bytecodes of 5, 1 and 9 words; versioned hash = SHA-256 of the code with the top 4 bytes replaced (mod.rs:187-213)
+    const size_t lens[3] = {5, 1, 9};
+    uint64_t seed = 0xCD;
+    CodeDecommitterCircuitInstanceWitness w;
+    size_t rounds = 0;
+    for (size_t k = 0; k < 3; k++) {
+        std::vector<uint32_t> be;  // the code as big-endian u32 words, the way SHA-256 consumes it
+        for (size_t i = 0; i < lens[k]; i++) {
+            std::array<uint32_t, 8> limbs;
+            for (auto &l : limbs) l = (uint32_t)sm64(seed);
+            w.code_words.push_back(limbs);
+            for (int j = 7; j >= 0; j--) be.push_back(limbs[j]);
+        }
+        be.push_back(0x80000000u);
+        while (be.size() % 16 != 15) be.push_back(0);
+        be.push_back((uint32_t)(lens[k] * 256));
+        uint32_t st[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+        for (size_t b = 0; b < be.size(); b += 16) orc_sha256_compress(st, be.data() + b);
+        zkc_decommit_query q;
+        std::memset(&q, 0, sizeof q);
+        for (int i = 0; i < 7; i++) q.code_hash[i] = st[7 - i];
+        q.code_hash[7] = (ZKC_CODE_HASH_VERSION_TOP16 << 16) | (uint32_t)lens[k];
+        q.page = 2048 + 8 * (uint32_t)k; q.timestamp = 77 + (uint32_t)k; q.is_first = 1;
+        w.sorted_requests_queue_witness.push_back(q);
+        rounds += (lens[k] + 1) / 2;
+    }
+    const size_t limit = rounds + 3;
+    w.closed_form_input.start_flag = 1;
+    w.closed_form_input.sorted_requests_queue_initial_state =
+        decommit_queue_simulate(e, w.sorted_requests_queue_witness, w.sorted_requests_queue_prev_states);
+    zkc_code_unpacker_closed_form io = w.closed_form_input;
+    std::vector<uint64_t> trace((size_t)ZKC_CU_NUM_COLS * limit), states(12 * (2 * limit + 1));
+    size_t n_states = 0;
+    uint64_t com[4];
+    zkc_status st;
+    const int rc = orc_code_unpacker_entry_point(&io, w.sorted_requests_queue_witness.data(), 3, w.code_words.front().data(),
+                                                 w.code_words.size(), limit, nullptr, trace.data(), states.data(), &n_states, com, &st);
+    CHECK(rc == ZKC_OK && io.completion_flag == 1 && n_states == 15);
+    const auto got = unpack_code_into_memory_entry_point(e, w, limit);
+    CHECK(got.status.code == ZKC_OK);
+    CHECK(std::memcmp(com, got.commitment.data(), 32) == 0);
+    CHECK(same_bytes(io.hidden_fsm_output, got.closed_form_input.hidden_fsm_output));
+    CHECK(same_bytes(io.memory_queue_final_state, got.closed_form_input.memory_queue_final_state));
+    CHECK(std::memcmp(trace.data(), got.trace.data(), trace.size() * 8) == 0);
+    std::printf("code_unpacker_sha256: 3 bytecodes, %zu words, %zu cycles\n", w.code_words.size(), limit);
+}
+
 int main(int argc, char **argv) {
     const std::string mode = argc > 1 ? argv[1] : "nodevice";
     std::printf("%s\n", Engine::version().c_str());
@@ -211,6 +260,7 @@ int main(int argc, char **argv) {
     ram_parity(e);
     decommit_parity(e);
     demux_parity(e);
+    code_unpacker_parity(e);
     std::printf(failures ? "%d check(s) FAILED\n" : "all checks passed\n", failures);
     return failures ? 1 : 0;
 }
