@@ -44,6 +44,16 @@ from .main_vm import (  # noqa: F401
     main_vm_check_trace,
     main_vm_entry_point,
     main_vm_entry_point_batch,
+    main_vm_entry_point_columns,
+    main_vm_rows_to_columns,
+    VmColumnInputs,
+    VmPackedTraceBuffers,
+    main_vm_entry_point_stream,
+    vm_decode_input_stream,
+    vm_encode_input_stream,
+    vm_expand_packed_trace,
+    vm_packed_layout,
+    vm_packed_trace_buffers,
     main_vm_initial_state,
     main_vm_simulate,
 )

@@ -206,6 +206,42 @@ class VmOptions(C.Structure):
                 ("sponge_records", C.c_void_p)]
 
 
+class VmColumns(C.Structure):
+    """zkc_vm_columns: the per-cycle inputs as device-resident columns (struct of arrays)"""
+    _fields_ = [("state_words", C.c_void_p), ("state_stride", C.c_size_t), ("witness_words", C.c_void_p), ("witness_stride", C.c_size_t)]
+
+
+VM_STATE_WORDS, VM_WITNESS_WORDS = 294, 44
+
+
+class VmSegmentHeader(C.Structure):
+    """zkc_vm_segment_header: the first bytes of a segment blob of the input stream"""
+    _fields_ = [(n, C.c_uint32) for n in (
+        "magic", "first_cycle", "n_cycles", "n_dense_state", "n_dense_witness", "n_sparse_state", "n_sparse_witness", "reserved",
+        "off_dense_state_word", "off_dense_witness_word", "off_dense_state", "off_dense_witness",
+        "off_sparse_state_offsets", "off_sparse_state_index", "off_sparse_state_value",
+        "off_sparse_witness_offsets", "off_sparse_witness_index", "off_sparse_witness_value", "blob_bytes", "reserved2")]
+
+
+class VmInputSegment(C.Structure):
+    _fields_ = [("blob", C.c_void_p), ("blob_bytes", C.c_uint64)]
+
+
+class VmInputStream(C.Structure):
+    _fields_ = [("limit", C.c_uint64), ("segment_cycles", C.c_uint32), ("n_segments", C.c_uint32), ("segments", C.POINTER(VmInputSegment))]
+
+
+class VmPackedTrace(C.Structure):
+    _fields_ = [("cols8", C.c_void_p), ("cols16", C.c_void_p), ("cols32", C.c_void_p), ("cols64", C.c_void_p),
+                ("aux_records", C.c_void_p), ("aux_capacity", C.c_uint64), ("n_aux_records", C.c_uint64),
+                ("sponge_records", C.c_void_p), ("sponge_capacity", C.c_uint64), ("n_sponge_records", C.c_uint64)]
+
+
+VM_SEGMENT_MAGIC = 0x5a4b5347
+VM_TRACE_PACKED = 2
+VM_PK_U8, VM_PK_U16, VM_PK_U32, VM_PK_U64, VM_PK_AUX_RECORD, VM_PK_SPONGE_RECORD = range(6)
+VM_AUX_RECORD_DTYPE = np.dtype([("row", "<u4"), ("reserved", "<u4"), ("op_aux", "<u8", (48,)), ("queue_ends", "<u8", (10,))])
+assert VM_AUX_RECORD_DTYPE.itemsize == 472 and C.sizeof(VmSegmentHeader) == 80
 VM_SPONGE_RECORD_DTYPE = np.dtype([("row", "<u4"), ("slot", "<u4"), ("out", "<u8", (12,))])
 assert VM_SPONGE_RECORD_DTYPE.itemsize == 104
 VM_TRACE_DENSE, VM_TRACE_COMPACT = 0, 1
@@ -447,6 +483,14 @@ SIGNATURES = {
                                           C.POINTER(VmOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
     "zkc_main_vm_entry_point_batch": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(VmIsa), _vp, _vp, _vp, C.c_size_t, C.c_size_t,
                                                 C.POINTER(VmOptions), C.c_int, _vp, _vp, _vp]),
+    "zkc_main_vm_entry_point_columns": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(VmIsa), C.POINTER(VmColumns), _vp, C.c_size_t, C.c_size_t,
+                                                  C.POINTER(VmOptions), C.c_int, _vp, _vp, _vp]),
+    "zkc_vm_encode_input_stream": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.POINTER(C.POINTER(VmInputStream)), _u64p]),
+    "zkc_vm_input_stream_free": (None, [C.POINTER(VmInputStream)]),
+    "zkc_vm_packed_layout": (None, [_vp, _vp, _vp]),
+    "zkc_main_vm_entry_point_stream": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t,
+                                                 C.POINTER(VmOptions), C.POINTER(VmPackedTrace), _vp, _vp]),
+    "zkc_main_vm_rows_to_columns": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t]),
     "zkc_main_vm_check_trace": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, C.c_size_t, C.c_size_t, C.c_int, _u64p, C.POINTER(Status)]),
     "zkc_main_vm_initial_state": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), C.POINTER(VmState)]),
     "zkc_main_vm_simulate": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp,

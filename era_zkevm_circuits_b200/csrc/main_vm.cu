@@ -533,11 +533,12 @@ __device__ void vm_log_encode(const uint32_t *address, const uint32_t *key, cons
 // the callstack witness, sponges run at once into `so`; otherwise answers come from `w` / `cw` and the sponges are
 // emitted as jobs into `penc`.  trace / limit / row: where to put the row (trace may be null; the sponge columns are
 // written by whoever runs the sponges).  next: the following snapshot (circuit mode; forward tail column only).
-template <bool SIM, typename W>
-__device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_vm_closed_form *gc, const zkc_vm_state &s, VmDelta &d, zkc_vm_context &nctx, W &w,
-                                 const zkc_vm_callstack_witness *__restrict__ cw, uint32_t n_cw, VmSim *sim, VmSimOut *so,
-                                 uint64_t *penc, const zkc_vm_state *next, uint64_t *__restrict__ trace, size_t limit, size_t row,
-                                 int aux_base = ZKC_VM_OP_AUX) {
+template <bool SIM, typename W, typename RS>
+__device__ __forceinline__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_vm_closed_form *gc, const zkc_vm_state &s, const RS &regs,
+                                                 VmDelta &d, zkc_vm_context &nctx, W &w,
+                                                 const zkc_vm_callstack_witness *__restrict__ cw, uint32_t n_cw, VmSim *sim, VmSimOut *so,
+                                                 uint64_t *penc, const uint64_t *next_fwd_tail, uint64_t *__restrict__ trace, size_t limit, size_t row,
+                                                 int aux_base = ZKC_VM_OP_AUX) {
 #define TR(col) trace[(size_t)(col) * limit + row]
     const bool wr = trace != nullptr;
     uint32_t checks = 0;
@@ -638,10 +639,10 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
         TR(ZKC_VM_IMM0) = imm0; TR(ZKC_VM_IMM1) = imm1;
     }
     // ---- operands -------------------------------------------------------------------------------------------------
-    const zkc_vm_register draft_src0 = src0_r ? s.registers[src0_r - 1] : reg_zero();
-    const zkc_vm_register src1_register = src1_r ? s.registers[src1_r - 1] : reg_zero();
+    const zkc_vm_register draft_src0 = src0_r ? regs.get(src0_r - 1) : reg_zero();
+    const zkc_vm_register src1_register = src1_r ? regs.get(src1_r - 1) : reg_zero();
     const uint32_t src0_low = draft_src0.value[0] & 0xFFFF;
-    const uint32_t dst0_low = (dst0_r ? s.registers[dst0_r - 1].value[0] : 0u) & 0xFFFF;
+    const uint32_t dst0_low = (dst0_r ? regs.low(dst0_r - 1) : 0u) & 0xFFFF;
     const uint32_t current_sp = ctx.sp, stack_page = ctx.base_page + 1, heap_page = ctx.base_page + 2, aux_heap_page = ctx.base_page + 3;
     const bool is_nop = TYPE(ZKC_OP_NOP);
     uint32_t src_page, src_index, sp_after_src0;
@@ -1097,7 +1098,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
             nctx.is_static_execution = is_static_call || cur_e.is_static_execution;
             nctx.is_kernel_mode = is_delegated ? cur_e.is_kernel_mode : (uint32_t)target_is_kernel;
             nctx.code_shard_id = dest_shard; nctx.this_shard_id = is_delegated ? caller_shard : dest_shard; nctx.caller_shard_id = caller_shard;
-            const zkc_vm_register &mimic_reg = s.registers[isa->call_implicit_parameter_reg_idx < ZKC_VM_REGISTERS ? isa->call_implicit_parameter_reg_idx : 0];
+            const zkc_vm_register mimic_reg = regs.get(isa->call_implicit_parameter_reg_idx < ZKC_VM_REGISTERS ? isa->call_implicit_parameter_reg_idx : 0);
             for (int i = 0; i < 5; i++) {
                 nctx.code_address[i] = b.v[i];
                 nctx.this_address[i] = is_delegated ? cur_e.this_address[i] : b.v[i];
@@ -1257,7 +1258,7 @@ __device__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ isa, const zkc_v
             uint64_t ft = d.fwd_tail_kind == 2 ? d.fwd_tail[i] : ctx.log_queue_forward_tail[i];
             if (d.fwd_tail_kind == 1) {
                 if constexpr (SIM) ft = so->fwd_tail[i];
-                else ft = next->current_context.log_queue_forward_tail[i];
+                else ft = next_fwd_tail[i];
             }
             TR(ZKC_VM_FORWARD_TAIL_OUT + i) = ft;
             TR(ZKC_VM_ROLLBACK_HEAD_OUT + i) = rep ? nctx.reverted_queue_head[i] : d.rb_head[i];
@@ -1287,7 +1288,7 @@ __global__ void vm_prologue_kernel(VmDev *devs, const zkc_vm_isa *isa, size_t n_
     d->start = d->io.start_flag != 0;
     if (d->start) vm_initial_bootloader_state(d->io, *isa, d->s0);  // mod.rs:85-97
     else d->s0 = d->io.hidden_fsm_input;
-    d->s_final = d->s0;
+    if (d->limit == 0) d->s_final = d->s0;  // with cycles, the last cycle's thread writes it (concurrently with this side-stream launch)
 }
 
 __device__ __forceinline__ void vm_report(VmDev *d, size_t row, uint32_t checks) {
@@ -1295,74 +1296,6 @@ __device__ __forceinline__ void vm_report(VmDev *d, size_t row, uint32_t checks)
     atomicOr(&d->failed_checks, checks);
     atomicMin(&d->first_bad, ((unsigned long long)row << 16) | checks);
 }
-
-// ---- one thread per cycle (of any instance of the batch) -----------------------------------------------------------------
-constexpr int VM_WORDS = (int)(sizeof(zkc_vm_state) / 4);
-constexpr int VM_DIFF_WORDS = (VM_WORDS + 31) / 32;
-static_assert(sizeof(zkc_vm_state) == 1176 && VM_DIFF_WORDS == 10, "snapshot layout");
-#define VW(f) ((int)(offsetof(zkc_vm_state, f) / 4))
-#define VWC(f) ((int)((offsetof(zkc_vm_state, current_context) + offsetof(zkc_vm_context, f)) / 4))
-
-struct VmMask { uint32_t w[VM_DIFF_WORDS]; };
-__host__ __device__ constexpr VmMask vm_mask_clear(VmMask m, int lo, int n) {
-    for (int i = lo; i < lo + n; i++) m.w[i >> 5] &= ~(1u << (i & 31));
-    return m;
-}
-__host__ __device__ constexpr VmMask vm_mask_set(VmMask m, int lo, int n) {
-    for (int i = lo; i < lo + n; i++) m.w[i >> 5] |= 1u << (i & 31);
-    return m;
-}
-// the words of the current context a cycle that keeps its frame may NOT change: everything except the alignment hole
-// and the scalars / queue ends that are compared with their expected values
-__host__ __device__ constexpr VmMask vm_ctx_keep_mask() {
-    VmMask m{};
-    m = vm_mask_set(m, VW(current_context), (int)(sizeof(zkc_vm_context) / 4));
-    m = vm_mask_clear(m, VWC(aux_heap_upper_bound) + 1, 1);  // alignment hole in front of reverted_queue_head
-    m = vm_mask_clear(m, VWC(pc), 1);
-    m = vm_mask_clear(m, VWC(sp), 1);
-    m = vm_mask_clear(m, VWC(ergs_remaining), 1);
-    m = vm_mask_clear(m, VWC(heap_upper_bound), 2);
-    m = vm_mask_clear(m, VWC(reverted_queue_head), 8);
-    m = vm_mask_clear(m, VWC(reverted_queue_segment_len), 1);
-    m = vm_mask_clear(m, VWC(log_queue_forward_part_length), 1);
-    m = vm_mask_clear(m, VWC(log_queue_forward_tail), 8);
-    return m;
-}
-// words outside the context that may only change through an explicit flag of the delta: not padding, not a register,
-// not one of the per-cycle scalars (compared with their expected value), not a sponge-derived queue state
-__host__ __device__ constexpr VmMask vm_keep_mask() {
-    VmMask m{};
-    m = vm_mask_set(m, 0, VM_WORDS);
-    m = vm_mask_clear(m, VW(_pad), VW(current_context) - VW(_pad));  // _pad + the alignment hole behind it
-    m = vm_mask_clear(m, VW(current_context), (int)(sizeof(zkc_vm_context) / 4));
-    m = vm_mask_clear(m, VW(previous_code_word), 8);
-    m = vm_mask_clear(m, VW(registers), 9 * ZKC_VM_REGISTERS);
-    m = vm_mask_clear(m, VW(flags), 3);
-    m = vm_mask_clear(m, VW(timestamp), 1);
-    m = vm_mask_clear(m, VW(previous_code_page), 1);
-    m = vm_mask_clear(m, VW(previous_super_pc), 1);
-    m = vm_mask_clear(m, VW(pending_exception), 1);
-    m = vm_mask_clear(m, VW(memory_queue_length), 1);
-    m = vm_mask_clear(m, VW(context_stack_depth), 1);
-    m = vm_mask_clear(m, VW(memory_queue_state), 24);
-    m = vm_mask_clear(m, VW(stack_sponge_state), 24);
-    m = vm_mask_clear(m, VW(code_decommittment_queue_state), 24);
-    m = vm_mask_clear(m, VW(code_decommittment_queue_length), 1);
-    m = vm_mask_clear(m, VW(memory_page_counter), 1);
-    return m;
-}
-__host__ __device__ constexpr VmMask vm_decommit_mask() { return vm_mask_set(VmMask{}, VW(code_decommittment_queue_state), 24); }
-__host__ __device__ constexpr VmMask vm_memq_mask() { return vm_mask_set(VmMask{}, VW(memory_queue_state), 24); }
-__host__ __device__ constexpr VmMask vm_stack_mask() { return vm_mask_set(VmMask{}, VW(stack_sponge_state), 24); }
-__host__ __device__ constexpr VmMask vm_fwd_tail_mask() { return vm_mask_set(VmMask{}, VWC(log_queue_forward_tail), 8); }
-static_assert(offsetof(zkc_vm_context, reverted_queue_head) == offsetof(zkc_vm_context, aux_heap_upper_bound) + 8, "context hole");
-template <int K> struct VmKeepWord { static constexpr uint32_t value = vm_keep_mask().w[K]; };
-template <int K> struct VmCtxKeepWord { static constexpr uint32_t value = vm_ctx_keep_mask().w[K]; };
-template <int K> struct VmMemqWord { static constexpr uint32_t value = vm_memq_mask().w[K]; };
-template <int K> struct VmStackWord { static constexpr uint32_t value = vm_stack_mask().w[K]; };
-template <int K> struct VmFwdTailWord { static constexpr uint32_t value = vm_fwd_tail_mask().w[K]; };
-template <int K> struct VmDecommitWord { static constexpr uint32_t value = vm_decommit_mask().w[K]; };
-#define VM_FOR10(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 
 __device__ __forceinline__ bool reg_equal(const zkc_vm_register &a, const zkc_vm_register &b) {
     bool eq = a.is_pointer == b.is_pointer;
@@ -1385,6 +1318,63 @@ __device__ bool vm_record_equal(const zkc_vm_context &c, const zkc_vm_context &e
     return eq;
 }
 
+// ---- one thread per cycle (of any instance of the batch) -----------------------------------------------------------------
+// The per-cycle inputs live in HBM as COLUMNS (struct of arrays): word w of snapshot i at st[w * st_stride + i], word w of the
+// oracle answers of cycle g at wt[w * wt_stride + g].  A warp's 32 consecutive cycles then read every word they need as ONE
+// 128-byte line -- the snapshot is 294 lines per warp instead of 32 records 1 176 bytes apart -- and "snapshot i + 1" is the
+// neighbouring element of the same lines.  Row-major (array of structs) inputs are transposed once per call
+// (vm_rows_to_columns_kernel); the host-buffer path expands its transport stream straight into this layout.
+constexpr int VM_WORDS = (int)(sizeof(zkc_vm_state) / 4);
+constexpr int VM_WIT_WORDS = (int)(sizeof(zkc_vm_cycle_witness) / 4);
+static_assert(sizeof(zkc_vm_state) == 1176 && sizeof(zkc_vm_cycle_witness) == 176, "snapshot / witness layout");
+static_assert(VM_WORDS == ZKC_VM_STATE_WORDS && VM_WIT_WORDS == ZKC_VM_WITNESS_WORDS, "header constants");
+#define VW(f) ((int)(offsetof(zkc_vm_state, f) / 4))
+#define VWC(f) ((int)((offsetof(zkc_vm_state, current_context) + offsetof(zkc_vm_context, f)) / 4))
+#define WW(f) ((int)(offsetof(zkc_vm_cycle_witness, f) / 4))
+static_assert(offsetof(zkc_vm_context, reverted_queue_head) == offsetof(zkc_vm_context, aux_heap_upper_bound) + 8, "context hole");
+
+struct VmCols {
+    const uint32_t *st; size_t st_stride;
+    const uint32_t *wt; size_t wt_stride;
+    __device__ __forceinline__ uint32_t sw(int w, size_t idx) const { return __ldg(st + (size_t)w * st_stride + idx); }
+    __device__ __forceinline__ uint64_t sw64(int w, size_t idx) const {
+        return (uint64_t)__ldg(st + (size_t)w * st_stride + idx) | ((uint64_t)__ldg(st + (size_t)(w + 1) * st_stride + idx) << 32);
+    }
+    __device__ __forceinline__ uint32_t ww(int w, size_t g) const { return __ldg(wt + (size_t)w * wt_stride + g); }
+};
+// the registers of snapshot idx, fetched on demand (a cycle reads at most three of the fifteen)
+struct VmRegsOfColumns {
+    const uint32_t *base; size_t stride;  // st + idx
+    __device__ __forceinline__ zkc_vm_register get(uint32_t r) const {
+        const uint32_t *p = base + (size_t)(VW(registers) + 9 * (int)r) * stride;
+        zkc_vm_register v;
+        v.is_pointer = __ldg(p);
+#pragma unroll
+        for (int i = 0; i < 8; i++) v.value[i] = __ldg(p + (size_t)(1 + i) * stride);
+        return v;
+    }
+    __device__ __forceinline__ uint32_t low(uint32_t r) const { return __ldg(base + (size_t)(VW(registers) + 9 * (int)r + 1) * stride); }
+};
+// the oracle answers of cycle g, fetched on demand: the member names of zkc_vm_cycle_witness
+struct VmWitWord { const uint32_t *p; __device__ __forceinline__ operator uint32_t() const { return __ldg(p); } };
+struct VmWitArr { const uint32_t *p; size_t stride; __device__ __forceinline__ uint32_t operator[](int i) const { return __ldg(p + (size_t)i * stride); } };
+struct VmWitArr64 {
+    const uint32_t *p; size_t stride;
+    __device__ __forceinline__ uint64_t operator[](int i) const {
+        return (uint64_t)__ldg(p + (size_t)(2 * i) * stride) | ((uint64_t)__ldg(p + (size_t)(2 * i + 1) * stride) << 32);
+    }
+};
+struct VmWitOfColumns {
+    VmWitArr code_word; VmWitWord src0_is_pointer; VmWitArr src0_value; VmWitWord callstack_index, refund, suggested_page;
+    VmWitArr value_a, value_b; VmWitArr64 rollback;
+    __device__ __forceinline__ VmWitOfColumns(const uint32_t *b, size_t s)
+        : code_word{b + WW(code_word) * s, s}, src0_is_pointer{b + WW(src0_is_pointer) * s}, src0_value{b + WW(src0_value) * s, s},
+          callstack_index{b + WW(callstack_index) * s}, refund{b + WW(refund) * s}, suggested_page{b + WW(suggested_page) * s},
+          value_a{b + WW(value_a) * s, s}, value_b{b + WW(value_b) * s, s}, rollback{b + WW(rollback) * s, s} {}
+};
+
+__device__ __forceinline__ uint32_t reg_word(const zkc_vm_register &r, int i) { return i == 0 ? r.is_pointer : r.value[i - 1]; }
+
 // scratch of one batch: what the cycle launch leaves for the sponge launches
 struct VmPushScratch {
     uint32_t *counts;  // [16] (VM_JOB_SLOTS used)
@@ -1404,21 +1394,59 @@ struct VmPushScratch {
     unsigned long long records_capacity;
 };
 
-// Every thread evaluates its cycle from snapshot `row` and checks that snapshot `row + 1` is the result.  The check
-// has two parts.  (1) The warp walks its 32 consecutive snapshot pairs together: lane l compares words l, l+32, ...
-// of snapshot c with snapshot c+1 -- fully coalesced, each snapshot is fetched once -- and the ballots of iteration c
-// (a 294-bit "which words differ" mask) stay with lane c.  (2) The owner then demands that only words its cycle is
-// allowed to change differ, and compares the changed ones (a few scalars, at most two registers, rarely the whole
-// frame) with the values the cycle produced.  The Poseidon2 relations are deferred: the cycle only emits their jobs.
-#ifndef VM_DIFF_GROUP
-#define VM_DIFF_GROUP 8
-#endif
+// Expected value of word w (>= VW(flags), outside the registers and the sponge-derived states) of the NEXT snapshot, given what
+// the cycle produced.  w is a compile-time constant at every call site (unrolled loops): the chain below folds to one case.
+#define CW(f) ((int)(offsetof(zkc_vm_context, f) / 4))
+__device__ __forceinline__ uint32_t vm_half(uint64_t v, int hi) { return hi ? (uint32_t)(v >> 32) : (uint32_t)v; }
+__device__ __forceinline__ uint32_t vm_expected_word(int w, const VmDelta &d, const zkc_vm_context &nctx, const uint64_t (&next_fwd_tail)[4],
+                                                     const uint32_t *cur, size_t stride) {
+#define KEEP __ldg(cur + (size_t)w * stride)
+    if (w >= VW(flags) && w < VW(flags) + 3) return d.flags[w - VW(flags)];
+    if (w == VW(timestamp)) return d.timestamp;
+    if (w == VW(memory_page_counter)) return d.page_counter;
+    if (w == VW(tx_number_in_block)) return KEEP + (d.inc_tx ? 1u : 0u);
+    if (w == VW(previous_code_page)) return d.prev_code_page;
+    if (w == VW(previous_super_pc)) return d.prev_super_pc;
+    if (w == VW(pending_exception)) return d.pending;
+    if (w == VW(ergs_per_pubdata_byte)) return d.set_pubdata ? d.pubdata : KEEP;
+    if (w == VW(context_stack_depth)) return d.depth;
+    if (w == VW(memory_queue_length)) return d.memq_len;
+    if (w == VW(code_decommittment_queue_length)) return d.decommit_len;
+    if (w >= VW(context_composite_u128) && w < VW(context_composite_u128) + 4) return d.set_u128 ? d.u128[(w - VW(context_composite_u128)) & 3] : KEEP;
+    if (w >= VW(current_context)) {
+        const int c = w - VW(current_context);
+        if (c == CW(log_queue_forward_part_length)) return d.fwd_len;
+        if (c >= CW(log_queue_forward_tail)) {  // kind 1: the log's forward sponge (slot 3 / 7) vouches for it
+            const int i = (c - CW(log_queue_forward_tail)) & 7;
+            return d.fwd_tail_kind == 2 ? vm_half(d.fwd_tail[i >> 1], i & 1) : (d.fwd_tail_kind == 1 ? vm_half(next_fwd_tail[i >> 1], i & 1) : KEEP);
+        }
+        if (d.ctx_replaced) return reinterpret_cast<const uint32_t *>(&nctx)[c];  // the whole record is the new frame's
+        if (c == CW(pc)) return d.pc;
+        if (c == CW(sp)) return d.sp;
+        if (c == CW(ergs_remaining)) return d.ergs;
+        if (c == CW(heap_upper_bound)) return d.heap_bound;
+        if (c == CW(aux_heap_upper_bound)) return d.aux_bound;
+        if (c == CW(reverted_queue_segment_len)) return d.rb_len;
+        if (c >= CW(reverted_queue_head) && c < CW(reverted_queue_head) + 8) {
+            const int i = (c - CW(reverted_queue_head)) & 7;
+            return vm_half(d.rb_head[i >> 1], i & 1);
+        }
+    }
+    return KEEP;
+#undef KEEP
+}
+
+// Every thread evaluates its cycle from snapshot `row` and checks that snapshot `row + 1` is the result: the words a cycle
+// can change are compared with what the cycle produced, every other word must carry over (the neighbouring element of the
+// same column: an L1 hit for 31 of the 32 lanes).  The three sponge-derived states are vouched for by the cycle's sponge jobs
+// when it has one (vm_sponge_kernel compares), and must not move otherwise.  The Poseidon2 relations are deferred: the cycle
+// only emits their jobs.
 #ifndef VM_CYCLES_MIN_BLOCKS
 #define VM_CYCLES_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(128, VM_CYCLES_MIN_BLOCKS)
-vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_state *__restrict__ snapshots,
-                 const zkc_vm_cycle_witness *__restrict__ witness, const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw,
+vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
+                 const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw,
                  uint64_t *__restrict__ trace, size_t limit, size_t n_instances, size_t row0, size_t row_count, VmPushScratch ps,
                  int ncols, int aux_base) {
     // this launch covers rows [row0, row0 + row_count) of every instance (one chunk of the pipelined host path, or all)
@@ -1429,158 +1457,113 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
     const size_t inst = valid ? l / row_count : 0, row = valid ? row0 + (l - inst * row_count) : 0;
     const size_t g = inst * limit + row;
     const size_t idx = inst * (limit + 1) + row;
-    // ---- (1) cooperative word diff --------------------------------------------------------------------------------
-    // Groups of VM_DIFF_GROUP consecutive cycles: the group's VM_DIFF_GROUP + 1 snapshots are contiguous in memory (one
-    // instance), so every lane first issues all of its loads for the group -- (G + 1) x 10 independent coalesced words
-    // in flight per lane -- and only then ballots; the memory latency is paid once per group, not once per cycle.
-    uint32_t diff[VM_DIFF_WORDS];
-#pragma unroll
-    for (int k = 0; k < VM_DIFF_WORDS; k++) diff[k] = 0;
-    {
-        constexpr int G = VM_DIFF_GROUP;
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-#pragma unroll 1
-        for (int c0 = 0; c0 < 32; c0 += G) {
-            if (!((vmask >> c0) & 1)) break;  // valid lanes are a prefix
-            const unsigned long long i0 = __shfl_sync(0xffffffffu, (unsigned long long)idx, c0);
-            // is the whole group valid and contiguous (same instance)?
-            const bool mine_ok = (int)lane < c0 || (int)lane >= c0 + G || (valid && (unsigned long long)idx == i0 + (lane - c0));
-            if (__all_sync(0xffffffffu, mine_ok)) {
-                const uint32_t *p0 = reinterpret_cast<const uint32_t *>(snapshots + i0);
-                uint32_t w[G + 1][VM_DIFF_WORDS];
-#pragma unroll
-                for (int j = 0; j <= G; j++)
-#pragma unroll
-                    for (int k = 0; k < VM_DIFF_WORDS; k++) {
-                        const int o = (int)lane + 32 * k;
-                        w[j][k] = o < VM_WORDS ? __ldg(p0 + (size_t)j * VM_WORDS + o) : 0u;
-                    }
-#pragma unroll
-                for (int j = 0; j < G; j++)
-#pragma unroll
-                    for (int k = 0; k < VM_DIFF_WORDS; k++) {
-                        const unsigned m = __ballot_sync(0xffffffffu, w[j][k] != w[j + 1][k]);
-                        if ((int)lane == c0 + j) diff[k] = m;
-                    }
-            } else {  // a group that straddles instances or the end of the launch: one cycle at a time
-#pragma unroll 1
-                for (int c = c0; c < c0 + G; c++) {
-                    if (!((vmask >> c) & 1)) break;
-                    const unsigned long long ic = __shfl_sync(0xffffffffu, (unsigned long long)idx, c);
-                    const uint32_t *pc = reinterpret_cast<const uint32_t *>(snapshots + ic), *pn = pc + VM_WORDS;
-#pragma unroll
-                    for (int k = 0; k < VM_DIFF_WORDS; k++) {
-                        const int o = (int)lane + 32 * k;
-                        const bool in = o < VM_WORDS;
-                        const uint32_t a = in ? __ldg(pc + o) : 0u, b = in ? __ldg(pn + o) : 0u;
-                        const unsigned m = __ballot_sync(0xffffffffu, a != b);
-                        if ((int)lane == c) diff[k] = m;
-                    }
-                }
-            }
-        }
-    }
-    // ---- the cycle ------------------------------------------------------------------------------------------------------
     VmDev *dev = devs + inst;
-    const zkc_vm_state &s = snapshots[idx], &next = snapshots[idx + 1];
     uint32_t checks = 0, jmask = 0;
     if (valid) {
+        const uint32_t *cur = cols.st + idx;  // word w of this snapshot: cur[w * stride]; of the next one: cur[w * stride + 1]
+        const size_t stride = cols.st_stride;
+#define CUR(w) __ldg(cur + (size_t)(w) * stride)
+#define NXT(w) __ldg(cur + (size_t)(w) * stride + 1)
+        // ---- the words a cycle reads outside the registers: scalars + the current context ---------------------------------
+        zkc_vm_state s;
+        uint32_t *sw = reinterpret_cast<uint32_t *>(&s);
+#pragma unroll
+        for (int w = 0; w < VW(registers); w++) sw[w] = CUR(w);
+#pragma unroll
+        for (int w = VW(flags); w < VW(stack_sponge_state); w++) sw[w] = CUR(w);
+        uint64_t next_fwd_tail[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) next_fwd_tail[i] = (uint64_t)NXT(VWC(log_queue_forward_tail) + 2 * i) | ((uint64_t)NXT(VWC(log_queue_forward_tail) + 2 * i + 1) << 32);
         VmDelta d;
         zkc_vm_context nctx;
         d.penc_hi = ps.enc_hi + g * (VM_JOB_SLOTS_HI * 8);
-        checks |= vm_cycle_dev<false>(isa, &dev->io, s, d, nctx, witness[g], cws + inst * (size_t)n_cw, n_cw, nullptr, nullptr,
-                                      ps.enc + g * (VM_JOB_SLOTS_LO * 8), &next,
+        const VmRegsOfColumns regs{cur, stride};
+        VmWitOfColumns wit(cols.wt + g, cols.wt_stride);
+        checks |= vm_cycle_dev<false>(isa, &dev->io, s, regs, d, nctx, wit, cws + inst * (size_t)n_cw, n_cw, nullptr, nullptr,
+                                      ps.enc + g * (VM_JOB_SLOTS_LO * 8), next_fwd_tail,
                                       trace ? trace + inst * (size_t)ncols * limit : nullptr, limit, row, aux_base);
         jmask = d.job_mask;
         ps.meta[g * 2] = (uint64_t)jmask | (d.cap_from << 16); ps.meta[g * 2 + 1] = d.chk;
-        // ---- (2) is snapshot row + 1 what this cycle produces? ---------------------------------------------------------
+        // ---- is snapshot row + 1 what this cycle produces? -----------------------------------------------------------------
+        // (1) scalars + context: the expected next value of every word (the current one unless the cycle changes it)
         bool bad = false;
-        if (d.set_u128) {
-            diff[VW(context_composite_u128) >> 5] &= ~(15u << (VW(context_composite_u128) & 31));
-            static_assert((VW(context_composite_u128) & 31) <= 28, "u128 words straddle a diff word");
-            for (int i = 0; i < 4; i++) bad |= next.context_composite_u128[i] != d.u128[i];
-        }
-        if (d.set_pubdata) {
-            diff[VW(ergs_per_pubdata_byte) >> 5] &= ~(1u << (VW(ergs_per_pubdata_byte) & 31));
-            bad |= next.ergs_per_pubdata_byte != d.pubdata;
-        }
-        if (d.inc_tx) {
-            diff[VW(tx_number_in_block) >> 5] &= ~(1u << (VW(tx_number_in_block) & 31));
-            bad |= next.tx_number_in_block != s.tx_number_in_block + 1;
-        }
-        // which sponge-derived words this cycle's jobs vouch for
-        bool memq_job = false, stack_job = false, decommit_job = false;
+        {
+            uint32_t acc = 0;
 #pragma unroll
-        for (int k = 0; k < VM_JOB_SLOTS; k++) {
-            const uint32_t c = (uint32_t)(d.chk >> (4 * k)) & 15;
-            memq_job |= c == VM_CHK_NEXT_MEMQ; stack_job |= c == VM_CHK_NEXT_STACK; decommit_job |= c == VM_CHK_NEXT_DECOMMIT;
-        }
-        uint32_t stray = 0, memq_diff = 0, stack_diff = 0, ctx_diff = 0, fwd_diff = 0, decommit_diff = 0;
-#define X(K) stray |= diff[K] & VmKeepWord<K>::value; memq_diff |= diff[K] & VmMemqWord<K>::value; \
-             stack_diff |= diff[K] & VmStackWord<K>::value; ctx_diff |= diff[K] & VmCtxKeepWord<K>::value; \
-             fwd_diff |= diff[K] & VmFwdTailWord<K>::value; decommit_diff |= diff[K] & VmDecommitWord<K>::value;
-        VM_FOR10(X)
-#undef X
-        bad |= stray != 0;
-        if (!memq_job) bad |= memq_diff != 0;  // otherwise the last memory queue job of the cycle compares (vm_sponge_kernel)
-        if (!decommit_job) bad |= decommit_diff != 0;
-        bad |= next.memory_page_counter != d.page_counter || next.code_decommittment_queue_length != d.decommit_len;
-        const zkc_vm_context &nc = next.current_context;
-        if (!d.ctx_replaced) {
-            bad |= ctx_diff != 0 || stack_diff != 0;
-            bad |= nc.pc != d.pc || nc.sp != d.sp || nc.ergs_remaining != d.ergs || nc.heap_upper_bound != d.heap_bound ||
-                   nc.aux_heap_upper_bound != d.aux_bound || nc.reverted_queue_segment_len != d.rb_len;
+            for (int w = 0; w < VW(registers); w++) acc |= NXT(w) ^ d.cw[w];
 #pragma unroll
-            for (int i = 0; i < 4; i++) bad |= nc.reverted_queue_head[i] != d.rb_head[i];
-        } else {
-            bad |= !vm_record_equal(nc, nctx);
-            if (d.ctx_replaced == 2) {  // ret: the stack state below the popped frame is the witness'
-                const uint64_t *p = cws[inst * (size_t)n_cw + (d.cw_index < n_cw ? d.cw_index : 0)].previous_sponge_state;
-                for (int i = 0; i < 12; i++) bad |= next.stack_sponge_state[i] != (d.cw_index < n_cw ? p[i] : 0ull);
-            } else if (!stack_job) bad |= stack_diff != 0;
+            for (int w = VW(flags); w < VW(stack_sponge_state); w++) {
+                if (w >= VW(_pad) && w < VW(current_context)) continue;  // padding is not state
+                if (w == VWC(aux_heap_upper_bound) + 1) continue;        // alignment hole in front of reverted_queue_head
+                acc |= NXT(w) ^ vm_expected_word(w, d, nctx, next_fwd_tail, cur, stride);
+            }
+            bad |= acc != 0;
         }
-        bad |= nc.log_queue_forward_part_length != d.fwd_len;
-        if (d.fwd_tail_kind == 0) bad |= fwd_diff != 0;
-        else if (d.fwd_tail_kind == 2) for (int i = 0; i < 4; i++) bad |= nc.log_queue_forward_tail[i] != d.fwd_tail[i];
-        if (d.far_ret) {
-            bad |= !reg_equal(next.registers[0], d.r1_val);
-            for (int r = 1; r < ZKC_VM_REGISTERS; r++) bad |= !reg_equal(next.registers[r], reg_zero());
-        } else if (d.far_call) {
-            for (int r = 0; r < ZKC_VM_REGISTERS; r++) bad |= !reg_equal(next.registers[r], vm_far_call_register(isa, d, r, s.registers[r]));
-        } else {
-            uint32_t regdiff = 0;
+        // (2) registers: only dst0 / dst1 may move (dst1 is applied last), to the values the cycle produced
+        if (!d.far_ret && !d.far_call) {
+            uint32_t acc = 0;
 #pragma unroll
             for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
-                const int lo = VW(registers) + 9 * r;
-                const uint32_t bits = __funnelshift_r(diff[lo >> 5], diff[(lo >> 5) + 1], lo & 31) & 0x1FFu;
-                regdiff |= (bits != 0) << r;
+                const bool is0 = (uint32_t)(r + 1) == d.idx0, is1 = (uint32_t)(r + 1) == d.idx1;
+#pragma unroll
+                for (int i = 0; i < 9; i++) {
+                    const int w = VW(registers) + 9 * r + i;
+                    const uint32_t c = CUR(w), n = NXT(w);
+                    const uint32_t want = is1 ? reg_word(d.val1, i) : (is0 ? reg_word(d.val0, i) : c);
+                    acc |= n ^ want;
+                }
             }
-            const uint32_t may = (d.idx0 ? 1u << (d.idx0 - 1) : 0u) | (d.idx1 ? 1u << (d.idx1 - 1) : 0u);
-            bad |= (regdiff & ~may) != 0;
-            if (d.idx1) bad |= !reg_equal(next.registers[d.idx1 - 1], d.val1);
-            if (d.idx0 && d.idx0 != d.idx1) bad |= !reg_equal(next.registers[d.idx0 - 1], d.val0);
+            bad |= acc != 0;
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
+                zkc_vm_register want = reg_zero();
+                if (d.far_ret) { if (r == 0) want = d.r1_val; }
+                else want = vm_far_call_register(isa, d, r, regs.get((uint32_t)r));
+                for (int i = 0; i < 9; i++) bad |= NXT(VW(registers) + 9 * r + i) != reg_word(want, i);
+            }
         }
-        bad |= next.pending_exception != d.pending || next.previous_code_page != d.prev_code_page ||
-               next.previous_super_pc != d.prev_super_pc || next.timestamp != d.timestamp || next.memory_queue_length != d.memq_len ||
-               next.context_stack_depth != d.depth;
+        // (3) the sponge-derived states: vouched for by the cycle's last job on them (vm_sponge_kernel), else unchanged
+        {
+            bool memq_job = false, stack_job = false, decommit_job = false;
 #pragma unroll
-        for (int i = 0; i < 3; i++) bad |= next.flags[i] != d.flags[i];
+            for (int k = 0; k < VM_JOB_SLOTS; k++) {
+                const uint32_t c = (uint32_t)(d.chk >> (4 * k)) & 15;
+                memq_job |= c == VM_CHK_NEXT_MEMQ; stack_job |= c == VM_CHK_NEXT_STACK; decommit_job |= c == VM_CHK_NEXT_DECOMMIT;
+            }
+            uint32_t memq_diff = 0, stack_diff = 0, decommit_diff = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) bad |= next.previous_code_word[i] != d.cw[i];
+            for (int i = 0; i < 24; i++) {
+                memq_diff |= CUR(VW(memory_queue_state) + i) ^ NXT(VW(memory_queue_state) + i);
+                stack_diff |= CUR(VW(stack_sponge_state) + i) ^ NXT(VW(stack_sponge_state) + i);
+                decommit_diff |= CUR(VW(code_decommittment_queue_state) + i) ^ NXT(VW(code_decommittment_queue_state) + i);
+            }
+            if (!memq_job) bad |= memq_diff != 0;
+            if (!decommit_job) bad |= decommit_diff != 0;
+            if (d.ctx_replaced == 2) {  // ret: the stack state below the popped frame is the witness'
+                const uint64_t *p = cws[inst * (size_t)n_cw + (d.cw_index < n_cw ? d.cw_index : 0)].previous_sponge_state;
+                for (int i = 0; i < 12; i++) {
+                    const uint64_t n = (uint64_t)NXT(VW(stack_sponge_state) + 2 * i) | ((uint64_t)NXT(VW(stack_sponge_state) + 2 * i + 1) << 32);
+                    bad |= n != (d.cw_index < n_cw ? p[i] : 0ull);
+                }
+            } else if (!stack_job) bad |= stack_diff != 0;
+        }
         if (bad) {
             // attribute the broken link to the cycle that would consume the wrong snapshot (what a sequential run sees)
             if (row + 1 < limit) vm_report(dev, row + 1, ZKC_VM_CHK_SNAPSHOT);
             else checks |= ZKC_VM_CHK_SNAPSHOT;
         }
         if (row + 1 == limit) {  // the state the circuit ends in, as computed (its sponge-derived parts: vm_sponge_kernel)
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(&s);
             uint32_t *dst = reinterpret_cast<uint32_t *>(&dev->s_final);
-            for (int i = 0; i < VM_WORDS; i++) dst[i] = src[i];
+#pragma unroll 1
+            for (int w = 0; w < VM_WORDS; w++) dst[w] = CUR(w);
             vm_apply_delta(dev->s_final, d, nctx, isa);
             if (d.ctx_replaced == 2 && d.cw_index < n_cw)
                 for (int i = 0; i < 12; i++) dev->s_final.stack_sponge_state[i] = cws[inst * (size_t)n_cw + d.cw_index].previous_sponge_state[i];
         }
         vm_report(dev, row, checks);
+#undef CUR
+#undef NXT
     }
     // ---- rows whose slot-k job runs, for the dense sponge launches ---------------------------------------------------------
 #pragma unroll
@@ -1596,17 +1579,72 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, const zkc_vm_s
     }
 }
 
+// ---- row-major (array of structs) inputs -> columns: one warp per tile of 32 records, through shared memory ---------------
+// records [n_inst][per_inst] of WORDS 32-bit words; rows [r0, r0 + cnt) of every instance.  The tile is CONTIGUOUS in the
+// row-major input (32 x WORDS words = 37 632 bytes of snapshots): one elected lane brings it in with a single bulk
+// asynchronous copy (TMA, cp.async.bulk global -> shared, completion on an mbarrier) -- 37 KB in flight per warp without a
+// register or an instruction per word -- and the warp then writes one 128-byte line per word.  Tiles that are not 16-byte
+// aligned (odd record index: 1 176 = 8 x 147) or not full take coalesced loads instead.
+__device__ __forceinline__ uint32_t vm_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int WORDS>
+__global__ void __launch_bounds__(32)
+vm_rows_to_columns_kernel(const uint32_t *__restrict__ rows, uint32_t *__restrict__ cols, size_t stride, size_t per_inst, size_t n_inst,
+                          size_t r0, size_t cnt) {
+    __shared__ alignas(128) uint32_t tile[32 * WORDS];
+    __shared__ alignas(8) unsigned long long bar;
+    const int lane = threadIdx.x;
+    const size_t tiles_per_inst = (cnt + 31) / 32;
+    const size_t t = blockIdx.x;
+    const size_t inst = t / tiles_per_inst, first = r0 + (t - inst * tiles_per_inst) * 32;
+    const int n = (int)min((size_t)32, r0 + cnt - first);
+    const size_t base = inst * per_inst + first;
+    const uint32_t *src = rows + base * WORDS;
+    constexpr uint32_t BYTES = 32u * WORDS * 4u;
+    if (n == 32 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const uint32_t bar_a = vm_smem_addr(&bar), tile_a = vm_smem_addr(tile);
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tile_a), "l"(src), "r"(BYTES), "r"(bar_a) : "memory");
+        }
+        __syncwarp();
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_a) : "memory");
+    } else {
+        for (int j = lane; j < n * WORDS; j += 32) tile[j] = __ldg(src + j);
+        __syncwarp();
+    }
+    if (lane < n) {
+        uint32_t *dst = cols + base + lane;
+#pragma unroll 6
+        for (int w = 0; w < WORDS; w++) dst[(size_t)w * stride] = tile[lane * WORDS + w];  // 2-way bank conflict at most (WORDS = 6, 12 mod 32)
+    }
+}
+
+// first and final snapshot of every instance as records: ends[2 * inst], ends[2 * inst + 1] (what the closed-form
+// commitments hash; vm_finalize_kernel).  One warp per record.
+__global__ void vm_gather_ends_kernel(VmCols cols, zkc_vm_state *__restrict__ ends, size_t limit, size_t n_instances) {
+    const size_t wi = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wi >= 2 * n_instances) return;
+    const size_t idx = (wi >> 1) * (limit + 1) + ((wi & 1) ? limit : 0);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(ends + wi);
+    for (int w = lane; w < VM_WORDS; w += 32) dst[w] = cols.sw(w, idx);
+}
+
 // slot k of every cycle that has one: out = P(enc || capacity), one thread per job, all lanes busy.  The capacity is a
 // previous job's output of the same cycle, zeros, or a queue state of the snapshot / the callstack witness; the output
 // of the last job of a chain must land on the next snapshot (or, for the joins the circuit enforces, on the current one).
 // One job: slot k of cycle g.  `flags` (persistent launch): per-job completion flags -- a job whose capacity is another
 // job's output waits for it, and publishes its own output when done.
-__device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
+__device__ __forceinline__ void vm_sponge_job(VmDev *devs, const VmCols &cols,
                                               const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, const VmPushScratch &ps, int k, size_t g,
                                               size_t limit, uint32_t *flags) {
     const size_t inst = g / limit, row = g - inst * limit, idx = inst * (limit + 1) + row;
     const uint32_t cap_from = (uint32_t)(ps.meta[g * 2] >> (16 + 4 * k)) & 15, chk = (uint32_t)(ps.meta[g * 2 + 1] >> (4 * k)) & 15;
-    const zkc_vm_state &s = snapshots[idx];
     uint64_t q[12];
 #pragma unroll
     for (int j = 0; j < 8; j++) q[j] = ps.enc_of(g, k)[j];
@@ -1623,20 +1661,21 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
     if (cap_from == VM_CAP_ZERO) {
 #pragma unroll
         for (int j = 8; j < 12; j++) q[j] = 0;
-    } else {
-        const uint64_t *from;
-        if (cap_from < VM_JOB_SLOTS) from = ps.state_of(g, (int)cap_from);
-        else if (cap_from == VM_CAP_MEMQ) from = s.memory_queue_state;
-        else if (cap_from == VM_CAP_STACK) from = s.stack_sponge_state;
-        else if (cap_from == VM_CAP_DECOMMIT) from = s.code_decommittment_queue_state;
-        else {
-            // an index outside the table was already reported by the cycle kernel (ZKC_VM_CHK_CALLSTACK);
-            // the job then runs from the all-zero capacity like the oracle does
-            const uint32_t cwi = witness[g].callstack_index;
-            from = cwi < n_cw ? cws[inst * (size_t)n_cw + cwi].previous_sponge_state : nullptr;
-        }
+    } else if (cap_from < VM_JOB_SLOTS) {
+        const uint64_t *from = ps.state_of(g, (int)cap_from);
+#pragma unroll
+        for (int j = 8; j < 12; j++) q[j] = from[j];
+    } else if (cap_from == VM_CAP_CALLSTACK_WITNESS) {
+        // an index outside the table was already reported by the cycle kernel (ZKC_VM_CHK_CALLSTACK);
+        // the job then runs from the all-zero capacity like the oracle does
+        const uint32_t cwi = cols.ww(WW(callstack_index), g);
+        const uint64_t *from = cwi < n_cw ? cws[inst * (size_t)n_cw + cwi].previous_sponge_state : nullptr;
 #pragma unroll
         for (int j = 8; j < 12; j++) q[j] = from ? from[j] : 0ull;
+    } else {
+        const int w0 = cap_from == VM_CAP_MEMQ ? VW(memory_queue_state) : (cap_from == VM_CAP_STACK ? VW(stack_sponge_state) : VW(code_decommittment_queue_state));
+#pragma unroll
+        for (int j = 8; j < 12; j++) q[j] = cols.sw64(w0 + 2 * j, idx);
     }
     poseidon2_permute(q);
     uint64_t *to = ps.state_of(g, k);
@@ -1659,19 +1698,18 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
     }
     if (chk == VM_CHK_NONE) return;
     VmDev *dev = devs + inst;
-    const zkc_vm_state &next = snapshots[idx + 1];
     const bool last_row = row + 1 == limit;
-    const uint64_t *want;
-    int n = 12;
-    if (chk == VM_CHK_NEXT_MEMQ) want = next.memory_queue_state;
-    else if (chk == VM_CHK_NEXT_STACK) want = next.stack_sponge_state;
-    else if (chk == VM_CHK_CUR_STACK) want = s.stack_sponge_state;
-    else if (chk == VM_CHK_NEXT_FWD_TAIL) { want = next.current_context.log_queue_forward_tail; n = 4; }
-    else if (chk == VM_CHK_NEXT_DECOMMIT) want = next.code_decommittment_queue_state;
-    else { want = s.current_context.reverted_queue_head; n = 4; }
+    int w0, n = 12;
+    size_t at = idx + 1;
+    if (chk == VM_CHK_NEXT_MEMQ) w0 = VW(memory_queue_state);
+    else if (chk == VM_CHK_NEXT_STACK) w0 = VW(stack_sponge_state);
+    else if (chk == VM_CHK_CUR_STACK) { w0 = VW(stack_sponge_state); at = idx; }
+    else if (chk == VM_CHK_NEXT_FWD_TAIL) { w0 = VWC(log_queue_forward_tail); n = 4; }
+    else if (chk == VM_CHK_NEXT_DECOMMIT) w0 = VW(code_decommittment_queue_state);
+    else { w0 = VWC(reverted_queue_head); n = 4; at = idx; }
     bool same = true;
 #pragma unroll
-    for (int j = 0; j < 12; j++) same &= j >= n || want[j] == q[j];
+    for (int j = 0; j < 12; j++) same &= j >= n || cols.sw64(w0 + 2 * j, at) == q[j];
     if (chk == VM_CHK_CUR_STACK) { if (!same) vm_report(dev, row, ZKC_VM_CHK_CALLSTACK); return; }
     if (chk == VM_CHK_CUR_RB_HEAD) { if (!same) vm_report(dev, row, ZKC_VM_CHK_ROLLBACK_QUEUE); return; }
     if (!same) vm_report(dev, last_row ? row : row + 1, ZKC_VM_CHK_SNAPSHOT);
@@ -1685,23 +1723,23 @@ __device__ __forceinline__ void vm_sponge_job(VmDev *devs, const zkc_vm_state *_
 
 // slot k of every cycle that has one, one thread per job (one launch per slot)
 __global__ void __launch_bounds__(128)
-vm_sponge_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
+vm_sponge_kernel(VmDev *devs, VmCols cols,
                  const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, VmPushScratch ps, int k, size_t limit, size_t total) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ps.counts[k]) return;
-    vm_sponge_job(devs, snapshots, witness, cws, n_cw, ps, k, ps.lists[(size_t)k * total + i], limit, nullptr);
+    vm_sponge_job(devs, cols, cws, n_cw, ps, k, ps.lists[(size_t)k * total + i], limit, nullptr);
 }
 
 // the far calls of the launch: slots 5, 6, 7 (code-hash read: a chain) and 8 (decommitment queue) of a cycle by one thread
 __global__ void __launch_bounds__(128)
-vm_sponge_far_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
+vm_sponge_far_kernel(VmDev *devs, VmCols cols,
                      const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, VmPushScratch ps, size_t limit, size_t total) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ps.counts[VM_JOB_SLOTS_LO]) return;
     const size_t g = ps.lists[(size_t)VM_JOB_SLOTS_LO * total + i];
     const uint32_t m = (uint32_t)ps.meta[g * 2] & 0xFFFFu;
     for (int k = VM_JOB_SLOTS_LO; k < VM_JOB_SLOTS; k++)
-        if ((m >> k) & 1) vm_sponge_job(devs, snapshots, witness, cws, n_cw, ps, k, g, limit, nullptr);
+        if ((m >> k) & 1) vm_sponge_job(devs, cols, cws, n_cw, ps, k, g, limit, nullptr);
 }
 
 // All slots in ONE persistent launch (grid = what is resident at once).  The jobs are numbered slot by slot (every
@@ -1710,7 +1748,7 @@ vm_sponge_far_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, co
 // out earlier to a warp that is resident and never waits on a larger number: no deadlock, and no launch boundary --
 // the tail of slot k overlaps the head of slot k + 1 instead of draining the machine five times.
 __global__ void __launch_bounds__(128)
-vm_sponge_persistent_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapshots, const zkc_vm_cycle_witness *__restrict__ witness,
+vm_sponge_persistent_kernel(VmDev *devs, VmCols cols,
                             const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw, VmPushScratch ps, unsigned long long *ticket,
                             uint32_t *flags, size_t limit, size_t total) {
     const unsigned lane = threadIdx.x & 31;
@@ -1727,7 +1765,7 @@ vm_sponge_persistent_kernel(VmDev *devs, const zkc_vm_state *__restrict__ snapsh
 #pragma unroll
         for (int j = 1; j < VM_JOB_SLOTS_LO; j++) k += t >= start[j];
         const unsigned long long i = t - start[k] + lane;
-        if (i < ps.counts[k]) vm_sponge_job(devs, snapshots, witness, cws, n_cw, ps, k, ps.lists[(size_t)k * total + i], limit, flags);
+        if (i < ps.counts[k]) vm_sponge_job(devs, cols, cws, n_cw, ps, k, ps.lists[(size_t)k * total + i], limit, flags);
     }
 }
 
@@ -1761,7 +1799,7 @@ vm_sponge_trace_kernel(VmPushScratch ps, uint64_t *__restrict__ trace, size_t li
 // starts at the circuit's own start state (snapshot 0 == s0), so that the cycle launch does not wait for the prologue.
 constexpr int VM_FLAT_STRIDE = 248;
 __global__ void __launch_bounds__(128)
-vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances, const zkc_vm_state *__restrict__ snapshots, size_t limit, int mode) {
+vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances, const zkc_vm_state *__restrict__ ends, size_t limit, int mode) {
     __shared__ uint64_t part[2][4][4];
     __shared__ uint64_t compact[2][24];
     const int slot = threadIdx.x >> 6, role = (threadIdx.x >> 4) & 3, i = threadIdx.x & 15;
@@ -1771,12 +1809,12 @@ vm_finalize_kernel(VmDev *devs, uint64_t *__restrict__ flat, size_t n_instances,
     VmDev *d = devs + (active ? inst : 0);
     zkc_vm_closed_form &io = d->io;
     const bool hint_mode = mode == 0;
-    const zkc_vm_state &state = hint_mode ? snapshots[(active ? inst : 0) * (limit + 1) + limit] : d->s_final;
+    const zkc_vm_state &state = hint_mode ? ends[2 * (active ? inst : 0) + 1] : d->s_final;
     const bool done = state.context_stack_depth == 0;  // mod.rs:113-122
     const bool start = hint_mode ? io.start_flag != 0 : d->start != 0;
     bool use_hint = false;
     if (!hint_mode && active) {
-        const bool chain_starts_right = limit == 0 || vm_state_equal(snapshots[inst * (limit + 1)], d->s0);
+        const bool chain_starts_right = limit == 0 || vm_state_equal(ends[2 * inst], d->s0);
         if (!chain_starts_right && threadIdx.x % 64 == 0) vm_report(d, 0, ZKC_VM_CHK_SNAPSHOT);
         use_hint = limit != 0 && chain_starts_right && d->hint_ok && !(d->failed_checks & ZKC_VM_CHK_SNAPSHOT);
     }
@@ -1911,6 +1949,12 @@ __device__ void vm_list_walk(VmLists &L, size_t depth, uint64_t (&cur)[4], zkc_v
     L.first[depth] = L.last[depth] = -1;
 }
 
+struct VmRegsOfState {
+    const zkc_vm_state &s;
+    __device__ __forceinline__ zkc_vm_register get(uint32_t r) const { return s.registers[r]; }
+    __device__ __forceinline__ uint32_t low(uint32_t r) const { return s.registers[r].value[0]; }
+};
+
 struct VmSimScratch {
     zkc_vm_register *pages;            // [n][4][VM_PAGE_WORDS]
     VmSlot *storage;                   // [n][VM_STORAGE_SLOTS]
@@ -1978,7 +2022,7 @@ vm_simulate_kernel(const zkc_vm_isa *__restrict__ isa, const zkc_vm_state *__res
         const size_t depth = s.context_stack_depth;
         uint64_t fwd_before[4];
         for (int i = 0; i < 4; i++) fwd_before[i] = s.current_context.log_queue_forward_tail[i];
-        const uint32_t checks = vm_cycle_dev<true>(isa, nullptr, s, d, nctx, w, nullptr, 0, &sim, &so, nullptr, nullptr, nullptr, 0, 0) & ~ignore;
+        const uint32_t checks = vm_cycle_dev<true>(isa, nullptr, s, VmRegsOfState{s}, d, nctx, w, nullptr, 0, &sim, &so, nullptr, nullptr, nullptr, 0, 0) & ~ignore;
         vm_apply_delta(s, d, nctx, isa);
         for (int i = 0; i < 12; i++) s.memory_queue_state[i] = so.memq[i];
         if (d.ctx_replaced) for (int i = 0; i < 12; i++) s.stack_sponge_state[i] = so.stack[i];
@@ -2051,40 +2095,120 @@ extern "C" int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form 
     return ZKC_OK;
 }
 
-extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa,
-                                             const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness,
-                                             const zkc_vm_callstack_witness *callstack_witness, size_t n_callstack_witness, size_t limit,
-                                             const zkc_vm_options *options, int on_device, uint64_t *trace, uint64_t *commitments,
-                                             zkc_status *statuses) {
-    if (!ctx || !ios || !isa || !commitments || !statuses || (limit && n_instances && (!snapshots || !witness)) ||
-        (n_callstack_witness && !callstack_witness) || n_callstack_witness > 0xFFFFFFFFull ||
+#include "main_vm_stream.cuh"
+
+namespace zkc {
+
+// what the per-cycle inputs of a call are: records (array of structs, host or device), columns (device) or segmented
+// streams (host); and where the witness goes: a DENSE / COMPACT trace (host or device) or the PACKED transport form (host)
+struct VmInput {
+    const zkc_vm_state *snapshots = nullptr;
+    const zkc_vm_cycle_witness *witness = nullptr;
+    bool rows_on_device = false;
+    const zkc_vm_columns *columns = nullptr;
+    const zkc_vm_input_stream *const *streams = nullptr;
+    const zkc_vm_callstack_witness *callstack_witness = nullptr;
+    size_t n_callstack_witness = 0;
+    bool callstack_on_device = false;
+    zkc_vm_packed_trace *packed = nullptr;
+};
+
+static inline size_t vm_round32(size_t n) { return (std::max<size_t>(n, 1) + 31) & ~(size_t)31; }
+
+// [lines] pieces of `width` bytes, src_pitch / dst_pitch apart
+static cudaError_t vm_copy_lines(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t lines, cudaMemcpyKind kind,
+                                 cudaStream_t st) {
+    if (!width || !lines) return cudaSuccess;
+    if (lines == 1 || (width == src_pitch && width == dst_pitch)) return cudaMemcpyAsync(dst, src, width * lines, kind, st);
+    if (src_pitch < (1ull << 31) && dst_pitch < (1ull << 31)) return cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, lines, kind, st);
+    for (size_t i = 0; i < lines; i++) {
+        const cudaError_t e = cudaMemcpyAsync((char *)dst + i * dst_pitch, (const char *)src + i * src_pitch, width, kind, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa, const VmInput &in, size_t limit,
+                          const zkc_vm_options *options, bool trace_dev, uint64_t *trace, uint64_t *commitments, zkc_status *statuses) {
+    const bool have_stream = in.streams != nullptr;
+    const bool have_rows = in.columns == nullptr && !have_stream;
+    if (!ctx || !ios || !isa || !commitments || !statuses ||
+        (limit && n_instances && have_rows && (!in.snapshots || !in.witness)) ||
+        (limit && n_instances && in.columns && (!in.columns->state_words || !in.columns->witness_words ||
+                                                in.columns->state_stride < n_instances * (limit + 1) || in.columns->witness_stride < n_instances * limit)) ||
+        (in.n_callstack_witness && !in.callstack_witness) || in.n_callstack_witness > 0xFFFFFFFFull ||
         limit > 0x0FFFFFFFull || n_instances > 0x00FFFFFFull || limit * n_instances > 0xFFFFFFFFull)
         return ZKC_ERR_INVALID_ARGUMENT;
     if (!n_instances) return ZKC_OK;
+    size_t seg_cycles = 0, n_segments = 0, blob_total = 0;
+    if (have_stream) {
+        for (size_t i = 0; i < n_instances; i++) {
+            const zkc_vm_input_stream *st = in.streams[i];
+            if (!st || st->limit != limit || !st->segment_cycles || !st->n_segments || !st->segments) return ZKC_ERR_INVALID_ARGUMENT;
+            if (i == 0) { seg_cycles = st->segment_cycles; n_segments = st->n_segments; }
+            if (st->segment_cycles != seg_cycles || st->n_segments != n_segments || n_segments != std::max<size_t>(1, (limit + seg_cycles - 1) / seg_cycles))
+                return ZKC_ERR_INVALID_ARGUMENT;
+            for (size_t k = 0; k < n_segments; k++) {
+                const zkc_vm_segment_header *h = (const zkc_vm_segment_header *)st->segments[k].blob;
+                if (!h || h->magic != ZKC_VM_SEGMENT_MAGIC || h->blob_bytes != st->segments[k].blob_bytes || h->first_cycle != k * seg_cycles ||
+                    h->n_cycles != std::min(seg_cycles, limit - k * seg_cycles))
+                    return ZKC_ERR_INVALID_ARGUMENT;
+                blob_total += (h->blob_bytes + 255) & ~(size_t)255;
+            }
+        }
+    }
     zkc_status *status = statuses;
     for (size_t i = 0; i < n_instances; i++) statuses[i] = zkc_status{ZKC_OK, 0, -1, 0, 0};
-    const bool in_dev = on_device & ZKC_INPUTS_ON_DEVICE, trace_dev = on_device & ZKC_TRACE_ON_DEVICE;
+    const bool rows_host = have_rows && !in.rows_on_device;
     ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
-    const size_t rows = limit * n_instances, n_cw = n_callstack_witness * n_instances;
-    size_t bytes = zkc_carver::bytes(n_instances, sizeof(VmDev)) + zkc_carver::bytes(1, sizeof(zkc_vm_isa));
-    if (!in_dev) bytes += zkc_carver::bytes(rows + n_instances, sizeof(zkc_vm_state)) + zkc_carver::bytes(rows + 1, sizeof(zkc_vm_cycle_witness)) +
-                          zkc_carver::bytes(n_cw + 1, sizeof(zkc_vm_callstack_witness));
-    const bool compact = options && options->trace_layout == ZKC_VM_TRACE_COMPACT && trace;
-    if (options && options->trace_layout > ZKC_VM_TRACE_COMPACT) return ZKC_ERR_INVALID_ARGUMENT;
-    if (compact && options->sponge_records_capacity && !options->sponge_records) return ZKC_ERR_INVALID_ARGUMENT;
+    const size_t rows = limit * n_instances, n_cw = in.n_callstack_witness * n_instances;
+    const bool own_cols = have_rows || have_stream;
+    const size_t st_stride = own_cols ? vm_round32(rows + n_instances) : in.columns->state_stride;
+    const size_t wt_stride = own_cols ? vm_round32(rows) : in.columns->witness_stride;
+    zkc_vm_packed_trace *packed = in.packed;
+    if (packed && (trace || (rows && (!packed->cols8 || !packed->cols16 || !packed->cols32 || !packed->cols64)) ||
+                   (packed->aux_capacity && !packed->aux_records) || (packed->sponge_capacity && !packed->sponge_records)))
+        return ZKC_ERR_INVALID_ARGUMENT;
+    const bool compact = packed || (options && options->trace_layout == ZKC_VM_TRACE_COMPACT && trace);
+    if (!packed && options && options->trace_layout > ZKC_VM_TRACE_COMPACT) return ZKC_ERR_INVALID_ARGUMENT;
+    if (!packed && compact && options->sponge_records_capacity && !options->sponge_records) return ZKC_ERR_INVALID_ARGUMENT;
     const int ncols = compact ? ZKC_VM_COMPACT_COLS : ZKC_VM_NUM_COLS, aux_base = compact ? ZKC_VM_COMPACT_OP_AUX : ZKC_VM_OP_AUX;
-    const size_t rec_cap = compact ? (size_t)options->sponge_records_capacity : 0;
-    if (trace && !trace_dev) bytes += zkc_carver::bytes((size_t)ncols * rows, 8) + zkc_carver::bytes(rec_cap + 1, sizeof(zkc_vm_sponge_record));
+    const size_t rec_cap = packed ? 0 : (compact ? (size_t)options->sponge_records_capacity : 0);
+    // Host buffers: the rows are cut into chunks and pipelined over three streams -- H2D of chunk i+1 | kernels of chunk i |
+    // D2H of chunk i-1 -- so that a step costs max(H2D, D2H) instead of their sum (PCIe is full duplex).  A stream's chunks
+    // are its segments.
+    size_t n_chunks = 1;
+    if ((rows_host || (trace && !trace_dev)) && limit >= 8192 && rows >= (1u << 16)) n_chunks = limit >= (1u << 18) ? 16 : 4;
+    if (have_stream) n_chunks = n_segments;
+    const bool side_streams = n_chunks > 1 || have_stream || packed;
+    if (side_streams && !ctx->copy_streams()) { if (!have_stream) n_chunks = 1; }
+    const size_t chunk_rows = have_stream ? seg_cycles : (limit + n_chunks - 1) / std::max<size_t>(n_chunks, 1);
+    const bool piped = side_streams && ctx->copy_in && ctx->copy_out;
+    size_t bytes = zkc_carver::bytes(n_instances, sizeof(VmDev)) + zkc_carver::bytes(1, sizeof(zkc_vm_isa)) + zkc_carver::bytes(2 * n_instances, sizeof(zkc_vm_state));
+    if (rows_host) bytes += zkc_carver::bytes(rows + n_instances, sizeof(zkc_vm_state)) + zkc_carver::bytes(rows + 1, sizeof(zkc_vm_cycle_witness));
+    if (!in.callstack_on_device) bytes += zkc_carver::bytes(n_cw + 1, sizeof(zkc_vm_callstack_witness));
+    if (own_cols) bytes += zkc_carver::bytes(st_stride * VM_WORDS, 4) + zkc_carver::bytes(wt_stride * VM_WIT_WORDS, 4);
+    if (have_stream) bytes += blob_total + 256;
+    if ((trace && !trace_dev) || packed) bytes += zkc_carver::bytes((size_t)ncols * rows, 8);
+    if (trace && !trace_dev) bytes += zkc_carver::bytes(rec_cap + 1, sizeof(zkc_vm_sponge_record));
+    const size_t chunk_cells = chunk_rows * n_instances;  // rows of one chunk over the batch
+    if (packed)
+        bytes += zkc_carver::bytes(rows * VM_PK_N8, 1) + zkc_carver::bytes(rows * VM_PK_N16, 2) + zkc_carver::bytes(rows * VM_PK_N32, 4) +
+                 zkc_carver::bytes(rows * VM_PK_N64, 8) + zkc_carver::bytes(n_chunks * chunk_cells + 1, sizeof(zkc_vm_aux_record)) +
+                 zkc_carver::bytes(n_chunks * chunk_cells * VM_JOB_SLOTS + 1, sizeof(zkc_vm_sponge_record)) + zkc_carver::bytes(2 * n_chunks, 8);
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
-    bytes += zkc_carver::bytes(16 * 16, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 2, 8) +
+    bytes += zkc_carver::bytes(16 * n_chunks, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 2, 8) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8) +
-             zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(32, 8) + 4096;  // + slack: the slot arrays are carved in two parts
+             zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(n_chunks + 32, 8) + 4096;  // + slack: the slot arrays are carved in two parts
     void *blk = ctx->scratch(bytes);
-    VmDev *h = (VmDev *)ctx->pinned(n_instances * sizeof(VmDev));
+    const size_t h_counts_off = (n_instances * sizeof(VmDev) + 63) & ~(size_t)63;
+    VmDev *h = (VmDev *)ctx->pinned(h_counts_off + 16 * n_chunks + 64);
     if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
+    unsigned long long *h_counts = (unsigned long long *)((char *)h + h_counts_off);  // [n_chunks][2]: aux, sponge records of a chunk
     zkc_carver cv(blk);
     VmDev *d = cv.take<VmDev>(n_instances);
     zkc_vm_isa *disa = cv.take<zkc_vm_isa>(1);
+    zkc_vm_state *ends = cv.take<zkc_vm_state>(2 * n_instances);
     cudaStream_t s = ctx->stream;
     memset(h, 0, n_instances * sizeof(VmDev));
     for (size_t i = 0; i < n_instances; i++) {
@@ -2095,18 +2219,10 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     }
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, n_instances * sizeof(VmDev), cudaMemcpyHostToDevice, s));
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(disa, isa, sizeof(zkc_vm_isa), cudaMemcpyHostToDevice, s));  // the ISA tables are always host data
-    const zkc_vm_state *dsnap = snapshots;
-    const zkc_vm_cycle_witness *dwit = witness;
-    const zkc_vm_callstack_witness *dcw = callstack_witness;
+    const zkc_vm_callstack_witness *dcw = in.callstack_witness;
     uint64_t *dtrace = trace;
     uint64_t *flat = cv.take<uint64_t>(n_instances * 4 * VM_FLAT_STRIDE);
-    // Host buffers: the rows are cut into chunks and pipelined over three streams -- H2D of chunk i+1 | kernels of chunk i |
-    // D2H of chunk i-1 -- so that a step costs max(H2D, D2H) instead of their sum (PCIe is full duplex).
-    size_t n_chunks = 1;
-    if ((!in_dev || (trace && !trace_dev)) && limit >= 8192 && rows >= (1u << 16)) n_chunks = limit >= (1u << 18) ? 16 : 4;
-    if (n_chunks > 1 && !ctx->copy_streams()) n_chunks = 1;
-    const size_t chunk_rows = (limit + n_chunks - 1) / n_chunks;
-    cudaStream_t s_in = n_chunks > 1 ? ctx->copy_in : s, s_out = n_chunks > 1 ? ctx->copy_out : s;
+    cudaStream_t s_in = piped ? ctx->copy_in : s, s_out = piped ? ctx->copy_out : s;
     uint32_t *counts = cv.take<uint32_t>(16 * n_chunks);
     uint32_t *lists = cv.take<uint32_t>(VM_JOB_SLOTS * rows);
     VmPushScratch ps;
@@ -2116,53 +2232,71 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
     ps.enc_hi = cv.take<uint64_t>(rows * VM_JOB_SLOTS_HI * 8);
     ps.state_hi = cv.take<uint64_t>(rows * VM_JOB_SLOTS_HI * 12);
     uint32_t *job_flags = cv.take<uint32_t>(rows * VM_JOB_SLOTS);
-    unsigned long long *tickets = cv.take<unsigned long long>(32);  // [0..15] chunk tickets, [31] record count
+    unsigned long long *tickets = cv.take<unsigned long long>(n_chunks + 32);  // [0 .. n_chunks) chunk tickets, [n_chunks + 31] record count
     ZKC_CUDA(ctx, status, cudaMemsetAsync(counts, 0, 64 * n_chunks, s));
-    ZKC_CUDA(ctx, status, cudaMemsetAsync(job_flags, 0, rows * VM_JOB_SLOTS * 4, s));
-    ZKC_CUDA(ctx, status, cudaMemsetAsync(tickets, 0, 32 * 8, s));
+    static const int sponge_mode = getenv("ZKC_VM_SPONGE_MODE") ? atoi(getenv("ZKC_VM_SPONGE_MODE")) : 0;
+    if (sponge_mode) ZKC_CUDA(ctx, status, cudaMemsetAsync(job_flags, 0, rows * VM_JOB_SLOTS * 4, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(tickets, 0, (n_chunks + 32) * 8, s));
     static int sponge_blocks_per_sm = 0;
     if (!sponge_blocks_per_sm) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sponge_blocks_per_sm, vm_sponge_persistent_kernel, 128, 0) != cudaSuccess || sponge_blocks_per_sm < 1)
             sponge_blocks_per_sm = 1;
     }
-    // [n] lines of `width` bytes, `pitch` apart on both sides
-    auto copy_lines = [&](void *dst, const void *src, size_t pitch, size_t width, size_t lines, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
-        if (lines == 1 || width == pitch) return cudaMemcpyAsync(dst, src, width * (width == pitch ? lines : 1), kind, st);
-        if (pitch < (1ull << 31)) return cudaMemcpy2DAsync(dst, pitch, src, pitch, width, lines, kind, st);
-        for (size_t i = 0; i < lines; i++) {
-            const cudaError_t e = cudaMemcpyAsync((char *)dst + i * pitch, (const char *)src + i * pitch, width, kind, st);
-            if (e != cudaSuccess) return e;
-        }
-        return cudaSuccess;
-    };
     std::vector<cudaEvent_t> used_events;
     auto event = [&]() { cudaEvent_t e = ctx->get_event(); used_events.push_back(e); return e; };
-    if (n_chunks > 1) {  // the copy streams start after what the main stream has queued so far (scratch reuse, VmDev upload)
+    if (piped) {  // the copy streams start after what the main stream has queued so far (scratch reuse, VmDev upload)
         cudaEvent_t e0 = event();
         ZKC_CUDA(ctx, status, cudaEventRecord(e0, s));
         ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_in, e0, 0));
         ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_out, e0, 0));
     }
+    // the records the transposition reads: the caller's (device) or a staging copy of the host's
+    const zkc_vm_state *rsnap = in.snapshots;
+    const zkc_vm_cycle_witness *rwit = in.witness;
     zkc_vm_state *bs = nullptr;
     zkc_vm_cycle_witness *bw = nullptr;
-    if (!in_dev && limit) {
+    if (rows_host && limit) {
         bs = cv.take<zkc_vm_state>(rows + n_instances);
         bw = cv.take<zkc_vm_cycle_witness>(rows + 1);
-        zkc_vm_callstack_witness *bc = cv.take<zkc_vm_callstack_witness>(n_cw + 1);
-        if (n_cw) ZKC_CUDA(ctx, status, cudaMemcpyAsync(bc, callstack_witness, n_cw * sizeof(zkc_vm_callstack_witness), cudaMemcpyHostToDevice, s_in));
-        dsnap = bs; dwit = bw; dcw = bc;
+        rsnap = bs; rwit = bw;
     }
-    if (trace && !trace_dev) dtrace = cv.take<uint64_t>((size_t)ncols * rows);
-    ps.records = nullptr; ps.n_records = tickets + 31; ps.records_capacity = rec_cap;
-    if (compact) ps.records = (trace_dev || !rec_cap) ? options->sponge_records : cv.take<zkc_vm_sponge_record>(rec_cap + 1);
-    if (compact && !ps.records) ps.records = (zkc_vm_sponge_record *)(tickets + 30);  // capacity 0: count only (never written)
+    if (!in.callstack_on_device) {
+        zkc_vm_callstack_witness *bc = cv.take<zkc_vm_callstack_witness>(n_cw + 1);
+        if (n_cw) ZKC_CUDA(ctx, status, cudaMemcpyAsync(bc, in.callstack_witness, n_cw * sizeof(zkc_vm_callstack_witness), cudaMemcpyHostToDevice, s));
+        dcw = bc;
+    }
+    VmCols cols;
+    if (own_cols) {
+        uint32_t *stc = cv.take<uint32_t>(st_stride * VM_WORDS), *wtc = cv.take<uint32_t>(wt_stride * VM_WIT_WORDS);
+        cols = VmCols{stc, st_stride, wtc, wt_stride};
+    } else cols = VmCols{in.columns->state_words, st_stride, in.columns->witness_words, wt_stride};
+    uint32_t *stc_w = const_cast<uint32_t *>(cols.st), *wtc_w = const_cast<uint32_t *>(cols.wt);  // written only when they are this call's scratch
+    char *dblobs = have_stream ? cv.take<char>(blob_total + 256) : nullptr;
+    if ((trace && !trace_dev) || packed) dtrace = cv.take<uint64_t>((size_t)ncols * rows);
+    ps.records = nullptr; ps.n_records = tickets + n_chunks + 31; ps.records_capacity = rec_cap;
+    if (compact && !packed) ps.records = (trace_dev || !rec_cap) ? options->sponge_records : cv.take<zkc_vm_sponge_record>(rec_cap + 1);
+    if (compact && !packed && !ps.records) ps.records = (zkc_vm_sponge_record *)(tickets + n_chunks + 30);  // capacity 0: count only (never written)
+    // PACKED: typed column blocks + per-chunk record regions (worst-case capacity: nothing is dropped on the device)
+    VmPackOut po{};
+    zkc_vm_sponge_record *sp_regions = nullptr;
+    unsigned long long *rec_counts = nullptr;  // [n_chunks][2]
+    if (packed) {
+        po.c8 = cv.take<uint8_t>(rows * VM_PK_N8); po.c16 = cv.take<uint16_t>(rows * VM_PK_N16);
+        po.c32 = cv.take<uint32_t>(rows * VM_PK_N32); po.c64 = cv.take<uint64_t>(rows * VM_PK_N64);
+        po.rows = rows;
+        po.aux = cv.take<zkc_vm_aux_record>(n_chunks * chunk_cells + 1);
+        sp_regions = cv.take<zkc_vm_sponge_record>(n_chunks * chunk_cells * VM_JOB_SLOTS + 1);
+        rec_counts = cv.take<unsigned long long>(2 * n_chunks);
+        ZKC_CUDA(ctx, status, cudaMemsetAsync(rec_counts, 0, 16 * n_chunks, s));
+        packed->n_aux_records = 0; packed->n_sponge_records = 0;
+    }
     // Side stream: the start state (4 dependent permutations) and the closed-form commitments from the host's final
     // snapshot (31 dependent permutations) run beside the cycle launches; the FINAL pass below takes them when every link
-    // verified.  Host inputs: the final snapshots are copied first (the chunk copies then leave them alone).
+    // verified.  `ends` = first and final snapshot of every instance as records (a stream's arrive with its last segment).
     cudaStream_t s_aux = ctx->aux_stream();
     if (!s_aux) s_aux = s;
-    cudaEvent_t e_final_snapshot = nullptr, e_hint = nullptr;
-    {
+    cudaEvent_t e_hint = nullptr;
+    auto launch_hint = [&](bool ends_from_columns) -> int {
         if (s_aux != s) {
             cudaEvent_t e = event();
             ZKC_CUDA(ctx, status, cudaEventRecord(e, s));
@@ -2171,77 +2305,165 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
         ctx->launches++;
         vm_prologue_kernel<<<(unsigned)((n_instances + 31) / 32), 32, 0, s_aux>>>(d, disa, n_instances);
         if (limit) {
-            if (!in_dev) {
-                ZKC_CUDA(ctx, status, copy_lines(bs + limit, snapshots + limit, (limit + 1) * sizeof(zkc_vm_state), sizeof(zkc_vm_state), n_instances,
-                                                 cudaMemcpyHostToDevice, s_aux));
-                e_final_snapshot = event();
-                ZKC_CUDA(ctx, status, cudaEventRecord(e_final_snapshot, s_aux));
+            if (!ends_from_columns) {
+                const cudaMemcpyKind kind = rows_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+                ZKC_CUDA(ctx, status, vm_copy_lines(ends, 2 * sizeof(zkc_vm_state), in.snapshots, (limit + 1) * sizeof(zkc_vm_state), sizeof(zkc_vm_state),
+                                                    n_instances, kind, s_aux));
+                ZKC_CUDA(ctx, status, vm_copy_lines(ends + 1, 2 * sizeof(zkc_vm_state), in.snapshots + limit, (limit + 1) * sizeof(zkc_vm_state),
+                                                    sizeof(zkc_vm_state), n_instances, kind, s_aux));
+            } else {
+                ctx->launches++;
+                vm_gather_ends_kernel<<<(unsigned)((2 * n_instances * 32 + 127) / 128), 128, 0, s_aux>>>(cols, ends, limit, n_instances);
             }
             ctx->launches++;
-            vm_finalize_kernel<<<(unsigned)((n_instances + 1) / 2), 128, 0, s_aux>>>(d, flat, n_instances, dsnap, limit, 0);
+            vm_finalize_kernel<<<(unsigned)((n_instances + 1) / 2), 128, 0, s_aux>>>(d, flat, n_instances, ends, limit, 0);
         }
         if (s_aux != s) {
             e_hint = event();
             ZKC_CUDA(ctx, status, cudaEventRecord(e_hint, s_aux));
         }
-    }
+        return ZKC_OK;
+    };
+    if (!have_stream || !limit) { const int rc = launch_hint(!have_rows && limit); if (rc) return rc; }
+    // PACKED: the records of a chunk go home two chunks later, when their count is known, without stalling the queue
+    std::vector<cudaEvent_t> count_events(n_chunks, nullptr);
+    size_t next_records = 0, aux_home = 0, sp_home = 0;
+    auto send_records_home = [&](size_t c) -> int {
+        ZKC_CUDA(ctx, status, cudaEventSynchronize(count_events[c]));
+        const unsigned long long na = h_counts[2 * c], nsp = h_counts[2 * c + 1];
+        const size_t ca = aux_home < packed->aux_capacity ? std::min<size_t>(na, packed->aux_capacity - aux_home) : 0;
+        const size_t cs = sp_home < packed->sponge_capacity ? std::min<size_t>(nsp, packed->sponge_capacity - sp_home) : 0;
+        if (ca) ZKC_CUDA(ctx, status, cudaMemcpyAsync(packed->aux_records + aux_home, po.aux + c * chunk_cells, ca * sizeof(zkc_vm_aux_record), cudaMemcpyDeviceToHost, s_out));
+        if (cs) ZKC_CUDA(ctx, status, cudaMemcpyAsync(packed->sponge_records + sp_home, sp_regions + c * chunk_cells * VM_JOB_SLOTS, cs * sizeof(zkc_vm_sponge_record),
+                                                      cudaMemcpyDeviceToHost, s_out));
+        aux_home += na; sp_home += nsp;
+        packed->n_aux_records += na; packed->n_sponge_records += nsp;
+        return ZKC_OK;
+    };
+    size_t blob_off = 0;
     for (size_t c = 0; c < n_chunks && limit; c++) {
         const size_t r0 = c * chunk_rows;
         if (r0 >= limit) break;
         const size_t cnt = std::min(chunk_rows, limit - r0), n_thr = cnt * n_instances;
-        if (!in_dev) {
-            const bool last_chunk = r0 + cnt == limit;  // its final snapshot came with the side stream
-            ZKC_CUDA(ctx, status, copy_lines(bs + r0, snapshots + r0, (limit + 1) * sizeof(zkc_vm_state), (cnt + (last_chunk ? 0 : 1)) * sizeof(zkc_vm_state),
-                                             n_instances, cudaMemcpyHostToDevice, s_in));
-            if (last_chunk && e_final_snapshot && s_aux != s) ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e_final_snapshot, 0));
-            ZKC_CUDA(ctx, status, copy_lines(bw + r0, witness + r0, limit * sizeof(zkc_vm_cycle_witness), cnt * sizeof(zkc_vm_cycle_witness), n_instances,
-                                             cudaMemcpyHostToDevice, s_in));
-            if (n_chunks > 1) {
+        if (rows_host) {
+            ZKC_CUDA(ctx, status, vm_copy_lines(bs + r0, (limit + 1) * sizeof(zkc_vm_state), in.snapshots + r0, (limit + 1) * sizeof(zkc_vm_state),
+                                                (cnt + 1) * sizeof(zkc_vm_state), n_instances, cudaMemcpyHostToDevice, s_in));
+            ZKC_CUDA(ctx, status, vm_copy_lines(bw + r0, limit * sizeof(zkc_vm_cycle_witness), in.witness + r0, limit * sizeof(zkc_vm_cycle_witness),
+                                                cnt * sizeof(zkc_vm_cycle_witness), n_instances, cudaMemcpyHostToDevice, s_in));
+            if (piped) {
                 cudaEvent_t e = event();
                 ZKC_CUDA(ctx, status, cudaEventRecord(e, s_in));
                 ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e, 0));
             }
         }
+        if (have_rows) {  // records -> columns (snapshot rows r0 .. r0 + cnt inclusive: the last one is the next chunk's first)
+            const size_t st_tiles = ((cnt + 1 + 31) / 32) * n_instances, wt_tiles = ((cnt + 31) / 32) * n_instances;
+            ZKC_LAUNCH(ctx, "vm_rows_to_columns", vm_rows_to_columns_kernel<VM_WORDS>, (unsigned)st_tiles, 32, 0,
+                       reinterpret_cast<const uint32_t *>(rsnap), stc_w, st_stride, limit + 1, n_instances, r0, cnt + 1);
+            ZKC_LAUNCH(ctx, "vm_rows_to_columns", vm_rows_to_columns_kernel<VM_WIT_WORDS>, (unsigned)wt_tiles, 32, 0,
+                       reinterpret_cast<const uint32_t *>(rwit), wtc_w, wt_stride, limit, n_instances, r0, cnt);
+        }
+        if (have_stream) {  // segment c of every instance: one copy per blob, then expansion into the columns
+            const size_t blob_off0 = blob_off;
+            for (size_t i = 0; i < n_instances; i++) {
+                const zkc_vm_input_segment &sg = in.streams[i]->segments[c];
+                ZKC_CUDA(ctx, status, cudaMemcpyAsync(dblobs + blob_off, sg.blob, sg.blob_bytes, cudaMemcpyHostToDevice, s_in));
+                blob_off += (sg.blob_bytes + 255) & ~(size_t)255;
+            }
+            if (piped) {
+                cudaEvent_t e = event();
+                ZKC_CUDA(ctx, status, cudaEventRecord(e, s_in));
+                ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e, 0));
+            }
+            size_t off = blob_off0;
+            for (size_t i = 0; i < n_instances; i++) {
+                const zkc_vm_input_segment &sg = in.streams[i]->segments[c];
+                const zkc_vm_segment_header &hd = *(const zkc_vm_segment_header *)sg.blob;
+                const char *db = dblobs + off;
+                off += (sg.blob_bytes + 255) & ~(size_t)255;
+                const size_t sbase = i * (limit + 1) + r0, wbase = i * limit + r0, n1 = cnt + 1;
+                if (hd.n_dense_state)
+                    ZKC_LAUNCH(ctx, "vm_expand", vm_expand_dense_kernel, dim3((unsigned)((n1 + 255) / 256), hd.n_dense_state), 256, 0,
+                               (const uint16_t *)(db + hd.off_dense_state_word), (const uint32_t *)(db + hd.off_dense_state), n1, stc_w, st_stride, sbase);
+                if (hd.n_sparse_state) {
+                    const uint32_t *offs = (const uint32_t *)((const char *)sg.blob + hd.off_sparse_state_offsets);
+                    uint32_t most = 0;
+                    for (int w = 0; w < ZKC_VM_STATE_WORDS; w++) most = std::max(most, offs[w + 1] - offs[w]);
+                    ZKC_LAUNCH(ctx, "vm_expand", vm_expand_runs_kernel, dim3((most + 127) / 128, ZKC_VM_STATE_WORDS), 128, 0,
+                               (const uint32_t *)(db + hd.off_sparse_state_offsets), (const uint32_t *)(db + hd.off_sparse_state_index),
+                               (const uint32_t *)(db + hd.off_sparse_state_value), (uint32_t)n1, stc_w, st_stride, sbase);
+                }
+                ZKC_CUDA(ctx, status, cudaMemset2DAsync(wtc_w + wbase, wt_stride * 4, 0, cnt * 4, VM_WIT_WORDS, s));
+                if (hd.n_dense_witness)
+                    ZKC_LAUNCH(ctx, "vm_expand", vm_expand_dense_kernel, dim3((unsigned)((cnt + 255) / 256), hd.n_dense_witness), 256, 0,
+                               (const uint16_t *)(db + hd.off_dense_witness_word), (const uint32_t *)(db + hd.off_dense_witness), cnt, wtc_w, wt_stride, wbase);
+                if (hd.n_sparse_witness)
+                    ZKC_LAUNCH(ctx, "vm_expand", vm_expand_scatter_kernel, (hd.n_sparse_witness + 255) / 256, 256, 0,
+                               (const uint32_t *)(db + hd.off_sparse_witness_offsets), (int)ZKC_VM_WITNESS_WORDS,
+                               (const uint32_t *)(db + hd.off_sparse_witness_index), (const uint32_t *)(db + hd.off_sparse_witness_value),
+                               hd.n_sparse_witness, wtc_w, wt_stride, wbase);
+            }
+            if (r0 + cnt == limit) { const int rc = launch_hint(true); if (rc) return rc; }  // the final snapshots are in the columns now
+        }
         ps.counts = counts + 16 * c;
         ps.lists = lists + n_instances * r0;
-        ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, dsnap, dwit, dcw,
-                   (uint32_t)n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base);
+        if (packed) {
+            ps.records = sp_regions + c * chunk_cells * VM_JOB_SLOTS;
+            ps.n_records = rec_counts + 2 * c + 1;
+            ps.records_capacity = chunk_cells * VM_JOB_SLOTS;
+        }
+        ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, cols, dcw,
+                   (uint32_t)in.n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base);
         // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists, or one launch per slot
-        static const int sponge_mode = getenv("ZKC_VM_SPONGE_MODE") ? atoi(getenv("ZKC_VM_SPONGE_MODE")) : 0;
         if (sponge_mode == 0) {
             for (int k = 0; k < VM_JOB_SLOTS_LO; k++)
-                ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, dsnap, dwit, dcw,
-                           (uint32_t)n_callstack_witness, ps, k, limit, rows);
+                ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, cols, dcw,
+                           (uint32_t)in.n_callstack_witness, ps, k, limit, rows);
         } else {
             const size_t max_blocks = (size_t)ctx->sm_count * sponge_blocks_per_sm, need_blocks = (n_thr * VM_JOB_SLOTS + 127) / 128;
-            ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_persistent_kernel, (unsigned)std::min(max_blocks, std::max<size_t>(need_blocks, 1)), 128, 0, d, dsnap,
-                       dwit, dcw, (uint32_t)n_callstack_witness, ps, tickets + c, job_flags, limit, rows);
+            ZKC_LAUNCH(ctx, "vm_sponge", vm_sponge_persistent_kernel, (unsigned)std::min(max_blocks, std::max<size_t>(need_blocks, 1)), 128, 0, d, cols,
+                       dcw, (uint32_t)in.n_callstack_witness, ps, tickets + c, job_flags, limit, rows);
         }
-        ZKC_LAUNCH(ctx, "vm_sponge_far", vm_sponge_far_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, dsnap, dwit, dcw,
-                   (uint32_t)n_callstack_witness, ps, limit, rows);
+        ZKC_LAUNCH(ctx, "vm_sponge_far", vm_sponge_far_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, cols, dcw,
+                   (uint32_t)in.n_callstack_witness, ps, limit, rows);
         if (dtrace && !compact)
             ZKC_LAUNCH(ctx, "vm_sponge_trace", vm_sponge_trace_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, ps, dtrace, limit, n_instances, r0, cnt);
-        if (trace && !trace_dev) {
-            if (n_chunks > 1) {
+        if (packed) {
+            VmPackOut pc = po;
+            pc.aux = po.aux + c * chunk_cells; pc.n_aux = rec_counts + 2 * c; pc.aux_cap = chunk_cells;
+            ZKC_LAUNCH(ctx, "vm_pack", vm_pack_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, dtrace, limit, n_instances, r0, cnt, pc);
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(h_counts + 2 * c, rec_counts + 2 * c, 16, cudaMemcpyDeviceToHost, s));
+            count_events[c] = event();
+            ZKC_CUDA(ctx, status, cudaEventRecord(count_events[c], s));
+            if (piped) ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_out, count_events[c], 0));
+            ZKC_CUDA(ctx, status, vm_copy_lines(packed->cols8 + r0, limit, po.c8 + r0, limit, cnt, n_instances * (size_t)VM_PK_N8, cudaMemcpyDeviceToHost, s_out));
+            ZKC_CUDA(ctx, status, vm_copy_lines(packed->cols16 + r0, limit * 2, po.c16 + r0, limit * 2, cnt * 2, n_instances * (size_t)VM_PK_N16, cudaMemcpyDeviceToHost, s_out));
+            ZKC_CUDA(ctx, status, vm_copy_lines(packed->cols32 + r0, limit * 4, po.c32 + r0, limit * 4, cnt * 4, n_instances * (size_t)VM_PK_N32, cudaMemcpyDeviceToHost, s_out));
+            ZKC_CUDA(ctx, status, vm_copy_lines(packed->cols64 + r0, limit * 8, po.c64 + r0, limit * 8, cnt * 8, n_instances * (size_t)VM_PK_N64, cudaMemcpyDeviceToHost, s_out));
+            while (next_records + 2 <= c) { const int rc = send_records_home(next_records++); if (rc) return rc; }
+        } else if (trace && !trace_dev) {
+            if (piped) {
                 cudaEvent_t e = event();
                 ZKC_CUDA(ctx, status, cudaEventRecord(e, s));
                 ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_out, e, 0));
             }
-            ZKC_CUDA(ctx, status, copy_lines(trace + r0, dtrace + r0, limit * 8, cnt * 8, n_instances * (size_t)ncols, cudaMemcpyDeviceToHost, s_out));
+            ZKC_CUDA(ctx, status, vm_copy_lines(trace + r0, limit * 8, dtrace + r0, limit * 8, cnt * 8, n_instances * (size_t)ncols, cudaMemcpyDeviceToHost, s_out));
         }
     }
     if (e_hint) ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e_hint, 0));
-    ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 1) / 2), 128, 0, d, flat, n_instances, dsnap, limit, 1);
+    ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 1) / 2), 128, 0, d, flat, n_instances, ends, limit, 1);
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, n_instances * sizeof(VmDev), cudaMemcpyDeviceToHost, s));
+    if (packed)
+        while (next_records < n_chunks && count_events[next_records]) { const int rc = send_records_home(next_records++); if (rc) return rc; }
     unsigned long long n_records = 0;
-    if (compact) ZKC_CUDA(ctx, status, cudaMemcpyAsync(&n_records, ps.n_records, 8, cudaMemcpyDeviceToHost, s));
+    if (compact && !packed) ZKC_CUDA(ctx, status, cudaMemcpyAsync(&n_records, ps.n_records, 8, cudaMemcpyDeviceToHost, s));
     ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
-    if (compact && !trace_dev && rec_cap && n_records)  // the records of the whole call, one copy (they are ~4 % of the dense sponge columns)
+    if (compact && !packed && !trace_dev && rec_cap && n_records)  // the records of the whole call, one copy (they are ~4 % of the dense sponge columns)
         ZKC_CUDA(ctx, status, cudaMemcpyAsync(options->sponge_records, ps.records, std::min<size_t>(n_records, rec_cap) * sizeof(zkc_vm_sponge_record),
                                               cudaMemcpyDeviceToHost, s));
-    if (compact) ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
-    if (n_chunks > 1) {
+    if (compact && !packed) ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    if (piped) {
         ZKC_CUDA(ctx, status, cudaStreamSynchronize(s_in));
         ZKC_CUDA(ctx, status, cudaStreamSynchronize(s_out));
     }
@@ -2257,8 +2479,61 @@ extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *i
         statuses[i] = h[i].status;
         if (statuses[i].code != ZKC_OK && worst == ZKC_OK) worst = statuses[i].code;
     }
-    if (compact) statuses[0].reserved = (uint32_t)std::min<unsigned long long>(n_records, 0xFFFFFFFFull);
+    if (compact && !packed) statuses[0].reserved = (uint32_t)std::min<unsigned long long>(n_records, 0xFFFFFFFFull);
     return worst;
+}
+
+}  // namespace zkc
+
+extern "C" int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa,
+                                             const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness,
+                                             const zkc_vm_callstack_witness *callstack_witness, size_t n_callstack_witness, size_t limit,
+                                             const zkc_vm_options *options, int on_device, uint64_t *trace, uint64_t *commitments,
+                                             zkc_status *statuses) {
+    VmInput in;
+    in.snapshots = snapshots; in.witness = witness; in.rows_on_device = (on_device & ZKC_INPUTS_ON_DEVICE) != 0;
+    in.callstack_witness = callstack_witness; in.n_callstack_witness = n_callstack_witness; in.callstack_on_device = in.rows_on_device;
+    return vm_entry_batch(ctx, ios, n_instances, isa, in, limit, options, (on_device & ZKC_TRACE_ON_DEVICE) != 0, trace, commitments, statuses);
+}
+
+extern "C" int zkc_main_vm_entry_point_columns(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa,
+                                               const zkc_vm_columns *columns, const zkc_vm_callstack_witness *callstack_witness,
+                                               size_t n_callstack_witness, size_t limit, const zkc_vm_options *options, int trace_on_device,
+                                               uint64_t *trace, uint64_t *commitments, zkc_status *statuses) {
+    if (!columns) return ZKC_ERR_INVALID_ARGUMENT;
+    VmInput in;
+    in.columns = columns;
+    in.callstack_witness = callstack_witness; in.n_callstack_witness = n_callstack_witness; in.callstack_on_device = true;
+    return vm_entry_batch(ctx, ios, n_instances, isa, in, limit, options, trace_on_device != 0, trace, commitments, statuses);
+}
+
+extern "C" int zkc_main_vm_entry_point_stream(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa,
+                                              const zkc_vm_input_stream *const *streams, const zkc_vm_callstack_witness *callstack_witness,
+                                              size_t n_callstack_witness, size_t limit, const zkc_vm_options *options, zkc_vm_packed_trace *out,
+                                              uint64_t *commitments, zkc_status *statuses) {
+    if (!streams) return ZKC_ERR_INVALID_ARGUMENT;
+    VmInput in;
+    in.streams = streams;
+    in.callstack_witness = callstack_witness; in.n_callstack_witness = n_callstack_witness; in.callstack_on_device = false;
+    in.packed = out;
+    return vm_entry_batch(ctx, ios, n_instances, isa, in, limit, options, false, nullptr, commitments, statuses);
+}
+
+extern "C" int zkc_main_vm_rows_to_columns(zkc_ctx *ctx, const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness, size_t n_instances,
+                                           size_t limit, uint32_t *state_words, size_t state_stride, uint32_t *witness_words, size_t witness_stride) {
+    if (!ctx || !snapshots || !witness || !state_words || !witness_words || state_stride < n_instances * (limit + 1) ||
+        witness_stride < n_instances * limit)
+        return ZKC_ERR_INVALID_ARGUMENT;
+    if (!n_instances) return ZKC_OK;
+    zkc_status *st = nullptr;
+    ZKC_CUDA(ctx, st, cudaSetDevice(ctx->device));
+    ZKC_LAUNCH(ctx, "vm_rows_to_columns", vm_rows_to_columns_kernel<VM_WORDS>, (unsigned)(((limit + 1 + 31) / 32) * n_instances), 32, 0,
+               reinterpret_cast<const uint32_t *>(snapshots), state_words, state_stride, limit + 1, n_instances, 0, limit + 1);
+    if (limit)
+        ZKC_LAUNCH(ctx, "vm_rows_to_columns", vm_rows_to_columns_kernel<VM_WIT_WORDS>, (unsigned)(((limit + 31) / 32) * n_instances), 32, 0,
+                   reinterpret_cast<const uint32_t *>(witness), witness_words, witness_stride, limit, n_instances, 0, limit);
+    ZKC_CUDA(ctx, st, cudaGetLastError());
+    return ZKC_OK;
 }
 
 extern "C" int zkc_main_vm_entry_point(zkc_ctx *ctx, zkc_vm_closed_form *io, const zkc_vm_isa *isa, const zkc_vm_state *snapshots,

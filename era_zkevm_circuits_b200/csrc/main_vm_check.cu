@@ -114,8 +114,10 @@ vm_check_kernel(VmCheckDev *out, const zkc_vm_isa *__restrict__ isa, const uint6
     if (TYPE(ZKC_OP_MUL) || TYPE(ZKC_OP_DIV)) {  // a * b + rem = lo + 2^256 * hi: enforce_mul_relation (8 x 8 u32 schoolbook)
         const bool div = TYPE(ZKC_OP_DIV);
         // mul: a * b = d0 + 2^256 d1.  div: d0 (quotient) * b + d1 (remainder) = a, remainder < b (b != 0); b == 0: both zero
-        const uint32_t *x = div ? d0 : a, *y = b;
-        uint32_t r[16];
+        uint32_t x[8], r[16];  // (a pointer select would push a / d0 into local memory)
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = div ? d0[i] : a[i];
+        const uint32_t (&y)[8] = b;
 #pragma unroll
         for (int i = 0; i < 16; i++) r[i] = 0;
 #pragma unroll
@@ -173,8 +175,8 @@ vm_check_kernel(VmCheckDev *out, const zkc_vm_isa *__restrict__ isa, const uint6
     if (upd0 && mem_write) bad |= ZKC_VMV_SELECTION;
     // ---- sponge columns: zeros unless enforced; the opcode-specific block is zero for the plain opcodes -------------------
     uint64_t stray = 0;
-#pragma unroll 1
-    for (int k = 0; k < ZKC_VM_NUM_SPONGES; k++) {
+#pragma unroll
+    for (int k = 0; k < ZKC_VM_NUM_SPONGES; k++) {  // fully unrolled: 117 independent loads, issued as far ahead as registers allow
         const uint64_t enf = TR(ZKC_VM_SPONGE_ENFORCE + k);
         if (enf > 1) bad |= ZKC_VMV_BOOLEAN;
         uint64_t any = 0;
@@ -193,7 +195,7 @@ vm_check_kernel(VmCheckDev *out, const zkc_vm_isa *__restrict__ isa, const uint6
                             prop_bit(props, ZKC_VM_BIT_TYPE(ZKC_OP_NEAR_CALL)) || prop_bit(props, ZKC_VM_BIT_TYPE(ZKC_OP_FAR_CALL)) ||
                             prop_bit(props, ZKC_VM_BIT_TYPE(ZKC_OP_RET));
         uint64_t any = 0;
-#pragma unroll 1
+#pragma unroll
         for (int i = 0; i < ZKC_VM_OP_AUX_COLS; i++) any |= TR(ZKC_VM_OP_AUX + i);
         if (!family && any) bad |= ZKC_VMV_SELECTION;
     }

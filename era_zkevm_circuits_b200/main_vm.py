@@ -128,6 +128,57 @@ def main_vm_entry_point_batch(engine: Engine, closed_form_inputs, isa: abi.VmIsa
     return commitments, ios, statuses, rc
 
 
+@dataclass
+class VmColumnInputs:
+    """zkc_vm_columns: torch int32 CUDA tensors state_words [294, state_stride], witness_words [44, witness_stride]; word w
+    of snapshot i of instance k at state_words[w, k * (limit + 1) + i], of cycle i's oracle answers at witness_words[w, k * limit + i]"""
+    state_words: object
+    witness_words: object
+
+    def struct(self):
+        return abi.VmColumns(self.state_words.data_ptr(), self.state_words.shape[1], self.witness_words.data_ptr(), self.witness_words.shape[1])
+
+
+def main_vm_rows_to_columns(engine: Engine, snapshots, witness_oracle, limit: int) -> VmColumnInputs:
+    """device records [n, limit + 1, 1176] / [n, limit, 176] (torch CUDA uint8) -> device columns"""
+    import torch
+    assert on_device(snapshots, witness_oracle)
+    n = int(snapshots.shape[0]) if snapshots.dim() == 3 else 1
+    ss, ws = (max(n * (limit + 1), 1) + 31) // 32 * 32, (max(n * limit, 1) + 31) // 32 * 32
+    st = torch.empty((abi.VM_STATE_WORDS, ss), dtype=torch.int32, device=snapshots.device)
+    wt = torch.empty((abi.VM_WITNESS_WORDS, ws), dtype=torch.int32, device=snapshots.device)
+    rc = engine.lib.zkc_main_vm_rows_to_columns(engine.h, ptr(snapshots), ptr(witness_oracle), n, limit, ptr(st), ss, ptr(wt), ws)
+    if rc:
+        raise ZkcError(rc, what="zkc_main_vm_rows_to_columns")
+    return VmColumnInputs(st, wt)
+
+
+def main_vm_entry_point_columns(engine: Engine, closed_form_inputs, isa: abi.VmIsa, columns: VmColumnInputs, limit: int, trace_out=None,
+                                compare_expected=False, callstack_witness=None, sponge_records_out=None):
+    """main_vm_entry_point_batch with the snapshots / oracle answers already in HBM as columns (and the popped frames as device
+    records [n, capacity, 336]).  Returns (commitments [n, 4], closed forms (updated), statuses, rc)."""
+    n = len(closed_form_inputs)
+    ios = (abi.VmClosedForm * n)(*[abi.VmClosedForm.from_buffer_copy(bytes(c)) for c in closed_form_inputs])
+    commitments = np.zeros((n, 4), dtype=np.uint64)
+    statuses = (abi.Status * n)()
+    opts = abi.VmOptions(int(compare_expected))
+    if sponge_records_out is not None:
+        assert trace_out is not None and on_device(sponge_records_out) == on_device(trace_out)
+        opts.trace_layout = abi.VM_TRACE_COMPACT
+        opts.sponge_records_capacity = len(sponge_records_out)
+        opts.sponge_records = ptr(sponge_records_out)
+    n_cw = _n_cw(callstack_witness)
+    assert not n_cw or on_device(callstack_witness)
+    cs = columns.struct()
+    rc = engine.lib.zkc_main_vm_entry_point_columns(engine.h, C.cast(ios, C.c_void_p), n, C.byref(isa), C.byref(cs),
+                                                    ptr(callstack_witness) if n_cw else None, n_cw, limit, C.byref(opts),
+                                                    int(trace_out is not None and on_device(trace_out)), ptr(trace_out), ptr(commitments),
+                                                    C.cast(statuses, C.c_void_p))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, statuses[0], "main_vm_entry_point_columns")
+    return commitments, ios, statuses, rc
+
+
 def main_vm_check_trace(engine: Engine, isa: abi.VmIsa, trace, limit: int, n_instances: int = 1):
     """Constraint evaluation of finished main_vm traces (DENSE layout): the row-local relations of vm_cycle.  trace:
     [NUM_COLS, limit] or [n, NUM_COLS, limit] uint64 (numpy: host, torch CUDA: device).  Returns (violating rows, status)."""
@@ -137,3 +188,173 @@ def main_vm_check_trace(engine: Engine, isa: abi.VmIsa, trace, limit: int, n_ins
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
         raise ZkcError(rc, st, "main_vm_check_trace")
     return viol.value, st
+
+
+# ---- transport forms over PCIe (include/zkc_b200.h, "transport forms of the main_vm call") ---------------------------------
+class VmInputStreamHandle:
+    """a zkc_vm_input_stream of ONE instance, in (pinned) host memory owned by the library"""
+
+    def __init__(self, lib, ptr_, nbytes):
+        self.lib, self.ptr, self.bytes = lib, ptr_, nbytes
+
+    @property
+    def struct(self):
+        return self.ptr.contents
+
+    def free(self):
+        if self.ptr:
+            self.lib.zkc_vm_input_stream_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def vm_encode_input_stream(lib, snapshots, witness_oracle, limit: int, segment_cycles: int = 0) -> VmInputStreamHandle:
+    """records of one instance (numpy uint8 [limit + 1, 1176], [limit, 176]) -> segmented stream (host encoder of the library)"""
+    snapshots, witness_oracle = np.ascontiguousarray(snapshots), np.ascontiguousarray(witness_oracle)
+    assert snapshots.shape[0] >= limit + 1 and witness_oracle.shape[0] >= limit
+    out = C.POINTER(abi.VmInputStream)()
+    nbytes = C.c_uint64()
+    rc = lib.zkc_vm_encode_input_stream(ptr(snapshots), ptr(witness_oracle), limit, segment_cycles, C.byref(out), C.byref(nbytes))
+    if rc:
+        raise ZkcError(rc, what="zkc_vm_encode_input_stream")
+    return VmInputStreamHandle(lib, out, nbytes.value)
+
+
+def vm_decode_input_stream(stream: VmInputStreamHandle):
+    """reference decoder of the stream format (numpy; tests): returns (state_words [294, limit + 1], witness_words [44, limit])"""
+    st = stream.struct
+    limit = int(st.limit)
+    state = np.zeros((abi.VM_STATE_WORDS, limit + 1), dtype=np.uint32)
+    wit = np.zeros((abi.VM_WITNESS_WORDS, limit), dtype=np.uint32)
+    for k in range(st.n_segments):
+        seg = st.segments[k]
+        raw = np.frombuffer((C.c_uint8 * seg.blob_bytes).from_address(seg.blob), dtype=np.uint8)
+        h = abi.VmSegmentHeader.from_buffer_copy(raw[:C.sizeof(abi.VmSegmentHeader)].tobytes())
+        assert h.magic == abi.VM_SEGMENT_MAGIC and h.blob_bytes == seg.blob_bytes and h.first_cycle == k * st.segment_cycles
+        n, f = h.n_cycles, h.first_cycle
+        arr = lambda off, cnt, dt: np.frombuffer(raw, dtype=dt, count=cnt, offset=off)
+        dsw, dww = arr(h.off_dense_state_word, h.n_dense_state, "<u2"), arr(h.off_dense_witness_word, h.n_dense_witness, "<u2")
+        state[dsw, f:f + n + 1] = arr(h.off_dense_state, h.n_dense_state * (n + 1), "<u4").reshape(h.n_dense_state, n + 1)
+        wit[dww, f:f + n] = arr(h.off_dense_witness, h.n_dense_witness * n, "<u4").reshape(h.n_dense_witness, n)
+        so = arr(h.off_sparse_state_offsets, abi.VM_STATE_WORDS + 1, "<u4")
+        si, sv = arr(h.off_sparse_state_index, h.n_sparse_state, "<u4"), arr(h.off_sparse_state_value, h.n_sparse_state, "<u4")
+        for w in range(abi.VM_STATE_WORDS):
+            lo, hi = int(so[w]), int(so[w + 1])
+            if hi > lo:
+                assert si[lo] == 0
+                runs = np.diff(np.append(si[lo:hi], n + 1).astype(np.int64))
+                state[w, f:f + n + 1] = np.repeat(sv[lo:hi], runs)
+        wo = arr(h.off_sparse_witness_offsets, abi.VM_WITNESS_WORDS + 1, "<u4")
+        wi, wv = arr(h.off_sparse_witness_index, h.n_sparse_witness, "<u4"), arr(h.off_sparse_witness_value, h.n_sparse_witness, "<u4")
+        for w in range(abi.VM_WITNESS_WORDS):
+            lo, hi = int(wo[w]), int(wo[w + 1])
+            if hi > lo:
+                assert w not in dww
+                wit[w, f + wi[lo:hi].astype(np.int64)] = wv[lo:hi]
+    return state, wit
+
+
+_PK_LAYOUT = None
+
+
+def vm_packed_layout(lib):
+    """(kind [276], slot [276], counts [6]) of the PACKED trace"""
+    global _PK_LAYOUT
+    if _PK_LAYOUT is None:
+        kind, slot, counts = np.zeros(abi.VM_COLS["NUM_COLS"], np.uint8), np.zeros(abi.VM_COLS["NUM_COLS"], np.uint16), np.zeros(6, np.uint32)
+        lib.zkc_vm_packed_layout(ptr(kind), ptr(slot), ptr(counts))
+        _PK_LAYOUT = (kind, slot, counts)
+    return _PK_LAYOUT
+
+
+@dataclass
+class VmPackedTraceBuffers:
+    """host buffers of a zkc_vm_packed_trace (numpy views, optionally of pinned memory): cols8 [N8, rows] ... and the records"""
+    cols8: np.ndarray
+    cols16: np.ndarray
+    cols32: np.ndarray
+    cols64: np.ndarray
+    aux_records: np.ndarray
+    sponge_records: np.ndarray
+    n_aux_records: int = 0
+    n_sponge_records: int = 0
+
+    @property
+    def nbytes_used(self):
+        return (self.cols8.nbytes + self.cols16.nbytes + self.cols32.nbytes + self.cols64.nbytes +
+                self.n_aux_records * abi.VM_AUX_RECORD_DTYPE.itemsize + self.n_sponge_records * abi.VM_SPONGE_RECORD_DTYPE.itemsize)
+
+
+def vm_packed_trace_buffers(engine: Engine, n: int, limit: int, aux_fraction=0.3, sponge_per_cycle=1.5, alloc=None) -> VmPackedTraceBuffers:
+    """alloc(shape, dtype) -> array (default numpy.zeros; pass a pinned allocator for asynchronous copies)"""
+    kind, slot, counts = vm_packed_layout(engine.lib)
+    rows = n * limit
+    alloc = alloc or (lambda shape, dt: np.zeros(shape, dtype=dt))
+    return VmPackedTraceBuffers(alloc((int(counts[0]), rows), np.uint8), alloc((int(counts[1]), rows), np.uint16), alloc((int(counts[2]), rows), np.uint32),
+                                alloc((int(counts[3]), rows), np.uint64), alloc((int(rows * aux_fraction) + 64,), abi.VM_AUX_RECORD_DTYPE),
+                                alloc((int(rows * sponge_per_cycle) + 64,), abi.VM_SPONGE_RECORD_DTYPE))
+
+
+def main_vm_entry_point_stream(engine: Engine, closed_form_inputs, isa: abi.VmIsa, streams, limit: int, callstack_witness=None,
+                               out: Optional[VmPackedTraceBuffers] = None, compare_expected=False):
+    """zkc_main_vm_entry_point_stream: host buffers in the transport forms.  streams: list of VmInputStreamHandle (one per
+    instance); callstack_witness: numpy [n, capacity, 336]; out: VmPackedTraceBuffers or None.  Returns (commitments,
+    closed forms, statuses, rc)."""
+    n = len(closed_form_inputs)
+    assert len(streams) == n
+    ios = (abi.VmClosedForm * n)(*[abi.VmClosedForm.from_buffer_copy(bytes(c)) for c in closed_form_inputs])
+    commitments = np.zeros((n, 4), dtype=np.uint64)
+    statuses = (abi.Status * n)()
+    opts = abi.VmOptions(int(compare_expected))
+    sp = (C.POINTER(abi.VmInputStream) * n)(*[s.ptr for s in streams])
+    pk = None
+    if out is not None:
+        opts.trace_layout = abi.VM_TRACE_PACKED
+        pk = abi.VmPackedTrace(out.cols8.ctypes.data, out.cols16.ctypes.data, out.cols32.ctypes.data, out.cols64.ctypes.data,
+                               out.aux_records.ctypes.data, len(out.aux_records), 0, out.sponge_records.ctypes.data, len(out.sponge_records), 0)
+    n_cw = _n_cw(callstack_witness)
+    assert not n_cw or not on_device(callstack_witness)
+    rc = engine.lib.zkc_main_vm_entry_point_stream(engine.h, C.cast(ios, C.c_void_p), n, C.byref(isa), C.cast(sp, C.c_void_p),
+                                                   ptr(callstack_witness) if n_cw else None, n_cw, limit, C.byref(opts),
+                                                   C.byref(pk) if pk is not None else None, ptr(commitments), C.cast(statuses, C.c_void_p))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, statuses[0], "main_vm_entry_point_stream")
+    if out is not None:
+        out.n_aux_records, out.n_sponge_records = int(pk.n_aux_records), int(pk.n_sponge_records)
+    return commitments, ios, statuses, rc
+
+
+def vm_expand_packed_trace(lib, out: VmPackedTraceBuffers, n: int, limit: int) -> np.ndarray:
+    """PACKED -> DENSE [n, 276, limit] uint64, bit-exactly (what the host shim does while it assigns the cells)"""
+    kind, slot, counts = vm_packed_layout(lib)
+    K = abi.VM_COLS
+    rows = n * limit
+    dense = np.zeros((n, K["NUM_COLS"], limit), dtype=np.uint64)
+    blocks = {abi.VM_PK_U8: out.cols8, abi.VM_PK_U16: out.cols16, abi.VM_PK_U32: out.cols32, abi.VM_PK_U64: out.cols64}
+    for c in range(K["NUM_COLS"]):
+        if int(kind[c]) in blocks:
+            dense[:, c, :] = blocks[int(kind[c])][int(slot[c])].reshape(n, limit)
+    assert out.n_aux_records <= len(out.aux_records) and out.n_sponge_records <= len(out.sponge_records), "record capacity exceeded"
+    rec = out.sponge_records[:out.n_sponge_records]
+    r, s_ = rec["row"].astype(np.int64), rec["slot"].astype(np.int64)
+    flat = dense.transpose(1, 0, 2).reshape(K["NUM_COLS"], rows)  # [col, g] view
+    flat[K["SPONGE_ENFORCE"] + s_, r] = 1
+    for j in range(12):
+        flat[K["SPONGE_FINAL"] + 12 * s_ + j, r] = rec["out"][:, j]
+    aux = out.aux_records[:out.n_aux_records]
+    aux = aux[np.argsort(aux["row"], kind="stable")]
+    ar = aux["row"].astype(np.int64)
+    flat[K["OP_AUX"]:K["OP_AUX"] + 48, ar] = aux["op_aux"].T
+    # queue ends: the record at or before each row (row 0 of every instance has one)
+    if rows:
+        has = np.zeros(rows, dtype=np.int64)
+        has[ar] = np.arange(1, len(ar) + 1)
+        last = np.maximum.accumulate(has)
+        assert (last > 0).all() and (has[::limit] > 0).all(), "row 0 of an instance without a record"
+        flat[K["FORWARD_TAIL_OUT"]:K["FORWARD_TAIL_OUT"] + 10, :] = aux["queue_ends"][last - 1].T
+    return np.ascontiguousarray(flat.reshape(K["NUM_COLS"], n, limit).transpose(1, 0, 2))

@@ -1090,6 +1090,8 @@ typedef struct zkc_vm_state {
     uint64_t code_decommittment_queue_state[12];
 } zkc_vm_state;
 #define ZKC_VM_STATE_FLAT 243
+#define ZKC_VM_STATE_WORDS 294   /* sizeof(zkc_vm_state) / 4 */
+#define ZKC_VM_WITNESS_WORDS 44  /* sizeof(zkc_vm_cycle_witness) / 4 */
 
 /* answers of the WitnessOracle (main_vm/witness_oracle.rs:45-91) one cycle consumes, flattened by the host before
  * the call.  Only one opcode executes per cycle, so the opcode-specific answers share fields. */
@@ -1257,6 +1259,121 @@ int zkc_main_vm_entry_point_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t 
                                   const zkc_vm_callstack_witness *callstack_witness, size_t n_callstack_witness, size_t limit,
                                   const zkc_vm_options *options, int on_device, uint64_t *trace, uint64_t *commitments,
                                   zkc_status *statuses);
+
+/* COLUMN (struct-of-arrays) form of the per-cycle inputs -- the layout the cycle kernel reads.  The 32-bit word w of
+ * zkc_vm_state (w = byte offset / 4; 64-bit members are two consecutive words, low half first) of snapshot i of instance k is
+ * state_words[w * state_stride + k * (limit + 1) + i]; word w of zkc_vm_cycle_witness of cycle i of instance k is
+ * witness_words[w * witness_stride + k * limit + i].  A warp's 32 consecutive cycles read every word as one 128-byte line
+ * and "the next snapshot" is the neighbouring element, which the record form (1 176-byte records) cannot offer; an
+ * out-of-circuit run that emits columns directly saves the transposition the record entry points do on the device.
+ * Device memory only; strides in elements, >= n_instances * (limit + 1) resp. n_instances * limit (multiples of 32 keep every
+ * line aligned). */
+typedef struct zkc_vm_columns {
+    const uint32_t *state_words;
+    size_t state_stride;
+    const uint32_t *witness_words;
+    size_t witness_stride;
+} zkc_vm_columns;
+
+/* main_vm_entry_point (main_vm/mod.rs:47-232) over a batch of instances whose snapshots / oracle answers are columns in HBM;
+ * callstack_witness is device memory too.  Everything else as zkc_main_vm_entry_point_batch. */
+int zkc_main_vm_entry_point_columns(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa,
+                                    const zkc_vm_columns *columns, const zkc_vm_callstack_witness *callstack_witness,
+                                    size_t n_callstack_witness, size_t limit, const zkc_vm_options *options, int trace_on_device,
+                                    uint64_t *trace, uint64_t *commitments, zkc_status *statuses);
+
+/* records -> columns on the device (what the record entry points run internally): snapshots [n_instances][limit + 1],
+ * witness [n_instances][limit], all four pointers device memory.  Asynchronous on the context's stream. */
+int zkc_main_vm_rows_to_columns(zkc_ctx *ctx, const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness, size_t n_instances,
+                                size_t limit, uint32_t *state_words, size_t state_stride, uint32_t *witness_words, size_t witness_stride);
+
+/* ---- transport forms of the main_vm call over PCIe (host buffers) ---------------------------------------------------
+ * The record form costs 1 176 + 176 bytes per cycle on the way in and 8 bytes per cell on the way out; both directions are
+ * PCIe-bound by a factor of ten against the kernels.  The STREAM forms carry the same values in fewer bytes:
+ *
+ * IN -- zkc_vm_input_stream: one instance's snapshots / oracle answers as a sequence of SEGMENTS of `segment_cycles` cycles
+ * (the last one may be shorter); segment s covers cycles [s * segment_cycles, ...) and the snapshots before each of them
+ * plus the one behind the last (a boundary snapshot is in both neighbours).  An out-of-circuit run emits a segment every
+ * `segment_cycles` cycles; the call copies, expands and evaluates them as they come (segment = pipeline chunk).
+ * A segment is ONE contiguous blob (one asynchronous copy): the columns of zkc_vm_columns restricted to the segment, each
+ * 32-bit word either DENSE (all its values) or SPARSE.  A sparse STATE word is a list of (local snapshot index, value)
+ * changes: record j of word w holds from index[j] up to the next record of w (or the end of the segment); the first record of
+ * a word is at local index 0.  A sparse WITNESS word is the list of (local cycle index, value) of its non-zero values.
+ * Blob layout (all offsets in bytes from the start of the blob, every array 16-byte aligned):
+ *   zkc_vm_segment_header
+ *   uint16_t dense_state_word[n_dense_state]        increasing
+ *   uint16_t dense_witness_word[n_dense_witness]
+ *   uint32_t dense_state[n_dense_state][n_cycles + 1]
+ *   uint32_t dense_witness[n_dense_witness][n_cycles]
+ *   uint32_t sparse_state_offsets[ZKC_VM_STATE_WORDS + 1]     records [offsets[w], offsets[w + 1]) belong to word w
+ *   uint32_t sparse_state_index[n_sparse_state], sparse_state_value[n_sparse_state]
+ *   uint32_t sparse_witness_offsets[ZKC_VM_WITNESS_WORDS + 1]
+ *   uint32_t sparse_witness_index[n_sparse_witness], sparse_witness_value[n_sparse_witness]
+ * zkc_vm_encode_input_stream derives the stream from records (a word goes dense when that is fewer bytes: 4 per value
+ * against 8 per change). */
+#define ZKC_VM_SEGMENT_MAGIC 0x5a4b5347u
+typedef struct zkc_vm_segment_header {
+    uint32_t magic, first_cycle, n_cycles, n_dense_state, n_dense_witness, n_sparse_state, n_sparse_witness, reserved;
+    uint32_t off_dense_state_word, off_dense_witness_word, off_dense_state, off_dense_witness;
+    uint32_t off_sparse_state_offsets, off_sparse_state_index, off_sparse_state_value;
+    uint32_t off_sparse_witness_offsets, off_sparse_witness_index, off_sparse_witness_value;
+    uint32_t blob_bytes, reserved2;
+} zkc_vm_segment_header;
+typedef struct zkc_vm_input_segment {
+    const void *blob;  /* starts with a zkc_vm_segment_header; pinned host memory makes the copy asynchronous */
+    uint64_t blob_bytes;
+} zkc_vm_input_segment;
+typedef struct zkc_vm_input_stream {
+    uint64_t limit;
+    uint32_t segment_cycles, n_segments;
+    const zkc_vm_input_segment *segments;
+} zkc_vm_input_stream;
+
+/* records of ONE instance (host memory: snapshots [limit + 1], witness [limit]) -> a stream in pinned host memory owned by
+ * the library; free with zkc_vm_input_stream_free.  segment_cycles = 0 picks the default (2^16).  bytes_out (may be NULL):
+ * what crosses PCIe. */
+int zkc_vm_encode_input_stream(const zkc_vm_state *snapshots, const zkc_vm_cycle_witness *witness, size_t limit, size_t segment_cycles,
+                               zkc_vm_input_stream **out, uint64_t *bytes_out);
+void zkc_vm_input_stream_free(zkc_vm_input_stream *stream);
+
+/* OUT -- the PACKED trace: the same cells as the DENSE layout, every column in the narrowest unsigned type its values fit
+ * (booleans / small integers u8, 16-bit values u16, limbs u32, field elements u64), column-major per type block:
+ * cols8[slot * rows + g] with g = instance * limit + row, rows = n_instances * limit.  zkc_vm_packed_layout gives
+ * (kind, slot) of every DENSE-layout column.  The opcode-family block (ZKC_VM_OP_AUX, zero on ~85 % of the rows) and the
+ * forward / rollback queue ends (which move only on log / call / ret rows) travel as one zkc_vm_aux_record per row that has
+ * either: a row without a record has a zero OP_AUX block and the queue ends of the row before it (row 0 of an instance always
+ * has a record).  The sponge columns travel as zkc_vm_sponge_record like in the COMPACT layout.  Records arrive in no
+ * particular order; the counts are written to n_aux_records / n_sponge_records (records beyond a capacity are dropped, the
+ * count still says how many there were). */
+#define ZKC_VM_TRACE_PACKED 2
+enum zkc_vm_packed_kind { ZKC_VM_PK_U8 = 0, ZKC_VM_PK_U16, ZKC_VM_PK_U32, ZKC_VM_PK_U64, ZKC_VM_PK_AUX_RECORD, ZKC_VM_PK_SPONGE_RECORD };
+typedef struct zkc_vm_aux_record {
+    uint32_t row;      /* instance * limit + cycle */
+    uint32_t reserved;
+    uint64_t op_aux[48];      /* ZKC_VM_OP_AUX .. + 47 */
+    uint64_t queue_ends[10];  /* ZKC_VM_FORWARD_TAIL_OUT .. + 4, ZKC_VM_ROLLBACK_HEAD_OUT .. + 4 */
+} zkc_vm_aux_record;
+typedef struct zkc_vm_packed_trace {
+    uint8_t *cols8;
+    uint16_t *cols16;
+    uint32_t *cols32;
+    uint64_t *cols64;
+    zkc_vm_aux_record *aux_records;
+    uint64_t aux_capacity, n_aux_records;        /* in, out */
+    zkc_vm_sponge_record *sponge_records;
+    uint64_t sponge_capacity, n_sponge_records;  /* in, out */
+} zkc_vm_packed_trace;
+/* kind[c], slot[c] for c < ZKC_VM_NUM_COLS; counts[k] = columns of kind k (k < 4: the heights of the four type blocks) */
+void zkc_vm_packed_layout(uint8_t kind[ZKC_VM_NUM_COLS], uint16_t slot[ZKC_VM_NUM_COLS], uint32_t counts[6]);
+
+/* main_vm_entry_point (main_vm/mod.rs:47-232) over host buffers in the stream forms: streams[n_instances] (equal limit and
+ * segment_cycles), callstack_witness [n_instances][n_callstack_witness] host records, `out` (may be NULL: no witness
+ * wanted) host buffers.  Segment by segment, H2D | expansion + kernels + packing | D2H overlap; everything else as
+ * zkc_main_vm_entry_point_batch. */
+int zkc_main_vm_entry_point_stream(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa,
+                                   const zkc_vm_input_stream *const *streams, const zkc_vm_callstack_witness *callstack_witness,
+                                   size_t n_callstack_witness, size_t limit, const zkc_vm_options *options, zkc_vm_packed_trace *out,
+                                   uint64_t *commitments, zkc_status *statuses);
 
 /* Constraint evaluation of finished main_vm traces (DENSE layout, [n_instances][ZKC_VM_NUM_COLS][limit]): every relation
  * that is local to a row -- booleanity / ranges of the allocated cells, opcode decoding against the ISA tables

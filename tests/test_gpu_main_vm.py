@@ -451,3 +451,97 @@ def test_check_trace_constraint_evaluation(engine, orc):
     two[1, K["CONDITION"], 5] = 3
     viol, stt = main_vm_check_trace(engine, isa.isa, two, cycles, n_instances=2)
     assert viol == 1 and stt.first_bad_row == cycles + 5
+
+
+def test_column_inputs_equal_record_inputs(engine, orc):
+    """zkc_main_vm_entry_point_columns (snapshots / oracle answers as device columns) == the record entry point == the oracle,
+    for a batch whose instance boundaries are not warp-aligned; hidden_fsm_output of every instance included"""
+    import torch
+    from era_zkevm_circuits_b200 import main_vm_entry_point_batch, main_vm_entry_point_columns, main_vm_rows_to_columns
+    n, cycles = 5, 1237
+    isa = I.Isa()
+    ios, snaps, wits, cws = [], [], [], []
+    for i in range(n):
+        io = abi.VmClosedForm(); io.start_flag = 1; io.rollback_queue_tail_for_block[1] = 31 + i
+        st = O.vm_initial_state(orc, io, isa.isa)
+        rc, sn, wi, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(I.random_program(isa, 700, seed=300 + i, far_calls=(i == 2))), cycles, full=True)
+        assert rc == 0
+        ios.append(with_tail(io, tail)); snaps.append(sn); wits.append(wi); cws.append(cw)
+    cap = max(1, max(len(c) for c in cws))
+    cwa = np.zeros((n, cap, C.sizeof(abi.VmCallstackWitness)), dtype=np.uint8)
+    for i, c in enumerate(cws):
+        cwa[i, :len(c)] = c
+    d_s, d_w, d_c = torch.from_numpy(np.stack(snaps)).cuda(), torch.from_numpy(np.stack(wits)).cuda(), torch.from_numpy(cwa).cuda()
+    t_rows = torch.empty((n, K["NUM_COLS"], cycles), dtype=torch.int64, device="cuda")
+    t_cols = torch.empty_like(t_rows)
+    c1, o1, s1, rc1 = main_vm_entry_point_batch(engine, ios, isa.isa, d_s, d_w, cycles, trace_out=t_rows, callstack_witness=d_c)
+    cols = main_vm_rows_to_columns(engine, d_s, d_w, cycles)
+    # the columns are what the header says: word w of snapshot i of instance k at [w, k * (limit + 1) + i]
+    hs = np.stack(snaps).view(np.uint32).reshape(n * (cycles + 1), -1)
+    assert np.array_equal(cols.state_words.cpu().numpy().view(np.uint32)[:, :n * (cycles + 1)], hs.T)
+    hw = np.stack(wits).view(np.uint32).reshape(n * cycles, -1)
+    assert np.array_equal(cols.witness_words.cpu().numpy().view(np.uint32)[:, :n * cycles], hw.T)
+    c2, o2, s2, rc2 = main_vm_entry_point_columns(engine, ios, isa.isa, cols, cycles, trace_out=t_cols, callstack_witness=d_c)
+    assert rc1 == 0 and rc2 == 0 and c1.tolist() == c2.tolist() and torch.equal(t_rows, t_cols)
+    lib = O.load()
+    for i in range(n):
+        want = O.vm_entry_point(orc, ios[i], isa.isa, snaps[i], wits[i], cycles, cw=cws[i])
+        assert want[0] == 0 and c2[i].tolist() == want[3].tolist()
+        assert np.array_equal(t_cols[i].cpu().numpy().view(np.uint64), want[2])
+        for o in (o1, o2):
+            assert np.array_equal(flat(lib, o[i].hidden_fsm_output), flat(lib, want[1].hidden_fsm_output)), i
+            assert o[i].completion_flag == want[1].completion_flag
+    # a broken link is found at its row through the columns too
+    bad = cols.state_words.clone()
+    bad[abi.VM_STATE_WORDS - 3, 2 * (cycles + 1) + 400] ^= 1  # decommitment queue state of instance 2, snapshot 400
+    c3, o3, s3, rc3 = main_vm_entry_point_columns(engine, ios, isa.isa, type(cols)(bad, cols.witness_words), cycles, callstack_witness=d_c)
+    assert rc3 == abi.ZKC_ERR_SNAPSHOT_MISMATCH and [s.code for s in s3] == [0, 0, abi.ZKC_ERR_SNAPSHOT_MISMATCH, 0, 0]
+    assert s3[2].first_bad_row in (399, 400)
+
+
+@pytest.mark.parametrize("n,cycles,segment", [(1, 3000, 0), (3, 5000, 1024), (2, 4096, 2048), (1, 1, 0)])
+def test_stream_inputs_and_packed_trace(engine, orc, n, cycles, segment):
+    """zkc_main_vm_entry_point_stream: segmented input streams (dense / sparse words, expanded on the device) in, PACKED trace
+    (typed columns + aux / sponge records) out == the oracle's dense trace, FSM output and commitment, bit-exactly"""
+    from era_zkevm_circuits_b200 import (main_vm_entry_point_stream, vm_encode_input_stream, vm_expand_packed_trace, vm_packed_trace_buffers)
+    isa = I.Isa()
+    ios, snaps, wits, cws = [], [], [], []
+    for i in range(n):
+        io = abi.VmClosedForm(); io.start_flag = 1; io.rollback_queue_tail_for_block[3] = 77 + i
+        st = O.vm_initial_state(orc, io, isa.isa)
+        rc, sn, wi, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(I.random_program(isa, 900, seed=500 + 7 * i + cycles, far_calls=(i == 1))), cycles, full=True)
+        assert rc == 0
+        ios.append(with_tail(io, tail)); snaps.append(sn); wits.append(wi); cws.append(cw)
+    cap = max(1, max(len(c) for c in cws))
+    cwa = np.zeros((n, cap, C.sizeof(abi.VmCallstackWitness)), dtype=np.uint8)
+    for i, c in enumerate(cws):
+        cwa[i, :len(c)] = c
+    streams = [vm_encode_input_stream(engine.lib, snaps[i], wits[i], cycles, segment) for i in range(n)]
+    out = vm_packed_trace_buffers(engine, n, cycles, aux_fraction=1.0, sponge_per_cycle=9.0)
+    coms, o, sts, rc = main_vm_entry_point_stream(engine, ios, isa.isa, streams, cycles, callstack_witness=cwa, out=out)
+    assert rc == 0, [(s.code, hex(s.failed_checks), s.first_bad_row) for s in sts]
+    dense = vm_expand_packed_trace(engine.lib, out, n, cycles)
+    lib = O.load()
+    n_aux = 0
+    for i in range(n):
+        want = O.vm_entry_point(orc, ios[i], isa.isa, snaps[i], wits[i], cycles, cw=cws[i])
+        assert want[0] == 0 and coms[i].tolist() == want[3].tolist()
+        bad = np.argwhere(dense[i] != want[2])
+        assert bad.size == 0, f"instance {i}: first differing (col,row): {bad[:8].tolist()}"
+        assert np.array_equal(flat(lib, o[i].hidden_fsm_output), flat(lib, want[1].hidden_fsm_output))
+        t = want[2]
+        moved = np.ones(cycles, dtype=bool)
+        moved[1:] = (t[K["FORWARD_TAIL_OUT"]:K["FORWARD_TAIL_OUT"] + 10, 1:] != t[K["FORWARD_TAIL_OUT"]:K["FORWARD_TAIL_OUT"] + 10, :-1]).any(axis=0)
+        n_aux += int((moved | (t[K["OP_AUX"]:K["OP_AUX"] + 48] != 0).any(axis=0)).sum())
+    assert out.n_aux_records == n_aux
+    assert out.n_sponge_records == int(sum(O.vm_entry_point(orc, ios[i], isa.isa, snaps[i], wits[i], cycles, cw=cws[i])[2][K["SPONGE_ENFORCE"]:K["SPONGE_ENFORCE"] + 9].sum() for i in range(n)))
+    # no witness wanted: commitments only
+    coms2, _, _, rc2 = main_vm_entry_point_stream(engine, ios, isa.isa, streams, cycles, callstack_witness=cwa, out=None)
+    assert rc2 == 0 and coms2.tolist() == coms.tolist()
+    # record buffers too small: the counts still say how many there were
+    small = vm_packed_trace_buffers(engine, n, cycles, aux_fraction=0.0, sponge_per_cycle=0.0)
+    coms3, _, _, rc3 = main_vm_entry_point_stream(engine, ios, isa.isa, streams, cycles, callstack_witness=cwa, out=small)
+    assert rc3 == 0 and small.n_aux_records == out.n_aux_records and small.n_sponge_records == out.n_sponge_records
+    assert np.array_equal(small.cols32, out.cols32) and np.array_equal(small.cols8, out.cols8)
+    for s in streams:
+        s.free()
