@@ -102,10 +102,10 @@ extern "C" int zkc_poseidon2_permute(zkc_ctx *ctx, const uint64_t *states_in, ui
     const uint64_t *din = states_in;
     uint64_t *dout = states_out;
     if (!on_device) {
-        uint64_t *buf = (uint64_t *)ctx->scratch(n * 96);
+        uint64_t *buf = (uint64_t *)ctx->scratch(2 * n * 96);  // separate output region: the kernel's pointers are __restrict__
         if (!buf) return ZKC_ERR_CUDA;
         ZKC_CUDA(ctx, st, cudaMemcpyAsync(buf, states_in, n * 96, cudaMemcpyHostToDevice, ctx->stream));
-        din = buf; dout = buf;
+        din = buf; dout = buf + n * 12;
     }
     ZKC_LAUNCH(ctx, "poseidon2_batch", poseidon2_batch_kernel, (unsigned)((n + 127) / 128), 128, 0, din, dout, n);
     ZKC_CUDA(ctx, st, cudaGetLastError());

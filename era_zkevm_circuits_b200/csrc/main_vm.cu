@@ -788,6 +788,7 @@ __device__ __forceinline__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; i++) d.u128[i] = a.v[i];
         d.pubdata = a.v[0];
+#ifndef VM_EXPERIMENT_LEAN
     } else if (TYPE(ZKC_OP_UMA)) {  // uma.rs:18-1084
         const bool heap_r = VAR(ZKC_VAR_UMA_HEAP_READ), heap_w = VAR(ZKC_VAR_UMA_HEAP_WRITE), aux_r = VAR(ZKC_VAR_UMA_AUX_HEAP_READ),
                    aux_w = VAR(ZKC_VAR_UMA_AUX_HEAP_WRITE), ptr_r = VAR(ZKC_VAR_UMA_FAT_PTR_READ);
@@ -1224,6 +1225,7 @@ __device__ __forceinline__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ 
             TR(aux_base + 42) = apply_near; TR(aux_base + 43) = apply_ret; TR(aux_base + 44) = is_panic_out;
             TR(aux_base + 45) = perform_revert; TR(aux_base + 46) = apply_far; TR(aux_base + 47) = far_exception;
         }
+#endif
     }
     // ---- state diffs ---------------------------------------------------------------------------------------------------
     // dst0 / dst1 are dot products of (flag, candidate) pairs (cycle.rs:199-246): zero when no candidate's flag is set
@@ -1487,6 +1489,7 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
         // ---- is snapshot row + 1 what this cycle produces? -----------------------------------------------------------------
         // (1) scalars + context: the expected next value of every word (the current one unless the cycle changes it)
         bool bad = false;
+#ifndef VM_EXPERIMENT_NOLINK
         {
             uint32_t acc = 0;
 #pragma unroll
@@ -1548,6 +1551,7 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
                 }
             } else if (!stack_job) bad |= stack_diff != 0;
         }
+#endif
         if (bad) {
             // attribute the broken link to the cycle that would consume the wrong snapshot (what a sequential run sees)
             if (row + 1 < limit) vm_report(dev, row + 1, ZKC_VM_CHK_SNAPSHOT);

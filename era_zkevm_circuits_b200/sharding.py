@@ -18,7 +18,7 @@ def gather_commitments(local_commitments: np.ndarray, n_total: int, rank: int, w
     import torch.distributed as dist
     per = (n_total + world - 1) // world
     buf = torch.zeros((per, 4), dtype=torch.int64, device=device)
-    mine = torch.from_numpy(np.ascontiguousarray(local_commitments, dtype=np.uint64).view(np.int64))
+    mine = torch.from_numpy(np.ascontiguousarray(local_commitments, dtype=np.uint64).reshape(-1, 4).view(np.int64))  # (0, 4) for a rank without instances
     buf[: mine.shape[0]] = mine.to(buf.device)
     out = torch.zeros((world * per, 4), dtype=torch.int64, device=device)
     if world > 1:

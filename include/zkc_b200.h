@@ -1416,6 +1416,61 @@ int zkc_main_vm_simulate(zkc_ctx *ctx, const zkc_vm_isa *isa, const zkc_vm_state
                          size_t callstack_capacity, uint32_t *n_callstack_out, uint64_t *rollback_tails_out,
                          zkc_status *status);
 
+/* ---- linear_hasher: Keccak-256 of the L2 -> L1 message queue ---------------------------------------------
+ * linear_hasher_entry_point, src/linear_hasher/mod.rs:35-214.  Every cycle pops one LogQuery (:107), serialises it into
+ * L2_TO_L1_MESSAGE_BYTE_LENGTH = 88 bytes (ByteSerializable::into_bytes, base_structures/log_query/mod.rs:645-686:
+ * shard_id, is_service, tx_number_in_block as 2 big-endian bytes, address 20, key 32, written_value 32, all big-endian),
+ * appends them to a byte buffer (:116), absorbs 136 bytes + keccak-f[1600] when the buffer holds that many (:120-137) and
+ * the padded remainder on the queue's last item (:142-168).  One instance per block: start_flag is enforced (:66).
+ * The buffer length before cycle c is (88 c) mod 136: a compile-time constant of the cycle in the reference, a function of
+ * the row index here. */
+#define ZKC_LH_MESSAGE_BYTES 88
+#define ZKC_KECCAK_RATE_BYTES 136
+typedef struct zkc_linear_hasher_closed_form {
+    uint32_t start_flag;      /* must be 1 (:66) */
+    uint32_t completion_flag; /* out */
+    zkc_queue_state4 queue_state;  /* LinearHasherInputData, input.rs:24-26 */
+    uint32_t keccak256_hash[32];   /* LinearHasherOutputData (input.rs:39-41), one byte per element (out; expected if compare_expected) */
+} zkc_linear_hasher_closed_form;
+
+/* trace columns of one loop iteration (mod.rs:103-171) */
+enum zkc_lh_col {
+    ZKC_LH_QUEUE_IS_EMPTY = 0,  /* :104 */
+    ZKC_LH_SHOULD_POP = 1,      /* :105 */
+    ZKC_LH_ITEM = 2,            /* 36: popped record, flatten order log_query/mod.rs:62-101 */
+    ZKC_LH_ENC = 38,            /* 20: LogQuery::encode (the pop's absorbed elements) */
+    ZKC_LH_HEAD = 58,           /* 4: queue head after the pop */
+    ZKC_LH_LEN = 62,            /* queue length after the pop */
+    ZKC_LH_NOW_EMPTY = 63,      /* :109 */
+    ZKC_LH_IS_LAST_SERIALIZATION = 64, /* :110 */
+    ZKC_LH_BYTES = 65,          /* 88: into_bytes (:112) */
+    ZKC_LH_CONTINUE_TO_ABSORB = 153, /* :118 */
+    ZKC_LH_ABSORB_FULL = 154,   /* condition of the full-block absorption of this cycle (0 when the buffer stays short, :120) */
+    ZKC_LH_ABSORB_LAST = 155,   /* absorb_as_last_round, :144-145 */
+    ZKC_LH_STATE_MID = 156,     /* 50: keccak state after the conditional full-block round (:131-136): lane x + 5y as (low, high) u32 halves */
+    ZKC_LH_STATE_OUT = 206,     /* 50: after the conditional last round (:162-167) */
+    ZKC_LH_DONE = 256,          /* :170 */
+    ZKC_LH_NUM_COLS = 257
+};
+
+#define ZKC_LH_CHK_START_FLAG (1u << 0)        /* :66 */
+#define ZKC_LH_CHK_TRIVIAL_HEAD (1u << 1)      /* :71 */
+#define ZKC_LH_CHK_TX_NUMBER_RANGE (1u << 2)   /* into_bytes: the two high bytes of tx_number_in_block are zero, log_query/mod.rs:666-668 */
+#define ZKC_LH_CHK_QUEUE_CONSISTENCY (1u << 3) /* :173 */
+#define ZKC_LH_CHK_NOT_COMPLETED (1u << 4)     /* :176: the queue must be empty after `limit` cycles */
+#define ZKC_LH_CHK_QUEUE_HINT (1u << 5)        /* prev_tails is not the hash chain of the records */
+#define ZKC_LH_CHK_STATE_HINT (1u << 6)        /* keccak_states is not the absorption chain */
+
+/*   records, prev_tails : the queue's witness in pop order (CircuitQueueRawWitness, input.rs:78-87), as for the demultiplexer
+ *   keccak_states       : NULL, or [limit][25] lanes: the keccak state AFTER every cycle (what an out-of-circuit run of the
+ *                         hasher holds; the state before cycle 0 is zero).  Verified row by row -- every cycle is then
+ *                         independent; when NULL the chain (one keccak-f per 136 bytes) is rebuilt sequentially on the device
+ *   trace               : column-major [ZKC_LH_NUM_COLS][limit] or NULL */
+int zkc_linear_hasher_entry_point(zkc_ctx *ctx, zkc_linear_hasher_closed_form *io, const zkc_log_query *records,
+                                  const uint64_t *prev_tails, size_t n_records, const uint64_t *keccak_states, size_t limit,
+                                  const zkc_sorter_options *options, int on_device, uint64_t *trace,
+                                  uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
+
 #ifdef __cplusplus
 }
 #endif
