@@ -27,6 +27,10 @@ from .demux_log_queue import (  # noqa: F401
     LogDemuxerCircuitInstanceWitness,
     demultiplex_storage_logs_enty_point,
 )
+from .linear_hasher import (  # noqa: F401
+    LinearHasherCircuitInstanceWitness,
+    linear_hasher_entry_point,
+)
 from .code_unpacker_sha256 import (  # noqa: F401
     CodeDecommitterCircuitInstanceWitness,
     unpack_code_into_memory_entry_point,

@@ -373,6 +373,19 @@ DMX_COLS = dict(
 DMX_CHK = dict(TRIVIAL_HEAD=1 << 0, PORTER_STORAGE=1 << 1, BITMASK=1 << 2, QUEUE_CONSISTENCY=1 << 3, QUEUE_HINT=1 << 4)
 
 
+class LinearHasherClosedForm(C.Structure):
+    """zkc_linear_hasher_closed_form: LinearHasherInputData / LinearHasherOutputData, linear_hasher/input.rs:24-41 (hidden FSM: `()`)"""
+    _fields_ = [("start_flag", C.c_uint32), ("completion_flag", C.c_uint32), ("queue_state", QueueState4),
+                ("keccak256_hash", C.c_uint32 * 32)]
+
+
+LH_MESSAGE_BYTES, KECCAK_RATE_BYTES = 88, 136
+LH_COLS = dict(QUEUE_IS_EMPTY=0, SHOULD_POP=1, ITEM=2, ENC=38, HEAD=58, LEN=62, NOW_EMPTY=63, IS_LAST_SERIALIZATION=64, BYTES=65,
+               CONTINUE_TO_ABSORB=153, ABSORB_FULL=154, ABSORB_LAST=155, STATE_MID=156, STATE_OUT=206, DONE=256, NUM_COLS=257)
+LH_CHK = dict(START_FLAG=1 << 0, TRIVIAL_HEAD=1 << 1, TX_NUMBER_RANGE=1 << 2, QUEUE_CONSISTENCY=1 << 3, NOT_COMPLETED=1 << 4,
+              QUEUE_HINT=1 << 5, STATE_HINT=1 << 6)
+
+
 class CodeDecommittmentFsm(C.Structure):
     _fields_ = [("sha256_inner_state", C.c_uint32 * 8), ("hash_to_compare_against", C.c_uint32 * 8), ("current_index", C.c_uint32),
                 ("current_page", C.c_uint32), ("timestamp", C.c_uint32), ("num_rounds_left", C.c_uint32),
@@ -467,6 +480,8 @@ SIGNATURES = {
     "zkc_demux_log_queue_entry_point": (C.c_int, [_vp, C.POINTER(DemuxClosedForm), _vp, _vp, C.c_size_t, _vp,
                                                   C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(DemuxOptions), C.c_int, _vp, _vp,
                                                   C.POINTER(Status)]),
+    "zkc_linear_hasher_entry_point": (C.c_int, [_vp, C.POINTER(LinearHasherClosedForm), _vp, _vp, C.c_size_t, _vp, C.c_size_t,
+                                                C.POINTER(SorterOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
     "zkc_code_unpacker_entry_point": (C.c_int, [_vp, C.POINTER(CodeUnpackerClosedForm), _vp, _vp, C.c_size_t, _vp, C.c_size_t, _vp,
                                                 C.c_size_t, C.c_size_t, C.POINTER(SorterOptions), C.c_int, _vp, _vp, C.POINTER(Status)]),
     "zkc_storage_validity_entry_point": (C.c_int, [_vp, C.POINTER(StorageClosedForm), _vp, _vp, C.c_size_t, _vp, _vp, _vp,

@@ -788,7 +788,6 @@ __device__ __forceinline__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ 
 #pragma unroll
         for (int i = 0; i < 4; i++) d.u128[i] = a.v[i];
         d.pubdata = a.v[0];
-#ifndef VM_EXPERIMENT_LEAN
     } else if (TYPE(ZKC_OP_UMA)) {  // uma.rs:18-1084
         const bool heap_r = VAR(ZKC_VAR_UMA_HEAP_READ), heap_w = VAR(ZKC_VAR_UMA_HEAP_WRITE), aux_r = VAR(ZKC_VAR_UMA_AUX_HEAP_READ),
                    aux_w = VAR(ZKC_VAR_UMA_AUX_HEAP_WRITE), ptr_r = VAR(ZKC_VAR_UMA_FAT_PTR_READ);
@@ -1225,7 +1224,6 @@ __device__ __forceinline__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ 
             TR(aux_base + 42) = apply_near; TR(aux_base + 43) = apply_ret; TR(aux_base + 44) = is_panic_out;
             TR(aux_base + 45) = perform_revert; TR(aux_base + 46) = apply_far; TR(aux_base + 47) = far_exception;
         }
-#endif
     }
     // ---- state diffs ---------------------------------------------------------------------------------------------------
     // dst0 / dst1 are dot products of (flag, candidate) pairs (cycle.rs:199-246): zero when no candidate's flag is set
@@ -1382,6 +1380,7 @@ struct VmPushScratch {
     uint32_t *counts;  // [16] (VM_JOB_SLOTS used)
     uint32_t *lists;   // [VM_JOB_SLOTS][rows]: the rows whose slot-k job runs, in no particular order
     uint64_t *meta;    // [rows][2]: job mask | capacity sources << 16 (nibble per slot), checks (nibble per slot)
+    uint32_t *link;    // [rows]: which words of the NEXT snapshot the cycle may change (VM_LINK_*), for vm_link_kernel
     uint64_t *enc, *enc_hi;      // [rows][5][8], [rows][4][8]
     uint64_t *state, *state_hi;  // [rows][5][12], [rows][4][12]: permutation outputs
     __device__ __forceinline__ uint64_t *enc_of(size_t g, int k) const {
@@ -1438,6 +1437,64 @@ __device__ __forceinline__ uint32_t vm_expected_word(int w, const VmDelta &d, co
 #undef KEEP
 }
 
+// ---- the snapshot link, split in two -----------------------------------------------------------------------------------------
+// Words of the current context no ordinary cycle moves (only a near / far call or a ret replaces them, with the whole record)
+__host__ __device__ constexpr bool vm_link_const_context_word(int w) {
+    const int c = w - VW(current_context);
+    return (c >= CW(this_address) && c < CW(heap_upper_bound)) ||                                   // addresses, code_page, base_page
+           (c >= CW(reverted_queue_tail) && c < CW(reverted_queue_tail) + 8) || c == CW(exception_handler_loc) ||
+           (c >= CW(is_static_execution) && c <= CW(is_local_call));                              // mode flags, shard ids, u128, is_local_call
+}
+enum : uint32_t { VM_LINK_ALL_REGISTERS = 1u << 8, VM_LINK_MEMQ = 1u << 9, VM_LINK_STACK = 1u << 10, VM_LINK_DECOMMIT = 1u << 11, VM_LINK_CONTEXT = 1u << 12 };
+
+// Carry-over half of the link check: every word group the cycle did NOT declare as changing (link[g]: dst0 / dst1 register
+// numbers, "all registers", the three sponge-derived states, "context replaced") must be equal in snapshots row and row + 1.
+// A pure stream over the state columns: lane i reads element i and i + 1 of each word's column (coalesced; the second an L1
+// hit), 243 of the 294 words; the words a cycle computes are compared by vm_cycles_kernel itself.
+__global__ void __launch_bounds__(256, 4)
+vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, size_t limit, size_t n_instances, size_t row0, size_t row_count) {
+    const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= row_count * n_instances) return;
+    const size_t inst = l / row_count, row = row0 + (l - inst * row_count);
+    const size_t g = inst * limit + row, idx = inst * (limit + 1) + row;
+    const uint32_t m = __ldg(link + g);
+    const uint32_t *cur = cols.st + idx;
+    const size_t stride = cols.st_stride;
+#define DIFF(w) (__ldg(cur + (size_t)(w) * stride) ^ __ldg(cur + (size_t)(w) * stride + 1))
+    bool bad = false;
+    {
+        const uint32_t idx0 = m & 15, idx1 = (m >> 4) & 15;
+        uint32_t moved = 0;  // bit r: register r differs
+#pragma unroll
+        for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
+            uint32_t dr = 0;
+#pragma unroll
+            for (int i = 0; i < 9; i++) dr |= DIFF(VW(registers) + 9 * r + i);
+            moved |= (dr != 0 ? 1u : 0u) << r;
+        }
+        const uint32_t allowed = (m & VM_LINK_ALL_REGISTERS) ? 0x7FFFu : ((idx0 ? 1u << (idx0 - 1) : 0u) | (idx1 ? 1u << (idx1 - 1) : 0u));
+        bad |= (moved & ~allowed) != 0;
+    }
+    {
+        uint32_t dc = 0;
+#pragma unroll
+        for (int w = VW(current_context); w < VW(stack_sponge_state); w++)
+            if (vm_link_const_context_word(w)) dc |= DIFF(w);
+        bad |= dc != 0 && !(m & VM_LINK_CONTEXT);
+    }
+    {
+        uint32_t dm = 0, ds = 0, dd = 0;
+#pragma unroll
+        for (int i = 0; i < 24; i++) {
+            dm |= DIFF(VW(memory_queue_state) + i); ds |= DIFF(VW(stack_sponge_state) + i); dd |= DIFF(VW(code_decommittment_queue_state) + i);
+        }
+        bad |= (dm != 0 && !(m & VM_LINK_MEMQ)) || (ds != 0 && !(m & VM_LINK_STACK)) || (dd != 0 && !(m & VM_LINK_DECOMMIT));
+    }
+#undef DIFF
+    // attribute the broken link to the cycle that would consume the wrong snapshot (what a sequential run sees)
+    if (bad) vm_report(devs + inst, row + 1 < limit ? row + 1 : row, ZKC_VM_CHK_SNAPSHOT);
+}
+
 // Every thread evaluates its cycle from snapshot `row` and checks that snapshot `row + 1` is the result: the words a cycle
 // can change are compared with what the cycle produced, every other word must carry over (the neighbouring element of the
 // same column: an L1 hit for 31 of the 32 lanes).  The three sponge-derived states are vouched for by the cycle's sponge jobs
@@ -1487,9 +1544,10 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
         jmask = d.job_mask;
         ps.meta[g * 2] = (uint64_t)jmask | (d.cap_from << 16); ps.meta[g * 2 + 1] = d.chk;
         // ---- is snapshot row + 1 what this cycle produces? -----------------------------------------------------------------
-        // (1) scalars + context: the expected next value of every word (the current one unless the cycle changes it)
+        // This thread compares the words its cycle CHANGES with what it computed; that every other word carries over unchanged
+        // is checked by vm_link_kernel (a stream over the columns) from the mask written here.
         bool bad = false;
-#ifndef VM_EXPERIMENT_NOLINK
+        // (1) scalars + the context fields an ordinary cycle moves; the whole record when the callstack moves
         {
             uint32_t acc = 0;
 #pragma unroll
@@ -1498,23 +1556,28 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
             for (int w = VW(flags); w < VW(stack_sponge_state); w++) {
                 if (w >= VW(_pad) && w < VW(current_context)) continue;  // padding is not state
                 if (w == VWC(aux_heap_upper_bound) + 1) continue;        // alignment hole in front of reverted_queue_head
+                if (vm_link_const_context_word(w)) continue;
                 acc |= NXT(w) ^ vm_expected_word(w, d, nctx, next_fwd_tail, cur, stride);
+            }
+            if (d.ctx_replaced) {
+#pragma unroll
+                for (int w = VW(current_context); w < VW(stack_sponge_state); w++)
+                    if (vm_link_const_context_word(w)) acc |= NXT(w) ^ reinterpret_cast<const uint32_t *>(&nctx)[w - VW(current_context)];
             }
             bad |= acc != 0;
         }
-        // (2) registers: only dst0 / dst1 may move (dst1 is applied last), to the values the cycle produced
+        // (2) registers: dst0 / dst1 (dst1 is applied last) hold the values the cycle produced; a far call / far return rewrites all
         if (!d.far_ret && !d.far_call) {
             uint32_t acc = 0;
+            if (d.idx1) {
+                const int base = VW(registers) + 9 * ((int)d.idx1 - 1);
 #pragma unroll
-            for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
-                const bool is0 = (uint32_t)(r + 1) == d.idx0, is1 = (uint32_t)(r + 1) == d.idx1;
+                for (int i = 0; i < 9; i++) acc |= NXT(base + i) ^ reg_word(d.val1, i);
+            }
+            if (d.idx0 && d.idx0 != d.idx1) {
+                const int base = VW(registers) + 9 * ((int)d.idx0 - 1);
 #pragma unroll
-                for (int i = 0; i < 9; i++) {
-                    const int w = VW(registers) + 9 * r + i;
-                    const uint32_t c = CUR(w), n = NXT(w);
-                    const uint32_t want = is1 ? reg_word(d.val1, i) : (is0 ? reg_word(d.val0, i) : c);
-                    acc |= n ^ want;
-                }
+                for (int i = 0; i < 9; i++) acc |= NXT(base + i) ^ reg_word(d.val0, i);
             }
             bad |= acc != 0;
         } else {
@@ -1526,7 +1589,7 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
                 for (int i = 0; i < 9; i++) bad |= NXT(VW(registers) + 9 * r + i) != reg_word(want, i);
             }
         }
-        // (3) the sponge-derived states: vouched for by the cycle's last job on them (vm_sponge_kernel), else unchanged
+        // (3) the sponge-derived states: vouched for by the cycle's last job on them (vm_sponge_kernel), else unchanged (vm_link_kernel)
         {
             bool memq_job = false, stack_job = false, decommit_job = false;
 #pragma unroll
@@ -1534,24 +1597,17 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
                 const uint32_t c = (uint32_t)(d.chk >> (4 * k)) & 15;
                 memq_job |= c == VM_CHK_NEXT_MEMQ; stack_job |= c == VM_CHK_NEXT_STACK; decommit_job |= c == VM_CHK_NEXT_DECOMMIT;
             }
-            uint32_t memq_diff = 0, stack_diff = 0, decommit_diff = 0;
-#pragma unroll
-            for (int i = 0; i < 24; i++) {
-                memq_diff |= CUR(VW(memory_queue_state) + i) ^ NXT(VW(memory_queue_state) + i);
-                stack_diff |= CUR(VW(stack_sponge_state) + i) ^ NXT(VW(stack_sponge_state) + i);
-                decommit_diff |= CUR(VW(code_decommittment_queue_state) + i) ^ NXT(VW(code_decommittment_queue_state) + i);
-            }
-            if (!memq_job) bad |= memq_diff != 0;
-            if (!decommit_job) bad |= decommit_diff != 0;
             if (d.ctx_replaced == 2) {  // ret: the stack state below the popped frame is the witness'
                 const uint64_t *p = cws[inst * (size_t)n_cw + (d.cw_index < n_cw ? d.cw_index : 0)].previous_sponge_state;
                 for (int i = 0; i < 12; i++) {
                     const uint64_t n = (uint64_t)NXT(VW(stack_sponge_state) + 2 * i) | ((uint64_t)NXT(VW(stack_sponge_state) + 2 * i + 1) << 32);
                     bad |= n != (d.cw_index < n_cw ? p[i] : 0ull);
                 }
-            } else if (!stack_job) bad |= stack_diff != 0;
+                stack_job = true;
+            }
+            ps.link[g] = d.idx0 | (d.idx1 << 4) | ((d.far_ret || d.far_call) ? VM_LINK_ALL_REGISTERS : 0u) | (memq_job ? VM_LINK_MEMQ : 0u) |
+                         (stack_job ? VM_LINK_STACK : 0u) | (decommit_job ? VM_LINK_DECOMMIT : 0u) | (d.ctx_replaced ? VM_LINK_CONTEXT : 0u);
         }
-#endif
         if (bad) {
             // attribute the broken link to the cycle that would consume the wrong snapshot (what a sequential run sees)
             if (row + 1 < limit) vm_report(dev, row + 1, ZKC_VM_CHK_SNAPSHOT);
@@ -2201,7 +2257,7 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
                  zkc_carver::bytes(rows * VM_PK_N64, 8) + zkc_carver::bytes(n_chunks * chunk_cells + 1, sizeof(zkc_vm_aux_record)) +
                  zkc_carver::bytes(n_chunks * chunk_cells * VM_JOB_SLOTS + 1, sizeof(zkc_vm_sponge_record)) + zkc_carver::bytes(2 * n_chunks, 8);
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
-    bytes += zkc_carver::bytes(16 * n_chunks, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 2, 8) +
+    bytes += zkc_carver::bytes(16 * n_chunks, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 2, 8) + zkc_carver::bytes(rows, 4) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(n_chunks + 32, 8) + 4096;  // + slack: the slot arrays are carved in two parts
     void *blk = ctx->scratch(bytes);
@@ -2231,6 +2287,7 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
     uint32_t *lists = cv.take<uint32_t>(VM_JOB_SLOTS * rows);
     VmPushScratch ps;
     ps.meta = cv.take<uint64_t>(rows * 2);
+    ps.link = cv.take<uint32_t>(rows);
     ps.enc = cv.take<uint64_t>(rows * VM_JOB_SLOTS_LO * 8);
     ps.state = cv.take<uint64_t>(rows * VM_JOB_SLOTS_LO * 12);
     ps.enc_hi = cv.take<uint64_t>(rows * VM_JOB_SLOTS_HI * 8);
@@ -2418,6 +2475,7 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
         }
         ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, cols, dcw,
                    (uint32_t)in.n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base);
+        ZKC_LAUNCH(ctx, "vm_link", vm_link_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, d, cols, (const uint32_t *)ps.link, limit, n_instances, r0, cnt);
         // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists, or one launch per slot
         if (sponge_mode == 0) {
             for (int k = 0; k < VM_JOB_SLOTS_LO; k++)

@@ -95,6 +95,11 @@ size_t orc_demux_encode_fsm(const zkc_demux_fsm *f, uint64_t *dst);
 int orc_demux_log_queue_entry_point(zkc_demux_closed_form *io, const zkc_log_query *records, size_t n_records, size_t limit,
                                     const zkc_demux_options *options, uint64_t *trace, uint64_t *output_tails,
                                     size_t n_output_tails[6], uint64_t commitment[4], zkc_status *status);
+/* linear_hasher.c; keccak_states (optional out): [limit][25], the keccak state after every cycle */
+int orc_log_query_into_bytes(const zkc_log_query *q, uint8_t out[ZKC_LH_MESSAGE_BYTES]);
+int orc_linear_hasher_entry_point(zkc_linear_hasher_closed_form *io, const zkc_log_query *records, size_t n_records, size_t limit,
+                                  const zkc_sorter_options *options, uint64_t *trace, uint64_t *keccak_states, uint64_t commitment[4],
+                                  zkc_status *status);
 /* code_unpacker_sha256.c; memory_states (optional out): memory queue tail [12] after each executed push */
 size_t orc_code_unpacker_encode_fsm(const zkc_code_unpacker_fsm *f, uint64_t *dst);
 int orc_code_unpacker_entry_point(zkc_code_unpacker_closed_form *io, const zkc_decommit_query *requests, size_t n_requests,

@@ -242,6 +242,29 @@ def demux_entry_point(lib, io, records, limit, want_trace=True, compare_expected
     return rc, io2, trace, com, st, [tails[q, :n_tails[q]].copy() for q in range(6)]
 
 
+def linear_hasher_closed_form(queue_state, start=True):
+    io = abi.LinearHasherClosedForm()
+    io.start_flag = int(start)
+    io.queue_state = queue_state
+    return io
+
+
+def linear_hasher_entry_point(lib, io, records, limit, want_trace=True, compare_expected=False):
+    """returns (rc, io_out, trace, commitment, status, keccak_states [limit, 25])"""
+    io2 = abi.LinearHasherClosedForm.from_buffer_copy(bytes(io))
+    records = np.ascontiguousarray(records)
+    trace = np.zeros((abi.LH_COLS["NUM_COLS"], limit), dtype=np.uint64) if want_trace else None
+    states = np.zeros((max(limit, 1), 25), dtype=np.uint64)
+    com = np.zeros(4, dtype=np.uint64)
+    st = abi.Status()
+    opts = abi.SorterOptions(int(compare_expected))
+    lib.orc_linear_hasher_entry_point.restype = C.c_int
+    lib.orc_linear_hasher_entry_point.argtypes = [C.POINTER(abi.LinearHasherClosedForm), _vp, C.c_size_t, C.c_size_t, C.POINTER(abi.SorterOptions),
+                                                  _vp, _vp, _vp, C.POINTER(abi.Status)]
+    rc = lib.orc_linear_hasher_entry_point(C.byref(io2), p(records), len(records), limit, C.byref(opts), p(trace), p(states), p(com), C.byref(st))
+    return rc, io2, trace, com, st, states[:limit].copy()
+
+
 def code_unpacker_closed_form(requests_state, memory_state=None, start=True, fsm_in=None):
     io = abi.CodeUnpackerClosedForm()
     io.start_flag = int(start)
