@@ -1465,8 +1465,8 @@ vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, size
     {
         const uint32_t idx0 = m & 15, idx1 = (m >> 4) & 15;
         uint32_t moved = 0;  // bit r: register r differs
-#pragma unroll
-        for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
+#pragma unroll 1
+        for (int r = 0; r < ZKC_VM_REGISTERS; r++) {  // 18 independent loads in flight per thread and iteration
             uint32_t dr = 0;
 #pragma unroll
             for (int i = 0; i < 9; i++) dr |= DIFF(VW(registers) + 9 * r + i);
@@ -1478,15 +1478,20 @@ vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, size
     {
         uint32_t dc = 0;
 #pragma unroll
-        for (int w = VW(current_context); w < VW(stack_sponge_state); w++)
+        for (int w = VW(current_context); w < VW(stack_sponge_state); w++) {
             if (vm_link_const_context_word(w)) dc |= DIFF(w);
+            if (w % 12 == 11) asm volatile("" ::: "memory");  // batches of <= 24 loads: keeps the register count of a stream kernel
+        }
         bad |= dc != 0 && !(m & VM_LINK_CONTEXT);
     }
     {
         uint32_t dm = 0, ds = 0, dd = 0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 24; i0 += 4) {
 #pragma unroll
-        for (int i = 0; i < 24; i++) {
-            dm |= DIFF(VW(memory_queue_state) + i); ds |= DIFF(VW(stack_sponge_state) + i); dd |= DIFF(VW(code_decommittment_queue_state) + i);
+            for (int i = 0; i < 4; i++) {
+                dm |= DIFF(VW(memory_queue_state) + i0 + i); ds |= DIFF(VW(stack_sponge_state) + i0 + i); dd |= DIFF(VW(code_decommittment_queue_state) + i0 + i);
+            }
         }
         bad |= (dm != 0 && !(m & VM_LINK_MEMQ)) || (ds != 0 && !(m & VM_LINK_STACK)) || (dd != 0 && !(m & VM_LINK_DECOMMIT));
     }
