@@ -285,7 +285,7 @@ def run_gpu(args):
     ms, t0, t1 = timed(step_device, args.steps)
     launches = eng.launches - l0
     eng.profile(False)
-    prof = {k: eng.profile_query(k) for k in ("vm_cycles", "vm_sponge", "vm_sponge_far", "vm_sponge_trace", "vm_finalize")}
+    prof = {k: eng.profile_query(k) for k in ("vm_cycles", "vm_link", "vm_sponge", "vm_sponge_far", "vm_sponge_trace", "vm_finalize")}
     value = n * cycles * world * args.steps / (ms / 1e3)
     # the timed region is K steps of a few ms: keep the same step running (untimed) until the sampler (10 Hz) has seen >= 1.5 s
     # of this load, and report the clocks over [start of the timed region, end of that tail]

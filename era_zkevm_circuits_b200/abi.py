@@ -442,7 +442,10 @@ RAM_COLS = dict(
     PAGE_IS_BOOTLOADER_HEAP=72, IS_NONDET_WRITE=73, NUM_NONDET_WRITES=74, CMP_DIFF=75, CMP_BORROW=78,
     CMP_LIMB_EQ=81, KEYS_EQUAL=84, PREV_KEY_SMALLER=85, SAME_CELL=86, VALUE_EQUAL=87, VALUE_IS_ZERO=88,
     IS_ZERO=89, PTR_EQUALITY=90, VALUE_AND_PTR_EQUAL=91, READ_UNINIT=92, CHECK_EQUALITY=93, GP_CHAIN=94,
-    GP_NEW=126, GP_ACC=130, NUM_COLS=134)
+    GP_NEW=126, GP_ACC=130, UNSORTED_ENC_BYTES=134, SORTED_ENC_BYTES=146, UNSORTED_LEN_INV=158, SORTED_LEN_INV=159, TS_INV=160,
+    PAGE_DIFF=161, PAGE_DIFF_INV=162, CMP_DIFF_INV=163, CELL_DIFF=166, CELL_DIFF_INV=168, CELL_LIMB_EQ=170, VALUE_DIFF=172,
+    VALUE_DIFF_INV=180, VALUE_LIMB_EQ=188, VALUE_ZERO_DIFF=196, VALUE_ZERO_DIFF_INV=204, VALUE_ZERO_LIMB_EQ=212, PTR_DIFF=220,
+    PTR_DIFF_INV=221, NUM_COLS=222)
 
 RAM_CHK = dict(LENGTHS_EQUAL=1 << 0, EMPTY_SYNC=1 << 1, ASCENDING=1 << 2, UNINIT_READ_ZERO=1 << 3,
                READ_CONSISTENT=1 << 4, QUEUE_CONSISTENCY=1 << 5, GRAND_PRODUCT=1 << 6, NONDET_COUNT=1 << 7,
@@ -519,7 +522,7 @@ SIGNATURES = {
 
 GATES_GENERAL, GATES_ROUND_FUNCTION = 1, 2
 RAMV = dict(BOOLEAN=1 << 0, QUEUE_LEN=1 << 1, ENCODING=1 << 2, ROUND_FUNCTION=1 << 3, NONDET=1 << 4, COMPARISON=1 << 5,
-            FLAGS=1 << 6, ENFORCE=1 << 7, GP_CHAIN=1 << 8, GP_ACC=1 << 9)
+            FLAGS=1 << 6, ENFORCE=1 << 7, GP_CHAIN=1 << 8, GP_ACC=1 << 9, GADGET_CELLS=1 << 10)
 
 
 def load_library(path=LIB_PATH):

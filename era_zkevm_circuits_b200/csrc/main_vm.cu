@@ -1381,6 +1381,7 @@ struct VmPushScratch {
     uint32_t *lists;   // [VM_JOB_SLOTS][rows]: the rows whose slot-k job runs, in no particular order
     uint64_t *meta;    // [rows][2]: job mask | capacity sources << 16 (nibble per slot), checks (nibble per slot)
     uint32_t *link;    // [rows]: which words of the NEXT snapshot the cycle may change (VM_LINK_*), for vm_link_kernel
+    uint32_t *exp;     // [VM_EXP_WORDS][rows]: the values the cycle computed for the words it moves (columns, for vm_link_kernel)
     uint64_t *enc, *enc_hi;      // [rows][5][8], [rows][4][8]
     uint64_t *state, *state_hi;  // [rows][5][12], [rows][4][12]: permutation outputs
     __device__ __forceinline__ uint64_t *enc_of(size_t g, int k) const {
@@ -1445,6 +1446,20 @@ __host__ __device__ constexpr bool vm_link_const_context_word(int w) {
            (c >= CW(reverted_queue_tail) && c < CW(reverted_queue_tail) + 8) || c == CW(exception_handler_loc) ||
            (c >= CW(is_static_execution) && c <= CW(is_local_call));                              // mode flags, shard ids, u128, is_local_call
 }
+// the words an ordinary cycle computes: previous_code_word, the scalars, the moving context fields
+__host__ __device__ constexpr bool vm_link_dyn_word(int w) {
+    if (w < VW(registers)) return true;
+    if (w < VW(flags) || w >= VW(stack_sponge_state)) return false;
+    if (w >= VW(_pad) && w < VW(current_context)) return false;  // padding is not state
+    if (w == VWC(aux_heap_upper_bound) + 1) return false;        // alignment hole in front of reverted_queue_head
+    return !(w >= VW(current_context) && vm_link_const_context_word(w));
+}
+__host__ __device__ constexpr int vm_exp_slot(int w) {
+    int n = 0;
+    for (int v = 0; v < w; v++) n += vm_link_dyn_word(v) ? 1 : 0;
+    return n;
+}
+constexpr int VM_EXP_DYN = vm_exp_slot(VM_WORDS), VM_EXP_WORDS = VM_EXP_DYN + 18;  // + dst0 / dst1 register values
 enum : uint32_t { VM_LINK_ALL_REGISTERS = 1u << 8, VM_LINK_MEMQ = 1u << 9, VM_LINK_STACK = 1u << 10, VM_LINK_DECOMMIT = 1u << 11, VM_LINK_CONTEXT = 1u << 12 };
 
 // Carry-over half of the link check: every word group the cycle did NOT declare as changing (link[g]: dst0 / dst1 register
@@ -1452,7 +1467,8 @@ enum : uint32_t { VM_LINK_ALL_REGISTERS = 1u << 8, VM_LINK_MEMQ = 1u << 9, VM_LI
 // A pure stream over the state columns: lane i reads element i and i + 1 of each word's column (coalesced; the second an L1
 // hit), 243 of the 294 words; the words a cycle computes are compared by vm_cycles_kernel itself.
 __global__ void __launch_bounds__(256, 4)
-vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, size_t limit, size_t n_instances, size_t row0, size_t row_count) {
+vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, const uint32_t *__restrict__ exp, size_t limit, size_t n_instances,
+               size_t row0, size_t row_count) {
     const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= row_count * n_instances) return;
     const size_t inst = l / row_count, row = row0 + (l - inst * row_count);
@@ -1461,19 +1477,35 @@ vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, size
     const uint32_t *cur = cols.st + idx;
     const size_t stride = cols.st_stride;
 #define DIFF(w) (__ldg(cur + (size_t)(w) * stride) ^ __ldg(cur + (size_t)(w) * stride + 1))
+#define EXP(slot) __ldg(exp + (size_t)(slot) * total + g)
+    const size_t total = limit * n_instances;
     bool bad = false;
-    {
+    {   // the words the cycle computed: snapshot row + 1 holds exactly those values
+        uint32_t dd = 0;
+#pragma unroll
+        for (int w = 0; w < VM_WORDS; w++) {
+            if (!vm_link_dyn_word(w)) continue;
+            dd |= __ldg(cur + (size_t)w * stride + 1) ^ EXP(vm_exp_slot(w));
+            if (vm_exp_slot(w) % 12 == 11) asm volatile("" ::: "memory");  // batches of 24 loads
+        }
+        bad |= dd != 0;
+    }
+    if (!(m & VM_LINK_ALL_REGISTERS)) {  // registers: dst1 / dst0 (dst1 is applied last) take the cycle's values, the others carry over
         const uint32_t idx0 = m & 15, idx1 = (m >> 4) & 15;
-        uint32_t moved = 0;  // bit r: register r differs
+        uint32_t v0[9], v1[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) { v0[i] = EXP(VM_EXP_DYN + i); v1[i] = EXP(VM_EXP_DYN + 9 + i); }
+        uint32_t dr = 0;
 #pragma unroll 1
         for (int r = 0; r < ZKC_VM_REGISTERS; r++) {  // 18 independent loads in flight per thread and iteration
-            uint32_t dr = 0;
+            const bool is0 = (uint32_t)(r + 1) == idx0, is1 = (uint32_t)(r + 1) == idx1;
 #pragma unroll
-            for (int i = 0; i < 9; i++) dr |= DIFF(VW(registers) + 9 * r + i);
-            moved |= (dr != 0 ? 1u : 0u) << r;
+            for (int i = 0; i < 9; i++) {
+                const uint32_t c = __ldg(cur + (size_t)(VW(registers) + 9 * r + i) * stride), n = __ldg(cur + (size_t)(VW(registers) + 9 * r + i) * stride + 1);
+                dr |= n ^ (is1 ? v1[i] : (is0 ? v0[i] : c));
+            }
         }
-        const uint32_t allowed = (m & VM_LINK_ALL_REGISTERS) ? 0x7FFFu : ((idx0 ? 1u << (idx0 - 1) : 0u) | (idx1 ? 1u << (idx1 - 1) : 0u));
-        bad |= (moved & ~allowed) != 0;
+        bad |= dr != 0;
     }
     {
         uint32_t dc = 0;
@@ -1496,6 +1528,7 @@ vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, size
         bad |= (dm != 0 && !(m & VM_LINK_MEMQ)) || (ds != 0 && !(m & VM_LINK_STACK)) || (dd != 0 && !(m & VM_LINK_DECOMMIT));
     }
 #undef DIFF
+#undef EXP
     // attribute the broken link to the cycle that would consume the wrong snapshot (what a sequential run sees)
     if (bad) vm_report(devs + inst, row + 1 < limit ? row + 1 : row, ZKC_VM_CHK_SNAPSHOT);
 }
@@ -1552,40 +1585,29 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
         // This thread compares the words its cycle CHANGES with what it computed; that every other word carries over unchanged
         // is checked by vm_link_kernel (a stream over the columns) from the mask written here.
         bool bad = false;
-        // (1) scalars + the context fields an ordinary cycle moves; the whole record when the callstack moves
+        // (1) scalars + the context fields an ordinary cycle moves: the computed values go to vm_link_kernel as columns; the rest of
+        // the context record only when the callstack moves (rare: compared here)
         {
-            uint32_t acc = 0;
 #pragma unroll
-            for (int w = 0; w < VW(registers); w++) acc |= NXT(w) ^ d.cw[w];
-#pragma unroll
-            for (int w = VW(flags); w < VW(stack_sponge_state); w++) {
-                if (w >= VW(_pad) && w < VW(current_context)) continue;  // padding is not state
-                if (w == VWC(aux_heap_upper_bound) + 1) continue;        // alignment hole in front of reverted_queue_head
-                if (vm_link_const_context_word(w)) continue;
-                acc |= NXT(w) ^ vm_expected_word(w, d, nctx, next_fwd_tail, cur, stride);
+            for (int w = 0; w < VM_WORDS; w++) {
+                if (!vm_link_dyn_word(w)) continue;
+                ps.exp[(size_t)vm_exp_slot(w) * total + g] = w < VW(registers) ? d.cw[w] : vm_expected_word(w, d, nctx, next_fwd_tail, cur, stride);
             }
             if (d.ctx_replaced) {
+                uint32_t acc = 0;
 #pragma unroll
                 for (int w = VW(current_context); w < VW(stack_sponge_state); w++)
                     if (vm_link_const_context_word(w)) acc |= NXT(w) ^ reinterpret_cast<const uint32_t *>(&nctx)[w - VW(current_context)];
+                bad |= acc != 0;
             }
-            bad |= acc != 0;
         }
-        // (2) registers: dst0 / dst1 (dst1 is applied last) hold the values the cycle produced; a far call / far return rewrites all
-        if (!d.far_ret && !d.far_call) {
-            uint32_t acc = 0;
-            if (d.idx1) {
-                const int base = VW(registers) + 9 * ((int)d.idx1 - 1);
+        // (2) registers: the values of dst0 / dst1 go to vm_link_kernel; a far call / far return rewrites all of them (compared here)
 #pragma unroll
-                for (int i = 0; i < 9; i++) acc |= NXT(base + i) ^ reg_word(d.val1, i);
-            }
-            if (d.idx0 && d.idx0 != d.idx1) {
-                const int base = VW(registers) + 9 * ((int)d.idx0 - 1);
-#pragma unroll
-                for (int i = 0; i < 9; i++) acc |= NXT(base + i) ^ reg_word(d.val0, i);
-            }
-            bad |= acc != 0;
-        } else {
+        for (int i = 0; i < 9; i++) {
+            ps.exp[(size_t)(VM_EXP_DYN + i) * total + g] = reg_word(d.val0, i);
+            ps.exp[(size_t)(VM_EXP_DYN + 9 + i) * total + g] = reg_word(d.val1, i);
+        }
+        if (d.far_ret || d.far_call) {
 #pragma unroll 1
             for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
                 zkc_vm_register want = reg_zero();
@@ -2262,7 +2284,7 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
                  zkc_carver::bytes(rows * VM_PK_N64, 8) + zkc_carver::bytes(n_chunks * chunk_cells + 1, sizeof(zkc_vm_aux_record)) +
                  zkc_carver::bytes(n_chunks * chunk_cells * VM_JOB_SLOTS + 1, sizeof(zkc_vm_sponge_record)) + zkc_carver::bytes(2 * n_chunks, 8);
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
-    bytes += zkc_carver::bytes(16 * n_chunks, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 2, 8) + zkc_carver::bytes(rows, 4) +
+    bytes += zkc_carver::bytes(16 * n_chunks, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 2, 8) + zkc_carver::bytes(rows, 4) + zkc_carver::bytes(rows * VM_EXP_WORDS, 4) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(n_chunks + 32, 8) + 4096;  // + slack: the slot arrays are carved in two parts
     void *blk = ctx->scratch(bytes);
@@ -2293,6 +2315,7 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
     VmPushScratch ps;
     ps.meta = cv.take<uint64_t>(rows * 2);
     ps.link = cv.take<uint32_t>(rows);
+    ps.exp = cv.take<uint32_t>(rows * VM_EXP_WORDS);
     ps.enc = cv.take<uint64_t>(rows * VM_JOB_SLOTS_LO * 8);
     ps.state = cv.take<uint64_t>(rows * VM_JOB_SLOTS_LO * 12);
     ps.enc_hi = cv.take<uint64_t>(rows * VM_JOB_SLOTS_HI * 8);
@@ -2480,7 +2503,8 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
         }
         ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, cols, dcw,
                    (uint32_t)in.n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base);
-        ZKC_LAUNCH(ctx, "vm_link", vm_link_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, d, cols, (const uint32_t *)ps.link, limit, n_instances, r0, cnt);
+        ZKC_LAUNCH(ctx, "vm_link", vm_link_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, d, cols, (const uint32_t *)ps.link, (const uint32_t *)ps.exp, limit,
+                   n_instances, r0, cnt);
         // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists, or one launch per slot
         if (sponge_mode == 0) {
             for (int k = 0; k < VM_JOB_SLOTS_LO; k++)

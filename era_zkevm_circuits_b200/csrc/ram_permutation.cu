@@ -241,6 +241,11 @@ ram_rows_kernel(RamDev *d, const zkc_memory_query *__restrict__ unsorted, const 
             const uint32_t len0 = k ? slen0 : ulen0;
             const size_t popped_now = row + 1 < active_rows ? row + 1 : active_rows;
             TR(base + 33) = len0 >= popped_now ? len0 - (uint32_t)popped_now : 0;
+            const int bytes = k ? ZKC_RAM_SORTED_ENC_BYTES : ZKC_RAM_UNSORTED_ENC_BYTES;  // memory_query/mod.rs:133-135
+#pragma unroll
+            for (int l = 0; l < 3; l++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) TR(bytes + 4 * l + b) = (it.value[5 + l] >> (8 * b)) & 0xFFu;
         }
         // utils.rs:104-129 contribution chains
 #pragma unroll
@@ -349,6 +354,16 @@ ram_rows_kernel(RamDev *d, const zkc_memory_query *__restrict__ unsorted, const 
             TR(ZKC_RAM_GP_NEW + i) = can_pop ? incl.p[i] : gl_mul(excl.p[i], contrib[i]);
             TR(ZKC_RAM_GP_ACC + i) = incl.p[i];
         }
+        // differences / per-limb flags of the equality gadgets; their inverse witnesses: ram_inverse_kernel
+        TR(ZKC_RAM_PAGE_DIFF) = gl_sub(si.memory_page, heap_page);
+        TR(ZKC_RAM_CELL_DIFF + 0) = gl_sub(si.index, prev_fk[0]); TR(ZKC_RAM_CELL_DIFF + 1) = gl_sub(si.memory_page, prev_fk[1]);
+        TR(ZKC_RAM_CELL_LIMB_EQ + 0) = si.index == prev_fk[0]; TR(ZKC_RAM_CELL_LIMB_EQ + 1) = si.memory_page == prev_fk[1];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            TR(ZKC_RAM_VALUE_DIFF + i) = gl_sub(si.value[i], prev_val[i]); TR(ZKC_RAM_VALUE_LIMB_EQ + i) = si.value[i] == prev_val[i];
+            TR(ZKC_RAM_VALUE_ZERO_DIFF + i) = si.value[i]; TR(ZKC_RAM_VALUE_ZERO_LIMB_EQ + i) = si.value[i] == 0;
+        }
+        TR(ZKC_RAM_PTR_DIFF) = gl_sub(prev_is_ptr, (uint32_t)is_ptr);
     }
     if (in_range && row == limit - 1) {
 #pragma unroll
@@ -358,6 +373,50 @@ ram_rows_kernel(RamDev *d, const zkc_memory_query *__restrict__ unsorted, const 
     }
     if (in_range) ram_report(d, row, checks);
 #undef TR
+}
+
+// ---- inverse witnesses of the zero checks (ZeroCheckGate: x * inv = 1 - is_zero) -------------------------------------------
+// 28 field inversions per row as ONE: Montgomery's trick over the row's values (zeros replaced by one and mapped back to a
+// zero witness), x^(p - 2) by an addition chain.  Reads the values from the trace the row kernel wrote.
+constexpr int RAM_INV_N = 28;
+__device__ constexpr int RAM_INV_SRC[RAM_INV_N] = {
+    -1, -2, ZKC_RAM_SORTED_ITEM + 0, ZKC_RAM_PAGE_DIFF, ZKC_RAM_CMP_DIFF, ZKC_RAM_CMP_DIFF + 1, ZKC_RAM_CMP_DIFF + 2, ZKC_RAM_CELL_DIFF,
+    ZKC_RAM_CELL_DIFF + 1, ZKC_RAM_VALUE_DIFF, ZKC_RAM_VALUE_DIFF + 1, ZKC_RAM_VALUE_DIFF + 2, ZKC_RAM_VALUE_DIFF + 3, ZKC_RAM_VALUE_DIFF + 4,
+    ZKC_RAM_VALUE_DIFF + 5, ZKC_RAM_VALUE_DIFF + 6, ZKC_RAM_VALUE_DIFF + 7, ZKC_RAM_VALUE_ZERO_DIFF, ZKC_RAM_VALUE_ZERO_DIFF + 1,
+    ZKC_RAM_VALUE_ZERO_DIFF + 2, ZKC_RAM_VALUE_ZERO_DIFF + 3, ZKC_RAM_VALUE_ZERO_DIFF + 4, ZKC_RAM_VALUE_ZERO_DIFF + 5,
+    ZKC_RAM_VALUE_ZERO_DIFF + 6, ZKC_RAM_VALUE_ZERO_DIFF + 7, ZKC_RAM_PTR_DIFF, -3, -3};
+__device__ constexpr int RAM_INV_DST[RAM_INV_N] = {
+    ZKC_RAM_UNSORTED_LEN_INV, ZKC_RAM_SORTED_LEN_INV, ZKC_RAM_TS_INV, ZKC_RAM_PAGE_DIFF_INV, ZKC_RAM_CMP_DIFF_INV, ZKC_RAM_CMP_DIFF_INV + 1,
+    ZKC_RAM_CMP_DIFF_INV + 2, ZKC_RAM_CELL_DIFF_INV, ZKC_RAM_CELL_DIFF_INV + 1, ZKC_RAM_VALUE_DIFF_INV, ZKC_RAM_VALUE_DIFF_INV + 1,
+    ZKC_RAM_VALUE_DIFF_INV + 2, ZKC_RAM_VALUE_DIFF_INV + 3, ZKC_RAM_VALUE_DIFF_INV + 4, ZKC_RAM_VALUE_DIFF_INV + 5, ZKC_RAM_VALUE_DIFF_INV + 6,
+    ZKC_RAM_VALUE_DIFF_INV + 7, ZKC_RAM_VALUE_ZERO_DIFF_INV, ZKC_RAM_VALUE_ZERO_DIFF_INV + 1, ZKC_RAM_VALUE_ZERO_DIFF_INV + 2,
+    ZKC_RAM_VALUE_ZERO_DIFF_INV + 3, ZKC_RAM_VALUE_ZERO_DIFF_INV + 4, ZKC_RAM_VALUE_ZERO_DIFF_INV + 5, ZKC_RAM_VALUE_ZERO_DIFF_INV + 6,
+    ZKC_RAM_VALUE_ZERO_DIFF_INV + 7, ZKC_RAM_PTR_DIFF_INV, -1, -1};
+__global__ void __launch_bounds__(128)
+ram_inverse_kernel(const RamDev *d, uint64_t *__restrict__ trace) {
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const uint32_t ulen0 = d->uq0.length, slen0 = d->sq0.length;
+    const size_t active_rows = limit < ulen0 ? limit : ulen0, popped_before = row < active_rows ? row : active_rows;
+    uint64_t x[RAM_INV_N], pre[RAM_INV_N];
+#pragma unroll
+    for (int i = 0; i < RAM_INV_N; i++) {
+        if (RAM_INV_SRC[i] == -1) x[i] = ulen0 - (uint32_t)popped_before;                           // queue lengths before the pop
+        else if (RAM_INV_SRC[i] == -2) x[i] = slen0 >= popped_before ? slen0 - (uint32_t)popped_before : 0;
+        else if (RAM_INV_SRC[i] == -3) x[i] = 1;                                                     // padding of the batch
+        else x[i] = trace[(size_t)RAM_INV_SRC[i] * limit + row];
+    }
+    uint64_t acc = 1;
+#pragma unroll
+    for (int i = 0; i < RAM_INV_N; i++) { pre[i] = acc; acc = gl_mul(acc, x[i] ? x[i] : 1ull); }
+    acc = gl_inv(acc);
+#pragma unroll
+    for (int i = RAM_INV_N - 1; i >= 0; i--) {
+        const uint64_t inv = gl_mul(acc, pre[i]);
+        acc = gl_mul(acc, x[i] ? x[i] : 1ull);
+        if (RAM_INV_DST[i] >= 0) trace[(size_t)RAM_INV_DST[i] * limit + row] = x[i] ? inv : 0ull;
+    }
 }
 
 // FullStateCircuitQueue::push of whole queues (the reference test builds its inputs this way,
@@ -611,6 +670,51 @@ ram_check_kernel(RamDev *d, const uint64_t *__restrict__ trace) {
     // conditional enforcements :312-316, :336, :340, :351, :356
     const uint64_t enforce_order = first ? (can_pop & not_start) : can_pop;
     if ((enforce_order & (1 - prev_smaller)) | (read_uninit & (1 - is_zero)) | (check_eq & (1 - vpe))) bad |= RAMV_ENFORCE;
+    // ---- gadget cells: byte decompositions, differences, zero-check witnesses (x * inv = 1 - flag, flag * x = 0) -------------
+    {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int base = k ? ZKC_RAM_SORTED_ITEM : ZKC_RAM_UNSORTED_ITEM, bytes = k ? ZKC_RAM_SORTED_ENC_BYTES : ZKC_RAM_UNSORTED_ENC_BYTES;
+#pragma unroll
+            for (int l = 0; l < 3; l++) {
+                uint64_t limb = 0, range = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) { const uint64_t v = TR(bytes + 4 * l + b); range |= v; limb |= v << (8 * b); }
+                ok &= (range >> 8) == 0 && limb == (k ? it[5 + 5 + l] : TR(base + 5 + 5 + l));
+            }
+        }
+        auto zero_check = [&](uint64_t x, uint64_t inv, uint64_t flag) {
+            return flag <= 1 && gl_mul(x, inv) == 1 - flag && (flag == 0 || x == 0);
+        };
+        const uint64_t ulen_prev = first ? d->uq0.length : TP(ZKC_RAM_UNSORTED_LEN), slen_prev = first ? d->sq0.length : TP(ZKC_RAM_SORTED_LEN);
+        ok &= zero_check(ulen_prev, TR(ZKC_RAM_UNSORTED_LEN_INV), u_empty) && zero_check(slen_prev, TR(ZKC_RAM_SORTED_LEN_INV), s_empty);
+        ok &= zero_check(it[0], TR(ZKC_RAM_TS_INV), ts_is_zero);
+        const uint64_t pd = TR(ZKC_RAM_PAGE_DIFF);
+        ok &= pd == gl_sub(it[1], heap_page) && zero_check(pd, TR(ZKC_RAM_PAGE_DIFF_INV), page_is_heap);
+#pragma unroll
+        for (int i = 0; i < 3; i++) ok &= zero_check(TR(ZKC_RAM_CMP_DIFF + i), TR(ZKC_RAM_CMP_DIFF_INV + i), TR(ZKC_RAM_CMP_LIMB_EQ + i));
+        uint64_t cell_and = 1, val_and = 1, zero_and = 1;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint64_t df = TR(ZKC_RAM_CELL_DIFF + i), eq = TR(ZKC_RAM_CELL_LIMB_EQ + i);
+            ok &= df == gl_sub(i ? it[1] : it[2], prev_fk[i]) && zero_check(df, TR(ZKC_RAM_CELL_DIFF_INV + i), eq);
+            cell_and &= eq;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint64_t df = TR(ZKC_RAM_VALUE_DIFF + i), eq = TR(ZKC_RAM_VALUE_LIMB_EQ + i);
+            ok &= df == gl_sub(it[5 + i], prev_val[i]) && zero_check(df, TR(ZKC_RAM_VALUE_DIFF_INV + i), eq);
+            val_and &= eq;
+            const uint64_t zf = TR(ZKC_RAM_VALUE_ZERO_DIFF + i), zq = TR(ZKC_RAM_VALUE_ZERO_LIMB_EQ + i);
+            ok &= zf == it[5 + i] && zero_check(zf, TR(ZKC_RAM_VALUE_ZERO_DIFF_INV + i), zq);
+            zero_and &= zq;
+        }
+        const uint64_t pdf = TR(ZKC_RAM_PTR_DIFF);
+        ok &= pdf == gl_sub(prev_is_ptr, is_ptr) && zero_check(pdf, TR(ZKC_RAM_PTR_DIFF_INV), ptr_eq);
+        ok &= cell_and == same_cell && val_and == value_equal && zero_and == value_is_zero;  // Boolean::multi_and of the limb flags
+        if (!ok) bad |= ZKC_RAMV_GADGET_CELLS;
+    }
     // utils.rs:104-135
 #pragma unroll
     for (int rep = 0; rep < 2; rep++) {
@@ -711,6 +815,7 @@ extern "C" int zkc_ram_permutation_entry_point(zkc_ctx *ctx, zkc_ram_closed_form
     ZKC_LAUNCH(ctx, "ram_prologue", ram_prologue_kernel, 1, 96, 0, d);
     if (need_chain) ZKC_LAUNCH(ctx, "ram_chain", ram_chain_kernel, 1, 64, 0, d, du, dsq, (uint64_t *)dup, (uint64_t *)dsp, need);
     if (tiles) ZKC_LAUNCH(ctx, "ram_rows", ram_rows_kernel, (unsigned)tiles, SCAN_THREADS, 0, d, du, dup, dsq, dsp, dtrace, sg, ts);
+    if (tiles && dtrace) ZKC_LAUNCH(ctx, "ram_inverse", ram_inverse_kernel, (unsigned)((limit + 127) / 128), 128, 0, d, dtrace);
     ZKC_LAUNCH(ctx, "ram_finalize", ram_finalize_kernel, 1, 32, 0, d);
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(RamDev), cudaMemcpyDeviceToHost, s));

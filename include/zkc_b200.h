@@ -220,7 +220,31 @@ enum zkc_ram_col {
     ZKC_RAM_GP_CHAIN = 94,  /* 32: fma partials, column (rep*2 + side)*8 + i, side 0 = lhs(unsorted); utils.rs:112-128 */
     ZKC_RAM_GP_NEW = 126,   /* 4: lhs.mul / rhs.mul results, rep*2 + side; utils.rs:131-132 */
     ZKC_RAM_GP_ACC = 130,   /* 4: accumulators after the select, rep*2 + side; utils.rs:134-135 */
-    ZKC_RAM_NUM_COLS = 134
+    /* ---- cells the gadgets called by the loop body allocate (boojum is un-vendored: what each gadget allocates is from its
+     * published construction -- Num::is_zero = ZeroCheckGate (flag + inverse witness, 0 for 0), Num::equals = is_zero of
+     * the difference, UInt32 / UInt256::equals = per-limb Num::equals + multi_and, decompose_into_bytes = 4 little-endian
+     * bytes).  include/zkc_b200_ram_variables.json maps every column to the reference line that allocates it and lists what
+     * stays host-resolved (range-check decompositions of allocated limbs, Poseidon2 round cells, linear-combination gates). */
+    ZKC_RAM_UNSORTED_ENC_BYTES = 134, /* 12: decompose_into_bytes of value limbs 5, 6, 7 (memory_query/mod.rs:133-135), 4 LE bytes each */
+    ZKC_RAM_SORTED_ENC_BYTES = 146,   /* 12 */
+    ZKC_RAM_UNSORTED_LEN_INV = 158,   /* :247 is_empty: inverse witness of the queue length before the pop */
+    ZKC_RAM_SORTED_LEN_INV = 159,     /* :248 */
+    ZKC_RAM_TS_INV = 160,             /* :261 */
+    ZKC_RAM_PAGE_DIFF = 161,          /* :263 UInt32::equals: memory_page - bootloader_heap_page (field) */
+    ZKC_RAM_PAGE_DIFF_INV = 162,
+    ZKC_RAM_CMP_DIFF_INV = 163,       /* 3: diff.is_zero() of unpacked_long_comparison, storage_validity.../mod.rs:937 */
+    ZKC_RAM_CELL_DIFF = 166,          /* 2: :318 long_equals: comparison_key[i] - previous_comparison_key[i] (field) */
+    ZKC_RAM_CELL_DIFF_INV = 168,      /* 2 */
+    ZKC_RAM_CELL_LIMB_EQ = 170,       /* 2 */
+    ZKC_RAM_VALUE_DIFF = 172,         /* 8: :319 UInt256::equals(value, previous_element_value), per limb */
+    ZKC_RAM_VALUE_DIFF_INV = 180,     /* 8 */
+    ZKC_RAM_VALUE_LIMB_EQ = 188,      /* 8 */
+    ZKC_RAM_VALUE_ZERO_DIFF = 196,    /* 8: :326 UInt256::equals(value, zero): value[i] - 0 */
+    ZKC_RAM_VALUE_ZERO_DIFF_INV = 204,/* 8 */
+    ZKC_RAM_VALUE_ZERO_LIMB_EQ = 212, /* 8 */
+    ZKC_RAM_PTR_DIFF = 220,           /* :330 Num::equals(previous_is_ptr, is_ptr): previous - current (field) */
+    ZKC_RAM_PTR_DIFF_INV = 221,
+    ZKC_RAM_NUM_COLS = 222
 };
 
 /* failed_checks bits for ram_permutation */
@@ -275,6 +299,7 @@ int zkc_ram_permutation_entry_point(zkc_ctx *ctx, zkc_ram_closed_form *io,
 #define ZKC_RAMV_FLAGS (1u << 6)
 #define ZKC_RAMV_ENFORCE (1u << 7)
 #define ZKC_RAMV_GP_CHAIN (1u << 8)
+#define ZKC_RAMV_GADGET_CELLS (1u << 10) /* bytes / differences / inverse witnesses of the gadget cells */
 #define ZKC_RAMV_GP_ACC (1u << 9)
 int zkc_ram_permutation_check_trace(zkc_ctx *ctx, const zkc_ram_closed_form *io, const uint64_t *trace,
                                     size_t limit, const zkc_ram_options *options, uint32_t gates, int on_device,

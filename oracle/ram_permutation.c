@@ -168,6 +168,7 @@ int orc_ram_permutation_entry_point(zkc_ram_closed_form *io, const zkc_memory_qu
     size_t upos = 0, spos = 0;
     for (size_t cyc = 0; cyc < limit; cyc++) {
         const int u_empty = uq.length == 0, s_empty = sq.length == 0; /* :247-248 */
+        const uint64_t ulen_before = uq.length, slen_before = sq.length;
         if (u_empty != s_empty) fail(&st, (int64_t)cyc, ZKC_RAM_CHK_EMPTY_SYNC); /* :252 */
         const int can_pop = !u_empty; /* :253 */
 
@@ -234,6 +235,9 @@ int orc_ram_permutation_entry_point(zkc_ram_closed_form *io, const zkc_memory_qu
         if (check_equality && !value_and_ptr_equal) fail(&st, (int64_t)cyc, ZKC_RAM_CHK_READ_CONSISTENT);
 
         /* :359-362 */
+        uint32_t old_fk[2], old_val[8];
+        const uint64_t old_is_ptr = prev_is_ptr;
+        memcpy(old_fk, prev_fk, sizeof old_fk); memcpy(old_val, prev_val, sizeof old_val);
         memcpy(prev_sk, sk, sizeof sk); memcpy(prev_fk, fk, sizeof fk);
         memcpy(prev_val, si.value, 32); prev_is_ptr = (uint32_t)is_ptr;
 
@@ -293,6 +297,30 @@ int orc_ram_permutation_entry_point(zkc_ram_closed_form *io, const zkc_memory_qu
             }
             T(ZKC_RAM_GP_ACC + 0, cyc) = lhs[0]; T(ZKC_RAM_GP_ACC + 1, cyc) = rhs[0];
             T(ZKC_RAM_GP_ACC + 2, cyc) = lhs[1]; T(ZKC_RAM_GP_ACC + 3, cyc) = rhs[1];
+            /* cells of the gadgets the loop body calls (un-vendored boojum, from the published constructions):
+             * decompose_into_bytes (memory_query/mod.rs:133-135), Num::is_zero = ZeroCheckGate (flag, inverse witness),
+             * Num::equals = is_zero(a - b), UInt32 / UInt256::equals per limb */
+            for (int k = 0; k < 2; k++)
+                for (int l = 0; l < 3; l++)
+                    for (int b = 0; b < 4; b++)
+                        T((k ? ZKC_RAM_SORTED_ENC_BYTES : ZKC_RAM_UNSORTED_ENC_BYTES) + 4 * l + b, cyc) = (items[k]->value[5 + l] >> (8 * b)) & 0xFF;
+            T(ZKC_RAM_UNSORTED_LEN_INV, cyc) = orc_gl_inv(ulen_before); T(ZKC_RAM_SORTED_LEN_INV, cyc) = orc_gl_inv(slen_before); /* :247-248 */
+            T(ZKC_RAM_TS_INV, cyc) = orc_gl_inv(si.timestamp);                                           /* :261 */
+            const uint64_t page_diff = gl_sub(si.memory_page, heap_page);                                /* :263 */
+            T(ZKC_RAM_PAGE_DIFF, cyc) = page_diff; T(ZKC_RAM_PAGE_DIFF_INV, cyc) = orc_gl_inv(page_diff);
+            for (int i = 0; i < 3; i++) T(ZKC_RAM_CMP_DIFF_INV + i, cyc) = orc_gl_inv(diff[i]);
+            for (int i = 0; i < 2; i++) {                                                                /* :318 */
+                const uint64_t df = gl_sub(fk[i], old_fk[i]);
+                T(ZKC_RAM_CELL_DIFF + i, cyc) = df; T(ZKC_RAM_CELL_DIFF_INV + i, cyc) = orc_gl_inv(df); T(ZKC_RAM_CELL_LIMB_EQ + i, cyc) = df == 0;
+            }
+            for (int i = 0; i < 8; i++) {                                                                /* :319, :326 */
+                const uint64_t df = gl_sub(si.value[i], old_val[i]);
+                T(ZKC_RAM_VALUE_DIFF + i, cyc) = df; T(ZKC_RAM_VALUE_DIFF_INV + i, cyc) = orc_gl_inv(df); T(ZKC_RAM_VALUE_LIMB_EQ + i, cyc) = df == 0;
+                T(ZKC_RAM_VALUE_ZERO_DIFF + i, cyc) = si.value[i]; T(ZKC_RAM_VALUE_ZERO_DIFF_INV + i, cyc) = orc_gl_inv(si.value[i]);
+                T(ZKC_RAM_VALUE_ZERO_LIMB_EQ + i, cyc) = si.value[i] == 0;
+            }
+            const uint64_t ptr_diff = gl_sub(old_is_ptr, (uint64_t)is_ptr);                              /* :330 */
+            T(ZKC_RAM_PTR_DIFF, cyc) = ptr_diff; T(ZKC_RAM_PTR_DIFF_INV, cyc) = orc_gl_inv(ptr_diff);
         }
     }
 

@@ -145,3 +145,62 @@ def test_golden_fixture(orc):
         json.dump(got, open(GOLDEN, "w"), indent=1)
     want = json.load(open(GOLDEN))
     assert got == want
+
+
+def test_gadget_cells_against_big_integers(orc):
+    """columns 134..221 (include/zkc_b200_ram_variables.json): byte decompositions, differences and ZeroCheckGate witnesses,
+    re-derived with Python integers from the item columns of the same trace"""
+    P = abi.GL_P
+    u, s = synthetic.ram_trace(400, seed=5, n_cells=25, n_nondet=3)
+    io, _, _ = H.ram_instance(orc, u, s, 3)
+    limit = 420
+    rc, io2, tr, com, st = O.ram_entry_point(orc, io, u, s, limit)
+    assert rc == abi.ZKC_OK
+    col = lambda name, i=0: [int(v) for v in tr[K[name] + i]]
+
+    def zero_check(x, inv, flag):
+        for a, b, f in zip(x, inv, flag):
+            assert f == int(a == 0) and (a * b) % P == (0 if a == 0 else 1) and (b < P) and (a != 0 or b == 0)
+
+    for side in ("UNSORTED", "SORTED"):
+        for l in range(3):
+            limb = col(side + "_ITEM", 5 + 5 + l)
+            by = [col(side + "_ENC_BYTES", 4 * l + b) for b in range(4)]
+            assert all(max(b) < 256 for b in by)
+            assert limb == [sum(by[b][r] << (8 * b) for b in range(4)) for r in range(limit)]
+    n = len(u)
+    len_before = [max(n - r, 0) for r in range(limit)]
+    zero_check(len_before, col("UNSORTED_LEN_INV"), col("UNSORTED_IS_EMPTY"))
+    zero_check(len_before, col("SORTED_LEN_INV"), col("SORTED_IS_EMPTY"))
+    zero_check(col("SORTED_ITEM", 0), col("TS_INV"), col("TS_IS_ZERO"))
+    page, index = col("SORTED_ITEM", 1), col("SORTED_ITEM", 2)
+    assert col("PAGE_DIFF") == [(p - 10) % P for p in page]
+    zero_check(col("PAGE_DIFF"), col("PAGE_DIFF_INV"), col("PAGE_IS_BOOTLOADER_HEAP"))
+    for i in range(3):
+        zero_check(col("CMP_DIFF", i), col("CMP_DIFF_INV", i), col("CMP_LIMB_EQ", i))
+    prev = lambda xs, first: [first] + xs[:-1]
+    for i, (cur, first) in enumerate([(index, 0), (page, 0)]):
+        assert col("CELL_DIFF", i) == [(a - b) % P for a, b in zip(cur, prev(cur, first))]
+        zero_check(col("CELL_DIFF", i), col("CELL_DIFF_INV", i), col("CELL_LIMB_EQ", i))
+    assert col("SAME_CELL") == [a & b for a, b in zip(col("CELL_LIMB_EQ", 0), col("CELL_LIMB_EQ", 1))]
+    veq, vz = [1] * limit, [1] * limit
+    for i in range(8):
+        v = col("SORTED_ITEM", 5 + i)
+        assert col("VALUE_DIFF", i) == [(a - b) % P for a, b in zip(v, prev(v, 0))] and col("VALUE_ZERO_DIFF", i) == v
+        zero_check(col("VALUE_DIFF", i), col("VALUE_DIFF_INV", i), col("VALUE_LIMB_EQ", i))
+        zero_check(v, col("VALUE_ZERO_DIFF_INV", i), col("VALUE_ZERO_LIMB_EQ", i))
+        veq = [a & b for a, b in zip(veq, col("VALUE_LIMB_EQ", i))]
+        vz = [a & b for a, b in zip(vz, col("VALUE_ZERO_LIMB_EQ", i))]
+    assert veq == col("VALUE_EQUAL") and vz == col("VALUE_IS_ZERO")
+    isp = col("SORTED_ITEM", 4)
+    assert col("PTR_DIFF") == [(b - a) % P for a, b in zip(isp, prev(isp, 0))]
+    zero_check(col("PTR_DIFF"), col("PTR_DIFF_INV"), col("PTR_EQUALITY"))
+
+
+def test_variable_map_covers_every_column():
+    doc = json.load(open(os.path.join(os.path.dirname(GOLDEN), "..", "..", "include", "zkc_b200_ram_variables.json")))
+    seen = np.zeros(K["NUM_COLS"], dtype=int)
+    for c in doc["columns"]:
+        assert K[c["name"][len("ZKC_RAM_"):]] == c["column"] and ".rs:" in c["reference"]
+        seen[c["column"]:c["column"] + c["width"]] += 1
+    assert (seen == 1).all() and len(doc["host_resolved"]) >= 5
