@@ -423,6 +423,26 @@ def run_gpu(args):
                           "bound": "hbm", "achieved": vchk_gbs, "peak": peak, "unit": "GB/s", "frac": vchk_gbs / peak if vchk_gbs else None,
                           "frac_of_nominal_8000": vchk_gbs / 8000.0 if vchk_gbs else None, "algorithmic_bytes_per_row": ncols * 8,
                           "avg_launch_ms": vchk_ms / vchk_n if vchk_n else None, "traffic": None}
+    # ---- integer-issue roofline of the Poseidon2-bound kernels: permutations/s against the issue-slot peak ----------
+    # One permutation costs ~19 000 thread instructions (472 64x64 multiplications with the 13-instruction Goldilocks reduction +
+    # the lazy 96-bit linear layers; measured: smsp__inst_executed of vm_sponge_kernel x 32 / jobs, profiles/r01_ncu_full_vm_kernels_raw.csv);
+    # the issue peak is SMs x 4 schedulers x 32 lanes x SM clock thread instructions/s.
+    P2_INSTR = 19000.0
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    p2_peak = sm_count * 128 * sm_hz / P2_INSTR
+    sponge_ms, sponge_n = prof["vm_sponge"]
+    sponge_perms = pk.n_sponge_records  # executed relations of one step (far-call slots included: ~0 in this mix)
+    int_roofline = {"unit": "Poseidon2 permutations/s", "bound": "integer issue slots", "thread_instructions_per_permutation": P2_INSTR,
+                    "peak": p2_peak, "peak_note": f"{sm_count} SMs x 128 lanes x {sm_hz / 1e6:.0f} MHz / {P2_INSTR:.0f}", "kernels": {}}
+    if sponge_n:
+        a = sponge_perms / (sponge_ms / args.steps * 1e-3)
+        int_roofline["kernels"]["vm_sponge_kernel (5 launches per step)"] = {"permutations_per_step": sponge_perms, "ms_per_step": sponge_ms / args.steps,
+                                                                              "achieved": a, "frac": a / p2_peak}
+    if rows_n:
+        a = 2.0 * rn / (rows_ms / rows_n * 1e-3)
+        int_roofline["kernels"]["ram_rows_kernel (2 queue pops per row + 4 x 8 FMA chains, scan)"] = {
+            "permutations_per_launch": 2 * rn, "ms_per_launch": rows_ms / rows_n, "achieved": a, "frac": a / p2_peak}
     kernels = {k + "_kernel": {"avg_launch_ms": v[0] / v[1], "launches_per_step": v[1] / args.steps,
                                "share_of_step": v[0] / ms} for k, v in prof.items() if v[1]}
     kernels["ram_rows_kernel (ram_permutation witness generation, 2^20 rows)"] = {"avg_launch_ms": rows_ms / rows_n if rows_n else None}
@@ -463,7 +483,7 @@ def run_gpu(args):
                 "input_stream_bytes_per_cycle": stream_bytes / (n * cycles), "packed_trace_bytes_per_cycle": pk.nbytes_used / (n * cycles),
                 "host_encode_s_setup": t_enc, "aux_records_per_step": pk.n_aux_records, "sponge_records_per_step": pk.n_sponge_records,
                 "records_form": e2e_records},
-        "roofline": roofline, "constraint_eval": constraint_eval, "constraint_eval_main_vm": constraint_eval_vm, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "constraint_eval": constraint_eval, "constraint_eval_main_vm": constraint_eval_vm, "int_roofline": int_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }))
     if world > 1:
         dist.destroy_process_group()

@@ -18,6 +18,9 @@
 // for a lane that hashes.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
+#include <utility>
+#include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no link dependency on libcuda)
 #include "ctx.cuh"
 #include "poseidon2.cuh"
 
@@ -1460,6 +1463,15 @@ __host__ __device__ constexpr int vm_exp_slot(int w) {
     return n;
 }
 constexpr int VM_EXP_DYN = vm_exp_slot(VM_WORDS), VM_EXP_WORDS = VM_EXP_DYN + 18;  // + dst0 / dst1 register values
+// one compile-time step of the word loops: W is a template argument, so slot numbers and word classes are constants of the code
+template <int W, typename F>
+__device__ __forceinline__ void vm_dyn_word_step(F &f) {
+    if constexpr (vm_link_dyn_word(W)) f(std::integral_constant<int, W>{}, std::integral_constant<int, vm_exp_slot(W)>{});
+}
+template <typename F, int... W>
+__device__ __forceinline__ void vm_for_dyn_words_impl(F &f, std::integer_sequence<int, W...>) { (vm_dyn_word_step<W>(f), ...); }
+template <typename F>
+__device__ __forceinline__ void vm_for_dyn_words(F &&f) { vm_for_dyn_words_impl(f, std::make_integer_sequence<int, VM_WORDS>{}); }
 enum : uint32_t { VM_LINK_ALL_REGISTERS = 1u << 8, VM_LINK_MEMQ = 1u << 9, VM_LINK_STACK = 1u << 10, VM_LINK_DECOMMIT = 1u << 11, VM_LINK_CONTEXT = 1u << 12 };
 
 // Carry-over half of the link check: every word group the cycle did NOT declare as changing (link[g]: dst0 / dst1 register
@@ -1482,12 +1494,10 @@ vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, cons
     bool bad = false;
     {   // the words the cycle computed: snapshot row + 1 holds exactly those values
         uint32_t dd = 0;
-#pragma unroll
-        for (int w = 0; w < VM_WORDS; w++) {
-            if (!vm_link_dyn_word(w)) continue;
-            dd |= __ldg(cur + (size_t)w * stride + 1) ^ EXP(vm_exp_slot(w));
-            if (vm_exp_slot(w) % 12 == 11) asm volatile("" ::: "memory");  // batches of 24 loads
-        }
+        vm_for_dyn_words([&](auto w, auto slot) {
+            dd |= __ldg(cur + (size_t)w.value * stride + 1) ^ EXP(slot.value);
+            if (slot.value % 12 == 11) asm volatile("" ::: "memory");  // batches of 24 loads
+        });
         bad |= dd != 0;
     }
     if (!(m & VM_LINK_ALL_REGISTERS)) {  // registers: dst1 / dst0 (dst1 is applied last) take the cycle's values, the others carry over
@@ -1541,11 +1551,23 @@ vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, cons
 #ifndef VM_CYCLES_MIN_BLOCKS
 #define VM_CYCLES_MIN_BLOCKS 2
 #endif
+// The words every cycle reads -- previous_code_word (8) and the scalars + current context (79) -- are staged per warp by TMA:
+// two tensor tiles [words x 32 consecutive snapshots] of the state columns land in shared memory (cp.async.bulk.tensor.2d,
+// completion on the warp's mbarrier), so the ~87 field reads of a cycle are shared-memory loads at their use sites instead of
+// global loads the compiler re-issues inside every divergent branch.  Registers of the snapshot, oracle answers and the rare
+// whole-record reads stay global loads.
+__device__ __forceinline__ uint32_t vm_smem_addr(const void *p);
+constexpr int VM_TILE_A = VW(registers), VM_TILE_B = VW(stack_sponge_state) - VW(flags), VM_TILE_WORDS = VM_TILE_A + VM_TILE_B;
+struct alignas(64) VmTmaps { CUtensorMap a, b; };  // boxes [32 x VM_TILE_A] and [32 x VM_TILE_B] over state_words [VM_WORDS][stride]
+__device__ __forceinline__ int vm_tile_slot(int w) { return w < VW(registers) ? w : VM_TILE_A + (w - VW(flags)); }
+
 __global__ void __launch_bounds__(128, VM_CYCLES_MIN_BLOCKS)
 vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
                  const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw,
                  uint64_t *__restrict__ trace, size_t limit, size_t n_instances, size_t row0, size_t row_count, VmPushScratch ps,
-                 int ncols, int aux_base) {
+                 int ncols, int aux_base, const __grid_constant__ VmTmaps tmaps, int use_tma) {
+    __shared__ alignas(128) uint32_t vm_tile[4][VM_TILE_WORDS * 32];
+    __shared__ alignas(8) unsigned long long vm_bar[4];
     // this launch covers rows [row0, row0 + row_count) of every instance (one chunk of the pipelined host path, or all)
     const size_t total = limit * n_instances;
     const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1556,6 +1578,32 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
     const size_t idx = inst * (limit + 1) + row;
     VmDev *dev = devs + inst;
     uint32_t checks = 0, jmask = 0;
+    // ---- TMA: the warp's tile, when its 32 cycles are 32 consecutive snapshots of one instance ------------------------------
+    const int wib = threadIdx.x >> 5;
+    const uint32_t *tile = vm_tile[wib] + lane;  // word slot k of this lane's snapshot: tile[k * 32]
+    bool staged = false;
+    if (use_tma) {
+        const unsigned long long idx0 = __shfl_sync(0xffffffffu, (unsigned long long)idx, 0);
+        const bool lane0_valid = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
+        staged = lane0_valid && __all_sync(0xffffffffu, !valid || (unsigned long long)idx == idx0 + lane);
+        if (staged) {
+            const uint32_t bar_a = vm_smem_addr(&vm_bar[wib]), tile_a = vm_smem_addr(vm_tile[wib]);
+            if (lane == 0) {
+                constexpr uint32_t BYTES = VM_TILE_WORDS * 32u * 4u;
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(BYTES) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                             ::"r"(tile_a), "l"(reinterpret_cast<uint64_t>(&tmaps.a)), "r"(bar_a), "r"((int)idx0), "r"(0) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                             ::"r"(tile_a + VM_TILE_A * 128u), "l"(reinterpret_cast<uint64_t>(&tmaps.b)), "r"(bar_a), "r"((int)idx0), "r"(VW(flags)) : "memory");
+            }
+            __syncwarp();
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_a) : "memory");
+        }
+    }
     if (valid) {
         const uint32_t *cur = cols.st + idx;  // word w of this snapshot: cur[w * stride]; of the next one: cur[w * stride + 1]
         const size_t stride = cols.st_stride;
@@ -1564,10 +1612,17 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
         // ---- the words a cycle reads outside the registers: scalars + the current context ---------------------------------
         zkc_vm_state s;
         uint32_t *sw = reinterpret_cast<uint32_t *>(&s);
+        if (staged) {
 #pragma unroll
-        for (int w = 0; w < VW(registers); w++) sw[w] = CUR(w);
+            for (int w = 0; w < VW(registers); w++) sw[w] = tile[vm_tile_slot(w) * 32];
 #pragma unroll
-        for (int w = VW(flags); w < VW(stack_sponge_state); w++) sw[w] = CUR(w);
+            for (int w = VW(flags); w < VW(stack_sponge_state); w++) sw[w] = tile[vm_tile_slot(w) * 32];
+        } else {
+#pragma unroll
+            for (int w = 0; w < VW(registers); w++) sw[w] = CUR(w);
+#pragma unroll
+            for (int w = VW(flags); w < VW(stack_sponge_state); w++) sw[w] = CUR(w);
+        }
         uint64_t next_fwd_tail[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) next_fwd_tail[i] = (uint64_t)NXT(VWC(log_queue_forward_tail) + 2 * i) | ((uint64_t)NXT(VWC(log_queue_forward_tail) + 2 * i + 1) << 32);
@@ -1588,11 +1643,12 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
         // (1) scalars + the context fields an ordinary cycle moves: the computed values go to vm_link_kernel as columns; the rest of
         // the context record only when the callstack moves (rare: compared here)
         {
-#pragma unroll
-            for (int w = 0; w < VM_WORDS; w++) {
-                if (!vm_link_dyn_word(w)) continue;
-                ps.exp[(size_t)vm_exp_slot(w) * total + g] = w < VW(registers) ? d.cw[w] : vm_expected_word(w, d, nctx, next_fwd_tail, cur, stride);
-            }
+            vm_for_dyn_words([&](auto w, auto slot) {
+                uint32_t v;
+                if constexpr (w.value < VW(registers)) v = d.cw[w.value];
+                else v = vm_expected_word(w.value, d, nctx, next_fwd_tail, cur, stride);
+                ps.exp[(size_t)slot.value * total + g] = v;
+            });
             if (d.ctx_replaced) {
                 uint32_t acc = 0;
 #pragma unroll
@@ -2215,6 +2271,28 @@ static cudaError_t vm_copy_lines(void *dst, size_t dst_pitch, const void *src, s
     return cudaSuccess;
 }
 
+// CUtensorMap of state_words [VM_WORDS][stride] (u32, row pitch stride * 4 bytes) with a [32 x rows] box; false when the driver
+// entry point is missing or the layout does not meet the 16-byte rules (the kernel then takes its plain-load path)
+static bool vm_make_tmaps(const uint32_t *st, size_t stride, VmTmaps *out) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = []() -> encode_fn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return (encode_fn)p;
+    }();
+    if (!encode || (reinterpret_cast<uintptr_t>(st) & 15) || (stride & 3) || stride >= (1ull << 31)) return false;
+    const cuuint64_t dims[2] = {stride, (cuuint64_t)VM_WORDS}, strides[1] = {stride * 4};
+    const cuuint32_t elem[2] = {1, 1};
+    const cuuint32_t box_a[2] = {32, (cuuint32_t)VM_TILE_A}, box_b[2] = {32, (cuuint32_t)VM_TILE_B};
+    void *base = const_cast<uint32_t *>(st);
+    return encode(&out->a, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box_a, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+           encode(&out->b, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box_b, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instances, const zkc_vm_isa *isa, const VmInput &in, size_t limit,
                           const zkc_vm_options *options, bool trace_dev, uint64_t *trace, uint64_t *commitments, zkc_status *statuses) {
     const bool have_stream = in.streams != nullptr;
@@ -2359,6 +2437,11 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
         uint32_t *stc = cv.take<uint32_t>(st_stride * VM_WORDS), *wtc = cv.take<uint32_t>(wt_stride * VM_WIT_WORDS);
         cols = VmCols{stc, st_stride, wtc, wt_stride};
     } else cols = VmCols{in.columns->state_words, st_stride, in.columns->witness_words, wt_stride};
+    // tensor maps of the state columns for the cycle kernel's TMA tiles (ZKC_VM_NO_TMA=1: plain loads, for comparison)
+    VmTmaps tmaps;
+    memset(&tmaps, 0, sizeof tmaps);
+    static const bool tma_disabled = getenv("ZKC_VM_NO_TMA") && atoi(getenv("ZKC_VM_NO_TMA"));
+    const int use_tma = !tma_disabled && vm_make_tmaps(cols.st, st_stride, &tmaps);
     uint32_t *stc_w = const_cast<uint32_t *>(cols.st), *wtc_w = const_cast<uint32_t *>(cols.wt);  // written only when they are this call's scratch
     char *dblobs = have_stream ? cv.take<char>(blob_total + 256) : nullptr;
     if ((trace && !trace_dev) || packed) dtrace = cv.take<uint64_t>((size_t)ncols * rows);
@@ -2502,7 +2585,7 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
             ps.records_capacity = chunk_cells * VM_JOB_SLOTS;
         }
         ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, cols, dcw,
-                   (uint32_t)in.n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base);
+                   (uint32_t)in.n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base, tmaps, use_tma);
         ZKC_LAUNCH(ctx, "vm_link", vm_link_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, d, cols, (const uint32_t *)ps.link, (const uint32_t *)ps.exp, limit,
                    n_instances, r0, cnt);
         // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists, or one launch per slot
