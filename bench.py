@@ -495,10 +495,14 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--instances", type=int, default=N_INSTANCES, help="main_vm instances per GPU per step")
+    ap.add_argument("--instances", type=int, default=0,
+                    help="main_vm instances per GPU per step; 0 = BASELINE.json's shapes: 1 (configs[1], one 2^20-cycle instance on one GPU) and, on "
+                         "8 GPUs, 8 (configs[4]: 64 instances of 2^20 cycles sharded over 8 GPUs, NCCL gather of the commitments)")
     ap.add_argument("--cycles", type=int, default=CYCLES_PER_INSTANCE, help="cycles per instance")
     ap.add_argument("--e2e-records", action="store_true", help="also time round 1's record-form host call (N = 1 only)")
     args = ap.parse_args()
+    if args.instances <= 0:
+        args.instances = 8 if int(os.environ.get("WORLD_SIZE", "1")) == 8 and args.gpus == 8 else N_INSTANCES
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -232,6 +232,49 @@ grand_product_kernel(GpParams *gp, const uint64_t *__restrict__ lhs, const uint6
 }
 }  // namespace zkc
 
+namespace zkc {
+// two rows per thread and column: 128-bit loads / stores over the column-major accumulators
+__global__ void __launch_bounds__(256)
+scale_accumulators_kernel(uint64_t *__restrict__ acc, size_t rows, uint64_t f0, uint64_t f1, uint64_t f2, uint64_t f3, int n_cols) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= rows) return;
+    const int c = blockIdx.y;
+    if (c >= n_cols) return;
+    const uint64_t f = c == 0 ? f0 : (c == 1 ? f1 : (c == 2 ? f2 : f3));
+    uint64_t *p = acc + (size_t)c * rows + i;
+    if (i + 1 < rows && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        ulonglong2 v = *reinterpret_cast<ulonglong2 *>(p);
+        v.x = gl_mul(v.x, f); v.y = gl_mul(v.y, f);
+        *reinterpret_cast<ulonglong2 *>(p) = v;
+    } else {
+        p[0] = gl_mul(p[0], f);
+        if (i + 1 < rows) p[1] = gl_mul(p[1], f);
+    }
+}
+}  // namespace zkc
+
+extern "C" int zkc_scale_accumulators(zkc_ctx *ctx, uint64_t *acc, size_t n_cols, size_t rows, const uint64_t *factors, int on_device) {
+    if (!ctx || !factors || n_cols > 4 || (n_cols && rows && !acc)) return ZKC_ERR_INVALID_ARGUMENT;
+    if (!rows || !n_cols) return ZKC_OK;
+    zkc_status *st = nullptr;
+    ZKC_CUDA(ctx, st, cudaSetDevice(ctx->device));
+    uint64_t f[4] = {1, 1, 1, 1};
+    for (size_t c = 0; c < n_cols; c++) f[c] = factors[c] % 0xFFFFFFFF00000001ull;
+    uint64_t *d = acc;
+    cudaStream_t s = ctx->stream;
+    if (!on_device) {
+        d = (uint64_t *)ctx->scratch(n_cols * rows * 8);
+        if (!d) return ZKC_ERR_CUDA;
+        ZKC_CUDA(ctx, st, cudaMemcpyAsync(d, acc, n_cols * rows * 8, cudaMemcpyHostToDevice, s));
+    }
+    ZKC_LAUNCH(ctx, "scale_accumulators", scale_accumulators_kernel, dim3((unsigned)((rows / 2 + 256) / 256), (unsigned)n_cols), 256, 0, d, rows, f[0], f[1],
+               f[2], f[3], (int)n_cols);
+    ZKC_CUDA(ctx, st, cudaGetLastError());
+    if (!on_device) ZKC_CUDA(ctx, st, cudaMemcpyAsync(acc, d, n_cols * rows * 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, st, cudaStreamSynchronize(s));
+    return ZKC_OK;
+}
+
 extern "C" int zkc_accumulate_grand_products(zkc_ctx *ctx, const uint64_t *lhs_enc, const uint64_t *rhs_enc,
                                              const uint8_t *should_acc, size_t enc_len, size_t rows,
                                              const uint64_t *challenges, const uint64_t acc_in[4], uint64_t *acc_out,

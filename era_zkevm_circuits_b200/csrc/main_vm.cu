@@ -1492,6 +1492,7 @@ vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, cons
 #define EXP(slot) __ldg(exp + (size_t)(slot) * total + g)
     const size_t total = limit * n_instances;
     bool bad = false;
+#if VM_LINK_EXP
     {   // the words the cycle computed: snapshot row + 1 holds exactly those values
         uint32_t dd = 0;
         vm_for_dyn_words([&](auto w, auto slot) {
@@ -1517,6 +1518,21 @@ vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, cons
         }
         bad |= dr != 0;
     }
+#else
+    {
+        const uint32_t idx0 = m & 15, idx1 = (m >> 4) & 15;
+        uint32_t moved = 0;  // bit r: register r differs
+#pragma unroll 1
+        for (int r = 0; r < ZKC_VM_REGISTERS; r++) {  // 18 independent loads in flight per thread and iteration
+            uint32_t dr = 0;
+#pragma unroll
+            for (int i = 0; i < 9; i++) dr |= DIFF(VW(registers) + 9 * r + i);
+            moved |= (dr != 0 ? 1u : 0u) << r;
+        }
+        const uint32_t allowed = (m & VM_LINK_ALL_REGISTERS) ? 0x7FFFu : ((idx0 ? 1u << (idx0 - 1) : 0u) | (idx1 ? 1u << (idx1 - 1) : 0u));
+        bad |= (moved & ~allowed) != 0;
+    }
+#endif
     {
         uint32_t dc = 0;
 #pragma unroll
@@ -1550,6 +1566,9 @@ vm_link_kernel(VmDev *devs, VmCols cols, const uint32_t *__restrict__ link, cons
 // only emits their jobs.
 #ifndef VM_CYCLES_MIN_BLOCKS
 #define VM_CYCLES_MIN_BLOCKS 2
+#endif
+#ifndef VM_LINK_EXP
+#define VM_LINK_EXP 0  // 1: the cycle kernel hands its computed words to vm_link_kernel as columns instead of comparing them itself (measured slower)
 #endif
 // The words every cycle reads -- previous_code_word (8) and the scalars + current context (79) -- are staged per warp by TMA:
 // two tensor tiles [words x 32 consecutive snapshots] of the state columns land in shared memory (cp.async.bulk.tensor.2d,
@@ -1585,7 +1604,8 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
     if (use_tma) {
         const unsigned long long idx0 = __shfl_sync(0xffffffffu, (unsigned long long)idx, 0);
         const bool lane0_valid = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
-        staged = lane0_valid && __all_sync(0xffffffffu, !valid || (unsigned long long)idx == idx0 + lane);
+        staged = lane0_valid && (idx0 & 3) == 0 &&  // the tile's first element must sit on a 16-byte boundary of its column
+                 __all_sync(0xffffffffu, !valid || (unsigned long long)idx == idx0 + lane);
         if (staged) {
             const uint32_t bar_a = vm_smem_addr(&vm_bar[wib]), tile_a = vm_smem_addr(vm_tile[wib]);
             if (lane == 0) {
@@ -1640,6 +1660,7 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
         // This thread compares the words its cycle CHANGES with what it computed; that every other word carries over unchanged
         // is checked by vm_link_kernel (a stream over the columns) from the mask written here.
         bool bad = false;
+#if VM_LINK_EXP
         // (1) scalars + the context fields an ordinary cycle moves: the computed values go to vm_link_kernel as columns; the rest of
         // the context record only when the callstack moves (rare: compared here)
         {
@@ -1672,6 +1693,50 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
                 for (int i = 0; i < 9; i++) bad |= NXT(VW(registers) + 9 * r + i) != reg_word(want, i);
             }
         }
+#else
+        // (1) scalars + the context fields an ordinary cycle moves; the whole record when the callstack moves
+        {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int w = 0; w < VW(registers); w++) acc |= NXT(w) ^ d.cw[w];
+#pragma unroll
+            for (int w = VW(flags); w < VW(stack_sponge_state); w++) {
+                if (w >= VW(_pad) && w < VW(current_context)) continue;  // padding is not state
+                if (w == VWC(aux_heap_upper_bound) + 1) continue;        // alignment hole in front of reverted_queue_head
+                if (vm_link_const_context_word(w)) continue;
+                acc |= NXT(w) ^ vm_expected_word(w, d, nctx, next_fwd_tail, cur, stride);
+            }
+            if (d.ctx_replaced) {
+#pragma unroll
+                for (int w = VW(current_context); w < VW(stack_sponge_state); w++)
+                    if (vm_link_const_context_word(w)) acc |= NXT(w) ^ reinterpret_cast<const uint32_t *>(&nctx)[w - VW(current_context)];
+            }
+            bad |= acc != 0;
+        }
+        // (2) registers: dst0 / dst1 (dst1 is applied last) hold the values the cycle produced; a far call / far return rewrites all
+        if (!d.far_ret && !d.far_call) {
+            uint32_t acc = 0;
+            if (d.idx1) {
+                const int base = VW(registers) + 9 * ((int)d.idx1 - 1);
+#pragma unroll
+                for (int i = 0; i < 9; i++) acc |= NXT(base + i) ^ reg_word(d.val1, i);
+            }
+            if (d.idx0 && d.idx0 != d.idx1) {
+                const int base = VW(registers) + 9 * ((int)d.idx0 - 1);
+#pragma unroll
+                for (int i = 0; i < 9; i++) acc |= NXT(base + i) ^ reg_word(d.val0, i);
+            }
+            bad |= acc != 0;
+        } else {
+#pragma unroll 1
+            for (int r = 0; r < ZKC_VM_REGISTERS; r++) {
+                zkc_vm_register want = reg_zero();
+                if (d.far_ret) { if (r == 0) want = d.r1_val; }
+                else want = vm_far_call_register(isa, d, r, regs.get((uint32_t)r));
+                for (int i = 0; i < 9; i++) bad |= NXT(VW(registers) + 9 * r + i) != reg_word(want, i);
+            }
+        }
+#endif
         // (3) the sponge-derived states: vouched for by the cycle's last job on them (vm_sponge_kernel), else unchanged (vm_link_kernel)
         {
             bool memq_job = false, stack_job = false, decommit_job = false;

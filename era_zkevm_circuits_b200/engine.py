@@ -152,6 +152,16 @@ class Engine:
             raise ZkcError(rc, what="zkc_accumulate_grand_products")
         return acc, chain, fin
 
+    def scale_accumulators(self, acc, factors):
+        """acc[c, :] *= factors[c] in place (zkc_scale_accumulators): the fix-up of a row range accumulated from the neutral
+        element once the product of everything before it is known (sharding.distributed_grand_products)."""
+        n_cols, rows = acc.shape
+        f = np.ascontiguousarray(factors, dtype=np.uint64)
+        rc = self.lib.zkc_scale_accumulators(self.h, ptr(acc), n_cols, rows, ptr(f), int(on_device(acc)))
+        if rc:
+            raise ZkcError(rc, what="zkc_scale_accumulators")
+        return acc
+
     def memory_queue_simulate(self, records, n_queues=1):
         """push every record into `n_queues` empty memory queues (records split evenly, in order).
         Returns (prev_states [n, 12] uint64, final_states: list/array of QueueState12)."""

@@ -115,6 +115,12 @@ int zkc_accumulate_grand_products(zkc_ctx *ctx, const uint64_t *lhs_enc, const u
                                   uint64_t *acc_out, uint64_t *chain_out, uint64_t acc_final[4],
                                   int on_device);
 
+/* acc[c][r] *= factors[c] for the `n_cols` column-major accumulator columns of `rows` rows: the fix-up of a row range whose
+ * running products were accumulated from the neutral element, once the product of everything before the range is known
+ * (the chained instance's hidden_fsm_input, ram_permutation/input.rs:52-62).  32 bytes of traffic per row and column pair
+ * instead of a second pass over the encodings.  factors: host, [n_cols]. */
+int zkc_scale_accumulators(zkc_ctx *ctx, uint64_t *acc, size_t n_cols, size_t rows, const uint64_t *factors, int on_device);
+
 /* ---- records shared by circuits --------------------------------------------------------------- */
 /* MemoryQuery witness, src/base_structures/memory_query/mod.rs:30-37 (64-byte record) */
 typedef struct zkc_memory_query {

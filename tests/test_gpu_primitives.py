@@ -92,3 +92,21 @@ def test_grand_product_permutation_invariance(engine):
     a = acc.cpu().numpy().view(np.uint64)
     assert a[:, -1].tolist() == fin.tolist()
     assert a.max() < P
+
+
+def test_scale_accumulators_host_and_device(engine):
+    """zkc_scale_accumulators: the 4-column fix-up multiply of a sharded grand product, against Python integers"""
+    import torch
+    P = abi.GL_P
+    rng = np.random.default_rng(3)
+    for rows in (1, 2, 7, 1000, 4097):
+        acc = rng.integers(0, P, size=(4, rows), dtype=np.uint64)
+        acc[0, 0] = P - 1
+        f = np.array([P - 1, 1, 0x123456789ABCDEF % P, 2], dtype=np.uint64)
+        want = np.array([[int(v) * int(f[c]) % P for v in acc[c]] for c in range(4)], dtype=np.uint64)
+        host = acc.copy()
+        engine.scale_accumulators(host, f)
+        assert np.array_equal(host, want)
+        dev = torch.from_numpy(acc.view(np.int64).copy()).cuda()
+        engine.scale_accumulators(dev, f)
+        assert np.array_equal(dev.cpu().numpy().view(np.uint64), want)
