@@ -13,6 +13,7 @@ from .ram_permutation import (  # noqa: F401
 from .log_sorter import (  # noqa: F401
     EventsDeduplicatorInstanceWitness,
     SorterResult,
+    log_sorter_check_trace,
     sort_and_deduplicate_events_entry_point,
 )
 from .storage_validity import (  # noqa: F401

@@ -225,23 +225,25 @@ dmx_rows_kernel(DmxDev *d, const zkc_log_query *__restrict__ recs, const uint64_
 #undef TR
 }
 
-// the six chains side by side when the caller supplies no tails: warp q, one lane, 1 permutation per push of queue q
+// the six chains side by side when the caller supplies no tails: warp q, 1 permutation per push of queue q, each on 12
+// cooperating lanes (poseidon2_permute_coop)
 __global__ void dmx_chain_kernel(const DmxDev *d, const uint64_t *__restrict__ r2in, const uint32_t *__restrict__ lists,
                                  uint64_t *__restrict__ tails) {
-    const int q = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) != 0 || q >= DMX_Q) return;
-    uint64_t tail[4];
-    for (int i = 0; i < 4; i++) tail[i] = d->oq0[q].tail[i];
+    const int q = threadIdx.x >> 5, i = threadIdx.x & 31;
+    if (i >= 16 || q >= DMX_Q) return;
+    const unsigned gm = 0xFFFFu;
+    uint64_t tail = i < 4 ? d->oq0[q].tail[i] : 0ull;  // lanes 0..3 hold the running tail
     const size_t n = d->counts_final[q], limit = d->limit;
     uint64_t *out = tails + 4 * d->tails_base[q];
     for (size_t k = 0; k < n; k++) {
         const size_t row = lists[(size_t)q * limit + k];
-        uint64_t s[12];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { s[i] = r2in[8 * row + i]; s[4 + i] = tail[i]; s[8 + i] = r2in[8 * row + 4 + i]; }
-        poseidon2_permute(s);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { tail[i] = s[i]; out[4 * k + i] = s[i]; }
+        const uint64_t from_tail = __shfl_sync(gm, tail, (i - 4) & 3, 16);
+        uint64_t x = 0;
+        if (i < 4) x = r2in[8 * row + i];
+        else if (i < 8) x = from_tail;
+        else if (i < 12) x = r2in[8 * row + 4 + (i - 8)];
+        x = poseidon2_permute_coop(gm, x, i);
+        if (i < 4) { tail = x; out[4 * k + i] = x; }
     }
 }
 

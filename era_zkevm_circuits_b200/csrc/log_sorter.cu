@@ -34,6 +34,7 @@ struct EvDev {
     // finalize
     uint64_t commitment[4];
     zkc_status status;
+    unsigned long long violations;  // zkc_log_sorter_check_trace
 };
 
 __device__ int ev_encode_fsm(const zkc_events_fsm &f, uint64_t *dst) {
@@ -451,6 +452,163 @@ __global__ void log_queue_simulate_kernel(const zkc_log_query *__restrict__ recs
     o._pad = 0;
 }
 
+// ---- constraint evaluation of a finished trace ------------------------------------------------------------------------------
+// One thread per row re-evaluates every relation the loop body of repack_and_prove_events_rollbacks_inner places that is local
+// to a row or to a row and its predecessor (the role of `check_if_satisfied` over these cells, log_sorter/mod.rs:626-634):
+// booleans / ranges of the allocated items, LogQuery::encode of both pops and of the pushed record, queue-length bookkeeping,
+// the 4 x 20 Num::fma chains and the accumulator update, the timestamp borrow chain, the flag algebra of :327-372, the
+// conditional enforcements, the result queue's length / tail selection.  Streams all ZKC_EV_NUM_COLS columns once (+ the
+// previous row of the carried ones, an L1 / L2 hit); with ZKC_GATES_ROUND_FUNCTION also the three permutations of the push.
+template <bool ROUND_FUNCTION>
+__global__ void __launch_bounds__(128)
+ev_check_kernel(EvDev *d, const uint64_t *__restrict__ trace) {
+    __shared__ uint64_t ch[2][21];
+    if (threadIdx.x < 42) ch[threadIdx.x / 21][threadIdx.x % 21] = d->ch[threadIdx.x / 21][threadIdx.x % 21];
+    __syncthreads();
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const bool first = row == 0;
+#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
+#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
+    uint32_t bad = 0;
+    const uint64_t o_empty = TR(ZKC_EV_ORIGINAL_IS_EMPTY), s_empty = TR(ZKC_EV_SORTED_IS_EMPTY), should_pop = TR(ZKC_EV_SHOULD_POP);
+    if ((o_empty | s_empty | should_pop) > 1 || o_empty != s_empty || should_pop != 1 - o_empty) bad |= ZKC_EVV_BOOLEAN;
+    zkc_log_query si = lq_zero(), pq = lq_zero();
+    uint64_t enc[2][20];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int base = k ? ZKC_EV_SORTED_ITEM : ZKC_EV_UNSORTED_ITEM;
+        const zkc_queue_state4 &q0 = k ? d->sq0 : d->uq0;
+        uint64_t f[36], limbs = 0;
+#pragma unroll
+        for (int i = 0; i < 36; i++) f[i] = TR(base + i);
+#pragma unroll
+        for (int i = 0; i < 29; i++) limbs |= f[i];
+        if ((limbs | f[34] | f[35]) >> 32 || (f[29] | f[33]) >> 8 || (f[30] | f[31] | f[32]) > 1) bad |= ZKC_EVV_BOOLEAN;
+        zkc_log_query q = lq_zero();
+#pragma unroll
+        for (int i = 0; i < 5; i++) q.address[i] = (uint32_t)f[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { q.key[i] = (uint32_t)f[5 + i]; q.read_value[i] = (uint32_t)f[13 + i]; q.written_value[i] = (uint32_t)f[21 + i]; }
+        q.flags = ZKC_LQ_FLAGS((uint32_t)f[29], (uint32_t)f[33], (uint32_t)f[30], (uint32_t)f[31], (uint32_t)f[32]);
+        q.tx_number_in_block = (uint32_t)f[34]; q.timestamp = (uint32_t)f[35];
+        uint64_t e[20];
+        lq_encode(q, e);
+#pragma unroll
+        for (int i = 0; i < 20; i++) { enc[k][i] = TR(base + 36 + i); if (enc[k][i] != e[i]) bad |= ZKC_EVV_ENCODING; }
+        // queue: is_empty <=> previous length == 0, length decrements on a pop, the head only moves on a pop
+        const uint64_t len_prev = first ? q0.length : TP(base + 60), len = TR(base + 60);
+        if ((k ? s_empty : o_empty) != (uint64_t)(len_prev == 0) || len + should_pop != len_prev) bad |= ZKC_EVV_QUEUE_LEN;
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint64_t h = TR(base + 56 + i);
+            same &= h == (first ? q0.head[i] : TP(base + 56 + i));
+            if (h >= GL_P) bad |= ZKC_EVV_BOOLEAN;
+        }
+        if (!should_pop && !same) bad |= ZKC_EVV_QUEUE_LEN;
+        if (should_pop && !ZKC_LQ_RW(q.flags)) bad |= ZKC_EVV_ENFORCE;  // :295-297, :318-320
+        if (k == 1) si = q;
+    }
+    // utils.rs:104-135
+#pragma unroll
+    for (int rep = 0; rep < 2; rep++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int g = rep * 2 + k;
+            uint64_t c = ch[rep][20];
+#pragma unroll
+            for (int i = 0; i < 20; i++) {
+                const uint64_t cell = TR(ZKC_EV_GP_CHAIN + g * 20 + i);
+                if (cell != gl_fma(enc[k][i], ch[rep][i], c)) bad |= ZKC_EVV_GP_CHAIN;
+                c = cell;
+            }
+            const uint64_t acc_prev = first ? d->acc0[g] : TP(ZKC_EV_GP_ACC + g);
+            const uint64_t nw = TR(ZKC_EV_GP_NEW + g), acc = TR(ZKC_EV_GP_ACC + g);
+            if (nw != gl_mul(acc_prev, c) || acc != (should_pop ? nw : acc_prev)) bad |= ZKC_EVV_GP_ACC;
+        }
+    }
+    // the previous item / key / triviality: the neighbouring row (row 0: the FSM input)
+    uint64_t previous_key, prev_trivial;
+    if (first) { pq = d->previous_item0; previous_key = d->previous_key0; prev_trivial = d->prev_trivial0; }
+    else {
+#pragma unroll
+        for (int i = 0; i < 5; i++) pq.address[i] = (uint32_t)TP(ZKC_EV_SORTED_ITEM + i);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { pq.key[i] = (uint32_t)TP(ZKC_EV_SORTED_ITEM + 5 + i); pq.written_value[i] = (uint32_t)TP(ZKC_EV_SORTED_ITEM + 21 + i); }
+        pq.flags = ZKC_LQ_FLAGS(0, (uint32_t)TP(ZKC_EV_SORTED_ITEM + 33), 0, (uint32_t)TP(ZKC_EV_SORTED_ITEM + 31), (uint32_t)TP(ZKC_EV_SORTED_ITEM + 32));
+        pq.tx_number_in_block = (uint32_t)TP(ZKC_EV_SORTED_ITEM + 34);
+        previous_key = TP(ZKC_EV_SORTED_ITEM + 35);
+        prev_trivial = TP(ZKC_EV_ORIGINAL_IS_EMPTY);
+    }
+    // :327 borrow chain: current - previous = diff - 2^32 * borrow
+    const uint64_t diff = TR(ZKC_EV_CMP_DIFF), borrow = TR(ZKC_EV_CMP_BORROW), keys_equal = TR(ZKC_EV_KEYS_EQUAL);
+    if ((diff >> 32) || borrow > 1 || keys_equal != (uint64_t)(diff == 0) || (uint64_t)si.timestamp + (borrow << 32) != diff + previous_key) bad |= ZKC_EVV_COMPARISON;
+    // :335-372 flags
+    const uint64_t same_nt = TR(ZKC_EV_SAME_NONTRIVIAL_LOG), diff_nt = TR(ZKC_EV_DIFFERENT_NONTRIVIAL_LOG), ike = TR(ZKC_EV_ITEM_KEYS_EQUAL),
+                   ve = TR(ZKC_EV_VALUES_EQUAL), same_body = TR(ZKC_EV_SAME_BODY), pit = TR(ZKC_EV_PREVIOUS_IS_TRIVIAL),
+                   should_enforce = TR(ZKC_EV_SHOULD_ENFORCE), maybe_add = TR(ZKC_EV_MAYBE_ADD), add = TR(ZKC_EV_ADD_TO_QUEUE);
+    bool keq = true, veq = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { keq &= si.key[i] == pq.key[i]; veq &= si.written_value[i] == pq.written_value[i]; }
+    const uint64_t rollback = ZKC_LQ_ROLLBACK(si.flags);
+    if ((same_nt | diff_nt | ike | ve | same_body | pit | should_enforce | maybe_add | add) > 1 || same_nt != (should_pop & keys_equal) ||
+        diff_nt != (should_pop & (1 - keys_equal)) || ike != (uint64_t)keq || ve != (uint64_t)veq || same_body != (ike & ve) || pit != prev_trivial ||
+        should_enforce != (keys_equal & (1 - pit)) || maybe_add != ((1 - keys_equal) | o_empty) ||
+        add != ((1 - pit) & maybe_add & (1 - (uint64_t)ZKC_LQ_ROLLBACK(pq.flags))))
+        bad |= ZKC_EVV_FLAGS;
+    // conditional enforcements :331, :342-343, :347-349, :362
+    if ((should_pop & borrow) | (diff_nt & rollback) | (same_nt & (1 - rollback)) | (should_enforce & (1 - same_body))) bad |= ZKC_EVV_ENFORCE;
+    // :381-397 the pushed record and the result queue
+    {
+        const zkc_log_query to_add = ev_cleaned_up(pq);
+        uint64_t pe[20], penc[20], s[12];
+        lq_encode(to_add, pe);
+#pragma unroll
+        for (int i = 0; i < 20; i++) { penc[i] = TR(ZKC_EV_PUSH_ENC + i); if (penc[i] != pe[i]) bad |= ZKC_EVV_ENCODING; }
+        uint64_t r0[12], r1[12], r2[12], tail_prev[4];
+#pragma unroll
+        for (int i = 0; i < 12; i++) { r0[i] = TR(ZKC_EV_PUSH_ROUND0 + i); r1[i] = TR(ZKC_EV_PUSH_ROUND1 + i); r2[i] = TR(ZKC_EV_PUSH_ROUND2 + i); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) tail_prev[i] = first ? d->rq0.tail[i] : TP(ZKC_EV_RESULT_TAIL + i);
+        const uint64_t len_prev = first ? d->rq0.length : TP(ZKC_EV_RESULT_LEN);
+        if (TR(ZKC_EV_RESULT_LEN) != len_prev + add) bad |= ZKC_EVV_RESULT_QUEUE;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (TR(ZKC_EV_RESULT_TAIL + i) != (add ? r2[i] : tail_prev[i])) bad |= ZKC_EVV_RESULT_QUEUE;
+        if (ROUND_FUNCTION) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = i < 8 ? penc[i] : 0;
+            poseidon2_permute(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (s[i] != r0[i]) bad |= ZKC_EVV_ROUND_FUNCTION;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s[i] = penc[8 + i];
+            poseidon2_permute(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (s[i] != r1[i]) bad |= ZKC_EVV_ROUND_FUNCTION;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { s[i] = penc[16 + i]; s[4 + i] = tail_prev[i]; }
+            poseidon2_permute(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (s[i] != r2[i]) bad |= ZKC_EVV_ROUND_FUNCTION;
+        } else {
+            uint64_t big = 0;
+#pragma unroll
+            for (int i = 0; i < 12; i++) big |= (uint64_t)(r0[i] >= GL_P) | (uint64_t)(r1[i] >= GL_P) | (uint64_t)(r2[i] >= GL_P);
+            if (big) bad |= ZKC_EVV_BOOLEAN;
+        }
+    }
+#undef TR
+#undef TP
+    if (bad) {
+        atomicAdd(&d->violations, 1ull);
+        atomicOr(&d->failed_checks, bad);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+    }
+}
+
 }  // namespace zkc
 
 using namespace zkc;
@@ -579,5 +737,49 @@ extern "C" int zkc_log_sorter_entry_point(zkc_ctx *ctx, zkc_events_closed_form *
     io->completion_flag = h->io.completion_flag;
     memcpy(commitment, h->commitment, 32);
     *status = h->status;
+    return status->code;
+}
+
+extern "C" int zkc_log_sorter_check_trace(zkc_ctx *ctx, const zkc_events_closed_form *io, const uint64_t *trace, size_t limit, uint32_t gates,
+                                          int on_device, uint64_t *violations, zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !violations || (limit && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(EvDev));
+    if (!on_device) bytes += zkc_carver::bytes((size_t)ZKC_EV_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    EvDev *h = (EvDev *)ctx->pinned(sizeof(EvDev));
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    EvDev *d = cv.take<EvDev>(1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(EvDev));
+    h->io = *io;
+    h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(EvDev), cudaMemcpyHostToDevice, s));
+    const uint64_t *dt = trace;
+    if (!on_device && limit) {
+        uint64_t *b = cv.take<uint64_t>((size_t)ZKC_EV_NUM_COLS * limit);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, (size_t)ZKC_EV_NUM_COLS * limit * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    ZKC_LAUNCH(ctx, "ev_prologue", ev_prologue_kernel, 1, 96, 0, d);
+    if (limit) {
+        const unsigned grid = (unsigned)((limit + 127) / 128);
+        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION)) ZKC_LAUNCH(ctx, "ev_check_rf", ev_check_kernel<true>, grid, 128, 0, d, dt);
+        else ZKC_LAUNCH(ctx, "ev_check", ev_check_kernel<false>, grid, 128, 0, d, dt);
+    }
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(EvDev), cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = h->violations;
+    status->failed_checks = h->failed_checks;
+    if (h->violations) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 16);
+    }
     return status->code;
 }

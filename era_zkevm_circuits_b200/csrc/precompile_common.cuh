@@ -22,20 +22,21 @@ __device__ __forceinline__ void mq_encode(uint32_t ts, uint32_t page, uint32_t i
 }
 
 
+// the chain when the caller supplies no states: one permutation per push on 12 cooperating lanes (poseidon2_permute_coop; the
+// full-state queue's next tail is the whole permutation output, so lane i simply keeps s[i]).  Launch with one warp.
 template <class Dev, int SLOTS>
 __global__ void pc_mem_chain_kernel(const Dev *d, const uint64_t *__restrict__ push_enc, const uint32_t *__restrict__ slot_meta,
                                     uint64_t *__restrict__ states) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t s[12];
-    for (int i = 0; i < 12; i++) s[i] = d->mq0.tail[i];
+    const int i = threadIdx.x;
+    if (blockIdx.x != 0 || i >= 16) return;
+    const unsigned gm = 0xFFFFu;
+    uint64_t x = i < 12 ? d->mq0.tail[i] : 0ull;
     const size_t limit = d->limit;
     const uint32_t n = limit ? (slot_meta[SLOTS * (limit - 1) + SLOTS - 1] & 0x7FFFFFFFu) : 0;
     for (uint32_t k = 0; k < n; k++) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = push_enc[8 * (size_t)k + i];
-        poseidon2_permute(s);
-#pragma unroll
-        for (int i = 0; i < 12; i++) states[12 * (size_t)k + i] = s[i];
+        if (i < 8) x = push_enc[8 * (size_t)k + i];
+        x = poseidon2_permute_coop(gm, x, i);
+        if (i < 12) states[12 * (size_t)k + i] = x;
     }
 }
 

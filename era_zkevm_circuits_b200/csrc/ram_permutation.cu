@@ -143,24 +143,25 @@ __global__ void ram_prologue_kernel(RamDev *d) {
     }
 }
 
-// sequential reconstruction of the previous-state column when the caller does not supply it
-// (2 threads, one hash chain each; only for callers without a raw queue witness)
+// sequential reconstruction of the previous-state column when the caller does not supply it (only for callers without a raw
+// queue witness): two warps, one hash chain each, every permutation on 12 cooperating lanes (poseidon2_permute_coop)
 __global__ void ram_chain_kernel(RamDev *d, const zkc_memory_query *unsorted, const zkc_memory_query *sorted,
                                  uint64_t *uprev, uint64_t *sprev, size_t rows) {
-    const int k = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) != 0 || k > 1) return;
+    const int k = threadIdx.x >> 5, i = threadIdx.x & 31;
+    if (i >= 16 || k > 1) return;
+    const unsigned gm = 0xFFFFu;
     const zkc_memory_query *q = k ? sorted : unsorted;
     uint64_t *out = k ? sprev : uprev;
     const zkc_queue_state12 &q0 = k ? d->sq0 : d->uq0;
-    uint64_t s[12];
-    for (int i = 0; i < 12; i++) s[i] = q0.head[i];
+    uint64_t x = i < 12 ? q0.head[i] : 0ull;
     for (size_t r = 0; r < rows; r++) {
-        for (int i = 0; i < 12; i++) out[12 * r + i] = s[i];
+        if (i < 12) out[12 * r + i] = x;
         zkc_memory_query it = q[r];
         uint64_t e[8];
         ram_encode(it, e);
-        for (int i = 0; i < 8; i++) s[i] = e[i];
-        poseidon2_permute(s);
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (i == j) x = e[j];
+        x = poseidon2_permute_coop(gm, x, i);
     }
 }
 

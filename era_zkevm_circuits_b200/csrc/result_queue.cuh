@@ -10,22 +10,27 @@
 
 namespace zkc {
 
+// The chain when the caller supplies no tails: one permutation per push, each consuming the previous tail.  The chain itself
+// cannot be cut, but ONE permutation can: it runs on 12 cooperating lanes (poseidon2_permute_coop: S-boxes of a full round side
+// by side, linear layers as shuffles), ~5x shorter than on one lane.  Launch with one warp; lanes 0..15 work.
 template <class Dev>
 __global__ void rq_chain_kernel(const Dev *d, const uint64_t *__restrict__ r2in, const uint32_t *__restrict__ meta,
                                 uint64_t *__restrict__ tails) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    uint64_t tail[4];
-    for (int i = 0; i < 4; i++) tail[i] = d->rq0.tail[i];
+    const int i = threadIdx.x;
+    if (blockIdx.x != 0 || i >= 16) return;
+    const unsigned gm = 0xFFFFu;
+    uint64_t tail = i < 4 ? d->rq0.tail[i] : 0ull;  // lanes 0..3 hold the running tail
     const size_t limit = d->limit;
     size_t k = 0;
     for (size_t row = 0; row < limit; row++) {
-        if (!(meta[row] & 1u)) continue;
-        uint64_t s[12];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { s[i] = r2in[8 * row + i]; s[4 + i] = tail[i]; s[8 + i] = r2in[8 * row + 4 + i]; }
-        poseidon2_permute(s);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { tail[i] = s[i]; tails[4 * k + i] = s[i]; }
+        if (!(meta[row] & 1u)) continue;  // uniform over the group
+        const uint64_t from_tail = __shfl_sync(gm, tail, (i - 4) & 3, 16);
+        uint64_t x = 0;
+        if (i < 4) x = r2in[8 * row + i];
+        else if (i < 8) x = from_tail;
+        else if (i < 12) x = r2in[8 * row + 4 + (i - 8)];
+        x = poseidon2_permute_coop(gm, x, i);
+        if (i < 4) { tail = x; tails[4 * k + i] = x; }
         k++;
     }
 }

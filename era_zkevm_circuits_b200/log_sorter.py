@@ -59,3 +59,15 @@ def sort_and_deduplicate_events_entry_point(engine: Engine, witness: EventsDedup
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE) or (rc and raise_on_unsatisfied):
         raise ZkcError(rc, st, "sort_and_deduplicate_events_entry_point")
     return SorterResult(commitment, io, trace, st)
+
+
+def log_sorter_check_trace(engine: Engine, closed_form_input: abi.EventsClosedForm, trace, limit: int, gates: int = 0):
+    """Constraint evaluation of a finished log_sorter trace [EV_COLS.NUM_COLS, limit] (numpy: host, torch CUDA: device): every
+    row-local relation of repack_and_prove_events_rollbacks_inner.  Returns (violating rows, status)."""
+    st = abi.Status()
+    viol = C.c_uint64()
+    io = abi.EventsClosedForm.from_buffer_copy(bytes(closed_form_input))
+    rc = engine.lib.zkc_log_sorter_check_trace(engine.h, C.byref(io), ptr(trace), limit, gates, on_device(trace), C.byref(viol), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, st, "log_sorter_check_trace")
+    return viol.value, st

@@ -434,6 +434,24 @@ int zkc_log_sorter_entry_point(zkc_ctx *ctx, zkc_events_closed_form *io, const z
                                size_t n_result_tails, size_t limit, const zkc_sorter_options *options, int on_device,
                                uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
+/* constraint evaluation of a finished log_sorter trace (as zkc_ram_permutation_check_trace): re-evaluates every relation of
+ * the loop body on every row and returns the number of violating rows; status->first_bad_row / failed_checks (ZKC_EVV_* bits)
+ * describe the first one.  io: start_flag, the observable input and hidden_fsm_input of the instance the trace belongs to.
+ * gates: ZKC_GATES_GENERAL = the streaming (HBM-bound) relations, ZKC_GATES_ROUND_FUNCTION adds the three permutations of the
+ * result-queue push; 0 = all. */
+#define ZKC_EVV_BOOLEAN (1u << 0)      /* booleans, u32 / u8 ranges, field range of hash outputs */
+#define ZKC_EVV_QUEUE_LEN (1u << 1)    /* is_empty / length / head bookkeeping of the two popped queues */
+#define ZKC_EVV_ENCODING (1u << 2)     /* LogQuery::encode of the popped items and of the pushed record */
+#define ZKC_EVV_ROUND_FUNCTION (1u << 3)
+#define ZKC_EVV_COMPARISON (1u << 4)   /* :327 borrow chain */
+#define ZKC_EVV_FLAGS (1u << 5)        /* :335-372 */
+#define ZKC_EVV_ENFORCE (1u << 6)      /* conditional enforcements */
+#define ZKC_EVV_GP_CHAIN (1u << 7)
+#define ZKC_EVV_GP_ACC (1u << 8)
+#define ZKC_EVV_RESULT_QUEUE (1u << 9) /* result queue length / tail selection */
+int zkc_log_sorter_check_trace(zkc_ctx *ctx, const zkc_events_closed_form *io, const uint64_t *trace, size_t limit, uint32_t gates,
+                               int on_device, uint64_t *violations, zkc_status *status);
+
 
 /* ---- storage_validity_by_grand_product (src/storage_validity_by_grand_product/mod.rs) ------------ */
 #define ZKC_PACKED_KEY_LENGTH 13 /* PACKED_KEY_LENGTH, input.rs:28 */

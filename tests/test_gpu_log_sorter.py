@@ -131,3 +131,55 @@ def test_device_resident_and_queue_simulate(engine, orc):
     torch.cuda.synchronize()
     assert got.commitment.tolist() == want[3].tolist()
     assert np.array_equal(got.trace.cpu().numpy().view(np.uint64), want[2])
+
+
+def test_check_trace_constraint_evaluation(engine, orc):
+    """zkc_log_sorter_check_trace: the ORACLE's trace (reference vector + synthetic, rollbacks included) satisfies every
+    relation with and without the round-function gates; a fault injected into any relation family is found at its row"""
+    from era_zkevm_circuits_b200 import log_sorter_check_trace
+    V_ = abi.EVV
+    u, s = V.log_sorter_reference_vector()
+    io, up, sp = instance(orc, u, s)
+    want = O.log_sorter_entry_point(orc, io, u, s, 16)
+    assert log_sorter_check_trace(engine, io, want[2], 16)[0] == 0
+    u, s = synthetic.events_trace(3000, seed=8, rollback_pct=20)
+    io, up, sp = instance(orc, u, s)
+    limit = 3100
+    want = O.log_sorter_entry_point(orc, io, u, s, limit)
+    assert want[0] == abi.ZKC_OK
+    trace = want[2]
+    for gates in (0, abi.GATES_GENERAL):
+        viol, st = log_sorter_check_trace(engine, io, trace, limit, gates)
+        assert viol == 0 and st.code == 0, (viol, hex(st.failed_checks), st.first_bad_row)
+    import torch
+    viol, st = log_sorter_check_trace(engine, io, torch.from_numpy(trace.view(np.int64)).cuda(), limit, abi.GATES_GENERAL)
+    assert viol == 0
+    pushes = np.flatnonzero(trace[K["ADD_TO_QUEUE"]])
+    faults = [
+        (K["SHOULD_POP"], 17, 2, V_["BOOLEAN"], 0),
+        (K["UNSORTED_ITEM"] + 7, 40, 1 << 33, V_["BOOLEAN"], 0),
+        (K["UNSORTED_ENC"] + 3, 99, None, V_["ENCODING"], 0),
+        (K["SORTED_LEN"], 123, None, V_["QUEUE_LEN"], 0),
+        (K["GP_CHAIN"] + 45, 200, None, V_["GP_CHAIN"], 0),
+        (K["GP_ACC"] + 2, 300, None, V_["GP_ACC"], 0),
+        (K["CMP_DIFF"], 400, None, V_["COMPARISON"], 0),
+        (K["SAME_BODY"], 500, None, V_["FLAGS"], 0),
+        (K["PUSH_ENC"] + 17, 600, None, V_["ENCODING"], 0),
+        (K["RESULT_LEN"], 700, None, V_["RESULT_QUEUE"], 0),
+        (K["PUSH_ROUND1"] + 5, int(pushes[10]), None, V_["ROUND_FUNCTION"], 0),
+    ]
+    for col, row, val, bit, gates in faults:
+        bad = trace.copy()
+        bad[col, row] = np.uint64(val) if val is not None else bad[col, row] ^ np.uint64(1)
+        viol, st = log_sorter_check_trace(engine, io, bad, limit, gates)
+        assert viol >= 1 and st.first_bad_row == row and st.failed_checks & bit, (col, row, viol, st.first_bad_row, hex(st.failed_checks))
+    # the engine's own trace of a chained second instance (start_flag = 0: accumulators / previous item from the FSM input)
+    cut = 1500
+    a = sort_and_deduplicate_events_entry_point(engine, EventsDeduplicatorInstanceWitness(io, u, up, s, sp), cut, raise_on_unsatisfied=False)
+    nxt = abi.EventsClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+    b = sort_and_deduplicate_events_entry_point(engine, EventsDeduplicatorInstanceWitness(nxt, u[cut:], up[cut:], s[cut:], sp[cut:]), limit - cut,
+                                                raise_on_unsatisfied=False)
+    assert b.status.code == 0
+    viol, st = log_sorter_check_trace(engine, nxt, b.trace, limit - cut)
+    assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)
