@@ -3,6 +3,7 @@ the zkSync Era zkEVM circuits (reference: matter-labs/era-zkevm_circuits).  The 
 csrc/ (hand-written sm_100a CUDA behind the C ABI of include/zkc_b200.h); this package is the
 host-side mirror of the reference's entry points."""
 from . import abi  # noqa: F401
+from . import wire  # noqa: F401
 from .engine import Engine, ZkcError  # noqa: F401
 from .ram_permutation import (  # noqa: F401
     RamPermutationCircuitInstanceWitness,

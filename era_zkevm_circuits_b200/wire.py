@@ -1,0 +1,334 @@
+"""Wire format of the reference's `*CircuitInstanceWitness` structs: what `bincode::serialize` (bincode 1.x,
+default options: little-endian, fixed-width integers, u64 sequence lengths) produces for the serde derives of
+
+    RamPermutationCircuitInstanceWitness   /root/reference/src/ram_permutation/input.rs:99-116
+    EventsDeduplicatorInstanceWitness      /root/reference/src/log_sorter/input.rs:98-106
+
+read into the host-side witness forms of this package (closed-form struct + struct-of-arrays queue witnesses), and written
+back (test_harness-style dumps for the round-trip tests).
+
+Field order = declaration order of the structs (serde derive); `()` occupies no bytes; `bool` is one byte; a field element
+(GoldilocksField, a newtype over u64) is 8 bytes; fixed arrays `[T; N]` are tuples (no length prefix; boojum's BigArraySerde
+for N > 32 likewise); `VecDeque` is a u64 length + elements; a tuple is its members back to back.  `U256` / `Address`
+(ethereum_types, serde through impl-serde) are STRINGS: u64 length + "0x" + hex, U256 without leading zeros ("0x0" for zero),
+H160 always 40 digits.
+
+The layouts of the witness structs boojum derives (QueueStateWitness { head, tail: QueueTailStateWitness { tail, length } },
+`(item_witness, previous_tail)` deque elements) follow the published boojum sources; boojum is not vendored in
+/root/reference, so no dump of the reference itself is available here to pin this reader against: PARITY UNPINNED, like the
+Poseidon2 constants.  The reader fails loudly (WireError) on trailing bytes, non-canonical field elements, bad booleans and
+malformed hex strings, so a layout drift shows up as an error, not as a silently wrong witness.
+"""
+import struct
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi
+
+
+class WireError(ValueError):
+    pass
+
+
+class Reader:
+    def __init__(self, data: bytes):
+        self.d, self.o = memoryview(data), 0
+
+    def take(self, n):
+        if self.o + n > len(self.d):
+            raise WireError(f"unexpected end of input at byte {self.o} (+{n})")
+        b = self.d[self.o:self.o + n]
+        self.o += n
+        return b
+
+    def u8(self):
+        return self.take(1)[0]
+
+    def u32(self):
+        return struct.unpack("<I", self.take(4))[0]
+
+    def u64(self):
+        return struct.unpack("<Q", self.take(8))[0]
+
+    def boolean(self):
+        v = self.u8()
+        if v > 1:
+            raise WireError(f"invalid bool {v} at byte {self.o - 1}")
+        return v
+
+    def field(self):
+        v = self.u64()
+        if v >= abi.GL_P:
+            raise WireError(f"non-canonical field element {v:#x} at byte {self.o - 8}")
+        return v
+
+    def fields(self, n):
+        return [self.field() for _ in range(n)]
+
+    def hex_string(self, max_digits, exact=False):
+        n = self.u64()
+        if n < 3 or n > 2 + max_digits:
+            raise WireError(f"hex string of length {n} at byte {self.o - 8}")
+        s = bytes(self.take(n)).decode("ascii", "replace")
+        if not s.startswith("0x") or (exact and n != 2 + max_digits):
+            raise WireError(f"malformed hex string {s!r}")
+        try:
+            return int(s[2:], 16)
+        except ValueError:
+            raise WireError(f"malformed hex string {s!r}") from None
+
+    def u256(self):
+        return self.hex_string(64)
+
+    def h160(self):
+        return self.hex_string(40, exact=True)
+
+    def done(self):
+        if self.o != len(self.d):
+            raise WireError(f"{len(self.d) - self.o} trailing bytes")
+
+
+class Writer:
+    def __init__(self):
+        self.b = bytearray()
+
+    def u8(self, v): self.b.append(int(v) & 0xFF)
+    def u32(self, v): self.b += struct.pack("<I", int(v))
+    def u64(self, v): self.b += struct.pack("<Q", int(v))
+    def boolean(self, v): self.u8(1 if v else 0)
+    def field(self, v): self.u64(v)
+
+    def fields(self, vs):
+        for v in vs:
+            self.u64(v)
+
+    def string(self, s):
+        raw = s.encode("ascii")
+        self.u64(len(raw))
+        self.b += raw
+
+    def u256(self, v): self.string(hex(int(v)))
+    def h160(self, v): self.string("0x%040x" % int(v))
+
+
+def _limbs(v, n):
+    return [(int(v) >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+
+
+def _from_limbs(limbs):
+    return sum(int(x) << (32 * i) for i, x in enumerate(limbs))
+
+
+# ---- QueueState<F, N> ------------------------------------------------------------------------------------------------------
+def _read_queue_state(r: Reader, q):
+    n = len(q.head)
+    for i, v in enumerate(r.fields(n)):
+        q.head[i] = v
+    for i, v in enumerate(r.fields(n)):
+        q.tail[i] = v
+    q.length = r.u32()
+
+
+def _write_queue_state(w: Writer, q):
+    w.fields(q.head)
+    w.fields(q.tail)
+    w.u32(q.length)
+
+
+# ---- MemoryQuery / LogQuery witnesses --------------------------------------------------------------------------------------
+def _read_memory_query(r: Reader, rec):
+    rec["timestamp"], rec["memory_page"], rec["index"] = r.u32(), r.u32(), r.u32()
+    rec["rw_flag"], rec["is_ptr"] = r.boolean(), r.boolean()
+    rec["value"] = _limbs(r.u256(), 8)
+
+
+def _write_memory_query(w: Writer, rec):
+    w.u32(rec["timestamp"]); w.u32(rec["memory_page"]); w.u32(rec["index"])
+    w.boolean(rec["rw_flag"]); w.boolean(rec["is_ptr"])
+    w.u256(_from_limbs(rec["value"]))
+
+
+def _read_log_query(r: Reader):
+    """-> (address[5], key[8], read_value[8], written_value[8], tx_number, timestamp, flags) as a LOG_QUERY_DTYPE tuple"""
+    address, key, rv, wv = _limbs(r.h160(), 5), _limbs(r.u256(), 8), _limbs(r.u256(), 8), _limbs(r.u256(), 8)
+    aux, rw, rollback, service, shard = r.u8(), r.boolean(), r.boolean(), r.boolean(), r.u8()
+    tx, ts = r.u32(), r.u32()
+    return address, key, rv, wv, tx, ts, abi.lq_flags(aux, shard, rw, rollback, service)
+
+
+def _write_log_query(w: Writer, rec):
+    fl = int(rec["flags"])
+    w.h160(_from_limbs(rec["address"])); w.u256(_from_limbs(rec["key"])); w.u256(_from_limbs(rec["read_value"]))
+    w.u256(_from_limbs(rec["written_value"]))
+    w.u8(fl & 0xFF); w.boolean((fl >> 16) & 1); w.boolean((fl >> 17) & 1); w.boolean((fl >> 18) & 1); w.u8((fl >> 8) & 0xFF)
+    w.u32(rec["tx_number_in_block"]); w.u32(rec["timestamp"])
+
+
+def _set_log_query_struct(dst, t):
+    address, key, rv, wv, tx, ts, flags = t
+    for i in range(5):
+        dst.address[i] = address[i]
+    for i in range(8):
+        dst.key[i], dst.read_value[i], dst.written_value[i] = key[i], rv[i], wv[i]
+    dst.tx_number_in_block, dst.timestamp, dst.flags = tx, ts, flags
+
+
+def _log_query_struct_as_record(src):
+    rec = np.zeros((), dtype=abi.LOG_QUERY_DTYPE)
+    rec["address"], rec["key"] = list(src.address), list(src.key)
+    rec["read_value"], rec["written_value"] = list(src.read_value), list(src.written_value)
+    rec["tx_number_in_block"], rec["timestamp"], rec["flags"] = src.tx_number_in_block, src.timestamp, src.flags
+    return rec
+
+
+# ---- ram_permutation ---------------------------------------------------------------------------------------------------------
+def _read_ram_fsm(r: Reader, f):
+    for name in ("lhs_accumulator", "rhs_accumulator"):
+        for i, v in enumerate(r.fields(2)):
+            getattr(f, name)[i] = v
+    _read_queue_state(r, f.current_unsorted_queue_state)
+    _read_queue_state(r, f.current_sorted_queue_state)
+    for i in range(3):
+        f.previous_sorting_key[i] = r.u32()
+    for i in range(2):
+        f.previous_full_key[i] = r.u32()
+    for i, v in enumerate(_limbs(r.u256(), 8)):
+        f.previous_value[i] = v
+    f.previous_is_ptr = r.boolean()
+    f.num_nondeterministic_writes = r.u32()
+
+
+def _write_ram_fsm(w: Writer, f):
+    w.fields(f.lhs_accumulator); w.fields(f.rhs_accumulator)
+    _write_queue_state(w, f.current_unsorted_queue_state)
+    _write_queue_state(w, f.current_sorted_queue_state)
+    for v in f.previous_sorting_key:
+        w.u32(v)
+    for v in f.previous_full_key:
+        w.u32(v)
+    w.u256(_from_limbs(f.previous_value))
+    w.boolean(f.previous_is_ptr)
+    w.u32(f.num_nondeterministic_writes)
+
+
+def _read_memory_queue(r: Reader):
+    n = r.u64()
+    if n > (len(r.d) - r.o) // 8:
+        raise WireError(f"queue witness claims {n} elements")
+    recs = np.zeros(n, dtype=abi.MEMORY_QUERY_DTYPE)
+    prev = np.zeros((n, 12), dtype=np.uint64)
+    for k in range(n):
+        _read_memory_query(r, recs[k])
+        prev[k] = r.fields(12)
+    return recs, prev
+
+
+def _write_memory_queue(w: Writer, recs, prev):
+    w.u64(len(recs))
+    for rec, p in zip(recs, prev):
+        _write_memory_query(w, rec)
+        w.fields(p)
+
+
+def read_ram_permutation_witness(data: bytes):
+    """bincode bytes of RamPermutationCircuitInstanceWitness<GoldilocksField> -> ram_permutation.RamPermutationCircuitInstanceWitness"""
+    from .ram_permutation import RamPermutationCircuitInstanceWitness
+    r = Reader(data)
+    io = abi.RamClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    _read_queue_state(r, io.observable_input.unsorted_queue_initial_state)
+    _read_queue_state(r, io.observable_input.sorted_queue_initial_state)
+    io.observable_input.non_deterministic_bootloader_memory_snapshot_length = r.u32()
+    # observable_output: `()`
+    _read_ram_fsm(r, io.hidden_fsm_input)
+    _read_ram_fsm(r, io.hidden_fsm_output)
+    u, up = _read_memory_queue(r)
+    s, sp = _read_memory_queue(r)
+    r.done()
+    return RamPermutationCircuitInstanceWitness(io, u, up, s, sp)
+
+
+def write_ram_permutation_witness(w_) -> bytes:
+    w = Writer()
+    io = w_.closed_form_input
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    _write_queue_state(w, io.observable_input.unsorted_queue_initial_state)
+    _write_queue_state(w, io.observable_input.sorted_queue_initial_state)
+    w.u32(io.observable_input.non_deterministic_bootloader_memory_snapshot_length)
+    _write_ram_fsm(w, io.hidden_fsm_input)
+    _write_ram_fsm(w, io.hidden_fsm_output)
+    _write_memory_queue(w, w_.unsorted_queue_witness, w_.unsorted_queue_prev_states)
+    _write_memory_queue(w, w_.sorted_queue_witness, w_.sorted_queue_prev_states)
+    return bytes(w.b)
+
+
+# ---- log_sorter --------------------------------------------------------------------------------------------------------------
+def _read_events_fsm(r: Reader, f):
+    for name in ("lhs_accumulator", "rhs_accumulator"):
+        for i, v in enumerate(r.fields(2)):
+            getattr(f, name)[i] = v
+    _read_queue_state(r, f.initial_unsorted_queue_state)
+    _read_queue_state(r, f.intermediate_sorted_queue_state)
+    _read_queue_state(r, f.final_result_queue_state)
+    f.previous_key = r.u32()
+    _set_log_query_struct(f.previous_item, _read_log_query(r))
+
+
+def _write_events_fsm(w: Writer, f):
+    w.fields(f.lhs_accumulator); w.fields(f.rhs_accumulator)
+    _write_queue_state(w, f.initial_unsorted_queue_state)
+    _write_queue_state(w, f.intermediate_sorted_queue_state)
+    _write_queue_state(w, f.final_result_queue_state)
+    w.u32(f.previous_key)
+    _write_log_query(w, _log_query_struct_as_record(f.previous_item))
+
+
+def _read_log_queue(r: Reader):
+    n = r.u64()
+    if n > (len(r.d) - r.o) // 8:
+        raise WireError(f"queue witness claims {n} elements")
+    recs = np.zeros(n, dtype=abi.LOG_QUERY_DTYPE)
+    prev = np.zeros((n, 4), dtype=np.uint64)
+    for k in range(n):
+        recs[k] = _read_log_query(r)
+        prev[k] = r.fields(4)
+    return recs, prev
+
+
+def _write_log_queue(w: Writer, recs, prev):
+    w.u64(len(recs))
+    for rec, p in zip(recs, prev):
+        _write_log_query(w, rec)
+        w.fields(p)
+
+
+def read_events_deduplicator_witness(data: bytes):
+    """bincode bytes of EventsDeduplicatorInstanceWitness<GoldilocksField> -> log_sorter.EventsDeduplicatorInstanceWitness"""
+    from .log_sorter import EventsDeduplicatorInstanceWitness
+    r = Reader(data)
+    io = abi.EventsClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    _read_queue_state(r, io.initial_log_queue_state)
+    _read_queue_state(r, io.intermediate_sorted_queue_state)
+    _read_queue_state(r, io.final_queue_state)
+    _read_events_fsm(r, io.hidden_fsm_input)
+    _read_events_fsm(r, io.hidden_fsm_output)
+    u, up = _read_log_queue(r)
+    s, sp = _read_log_queue(r)
+    r.done()
+    return EventsDeduplicatorInstanceWitness(io, u, up, s, sp)
+
+
+def write_events_deduplicator_witness(w_) -> bytes:
+    w = Writer()
+    io = w_.closed_form_input
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    _write_queue_state(w, io.initial_log_queue_state)
+    _write_queue_state(w, io.intermediate_sorted_queue_state)
+    _write_queue_state(w, io.final_queue_state)
+    _write_events_fsm(w, io.hidden_fsm_input)
+    _write_events_fsm(w, io.hidden_fsm_output)
+    _write_log_queue(w, w_.initial_queue_witness, w_.initial_queue_prev_tails)
+    _write_log_queue(w, w_.intermediate_sorted_queue_witness, w_.intermediate_sorted_queue_prev_tails)
+    return bytes(w.b)

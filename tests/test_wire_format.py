@@ -1,0 +1,94 @@
+"""bincode wire format of the reference's *CircuitInstanceWitness structs (era_zkevm_circuits_b200/wire.py): a hand-assembled
+byte string of every primitive (what serde + bincode 1.x emit for bool / u32 / field element / U256 / Address / VecDeque),
+write -> read round trips of whole witnesses, ingestion of a dump by the ORACLE (the ingested witness proves like the
+original), and loud failures on malformed input."""
+import struct
+
+import numpy as np
+import pytest
+
+import helpers as H
+import orc as O
+import vectors as V
+from era_zkevm_circuits_b200 import abi, synthetic, wire
+
+
+def test_primitives_byte_for_byte():
+    w = wire.Writer()
+    w.boolean(True); w.u32(0x01020304); w.field(abi.GL_P - 1); w.u256(0); w.u256(0xABC << 200); w.h160(0x8010)
+    want = (b"\x01" + b"\x04\x03\x02\x01" + struct.pack("<Q", abi.GL_P - 1) +
+            struct.pack("<Q", 3) + b"0x0" +                                  # U256: hex string without leading zeros
+            struct.pack("<Q", 2 + 53) + b"0xabc" + b"0" * 50 +
+            struct.pack("<Q", 42) + b"0x" + b"0" * 36 + b"8010")             # H160: always 40 digits
+    assert bytes(w.b) == want
+    r = wire.Reader(want)
+    assert (r.boolean(), r.u32(), r.field(), r.u256(), r.u256(), r.h160()) == (1, 0x01020304, abi.GL_P - 1, 0, 0xABC << 200, 0x8010)
+    r.done()
+
+
+def test_ram_permutation_dump_round_trip_and_ingestion(orc):
+    from era_zkevm_circuits_b200 import RamPermutationCircuitInstanceWitness
+    u, s = V.ram_reference_vector()
+    io, up, sp = H.ram_instance(orc, u, s, nondet_len=1)
+    dump = wire.write_ram_permutation_witness(RamPermutationCircuitInstanceWitness(io, u, up, s, sp))
+    # header: start_flag, completion_flag, then the unsorted queue's head (12 field elements)
+    assert dump[:2] == b"\x01\x00" and dump[2:2 + 96] == bytes(96)
+    got = wire.read_ram_permutation_witness(dump)
+    assert bytes(got.closed_form_input) == bytes(io)
+    for a, b in ((got.unsorted_queue_witness, u), (got.sorted_queue_witness, s)):
+        for name in ("timestamp", "memory_page", "index", "rw_flag", "is_ptr", "value"):
+            assert np.array_equal(a[name], b[name]), name
+    assert np.array_equal(got.unsorted_queue_prev_states, up) and np.array_equal(got.sorted_queue_prev_states, sp)
+    assert wire.write_ram_permutation_witness(got) == dump
+    # the ingested witness proves exactly like the original
+    want = O.ram_entry_point(orc, io, u, s, 16)
+    have = O.ram_entry_point(orc, got.closed_form_input, got.unsorted_queue_witness, got.sorted_queue_witness, 16)
+    assert want[0] == have[0] == abi.ZKC_OK and have[3].tolist() == want[3].tolist() and np.array_equal(have[2], want[2])
+    # a chained (not start) instance with a non-trivial FSM input
+    u2, s2 = synthetic.ram_trace(300, seed=4, n_cells=30, n_nondet=2)
+    io2, up2, sp2 = H.ram_instance(orc, u2, s2, 2)
+    first = O.ram_entry_point(orc, io2, u2, s2, 100)
+    nxt = abi.RamClosedForm.from_buffer_copy(bytes(first[1])); nxt.start_flag = 0
+    nxt.hidden_fsm_input = first[1].hidden_fsm_output
+    w2 = RamPermutationCircuitInstanceWitness(nxt, u2[100:], up2[100:], s2[100:], sp2[100:])
+    back = wire.read_ram_permutation_witness(wire.write_ram_permutation_witness(w2))
+    assert bytes(back.closed_form_input) == bytes(nxt) and len(back.unsorted_queue_witness) == 200
+
+
+def test_events_deduplicator_dump_round_trip(orc):
+    from era_zkevm_circuits_b200 import EventsDeduplicatorInstanceWitness
+    u, s = synthetic.events_trace(200, seed=6, rollback_pct=20)
+    up, ufin = O.log_queue_simulate(orc, u)
+    sp, sfin = O.log_queue_simulate(orc, s)
+    io = O.events_closed_form(ufin, sfin, True)
+    first = O.log_sorter_entry_point(orc, io, u, s, 120)
+    nxt = abi.EventsClosedForm.from_buffer_copy(bytes(first[1])); nxt.start_flag = 0
+    nxt.hidden_fsm_input = first[1].hidden_fsm_output  # carries a previous_item: Address / U256 strings of a real record
+    w = EventsDeduplicatorInstanceWitness(nxt, u[120:], up[120:], s[120:], sp[120:])
+    dump = wire.write_events_deduplicator_witness(w)
+    got = wire.read_events_deduplicator_witness(dump)
+    assert bytes(got.closed_form_input) == bytes(nxt)
+    assert got.initial_queue_witness.tobytes() == np.ascontiguousarray(u[120:]).tobytes()
+    assert got.intermediate_sorted_queue_witness.tobytes() == np.ascontiguousarray(s[120:]).tobytes()
+    assert np.array_equal(got.initial_queue_prev_tails, up[120:]) and np.array_equal(got.intermediate_sorted_queue_prev_tails, sp[120:])
+    assert wire.write_events_deduplicator_witness(got) == dump
+    have = O.log_sorter_entry_point(orc, got.closed_form_input, got.initial_queue_witness, got.intermediate_sorted_queue_witness, 100)
+    want = O.log_sorter_entry_point(orc, nxt, u[120:], s[120:], 100)
+    assert have[0] == want[0] == abi.ZKC_OK and have[3].tolist() == want[3].tolist()
+
+
+def test_malformed_dumps_fail_loudly(orc):
+    from era_zkevm_circuits_b200 import RamPermutationCircuitInstanceWitness
+    u, s = V.ram_reference_vector()
+    io, up, sp = H.ram_instance(orc, u, s, nondet_len=1)
+    dump = bytearray(wire.write_ram_permutation_witness(RamPermutationCircuitInstanceWitness(io, u, up, s, sp)))
+    with pytest.raises(wire.WireError):
+        wire.read_ram_permutation_witness(bytes(dump) + b"\x00")            # trailing bytes
+    with pytest.raises(wire.WireError):
+        wire.read_ram_permutation_witness(bytes(dump[:-5]))                 # truncated
+    bad = bytearray(dump); bad[0] = 2
+    with pytest.raises(wire.WireError):
+        wire.read_ram_permutation_witness(bytes(bad))                       # bool out of range
+    bad = bytearray(dump); bad[2:10] = struct.pack("<Q", abi.GL_P)
+    with pytest.raises(wire.WireError):
+        wire.read_ram_permutation_witness(bytes(bad))                       # non-canonical field element
