@@ -48,6 +48,7 @@ from .sha256_round_function import (  # noqa: F401
 from .main_vm import (  # noqa: F401
     VmCircuitWitness,
     main_vm_check_trace,
+    main_vm_gadget_cells,
     main_vm_entry_point,
     main_vm_entry_point_batch,
     main_vm_entry_point_columns,

@@ -511,6 +511,7 @@ SIGNATURES = {
     "zkc_main_vm_entry_point_stream": (C.c_int, [_vp, _vp, C.c_size_t, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t,
                                                  C.POINTER(VmOptions), C.POINTER(VmPackedTrace), _vp, _vp]),
     "zkc_main_vm_rows_to_columns": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_size_t, _vp, C.c_size_t]),
+    "zkc_main_vm_gadget_cells": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),
     "zkc_main_vm_check_trace": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, C.c_size_t, C.c_size_t, C.c_int, _u64p, C.POINTER(Status)]),
     "zkc_main_vm_initial_state": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), C.POINTER(VmState)]),
     "zkc_main_vm_simulate": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp,
@@ -523,6 +524,22 @@ SIGNATURES = {
 }
 
 GATES_GENERAL, GATES_ROUND_FUNCTION = 1, 2
+
+
+def _gadget_columns():
+    """ZKC_VM_GADGET_COLUMNS of include/zkc_b200.h (the X-macro list is the single source): name -> first column, + NUM_COLS"""
+    import re
+    text = open(os.path.join(os.path.dirname(_HERE), "include", "zkc_b200.h")).read()
+    body = text[text.index("#define ZKC_VM_GADGET_COLUMNS(X)"):text.index("enum zkc_vm_gadget_col {")]
+    cols, widths, n = {}, {}, 0
+    for name, width in re.findall(r"X\((\w+), (\d+)\)", body):
+        cols[name], widths[name] = n, int(width)
+        n += int(width)
+    cols["NUM_COLS"] = n
+    return cols, widths
+
+
+VMG_COLS, VMG_WIDTHS = _gadget_columns()
 EVV = dict(BOOLEAN=1 << 0, QUEUE_LEN=1 << 1, ENCODING=1 << 2, ROUND_FUNCTION=1 << 3, COMPARISON=1 << 4, FLAGS=1 << 5, ENFORCE=1 << 6,
            GP_CHAIN=1 << 7, GP_ACC=1 << 8, RESULT_QUEUE=1 << 9)
 RAMV = dict(BOOLEAN=1 << 0, QUEUE_LEN=1 << 1, ENCODING=1 << 2, ROUND_FUNCTION=1 << 3, NONDET=1 << 4, COMPARISON=1 << 5,

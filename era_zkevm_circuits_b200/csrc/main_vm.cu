@@ -23,6 +23,7 @@
 #include <cuda.h>  // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no link dependency on libcuda)
 #include "ctx.cuh"
 #include "poseidon2.cuh"
+#include "u256.cuh"
 
 namespace zkc {
 
@@ -40,130 +41,6 @@ struct VmDev {
     uint64_t hint_commitment[4];  // commitment computed ahead of time from the host's final snapshot (vm_finalize_kernel, mode 0)
     uint32_t hint_ok, pad2;
 };
-
-// ---- 256-bit helpers on little-endian u32 limbs -------------------------------------------------------------
-struct U256 {
-    uint32_t v[8];
-};
-__device__ __forceinline__ bool u256_is_zero(const U256 &a) {
-    uint32_t o = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) o |= a.v[i];
-    return o == 0;
-}
-__device__ __forceinline__ uint32_t u256_add(const U256 &a, const U256 &b, U256 &c) {
-    uint64_t carry = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { const uint64_t t = (uint64_t)a.v[i] + b.v[i] + carry; c.v[i] = (uint32_t)t; carry = t >> 32; }
-    return (uint32_t)carry;
-}
-__device__ __forceinline__ uint32_t u256_sub(const U256 &a, const U256 &b, U256 &c) {
-    uint64_t borrow = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { const uint64_t t = (uint64_t)a.v[i] - b.v[i] - borrow; c.v[i] = (uint32_t)t; borrow = (t >> 32) & 1; }
-    return (uint32_t)borrow;
-}
-__device__ void u256_mul(const U256 &a, const U256 &b, U256 &lo, U256 &hi) {
-    uint32_t r[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) r[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint64_t carry = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint64_t t = (uint64_t)a.v[i] * b.v[j] + r[i + j] + carry;
-            r[i + j] = (uint32_t)t; carry = t >> 32;
-        }
-        r[i + 8] = (uint32_t)carry;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) { lo.v[i] = r[i]; hi.v[i] = r[i + 8]; }
-}
-__device__ __forceinline__ bool u256_ge(const U256 &a, const U256 &b) {
-    U256 t;
-    return u256_sub(a, b, t) == 0;
-}
-// q = a / b, r = a % b for b != 0: Knuth's algorithm D on 32-bit limbs (at most 8 quotient digits, each one 64/32
-// division + a multiply-subtract), instead of 256 shift-subtract steps that every lane of a warp would wait for
-__device__ void u256_divrem(const U256 &a, const U256 &b, U256 &q, U256 &r) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) { q.v[i] = 0; r.v[i] = 0; }
-    int n = 8;
-    while (n > 1 && b.v[n - 1] == 0) n--;
-    if (n == 1) {
-        uint64_t rem = 0;
-        const uint32_t d = b.v[0];
-        for (int i = 7; i >= 0; i--) {
-            const uint64_t cur = (rem << 32) | a.v[i];
-            q.v[i] = (uint32_t)(cur / d);
-            rem = cur % d;
-        }
-        r.v[0] = (uint32_t)rem;
-        return;
-    }
-    const int sh = __clz(b.v[n - 1]);
-    uint32_t v[8], u[9];
-    for (int i = n - 1; i > 0; i--) v[i] = sh ? (b.v[i] << sh) | (b.v[i - 1] >> (32 - sh)) : b.v[i];
-    v[0] = b.v[0] << sh;
-    u[8] = sh ? a.v[7] >> (32 - sh) : 0;
-    for (int i = 7; i > 0; i--) u[i] = sh ? (a.v[i] << sh) | (a.v[i - 1] >> (32 - sh)) : a.v[i];
-    u[0] = a.v[0] << sh;
-    for (int j = 8 - n; j >= 0; j--) {
-        const uint64_t num = ((uint64_t)u[j + n] << 32) | u[j + n - 1];
-        uint64_t qhat = num / v[n - 1], rhat = num % v[n - 1];
-        while (qhat >= (1ull << 32) || qhat * v[n - 2] > ((rhat << 32) | u[j + n - 2])) {
-            qhat--;
-            rhat += v[n - 1];
-            if (rhat >= (1ull << 32)) break;
-        }
-        // u[j .. j+n] -= qhat * v
-        int64_t borrow = 0;
-        uint64_t carry = 0;
-        for (int i = 0; i < n; i++) {
-            const uint64_t p = qhat * v[i] + carry;
-            carry = p >> 32;
-            const int64_t t = (int64_t)u[i + j] - (int64_t)(uint32_t)p + borrow;
-            u[i + j] = (uint32_t)t;
-            borrow = t >> 32;  // 0 or -1
-        }
-        const int64_t t = (int64_t)u[j + n] - (int64_t)carry + borrow;
-        u[j + n] = (uint32_t)t;
-        if (t < 0) {  // qhat was one too large: add the divisor back
-            qhat--;
-            uint64_t c = 0;
-            for (int i = 0; i < n; i++) {
-                const uint64_t x = (uint64_t)u[i + j] + v[i] + c;
-                u[i + j] = (uint32_t)x;
-                c = x >> 32;
-            }
-            u[j + n] += (uint32_t)c;
-        }
-        q.v[j] = (uint32_t)qhat;
-    }
-    for (int i = 0; i < n; i++) r.v[i] = sh ? (u[i] >> sh) | ((uint64_t)u[i + 1] << (32 - sh)) : u[i];
-}
-// (a << s) mod 2^256 and a >> (256 - s) for s in [0, 255]: the two halves of a * 2^s (shifts.rs:95-96)
-__device__ void u256_shl_wide(const U256 &a, uint32_t s, U256 &lo, U256 &hi) {
-    const uint32_t limbs = s >> 5, bits = s & 31;
-    uint32_t w[17];
-#pragma unroll
-    for (int i = 0; i < 17; i++) w[i] = 0;
-    for (int i = 0; i < 8; i++) {  // dynamic limb offset: small loop in local memory
-        const uint64_t t = (uint64_t)a.v[i] << bits;
-        w[i + limbs] |= (uint32_t)t;
-        w[i + limbs + 1] |= (uint32_t)(t >> 32);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) { lo.v[i] = w[i]; hi.v[i] = w[i + 8]; }
-}
-__device__ void u256_shr(const U256 &a, uint32_t s, U256 &q) {
-    const uint32_t limbs = s >> 5, bits = s & 31;
-    for (int i = 0; i < 8; i++) {
-        const uint32_t lo = i + limbs < 8 ? a.v[i + limbs] : 0, hi = i + limbs + 1 < 8 ? a.v[i + limbs + 1] : 0;
-        q.v[i] = bits ? (lo >> bits) | (hi << (32 - bits)) : lo;
-    }
-}
 
 // ---- encodings / queue -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void vm_mq_encode(uint32_t ts, uint32_t page, uint32_t index, uint32_t rw, const zkc_vm_register &r, uint64_t (&e)[8]) {
@@ -1580,12 +1457,17 @@ constexpr int VM_TILE_A = VW(registers), VM_TILE_B = VW(stack_sponge_state) - VW
 struct alignas(64) VmTmaps { CUtensorMap a, b; };  // boxes [32 x VM_TILE_A] and [32 x VM_TILE_B] over state_words [VM_WORDS][stride]
 __device__ __forceinline__ int vm_tile_slot(int w) { return w < VW(registers) ? w : VM_TILE_A + (w - VW(flags)); }
 
+// Two instantiations, selected per call: VM_USE_TMA = false reads the state words with plain (non-coherent) global loads the
+// compiler places at their use sites -- measured 3 % FASTER on B200 (1.42 vs 1.46 ms per 2^20 cycles, profiles/README.md) because
+// the column layout already makes every such load one full 128-byte line per warp and L1 holds the tile; the TMA variant
+// (ZKC_VM_TMA=1) is kept for layouts / sizes where the tile does not stay in L1.
+template <bool VM_USE_TMA>
 __global__ void __launch_bounds__(128, VM_CYCLES_MIN_BLOCKS)
 vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
                  const zkc_vm_callstack_witness *__restrict__ cws, uint32_t n_cw,
                  uint64_t *__restrict__ trace, size_t limit, size_t n_instances, size_t row0, size_t row_count, VmPushScratch ps,
                  int ncols, int aux_base, const __grid_constant__ VmTmaps tmaps, int use_tma) {
-    __shared__ alignas(128) uint32_t vm_tile[4][VM_TILE_WORDS * 32];
+    __shared__ alignas(128) uint32_t vm_tile[VM_USE_TMA ? 4 : 1][VM_USE_TMA ? VM_TILE_WORDS * 32 : 32];
     __shared__ alignas(8) unsigned long long vm_bar[4];
     // this launch covers rows [row0, row0 + row_count) of every instance (one chunk of the pipelined host path, or all)
     const size_t total = limit * n_instances;
@@ -1598,10 +1480,10 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
     VmDev *dev = devs + inst;
     uint32_t checks = 0, jmask = 0;
     // ---- TMA: the warp's tile, when its 32 cycles are 32 consecutive snapshots of one instance ------------------------------
-    const int wib = threadIdx.x >> 5;
+    const int wib = VM_USE_TMA ? threadIdx.x >> 5 : 0;
     const uint32_t *tile = vm_tile[wib] + lane;  // word slot k of this lane's snapshot: tile[k * 32]
     bool staged = false;
-    if (use_tma) {
+    if (VM_USE_TMA && use_tma) {
         const unsigned long long idx0 = __shfl_sync(0xffffffffu, (unsigned long long)idx, 0);
         const bool lane0_valid = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
         staged = lane0_valid && (idx0 & 3) == 0 &&  // the tile's first element must sit on a 16-byte boundary of its column
@@ -1632,7 +1514,17 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
         // ---- the words a cycle reads outside the registers: scalars + the current context ---------------------------------
         zkc_vm_state s;
         uint32_t *sw = reinterpret_cast<uint32_t *>(&s);
-        if (staged) {
+        if constexpr (VM_USE_TMA) {
+            // one source for every warp: a warp without a TMA tile (it straddles two instances, or its tile is not 16-byte aligned)
+            // fills its lanes' slots of the shared tile with plain loads; the field reads below are then shared-memory loads the
+            // compiler is free to place at their use sites
+            if (!staged) {
+                uint32_t *mine = vm_tile[wib] + lane;
+#pragma unroll
+                for (int w = 0; w < VW(registers); w++) mine[vm_tile_slot(w) * 32] = CUR(w);
+#pragma unroll
+                for (int w = VW(flags); w < VW(stack_sponge_state); w++) mine[vm_tile_slot(w) * 32] = CUR(w);
+            }
 #pragma unroll
             for (int w = 0; w < VW(registers); w++) sw[w] = tile[vm_tile_slot(w) * 32];
 #pragma unroll
@@ -2502,11 +2394,11 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
         uint32_t *stc = cv.take<uint32_t>(st_stride * VM_WORDS), *wtc = cv.take<uint32_t>(wt_stride * VM_WIT_WORDS);
         cols = VmCols{stc, st_stride, wtc, wt_stride};
     } else cols = VmCols{in.columns->state_words, st_stride, in.columns->witness_words, wt_stride};
-    // tensor maps of the state columns for the cycle kernel's TMA tiles (ZKC_VM_NO_TMA=1: plain loads, for comparison)
+    // tensor maps of the state columns for the cycle kernel's TMA tiles (ZKC_VM_TMA=1 selects that variant; default: plain loads, measured faster)
     VmTmaps tmaps;
     memset(&tmaps, 0, sizeof tmaps);
-    static const bool tma_disabled = getenv("ZKC_VM_NO_TMA") && atoi(getenv("ZKC_VM_NO_TMA"));
-    const int use_tma = !tma_disabled && vm_make_tmaps(cols.st, st_stride, &tmaps);
+    static const bool tma_wanted = getenv("ZKC_VM_TMA") && atoi(getenv("ZKC_VM_TMA"));
+    const int use_tma = tma_wanted && vm_make_tmaps(cols.st, st_stride, &tmaps);
     uint32_t *stc_w = const_cast<uint32_t *>(cols.st), *wtc_w = const_cast<uint32_t *>(cols.wt);  // written only when they are this call's scratch
     char *dblobs = have_stream ? cv.take<char>(blob_total + 256) : nullptr;
     if ((trace && !trace_dev) || packed) dtrace = cv.take<uint64_t>((size_t)ncols * rows);
@@ -2649,8 +2541,12 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
             ps.n_records = rec_counts + 2 * c + 1;
             ps.records_capacity = chunk_cells * VM_JOB_SLOTS;
         }
-        ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, cols, dcw,
-                   (uint32_t)in.n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base, tmaps, use_tma);
+        if (use_tma)
+            ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel<true>, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, cols, dcw,
+                       (uint32_t)in.n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base, tmaps, use_tma);
+        else
+            ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel<false>, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, cols, dcw,
+                       (uint32_t)in.n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base, tmaps, use_tma);
         ZKC_LAUNCH(ctx, "vm_link", vm_link_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, d, cols, (const uint32_t *)ps.link, (const uint32_t *)ps.exp, limit,
                    n_instances, r0, cnt);
         // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists, or one launch per slot

@@ -190,6 +190,24 @@ def main_vm_check_trace(engine: Engine, isa: abi.VmIsa, trace, limit: int, n_ins
     return viol.value, st
 
 
+def main_vm_gadget_cells(engine: Engine, trace, limit: int, n_instances: int = 1):
+    """The cells the add/sub, binop, mul/div and shift gadgets allocate on every cycle whatever the opcode, and the relations
+    vm_cycle enforces once per cycle (include/zkc_b200.h, ZKC_VM_GADGET_COLUMNS), from finished DENSE traces [NUM_COLS, limit] /
+    [n, NUM_COLS, limit].  Returns [VMG_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory space of `trace`."""
+    dev = on_device(trace)
+    shape = tuple(trace.shape[:-2]) + (abi.VMG_COLS["NUM_COLS"], limit)
+    if dev:
+        import torch
+        out = torch.empty(shape, dtype=trace.dtype, device=trace.device)
+    else:
+        trace = np.ascontiguousarray(trace, dtype=np.uint64)
+        out = np.empty(shape, dtype=np.uint64)
+    rc = engine.lib.zkc_main_vm_gadget_cells(engine.h, ptr(trace), limit, n_instances, dev, ptr(out))
+    if rc:
+        raise ZkcError(rc, what="zkc_main_vm_gadget_cells")
+    return out
+
+
 # ---- transport forms over PCIe (include/zkc_b200.h, "transport forms of the main_vm call") ---------------------------------
 class VmInputStreamHandle:
     """a zkc_vm_input_stream of ONE instance, in (pinned) host memory owned by the library"""

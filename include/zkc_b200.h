@@ -1444,6 +1444,53 @@ int zkc_main_vm_entry_point_stream(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t
 int zkc_main_vm_check_trace(zkc_ctx *ctx, const zkc_vm_isa *isa, const uint64_t *trace, size_t limit, size_t n_instances,
                             int on_device, uint64_t *violations, zkc_status *status);
 
+/* ---- cells of the arithmetic opcode gadgets, evaluated OBLIVIOUSLY --------------------------------------------------------
+ * The reference runs every opcode gadget on every cycle and selects afterwards (main_vm/cycle.rs:73-156); the DENSE trace
+ * (zkc_vm_col) carries the selected path.  zkc_main_vm_gadget_cells produces, for every cycle, the cells the add/sub, binop,
+ * mul/div and shift gadgets allocate regardless of the opcode, and the relations vm_cycle enforces once per cycle:
+ *   register_input_view.rs:27-53   byte views of src0 / src1
+ *   opcodes/add_sub.rs:8-166       both results, the selected result, the shuffled AddSubRelation, flags
+ *   opcodes/binop.rs:14-244        the 32 composite lookups, their 96-cell decomposition, and / or / xor limbs, result, flags
+ *   opcodes/mul_div.rs:199-417     product, quotient / remainder (divisor 0: quotient 0, remainder = src0, :119-123), selections,
+ *                                  the MulDivRelation and the remainder < divisor AddSubRelation, flags
+ *   opcodes/shifts.rs:8-198        shift constant (tables/bitshift.rs), both shift directions, relations, result, flags
+ *   cycle.rs:619-670               the conditional range check, the ONE enforced AddSubRelation (candidates add_sub, mul_div,
+ *                                  shifts; the last pushed is the default, opcodes/mod.rs:101-125: 8 carries) and the ONE enforced
+ *                                  MulDivRelation (candidates mul_div, shifts; opcodes/mod.rs:129-180: 64 (low, high) partial
+ *                                  products of UInt32::fma_with_carry + 8 row-end sums)
+ * Inputs are the src0 / src1 operand and property-bit columns of the DENSE trace (ZKC_VM_SRC0, ZKC_VM_SRC1, ZKC_VM_PROPS).
+ * The UMA, log, context, ptr, jump, nop and call/ret gadgets' non-selected cells are not produced.
+ * X(name, width): column ZKC_VMG_<name> .. + width - 1 of the gadget block [ZKC_VMG_NUM_COLS][limit]. */
+#define ZKC_VM_GADGET_COLUMNS(X) \
+    X(SRC0_BYTES, 32) X(SRC1_BYTES, 32) \
+    X(ADD_RESULT, 8) X(ADD_OF, 1) X(SUB_RESULT, 8) X(SUB_UF, 1) X(ADDSUB_RESULT, 8) X(ADDSUB_NEW_B, 8) X(ADDSUB_NEW_C, 8) \
+    X(ADDSUB_NEW_OF, 1) X(ADDSUB_LIMB_IS_ZERO, 8) X(ADDSUB_RESULT_IS_ZERO, 1) X(ADDSUB_GT, 1) X(ADDSUB_APPLY_ANY, 1) \
+    X(ADDSUB_UPDATE_FLAGS, 1) \
+    X(BINOP_COMPOSITE, 32) X(BINOP_ALL_RESULTS, 96) X(BINOP_AND, 8) X(BINOP_OR, 8) X(BINOP_XOR, 8) X(BINOP_RESULT, 8) \
+    X(BINOP_LIMB_IS_ZERO, 8) X(BINOP_RESULT_IS_ZERO, 1) X(BINOP_UPDATE_FLAGS, 1) \
+    X(MUL_LOW, 8) X(MUL_HIGH, 8) X(DIV_QUOTIENT, 8) X(DIV_REMAINDER, 8) X(MULDIV_RESULT_0, 8) X(MULDIV_RESULT_1_UNMASKED, 8) \
+    X(MULDIV_REM_TO_ENFORCE, 8) X(MULDIV_A_TO_ENFORCE, 8) X(MULDIV_MUL_LOW_TO_ENFORCE, 8) X(MULDIV_MUL_HIGH_TO_ENFORCE, 8) \
+    X(MUL_HIGH_IS_ZERO, 1) X(MUL_LOW_IS_ZERO, 1) X(MUL_OF, 1) X(MUL_GT, 1) X(DIV_DIVISOR_IS_ZERO, 1) X(DIV_QUOTIENT_IS_ZERO, 1) \
+    X(DIV_REMAINDER_IS_ZERO, 1) X(DIV_SUB_RESULT, 8) X(DIV_REMAINDER_IS_LESS, 1) X(DIV_MASK_REMAINDER, 1) X(MULDIV_RESULT_1, 8) \
+    X(DIV_EQ, 1) X(DIV_GT, 1) X(MULDIV_OF, 1) X(MULDIV_EQ, 1) X(MULDIV_GT, 1) X(MULDIV_APPLY_ANY, 1) X(MULDIV_SET_FLAGS, 1) \
+    X(SHIFT_AMOUNT, 1) X(SHIFT_IS_ZERO, 1) X(SHIFT_INVERTED, 1) X(SHIFT_CHANGE_FLAG, 1) X(SHIFT_FULL, 1) X(SHIFT_CONSTANT, 8) \
+    X(SHIFT_IS_RIGHT, 1) X(SHIFT_RSHIFT_Q, 8) X(SHIFT_RSHIFT_R, 8) X(SHIFT_APPLY_LEFT, 1) X(SHIFT_LSHIFT_LOW, 8) \
+    X(SHIFT_LSHIFT_HIGH, 8) X(SHIFT_REM_TO_ENFORCE, 8) X(SHIFT_A_TO_ENFORCE, 8) X(SHIFT_MUL_LOW_TO_ENFORCE, 8) \
+    X(SHIFT_MUL_HIGH_TO_ENFORCE, 8) X(SHIFT_SUB_RESULT, 8) X(SHIFT_REMAINDER_IS_LESS, 1) X(SHIFT_TEMP_RESULT, 8) \
+    X(SHIFT_RESULT, 8) X(SHIFT_RESULT_IS_ZERO, 1) X(SHIFT_SET_FLAGS, 1) \
+    X(RANGE_CHECK, 8) X(ADDREL_A, 8) X(ADDREL_B, 8) X(ADDREL_C, 8) X(ADDREL_OF, 1) X(ADDREL_CARRY, 8) \
+    X(MULREL_A, 8) X(MULREL_B, 8) X(MULREL_REM, 8) X(MULREL_LOW, 8) X(MULREL_HIGH, 8) X(MULREL_PARTIAL_LOW, 64) \
+    X(MULREL_PARTIAL_HIGH, 64) X(MULREL_ROW_END, 8)
+enum zkc_vm_gadget_col {
+#define ZKC_VMG_X(name, width) ZKC_VMG_##name, ZKC_VMG_##name##_LAST = ZKC_VMG_##name + (width)-1,
+    ZKC_VM_GADGET_COLUMNS(ZKC_VMG_X)
+#undef ZKC_VMG_X
+    ZKC_VMG_NUM_COLS
+};
+/* trace: DENSE traces [n_instances][ZKC_VM_NUM_COLS][limit] (host, or device with on_device != 0);
+ * gadget_trace: out, [n_instances][ZKC_VMG_NUM_COLS][limit] in the same memory space */
+int zkc_main_vm_gadget_cells(zkc_ctx *ctx, const uint64_t *trace, size_t limit, size_t n_instances, int on_device, uint64_t *gadget_trace);
+
 /* the state main_vm_entry_point starts from when start_flag is set: initial_bootloader_state, main_vm/loading.rs:13-226 */
 int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *out);
 

@@ -1,0 +1,221 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see gl.h header).
+ *
+ * The cells the arithmetic opcode gadgets of the reference allocate on EVERY cycle, whatever the opcode, and the relations
+ * vm_cycle enforces once per cycle (one cycle at a time, in the order the reference evaluates them):
+ *   RegisterInputView::from_input_value   /root/reference/src/main_vm/register_input_view.rs:27-53
+ *   apply_add_sub                         /root/reference/src/main_vm/opcodes/add_sub.rs:8-166 (+ :168-282 the unchecked results)
+ *   apply_binop, get_binop_subresults     /root/reference/src/main_vm/opcodes/binop.rs:14-244
+ *   apply_mul_div                         /root/reference/src/main_vm/opcodes/mul_div.rs:199-417 (+ :20-163 the unchecked results)
+ *   apply_shifts, get_shift_constant      /root/reference/src/main_vm/opcodes/shifts.rs:8-221, /root/reference/src/tables/bitshift.rs
+ *   relation selection                    /root/reference/src/main_vm/cycle.rs:619-670
+ *   enforce_addition_relation / enforce_mul_relation   /root/reference/src/main_vm/opcodes/mod.rs:101-180
+ * Column meaning: include/zkc_b200.h, ZKC_VM_GADGET_COLUMNS.  Pinning: PARITY UNPINNED against the reference (no main_vm vector
+ * in it); the arithmetic itself is checked against Python integers (tests/test_oracle_main_vm_gadgets.py).
+ */
+#include "oracle.h"
+#include <string.h>
+
+static int add256(const uint32_t *a, const uint32_t *b, uint32_t *c) {  /* add_sub.rs:181-194 */
+    uint64_t carry = 0;
+    for (int i = 0; i < 8; i++) { const uint64_t s = (uint64_t)a[i] + b[i] + carry; c[i] = (uint32_t)s; carry = s >> 32; }
+    return (int)carry;
+}
+static int sub256(const uint32_t *a, const uint32_t *b, uint32_t *c) {  /* add_sub.rs:239-252 */
+    uint64_t borrow = 0;
+    for (int i = 0; i < 8; i++) { const uint64_t d = (uint64_t)a[i] - b[i] - borrow; c[i] = (uint32_t)d; borrow = (d >> 32) & 1; }
+    return (int)borrow;
+}
+static void mul256(const uint32_t *a, const uint32_t *b, uint32_t *lo, uint32_t *hi) {  /* U256::full_mul */
+    uint32_t r[16];
+    memset(r, 0, sizeof r);
+    for (int i = 0; i < 8; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 8; j++) { const uint64_t t = (uint64_t)a[i] * b[j] + r[i + j] + carry; r[i + j] = (uint32_t)t; carry = t >> 32; }
+        r[i + 8] = (uint32_t)carry;
+    }
+    memcpy(lo, r, 32); memcpy(hi, r + 8, 32);
+}
+static int is_zero256(const uint32_t *a) { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= a[i]; return o == 0; }
+static int ge256(const uint32_t *a, const uint32_t *b) {
+    for (int i = 7; i >= 0; i--) if (a[i] != b[i]) return a[i] > b[i];
+    return 1;
+}
+/* mul_div.rs:110-123: (0, a) for a zero divisor; schoolbook binary long division otherwise */
+static void divrem256(const uint32_t *a, const uint32_t *b, uint32_t *q, uint32_t *r) {
+    memset(q, 0, 32); memset(r, 0, 32);
+    if (is_zero256(b)) { memcpy(r, a, 32); return; }
+    for (int bit = 255; bit >= 0; bit--) {
+        uint32_t top = r[7] >> 31;
+        for (int i = 7; i > 0; i--) r[i] = (r[i] << 1) | (r[i - 1] >> 31);
+        r[0] = (r[0] << 1) | ((a[bit >> 5] >> (bit & 31)) & 1);
+        if (top || ge256(r, b)) { uint32_t t[8]; sub256(r, b, t); memcpy(r, t, 32); q[bit >> 5] |= 1u << (bit & 31); }
+    }
+}
+static void sel8(int flag, const uint32_t *a, const uint32_t *b, uint32_t *out) { memcpy(out, flag ? a : b, 32); }  /* UInt32::parallel_select */
+
+#define G(col, i) out[(size_t)((col) + (i)) * limit + row]
+static void put8(uint64_t *out, size_t limit, size_t row, int col, const uint32_t *v) { for (int i = 0; i < 8; i++) G(col, i) = v[i]; }
+
+static void gadget_row(uint64_t props, const uint32_t *a, const uint32_t *b, uint64_t *out, size_t limit, size_t row) {
+#define BIT(n) (int)((props >> (n)) & 1)
+    static const uint32_t zero8[8] = {0};
+    const int set_flags = BIT(ZKC_VM_BIT_FLAG(ZKC_VM_SET_FLAGS_FLAG_IDX));
+    /* register_input_view.rs:36-46 */
+    for (int i = 0; i < 32; i++) { G(ZKC_VMG_SRC0_BYTES, i) = (a[i / 4] >> (8 * (i % 4))) & 0xFF; G(ZKC_VMG_SRC1_BYTES, i) = (b[i / 4] >> (8 * (i % 4))) & 0xFF; }
+
+    /* ---- add_sub.rs ------------------------------------------------------------------------------------------------ */
+    uint32_t add_r[8], sub_r[8], as_result[8], new_b[8], new_c[8];
+    const int add_of = add256(a, b, add_r), sub_uf = sub256(a, b, sub_r);
+    const int apply_add = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_ADD)), apply_sub = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_SUB));
+    sel8(apply_add, add_r, sub_r, as_result);          /* :51-56 */
+    sel8(apply_add, a, sub_r, new_b);                  /* :91-96: relation a = src1, b, c, of */
+    sel8(apply_add, add_r, a, new_c);                  /* :98-103 */
+    const int new_of = apply_add ? add_of : sub_uf;
+    int as_zero = 1;
+    for (int i = 0; i < 8; i++) { G(ZKC_VMG_ADDSUB_LIMB_IS_ZERO, i) = as_result[i] == 0; as_zero &= as_result[i] == 0; }
+    const int as_gt = !(new_of || as_zero), as_any = apply_add || apply_sub;
+    put8(out, limit, row, ZKC_VMG_ADD_RESULT, add_r); G(ZKC_VMG_ADD_OF, 0) = add_of;
+    put8(out, limit, row, ZKC_VMG_SUB_RESULT, sub_r); G(ZKC_VMG_SUB_UF, 0) = sub_uf;
+    put8(out, limit, row, ZKC_VMG_ADDSUB_RESULT, as_result); put8(out, limit, row, ZKC_VMG_ADDSUB_NEW_B, new_b);
+    put8(out, limit, row, ZKC_VMG_ADDSUB_NEW_C, new_c);
+    G(ZKC_VMG_ADDSUB_NEW_OF, 0) = new_of; G(ZKC_VMG_ADDSUB_RESULT_IS_ZERO, 0) = as_zero; G(ZKC_VMG_ADDSUB_GT, 0) = as_gt;
+    G(ZKC_VMG_ADDSUB_APPLY_ANY, 0) = as_any; G(ZKC_VMG_ADDSUB_UPDATE_FLAGS, 0) = as_any && set_flags;
+
+    /* ---- binop.rs ---------------------------------------------------------------------------------------------------- */
+    {
+        uint32_t and_c[8] = {0}, or_c[8] = {0}, xor_c[8] = {0}, res[8];
+        for (int i = 0; i < 32; i++) {
+            const uint32_t x = (a[i / 4] >> (8 * (i % 4))) & 0xFF, y = (b[i / 4] >> (8 * (i % 4))) & 0xFF;
+            const uint64_t an = x & y, orr = x | y, xo = x ^ y;
+            G(ZKC_VMG_BINOP_COMPOSITE, i) = an | (orr << 16) | (xo << 32);  /* BinopTable row, split at :171-178 */
+            G(ZKC_VMG_BINOP_ALL_RESULTS, 3 * i) = an; G(ZKC_VMG_BINOP_ALL_RESULTS, 3 * i + 1) = orr; G(ZKC_VMG_BINOP_ALL_RESULTS, 3 * i + 2) = xo;
+            and_c[i / 4] |= (uint32_t)an << (8 * (i % 4)); or_c[i / 4] |= (uint32_t)orr << (8 * (i % 4)); xor_c[i / 4] |= (uint32_t)xo << (8 * (i % 4));
+        }
+        const int is_and = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_BINOP_AND)), is_or = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_BINOP_OR));
+        sel8(is_and, and_c, xor_c, res);               /* :85 */
+        if (is_or) memcpy(res, or_c, 32);              /* :86 */
+        int z = 1;
+        for (int i = 0; i < 8; i++) { G(ZKC_VMG_BINOP_LIMB_IS_ZERO, i) = res[i] == 0; z &= res[i] == 0; }
+        put8(out, limit, row, ZKC_VMG_BINOP_AND, and_c); put8(out, limit, row, ZKC_VMG_BINOP_OR, or_c); put8(out, limit, row, ZKC_VMG_BINOP_XOR, xor_c);
+        put8(out, limit, row, ZKC_VMG_BINOP_RESULT, res);
+        G(ZKC_VMG_BINOP_RESULT_IS_ZERO, 0) = z;
+        G(ZKC_VMG_BINOP_UPDATE_FLAGS, 0) = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_BINOP)) && set_flags;
+    }
+
+    /* ---- mul_div.rs -------------------------------------------------------------------------------------------------- */
+    uint32_t mul_lo[8], mul_hi[8], quot[8], rem[8], md_rem[8], md_a[8], md_low[8], md_high[8], div_sub[8];
+    const int apply_mul = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_MUL)), apply_div = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_DIV)), md_any = apply_mul || apply_div;
+    int div_less;
+    {
+        uint32_t r0[8], r1[8], r1m[8];
+        mul256(a, b, mul_lo, mul_hi);
+        divrem256(a, b, quot, rem);
+        sel8(apply_mul, mul_lo, quot, r0); sel8(apply_mul, mul_hi, rem, r1);              /* :258-269 */
+        sel8(apply_mul, zero8, rem, md_rem); sel8(apply_mul, a, quot, md_a);              /* :281-288 */
+        sel8(apply_mul, mul_lo, a, md_low); sel8(apply_mul, mul_hi, zero8, md_high);      /* :290-297 */
+        const int high_z = is_zero256(mul_hi), low_z = is_zero256(mul_lo), of_mul = !high_z, eq_mul = low_z, gt_mul = !of_mul && !eq_mul;
+        const int divisor_z = is_zero256(b), quot_z = is_zero256(quot), rem_z = is_zero256(rem);
+        div_less = sub256(rem, b, div_sub);                                               /* :330-331 */
+        const int mask = apply_div && divisor_z;                                          /* :354 */
+        for (int i = 0; i < 8; i++) r1m[i] = mask ? 0 : r1[i];
+        const int of_div = divisor_z, eq_div = !divisor_z && quot_z, gt_div = !divisor_z && rem_z;
+        put8(out, limit, row, ZKC_VMG_MUL_LOW, mul_lo); put8(out, limit, row, ZKC_VMG_MUL_HIGH, mul_hi);
+        put8(out, limit, row, ZKC_VMG_DIV_QUOTIENT, quot); put8(out, limit, row, ZKC_VMG_DIV_REMAINDER, rem);
+        put8(out, limit, row, ZKC_VMG_MULDIV_RESULT_0, r0); put8(out, limit, row, ZKC_VMG_MULDIV_RESULT_1_UNMASKED, r1);
+        put8(out, limit, row, ZKC_VMG_MULDIV_REM_TO_ENFORCE, md_rem); put8(out, limit, row, ZKC_VMG_MULDIV_A_TO_ENFORCE, md_a);
+        put8(out, limit, row, ZKC_VMG_MULDIV_MUL_LOW_TO_ENFORCE, md_low); put8(out, limit, row, ZKC_VMG_MULDIV_MUL_HIGH_TO_ENFORCE, md_high);
+        G(ZKC_VMG_MUL_HIGH_IS_ZERO, 0) = high_z; G(ZKC_VMG_MUL_LOW_IS_ZERO, 0) = low_z; G(ZKC_VMG_MUL_OF, 0) = of_mul; G(ZKC_VMG_MUL_GT, 0) = gt_mul;
+        G(ZKC_VMG_DIV_DIVISOR_IS_ZERO, 0) = divisor_z; G(ZKC_VMG_DIV_QUOTIENT_IS_ZERO, 0) = quot_z; G(ZKC_VMG_DIV_REMAINDER_IS_ZERO, 0) = rem_z;
+        put8(out, limit, row, ZKC_VMG_DIV_SUB_RESULT, div_sub); G(ZKC_VMG_DIV_REMAINDER_IS_LESS, 0) = div_less;
+        G(ZKC_VMG_DIV_MASK_REMAINDER, 0) = mask; put8(out, limit, row, ZKC_VMG_MULDIV_RESULT_1, r1m);
+        G(ZKC_VMG_DIV_EQ, 0) = eq_div; G(ZKC_VMG_DIV_GT, 0) = gt_div;
+        G(ZKC_VMG_MULDIV_OF, 0) = apply_mul ? of_mul : of_div; G(ZKC_VMG_MULDIV_EQ, 0) = apply_mul ? eq_mul : eq_div;
+        G(ZKC_VMG_MULDIV_GT, 0) = apply_mul ? gt_mul : gt_div;
+        G(ZKC_VMG_MULDIV_APPLY_ANY, 0) = md_any; G(ZKC_VMG_MULDIV_SET_FLAGS, 0) = md_any && set_flags;
+    }
+
+    /* ---- shifts.rs ----------------------------------------------------------------------------------------------------- */
+    uint32_t shc[8], sh_rem[8], sh_a[8], sh_low[8], sh_high[8], sh_sub[8], sh_rr[8];
+    const int apply_shift = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_SHIFT));
+    int sh_less;
+    {
+        const int is_rol = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_SHIFT_ROL)), is_ror = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_SHIFT_ROR)),
+                  is_shr = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_SHIFT_SHR));
+        const int is_cyclic = is_rol || is_ror, is_right = is_ror || is_shr;
+        const uint32_t shift = b[0] & 0xFF;                                                /* :57 */
+        const int shift_z = shift == 0;
+        const uint32_t inverted = 256 - shift;                                             /* :65, a field element (256 for shift 0) */
+        const int change = is_ror && !shift_z;
+        const uint32_t full = change ? inverted : shift;                                   /* :71, 8 bits again */
+        memset(shc, 0, sizeof shc); shc[full >> 5] = 1u << (full & 31);                    /* tables/bitshift.rs:22-33: 2^full */
+        const int is_right_shift = is_right && !is_cyclic;                                 /* :78-81 */
+        const int apply_left = apply_shift && !is_right_shift;                             /* :84-87 */
+        uint32_t rq[8], rr[8], ll[8], lh[8], temp[8], fin[8];
+        divrem256(a, shc, rq, rr); mul256(a, shc, ll, lh);
+        memcpy(sh_rr, rr, 32);
+        sel8(apply_left, zero8, rr, sh_rem); sel8(apply_left, a, rq, sh_a);                /* :99-101 */
+        sel8(apply_left, ll, a, sh_low); sel8(apply_left, lh, zero8, sh_high);             /* :103-105 */
+        sh_less = sub256(rr, shc, sh_sub);                                                 /* :117-118 */
+        sel8(is_right_shift, rq, ll, temp);                                                /* :136 */
+        for (int i = 0; i < 8; i++) fin[i] = (is_cyclic ? lh[i] : 0u) + temp[i];           /* :141-152 */
+        G(ZKC_VMG_SHIFT_AMOUNT, 0) = shift; G(ZKC_VMG_SHIFT_IS_ZERO, 0) = shift_z; G(ZKC_VMG_SHIFT_INVERTED, 0) = inverted;
+        G(ZKC_VMG_SHIFT_CHANGE_FLAG, 0) = change; G(ZKC_VMG_SHIFT_FULL, 0) = full; put8(out, limit, row, ZKC_VMG_SHIFT_CONSTANT, shc);
+        G(ZKC_VMG_SHIFT_IS_RIGHT, 0) = is_right_shift; put8(out, limit, row, ZKC_VMG_SHIFT_RSHIFT_Q, rq); put8(out, limit, row, ZKC_VMG_SHIFT_RSHIFT_R, rr);
+        G(ZKC_VMG_SHIFT_APPLY_LEFT, 0) = apply_left; put8(out, limit, row, ZKC_VMG_SHIFT_LSHIFT_LOW, ll); put8(out, limit, row, ZKC_VMG_SHIFT_LSHIFT_HIGH, lh);
+        put8(out, limit, row, ZKC_VMG_SHIFT_REM_TO_ENFORCE, sh_rem); put8(out, limit, row, ZKC_VMG_SHIFT_A_TO_ENFORCE, sh_a);
+        put8(out, limit, row, ZKC_VMG_SHIFT_MUL_LOW_TO_ENFORCE, sh_low); put8(out, limit, row, ZKC_VMG_SHIFT_MUL_HIGH_TO_ENFORCE, sh_high);
+        put8(out, limit, row, ZKC_VMG_SHIFT_SUB_RESULT, sh_sub); G(ZKC_VMG_SHIFT_REMAINDER_IS_LESS, 0) = sh_less;
+        put8(out, limit, row, ZKC_VMG_SHIFT_TEMP_RESULT, temp); put8(out, limit, row, ZKC_VMG_SHIFT_RESULT, fin);
+        G(ZKC_VMG_SHIFT_RESULT_IS_ZERO, 0) = is_zero256(fin); G(ZKC_VMG_SHIFT_SET_FLAGS, 0) = apply_shift && set_flags;
+    }
+
+    /* ---- cycle.rs:619-670: the candidates in push order add_sub, mul_div, shifts; the LAST pushed is the default ----------- */
+    {
+        uint32_t rc[8], ra_[8], rb_[8], rcc[8];
+        memcpy(rc, sh_sub, 32);                                    /* :620-627 */
+        if (as_any) memcpy(rc, as_result, 32);
+        if (md_any) memcpy(rc, div_sub, 32);
+        put8(out, limit, row, ZKC_VMG_RANGE_CHECK, rc);
+        /* AddSubRelation { a, b, c, of }: shifts (a = shift constant, b = sub result, c = rshift_r), add_sub (a = src1, new_b, new_c),
+         * mul_div (a = src1, b = sub result, c = remainder) */
+        int of = sh_less;
+        memcpy(ra_, shc, 32); memcpy(rb_, sh_sub, 32); memcpy(rcc, sh_rr, 32);
+        if (as_any) { memcpy(ra_, b, 32); memcpy(rb_, new_b, 32); memcpy(rcc, new_c, 32); of = new_of; }
+        if (md_any) { memcpy(ra_, b, 32); memcpy(rb_, div_sub, 32); memcpy(rcc, rem, 32); of = div_less; }
+        put8(out, limit, row, ZKC_VMG_ADDREL_A, ra_); put8(out, limit, row, ZKC_VMG_ADDREL_B, rb_); put8(out, limit, row, ZKC_VMG_ADDREL_C, rcc);
+        G(ZKC_VMG_ADDREL_OF, 0) = of;
+        uint64_t carry = 0;                                        /* opcodes/mod.rs:107-117 */
+        for (int i = 0; i < 8; i++) { carry = ((uint64_t)ra_[i] + rb_[i] + carry) >> 32; G(ZKC_VMG_ADDREL_CARRY, i) = carry; }
+        /* MulDivRelation { a, b, rem, mul_low, mul_high }: shifts by default, mul_div when it applies */
+        uint32_t ma[8], mb[8], mrem[8], mlow[8], mhigh[8];
+        memcpy(ma, sh_a, 32); memcpy(mb, shc, 32); memcpy(mrem, sh_rem, 32); memcpy(mlow, sh_low, 32); memcpy(mhigh, sh_high, 32);
+        if (md_any) { memcpy(ma, md_a, 32); memcpy(mb, b, 32); memcpy(mrem, md_rem, 32); memcpy(mlow, md_low, 32); memcpy(mhigh, md_high, 32); }
+        put8(out, limit, row, ZKC_VMG_MULREL_A, ma); put8(out, limit, row, ZKC_VMG_MULREL_B, mb); put8(out, limit, row, ZKC_VMG_MULREL_REM, mrem);
+        put8(out, limit, row, ZKC_VMG_MULREL_LOW, mlow); put8(out, limit, row, ZKC_VMG_MULREL_HIGH, mhigh);
+        uint32_t partial[16];                                      /* opcodes/mod.rs:146-169 */
+        memset(partial, 0, sizeof partial); memcpy(partial, mrem, 32);
+        for (int ai = 0; ai < 8; ai++) {
+            uint32_t overflow = 0;
+            for (int bi = 0; bi < 8; bi++) {
+                const uint64_t t = (uint64_t)ma[ai] * mb[bi] + partial[ai + bi] + overflow;  /* UInt32::fma_with_carry */
+                partial[ai + bi] = (uint32_t)t; overflow = (uint32_t)(t >> 32);
+                G(ZKC_VMG_MULREL_PARTIAL_LOW, 8 * ai + bi) = (uint32_t)t; G(ZKC_VMG_MULREL_PARTIAL_HIGH, 8 * ai + bi) = overflow;
+            }
+            partial[ai + 8] += overflow;                           /* add_no_overflow */
+            G(ZKC_VMG_MULREL_ROW_END, ai) = partial[ai + 8];
+        }
+    }
+#undef BIT
+}
+
+void orc_main_vm_gadget_cells(const uint64_t *trace, size_t limit, size_t n_instances, uint64_t *out_all) {
+    for (size_t inst = 0; inst < n_instances; inst++) {
+        const uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit;
+        uint64_t *out = out_all + inst * (size_t)ZKC_VMG_NUM_COLS * limit;
+        for (size_t row = 0; row < limit; row++) {
+            uint32_t a[8], b[8];
+            for (int i = 0; i < 8; i++) { a[i] = (uint32_t)t[(size_t)(ZKC_VM_SRC0 + 1 + i) * limit + row]; b[i] = (uint32_t)t[(size_t)(ZKC_VM_SRC1 + 1 + i) * limit + row]; }
+            gadget_row(t[(size_t)ZKC_VM_PROPS * limit + row], a, b, out, limit, row);
+        }
+    }
+}

@@ -132,4 +132,6 @@ int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const
                             const zkc_vm_cycle_witness *witness, const zkc_vm_callstack_witness *callstack_witness,
                             size_t n_callstack_witness, size_t limit, const zkc_vm_options *options,
                             uint64_t *trace, uint64_t commitment[4], zkc_status *status);
+/* main_vm_gadgets.c: trace [n_instances][ZKC_VM_NUM_COLS][limit] -> out [n_instances][ZKC_VMG_NUM_COLS][limit] */
+void orc_main_vm_gadget_cells(const uint64_t *trace, size_t limit, size_t n_instances, uint64_t *out);
 #endif

@@ -411,3 +411,13 @@ def vm_entry_point(lib, io, isa, snaps, wit, limit, want_trace=True, compare_exp
                                      p(np.ascontiguousarray(cw)) if n_cw else None, n_cw, limit,
                                      C.byref(opts), p(trace), p(com), C.byref(st))
     return rc, io2, trace, com, st
+
+
+def vm_gadget_cells(lib, trace, limit, n_instances=1):
+    """orc_main_vm_gadget_cells: DENSE trace(s) -> [n?, VMG_COLS.NUM_COLS, limit]"""
+    trace = np.ascontiguousarray(trace, dtype=np.uint64)
+    out = np.zeros(tuple(trace.shape[:-2]) + (abi.VMG_COLS["NUM_COLS"], limit), dtype=np.uint64)
+    lib.orc_main_vm_gadget_cells.restype = None
+    lib.orc_main_vm_gadget_cells.argtypes = [_vp, C.c_size_t, C.c_size_t, _vp]
+    lib.orc_main_vm_gadget_cells(p(trace), limit, n_instances, p(out))
+    return out

@@ -545,3 +545,27 @@ def test_stream_inputs_and_packed_trace(engine, orc, n, cycles, segment):
     assert np.array_equal(small.cols32, out.cols32) and np.array_equal(small.cols8, out.cols8)
     for s in streams:
         s.free()
+
+
+@pytest.mark.parametrize("n,cycles,seed,far", [(1, 1, 1, False), (1, 5000, 2, False), (3, 4097, 3, True)])
+def test_gadget_cells_bit_exact(engine, orc, n, cycles, seed, far):
+    """zkc_main_vm_gadget_cells: the oblivious add/sub, binop, mul/div, shift cells and the per-cycle relations, CUDA vs the oracle
+    (which tests/test_oracle_main_vm_gadgets.py pins on Python integers), host and device buffers, batches"""
+    import torch
+    from era_zkevm_circuits_b200 import main_vm_gadget_cells
+    isa, io, st = fresh(orc)
+    traces = []
+    for k in range(n):
+        ops = I.random_program(isa, 1024, seed=seed + k, far_calls=far)
+        rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+        assert rc == 0
+        want = O.vm_entry_point(orc, with_tail(io, tail), isa.isa, snaps, wit, cycles, cw=cw)
+        assert want[0] == 0
+        traces.append(want[2])
+    trace = np.ascontiguousarray(np.stack(traces))
+    want = O.vm_gadget_cells(orc, trace, cycles, n)
+    got = main_vm_gadget_cells(engine, trace, cycles, n)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"first differing (instance, column, row): {bad[:5].tolist()}"
+    dev = main_vm_gadget_cells(engine, torch.from_numpy(trace.view(np.int64)).cuda(), cycles, n)
+    assert np.array_equal(dev.cpu().numpy().view(np.uint64), want)

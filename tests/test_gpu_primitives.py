@@ -95,6 +95,7 @@ def test_grand_product_permutation_invariance(engine):
 
 
 def test_scale_accumulators_host_and_device(engine):
+    from era_zkevm_circuits_b200 import abi
     """zkc_scale_accumulators: the 4-column fix-up multiply of a sharded grand product, against Python integers"""
     import torch
     P = abi.GL_P
