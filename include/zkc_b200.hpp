@@ -287,6 +287,34 @@ inline Result<zkc_demux_closed_form> demultiplex_storage_logs_enty_point(Engine 
     return r;
 }
 
+// ---- linear_hasher -----------------------------------------------------------------------------------------------------
+// LinearHasherCircuitInstanceWitness, /root/reference/src/linear_hasher/input.rs:74-87
+struct LinearHasherCircuitInstanceWitness {
+    zkc_linear_hasher_closed_form closed_form_input{};
+    std::vector<zkc_log_query> queue_witness;
+    std::vector<State4> queue_prev_tails;
+    // optional hint: the keccak state (25 lanes) after every cycle ([limit] entries); empty = rebuilt on the device
+    std::vector<std::array<uint64_t, 25>> keccak_states;
+};
+
+// linear_hasher_entry_point, /root/reference/src/linear_hasher/mod.rs:35-214
+inline Result<zkc_linear_hasher_closed_form> linear_hasher_entry_point(Engine &e, const LinearHasherCircuitInstanceWitness &w, size_t limit,
+                                                                       bool want_trace = true, const zkc_sorter_options *options = nullptr,
+                                                                       bool throw_if_unsatisfied = false) {
+    detail::same_length("linear_hasher_entry_point", w.queue_witness.size(), w.queue_prev_tails.size());
+    if (!w.keccak_states.empty() && w.keccak_states.size() < limit)
+        throw Error("linear_hasher_entry_point: keccak_states holds the state after EVERY cycle", ZKC_ERR_INVALID_ARGUMENT,
+                    zkc_status{ZKC_ERR_INVALID_ARGUMENT, 0, -1, 0, 0});
+    Result<zkc_linear_hasher_closed_form> r;
+    r.closed_form_input = w.closed_form_input;
+    uint64_t *trace = detail::make_trace(r, ZKC_LH_NUM_COLS, limit, want_trace);
+    const int rc = zkc_linear_hasher_entry_point(e.handle(), &r.closed_form_input, detail::ptr(w.queue_witness), detail::flat(w.queue_prev_tails),
+                                                 w.queue_witness.size(), w.keccak_states.empty() ? nullptr : w.keccak_states.front().data(), limit,
+                                                 options, 0, trace, r.commitment.data(), &r.status);
+    detail::finish("linear_hasher_entry_point", rc, r, throw_if_unsatisfied);
+    return r;
+}
+
 // ---- precompile round-function circuits ------------------------------------------------------------------------------------
 // Keccak256RoundFunctionCircuitInstanceWitness (keccak256_round_function/input.rs:92-99) and its sha256 twin
 // (sha256_round_function/input.rs): requests queue witness + the memory reads the circuit pops conditionally
@@ -398,6 +426,33 @@ inline zkc_vm_state main_vm_initial_state(Engine &e, const zkc_vm_closed_form &i
     const int rc = zkc_main_vm_initial_state(e.handle(), &io, &isa, &st);
     if (rc != ZKC_OK) throw Error("zkc_main_vm_initial_state", rc, zkc_status{rc, 0, -1, 0, 0});
     return st;
+}
+
+// the cells the add/sub, binop, mul/div and shift gadgets allocate on every cycle + the per-cycle relations (zkc_b200.h,
+// ZKC_VM_GADGET_COLUMNS), from a finished DENSE trace [ZKC_VM_NUM_COLS][limit] (host)
+inline std::vector<uint64_t> main_vm_gadget_cells(Engine &e, const std::vector<uint64_t> &trace, size_t limit) {
+    std::vector<uint64_t> out((size_t)ZKC_VMG_NUM_COLS * limit);
+    const int rc = zkc_main_vm_gadget_cells(e.handle(), trace.data(), limit, 1, 0, out.data());
+    if (rc != ZKC_OK) throw Error("zkc_main_vm_gadget_cells", rc, zkc_status{rc, 0, -1, 0, 0});
+    return out;
+}
+
+// constraint evaluation of finished traces (host buffers): violating rows; st describes the first one
+inline uint64_t ram_permutation_check_trace(Engine &e, const zkc_ram_closed_form &io, const std::vector<uint64_t> &trace, size_t limit,
+                                            uint32_t gates = 0, zkc_status *st = nullptr) {
+    uint64_t v = 0;
+    zkc_status local;
+    const int rc = zkc_ram_permutation_check_trace(e.handle(), &io, trace.data(), limit, nullptr, gates, 0, &v, st ? st : &local);
+    if (rc != ZKC_OK && rc != ZKC_ERR_UNSATISFIED) throw Error("zkc_ram_permutation_check_trace", rc, st ? *st : local);
+    return v;
+}
+inline uint64_t log_sorter_check_trace(Engine &e, const zkc_events_closed_form &io, const std::vector<uint64_t> &trace, size_t limit,
+                                       uint32_t gates = 0, zkc_status *st = nullptr) {
+    uint64_t v = 0;
+    zkc_status local;
+    const int rc = zkc_log_sorter_check_trace(e.handle(), &io, trace.data(), limit, gates, 0, &v, st ? st : &local);
+    if (rc != ZKC_OK && rc != ZKC_ERR_UNSATISFIED) throw Error("zkc_log_sorter_check_trace", rc, st ? *st : local);
+    return v;
 }
 
 }  // namespace zkc_b200

@@ -3,7 +3,7 @@
 // push the inputs into fresh queues, run the entry point, check the outcome.  TEST INFRASTRUCTURE: links oracle/liborc.so as
 // the checker.
 //   host_mirror_test nodevice   no GPU required: the engine must refuse to start (no CPU fallback) and say why
-//   host_mirror_test parity     on a GPU: ram_permutation, sort_decommittment_requests, demux_log_queue, code_unpacker_sha256
+//   host_mirror_test parity     on a GPU: ram_permutation, sort_decommittment_requests, demux_log_queue, code_unpacker_sha256, linear_hasher
 //                               bit-exact vs the oracle
 #include <algorithm>
 #include <cstdio>
@@ -188,6 +188,49 @@ static void demux_parity(Engine &e) {
                 counts[4], counts[5]);
 }
 
+static void linear_hasher_parity(Engine &e) {
+    const size_t n = 300, limit = 320;
+    uint64_t seed = 0x1A;
+    std::vector<zkc_log_query> recs(n);
+    for (size_t i = 0; i < n; i++) {
+        zkc_log_query &q = recs[i];
+        std::memset(&q, 0, sizeof q);
+        for (auto &l : q.address) l = (uint32_t)sm64(seed);
+        for (auto &l : q.key) l = (uint32_t)sm64(seed);
+        for (auto &l : q.written_value) l = (uint32_t)sm64(seed);
+        q.tx_number_in_block = (uint32_t)(sm64(seed) & 0xFFFF); q.timestamp = (uint32_t)i + 1;
+        q.flags = ZKC_LQ_FLAGS(2, 0, 1, 0, (uint32_t)(sm64(seed) & 1));
+    }
+    LinearHasherCircuitInstanceWitness w;
+    w.queue_witness = recs;
+    w.closed_form_input.start_flag = 1;
+    w.closed_form_input.queue_state = log_queue_simulate(e, recs, w.queue_prev_tails);
+    zkc_linear_hasher_closed_form io = w.closed_form_input;
+    std::vector<uint64_t> trace((size_t)ZKC_LH_NUM_COLS * limit), states(25 * limit);
+    uint64_t com[4];
+    zkc_status st;
+    const int rc = orc_linear_hasher_entry_point(&io, recs.data(), n, limit, nullptr, trace.data(), states.data(), com, &st);
+    CHECK(rc == ZKC_OK && io.completion_flag == 1);
+    // the digest is Keccak-256 of the concatenated serialisations
+    std::vector<uint8_t> stream(n * ZKC_LH_MESSAGE_BYTES);
+    for (size_t i = 0; i < n; i++) orc_log_query_into_bytes(&recs[i], stream.data() + i * ZKC_LH_MESSAGE_BYTES);
+    uint8_t digest[32];
+    orc_keccak256(stream.data(), stream.size(), digest);
+    for (int i = 0; i < 32; i++) CHECK(io.keccak256_hash[i] == digest[i]);
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass) {
+            w.keccak_states.resize(limit);
+            std::memcpy(w.keccak_states.front().data(), states.data(), states.size() * 8);
+        }
+        const auto got = linear_hasher_entry_point(e, w, limit);
+        CHECK(got.status.code == ZKC_OK);
+        CHECK(std::memcmp(com, got.commitment.data(), 32) == 0);
+        CHECK(std::memcmp(io.keccak256_hash, got.closed_form_input.keccak256_hash, sizeof io.keccak256_hash) == 0);
+        CHECK(std::memcmp(trace.data(), got.trace.data(), trace.size() * 8) == 0);
+    }
+    std::printf("linear_hasher: %zu messages, %zu cycles\n", n, limit);
+}
+
 static void code_unpacker_parity(Engine &e) {
     // three bytecodes of 5, 1 and 9 words; versioned hash = SHA-256 of the code with the top 4 bytes replaced (mod.rs:187-213)
     const size_t lens[3] = {5, 1, 9};
@@ -244,7 +287,8 @@ int main(int argc, char **argv) {
                             (void *)&sort_and_deduplicate_storage_access_entry_point,
                             (void *)&sort_and_deduplicate_code_decommittments_entry_point, (void *)&demultiplex_storage_logs_enty_point,
                             (void *)&unpack_code_into_memory_entry_point, (void *)&keccak256_round_function_entry_point, (void *)&sha256_round_function_entry_point,
-                            (void *)&main_vm_entry_point, (void *)&main_vm_initial_state};
+                            (void *)&main_vm_entry_point, (void *)&main_vm_initial_state, (void *)&linear_hasher_entry_point,
+                            (void *)&main_vm_gadget_cells, (void *)&ram_permutation_check_trace, (void *)&log_sorter_check_trace};
     std::printf("%zu entry points\n", sizeof instantiated / sizeof instantiated[0]);
     if (mode == "nodevice") {
         try {
@@ -261,6 +305,7 @@ int main(int argc, char **argv) {
     decommit_parity(e);
     demux_parity(e);
     code_unpacker_parity(e);
+    linear_hasher_parity(e);
     std::printf(failures ? "%d check(s) FAILED\n" : "all checks passed\n", failures);
     return failures ? 1 : 0;
 }
