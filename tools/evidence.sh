@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round-end evidence on one B200 (run under gpurun): full GPU test suite, smoke, bench (both arms), the ncu launch list of the
+# bench command, --set full captures of every kernel family, SASS excerpts.  Outputs under gpurun_out/<tag>_*.
+tag=${1:-r02_final}
+python -m pytest tests -m gpu -q --durations=8 > gpurun_out/${tag}_tests.log 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${tag}_bench_reference.log 2>&1
+python bench.py > gpurun_out/${tag}_bench.log 2> gpurun_out/${tag}_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches_bench.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${tag}_launches_bench.out 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'vm_cycles|vm_link|vm_sponge_kernel|vm_sponge_trace|vm_check|vm_gadgets|ram_rows|ram_inverse|ram_check|ev_rows|ev_check|rq_push|lh_rows|lh_chain' -c 24 -o gpurun_out/${tag}_ncu_full python tools/profile_all.py 18 > gpurun_out/${tag}_ncu_full.log 2>&1
+tail -3 gpurun_out/${tag}_tests.log; tail -2 gpurun_out/${tag}_smoke.log; tail -c 600 gpurun_out/${tag}_bench.log; tail -3 gpurun_out/${tag}_ncu_full.log
