@@ -234,12 +234,16 @@ class VmInputStream(C.Structure):
 class VmPackedTrace(C.Structure):
     _fields_ = [("cols8", C.c_void_p), ("cols16", C.c_void_p), ("cols32", C.c_void_p), ("cols64", C.c_void_p),
                 ("aux_records", C.c_void_p), ("aux_capacity", C.c_uint64), ("n_aux_records", C.c_uint64),
-                ("sponge_records", C.c_void_p), ("sponge_capacity", C.c_uint64), ("n_sponge_records", C.c_uint64)]
+                ("sponge_records", C.c_void_p), ("sponge_capacity", C.c_uint64), ("n_sponge_records", C.c_uint64),
+                ("limb_records", C.c_void_p), ("limb_capacity", C.c_uint64), ("n_limb_records", C.c_uint64)]
 
 
 VM_SEGMENT_MAGIC = 0x5a4b5347
 VM_TRACE_PACKED = 2
-VM_PK_U8, VM_PK_U16, VM_PK_U32, VM_PK_U64, VM_PK_AUX_RECORD, VM_PK_SPONGE_RECORD = range(6)
+VM_PK_U8, VM_PK_U16, VM_PK_U32, VM_PK_U64, VM_PK_AUX_RECORD, VM_PK_SPONGE_RECORD, VM_PK_LIMB_RECORD = range(7)
+VM_LIMB_CODE_WORD, VM_LIMB_SRC0_FROM_MEMORY, VM_LIMB_DST1 = range(3)
+VM_LIMB_RECORD_DTYPE = np.dtype([("row", "<u4"), ("kind", "<u4"), ("v", "<u4", (9,)), ("reserved", "<u4")])
+assert VM_LIMB_RECORD_DTYPE.itemsize == 48
 VM_AUX_RECORD_DTYPE = np.dtype([("row", "<u4"), ("reserved", "<u4"), ("op_aux", "<u8", (48,)), ("queue_ends", "<u8", (10,))])
 assert VM_AUX_RECORD_DTYPE.itemsize == 472 and C.sizeof(VmSegmentHeader) == 80
 VM_SPONGE_RECORD_DTYPE = np.dtype([("row", "<u4"), ("slot", "<u4"), ("out", "<u8", (12,))])

@@ -2289,7 +2289,8 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
     const size_t wt_stride = own_cols ? vm_round32(rows) : in.columns->witness_stride;
     zkc_vm_packed_trace *packed = in.packed;
     if (packed && (trace || (rows && (!packed->cols8 || !packed->cols16 || !packed->cols32 || !packed->cols64)) ||
-                   (packed->aux_capacity && !packed->aux_records) || (packed->sponge_capacity && !packed->sponge_records)))
+                   (packed->aux_capacity && !packed->aux_records) || (packed->sponge_capacity && !packed->sponge_records) ||
+                   (packed->limb_capacity && !packed->limb_records)))
         return ZKC_ERR_INVALID_ARGUMENT;
     const bool compact = packed || (options && options->trace_layout == ZKC_VM_TRACE_COMPACT && trace);
     if (!packed && options && options->trace_layout > ZKC_VM_TRACE_COMPACT) return ZKC_ERR_INVALID_ARGUMENT;
@@ -2317,16 +2318,17 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
     if (packed)
         bytes += zkc_carver::bytes(rows * VM_PK_N8, 1) + zkc_carver::bytes(rows * VM_PK_N16, 2) + zkc_carver::bytes(rows * VM_PK_N32, 4) +
                  zkc_carver::bytes(rows * VM_PK_N64, 8) + zkc_carver::bytes(n_chunks * chunk_cells + 1, sizeof(zkc_vm_aux_record)) +
-                 zkc_carver::bytes(n_chunks * chunk_cells * VM_JOB_SLOTS + 1, sizeof(zkc_vm_sponge_record)) + zkc_carver::bytes(2 * n_chunks, 8);
+                 zkc_carver::bytes(n_chunks * chunk_cells * VM_JOB_SLOTS + 1, sizeof(zkc_vm_sponge_record)) +
+                 zkc_carver::bytes(n_chunks * chunk_cells * 3 + 1, sizeof(zkc_vm_limb_record)) + zkc_carver::bytes(4 * n_chunks, 8);
     bytes += zkc_carver::bytes(n_instances * 4 * VM_FLAT_STRIDE, 8);
     bytes += zkc_carver::bytes(16 * n_chunks, 4) + zkc_carver::bytes(VM_JOB_SLOTS * rows, 4) + zkc_carver::bytes(rows * 2, 8) + zkc_carver::bytes(rows, 4) + zkc_carver::bytes(rows * VM_EXP_WORDS, 4) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS * 8, 8) + zkc_carver::bytes(rows * VM_JOB_SLOTS * 12, 8) +
              zkc_carver::bytes(rows * VM_JOB_SLOTS, 4) + zkc_carver::bytes(n_chunks + 32, 8) + 4096;  // + slack: the slot arrays are carved in two parts
     void *blk = ctx->scratch(bytes);
     const size_t h_counts_off = (n_instances * sizeof(VmDev) + 63) & ~(size_t)63;
-    VmDev *h = (VmDev *)ctx->pinned(h_counts_off + 16 * n_chunks + 64);
+    VmDev *h = (VmDev *)ctx->pinned(h_counts_off + 32 * n_chunks + 64);
     if (!blk || !h) { status->code = ZKC_ERR_CUDA; status->cuda_error = (int)cudaErrorMemoryAllocation; return ZKC_ERR_CUDA; }
-    unsigned long long *h_counts = (unsigned long long *)((char *)h + h_counts_off);  // [n_chunks][2]: aux, sponge records of a chunk
+    unsigned long long *h_counts = (unsigned long long *)((char *)h + h_counts_off);  // [n_chunks][4]: aux, sponge, limb records of a chunk
     zkc_carver cv(blk);
     VmDev *d = cv.take<VmDev>(n_instances);
     zkc_vm_isa *disa = cv.take<zkc_vm_isa>(1);
@@ -2408,16 +2410,17 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
     // PACKED: typed column blocks + per-chunk record regions (worst-case capacity: nothing is dropped on the device)
     VmPackOut po{};
     zkc_vm_sponge_record *sp_regions = nullptr;
-    unsigned long long *rec_counts = nullptr;  // [n_chunks][2]
+    unsigned long long *rec_counts = nullptr;  // [n_chunks][4]: aux, sponge, limb, -
     if (packed) {
         po.c8 = cv.take<uint8_t>(rows * VM_PK_N8); po.c16 = cv.take<uint16_t>(rows * VM_PK_N16);
         po.c32 = cv.take<uint32_t>(rows * VM_PK_N32); po.c64 = cv.take<uint64_t>(rows * VM_PK_N64);
         po.rows = rows;
         po.aux = cv.take<zkc_vm_aux_record>(n_chunks * chunk_cells + 1);
         sp_regions = cv.take<zkc_vm_sponge_record>(n_chunks * chunk_cells * VM_JOB_SLOTS + 1);
-        rec_counts = cv.take<unsigned long long>(2 * n_chunks);
-        ZKC_CUDA(ctx, status, cudaMemsetAsync(rec_counts, 0, 16 * n_chunks, s));
-        packed->n_aux_records = 0; packed->n_sponge_records = 0;
+        po.limb = cv.take<zkc_vm_limb_record>(n_chunks * chunk_cells * 3 + 1);
+        rec_counts = cv.take<unsigned long long>(4 * n_chunks);
+        ZKC_CUDA(ctx, status, cudaMemsetAsync(rec_counts, 0, 32 * n_chunks, s));
+        packed->n_aux_records = 0; packed->n_sponge_records = 0; packed->n_limb_records = 0;
     }
     // Side stream: the start state (4 dependent permutations) and the closed-form commitments from the host's final
     // snapshot (31 dependent permutations) run beside the cycle launches; the FINAL pass below takes them when every link
@@ -2456,17 +2459,20 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
     if (!have_stream || !limit) { const int rc = launch_hint(!have_rows && limit); if (rc) return rc; }
     // PACKED: the records of a chunk go home two chunks later, when their count is known, without stalling the queue
     std::vector<cudaEvent_t> count_events(n_chunks, nullptr);
-    size_t next_records = 0, aux_home = 0, sp_home = 0;
+    size_t next_records = 0, aux_home = 0, sp_home = 0, limb_home = 0;
     auto send_records_home = [&](size_t c) -> int {
         ZKC_CUDA(ctx, status, cudaEventSynchronize(count_events[c]));
-        const unsigned long long na = h_counts[2 * c], nsp = h_counts[2 * c + 1];
+        const unsigned long long na = h_counts[4 * c], nsp = h_counts[4 * c + 1], nl = h_counts[4 * c + 2];
         const size_t ca = aux_home < packed->aux_capacity ? std::min<size_t>(na, packed->aux_capacity - aux_home) : 0;
         const size_t cs = sp_home < packed->sponge_capacity ? std::min<size_t>(nsp, packed->sponge_capacity - sp_home) : 0;
         if (ca) ZKC_CUDA(ctx, status, cudaMemcpyAsync(packed->aux_records + aux_home, po.aux + c * chunk_cells, ca * sizeof(zkc_vm_aux_record), cudaMemcpyDeviceToHost, s_out));
         if (cs) ZKC_CUDA(ctx, status, cudaMemcpyAsync(packed->sponge_records + sp_home, sp_regions + c * chunk_cells * VM_JOB_SLOTS, cs * sizeof(zkc_vm_sponge_record),
                                                       cudaMemcpyDeviceToHost, s_out));
-        aux_home += na; sp_home += nsp;
-        packed->n_aux_records += na; packed->n_sponge_records += nsp;
+        const size_t cl = limb_home < packed->limb_capacity ? std::min<size_t>(nl, packed->limb_capacity - limb_home) : 0;
+        if (cl) ZKC_CUDA(ctx, status, cudaMemcpyAsync(packed->limb_records + limb_home, po.limb + c * chunk_cells * 3, cl * sizeof(zkc_vm_limb_record),
+                                                      cudaMemcpyDeviceToHost, s_out));
+        aux_home += na; sp_home += nsp; limb_home += nl;
+        packed->n_aux_records += na; packed->n_sponge_records += nsp; packed->n_limb_records += nl;
         return ZKC_OK;
     };
     size_t blob_off = 0;
@@ -2538,7 +2544,7 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
         ps.lists = lists + n_instances * r0;
         if (packed) {
             ps.records = sp_regions + c * chunk_cells * VM_JOB_SLOTS;
-            ps.n_records = rec_counts + 2 * c + 1;
+            ps.n_records = rec_counts + 4 * c + 1;
             ps.records_capacity = chunk_cells * VM_JOB_SLOTS;
         }
         if (use_tma)
@@ -2565,9 +2571,10 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
             ZKC_LAUNCH(ctx, "vm_sponge_trace", vm_sponge_trace_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, ps, dtrace, limit, n_instances, r0, cnt);
         if (packed) {
             VmPackOut pc = po;
-            pc.aux = po.aux + c * chunk_cells; pc.n_aux = rec_counts + 2 * c; pc.aux_cap = chunk_cells;
+            pc.aux = po.aux + c * chunk_cells; pc.n_aux = rec_counts + 4 * c; pc.aux_cap = chunk_cells;
+            pc.limb = po.limb + c * chunk_cells * 3; pc.n_limb = rec_counts + 4 * c + 2;
             ZKC_LAUNCH(ctx, "vm_pack", vm_pack_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, dtrace, limit, n_instances, r0, cnt, pc);
-            ZKC_CUDA(ctx, status, cudaMemcpyAsync(h_counts + 2 * c, rec_counts + 2 * c, 16, cudaMemcpyDeviceToHost, s));
+            ZKC_CUDA(ctx, status, cudaMemcpyAsync(h_counts + 4 * c, rec_counts + 4 * c, 32, cudaMemcpyDeviceToHost, s));
             count_events[c] = event();
             ZKC_CUDA(ctx, status, cudaEventRecord(count_events[c], s));
             if (piped) ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_out, count_events[c], 0));

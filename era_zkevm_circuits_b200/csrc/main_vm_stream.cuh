@@ -11,12 +11,15 @@ namespace zkc {
 struct VmPkTable {
     uint8_t kind[ZKC_VM_NUM_COLS];
     uint16_t slot[ZKC_VM_NUM_COLS];
-    uint32_t counts[6];
+    uint32_t counts[7];
 };
 __host__ __device__ constexpr int vm_pk_kind_of(int c) {
     if (c >= ZKC_VM_OP_AUX) return ZKC_VM_PK_AUX_RECORD;
     if (c >= ZKC_VM_SPONGE_ENFORCE) return ZKC_VM_PK_SPONGE_RECORD;
     if (c >= ZKC_VM_FORWARD_TAIL_OUT) return ZKC_VM_PK_AUX_RECORD;  // forward tail (4 + length), rollback head (4 + length)
+    if ((c >= ZKC_VM_CODE_WORD && c < ZKC_VM_CODE_WORD + 8) || (c >= ZKC_VM_SRC0_FROM_MEMORY && c < ZKC_VM_SRC0_FROM_MEMORY + 9) ||
+        (c >= ZKC_VM_DST1 && c < ZKC_VM_DST1 + 9))
+        return ZKC_VM_PK_LIMB_RECORD;
     if (c == ZKC_VM_PROPS) return ZKC_VM_PK_U64;
     if (c == ZKC_VM_SUPER_PC || c == ZKC_VM_VARIANT || c == ZKC_VM_IMM0 || c == ZKC_VM_IMM1 || c == ZKC_VM_SRC0_INDEX ||
         c == ZKC_VM_SP_AFTER_SRC0 || c == ZKC_VM_DST0_INDEX || c == ZKC_VM_NEW_SP || c == ZKC_VM_PC_OUT)
@@ -34,19 +37,25 @@ __host__ __device__ constexpr VmPkTable vm_pk_make() {
     for (int c = 0; c < ZKC_VM_NUM_COLS; c++) {
         const int k = vm_pk_kind_of(c);
         t.kind[c] = (uint8_t)k;
-        t.slot[c] = (uint16_t)t.counts[k]++;
+        if (k == ZKC_VM_PK_LIMB_RECORD) {  // slot = 9 * record kind + index in v[]
+            t.slot[c] = (uint16_t)(c >= ZKC_VM_DST1 ? 9 * ZKC_VM_LIMB_DST1 + (c - ZKC_VM_DST1)
+                                   : (c >= ZKC_VM_SRC0_FROM_MEMORY ? 9 * ZKC_VM_LIMB_SRC0_FROM_MEMORY + (c - ZKC_VM_SRC0_FROM_MEMORY) : c - ZKC_VM_CODE_WORD));
+            t.counts[k]++;
+        } else t.slot[c] = (uint16_t)t.counts[k]++;
     }
     return t;
 }
 constexpr VmPkTable VM_PK = vm_pk_make();
 constexpr int VM_PK_N8 = (int)VM_PK.counts[0], VM_PK_N16 = (int)VM_PK.counts[1], VM_PK_N32 = (int)VM_PK.counts[2], VM_PK_N64 = (int)VM_PK.counts[3];
-static_assert(VM_PK.counts[ZKC_VM_PK_AUX_RECORD] == 58 && VM_PK.counts[ZKC_VM_PK_SPONGE_RECORD] == 117, "record columns");
+static_assert(VM_PK.counts[ZKC_VM_PK_AUX_RECORD] == 58 && VM_PK.counts[ZKC_VM_PK_SPONGE_RECORD] == 117 && VM_PK.counts[ZKC_VM_PK_LIMB_RECORD] == 26, "record columns");
+static_assert(sizeof(zkc_vm_limb_record) == 48, "limb record layout");
 static_assert(sizeof(zkc_vm_aux_record) == 8 + 58 * 8, "aux record layout");
 
 struct VmPackOut {
     uint8_t *c8; uint16_t *c16; uint32_t *c32; uint64_t *c64;
     size_t rows;  // column pitch of the four blocks (n_instances * limit)
     zkc_vm_aux_record *aux; unsigned long long *n_aux; unsigned long long aux_cap;
+    zkc_vm_limb_record *limb; unsigned long long *n_limb;  // capacity: 3 per row of the chunk (nothing is dropped on the device)
 };
 
 template <int C, int END>
@@ -92,20 +101,52 @@ vm_pack_kernel(const uint64_t *__restrict__ dense, size_t limit, size_t n_inst, 
         emit = (any | moved) != 0;
     }
     const unsigned b = __ballot_sync(0xffffffffu, emit);
-    if (!b) return;
-    const int leader = __ffs(b) - 1;
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(o.n_aux, (unsigned long long)__popc(b));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (emit) {
-        const unsigned long long pos = base + __popc(b & ((1u << lane) - 1));
-        if (pos < o.aux_cap) {
-            zkc_vm_aux_record &r = o.aux[pos];
-            r.row = (uint32_t)g; r.reserved = 0;
-            for (int i = 0; i < ZKC_VM_OP_AUX_COLS; i++) r.op_aux[i] = __ldg(t + (size_t)(ZKC_VM_COMPACT_OP_AUX + i) * limit);
-            for (int i = 0; i < 10; i++) r.queue_ends[i] = __ldg(t + (size_t)(ZKC_VM_FORWARD_TAIL_OUT + i) * limit);
+    if (b) {
+        const int leader = __ffs(b) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(o.n_aux, (unsigned long long)__popc(b));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (emit) {
+            const unsigned long long pos = base + __popc(b & ((1u << lane) - 1));
+            if (pos < o.aux_cap) {
+                zkc_vm_aux_record &r = o.aux[pos];
+                r.row = (uint32_t)g; r.reserved = 0;
+                for (int i = 0; i < ZKC_VM_OP_AUX_COLS; i++) r.op_aux[i] = __ldg(t + (size_t)(ZKC_VM_COMPACT_OP_AUX + i) * limit);
+                for (int i = 0; i < 10; i++) r.queue_ends[i] = __ldg(t + (size_t)(ZKC_VM_FORWARD_TAIL_OUT + i) * limit);
+            }
         }
     }
+    // ---- limb records: code word (on an opcode fetch / row 0), src0 memory operand, dst1 (when not zero) -------------------
+    uint32_t cw[9], sm[9], d1[9];
+    bool e_cw = false, e_sm = false, e_d1 = false;
+    if (valid) {
+        const size_t row = g % limit;
+        uint32_t any_sm = 0, any_d1 = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            cw[i] = i < 8 ? (uint32_t)__ldg(t + (size_t)(ZKC_VM_CODE_WORD + i) * limit) : 0u;
+            sm[i] = (uint32_t)__ldg(t + (size_t)(ZKC_VM_SRC0_FROM_MEMORY + i) * limit); any_sm |= sm[i];
+            d1[i] = (uint32_t)__ldg(t + (size_t)(ZKC_VM_DST1 + i) * limit); any_d1 |= d1[i];
+        }
+        e_cw = row == 0 || __ldg(t + (size_t)ZKC_VM_SHOULD_READ_OPCODE * limit) != 0;
+        e_sm = any_sm != 0; e_d1 = any_d1 != 0;
+    }
+    const unsigned b0 = __ballot_sync(0xffffffffu, e_cw), b1 = __ballot_sync(0xffffffffu, e_sm), b2 = __ballot_sync(0xffffffffu, e_d1);
+    const unsigned total = __popc(b0) + __popc(b1) + __popc(b2);
+    if (!total) return;
+    unsigned long long lbase = 0;
+    if (lane == 0) lbase = atomicAdd(o.n_limb, (unsigned long long)total);
+    lbase = __shfl_sync(0xffffffffu, lbase, 0);
+    const unsigned below = (1u << lane) - 1;
+    auto put = [&](unsigned long long pos, uint32_t kind, const uint32_t (&v)[9]) {
+        zkc_vm_limb_record &r = o.limb[pos];
+        r.row = (uint32_t)g; r.kind = kind; r.reserved = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) r.v[i] = v[i];
+    };
+    if (e_cw) put(lbase + __popc(b0 & below), ZKC_VM_LIMB_CODE_WORD, cw);
+    if (e_sm) put(lbase + __popc(b0) + __popc(b1 & below), ZKC_VM_LIMB_SRC0_FROM_MEMORY, sm);
+    if (e_d1) put(lbase + __popc(b0) + __popc(b1) + __popc(b2 & below), ZKC_VM_LIMB_DST1, d1);
 }
 
 // ---- expansion of a segment blob into the columns ---------------------------------------------------------------------------------
@@ -304,7 +345,7 @@ extern "C" void zkc_vm_input_stream_free(zkc_vm_input_stream *stream) {
     delete o;
 }
 
-extern "C" void zkc_vm_packed_layout(uint8_t kind[ZKC_VM_NUM_COLS], uint16_t slot[ZKC_VM_NUM_COLS], uint32_t counts[6]) {
+extern "C" void zkc_vm_packed_layout(uint8_t kind[ZKC_VM_NUM_COLS], uint16_t slot[ZKC_VM_NUM_COLS], uint32_t counts[7]) {
     for (int c = 0; c < ZKC_VM_NUM_COLS; c++) { kind[c] = zkc::VM_PK.kind[c]; slot[c] = zkc::VM_PK.slot[c]; }
-    for (int k = 0; k < 6; k++) counts[k] = zkc::VM_PK.counts[k];
+    for (int k = 0; k < 7; k++) counts[k] = zkc::VM_PK.counts[k];
 }

@@ -284,7 +284,7 @@ def vm_packed_layout(lib):
     """(kind [276], slot [276], counts [6]) of the PACKED trace"""
     global _PK_LAYOUT
     if _PK_LAYOUT is None:
-        kind, slot, counts = np.zeros(abi.VM_COLS["NUM_COLS"], np.uint8), np.zeros(abi.VM_COLS["NUM_COLS"], np.uint16), np.zeros(6, np.uint32)
+        kind, slot, counts = np.zeros(abi.VM_COLS["NUM_COLS"], np.uint8), np.zeros(abi.VM_COLS["NUM_COLS"], np.uint16), np.zeros(7, np.uint32)
         lib.zkc_vm_packed_layout(ptr(kind), ptr(slot), ptr(counts))
         _PK_LAYOUT = (kind, slot, counts)
     return _PK_LAYOUT
@@ -299,23 +299,27 @@ class VmPackedTraceBuffers:
     cols64: np.ndarray
     aux_records: np.ndarray
     sponge_records: np.ndarray
+    limb_records: np.ndarray
     n_aux_records: int = 0
     n_sponge_records: int = 0
+    n_limb_records: int = 0
 
     @property
     def nbytes_used(self):
         return (self.cols8.nbytes + self.cols16.nbytes + self.cols32.nbytes + self.cols64.nbytes +
-                self.n_aux_records * abi.VM_AUX_RECORD_DTYPE.itemsize + self.n_sponge_records * abi.VM_SPONGE_RECORD_DTYPE.itemsize)
+                self.n_aux_records * abi.VM_AUX_RECORD_DTYPE.itemsize + self.n_sponge_records * abi.VM_SPONGE_RECORD_DTYPE.itemsize +
+                self.n_limb_records * abi.VM_LIMB_RECORD_DTYPE.itemsize)
 
 
-def vm_packed_trace_buffers(engine: Engine, n: int, limit: int, aux_fraction=0.3, sponge_per_cycle=1.5, alloc=None) -> VmPackedTraceBuffers:
+def vm_packed_trace_buffers(engine: Engine, n: int, limit: int, aux_fraction=0.3, sponge_per_cycle=1.5, limb_per_cycle=1.0, alloc=None) -> VmPackedTraceBuffers:
     """alloc(shape, dtype) -> array (default numpy.zeros; pass a pinned allocator for asynchronous copies)"""
     kind, slot, counts = vm_packed_layout(engine.lib)
     rows = n * limit
     alloc = alloc or (lambda shape, dt: np.zeros(shape, dtype=dt))
     return VmPackedTraceBuffers(alloc((int(counts[0]), rows), np.uint8), alloc((int(counts[1]), rows), np.uint16), alloc((int(counts[2]), rows), np.uint32),
                                 alloc((int(counts[3]), rows), np.uint64), alloc((int(rows * aux_fraction) + 64,), abi.VM_AUX_RECORD_DTYPE),
-                                alloc((int(rows * sponge_per_cycle) + 64,), abi.VM_SPONGE_RECORD_DTYPE))
+                                alloc((int(rows * sponge_per_cycle) + 64,), abi.VM_SPONGE_RECORD_DTYPE),
+                                alloc((int(rows * limb_per_cycle) + 64 + n,), abi.VM_LIMB_RECORD_DTYPE))
 
 
 def main_vm_entry_point_stream(engine: Engine, closed_form_inputs, isa: abi.VmIsa, streams, limit: int, callstack_witness=None,
@@ -334,7 +338,8 @@ def main_vm_entry_point_stream(engine: Engine, closed_form_inputs, isa: abi.VmIs
     if out is not None:
         opts.trace_layout = abi.VM_TRACE_PACKED
         pk = abi.VmPackedTrace(out.cols8.ctypes.data, out.cols16.ctypes.data, out.cols32.ctypes.data, out.cols64.ctypes.data,
-                               out.aux_records.ctypes.data, len(out.aux_records), 0, out.sponge_records.ctypes.data, len(out.sponge_records), 0)
+                               out.aux_records.ctypes.data, len(out.aux_records), 0, out.sponge_records.ctypes.data, len(out.sponge_records), 0,
+                               out.limb_records.ctypes.data, len(out.limb_records), 0)
     n_cw = _n_cw(callstack_witness)
     assert not n_cw or not on_device(callstack_witness)
     rc = engine.lib.zkc_main_vm_entry_point_stream(engine.h, C.cast(ios, C.c_void_p), n, C.byref(isa), C.cast(sp, C.c_void_p),
@@ -343,7 +348,7 @@ def main_vm_entry_point_stream(engine: Engine, closed_form_inputs, isa: abi.VmIs
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
         raise ZkcError(rc, statuses[0], "main_vm_entry_point_stream")
     if out is not None:
-        out.n_aux_records, out.n_sponge_records = int(pk.n_aux_records), int(pk.n_sponge_records)
+        out.n_aux_records, out.n_sponge_records, out.n_limb_records = int(pk.n_aux_records), int(pk.n_sponge_records), int(pk.n_limb_records)
     return commitments, ios, statuses, rc
 
 
@@ -357,13 +362,29 @@ def vm_expand_packed_trace(lib, out: VmPackedTraceBuffers, n: int, limit: int) -
     for c in range(K["NUM_COLS"]):
         if int(kind[c]) in blocks:
             dense[:, c, :] = blocks[int(kind[c])][int(slot[c])].reshape(n, limit)
-    assert out.n_aux_records <= len(out.aux_records) and out.n_sponge_records <= len(out.sponge_records), "record capacity exceeded"
+    assert out.n_aux_records <= len(out.aux_records) and out.n_sponge_records <= len(out.sponge_records) and \
+        out.n_limb_records <= len(out.limb_records), "record capacity exceeded"
     rec = out.sponge_records[:out.n_sponge_records]
     r, s_ = rec["row"].astype(np.int64), rec["slot"].astype(np.int64)
     flat = dense.transpose(1, 0, 2).reshape(K["NUM_COLS"], rows)  # [col, g] view
     flat[K["SPONGE_ENFORCE"] + s_, r] = 1
     for j in range(12):
         flat[K["SPONGE_FINAL"] + 12 * s_ + j, r] = rec["out"][:, j]
+    # limb records: src0 memory operand / dst1 (zeros elsewhere), code word (held until the next record of its instance)
+    limb = out.limb_records[:out.n_limb_records]
+    lrow, lkind = limb["row"].astype(np.int64), limb["kind"]
+    for k_, base, width in ((abi.VM_LIMB_SRC0_FROM_MEMORY, K["SRC0_FROM_MEMORY"], 9), (abi.VM_LIMB_DST1, K["DST1"], 9)):
+        sel = lkind == k_
+        flat[base:base + width, lrow[sel]] = limb["v"][sel][:, :width].T
+    if rows:
+        sel = lkind == abi.VM_LIMB_CODE_WORD
+        cw_rows, cw_vals = lrow[sel], limb["v"][sel][:, :8]
+        order = np.argsort(cw_rows, kind="stable")
+        cw_rows, cw_vals = cw_rows[order], cw_vals[order]
+        has = np.zeros(rows, dtype=np.int64)
+        has[cw_rows] = np.arange(1, len(cw_rows) + 1)
+        assert (has[::limit] > 0).all(), "row 0 of an instance without a code-word record"
+        flat[K["CODE_WORD"]:K["CODE_WORD"] + 8, :] = cw_vals[np.maximum.accumulate(has) - 1].T
     aux = out.aux_records[:out.n_aux_records]
     aux = aux[np.argsort(aux["row"], kind="stable")]
     ar = aux["row"].astype(np.int64)

@@ -1395,7 +1395,20 @@ void zkc_vm_input_stream_free(zkc_vm_input_stream *stream);
  * particular order; the counts are written to n_aux_records / n_sponge_records (records beyond a capacity are dropped, the
  * count still says how many there were). */
 #define ZKC_VM_TRACE_PACKED 2
-enum zkc_vm_packed_kind { ZKC_VM_PK_U8 = 0, ZKC_VM_PK_U16, ZKC_VM_PK_U32, ZKC_VM_PK_U64, ZKC_VM_PK_AUX_RECORD, ZKC_VM_PK_SPONGE_RECORD };
+enum zkc_vm_packed_kind { ZKC_VM_PK_U8 = 0, ZKC_VM_PK_U16, ZKC_VM_PK_U32, ZKC_VM_PK_U64, ZKC_VM_PK_AUX_RECORD, ZKC_VM_PK_SPONGE_RECORD,
+                          ZKC_VM_PK_LIMB_RECORD };
+/* Three 9-column groups of u32 limbs that are constant or zero on most rows travel as one zkc_vm_limb_record per row that
+ * changes them: the code word (rows without a record carry the code word of the row before; a row that fetches its opcode and
+ * row 0 of an instance always have one), the src0 memory operand and dst1 (rows without a record hold zeros). */
+#define ZKC_VM_LIMB_CODE_WORD 0        /* v[0..8) = ZKC_VM_CODE_WORD .. + 7, v[8] = 0 */
+#define ZKC_VM_LIMB_SRC0_FROM_MEMORY 1 /* v[0..9) = ZKC_VM_SRC0_FROM_MEMORY .. + 8 (is_pointer, 8 limbs) */
+#define ZKC_VM_LIMB_DST1 2             /* v[0..9) = ZKC_VM_DST1 .. + 8 */
+typedef struct zkc_vm_limb_record {
+    uint32_t row;  /* instance * limit + cycle */
+    uint32_t kind; /* ZKC_VM_LIMB_* */
+    uint32_t v[9];
+    uint32_t reserved;
+} zkc_vm_limb_record;
 typedef struct zkc_vm_aux_record {
     uint32_t row;      /* instance * limit + cycle */
     uint32_t reserved;
@@ -1411,9 +1424,12 @@ typedef struct zkc_vm_packed_trace {
     uint64_t aux_capacity, n_aux_records;        /* in, out */
     zkc_vm_sponge_record *sponge_records;
     uint64_t sponge_capacity, n_sponge_records;  /* in, out */
+    zkc_vm_limb_record *limb_records;
+    uint64_t limb_capacity, n_limb_records;      /* in, out */
 } zkc_vm_packed_trace;
-/* kind[c], slot[c] for c < ZKC_VM_NUM_COLS; counts[k] = columns of kind k (k < 4: the heights of the four type blocks) */
-void zkc_vm_packed_layout(uint8_t kind[ZKC_VM_NUM_COLS], uint16_t slot[ZKC_VM_NUM_COLS], uint32_t counts[6]);
+/* kind[c], slot[c] for c < ZKC_VM_NUM_COLS; counts[k] = columns of kind k (k < 4: the heights of the four type blocks; a
+ * LIMB_RECORD column's slot = 9 * ZKC_VM_LIMB_* kind + its index in v[]) */
+void zkc_vm_packed_layout(uint8_t kind[ZKC_VM_NUM_COLS], uint16_t slot[ZKC_VM_NUM_COLS], uint32_t counts[7]);
 
 /* main_vm_entry_point (main_vm/mod.rs:47-232) over host buffers in the stream forms: streams[n_instances] (equal limit and
  * segment_cycles), callstack_witness [n_instances][n_callstack_witness] host records, `out` (may be NULL: no witness

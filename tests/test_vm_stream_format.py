@@ -58,8 +58,10 @@ def test_packed_layout_covers_every_column():
     assert int(counts.sum()) == K["NUM_COLS"] and counts[abi.VM_PK_SPONGE_RECORD] == 117 and counts[abi.VM_PK_AUX_RECORD] == 58
     for k in range(6):
         assert sorted(slot[kind == k].tolist()) == list(range(int(counts[k])))
-    assert kind[K["PROPS"]] == abi.VM_PK_U64 and kind[K["CODE_WORD"]] == abi.VM_PK_U32 and kind[K["IMM0"]] == abi.VM_PK_U16
+    assert counts[abi.VM_PK_LIMB_RECORD] == 26 and kind[K["CODE_WORD"] + 7] == kind[K["SRC0_FROM_MEMORY"]] == kind[K["DST1"] + 8] == abi.VM_PK_LIMB_RECORD
+    assert slot[K["CODE_WORD"] + 3] == 3 and slot[K["SRC0_FROM_MEMORY"] + 2] == 9 + 2 and slot[K["DST1"]] == 18
+    assert kind[K["PROPS"]] == abi.VM_PK_U64 and kind[K["OPCODE"]] == abi.VM_PK_U32 and kind[K["IMM0"]] == abi.VM_PK_U16
     assert kind[K["CONDITION"]] == abi.VM_PK_U8 and kind[K["OP_AUX"] + 47] == abi.VM_PK_AUX_RECORD
     assert all(kind[K["FORWARD_TAIL_OUT"] + i] == abi.VM_PK_AUX_RECORD for i in range(10))
     # bytes per cycle of the four typed blocks
-    assert int(counts[0]) + 2 * int(counts[1]) + 4 * int(counts[2]) + 8 * int(counts[3]) < 320
+    assert int(counts[0]) + 2 * int(counts[1]) + 4 * int(counts[2]) + 8 * int(counts[3]) < 220
