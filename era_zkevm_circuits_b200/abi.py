@@ -475,6 +475,7 @@ SIGNATURES = {
     "zkc_commit_encoding": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_int]),
     "zkc_field_ops": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "zkc_accumulate_grand_products": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "zkc_check_trace_columns": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_int, _u64p, C.POINTER(C.c_uint32), C.POINTER(Status)]),
     "zkc_scale_accumulators": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, C.c_int]),
     "zkc_memory_queue_simulate": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, C.c_int]),
     "zkc_log_queue_simulate": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, C.c_int]),

@@ -275,6 +275,90 @@ extern "C" int zkc_scale_accumulators(zkc_ctx *ctx, uint64_t *acc, size_t n_cols
     return ZKC_OK;
 }
 
+namespace zkc {
+struct ColCheckDev { unsigned long long violations, first_bad; uint32_t failed_checks, pad; };
+// the allocation checks of a whole trace: thread = R consecutive rows (R = 2: one 128-bit load per column), loop over the
+// columns with the class table in shared memory, 8 independent loads in flight per iteration; a pure HBM stream
+template <int R>
+__global__ void __launch_bounds__(256)
+check_columns_kernel(ColCheckDev *out, const uint64_t *__restrict__ trace, size_t n_cols, size_t rows, const uint8_t *__restrict__ col_class) {
+    extern __shared__ uint8_t cls[];
+    for (size_t c = threadIdx.x; c < n_cols; c += blockDim.x) cls[c] = col_class[c];
+    __syncthreads();
+    const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * R;
+    if (row >= rows) return;
+    uint32_t bad[R];
+    unsigned long long where[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) { bad[r] = 0; where[r] = ~0ull; }
+    constexpr uint64_t BOUND[ZKC_COL_NUM_CLASSES] = {GL_P, 2ull, 1ull << 8, 1ull << 16, 1ull << 32};
+    const uint64_t *t = trace + row;
+#pragma unroll 8
+    for (size_t c = 0; c < n_cols; c++) {
+        uint64_t v[R];
+        if constexpr (R == 2) { const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2 *>(t + c * rows)); v[0] = q.x; v[1] = q.y; }
+        else v[0] = __ldg(t + c * rows);
+        const uint32_t k = cls[c] < ZKC_COL_NUM_CLASSES ? cls[c] : 0u;
+        const uint64_t bound = k == 0 ? BOUND[0] : (k == 1 ? BOUND[1] : (k == 2 ? BOUND[2] : (k == 3 ? BOUND[3] : BOUND[4])));
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (v[r] >= bound) { bad[r] |= 1u << k; if (where[r] == ~0ull) where[r] = c; }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+        if (bad[r] && row + r < rows) {
+            atomicAdd(&out->violations, 1ull);
+            atomicOr(&out->failed_checks, bad[r]);
+            atomicMin(&out->first_bad, ((unsigned long long)(row + r) << 20) | (where[r] & 0xFFFFFull));
+        }
+}
+}  // namespace zkc
+
+extern "C" int zkc_check_trace_columns(zkc_ctx *ctx, const uint64_t *trace, size_t n_cols, size_t rows, const uint8_t *col_class, int on_device,
+                                       uint64_t *violations, uint32_t *first_bad_column, zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !violations || !col_class || n_cols > 40000 || ((n_cols * rows) && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    *violations = 0;
+    if (first_bad_column) *first_bad_column = 0;
+    if (!rows || !n_cols) return ZKC_OK;
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(ColCheckDev)) + zkc_carver::bytes(n_cols, 1);
+    if (!on_device) bytes += zkc_carver::bytes(n_cols * rows, 8);
+    void *blk = ctx->scratch(bytes);
+    ColCheckDev *h = (ColCheckDev *)ctx->pinned(sizeof(ColCheckDev));
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    ColCheckDev *d = cv.take<ColCheckDev>(1);
+    uint8_t *dcls = cv.take<uint8_t>(n_cols);
+    cudaStream_t s = ctx->stream;
+    h->violations = 0; h->first_bad = ~0ull; h->failed_checks = 0; h->pad = 0;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof *h, cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(dcls, col_class, n_cols, cudaMemcpyHostToDevice, s));  // the class table is always host data
+    const uint64_t *dt = trace;
+    if (!on_device) {
+        uint64_t *b = cv.take<uint64_t>(n_cols * rows);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, n_cols * rows * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    if (rows % 2 == 0 && (reinterpret_cast<uintptr_t>(dt) & 15) == 0)
+        ZKC_LAUNCH(ctx, "check_columns", check_columns_kernel<2>, (unsigned)((rows / 2 + 255) / 256), 256, n_cols, d, dt, n_cols, rows, dcls);
+    else
+        ZKC_LAUNCH(ctx, "check_columns", check_columns_kernel<1>, (unsigned)((rows + 255) / 256), 256, n_cols, d, dt, n_cols, rows, dcls);
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof *h, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = h->violations;
+    status->failed_checks = h->failed_checks;
+    if (h->violations) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 20);
+        if (first_bad_column) *first_bad_column = (uint32_t)(h->first_bad & 0xFFFFFull);
+    }
+    return status->code;
+}
+
 extern "C" int zkc_accumulate_grand_products(zkc_ctx *ctx, const uint64_t *lhs_enc, const uint64_t *rhs_enc,
                                              const uint8_t *should_acc, size_t enc_len, size_t rows,
                                              const uint64_t *challenges, const uint64_t acc_in[4], uint64_t *acc_out,

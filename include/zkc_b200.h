@@ -1528,6 +1528,17 @@ int zkc_main_vm_simulate(zkc_ctx *ctx, const zkc_vm_isa *isa, const zkc_vm_state
                          size_t callstack_capacity, uint32_t *n_callstack_out, uint64_t *rollback_tails_out,
                          zkc_status *status);
 
+/* ---- generic allocation-check evaluator -----------------------------------------------------------------------------------
+ * Every variable the reference allocates carries the range relation of its gadget type (Boolean::allocate -> x (x - 1) = 0,
+ * UInt8 / UInt16 / UInt32::allocate_checked -> range-check lookups, Num -> a canonical field element).  This evaluator streams
+ * ANY finished column-major trace [n_cols][rows] once (row pairs, 128-bit loads) and re-evaluates those relations from a
+ * per-column class table; the circuits' row-local arithmetic relations have their own evaluators (zkc_ram_permutation_check_trace,
+ * zkc_log_sorter_check_trace, zkc_main_vm_check_trace).  Returns the number of violating rows; status->first_bad_row and
+ * status->failed_checks (bit k: a cell of class k is out of range) describe the first one; first_bad_column (may be NULL). */
+enum zkc_col_class { ZKC_COL_FIELD = 0, ZKC_COL_BOOLEAN, ZKC_COL_U8, ZKC_COL_U16, ZKC_COL_U32, ZKC_COL_NUM_CLASSES };
+int zkc_check_trace_columns(zkc_ctx *ctx, const uint64_t *trace, size_t n_cols, size_t rows, const uint8_t *col_class, int on_device,
+                            uint64_t *violations, uint32_t *first_bad_column, zkc_status *status);
+
 /* ---- linear_hasher: Keccak-256 of the L2 -> L1 message queue ---------------------------------------------
  * linear_hasher_entry_point, src/linear_hasher/mod.rs:35-214.  Every cycle pops one LogQuery (:107), serialises it into
  * L2_TO_L1_MESSAGE_BYTE_LENGTH = 88 bytes (ByteSerializable::into_bytes, base_structures/log_query/mod.rs:645-686:
