@@ -47,6 +47,60 @@ VM_CYCLES_TRAFFIC_NOTE = ("ncu --set full dram__bytes_read+write of vm_cycles_ke
                           "final kernel of the round), scaled x4 to 2^20 cycles: 1.14x the algorithmic bytes")
 
 
+def sorter_check_rooflines(eng, log2rows, peak):
+    """Constraint evaluation of the two LogQuery sorter traces (C4's circuits) at 2^log2rows rows, device resident: the traces come from
+    the entry points themselves (queue-state hints built on the device), the evaluators stream them once (general-purpose gates)."""
+    import torch
+    from era_zkevm_circuits_b200 import (EventsDeduplicatorInstanceWitness, StorageDeduplicatorInstanceWitness, abi, log_sorter_check_trace, synthetic,
+                                         sort_and_deduplicate_events_entry_point, sort_and_deduplicate_storage_access_entry_point,
+                                         storage_validity_check_trace)
+    n = 1 << log2rows
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)).cuda()
+    out = {}
+
+    def measure(name, key, ncols, rewrite, check):
+        for _ in range(2):
+            viol, st_ = check()
+            assert viol == 0, (name, hex(st_.failed_checks), st_.first_bad_row)
+        eng.profile_reset(); eng.profile(True)
+        for _ in range(5):
+            rewrite()  # rewrites the trace: the next check reads cold HBM
+            check()
+        eng.profile(False)
+        ms, k = eng.profile_query(key)
+        gbs = ncols * 8 * n / (ms / k * 1e-3) / 1e9
+        out[name] = {"rows": n, "algorithmic_bytes_per_row": ncols * 8, "avg_launch_ms": ms / k, "achieved": gbs, "unit": "GB/s", "peak": peak,
+                     "frac": gbs / peak, "bound": "hbm"}
+
+    u, s = synthetic.events_trace(n, seed=0xC4, rollback_pct=10)
+    prev, fin = eng.log_queue_simulate(dev(np.concatenate([u, s])), n_queues=2)
+    io = abi.EventsClosedForm(); io.start_flag = 1
+    io.initial_log_queue_state = fin[0]; io.intermediate_sorted_queue_state = fin[1]
+    w = EventsDeduplicatorInstanceWitness(io, dev(u), prev[:n], dev(s), prev[n:], None)
+    trace = torch.empty((abi.EV_COLS["NUM_COLS"], n), dtype=torch.int64, device="cuda")
+    run = lambda: sort_and_deduplicate_events_entry_point(eng, w, n, trace_out=trace, raise_on_unsatisfied=False)
+    assert run().status.code == 0
+    K = abi.EV_COLS
+    w.result_queue_tails = trace[K["RESULT_TAIL"]:K["RESULT_TAIL"] + 4].t()[trace[K["ADD_TO_QUEUE"]] != 0].contiguous()  # hints: the pushes go row-parallel
+    measure("ev_check_kernel<false> (log_sorter trace)", "ev_check", K["NUM_COLS"], run, lambda: log_sorter_check_trace(eng, io, trace, n, abi.GATES_GENERAL))
+    del trace, w
+    u, s, ts = synthetic.storage_trace(n, seed=0xC4, n_cells=1 << 12)
+    d_ts = torch.from_numpy(ts.astype(np.uint32).view(np.int32)).cuda()
+    pu, fu = eng.log_queue_simulate(dev(u))
+    psd, fs = eng.log_queue_simulate(dev(s), d_ts)
+    sio = abi.StorageClosedForm(); sio.start_flag = 1
+    sio.unsorted_log_queue_state = fu[0]; sio.intermediate_sorted_queue_state = fs[0]
+    sw = StorageDeduplicatorInstanceWitness(sio, dev(u), pu, dev(s), d_ts, psd, None)
+    strace = torch.empty((abi.ST_COLS["NUM_COLS"], n), dtype=torch.int64, device="cuda")
+    srun = lambda: sort_and_deduplicate_storage_access_entry_point(eng, sw, n, trace_out=strace, raise_on_unsatisfied=False)
+    assert srun().status.code == 0
+    K = abi.ST_COLS
+    sw.result_queue_tails = strace[K["RESULT_TAIL"]:K["RESULT_TAIL"] + 4].t()[strace[K["SHOULD_PUSH"]] != 0].contiguous()
+    measure("st_check_kernel<false> (storage_validity trace)", "st_check", K["NUM_COLS"], srun,
+            lambda: storage_validity_check_trace(eng, sio, strace, n, abi.GATES_GENERAL))
+    return out
+
+
 def measured_peaks():
     try:
         j = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -336,6 +390,14 @@ def run_gpu(args):
     rows_ms, rows_n = eng.profile_query("ram_rows")
     del d_both, prev, rtrace
 
+    # ---- constraint evaluation of the two LogQuery sorter traces (C4's circuits), 2^17 rows each; rank 0 of a 1-GPU run only -------
+    sorter_eval = None
+    if world == 1:
+        try:
+            sorter_eval = sorter_check_rooflines(eng, 17, measured_peaks()[0])
+        except Exception as ex:  # reported, never fatal for the headline numbers
+            sorter_eval = {"error": repr(ex)[:300]}
+
     # ---- e2e: pinned host inputs -> H2D -> kernels -> D2H of witness columns + closed forms ------------------------------------
     # The reference-facing call over HOST buffers in the C ABI's transport forms (include/zkc_b200.h): the out-of-circuit run's
     # snapshots / oracle answers as a segmented input stream (dense words + change lists: what a VM run emits natively), the
@@ -483,7 +545,7 @@ def run_gpu(args):
                 "input_stream_bytes_per_cycle": stream_bytes / (n * cycles), "packed_trace_bytes_per_cycle": pk.nbytes_used / (n * cycles),
                 "host_encode_s_setup": t_enc, "aux_records_per_step": pk.n_aux_records, "sponge_records_per_step": pk.n_sponge_records,
                 "records_form": e2e_records},
-        "roofline": roofline, "constraint_eval": constraint_eval, "constraint_eval_main_vm": constraint_eval_vm, "int_roofline": int_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "constraint_eval": constraint_eval, "constraint_eval_main_vm": constraint_eval_vm, "constraint_eval_sorters": sorter_eval, "int_roofline": int_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }))
     if world > 1:
         dist.destroy_process_group()

@@ -20,6 +20,7 @@ from .log_sorter import (  # noqa: F401
 from .storage_validity import (  # noqa: F401
     StorageDeduplicatorInstanceWitness,
     sort_and_deduplicate_storage_access_entry_point,
+    storage_validity_check_trace,
 )
 from .sort_decommittment_requests import (  # noqa: F401
     CodeDecommittmentsDeduplicatorInstanceWitness,

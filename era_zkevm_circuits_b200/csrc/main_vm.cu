@@ -2427,7 +2427,7 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
     // verified.  `ends` = first and final snapshot of every instance as records (a stream's arrive with its last segment).
     cudaStream_t s_aux = ctx->aux_stream();
     if (!s_aux) s_aux = s;
-    cudaEvent_t e_hint = nullptr;
+    cudaEvent_t e_hint = nullptr, e_link = nullptr;
     auto launch_hint = [&](bool ends_from_columns) -> int {
         if (s_aux != s) {
             cudaEvent_t e = event();
@@ -2553,8 +2553,21 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
         else
             ZKC_LAUNCH(ctx, "vm_cycles", vm_cycles_kernel<false>, (unsigned)((n_thr + 127) / 128), 128, 0, d, disa, cols, dcw,
                        (uint32_t)in.n_callstack_witness, dtrace, limit, n_instances, r0, cnt, ps, ncols, aux_base, tmaps, use_tma);
-        ZKC_LAUNCH(ctx, "vm_link", vm_link_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, d, cols, (const uint32_t *)ps.link, (const uint32_t *)ps.exp, limit,
-                   n_instances, r0, cnt);
+        // The link check streams the state columns (HBM-bound) while the sponge kernels below are integer-bound: it runs beside
+        // them on the side stream (in line when per-kernel profiling wants one kernel at a time).
+        static const bool link_in_line = getenv("ZKC_VM_LINK_IN_LINE") != nullptr;  // for A/B timing
+        if (s_aux != s && !ctx->profiling && !link_in_line) {
+            cudaEvent_t e = event();
+            ZKC_CUDA(ctx, status, cudaEventRecord(e, s));
+            ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s_aux, e, 0));
+            ctx->launches++;
+            vm_link_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, s_aux>>>(d, cols, (const uint32_t *)ps.link, (const uint32_t *)ps.exp, limit, n_instances, r0, cnt);
+            e_link = event();
+            ZKC_CUDA(ctx, status, cudaEventRecord(e_link, s_aux));
+        } else {
+            ZKC_LAUNCH(ctx, "vm_link", vm_link_kernel, (unsigned)((n_thr + 255) / 256), 256, 0, d, cols, (const uint32_t *)ps.link, (const uint32_t *)ps.exp, limit,
+                       n_instances, r0, cnt);
+        }
         // every Poseidon2 relation of the chunk: one persistent launch over the per-slot job lists, or one launch per slot
         if (sponge_mode == 0) {
             for (int k = 0; k < VM_JOB_SLOTS_LO; k++)
@@ -2593,6 +2606,7 @@ static int vm_entry_batch(zkc_ctx *ctx, zkc_vm_closed_form *ios, size_t n_instan
         }
     }
     if (e_hint) ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e_hint, 0));
+    if (e_link) ZKC_CUDA(ctx, status, cudaStreamWaitEvent(s, e_link, 0));  // the side stream is in order: the last link covers all
     ZKC_LAUNCH(ctx, "vm_finalize", vm_finalize_kernel, (unsigned)((n_instances + 1) / 2), 128, 0, d, flat, n_instances, ends, limit, 1);
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, n_instances * sizeof(VmDev), cudaMemcpyDeviceToHost, s));

@@ -559,187 +559,312 @@ enum : uint32_t {
     RAMV_FLAGS = ZKC_RAMV_FLAGS, RAMV_ENFORCE = ZKC_RAMV_ENFORCE, RAMV_GP_CHAIN = ZKC_RAMV_GP_CHAIN, RAMV_GP_ACC = ZKC_RAMV_GP_ACC,
 };
 
-template <bool ROUND_FUNCTION>
-__global__ void __launch_bounds__(256)
+#ifndef RAM_CHECK_THREADS
+#define RAM_CHECK_THREADS 128
+#endif
+#ifndef RAM_CHECK_MIN_BLOCKS
+#define RAM_CHECK_MIN_BLOCKS 3
+#endif
+#ifndef RAM_CHECK_PREFETCH
+#define RAM_CHECK_PREFETCH 0  // measured slower on B200 (0.78 vs 0.53 ms per 2^20 rows): kept for the record
+#endif
+#ifndef RAM_CHECK_GP_MERGE
+#define RAM_CHECK_GP_MERGE 0
+#endif
+#ifndef RAM_CHECK_PAIRS
+#define RAM_CHECK_PAIRS 1
+#endif
+// R rows per thread.  R = 2: the thread owns the row pair (2k, 2k + 1) and reads every column with ONE 128-bit load (LDG.E.128);
+// the value a relation takes from the previous row is the pair's other element, or one 8-byte load of row 2k - 1 (the
+// neighbouring thread's line: an L1 hit).  R = 1 (odd limit, or with the Poseidon2 link, whose 12-element states would not fit
+// twice): 64-bit loads.  The relations run in stages -- flags, the two queue pops (item, packing, byte decomposition, the FMA
+// chains, the head), ordering, value flags, zero-check witnesses -- and the loads of a stage are not hoisted above the previous
+// one (STAGE), so the register count allows 3 CTAs of 128 threads per SM.
+template <int R> struct RamCells { uint64_t v[R]; };
+template <int R> __device__ __forceinline__ RamCells<R> ram_ld(const uint64_t *p);
+template <> __device__ __forceinline__ RamCells<1> ram_ld<1>(const uint64_t *p) { return RamCells<1>{{__ldg(p)}}; }
+template <> __device__ __forceinline__ RamCells<2> ram_ld<2>(const uint64_t *p) {
+    const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+    return RamCells<2>{{q.x, q.y}};
+}
+
+template <bool ROUND_FUNCTION, int R>
+__global__ void __launch_bounds__(RAM_CHECK_THREADS, RAM_CHECK_MIN_BLOCKS)
 ram_check_kernel(RamDev *d, const uint64_t *__restrict__ trace) {
     __shared__ uint64_t ch[2][9];
     if (threadIdx.x < 18) ch[threadIdx.x / 9][threadIdx.x % 9] = d->ch[threadIdx.x / 9][threadIdx.x % 9];
     __syncthreads();
     const size_t limit = d->limit;
-    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= limit) return;
-    const bool first = row == 0;
+    const size_t row0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * R;  // R == 2: limit is even
+    if (row0 >= limit) return;
+    const bool first = row0 == 0;
     const bool start = d->start;
-#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
-#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
-    uint32_t bad = 0;
-    const uint64_t u_empty = TR(ZKC_RAM_UNSORTED_IS_EMPTY), s_empty = TR(ZKC_RAM_SORTED_IS_EMPTY), can_pop = TR(ZKC_RAM_CAN_POP);
-    if ((u_empty | s_empty | can_pop) > 1 || u_empty != s_empty || can_pop != 1 - u_empty) bad |= RAMV_BOOLEAN;
+    const uint64_t *t = trace + row0;
+    typedef RamCells<R> Cells;
+#define LD(col) ram_ld<R>(t + (size_t)(col) * limit)
+#define PRV(col, at_first) (first ? (uint64_t)(at_first) : __ldg(t + (size_t)(col) * limit - 1))  // the cell of row0 - 1
+#define FOR_R _Pragma("unroll") for (int r = 0; r < R; r++)
+#define STAGE asm volatile("" ::: "memory")
+#if RAM_CHECK_PREFETCH
+    // L2 prefetch of the columns two stages ahead: the loads of a stage then cost an L2 round trip instead of an HBM one, with no
+    // registers held while the line is on its way
+#define PF(col0, n) _Pragma("unroll 1") for (int c_ = 0; c_ < (n); c_++) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + (size_t)((col0) + c_) * limit))
+#else
+#define PF(col0, n)
+#endif
+    PF(ZKC_RAM_UNSORTED_IS_EMPTY, 3 + 13 + 8); PF(ZKC_RAM_UNSORTED_LEN, 1); PF(ZKC_RAM_UNSORTED_LEN_INV, 1); PF(ZKC_RAM_UNSORTED_ENC_BYTES, 12);
+    PF(ZKC_RAM_GP_CHAIN, 8); PF(ZKC_RAM_GP_CHAIN + 16, 8); PF(ZKC_RAM_GP_NEW, 8);
+    PF(ZKC_RAM_UNSORTED_HEAD, 12);
+    uint32_t bad[R];
+    uint64_t u_empty[R], s_empty[R], can_pop[R];
+    {
+        const Cells ue = LD(ZKC_RAM_UNSORTED_IS_EMPTY), se = LD(ZKC_RAM_SORTED_IS_EMPTY), cp = LD(ZKC_RAM_CAN_POP);
+        FOR_R {
+            u_empty[r] = ue.v[r]; s_empty[r] = se.v[r]; can_pop[r] = cp.v[r];
+            bad[r] = ((u_empty[r] | s_empty[r] | can_pop[r]) > 1 || u_empty[r] != s_empty[r] || can_pop[r] != 1 - u_empty[r]) ? RAMV_BOOLEAN : 0u;
+        }
+    }
     const uint32_t heap_page = d->opt.bootloader_heap_page ? d->opt.bootloader_heap_page : ZKC_BOOTLOADER_HEAP_PAGE_DEFAULT;
-    uint64_t enc[2][8];
-    uint64_t it[13];  // the sorted item survives the loop
+    uint32_t it[R][13];     // u32 cells (range-checked below); the sorted item survives the loop
+    bool cells_ok[R];
+    FOR_R cells_ok[r] = true;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const int base = k ? ZKC_RAM_SORTED_ITEM : ZKC_RAM_UNSORTED_ITEM;
         const zkc_queue_state12 &q0 = k ? d->sq0 : d->uq0;
-        uint64_t range = 0;
+        if (k == 0) { PF(ZKC_RAM_SORTED_ITEM, 13 + 8); PF(ZKC_RAM_SORTED_LEN, 1); PF(ZKC_RAM_SORTED_LEN_INV, 1); PF(ZKC_RAM_SORTED_ENC_BYTES, 12); }
+        else { PF(ZKC_RAM_TS_IS_ZERO, 4); PF(ZKC_RAM_TS_INV, 3); PF(ZKC_RAM_CMP_DIFF, 11); PF(ZKC_RAM_CMP_DIFF_INV, 3); }
+        {
+            uint64_t range[R];
+            FOR_R range[r] = 0;
 #pragma unroll
-        for (int i = 0; i < 13; i++) { it[i] = TR(base + i); range |= it[i]; }
-        if ((range >> 32) || (it[3] | it[4]) > 1) bad |= RAMV_BOOLEAN;
-        // queue length: is_empty <=> previous length == 0, length decrements on a pop
-        const uint64_t len_prev = first ? q0.length : TP(base + 33);
-        const uint64_t len = TR(base + 33);
-        if ((k ? s_empty : u_empty) != (len_prev == 0) || len + can_pop != len_prev) bad |= RAMV_QUEUE_LEN;
-        // MemoryQuery::encode, memory_query/mod.rs:103-221
-        zkc_memory_query q;
-        q.timestamp = (uint32_t)it[0]; q.memory_page = (uint32_t)it[1]; q.index = (uint32_t)it[2];
-        q.rw_flag = (uint32_t)it[3]; q.is_ptr = (uint32_t)it[4];
-#pragma unroll
-        for (int i = 0; i < 8; i++) q.value[i] = (uint32_t)it[5 + i];
-        uint64_t e[8];
-        ram_encode(q, e);
-#pragma unroll
-        for (int i = 0; i < 8; i++) { enc[k][i] = TR(base + 13 + i); if (enc[k][i] != e[i]) bad |= RAMV_ENCODING; }
-        // head' = can_pop ? P(enc || head[8..12]) : head
-        uint64_t s[12], hcur[12];
-        bool same = true;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            const uint64_t hp = first ? q0.head[i] : TP(base + 21 + i);
-            hcur[i] = TR(base + 21 + i);
-            same &= hp == hcur[i];
-            s[i] = i < 8 ? enc[k][i] : hp;
-        }
-        if (!can_pop && !same) bad |= RAMV_ROUND_FUNCTION;
-        if (ROUND_FUNCTION && can_pop) {
-            poseidon2_permute(s);
-#pragma unroll
-            for (int i = 0; i < 12; i++) if (s[i] != hcur[i]) bad |= RAMV_ROUND_FUNCTION;
-        }
-    }
-    // :260-290
-    const uint64_t ts_is_zero = TR(ZKC_RAM_TS_IS_ZERO), page_is_heap = TR(ZKC_RAM_PAGE_IS_BOOTLOADER_HEAP);
-    const uint64_t is_nondet = TR(ZKC_RAM_IS_NONDET_WRITE), nnw = TR(ZKC_RAM_NUM_NONDET_WRITES);
-    const uint64_t nnw_prev = first ? d->nnw0 : TP(ZKC_RAM_NUM_NONDET_WRITES);
-    const uint64_t rw = it[3], is_ptr = it[4];
-    if (ts_is_zero != (it[0] == 0) || page_is_heap != (it[1] == heap_page) ||
-        is_nondet != (can_pop & ts_is_zero & page_is_heap & rw & (1 - is_ptr)) || nnw != nnw_prev + is_nondet)
-        bad |= RAMV_NONDET;
-    // :296-304 borrow chain: prev - cur - borrow_in = diff - 2^32 * borrow_out
-    uint64_t prev_sk[3], prev_fk[2], prev_val[8], prev_is_ptr;
-    if (first) {
-        const zkc_ram_fsm &f = d->io.hidden_fsm_input;
-#pragma unroll
-        for (int i = 0; i < 3; i++) prev_sk[i] = f.previous_sorting_key[i];
-        prev_fk[0] = f.previous_full_key[0]; prev_fk[1] = f.previous_full_key[1];
-#pragma unroll
-        for (int i = 0; i < 8; i++) prev_val[i] = f.previous_value[i];
-        prev_is_ptr = f.previous_is_ptr & 1;
-    } else {
-        prev_sk[0] = TP(ZKC_RAM_SORTED_ITEM + 0); prev_sk[1] = TP(ZKC_RAM_SORTED_ITEM + 2); prev_sk[2] = TP(ZKC_RAM_SORTED_ITEM + 1);
-        prev_fk[0] = prev_sk[1]; prev_fk[1] = prev_sk[2];
-#pragma unroll
-        for (int i = 0; i < 8; i++) prev_val[i] = TP(ZKC_RAM_SORTED_ITEM + 5 + i);
-        prev_is_ptr = TP(ZKC_RAM_SORTED_ITEM + 4);
-    }
-    const uint64_t sk[3] = {it[0], it[2], it[1]};
-    uint64_t borrow = 0, all_eq = 1;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const uint64_t diff = TR(ZKC_RAM_CMP_DIFF + i), bo = TR(ZKC_RAM_CMP_BORROW + i), leq = TR(ZKC_RAM_CMP_LIMB_EQ + i);
-        if ((diff >> 32) || bo > 1 || leq != (diff == 0) || prev_sk[i] + (bo << 32) != diff + sk[i] + borrow) bad |= RAMV_COMPARISON;
-        borrow = bo;
-        all_eq &= leq;
-    }
-    const uint64_t keys_equal = TR(ZKC_RAM_KEYS_EQUAL), prev_smaller = TR(ZKC_RAM_PREV_KEY_SMALLER);
-    if (keys_equal != all_eq || prev_smaller != borrow) bad |= RAMV_COMPARISON;
-    // :318-357 flags
-    const uint64_t same_cell = TR(ZKC_RAM_SAME_CELL), value_equal = TR(ZKC_RAM_VALUE_EQUAL), value_is_zero = TR(ZKC_RAM_VALUE_IS_ZERO);
-    const uint64_t is_zero = TR(ZKC_RAM_IS_ZERO), ptr_eq = TR(ZKC_RAM_PTR_EQUALITY), vpe = TR(ZKC_RAM_VALUE_AND_PTR_EQUAL);
-    const uint64_t read_uninit = TR(ZKC_RAM_READ_UNINIT), check_eq = TR(ZKC_RAM_CHECK_EQUALITY);
-    bool veq = true, vz = true;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { veq &= it[5 + i] == prev_val[i]; vz &= it[5 + i] == 0; }
-    const uint64_t not_rw = 1 - rw, not_start = start ? 0 : 1;
-    uint64_t ru, ce;
-    if (!first) { ru = (1 - same_cell) & not_rw; ce = same_cell & not_rw; }
-    else { ru = (not_start & (1 - same_cell) & not_rw) | ((1 - not_start) & not_rw); ce = same_cell & not_rw & not_start; }
-    if (same_cell != (uint64_t)(it[2] == prev_fk[0] && it[1] == prev_fk[1]) || value_equal != (uint64_t)veq ||
-        value_is_zero != (uint64_t)vz || is_zero != (value_is_zero & (1 - is_ptr)) || ptr_eq != (uint64_t)(prev_is_ptr == is_ptr) ||
-        vpe != (value_equal & ptr_eq) || read_uninit != ru || check_eq != ce)
-        bad |= RAMV_FLAGS;
-    // conditional enforcements :312-316, :336, :340, :351, :356
-    const uint64_t enforce_order = first ? (can_pop & not_start) : can_pop;
-    if ((enforce_order & (1 - prev_smaller)) | (read_uninit & (1 - is_zero)) | (check_eq & (1 - vpe))) bad |= RAMV_ENFORCE;
-    // ---- gadget cells: byte decompositions, differences, zero-check witnesses (x * inv = 1 - flag, flag * x = 0) -------------
-    {
-        bool ok = true;
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int base = k ? ZKC_RAM_SORTED_ITEM : ZKC_RAM_UNSORTED_ITEM, bytes = k ? ZKC_RAM_SORTED_ENC_BYTES : ZKC_RAM_UNSORTED_ENC_BYTES;
-#pragma unroll
-            for (int l = 0; l < 3; l++) {
-                uint64_t limb = 0, range = 0;
-#pragma unroll
-                for (int b = 0; b < 4; b++) { const uint64_t v = TR(bytes + 4 * l + b); range |= v; limb |= v << (8 * b); }
-                ok &= (range >> 8) == 0 && limb == (k ? it[5 + 5 + l] : TR(base + 5 + 5 + l));
+            for (int i = 0; i < 13; i++) {
+                const Cells c = LD(base + i);
+                FOR_R { it[r][i] = (uint32_t)c.v[r]; range[r] |= c.v[r]; }
+            }
+            FOR_R if ((range[r] >> 32) || (it[r][3] | it[r][4]) > 1) bad[r] |= RAMV_BOOLEAN;
+            // queue length: is_empty <=> previous length == 0, length decrements on a pop
+            const Cells len = LD(base + 33), inv = LD(k ? ZKC_RAM_SORTED_LEN_INV : ZKC_RAM_UNSORTED_LEN_INV);
+            const uint64_t p0 = PRV(base + 33, q0.length);
+            FOR_R {
+                const uint64_t lp = r ? len.v[r ? r - 1 : 0] : p0;
+                if ((k ? s_empty[r] : u_empty[r]) != (uint64_t)(lp == 0) || len.v[r] + can_pop[r] != lp) bad[r] |= RAMV_QUEUE_LEN;
+                const uint64_t flag = k ? s_empty[r] : u_empty[r];  // :247 / :248 is_empty: the inverse witness of the length before the pop
+                cells_ok[r] &= flag <= 1 && gl_mul(lp, inv.v[r]) == 1 - flag && (flag == 0 || lp == 0);
             }
         }
-        auto zero_check = [&](uint64_t x, uint64_t inv, uint64_t flag) {
-            return flag <= 1 && gl_mul(x, inv) == 1 - flag && (flag == 0 || x == 0);
-        };
-        const uint64_t ulen_prev = first ? d->uq0.length : TP(ZKC_RAM_UNSORTED_LEN), slen_prev = first ? d->sq0.length : TP(ZKC_RAM_SORTED_LEN);
-        ok &= zero_check(ulen_prev, TR(ZKC_RAM_UNSORTED_LEN_INV), u_empty) && zero_check(slen_prev, TR(ZKC_RAM_SORTED_LEN_INV), s_empty);
-        ok &= zero_check(it[0], TR(ZKC_RAM_TS_INV), ts_is_zero);
-        const uint64_t pd = TR(ZKC_RAM_PAGE_DIFF);
-        ok &= pd == gl_sub(it[1], heap_page) && zero_check(pd, TR(ZKC_RAM_PAGE_DIFF_INV), page_is_heap);
+        // MemoryQuery::encode, memory_query/mod.rs:103-221, and the byte decomposition of value limbs 5, 6, 7 (:133-135)
+        uint64_t enc[R][8];
+        {
+            uint64_t e[R][8];
+            FOR_R {
+                zkc_memory_query q;
+                q.timestamp = (uint32_t)it[r][0]; q.memory_page = (uint32_t)it[r][1]; q.index = (uint32_t)it[r][2];
+                q.rw_flag = (uint32_t)it[r][3]; q.is_ptr = (uint32_t)it[r][4];
 #pragma unroll
-        for (int i = 0; i < 3; i++) ok &= zero_check(TR(ZKC_RAM_CMP_DIFF + i), TR(ZKC_RAM_CMP_DIFF_INV + i), TR(ZKC_RAM_CMP_LIMB_EQ + i));
-        uint64_t cell_and = 1, val_and = 1, zero_and = 1;
+                for (int i = 0; i < 8; i++) q.value[i] = (uint32_t)it[r][5 + i];
+                ram_encode(q, e[r]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const Cells c = LD(base + 13 + i);
+                FOR_R { enc[r][i] = c.v[r]; if (c.v[r] != e[r][i]) bad[r] |= RAMV_ENCODING; }
+            }
+            const int bytes = k ? ZKC_RAM_SORTED_ENC_BYTES : ZKC_RAM_UNSORTED_ENC_BYTES;
+#pragma unroll
+            for (int l = 0; l < 3; l++) {
+                uint64_t limb[R], range[R];
+                FOR_R { limb[r] = 0; range[r] = 0; }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const Cells c = LD(bytes + 4 * l + b);
+                    FOR_R { range[r] |= c.v[r]; limb[r] |= c.v[r] << (8 * b); }
+                }
+                FOR_R cells_ok[r] &= (range[r] >> 8) == 0 && limb[r] == it[r][5 + 5 + l];
+            }
+        }
+        STAGE;
+        if (k == 0) { PF(ZKC_RAM_GP_CHAIN + 8, 8); PF(ZKC_RAM_GP_CHAIN + 24, 8); PF(ZKC_RAM_SORTED_HEAD, 12); }
+        else { PF(ZKC_RAM_SAME_CELL, 8); PF(ZKC_RAM_CELL_DIFF, 6); PF(ZKC_RAM_VALUE_DIFF, 24); }
+        // utils.rs:104-135: the two FMA chains over this queue's encoding and the accumulator update
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+            const int g = rep * 2 + k;
+            uint64_t c[R];
+            FOR_R c[r] = ch[rep][8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const Cells cell = LD(ZKC_RAM_GP_CHAIN + g * 8 + i);
+                FOR_R { if (cell.v[r] != gl_fma(enc[r][i], ch[rep][i], c[r])) bad[r] |= RAMV_GP_CHAIN; c[r] = cell.v[r]; }
+            }
+            const Cells nw = LD(ZKC_RAM_GP_NEW + g), acc = LD(ZKC_RAM_GP_ACC + g);
+            const uint64_t p0 = PRV(ZKC_RAM_GP_ACC + g, d->acc0[g]);
+            FOR_R {
+                const uint64_t acc_prev = r ? acc.v[r ? r - 1 : 0] : p0;
+                if (nw.v[r] != gl_mul(acc_prev, c[r]) || acc.v[r] != (can_pop[r] ? nw.v[r] : acc_prev)) bad[r] |= RAMV_GP_ACC;
+            }
+#if !RAM_CHECK_GP_MERGE
+            STAGE;
+#endif
+        }
+        STAGE;
+        // head' = can_pop ? P(enc || head[8..12]) : head
+        {
+            bool same[R];
+            FOR_R same[r] = true;
+            uint64_t st[ROUND_FUNCTION ? R : 1][12], hcur[ROUND_FUNCTION ? R : 1][12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const Cells c = LD(base + 21 + i);
+                const uint64_t p0 = PRV(base + 21 + i, q0.head[i]);
+                FOR_R {
+                    const uint64_t hp = r ? c.v[r ? r - 1 : 0] : p0;
+                    same[r] &= hp == c.v[r];
+                    if (ROUND_FUNCTION) { st[r][i] = i < 8 ? enc[r][i] : hp; hcur[r][i] = c.v[r]; }
+                }
+            }
+            FOR_R {
+                if (!can_pop[r] && !same[r]) bad[r] |= RAMV_ROUND_FUNCTION;
+                if (ROUND_FUNCTION && can_pop[r]) {
+                    poseidon2_permute(st[r]);
+#pragma unroll
+                    for (int i = 0; i < 12; i++) if (st[r][i] != hcur[r][i]) bad[r] |= RAMV_ROUND_FUNCTION;
+                }
+            }
+        }
+        STAGE;
+    }
+    PF(ZKC_RAM_VALUE_ZERO_DIFF, 24); PF(ZKC_RAM_PTR_DIFF, 2);
+    // ---- the row before: the sorted item of row - 1 (the pair's other element, one load per column for the pair's first row) ----
+    uint32_t prev_sk[R][3], prev_fk[R][2], prev_val[R][8], prev_is_ptr[R];  // u32 cells of the row before (range-checked on their own row)
+    {
+        const zkc_ram_fsm &f = d->io.hidden_fsm_input;
+        prev_sk[0][0] = (uint32_t)PRV(ZKC_RAM_SORTED_ITEM + 0, f.previous_sorting_key[0]);
+        prev_sk[0][1] = (uint32_t)PRV(ZKC_RAM_SORTED_ITEM + 2, f.previous_sorting_key[1]);
+        prev_sk[0][2] = (uint32_t)PRV(ZKC_RAM_SORTED_ITEM + 1, f.previous_sorting_key[2]);
+        prev_fk[0][0] = first ? f.previous_full_key[0] : prev_sk[0][1];
+        prev_fk[0][1] = first ? f.previous_full_key[1] : prev_sk[0][2];
+#pragma unroll
+        for (int i = 0; i < 8; i++) prev_val[0][i] = (uint32_t)PRV(ZKC_RAM_SORTED_ITEM + 5 + i, f.previous_value[i]);
+        prev_is_ptr[0] = (uint32_t)PRV(ZKC_RAM_SORTED_ITEM + 4, f.previous_is_ptr & 1);
+#pragma unroll
+        for (int r = 1; r < R; r++) {
+            prev_sk[r][0] = it[r - 1][0]; prev_sk[r][1] = it[r - 1][2]; prev_sk[r][2] = it[r - 1][1];
+            prev_fk[r][0] = it[r - 1][2]; prev_fk[r][1] = it[r - 1][1];
+#pragma unroll
+            for (int i = 0; i < 8; i++) prev_val[r][i] = it[r - 1][5 + i];
+            prev_is_ptr[r] = it[r - 1][4];
+        }
+    }
+    // ---- :260-290 non-deterministic writes; :296-304 borrow chain: prev - cur - borrow_in = diff - 2^32 * borrow_out ------------
+    uint64_t prev_smaller[R];
+    {
+        const Cells tz = LD(ZKC_RAM_TS_IS_ZERO), ph = LD(ZKC_RAM_PAGE_IS_BOOTLOADER_HEAP), nd = LD(ZKC_RAM_IS_NONDET_WRITE), nnw = LD(ZKC_RAM_NUM_NONDET_WRITES);
+        const uint64_t nnw0 = PRV(ZKC_RAM_NUM_NONDET_WRITES, d->nnw0);
+        const Cells tsi = LD(ZKC_RAM_TS_INV), pd = LD(ZKC_RAM_PAGE_DIFF), pdi = LD(ZKC_RAM_PAGE_DIFF_INV);
+        FOR_R {
+            auto zero_check = [&](uint64_t x, uint64_t inv, uint64_t flag) { return flag <= 1 && gl_mul(x, inv) == 1 - flag && (flag == 0 || x == 0); };
+            const uint64_t rw = it[r][3], is_ptr = it[r][4];
+            const uint64_t nnw_prev = r ? nnw.v[r ? r - 1 : 0] : nnw0;
+            if (tz.v[r] != (uint64_t)(it[r][0] == 0) || ph.v[r] != (uint64_t)(it[r][1] == heap_page) ||
+                nd.v[r] != (can_pop[r] & tz.v[r] & ph.v[r] & rw & (1 - is_ptr)) || nnw.v[r] != nnw_prev + nd.v[r])
+                bad[r] |= RAMV_NONDET;
+            cells_ok[r] &= zero_check(it[r][0], tsi.v[r], tz.v[r]);
+            cells_ok[r] &= pd.v[r] == gl_sub(it[r][1], heap_page) && zero_check(pd.v[r], pdi.v[r], ph.v[r]);
+        }
+    }
+    STAGE;
+    {
+        uint64_t borrow[R], all_eq[R];
+        FOR_R { borrow[r] = 0; all_eq[r] = 1; }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const Cells diff = LD(ZKC_RAM_CMP_DIFF + i), bo = LD(ZKC_RAM_CMP_BORROW + i), leq = LD(ZKC_RAM_CMP_LIMB_EQ + i), dinv = LD(ZKC_RAM_CMP_DIFF_INV + i);
+            FOR_R {
+                const uint64_t df = diff.v[r], b = bo.v[r], le = leq.v[r];
+                const uint64_t sk = i == 0 ? it[r][0] : (i == 1 ? it[r][2] : it[r][1]);
+                if ((df >> 32) || b > 1 || le != (uint64_t)(df == 0) || (uint64_t)prev_sk[r][i] + (b << 32) != df + sk + borrow[r]) bad[r] |= RAMV_COMPARISON;
+                borrow[r] = b;
+                all_eq[r] &= le;
+                cells_ok[r] &= le <= 1 && gl_mul(df, dinv.v[r]) == 1 - le && (le == 0 || df == 0);
+            }
+        }
+        const Cells ke = LD(ZKC_RAM_KEYS_EQUAL), ps = LD(ZKC_RAM_PREV_KEY_SMALLER);
+        FOR_R {
+            prev_smaller[r] = ps.v[r];
+            if (ke.v[r] != all_eq[r] || ps.v[r] != borrow[r]) bad[r] |= RAMV_COMPARISON;
+        }
+    }
+    STAGE;
+    // ---- :318-357 flags and the conditional enforcements :312-316, :336, :340, :351, :356 ---------------------------------------
+    uint64_t same_cell[R], value_equal[R], value_is_zero[R], ptr_eq[R];
+    {
+        const Cells sc = LD(ZKC_RAM_SAME_CELL), ve = LD(ZKC_RAM_VALUE_EQUAL), vz_ = LD(ZKC_RAM_VALUE_IS_ZERO), iz = LD(ZKC_RAM_IS_ZERO);
+        const Cells pe = LD(ZKC_RAM_PTR_EQUALITY), vp = LD(ZKC_RAM_VALUE_AND_PTR_EQUAL), ru_ = LD(ZKC_RAM_READ_UNINIT), ce_ = LD(ZKC_RAM_CHECK_EQUALITY);
+        FOR_R {
+            same_cell[r] = sc.v[r]; value_equal[r] = ve.v[r]; value_is_zero[r] = vz_.v[r]; ptr_eq[r] = pe.v[r];
+            const uint64_t rw = it[r][3], is_ptr = it[r][4];
+            bool veq = true, vz = true;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { veq &= it[r][5 + i] == prev_val[r][i]; vz &= it[r][5 + i] == 0; }
+            const uint64_t not_rw = 1 - rw, not_start = start ? 0 : 1;
+            const bool row_is_first = first && r == 0;
+            uint64_t ru, ce;
+            if (!row_is_first) { ru = (1 - sc.v[r]) & not_rw; ce = sc.v[r] & not_rw; }
+            else { ru = (not_start & (1 - sc.v[r]) & not_rw) | ((1 - not_start) & not_rw); ce = sc.v[r] & not_rw & not_start; }
+            if (sc.v[r] != (uint64_t)(it[r][2] == prev_fk[r][0] && it[r][1] == prev_fk[r][1]) || ve.v[r] != (uint64_t)veq ||
+                vz_.v[r] != (uint64_t)vz || iz.v[r] != (vz_.v[r] & (1 - is_ptr)) || pe.v[r] != (uint64_t)(prev_is_ptr[r] == is_ptr) ||
+                vp.v[r] != (ve.v[r] & pe.v[r]) || ru_.v[r] != ru || ce_.v[r] != ce)
+                bad[r] |= RAMV_FLAGS;
+            const uint64_t enforce_order = row_is_first ? (can_pop[r] & not_start) : can_pop[r];
+            if ((enforce_order & (1 - prev_smaller[r])) | (ru_.v[r] & (1 - iz.v[r])) | (ce_.v[r] & (1 - vp.v[r]))) bad[r] |= RAMV_ENFORCE;
+        }
+    }
+    STAGE;
+    // ---- gadget cells: differences and zero-check witnesses (x * inv = 1 - flag, flag * x = 0) of the equality gadgets ---------
+    {
+        auto zero_check = [&](uint64_t x, uint64_t inv, uint64_t flag) { return flag <= 1 && gl_mul(x, inv) == 1 - flag && (flag == 0 || x == 0); };
+        uint64_t cell_and[R], val_and[R], zero_and[R];
+        FOR_R { cell_and[r] = 1; val_and[r] = 1; zero_and[r] = 1; }
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-            const uint64_t df = TR(ZKC_RAM_CELL_DIFF + i), eq = TR(ZKC_RAM_CELL_LIMB_EQ + i);
-            ok &= df == gl_sub(i ? it[1] : it[2], prev_fk[i]) && zero_check(df, TR(ZKC_RAM_CELL_DIFF_INV + i), eq);
-            cell_and &= eq;
+            const Cells df = LD(ZKC_RAM_CELL_DIFF + i), eq = LD(ZKC_RAM_CELL_LIMB_EQ + i), inv = LD(ZKC_RAM_CELL_DIFF_INV + i);
+            FOR_R {
+                cells_ok[r] &= df.v[r] == gl_sub(i ? it[r][1] : it[r][2], prev_fk[r][i]) && zero_check(df.v[r], inv.v[r], eq.v[r]);
+                cell_and[r] &= eq.v[r];
+            }
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const uint64_t df = TR(ZKC_RAM_VALUE_DIFF + i), eq = TR(ZKC_RAM_VALUE_LIMB_EQ + i);
-            ok &= df == gl_sub(it[5 + i], prev_val[i]) && zero_check(df, TR(ZKC_RAM_VALUE_DIFF_INV + i), eq);
-            val_and &= eq;
-            const uint64_t zf = TR(ZKC_RAM_VALUE_ZERO_DIFF + i), zq = TR(ZKC_RAM_VALUE_ZERO_LIMB_EQ + i);
-            ok &= zf == it[5 + i] && zero_check(zf, TR(ZKC_RAM_VALUE_ZERO_DIFF_INV + i), zq);
-            zero_and &= zq;
-        }
-        const uint64_t pdf = TR(ZKC_RAM_PTR_DIFF);
-        ok &= pdf == gl_sub(prev_is_ptr, is_ptr) && zero_check(pdf, TR(ZKC_RAM_PTR_DIFF_INV), ptr_eq);
-        ok &= cell_and == same_cell && val_and == value_equal && zero_and == value_is_zero;  // Boolean::multi_and of the limb flags
-        if (!ok) bad |= ZKC_RAMV_GADGET_CELLS;
-    }
-    // utils.rs:104-135
-#pragma unroll
-    for (int rep = 0; rep < 2; rep++) {
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int g = rep * 2 + k;
-            uint64_t c = ch[rep][8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint64_t cell = TR(ZKC_RAM_GP_CHAIN + g * 8 + i);
-                if (cell != gl_fma(enc[k][i], ch[rep][i], c)) bad |= RAMV_GP_CHAIN;
-                c = cell;
+            const Cells df = LD(ZKC_RAM_VALUE_DIFF + i), eq = LD(ZKC_RAM_VALUE_LIMB_EQ + i), inv = LD(ZKC_RAM_VALUE_DIFF_INV + i);
+            const Cells zf = LD(ZKC_RAM_VALUE_ZERO_DIFF + i), zq = LD(ZKC_RAM_VALUE_ZERO_LIMB_EQ + i), zinv = LD(ZKC_RAM_VALUE_ZERO_DIFF_INV + i);
+            FOR_R {
+                cells_ok[r] &= df.v[r] == gl_sub(it[r][5 + i], prev_val[r][i]) && zero_check(df.v[r], inv.v[r], eq.v[r]);
+                val_and[r] &= eq.v[r];
+                cells_ok[r] &= zf.v[r] == it[r][5 + i] && zero_check(zf.v[r], zinv.v[r], zq.v[r]);
+                zero_and[r] &= zq.v[r];
             }
-            const uint64_t acc_prev = first ? d->acc0[g] : TP(ZKC_RAM_GP_ACC + g);
-            const uint64_t nw = TR(ZKC_RAM_GP_NEW + g), acc = TR(ZKC_RAM_GP_ACC + g);
-            if (nw != gl_mul(acc_prev, c) || acc != (can_pop ? nw : acc_prev)) bad |= RAMV_GP_ACC;
+            if (i == 3) STAGE;
+        }
+        const Cells pdf = LD(ZKC_RAM_PTR_DIFF), pdi = LD(ZKC_RAM_PTR_DIFF_INV);
+        FOR_R {
+            cells_ok[r] &= pdf.v[r] == gl_sub(prev_is_ptr[r], it[r][4]) && zero_check(pdf.v[r], pdi.v[r], ptr_eq[r]);
+            cells_ok[r] &= cell_and[r] == same_cell[r] && val_and[r] == value_equal[r] && zero_and[r] == value_is_zero[r];  // Boolean::multi_and of the limb flags
+            if (!cells_ok[r]) bad[r] |= ZKC_RAMV_GADGET_CELLS;
         }
     }
-#undef TR
-#undef TP
-    if (bad) {
-        atomicAdd(&d->violations, 1ull);
-        atomicOr(&d->failed_checks, bad);
-        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+#undef LD
+#undef PF
+#undef PRV
+#undef FOR_R
+#undef STAGE
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (bad[r]) {
+            atomicAdd(&d->violations, 1ull);
+            atomicOr(&d->failed_checks, bad[r]);
+            atomicMin(&d->first_bad, ((unsigned long long)(row0 + r) << 16) | bad[r]);
+        }
     }
 }
 
@@ -895,11 +1020,13 @@ extern "C" int zkc_ram_permutation_check_trace(zkc_ctx *ctx, const zkc_ram_close
     }
     ZKC_LAUNCH(ctx, "ram_prologue", ram_prologue_kernel, 1, 96, 0, d);
     if (limit) {
-        const unsigned grid = (unsigned)((limit + 255) / 256);
-        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION))
-            ZKC_LAUNCH(ctx, "ram_check_rf", ram_check_kernel<true>, grid, 256, 0, d, dt);
-        else
-            ZKC_LAUNCH(ctx, "ram_check", ram_check_kernel<false>, grid, 256, 0, d, dt);
+        const bool rf = gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION);
+        const bool pairs = RAM_CHECK_PAIRS && !rf && limit % 2 == 0 && ((uintptr_t)dt & 15) == 0;  // row pairs: 128-bit loads
+        const size_t threads = pairs ? limit / 2 : limit;
+        const unsigned grid = (unsigned)((threads + RAM_CHECK_THREADS - 1) / RAM_CHECK_THREADS);
+        if (rf) ZKC_LAUNCH(ctx, "ram_check_rf", (ram_check_kernel<true, 1>), grid, RAM_CHECK_THREADS, 0, d, dt);
+        else if (pairs) ZKC_LAUNCH(ctx, "ram_check", (ram_check_kernel<false, 2>), grid, RAM_CHECK_THREADS, 0, d, dt);
+        else ZKC_LAUNCH(ctx, "ram_check", (ram_check_kernel<false, 1>), grid, RAM_CHECK_THREADS, 0, d, dt);
     }
     ZKC_CUDA(ctx, status, cudaGetLastError());
     ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(RamDev), cudaMemcpyDeviceToHost, s));

@@ -700,6 +700,261 @@ __global__ void st_finalize_kernel(StDev *d, const zkc_log_query *__restrict__ s
     }
 }
 
+
+// ---- constraint evaluation of a finished trace ------------------------------------------------------------------------------
+// One thread per row re-evaluates every relation the loop body of sort_and_deduplicate_storage_access_inner places that is local
+// to a row or to a row and its predecessor (mod.rs:560-800; the role of `check_if_satisfied` over these cells): booleans / ranges
+// of the allocated items, LogQuery::encode of both pops (the timestamped forms of :98-109 and :605-610) and of the pushed net
+// query, queue-length / head bookkeeping, the 4 x 20 Num::fma chains and the accumulator update, the 13-limb key comparison and
+// the timestamp comparison, the flag algebra, the per-cell state machine (base / current value, rollback depth, the explicit-read
+// flag) from the previous row's state, the push decision, the result queue's length / tail selection, the conditional
+// enforcements.  Streams all ZKC_ST_NUM_COLS columns once (+ the previous row of the carried ones); with
+// ZKC_GATES_ROUND_FUNCTION also the permutations: 3 per popped item and queue, 3 of the push.
+template <bool ROUND_FUNCTION>
+__global__ void __launch_bounds__(128)
+st_check_kernel(StDev *d, unsigned long long *violations, const uint64_t *__restrict__ trace) {
+    __shared__ uint64_t ch[2][21];
+    if (threadIdx.x < 42) ch[threadIdx.x / 21][threadIdx.x % 21] = d->ch[threadIdx.x / 21][threadIdx.x % 21];
+    __syncthreads();
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const bool first = row == 0;
+    const zkc_storage_fsm &fsm = d->io.hidden_fsm_input;
+#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
+#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
+    uint32_t bad = 0;
+    const uint64_t o_empty = TR(ZKC_ST_ORIGINAL_IS_EMPTY), s_empty = TR(ZKC_ST_SORTED_IS_EMPTY), should_pop = TR(ZKC_ST_SHOULD_POP);
+    if ((o_empty | s_empty | should_pop) > 1 || o_empty != s_empty || should_pop != 1 - o_empty) bad |= ZKC_STV_BOOLEAN;
+    const uint64_t original_ts = TR(ZKC_ST_ORIGINAL_TIMESTAMP);
+    if (original_ts != (first ? (uint64_t)d->cycle0 : TP(ZKC_ST_ORIGINAL_TIMESTAMP) + 1) || original_ts >> 32) bad |= ZKC_STV_BOOLEAN;  // cycle_idx, :585-589
+    zkc_log_query si = lq_zero();
+    uint64_t sorted_ts = 0;
+    uint64_t enc[2][20];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int base = k ? ZKC_ST_SORTED_ITEM : ZKC_ST_UNSORTED_ITEM, enc_base = k ? ZKC_ST_SORTED_ENC : ZKC_ST_UNSORTED_ENC;
+        const int head_base = k ? ZKC_ST_SORTED_HEAD : ZKC_ST_UNSORTED_HEAD;
+        const zkc_queue_state4 &q0 = k ? d->sq0 : d->uq0;
+        uint64_t f[36], limbs = 0;
+#pragma unroll
+        for (int i = 0; i < 36; i++) f[i] = TR(base + i);
+#pragma unroll
+        for (int i = 0; i < 29; i++) limbs |= f[i];
+        if ((limbs | f[34] | f[35]) >> 32 || (f[29] | f[33]) >> 8 || (f[30] | f[31] | f[32]) > 1) bad |= ZKC_STV_BOOLEAN;
+        zkc_log_query q = lq_zero();
+#pragma unroll
+        for (int i = 0; i < 5; i++) q.address[i] = (uint32_t)f[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { q.key[i] = (uint32_t)f[5 + i]; q.read_value[i] = (uint32_t)f[13 + i]; q.written_value[i] = (uint32_t)f[21 + i]; }
+        q.flags = ZKC_LQ_FLAGS((uint32_t)f[29], (uint32_t)f[33], (uint32_t)f[30], (uint32_t)f[31], (uint32_t)f[32]);
+        q.tx_number_in_block = (uint32_t)f[34]; q.timestamp = (uint32_t)f[35];
+        uint64_t e[20];
+        lq_encode(q, e);
+        if (k) {  // TimestampedStorageLogRecord::encode, :98-109
+            sorted_ts = TR(ZKC_ST_SORTED_ITEM + 36);
+            if (sorted_ts >> 32) bad |= ZKC_STV_BOOLEAN;
+            e[19] += sorted_ts << 8;
+        }
+#pragma unroll
+        for (int i = 0; i < 20; i++) { enc[k][i] = TR(enc_base + i); if (enc[k][i] != e[i]) bad |= ZKC_STV_ENCODING; }
+        // queue: is_empty <=> previous length == 0, length decrements on a pop, the head only moves on a pop
+        const uint64_t len_prev = first ? q0.length : TP(head_base + 4), len = TR(head_base + 4);
+        if ((k ? s_empty : o_empty) != (uint64_t)(len_prev == 0) || len + should_pop != len_prev) bad |= ZKC_STV_QUEUE_LEN;
+        bool same = true;
+        uint64_t head_prev[4], head[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            head[i] = TR(head_base + i);
+            head_prev[i] = first ? q0.head[i] : TP(head_base + i);
+            same &= head[i] == head_prev[i];
+            if (head[i] >= GL_P) bad |= ZKC_STV_BOOLEAN;
+        }
+        if (!should_pop && !same) bad |= ZKC_STV_QUEUE_LEN;
+        if (ROUND_FUNCTION && should_pop) {  // the popped item's absorption from the head before the pop
+            uint64_t st[12];
+            lq_absorb_head(enc[k], st);
+            lq_absorb_tail(enc[k], head_prev, st);
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (st[i] != head[i]) bad |= ZKC_STV_ROUND_FUNCTION;
+        }
+        if (!k) {  // append_timestamp_to_raw_query_encoding, :605-610: the lhs of the grand product carries the pop index
+            const uint64_t ext = TR(ZKC_ST_UNSORTED_EXT19);
+            if (ext != enc[0][19] + (original_ts << 8)) bad |= ZKC_STV_ENCODING;
+            enc[0][19] = ext;
+        }
+        if (k == 1) si = q;
+    }
+    // utils.rs:104-135
+#pragma unroll
+    for (int rep = 0; rep < 2; rep++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int g = rep * 2 + k;
+            uint64_t c = ch[rep][20];
+#pragma unroll
+            for (int i = 0; i < 20; i++) {
+                const uint64_t cell = TR(ZKC_ST_GP_CHAIN + g * 20 + i);
+                if (cell != gl_fma(enc[k][i], ch[rep][i], c)) bad |= ZKC_STV_GP_CHAIN;
+                c = cell;
+            }
+            const uint64_t acc_prev = first ? d->acc0[g] : TP(ZKC_ST_GP_ACC + g);
+            const uint64_t nw = TR(ZKC_ST_GP_NEW + g), acc = TR(ZKC_ST_GP_ACC + g);
+            if (nw != gl_mul(acc_prev, c) || acc != (should_pop ? nw : acc_prev)) bad |= ZKC_STV_GP_ACC;
+        }
+    }
+    // ---- :612-661 shard id, ordering against the previous row (row 0: the FSM input) ---------------------------------------------
+    const uint64_t shard_ok = TR(ZKC_ST_SHARD_ID_IS_VALID);
+    if (shard_ok != (uint64_t)(ZKC_LQ_SHARD(si.flags) == d->shard)) bad |= ZKC_STV_FLAGS;
+    uint32_t prev_pk[13], prev_address[5], prev_key[8];
+    uint64_t prev_ts, prev_trivial;
+    if (first) {
+#pragma unroll
+        for (int i = 0; i < 13; i++) prev_pk[i] = d->packed_key0[i];
+#pragma unroll
+        for (int i = 0; i < 5; i++) prev_address[i] = fsm.previous_address[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) prev_key[i] = fsm.previous_key[i];
+        prev_ts = fsm.previous_timestamp;
+        prev_trivial = d->prev_trivial0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 5; i++) { prev_address[i] = (uint32_t)TP(ZKC_ST_SORTED_ITEM + i); prev_pk[8 + i] = prev_address[i]; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) { prev_key[i] = (uint32_t)TP(ZKC_ST_SORTED_ITEM + 5 + i); prev_pk[i] = prev_key[i]; }
+        prev_ts = TP(ZKC_ST_SORTED_ITEM + 36);
+        prev_trivial = TP(ZKC_ST_ORIGINAL_IS_EMPTY);
+    }
+    uint64_t borrow = 0, all_eq = 1;
+#pragma unroll
+    for (int i = 0; i < 13; i++) {  // packed_key - previous_packed_key, least significant limb first: cur + 2^32 * borrow_out = diff + prev + borrow_in
+        const uint64_t cur = i < 8 ? si.key[i] : si.address[i - 8];
+        const uint64_t diff = TR(ZKC_ST_CMP_DIFF + i), bo = TR(ZKC_ST_CMP_BORROW + i), leq = TR(ZKC_ST_CMP_LIMB_EQ + i);
+        if ((diff >> 32) || bo > 1 || leq != (uint64_t)(diff == 0) || cur + (bo << 32) != diff + prev_pk[i] + borrow) bad |= ZKC_STV_COMPARISON;
+        borrow = bo;
+        all_eq &= leq;
+    }
+    const uint64_t keys_equal = TR(ZKC_ST_KEYS_ARE_EQUAL), prev_greater = TR(ZKC_ST_PREVIOUS_KEY_IS_GREATER);
+    const uint64_t ts_diff = TR(ZKC_ST_TS_DIFF), prev_ts_less = TR(ZKC_ST_PREVIOUS_TIMESTAMP_IS_LESS);
+    if (keys_equal != all_eq || prev_greater != borrow || (ts_diff >> 32) || prev_ts_less > 1 || prev_ts + (prev_ts_less << 32) != ts_diff + sorted_ts)
+        bad |= ZKC_STV_COMPARISON;
+    // ---- flags ---------------------------------------------------------------------------------------------------------------------
+    const uint64_t trivial = o_empty, not_trivial = 1 - (o_empty & 1);
+    const uint64_t rw = ZKC_LQ_RW(si.flags), rollback = ZKC_LQ_ROLLBACK(si.flags);
+    const uint64_t must_enforce = TR(ZKC_ST_MUST_ENFORCE), new_cell = TR(ZKC_ST_NEW_NON_TRIVIAL_CELL), nt_same = TR(ZKC_ST_NON_TRIVIAL_AND_SAME_CELL);
+    const uint64_t read_same = TR(ZKC_ST_READ_OF_SAME_CELL), write_same = TR(ZKC_ST_WRITE_OF_SAME_CELL), wnr = TR(ZKC_ST_WRITE_NO_ROLLBACK), wrb = TR(ZKC_ST_WRITE_ROLLBACK);
+    if (must_enforce != (keys_equal & not_trivial) || new_cell != (not_trivial & (1 - (keys_equal & 1))) || nt_same != (not_trivial & keys_equal) ||
+        read_same != (nt_same & (1 - rw)) || write_same != (nt_same & rw) || wnr != (write_same & (1 - rollback)) || wrb != (write_same & rollback))
+        bad |= ZKC_STV_FLAGS;
+    (void)trivial;
+    // ---- the cell state machine: state left by the previous row -> state after this one ------------------------------------------
+    uint32_t b_base[8], b_cur[8], a_base[8], a_cur[8];
+    uint64_t b_depth, b_flag;
+    {
+        uint64_t range = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint64_t ab = TR(ZKC_ST_CELL_BASE_VALUE + i), ac = TR(ZKC_ST_CELL_CURRENT_VALUE + i);
+            range |= ab | ac;
+            a_base[i] = (uint32_t)ab; a_cur[i] = (uint32_t)ac;
+            b_base[i] = first ? fsm.this_cell_base_value[i] : (uint32_t)TP(ZKC_ST_CELL_BASE_VALUE + i);
+            b_cur[i] = first ? fsm.this_cell_current_value[i] : (uint32_t)TP(ZKC_ST_CELL_CURRENT_VALUE + i);
+        }
+        if (range >> 32) bad |= ZKC_STV_BOOLEAN;
+        b_depth = first ? (uint64_t)fsm.this_cell_current_depth : TP(ZKC_ST_CELL_CURRENT_DEPTH);
+        b_flag = first ? (uint64_t)(fsm.this_cell_has_explicit_read_and_rollback_depth_zero & 1) : TP(ZKC_ST_CELL_HAS_READ_AT_DEPTH_ZERO);
+    }
+    // the finished cell's net query: decided on the state BEFORE this row's update (:663-705)
+    const uint64_t viu = TR(ZKC_ST_VALUE_IS_UNCHANGED), dz = TR(ZKC_ST_CURRENT_DEPTH_IS_ZERO), ubnr = TR(ZKC_ST_UNCHANGED_BUT_NOT_BY_ROLLBACK);
+    const uint64_t ipr = TR(ZKC_ST_ISSUE_PROTECTIVE_READ), should_write = TR(ZKC_ST_SHOULD_WRITE), should_update = TR(ZKC_ST_SHOULD_UPDATE);
+    const uint64_t should_push = TR(ZKC_ST_SHOULD_PUSH);
+    {
+        bool unchanged = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) unchanged &= b_cur[i] == b_base[i];
+        if (viu != (uint64_t)unchanged || dz != (uint64_t)(b_depth == 0) || ubnr != (viu & (1 - (dz & 1))) || ipr != (b_flag | ubnr) || should_write != 1 - (viu & 1) ||
+            should_update != (ipr | should_write) || should_push != ((1 - (prev_trivial & 1)) & (1 - (keys_equal & 1)) & should_update) || prev_trivial > 1 || b_flag > 1)
+            bad |= ZKC_STV_FLAGS;
+    }
+    // this row's update of the state (:707-800)
+    const uint64_t a_depth = TR(ZKC_ST_CELL_CURRENT_DEPTH), a_flag = TR(ZKC_ST_CELL_HAS_READ_AT_DEPTH_ZERO);
+    const uint64_t depth_zero_after = TR(ZKC_ST_ROLLBACK_DEPTH_IS_ZERO), r0 = TR(ZKC_ST_READ_AT_DEPTH_ZERO_OF_SAME_CELL);
+    const uint64_t read_is_equal = TR(ZKC_ST_READ_IS_EQUAL_TO_CURRENT), check_read = TR(ZKC_ST_CHECK_READ_CONSISTENCY);
+    {
+        const uint64_t want_depth = new_cell ? rw : (uint64_t)(uint32_t)((uint32_t)b_depth + (uint32_t)wnr - (uint32_t)wrb);
+        bool ok = a_depth == want_depth && (a_depth >> 32) == 0 && depth_zero_after == (uint64_t)(a_depth == 0) && r0 == (depth_zero_after & read_same) &&
+                  a_flag == (new_cell ? 1 - rw : (b_flag | r0)) && check_read == (read_same | wnr);
+        bool req = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t rv = si.read_value[i], wv = si.written_value[i];
+            const uint32_t cur1 = new_cell ? (rw ? wv : rv) : b_cur[i];  // after the new-cell select
+            req &= cur1 == rv;
+            ok &= a_cur[i] == (new_cell ? cur1 : (wnr ? wv : (wrb ? rv : b_cur[i])));
+            ok &= a_base[i] == ((new_cell | r0) ? rv : b_base[i]);
+        }
+        ok &= read_is_equal == (uint64_t)req;
+        if (!ok) bad |= ZKC_STV_CELL_STATE;
+    }
+    // conditional enforcements: :612-614 shard, :638-639 key order, :645-648 timestamp order, :657-661 first key, :787-792 read
+    // consistency; a rollback below depth 0 (decrement_unchecked, :774)
+    if ((should_pop & (1 - (shard_ok & 1))) | (not_trivial & prev_greater) | (must_enforce & (1 - (prev_ts_less & 1))) | (check_read & (1 - (read_is_equal & 1))) |
+        (uint64_t)(first && d->start && should_pop && keys_equal) | (wrb & (uint64_t)(b_depth == 0)))
+        bad |= ZKC_STV_ENFORCE;
+    // ---- the pushed net query and the result queue (:676-705) ----------------------------------------------------------------------
+    {
+        zkc_log_query q = lq_zero();
+#pragma unroll
+        for (int i = 0; i < 5; i++) q.address[i] = prev_address[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { q.key[i] = prev_key[i]; q.read_value[i] = b_base[i]; q.written_value[i] = b_cur[i]; }
+        q.flags = ZKC_LQ_FLAGS(0, d->shard, (uint32_t)(should_write & 1), 0, 0);
+        uint64_t pe[20], penc[20], s[12];
+        lq_encode(q, pe);
+#pragma unroll
+        for (int i = 0; i < 20; i++) { penc[i] = TR(ZKC_ST_PUSH_ENC + i); if (penc[i] != pe[i]) bad |= ZKC_STV_ENCODING; }
+        uint64_t r0s[12], r1s[12], r2s[12], tail_prev[4];
+#pragma unroll
+        for (int i = 0; i < 12; i++) { r0s[i] = TR(ZKC_ST_PUSH_ROUND0 + i); r1s[i] = TR(ZKC_ST_PUSH_ROUND1 + i); r2s[i] = TR(ZKC_ST_PUSH_ROUND2 + i); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) tail_prev[i] = first ? d->rq0.tail[i] : TP(ZKC_ST_RESULT_TAIL + i);
+        const uint64_t len_prev = first ? d->rq0.length : TP(ZKC_ST_RESULT_LEN);
+        if (TR(ZKC_ST_RESULT_LEN) != len_prev + should_push) bad |= ZKC_STV_RESULT_QUEUE;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (TR(ZKC_ST_RESULT_TAIL + i) != (should_push ? r2s[i] : tail_prev[i])) bad |= ZKC_STV_RESULT_QUEUE;
+        if (ROUND_FUNCTION) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = i < 8 ? penc[i] : 0;
+            poseidon2_permute(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (s[i] != r0s[i]) bad |= ZKC_STV_ROUND_FUNCTION;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s[i] = penc[8 + i];
+            poseidon2_permute(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (s[i] != r1s[i]) bad |= ZKC_STV_ROUND_FUNCTION;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { s[i] = penc[16 + i]; s[4 + i] = tail_prev[i]; }
+            poseidon2_permute(s);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (s[i] != r2s[i]) bad |= ZKC_STV_ROUND_FUNCTION;
+        } else {
+            uint64_t big = 0;
+#pragma unroll
+            for (int i = 0; i < 12; i++) big |= (uint64_t)(r0s[i] >= GL_P) | (uint64_t)(r1s[i] >= GL_P) | (uint64_t)(r2s[i] >= GL_P);
+            if (big) bad |= ZKC_STV_BOOLEAN;
+        }
+    }
+#undef TR
+#undef TP
+    if (bad) {
+        atomicAdd(violations, 1ull);
+        atomicOr(&d->failed_checks, bad);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+    }
+}
+
 }  // namespace zkc
 
 using namespace zkc;
@@ -810,5 +1065,53 @@ extern "C" int zkc_storage_validity_entry_point(zkc_ctx *ctx, zkc_storage_closed
     io->completion_flag = h->io.completion_flag;
     memcpy(commitment, h->commitment, 32);
     *status = h->status;
+    return status->code;
+}
+
+extern "C" int zkc_storage_validity_check_trace(zkc_ctx *ctx, const zkc_storage_closed_form *io, const uint64_t *trace, size_t limit, uint32_t gates,
+                                                int on_device, uint64_t *violations, zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !violations || (limit && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(StDev)) + zkc_carver::bytes(1, 8);
+    if (!on_device) bytes += zkc_carver::bytes((size_t)ZKC_ST_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    StDev *h = (StDev *)ctx->pinned(sizeof(StDev) + 8);
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    StDev *d = cv.take<StDev>(1);
+    unsigned long long *dviol = cv.take<unsigned long long>(1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(StDev));
+    h->io = *io;
+    h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(StDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(dviol, 0, 8, s));
+    const uint64_t *dt = trace;
+    if (!on_device && limit) {
+        uint64_t *b = cv.take<uint64_t>((size_t)ZKC_ST_NUM_COLS * limit);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, (size_t)ZKC_ST_NUM_COLS * limit * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    ZKC_LAUNCH(ctx, "st_prologue", st_prologue_kernel, 1, 96, 0, d);
+    if (limit) {
+        const unsigned grid = (unsigned)((limit + 127) / 128);
+        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION)) ZKC_LAUNCH(ctx, "st_check_rf", st_check_kernel<true>, grid, 128, 0, d, dviol, dt);
+        else ZKC_LAUNCH(ctx, "st_check", st_check_kernel<false>, grid, 128, 0, d, dviol, dt);
+    }
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    unsigned long long *hviol = (unsigned long long *)(h + 1);
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(StDev), cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(hviol, dviol, 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = *hviol;
+    status->failed_checks = h->failed_checks;
+    if (*hviol) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 16);
+    }
     return status->code;
 }

@@ -571,6 +571,27 @@ int zkc_storage_validity_entry_point(zkc_ctx *ctx, zkc_storage_closed_form *io, 
                                      zkc_status *status);
 
 
+/* constraint evaluation of a finished storage_validity trace (as zkc_log_sorter_check_trace): every relation of the loop body
+ * (mod.rs:560-800) on every row -- item ranges, the three encodings, queue bookkeeping, the 4 x 20 fma chains, the 13-limb key
+ * and the timestamp comparison, the flag algebra, the per-cell state machine from the previous row's state, the push decision,
+ * the result queue -- returns the number of violating rows; status->first_bad_row / failed_checks (ZKC_STV_* bits) describe the
+ * first one.  gates: ZKC_GATES_GENERAL = the streaming (HBM-bound) relations; ZKC_GATES_ROUND_FUNCTION adds the permutations
+ * (3 per popped item and queue, 3 of the push); 0 = all. */
+#define ZKC_STV_BOOLEAN (1u << 0)      /* booleans, u32 / u8 ranges, field range of hash outputs, the cycle counter */
+#define ZKC_STV_QUEUE_LEN (1u << 1)    /* is_empty / length / head bookkeeping of the two popped queues */
+#define ZKC_STV_ENCODING (1u << 2)     /* LogQuery::encode of the popped items (+ timestamps) and of the pushed net query */
+#define ZKC_STV_ROUND_FUNCTION (1u << 3)
+#define ZKC_STV_COMPARISON (1u << 4)   /* :635-648 borrow chains */
+#define ZKC_STV_FLAGS (1u << 5)        /* flag algebra, the push decision */
+#define ZKC_STV_ENFORCE (1u << 6)      /* conditional enforcements */
+#define ZKC_STV_GP_CHAIN (1u << 7)
+#define ZKC_STV_GP_ACC (1u << 8)
+#define ZKC_STV_RESULT_QUEUE (1u << 9) /* result queue length / tail selection */
+#define ZKC_STV_CELL_STATE (1u << 10)  /* base / current value, rollback depth, explicit-read flag: the update from the previous row's state */
+int zkc_storage_validity_check_trace(zkc_ctx *ctx, const zkc_storage_closed_form *io, const uint64_t *trace, size_t limit, uint32_t gates,
+                                     int on_device, uint64_t *violations, zkc_status *status);
+
+
 /* ---- sort_decommittment_requests (src/sort_decommittment_requests/mod.rs) ------------------------ */
 /* DecommitQuery witness, src/base_structures/decommit_query/mod.rs:20-27 (48-byte record) */
 typedef struct zkc_decommit_query {

@@ -208,6 +208,53 @@ def test_error_cases_match_oracle(engine, orc):
     assert_same(want, got, check_trace=False)
 
 
+@pytest.mark.parametrize("want_trace", [True, False])
+def test_snapshot_link_covers_every_state_word(engine, orc, want_trace):
+    """One flipped bit in each 32-bit word of a mid-trace snapshot, one word at a time: with a trace the link check reads what the
+    cycle produced back from the trace columns (vm_link_kernel), without one the cycle's thread compares -- same verdicts as the oracle,
+    which compares the whole record (main_vm/mod.rs:126-208: each cycle starts from the state the previous one left)."""
+    isa, io, st = fresh(orc)
+    ops = I.random_program(isa, 256, seed=29)
+    cycles = 600
+    rc, snaps, wit, _, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+    io = with_tail(io, tail)
+    n_words = snaps.shape[1] // 4
+    caught = 0
+    for w in range(n_words):
+        idx = 1 + (w * 37) % (cycles - 1)
+        bad = snaps.copy(); bad[idx, 4 * w + (w % 4)] ^= 1 << (w % 8)
+        want = O.vm_entry_point(orc, io, isa.isa, bad, wit, cycles, cw=cw)
+        got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, bad, wit, cw), cycles, want_trace=want_trace, raise_on_unsatisfied=False)
+        assert got.status.code == want[0] and got.status.first_bad_row == want[4].first_bad_row, (w, idx, got.status.code, want[0])
+        assert got.status.failed_checks == want[4].failed_checks, (w, idx)
+        caught += want[0] == abi.ZKC_ERR_SNAPSHOT_MISMATCH
+    assert caught >= n_words - 8  # only padding words may go unnoticed
+
+
+@pytest.mark.parametrize("want_trace", [True, False])
+def test_snapshot_link_after_calls_and_rets(engine, orc, want_trace):
+    """the same, on the snapshots right after far calls, near calls and rets (the cycles that replace the whole context record)"""
+    isa, io, st = fresh(orc)
+    io.default_aa_code_hash[7] = (1 << 24) | 5; io.default_aa_code_hash[2] = 0xA1
+    ops = I.random_program(isa, 512, seed=8, far_calls=True)
+    cycles = 3000
+    rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True, gc=io)
+    assert rc == 0
+    io = with_tail(io, tail)
+    good = O.vm_entry_point(orc, io, isa.isa, snaps, wit, cycles, cw=cw)
+    assert good[0] == 0
+    moved = np.flatnonzero(good[2][K["DEPTH_OUT"]][:-1] != np.concatenate([[0], good[2][K["DEPTH_OUT"]][:-2]]))  # rows that push / pop a frame
+    assert len(moved) > 20
+    n_words = snaps.shape[1] // 4
+    for j, w in enumerate(range(0, n_words, 3)):
+        idx = int(moved[j % len(moved)]) + 1
+        bad = snaps.copy(); bad[idx, 4 * w] ^= 0x10
+        want = O.vm_entry_point(orc, io, isa.isa, bad, wit, cycles, cw=cw)
+        got = main_vm_entry_point(engine, VmCircuitWitness(io, isa.isa, bad, wit, cw), cycles, want_trace=want_trace, raise_on_unsatisfied=False)
+        assert got.status.code == want[0] and got.status.first_bad_row == want[4].first_bad_row, (w, idx, got.status.code, want[0])
+        assert got.status.failed_checks == want[4].failed_checks, (w, idx)
+
+
 def test_batch_of_instances(engine, orc):
     from era_zkevm_circuits_b200 import main_vm_entry_point_batch
     n, cycles = 6, 500

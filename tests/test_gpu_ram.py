@@ -141,14 +141,15 @@ def test_device_resident_inputs_and_missing_prev_states(engine, orc):
     assert np.array_equal(prev, up) and bytes(fin[0]) == bytes(io.observable_input.unsorted_queue_initial_state)
 
 
-def test_check_trace_accepts_valid_and_localises_corruption(engine, orc):
+@pytest.mark.parametrize("limit", [3100, 3101])  # even: row pairs per thread (128-bit loads); odd: one row per thread
+def test_check_trace_accepts_valid_and_localises_corruption(engine, orc, limit):
     from era_zkevm_circuits_b200 import ram_permutation_check_trace
     n = 3000
     u, s = synthetic.ram_trace(n, seed=21, n_cells=50, n_nondet=2)
     io, up, sp = H.ram_instance(orc, u, s, 2)
-    _, _, trace, _, _ = O.ram_entry_point(orc, io, u, s, 3100)  # the ORACLE's trace satisfies the CUDA checker
+    _, _, trace, _, _ = O.ram_entry_point(orc, io, u, s, limit)  # the ORACLE's trace satisfies the CUDA checker
     for gates in (0, abi.GATES_GENERAL):
-        viol, st = ram_permutation_check_trace(engine, io, trace, 3100, gates)
+        viol, st = ram_permutation_check_trace(engine, io, trace, limit, gates)
         assert viol == 0 and st.code == 0, (gates, hex(st.failed_checks), st.first_bad_row)
     probes = [(K["GP_CHAIN"] + 13, 1234, abi.RAMV["GP_CHAIN"], 0), (K["GP_ACC"] + 1, 77, abi.RAMV["GP_ACC"], 0),
               (K["SORTED_ENC"] + 3, 5, abi.RAMV["ENCODING"], 0), (K["CMP_DIFF"] + 1, 2999, abi.RAMV["COMPARISON"], 0),
@@ -158,18 +159,31 @@ def test_check_trace_accepts_valid_and_localises_corruption(engine, orc):
     for col, row, bit, gates in probes:
         t = trace.copy()
         t[col, row] ^= 1
-        viol, st = ram_permutation_check_trace(engine, io, t, 3100, gates)
+        viol, st = ram_permutation_check_trace(engine, io, t, limit, gates)
         assert viol >= 1 and st.code == abi.ZKC_ERR_UNSATISFIED
         assert st.first_bad_row == row and st.failed_checks & bit, (col, row, hex(st.failed_checks), st.first_bad_row)
     # a head corruption is invisible to the streaming pass only when the row pops (needs the round function)
     t = trace.copy(); t[K["UNSORTED_HEAD"] + 2, 100] ^= 1
-    viol, st = ram_permutation_check_trace(engine, io, t, 3100, abi.GATES_GENERAL)
+    viol, st = ram_permutation_check_trace(engine, io, t, limit, abi.GATES_GENERAL)
     assert viol == 0
+    # the gadget cells: byte decompositions, differences, inverse witnesses (where the inverted value is not zero), limb flags
+    for name in ("UNSORTED_ENC_BYTES", "SORTED_ENC_BYTES", "UNSORTED_LEN_INV", "SORTED_LEN_INV", "TS_INV", "PAGE_DIFF", "PAGE_DIFF_INV", "CMP_DIFF_INV",
+                 "CELL_DIFF", "CELL_DIFF_INV", "CELL_LIMB_EQ", "VALUE_DIFF", "VALUE_DIFF_INV", "VALUE_LIMB_EQ", "VALUE_ZERO_DIFF", "VALUE_ZERO_DIFF_INV",
+                 "VALUE_ZERO_LIMB_EQ", "PTR_DIFF", "PTR_DIFF_INV"):
+        col = K[name] + (1 if name in ("CMP_DIFF_INV", "CELL_DIFF", "CELL_DIFF_INV", "CELL_LIMB_EQ") else 0)
+        rows = np.flatnonzero(trace[col, 1:n] != 0) + 1
+        if name.endswith("_EQ") or not len(rows):
+            rows = np.arange(1, n)
+        row = int(rows[len(rows) // 2])
+        t = trace.copy()
+        t[col, row] ^= 1
+        viol, st = ram_permutation_check_trace(engine, io, t, limit, abi.GATES_GENERAL)
+        assert viol >= 1 and st.first_bad_row == row and st.failed_checks & abi.RAMV["GADGET_CELLS"], (name, row, hex(st.failed_checks), st.first_bad_row)
     # an unsatisfiable input (order violated) is caught as an enforcement failure of its own trace
     s2 = s.copy(); s2[[700, 701]] = s2[[701, 700]]
     io2, up2, sp2 = H.ram_instance(orc, u, s2, 2)
-    r = ram_permutation_entry_point(engine, RamPermutationCircuitInstanceWitness(io2, u, up2, s2, sp2), 3100, raise_on_unsatisfied=False)
-    viol, st = ram_permutation_check_trace(engine, io2, r.trace, 3100, abi.GATES_GENERAL)
+    r = ram_permutation_entry_point(engine, RamPermutationCircuitInstanceWitness(io2, u, up2, s2, sp2), limit, raise_on_unsatisfied=False)
+    viol, st = ram_permutation_check_trace(engine, io2, r.trace, limit, abi.GATES_GENERAL)
     assert viol >= 1 and st.failed_checks == abi.RAMV["ENFORCE"] and st.first_bad_row == r.status.first_bad_row
 
 

@@ -122,3 +122,66 @@ def test_device_resident(engine, orc):
     torch.cuda.synchronize()
     assert got.commitment.tolist() == want[3].tolist()
     assert np.array_equal(got.trace.cpu().numpy().view(np.uint64), want[2])
+
+
+def test_check_trace_constraint_evaluation(engine, orc):
+    """zkc_storage_validity_check_trace: the ORACLE's trace (reads, writes, rollbacks, protective reads over 40 cells) satisfies
+    every relation with and without the round-function gates; a fault injected into any relation family is found at its row"""
+    from era_zkevm_circuits_b200 import storage_validity_check_trace
+    V_ = abi.STV
+    u, s, ts = synthetic.storage_trace(3000, seed=8, n_cells=40)
+    io, up, sp = instance(orc, u, s, ts)
+    limit = 3100
+    want = O.storage_validity_entry_point(orc, io, u, s, ts, limit)
+    assert want[0] == abi.ZKC_OK
+    trace = want[2]
+    for gates in (0, abi.GATES_GENERAL):
+        viol, st = storage_validity_check_trace(engine, io, trace, limit, gates)
+        assert viol == 0 and st.code == 0, (gates, viol, hex(st.failed_checks), st.first_bad_row)
+    import torch
+    viol, st = storage_validity_check_trace(engine, io, torch.from_numpy(trace.view(np.int64)).cuda(), limit, abi.GATES_GENERAL)
+    assert viol == 0
+    pushes = np.flatnonzero(trace[K["SHOULD_PUSH"]])
+    same = np.flatnonzero(trace[K["NON_TRIVIAL_AND_SAME_CELL"]])
+    faults = [
+        (K["SHOULD_POP"], 17, 2, V_["BOOLEAN"], 0),
+        (K["UNSORTED_ITEM"] + 7, 40, 1 << 33, V_["BOOLEAN"], 0),
+        (K["ORIGINAL_TIMESTAMP"], 55, None, V_["BOOLEAN"], 0),
+        (K["UNSORTED_ENC"] + 3, 99, None, V_["ENCODING"], 0),
+        (K["UNSORTED_EXT19"], 98, None, V_["ENCODING"], 0),
+        (K["SORTED_ENC"] + 19, 97, None, V_["ENCODING"], 0),
+        (K["SORTED_LEN"], 123, None, V_["QUEUE_LEN"], 0),
+        (K["UNSORTED_HEAD"] + 1, 3050, None, V_["QUEUE_LEN"], 0),
+        (K["UNSORTED_HEAD"] + 1, 150, None, V_["ROUND_FUNCTION"], 0),
+        (K["GP_CHAIN"] + 45, 200, None, V_["GP_CHAIN"], 0),
+        (K["GP_ACC"] + 2, 300, None, V_["GP_ACC"], 0),
+        (K["CMP_DIFF"] + 9, 400, None, V_["COMPARISON"], 0),
+        (K["TS_DIFF"], 410, None, V_["COMPARISON"], 0),
+        (K["WRITE_ROLLBACK"], 500, None, V_["FLAGS"], 0),
+        (K["SHOULD_UPDATE"], 510, None, V_["FLAGS"], 0),
+        (K["SHARD_ID_IS_VALID"], 520, None, V_["FLAGS"], 0),
+        (K["CELL_CURRENT_VALUE"] + 3, int(same[20]), None, V_["CELL_STATE"], 0),
+        (K["CELL_BASE_VALUE"] + 1, 530, None, V_["CELL_STATE"], 0),
+        (K["CELL_CURRENT_DEPTH"], int(same[30]), None, V_["CELL_STATE"], 0),
+        (K["CELL_HAS_READ_AT_DEPTH_ZERO"], 540, None, V_["CELL_STATE"], 0),
+        (K["READ_IS_EQUAL_TO_CURRENT"], 550, None, V_["CELL_STATE"], 0),
+        (K["PUSH_ENC"] + 17, 600, None, V_["ENCODING"], 0),
+        (K["RESULT_LEN"], 700, None, V_["RESULT_QUEUE"], 0),
+        (K["RESULT_TAIL"] + 2, int(pushes[5]), None, V_["RESULT_QUEUE"], 0),
+        (K["PUSH_ROUND1"] + 5, int(pushes[10]), None, V_["ROUND_FUNCTION"], 0),
+    ]
+    for col, row, val, bit, gates in faults:
+        bad = trace.copy()
+        bad[col, row] = np.uint64(val) if val is not None else bad[col, row] ^ np.uint64(1)
+        viol, st = storage_validity_check_trace(engine, io, bad, limit, gates)
+        assert viol >= 1 and st.first_bad_row == row and st.failed_checks & bit, (col, row, viol, st.first_bad_row, hex(st.failed_checks))
+    # the engine's own trace of a chained second instance (start_flag = 0: cell state / previous key from the FSM input)
+    cut = 1500
+    a = sort_and_deduplicate_storage_access_entry_point(engine, StorageDeduplicatorInstanceWitness(io, u, up, s, ts, sp), cut, raise_on_unsatisfied=False)
+    nxt = abi.StorageClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+    b = sort_and_deduplicate_storage_access_entry_point(engine, StorageDeduplicatorInstanceWitness(nxt, u[cut:], up[cut:], s[cut:], ts[cut:], sp[cut:]),
+                                                        limit - cut, raise_on_unsatisfied=False)
+    assert b.status.code == 0
+    viol, st = storage_validity_check_trace(engine, nxt, b.trace, limit - cut)
+    assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)

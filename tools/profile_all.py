@@ -2,7 +2,7 @@
 """One or two launches of every kernel family, for ncu captures (round 2 evidence):
   ncu --set full --clock-control none --import-source on -k regex:'<names>' -o gpurun_out/prof python tools/profile_all.py [log2 cycles]
 main_vm (columns, 2^k cycles) + its constraint evaluator + gadget cells; ram_permutation + evaluator; log_sorter + evaluator;
-storage_validity; sort_decommittment_requests; demux_log_queue; keccak256 / sha256 round functions; linear_hasher.
+storage_validity + evaluator + the generic allocation-check evaluator; keccak256 / sha256 round functions; linear_hasher.
 Queue-state hints come from the engine's own un-hinted first run (verified chains), as in tools/bench_configs.py."""
 import os
 import sys
@@ -81,6 +81,26 @@ assert got.status.code == 0
 assert log_sorter_check_trace(eng, eio, etrace, en, abi.GATES_GENERAL)[0] == 0
 assert log_sorter_check_trace(eng, eio, etrace, en, 0)[0] == 0
 del etrace
+
+# ---- storage_validity + evaluator, the generic allocation-check evaluator --------------------------------------------------------
+from era_zkevm_circuits_b200 import (StorageDeduplicatorInstanceWitness, check_trace_columns, sort_and_deduplicate_storage_access_entry_point,  # noqa: E402
+                                     storage_validity_check_trace)
+su, ss, sts = synthetic.storage_trace(en, seed=0xC4, n_cells=1 << 10)
+d_ts = torch.from_numpy(sts.astype(np.uint32).view(np.int32)).cuda()
+spu, sfu = eng.log_queue_simulate(dev(su))
+sps, sfs = eng.log_queue_simulate(dev(ss), d_ts)
+sio = abi.StorageClosedForm(); sio.start_flag = 1
+sio.unsorted_log_queue_state = sfu[0]; sio.intermediate_sorted_queue_state = sfs[0]
+sw = StorageDeduplicatorInstanceWitness(sio, dev(su), spu, dev(ss), d_ts, sps, None)
+strace = torch.empty((abi.ST_COLS["NUM_COLS"], en), dtype=torch.int64, device="cuda")
+assert sort_and_deduplicate_storage_access_entry_point(eng, sw, en, trace_out=strace).status.code == 0
+KS = abi.ST_COLS
+sw.result_queue_tails = strace[KS["RESULT_TAIL"]:KS["RESULT_TAIL"] + 4].t()[strace[KS["SHOULD_PUSH"]] != 0].contiguous()
+assert sort_and_deduplicate_storage_access_entry_point(eng, sw, en, trace_out=strace).status.code == 0
+assert storage_validity_check_trace(eng, sio, strace, en, abi.GATES_GENERAL)[0] == 0
+assert storage_validity_check_trace(eng, sio, strace, en, 0)[0] == 0
+assert check_trace_columns(eng, "storage_validity", strace)[0] == 0
+del strace
 
 # ---- linear_hasher ---------------------------------------------------------------------------------------------------------------
 ln = 1 << (k - 4)
