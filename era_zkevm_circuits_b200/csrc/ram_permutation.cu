@@ -563,7 +563,7 @@ enum : uint32_t {
 #define RAM_CHECK_THREADS 128
 #endif
 #ifndef RAM_CHECK_MIN_BLOCKS
-#define RAM_CHECK_MIN_BLOCKS 3
+#define RAM_CHECK_MIN_BLOCKS 2  // measured per 2^20 rows (profiles/README.md): 2 CTAs / SM 0.51 ms, 3: 0.53 - 0.54, 4 (spills): 0.61; one row per thread at 4 / 5 / 6 CTAs: 0.60 / 0.55 / 0.55
 #endif
 #ifndef RAM_CHECK_PREFETCH
 #define RAM_CHECK_PREFETCH 0  // measured slower on B200 (0.78 vs 0.53 ms per 2^20 rows): kept for the record
@@ -579,7 +579,7 @@ enum : uint32_t {
 // neighbouring thread's line: an L1 hit).  R = 1 (odd limit, or with the Poseidon2 link, whose 12-element states would not fit
 // twice): 64-bit loads.  The relations run in stages -- flags, the two queue pops (item, packing, byte decomposition, the FMA
 // chains, the head), ordering, value flags, zero-check witnesses -- and the loads of a stage are not hoisted above the previous
-// one (STAGE), so the register count allows 3 CTAs of 128 threads per SM.
+// one (STAGE): the compiler keeps a stage's loads together and in flight while the previous stage's field arithmetic runs.
 template <int R> struct RamCells { uint64_t v[R]; };
 template <int R> __device__ __forceinline__ RamCells<R> ram_ld(const uint64_t *p);
 template <> __device__ __forceinline__ RamCells<1> ram_ld<1>(const uint64_t *p) { return RamCells<1>{{__ldg(p)}}; }

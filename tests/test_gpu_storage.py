@@ -185,3 +185,49 @@ def test_check_trace_constraint_evaluation(engine, orc):
     assert b.status.code == 0
     viol, st = storage_validity_check_trace(engine, nxt, b.trace, limit - cut)
     assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)
+
+
+@pytest.mark.parametrize("world,on_dev", [(2, False), (4, False), (3, True)])
+def test_one_instance_cut_by_rows_over_ranks(engine, orc, world, on_dev):
+    """sharding.storage_rows_local / storage_rows_finish with the ENGINE as the backend (the ranks run one after the other on this
+    GPU; tests/test_sharding_gloo.py runs the same phases over a real process group): the rank traces, with their accumulator
+    columns scaled after the exchange, concatenate to the whole instance's trace; every rank ends with the whole instance's
+    closed form, status and commitment.  Cells span ~150 rows, so every cut lands inside a cell."""
+    import torch
+    from era_zkevm_circuits_b200 import sharding
+    n, limit = 6000, 6100
+    u, s, ts = synthetic.storage_trace(n, seed=33, n_cells=40)
+    io, up, sp = instance(orc, u, s, ts)
+    want = O.storage_validity_entry_point(orc, io, u, s, ts, limit)
+    assert want[0] == abi.ZKC_OK
+    tails = want[5]
+    if on_dev:
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)).cuda()
+        i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+        w = StorageDeduplicatorInstanceWitness(io, dev(u), i64(up), dev(s), torch.from_numpy(ts.astype(np.uint32).view(np.int32)).cuda(), i64(sp), i64(tails))
+    else:
+        w = StorageDeduplicatorInstanceWitness(io, u, up, s, ts, sp, tails)
+    cum = np.concatenate([[0], np.cumsum(want[2][K["SHOULD_PUSH"]])]).astype(np.int64)
+    offs = [int(cum[sharding.row_range(n, r, world)[0]]) for r in range(world)]
+
+    def run(io_, u_, up_, s_, ts_, sp_, tails_, lim, want_trace):
+        return sort_and_deduplicate_storage_access_entry_point(engine, StorageDeduplicatorInstanceWitness(io_, u_, up_, s_, ts_, sp_, tails_), lim,
+                                                               want_trace=want_trace, raise_on_unsatisfied=False)
+
+    commit = lambda e: engine.commit_encoding(np.ascontiguousarray(e, dtype=np.uint64).reshape(1, -1))[0]
+    locs = [sharding.storage_rows_local(run, w, limit, r, world, offs) for r in range(world)]
+    recs = np.stack([l[3] for l in locs])
+    traces = []
+    for r in range(world):
+        com, io_g, trace, st = sharding.storage_rows_finish(locs[r][0], r, world, recs, io, offs, engine.scale_accumulators, commit)
+        assert st.code == 0, (r, st.code, hex(st.failed_checks), st.first_bad_row)
+        assert com.tolist() == want[3].tolist()
+        assert bytes(io_g.hidden_fsm_output) == bytes(want[1].hidden_fsm_output) and io_g.completion_flag == want[1].completion_flag
+        assert bytes(io_g.final_sorted_queue_state) == bytes(want[1].final_sorted_queue_state)
+        traces.append(trace.cpu().numpy().view(np.uint64) if on_dev else trace)
+    bad = np.argwhere(np.concatenate(traces, axis=1) != want[2])
+    assert bad.size == 0, f"first differing (col,row): {bad[:8].tolist()}"
+    # a wrong push offset is a wrong result-queue tail for that rank: its own hint verification fails
+    wrong = list(offs); wrong[1] += 1
+    res, lo, hi, rec = sharding.storage_rows_local(run, w, limit, 1, world, wrong)
+    assert res.status.code == abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT

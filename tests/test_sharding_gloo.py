@@ -108,3 +108,108 @@ def test_grand_product_over_row_ranges(tmp_path):
     assert np.array_equal(got, want)
     for r in range(world):
         assert np.load(os.path.join(str(tmp_path), f"gpt{r}.npy")).tolist() == fin.tolist()
+
+
+# ---- ONE storage_validity instance cut by row range over two gloo ranks (the CPU oracle stands in for the engine) -----------------
+def _storage_instance():
+    sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+    import orc as O
+    from era_zkevm_circuits_b200 import StorageDeduplicatorInstanceWitness, abi, synthetic
+    lib = O.load()
+    n, limit = 1200, 1250
+    u, s, ts = synthetic.storage_trace(n, seed=5, n_cells=12)  # ~100 rows per cell: every cut lands inside a cell
+    up, ufin = O.log_queue_simulate(lib, u)
+    sp, sfin = O.log_queue_simulate(lib, s, ts)
+    io = O.storage_closed_form(ufin, sfin, 0, True)
+    whole = O.storage_validity_entry_point(lib, io, u, s, ts, limit)
+    assert whole[0] == 0
+    return lib, StorageDeduplicatorInstanceWitness(io, u, up, s, ts, sp, whole[5]), n, limit, whole
+
+
+def _oracle_backend(lib):
+    from types import SimpleNamespace
+    import orc as O
+    from era_zkevm_circuits_b200 import sharding
+
+    def run(io, u, up, s, ts, sp, tails, limit, want_trace):
+        rc, io2, trace, com, st, _ = O.storage_validity_entry_point(lib, io, u, s, ts, limit, want_trace=want_trace)
+        return SimpleNamespace(closed_form_input=io2, trace=trace, status=st, commitment=com)
+
+    def scale(cols, seed):
+        for c in range(4):
+            cols[c] = np.array([int(v) * int(seed[c]) % sharding.GL_P for v in cols[c]], dtype=np.uint64)
+
+    return run, scale, (lambda e: O.commit_encoding(lib, e))
+
+
+def _push_offsets(whole_trace, n, world):
+    from era_zkevm_circuits_b200 import abi, sharding
+    cum = np.concatenate([[0], np.cumsum(whole_trace[abi.ST_COLS["SHOULD_PUSH"]])]).astype(np.int64)
+    return [int(cum[sharding.row_range(n, r, world)[0]]) for r in range(world)]
+
+
+def _storage_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    lib, w, n, limit, whole = _storage_instance()
+    from era_zkevm_circuits_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    run, scale, commit = _oracle_backend(lib)
+    offs = _push_offsets(whole[2], n, world)
+    res, lo, hi, rec = sharding.storage_rows_local(run, w, limit, rank, world, offs)
+    allr = torch.zeros((world, len(rec)), dtype=torch.int64)
+    dist.all_gather_into_tensor(allr, torch.from_numpy(rec.copy()).reshape(1, -1))  # the path's ONE collective
+    com, io, trace, st = sharding.storage_rows_finish(res, rank, world, allr.numpy(), w.closed_form_input, offs, scale, commit)
+    np.savez(os.path.join(out_dir, f"st{rank}.npz"), com=com, trace=trace, lo=lo, hi=hi, code=st.code, failed=st.failed_checks,
+             fsm=np.frombuffer(bytes(io.hidden_fsm_output), dtype=np.uint8), done=io.completion_flag)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_one_storage_instance_by_rows(tmp_path):
+    world = 2
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_storage_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    lib, w, n, limit, whole = _storage_instance()
+    parts = [np.load(os.path.join(str(tmp_path), f"st{r}.npz")) for r in range(world)]
+    for p in parts:
+        assert int(p["code"]) == 0 and int(p["failed"]) == 0
+        assert np.array_equal(p["com"], whole[3])  # every rank ends with the WHOLE instance's commitment
+        assert p["fsm"].tobytes() == bytes(whole[1].hidden_fsm_output) and int(p["done"]) == whole[1].completion_flag
+    assert [(int(p["lo"]), int(p["hi"])) for p in parts] == [(0, 600), (600, limit)]
+    assert np.array_equal(np.concatenate([p["trace"] for p in parts], axis=1), whole[2])  # scaled accumulator columns included
+
+
+def test_row_sharded_storage_chained_instance_and_bad_offsets():
+    """single process, three virtual ranks: a chained (start_flag = 0) instance cut by rows, and wrong push offsets"""
+    lib, w, n, limit, whole = _storage_instance()
+    import orc as O
+    from era_zkevm_circuits_b200 import StorageDeduplicatorInstanceWitness, abi, sharding
+    run, scale, commit = _oracle_backend(lib)
+    # second instance of a chain: rows [400, ...) with the FSM state the first instance left
+    first = O.storage_validity_entry_point(lib, w.closed_form_input, w.unsorted_queue_witness, w.intermediate_sorted_queue_witness,
+                                           w.intermediate_sorted_queue_timestamps, 400)
+    nxt = abi.StorageClosedForm.from_buffer_copy(bytes(first[1])); nxt.start_flag = 0
+    nxt.hidden_fsm_input = first[1].hidden_fsm_output
+    cut = lambda a: a[400:]
+    rest = O.storage_validity_entry_point(lib, nxt, cut(w.unsorted_queue_witness), cut(w.intermediate_sorted_queue_witness),
+                                          cut(w.intermediate_sorted_queue_timestamps), limit - 400)
+    assert rest[0] == 0
+    w2 = StorageDeduplicatorInstanceWitness(nxt, cut(w.unsorted_queue_witness), cut(w.unsorted_queue_prev_tails), cut(w.intermediate_sorted_queue_witness),
+                                            cut(w.intermediate_sorted_queue_timestamps), cut(w.intermediate_sorted_queue_prev_tails), rest[5])
+    world = 3
+    offs = _push_offsets(rest[2], n - 400, world)
+    locs = [sharding.storage_rows_local(run, w2, limit - 400, r, world, offs) for r in range(world)]
+    recs = np.stack([l[3] for l in locs])
+    traces = []
+    for r in range(world):
+        com, io, trace, st = sharding.storage_rows_finish(locs[r][0], r, world, recs, nxt, offs, scale, commit)
+        assert st.code == 0 and np.array_equal(com, rest[3]) and bytes(io.hidden_fsm_output) == bytes(rest[1].hidden_fsm_output)
+        traces.append(trace)
+    assert np.array_equal(np.concatenate(traces, axis=1), rest[2])
+    bad = list(offs); bad[2] += 1  # the host's push count before rank 2 is off by one: found when the counts are exchanged
+    locs = [sharding.storage_rows_local(run, w2, limit - 400, r, world, bad) for r in range(world)]
+    com, io, trace, st = sharding.storage_rows_finish(locs[0][0], 0, world, np.stack([l[3] for l in locs]), nxt, bad, scale, commit)
+    assert st.code != 0 and st.failed_checks & abi.ST_CHK["QUEUE_HINT"]

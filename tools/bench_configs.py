@@ -300,6 +300,73 @@ def gp(eng, log2rows):
         dist.destroy_process_group()
 
 
+def c4rows(eng, log2rows):
+    """ONE storage_validity instance of 2^log2rows rows cut by row range over the ranks (sharding.storage_validity_row_sharded):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_configs.py c4rows 20
+    Every rank builds the same synthetic instance and its hints (queue states: two device chains, ~20 s each at 2^20 rows; the
+    result-queue tails and the push offsets come from one whole-instance run, which is also the 1-GPU time the cut is compared
+    with); the timed step is phase 1 (cell replay + the rank's rows) + the all-gather + phase 2 (fix-up, closed form, commitment)."""
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    n = 1 << log2rows
+    u, s, ts = synthetic.storage_trace(n, seed=0xC4, n_cells=1 << max(4, log2rows - 4))
+    d_ts2 = torch.from_numpy(np.concatenate([np.zeros(n, dtype=np.uint32), ts.astype(np.uint32)]).view(np.int32)).cuda()
+    d_ts = d_ts2[n:].contiguous()
+    t0 = time.perf_counter()
+    prev, fin = eng.log_queue_simulate(dev(np.concatenate([u, s])), d_ts2, n_queues=2)  # both chains side by side (timestamp 0 = plain record)
+    pu, psd = prev[:n].contiguous(), prev[n:].contiguous()
+    setup = time.perf_counter() - t0
+    io = abi.StorageClosedForm(); io.start_flag = 1
+    io.unsorted_log_queue_state = fin[0]; io.intermediate_sorted_queue_state = fin[1]
+    w = StorageDeduplicatorInstanceWitness(io, dev(u), pu, dev(s), d_ts, psd, None)
+    trace = torch.empty((abi.ST_COLS["NUM_COLS"], n), dtype=torch.int64, device="cuda")
+    K = abi.ST_COLS
+    whole = sort_and_deduplicate_storage_access_entry_point(eng, w, n, trace_out=trace, raise_on_unsatisfied=False)  # un-hinted result queue: builds the tails
+    assert whole.status.code == 0, (whole.status.code, hex(whole.status.failed_checks))
+    tails = pushes_from_trace(trace, None, [K["SHOULD_PUSH"]], [K["RESULT_TAIL"]], 4)
+    fin_tail = torch.tensor(np.array(list(whole.closed_form_input.final_sorted_queue_state.tail), dtype=np.uint64).view(np.int64), device="cuda").reshape(1, 4)
+    if int(whole.closed_form_input.final_sorted_queue_state.length) == len(tails) + 1:
+        tails = torch.cat([tails, fin_tail])
+    w.result_queue_tails = tails.contiguous()
+    cum = torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), torch.cumsum((trace[K["SHOULD_PUSH"]] != 0).to(torch.int64), 0)])
+    offs = [int(cum[sharding.row_range(n, r, world)[0]]) for r in range(world)]
+    ms_whole, whole = timed(lambda: sort_and_deduplicate_storage_access_entry_point(eng, w, n, trace_out=trace, raise_on_unsatisfied=False), steps=3, warmup=1)
+    assert whole.status.code == 0
+    del trace
+    torch.cuda.empty_cache()
+
+    def step():
+        return sharding.storage_validity_row_sharded(eng, w, n, rank, world, offs, device="cuda")
+
+    for _ in range(2):
+        got, (lo, hi) = step()
+    assert got.status.code == 0, (rank, got.status.code, hex(got.status.failed_checks), got.status.first_bad_row)
+    assert got.commitment.tolist() == whole.commitment.tolist(), "the cut instance must end with the whole instance's commitment"
+    assert bytes(got.closed_form_input.hidden_fsm_output) == bytes(whole.closed_form_input.hidden_fsm_output)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"config": f"C4 storage_validity_by_grand_product, ONE instance of 2^{log2rows} rows cut by row range over {world} GPU(s)",
+                          "ms": float(ms.item()), "rows_per_s": n / float(ms.item()) * 1e3, "ms_whole_instance_one_gpu": ms_whole,
+                          "speedup_vs_one_gpu": ms_whole / float(ms.item()), "push_offsets": offs, "result_pushes": len(tails),
+                          "same_commitment_and_fsm_output_as_the_whole_instance": True, "queue_hint_setup_s": setup,
+                          "collective": "one all-gather of {4 products, push count, status, FSM output record} per rank; fix-up: 8 columns x 4 field elements"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "c1"
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
@@ -311,6 +378,8 @@ if __name__ == "__main__":
         c3(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 18)
     elif what == "c4":
         c4(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 20)
+    elif what == "c4rows":
+        c4rows(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 20)
     elif what == "dq":
         dq(eng, int(sys.argv[2]) if len(sys.argv) > 2 else 20)
     elif what == "dmx":
