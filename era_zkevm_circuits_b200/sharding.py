@@ -85,18 +85,19 @@ def distributed_grand_products(local_fn, rank: int, world: int, acc_in=(1, 1, 1,
     return acc_out, acc_final, np.array(grand, dtype=np.uint64)
 
 
-# ---- ONE storage_validity instance cut over the ranks by row range -----------------------------------------
-# The loop of sort_and_deduplicate_storage_access_inner (storage_validity_by_grand_product/mod.rs:560-800) carries a small
-# state from row to row: the two grand-product accumulators per repetition, the three queue states, the cycle counter, the
-# previous key / timestamp and the state of the storage cell under construction (input.rs:37-52: exactly the hidden FSM record
-# the reference itself uses to chain circuit instances).  Cut at row `lo`, everything in that record except the accumulators is
-# known WITHOUT running rows [0, lo):
+# ---- ONE sorter instance cut over the ranks by row range -----------------------------------------------------
+# The loops of sort_and_deduplicate_storage_access_inner (storage_validity_by_grand_product/mod.rs:560-800) and
+# repack_and_prove_events_rollbacks_inner (log_sorter/mod.rs:234-420) carry a small state from row to row: the two grand-product
+# accumulators per repetition, the three queue states, the previous key / item and -- storage only -- the cycle counter and the
+# state of the storage cell under construction (input.rs:37-52 / log_sorter/input.rs:26-38: exactly the hidden FSM record the
+# reference itself uses to chain circuit instances).  Cut at row `lo`, everything in that record except the accumulators is known
+# WITHOUT running rows [0, lo):
 #   * queue heads / lengths: the host's queue-state hints (prev_tails[lo]) and `lo` itself;
 #   * the result queue: the host's tail hints, indexed by the number of pushes before the cut (push_offsets, a hint like the
 #     tails: verified after the exchange against the counts the ranks measured);
-#   * previous key / timestamp: the sorted record at lo - 1;
-#   * the cell state: a cell's state is reset by its first row, so replaying the rows of the cell that straddles the cut,
-#     [cell_start, lo), reproduces it exactly -- a short run through the same entry point;
+#   * previous key / item / timestamp and the storage cell state: a cell's state is reset by its first row, so replaying the rows
+#     of the cell that straddles the cut, [cell_start, lo) -- for log_sorter just row lo - 1 -- through the same entry point
+#     reproduces them exactly (its FSM output IS the record, accumulators and result queue apart);
 #   * the accumulators are running products: every rank starts from 1 and the columns are scaled after ONE all-gather.
 # Each rank then runs the stock entry point over its rows as a chained instance; the exchange carries {4 products, push
 # count, status, the FSM output record} per rank; the fix-up is 8 columns (GP_NEW, GP_ACC) times 4 field elements.
@@ -115,58 +116,158 @@ def _qs4(head, tail, length):
     return q
 
 
-def storage_start_state(io):
-    """the selection the entry point makes between the observable input and the hidden FSM input (mod.rs:190-395)"""
+def _qs_list(q):
+    return list(q.head) + list(q.tail) + [q.length]
+
+
+def _packed_keys(recs):
+    """[m, 13] u32: address (5 limbs) then key (8 limbs) of LogQuery records (numpy structured or byte rows)"""
+    a = _np(recs)
+    if a.dtype.names:
+        return np.concatenate([a["address"], a["key"]], axis=1)
+    return np.concatenate([a[:, :20].view(np.uint32), a[:, 20:52].view(np.uint32)], axis=1)
+
+
+class _StorageCut:
+    """storage_validity_by_grand_product: field names, the replay window, the encodings of the commitments"""
+    name = "storage_validity"
+    fsm_queues = ("current_unsorted_queue_state", "current_intermediate_sorted_queue_state", "current_final_sorted_queue_state")
+    obs_queues = ("unsorted_log_queue_state", "intermediate_sorted_queue_state")
+    final_queue = "final_sorted_queue_state"
+
+    def __init__(self):
+        from . import abi
+        self.ClosedForm, self.Fsm, self.cols, self.chk = abi.StorageClosedForm, abi.StorageFsm, abi.ST_COLS, abi.ST_CHK
+
+    def arrays(self, w):
+        """(unsorted records, unsorted prev tails, sorted records, sorted prev tails, extra per-row arrays of the sorted queue)"""
+        return w.unsorted_queue_witness, w.unsorted_queue_prev_tails, w.intermediate_sorted_queue_witness, w.intermediate_sorted_queue_prev_tails, \
+            (w.intermediate_sorted_queue_timestamps,)
+
+    def cycle0(self, io):
+        return 0 if io.start_flag else int(io.hidden_fsm_input.cycle_idx)
+
+    def replay_start(self, w, lo):
+        """first row of the cell that holds row lo - 1: rows [cs, lo) share its packed key (address, key)"""
+        win = 256
+        while True:
+            a0 = max(0, lo - win)
+            keys = _packed_keys(w.intermediate_sorted_queue_witness[a0:lo])
+            other = np.flatnonzero(~(keys == keys[-1]).all(axis=1))
+            if len(other) or a0 == 0:
+                return a0 + (int(other[-1]) + 1 if len(other) else 0)
+            win *= 4
+
+    def fill_replay_fsm(self, f, w, io0, cs):
+        f.cycle_idx = self.cycle0(io0) + cs
+        prev = _packed_keys(w.intermediate_sorted_queue_witness[cs - 1:cs])[0]
+        for i in range(5):
+            f.previous_address[i] = int(prev[i]); f.previous_packed_key[8 + i] = int(prev[i])
+        for i in range(8):
+            f.previous_key[i] = int(prev[5 + i]); f.previous_packed_key[i] = int(prev[5 + i])
+        f.previous_timestamp = int(_np(w.intermediate_sorted_queue_timestamps[cs - 1:cs]).view(np.uint32)[0])
+
+    def fsm_encoding(self, f):
+        """77 field elements, StorageDeduplicatorFSMInputOutput's encoding order (input.rs:37-52)"""
+        e = [f.lhs_accumulator[0], f.lhs_accumulator[1], f.rhs_accumulator[0], f.rhs_accumulator[1]]
+        for q in self.fsm_queues:
+            e += _qs_list(getattr(f, q))
+        e += [f.cycle_idx] + list(f.previous_packed_key) + list(f.previous_key) + list(f.previous_address) + [f.previous_timestamp]
+        e += [f.this_cell_has_explicit_read_and_rollback_depth_zero] + list(f.this_cell_base_value) + list(f.this_cell_current_value) + [f.this_cell_current_depth]
+        return np.array([int(x) for x in e], dtype=np.uint64)
+
+    def obs_in_encoding(self, io):
+        return np.array([io.shard_id_to_process & 0xFF] + _qs_list(io.unsorted_log_queue_state) + _qs_list(io.intermediate_sorted_queue_state), dtype=np.uint64)
+
+
+class _EventsCut:
+    """log_sorter: the FSM record is the previous key and item -- the replay window is row lo - 1 alone"""
+    name = "log_sorter"
+    fsm_queues = ("initial_unsorted_queue_state", "intermediate_sorted_queue_state", "final_result_queue_state")
+    obs_queues = ("initial_log_queue_state", "intermediate_sorted_queue_state")
+    final_queue = "final_queue_state"
+
+    def __init__(self):
+        from . import abi
+        self.ClosedForm, self.Fsm, self.cols, self.chk = abi.EventsClosedForm, abi.EventsFsm, abi.EV_COLS, abi.EV_CHK
+
+    def arrays(self, w):
+        return w.initial_queue_witness, w.initial_queue_prev_tails, w.intermediate_sorted_queue_witness, w.intermediate_sorted_queue_prev_tails, ()
+
+    def replay_start(self, w, lo):
+        return lo - 1
+
+    def fill_replay_fsm(self, f, w, io0, cs):
+        pass
+
+    def fsm_encoding(self, f):
+        """68 field elements (log_sorter/input.rs:26-38): accumulators, 3 queue states, previous key, the previous item's 36 variables"""
+        from . import abi
+        e = [f.lhs_accumulator[0], f.lhs_accumulator[1], f.rhs_accumulator[0], f.rhs_accumulator[1]]
+        for q in self.fsm_queues:
+            e += _qs_list(getattr(f, q))
+        p = f.previous_item
+        fl = int(p.flags)
+        e += [f.previous_key] + list(p.address) + list(p.key) + list(p.read_value) + list(p.written_value)
+        e += [fl & 0xFF, (fl >> 16) & 1, (fl >> 17) & 1, (fl >> 18) & 1, (fl >> 8) & 0xFF, p.tx_number_in_block, p.timestamp]
+        return np.array([int(x) for x in e], dtype=np.uint64)
+
+    def obs_in_encoding(self, io):
+        return np.array(_qs_list(io.initial_log_queue_state) + _qs_list(io.intermediate_sorted_queue_state), dtype=np.uint64)
+
+
+def _start_state(cut, io):
+    """the selection the entry points make between the observable input and the hidden FSM input (storage mod.rs:190-395)"""
     f = io.hidden_fsm_input
     start = bool(io.start_flag)
-    uq0 = io.unsorted_log_queue_state if start else f.current_unsorted_queue_state
-    sq0 = io.intermediate_sorted_queue_state if start else f.current_intermediate_sorted_queue_state
-    rq0 = _qs4([0] * 4, [0] * 4, 0) if start else f.current_final_sorted_queue_state
-    acc0 = [1, 1, 1, 1] if start else [int(f.lhs_accumulator[0]), int(f.rhs_accumulator[0]), int(f.lhs_accumulator[1]), int(f.rhs_accumulator[1])]
-    return uq0, sq0, rq0, acc0, (0 if start else int(f.cycle_idx))
+    uq0 = getattr(io, cut.obs_queues[0]) if start else getattr(f, cut.fsm_queues[0])
+    sq0 = getattr(io, cut.obs_queues[1]) if start else getattr(f, cut.fsm_queues[1])
+    rq0 = _qs4([0] * 4, [0] * 4, 0) if start else getattr(f, cut.fsm_queues[2])
+    return uq0, sq0, rq0
 
 
-def storage_fsm_encoding(f):
-    """77 field elements, StorageDeduplicatorFSMInputOutput's encoding order (input.rs:37-52)"""
-    e = [f.lhs_accumulator[0], f.lhs_accumulator[1], f.rhs_accumulator[0], f.rhs_accumulator[1]]
-    for q in (f.current_unsorted_queue_state, f.current_intermediate_sorted_queue_state, f.current_final_sorted_queue_state):
-        e += list(q.head) + list(q.tail) + [q.length]
-    e += [f.cycle_idx] + list(f.previous_packed_key) + list(f.previous_key) + list(f.previous_address) + [f.previous_timestamp]
-    e += [f.this_cell_has_explicit_read_and_rollback_depth_zero] + list(f.this_cell_base_value) + list(f.this_cell_current_value) + [f.this_cell_current_depth]
-    return np.array([int(x) for x in e], dtype=np.uint64)
+def storage_start_state(io):
+    return _start_state(_StorageCut(), io)
 
 
-def storage_closed_form_commitment(commit_fn, io):
-    """ClosedFormInputCompactForm::from_full_form + commit (fsm_input_output/mod.rs:281-326) of a finished storage_validity closed
-    form; commit_fn(elements [len] uint64) -> [4] is the variable-length Poseidon2 commitment (Engine.commit_encoding)."""
-    qs = lambda q: list(q.head) + list(q.tail) + [q.length]
-    obs_in = np.array([io.shard_id_to_process & 0xFF] + qs(io.unsorted_log_queue_state) + qs(io.intermediate_sorted_queue_state), dtype=np.uint64)
+def closed_form_commitment(cut, commit_fn, io):
+    """ClosedFormInputCompactForm::from_full_form + commit (fsm_input_output/mod.rs:281-326) of a finished closed form;
+    commit_fn(elements [len] uint64) -> [4] is the variable-length Poseidon2 commitment (Engine.commit_encoding)."""
     compact = np.zeros(18, dtype=np.uint64)
     compact[0], compact[1] = int(bool(io.start_flag)), int(bool(io.completion_flag))
-    compact[2:6] = commit_fn(obs_in)
+    compact[2:6] = commit_fn(cut.obs_in_encoding(io))
     if io.completion_flag:
-        compact[6:10] = commit_fn(np.array(qs(io.final_sorted_queue_state), dtype=np.uint64))
+        compact[6:10] = commit_fn(np.array(_qs_list(getattr(io, cut.final_queue)), dtype=np.uint64))
     else:
-        compact[14:18] = commit_fn(storage_fsm_encoding(io.hidden_fsm_output))
+        compact[14:18] = commit_fn(cut.fsm_encoding(io.hidden_fsm_output))
     if not io.start_flag:
-        compact[10:14] = commit_fn(storage_fsm_encoding(io.hidden_fsm_input))
+        compact[10:14] = commit_fn(cut.fsm_encoding(io.hidden_fsm_input))
     return commit_fn(compact)
 
 
-_ST_LOCAL_WORDS = 16  # int64 words of the fixed part of a rank's exchange record
+def storage_closed_form_commitment(commit_fn, io):
+    return closed_form_commitment(_StorageCut(), commit_fn, io)
 
 
-def storage_rows_local(run_fn, witness, limit, rank, world, push_offsets):
+def events_closed_form_commitment(commit_fn, io):
+    return closed_form_commitment(_EventsCut(), commit_fn, io)
+
+
+_LOCAL_WORDS = 16  # int64 words of the fixed part of a rank's exchange record
+
+
+def rows_local(cut, run_fn, witness, limit, rank, world, push_offsets):
     """Phase 1 on rank `rank`: derive the FSM input at the rank's first row, run the rank's rows through the entry point.
-    run_fn(io, unsorted, unsorted_prev_tails, sorted, sorted_ts, sorted_prev_tails, result_tails, limit, want_trace) ->
-    SorterResult-like (closed_form_input, trace, status).  Returns (result of the rank's rows, lo, hi, exchange record int64)."""
+    run_fn(io, unsorted, unsorted_prev_tails, sorted, sorted_prev_tails, extras, result_tails, limit, want_trace) ->
+    SorterResult-like (closed_form_input, trace, status, commitment).  Returns (result of the rank's rows, lo, hi, exchange
+    record int64)."""
     import ctypes as C
     from . import abi
-    from .storage_validity import ST_CHK_GRAND_PRODUCT
     w = witness
     io0 = w.closed_form_input
-    uq0, sq0, rq0, acc0, cycle0 = storage_start_state(io0)
-    n_active = min(limit, int(uq0.length), int(sq0.length), len(w.unsorted_queue_witness), len(w.intermediate_sorted_queue_witness))
+    uq0, sq0, rq0 = _start_state(cut, io0)
+    u, up, s, sp, extras = cut.arrays(w)
+    n_active = min(limit, int(uq0.length), int(sq0.length), len(u), len(s))
     if world > 1 and (w.result_queue_tails is None or push_offsets is None or len(push_offsets) != world):
         raise ValueError("a row-sharded run needs the result-queue tail hints and one push offset per rank")
     if world > 1 and n_active < world:
@@ -175,149 +276,155 @@ def storage_rows_local(run_fn, witness, limit, rank, world, push_offsets):
     if rank == world - 1:
         hi = limit  # the padding rows after the queues run empty stay with the last rank
     k_lo = int(push_offsets[rank]) if world > 1 else 0
-    io = abi.StorageClosedForm.from_buffer_copy(bytes(io0))
+    io = cut.ClosedForm.from_buffer_copy(bytes(io0))
     sl = lambda a, a0, a1: None if a is None else a[a0:a1]
+    args = lambda a0, a1: (sl(u, a0, a1), sl(up, a0, a1), sl(s, a0, a1), sl(sp, a0, a1), tuple(sl(x, a0, a1) for x in extras))
     if rank > 0:
-        # the cell that straddles the cut: rows [cs, lo) share the packed key (address, key) of row lo - 1
-        cs = lo - 1
-        win = 256
-        key_of = lambda recs: np.concatenate([_np(recs)["address"] if _np(recs).dtype.names else _np(recs)[:, :20].view(np.uint32),
-                                              _np(recs)["key"] if _np(recs).dtype.names else _np(recs)[:, 20:52].view(np.uint32)], axis=1)
-        while True:
-            a0 = max(0, lo - win)
-            keys = key_of(w.intermediate_sorted_queue_witness[a0:lo])
-            same = (keys == keys[-1]).all(axis=1)
-            first_other = np.flatnonzero(~same)
-            if len(first_other) or a0 == 0:
-                cs = a0 + (int(first_other[-1]) + 1 if len(first_other) else 0)
-                break
-            win *= 4
-        mini = abi.StorageClosedForm.from_buffer_copy(bytes(io0))
+        cs = cut.replay_start(w, lo)
+        mini = cut.ClosedForm.from_buffer_copy(bytes(io0))
         if cs > 0:
             mini.start_flag = 0
             f = mini.hidden_fsm_input
             C.memset(C.byref(f), 0, C.sizeof(f))
             f.lhs_accumulator[0] = f.lhs_accumulator[1] = f.rhs_accumulator[0] = f.rhs_accumulator[1] = 1
-            f.current_unsorted_queue_state = _qs4(_np(w.unsorted_queue_prev_tails[cs:cs + 1]).view(np.uint64)[0], uq0.tail, int(uq0.length) - cs)
-            f.current_intermediate_sorted_queue_state = _qs4(_np(w.intermediate_sorted_queue_prev_tails[cs:cs + 1]).view(np.uint64)[0], sq0.tail, int(sq0.length) - cs)
-            f.cycle_idx = cycle0 + cs
-            prev = key_of(w.intermediate_sorted_queue_witness[cs - 1:cs])[0]
-            for i in range(5):
-                f.previous_address[i] = int(prev[i]); f.previous_packed_key[8 + i] = int(prev[i])
-            for i in range(8):
-                f.previous_key[i] = int(prev[5 + i]); f.previous_packed_key[i] = int(prev[5 + i])
-            f.previous_timestamp = int(_np(w.intermediate_sorted_queue_timestamps[cs - 1:cs]).view(np.uint32)[0])
-        m = run_fn(mini, sl(w.unsorted_queue_witness, cs, lo), sl(w.unsorted_queue_prev_tails, cs, lo), sl(w.intermediate_sorted_queue_witness, cs, lo),
-                   sl(w.intermediate_sorted_queue_timestamps, cs, lo), sl(w.intermediate_sorted_queue_prev_tails, cs, lo), None, lo - cs, False)
+            setattr(f, cut.fsm_queues[0], _qs4(_np(up[cs:cs + 1]).view(np.uint64)[0], uq0.tail, int(uq0.length) - cs))
+            setattr(f, cut.fsm_queues[1], _qs4(_np(sp[cs:cs + 1]).view(np.uint64)[0], sq0.tail, int(sq0.length) - cs))
+            cut.fill_replay_fsm(f, w, io0, cs)
+        m = run_fn(mini, *args(cs, lo), None, lo - cs, False)
         if m.status.code not in (abi.ZKC_OK, abi.ZKC_ERR_UNSATISFIED):
-            raise RuntimeError(f"replay of the straddling cell [{cs}, {lo}) failed: code {m.status.code}")
+            raise RuntimeError(f"replay of rows [{cs}, {lo}) failed: code {m.status.code}")
         io.start_flag = 0
         io.hidden_fsm_input = m.closed_form_input.hidden_fsm_output
         f = io.hidden_fsm_input
         f.lhs_accumulator[0] = f.lhs_accumulator[1] = f.rhs_accumulator[0] = f.rhs_accumulator[1] = 1
         tail = _np(w.result_queue_tails[k_lo - 1:k_lo]).view(np.uint64)[0] if k_lo > 0 else rq0.tail
-        f.current_final_sorted_queue_state = _qs4(rq0.head, tail, int(rq0.length) + k_lo)
-    res = run_fn(io, sl(w.unsorted_queue_witness, lo, hi), sl(w.unsorted_queue_prev_tails, lo, hi), sl(w.intermediate_sorted_queue_witness, lo, hi),
-                 sl(w.intermediate_sorted_queue_timestamps, lo, hi), sl(w.intermediate_sorted_queue_prev_tails, lo, hi),
-                 None if w.result_queue_tails is None else w.result_queue_tails[k_lo:], hi - lo, True)
+        setattr(f, cut.fsm_queues[2], _qs4(rq0.head, tail, int(rq0.length) + k_lo))
+    res = run_fn(io, *args(lo, hi), None if w.result_queue_tails is None else w.result_queue_tails[k_lo:], hi - lo, True)
     out = res.closed_form_input.hidden_fsm_output
     st = res.status
     failed = int(st.failed_checks)
     if world > 1:
-        failed &= ~ST_CHK_GRAND_PRODUCT  # lhs == rhs holds for the WHOLE loop: re-evaluated on the exchanged products
+        failed &= ~cut.chk["GRAND_PRODUCT"]  # lhs == rhs holds for the WHOLE loop: re-evaluated on the exchanged products
     code = int(st.code) if (failed or st.code != abi.ZKC_ERR_UNSATISFIED) else 0
-    fsm_bytes = np.frombuffer(bytes(out) + bytes(res.closed_form_input.final_sorted_queue_state), dtype=np.uint8)
+    fsm_bytes = np.frombuffer(bytes(out) + bytes(getattr(res.closed_form_input, cut.final_queue)), dtype=np.uint8)
     pad = (-len(fsm_bytes)) % 8
-    rec = np.zeros(_ST_LOCAL_WORDS + (len(fsm_bytes) + pad) // 8, dtype=np.int64)
+    rec = np.zeros(_LOCAL_WORDS + (len(fsm_bytes) + pad) // 8, dtype=np.int64)
     loc = np.array([out.lhs_accumulator[0], out.rhs_accumulator[0], out.lhs_accumulator[1], out.rhs_accumulator[1]], dtype=np.uint64)
-    f_in = io.hidden_fsm_input
-    pushes_in = int(f_in.current_final_sorted_queue_state.length) if not io.start_flag else 0
+    pushes_in = int(getattr(io.hidden_fsm_input, cut.fsm_queues[2]).length) if not io.start_flag else 0
     rec[0:4] = loc.view(np.int64)
-    rec[4] = int(out.current_final_sorted_queue_state.length) - pushes_in  # pushes of this rank's rows (+ the finalisation push on the last)
+    rec[4] = int(getattr(out, cut.fsm_queues[2]).length) - pushes_in  # pushes of this rank's rows (+ the finalisation push on the last)
     rec[5], rec[6], rec[7] = code, failed, int(st.first_bad_row) + lo if st.first_bad_row >= 0 else -1
     rec[8] = int(res.closed_form_input.completion_flag)
     rec[9], rec[10] = lo, hi
-    rec[_ST_LOCAL_WORDS:] = np.concatenate([fsm_bytes, np.zeros(pad, np.uint8)]).view(np.int64)
+    rec[_LOCAL_WORDS:] = np.concatenate([fsm_bytes, np.zeros(pad, np.uint8)]).view(np.int64)
     return res, lo, hi, rec
 
 
-def storage_rows_finish(res, rank, world, records, io0, push_offsets, scale_fn, commit_fn):
+def rows_finish(cut, res, rank, world, records, io0, push_offsets, scale_fn, commit_fn):
     """Phase 2: `records` [world, words] = every rank's exchange record.  Scales this rank's GP_NEW / GP_ACC columns by the
     product of everything before its rows, verifies the push offsets, assembles the WHOLE instance's closed form, status and
     commitment (identical on every rank).  Returns (commitment, closed form, trace of this rank's rows, status)."""
     import ctypes as C
     from . import abi
-    from .storage_validity import ST_CHK_GRAND_PRODUCT
+    if world == 1:
+        return res.commitment, res.closed_form_input, res.trace, res.status
     records = np.asarray(records, dtype=np.int64).reshape(world, -1)
     totals = records[:, 0:4].copy().view(np.uint64)
     seed = [1, 1, 1, 1]  # rank 0 runs from the instance's own accumulators: its totals carry them
     for r in range(rank):
         seed = [s * int(t) % GL_P for s, t in zip(seed, totals[r])]
-    K = abi.ST_COLS
-    if world > 1 and rank > 0 and res.trace is not None and any(s != 1 for s in seed):
+    K = cut.cols
+    if rank > 0 and res.trace is not None and any(s != 1 for s in seed):
         scale_fn(res.trace[K["GP_NEW"]:K["GP_NEW"] + 4], np.array(seed, dtype=np.uint64))
         scale_fn(res.trace[K["GP_ACC"]:K["GP_ACC"] + 4], np.array(seed, dtype=np.uint64))
-    io = abi.StorageClosedForm.from_buffer_copy(bytes(io0))
+    io = cut.ClosedForm.from_buffer_copy(bytes(io0))
     last = records[world - 1]
-    fsm_len = C.sizeof(abi.StorageFsm)
-    tail_bytes = last[_ST_LOCAL_WORDS:].view(np.uint8)
-    io.hidden_fsm_output = abi.StorageFsm.from_buffer_copy(tail_bytes[:fsm_len].tobytes())
-    io.final_sorted_queue_state = abi.QueueState4.from_buffer_copy(tail_bytes[fsm_len:fsm_len + C.sizeof(abi.QueueState4)].tobytes())
+    fsm_len = C.sizeof(cut.Fsm)
+    tail_bytes = last[_LOCAL_WORDS:].view(np.uint8)
+    io.hidden_fsm_output = cut.Fsm.from_buffer_copy(tail_bytes[:fsm_len].tobytes())
+    setattr(io, cut.final_queue, abi.QueueState4.from_buffer_copy(tail_bytes[fsm_len:fsm_len + C.sizeof(abi.QueueState4)].tobytes()))
     io.completion_flag = int(last[8])
+    grand = [1, 1, 1, 1]
+    for r in range(world):
+        grand = [g * int(t) % GL_P for g, t in zip(grand, totals[r])]
+    out = io.hidden_fsm_output
+    out.lhs_accumulator[0], out.rhs_accumulator[0], out.lhs_accumulator[1], out.rhs_accumulator[1] = grand
+    failed, code, first_bad = 0, 0, -1
+    for r in range(world):
+        failed |= int(records[r, 6])
+        if records[r, 5] and not code:
+            code = int(records[r, 5])
+        if records[r, 7] >= 0 and first_bad < 0:
+            first_bad = int(records[r, 7])
+        if r + 1 < world and int(push_offsets[r]) + int(records[r, 4]) != int(push_offsets[r + 1]):
+            failed |= cut.chk["QUEUE_HINT"]
+            code = code or abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT
+    if io.completion_flag and (grand[0] != grand[1] or grand[2] != grand[3]):
+        failed |= cut.chk["GRAND_PRODUCT"]
+    if failed and not code:
+        code = abi.ZKC_ERR_UNSATISFIED
     st = abi.Status()
-    st.first_bad_row = -1
+    st.code, st.failed_checks, st.first_bad_row = code, failed, first_bad
+    return closed_form_commitment(cut, commit_fn, io), io, res.trace, st
+
+
+def storage_rows_local(run_fn, witness, limit, rank, world, push_offsets):
+    """rows_local for storage_validity; run_fn(io, u, up, s, ts, sp, tails, limit, want_trace)"""
+    return rows_local(_StorageCut(), lambda io, u, up, s, sp, ex, tails, lim, wt: run_fn(io, u, up, s, ex[0], sp, tails, lim, wt),
+                      witness, limit, rank, world, push_offsets)
+
+
+def storage_rows_finish(res, rank, world, records, io0, push_offsets, scale_fn, commit_fn):
+    return rows_finish(_StorageCut(), res, rank, world, records, io0, push_offsets, scale_fn, commit_fn)
+
+
+def events_rows_local(run_fn, witness, limit, rank, world, push_offsets):
+    """rows_local for log_sorter; run_fn(io, u, up, s, sp, tails, limit, want_trace)"""
+    return rows_local(_EventsCut(), lambda io, u, up, s, sp, ex, tails, lim, wt: run_fn(io, u, up, s, sp, tails, lim, wt),
+                      witness, limit, rank, world, push_offsets)
+
+
+def events_rows_finish(res, rank, world, records, io0, push_offsets, scale_fn, commit_fn):
+    return rows_finish(_EventsCut(), res, rank, world, records, io0, push_offsets, scale_fn, commit_fn)
+
+
+def _row_sharded(engine, local_fn, finish_fn, run_fn, witness, limit, rank, world, push_offsets, device):
+    import torch
+    import torch.distributed as dist
+    from .log_sorter import SorterResult
+    res, lo, hi, rec = local_fn(run_fn, witness, limit, rank, world, push_offsets)
+    mine = torch.from_numpy(rec.copy())
+    if device is not None:
+        mine = mine.to(device)
+    allr = torch.zeros((world, len(rec)), dtype=torch.int64, device=mine.device)
     if world > 1:
-        grand = [1, 1, 1, 1]
-        for r in range(world):
-            grand = [g * int(t) % GL_P for g, t in zip(grand, totals[r])]
-        out = io.hidden_fsm_output
-        out.lhs_accumulator[0], out.rhs_accumulator[0], out.lhs_accumulator[1], out.rhs_accumulator[1] = grand
-        failed, code, first_bad = 0, 0, -1
-        for r in range(world):
-            failed |= int(records[r, 6])
-            if records[r, 5] and not code:
-                code = int(records[r, 5])
-            if records[r, 7] >= 0 and first_bad < 0:
-                first_bad = int(records[r, 7])
-            expect = int(push_offsets[r + 1]) if r + 1 < world else None
-            if expect is not None and int(push_offsets[r]) + int(records[r, 4]) != expect:
-                failed |= abi.ST_CHK["QUEUE_HINT"]
-                code = code or abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT
-        if io.completion_flag and (grand[0] != grand[1] or grand[2] != grand[3]):
-            failed |= ST_CHK_GRAND_PRODUCT
-        if failed and not code:
-            code = abi.ZKC_ERR_UNSATISFIED
-        st.code, st.failed_checks, st.first_bad_row = code, failed, first_bad
-        commitment = storage_closed_form_commitment(commit_fn, io)
+        dist.all_gather_into_tensor(allr, mine.reshape(1, -1))  # the path's ONE collective
     else:
-        st = res.status
-        commitment = res.commitment
-    return commitment, io, res.trace, st
+        allr.copy_(mine.reshape(1, -1))
+    commit_fn = lambda e: engine.commit_encoding(np.ascontiguousarray(e, dtype=np.uint64).reshape(1, -1))[0]
+    com, io, trace, st = finish_fn(res, rank, world, allr.cpu().numpy(), witness.closed_form_input, push_offsets, engine.scale_accumulators, commit_fn)
+    return SorterResult(com, io, trace, st), (lo, hi)
 
 
 def storage_validity_row_sharded(engine, witness, limit, rank, world, push_offsets=None, device=None):
     """sort_and_deduplicate_storage_access_entry_point of ONE instance over `world` ranks (one process per GPU, torch.distributed
     initialised by the caller): phase 1, the single all-gather, phase 2.  Every rank holds (or can slice) the whole witness;
     push_offsets[r] = result-queue pushes in the rows before rank r's first row (row_range over the active rows)."""
-    import torch
-    import torch.distributed as dist
-    from .log_sorter import SorterResult
     from .storage_validity import StorageDeduplicatorInstanceWitness, sort_and_deduplicate_storage_access_entry_point
 
     def run_fn(io, u, up, s, ts, sp, tails, lim, want_trace):
         wit = StorageDeduplicatorInstanceWitness(io, u, up, s, ts, sp, tails)
         return sort_and_deduplicate_storage_access_entry_point(engine, wit, lim, want_trace=want_trace, raise_on_unsatisfied=False)
 
-    res, lo, hi, rec = storage_rows_local(run_fn, witness, limit, rank, world, push_offsets)
-    mine = torch.from_numpy(rec.copy())
-    if device is not None:
-        mine = mine.to(device)
-    allr = torch.zeros((world, len(rec)), dtype=torch.int64, device=mine.device)
-    if world > 1:
-        dist.all_gather_into_tensor(allr, mine.reshape(1, -1))
-    else:
-        allr.copy_(mine.reshape(1, -1))
-    commit_fn = lambda e: engine.commit_encoding(np.ascontiguousarray(e, dtype=np.uint64).reshape(1, -1))[0]
-    com, io, trace, st = storage_rows_finish(res, rank, world, allr.cpu().numpy(), witness.closed_form_input, push_offsets,
-                                             engine.scale_accumulators, commit_fn)
-    return SorterResult(com, io, trace, st), (lo, hi)
+    return _row_sharded(engine, storage_rows_local, storage_rows_finish, run_fn, witness, limit, rank, world, push_offsets, device)
+
+
+def log_sorter_row_sharded(engine, witness, limit, rank, world, push_offsets=None, device=None):
+    """sort_and_deduplicate_events_entry_point of ONE instance over `world` ranks, as storage_validity_row_sharded"""
+    from .log_sorter import EventsDeduplicatorInstanceWitness, sort_and_deduplicate_events_entry_point
+
+    def run_fn(io, u, up, s, sp, tails, lim, want_trace):
+        wit = EventsDeduplicatorInstanceWitness(io, u, up, s, sp, tails)
+        return sort_and_deduplicate_events_entry_point(engine, wit, lim, want_trace=want_trace, raise_on_unsatisfied=False)
+
+    return _row_sharded(engine, events_rows_local, events_rows_finish, run_fn, witness, limit, rank, world, push_offsets, device)

@@ -10,7 +10,6 @@ from . import abi
 from .engine import Engine, ZkcError, on_device, ptr
 from .log_sorter import SorterResult
 
-ST_CHK_GRAND_PRODUCT = abi.ST_CHK["GRAND_PRODUCT"]
 
 
 @dataclass

@@ -183,3 +183,35 @@ def test_check_trace_constraint_evaluation(engine, orc):
     assert b.status.code == 0
     viol, st = log_sorter_check_trace(engine, nxt, b.trace, limit - cut)
     assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)
+
+
+def test_one_instance_cut_by_rows_over_ranks(engine, orc):
+    """sharding.events_rows_local / events_rows_finish with the ENGINE as the backend, 3 virtual ranks on this GPU: rank traces (accumulator
+    columns scaled after the exchange) concatenate to the whole instance's trace; every rank ends with the whole closed form + commitment"""
+    from era_zkevm_circuits_b200 import sharding
+    n, limit = 5000, 5100
+    u, s = synthetic.events_trace(n, seed=12, rollback_pct=15)
+    io, up, sp = instance(orc, u, s)
+    want = O.log_sorter_entry_point(orc, io, u, s, limit)
+    assert want[0] == abi.ZKC_OK
+    w = EventsDeduplicatorInstanceWitness(io, u, up, s, sp, want[5])
+    world = 3
+    cum = np.concatenate([[0], np.cumsum(want[2][K["ADD_TO_QUEUE"]])]).astype(np.int64)
+    offs = [int(cum[sharding.row_range(n, r, world)[0]]) for r in range(world)]
+
+    def run(io_, u_, up_, s_, sp_, tails_, lim, want_trace):
+        return sort_and_deduplicate_events_entry_point(engine, EventsDeduplicatorInstanceWitness(io_, u_, up_, s_, sp_, tails_), lim,
+                                                       want_trace=want_trace, raise_on_unsatisfied=False)
+
+    commit = lambda e: engine.commit_encoding(np.ascontiguousarray(e, dtype=np.uint64).reshape(1, -1))[0]
+    locs = [sharding.events_rows_local(run, w, limit, r, world, offs) for r in range(world)]
+    recs = np.stack([l[3] for l in locs])
+    traces = []
+    for r in range(world):
+        com, io_g, trace, st = sharding.events_rows_finish(locs[r][0], r, world, recs, io, offs, engine.scale_accumulators, commit)
+        assert st.code == 0, (r, st.code, hex(st.failed_checks), st.first_bad_row)
+        assert com.tolist() == want[3].tolist()
+        assert bytes(io_g.hidden_fsm_output) == bytes(want[1].hidden_fsm_output) and bytes(io_g.final_queue_state) == bytes(want[1].final_queue_state)
+        traces.append(trace)
+    bad = np.argwhere(np.concatenate(traces, axis=1) != want[2])
+    assert bad.size == 0, f"first differing (col,row): {bad[:8].tolist()}"

@@ -213,3 +213,40 @@ def test_row_sharded_storage_chained_instance_and_bad_offsets():
     locs = [sharding.storage_rows_local(run, w2, limit - 400, r, world, bad) for r in range(world)]
     com, io, trace, st = sharding.storage_rows_finish(locs[0][0], 0, world, np.stack([l[3] for l in locs]), nxt, bad, scale, commit)
     assert st.code != 0 and st.failed_checks & abi.ST_CHK["QUEUE_HINT"]
+
+
+def test_row_sharded_log_sorter_virtual_ranks():
+    """ONE log_sorter instance cut by rows (its FSM record is the previous key / item: the replay window is row lo - 1 alone);
+    2 and 4 virtual ranks with the oracle as the backend"""
+    sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+    from types import SimpleNamespace
+    import orc as O
+    from era_zkevm_circuits_b200 import EventsDeduplicatorInstanceWitness, abi, sharding, synthetic
+    lib = O.load()
+    n, limit = 1500, 1530
+    u, s = synthetic.events_trace(n, seed=8, rollback_pct=20)
+    up, ufin = O.log_queue_simulate(lib, u)
+    sp, sfin = O.log_queue_simulate(lib, s)
+    io = O.events_closed_form(ufin, sfin, True)
+    whole = O.log_sorter_entry_point(lib, io, u, s, limit)
+    assert whole[0] == 0
+    assert np.array_equal(sharding.events_closed_form_commitment(lambda e: O.commit_encoding(lib, e), whole[1]), whole[3])
+    w = EventsDeduplicatorInstanceWitness(io, u, up, s, sp, whole[5])
+
+    def run(io_, u_, up_, s_, sp_, tails, lim, want_trace):
+        rc, io2, trace, com, st, _ = O.log_sorter_entry_point(lib, io_, u_, s_, lim, want_trace=want_trace)
+        return SimpleNamespace(closed_form_input=io2, trace=trace, status=st, commitment=com)
+
+    _, scale, commit = _oracle_backend(lib)
+    cum = np.concatenate([[0], np.cumsum(whole[2][abi.EV_COLS["ADD_TO_QUEUE"]])]).astype(np.int64)
+    for world in (2, 4):
+        offs = [int(cum[sharding.row_range(n, r, world)[0]]) for r in range(world)]
+        locs = [sharding.events_rows_local(run, w, limit, r, world, offs) for r in range(world)]
+        recs = np.stack([l[3] for l in locs])
+        traces = []
+        for r in range(world):
+            com, io_g, trace, st = sharding.events_rows_finish(locs[r][0], r, world, recs, io, offs, scale, commit)
+            assert st.code == 0 and np.array_equal(com, whole[3])
+            assert bytes(io_g.hidden_fsm_output) == bytes(whole[1].hidden_fsm_output) and bytes(io_g.final_queue_state) == bytes(whole[1].final_queue_state)
+            traces.append(trace)
+        assert np.array_equal(np.concatenate(traces, axis=1), whole[2])
