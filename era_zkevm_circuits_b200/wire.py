@@ -3,6 +3,7 @@ default options: little-endian, fixed-width integers, u64 sequence lengths) prod
 
     RamPermutationCircuitInstanceWitness   /root/reference/src/ram_permutation/input.rs:99-116
     EventsDeduplicatorInstanceWitness      /root/reference/src/log_sorter/input.rs:98-106
+    StorageDeduplicatorInstanceWitness     /root/reference/src/storage_validity_by_grand_product/input.rs:128-136
 
 read into the host-side witness forms of this package (closed-form struct + struct-of-arrays queue witnesses), and written
 back (test_harness-style dumps for the round-trip tests).
@@ -331,4 +332,90 @@ def write_events_deduplicator_witness(w_) -> bytes:
     _write_events_fsm(w, io.hidden_fsm_output)
     _write_log_queue(w, w_.initial_queue_witness, w_.initial_queue_prev_tails)
     _write_log_queue(w, w_.intermediate_sorted_queue_witness, w_.intermediate_sorted_queue_prev_tails)
+    return bytes(w.b)
+
+
+# ---- storage_validity_by_grand_product ---------------------------------------------------------------------------------------
+def _read_storage_fsm(r: Reader, f):
+    """StorageDeduplicatorFSMInputOutput, storage_validity_by_grand_product/input.rs:37-52"""
+    for name in ("lhs_accumulator", "rhs_accumulator"):
+        for i, v in enumerate(r.fields(2)):
+            getattr(f, name)[i] = v
+    _read_queue_state(r, f.current_unsorted_queue_state)
+    _read_queue_state(r, f.current_intermediate_sorted_queue_state)
+    _read_queue_state(r, f.current_final_sorted_queue_state)
+    f.cycle_idx = r.u32()
+    for i in range(13):
+        f.previous_packed_key[i] = r.u32()
+    for i, v in enumerate(_limbs(r.u256(), 8)):
+        f.previous_key[i] = v
+    for i, v in enumerate(_limbs(r.h160(), 5)):
+        f.previous_address[i] = v
+    f.previous_timestamp = r.u32()
+    f.this_cell_has_explicit_read_and_rollback_depth_zero = r.boolean()
+    for i, v in enumerate(_limbs(r.u256(), 8)):
+        f.this_cell_base_value[i] = v
+    for i, v in enumerate(_limbs(r.u256(), 8)):
+        f.this_cell_current_value[i] = v
+    f.this_cell_current_depth = r.u32()
+
+
+def _write_storage_fsm(w: Writer, f):
+    w.fields(f.lhs_accumulator); w.fields(f.rhs_accumulator)
+    _write_queue_state(w, f.current_unsorted_queue_state)
+    _write_queue_state(w, f.current_intermediate_sorted_queue_state)
+    _write_queue_state(w, f.current_final_sorted_queue_state)
+    w.u32(f.cycle_idx)
+    for v in f.previous_packed_key:
+        w.u32(v)
+    w.u256(_from_limbs(f.previous_key)); w.h160(_from_limbs(f.previous_address)); w.u32(f.previous_timestamp)
+    w.boolean(f.this_cell_has_explicit_read_and_rollback_depth_zero)
+    w.u256(_from_limbs(f.this_cell_base_value)); w.u256(_from_limbs(f.this_cell_current_value)); w.u32(f.this_cell_current_depth)
+
+
+def read_storage_deduplicator_witness(data: bytes):
+    """bincode bytes of StorageDeduplicatorInstanceWitness<GoldilocksField> (input.rs:128-136) ->
+    storage_validity.StorageDeduplicatorInstanceWitness.  The sorted queue's elements are TimestampedStorageLogRecord witnesses
+    (mod.rs:63-66): the LogQuery witness followed by its u32 timestamp, then the previous tail."""
+    from .storage_validity import StorageDeduplicatorInstanceWitness
+    r = Reader(data)
+    io = abi.StorageClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    io.shard_id_to_process = r.u8()
+    _read_queue_state(r, io.unsorted_log_queue_state)
+    _read_queue_state(r, io.intermediate_sorted_queue_state)
+    _read_queue_state(r, io.final_sorted_queue_state)
+    _read_storage_fsm(r, io.hidden_fsm_input)
+    _read_storage_fsm(r, io.hidden_fsm_output)
+    u, up = _read_log_queue(r)
+    n = r.u64()
+    if n > (len(r.d) - r.o) // 8:
+        raise WireError(f"queue witness claims {n} elements")
+    s = np.zeros(n, dtype=abi.LOG_QUERY_DTYPE)
+    ts = np.zeros(n, dtype=np.uint32)
+    sp = np.zeros((n, 4), dtype=np.uint64)
+    for k in range(n):
+        s[k] = _read_log_query(r)
+        ts[k] = r.u32()
+        sp[k] = r.fields(4)
+    r.done()
+    return StorageDeduplicatorInstanceWitness(io, u, up, s, ts, sp)
+
+
+def write_storage_deduplicator_witness(w_) -> bytes:
+    w = Writer()
+    io = w_.closed_form_input
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    w.u8(io.shard_id_to_process)
+    _write_queue_state(w, io.unsorted_log_queue_state)
+    _write_queue_state(w, io.intermediate_sorted_queue_state)
+    _write_queue_state(w, io.final_sorted_queue_state)
+    _write_storage_fsm(w, io.hidden_fsm_input)
+    _write_storage_fsm(w, io.hidden_fsm_output)
+    _write_log_queue(w, w_.unsorted_queue_witness, w_.unsorted_queue_prev_tails)
+    w.u64(len(w_.intermediate_sorted_queue_witness))
+    for rec, t, p in zip(w_.intermediate_sorted_queue_witness, w_.intermediate_sorted_queue_timestamps, w_.intermediate_sorted_queue_prev_tails):
+        _write_log_query(w, rec)
+        w.u32(t)
+        w.fields(p)
     return bytes(w.b)

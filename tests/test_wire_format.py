@@ -92,3 +92,32 @@ def test_malformed_dumps_fail_loudly(orc):
     bad = bytearray(dump); bad[2:10] = struct.pack("<Q", abi.GL_P)
     with pytest.raises(wire.WireError):
         wire.read_ram_permutation_witness(bytes(bad))                       # non-canonical field element
+
+
+def test_storage_deduplicator_dump_round_trip_and_ingestion(orc):
+    """a chained (start_flag = 0) storage_validity instance: every field of the 77-element FSM record is populated; the ingested dump
+    proves like the original under the oracle"""
+    from era_zkevm_circuits_b200 import StorageDeduplicatorInstanceWitness
+    u, s, ts = synthetic.storage_trace(300, seed=4, n_cells=9)
+    up, ufin = O.log_queue_simulate(orc, u)
+    sp, sfin = O.log_queue_simulate(orc, s, ts)
+    io = O.storage_closed_form(ufin, sfin, 0, True)
+    first = O.storage_validity_entry_point(orc, io, u, s, ts, 120)
+    nxt = abi.StorageClosedForm.from_buffer_copy(bytes(first[1])); nxt.start_flag = 0
+    nxt.hidden_fsm_input = first[1].hidden_fsm_output
+    w = StorageDeduplicatorInstanceWitness(nxt, u[120:], up[120:], s[120:], ts[120:], sp[120:])
+    dump = wire.write_storage_deduplicator_witness(w)
+    assert dump[:3] == b"\x00\x00\x00"  # start_flag, completion_flag, shard id
+    got = wire.read_storage_deduplicator_witness(dump)
+    assert bytes(got.closed_form_input) == bytes(nxt)
+    for a, b in ((got.unsorted_queue_witness, w.unsorted_queue_witness), (got.intermediate_sorted_queue_witness, w.intermediate_sorted_queue_witness)):
+        assert a.tobytes() == np.ascontiguousarray(b).tobytes()
+    assert np.array_equal(got.intermediate_sorted_queue_timestamps, ts[120:])
+    assert np.array_equal(got.unsorted_queue_prev_tails, up[120:]) and np.array_equal(got.intermediate_sorted_queue_prev_tails, sp[120:])
+    assert wire.write_storage_deduplicator_witness(got) == dump
+    want = O.storage_validity_entry_point(orc, nxt, u[120:], s[120:], ts[120:], 200)
+    have = O.storage_validity_entry_point(orc, got.closed_form_input, got.unsorted_queue_witness, got.intermediate_sorted_queue_witness,
+                                          got.intermediate_sorted_queue_timestamps, 200)
+    assert want[0] == have[0] == 0 and np.array_equal(want[3], have[3]) and np.array_equal(want[2], have[2])
+    with pytest.raises(wire.WireError):
+        wire.read_storage_deduplicator_witness(dump[:-3])
