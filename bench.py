@@ -343,8 +343,8 @@ def run_gpu(args):
     value = n * cycles * world * args.steps / (ms / 1e3)
     # the timed region is K steps of a few ms: keep the same step running (untimed) until the sampler (10 Hz) has seen >= 1.5 s
     # of this load, and report the clocks over [start of the timed region, end of that tail]
-    t_tail = time.perf_counter()
-    while time.perf_counter() - t_tail < (1.5 if rank == 0 else 0.0):
+    # (the step holds a collective when n_gpus > 1: every rank runs the SAME number of tail steps, derived from the max-over-ranks time)
+    for _ in range(int(1500.0 / max(ms / args.steps, 0.05)) + 1):
         step_device()
     torch.cuda.synchronize()
     clocks = sampler.stop(t0, time.perf_counter()) if rank == 0 else None

@@ -6,7 +6,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import abi
-from .engine import Engine, ZkcError, on_device, ptr
+from .engine import Engine, ZkcError, check_hint_rows, on_device, ptr
 from .log_sorter import SorterResult
 
 
@@ -26,6 +26,7 @@ def demultiplex_storage_logs_enty_point(engine: Engine, witness: LogDemuxerCircu
                                         compare_expected=False, raise_on_unsatisfied=True, trace_out=None,
                                         options: Optional[abi.DemuxOptions] = None) -> SorterResult:
     w = witness
+    check_hint_rows("demultiplex_storage_logs_enty_point", w.initial_queue_witness, w.initial_queue_prev_tails)
     dev = on_device(w.initial_queue_witness, w.initial_queue_prev_tails, w.output_queue_tails)
     if trace_out is not None:
         dev |= 2 * on_device(trace_out)

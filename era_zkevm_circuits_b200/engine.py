@@ -36,6 +36,15 @@ def ptr(x):
     return C.c_void_p(x.ctypes.data)
 
 
+def check_hint_rows(what, records, *hints):
+    """the C ABI takes queue-state hints without a length: they must cover every record (a short hint array would be
+    read out of bounds)"""
+    n = 0 if records is None else len(records)
+    for h in hints:
+        if h is not None and len(h) < n:
+            raise ValueError(f"{what}: a queue-state hint array has {len(h)} rows for {n} records")
+
+
 def on_device(*xs):
     flags = {bool(x.is_cuda) if _is_torch(x) else False for x in xs if x is not None}
     if len(flags) > 1:

@@ -7,7 +7,7 @@ from typing import Optional
 import numpy as np
 
 from . import abi
-from .engine import Engine, ZkcError, on_device, ptr
+from .engine import Engine, ZkcError, check_hint_rows, on_device, ptr
 
 
 @dataclass
@@ -33,6 +33,8 @@ def sort_and_deduplicate_events_entry_point(engine: Engine, witness: EventsDedup
                                             want_trace=True, compare_expected=False, raise_on_unsatisfied=True,
                                             trace_out=None) -> SorterResult:
     w = witness
+    check_hint_rows("sort_and_deduplicate_events_entry_point", w.initial_queue_witness, w.initial_queue_prev_tails)
+    check_hint_rows("sort_and_deduplicate_events_entry_point", w.intermediate_sorted_queue_witness, w.intermediate_sorted_queue_prev_tails)
     dev = on_device(w.initial_queue_witness, w.intermediate_sorted_queue_witness, w.initial_queue_prev_tails,
                     w.intermediate_sorted_queue_prev_tails, w.result_queue_tails)
     if trace_out is not None:

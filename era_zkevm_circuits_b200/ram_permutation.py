@@ -9,7 +9,7 @@ from typing import Optional
 import numpy as np
 
 from . import abi
-from .engine import Engine, ZkcError, on_device, ptr
+from .engine import Engine, ZkcError, check_hint_rows, on_device, ptr
 
 
 @dataclass
@@ -35,6 +35,8 @@ def ram_permutation_entry_point(engine: Engine, witness: RamPermutationCircuitIn
                                 want_trace=True, compare_expected=False, bootloader_heap_page=0,
                                 raise_on_unsatisfied=True, trace_out=None) -> RamPermutationResult:
     w = witness
+    check_hint_rows("ram_permutation_entry_point", w.unsorted_queue_witness, w.unsorted_queue_prev_states)
+    check_hint_rows("ram_permutation_entry_point", w.sorted_queue_witness, w.sorted_queue_prev_states)
     dev = on_device(w.unsorted_queue_witness, w.sorted_queue_witness, w.unsorted_queue_prev_states,
                     w.sorted_queue_prev_states)
     if trace_out is not None:

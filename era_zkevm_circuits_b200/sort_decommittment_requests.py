@@ -7,7 +7,7 @@ from typing import Optional
 import numpy as np
 
 from . import abi
-from .engine import Engine, ZkcError, on_device, ptr
+from .engine import Engine, ZkcError, check_hint_rows, on_device, ptr
 from .log_sorter import SorterResult
 
 
@@ -26,6 +26,8 @@ def sort_and_deduplicate_code_decommittments_entry_point(engine: Engine, witness
                                                          limit: int, want_trace=True, compare_expected=False,
                                                          raise_on_unsatisfied=True, trace_out=None) -> SorterResult:
     w = witness
+    check_hint_rows("sort_and_deduplicate_code_decommittments_entry_point", w.initial_queue_witness, w.initial_queue_prev_states)
+    check_hint_rows("sort_and_deduplicate_code_decommittments_entry_point", w.sorted_queue_witness, w.sorted_queue_prev_states)
     dev = on_device(w.initial_queue_witness, w.sorted_queue_witness, w.initial_queue_prev_states, w.sorted_queue_prev_states,
                     w.result_queue_states)
     if trace_out is not None:

@@ -7,7 +7,7 @@ from typing import Optional
 import numpy as np
 
 from . import abi
-from .engine import Engine, ZkcError, on_device, ptr
+from .engine import Engine, ZkcError, check_hint_rows, on_device, ptr
 from .log_sorter import SorterResult
 
 
@@ -29,6 +29,9 @@ def sort_and_deduplicate_storage_access_entry_point(engine: Engine, witness: Sto
                                                     want_trace=True, compare_expected=False, raise_on_unsatisfied=True,
                                                     trace_out=None) -> SorterResult:
     w = witness
+    check_hint_rows("sort_and_deduplicate_storage_access_entry_point", w.unsorted_queue_witness, w.unsorted_queue_prev_tails)
+    check_hint_rows("sort_and_deduplicate_storage_access_entry_point", w.intermediate_sorted_queue_witness, w.intermediate_sorted_queue_prev_tails,
+                    w.intermediate_sorted_queue_timestamps)
     dev = on_device(w.unsorted_queue_witness, w.intermediate_sorted_queue_witness, w.unsorted_queue_prev_tails,
                     w.intermediate_sorted_queue_prev_tails, w.intermediate_sorted_queue_timestamps, w.result_queue_tails)
     if trace_out is not None:
