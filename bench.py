@@ -472,16 +472,17 @@ def run_gpu(args):
                 "algorithmic_bytes_per_cycle": vm_bytes_per_cycle, "avg_launch_ms": cyc_ms / cyc_n if cyc_n else None,
                 "share_of_step": (cyc_ms / cyc_n) / (ms / args.steps) if cyc_n else None,
                 "traffic": VM_CYCLES_TRAFFIC, "traffic_note": VM_CYCLES_TRAFFIC_NOTE}
-    constraint_eval = {"kernel": "ram_check_kernel<false> (constraint evaluation of a 2^20-row ram_permutation trace, streaming relations)",
+    constraint_eval = {"kernel": "ram_check_kernel<false, 2> (constraint evaluation of a 2^20-row ram_permutation trace, 222 columns incl. the gadget cells: "
+                                 "63 field multiplications per row; latency-bound, profiles/README.md)",
                        "bound": "hbm", "achieved": chk_gbs, "peak": peak, "unit": "GB/s",
                        "frac": chk_gbs / peak if chk_gbs else None, "frac_of_nominal_8000": chk_gbs / 8000.0 if chk_gbs else None,
                        "algorithmic_bytes_per_row": abi.RAM_COLS["NUM_COLS"] * 8, "avg_launch_ms": chk_ms / chk_n if chk_n else None,
-                       "traffic": (281072896 + 4868864) * 4,
-                       "traffic_note": "ncu --set full dram__bytes_read+write of this kernel at 2^18 rows (profiles/r01_ncu_full_ram_kernels_raw.csv), "
-                                       "scaled x4 to 2^20 rows: equals the algorithmic bytes (no re-reads)"}
+                       "traffic": int((473.7e6 + 24.0e6) * 4),
+                       "traffic_note": "ncu --set full dram__bytes_read+write of this kernel at 2^18 rows (profiles/r02_run19_ncu_ram_check_summary.txt), "
+                                       "scaled x4 to 2^20 rows: 1.07x the algorithmic bytes (no re-reads)"}
     vchk_gbs = ncols * 8 * n * cycles / (vchk_ms / vchk_n * 1e-3) / 1e9 if vchk_n else None
-    constraint_eval_vm = {"kernel": "vm_check_kernel (constraint evaluation of the main_vm trace: decoding, exception masks, add/sub, mul/div, "
-                                    "bitwise relations, selection, sponge columns; every cell read once)",
+    constraint_eval_vm = {"kernel": "vm_check_kernel<2> (constraint evaluation of the main_vm trace the timed step wrote: decoding, exception masks, add/sub, "
+                                    "mul/div, bitwise relations, selection, sponge columns; every cell read once, row pairs with 128-bit loads)",
                           "bound": "hbm", "achieved": vchk_gbs, "peak": peak, "unit": "GB/s", "frac": vchk_gbs / peak if vchk_gbs else None,
                           "frac_of_nominal_8000": vchk_gbs / 8000.0 if vchk_gbs else None, "algorithmic_bytes_per_row": ncols * 8,
                           "avg_launch_ms": vchk_ms / vchk_n if vchk_n else None, "traffic": None}
@@ -545,7 +546,7 @@ def run_gpu(args):
                 "input_stream_bytes_per_cycle": stream_bytes / (n * cycles), "packed_trace_bytes_per_cycle": pk.nbytes_used / (n * cycles),
                 "host_encode_s_setup": t_enc, "aux_records_per_step": pk.n_aux_records, "sponge_records_per_step": pk.n_sponge_records,
                 "records_form": e2e_records},
-        "roofline": roofline, "constraint_eval": constraint_eval, "constraint_eval_main_vm": constraint_eval_vm, "constraint_eval_sorters": sorter_eval, "int_roofline": int_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "constraint_eval": constraint_eval_vm, "constraint_eval_ram_permutation": constraint_eval, "constraint_eval_sorters": sorter_eval, "int_roofline": int_roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }))
     if world > 1:
         dist.destroy_process_group()
