@@ -4,6 +4,7 @@ default options: little-endian, fixed-width integers, u64 sequence lengths) prod
     RamPermutationCircuitInstanceWitness   /root/reference/src/ram_permutation/input.rs:99-116
     EventsDeduplicatorInstanceWitness      /root/reference/src/log_sorter/input.rs:98-106
     StorageDeduplicatorInstanceWitness     /root/reference/src/storage_validity_by_grand_product/input.rs:128-136
+    Sha256RoundFunctionCircuitInstanceWitness /root/reference/src/sha256_round_function/input.rs:85-89
 
 read into the host-side witness forms of this package (closed-form struct + struct-of-arrays queue witnesses), and written
 back (test_harness-style dumps for the round-trip tests).
@@ -418,4 +419,65 @@ def write_storage_deduplicator_witness(w_) -> bytes:
         _write_log_query(w, rec)
         w.u32(t)
         w.fields(p)
+    return bytes(w.b)
+
+
+# ---- sha256_round_function -----------------------------------------------------------------------------------------------------
+def _read_sha256_fsm(r: Reader, f):
+    """Sha256RoundFunctionFSMInputOutput (sha256_round_function/input.rs:24-57): internal_fsm, then the two queue states"""
+    f.read_precompile_call, f.read_words_for_round, f.completed = r.boolean(), r.boolean(), r.boolean()
+    for i in range(8):
+        f.sha256_inner_state[i] = r.u32()
+    f.timestamp_to_use_for_read, f.timestamp_to_use_for_write = r.u32(), r.u32()
+    f.input_page, f.input_offset, f.output_page, f.output_offset, f.num_rounds = r.u32(), r.u32(), r.u32(), r.u32(), r.u32()  # mod.rs:44-50
+    _read_queue_state(r, f.log_queue_state)
+    _read_queue_state(r, f.memory_queue_state)
+
+
+def _write_sha256_fsm(w: Writer, f):
+    w.boolean(f.read_precompile_call); w.boolean(f.read_words_for_round); w.boolean(f.completed)
+    for v in f.sha256_inner_state:
+        w.u32(v)
+    for v in (f.timestamp_to_use_for_read, f.timestamp_to_use_for_write, f.input_page, f.input_offset, f.output_page, f.output_offset, f.num_rounds):
+        w.u32(v)
+    _write_queue_state(w, f.log_queue_state)
+    _write_queue_state(w, f.memory_queue_state)
+
+
+def read_sha256_round_function_witness(data: bytes):
+    """bincode bytes of Sha256RoundFunctionCircuitInstanceWitness<GoldilocksField> (input.rs:85-89) ->
+    sha256_round_function.Sha256RoundFunctionCircuitInstanceWitness; memory_reads_witness (VecDeque<U256>) becomes [n, 8] u32 limbs"""
+    from .sha256_round_function import Sha256RoundFunctionCircuitInstanceWitness
+    r = Reader(data)
+    io = abi.Sha256ClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    _read_queue_state(r, io.initial_log_queue_state)
+    _read_queue_state(r, io.initial_memory_queue_state)
+    _read_queue_state(r, io.final_memory_state)
+    _read_sha256_fsm(r, io.hidden_fsm_input)
+    _read_sha256_fsm(r, io.hidden_fsm_output)
+    reqs, prev = _read_log_queue(r)
+    n = r.u64()
+    if n > (len(r.d) - r.o) // 11:  # a U256 string is at least 8 + 3 bytes
+        raise WireError(f"memory_reads_witness claims {n} elements")
+    reads = np.zeros((n, 8), dtype=np.uint32)
+    for k in range(n):
+        reads[k] = _limbs(r.u256(), 8)
+    r.done()
+    return Sha256RoundFunctionCircuitInstanceWitness(io, reqs, prev, reads)
+
+
+def write_sha256_round_function_witness(w_) -> bytes:
+    w = Writer()
+    io = w_.closed_form_input
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    _write_queue_state(w, io.initial_log_queue_state)
+    _write_queue_state(w, io.initial_memory_queue_state)
+    _write_queue_state(w, io.final_memory_state)
+    _write_sha256_fsm(w, io.hidden_fsm_input)
+    _write_sha256_fsm(w, io.hidden_fsm_output)
+    _write_log_queue(w, w_.requests_queue_witness, w_.requests_queue_prev_tails)
+    w.u64(len(w_.memory_reads_witness))
+    for word in w_.memory_reads_witness:
+        w.u256(_from_limbs(word))
     return bytes(w.b)

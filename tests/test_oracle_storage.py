@@ -73,3 +73,51 @@ def test_negative_cases(orc):
     io5, _, _ = instance(orc, u, s, ts5)
     rc, _, _, _, st, _ = O.storage_validity_entry_point(orc, io5, u, s, ts5, 800)
     assert st.failed_checks & CHK["GRAND_PRODUCT"]
+
+
+def test_row_relations_of_the_trace(orc):
+    """The row-to-row relations zkc_storage_validity_check_trace evaluates on the device (st_check_kernel), restated in numpy and
+    held against the oracle's trace: the per-cell state machine (base / current value, rollback depth, explicit-read flag), the push
+    decision, the timestamp / cycle-counter bookkeeping.  Pins the evaluator's reading of mod.rs:560-800 without a GPU."""
+    n, limit = 3000, 3100
+    u, s, ts = synthetic.storage_trace(n, seed=8, n_cells=40)
+    io, _, _ = instance(orc, u, s, ts)
+    rc, out, T, _, st, _ = O.storage_validity_entry_point(orc, io, u, s, ts, limit)
+    assert rc == 0
+    f = io.hidden_fsm_input
+    col = lambda name, i=0: T[K[name] + i]
+    prev = lambda a, first: np.concatenate([[first], a[:-1]]).astype(np.uint64)
+    S = K["SORTED_ITEM"]
+    rw = T[S + 30]
+    new_cell, read_same, wnr, wrb = col("NEW_NON_TRIVIAL_CELL"), col("READ_OF_SAME_CELL"), col("WRITE_NO_ROLLBACK"), col("WRITE_ROLLBACK")
+    b_depth, b_flag = prev(col("CELL_CURRENT_DEPTH"), f.this_cell_current_depth), prev(col("CELL_HAS_READ_AT_DEPTH_ZERO"), 0)
+    a_depth = col("CELL_CURRENT_DEPTH")
+    assert np.array_equal(a_depth, np.where(new_cell == 1, rw, (b_depth + wnr - wrb) & 0xFFFFFFFF))
+    depth_zero, r0 = col("ROLLBACK_DEPTH_IS_ZERO"), col("READ_AT_DEPTH_ZERO_OF_SAME_CELL")
+    assert np.array_equal(depth_zero, a_depth == 0) and np.array_equal(r0, depth_zero & read_same)
+    assert np.array_equal(col("CELL_HAS_READ_AT_DEPTH_ZERO"), np.where(new_cell == 1, 1 - rw, b_flag | r0))
+    req, unchanged = np.ones(limit, bool), np.ones(limit, bool)
+    for i in range(8):
+        rv, wv = T[S + 13 + i], T[S + 21 + i]
+        b_cur, b_base = prev(col("CELL_CURRENT_VALUE", i), 0), prev(col("CELL_BASE_VALUE", i), 0)
+        cur1 = np.where(new_cell == 1, np.where(rw == 1, wv, rv), b_cur)
+        req &= cur1 == rv
+        assert np.array_equal(col("CELL_CURRENT_VALUE", i), np.where(new_cell == 1, cur1, np.where(wnr == 1, wv, np.where(wrb == 1, rv, b_cur))))
+        assert np.array_equal(col("CELL_BASE_VALUE", i), np.where((new_cell | r0) == 1, rv, b_base))
+        unchanged &= b_cur == b_base
+    assert np.array_equal(col("READ_IS_EQUAL_TO_CURRENT"), req) and np.array_equal(col("CHECK_READ_CONSISTENCY"), read_same | wnr)
+    viu, dz = col("VALUE_IS_UNCHANGED"), col("CURRENT_DEPTH_IS_ZERO")
+    assert np.array_equal(viu, unchanged) and np.array_equal(dz, b_depth == 0)
+    ubnr, ipr, sw, su = col("UNCHANGED_BUT_NOT_BY_ROLLBACK"), col("ISSUE_PROTECTIVE_READ"), col("SHOULD_WRITE"), col("SHOULD_UPDATE")
+    assert np.array_equal(ubnr, viu & (1 - dz)) and np.array_equal(ipr, b_flag | ubnr) and np.array_equal(sw, 1 - viu) and np.array_equal(su, ipr | sw)
+    keys_equal, trivial = col("KEYS_ARE_EQUAL"), col("ORIGINAL_IS_EMPTY")
+    prev_trivial = prev(trivial, 1)  # start_flag: the first row has no previous item (:574-575)
+    push = col("SHOULD_PUSH")
+    assert np.array_equal(push, (1 - prev_trivial) & (1 - keys_equal) & su) and push.sum() == 40
+    assert np.array_equal(col("RESULT_LEN"), np.cumsum(push))
+    ots = col("ORIGINAL_TIMESTAMP")
+    assert np.array_equal(ots, np.arange(limit, dtype=np.uint64)) and np.array_equal(col("UNSORTED_EXT19"), col("UNSORTED_ENC", 19) + (ots << np.uint64(8)))
+    sts = T[S + 36]
+    assert np.array_equal(prev(sts, f.previous_timestamp) + (col("PREVIOUS_TIMESTAMP_IS_LESS") << np.uint64(32)), col("TS_DIFF") + sts)
+    nt = 1 - trivial
+    assert np.array_equal(col("MUST_ENFORCE"), keys_equal & nt) and np.array_equal(new_cell, nt & (1 - keys_equal))

@@ -121,3 +121,30 @@ def test_storage_deduplicator_dump_round_trip_and_ingestion(orc):
     assert want[0] == have[0] == 0 and np.array_equal(want[3], have[3]) and np.array_equal(want[2], have[2])
     with pytest.raises(wire.WireError):
         wire.read_storage_deduplicator_witness(dump[:-3])
+
+
+def test_sha256_round_function_dump_round_trip_and_ingestion(orc):
+    """a chained (start_flag = 0) sha256 instance: mid-message FSM state (inner state, call parameters) populated; the ingested dump
+    proves like the original under the oracle"""
+    from era_zkevm_circuits_b200 import Sha256RoundFunctionCircuitInstanceWitness
+    reqs, reads, msgs = synthetic.sha256_calls(12, seed=3, max_rounds=9)
+    prev, rfin = O.log_queue_simulate(orc, reqs)
+    io = O.sha256_closed_form(rfin)
+    total = len(reads) // 2
+    cut = total // 2
+    first = O.sha256_entry_point(orc, io, reqs, reads, cut)
+    nxt = abi.Sha256ClosedForm.from_buffer_copy(bytes(first[1])); nxt.start_flag = 0
+    nxt.hidden_fsm_input = first[1].hidden_fsm_output
+    used = len(reqs) - first[1].hidden_fsm_output.log_queue_state.length
+    w = Sha256RoundFunctionCircuitInstanceWitness(nxt, reqs[used:], prev[used:], np.ascontiguousarray(reads, dtype=np.uint32).reshape(-1, 8)[2 * cut:])
+    dump = wire.write_sha256_round_function_witness(w)
+    got = wire.read_sha256_round_function_witness(dump)
+    assert bytes(got.closed_form_input) == bytes(nxt)
+    assert got.requests_queue_witness.tobytes() == np.ascontiguousarray(w.requests_queue_witness).tobytes()
+    assert np.array_equal(got.requests_queue_prev_tails, w.requests_queue_prev_tails) and np.array_equal(got.memory_reads_witness, w.memory_reads_witness)
+    assert wire.write_sha256_round_function_witness(got) == dump
+    want = O.sha256_entry_point(orc, nxt, w.requests_queue_witness, w.memory_reads_witness, total + 3 - cut)
+    have = O.sha256_entry_point(orc, got.closed_form_input, got.requests_queue_witness, got.memory_reads_witness, total + 3 - cut)
+    assert want[0] == have[0] == 0 and np.array_equal(want[3], have[3]) and np.array_equal(want[2], have[2])
+    with pytest.raises(wire.WireError):
+        wire.read_sha256_round_function_witness(dump + b"\x00")
