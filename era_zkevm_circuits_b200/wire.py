@@ -5,6 +5,7 @@ default options: little-endian, fixed-width integers, u64 sequence lengths) prod
     EventsDeduplicatorInstanceWitness      /root/reference/src/log_sorter/input.rs:98-106
     StorageDeduplicatorInstanceWitness     /root/reference/src/storage_validity_by_grand_product/input.rs:128-136
     Sha256RoundFunctionCircuitInstanceWitness /root/reference/src/sha256_round_function/input.rs:85-89
+    Keccak256RoundFunctionCircuitInstanceWitness /root/reference/src/keccak256_round_function/input.rs:95-99
 
 read into the host-side witness forms of this package (closed-form struct + struct-of-arrays queue witnesses), and written
 back (test_harness-style dumps for the round-trip tests).
@@ -476,6 +477,77 @@ def write_sha256_round_function_witness(w_) -> bytes:
     _write_queue_state(w, io.final_memory_state)
     _write_sha256_fsm(w, io.hidden_fsm_input)
     _write_sha256_fsm(w, io.hidden_fsm_output)
+    _write_log_queue(w, w_.requests_queue_witness, w_.requests_queue_prev_tails)
+    w.u64(len(w_.memory_reads_witness))
+    for word in w_.memory_reads_witness:
+        w.u256(_from_limbs(word))
+    return bytes(w.b)
+
+
+# ---- keccak256_round_function --------------------------------------------------------------------------------------------------
+def _read_keccak_fsm(r: Reader, f):
+    """Keccak256RoundFunctionFSMInputOutput (keccak256_round_function/input.rs:29-67): internal_fsm { 4 flags, the 5 x 5 x 8 byte
+    state (nested fixed arrays: 200 bytes, no prefixes), 2 timestamps, Keccak256PrecompileCallParams (mod.rs:48-55), ByteBuffer
+    { bytes [u8; 192] (BigArraySerde: a tuple), filled: u8 } (buffer/mod.rs:8-11) }, then the two queue states"""
+    f.read_precompile_call, f.read_unaligned_words_for_round, f.padding_round, f.completed = r.boolean(), r.boolean(), r.boolean(), r.boolean()
+    for i, b in enumerate(bytes(r.take(200))):
+        f.keccak_internal_state[i] = b
+    f.timestamp_to_use_for_read, f.timestamp_to_use_for_write = r.u32(), r.u32()
+    f.input_page, f.input_memory_byte_offset, f.input_memory_byte_length, f.output_page, f.output_word_offset = r.u32(), r.u32(), r.u32(), r.u32(), r.u32()
+    f.needs_full_padding_round = r.boolean()
+    for i, b in enumerate(bytes(r.take(192))):
+        f.buffer_bytes[i] = b
+    f.buffer_filled = r.u8()
+    _read_queue_state(r, f.log_queue_state)
+    _read_queue_state(r, f.memory_queue_state)
+
+
+def _write_keccak_fsm(w: Writer, f):
+    for v in (f.read_precompile_call, f.read_unaligned_words_for_round, f.padding_round, f.completed):
+        w.boolean(v)
+    w.b += bytes(f.keccak_internal_state)
+    for v in (f.timestamp_to_use_for_read, f.timestamp_to_use_for_write, f.input_page, f.input_memory_byte_offset, f.input_memory_byte_length,
+              f.output_page, f.output_word_offset):
+        w.u32(v)
+    w.boolean(f.needs_full_padding_round)
+    w.b += bytes(f.buffer_bytes)
+    w.u8(f.buffer_filled)
+    _write_queue_state(w, f.log_queue_state)
+    _write_queue_state(w, f.memory_queue_state)
+
+
+def read_keccak256_round_function_witness(data: bytes):
+    """bincode bytes of Keccak256RoundFunctionCircuitInstanceWitness<GoldilocksField> (input.rs:95-99) ->
+    keccak256_round_function.Keccak256RoundFunctionCircuitInstanceWitness; memory_reads_witness (VecDeque<U256>) becomes [n, 8] u32 limbs"""
+    from .keccak256_round_function import Keccak256RoundFunctionCircuitInstanceWitness
+    r = Reader(data)
+    io = abi.KeccakClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    _read_queue_state(r, io.initial_log_queue_state)
+    _read_queue_state(r, io.initial_memory_queue_state)
+    _read_queue_state(r, io.final_memory_state)
+    _read_keccak_fsm(r, io.hidden_fsm_input)
+    _read_keccak_fsm(r, io.hidden_fsm_output)
+    reqs, prev = _read_log_queue(r)
+    n = r.u64()
+    if n > (len(r.d) - r.o) // 11:
+        raise WireError(f"memory_reads_witness claims {n} elements")
+    reads = np.zeros((n, 8), dtype=np.uint32)
+    for k in range(n):
+        reads[k] = _limbs(r.u256(), 8)
+    r.done()
+    return Keccak256RoundFunctionCircuitInstanceWitness(io, reqs, prev, reads)
+
+
+def write_keccak256_round_function_witness(w_) -> bytes:
+    w = Writer()
+    io = w_.closed_form_input
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    _write_queue_state(w, io.initial_log_queue_state)
+    _write_queue_state(w, io.initial_memory_queue_state)
+    _write_queue_state(w, io.final_memory_state)
+    _write_keccak_fsm(w, io.hidden_fsm_input)
+    _write_keccak_fsm(w, io.hidden_fsm_output)
     _write_log_queue(w, w_.requests_queue_witness, w_.requests_queue_prev_tails)
     w.u64(len(w_.memory_reads_witness))
     for word in w_.memory_reads_witness:

@@ -148,3 +148,32 @@ def test_sha256_round_function_dump_round_trip_and_ingestion(orc):
     assert want[0] == have[0] == 0 and np.array_equal(want[3], have[3]) and np.array_equal(want[2], have[2])
     with pytest.raises(wire.WireError):
         wire.read_sha256_round_function_witness(dump + b"\x00")
+
+
+def test_keccak256_round_function_dump_round_trip_and_ingestion(orc):
+    """a chained keccak256 instance cut in the middle of a call: the 200-byte internal state, the byte buffer and its fill count
+    are populated; the ingested dump proves like the original under the oracle"""
+    from era_zkevm_circuits_b200 import Keccak256RoundFunctionCircuitInstanceWitness
+    KC = abi.KC_COLS
+    reqs, reads, msgs = synthetic.keccak_calls(10, seed=3, max_len=700)
+    prev, rfin = O.log_queue_simulate(orc, reqs)
+    io = O.keccak_closed_form(rfin)
+    limit = sum(len(m) // 136 + 1 for m in msgs) + 5
+    whole = O.keccak_entry_point(orc, io, reqs, reads, limit)
+    cut = int(np.flatnonzero(whole[2][KC["WRITE_RESULT"]])[4]) - 1
+    first = O.keccak_entry_point(orc, io, reqs, reads, cut)
+    nxt = abi.KeccakClosedForm.from_buffer_copy(bytes(first[1])); nxt.start_flag = 0
+    nxt.hidden_fsm_input = first[1].hidden_fsm_output
+    assert any(nxt.hidden_fsm_input.keccak_internal_state) and nxt.hidden_fsm_input.completed == 0
+    used_req = len(reqs) - first[1].hidden_fsm_output.log_queue_state.length
+    used_reads = int(first[2][KC["QUERY"] + 3::KC["QUERY_STRIDE"]][:6].sum())
+    w = Keccak256RoundFunctionCircuitInstanceWitness(nxt, reqs[used_req:], prev[used_req:], np.ascontiguousarray(reads, dtype=np.uint32).reshape(-1, 8)[used_reads:])
+    dump = wire.write_keccak256_round_function_witness(w)
+    got = wire.read_keccak256_round_function_witness(dump)
+    assert bytes(got.closed_form_input) == bytes(nxt)
+    assert got.requests_queue_witness.tobytes() == np.ascontiguousarray(w.requests_queue_witness).tobytes()
+    assert np.array_equal(got.memory_reads_witness, w.memory_reads_witness) and wire.write_keccak256_round_function_witness(got) == dump
+    want = O.keccak_entry_point(orc, nxt, w.requests_queue_witness, w.memory_reads_witness, limit - cut)
+    have = O.keccak_entry_point(orc, got.closed_form_input, got.requests_queue_witness, got.memory_reads_witness, limit - cut)
+    assert want[0] == have[0] == 0 and np.array_equal(want[3], have[3]) and np.array_equal(want[2], have[2])
+    assert bytes(have[1].hidden_fsm_output) == bytes(whole[1].hidden_fsm_output)
