@@ -42,9 +42,9 @@ def workload(n, cycles):
 
 
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of vm_cycles_kernel per launch (profiles/README.md); None until captured
-VM_CYCLES_TRAFFIC = (416582912 + 368345600) * 4
-VM_CYCLES_TRAFFIC_NOTE = ("ncu --set full dram__bytes_read+write of vm_cycles_kernel at 2^18 cycles (profiles/r01_ncu_full_vm_kernels_raw.csv, "
-                          "final kernel of the round), scaled x4 to 2^20 cycles: 1.14x the algorithmic bytes")
+VM_CYCLES_TRAFFIC = int((373.3e6 + 382.1e6) * 4)
+VM_CYCLES_TRAFFIC_NOTE = ("ncu --set full dram__bytes_read+write of vm_cycles_kernel<false> at 2^18 cycles (profiles/r02_final_ncu_summary.txt, the final "
+                          "kernel of round 2), scaled x4 to 2^20 cycles: 1.10x the algorithmic bytes")
 
 
 def sorter_check_rooflines(eng, log2rows, peak):
