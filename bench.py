@@ -58,7 +58,7 @@ def sorter_check_rooflines(eng, log2rows, peak):
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)).cuda()
     out = {}
 
-    def measure(name, key, ncols, rewrite, check):
+    def measure(name, key, ncols, rewrite, check, row_kernels=()):
         for _ in range(2):
             viol, st_ = check()
             assert viol == 0, (name, hex(st_.failed_checks), st_.first_bad_row)
@@ -71,6 +71,10 @@ def sorter_check_rooflines(eng, log2rows, peak):
         gbs = ncols * 8 * n / (ms / k * 1e-3) / 1e9
         out[name] = {"rows": n, "algorithmic_bytes_per_row": ncols * 8, "avg_launch_ms": ms / k, "achieved": gbs, "unit": "GB/s", "peak": peak,
                      "frac": gbs / peak, "bound": "hbm"}
+        for kern, perms in row_kernels:  # the witness-generation kernels of the same circuit: Poseidon2 permutations per row (integer roofline)
+            kms, kk = eng.profile_query(kern)
+            if kk:
+                out.setdefault("_int", {})[kern + "_kernel"] = {"permutations_per_launch": perms * n, "ms_per_launch": kms / kk}
 
     u, s = synthetic.events_trace(n, seed=0xC4, rollback_pct=10)
     prev, fin = eng.log_queue_simulate(dev(np.concatenate([u, s])), n_queues=2)
@@ -82,7 +86,8 @@ def sorter_check_rooflines(eng, log2rows, peak):
     assert run().status.code == 0
     K = abi.EV_COLS
     w.result_queue_tails = trace[K["RESULT_TAIL"]:K["RESULT_TAIL"] + 4].t()[trace[K["ADD_TO_QUEUE"]] != 0].contiguous()  # hints: the pushes go row-parallel
-    measure("ev_check_kernel<false> (log_sorter trace)", "ev_check", K["NUM_COLS"], run, lambda: log_sorter_check_trace(eng, io, trace, n, abi.GATES_GENERAL))
+    measure("ev_check_kernel<false> (log_sorter trace)", "ev_check", K["NUM_COLS"], run, lambda: log_sorter_check_trace(eng, io, trace, n, abi.GATES_GENERAL),
+            row_kernels=(("ev_rows", 8), ("ev_push", 1)))  # 2 pops x 3 + rounds 0-1 of the push; round 2 of the push
     del trace, w
     u, s, ts = synthetic.storage_trace(n, seed=0xC4, n_cells=1 << 12)
     d_ts = torch.from_numpy(ts.astype(np.uint32).view(np.int32)).cuda()
@@ -97,7 +102,8 @@ def sorter_check_rooflines(eng, log2rows, peak):
     K = abi.ST_COLS
     sw.result_queue_tails = strace[K["RESULT_TAIL"]:K["RESULT_TAIL"] + 4].t()[strace[K["SHOULD_PUSH"]] != 0].contiguous()
     measure("st_check_kernel<false> (storage_validity trace)", "st_check", K["NUM_COLS"], srun,
-            lambda: storage_validity_check_trace(eng, sio, strace, n, abi.GATES_GENERAL))
+            lambda: storage_validity_check_trace(eng, sio, strace, n, abi.GATES_GENERAL),
+            row_kernels=(("st_rows", 6), ("st_push_rows", 2), ("st_push", 1)))
     return out
 
 
@@ -506,6 +512,10 @@ def run_gpu(args):
         a = 2.0 * rn / (rows_ms / rows_n * 1e-3)
         int_roofline["kernels"]["ram_rows_kernel (2 queue pops per row + 4 x 8 FMA chains, scan)"] = {
             "permutations_per_launch": 2 * rn, "ms_per_launch": rows_ms / rows_n, "achieved": a, "frac": a / p2_peak}
+    if isinstance(sorter_eval, dict):
+        for kern, v in (sorter_eval.pop("_int", None) or {}).items():
+            a = v["permutations_per_launch"] / (v["ms_per_launch"] * 1e-3)
+            int_roofline["kernels"][kern + " (2^17 rows)"] = dict(v, achieved=a, frac=a / p2_peak)
     kernels = {k + "_kernel": {"avg_launch_ms": v[0] / v[1], "launches_per_step": v[1] / args.steps,
                                "share_of_step": v[0] / ms} for k, v in prof.items() if v[1]}
     kernels["ram_rows_kernel (ram_permutation witness generation, 2^20 rows)"] = {"avg_launch_ms": rows_ms / rows_n if rows_n else None}
