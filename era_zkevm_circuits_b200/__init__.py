@@ -25,6 +25,7 @@ from .storage_validity import (  # noqa: F401
 from .sort_decommittment_requests import (  # noqa: F401
     CodeDecommittmentsDeduplicatorInstanceWitness,
     sort_and_deduplicate_code_decommittments_entry_point,
+    sort_decommittments_check_trace,
 )
 from .demux_log_queue import (  # noqa: F401
     LogDemuxerCircuitInstanceWitness,

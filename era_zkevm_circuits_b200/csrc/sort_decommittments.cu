@@ -586,6 +586,172 @@ __global__ void decommit_queue_simulate_kernel(const zkc_decommit_query *__restr
     o._pad = 0;
 }
 
+
+// ---- constraint evaluation of a finished trace ------------------------------------------------------------------------------
+// One thread per row re-evaluates every relation the loop body of sort_and_deduplicate_code_decommittments_inner (mod.rs:235-381)
+// places that is local to a row or to a row and its predecessor: booleans / ranges of the allocated items, DecommitQuery::encode of
+// both pops and of the pushed record, queue-length / head bookkeeping, the 4 x 8 Num::fma chains and the accumulator update, the
+// 9-limb key comparison, same-hash / first-marker / same-page flags and their enforcements, the record to add (previous record with
+// the first-encountered timestamp), the carried first-encountered timestamp, the result queue's length / tail selection.  Streams
+// all ZKC_DQ_NUM_COLS columns once; with ZKC_GATES_ROUND_FUNCTION also the three permutations (two pops, one push).
+template <bool ROUND_FUNCTION>
+__global__ void __launch_bounds__(128)
+dq_check_kernel(DqDev *d, unsigned long long *violations, const uint64_t *__restrict__ trace) {
+    __shared__ uint64_t ch[2][9];
+    if (threadIdx.x < 18) ch[threadIdx.x / 9][threadIdx.x % 9] = d->ch[threadIdx.x / 9][threadIdx.x % 9];
+    __syncthreads();
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const bool first = row == 0;
+#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
+#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
+    uint32_t bad = 0;
+    const uint64_t o_empty = TR(ZKC_DQ_ORIGINAL_IS_EMPTY), s_empty = TR(ZKC_DQ_SORTED_IS_EMPTY), should_pop = TR(ZKC_DQ_SHOULD_POP);
+    if ((o_empty | s_empty | should_pop) > 1 || o_empty != s_empty || should_pop != 1 - o_empty) bad |= ZKC_DQV_BOOLEAN;
+    zkc_decommit_query si = dq_zero();
+    uint64_t enc[2][8];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int base = k ? ZKC_DQ_SORTED_ITEM : ZKC_DQ_UNSORTED_ITEM;
+        const zkc_queue_state12 &q0 = k ? d->sq0 : d->uq0;
+        uint64_t f[11], limbs = 0;
+#pragma unroll
+        for (int i = 0; i < 11; i++) { f[i] = TR(base + i); limbs |= f[i]; }
+        if ((limbs >> 32) || f[9] > 1) bad |= ZKC_DQV_BOOLEAN;
+        zkc_decommit_query q = dq_zero();
+#pragma unroll
+        for (int i = 0; i < 8; i++) q.code_hash[i] = (uint32_t)f[i];
+        q.page = (uint32_t)f[8]; q.is_first = (uint32_t)f[9] & 1u; q.timestamp = (uint32_t)f[10];
+        uint64_t e[8];
+        dq_encode(q, e);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { enc[k][i] = TR(base + 11 + i); if (enc[k][i] != e[i]) bad |= ZKC_DQV_ENCODING; }
+        const uint64_t len_prev = first ? q0.length : TP(base + 31), len = TR(base + 31);
+        if ((k ? s_empty : o_empty) != (uint64_t)(len_prev == 0) || len + should_pop != len_prev) bad |= ZKC_DQV_QUEUE_LEN;
+        bool same = true;
+        uint64_t st[12], head[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            head[i] = TR(base + 19 + i);
+            const uint64_t hp = first ? q0.head[i] : TP(base + 19 + i);
+            same &= head[i] == hp;
+            st[i] = i < 8 ? enc[k][i] : hp;
+            if (head[i] >= GL_P) bad |= ZKC_DQV_BOOLEAN;
+        }
+        if (!should_pop && !same) bad |= ZKC_DQV_QUEUE_LEN;
+        if (ROUND_FUNCTION && should_pop) {  // head' = P(enc || head[8..12])
+            poseidon2_permute(st);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (st[i] != head[i]) bad |= ZKC_DQV_ROUND_FUNCTION;
+        }
+        if (k == 1) si = q;
+    }
+    // utils.rs:104-135
+#pragma unroll
+    for (int rep = 0; rep < 2; rep++) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int g = rep * 2 + k;
+            uint64_t c = ch[rep][8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint64_t cell = TR(ZKC_DQ_GP_CHAIN + g * 8 + i);
+                if (cell != gl_fma(enc[k][i], ch[rep][i], c)) bad |= ZKC_DQV_GP_CHAIN;
+                c = cell;
+            }
+            const uint64_t acc_prev = first ? d->acc0[g] : TP(ZKC_DQ_GP_ACC + g);
+            const uint64_t nw = TR(ZKC_DQ_GP_NEW + g), acc = TR(ZKC_DQ_GP_ACC + g);
+            if (nw != gl_mul(acc_prev, c) || acc != (should_pop ? nw : acc_prev)) bad |= ZKC_DQV_GP_ACC;
+        }
+    }
+    // the previous record / key / triviality / first-encountered timestamp: the neighbouring row (row 0: the FSM input)
+    zkc_decommit_query pq = dq_zero();
+    uint32_t prev_key[ZKC_DQ_PACKED_KEY_LENGTH];
+    uint64_t prev_trivial, prev_first_ts;
+    if (first) {
+        pq = d->previous_record0;
+#pragma unroll
+        for (int i = 0; i < ZKC_DQ_PACKED_KEY_LENGTH; i++) prev_key[i] = d->previous_packed_key0[i];
+        prev_trivial = d->prev_trivial0;
+        prev_first_ts = d->first_ts0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) pq.code_hash[i] = (uint32_t)TP(ZKC_DQ_SORTED_ITEM + i);
+        pq.page = (uint32_t)TP(ZKC_DQ_SORTED_ITEM + 8); pq.is_first = (uint32_t)TP(ZKC_DQ_SORTED_ITEM + 9) & 1u; pq.timestamp = (uint32_t)TP(ZKC_DQ_SORTED_ITEM + 10);
+        prev_key[0] = pq.timestamp;
+#pragma unroll
+        for (int i = 0; i < 8; i++) prev_key[1 + i] = pq.code_hash[i];
+        prev_trivial = TP(ZKC_DQ_ORIGINAL_IS_EMPTY);
+        prev_first_ts = TP(ZKC_DQ_FIRST_TIMESTAMP);
+    }
+    // :309-310 borrow chain, previous - current, least significant limb first: prev + 2^32 * borrow_out = diff + cur + borrow_in
+    uint64_t borrow = 0, all_eq = 1;
+#pragma unroll
+    for (int i = 0; i < ZKC_DQ_PACKED_KEY_LENGTH; i++) {
+        const uint64_t cur = i == 0 ? si.timestamp : si.code_hash[i - 1];
+        const uint64_t diff = TR(ZKC_DQ_CMP_DIFF + i), bo = TR(ZKC_DQ_CMP_BORROW + i), leq = TR(ZKC_DQ_CMP_LIMB_EQ + i);
+        if ((diff >> 32) || bo > 1 || leq != (uint64_t)(diff == 0) || (uint64_t)prev_key[i] + (bo << 32) != diff + cur + borrow) bad |= ZKC_DQV_COMPARISON;
+        borrow = bo;
+        all_eq &= leq;
+    }
+    const uint64_t new_key_is_greater = borrow;
+    // :314-341 flags
+    const uint64_t keys_equal = TR(ZKC_DQ_KEYS_ARE_EQUAL), same_hash = TR(ZKC_DQ_SAME_HASH), must_be_first = TR(ZKC_DQ_ENFORCE_MUST_BE_FIRST),
+                   pit = TR(ZKC_DQ_PREVIOUS_IS_TRIVIAL), same_page = TR(ZKC_DQ_ENFORCE_SAME_MEMORY_PAGE), add = TR(ZKC_DQ_ADD_TO_QUEUE);
+    bool heq = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) heq &= pq.code_hash[i] == si.code_hash[i];
+    if ((keys_equal | same_hash | must_be_first | pit | same_page | add) > 1 || keys_equal != all_eq || same_hash != (uint64_t)heq ||
+        must_be_first != ((1 - same_hash) & should_pop) || pit != prev_trivial || same_page != (same_hash & (1 - pit)) || add != ((1 - pit) & (1 - same_hash)))
+        bad |= ZKC_DQV_FLAGS;
+    // conditional enforcements :312, :319-321, :328-333
+    if ((should_pop & (1 - (new_key_is_greater & 1))) | (must_be_first & (1 - (uint64_t)(si.is_first & 1u))) | (same_page & (uint64_t)(si.page != pq.page))) bad |= ZKC_DQV_ENFORCE;
+    // :338-350 record_to_add = the previous record with is_first = 1 and the first-encountered timestamp of its hash; the carried timestamp
+    const uint64_t first_ts = TR(ZKC_DQ_FIRST_TIMESTAMP);
+    if (first_ts != (same_hash ? prev_first_ts : (uint64_t)si.timestamp) || (first_ts >> 32)) bad |= ZKC_DQV_FLAGS;
+    uint64_t penc[8];
+    {
+        zkc_decommit_query to_add = pq;
+        to_add.is_first = 1;
+        to_add.timestamp = (uint32_t)prev_first_ts;
+#pragma unroll
+        for (int i = 0; i < 11; i++) if (TR(ZKC_DQ_PUSH_ITEM + i) != dq_flat(to_add, i)) bad |= ZKC_DQV_RESULT_QUEUE;
+        uint64_t pe[8];
+        dq_encode(to_add, pe);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { penc[i] = TR(ZKC_DQ_PUSH_ENC + i); if (penc[i] != pe[i]) bad |= ZKC_DQV_ENCODING; }
+    }
+    // the result queue: length counts the pushes; the tail moves only on a push (to P(enc || tail[8..12]))
+    {
+        const uint64_t len_prev = first ? d->rq0.length : TP(ZKC_DQ_RESULT_LEN);
+        if (TR(ZKC_DQ_RESULT_LEN) != len_prev + add) bad |= ZKC_DQV_RESULT_QUEUE;
+        uint64_t st[12], tail[12];
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            tail[i] = TR(ZKC_DQ_RESULT_TAIL + i);
+            const uint64_t tp = first ? d->rq0.tail[i] : TP(ZKC_DQ_RESULT_TAIL + i);
+            same &= tail[i] == tp;
+            st[i] = i < 8 ? penc[i] : tp;
+            if (tail[i] >= GL_P) bad |= ZKC_DQV_BOOLEAN;
+        }
+        if (!add && !same) bad |= ZKC_DQV_RESULT_QUEUE;
+        if (ROUND_FUNCTION && add) {
+            poseidon2_permute(st);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (st[i] != tail[i]) bad |= ZKC_DQV_ROUND_FUNCTION;
+        }
+    }
+#undef TR
+#undef TP
+    if (bad) {
+        atomicAdd(violations, 1ull);
+        atomicOr(&d->failed_checks, bad);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+    }
+}
+
 }  // namespace zkc
 
 using namespace zkc;
@@ -712,5 +878,53 @@ extern "C" int zkc_sort_decommittments_entry_point(zkc_ctx *ctx, zkc_decommit_so
     io->completion_flag = h->io.completion_flag;
     memcpy(commitment, h->commitment, 32);
     *status = h->status;
+    return status->code;
+}
+
+extern "C" int zkc_sort_decommittments_check_trace(zkc_ctx *ctx, const zkc_decommit_sorter_closed_form *io, const uint64_t *trace, size_t limit,
+                                                   uint32_t gates, int on_device, uint64_t *violations, zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !violations || (limit && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(DqDev)) + zkc_carver::bytes(1, 8);
+    if (!on_device) bytes += zkc_carver::bytes((size_t)ZKC_DQ_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    DqDev *h = (DqDev *)ctx->pinned(sizeof(DqDev) + 8);
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    DqDev *d = cv.take<DqDev>(1);
+    unsigned long long *dviol = cv.take<unsigned long long>(1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(DqDev));
+    h->io = *io;
+    h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(DqDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(dviol, 0, 8, s));
+    const uint64_t *dt = trace;
+    if (!on_device && limit) {
+        uint64_t *b = cv.take<uint64_t>((size_t)ZKC_DQ_NUM_COLS * limit);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, (size_t)ZKC_DQ_NUM_COLS * limit * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    ZKC_LAUNCH(ctx, "dq_prologue", dq_prologue_kernel, 1, 96, 0, d);
+    if (limit) {
+        const unsigned grid = (unsigned)((limit + 127) / 128);
+        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION)) ZKC_LAUNCH(ctx, "dq_check_rf", dq_check_kernel<true>, grid, 128, 0, d, dviol, dt);
+        else ZKC_LAUNCH(ctx, "dq_check", dq_check_kernel<false>, grid, 128, 0, d, dviol, dt);
+    }
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    unsigned long long *hviol = (unsigned long long *)(h + 1);
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(DqDev), cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(hviol, dviol, 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = *hviol;
+    status->failed_checks = h->failed_checks;
+    if (*hviol) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 16);
+    }
     return status->code;
 }

@@ -53,3 +53,16 @@ def sort_and_deduplicate_code_decommittments_entry_point(engine: Engine, witness
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE) or (rc and raise_on_unsatisfied):
         raise ZkcError(rc, st, "sort_and_deduplicate_code_decommittments_entry_point")
     return SorterResult(commitment, io, trace, st)
+
+
+def sort_decommittments_check_trace(engine: Engine, closed_form_input: abi.DecommitSorterClosedForm, trace, limit: int, gates: int = 0):
+    """Constraint evaluation of a finished sort_decommittment_requests trace [DQ_COLS.NUM_COLS, limit] (numpy: host, torch CUDA:
+    device): every row-local relation of sort_and_deduplicate_code_decommittments_inner (mod.rs:235-381).  Returns (violating rows,
+    status); status.failed_checks holds abi.DQV bits."""
+    st = abi.Status()
+    viol = C.c_uint64()
+    io = abi.DecommitSorterClosedForm.from_buffer_copy(bytes(closed_form_input))
+    rc = engine.lib.zkc_sort_decommittments_check_trace(engine.h, C.byref(io), ptr(trace), limit, gates, on_device(trace), C.byref(viol), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, st, "sort_decommittments_check_trace")
+    return viol.value, st

@@ -691,6 +691,23 @@ int zkc_sort_decommittments_entry_point(zkc_ctx *ctx, zkc_decommit_sorter_closed
                                         size_t limit, const zkc_sorter_options *options, int on_device, uint64_t *trace,
                                         uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
+/* constraint evaluation of a finished sort_decommittment_requests trace (as zkc_log_sorter_check_trace): every relation of the loop
+ * body (mod.rs:235-381) on every row; returns the number of violating rows, status->first_bad_row / failed_checks (ZKC_DQV_* bits)
+ * describe the first one.  gates: ZKC_GATES_GENERAL = the streaming relations; ZKC_GATES_ROUND_FUNCTION adds the permutations of
+ * the two pops and of the push; 0 = all. */
+#define ZKC_DQV_BOOLEAN (1u << 0)      /* booleans, u32 ranges, field range of hash outputs */
+#define ZKC_DQV_QUEUE_LEN (1u << 1)    /* is_empty / length / head bookkeeping of the two popped queues */
+#define ZKC_DQV_ENCODING (1u << 2)     /* DecommitQuery::encode of the popped items and of the pushed record */
+#define ZKC_DQV_ROUND_FUNCTION (1u << 3)
+#define ZKC_DQV_COMPARISON (1u << 4)   /* :309-310 borrow chain */
+#define ZKC_DQV_FLAGS (1u << 5)        /* same hash / first marker / same page / add flags, the carried first-encountered timestamp */
+#define ZKC_DQV_ENFORCE (1u << 6)      /* conditional enforcements */
+#define ZKC_DQV_GP_CHAIN (1u << 7)
+#define ZKC_DQV_GP_ACC (1u << 8)
+#define ZKC_DQV_RESULT_QUEUE (1u << 9) /* the record to add, result queue length / tail selection */
+int zkc_sort_decommittments_check_trace(zkc_ctx *ctx, const zkc_decommit_sorter_closed_form *io, const uint64_t *trace, size_t limit,
+                                        uint32_t gates, int on_device, uint64_t *violations, zkc_status *status);
+
 
 /* ---- demux_log_queue (src/demux_log_queue/mod.rs) ------------------------------------------------- */
 #define ZKC_DEMUX_NUM_QUEUES 6 /* NUM_SEPARATE_QUEUES, mod.rs:221; queue order = enum LogType, mod.rs:224-232:

@@ -177,3 +177,55 @@ def test_full_size_properties(engine, orc):
     firsts["is_first"] = 1
     _, fin2 = engine.decommit_queue_simulate(tod(firsts))
     assert list(fin2[0].tail) == list(out.final_queue_state.tail)
+
+
+def test_check_trace_constraint_evaluation(engine, orc):
+    """zkc_sort_decommittments_check_trace: the ORACLE's trace satisfies every relation with and without the round-function gates; a
+    fault injected into any relation family is found at its row; the engine's own trace of a chained second instance passes"""
+    from era_zkevm_circuits_b200 import sort_decommittments_check_trace
+    V_ = abi.DQV
+    n, limit = 3000, 3100
+    u, s = synthetic.decommit_requests_trace(n, seed=8, n_hashes=70)
+    io, up, sp = instance(orc, u, s)
+    want = O.sort_decommittments_entry_point(orc, io, u, s, limit)
+    assert want[0] == abi.ZKC_OK
+    trace = want[2]
+    for gates in (0, abi.GATES_GENERAL):
+        viol, st = sort_decommittments_check_trace(engine, io, trace, limit, gates)
+        assert viol == 0 and st.code == 0, (gates, viol, hex(st.failed_checks), st.first_bad_row)
+    import torch
+    viol, st = sort_decommittments_check_trace(engine, io, torch.from_numpy(trace.view(np.int64)).cuda(), limit, abi.GATES_GENERAL)
+    assert viol == 0
+    pushes = np.flatnonzero(trace[K["ADD_TO_QUEUE"]])
+    faults = [
+        (K["SHOULD_POP"], 17, 2, V_["BOOLEAN"], 0),
+        (K["UNSORTED_ITEM"] + 3, 40, 1 << 33, V_["BOOLEAN"], 0),
+        (K["UNSORTED_ENC"] + 2, 99, None, V_["ENCODING"], 0),
+        (K["SORTED_LEN"], 123, None, V_["QUEUE_LEN"], 0),
+        (K["SORTED_HEAD"] + 5, 3050, None, V_["QUEUE_LEN"], 0),
+        (K["SORTED_HEAD"] + 5, 150, None, V_["ROUND_FUNCTION"], 0),
+        (K["GP_CHAIN"] + 21, 200, None, V_["GP_CHAIN"], 0),
+        (K["GP_ACC"] + 2, 300, None, V_["GP_ACC"], 0),
+        (K["CMP_DIFF"] + 4, 400, None, V_["COMPARISON"], 0),
+        (K["SAME_HASH"], 500, None, V_["FLAGS"], 0),
+        (K["ADD_TO_QUEUE"], 510, None, V_["FLAGS"], 0),
+        (K["FIRST_TIMESTAMP"], 520, None, V_["FLAGS"], 0),
+        (K["PUSH_ITEM"] + 10, 530, None, V_["RESULT_QUEUE"], 0),
+        (K["PUSH_ENC"] + 6, 600, None, V_["ENCODING"], 0),
+        (K["RESULT_LEN"], 700, None, V_["RESULT_QUEUE"], 0),
+        (K["RESULT_TAIL"] + 7, 700 + int(np.flatnonzero(trace[K["ADD_TO_QUEUE"], 700:] == 0)[0]), None, V_["RESULT_QUEUE"], abi.GATES_GENERAL),
+        (K["RESULT_TAIL"] + 7, int(pushes[10]), None, V_["ROUND_FUNCTION"], 0),
+    ]
+    for col, row, val, bit, gates in faults:
+        bad = trace.copy()
+        bad[col, row] = np.uint64(val) if val is not None else bad[col, row] ^ np.uint64(1)
+        viol, st = sort_decommittments_check_trace(engine, io, bad, limit, gates)
+        assert viol >= 1 and st.first_bad_row == row and st.failed_checks & bit, (col, row, viol, st.first_bad_row, hex(st.failed_checks))
+    cut = 1500
+    a = entry_point(engine, Witness(io, u, up, s, sp), cut, raise_on_unsatisfied=False)
+    nxt = abi.DecommitSorterClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+    b = entry_point(engine, Witness(nxt, u[cut:], up[cut:], s[cut:], sp[cut:]), limit - cut, raise_on_unsatisfied=False)
+    assert b.status.code == 0
+    viol, st = sort_decommittments_check_trace(engine, nxt, b.trace, limit - cut)
+    assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)

@@ -145,3 +145,52 @@ def test_negative_cases(orc):
     io7.initial_queue_state.head[3] = 1
     rc, _, _, _, st, _ = O.sort_decommittments_entry_point(orc, io7, u, s, 256)
     assert st.failed_checks & CHK["TRIVIAL_HEAD"]
+
+
+def test_row_relations_of_the_trace(orc):
+    """The row-to-row relations zkc_sort_decommittments_check_trace evaluates on the device (dq_check_kernel), restated in numpy and
+    held against the oracle's trace: key comparison, same-hash / first-marker / same-page flags, the record to add with the
+    first-encountered timestamp, queue bookkeeping.  Pins the evaluator's reading of mod.rs:235-381 without a GPU."""
+    n, limit = 2000, 2100
+    u, s = synthetic.decommit_requests_trace(n, seed=5, n_hashes=60)
+    io, _, _ = instance(orc, u, s)
+    rc, out, T, _, st, _ = O.sort_decommittments_entry_point(orc, io, u, s, limit)
+    assert rc == 0
+    K = abi.DQ_COLS
+    col = lambda name, i=0: T[K[name] + i]
+    prev = lambda a, first: np.concatenate([np.array([first], dtype=np.uint64), a[:-1].astype(np.uint64)])
+    S = K["SORTED_ITEM"]
+    ts, page = T[S + 10], T[S + 8]
+    cur = [ts] + [T[S + i] for i in range(8)]
+    pk = [prev(c, 0) for c in cur]
+    borrow, all_eq = np.zeros(limit, np.uint64), np.ones(limit, np.uint64)
+    for i in range(9):
+        df, bo, le = col("CMP_DIFF", i), col("CMP_BORROW", i), col("CMP_LIMB_EQ", i)
+        assert np.array_equal(pk[i] + (bo << np.uint64(32)), df + cur[i] + borrow) and np.array_equal(le, df == 0)
+        borrow, all_eq = bo, all_eq & le
+    assert np.array_equal(col("KEYS_ARE_EQUAL"), all_eq)
+    same = np.ones(limit, bool)
+    for i in range(8):
+        same &= prev(T[S + i], 0) == T[S + i]
+    same_hash, pop, trivial = col("SAME_HASH"), col("SHOULD_POP"), col("ORIGINAL_IS_EMPTY")
+    pit = prev(trivial, 1)
+    assert np.array_equal(same_hash, same) and np.array_equal(col("PREVIOUS_IS_TRIVIAL"), pit)
+    assert np.array_equal(col("ENFORCE_MUST_BE_FIRST"), (1 - same_hash) & pop) and np.array_equal(col("ENFORCE_SAME_MEMORY_PAGE"), same_hash & (1 - pit))
+    add = col("ADD_TO_QUEUE")
+    assert np.array_equal(add, (1 - pit) & (1 - same_hash)) and add.sum() == 60  # 60 hashes: the last one is pushed by the first padding row (zero hash, previous item not trivial)
+    fts = col("FIRST_TIMESTAMP")
+    assert np.array_equal(fts, np.where(same_hash == 0, ts, prev(fts, 0)))
+    P = K["PUSH_ITEM"]
+    for i in range(8):
+        assert np.array_equal(T[P + i], prev(T[S + i], 0))
+    assert np.array_equal(T[P + 8], prev(page, 0)) and (T[P + 9] == 1).all() and np.array_equal(T[P + 10], prev(fts, 0))
+    assert np.array_equal(col("RESULT_LEN"), np.cumsum(add))
+    for i in range(12):
+        t = col("RESULT_TAIL", i)
+        assert np.array_equal(t[add == 0], prev(t, 0)[add == 0])
+    for k, base, q0 in ((0, K["UNSORTED_ITEM"], io.initial_queue_state), (1, K["SORTED_ITEM"], io.sorted_queue_initial_state)):
+        ln = T[base + 31]
+        assert np.array_equal(ln + pop, prev(ln, q0.length))
+        for i in range(12):
+            h = T[base + 19 + i]
+            assert np.array_equal(h[pop == 0], prev(h, q0.head[i])[pop == 0])
