@@ -30,6 +30,7 @@ from .sort_decommittment_requests import (  # noqa: F401
 from .demux_log_queue import (  # noqa: F401
     LogDemuxerCircuitInstanceWitness,
     demultiplex_storage_logs_enty_point,
+    demux_log_queue_check_trace,
 )
 from .linear_hasher import (  # noqa: F401
     LinearHasherCircuitInstanceWitness,

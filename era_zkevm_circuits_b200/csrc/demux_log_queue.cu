@@ -396,6 +396,148 @@ __global__ void dmx_finalize_kernel(DmxDev *d, const uint64_t *__restrict__ tail
     }
 }
 
+
+// ---- constraint evaluation of a finished trace ------------------------------------------------------------------------------
+// One thread per row re-evaluates every relation the loop body of demultiplex_storage_logs_inner (mod.rs:268-393) and
+// push_with_optimize (:401-447) place that is local to a row or to a row and its predecessor: booleans / ranges of the popped item,
+// LogQuery::encode, queue-length / head bookkeeping, the aux-byte / address / shard classification, the six execute bits and the
+// bitmask check, the selected output queue's state before the push, every output queue's tail / length after it.  With
+// ZKC_GATES_ROUND_FUNCTION also the permutations: rounds 0-1 (shared by the pop and the push), the pop's round 2, the push's round 2.
+template <bool ROUND_FUNCTION>
+__global__ void __launch_bounds__(128)
+dmx_check_kernel(DmxDev *d, unsigned long long *violations, const uint64_t *__restrict__ trace) {
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const bool first = row == 0;
+#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
+#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
+    uint32_t bad = 0;
+    const uint64_t is_empty = TR(ZKC_DMX_QUEUE_IS_EMPTY), execute = TR(ZKC_DMX_EXECUTE);
+    if ((is_empty | execute) > 1 || execute != 1 - is_empty) bad |= ZKC_DMXV_BOOLEAN;
+    uint64_t f[36], limbs = 0;
+#pragma unroll
+    for (int i = 0; i < 36; i++) f[i] = TR(ZKC_DMX_ITEM + i);
+#pragma unroll
+    for (int i = 0; i < 29; i++) limbs |= f[i];
+    if ((limbs | f[34] | f[35]) >> 32 || (f[29] | f[33]) >> 8 || (f[30] | f[31] | f[32]) > 1) bad |= ZKC_DMXV_BOOLEAN;
+    zkc_log_query q = lq_zero();
+#pragma unroll
+    for (int i = 0; i < 5; i++) q.address[i] = (uint32_t)f[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { q.key[i] = (uint32_t)f[5 + i]; q.read_value[i] = (uint32_t)f[13 + i]; q.written_value[i] = (uint32_t)f[21 + i]; }
+    q.flags = ZKC_LQ_FLAGS((uint32_t)f[29], (uint32_t)f[33], (uint32_t)f[30], (uint32_t)f[31], (uint32_t)f[32]);
+    q.tx_number_in_block = (uint32_t)f[34]; q.timestamp = (uint32_t)f[35];
+    uint64_t e[20], enc[20];
+    lq_encode(q, e);
+#pragma unroll
+    for (int i = 0; i < 20; i++) { enc[i] = TR(ZKC_DMX_ENC + i); if (enc[i] != e[i]) bad |= ZKC_DMXV_ENCODING; }
+    // the popped queue: is_empty <=> previous length == 0, length decrements on a pop, the head only moves on a pop
+    const uint64_t len_prev = first ? d->iq0.length : TP(ZKC_DMX_LEN), len = TR(ZKC_DMX_LEN);
+    if (is_empty != (uint64_t)(len_prev == 0) || len + execute != len_prev) bad |= ZKC_DMXV_QUEUE_LEN;
+    uint64_t head[4], head_prev[4];
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        head[i] = TR(ZKC_DMX_HEAD + i);
+        head_prev[i] = first ? d->iq0.head[i] : TP(ZKC_DMX_HEAD + i);
+        same &= head[i] == head_prev[i];
+        if (head[i] >= GL_P) bad |= ZKC_DMXV_BOOLEAN;
+    }
+    if (!execute && !same) bad |= ZKC_DMXV_QUEUE_LEN;
+    // :285-360 classification
+    const uint64_t aux = f[29], shard = f[33];
+    uint64_t is_aux[4], is_addr[3], sum_aux = 0;
+    const bool small = (f[1] | f[2] | f[3] | f[4]) == 0;
+    uint64_t flags_or = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        is_aux[i] = TR(ZKC_DMX_IS_AUX + i); flags_or |= is_aux[i]; sum_aux += is_aux[i];
+        if (is_aux[i] != (uint64_t)(aux == d->opt.aux_bytes[i])) bad |= ZKC_DMXV_FLAGS;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        is_addr[i] = TR(ZKC_DMX_IS_ADDRESS + i); flags_or |= is_addr[i];
+        if (is_addr[i] != (uint64_t)(small && f[0] == d->opt.precompile_addresses[i])) bad |= ZKC_DMXV_FLAGS;
+    }
+    const uint64_t rollup = TR(ZKC_DMX_IS_ROLLUP_SHARD), porter = TR(ZKC_DMX_EXECUTE_PORTER_STORAGE), is_bitmask = TR(ZKC_DMX_IS_BITMASK);
+    if ((flags_or | rollup | porter | is_bitmask) > 1 || rollup != (uint64_t)(shard == 0) || porter != (is_aux[0] & (1 - rollup) & execute) ||
+        is_bitmask != (uint64_t)(sum_aux == 1))
+        bad |= ZKC_DMXV_FLAGS;
+    const uint64_t want_bit[DMX_Q] = {is_aux[0] & rollup & execute, is_aux[1] & execute, is_aux[2] & execute,
+                                      is_aux[3] & is_addr[0] & execute, is_aux[3] & is_addr[1] & execute, is_aux[3] & is_addr[2] & execute};
+    uint64_t bit[DMX_Q];
+    int sel = 0;
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < DMX_Q; k++) {
+        bit[k] = TR(ZKC_DMX_BITMASK + k);
+        if (bit[k] != want_bit[k]) bad |= ZKC_DMXV_FLAGS;
+        if (bit[k] & 1) { sel = k; any = true; }
+    }
+    // enforcements: no porter storage (:304-305), exactly one aux class on an executed row (:383-384)
+    if (porter | (execute & (1 - (is_bitmask & 1)))) bad |= ZKC_DMXV_ENFORCE;
+    // push_with_optimize (:401-447): the selected queue's state before the push, every queue's tail / length after it
+    uint64_t r0[12], r1[12], r2[12], exec_tail[4];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { r0[i] = TR(ZKC_DMX_PUSH_ROUND0 + i); r1[i] = TR(ZKC_DMX_PUSH_ROUND1 + i); r2[i] = TR(ZKC_DMX_PUSH_ROUND2 + i); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) exec_tail[i] = TR(ZKC_DMX_EXEC_TAIL + i);
+    const uint64_t exec_len = TR(ZKC_DMX_EXEC_LEN);
+#pragma unroll
+    for (int k = 0; k < DMX_Q; k++) {
+        const uint64_t lp = first ? d->oq0[k].length : TP(ZKC_DMX_QUEUE_LENS + k);
+        if (TR(ZKC_DMX_QUEUE_LENS + k) != lp + bit[k]) bad |= ZKC_DMXV_OUTPUT_QUEUES;
+        if (k == sel && exec_len != lp) bad |= ZKC_DMXV_OUTPUT_QUEUES;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint64_t tp = first ? d->oq0[k].tail[i] : TP(ZKC_DMX_QUEUE_TAILS + 4 * k + i);
+            if (k == sel && exec_tail[i] != tp) bad |= ZKC_DMXV_OUTPUT_QUEUES;
+            if (TR(ZKC_DMX_QUEUE_TAILS + 4 * k + i) != ((any && k == sel) ? r2[i] : tp)) bad |= ZKC_DMXV_OUTPUT_QUEUES;
+        }
+    }
+    if (ROUND_FUNCTION) {
+        uint64_t st[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) st[i] = i < 8 ? enc[i] : 0;
+        poseidon2_permute(st);
+#pragma unroll
+        for (int i = 0; i < 12; i++) if (st[i] != r0[i]) bad |= ZKC_DMXV_ROUND_FUNCTION;
+#pragma unroll
+        for (int i = 0; i < 8; i++) st[i] = enc[8 + i];
+        poseidon2_permute(st);
+#pragma unroll
+        for (int i = 0; i < 12; i++) if (st[i] != r1[i]) bad |= ZKC_DMXV_ROUND_FUNCTION;
+        uint64_t sp[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) sp[i] = st[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { st[i] = enc[16 + i]; st[4 + i] = exec_tail[i]; }  // the push: absorbs the selected queue's tail
+        poseidon2_permute(st);
+#pragma unroll
+        for (int i = 0; i < 12; i++) if (st[i] != r2[i]) bad |= ZKC_DMXV_ROUND_FUNCTION;
+        if (execute) {  // the pop: the same two rounds, then the head before the pop
+#pragma unroll
+            for (int i = 0; i < 4; i++) { sp[i] = enc[16 + i]; sp[4 + i] = head_prev[i]; }
+            poseidon2_permute(sp);
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (sp[i] != head[i]) bad |= ZKC_DMXV_ROUND_FUNCTION;
+        }
+    } else {
+        uint64_t big = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) big |= (uint64_t)(r0[i] >= GL_P) | (uint64_t)(r1[i] >= GL_P) | (uint64_t)(r2[i] >= GL_P);
+        if (big) bad |= ZKC_DMXV_BOOLEAN;
+    }
+#undef TR
+#undef TP
+    if (bad) {
+        atomicAdd(violations, 1ull);
+        atomicOr(&d->failed_checks, bad);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+    }
+}
+
 }  // namespace zkc
 
 using namespace zkc;
@@ -504,5 +646,62 @@ extern "C" int zkc_demux_log_queue_entry_point(zkc_ctx *ctx, zkc_demux_closed_fo
     io->completion_flag = h->io.completion_flag;
     memcpy(commitment, h->commitment, 32);
     *status = h->status;
+    return status->code;
+}
+
+extern "C" int zkc_demux_log_queue_check_trace(zkc_ctx *ctx, const zkc_demux_closed_form *io, const zkc_demux_options *options, const uint64_t *trace,
+                                               size_t limit, uint32_t gates, int on_device, uint64_t *violations, zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !violations || (limit && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    zkc_demux_options opt;
+    memset(&opt, 0, sizeof opt);
+    if (options) opt = *options;
+    if (!opt.custom_constants) {
+        const uint32_t aux[4] = {0, 1, 2, 3}, addr[3] = {0x8010u, 0x02u, 0x01u};
+        memcpy(opt.aux_bytes, aux, sizeof aux);
+        memcpy(opt.precompile_addresses, addr, sizeof addr);
+    }
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(DmxDev)) + zkc_carver::bytes(1, 8);
+    if (!on_device) bytes += zkc_carver::bytes((size_t)ZKC_DMX_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    DmxDev *h = (DmxDev *)ctx->pinned(sizeof(DmxDev) + 8);
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    DmxDev *d = cv.take<DmxDev>(1);
+    unsigned long long *dviol = cv.take<unsigned long long>(1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(DmxDev));
+    h->io = *io;
+    h->opt = opt;
+    h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(DmxDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(dviol, 0, 8, s));
+    const uint64_t *dt = trace;
+    if (!on_device && limit) {
+        uint64_t *b = cv.take<uint64_t>((size_t)ZKC_DMX_NUM_COLS * limit);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, (size_t)ZKC_DMX_NUM_COLS * limit * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    ZKC_LAUNCH(ctx, "dmx_prologue", dmx_prologue_kernel, 1, 96, 0, d);
+    if (limit) {
+        const unsigned grid = (unsigned)((limit + 127) / 128);
+        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION)) ZKC_LAUNCH(ctx, "dmx_check_rf", dmx_check_kernel<true>, grid, 128, 0, d, dviol, dt);
+        else ZKC_LAUNCH(ctx, "dmx_check", dmx_check_kernel<false>, grid, 128, 0, d, dviol, dt);
+    }
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    unsigned long long *hviol = (unsigned long long *)(h + 1);
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(DmxDev), cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(hviol, dviol, 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = *hviol;
+    status->failed_checks = h->failed_checks;
+    if (*hviol) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 16);
+    }
     return status->code;
 }

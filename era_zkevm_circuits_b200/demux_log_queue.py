@@ -53,3 +53,18 @@ def demultiplex_storage_logs_enty_point(engine: Engine, witness: LogDemuxerCircu
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE) or (rc and raise_on_unsatisfied):
         raise ZkcError(rc, st, "demultiplex_storage_logs_enty_point")
     return SorterResult(commitment, io, trace, st)
+
+
+def demux_log_queue_check_trace(engine: Engine, closed_form_input: abi.DemuxClosedForm, trace, limit: int, gates: int = 0,
+                                options: Optional[abi.DemuxOptions] = None):
+    """Constraint evaluation of a finished demux_log_queue trace [DMX_COLS.NUM_COLS, limit] (numpy: host, torch CUDA: device): every
+    row-local relation of demultiplex_storage_logs_inner and push_with_optimize (mod.rs:268-447).  Returns (violating rows, status);
+    status.failed_checks holds abi.DMXV bits."""
+    st = abi.Status()
+    viol = C.c_uint64()
+    io = abi.DemuxClosedForm.from_buffer_copy(bytes(closed_form_input))
+    opts = abi.DemuxOptions.from_buffer_copy(bytes(options)) if options is not None else abi.DemuxOptions()
+    rc = engine.lib.zkc_demux_log_queue_check_trace(engine.h, C.byref(io), C.byref(opts), ptr(trace), limit, gates, on_device(trace), C.byref(viol), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, st, "demux_log_queue_check_trace")
+    return viol.value, st

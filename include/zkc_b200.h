@@ -782,6 +782,19 @@ int zkc_demux_log_queue_entry_point(zkc_ctx *ctx, zkc_demux_closed_form *io, con
                                     const zkc_demux_options *options, int on_device, uint64_t *trace,
                                     uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
+/* constraint evaluation of a finished demux_log_queue trace (as zkc_log_sorter_check_trace): every relation of the loop body
+ * (mod.rs:268-393) and of push_with_optimize (:401-447) on every row; options as for the entry point (the aux bytes / formal
+ * addresses).  gates: ZKC_GATES_GENERAL = the streaming relations; ZKC_GATES_ROUND_FUNCTION adds the four permutations; 0 = all. */
+#define ZKC_DMXV_BOOLEAN (1u << 0)       /* booleans, u32 / u8 ranges, field range of hash outputs */
+#define ZKC_DMXV_QUEUE_LEN (1u << 1)     /* is_empty / length / head bookkeeping of the popped queue */
+#define ZKC_DMXV_ENCODING (1u << 2)      /* LogQuery::encode */
+#define ZKC_DMXV_ROUND_FUNCTION (1u << 3)
+#define ZKC_DMXV_FLAGS (1u << 4)         /* classification flags, execute bits, the bitmask flag */
+#define ZKC_DMXV_ENFORCE (1u << 5)       /* no porter storage, one class per executed row */
+#define ZKC_DMXV_OUTPUT_QUEUES (1u << 6) /* selected state before the push, the six tails / lengths after it */
+int zkc_demux_log_queue_check_trace(zkc_ctx *ctx, const zkc_demux_closed_form *io, const zkc_demux_options *options, const uint64_t *trace,
+                                    size_t limit, uint32_t gates, int on_device, uint64_t *violations, zkc_status *status);
+
 
 /* ---- keccak256_round_function (src/keccak256_round_function/mod.rs) -------------------------------- */
 #define ZKC_KECCAK_RATE_BYTES 136            /* boojum KECCAK_RATE_BYTES */

@@ -150,3 +150,55 @@ def test_device_resident_feeds_the_sorters(engine, orc):
     for q, sel in ((1, aux == 1), (2, aux == 2), (0, aux == 0)):
         _, f = engine.log_queue_simulate(tod(np.ascontiguousarray(recs[sel])))
         assert bytes(f[0]) == bytes(out.output_queue_states[q]), q
+
+
+def test_check_trace_constraint_evaluation(engine, orc):
+    """zkc_demux_log_queue_check_trace: the ORACLE's trace satisfies every relation with and without the round-function gates; a fault
+    injected into any relation family is found at its row; the engine's own trace of a chained second instance passes"""
+    from era_zkevm_circuits_b200 import demux_log_queue_check_trace
+    V_ = abi.DMXV
+    n, limit = 3000, 3100
+    recs = synthetic.vm_log_queue_trace(n, seed=8)
+    io, prev = instance(orc, recs)
+    want = O.demux_entry_point(orc, io, recs, limit)
+    assert want[0] == abi.ZKC_OK
+    trace = want[2]
+    for gates in (0, abi.GATES_GENERAL):
+        viol, st = demux_log_queue_check_trace(engine, io, trace, limit, gates)
+        assert viol == 0 and st.code == 0, (gates, viol, hex(st.failed_checks), st.first_bad_row)
+    import torch
+    viol, st = demux_log_queue_check_trace(engine, io, torch.from_numpy(trace.view(np.int64)).cuda(), limit, abi.GATES_GENERAL)
+    assert viol == 0
+    events = np.flatnonzero(trace[K["BITMASK"] + 1])
+    faults = [
+        (K["EXECUTE"], 17, 2, V_["BOOLEAN"], 0),
+        (K["ITEM"] + 7, 40, 1 << 33, V_["BOOLEAN"], 0),
+        (K["ENC"] + 3, 99, None, V_["ENCODING"], 0),
+        (K["LEN"], 123, None, V_["QUEUE_LEN"], 0),
+        (K["HEAD"] + 1, 3050, None, V_["QUEUE_LEN"], 0),
+        (K["HEAD"] + 1, 150, None, V_["ROUND_FUNCTION"], 0),
+        (K["IS_AUX"] + 2, 200, None, V_["FLAGS"], 0),
+        (K["IS_ADDRESS"] + 1, 210, None, V_["FLAGS"], 0),
+        (K["IS_ROLLUP_SHARD"], 220, None, V_["FLAGS"], 0),
+        (K["BITMASK"] + 4, 230, None, V_["FLAGS"], 0),
+        (K["IS_BITMASK"], 240, None, V_["FLAGS"], 0),
+        (K["EXEC_TAIL"] + 2, 300, None, V_["OUTPUT_QUEUES"], 0),
+        (K["EXEC_LEN"], 310, None, V_["OUTPUT_QUEUES"], 0),
+        (K["QUEUE_LENS"] + 3, 320, None, V_["OUTPUT_QUEUES"], 0),
+        (K["QUEUE_TAILS"] + 4 * 1 + 2, int(events[20]), None, V_["OUTPUT_QUEUES"], abi.GATES_GENERAL),
+        (K["PUSH_ROUND0"] + 5, 400, None, V_["ROUND_FUNCTION"], 0),
+        (K["PUSH_ROUND2"] + 9, 410, None, V_["ROUND_FUNCTION"], 0),
+    ]
+    for col, row, val, bit, gates in faults:
+        bad = trace.copy()
+        bad[col, row] = np.uint64(val) if val is not None else bad[col, row] ^ np.uint64(1)
+        viol, st = demux_log_queue_check_trace(engine, io, bad, limit, gates)
+        assert viol >= 1 and st.first_bad_row == row and st.failed_checks & bit, (col, row, viol, st.first_bad_row, hex(st.failed_checks))
+    cut = 1500
+    a = entry_point(engine, Witness(io, recs, prev, None, None), cut, raise_on_unsatisfied=False)
+    nxt = abi.DemuxClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+    b = entry_point(engine, Witness(nxt, recs[cut:], prev[cut:], None, None), limit - cut, raise_on_unsatisfied=False)
+    assert b.status.code == 0
+    viol, st = demux_log_queue_check_trace(engine, nxt, b.trace, limit - cut)
+    assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)

@@ -113,3 +113,45 @@ def test_edge_and_negative_cases(orc):
     io, _ = instance(orc, recs); io.initial_log_queue_state.head[0] = 9
     rc, _, _, _, st, _ = O.demux_entry_point(orc, io, recs, 128)
     assert st.failed_checks & CHK["TRIVIAL_HEAD"]
+
+
+def test_row_relations_of_the_trace(orc):
+    """The row-to-row relations zkc_demux_log_queue_check_trace evaluates on the device (dmx_check_kernel), restated in numpy and held
+    against the oracle's trace: classification, the six execute bits, the state push_with_optimize selects, the output queues'
+    tails / lengths.  Pins the evaluator's reading of mod.rs:268-447 without a GPU."""
+    n, limit = 2000, 2100
+    recs = synthetic.vm_log_queue_trace(n, seed=5)
+    io, _ = instance(orc, recs)
+    rc, out, T, _, st, _ = O.demux_entry_point(orc, io, recs, limit)
+    assert rc == 0
+    K = abi.DMX_COLS
+    col = lambda name, i=0: T[K[name] + i]
+    prev = lambda a, first: np.concatenate([np.array([first], dtype=np.uint64), a[:-1].astype(np.uint64)])
+    ex, emp, ln = col("EXECUTE"), col("QUEUE_IS_EMPTY"), col("LEN")
+    len0 = io.initial_log_queue_state.length
+    assert np.array_equal(ln + ex, prev(ln, len0)) and np.array_equal(emp, prev(ln, len0) == 0) and np.array_equal(ex, 1 - emp)
+    I = K["ITEM"]
+    aux, shard, small = T[I + 29], T[I + 33], (T[I + 1] | T[I + 2] | T[I + 3] | T[I + 4]) == 0
+    ia = [col("IS_AUX", i) for i in range(4)]
+    iad = [col("IS_ADDRESS", i) for i in range(3)]
+    assert all(np.array_equal(ia[i], aux == i) for i in range(4))
+    assert all(np.array_equal(iad[i], small & (T[I] == a)) for i, a in enumerate((0x8010, 2, 1)))
+    rollup = col("IS_ROLLUP_SHARD")
+    assert np.array_equal(rollup, shard == 0) and np.array_equal(col("EXECUTE_PORTER_STORAGE"), ia[0] & (1 - rollup) & ex)
+    bits = [ia[0] & rollup & ex, ia[1] & ex, ia[2] & ex, ia[3] & iad[0] & ex, ia[3] & iad[1] & ex, ia[3] & iad[2] & ex]
+    assert all(np.array_equal(col("BITMASK", q), bits[q]) for q in range(6))
+    assert np.array_equal(col("IS_BITMASK"), (ia[0] + ia[1] + ia[2] + ia[3]) == 1)
+    sel, anyb = np.zeros(limit, int), np.zeros(limit, bool)
+    for q in range(6):
+        sel = np.where(bits[q] == 1, q, sel); anyb |= bits[q] == 1
+    ql = [col("QUEUE_LENS", q) for q in range(6)]
+    assert all(np.array_equal(ql[q], prev(ql[q], 0) + bits[q]) for q in range(6))
+    rows = np.arange(limit)
+    assert np.array_equal(col("EXEC_LEN"), np.stack([prev(ql[q], 0) for q in range(6)])[sel, rows])
+    for i in range(4):
+        pt = np.stack([prev(col("QUEUE_TAILS", 4 * q + i), 0) for q in range(6)])
+        assert np.array_equal(col("EXEC_TAIL", i), pt[sel, rows])
+        for q in range(6):
+            assert np.array_equal(col("QUEUE_TAILS", 4 * q + i), np.where(anyb & (sel == q), col("PUSH_ROUND2", i), pt[q]))
+        h = col("HEAD", i)
+        assert np.array_equal(h[ex == 0], prev(h, 0)[ex == 0])
