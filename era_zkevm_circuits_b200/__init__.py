@@ -47,6 +47,7 @@ from .keccak256_round_function import (  # noqa: F401
 from .sha256_round_function import (  # noqa: F401
     Sha256RoundFunctionCircuitInstanceWitness,
     sha256_round_function_entry_point,
+    sha256_round_function_check_trace,
 )
 from .main_vm import (  # noqa: F401
     VmCircuitWitness,

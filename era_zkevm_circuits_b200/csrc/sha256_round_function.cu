@@ -411,6 +411,184 @@ __global__ void sh_finalize_kernel(ShDev *d, const uint32_t *__restrict__ slot_m
     }
 }
 
+
+// ---- constraint evaluation of a finished trace ------------------------------------------------------------------------------
+// One thread per cycle re-evaluates every relation sha256_precompile_inner (mod.rs:146-330) places that is local to a cycle or to a
+// cycle and its predecessor: the FSM flags carried from the previous cycle, the conditional pop (ranges, aux byte / formal address
+// enforcement, queue length / head), Sha256PrecompileCallParams::from_encoding and the selects on the call parameters and
+// timestamps, reset / should_read, the two read queries (offset increments, big-endian message words), the round counter, the
+// state the compression starts from and the SHA-256 compression itself, the result word, write_result and the next FSM flags, the
+// memory queue's length / tail bookkeeping over the three conditional pushes.  With ZKC_GATES_ROUND_FUNCTION also the Poseidon2
+// permutations (3 of the pop, 1 per executed memory push).
+template <bool ROUND_FUNCTION>
+__global__ void __launch_bounds__(128)
+sh_check_kernel(ShDev *d, unsigned long long *violations, const uint64_t *__restrict__ trace) {
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const bool first = row == 0;
+    const zkc_sha256_fsm &s0 = d->s0;
+#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
+#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
+    uint32_t bad = 0;
+    const uint32_t aux_byte = d->opt.aux_byte ? d->opt.aux_byte : ZKC_PRECOMPILE_AUX_BYTE_DEFAULT;
+    const uint32_t formal = d->opt.precompile_address ? d->opt.precompile_address : ZKC_SHA256_PRECOMPILE_ADDRESS_DEFAULT;
+    // FSM flags on entry = the flags the previous cycle left
+    const uint64_t rpc = TR(ZKC_SH_FLAGS_IN + 0), rwr_in = TR(ZKC_SH_FLAGS_IN + 1), completed_in = TR(ZKC_SH_FLAGS_IN + 2);
+    if ((rpc | rwr_in | completed_in) > 1 || rpc != (first ? (uint64_t)s0.read_precompile_call : TP(ZKC_SH_FLAGS_OUT + 0)) ||
+        rwr_in != (first ? (uint64_t)s0.read_words_for_round : TP(ZKC_SH_FLAGS_OUT + 1)) || completed_in != (first ? (uint64_t)s0.completed : TP(ZKC_SH_FLAGS_OUT + 2)))
+        bad |= ZKC_SHV_FSM;
+    // the conditional pop
+    uint64_t f[36], limbs = 0;
+#pragma unroll
+    for (int i = 0; i < 36; i++) f[i] = TR(ZKC_SH_CALL_ITEM + i);
+#pragma unroll
+    for (int i = 0; i < 29; i++) limbs |= f[i];
+    if ((limbs | f[34] | f[35]) >> 32 || (f[29] | f[33]) >> 8 || (f[30] | f[31] | f[32]) > 1) bad |= ZKC_SHV_BOOLEAN;
+    if (rpc && (f[29] != aux_byte || f[0] != formal || (f[1] | f[2] | f[3] | f[4]))) bad |= ZKC_SHV_ENFORCE;
+    const uint64_t len_prev = first ? d->rq0.length : TP(ZKC_SH_REQ_LEN), len = TR(ZKC_SH_REQ_LEN);
+    if (len + rpc != len_prev || (len >> 32)) bad |= ZKC_SHV_QUEUE;
+    uint64_t head[4], head_prev[4];
+    bool same = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        head[i] = TR(ZKC_SH_REQ_HEAD + i);
+        head_prev[i] = first ? d->rq0.head[i] : TP(ZKC_SH_REQ_HEAD + i);
+        same &= head[i] == head_prev[i];
+        if (head[i] >= GL_P) bad |= ZKC_SHV_BOOLEAN;
+    }
+    if (!rpc && !same) bad |= ZKC_SHV_QUEUE;
+    if (ROUND_FUNCTION && rpc) {
+        zkc_log_query q = lq_zero();
+#pragma unroll
+        for (int i = 0; i < 5; i++) q.address[i] = (uint32_t)f[i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { q.key[i] = (uint32_t)f[5 + i]; q.read_value[i] = (uint32_t)f[13 + i]; q.written_value[i] = (uint32_t)f[21 + i]; }
+        q.flags = ZKC_LQ_FLAGS((uint32_t)f[29], (uint32_t)f[33], (uint32_t)f[30], (uint32_t)f[31], (uint32_t)f[32]);
+        q.tx_number_in_block = (uint32_t)f[34]; q.timestamp = (uint32_t)f[35];
+        uint64_t e[20], st[12];
+        lq_encode(q, e);
+        lq_absorb_head(e, st);
+        lq_absorb_tail(e, head_prev, st);
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (st[i] != head[i]) bad |= ZKC_SHV_ROUND_FUNCTION;
+    }
+    // call parameters and timestamps after the selects (:175-200); carried: page / offsets / rounds as the previous cycle left them
+    uint64_t p[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) p[i] = TR(ZKC_SH_PARAMS + i);
+    const uint64_t ts_read = TR(ZKC_SH_TS_READ), ts_write = TR(ZKC_SH_TS_WRITE);
+    {
+        const uint64_t prev_p[5] = {first ? (uint64_t)s0.input_page : TP(ZKC_SH_PARAMS + 0),
+                                    first ? (uint64_t)s0.input_offset : TP(ZKC_SH_QUERY + ZKC_SH_QUERY_STRIDE + 21),
+                                    first ? (uint64_t)s0.output_page : TP(ZKC_SH_PARAMS + 2), first ? (uint64_t)s0.output_offset : TP(ZKC_SH_PARAMS + 3),
+                                    first ? (uint64_t)s0.num_rounds : TP(ZKC_SH_NUM_ROUNDS)};
+        const uint64_t from_call[5] = {f[5 + 4], f[5 + 0], f[5 + 5], f[5 + 2], f[5 + 6]};  // from_encoding: key limbs 4, 0, 5, 2, 6
+        uint64_t range = ts_read | ts_write;
+#pragma unroll
+        for (int i = 0; i < 5; i++) { range |= p[i]; if (p[i] != (rpc ? from_call[i] : prev_p[i])) bad |= ZKC_SHV_PARAMS; }
+        const uint64_t tr_prev = first ? (uint64_t)s0.timestamp_to_use_for_read : TP(ZKC_SH_TS_READ), tw_prev = first ? (uint64_t)s0.timestamp_to_use_for_write : TP(ZKC_SH_TS_WRITE);
+        if (ts_read != (rpc ? f[35] : tr_prev) || ts_write != (rpc ? (uint64_t)(uint32_t)(ts_read + 1) : tw_prev) || (range >> 32)) bad |= ZKC_SHV_PARAMS;
+    }
+    const uint64_t reset = TR(ZKC_SH_RESET_BUFFER), should_read = TR(ZKC_SH_SHOULD_READ);
+    const uint64_t rwr = rpc | rwr_in;  // read_words_for_round after :205-208
+    if ((reset | should_read) > 1 || reset != (rpc | completed_in) || should_read != (uint64_t)(p[4] != 0)) bad |= ZKC_SHV_FSM;
+    // the two reads: offsets, message words, the memory queue (tail / length chain: previous write -> read 0 -> read 1 -> write)
+    uint32_t m[16];
+    uint64_t mt_prev[12], ml_prev;
+#pragma unroll
+    for (int i = 0; i < 12; i++) mt_prev[i] = first ? d->mq0.tail[i] : TP(ZKC_SH_WRITE_TAIL + i);
+    ml_prev = first ? d->mq0.length : TP(ZKC_SH_WRITE_LEN);
+    uint64_t offset = p[1];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int b = ZKC_SH_QUERY + q * ZKC_SH_QUERY_STRIDE;
+        uint32_t value[8];
+        uint64_t vr = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const uint64_t v = TR(b + i); vr |= v; value[i] = (uint32_t)v; }
+        if ((vr >> 32) || (!should_read && vr)) bad |= ZKC_SHV_BOOLEAN;  // conditionally_allocate: zero when nothing is read
+        const uint64_t off_after = TR(b + 21);
+        if (off_after != (uint64_t)(uint32_t)(offset + rwr)) bad |= ZKC_SHV_PARAMS;
+#pragma unroll
+        for (int i = 0; i < 8; i++) m[8 * q + i] = value[7 - i];
+        uint64_t mt[12], st[12];
+        bool msame = true;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { mt[i] = TR(b + 8 + i); msame &= mt[i] == mt_prev[i]; if (mt[i] >= GL_P) bad |= ZKC_SHV_BOOLEAN; }
+        const uint64_t ml = TR(b + 20);
+        if (ml != ml_prev + should_read || (!should_read && !msame)) bad |= ZKC_SHV_MEMORY_QUEUE;
+        if (ROUND_FUNCTION && should_read) {
+            mq_encode((uint32_t)ts_read, (uint32_t)p[0], (uint32_t)offset, 0, value, st);
+#pragma unroll
+            for (int i = 8; i < 12; i++) st[i] = mt_prev[i];
+            poseidon2_permute(st);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (st[i] != mt[i]) bad |= ZKC_SHV_ROUND_FUNCTION;
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) mt_prev[i] = mt[i];
+        ml_prev = ml;
+        offset = off_after;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) if (TR(ZKC_SH_MESSAGE + i) != m[i]) bad |= ZKC_SHV_COMPRESSION;
+    const uint64_t rounds_after = TR(ZKC_SH_NUM_ROUNDS);
+    if (rounds_after != (uint64_t)(uint32_t)(p[4] - rwr)) bad |= ZKC_SHV_PARAMS;
+    // the compression
+    uint32_t cur[8], result[8];
+    {
+        uint64_t range = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint64_t si = TR(ZKC_SH_STATE_IN + i);
+            range |= si;
+            if (si != (reset ? (uint64_t)SHA_IV[i] : (first ? (uint64_t)s0.sha256_inner_state[i] : TP(ZKC_SH_STATE_OUT + i)))) bad |= ZKC_SHV_COMPRESSION;
+            cur[i] = (uint32_t)si;
+        }
+        if (range >> 32) bad |= ZKC_SHV_BOOLEAN;
+        sha256_compress(cur, m);
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (TR(ZKC_SH_STATE_OUT + i) != cur[i]) bad |= ZKC_SHV_COMPRESSION;
+#pragma unroll
+        for (int k = 0; k < 8; k++) result[7 - k] = cur[k];
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (TR(ZKC_SH_RESULT + i) != result[i]) bad |= ZKC_SHV_COMPRESSION;
+    }
+    // the write and the next FSM flags
+    const uint64_t write_result = TR(ZKC_SH_WRITE_RESULT);
+    if (write_result != (rwr & (uint64_t)(rounds_after == 0))) bad |= ZKC_SHV_FSM;
+    {
+        uint64_t mt[12], st[12];
+        bool msame = true;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { mt[i] = TR(ZKC_SH_WRITE_TAIL + i); msame &= mt[i] == mt_prev[i]; if (mt[i] >= GL_P) bad |= ZKC_SHV_BOOLEAN; }
+        if (TR(ZKC_SH_WRITE_LEN) != ml_prev + write_result || (!write_result && !msame)) bad |= ZKC_SHV_MEMORY_QUEUE;
+        if (ROUND_FUNCTION && write_result) {
+            mq_encode((uint32_t)ts_write, (uint32_t)p[2], (uint32_t)p[3], 1, result, st);
+#pragma unroll
+            for (int i = 8; i < 12; i++) st[i] = mt_prev[i];
+            poseidon2_permute(st);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (st[i] != mt[i]) bad |= ZKC_SHV_ROUND_FUNCTION;
+        }
+    }
+    {
+        const uint64_t empty = len == 0;
+        const uint64_t o_rpc = TR(ZKC_SH_FLAGS_OUT + 0), o_rwr = TR(ZKC_SH_FLAGS_OUT + 1), o_completed = TR(ZKC_SH_FLAGS_OUT + 2);
+        if (o_rpc != (write_result & (1 - empty)) || o_completed != ((write_result & empty) | completed_in) || o_rwr != 1 - ((o_rpc | o_completed) & 1) ||
+            (o_rpc | o_rwr | o_completed) > 1)
+            bad |= ZKC_SHV_FSM;
+    }
+#undef TR
+#undef TP
+    if (bad) {
+        atomicAdd(violations, 1ull);
+        atomicOr(&d->failed_checks, bad);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+    }
+}
+
 }  // namespace zkc
 
 using namespace zkc;
@@ -507,5 +685,55 @@ extern "C" int zkc_sha256_round_function_entry_point(zkc_ctx *ctx, zkc_sha256_cl
     io->completion_flag = h->io.completion_flag;
     memcpy(commitment, h->commitment, 32);
     *status = h->status;
+    return status->code;
+}
+
+extern "C" int zkc_sha256_round_function_check_trace(zkc_ctx *ctx, const zkc_sha256_closed_form *io, const zkc_precompile_options *options,
+                                                     const uint64_t *trace, size_t limit, uint32_t gates, int on_device, uint64_t *violations,
+                                                     zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !violations || (limit && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(ShDev)) + zkc_carver::bytes(1, 8);
+    if (!on_device) bytes += zkc_carver::bytes((size_t)ZKC_SH_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    ShDev *h = (ShDev *)ctx->pinned(sizeof(ShDev) + 8);
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    ShDev *d = cv.take<ShDev>(1);
+    unsigned long long *dviol = cv.take<unsigned long long>(1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(ShDev));
+    h->io = *io;
+    if (options) h->opt = *options;
+    h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(ShDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(dviol, 0, 8, s));
+    const uint64_t *dt = trace;
+    if (!on_device && limit) {
+        uint64_t *b = cv.take<uint64_t>((size_t)ZKC_SH_NUM_COLS * limit);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, (size_t)ZKC_SH_NUM_COLS * limit * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    ZKC_LAUNCH(ctx, "sh_prologue", sh_prologue_kernel, 1, 96, 0, d);
+    if (limit) {
+        const unsigned grid = (unsigned)((limit + 127) / 128);
+        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION)) ZKC_LAUNCH(ctx, "sh_check_rf", sh_check_kernel<true>, grid, 128, 0, d, dviol, dt);
+        else ZKC_LAUNCH(ctx, "sh_check", sh_check_kernel<false>, grid, 128, 0, d, dviol, dt);
+    }
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    unsigned long long *hviol = (unsigned long long *)(h + 1);
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(ShDev), cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(hviol, dviol, 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = *hviol;
+    status->failed_checks = h->failed_checks;
+    if (*hviol) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 16);
+    }
     return status->code;
 }

@@ -52,3 +52,19 @@ def sha256_round_function_entry_point(engine: Engine, witness: Sha256RoundFuncti
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE) or (rc and raise_on_unsatisfied):
         raise ZkcError(rc, st, "sha256_round_function_entry_point")
     return SorterResult(commitment, io, trace, st)
+
+
+def sha256_round_function_check_trace(engine: Engine, closed_form_input: abi.Sha256ClosedForm, trace, limit: int, gates: int = 0,
+                                      options: Optional[abi.PrecompileOptions] = None):
+    """Constraint evaluation of a finished sha256_round_function trace [SH_COLS.NUM_COLS, limit] (numpy: host, torch CUDA: device):
+    every relation of sha256_precompile_inner (mod.rs:146-330), the compression included.  Returns (violating rows, status);
+    status.failed_checks holds abi.SHV bits."""
+    st = abi.Status()
+    viol = C.c_uint64()
+    io = abi.Sha256ClosedForm.from_buffer_copy(bytes(closed_form_input))
+    opts = abi.PrecompileOptions.from_buffer_copy(bytes(options)) if options is not None else abi.PrecompileOptions()
+    rc = engine.lib.zkc_sha256_round_function_check_trace(engine.h, C.byref(io), C.byref(opts), ptr(trace), limit, gates, on_device(trace),
+                                                          C.byref(viol), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, st, "sha256_round_function_check_trace")
+    return viol.value, st

@@ -967,6 +967,21 @@ int zkc_sha256_round_function_entry_point(zkc_ctx *ctx, zkc_sha256_closed_form *
                                           int on_device, uint64_t *trace, uint64_t commitment[ZKC_COMMITMENT_LEN],
                                           zkc_status *status);
 
+/* constraint evaluation of a finished sha256_round_function trace: every relation of sha256_precompile_inner (mod.rs:146-330) on
+ * every cycle, the SHA-256 compression included; options as for the entry point (aux byte / formal address).  gates:
+ * ZKC_GATES_GENERAL = everything but the Poseidon2 permutations of the queues; ZKC_GATES_ROUND_FUNCTION adds them; 0 = all. */
+#define ZKC_SHV_BOOLEAN (1u << 0)        /* booleans, u32 / u8 ranges, field range of hash outputs, zero values when nothing is read */
+#define ZKC_SHV_QUEUE (1u << 1)          /* length / head bookkeeping of the requests queue */
+#define ZKC_SHV_FSM (1u << 2)            /* FSM flags carried between cycles, reset / should_read / write_result, the next flags */
+#define ZKC_SHV_ROUND_FUNCTION (1u << 3)
+#define ZKC_SHV_PARAMS (1u << 4)         /* call parameters / timestamps after the selects, offset increments, the round counter */
+#define ZKC_SHV_ENFORCE (1u << 5)        /* aux byte / formal address of a popped call */
+#define ZKC_SHV_COMPRESSION (1u << 6)    /* message words, starting state, SHA-256 compression, result word */
+#define ZKC_SHV_MEMORY_QUEUE (1u << 7)   /* memory queue length / tail over the three conditional pushes */
+int zkc_sha256_round_function_check_trace(zkc_ctx *ctx, const zkc_sha256_closed_form *io, const zkc_precompile_options *options,
+                                          const uint64_t *trace, size_t limit, uint32_t gates, int on_device, uint64_t *violations,
+                                          zkc_status *status);
+
 
 /* ---- code_unpacker_sha256 (src/code_unpacker_sha256/mod.rs) --------------------------------------------- */
 /* CodeDecommittmentFSM, code_unpacker_sha256/input.rs:27-38 */

@@ -62,3 +62,50 @@ def test_negative(orc):
     _, rfin = O.log_queue_simulate(orc, e)
     rc, out, _, _, st, _ = O.sha256_entry_point(orc, O.sha256_closed_form(rfin), e, np.zeros((0, 8), dtype=np.uint32), 4)
     assert rc == 0 and out.completion_flag == 1
+
+
+def test_cycle_relations_of_the_trace(orc):
+    """The cycle-to-cycle relations zkc_sha256_round_function_check_trace evaluates on the device (sh_check_kernel), restated in numpy
+    and held against the oracle's trace: FSM flags, parameter / timestamp selects, offsets, round counter, state chaining, message
+    words, result word, memory-queue bookkeeping.  Pins the evaluator's reading of mod.rs:146-330 without a GPU."""
+    reqs, reads, msgs = synthetic.sha256_calls(200, seed=3, max_rounds=9)
+    _, rfin = O.log_queue_simulate(orc, reqs)
+    io = O.sha256_closed_form(rfin)
+    limit = len(reads) // 2 + 20
+    rc, out, T, com, st, states = O.sha256_entry_point(orc, io, reqs, reads, limit)
+    assert rc == 0
+    col = lambda name, i=0: T[K[name] + i]
+    prev = lambda a, first: np.concatenate([np.array([first], dtype=np.uint64), a[:-1].astype(np.uint64)])
+    rpc, rwr_in, comp = col("FLAGS_IN", 0), col("FLAGS_IN", 1), col("FLAGS_IN", 2)
+    fo = [col("FLAGS_OUT", i) for i in range(3)]
+    assert all(np.array_equal(x[1:], y[:-1]) for x, y in zip((rpc, rwr_in, comp), fo)) and (rpc[0], rwr_in[0], comp[0]) == (1, 0, 0)
+    I = K["CALL_ITEM"]
+    key, call_ts = [T[I + 5 + i] for i in range(8)], T[I + 35]
+    P = [col("PARAMS", i) for i in range(5)]
+    Q0, Q1 = K["QUERY"], K["QUERY"] + K["QUERY_STRIDE"]
+    carried = [prev(P[0], 0), prev(T[Q1 + 21], 0), prev(P[2], 0), prev(P[3], 0), prev(col("NUM_ROUNDS"), 0)]
+    from_call = [key[4], key[0], key[5], key[2], key[6]]
+    assert all(np.array_equal(P[i], np.where(rpc == 1, from_call[i], carried[i])) for i in range(5))
+    tsr, tsw = col("TS_READ"), col("TS_WRITE")
+    assert np.array_equal(tsr, np.where(rpc == 1, call_ts, prev(tsr, 0))) and np.array_equal(tsw, np.where(rpc == 1, (tsr + 1) & 0xFFFFFFFF, prev(tsw, 0)))
+    reset, should_read, rwr = col("RESET_BUFFER"), col("SHOULD_READ"), rpc | rwr_in
+    assert np.array_equal(reset, rpc | comp) and np.array_equal(should_read, P[4] != 0)
+    assert np.array_equal(T[Q0 + 21], (P[1] + rwr) & 0xFFFFFFFF) and np.array_equal(T[Q1 + 21], (T[Q0 + 21] + rwr) & 0xFFFFFFFF)
+    rounds = col("NUM_ROUNDS")
+    write = col("WRITE_RESULT")
+    assert np.array_equal(rounds, (P[4] - rwr) & 0xFFFFFFFF) and np.array_equal(write, rwr & (rounds == 0))
+    ln = col("REQ_LEN")
+    empty = ln == 0
+    assert np.array_equal(ln + rpc, prev(ln, rfin.length))
+    assert np.array_equal(fo[0], write & ~empty) and np.array_equal(fo[2], (write & empty) | comp) and np.array_equal(fo[1], 1 - (fo[0] | fo[2]))
+    IV = [0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19]
+    assert all(np.array_equal(col("STATE_IN", i), np.where(reset == 1, IV[i], prev(col("STATE_OUT", i), 0))) for i in range(8))
+    assert all(np.array_equal(col("RESULT", 7 - k), col("STATE_OUT", k)) for k in range(8))
+    assert all(np.array_equal(col("MESSAGE", 8 * q + i), T[K["QUERY"] + K["QUERY_STRIDE"] * q + 7 - i]) for q in range(2) for i in range(8))
+    l0, l1, lw = T[Q0 + 20], T[Q1 + 20], col("WRITE_LEN")
+    assert np.array_equal(l0, prev(lw, 0) + should_read) and np.array_equal(l1, l0 + should_read) and np.array_equal(lw, l1 + write)
+    for i in range(12):
+        t0, t1, tw = T[Q0 + 8 + i], T[Q1 + 8 + i], col("WRITE_TAIL", i)
+        idle = should_read == 0
+        assert np.array_equal(t0[idle], prev(tw, 0)[idle]) and np.array_equal(t1[idle], t0[idle]) and np.array_equal(tw[write == 0], t1[write == 0])
+    assert all((T[K["QUERY"] + K["QUERY_STRIDE"] * q + i][should_read == 0] == 0).all() for q in range(2) for i in range(8))
