@@ -39,6 +39,7 @@ from .linear_hasher import (  # noqa: F401
 from .code_unpacker_sha256 import (  # noqa: F401
     CodeDecommitterCircuitInstanceWitness,
     unpack_code_into_memory_entry_point,
+    code_unpacker_check_trace,
 )
 from .keccak256_round_function import (  # noqa: F401
     Keccak256RoundFunctionCircuitInstanceWitness,

@@ -50,3 +50,16 @@ def unpack_code_into_memory_entry_point(engine: Engine, witness: CodeDecommitter
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE) or (rc and raise_on_unsatisfied):
         raise ZkcError(rc, st, "unpack_code_into_memory_entry_point")
     return SorterResult(commitment, io, trace, st)
+
+
+def code_unpacker_check_trace(engine: Engine, closed_form_input: abi.CodeUnpackerClosedForm, trace, limit: int, gates: int = 0):
+    """Constraint evaluation of a finished code_unpacker_sha256 trace [CU_COLS.NUM_COLS, limit] (numpy: host, torch CUDA: device):
+    every relation of unpack_code_into_memory_inner (mod.rs:191-447), the compression and the hash comparison included.  Returns
+    (violating rows, status); status.failed_checks holds abi.CUV bits."""
+    st = abi.Status()
+    viol = C.c_uint64()
+    io = abi.CodeUnpackerClosedForm.from_buffer_copy(bytes(closed_form_input))
+    rc = engine.lib.zkc_code_unpacker_check_trace(engine.h, C.byref(io), ptr(trace), limit, gates, on_device(trace), C.byref(viol), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, st, "code_unpacker_check_trace")
+    return viol.value, st

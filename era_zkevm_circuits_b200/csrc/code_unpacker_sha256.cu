@@ -524,6 +524,181 @@ __global__ void cu_finalize_kernel(CuDev *d, const uint32_t *__restrict__ slot_m
     }
 }
 
+
+// ---- constraint evaluation of a finished trace ------------------------------------------------------------------------------
+// One thread per cycle re-evaluates every relation unpack_code_into_memory_inner (mod.rs:191-447) places that is local to a cycle
+// or to a cycle and its predecessor: the FSM flags carried from the previous cycle, the conditional pop (ranges, queue length /
+// head), the versioned-hash decomposition (version match, length in words / rounds / bits), the selects on timestamp / page / hash /
+// index / SHA-256 state, the round counter, last_round / finalize / process_second_word, the two conditional code words and their
+// indices, the SHA-256 block (padding selected in on finalize) and the compression, the state select, the hash comparison on
+// finalize, the next FSM flags, the memory queue's length / tail over the two conditional writes.  With
+// ZKC_GATES_ROUND_FUNCTION also the Poseidon2 permutations (the pop, every executed memory write).
+template <bool ROUND_FUNCTION>
+__global__ void __launch_bounds__(128)
+cu_check_kernel(CuDev *d, unsigned long long *violations, const uint64_t *__restrict__ trace) {
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const bool first = row == 0;
+    const zkc_code_decommittment_fsm &s0 = d->s0;
+#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
+#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
+    uint32_t bad = 0;
+    const uint64_t get = TR(ZKC_CU_FLAGS_IN + 0), decommit_in = TR(ZKC_CU_FLAGS_IN + 1), finished_in = TR(ZKC_CU_FLAGS_IN + 2);
+    if ((get | decommit_in | finished_in) > 1 || get != (first ? (uint64_t)s0.state_get_from_queue : TP(ZKC_CU_FLAGS_OUT + 0)) ||
+        decommit_in != (first ? (uint64_t)s0.state_decommit : TP(ZKC_CU_FLAGS_OUT + 1)) || finished_in != (first ? (uint64_t)s0.finished : TP(ZKC_CU_FLAGS_OUT + 2)))
+        bad |= ZKC_CUV_FSM;
+    // the conditional pop
+    uint64_t f[11], limbs = 0;
+#pragma unroll
+    for (int i = 0; i < 11; i++) { f[i] = TR(ZKC_CU_REQUEST + i); limbs |= f[i]; }
+    if ((limbs >> 32) || f[9] > 1) bad |= ZKC_CUV_BOOLEAN;
+    const uint64_t len_prev = first ? d->rq0.length : TP(ZKC_CU_REQ_LEN), len = TR(ZKC_CU_REQ_LEN);
+    if (len + get != len_prev || (len >> 32)) bad |= ZKC_CUV_QUEUE;
+    {
+        uint64_t head[12], st[12];
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            head[i] = TR(ZKC_CU_REQ_HEAD + i);
+            const uint64_t hp = first ? d->rq0.head[i] : TP(ZKC_CU_REQ_HEAD + i);
+            same &= head[i] == hp;
+            st[i] = hp;
+            if (head[i] >= GL_P) bad |= ZKC_CUV_BOOLEAN;
+        }
+        if (!get && !same) bad |= ZKC_CUV_QUEUE;
+        if (ROUND_FUNCTION && get) {
+            zkc_decommit_query q;
+#pragma unroll
+            for (int i = 0; i < 8; i++) q.code_hash[i] = (uint32_t)f[i];
+            q.page = (uint32_t)f[8]; q.is_first = (uint32_t)f[9] & 1u; q.timestamp = (uint32_t)f[10]; q._pad = 0;
+            uint64_t e[8];
+            cu_encode_request(q, e);
+#pragma unroll
+            for (int i = 0; i < 8; i++) st[i] = e[i];
+            poseidon2_permute(st);
+#pragma unroll
+            for (int i = 0; i < 12; i++) if (st[i] != head[i]) bad |= ZKC_CUV_ROUND_FUNCTION;
+        }
+    }
+    // :198-221 the versioned hash: top 16 bits = version, low 16 bits of limb 7 = length in words (odd), rounds = (words + 1) / 2
+    const uint64_t version_matches = TR(ZKC_CU_VERSION_MATCHES), words = TR(ZKC_CU_LENGTH_IN_WORDS), rounds = TR(ZKC_CU_LENGTH_IN_ROUNDS);
+    if (version_matches != (uint64_t)((f[7] >> 16) == ZKC_CODE_HASH_VERSION_TOP16) || words != (get ? (f[7] & 0xFFFFu) : 1ull) || 2 * rounds != words + 1 ||
+        (rounds >> 16))
+        bad |= ZKC_CUV_LENGTH;
+    if (get & (1 - (version_matches & 1))) bad |= ZKC_CUV_ENFORCE;
+    // :226-275 the selects
+    const uint64_t bits = TR(ZKC_CU_LENGTH_IN_BITS), ts = TR(ZKC_CU_TIMESTAMP), page = TR(ZKC_CU_PAGE), index0 = TR(ZKC_CU_INDEX0);
+    uint64_t hash_cmp[8];
+    {
+        bool ok = bits == (get ? (uint64_t)(uint32_t)(words * 256) : (first ? (uint64_t)s0.length_in_bits : TP(ZKC_CU_LENGTH_IN_BITS)));
+        ok &= ts == (get ? f[10] : (first ? (uint64_t)s0.timestamp : TP(ZKC_CU_TIMESTAMP)));
+        ok &= page == (get ? f[8] : (first ? (uint64_t)s0.current_page : TP(ZKC_CU_PAGE)));
+        ok &= index0 == (get ? 0ull : (first ? (uint64_t)s0.current_index : TP(ZKC_CU_INDEX_OUT)));
+        uint64_t range = bits | ts | page | index0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            hash_cmp[i] = TR(ZKC_CU_HASH_TO_COMPARE + i);
+            range |= hash_cmp[i];
+            ok &= hash_cmp[i] == (get ? (i < 7 ? f[i] : 0ull) : (first ? (uint64_t)s0.hash_to_compare_against[i] : TP(ZKC_CU_HASH_TO_COMPARE + i)));
+        }
+        if (!ok || (range >> 32)) bad |= ZKC_CUV_SELECTS;
+    }
+    // :277-291 decommit flag, round counter, the three phase flags
+    const uint64_t decommit = TR(ZKC_CU_DECOMMIT), rounds_left = TR(ZKC_CU_NUM_ROUNDS_LEFT), last = TR(ZKC_CU_LAST_ROUND), finalize = TR(ZKC_CU_FINALIZE),
+                   second = TR(ZKC_CU_PROCESS_SECOND_WORD);
+    {
+        const uint64_t selected = get ? rounds : (first ? (uint64_t)s0.num_rounds_left : TP(ZKC_CU_NUM_ROUNDS_LEFT));
+        if ((decommit | last | finalize | second) > 1 || decommit != (decommit_in | get) || rounds_left != (decommit ? ((selected - 1) & 0xFFFFu) : selected) ||
+            last != (uint64_t)(rounds_left == 0) || finalize != (last & decommit) || second != ((1 - last) & decommit))
+            bad |= ZKC_CUV_FSM;
+    }
+    // :293-352 the two code words, their indices, the two conditional memory writes
+    uint32_t w0[8], w1[8], m[16];
+    {
+        uint64_t r0 = 0, r1 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const uint64_t a = TR(ZKC_CU_WORD0 + i), b = TR(ZKC_CU_WORD1 + i); r0 |= a; r1 |= b; w0[i] = (uint32_t)a; w1[i] = (uint32_t)b; }
+        if (((r0 | r1) >> 32) || (!decommit && r0) || (!second && r1)) bad |= ZKC_CUV_BOOLEAN;  // conditionally_allocate: zero when not taken
+    }
+    const uint64_t index1 = TR(ZKC_CU_INDEX1), index_out = TR(ZKC_CU_INDEX_OUT);
+    if (index1 != (uint64_t)(uint32_t)(index0 + decommit) || index_out != (uint64_t)(uint32_t)(index1 + second)) bad |= ZKC_CUV_SELECTS;
+    {
+        uint64_t mt_prev[12], ml_prev = first ? d->mq0.length : TP(ZKC_CU_MEM_TAIL1 + 12);
+#pragma unroll
+        for (int i = 0; i < 12; i++) mt_prev[i] = first ? d->mq0.tail[i] : TP(ZKC_CU_MEM_TAIL1 + i);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int b = q ? ZKC_CU_MEM_TAIL1 : ZKC_CU_MEM_TAIL0;
+            const uint64_t pushed = q ? second : decommit;
+            uint64_t mt[12], st[12];
+            bool msame = true;
+#pragma unroll
+            for (int i = 0; i < 12; i++) { mt[i] = TR(b + i); msame &= mt[i] == mt_prev[i]; if (mt[i] >= GL_P) bad |= ZKC_CUV_BOOLEAN; }
+            const uint64_t ml = TR(b + 12);
+            if (ml != ml_prev + pushed || (!pushed && !msame)) bad |= ZKC_CUV_MEMORY_QUEUE;
+            if (ROUND_FUNCTION && pushed) {
+                mq_encode((uint32_t)ts, (uint32_t)page, (uint32_t)(q ? index1 : index0), 1, q ? w1 : w0, st);
+#pragma unroll
+                for (int i = 8; i < 12; i++) st[i] = mt_prev[i];
+                poseidon2_permute(st);
+#pragma unroll
+                for (int i = 0; i < 12; i++) if (st[i] != mt[i]) bad |= ZKC_CUV_ROUND_FUNCTION;
+            }
+#pragma unroll
+            for (int i = 0; i < 12; i++) mt_prev[i] = mt[i];
+            ml_prev = ml;
+        }
+    }
+    // :354-391 the SHA-256 block (big-endian words; the padding block selected in on finalize), the compression, the state select
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        m[i] = w0[7 - i];
+        const uint32_t pad = i == 0 ? 0x80000000u : (i == 7 ? (uint32_t)bits : 0u);
+        m[8 + i] = finalize ? pad : w1[7 - i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) if (TR(ZKC_CU_MESSAGE + i) != m[i]) bad |= ZKC_CUV_COMPRESSION;
+    uint32_t cur[8];
+    {
+        uint64_t range = 0;
+        uint64_t st_in[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            st_in[i] = TR(ZKC_CU_STATE_IN + i);
+            range |= st_in[i];
+            if (st_in[i] != (get ? (uint64_t)SHA_IV[i] : (first ? (uint64_t)s0.sha256_inner_state[i] : TP(ZKC_CU_STATE_OUT + i)))) bad |= ZKC_CUV_COMPRESSION;
+            cur[i] = (uint32_t)st_in[i];
+        }
+        if (range >> 32) bad |= ZKC_CUV_BOOLEAN;
+        sha256_compress(cur, m);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (TR(ZKC_CU_STATE_NEW + i) != cur[i]) bad |= ZKC_CUV_COMPRESSION;
+            if (TR(ZKC_CU_STATE_OUT + i) != (decommit ? (uint64_t)cur[i] : st_in[i])) bad |= ZKC_CUV_COMPRESSION;
+        }
+    }
+    // :393-420 on finalize the digest (top 4 bytes ignored) is the hash of the request
+    if (finalize) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (hash_cmp[i] != (i < 7 ? (uint64_t)cur[7 - i] : 0ull)) bad |= ZKC_CUV_ENFORCE;
+    }
+    // :422-430 the next FSM flags
+    {
+        const uint64_t empty = len == 0;
+        const uint64_t o_get = TR(ZKC_CU_FLAGS_OUT + 0), o_decommit = TR(ZKC_CU_FLAGS_OUT + 1), o_finished = TR(ZKC_CU_FLAGS_OUT + 2);
+        if ((o_get | o_decommit | o_finished) > 1 || o_get != ((1 - empty) & finalize) || o_decommit != second || o_finished != (finished_in | (empty & finalize)))
+            bad |= ZKC_CUV_FSM;
+    }
+#undef TR
+#undef TP
+    if (bad) {
+        atomicAdd(violations, 1ull);
+        atomicOr(&d->failed_checks, bad);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+    }
+}
+
 }  // namespace zkc
 
 using namespace zkc;
@@ -624,5 +799,53 @@ extern "C" int zkc_code_unpacker_entry_point(zkc_ctx *ctx, zkc_code_unpacker_clo
     io->completion_flag = h->io.completion_flag;
     memcpy(commitment, h->commitment, 32);
     *status = h->status;
+    return status->code;
+}
+
+extern "C" int zkc_code_unpacker_check_trace(zkc_ctx *ctx, const zkc_code_unpacker_closed_form *io, const uint64_t *trace, size_t limit, uint32_t gates,
+                                             int on_device, uint64_t *violations, zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !violations || (limit && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(CuDev)) + zkc_carver::bytes(1, 8);
+    if (!on_device) bytes += zkc_carver::bytes((size_t)ZKC_CU_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    CuDev *h = (CuDev *)ctx->pinned(sizeof(CuDev) + 8);
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    CuDev *d = cv.take<CuDev>(1);
+    unsigned long long *dviol = cv.take<unsigned long long>(1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(CuDev));
+    h->io = *io;
+    h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(CuDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(dviol, 0, 8, s));
+    const uint64_t *dt = trace;
+    if (!on_device && limit) {
+        uint64_t *b = cv.take<uint64_t>((size_t)ZKC_CU_NUM_COLS * limit);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, (size_t)ZKC_CU_NUM_COLS * limit * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    ZKC_LAUNCH(ctx, "cu_prologue", cu_prologue_kernel, 1, 96, 0, d);
+    if (limit) {
+        const unsigned grid = (unsigned)((limit + 127) / 128);
+        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION)) ZKC_LAUNCH(ctx, "cu_check_rf", cu_check_kernel<true>, grid, 128, 0, d, dviol, dt);
+        else ZKC_LAUNCH(ctx, "cu_check", cu_check_kernel<false>, grid, 128, 0, d, dviol, dt);
+    }
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    unsigned long long *hviol = (unsigned long long *)(h + 1);
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(CuDev), cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(hviol, dviol, 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = *hviol;
+    status->failed_checks = h->failed_checks;
+    if (*hviol) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 16);
+    }
     return status->code;
 }

@@ -1072,6 +1072,21 @@ int zkc_code_unpacker_entry_point(zkc_ctx *ctx, zkc_code_unpacker_closed_form *i
                                   const zkc_sorter_options *options, int on_device, uint64_t *trace,
                                   uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
+/* constraint evaluation of a finished code_unpacker_sha256 trace: every relation of unpack_code_into_memory_inner (mod.rs:191-447)
+ * on every cycle, the SHA-256 compression and the hash comparison included.  gates: ZKC_GATES_GENERAL = everything but the
+ * Poseidon2 permutations of the queues; ZKC_GATES_ROUND_FUNCTION adds them; 0 = all. */
+#define ZKC_CUV_BOOLEAN (1u << 0)        /* booleans, u32 ranges, field range of hash outputs, zero words when not taken */
+#define ZKC_CUV_QUEUE (1u << 1)          /* length / head bookkeeping of the requests queue */
+#define ZKC_CUV_FSM (1u << 2)            /* FSM flags carried between cycles, decommit, round counter, phase flags, next flags */
+#define ZKC_CUV_ROUND_FUNCTION (1u << 3)
+#define ZKC_CUV_LENGTH (1u << 4)         /* version match, length in words / rounds */
+#define ZKC_CUV_ENFORCE (1u << 5)        /* version of a popped request; digest = requested hash on finalize */
+#define ZKC_CUV_COMPRESSION (1u << 6)    /* SHA-256 block, starting state, compression, state select */
+#define ZKC_CUV_MEMORY_QUEUE (1u << 7)   /* memory queue length / tail over the two conditional writes */
+#define ZKC_CUV_SELECTS (1u << 8)        /* length in bits, timestamp, page, hash, indices after the selects */
+int zkc_code_unpacker_check_trace(zkc_ctx *ctx, const zkc_code_unpacker_closed_form *io, const uint64_t *trace, size_t limit, uint32_t gates,
+                                  int on_device, uint64_t *violations, zkc_status *status);
+
 
 /* ---- main_vm (src/main_vm/) ------------------------------------------------------------------------- */
 /* The ISA tables (zkevm_opcode_defs, un-vendored) are INPUT DATA: opcode -> (price, 48-bit property bit spread +

@@ -142,3 +142,65 @@ def test_device_resident(engine, orc):
     torch.cuda.synchronize()
     assert got.commitment.tolist() == want[3].tolist() and got.status.code == 0
     assert np.array_equal(got.trace.cpu().numpy().view(np.uint64), want[2])
+
+
+def test_check_trace_constraint_evaluation(engine, orc):
+    """zkc_code_unpacker_check_trace: the ORACLE's trace satisfies every relation with and without the queue permutations; a fault
+    injected into any relation family is found at its cycle; the engine's trace of a chained second instance (cut inside a bytecode)
+    passes"""
+    from era_zkevm_circuits_b200 import code_unpacker_check_trace
+    V_ = abi.CUV
+    reqs, words = synthetic.code_decommit_requests(80, seed=8, max_words=41)
+    io, prev = instance(orc, reqs)
+    limit = int(rounds_of(reqs).sum()) + 20
+    want = O.code_unpacker_entry_point(orc, io, reqs, words, limit)
+    assert want[0] == abi.ZKC_OK
+    trace = want[2]
+    for gates in (0, abi.GATES_GENERAL):
+        viol, st = code_unpacker_check_trace(engine, io, trace, limit, gates)
+        assert viol == 0 and st.code == 0, (gates, viol, hex(st.failed_checks), st.first_bad_row)
+    import torch
+    viol, st = code_unpacker_check_trace(engine, io, torch.from_numpy(trace.view(np.int64)).cuda(), limit, abi.GATES_GENERAL)
+    assert viol == 0
+    pops = np.flatnonzero(trace[K["FLAGS_IN"]])
+    fins = np.flatnonzero(trace[K["FINALIZE"]])
+    mid = int(np.flatnonzero((trace[K["FLAGS_IN"]] == 0) & (trace[K["PROCESS_SECOND_WORD"]] == 1))[50])  # in the middle of a bytecode
+    faults = [
+        (K["FLAGS_IN"] + 1, mid, None, V_["FSM"], 0),
+        (K["REQUEST"] + 3, int(pops[5]), 1 << 33, V_["BOOLEAN"], 0),
+        (K["REQ_LEN"], mid, None, V_["QUEUE"], 0),
+        (K["REQ_HEAD"] + 7, mid, None, V_["QUEUE"], 0),
+        (K["REQ_HEAD"] + 7, int(pops[6]), None, V_["ROUND_FUNCTION"], 0),
+        (K["VERSION_MATCHES"], int(pops[7]), None, V_["LENGTH"], 0),
+        (K["LENGTH_IN_ROUNDS"], int(pops[8]), None, V_["LENGTH"], 0),
+        (K["LENGTH_IN_BITS"], mid, None, V_["SELECTS"], 0),
+        (K["PAGE"], mid, None, V_["SELECTS"], 0),
+        (K["HASH_TO_COMPARE"] + 2, mid, None, V_["SELECTS"], 0),
+        (K["DECOMMIT"], limit - 3, None, V_["FSM"], 0),
+        (K["NUM_ROUNDS_LEFT"], mid, None, V_["FSM"], 0),
+        (K["WORD1"] + 4, int(fins[9]), None, V_["BOOLEAN"], 0),
+        (K["INDEX1"], mid, None, V_["SELECTS"], 0),
+        (K["MEM_TAIL0"] + 12, mid, None, V_["MEMORY_QUEUE"], 0),
+        (K["MEM_TAIL1"] + 3, mid, None, V_["ROUND_FUNCTION"], 0),
+        (K["MEM_TAIL1"] + 3, limit - 3, None, V_["MEMORY_QUEUE"], abi.GATES_GENERAL),
+        (K["MESSAGE"] + 15, int(fins[10]), None, V_["COMPRESSION"], 0),
+        (K["STATE_IN"] + 4, mid, None, V_["COMPRESSION"], 0),
+        (K["STATE_NEW"] + 6, mid, None, V_["COMPRESSION"], 0),
+        (K["WORD0"] + 1, int(fins[11]), None, V_["ENFORCE"], abi.GATES_GENERAL),
+        (K["FLAGS_OUT"], int(fins[12]), None, V_["FSM"], 0),
+    ]
+    for col, row, val, bit, gates in faults:
+        bad = trace.copy()
+        bad[col, row] = np.uint64(val) if val is not None else bad[col, row] ^ np.uint64(1)
+        viol, st = code_unpacker_check_trace(engine, io, bad, limit, gates)
+        assert viol >= 1 and st.first_bad_row == row and st.failed_checks & bit, (col, row, viol, st.first_bad_row, hex(st.failed_checks))
+    cut = mid
+    a = entry_point(engine, Witness(io, reqs, prev, words, None), cut)
+    nxt = abi.CodeUnpackerClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+    used_req = len(reqs) - a.closed_form_input.hidden_fsm_output.decommittment_requests_queue_state.length
+    used_words = int(a.closed_form_input.hidden_fsm_output.memory_queue_state.length)
+    b = entry_point(engine, Witness(nxt, reqs[used_req:], prev[used_req:], words[used_words:], None), limit - cut)
+    assert b.status.code == 0
+    viol, st = code_unpacker_check_trace(engine, nxt, b.trace, limit - cut)
+    assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)

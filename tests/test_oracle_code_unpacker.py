@@ -118,3 +118,56 @@ def test_negative_cases(orc):
     io0, _ = instance(orc, e)
     rc, out, _, _, st, _ = O.code_unpacker_entry_point(orc, io0, e, words[:0], 4)
     assert st.failed_checks & CHK["WITNESS_EXHAUSTED"] and st.first_bad_row == 0
+
+
+def test_cycle_relations_of_the_trace(orc):
+    """The cycle-to-cycle relations zkc_code_unpacker_check_trace evaluates on the device (cu_check_kernel), restated in numpy and held
+    against the oracle's trace: FSM flags, versioned-hash decomposition, selects, round counter, indices, SHA-256 block with the
+    padding selected in on finalize, state chaining, the hash comparison, memory-queue bookkeeping.  Pins the evaluator's reading of
+    mod.rs:191-447 without a GPU."""
+    reqs, words = synthetic.code_decommit_requests(60, seed=4, max_words=41)
+    io, _ = instance(orc, reqs)
+    limit = int((((reqs["code_hash"][:, 7] & 0xFFFF).astype(np.int64) + 1) // 2).sum()) + 15
+    rc, out, T, com, st, states = O.code_unpacker_entry_point(orc, io, reqs, words, limit)
+    assert rc == 0
+    col = lambda name, i=0: T[K[name] + i]
+    prev = lambda a, first: np.concatenate([np.array([first], dtype=np.uint64), a[:-1].astype(np.uint64)])
+    get, dc_in, fin_in = col("FLAGS_IN", 0), col("FLAGS_IN", 1), col("FLAGS_IN", 2)
+    fo = [col("FLAGS_OUT", i) for i in range(3)]
+    assert all(np.array_equal(x[1:], y[:-1]) for x, y in zip((get, dc_in, fin_in), fo)) and (get[0], dc_in[0], fin_in[0]) == (1, 0, 0)
+    R = K["REQUEST"]
+    h7 = T[R + 7]
+    assert np.array_equal(col("VERSION_MATCHES"), (h7 >> np.uint64(16)) == abi.CODE_HASH_VERSION_TOP16)
+    liw, lir, bits = col("LENGTH_IN_WORDS"), col("LENGTH_IN_ROUNDS"), col("LENGTH_IN_BITS")
+    assert np.array_equal(liw, np.where(get == 1, h7 & 0xFFFF, 1)) and np.array_equal(2 * lir, liw + 1)
+    assert np.array_equal(bits, np.where(get == 1, (liw * 256) & 0xFFFFFFFF, prev(bits, 0)))
+    assert np.array_equal(col("TIMESTAMP"), np.where(get == 1, T[R + 10], prev(col("TIMESTAMP"), 0)))
+    assert np.array_equal(col("PAGE"), np.where(get == 1, T[R + 8], prev(col("PAGE"), 0)))
+    for i in range(8):
+        assert np.array_equal(col("HASH_TO_COMPARE", i), np.where(get == 1, T[R + i] if i < 7 else 0 * h7, prev(col("HASH_TO_COMPARE", i), 0)))
+    dcm, nrl = col("DECOMMIT"), col("NUM_ROUNDS_LEFT")
+    sel = np.where(get == 1, lir, prev(nrl, 0))
+    assert np.array_equal(dcm, dc_in | get) and np.array_equal(nrl, np.where(dcm == 1, (sel - 1) & 0xFFFF, sel))
+    last, fz, second = col("LAST_ROUND"), col("FINALIZE"), col("PROCESS_SECOND_WORD")
+    assert np.array_equal(last, nrl == 0) and np.array_equal(fz, last & dcm) and np.array_equal(second, (1 - last) & dcm)
+    i0, i1, iout = col("INDEX0"), col("INDEX1"), col("INDEX_OUT")
+    assert np.array_equal(i0, np.where(get == 1, 0, prev(iout, 0))) and np.array_equal(i1, i0 + dcm) and np.array_equal(iout, i1 + second)
+    assert all((col("WORD0", i)[dcm == 0] == 0).all() and (col("WORD1", i)[second == 0] == 0).all() for i in range(8))
+    l0, l1 = T[K["MEM_TAIL0"] + 12], T[K["MEM_TAIL1"] + 12]
+    assert np.array_equal(l0, prev(l1, 0) + dcm) and np.array_equal(l1, l0 + second)
+    for i in range(12):
+        t0, t1 = T[K["MEM_TAIL0"] + i], T[K["MEM_TAIL1"] + i]
+        assert np.array_equal(t0[dcm == 0], prev(t1, 0)[dcm == 0]) and np.array_equal(t1[second == 0], t0[second == 0])
+    pad = [np.full(limit, 1 << 31, dtype=np.uint64)] + [np.zeros(limit, np.uint64)] * 6 + [bits]
+    for i in range(8):
+        assert np.array_equal(col("MESSAGE", i), col("WORD0", 7 - i)) and np.array_equal(col("MESSAGE", 8 + i), np.where(fz == 1, pad[i], col("WORD1", 7 - i)))
+    IV = [0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19]
+    for i in range(8):
+        si, sn, so = col("STATE_IN", i), col("STATE_NEW", i), col("STATE_OUT", i)
+        assert np.array_equal(si, np.where(get == 1, IV[i], prev(so, 0))) and np.array_equal(so, np.where(dcm == 1, sn, si))
+        digest_limb = col("STATE_NEW", 7 - i) if i < 7 else 0 * si
+        assert np.array_equal(digest_limb[fz == 1], col("HASH_TO_COMPARE", i)[fz == 1])
+    ln = col("REQ_LEN")
+    empty = ln == 0
+    assert np.array_equal(ln + get, prev(ln, io.sorted_requests_queue_initial_state.length))
+    assert np.array_equal(fo[0], fz & ~empty) and np.array_equal(fo[1], second) and np.array_equal(fo[2], fin_in | (fz & empty))
