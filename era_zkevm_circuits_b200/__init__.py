@@ -35,6 +35,7 @@ from .demux_log_queue import (  # noqa: F401
 from .linear_hasher import (  # noqa: F401
     LinearHasherCircuitInstanceWitness,
     linear_hasher_entry_point,
+    linear_hasher_check_trace,
 )
 from .code_unpacker_sha256 import (  # noqa: F401
     CodeDecommitterCircuitInstanceWitness,

@@ -278,6 +278,131 @@ __global__ void lh_finalize_kernel(LhDev *d, const uint64_t *__restrict__ states
     if (i < 4) d->commitment[i] = f;
 }
 
+
+// ---- constraint evaluation of a finished trace ------------------------------------------------------------------------------
+// One thread per cycle re-evaluates every relation of the loop of linear_hasher_entry_point (mod.rs:103-171) that is local to a
+// cycle or to a cycle and its predecessors: the conditional pop (ranges, LogQuery::encode, queue length / head), into_bytes and its
+// tx-number range, now_empty / is_last_serialization / done / continue_to_absorb, the two absorption conditions, and the keccak
+// sponge itself: the buffer before the cycle is the last (88 c) mod 136 bytes of the serialisation stream, i.e. of the BYTES columns
+// of cycles c - 2 and c - 1; STATE_MID / STATE_OUT are the previous cycle's state after the conditional full-block round and the
+// conditional padded last round (keccak-f[1600] recomputed).  With ZKC_GATES_ROUND_FUNCTION also the three Poseidon2 permutations
+// of the pop.
+template <bool ROUND_FUNCTION>
+__global__ void __launch_bounds__(128)
+lh_check_kernel(LhDev *d, unsigned long long *violations, const uint64_t *__restrict__ trace) {
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const bool first = row == 0;
+    const zkc_queue_state4 &q0 = d->io.queue_state;
+#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
+#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
+    uint32_t bad = 0;
+    const uint64_t is_empty = TR(ZKC_LH_QUEUE_IS_EMPTY), should_pop = TR(ZKC_LH_SHOULD_POP);
+    if ((is_empty | should_pop) > 1 || should_pop != 1 - is_empty) bad |= ZKC_LHV_BOOLEAN;
+    uint64_t f[36], limbs = 0;
+#pragma unroll
+    for (int i = 0; i < 36; i++) f[i] = TR(ZKC_LH_ITEM + i);
+#pragma unroll
+    for (int i = 0; i < 29; i++) limbs |= f[i];
+    if ((limbs | f[34] | f[35]) >> 32 || (f[29] | f[33]) >> 8 || (f[30] | f[31] | f[32]) > 1) bad |= ZKC_LHV_BOOLEAN;
+    if (f[34] >> 16) bad |= ZKC_LHV_ENFORCE;  // into_bytes: tx_number_in_block is two bytes on the wire (log_query/mod.rs:666-668)
+    zkc_log_query q = lq_zero();
+#pragma unroll
+    for (int i = 0; i < 5; i++) q.address[i] = (uint32_t)f[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { q.key[i] = (uint32_t)f[5 + i]; q.read_value[i] = (uint32_t)f[13 + i]; q.written_value[i] = (uint32_t)f[21 + i]; }
+    q.flags = ZKC_LQ_FLAGS((uint32_t)f[29], (uint32_t)f[33], (uint32_t)f[30], (uint32_t)f[31], (uint32_t)f[32]);
+    q.tx_number_in_block = (uint32_t)f[34]; q.timestamp = (uint32_t)f[35];
+    uint64_t e[20], enc[20];
+    lq_encode(q, e);
+#pragma unroll
+    for (int i = 0; i < 20; i++) { enc[i] = TR(ZKC_LH_ENC + i); if (enc[i] != e[i]) bad |= ZKC_LHV_ENCODING; }
+    const uint64_t len_prev = first ? q0.length : TP(ZKC_LH_LEN), len = TR(ZKC_LH_LEN);
+    if (is_empty != (uint64_t)(len_prev == 0) || len + should_pop != len_prev) bad |= ZKC_LHV_QUEUE;
+    {
+        uint64_t head[4], head_prev[4];
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            head[i] = TR(ZKC_LH_HEAD + i);
+            head_prev[i] = first ? q0.head[i] : TP(ZKC_LH_HEAD + i);
+            same &= head[i] == head_prev[i];
+            if (head[i] >= GL_P) bad |= ZKC_LHV_BOOLEAN;
+        }
+        if (!should_pop && !same) bad |= ZKC_LHV_QUEUE;
+        if (ROUND_FUNCTION && should_pop) {
+            uint64_t st[12];
+            lq_absorb_head(enc, st);
+            lq_absorb_tail(enc, head_prev, st);
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (st[i] != head[i]) bad |= ZKC_LHV_ROUND_FUNCTION;
+        }
+    }
+    // the flags of :104-118 and :170
+    const uint64_t now_empty = TR(ZKC_LH_NOW_EMPTY), is_last = TR(ZKC_LH_IS_LAST_SERIALIZATION), cont = TR(ZKC_LH_CONTINUE_TO_ABSORB),
+                   absorb_full = TR(ZKC_LH_ABSORB_FULL), absorb_last = TR(ZKC_LH_ABSORB_LAST), done = TR(ZKC_LH_DONE);
+    const uint64_t done_prev = first ? (uint64_t)(q0.length == 0) : TP(ZKC_LH_DONE);
+    const int lb = (int)((row * LH_MSG) % LH_RATE);  // buffer length before the cycle: a function of the cycle index (:114-125)
+    const bool has_full = lb + LH_MSG >= LH_RATE;
+    if ((now_empty | is_last | cont | absorb_full | absorb_last | done) > 1 || now_empty != (uint64_t)(len == 0) || is_last != (should_pop & now_empty) ||
+        cont != 1 - (done_prev & 1) || done != (done_prev | is_last) || absorb_full != ((uint64_t)has_full & cont) || absorb_last != (cont & is_last))
+        bad |= ZKC_LHV_FLAGS;
+    // the byte window: BYTES of cycles row - 2, row - 1, row; this cycle's bytes are into_bytes of the popped item
+    uint8_t win[3 * LH_MSG], last[LH_RATE];
+    {
+        uint8_t want[LH_MSG];
+        lh_into_bytes(q, want);
+        uint64_t range = 0;
+        for (int i = 0; i < LH_MSG; i++) {
+            const uint64_t b2 = row >= 2 ? __ldg(trace + (size_t)(ZKC_LH_BYTES + i) * limit + row - 2) : 0ull;
+            const uint64_t b1 = row >= 1 ? TP(ZKC_LH_BYTES + i) : 0ull;
+            const uint64_t b0 = TR(ZKC_LH_BYTES + i);
+            range |= b0;
+            if (b0 != want[i]) bad |= ZKC_LHV_ENCODING;
+            win[i] = (uint8_t)b2; win[LH_MSG + i] = (uint8_t)b1; win[2 * LH_MSG + i] = (uint8_t)b0;
+        }
+        if (range >> 8) bad |= ZKC_LHV_BOOLEAN;
+    }
+    // the sponge: previous state -> (full block?) -> STATE_MID -> (padded last block?) -> STATE_OUT
+    uint64_t A[25];
+    {
+        uint64_t range = 0;
+#pragma unroll
+        for (int i = 0; i < 25; i++) {
+            const uint64_t lo = first ? 0ull : TP(ZKC_LH_STATE_OUT + 2 * i), hi = first ? 0ull : TP(ZKC_LH_STATE_OUT + 2 * i + 1);
+            A[i] = lo | (hi << 32);
+        }
+        const uint8_t *buf = win + 2 * LH_MSG - lb;
+        if (absorb_full) lh_absorb(A, buf);
+#pragma unroll
+        for (int i = 0; i < 25; i++) {
+            const uint64_t lo = TR(ZKC_LH_STATE_MID + 2 * i), hi = TR(ZKC_LH_STATE_MID + 2 * i + 1);
+            range |= lo | hi;
+            if ((lo | (hi << 32)) != A[i]) bad |= ZKC_LHV_SPONGE;
+        }
+        if (absorb_last) {
+            const int rest = has_full ? lb + LH_MSG - LH_RATE : lb + LH_MSG;
+            lh_pad(has_full ? buf + LH_RATE : buf, rest, last);
+            lh_absorb(A, last);
+        }
+#pragma unroll
+        for (int i = 0; i < 25; i++) {
+            const uint64_t lo = TR(ZKC_LH_STATE_OUT + 2 * i), hi = TR(ZKC_LH_STATE_OUT + 2 * i + 1);
+            range |= lo | hi;
+            if ((lo | (hi << 32)) != A[i]) bad |= ZKC_LHV_SPONGE;
+        }
+        if (range >> 32) bad |= ZKC_LHV_BOOLEAN;
+    }
+#undef TR
+#undef TP
+    if (bad) {
+        atomicAdd(violations, 1ull);
+        atomicOr(&d->failed_checks, bad);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+    }
+}
+
 }  // namespace zkc
 
 using namespace zkc;
@@ -346,5 +471,52 @@ extern "C" int zkc_linear_hasher_entry_point(zkc_ctx *ctx, zkc_linear_hasher_clo
     io->completion_flag = h->io.completion_flag;
     memcpy(commitment, h->commitment, 32);
     *status = h->status;
+    return status->code;
+}
+
+extern "C" int zkc_linear_hasher_check_trace(zkc_ctx *ctx, const zkc_linear_hasher_closed_form *io, const uint64_t *trace, size_t limit, uint32_t gates,
+                                             int on_device, uint64_t *violations, zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !violations || (limit && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(LhDev)) + zkc_carver::bytes(1, 8);
+    if (!on_device) bytes += zkc_carver::bytes((size_t)ZKC_LH_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    LhDev *h = (LhDev *)ctx->pinned(sizeof(LhDev) + 8);
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    LhDev *d = cv.take<LhDev>(1);
+    unsigned long long *dviol = cv.take<unsigned long long>(1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(LhDev));
+    h->io = *io;
+    h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(LhDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(dviol, 0, 8, s));
+    const uint64_t *dt = trace;
+    if (!on_device && limit) {
+        uint64_t *b = cv.take<uint64_t>((size_t)ZKC_LH_NUM_COLS * limit);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, (size_t)ZKC_LH_NUM_COLS * limit * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    if (limit) {
+        const unsigned grid = (unsigned)((limit + 127) / 128);
+        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION)) ZKC_LAUNCH(ctx, "lh_check_rf", lh_check_kernel<true>, grid, 128, 0, d, dviol, dt);
+        else ZKC_LAUNCH(ctx, "lh_check", lh_check_kernel<false>, grid, 128, 0, d, dviol, dt);
+    }
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    unsigned long long *hviol = (unsigned long long *)(h + 1);
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(LhDev), cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(hviol, dviol, 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = *hviol;
+    status->failed_checks = h->failed_checks;
+    if (*hviol) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 16);
+    }
     return status->code;
 }

@@ -46,3 +46,16 @@ def linear_hasher_entry_point(engine: Engine, witness: LinearHasherCircuitInstan
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE) or (rc and raise_on_unsatisfied):
         raise ZkcError(rc, st, "linear_hasher_entry_point")
     return SorterResult(commitment, io, trace, st)
+
+
+def linear_hasher_check_trace(engine: Engine, closed_form_input: abi.LinearHasherClosedForm, trace, limit: int, gates: int = 0):
+    """Constraint evaluation of a finished linear_hasher trace [LH_COLS.NUM_COLS, limit] (numpy: host, torch CUDA: device): every
+    relation of the loop of linear_hasher_entry_point (mod.rs:103-171), the keccak sponge included.  Returns (violating rows, status);
+    status.failed_checks holds abi.LHV bits."""
+    st = abi.Status()
+    viol = C.c_uint64()
+    io = abi.LinearHasherClosedForm.from_buffer_copy(bytes(closed_form_input))
+    rc = engine.lib.zkc_linear_hasher_check_trace(engine.h, C.byref(io), ptr(trace), limit, gates, on_device(trace), C.byref(viol), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, st, "linear_hasher_check_trace")
+    return viol.value, st

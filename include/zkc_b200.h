@@ -1675,6 +1675,19 @@ int zkc_linear_hasher_entry_point(zkc_ctx *ctx, zkc_linear_hasher_closed_form *i
                                   const zkc_sorter_options *options, int on_device, uint64_t *trace,
                                   uint64_t commitment[ZKC_COMMITMENT_LEN], zkc_status *status);
 
+/* constraint evaluation of a finished linear_hasher trace: every relation of the loop (mod.rs:103-171) on every cycle, the keccak
+ * sponge included (buffer = the BYTES columns of the two previous cycles).  gates: ZKC_GATES_GENERAL = everything but the Poseidon2
+ * permutations of the pop; ZKC_GATES_ROUND_FUNCTION adds them; 0 = all. */
+#define ZKC_LHV_BOOLEAN (1u << 0)        /* booleans, u32 / u8 ranges, field range of hash outputs */
+#define ZKC_LHV_QUEUE (1u << 1)          /* is_empty / length / head bookkeeping of the popped queue */
+#define ZKC_LHV_ENCODING (1u << 2)       /* LogQuery::encode, into_bytes */
+#define ZKC_LHV_ROUND_FUNCTION (1u << 3)
+#define ZKC_LHV_FLAGS (1u << 4)          /* now_empty, is_last_serialization, continue_to_absorb, the absorption conditions, done */
+#define ZKC_LHV_ENFORCE (1u << 5)        /* tx_number_in_block fits two bytes */
+#define ZKC_LHV_SPONGE (1u << 6)         /* keccak state after the conditional full-block and padded last rounds */
+int zkc_linear_hasher_check_trace(zkc_ctx *ctx, const zkc_linear_hasher_closed_form *io, const uint64_t *trace, size_t limit, uint32_t gates,
+                                  int on_device, uint64_t *violations, zkc_status *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -494,5 +494,13 @@ inline uint64_t code_unpacker_check_trace(Engine &e, const zkc_code_unpacker_clo
     if (rc != ZKC_OK && rc != ZKC_ERR_UNSATISFIED) throw Error("zkc_code_unpacker_check_trace", rc, st ? *st : local);
     return v;
 }
+inline uint64_t linear_hasher_check_trace(Engine &e, const zkc_linear_hasher_closed_form &io, const std::vector<uint64_t> &trace, size_t limit,
+                                          uint32_t gates = 0, zkc_status *st = nullptr) {
+    uint64_t v = 0;
+    zkc_status local;
+    const int rc = zkc_linear_hasher_check_trace(e.handle(), &io, trace.data(), limit, gates, 0, &v, st ? st : &local);
+    if (rc != ZKC_OK && rc != ZKC_ERR_UNSATISFIED) throw Error("zkc_linear_hasher_check_trace", rc, st ? *st : local);
+    return v;
+}
 
 }  // namespace zkc_b200

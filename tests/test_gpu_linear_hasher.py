@@ -66,3 +66,53 @@ def test_enforcements_match_oracle(engine, orc):
     want = O.linear_hasher_entry_point(orc, io3, bad, 40)
     got = entry_point(engine, Witness(io3, bad, prev3), 40, raise_on_unsatisfied=False)
     assert_same(want, got)
+
+
+def test_check_trace_constraint_evaluation(engine, orc):
+    """zkc_linear_hasher_check_trace: the ORACLE's trace satisfies every relation with and without the pop's permutations; a fault
+    injected into any relation family is found at its cycle (a byte of the serialisation also breaks the sponge of the cycle that
+    absorbs it)"""
+    from era_zkevm_circuits_b200 import linear_hasher_check_trace
+    K = abi.LH_COLS
+    V_ = abi.LHV
+    recs = messages(700, seed=8)
+    io, prev = instance(orc, recs)
+    limit = 730
+    want = O.linear_hasher_entry_point(orc, io, recs, limit)
+    assert want[0] == abi.ZKC_OK
+    trace = want[2]
+    for gates in (0, abi.GATES_GENERAL):
+        viol, st = linear_hasher_check_trace(engine, io, trace, limit, gates)
+        assert viol == 0 and st.code == 0, (gates, viol, hex(st.failed_checks), st.first_bad_row)
+    import torch
+    viol, st = linear_hasher_check_trace(engine, io, torch.from_numpy(trace.view(np.int64)).cuda(), limit, abi.GATES_GENERAL)
+    assert viol == 0
+    full = np.flatnonzero(trace[K["ABSORB_FULL"]])
+    faults = [
+        (K["SHOULD_POP"], 17, 2, V_["BOOLEAN"], 0),
+        (K["ITEM"] + 7, 40, 1 << 33, V_["BOOLEAN"], 0),
+        (K["ITEM"] + 34, 41, 1 << 16, V_["ENFORCE"], 0),
+        (K["ENC"] + 3, 99, None, V_["ENCODING"], 0),
+        (K["BYTES"] + 50, 100, None, V_["ENCODING"], 0),
+        (K["LEN"], 123, None, V_["QUEUE"], 0),
+        (K["HEAD"] + 1, 715, None, V_["QUEUE"], 0),
+        (K["HEAD"] + 1, 150, None, V_["ROUND_FUNCTION"], 0),
+        (K["NOW_EMPTY"], 200, None, V_["FLAGS"], 0),
+        (K["IS_LAST_SERIALIZATION"], 699, None, V_["FLAGS"], 0),
+        (K["CONTINUE_TO_ABSORB"], 710, None, V_["FLAGS"], 0),
+        (K["ABSORB_FULL"], int(full[30]), None, V_["FLAGS"], 0),
+        (K["DONE"], 300, None, V_["FLAGS"], 0),
+        (K["STATE_MID"] + 13, int(full[40]), None, V_["SPONGE"], 0),
+        (K["STATE_OUT"] + 27, 400, None, V_["SPONGE"], 0),
+    ]
+    for col, row, val, bit, gates in faults:
+        bad = trace.copy()
+        bad[col, row] = np.uint64(val) if val is not None else bad[col, row] ^ np.uint64(1)
+        viol, st = linear_hasher_check_trace(engine, io, bad, limit, gates)
+        assert viol >= 1 and st.first_bad_row == row and st.failed_checks & bit, (col, row, viol, st.first_bad_row, hex(st.failed_checks))
+    # the engine's own trace (device resident, state hints from the oracle)
+    i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)).cuda()
+    got = entry_point(engine, Witness(io, dev(recs), i64(prev), i64(want[5])), limit)
+    viol, st = linear_hasher_check_trace(engine, io, got.trace, limit)
+    assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)

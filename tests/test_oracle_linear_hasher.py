@@ -84,3 +84,29 @@ def test_enforcements(orc):
     assert O.linear_hasher_entry_point(orc, exp, recs, 20, compare_expected=True)[0] == abi.ZKC_OK
     exp.keccak256_hash[3] ^= 1
     assert O.linear_hasher_entry_point(orc, exp, recs, 20, compare_expected=True)[0] == abi.ZKC_ERR_FSM_OUTPUT_MISMATCH
+
+
+def test_cycle_relations_of_the_trace(orc):
+    """The cycle-to-cycle flag relations zkc_linear_hasher_check_trace evaluates on the device (lh_check_kernel), restated in numpy and
+    held against the oracle's trace (the sponge itself is pinned by the digest tests above): queue bookkeeping, now_empty /
+    is_last_serialization / done / continue_to_absorb, the absorption conditions as functions of the cycle index, state carry-over."""
+    K = abi.LH_COLS
+    recs = messages(500, seed=5)
+    io, _ = instance(orc, recs)
+    limit = 520
+    rc, out, T, com, st, states = O.linear_hasher_entry_point(orc, io, recs, limit)
+    assert rc == 0
+    col = lambda name, i=0: T[K[name] + i]
+    prev = lambda a, first: np.concatenate([np.array([first], dtype=np.uint64), a[:-1].astype(np.uint64)])
+    emp, pop, ln, len0 = col("QUEUE_IS_EMPTY"), col("SHOULD_POP"), col("LEN"), io.queue_state.length
+    assert np.array_equal(ln + pop, prev(ln, len0)) and np.array_equal(emp, prev(ln, len0) == 0) and np.array_equal(pop, 1 - emp)
+    now, last, done, cont = col("NOW_EMPTY"), col("IS_LAST_SERIALIZATION"), col("DONE"), col("CONTINUE_TO_ABSORB")
+    done_prev = prev(done, int(len0 == 0))
+    assert np.array_equal(now, ln == 0) and np.array_equal(last, pop & now) and np.array_equal(done, done_prev | last) and np.array_equal(cont, 1 - done_prev)
+    lb = (np.arange(limit) * abi.LH_MESSAGE_BYTES) % 136
+    full, final = col("ABSORB_FULL"), col("ABSORB_LAST")
+    assert np.array_equal(full, (lb + abi.LH_MESSAGE_BYTES >= 136) & (cont == 1)) and np.array_equal(final, cont & last)
+    for i in range(50):
+        mid, so = col("STATE_MID", i), col("STATE_OUT", i)
+        assert np.array_equal(mid[full == 0], prev(so, 0)[full == 0]) and np.array_equal(so[final == 0], mid[final == 0])
+    assert (T[K["BYTES"]:K["BYTES"] + abi.LH_MESSAGE_BYTES] < 256).all()
