@@ -45,6 +45,7 @@ from .code_unpacker_sha256 import (  # noqa: F401
 from .keccak256_round_function import (  # noqa: F401
     Keccak256RoundFunctionCircuitInstanceWitness,
     keccak256_round_function_entry_point,
+    keccak256_round_function_check_trace,
 )
 from .sha256_round_function import (  # noqa: F401
     Sha256RoundFunctionCircuitInstanceWitness,

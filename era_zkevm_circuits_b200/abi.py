@@ -484,6 +484,7 @@ SIGNATURES = {
                                              C.POINTER(Status)]),
     "zkc_log_sorter_check_trace": (C.c_int, [_vp, C.POINTER(EventsClosedForm), _vp, C.c_size_t, C.c_uint32, C.c_int, _u64p, C.POINTER(Status)]),
     "zkc_storage_validity_check_trace": (C.c_int, [_vp, C.POINTER(StorageClosedForm), _vp, C.c_size_t, C.c_uint32, C.c_int, _u64p, C.POINTER(Status)]),
+    "zkc_keccak256_round_function_check_trace": (C.c_int, [_vp, C.POINTER(KeccakClosedForm), C.POINTER(PrecompileOptions), _vp, C.c_size_t, C.c_uint32, C.c_int, _u64p, C.POINTER(Status)]),
     "zkc_linear_hasher_check_trace": (C.c_int, [_vp, C.POINTER(LinearHasherClosedForm), _vp, C.c_size_t, C.c_uint32, C.c_int, _u64p, C.POINTER(Status)]),
     "zkc_code_unpacker_check_trace": (C.c_int, [_vp, C.POINTER(CodeUnpackerClosedForm), _vp, C.c_size_t, C.c_uint32, C.c_int, _u64p, C.POINTER(Status)]),
     "zkc_sha256_round_function_check_trace": (C.c_int, [_vp, C.POINTER(Sha256ClosedForm), C.POINTER(PrecompileOptions), _vp, C.c_size_t, C.c_uint32, C.c_int, _u64p, C.POINTER(Status)]),
@@ -553,6 +554,8 @@ def _gadget_columns():
 VMG_COLS, VMG_WIDTHS = _gadget_columns()
 EVV = dict(BOOLEAN=1 << 0, QUEUE_LEN=1 << 1, ENCODING=1 << 2, ROUND_FUNCTION=1 << 3, COMPARISON=1 << 4, FLAGS=1 << 5, ENFORCE=1 << 6,
            GP_CHAIN=1 << 7, GP_ACC=1 << 8, RESULT_QUEUE=1 << 9)
+KCV = dict(BOOLEAN=1 << 0, QUEUE=1 << 1, FSM=1 << 2, ROUND_FUNCTION=1 << 3, PARAMS=1 << 4, ENFORCE=1 << 5, SPONGE=1 << 6, MEMORY_QUEUE=1 << 7,
+           QUERIES=1 << 8, BUFFER=1 << 9)  # ZKC_KCV_*
 LHV = dict(BOOLEAN=1 << 0, QUEUE=1 << 1, ENCODING=1 << 2, ROUND_FUNCTION=1 << 3, FLAGS=1 << 4, ENFORCE=1 << 5, SPONGE=1 << 6)  # ZKC_LHV_*
 CUV = dict(BOOLEAN=1 << 0, QUEUE=1 << 1, FSM=1 << 2, ROUND_FUNCTION=1 << 3, LENGTH=1 << 4, ENFORCE=1 << 5, COMPRESSION=1 << 6, MEMORY_QUEUE=1 << 7,
            SELECTS=1 << 8)  # ZKC_CUV_*

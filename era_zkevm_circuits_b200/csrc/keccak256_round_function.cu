@@ -90,20 +90,36 @@ struct KcCycleOut {
     bool write_result;
 };
 
+// relation family of a trace column, for the constraint evaluator (ZKC_KCV_* bits)
+__device__ __forceinline__ uint32_t kc_col_family(int col) {
+    if (col < ZKC_KC_CALL_ITEM || (col >= ZKC_KC_RESET_BUFFER && col < ZKC_KC_QUERY) || (col >= ZKC_KC_ZERO_BYTES_LEFT && col < ZKC_KC_INPUT) ||
+        col == ZKC_KC_WRITE_RESULT || (col >= ZKC_KC_FLAGS_OUT && col < ZKC_KC_BUFFER_OUT))
+        return ZKC_KCV_FSM;
+    if (col >= ZKC_KC_PARAMS && col < ZKC_KC_RESET_BUFFER) return ZKC_KCV_PARAMS;
+    if (col >= ZKC_KC_QUERY && col < ZKC_KC_ZERO_BYTES_LEFT) return ZKC_KCV_QUERIES;
+    if (col >= ZKC_KC_BUFFER_OUT) return ZKC_KCV_BUFFER;
+    return ZKC_KCV_SPONGE;  // INPUT, STATE_OUT, RESULT
+}
+
 // One iteration of the main work cycle (mod.rs:230-665).  DRY: control only (no witness, no sponge, no trace).
 // `call` is the precompile call popped this cycle (zero item when none is popped); cursors advance.
-template <bool DRY>
+// CHECK: constraint evaluation -- `trace` is a finished trace: the words read from memory are taken from its QUERY columns and
+// every cell the cycle would write is COMPARED with the trace instead (a mismatch sets the cell's ZKC_KCV_* family bit in `checks`).
+template <bool DRY, bool CHECK = false>
 __device__ __forceinline__ KcCycleOut kc_cycle(KcState &s, const zkc_log_query &call, bool input_queue_empty_after_pop,
                                                const uint32_t *__restrict__ reads, size_t n_reads, size_t &read_cursor,
                                                uint64_t *__restrict__ push_enc, uint32_t *__restrict__ slot_meta, uint32_t &push_ordinal,
                                                uint64_t *__restrict__ trace, size_t limit, size_t row, uint32_t &checks) {
     KcCycleOut out{0, 0, false};
-#define TR(col) trace[(size_t)(col) * limit + row]
     const bool wr = !DRY && trace != nullptr;
+    auto put = [&](int col, uint64_t v) {
+        if constexpr (CHECK) { if (__ldg(trace + (size_t)col * limit + row) != v) checks |= kc_col_family(col); }
+        else trace[(size_t)col * limit + row] = v;
+    };
     const bool read_call = s.read_precompile_call;
     if (wr) {
-        TR(ZKC_KC_FLAGS_IN + 0) = s.read_precompile_call; TR(ZKC_KC_FLAGS_IN + 1) = s.read_unaligned;
-        TR(ZKC_KC_FLAGS_IN + 2) = s.padding_round; TR(ZKC_KC_FLAGS_IN + 3) = s.completed;
+        put(ZKC_KC_FLAGS_IN + 0, s.read_precompile_call); put(ZKC_KC_FLAGS_IN + 1, s.read_unaligned);
+        put(ZKC_KC_FLAGS_IN + 2, s.padding_round); put(ZKC_KC_FLAGS_IN + 3, s.completed);
     }
     const uint32_t new_len = call.key[1];
     if (read_call) {
@@ -125,29 +141,34 @@ __device__ __forceinline__ KcCycleOut kc_cycle(KcState &s, const zkc_log_query &
         }
     }
     if (wr) {
-        TR(ZKC_KC_PARAMS + 0) = s.input_page; TR(ZKC_KC_PARAMS + 1) = s.byte_offset; TR(ZKC_KC_PARAMS + 2) = s.byte_length;
-        TR(ZKC_KC_PARAMS + 3) = s.output_page; TR(ZKC_KC_PARAMS + 4) = s.output_word_offset; TR(ZKC_KC_PARAMS + 5) = s.needs_full_padding;
-        TR(ZKC_KC_TS_READ) = s.ts_read; TR(ZKC_KC_TS_WRITE) = s.ts_write;
-        TR(ZKC_KC_RESET_BUFFER) = reset_buffer; TR(ZKC_KC_READ_ZERO_LENGTH) = read_zero; TR(ZKC_KC_READ_NON_ZERO_LENGTH) = read_nonzero;
+        put(ZKC_KC_PARAMS + 0, s.input_page); put(ZKC_KC_PARAMS + 1, s.byte_offset); put(ZKC_KC_PARAMS + 2, s.byte_length);
+        put(ZKC_KC_PARAMS + 3, s.output_page); put(ZKC_KC_PARAMS + 4, s.output_word_offset); put(ZKC_KC_PARAMS + 5, s.needs_full_padding);
+        put(ZKC_KC_TS_READ, s.ts_read); put(ZKC_KC_TS_WRITE, s.ts_write);
+        put(ZKC_KC_RESET_BUFFER, reset_buffer); put(ZKC_KC_READ_ZERO_LENGTH, read_zero); put(ZKC_KC_READ_NON_ZERO_LENGTH, read_nonzero);
     }
 #pragma unroll 1
     for (int q = 0; q < ZKC_KECCAK_MEMORY_QUERIES_PER_CYCLE; q++) {
         const uint32_t aligned = s.byte_offset / 32, unal = s.byte_offset % 32, at_most = 32 - unal;
         const uint32_t meaningful = s.byte_length < at_most ? s.byte_length : at_most;
         const uint32_t next_filled = s.filled + meaningful;
-        if (next_filled > 255) checks |= ZKC_KC_CHK_BUFFER_OVERFLOW;
+        if (next_filled > 255) checks |= CHECK ? ZKC_KCV_ENFORCE : ZKC_KC_CHK_BUFFER_OVERFLOW;
         const bool should_read = meaningful != 0 && next_filled <= ZKC_KECCAK_BUFFER_SIZE && s.read_unaligned;
         uint32_t value[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (should_read) {
             if (!DRY) {
-                if (read_cursor < n_reads) {
+                if constexpr (CHECK) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) value[i] = __ldg(reads + 8 * read_cursor + i);
-                } else checks |= ZKC_KC_CHK_WITNESS_EXHAUSTED;
-                uint64_t e[8];
-                mq_encode(s.ts_read, s.input_page, aligned, 0, value, e);
+                    for (int i = 0; i < 8; i++) value[i] = (uint32_t)__ldg(trace + (size_t)(ZKC_KC_QUERY + q * ZKC_KC_QUERY_STRIDE + 4 + i) * limit + row);
+                } else {
+                    if (read_cursor < n_reads) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) push_enc[8 * (size_t)push_ordinal + i] = e[i];
+                        for (int i = 0; i < 8; i++) value[i] = __ldg(reads + 8 * read_cursor + i);
+                    } else checks |= ZKC_KC_CHK_WITNESS_EXHAUSTED;
+                    uint64_t e[8];
+                    mq_encode(s.ts_read, s.input_page, aligned, 0, value, e);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) push_enc[8 * (size_t)push_ordinal + i] = e[i];
+                }
                 // fill_with_bytes(be_bytes, offset = unal, meaningful), buffer/mod.rs:73-136
                 for (uint32_t idx = 0; idx < 32; idx++) {
                     const uint32_t pos = s.filled + idx;
@@ -159,13 +180,13 @@ __device__ __forceinline__ KcCycleOut kc_cycle(KcState &s, const zkc_log_query &
             read_cursor++; push_ordinal++; out.reads++; out.pushes++;
             s.byte_offset += meaningful; s.byte_length -= meaningful; s.filled += meaningful;
         }
-        if (!DRY) slot_meta[7 * row + q] = push_ordinal | (should_read ? 0x80000000u : 0u);
+        if (!DRY && !CHECK) slot_meta[7 * row + q] = push_ordinal | (should_read ? 0x80000000u : 0u);
         if (wr) {
             const int b = ZKC_KC_QUERY + q * ZKC_KC_QUERY_STRIDE;
-            TR(b + 0) = aligned; TR(b + 1) = unal; TR(b + 2) = meaningful; TR(b + 3) = should_read;
+            put(b + 0, aligned); put(b + 1, unal); put(b + 2, meaningful); put(b + 3, should_read);
 #pragma unroll
-            for (int i = 0; i < 8; i++) TR(b + 4 + i) = value[i];
-            TR(b + 25) = s.byte_offset; TR(b + 26) = s.byte_length; TR(b + 27) = s.filled;
+            for (int i = 0; i < 8; i++) put(b + 4 + i, value[i]);
+            put(b + 25, s.byte_offset); put(b + 26, s.byte_length); put(b + 27, s.filled);
         }
     }
     const bool zero_bytes_left = s.byte_length == 0;
@@ -193,7 +214,7 @@ __device__ __forceinline__ KcCycleOut kc_cycle(KcState &s, const zkc_log_query &
                         if (k == 135) byte = do_one_byte ? 0x81 : 0x80;
                     }
                     if (s.padding_round) byte = k == 0 ? 0x01 : (k == 135 ? 0x80 : 0);
-                    if (wr) TR(ZKC_KC_INPUT + k) = byte;
+                    if (wr) put(ZKC_KC_INPUT + k, byte);
                     lane ^= (uint64_t)byte << (8 * b);
                 }
             }
@@ -208,7 +229,7 @@ __device__ __forceinline__ KcCycleOut kc_cycle(KcState &s, const zkc_log_query &
             for (int b = 0; b < 8; b++) {
                 const uint8_t byte = (uint8_t)(A[idx] >> (8 * b));
                 s.sponge[(i * 5 + j) * 8 + b] = byte;
-                if (wr) TR(ZKC_KC_STATE_OUT + (i * 5 + j) * 8 + b) = byte;
+                if (wr) put(ZKC_KC_STATE_OUT + (i * 5 + j) * 8 + b, byte);
             }
         }
         // UInt256::from_be_bytes(state[0..4][0]): digest byte d = lane d/8, byte d%8; limb l = BE bytes 28-4l..31-4l
@@ -222,7 +243,7 @@ __device__ __forceinline__ KcCycleOut kc_cycle(KcState &s, const zkc_log_query &
             }
             result[l] = w;
         }
-        if (write_result) {
+        if (write_result && !CHECK) {
             uint64_t e[8];
             mq_encode(s.ts_write, s.output_page, s.output_word_offset, 1, result, e);
 #pragma unroll
@@ -230,7 +251,7 @@ __device__ __forceinline__ KcCycleOut kc_cycle(KcState &s, const zkc_log_query &
         }
     }
     if (write_result) { push_ordinal++; out.pushes++; }
-    if (!DRY) slot_meta[7 * row + 6] = push_ordinal | (write_result ? 0x80000000u : 0u);
+    if (!DRY && !CHECK) slot_meta[7 * row + 6] = push_ordinal | (write_result ? 0x80000000u : 0u);
     out.write_result = write_result;
     const bool nothing_left = write_result && input_queue_empty_after_pop, process_next = write_result && !input_queue_empty_after_pop;
     s.read_precompile_call = process_next;
@@ -238,16 +259,15 @@ __device__ __forceinline__ KcCycleOut kc_cycle(KcState &s, const zkc_log_query &
     s.padding_round = s.read_unaligned && zero_bytes_left && buffer_now_empty && s.needs_full_padding;
     s.read_unaligned = !(s.read_precompile_call || s.padding_round || s.completed);
     if (wr) {
-        TR(ZKC_KC_ZERO_BYTES_LEFT) = zero_bytes_left; TR(ZKC_KC_CURRENTLY_FILLED) = currently_filled;
-        TR(ZKC_KC_DO_ONE_BYTE_OF_PADDING) = do_one_byte; TR(ZKC_KC_BUFFER_NOW_EMPTY) = buffer_now_empty;
-        TR(ZKC_KC_APPLY_PADDING) = apply_padding; TR(ZKC_KC_WRITE_RESULT) = write_result;
+        put(ZKC_KC_ZERO_BYTES_LEFT, zero_bytes_left); put(ZKC_KC_CURRENTLY_FILLED, currently_filled);
+        put(ZKC_KC_DO_ONE_BYTE_OF_PADDING, do_one_byte); put(ZKC_KC_BUFFER_NOW_EMPTY, buffer_now_empty);
+        put(ZKC_KC_APPLY_PADDING, apply_padding); put(ZKC_KC_WRITE_RESULT, write_result);
 #pragma unroll
-        for (int i = 0; i < 8; i++) TR(ZKC_KC_RESULT + i) = result[i];
-        TR(ZKC_KC_FLAGS_OUT + 0) = s.read_precompile_call; TR(ZKC_KC_FLAGS_OUT + 1) = s.read_unaligned;
-        TR(ZKC_KC_FLAGS_OUT + 2) = s.padding_round; TR(ZKC_KC_FLAGS_OUT + 3) = s.completed;
-        for (int i = 0; i < ZKC_KECCAK_BUFFER_SIZE; i++) TR(ZKC_KC_BUFFER_OUT + i) = s.buffer[i];
+        for (int i = 0; i < 8; i++) put(ZKC_KC_RESULT + i, result[i]);
+        put(ZKC_KC_FLAGS_OUT + 0, s.read_precompile_call); put(ZKC_KC_FLAGS_OUT + 1, s.read_unaligned);
+        put(ZKC_KC_FLAGS_OUT + 2, s.padding_round); put(ZKC_KC_FLAGS_OUT + 3, s.completed);
+        for (int i = 0; i < ZKC_KECCAK_BUFFER_SIZE; i++) put(ZKC_KC_BUFFER_OUT + i, s.buffer[i]);
     }
-#undef TR
     return out;
 }
 
@@ -545,6 +565,130 @@ __global__ void kc_finalize_kernel(KcDev *d, const KcPlan *__restrict__ starts, 
     }
 }
 
+
+// ---- constraint evaluation of a finished trace ------------------------------------------------------------------------------
+// One thread per cycle: the FSM state on entry is rebuilt from the PREVIOUS cycle's cells (flags, call parameters, offsets, buffer
+// bytes and fill count, keccak state; cycle 0: the start state), the free inputs of the cycle are taken from its own cells (the
+// popped call, the words read from memory), and the cycle function itself (kc_cycle, the code that generates the trace) runs in CHECK
+// mode: every cell it would write -- selects, the six unaligned reads and the buffer fills, padding decisions, the absorbed block,
+// keccak-f[1600], the digest word, the next flags, the buffer after the cycle -- is compared with the trace.  Around it: the
+// conditional pop (ranges, aux byte / formal address, queue length / head) and the memory queue's length / tail chain over the
+// seven conditional pushes.  With ZKC_GATES_ROUND_FUNCTION also the Poseidon2 permutations (the pop, every executed push).
+template <bool ROUND_FUNCTION>
+__global__ void __launch_bounds__(64)
+kc_check_kernel(KcDev *d, unsigned long long *violations, const uint64_t *__restrict__ trace) {
+    const size_t limit = d->limit;
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= limit) return;
+    const bool first = row == 0;
+#define TR(col) __ldg(trace + (size_t)(col) * limit + row)
+#define TP(col) __ldg(trace + (size_t)(col) * limit + row - 1)
+    uint32_t bad = 0;
+    const uint32_t aux_byte = d->opt.aux_byte ? d->opt.aux_byte : ZKC_PRECOMPILE_AUX_BYTE_DEFAULT;
+    const uint32_t formal = d->opt.precompile_address ? d->opt.precompile_address : ZKC_KECCAK256_PRECOMPILE_ADDRESS_DEFAULT;
+    KcState s;
+    if (first) kc_load_state(d->s0, s);
+    else {
+        const int lastq = ZKC_KC_QUERY + 5 * ZKC_KC_QUERY_STRIDE;
+        s.read_precompile_call = (uint32_t)TP(ZKC_KC_FLAGS_OUT + 0); s.read_unaligned = (uint32_t)TP(ZKC_KC_FLAGS_OUT + 1);
+        s.padding_round = (uint32_t)TP(ZKC_KC_FLAGS_OUT + 2); s.completed = (uint32_t)TP(ZKC_KC_FLAGS_OUT + 3);
+        s.ts_read = (uint32_t)TP(ZKC_KC_TS_READ); s.ts_write = (uint32_t)TP(ZKC_KC_TS_WRITE);
+        s.input_page = (uint32_t)TP(ZKC_KC_PARAMS + 0); s.byte_offset = (uint32_t)TP(lastq + 25); s.byte_length = (uint32_t)TP(lastq + 26);
+        s.output_page = (uint32_t)TP(ZKC_KC_PARAMS + 3); s.output_word_offset = (uint32_t)TP(ZKC_KC_PARAMS + 4); s.needs_full_padding = (uint32_t)TP(ZKC_KC_PARAMS + 5);
+        const uint32_t cf = (uint32_t)TP(ZKC_KC_CURRENTLY_FILLED);
+        s.filled = cf < ZKC_KECCAK_RATE_BYTES ? 0 : cf - ZKC_KECCAK_RATE_BYTES;  // consume::<136>(allow_partial)
+        for (int i = 0; i < ZKC_KECCAK_BUFFER_SIZE; i++) s.buffer[i] = (uint8_t)TP(ZKC_KC_BUFFER_OUT + i);
+        for (int i = 0; i < 200; i++) s.sponge[i] = (uint8_t)TP(ZKC_KC_STATE_OUT + i);
+    }
+    const bool read_call = s.read_precompile_call;
+    // the conditional pop
+    uint64_t f[36], limbs = 0, any = 0;
+#pragma unroll
+    for (int i = 0; i < 36; i++) { f[i] = TR(ZKC_KC_CALL_ITEM + i); any |= f[i]; }
+#pragma unroll
+    for (int i = 0; i < 29; i++) limbs |= f[i];
+    if ((limbs | f[34] | f[35]) >> 32 || (f[29] | f[33]) >> 8 || (f[30] | f[31] | f[32]) > 1 || (!read_call && any)) bad |= ZKC_KCV_BOOLEAN;
+    if (read_call && (f[29] != aux_byte || f[0] != formal || (f[1] | f[2] | f[3] | f[4]))) bad |= ZKC_KCV_ENFORCE;
+    zkc_log_query call = lq_zero();
+#pragma unroll
+    for (int i = 0; i < 5; i++) call.address[i] = (uint32_t)f[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { call.key[i] = (uint32_t)f[5 + i]; call.read_value[i] = (uint32_t)f[13 + i]; call.written_value[i] = (uint32_t)f[21 + i]; }
+    call.flags = ZKC_LQ_FLAGS((uint32_t)f[29], (uint32_t)f[33], (uint32_t)f[30], (uint32_t)f[31], (uint32_t)f[32]);
+    call.tx_number_in_block = (uint32_t)f[34]; call.timestamp = (uint32_t)f[35];
+    const uint64_t len_prev = first ? d->rq0.length : TP(ZKC_KC_REQ_LEN), len = TR(ZKC_KC_REQ_LEN);
+    if (len + (read_call ? 1u : 0u) != len_prev || (len >> 32)) bad |= ZKC_KCV_QUEUE;
+    {
+        uint64_t head[4], head_prev[4];
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            head[i] = TR(ZKC_KC_REQ_HEAD + i);
+            head_prev[i] = first ? d->rq0.head[i] : TP(ZKC_KC_REQ_HEAD + i);
+            same &= head[i] == head_prev[i];
+            if (head[i] >= GL_P) bad |= ZKC_KCV_BOOLEAN;
+        }
+        if (!read_call && !same) bad |= ZKC_KCV_QUEUE;
+        if (ROUND_FUNCTION && read_call) {
+            uint64_t e[20], st[12];
+            lq_encode(call, e);
+            lq_absorb_head(e, st);
+            lq_absorb_tail(e, head_prev, st);
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (st[i] != head[i]) bad |= ZKC_KCV_ROUND_FUNCTION;
+        }
+    }
+    // the cycle function in CHECK mode: compares every cell it computes with the trace
+    {
+        size_t read_cursor = 0;
+        uint32_t push_ordinal = 0, checks = 0;
+        kc_cycle<false, true>(s, call, len == 0, nullptr, 0, read_cursor, nullptr, nullptr, push_ordinal, const_cast<uint64_t *>(trace), limit, row, checks);
+        bad |= checks;
+    }
+    // the memory queue: previous write -> six conditional reads -> conditional digest write
+    {
+        uint64_t mt_prev[12], ml_prev = first ? d->mq0.length : TP(ZKC_KC_WRITE_LEN);
+#pragma unroll
+        for (int i = 0; i < 12; i++) mt_prev[i] = first ? d->mq0.tail[i] : TP(ZKC_KC_WRITE_TAIL + i);
+        const uint32_t ts_read = (uint32_t)TR(ZKC_KC_TS_READ), ts_write = (uint32_t)TR(ZKC_KC_TS_WRITE);
+        const uint32_t in_page = (uint32_t)TR(ZKC_KC_PARAMS + 0), out_page = (uint32_t)TR(ZKC_KC_PARAMS + 3), out_offset = (uint32_t)TR(ZKC_KC_PARAMS + 4);
+#pragma unroll 1
+        for (int q = 0; q < 7; q++) {
+            const int b = ZKC_KC_QUERY + q * ZKC_KC_QUERY_STRIDE;
+            const int tail_col = q < 6 ? b + 12 : ZKC_KC_WRITE_TAIL, len_col = q < 6 ? b + 24 : ZKC_KC_WRITE_LEN;
+            const uint64_t pushed = q < 6 ? TR(b + 3) : TR(ZKC_KC_WRITE_RESULT);
+            uint64_t mt[12], st[12];
+            bool msame = true;
+#pragma unroll
+            for (int i = 0; i < 12; i++) { mt[i] = TR(tail_col + i); msame &= mt[i] == mt_prev[i]; if (mt[i] >= GL_P) bad |= ZKC_KCV_BOOLEAN; }
+            const uint64_t ml = TR(len_col);
+            if (pushed > 1 || ml != ml_prev + pushed || (!pushed && !msame)) bad |= ZKC_KCV_MEMORY_QUEUE;
+            if (ROUND_FUNCTION && pushed) {
+                uint32_t value[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) value[i] = (uint32_t)(q < 6 ? TR(b + 4 + i) : TR(ZKC_KC_RESULT + i));
+                if (q < 6) mq_encode(ts_read, in_page, (uint32_t)TR(b + 0), 0, value, st);
+                else mq_encode(ts_write, out_page, out_offset, 1, value, st);
+#pragma unroll
+                for (int i = 8; i < 12; i++) st[i] = mt_prev[i];
+                poseidon2_permute(st);
+#pragma unroll
+                for (int i = 0; i < 12; i++) if (st[i] != mt[i]) bad |= ZKC_KCV_ROUND_FUNCTION;
+            }
+#pragma unroll
+            for (int i = 0; i < 12; i++) mt_prev[i] = mt[i];
+            ml_prev = ml;
+        }
+    }
+#undef TR
+#undef TP
+    if (bad) {
+        atomicAdd(violations, 1ull);
+        atomicOr(&d->failed_checks, bad);
+        atomicMin(&d->first_bad, ((unsigned long long)row << 16) | bad);
+    }
+}
+
 }  // namespace zkc
 
 using namespace zkc;
@@ -641,5 +785,55 @@ extern "C" int zkc_keccak256_round_function_entry_point(zkc_ctx *ctx, zkc_keccak
     io->completion_flag = h->io.completion_flag;
     memcpy(commitment, h->commitment, 32);
     *status = h->status;
+    return status->code;
+}
+
+extern "C" int zkc_keccak256_round_function_check_trace(zkc_ctx *ctx, const zkc_keccak_closed_form *io, const zkc_precompile_options *options,
+                                                        const uint64_t *trace, size_t limit, uint32_t gates, int on_device, uint64_t *violations,
+                                                        zkc_status *status) {
+    zkc_status local;
+    if (!status) status = &local;
+    *status = zkc_status{ZKC_OK, 0, -1, 0, 0};
+    if (!ctx || !io || !violations || (limit && !trace)) { status->code = ZKC_ERR_INVALID_ARGUMENT; return ZKC_ERR_INVALID_ARGUMENT; }
+    ZKC_CUDA(ctx, status, cudaSetDevice(ctx->device));
+    size_t bytes = zkc_carver::bytes(1, sizeof(KcDev)) + zkc_carver::bytes(1, 8);
+    if (!on_device) bytes += zkc_carver::bytes((size_t)ZKC_KC_NUM_COLS * limit, 8);
+    void *blk = ctx->scratch(bytes);
+    KcDev *h = (KcDev *)ctx->pinned(sizeof(KcDev) + 8);
+    if (!blk || !h) { status->code = ZKC_ERR_CUDA; return ZKC_ERR_CUDA; }
+    zkc_carver cv(blk);
+    KcDev *d = cv.take<KcDev>(1);
+    unsigned long long *dviol = cv.take<unsigned long long>(1);
+    cudaStream_t s = ctx->stream;
+    memset(h, 0, sizeof(KcDev));
+    h->io = *io;
+    if (options) h->opt = *options;
+    h->limit = limit;
+    h->first_bad = ~0ull;
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(d, h, sizeof(KcDev), cudaMemcpyHostToDevice, s));
+    ZKC_CUDA(ctx, status, cudaMemsetAsync(dviol, 0, 8, s));
+    const uint64_t *dt = trace;
+    if (!on_device && limit) {
+        uint64_t *b = cv.take<uint64_t>((size_t)ZKC_KC_NUM_COLS * limit);
+        ZKC_CUDA(ctx, status, cudaMemcpyAsync(b, trace, (size_t)ZKC_KC_NUM_COLS * limit * 8, cudaMemcpyHostToDevice, s));
+        dt = b;
+    }
+    ZKC_LAUNCH(ctx, "kc_prologue", kc_prologue_kernel, 1, 96, 0, d);
+    if (limit) {
+        const unsigned grid = (unsigned)((limit + 63) / 64);
+        if (gates == 0 || (gates & ZKC_GATES_ROUND_FUNCTION)) ZKC_LAUNCH(ctx, "kc_check_rf", kc_check_kernel<true>, grid, 64, 0, d, dviol, dt);
+        else ZKC_LAUNCH(ctx, "kc_check", kc_check_kernel<false>, grid, 64, 0, d, dviol, dt);
+    }
+    ZKC_CUDA(ctx, status, cudaGetLastError());
+    unsigned long long *hviol = (unsigned long long *)(h + 1);
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(h, d, sizeof(KcDev), cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaMemcpyAsync(hviol, dviol, 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, status, cudaStreamSynchronize(s));
+    *violations = *hviol;
+    status->failed_checks = h->failed_checks;
+    if (*hviol) {
+        status->code = ZKC_ERR_UNSATISFIED;
+        status->first_bad_row = (int64_t)(h->first_bad >> 16);
+    }
     return status->code;
 }

@@ -52,3 +52,19 @@ def keccak256_round_function_entry_point(engine: Engine, witness: Keccak256Round
     if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE) or (rc and raise_on_unsatisfied):
         raise ZkcError(rc, st, "keccak256_round_function_entry_point")
     return SorterResult(commitment, io, trace, st)
+
+
+def keccak256_round_function_check_trace(engine: Engine, closed_form_input: abi.KeccakClosedForm, trace, limit: int, gates: int = 0,
+                                         options: Optional[abi.PrecompileOptions] = None):
+    """Constraint evaluation of a finished keccak256_round_function trace [KC_COLS.NUM_COLS, limit] (numpy: host, torch CUDA: device):
+    the cycle function re-run on every cycle from the previous cycle's cells and compared cell by cell, the pop and the memory queue
+    bookkeeping.  Returns (violating rows, status); status.failed_checks holds abi.KCV bits."""
+    st = abi.Status()
+    viol = C.c_uint64()
+    io = abi.KeccakClosedForm.from_buffer_copy(bytes(closed_form_input))
+    opts = abi.PrecompileOptions.from_buffer_copy(bytes(options)) if options is not None else abi.PrecompileOptions()
+    rc = engine.lib.zkc_keccak256_round_function_check_trace(engine.h, C.byref(io), C.byref(opts), ptr(trace), limit, gates, on_device(trace),
+                                                             C.byref(viol), C.byref(st))
+    if rc in (abi.ZKC_ERR_INVALID_ARGUMENT, abi.ZKC_ERR_CUDA, abi.ZKC_ERR_NO_DEVICE):
+        raise ZkcError(rc, st, "keccak256_round_function_check_trace")
+    return viol.value, st

@@ -888,6 +888,25 @@ typedef struct zkc_precompile_options {
     uint32_t _pad;
 } zkc_precompile_options;
 
+/* constraint evaluation of a finished keccak256_round_function trace: the FSM state on entry to a cycle is rebuilt from the
+ * previous cycle's cells, the cycle function (mod.rs:230-665) is re-run on the cycle's free inputs (popped call, words read) and
+ * every cell it produces is compared with the trace; plus the conditional pop and the memory queue's length / tail chain over the
+ * seven conditional pushes.  gates: ZKC_GATES_GENERAL = everything but the Poseidon2 permutations of the queues;
+ * ZKC_GATES_ROUND_FUNCTION adds them; 0 = all. */
+#define ZKC_KCV_BOOLEAN (1u << 0)        /* booleans, u32 / u8 ranges, field range of hash outputs, a call item where nothing is popped */
+#define ZKC_KCV_QUEUE (1u << 1)          /* length / head bookkeeping of the requests queue */
+#define ZKC_KCV_FSM (1u << 2)            /* flags on entry / exit, reset / read flags, padding decisions, write_result */
+#define ZKC_KCV_ROUND_FUNCTION (1u << 3)
+#define ZKC_KCV_PARAMS (1u << 4)         /* call parameters / timestamps after the selects */
+#define ZKC_KCV_ENFORCE (1u << 5)        /* aux byte / formal address of a popped call; buffer fill within range */
+#define ZKC_KCV_SPONGE (1u << 6)         /* absorbed block, keccak state after the permutation, digest word */
+#define ZKC_KCV_MEMORY_QUEUE (1u << 7)   /* memory queue length / tail over the seven conditional pushes */
+#define ZKC_KCV_QUERIES (1u << 8)        /* the six read slots: aligned index, unalignment, meaningful bytes, should_read, value, offsets, fill */
+#define ZKC_KCV_BUFFER (1u << 9)         /* buffer bytes after the cycle */
+int zkc_keccak256_round_function_check_trace(zkc_ctx *ctx, const zkc_keccak_closed_form *io, const zkc_precompile_options *options,
+                                             const uint64_t *trace, size_t limit, uint32_t gates, int on_device, uint64_t *violations,
+                                             zkc_status *status);
+
 /* keccak256_round_function_entry_point, mod.rs:673-794.
  *   requests, requests_prev_tails : precompile calls queue witness in pop order (CircuitQueueRawWitness, input.rs:97)
  *   memory_reads                  : memory_reads_witness (input.rs:98), n_reads x 8 little-endian u32 limbs, FIFO order

@@ -502,5 +502,13 @@ inline uint64_t linear_hasher_check_trace(Engine &e, const zkc_linear_hasher_clo
     if (rc != ZKC_OK && rc != ZKC_ERR_UNSATISFIED) throw Error("zkc_linear_hasher_check_trace", rc, st ? *st : local);
     return v;
 }
+inline uint64_t keccak256_round_function_check_trace(Engine &e, const zkc_keccak_closed_form &io, const std::vector<uint64_t> &trace, size_t limit,
+                                                     uint32_t gates = 0, const zkc_precompile_options *options = nullptr, zkc_status *st = nullptr) {
+    uint64_t v = 0;
+    zkc_status local;
+    const int rc = zkc_keccak256_round_function_check_trace(e.handle(), &io, options, trace.data(), limit, gates, 0, &v, st ? st : &local);
+    if (rc != ZKC_OK && rc != ZKC_ERR_UNSATISFIED) throw Error("zkc_keccak256_round_function_check_trace", rc, st ? *st : local);
+    return v;
+}
 
 }  // namespace zkc_b200

@@ -291,7 +291,8 @@ int main(int argc, char **argv) {
                             (void *)&main_vm_gadget_cells, (void *)&ram_permutation_check_trace, (void *)&log_sorter_check_trace,
                             (void *)&storage_validity_check_trace, (void *)&sort_decommittments_check_trace,
                             (void *)&demux_log_queue_check_trace, (void *)&sha256_round_function_check_trace,
-                            (void *)&code_unpacker_check_trace, (void *)&linear_hasher_check_trace};
+                            (void *)&code_unpacker_check_trace, (void *)&linear_hasher_check_trace,
+                            (void *)&keccak256_round_function_check_trace};
     std::printf("%zu entry points\n", sizeof instantiated / sizeof instantiated[0]);
     if (mode == "nodevice") {
         try {

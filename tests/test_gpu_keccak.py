@@ -113,3 +113,68 @@ def test_negative_and_empty(engine, orc):
     prev, _ = O.log_queue_simulate(orc, req)
     r = keccak256_round_function_entry_point(engine, W(io, req, prev, reads, s), 4, raise_on_unsatisfied=False)
     assert r.status.code == abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT
+
+
+def test_check_trace_constraint_evaluation(engine, orc):
+    """zkc_keccak256_round_function_check_trace: the ORACLE's trace (many calls, every length / unalignment class, full padding rounds)
+    satisfies every relation with and without the queue permutations; a fault injected into any cell family is found at its cycle;
+    the engine's trace of a chained second instance (cut inside a message: buffer, fill count and keccak state carried) passes"""
+    from era_zkevm_circuits_b200 import keccak256_round_function_check_trace
+    V_ = abi.KCV
+    reqs, reads, msgs = synthetic.keccak_calls(120, seed=8, max_len=700)
+    prev, rfin = O.log_queue_simulate(orc, reqs)
+    io = O.keccak_closed_form(rfin)
+    limit = sum(len(m) // 136 + 1 for m in msgs) + 12
+    want = O.keccak_entry_point(orc, io, reqs, reads, limit)
+    assert want[0] == abi.ZKC_OK
+    trace = want[2]
+    for gates in (0, abi.GATES_GENERAL):
+        viol, st = keccak256_round_function_check_trace(engine, io, trace, limit, gates)
+        assert viol == 0 and st.code == 0, (gates, viol, hex(st.failed_checks), st.first_bad_row)
+    import torch
+    viol, st = keccak256_round_function_check_trace(engine, io, torch.from_numpy(trace.view(np.int64)).cuda(), limit, abi.GATES_GENERAL)
+    assert viol == 0
+    Q, QS = K["QUERY"], K["QUERY_STRIDE"]
+    pops = np.flatnonzero(trace[K["FLAGS_IN"]])
+    writes = np.flatnonzero(trace[K["WRITE_RESULT"]])
+    mid = int(np.flatnonzero((trace[K["FLAGS_IN"]] == 0) & (trace[Q + 3] == 1) & (trace[K["WRITE_RESULT"]] == 0))[30])  # reading, mid-message
+    faults = [
+        (K["FLAGS_IN"] + 1, mid, None, V_["FSM"], 0),
+        (K["CALL_ITEM"] + 9, int(pops[5]), 1 << 33, V_["BOOLEAN"], 0),
+        (K["CALL_ITEM"] + 3, mid, None, V_["BOOLEAN"], 0),
+        (K["CALL_ITEM"], int(pops[6]), None, V_["ENFORCE"], 0),
+        (K["REQ_LEN"], mid, None, V_["QUEUE"], 0),
+        (K["REQ_HEAD"] + 2, mid, None, V_["QUEUE"], 0),
+        (K["REQ_HEAD"] + 2, int(pops[7]), None, V_["ROUND_FUNCTION"], 0),
+        (K["PARAMS"] + 4, mid, None, V_["PARAMS"], 0),
+        (K["TS_WRITE"], mid, None, V_["PARAMS"], 0),
+        (K["READ_NON_ZERO_LENGTH"], mid, None, V_["FSM"], 0),
+        (Q + 2 * QS + 2, mid, None, V_["QUERIES"], 0),
+        (Q + 4 + 1, mid, None, V_["SPONGE"] | V_["BUFFER"], abi.GATES_GENERAL),  # a word read from memory is a free input: what it feeds no longer matches
+        (Q + 3 * QS + 24, mid, None, V_["MEMORY_QUEUE"], 0),
+        (Q + 12 + 3, mid, None, V_["ROUND_FUNCTION"], 0),
+        (Q + 12 + 3, limit - 3, None, V_["MEMORY_QUEUE"], abi.GATES_GENERAL),
+        (K["CURRENTLY_FILLED"], mid, None, V_["FSM"], 0),
+        (K["INPUT"] + 77, mid, None, V_["SPONGE"], 0),
+        (K["STATE_OUT"] + 123, mid, None, V_["SPONGE"], 0),
+        (K["RESULT"] + 2, int(writes[9]), None, V_["SPONGE"], abi.GATES_GENERAL),
+        (K["WRITE_RESULT"], mid, None, V_["FSM"], 0),
+        (K["WRITE_TAIL"] + 5, int(writes[10]), None, V_["ROUND_FUNCTION"], 0),
+        (K["FLAGS_OUT"] + 3, mid, None, V_["FSM"], 0),
+        (K["BUFFER_OUT"] + 20, mid, None, V_["BUFFER"], 0),
+    ]
+    for col, row, val, bit, gates in faults:
+        bad = trace.copy()
+        bad[col, row] = np.uint64(val) if val is not None else bad[col, row] ^ np.uint64(1)
+        viol, st = keccak256_round_function_check_trace(engine, io, bad, limit, gates)
+        assert viol >= 1 and st.first_bad_row == row and st.failed_checks & bit, (col, row, viol, st.first_bad_row, hex(st.failed_checks))
+    cut = mid
+    a = keccak256_round_function_entry_point(engine, W(io, reqs, prev, reads), cut)
+    nxt = abi.KeccakClosedForm.from_buffer_copy(bytes(a.closed_form_input)); nxt.start_flag = 0
+    nxt.hidden_fsm_input = a.closed_form_input.hidden_fsm_output
+    used_req = len(reqs) - a.closed_form_input.hidden_fsm_output.log_queue_state.length
+    used_reads = int(a.trace[K["QUERY"] + 3::K["QUERY_STRIDE"]][:6].sum())
+    b = keccak256_round_function_entry_point(engine, W(nxt, reqs[used_req:], prev[used_req:], reads[used_reads:]), limit - cut)
+    assert b.status.code == 0
+    viol, st = keccak256_round_function_check_trace(engine, nxt, b.trace, limit - cut)
+    assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)
