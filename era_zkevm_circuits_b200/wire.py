@@ -6,6 +6,10 @@ default options: little-endian, fixed-width integers, u64 sequence lengths) prod
     StorageDeduplicatorInstanceWitness     /root/reference/src/storage_validity_by_grand_product/input.rs:128-136
     Sha256RoundFunctionCircuitInstanceWitness /root/reference/src/sha256_round_function/input.rs:85-89
     Keccak256RoundFunctionCircuitInstanceWitness /root/reference/src/keccak256_round_function/input.rs:95-99
+    CodeDecommittmentsDeduplicatorInstanceWitness /root/reference/src/sort_decommittment_requests/input.rs:110-125
+    CodeDecommitterCircuitInstanceWitness  /root/reference/src/code_unpacker_sha256/input.rs:134-140
+    LogDemuxerCircuitInstanceWitness       /root/reference/src/demux_log_queue/input.rs:118-121
+    LinearHasherCircuitInstanceWitness     /root/reference/src/linear_hasher/input.rs:71-80
 
 read into the host-side witness forms of this package (closed-form struct + struct-of-arrays queue witnesses), and written
 back (test_harness-style dumps for the round-trip tests).
@@ -552,4 +556,229 @@ def write_keccak256_round_function_witness(w_) -> bytes:
     w.u64(len(w_.memory_reads_witness))
     for word in w_.memory_reads_witness:
         w.u256(_from_limbs(word))
+    return bytes(w.b)
+
+
+# ---- DecommitQuery witnesses: sort_decommittment_requests, code_unpacker_sha256 ------------------------------------------------------
+def _read_decommit_query(r: Reader):
+    """DecommitQuery witness (base_structures/decommit_query/mod.rs:22-27) as a DECOMMIT_QUERY_DTYPE tuple"""
+    code_hash = _limbs(r.u256(), 8)
+    page, is_first, ts = r.u32(), r.boolean(), r.u32()
+    return code_hash, page, is_first, ts, 0
+
+
+def _write_decommit_query(w: Writer, rec):
+    w.u256(_from_limbs(rec["code_hash"])); w.u32(rec["page"]); w.boolean(rec["is_first"]); w.u32(rec["timestamp"])
+
+
+def _read_decommit_queue(r: Reader):
+    """FullStateCircuitQueueRawWitness<DecommitQuery>: u64 count, then (item, previous 12-element state)"""
+    n = r.u64()
+    if n > (len(r.d) - r.o) // 8:
+        raise WireError(f"queue witness claims {n} elements")
+    recs = np.zeros(n, dtype=abi.DECOMMIT_QUERY_DTYPE)
+    prev = np.zeros((n, 12), dtype=np.uint64)
+    for k in range(n):
+        recs[k] = _read_decommit_query(r)
+        prev[k] = r.fields(12)
+    return recs, prev
+
+
+def _write_decommit_queue(w: Writer, recs, prev):
+    w.u64(len(recs))
+    for rec, p in zip(recs, prev):
+        _write_decommit_query(w, rec)
+        w.fields(p)
+
+
+def _read_decommit_sorter_fsm(r: Reader, f):
+    """CodeDecommittmentsDeduplicatorFSMInputOutput, sort_decommittment_requests/input.rs:26-37"""
+    _read_queue_state(r, f.initial_queue_state); _read_queue_state(r, f.sorted_queue_state); _read_queue_state(r, f.final_queue_state)
+    for name in ("lhs_accumulator", "rhs_accumulator"):
+        for i, v in enumerate(r.fields(2)):
+            getattr(f, name)[i] = v
+    for i in range(9):
+        f.previous_packed_key[i] = r.u32()
+    f.first_encountered_timestamp = r.u32()
+    code_hash, page, is_first, ts, _ = _read_decommit_query(r)
+    for i in range(8):
+        f.previous_record.code_hash[i] = code_hash[i]
+    f.previous_record.page, f.previous_record.is_first, f.previous_record.timestamp = page, is_first, ts
+
+
+def _write_decommit_sorter_fsm(w: Writer, f):
+    _write_queue_state(w, f.initial_queue_state); _write_queue_state(w, f.sorted_queue_state); _write_queue_state(w, f.final_queue_state)
+    w.fields(f.lhs_accumulator); w.fields(f.rhs_accumulator)
+    for v in f.previous_packed_key:
+        w.u32(v)
+    w.u32(f.first_encountered_timestamp)
+    p = f.previous_record
+    w.u256(_from_limbs(p.code_hash)); w.u32(p.page); w.boolean(p.is_first); w.u32(p.timestamp)
+
+
+def read_decommit_sorter_witness(data: bytes):
+    """bincode bytes of CodeDecommittmentsDeduplicatorInstanceWitness<GoldilocksField> (input.rs:110-125)"""
+    from .sort_decommittment_requests import CodeDecommittmentsDeduplicatorInstanceWitness
+    r = Reader(data)
+    io = abi.DecommitSorterClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    _read_queue_state(r, io.initial_queue_state); _read_queue_state(r, io.sorted_queue_initial_state)
+    _read_queue_state(r, io.final_queue_state)
+    _read_decommit_sorter_fsm(r, io.hidden_fsm_input); _read_decommit_sorter_fsm(r, io.hidden_fsm_output)
+    u, up = _read_decommit_queue(r)
+    s, sp = _read_decommit_queue(r)
+    r.done()
+    return CodeDecommittmentsDeduplicatorInstanceWitness(io, u, up, s, sp)
+
+
+def write_decommit_sorter_witness(w_) -> bytes:
+    w = Writer()
+    io = w_.closed_form_input
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    _write_queue_state(w, io.initial_queue_state); _write_queue_state(w, io.sorted_queue_initial_state)
+    _write_queue_state(w, io.final_queue_state)
+    _write_decommit_sorter_fsm(w, io.hidden_fsm_input); _write_decommit_sorter_fsm(w, io.hidden_fsm_output)
+    _write_decommit_queue(w, w_.initial_queue_witness, w_.initial_queue_prev_states)
+    _write_decommit_queue(w, w_.sorted_queue_witness, w_.sorted_queue_prev_states)
+    return bytes(w.b)
+
+
+def _read_code_unpacker_fsm(r: Reader, f):
+    """CodeDecommitterFSMInputOutput (code_unpacker_sha256/input.rs:23-65): internal_fsm, then the two queue states"""
+    s = f.internal_fsm
+    for i in range(8):
+        s.sha256_inner_state[i] = r.u32()
+    for i, v in enumerate(_limbs(r.u256(), 8)):
+        s.hash_to_compare_against[i] = v
+    s.current_index, s.current_page, s.timestamp = r.u32(), r.u32(), r.u32()
+    s.num_rounds_left = struct.unpack("<H", r.take(2))[0]  # UInt16
+    s.length_in_bits = r.u32()
+    s.state_get_from_queue, s.state_decommit, s.finished = r.boolean(), r.boolean(), r.boolean()
+    _read_queue_state(r, f.decommittment_requests_queue_state)
+    _read_queue_state(r, f.memory_queue_state)
+
+
+def _write_code_unpacker_fsm(w: Writer, f):
+    s = f.internal_fsm
+    for v in s.sha256_inner_state:
+        w.u32(v)
+    w.u256(_from_limbs(s.hash_to_compare_against))
+    w.u32(s.current_index); w.u32(s.current_page); w.u32(s.timestamp)
+    w.b += struct.pack("<H", int(s.num_rounds_left))
+    w.u32(s.length_in_bits)
+    w.boolean(s.state_get_from_queue); w.boolean(s.state_decommit); w.boolean(s.finished)
+    _write_queue_state(w, f.decommittment_requests_queue_state)
+    _write_queue_state(w, f.memory_queue_state)
+
+
+def read_code_decommitter_witness(data: bytes):
+    """bincode bytes of CodeDecommitterCircuitInstanceWitness<GoldilocksField> (input.rs:134-140); code_words (Vec<Vec<U256>>, one inner
+    vector per request) is flattened into [total_words, 8] u32 limbs in pop order.  Returns (witness, words per request)."""
+    from .code_unpacker_sha256 import CodeDecommitterCircuitInstanceWitness
+    r = Reader(data)
+    io = abi.CodeUnpackerClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    _read_queue_state(r, io.memory_queue_initial_state); _read_queue_state(r, io.sorted_requests_queue_initial_state)
+    _read_queue_state(r, io.memory_queue_final_state)
+    _read_code_unpacker_fsm(r, io.hidden_fsm_input); _read_code_unpacker_fsm(r, io.hidden_fsm_output)
+    reqs, prev = _read_decommit_queue(r)
+    n_outer = r.u64()
+    if n_outer > (len(r.d) - r.o) // 8:
+        raise WireError(f"code_words claims {n_outer} vectors")
+    words, per_request = [], []
+    for _ in range(n_outer):
+        n = r.u64()
+        if n > (len(r.d) - r.o) // 11:
+            raise WireError(f"a code vector claims {n} words")
+        per_request.append(n)
+        words += [_limbs(r.u256(), 8) for _ in range(n)]
+    r.done()
+    arr = np.array(words, dtype=np.uint32).reshape(-1, 8)
+    return CodeDecommitterCircuitInstanceWitness(io, reqs, prev, arr), per_request
+
+
+def write_code_decommitter_witness(w_, words_per_request) -> bytes:
+    """words_per_request: how code_words splits over the requests in pop order (a request in progress on entry comes first)"""
+    w = Writer()
+    io = w_.closed_form_input
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    _write_queue_state(w, io.memory_queue_initial_state); _write_queue_state(w, io.sorted_requests_queue_initial_state)
+    _write_queue_state(w, io.memory_queue_final_state)
+    _write_code_unpacker_fsm(w, io.hidden_fsm_input); _write_code_unpacker_fsm(w, io.hidden_fsm_output)
+    _write_decommit_queue(w, w_.sorted_requests_queue_witness, w_.sorted_requests_queue_prev_states)
+    assert sum(words_per_request) == len(w_.code_words)
+    w.u64(len(words_per_request))
+    k = 0
+    for n in words_per_request:
+        w.u64(n)
+        for word in w_.code_words[k:k + n]:
+            w.u256(_from_limbs(word))
+        k += n
+    return bytes(w.b)
+
+
+# ---- demux_log_queue, linear_hasher ------------------------------------------------------------------------------------------------
+def _read_demux_fsm(r: Reader, f):
+    """LogDemuxerFSMInputOutput, demux_log_queue/input.rs:24-32: the input queue, then storage / events / l1 messages / keccak256 /
+    sha256 / ecrecover"""
+    _read_queue_state(r, f.initial_log_queue_state)
+    for q in range(6):
+        _read_queue_state(r, f.output_queue_states[q])
+
+
+def _write_demux_fsm(w: Writer, f):
+    _write_queue_state(w, f.initial_log_queue_state)
+    for q in range(6):
+        _write_queue_state(w, f.output_queue_states[q])
+
+
+def read_log_demuxer_witness(data: bytes):
+    """bincode bytes of LogDemuxerCircuitInstanceWitness<GoldilocksField> (input.rs:118-121)"""
+    from .demux_log_queue import LogDemuxerCircuitInstanceWitness
+    r = Reader(data)
+    io = abi.DemuxClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    _read_queue_state(r, io.initial_log_queue_state)
+    for q in range(6):
+        _read_queue_state(r, io.output_queue_states[q])
+    _read_demux_fsm(r, io.hidden_fsm_input); _read_demux_fsm(r, io.hidden_fsm_output)
+    recs, prev = _read_log_queue(r)
+    r.done()
+    return LogDemuxerCircuitInstanceWitness(io, recs, prev)
+
+
+def write_log_demuxer_witness(w_) -> bytes:
+    w = Writer()
+    io = w_.closed_form_input
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    _write_queue_state(w, io.initial_log_queue_state)
+    for q in range(6):
+        _write_queue_state(w, io.output_queue_states[q])
+    _write_demux_fsm(w, io.hidden_fsm_input); _write_demux_fsm(w, io.hidden_fsm_output)
+    _write_log_queue(w, w_.initial_queue_witness, w_.initial_queue_prev_tails)
+    return bytes(w.b)
+
+
+def read_linear_hasher_witness(data: bytes):
+    """bincode bytes of LinearHasherCircuitInstanceWitness<GoldilocksField> (input.rs:71-80): the hidden FSM is `()` (no bytes), the
+    observable output 32 digest bytes"""
+    from .linear_hasher import LinearHasherCircuitInstanceWitness
+    r = Reader(data)
+    io = abi.LinearHasherClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    _read_queue_state(r, io.queue_state)
+    for i, b in enumerate(bytes(r.take(32))):
+        io.keccak256_hash[i] = b
+    recs, prev = _read_log_queue(r)
+    r.done()
+    return LinearHasherCircuitInstanceWitness(io, recs, prev)
+
+
+def write_linear_hasher_witness(w_) -> bytes:
+    w = Writer()
+    io = w_.closed_form_input
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    _write_queue_state(w, io.queue_state)
+    w.b += bytes(int(b) & 0xFF for b in io.keccak256_hash)
+    _write_log_queue(w, w_.queue_witness, w_.queue_prev_tails)
     return bytes(w.b)

@@ -177,3 +177,76 @@ def test_keccak256_round_function_dump_round_trip_and_ingestion(orc):
     have = O.keccak_entry_point(orc, got.closed_form_input, got.requests_queue_witness, got.memory_reads_witness, limit - cut)
     assert want[0] == have[0] == 0 and np.array_equal(want[3], have[3]) and np.array_equal(want[2], have[2])
     assert bytes(have[1].hidden_fsm_output) == bytes(whole[1].hidden_fsm_output)
+
+
+def test_decommit_sorter_dump_round_trip_and_ingestion(orc):
+    from era_zkevm_circuits_b200 import CodeDecommittmentsDeduplicatorInstanceWitness as W
+    u, s = synthetic.decommit_requests_trace(300, seed=4, n_hashes=20)
+    up, ufin = O.decommit_queue_simulate(orc, u)
+    sp, sfin = O.decommit_queue_simulate(orc, s)
+    io = O.decommit_sorter_closed_form(ufin, sfin, True)
+    first = O.sort_decommittments_entry_point(orc, io, u, s, 120)
+    nxt = abi.DecommitSorterClosedForm.from_buffer_copy(bytes(first[1])); nxt.start_flag = 0
+    nxt.hidden_fsm_input = first[1].hidden_fsm_output  # carries previous_record / previous_packed_key / first_encountered_timestamp
+    w = W(nxt, u[120:], up[120:], s[120:], sp[120:])
+    dump = wire.write_decommit_sorter_witness(w)
+    got = wire.read_decommit_sorter_witness(dump)
+    assert bytes(got.closed_form_input) == bytes(nxt) and wire.write_decommit_sorter_witness(got) == dump
+    assert got.sorted_queue_witness.tobytes() == np.ascontiguousarray(s[120:]).tobytes() and np.array_equal(got.initial_queue_prev_states, up[120:])
+    want = O.sort_decommittments_entry_point(orc, nxt, u[120:], s[120:], 200)
+    have = O.sort_decommittments_entry_point(orc, got.closed_form_input, got.initial_queue_witness, got.sorted_queue_witness, 200)
+    assert want[0] == have[0] == 0 and np.array_equal(want[3], have[3]) and np.array_equal(want[2], have[2])
+
+
+def test_code_decommitter_dump_round_trip_and_ingestion(orc):
+    from era_zkevm_circuits_b200 import CodeDecommitterCircuitInstanceWitness as W
+    reqs, words = synthetic.code_decommit_requests(12, seed=4, max_words=21)
+    prev, fin = O.decommit_queue_simulate(orc, reqs)
+    io = O.code_unpacker_closed_form(fin, None, True)
+    per_request = [int(h[7]) & 0xFFFF for h in reqs["code_hash"]]
+    limit = sum((n + 1) // 2 for n in per_request) + 3
+    cut = limit // 2
+    first = O.code_unpacker_entry_point(orc, io, reqs, words, cut)
+    nxt = abi.CodeUnpackerClosedForm.from_buffer_copy(bytes(first[1])); nxt.start_flag = 0
+    nxt.hidden_fsm_input = first[1].hidden_fsm_output  # mid-bytecode: SHA-256 state, hash to compare, UInt16 round counter
+    used_req = len(reqs) - first[1].hidden_fsm_output.decommittment_requests_queue_state.length
+    used_words = int(first[1].hidden_fsm_output.memory_queue_state.length)
+    rest = np.ascontiguousarray(words, dtype=np.uint32).reshape(-1, 8)[used_words:]
+    split = [sum(per_request[:used_req]) - used_words] + per_request[used_req:]  # the request in progress first
+    w = W(nxt, reqs[used_req:], prev[used_req:], rest)
+    dump = wire.write_code_decommitter_witness(w, split)
+    got, got_split = wire.read_code_decommitter_witness(dump)
+    assert bytes(got.closed_form_input) == bytes(nxt) and got_split == split and wire.write_code_decommitter_witness(got, got_split) == dump
+    assert np.array_equal(got.code_words, rest) and got.sorted_requests_queue_witness.tobytes() == np.ascontiguousarray(reqs[used_req:]).tobytes()
+    want = O.code_unpacker_entry_point(orc, nxt, reqs[used_req:], rest, limit - cut)
+    have = O.code_unpacker_entry_point(orc, got.closed_form_input, got.sorted_requests_queue_witness, got.code_words, limit - cut)
+    assert want[0] == have[0] == 0 and np.array_equal(want[3], have[3]) and np.array_equal(want[2], have[2])
+
+
+def test_log_demuxer_and_linear_hasher_dump_round_trips(orc):
+    from era_zkevm_circuits_b200 import LinearHasherCircuitInstanceWitness, LogDemuxerCircuitInstanceWitness
+    recs = synthetic.vm_log_queue_trace(200, seed=6)
+    prev, fin = O.log_queue_simulate(orc, recs)
+    io = O.demux_closed_form(fin, True)
+    first = O.demux_entry_point(orc, io, recs, 90)
+    nxt = abi.DemuxClosedForm.from_buffer_copy(bytes(first[1])); nxt.start_flag = 0
+    nxt.hidden_fsm_input = first[1].hidden_fsm_output  # six non-trivial output queue states
+    w = LogDemuxerCircuitInstanceWitness(nxt, recs[90:], prev[90:])
+    dump = wire.write_log_demuxer_witness(w)
+    got = wire.read_log_demuxer_witness(dump)
+    assert bytes(got.closed_form_input) == bytes(nxt) and wire.write_log_demuxer_witness(got) == dump
+    want = O.demux_entry_point(orc, nxt, recs[90:], 120)
+    have = O.demux_entry_point(orc, got.closed_form_input, got.initial_queue_witness, 120)
+    assert want[0] == have[0] == 0 and np.array_equal(want[3], have[3]) and np.array_equal(want[2], have[2])
+    msgs = recs.copy(); msgs["tx_number_in_block"] &= 0xFFFF
+    mprev, mfin = O.log_queue_simulate(orc, msgs)
+    lio = O.linear_hasher_closed_form(mfin)
+    done = O.linear_hasher_entry_point(orc, lio, msgs, 210)
+    assert done[0] == 0
+    lw = LinearHasherCircuitInstanceWitness(done[1], msgs, mprev)  # the finished closed form carries the 32 digest bytes
+    dump = wire.write_linear_hasher_witness(lw)
+    got = wire.read_linear_hasher_witness(dump)
+    assert bytes(got.closed_form_input) == bytes(done[1]) and wire.write_linear_hasher_witness(got) == dump
+    assert got.queue_witness.tobytes() == msgs.tobytes() and np.array_equal(got.queue_prev_tails, mprev)
+    again = O.linear_hasher_entry_point(orc, got.closed_form_input, got.queue_witness, 210)
+    assert again[0] == 0 and np.array_equal(again[3], done[3])
