@@ -107,13 +107,18 @@ def _np(x):
     return x.cpu().numpy() if type(x).__module__.startswith("torch") else np.asarray(x)
 
 
-def _qs4(head, tail, length):
-    from . import abi
-    q = abi.QueueState4()
-    for i in range(4):
+def _qs(cls, head, tail, length):
+    """a QueueState4 / QueueState12 from head / tail element sequences"""
+    q = cls()
+    for i in range(len(q.head)):
         q.head[i] = int(head[i]); q.tail[i] = int(tail[i])
     q.length = int(length)
     return q
+
+
+def _qs4(head, tail, length):
+    from . import abi
+    return _qs(abi.QueueState4, head, tail, length)
 
 
 def _qs_list(q):
@@ -137,7 +142,10 @@ class _StorageCut:
 
     def __init__(self):
         from . import abi
-        self.ClosedForm, self.Fsm, self.cols, self.chk = abi.StorageClosedForm, abi.StorageFsm, abi.ST_COLS, abi.ST_CHK
+        self.ClosedForm, self.Fsm, self.cols, self.chk, self.Queue = abi.StorageClosedForm, abi.StorageFsm, abi.ST_COLS, abi.ST_CHK, abi.QueueState4
+
+    def result_tails(self, w):
+        return w.result_queue_tails
 
     def arrays(self, w):
         """(unsorted records, unsorted prev tails, sorted records, sorted prev tails, extra per-row arrays of the sorted queue)"""
@@ -189,7 +197,10 @@ class _EventsCut:
 
     def __init__(self):
         from . import abi
-        self.ClosedForm, self.Fsm, self.cols, self.chk = abi.EventsClosedForm, abi.EventsFsm, abi.EV_COLS, abi.EV_CHK
+        self.ClosedForm, self.Fsm, self.cols, self.chk, self.Queue = abi.EventsClosedForm, abi.EventsFsm, abi.EV_COLS, abi.EV_CHK, abi.QueueState4
+
+    def result_tails(self, w):
+        return w.result_queue_tails
 
     def arrays(self, w):
         return w.initial_queue_witness, w.initial_queue_prev_tails, w.intermediate_sorted_queue_witness, w.intermediate_sorted_queue_prev_tails, ()
@@ -216,13 +227,71 @@ class _EventsCut:
         return np.array(_qs_list(io.initial_log_queue_state) + _qs_list(io.intermediate_sorted_queue_state), dtype=np.uint64)
 
 
+class _DecommitCut:
+    """sort_decommittment_requests: full-state (12-element) queues; the carried first-encountered timestamp belongs to the run of
+    equal code hashes that straddles the cut, so the replay window is that run (as the storage cell)"""
+    name = "sort_decommittment_requests"
+    fsm_queues = ("initial_queue_state", "sorted_queue_state", "final_queue_state")
+    obs_queues = ("initial_queue_state", "sorted_queue_initial_state")
+    final_queue = "final_queue_state"
+
+    def __init__(self):
+        from . import abi
+        self.ClosedForm, self.Fsm, self.cols, self.chk, self.Queue = abi.DecommitSorterClosedForm, abi.DecommitSorterFsm, abi.DQ_COLS, abi.DQ_CHK, abi.QueueState12
+
+    def arrays(self, w):
+        return w.initial_queue_witness, w.initial_queue_prev_states, w.sorted_queue_witness, w.sorted_queue_prev_states, ()
+
+    def result_tails(self, w):
+        return w.result_queue_states
+
+    @staticmethod
+    def _fields(recs):
+        """[m, 11] u32: code_hash (8 limbs), page, is_first, timestamp of DecommitQuery records (numpy structured or byte rows)"""
+        a = _np(recs)
+        if a.dtype.names:
+            return np.concatenate([a["code_hash"], a["page"][:, None], a["is_first"][:, None], a["timestamp"][:, None]], axis=1).astype(np.uint32)
+        return a[:, :44].view(np.uint32)
+
+    def replay_start(self, w, lo):
+        win = 256
+        while True:
+            a0 = max(0, lo - win)
+            h = self._fields(w.sorted_queue_witness[a0:lo])[:, :8]
+            other = np.flatnonzero(~(h == h[-1]).all(axis=1))
+            if len(other) or a0 == 0:
+                return a0 + (int(other[-1]) + 1 if len(other) else 0)
+            win *= 4
+
+    def fill_replay_fsm(self, f, w, io0, cs):
+        prev = self._fields(w.sorted_queue_witness[cs - 1:cs])[0]
+        f.previous_packed_key[0] = int(prev[10])
+        for i in range(8):
+            f.previous_packed_key[1 + i] = int(prev[i]); f.previous_record.code_hash[i] = int(prev[i])
+        f.previous_record.page, f.previous_record.is_first, f.previous_record.timestamp = int(prev[8]), int(prev[9]) & 1, int(prev[10])
+
+    def fsm_encoding(self, f):
+        """100 field elements (sort_decommittment_requests/input.rs:26-37)"""
+        e = []
+        for q in self.fsm_queues:
+            e += _qs_list(getattr(f, q))
+        e += [f.lhs_accumulator[0], f.lhs_accumulator[1], f.rhs_accumulator[0], f.rhs_accumulator[1]]
+        p = f.previous_record
+        e += list(f.previous_packed_key) + [f.first_encountered_timestamp] + list(p.code_hash) + [p.page, p.is_first & 1, p.timestamp]
+        return np.array([int(x) for x in e], dtype=np.uint64)
+
+    def obs_in_encoding(self, io):
+        return np.array(_qs_list(io.initial_queue_state) + _qs_list(io.sorted_queue_initial_state), dtype=np.uint64)
+
+
 def _start_state(cut, io):
     """the selection the entry points make between the observable input and the hidden FSM input (storage mod.rs:190-395)"""
     f = io.hidden_fsm_input
     start = bool(io.start_flag)
     uq0 = getattr(io, cut.obs_queues[0]) if start else getattr(f, cut.fsm_queues[0])
     sq0 = getattr(io, cut.obs_queues[1]) if start else getattr(f, cut.fsm_queues[1])
-    rq0 = _qs4([0] * 4, [0] * 4, 0) if start else getattr(f, cut.fsm_queues[2])
+    width = len(cut.Queue().head)
+    rq0 = _qs(cut.Queue, [0] * width, [0] * width, 0) if start else getattr(f, cut.fsm_queues[2])
     return uq0, sq0, rq0
 
 
@@ -268,7 +337,8 @@ def rows_local(cut, run_fn, witness, limit, rank, world, push_offsets):
     uq0, sq0, rq0 = _start_state(cut, io0)
     u, up, s, sp, extras = cut.arrays(w)
     n_active = min(limit, int(uq0.length), int(sq0.length), len(u), len(s))
-    if world > 1 and (w.result_queue_tails is None or push_offsets is None or len(push_offsets) != world):
+    tails_hint = cut.result_tails(w)
+    if world > 1 and (tails_hint is None or push_offsets is None or len(push_offsets) != world):
         raise ValueError("a row-sharded run needs the result-queue tail hints and one push offset per rank")
     if world > 1 and n_active < world:
         raise ValueError("fewer active rows than ranks")
@@ -287,8 +357,8 @@ def rows_local(cut, run_fn, witness, limit, rank, world, push_offsets):
             f = mini.hidden_fsm_input
             C.memset(C.byref(f), 0, C.sizeof(f))
             f.lhs_accumulator[0] = f.lhs_accumulator[1] = f.rhs_accumulator[0] = f.rhs_accumulator[1] = 1
-            setattr(f, cut.fsm_queues[0], _qs4(_np(up[cs:cs + 1]).view(np.uint64)[0], uq0.tail, int(uq0.length) - cs))
-            setattr(f, cut.fsm_queues[1], _qs4(_np(sp[cs:cs + 1]).view(np.uint64)[0], sq0.tail, int(sq0.length) - cs))
+            setattr(f, cut.fsm_queues[0], _qs(cut.Queue, _np(up[cs:cs + 1]).view(np.uint64)[0], uq0.tail, int(uq0.length) - cs))
+            setattr(f, cut.fsm_queues[1], _qs(cut.Queue, _np(sp[cs:cs + 1]).view(np.uint64)[0], sq0.tail, int(sq0.length) - cs))
             cut.fill_replay_fsm(f, w, io0, cs)
         m = run_fn(mini, *args(cs, lo), None, lo - cs, False)
         if m.status.code not in (abi.ZKC_OK, abi.ZKC_ERR_UNSATISFIED):
@@ -297,9 +367,9 @@ def rows_local(cut, run_fn, witness, limit, rank, world, push_offsets):
         io.hidden_fsm_input = m.closed_form_input.hidden_fsm_output
         f = io.hidden_fsm_input
         f.lhs_accumulator[0] = f.lhs_accumulator[1] = f.rhs_accumulator[0] = f.rhs_accumulator[1] = 1
-        tail = _np(w.result_queue_tails[k_lo - 1:k_lo]).view(np.uint64)[0] if k_lo > 0 else rq0.tail
-        setattr(f, cut.fsm_queues[2], _qs4(rq0.head, tail, int(rq0.length) + k_lo))
-    res = run_fn(io, *args(lo, hi), None if w.result_queue_tails is None else w.result_queue_tails[k_lo:], hi - lo, True)
+        tail = _np(tails_hint[k_lo - 1:k_lo]).view(np.uint64)[0] if k_lo > 0 else rq0.tail
+        setattr(f, cut.fsm_queues[2], _qs(cut.Queue, rq0.head, tail, int(rq0.length) + k_lo))
+    res = run_fn(io, *args(lo, hi), None if tails_hint is None else tails_hint[k_lo:], hi - lo, True)
     out = res.closed_form_input.hidden_fsm_output
     st = res.status
     failed = int(st.failed_checks)
@@ -342,7 +412,7 @@ def rows_finish(cut, res, rank, world, records, io0, push_offsets, scale_fn, com
     fsm_len = C.sizeof(cut.Fsm)
     tail_bytes = last[_LOCAL_WORDS:].view(np.uint8)
     io.hidden_fsm_output = cut.Fsm.from_buffer_copy(tail_bytes[:fsm_len].tobytes())
-    setattr(io, cut.final_queue, abi.QueueState4.from_buffer_copy(tail_bytes[fsm_len:fsm_len + C.sizeof(abi.QueueState4)].tobytes()))
+    setattr(io, cut.final_queue, cut.Queue.from_buffer_copy(tail_bytes[fsm_len:fsm_len + C.sizeof(cut.Queue)].tobytes()))
     io.completion_flag = int(last[8])
     grand = [1, 1, 1, 1]
     for r in range(world):
@@ -388,6 +458,20 @@ def events_rows_finish(res, rank, world, records, io0, push_offsets, scale_fn, c
     return rows_finish(_EventsCut(), res, rank, world, records, io0, push_offsets, scale_fn, commit_fn)
 
 
+def decommit_rows_local(run_fn, witness, limit, rank, world, push_offsets):
+    """rows_local for sort_decommittment_requests; run_fn(io, u, up, s, sp, states, limit, want_trace)"""
+    return rows_local(_DecommitCut(), lambda io, u, up, s, sp, ex, tails, lim, wt: run_fn(io, u, up, s, sp, tails, lim, wt),
+                      witness, limit, rank, world, push_offsets)
+
+
+def decommit_rows_finish(res, rank, world, records, io0, push_offsets, scale_fn, commit_fn):
+    return rows_finish(_DecommitCut(), res, rank, world, records, io0, push_offsets, scale_fn, commit_fn)
+
+
+def decommit_sorter_closed_form_commitment(commit_fn, io):
+    return closed_form_commitment(_DecommitCut(), commit_fn, io)
+
+
 def _row_sharded(engine, local_fn, finish_fn, run_fn, witness, limit, rank, world, push_offsets, device):
     import torch
     import torch.distributed as dist
@@ -428,3 +512,14 @@ def log_sorter_row_sharded(engine, witness, limit, rank, world, push_offsets=Non
         return sort_and_deduplicate_events_entry_point(engine, wit, lim, want_trace=want_trace, raise_on_unsatisfied=False)
 
     return _row_sharded(engine, events_rows_local, events_rows_finish, run_fn, witness, limit, rank, world, push_offsets, device)
+
+
+def sort_decommittments_row_sharded(engine, witness, limit, rank, world, push_offsets=None, device=None):
+    """sort_and_deduplicate_code_decommittments_entry_point of ONE instance over `world` ranks, as storage_validity_row_sharded"""
+    from .sort_decommittment_requests import CodeDecommittmentsDeduplicatorInstanceWitness, sort_and_deduplicate_code_decommittments_entry_point
+
+    def run_fn(io, u, up, s, sp, states, lim, want_trace):
+        wit = CodeDecommittmentsDeduplicatorInstanceWitness(io, u, up, s, sp, states)
+        return sort_and_deduplicate_code_decommittments_entry_point(engine, wit, lim, want_trace=want_trace, raise_on_unsatisfied=False)
+
+    return _row_sharded(engine, decommit_rows_local, decommit_rows_finish, run_fn, witness, limit, rank, world, push_offsets, device)

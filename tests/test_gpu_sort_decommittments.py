@@ -229,3 +229,39 @@ def test_check_trace_constraint_evaluation(engine, orc):
     assert b.status.code == 0
     viol, st = sort_decommittments_check_trace(engine, nxt, b.trace, limit - cut)
     assert viol == 0, (viol, hex(st.failed_checks), st.first_bad_row)
+
+
+def test_one_instance_cut_by_rows_over_ranks(engine, orc):
+    """sharding.decommit_rows_local / decommit_rows_finish with the ENGINE as the backend, 3 virtual ranks on this GPU (host buffers
+    and device tensors): the rank traces concatenate to the whole instance's trace; every rank ends with the whole closed form +
+    commitment"""
+    import torch
+    from era_zkevm_circuits_b200 import sharding
+    n, limit = 5000, 5100
+    u, s = synthetic.decommit_requests_trace(n, seed=12, n_hashes=40)
+    io, up, sp = instance(orc, u, s)
+    want = O.sort_decommittments_entry_point(orc, io, u, s, limit)
+    assert want[0] == abi.ZKC_OK
+    world = 3
+    cum = np.concatenate([[0], np.cumsum(want[2][K["ADD_TO_QUEUE"]])]).astype(np.int64)
+    offs = [int(cum[sharding.row_range(n, r, world)[0]]) for r in range(world)]
+
+    def run(io_, u_, up_, s_, sp_, states_, lim, want_trace):
+        return entry_point(engine, Witness(io_, u_, up_, s_, sp_, states_), lim, want_trace=want_trace, raise_on_unsatisfied=False)
+
+    commit = lambda e: engine.commit_encoding(np.ascontiguousarray(e, dtype=np.uint64).reshape(1, -1))[0]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)).cuda()
+    i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+    for on_dev in (False, True):
+        w = Witness(io, dev(u), i64(up), dev(s), i64(sp), i64(want[5])) if on_dev else Witness(io, u, up, s, sp, want[5])
+        locs = [sharding.decommit_rows_local(run, w, limit, r, world, offs) for r in range(world)]
+        recs = np.stack([l[3] for l in locs])
+        traces = []
+        for r in range(world):
+            com, io_g, trace, st = sharding.decommit_rows_finish(locs[r][0], r, world, recs, io, offs, engine.scale_accumulators, commit)
+            assert st.code == 0, (r, st.code, hex(st.failed_checks), st.first_bad_row)
+            assert com.tolist() == want[3].tolist()
+            assert bytes(io_g.hidden_fsm_output) == bytes(want[1].hidden_fsm_output) and bytes(io_g.final_queue_state) == bytes(want[1].final_queue_state)
+            traces.append(trace.cpu().numpy().view(np.uint64) if on_dev else trace)
+        bad = np.argwhere(np.concatenate(traces, axis=1) != want[2])
+        assert bad.size == 0, f"first differing (col,row): {bad[:8].tolist()}"

@@ -250,3 +250,40 @@ def test_row_sharded_log_sorter_virtual_ranks():
             assert bytes(io_g.hidden_fsm_output) == bytes(whole[1].hidden_fsm_output) and bytes(io_g.final_queue_state) == bytes(whole[1].final_queue_state)
             traces.append(trace)
         assert np.array_equal(np.concatenate(traces, axis=1), whole[2])
+
+
+def test_row_sharded_decommit_sorter_virtual_ranks():
+    """ONE sort_decommittment_requests instance cut by rows (12-element full-state queues; the replay window is the run of equal code
+    hashes that straddles the cut, which owns the carried first-encountered timestamp); 2 and 4 virtual ranks, oracle backend"""
+    sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+    from types import SimpleNamespace
+    import orc as O
+    from era_zkevm_circuits_b200 import CodeDecommittmentsDeduplicatorInstanceWitness, abi, sharding, synthetic
+    lib = O.load()
+    n, limit = 1500, 1530
+    u, s = synthetic.decommit_requests_trace(n, seed=5, n_hashes=14)  # ~100 requests per hash: every cut lands inside a run
+    up, ufin = O.decommit_queue_simulate(lib, u)
+    sp, sfin = O.decommit_queue_simulate(lib, s)
+    io = O.decommit_sorter_closed_form(ufin, sfin, True)
+    whole = O.sort_decommittments_entry_point(lib, io, u, s, limit)
+    assert whole[0] == 0
+    assert np.array_equal(sharding.decommit_sorter_closed_form_commitment(lambda e: O.commit_encoding(lib, e), whole[1]), whole[3])
+    w = CodeDecommittmentsDeduplicatorInstanceWitness(io, u, up, s, sp, whole[5])
+
+    def run(io_, u_, up_, s_, sp_, states, lim, want_trace):
+        rc, io2, trace, com, st, _ = O.sort_decommittments_entry_point(lib, io_, u_, s_, lim, want_trace=want_trace)
+        return SimpleNamespace(closed_form_input=io2, trace=trace, status=st, commitment=com)
+
+    _, scale, commit = _oracle_backend(lib)
+    cum = np.concatenate([[0], np.cumsum(whole[2][abi.DQ_COLS["ADD_TO_QUEUE"]])]).astype(np.int64)
+    for world in (2, 4):
+        offs = [int(cum[sharding.row_range(n, r, world)[0]]) for r in range(world)]
+        locs = [sharding.decommit_rows_local(run, w, limit, r, world, offs) for r in range(world)]
+        recs = np.stack([l[3] for l in locs])
+        traces = []
+        for r in range(world):
+            com, io_g, trace, st = sharding.decommit_rows_finish(locs[r][0], r, world, recs, io, offs, scale, commit)
+            assert st.code == 0 and np.array_equal(com, whole[3])
+            assert bytes(io_g.hidden_fsm_output) == bytes(whole[1].hidden_fsm_output) and bytes(io_g.final_queue_state) == bytes(whole[1].final_queue_state)
+            traces.append(trace)
+        assert np.array_equal(np.concatenate(traces, axis=1), whole[2])
