@@ -284,14 +284,75 @@ class _DecommitCut:
         return np.array(_qs_list(io.initial_queue_state) + _qs_list(io.sorted_queue_initial_state), dtype=np.uint64)
 
 
+class _RamCut:
+    """ram_permutation: no result queue; besides the accumulators the loop carries a COUNTER (num_nondeterministic_writes, :260-290):
+    every rank counts from 0 and the column / FSM field get the sum of the lower ranks' counts added after the exchange"""
+    name = "ram_permutation"
+    fsm_queues = ("current_unsorted_queue_state", "current_sorted_queue_state")
+    final_queue = None
+    counters = (("NUM_NONDET_WRITES", "num_nondeterministic_writes"),)  # (trace column, FSM field)
+
+    def __init__(self):
+        from . import abi
+        self.ClosedForm, self.Fsm, self.cols, self.chk, self.Queue = abi.RamClosedForm, abi.RamFsm, abi.RAM_COLS, abi.RAM_CHK, abi.QueueState12
+
+    def obs_queue(self, io, k):
+        return io.observable_input.sorted_queue_initial_state if k else io.observable_input.unsorted_queue_initial_state
+
+    def arrays(self, w):
+        return w.unsorted_queue_witness, w.unsorted_queue_prev_states, w.sorted_queue_witness, w.sorted_queue_prev_states, ()
+
+    def result_tails(self, w):
+        return None
+
+    def replay_start(self, w, lo):
+        return lo - 1  # previous sorting key / value / is_ptr: the sorted record at lo - 1
+
+    def fill_replay_fsm(self, f, w, io0, cs):
+        pass
+
+    def masked_checks(self):
+        return self.chk["GRAND_PRODUCT"] | self.chk["NONDET_COUNT"]
+
+    def completion_checks(self, io, grand):
+        bad = 0
+        if grand[0] != grand[1] or grand[2] != grand[3]:
+            bad |= self.chk["GRAND_PRODUCT"]
+        if int(io.hidden_fsm_output.num_nondeterministic_writes) != int(io.observable_input.non_deterministic_bootloader_memory_snapshot_length):
+            bad |= self.chk["NONDET_COUNT"]
+        return bad
+
+    def fsm_encoding(self, f):
+        """69 field elements (ram_permutation/input.rs:52-62)"""
+        e = [f.lhs_accumulator[0], f.lhs_accumulator[1], f.rhs_accumulator[0], f.rhs_accumulator[1]]
+        e += _qs_list(f.current_unsorted_queue_state) + _qs_list(f.current_sorted_queue_state)
+        e += list(f.previous_sorting_key) + list(f.previous_full_key) + list(f.previous_value) + [f.previous_is_ptr, f.num_nondeterministic_writes]
+        return np.array([int(x) for x in e], dtype=np.uint64)
+
+    def obs_in_encoding(self, io):
+        o = io.observable_input
+        return np.array(_qs_list(o.unsorted_queue_initial_state) + _qs_list(o.sorted_queue_initial_state) +
+                        [o.non_deterministic_bootloader_memory_snapshot_length], dtype=np.uint64)
+
+
+def _obs_queue(cut, io, k):
+    return cut.obs_queue(io, k) if hasattr(cut, "obs_queue") else getattr(io, cut.obs_queues[k])
+
+
+def _has_result_queue(cut):
+    return len(cut.fsm_queues) > 2
+
+
 def _start_state(cut, io):
     """the selection the entry points make between the observable input and the hidden FSM input (storage mod.rs:190-395)"""
     f = io.hidden_fsm_input
     start = bool(io.start_flag)
-    uq0 = getattr(io, cut.obs_queues[0]) if start else getattr(f, cut.fsm_queues[0])
-    sq0 = getattr(io, cut.obs_queues[1]) if start else getattr(f, cut.fsm_queues[1])
-    width = len(cut.Queue().head)
-    rq0 = _qs(cut.Queue, [0] * width, [0] * width, 0) if start else getattr(f, cut.fsm_queues[2])
+    uq0 = _obs_queue(cut, io, 0) if start else getattr(f, cut.fsm_queues[0])
+    sq0 = _obs_queue(cut, io, 1) if start else getattr(f, cut.fsm_queues[1])
+    rq0 = None
+    if _has_result_queue(cut):
+        width = len(cut.Queue().head)
+        rq0 = _qs(cut.Queue, [0] * width, [0] * width, 0) if start else getattr(f, cut.fsm_queues[2])
     return uq0, sq0, rq0
 
 
@@ -306,7 +367,8 @@ def closed_form_commitment(cut, commit_fn, io):
     compact[0], compact[1] = int(bool(io.start_flag)), int(bool(io.completion_flag))
     compact[2:6] = commit_fn(cut.obs_in_encoding(io))
     if io.completion_flag:
-        compact[6:10] = commit_fn(np.array(_qs_list(getattr(io, cut.final_queue)), dtype=np.uint64))
+        if cut.final_queue is not None:  # an observable output of `()` commits to zeros
+            compact[6:10] = commit_fn(np.array(_qs_list(getattr(io, cut.final_queue)), dtype=np.uint64))
     else:
         compact[14:18] = commit_fn(cut.fsm_encoding(io.hidden_fsm_output))
     if not io.start_flag:
@@ -338,14 +400,15 @@ def rows_local(cut, run_fn, witness, limit, rank, world, push_offsets):
     u, up, s, sp, extras = cut.arrays(w)
     n_active = min(limit, int(uq0.length), int(sq0.length), len(u), len(s))
     tails_hint = cut.result_tails(w)
-    if world > 1 and (tails_hint is None or push_offsets is None or len(push_offsets) != world):
+    has_rq = _has_result_queue(cut)
+    if world > 1 and has_rq and (tails_hint is None or push_offsets is None or len(push_offsets) != world):
         raise ValueError("a row-sharded run needs the result-queue tail hints and one push offset per rank")
     if world > 1 and n_active < world:
         raise ValueError("fewer active rows than ranks")
     lo, hi = row_range(n_active, rank, world)
     if rank == world - 1:
         hi = limit  # the padding rows after the queues run empty stay with the last rank
-    k_lo = int(push_offsets[rank]) if world > 1 else 0
+    k_lo = int(push_offsets[rank]) if (world > 1 and has_rq) else 0
     io = cut.ClosedForm.from_buffer_copy(bytes(io0))
     sl = lambda a, a0, a1: None if a is None else a[a0:a1]
     args = lambda a0, a1: (sl(u, a0, a1), sl(up, a0, a1), sl(s, a0, a1), sl(sp, a0, a1), tuple(sl(x, a0, a1) for x in extras))
@@ -367,22 +430,28 @@ def rows_local(cut, run_fn, witness, limit, rank, world, push_offsets):
         io.hidden_fsm_input = m.closed_form_input.hidden_fsm_output
         f = io.hidden_fsm_input
         f.lhs_accumulator[0] = f.lhs_accumulator[1] = f.rhs_accumulator[0] = f.rhs_accumulator[1] = 1
-        tail = _np(tails_hint[k_lo - 1:k_lo]).view(np.uint64)[0] if k_lo > 0 else rq0.tail
-        setattr(f, cut.fsm_queues[2], _qs(cut.Queue, rq0.head, tail, int(rq0.length) + k_lo))
+        if has_rq:
+            tail = _np(tails_hint[k_lo - 1:k_lo]).view(np.uint64)[0] if k_lo > 0 else rq0.tail
+            setattr(f, cut.fsm_queues[2], _qs(cut.Queue, rq0.head, tail, int(rq0.length) + k_lo))
+        for _col, field in getattr(cut, "counters", ()):
+            setattr(f, field, 0)  # counted from 0: the lower ranks' counts are added after the exchange
     res = run_fn(io, *args(lo, hi), None if tails_hint is None else tails_hint[k_lo:], hi - lo, True)
     out = res.closed_form_input.hidden_fsm_output
     st = res.status
     failed = int(st.failed_checks)
-    if world > 1:
-        failed &= ~cut.chk["GRAND_PRODUCT"]  # lhs == rhs holds for the WHOLE loop: re-evaluated on the exchanged products
+    if world > 1:  # lhs == rhs (and the counters' final values) hold for the WHOLE loop: re-evaluated after the exchange
+        failed &= ~(cut.masked_checks() if hasattr(cut, "masked_checks") else cut.chk["GRAND_PRODUCT"])
     code = int(st.code) if (failed or st.code != abi.ZKC_ERR_UNSATISFIED) else 0
-    fsm_bytes = np.frombuffer(bytes(out) + bytes(getattr(res.closed_form_input, cut.final_queue)), dtype=np.uint8)
+    fsm_bytes = np.frombuffer(bytes(out) + (bytes(getattr(res.closed_form_input, cut.final_queue)) if cut.final_queue else b""), dtype=np.uint8)
     pad = (-len(fsm_bytes)) % 8
     rec = np.zeros(_LOCAL_WORDS + (len(fsm_bytes) + pad) // 8, dtype=np.int64)
     loc = np.array([out.lhs_accumulator[0], out.rhs_accumulator[0], out.lhs_accumulator[1], out.rhs_accumulator[1]], dtype=np.uint64)
-    pushes_in = int(getattr(io.hidden_fsm_input, cut.fsm_queues[2]).length) if not io.start_flag else 0
     rec[0:4] = loc.view(np.int64)
-    rec[4] = int(getattr(out, cut.fsm_queues[2]).length) - pushes_in  # pushes of this rank's rows (+ the finalisation push on the last)
+    if has_rq:
+        pushes_in = int(getattr(io.hidden_fsm_input, cut.fsm_queues[2]).length) if not io.start_flag else 0
+        rec[4] = int(getattr(out, cut.fsm_queues[2]).length) - pushes_in  # pushes of this rank's rows (+ the finalisation push on the last)
+    for j, (_col, field) in enumerate(getattr(cut, "counters", ())):
+        rec[11 + j] = int(getattr(out, field))  # rank 0 counts from the instance's own value, the others from 0
     rec[5], rec[6], rec[7] = code, failed, int(st.first_bad_row) + lo if st.first_bad_row >= 0 else -1
     rec[8] = int(res.closed_form_input.completion_flag)
     rec[9], rec[10] = lo, hi
@@ -407,13 +476,21 @@ def rows_finish(cut, res, rank, world, records, io0, push_offsets, scale_fn, com
     if rank > 0 and res.trace is not None and any(s != 1 for s in seed):
         scale_fn(res.trace[K["GP_NEW"]:K["GP_NEW"] + 4], np.array(seed, dtype=np.uint64))
         scale_fn(res.trace[K["GP_ACC"]:K["GP_ACC"] + 4], np.array(seed, dtype=np.uint64))
+    counters = getattr(cut, "counters", ())
+    for j, (col, _field) in enumerate(counters):
+        offset = int(sum(int(records[r, 11 + j]) for r in range(rank)))
+        if offset and res.trace is not None:
+            res.trace[K[col]] += offset  # the column is a running count: additive fix-up (numpy and torch both add in place)
     io = cut.ClosedForm.from_buffer_copy(bytes(io0))
     last = records[world - 1]
     fsm_len = C.sizeof(cut.Fsm)
     tail_bytes = last[_LOCAL_WORDS:].view(np.uint8)
     io.hidden_fsm_output = cut.Fsm.from_buffer_copy(tail_bytes[:fsm_len].tobytes())
-    setattr(io, cut.final_queue, cut.Queue.from_buffer_copy(tail_bytes[fsm_len:fsm_len + C.sizeof(cut.Queue)].tobytes()))
+    if cut.final_queue is not None:
+        setattr(io, cut.final_queue, cut.Queue.from_buffer_copy(tail_bytes[fsm_len:fsm_len + C.sizeof(cut.Queue)].tobytes()))
     io.completion_flag = int(last[8])
+    for j, (_col, field) in enumerate(counters):
+        setattr(io.hidden_fsm_output, field, int(sum(int(records[r, 11 + j]) for r in range(world))))
     grand = [1, 1, 1, 1]
     for r in range(world):
         grand = [g * int(t) % GL_P for g, t in zip(grand, totals[r])]
@@ -426,11 +503,14 @@ def rows_finish(cut, res, rank, world, records, io0, push_offsets, scale_fn, com
             code = int(records[r, 5])
         if records[r, 7] >= 0 and first_bad < 0:
             first_bad = int(records[r, 7])
-        if r + 1 < world and int(push_offsets[r]) + int(records[r, 4]) != int(push_offsets[r + 1]):
+        if _has_result_queue(cut) and r + 1 < world and int(push_offsets[r]) + int(records[r, 4]) != int(push_offsets[r + 1]):
             failed |= cut.chk["QUEUE_HINT"]
             code = code or abi.ZKC_ERR_QUEUE_WITNESS_INCONSISTENT
-    if io.completion_flag and (grand[0] != grand[1] or grand[2] != grand[3]):
-        failed |= cut.chk["GRAND_PRODUCT"]
+    if io.completion_flag:
+        if hasattr(cut, "completion_checks"):
+            failed |= cut.completion_checks(io, grand)
+        elif grand[0] != grand[1] or grand[2] != grand[3]:
+            failed |= cut.chk["GRAND_PRODUCT"]
     if failed and not code:
         code = abi.ZKC_ERR_UNSATISFIED
     st = abi.Status()
@@ -470,6 +550,19 @@ def decommit_rows_finish(res, rank, world, records, io0, push_offsets, scale_fn,
 
 def decommit_sorter_closed_form_commitment(commit_fn, io):
     return closed_form_commitment(_DecommitCut(), commit_fn, io)
+
+
+def ram_rows_local(run_fn, witness, limit, rank, world):
+    """rows_local for ram_permutation (no result queue: no push offsets); run_fn(io, u, up, s, sp, limit, want_trace)"""
+    return rows_local(_RamCut(), lambda io, u, up, s, sp, ex, tails, lim, wt: run_fn(io, u, up, s, sp, lim, wt), witness, limit, rank, world, None)
+
+
+def ram_rows_finish(res, rank, world, records, io0, scale_fn, commit_fn):
+    return rows_finish(_RamCut(), res, rank, world, records, io0, None, scale_fn, commit_fn)
+
+
+def ram_closed_form_commitment(commit_fn, io):
+    return closed_form_commitment(_RamCut(), commit_fn, io)
 
 
 def _row_sharded(engine, local_fn, finish_fn, run_fn, witness, limit, rank, world, push_offsets, device):
@@ -523,3 +616,16 @@ def sort_decommittments_row_sharded(engine, witness, limit, rank, world, push_of
         return sort_and_deduplicate_code_decommittments_entry_point(engine, wit, lim, want_trace=want_trace, raise_on_unsatisfied=False)
 
     return _row_sharded(engine, decommit_rows_local, decommit_rows_finish, run_fn, witness, limit, rank, world, push_offsets, device)
+
+
+def ram_permutation_row_sharded(engine, witness, limit, rank, world, device=None):
+    """ram_permutation_entry_point of ONE instance over `world` ranks: as storage_validity_row_sharded, without a result queue and
+    with the non-deterministic-write counter fixed up additively"""
+    from .ram_permutation import RamPermutationCircuitInstanceWitness, ram_permutation_entry_point
+
+    def run_fn(io, u, up, s, sp, lim, want_trace):
+        return ram_permutation_entry_point(engine, RamPermutationCircuitInstanceWitness(io, u, up, s, sp), lim, want_trace=want_trace, raise_on_unsatisfied=False)
+
+    local = lambda rf, w, lim, r, n, _offs: ram_rows_local(rf, w, lim, r, n)
+    finish = lambda res, r, n, recs, io0, _offs, sc, cm: ram_rows_finish(res, r, n, recs, io0, sc, cm)
+    return _row_sharded(engine, local, finish, run_fn, witness, limit, rank, world, None, device)

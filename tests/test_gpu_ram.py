@@ -212,3 +212,38 @@ def test_full_size_properties(engine):
         H.continue_io(a.closed_form_input), du[half:], up[half:], ds[half:], sp[half:]), half, want_trace=False)
     assert H.fsm_equal(b.closed_form_input.hidden_fsm_output, out)
     assert b.commitment.tolist() != r.commitment.tolist()  # different closed forms commit differently
+
+
+def test_one_instance_cut_by_rows_over_ranks(engine, orc):
+    """sharding.ram_rows_local / ram_rows_finish with the ENGINE as the backend, 3 virtual ranks on this GPU (host buffers and device
+    tensors): accumulator columns scaled and the non-deterministic-write counter offset after the exchange; the rank traces
+    concatenate to the whole instance's trace, every rank ends with the whole closed form + commitment"""
+    import torch
+    from era_zkevm_circuits_b200 import sharding
+    n, limit = 6000, 6100
+    u, s = synthetic.ram_trace(n, seed=33, n_cells=80, n_nondet=3500)
+    io, up, sp = H.ram_instance(orc, u, s, 3500)
+    want = O.ram_entry_point(orc, io, u, s, limit)
+    assert want[0] == abi.ZKC_OK
+    world = 3
+
+    def run(io_, u_, up_, s_, sp_, lim, want_trace):
+        return ram_permutation_entry_point(engine, RamPermutationCircuitInstanceWitness(io_, u_, up_, s_, sp_), lim, want_trace=want_trace,
+                                           raise_on_unsatisfied=False)
+
+    commit = lambda e: engine.commit_encoding(np.ascontiguousarray(e, dtype=np.uint64).reshape(1, -1))[0]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)).cuda()
+    i64 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+    for on_dev in (False, True):
+        w = RamPermutationCircuitInstanceWitness(io, dev(u), i64(up), dev(s), i64(sp)) if on_dev else RamPermutationCircuitInstanceWitness(io, u, up, s, sp)
+        locs = [sharding.ram_rows_local(run, w, limit, r, world) for r in range(world)]
+        recs = np.stack([l[3] for l in locs])
+        assert int(recs[:, 11].sum()) == 3500 and np.count_nonzero(recs[:, 11]) >= 2
+        traces = []
+        for r in range(world):
+            com, io_g, trace, st = sharding.ram_rows_finish(locs[r][0], r, world, recs, io, engine.scale_accumulators, commit)
+            assert st.code == 0, (r, st.code, hex(st.failed_checks), st.first_bad_row)
+            assert com.tolist() == want[3].tolist() and bytes(io_g.hidden_fsm_output) == bytes(want[1].hidden_fsm_output)
+            traces.append(trace.cpu().numpy().view(np.uint64) if on_dev else trace)
+        bad = np.argwhere(np.concatenate(traces, axis=1) != want[2])
+        assert bad.size == 0, f"first differing (col,row): {bad[:8].tolist()}"

@@ -287,3 +287,45 @@ def test_row_sharded_decommit_sorter_virtual_ranks():
             assert bytes(io_g.hidden_fsm_output) == bytes(whole[1].hidden_fsm_output) and bytes(io_g.final_queue_state) == bytes(whole[1].final_queue_state)
             traces.append(trace)
         assert np.array_equal(np.concatenate(traces, axis=1), whole[2])
+
+
+def test_row_sharded_ram_permutation_virtual_ranks():
+    """ONE ram_permutation instance cut by rows: no result queue, but a COUNTER in the FSM record (num_nondeterministic_writes): every
+    rank counts from 0 and the column gets the lower ranks' counts added after the exchange.  1800 of the 3000 queries are
+    non-deterministic bootloader writes, so every cut has writes on both sides; 2 and 4 virtual ranks, oracle backend."""
+    sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+    from types import SimpleNamespace
+    import helpers as H
+    import orc as O
+    from era_zkevm_circuits_b200 import RamPermutationCircuitInstanceWitness, abi, sharding, synthetic
+    lib = O.load()
+    n, limit = 3000, 3100
+    u, s = synthetic.ram_trace(n, seed=21, n_cells=50, n_nondet=1800)
+    io, up, sp = H.ram_instance(lib, u, s, 1800)
+    whole = O.ram_entry_point(lib, io, u, s, limit)
+    assert whole[0] == 0 and whole[1].hidden_fsm_output.num_nondeterministic_writes == 1800
+    commit = lambda e: O.commit_encoding(lib, e)
+    assert np.array_equal(sharding.ram_closed_form_commitment(commit, whole[1]), whole[3])
+    w = RamPermutationCircuitInstanceWitness(io, u, up, s, sp)
+
+    def run(io_, u_, up_, s_, sp_, lim, want_trace):
+        rc, io2, trace, com, st = O.ram_entry_point(lib, io_, u_, s_, lim, want_trace=want_trace)
+        return SimpleNamespace(closed_form_input=io2, trace=trace, status=st, commitment=com)
+
+    _, scale, _ = _oracle_backend(lib)
+    for world in (2, 4):
+        locs = [sharding.ram_rows_local(run, w, limit, r, world) for r in range(world)]
+        recs = np.stack([l[3] for l in locs])
+        assert int(recs[:, 11].sum()) == 1800 and np.count_nonzero(recs[:, 11]) >= 2  # counts on both sides of a cut
+        traces = []
+        for r in range(world):
+            com, io_g, trace, st = sharding.ram_rows_finish(locs[r][0], r, world, recs, io, scale, commit)
+            assert st.code == 0 and np.array_equal(com, whole[3]) and bytes(io_g.hidden_fsm_output) == bytes(whole[1].hidden_fsm_output)
+            traces.append(trace)
+        assert np.array_equal(np.concatenate(traces, axis=1), whole[2])
+    # a wrong snapshot length is found on the exchanged counts (the per-rank check is masked: only the sum is meaningful)
+    io_bad = abi.RamClosedForm.from_buffer_copy(bytes(io)); io_bad.observable_input.non_deterministic_bootloader_memory_snapshot_length = 1799
+    w_bad = RamPermutationCircuitInstanceWitness(io_bad, u, up, s, sp)
+    locs = [sharding.ram_rows_local(run, w_bad, limit, r, 2) for r in range(2)]
+    com, io_g, trace, st = sharding.ram_rows_finish(locs[0][0], 0, 2, np.stack([l[3] for l in locs]), io_bad, scale, commit)
+    assert st.code == abi.ZKC_ERR_UNSATISFIED and st.failed_checks == abi.RAM_CHK["NONDET_COUNT"]
