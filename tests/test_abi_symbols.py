@@ -143,3 +143,13 @@ def test_code_unpacker_mirrors_header():
         subprocess.check_call(["gcc", "-o", exe, src])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(abi.CodeDecommittmentFsm), C.sizeof(abi.CodeUnpackerFsm), C.sizeof(abi.CodeUnpackerClosedForm)]
+
+
+def test_evaluator_violation_bits_mirror_header():
+    """the relation-family bits of the ten trace evaluators (ZKC_<X>V_*): abi.py's hand-written dicts against the header's defines"""
+    text = open(os.path.join(ROOT, "include", "zkc_b200.h")).read()
+    for prefix, mirror in (("RAMV", abi.RAMV), ("EVV", abi.EVV), ("STV", abi.STV), ("DQV", abi.DQV), ("DMXV", abi.DMXV), ("SHV", abi.SHV),
+                           ("CUV", abi.CUV), ("LHV", abi.LHV), ("KCV", abi.KCV)):
+        bits = {m.group(1): 1 << int(m.group(2)) for m in re.finditer(r"#define ZKC_%s_([A-Z_]+) \(1u << (\d+)\)" % prefix, text)}
+        assert bits and bits == mirror, (prefix, bits, mirror)
+        assert len(set(bits.values())) == len(bits)
