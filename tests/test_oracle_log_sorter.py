@@ -88,3 +88,45 @@ def test_negative_cases(orc):
     io5, _, _ = instance(orc, u5, s)
     rc, _, _, _, st, _ = O.log_sorter_entry_point(orc, io5, u5, s, 256)
     assert st.failed_checks == CHK["GRAND_PRODUCT"]
+
+
+def test_row_relations_of_the_trace(orc):
+    """The row-to-row relations zkc_log_sorter_check_trace evaluates on the device (ev_check_kernel), restated in numpy and held against
+    the oracle's trace: queue bookkeeping, the timestamp borrow chain, the flag algebra of :327-372, the pushed record, the result
+    queue's length / tail selection.  Pins the evaluator's reading of log_sorter/mod.rs:283-403 without a GPU."""
+    n, limit = 2000, 2100
+    u, s = synthetic.events_trace(n, seed=5, rollback_pct=20)
+    io, _, _ = instance(orc, u, s)
+    rc, out, T, _, st, _ = O.log_sorter_entry_point(orc, io, u, s, limit)
+    assert rc == 0
+    K = abi.EV_COLS
+    col = lambda name, i=0: T[K[name] + i]
+    prev = lambda a, first: np.concatenate([np.array([first], dtype=np.uint64), a[:-1].astype(np.uint64)])
+    pop, emp = col("SHOULD_POP"), col("ORIGINAL_IS_EMPTY")
+    for base, q0 in ((K["UNSORTED_ITEM"], io.initial_log_queue_state), (K["SORTED_ITEM"], io.intermediate_sorted_queue_state)):
+        ln = T[base + 60]
+        assert np.array_equal(ln + pop, prev(ln, q0.length))
+        for i in range(4):
+            h = T[base + 56 + i]
+            assert np.array_equal(h[pop == 0], prev(h, q0.head[i])[pop == 0])
+    S = K["SORTED_ITEM"]
+    ts, rollback = T[S + 35], T[S + 31]
+    diff, borrow, keys_equal = col("CMP_DIFF"), col("CMP_BORROW"), col("KEYS_EQUAL")
+    assert np.array_equal(ts + (borrow << np.uint64(32)), diff + prev(ts, 0)) and np.array_equal(keys_equal, diff == 0)  # current - previous
+    same_nt, diff_nt, ike, ve = col("SAME_NONTRIVIAL_LOG"), col("DIFFERENT_NONTRIVIAL_LOG"), col("ITEM_KEYS_EQUAL"), col("VALUES_EQUAL")
+    keq, veq = np.ones(limit, bool), np.ones(limit, bool)
+    for i in range(8):
+        keq &= T[S + 5 + i] == prev(T[S + 5 + i], 0)
+        veq &= T[S + 21 + i] == prev(T[S + 21 + i], 0)
+    pit = col("PREVIOUS_IS_TRIVIAL")
+    assert np.array_equal(same_nt, pop & keys_equal) and np.array_equal(diff_nt, pop & (1 - keys_equal)) and np.array_equal(ike, keq) and np.array_equal(ve, veq)
+    assert np.array_equal(col("SAME_BODY"), ike & ve) and np.array_equal(pit, prev(emp, 1))
+    should_enforce, maybe_add, add = col("SHOULD_ENFORCE"), col("MAYBE_ADD"), col("ADD_TO_QUEUE")
+    assert np.array_equal(should_enforce, keys_equal & (1 - pit)) and np.array_equal(maybe_add, (1 - keys_equal) | emp)
+    assert np.array_equal(add, (1 - pit) & maybe_add & (1 - prev(rollback, 0)))
+    # enforcements: ascending keys, a fresh key is not a rollback, a repeated key is one with the same body
+    assert not ((pop & borrow) | (diff_nt & rollback) | (same_nt & (1 - rollback)) | (should_enforce & (1 - col("SAME_BODY")))).any()
+    assert np.array_equal(col("RESULT_LEN"), np.cumsum(add))
+    for i in range(4):
+        t = col("RESULT_TAIL", i)
+        assert np.array_equal(t, np.where(add == 1, col("PUSH_ROUND2", i), prev(t, 0)))
