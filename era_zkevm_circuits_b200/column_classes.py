@@ -45,6 +45,22 @@ def _gadget_block():
     return np.array(cls, dtype=np.uint8)
 
 
+def _state_gadget_block():
+    """ZKC_VM_STATE_GADGET_COLUMNS: booleans everywhere except the UInt32 results / selected limbs, the UInt16 jump destination"""
+    u32 = {"PTR_ADD_RESULT", "PTR_SUB_RESULT", "PTR_SHRINK_RESULT", "PTR_LOW_IF_ADD", "PTR_LOW_IF_ADD_OR_SUB", "PTR_96_128_IF_SHRINK", "PTR_HIGHEST_128",
+           "PTR_LOWEST32", "PTR_96_128", "CTX_INCREMENTED_TX_NUMBER", "CTX_META_HIGHEST", "CTX_LOW_U32", "CTX_RESULT_128", "CTX_RESULT_160_THIS",
+           "CTX_RESULT_160_CALLER", "CTX_RESULT_160_CODE", "CTX_RESULT_256"}
+    cls = []
+    for name, width in abi.VMS_WIDTHS.items():
+        if name == "PTR_DST0":
+            cls += [B] + [U32] * 8
+        elif name == "JUMP_DST":
+            cls += [U16]
+        else:
+            cls += [U32 if name in u32 else B] * width
+    return np.array(cls, dtype=np.uint8)
+
+
 TABLES = {
     "ram_permutation": lambda: _table([[B] * 3, MEMORY_ITEM, [F] * 8, [F] * 12, [U32], MEMORY_ITEM, [F] * 8, [F] * 12, [U32], [B] * 3, [U32],
                                        [U32] * 3, [B] * 3, [B] * 3, [B] * 10, [F] * 32, [F] * 4, [F] * 4, [U8] * 24, [F] * 2, [F], [F, F], [F] * 3,
@@ -69,6 +85,7 @@ TABLES = {
                                            abi.CU_COLS["NUM_COLS"]),
     "linear_hasher": lambda: _table([[B] * 2, LOG_ITEM, [F] * 20, [F] * 4, [U32], [B, B], [U8] * 88, [B] * 3, [U32] * 100, [B]], abi.LH_COLS["NUM_COLS"]),
     "main_vm_gadget_cells": _gadget_block,
+    "main_vm_state_gadget_cells": _state_gadget_block,
 }
 
 

@@ -184,6 +184,109 @@ vm_gadgets_kernel(const uint64_t *__restrict__ trace, size_t limit, size_t n_ins
 #undef PUT8
 }
 
+
+// ---- the second block (ZKC_VM_STATE_GADGET_COLUMNS): ptr, jump and context gadgets, which read the state the cycle starts from ------
+//   apply_ptr      /root/reference/src/main_vm/opcodes/ptr.rs:8-183
+//   apply_jump     /root/reference/src/main_vm/opcodes/jump.rs:3-38
+//   apply_context  /root/reference/src/main_vm/opcodes/context.rs:8-307
+// One thread per cycle: 21 coalesced trace columns + 27 words of its snapshot record in, 87 columns out.
+__global__ void __launch_bounds__(128)
+vm_state_gadgets_kernel(const uint64_t *__restrict__ trace, const zkc_vm_state *__restrict__ snapshots, size_t limit, size_t n_instances,
+                        uint64_t *__restrict__ out_all) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= limit * n_instances) return;
+    const size_t inst = g / limit, row = g - inst * limit;
+    const uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit + row;
+    const zkc_vm_state *st = snapshots + inst * (limit + 1) + row;
+    uint64_t *out = out_all + inst * (size_t)ZKC_VMS_NUM_COLS * limit + row;
+#define S(col, i) out[(size_t)((col) + (i)) * limit]
+    const uint64_t props = __ldg(t + (size_t)ZKC_VM_PROPS * limit);
+#define BIT(n) (((props >> (n)) & 1) != 0)
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        a[i] = (uint32_t)__ldg(t + (size_t)(ZKC_VM_SRC0 + 1 + i) * limit); b[i] = (uint32_t)__ldg(t + (size_t)(ZKC_VM_SRC1 + 1 + i) * limit);
+    }
+    const bool a_ptr = __ldg(t + (size_t)ZKC_VM_SRC0 * limit) != 0, b_ptr = __ldg(t + (size_t)ZKC_VM_SRC1 * limit) != 0;
+
+    // ---- ptr.rs ------------------------------------------------------------------------------------------------------------
+    {
+        const bool should_apply = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_PTR));
+        const bool v_add = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_ADD)), v_sub = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_SUB)),
+                   v_pack = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_PACK)), v_shrink = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_SHRINK));
+        const bool src1_is_integer = !b_ptr, args_valid = a_ptr && src1_is_integer, args_invalid = !args_valid;
+        bool hi_zero = true, lo_zero = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const bool z = b[i] == 0;
+            S(ZKC_VMS_PTR_SRC1_LIMB_IS_ZERO, i) = z;
+            if (i >= 1) hi_zero &= z;
+            if (i < 4) lo_zero &= z;
+        }
+        const bool arith = v_add || v_sub, too_large = !hi_zero && arith, dirty_pack = !lo_zero && v_pack;
+        const uint32_t add_r = a[0] + b[0], sub_r = a[0] - b[0], shr_r = a[3] - b[0];
+        const bool add_of = add_r < a[0], sub_uf = a[0] < b[0], shr_uf = a[3] < b[0];
+        const bool add_panic = v_add && add_of, sub_panic = v_sub && sub_uf, shr_panic = v_shrink && shr_uf;
+        const bool any_panic = args_invalid || too_large || dirty_pack || add_panic || sub_panic || shr_panic;
+        const uint32_t low_if_add = v_add ? add_r : a[0], low_if_add_or_sub = v_sub ? sub_r : low_if_add, b96_if_shrink = v_shrink ? shr_r : a[3];
+        const uint32_t lowest32 = v_pack ? a[0] : low_if_add_or_sub, b96 = v_pack ? a[3] : b96_if_shrink;
+        S(ZKC_VMS_PTR_SRC1_IS_INTEGER, 0) = src1_is_integer; S(ZKC_VMS_PTR_ARGS_VALID, 0) = args_valid; S(ZKC_VMS_PTR_ARGS_INVALID, 0) = args_invalid;
+        S(ZKC_VMS_PTR_SRC1_32_256_IS_ZERO, 0) = hi_zero; S(ZKC_VMS_PTR_SRC1_0_128_IS_ZERO, 0) = lo_zero; S(ZKC_VMS_PTR_SRC1_32_256_IS_NONZERO, 0) = !hi_zero;
+        S(ZKC_VMS_PTR_ARITH_VARIANT, 0) = arith; S(ZKC_VMS_PTR_TOO_LARGE_OFFSET, 0) = too_large; S(ZKC_VMS_PTR_SRC1_0_128_IS_NONZERO, 0) = !lo_zero;
+        S(ZKC_VMS_PTR_DIRTY_PACK, 0) = dirty_pack; S(ZKC_VMS_PTR_ADD_RESULT, 0) = add_r; S(ZKC_VMS_PTR_ADD_OF, 0) = add_of; S(ZKC_VMS_PTR_ADD_PANIC, 0) = add_panic;
+        S(ZKC_VMS_PTR_SUB_RESULT, 0) = sub_r; S(ZKC_VMS_PTR_SUB_UF, 0) = sub_uf; S(ZKC_VMS_PTR_SUB_PANIC, 0) = sub_panic;
+        S(ZKC_VMS_PTR_SHRINK_RESULT, 0) = shr_r; S(ZKC_VMS_PTR_SHRINK_UF, 0) = shr_uf; S(ZKC_VMS_PTR_SHRINK_PANIC, 0) = shr_panic;
+        S(ZKC_VMS_PTR_ANY_PANIC, 0) = any_panic; S(ZKC_VMS_PTR_SHOULD_PANIC, 0) = should_apply && any_panic; S(ZKC_VMS_PTR_OK, 0) = !any_panic;
+        S(ZKC_VMS_PTR_UPDATE_REGISTER, 0) = should_apply && !any_panic;
+        S(ZKC_VMS_PTR_LOW_IF_ADD, 0) = low_if_add; S(ZKC_VMS_PTR_LOW_IF_ADD_OR_SUB, 0) = low_if_add_or_sub; S(ZKC_VMS_PTR_96_128_IF_SHRINK, 0) = b96_if_shrink;
+        S(ZKC_VMS_PTR_LOWEST32, 0) = lowest32; S(ZKC_VMS_PTR_96_128, 0) = b96;
+        S(ZKC_VMS_PTR_DST0, 0) = a_ptr; S(ZKC_VMS_PTR_DST0, 1) = lowest32; S(ZKC_VMS_PTR_DST0, 2) = a[1]; S(ZKC_VMS_PTR_DST0, 3) = a[2]; S(ZKC_VMS_PTR_DST0, 4) = b96;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const uint32_t h = v_pack ? b[4 + i] : a[4 + i]; S(ZKC_VMS_PTR_HIGHEST_128, i) = h; S(ZKC_VMS_PTR_DST0, 5 + i) = h; }
+    }
+
+    // ---- jump.rs ---------------------------------------------------------------------------------------------------------
+    S(ZKC_VMS_JUMP_DST, 0) = a[0] & 0xFFFFu;
+
+    // ---- context.rs ------------------------------------------------------------------------------------------------------
+    {
+        const zkc_vm_context *c = &st->current_context;
+        const bool should_apply = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_CONTEXT));
+        const bool is_this = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_THIS)), is_caller = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_CALLER)),
+                   is_code = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_CODE_ADDRESS)), is_meta = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_META)),
+                   is_ergs = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_ERGS_LEFT)), is_get_u128 = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_GET_U128)),
+                   is_set_u128 = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_SET_U128)),
+                   is_set_ergs = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_SET_ERGS_PER_PUBDATA)),
+                   is_inc_tx = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_INC_TX_NUMBER));
+        const bool read_only = is_set_u128 || is_set_ergs || is_inc_tx;
+        S(ZKC_VMS_CTX_WRITE_TO_CONTEXT, 0) = should_apply && is_set_u128; S(ZKC_VMS_CTX_SET_PUBDATA_ERGS, 0) = should_apply && is_set_ergs;
+        S(ZKC_VMS_CTX_INCREMENT_TX, 0) = should_apply && is_inc_tx; S(ZKC_VMS_CTX_READ_ONLY, 0) = read_only; S(ZKC_VMS_CTX_WRITE_LIKE, 0) = !read_only;
+        S(ZKC_VMS_CTX_WRITE_TO_DST0, 0) = should_apply && !read_only;
+        const uint32_t tx = __ldg(&st->tx_number_in_block);
+        S(ZKC_VMS_CTX_INCREMENTED_TX_NUMBER, 0) = tx + 1u; S(ZKC_VMS_CTX_TX_OF, 0) = tx == 0xFFFFFFFFu;
+        const uint32_t meta_hi = (__ldg(&c->this_shard_id) & 0xFFu) | (__ldg(&c->caller_shard_id) & 0xFFu) << 8 | (__ldg(&c->code_shard_id) & 0xFFu) << 16;
+        S(ZKC_VMS_CTX_META_HIGHEST, 0) = meta_hi;
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = 0;
+        r[0] = is_ergs ? (uint32_t)__ldg(t + (size_t)ZKC_VM_DIRTY_ERGS_LEFT * limit) : (uint32_t)__ldg(t + (size_t)ZKC_VM_NEW_SP * limit);
+        S(ZKC_VMS_CTX_LOW_U32, 0) = r[0];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const uint32_t v = __ldg(&c->context_u128_value_composite[i]); if (is_get_u128) r[i] = v; S(ZKC_VMS_CTX_RESULT_128, i) = r[i]; }
+#pragma unroll
+        for (int i = 0; i < 5; i++) { const uint32_t v = __ldg(&c->this_address[i]); if (is_this) r[i] = v; S(ZKC_VMS_CTX_RESULT_160_THIS, i) = r[i]; }
+#pragma unroll
+        for (int i = 0; i < 5; i++) { const uint32_t v = __ldg(&c->caller[i]); if (is_caller) r[i] = v; S(ZKC_VMS_CTX_RESULT_160_CALLER, i) = r[i]; }
+#pragma unroll
+        for (int i = 0; i < 5; i++) { const uint32_t v = __ldg(&c->code_address[i]); if (is_code) r[i] = v; S(ZKC_VMS_CTX_RESULT_160_CODE, i) = r[i]; }
+        const uint32_t meta[8] = {__ldg(&st->ergs_per_pubdata_byte), 0u, __ldg(&c->heap_upper_bound), __ldg(&c->aux_heap_upper_bound), 0u, 0u, 0u, meta_hi};
+#pragma unroll
+        for (int i = 0; i < 8; i++) S(ZKC_VMS_CTX_RESULT_256, i) = is_meta ? meta[i] : r[i];
+    }
+#undef BIT
+#undef S
+}
+
 }  // namespace zkc
 
 using namespace zkc;
@@ -209,6 +312,36 @@ extern "C" int zkc_main_vm_gadget_cells(zkc_ctx *ctx, const uint64_t *trace, siz
     ZKC_LAUNCH(ctx, "vm_gadgets", vm_gadgets_kernel, (unsigned)((rows + 127) / 128), 128, 0, dt, limit, n_instances, dg);
     ZKC_CUDA(ctx, st, cudaGetLastError());
     if (!on_device) ZKC_CUDA(ctx, st, cudaMemcpyAsync(gadget_trace, dg, rows * ZKC_VMG_NUM_COLS * 8, cudaMemcpyDeviceToHost, s));
+    ZKC_CUDA(ctx, st, cudaStreamSynchronize(s));
+    return ZKC_OK;
+}
+
+extern "C" int zkc_main_vm_state_gadget_cells(zkc_ctx *ctx, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances,
+                                              int on_device, uint64_t *gadget_trace) {
+    if (!ctx || ((limit * n_instances) && (!trace || !snapshots || !gadget_trace))) return ZKC_ERR_INVALID_ARGUMENT;
+    const size_t rows = limit * n_instances, n_snaps = (limit + 1) * n_instances;
+    if (!rows) return ZKC_OK;
+    zkc_status *st = nullptr;
+    ZKC_CUDA(ctx, st, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint64_t *dt = trace;
+    const zkc_vm_state *ds = snapshots;
+    uint64_t *dg = gadget_trace;
+    if (!on_device) {
+        char *blk = (char *)ctx->scratch(zkc_carver::bytes(rows * ZKC_VM_NUM_COLS, 8) + zkc_carver::bytes(n_snaps, sizeof(zkc_vm_state)) +
+                                         zkc_carver::bytes(rows * ZKC_VMS_NUM_COLS, 8));
+        if (!blk) return ZKC_ERR_CUDA;
+        zkc_carver cv(blk);
+        uint64_t *bt = cv.take<uint64_t>(rows * ZKC_VM_NUM_COLS);
+        zkc_vm_state *bs = cv.take<zkc_vm_state>(n_snaps);
+        dg = cv.take<uint64_t>(rows * ZKC_VMS_NUM_COLS);
+        ZKC_CUDA(ctx, st, cudaMemcpyAsync(bt, trace, rows * ZKC_VM_NUM_COLS * 8, cudaMemcpyHostToDevice, s));
+        ZKC_CUDA(ctx, st, cudaMemcpyAsync(bs, snapshots, n_snaps * sizeof(zkc_vm_state), cudaMemcpyHostToDevice, s));
+        dt = bt; ds = bs;
+    }
+    ZKC_LAUNCH(ctx, "vm_state_gadgets", vm_state_gadgets_kernel, (unsigned)((rows + 127) / 128), 128, 0, dt, ds, limit, n_instances, dg);
+    ZKC_CUDA(ctx, st, cudaGetLastError());
+    if (!on_device) ZKC_CUDA(ctx, st, cudaMemcpyAsync(gadget_trace, dg, rows * ZKC_VMS_NUM_COLS * 8, cudaMemcpyDeviceToHost, s));
     ZKC_CUDA(ctx, st, cudaStreamSynchronize(s));
     return ZKC_OK;
 }

@@ -208,6 +208,34 @@ def main_vm_gadget_cells(engine: Engine, trace, limit: int, n_instances: int = 1
     return out
 
 
+def main_vm_state_gadget_cells(engine: Engine, trace, snapshots, limit: int, n_instances: int = 1):
+    """The cells the ptr, jump and context gadgets allocate on every cycle whatever the opcode (include/zkc_b200.h,
+    ZKC_VM_STATE_GADGET_COLUMNS; opcodes/ptr.rs:8-183, jump.rs:3-38, context.rs:8-307), from finished DENSE traces
+    [NUM_COLS, limit] / [n, NUM_COLS, limit] and the snapshots the entry point took ([limit + 1] / [n, limit + 1] records,
+    abi.VM_STATE_DTYPE or a byte tensor on the device).  Returns [VMS_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory
+    space of `trace`."""
+    dev = on_device(trace)
+    if dev != on_device(snapshots):
+        raise ZkcError(abi.ZKC_ERR_INVALID_ARGUMENT, what="main_vm_state_gadget_cells: trace and snapshots in different memory spaces")
+    shape = tuple(trace.shape[:-2]) + (abi.VMS_COLS["NUM_COLS"], limit)
+    need = (limit + 1) * n_instances * C.sizeof(abi.VmState)
+    if dev:
+        import torch
+        have = snapshots.numel() * snapshots.element_size()
+        out = torch.empty(shape, dtype=trace.dtype, device=trace.device)
+    else:
+        trace = np.ascontiguousarray(trace, dtype=np.uint64)
+        snapshots = np.ascontiguousarray(snapshots)
+        have = snapshots.nbytes
+        out = np.empty(shape, dtype=np.uint64)
+    if have < need or trace.shape[-2] != abi.VM_COLS["NUM_COLS"] or trace.shape[-1] != limit:
+        raise ZkcError(abi.ZKC_ERR_INVALID_ARGUMENT, what="main_vm_state_gadget_cells: trace / snapshots shorter than limit")
+    rc = engine.lib.zkc_main_vm_state_gadget_cells(engine.h, ptr(trace), ptr(snapshots), limit, n_instances, dev, ptr(out))
+    if rc:
+        raise ZkcError(rc, what="zkc_main_vm_state_gadget_cells")
+    return out
+
+
 # ---- transport forms over PCIe (include/zkc_b200.h, "transport forms of the main_vm call") ---------------------------------
 class VmInputStreamHandle:
     """a zkc_vm_input_stream of ONE instance, in (pinned) host memory owned by the library"""

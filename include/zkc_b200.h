@@ -1575,7 +1575,8 @@ int zkc_main_vm_check_trace(zkc_ctx *ctx, const zkc_vm_isa *isa, const uint64_t 
  *                                  MulDivRelation (candidates mul_div, shifts; opcodes/mod.rs:129-180: 64 (low, high) partial
  *                                  products of UInt32::fma_with_carry + 8 row-end sums)
  * Inputs are the src0 / src1 operand and property-bit columns of the DENSE trace (ZKC_VM_SRC0, ZKC_VM_SRC1, ZKC_VM_PROPS).
- * The UMA, log, context, ptr, jump, nop and call/ret gadgets' non-selected cells are not produced.
+ * The ptr, jump and context gadgets' cells are the second block (zkc_main_vm_state_gadget_cells below); the UMA, log and
+ * call/ret gadgets' non-selected cells are not produced.
  * X(name, width): column ZKC_VMG_<name> .. + width - 1 of the gadget block [ZKC_VMG_NUM_COLS][limit]. */
 #define ZKC_VM_GADGET_COLUMNS(X) \
     X(SRC0_BYTES, 32) X(SRC1_BYTES, 32) \
@@ -1606,6 +1607,44 @@ enum zkc_vm_gadget_col {
 /* trace: DENSE traces [n_instances][ZKC_VM_NUM_COLS][limit] (host, or device with on_device != 0);
  * gadget_trace: out, [n_instances][ZKC_VMG_NUM_COLS][limit] in the same memory space */
 int zkc_main_vm_gadget_cells(zkc_ctx *ctx, const uint64_t *trace, size_t limit, size_t n_instances, int on_device, uint64_t *gadget_trace);
+
+/* ---- cells of the ptr, jump and context opcode gadgets, evaluated OBLIVIOUSLY ------------------------------------------------
+ * The second gadget-cell block: what apply_ptr, apply_jump and apply_context allocate on EVERY cycle whatever the opcode
+ * (apply_nop allocates nothing, opcodes/nop.rs:4-24).  Unlike the arithmetic gadgets these read the VM state the cycle starts
+ * from, so the call takes the per-cycle snapshots next to the finished DENSE trace:
+ *   opcodes/ptr.rs:8-183      operand type / range checks of src1, the three overflowing add / sub results, the panic conditions,
+ *                             the selected limbs and the dst0 candidate (is_pointer of src0 + 8 limbs)
+ *   opcodes/jump.rs:3-38      the UInt16 destination recomposed from the two low bytes of src0
+ *   opcodes/context.rs:8-307  the three state-update flags, read_only / write_like / write_to_dst0, tx_number_in_block + 1, the
+ *                             meta word's highest limb, and the widening select chain low_u32 -> 128 -> 160 (this, caller, code
+ *                             address) -> 256 (meta) that ends in the dst0 candidate
+ * Inputs: ZKC_VM_SRC0 / ZKC_VM_SRC1 (is_pointer + limbs, after swap and fat-pointer erasure), ZKC_VM_PROPS, ZKC_VM_NEW_SP (the
+ * draft state's sp, pre_state.rs:370) and ZKC_VM_DIRTY_ERGS_LEFT (preliminary_ergs_left, pre_state.rs:513) of the DENSE trace;
+ * tx_number_in_block, ergs_per_pubdata_byte and the current context's addresses, shard ids, heap bounds and context_u128 of
+ * snapshot i (pre_state.rs does not touch them).
+ * X(name, width): column ZKC_VMS_<name> .. + width - 1 of the block [ZKC_VMS_NUM_COLS][limit]. */
+#define ZKC_VM_STATE_GADGET_COLUMNS(X) \
+    X(PTR_SRC1_IS_INTEGER, 1) X(PTR_ARGS_VALID, 1) X(PTR_ARGS_INVALID, 1) X(PTR_SRC1_LIMB_IS_ZERO, 8) X(PTR_SRC1_32_256_IS_ZERO, 1) \
+    X(PTR_SRC1_0_128_IS_ZERO, 1) X(PTR_SRC1_32_256_IS_NONZERO, 1) X(PTR_ARITH_VARIANT, 1) X(PTR_TOO_LARGE_OFFSET, 1) \
+    X(PTR_SRC1_0_128_IS_NONZERO, 1) X(PTR_DIRTY_PACK, 1) X(PTR_ADD_RESULT, 1) X(PTR_ADD_OF, 1) X(PTR_ADD_PANIC, 1) \
+    X(PTR_SUB_RESULT, 1) X(PTR_SUB_UF, 1) X(PTR_SUB_PANIC, 1) X(PTR_SHRINK_RESULT, 1) X(PTR_SHRINK_UF, 1) X(PTR_SHRINK_PANIC, 1) \
+    X(PTR_ANY_PANIC, 1) X(PTR_SHOULD_PANIC, 1) X(PTR_OK, 1) X(PTR_UPDATE_REGISTER, 1) X(PTR_LOW_IF_ADD, 1) X(PTR_LOW_IF_ADD_OR_SUB, 1) \
+    X(PTR_96_128_IF_SHRINK, 1) X(PTR_HIGHEST_128, 4) X(PTR_LOWEST32, 1) X(PTR_96_128, 1) X(PTR_DST0, 9) \
+    X(JUMP_DST, 1) \
+    X(CTX_WRITE_TO_CONTEXT, 1) X(CTX_SET_PUBDATA_ERGS, 1) X(CTX_INCREMENT_TX, 1) X(CTX_READ_ONLY, 1) X(CTX_WRITE_LIKE, 1) \
+    X(CTX_WRITE_TO_DST0, 1) X(CTX_INCREMENTED_TX_NUMBER, 1) X(CTX_TX_OF, 1) X(CTX_META_HIGHEST, 1) X(CTX_LOW_U32, 1) \
+    X(CTX_RESULT_128, 4) X(CTX_RESULT_160_THIS, 5) X(CTX_RESULT_160_CALLER, 5) X(CTX_RESULT_160_CODE, 5) X(CTX_RESULT_256, 8)
+enum zkc_vm_state_gadget_col {
+#define ZKC_VMS_X(name, width) ZKC_VMS_##name, ZKC_VMS_##name##_LAST = ZKC_VMS_##name + (width)-1,
+    ZKC_VM_STATE_GADGET_COLUMNS(ZKC_VMS_X)
+#undef ZKC_VMS_X
+    ZKC_VMS_NUM_COLS
+};
+/* trace: DENSE traces [n_instances][ZKC_VM_NUM_COLS][limit]; snapshots: [n_instances][limit + 1] records (the ones
+ * zkc_main_vm_entry_point took); both host, or both device with on_device != 0;
+ * gadget_trace: out, [n_instances][ZKC_VMS_NUM_COLS][limit] in the same memory space */
+int zkc_main_vm_state_gadget_cells(zkc_ctx *ctx, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances,
+                                   int on_device, uint64_t *gadget_trace);
 
 /* the state main_vm_entry_point starts from when start_flag is set: initial_bootloader_state, main_vm/loading.rs:13-226 */
 int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *out);

@@ -437,6 +437,18 @@ inline std::vector<uint64_t> main_vm_gadget_cells(Engine &e, const std::vector<u
     return out;
 }
 
+// the cells the ptr, jump and context gadgets allocate on every cycle (zkc_b200.h, ZKC_VM_STATE_GADGET_COLUMNS), from a finished DENSE
+// trace [ZKC_VM_NUM_COLS][limit] and the [limit + 1] snapshots the entry point took (host)
+inline std::vector<uint64_t> main_vm_state_gadget_cells(Engine &e, const std::vector<uint64_t> &trace, const std::vector<zkc_vm_state> &snapshots,
+                                                        size_t limit) {
+    if (trace.size() < (size_t)ZKC_VM_NUM_COLS * limit || snapshots.size() < limit + 1)
+        throw Error("main_vm_state_gadget_cells", ZKC_ERR_INVALID_ARGUMENT, zkc_status{ZKC_ERR_INVALID_ARGUMENT, 0, -1, 0, 0});
+    std::vector<uint64_t> out((size_t)ZKC_VMS_NUM_COLS * limit);
+    const int rc = zkc_main_vm_state_gadget_cells(e.handle(), trace.data(), snapshots.data(), limit, 1, 0, out.data());
+    if (rc != ZKC_OK) throw Error("zkc_main_vm_state_gadget_cells", rc, zkc_status{rc, 0, -1, 0, 0});
+    return out;
+}
+
 // constraint evaluation of finished traces (host buffers): violating rows; st describes the first one
 inline uint64_t ram_permutation_check_trace(Engine &e, const zkc_ram_closed_form &io, const std::vector<uint64_t> &trace, size_t limit,
                                             uint32_t gates = 0, zkc_status *st = nullptr) {

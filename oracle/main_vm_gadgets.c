@@ -219,3 +219,108 @@ void orc_main_vm_gadget_cells(const uint64_t *trace, size_t limit, size_t n_inst
         }
     }
 }
+
+/* ---- the second block: apply_ptr, apply_jump, apply_context (ZKC_VM_STATE_GADGET_COLUMNS) --------------------------------------
+ *   apply_ptr      /root/reference/src/main_vm/opcodes/ptr.rs:8-183
+ *   apply_jump     /root/reference/src/main_vm/opcodes/jump.rs:3-38
+ *   apply_context  /root/reference/src/main_vm/opcodes/context.rs:8-307
+ *   apply_nop      /root/reference/src/main_vm/opcodes/nop.rs:4-24 (allocates nothing)
+ * Pinning: PARITY UNPINNED against the reference; the values are checked against an independent Python statement
+ * (tests/test_oracle_main_vm_gadgets.py). */
+#define S(col, i) out[(size_t)((col) + (i)) * limit + row]
+static void state_gadget_row(uint64_t props, int a_ptr, const uint32_t *a, int b_ptr, const uint32_t *b, uint32_t new_sp, uint32_t ergs_left,
+                             const zkc_vm_state *st, uint64_t *out, size_t limit, size_t row) {
+#define BIT(n) (int)((props >> (n)) & 1)
+    /* ---- ptr.rs ---- */
+    {
+        const int should_apply = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_PTR));
+        const int v_add = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_ADD)), v_sub = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_SUB)),
+                  v_pack = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_PACK)), v_shrink = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_SHRINK));
+        const int src1_is_integer = !b_ptr;                                   /* :50 */
+        const int args_valid = a_ptr && src1_is_integer, args_invalid = !args_valid;   /* :53-54 */
+        int lz[8], hi_zero = 1, lo_zero = 1;
+        for (int i = 0; i < 8; i++) { lz[i] = b[i] == 0; S(ZKC_VMS_PTR_SRC1_LIMB_IS_ZERO, i) = lz[i]; }
+        for (int i = 1; i < 8; i++) hi_zero &= lz[i];                         /* :61 */
+        for (int i = 0; i < 4; i++) lo_zero &= lz[i];                         /* :62 */
+        const int hi_nonzero = !hi_zero, arith = v_add || v_sub, too_large = hi_nonzero && arith;   /* :64-68 */
+        const int lo_nonzero = !lo_zero, dirty_pack = lo_nonzero && v_pack;   /* :71-73 */
+        const uint64_t sum = (uint64_t)a[0] + b[0];                           /* :76 */
+        const uint32_t add_r = (uint32_t)sum; const int add_of = (int)(sum >> 32), add_panic = v_add && add_of;
+        const uint32_t sub_r = a[0] - b[0]; const int sub_uf = a[0] < b[0], sub_panic = v_sub && sub_uf;          /* :79-80 */
+        const uint32_t shr_r = a[3] - b[0]; const int shr_uf = a[3] < b[0], shr_panic = v_shrink && shr_uf;       /* :82-83 */
+        const int any_panic = args_invalid || too_large || dirty_pack || add_panic || sub_panic || shr_panic;    /* :85-95 */
+        const int should_panic = should_apply && any_panic, ok = !any_panic, update = should_apply && ok;        /* :97-99 */
+        const uint32_t low_if_add = v_add ? add_r : a[0];                     /* :104-109 */
+        const uint32_t low_if_add_or_sub = v_sub ? sub_r : low_if_add;        /* :112-117 */
+        const uint32_t b96_if_shrink = v_shrink ? shr_r : a[3];               /* :120-125 */
+        uint32_t highest[4];
+        for (int i = 0; i < 4; i++) highest[i] = v_pack ? b[4 + i] : a[4 + i];   /* :127-142 */
+        const uint32_t lowest32 = v_pack ? a[0] : low_if_add_or_sub;          /* :144-149 */
+        const uint32_t b96 = v_pack ? a[3] : b96_if_shrink;                   /* :151-156 */
+        S(ZKC_VMS_PTR_SRC1_IS_INTEGER, 0) = src1_is_integer; S(ZKC_VMS_PTR_ARGS_VALID, 0) = args_valid; S(ZKC_VMS_PTR_ARGS_INVALID, 0) = args_invalid;
+        S(ZKC_VMS_PTR_SRC1_32_256_IS_ZERO, 0) = hi_zero; S(ZKC_VMS_PTR_SRC1_0_128_IS_ZERO, 0) = lo_zero; S(ZKC_VMS_PTR_SRC1_32_256_IS_NONZERO, 0) = hi_nonzero;
+        S(ZKC_VMS_PTR_ARITH_VARIANT, 0) = arith; S(ZKC_VMS_PTR_TOO_LARGE_OFFSET, 0) = too_large; S(ZKC_VMS_PTR_SRC1_0_128_IS_NONZERO, 0) = lo_nonzero;
+        S(ZKC_VMS_PTR_DIRTY_PACK, 0) = dirty_pack; S(ZKC_VMS_PTR_ADD_RESULT, 0) = add_r; S(ZKC_VMS_PTR_ADD_OF, 0) = add_of; S(ZKC_VMS_PTR_ADD_PANIC, 0) = add_panic;
+        S(ZKC_VMS_PTR_SUB_RESULT, 0) = sub_r; S(ZKC_VMS_PTR_SUB_UF, 0) = sub_uf; S(ZKC_VMS_PTR_SUB_PANIC, 0) = sub_panic;
+        S(ZKC_VMS_PTR_SHRINK_RESULT, 0) = shr_r; S(ZKC_VMS_PTR_SHRINK_UF, 0) = shr_uf; S(ZKC_VMS_PTR_SHRINK_PANIC, 0) = shr_panic;
+        S(ZKC_VMS_PTR_ANY_PANIC, 0) = any_panic; S(ZKC_VMS_PTR_SHOULD_PANIC, 0) = should_panic; S(ZKC_VMS_PTR_OK, 0) = ok; S(ZKC_VMS_PTR_UPDATE_REGISTER, 0) = update;
+        S(ZKC_VMS_PTR_LOW_IF_ADD, 0) = low_if_add; S(ZKC_VMS_PTR_LOW_IF_ADD_OR_SUB, 0) = low_if_add_or_sub; S(ZKC_VMS_PTR_96_128_IF_SHRINK, 0) = b96_if_shrink;
+        for (int i = 0; i < 4; i++) S(ZKC_VMS_PTR_HIGHEST_128, i) = highest[i];
+        S(ZKC_VMS_PTR_LOWEST32, 0) = lowest32; S(ZKC_VMS_PTR_96_128, 0) = b96;
+        S(ZKC_VMS_PTR_DST0, 0) = a_ptr;                                       /* :158-173 */
+        S(ZKC_VMS_PTR_DST0, 1) = lowest32; S(ZKC_VMS_PTR_DST0, 2) = a[1]; S(ZKC_VMS_PTR_DST0, 3) = a[2]; S(ZKC_VMS_PTR_DST0, 4) = b96;
+        for (int i = 0; i < 4; i++) S(ZKC_VMS_PTR_DST0, 5 + i) = highest[i];
+    }
+    /* ---- jump.rs:27-33: UInt16::from_le_bytes of the two low bytes of src0 ---- */
+    S(ZKC_VMS_JUMP_DST, 0) = a[0] & 0xFFFF;
+    /* ---- context.rs ---- */
+    {
+        const zkc_vm_context *c = &st->current_context;
+        const int should_apply = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_CONTEXT));
+        const int is_this = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_THIS)), is_caller = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_CALLER)),
+                  is_code = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_CODE_ADDRESS)), is_meta = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_META)),
+                  is_ergs = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_ERGS_LEFT)), is_get_u128 = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_GET_U128)),
+                  is_set_u128 = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_SET_U128)),
+                  is_set_ergs = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_SET_ERGS_PER_PUBDATA)), is_inc_tx = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_INC_TX_NUMBER));
+        const int read_only = is_set_u128 || is_set_ergs || is_inc_tx, write_like = !read_only;   /* :113-117 */
+        S(ZKC_VMS_CTX_WRITE_TO_CONTEXT, 0) = should_apply && is_set_u128; S(ZKC_VMS_CTX_SET_PUBDATA_ERGS, 0) = should_apply && is_set_ergs;   /* :108-109 */
+        S(ZKC_VMS_CTX_INCREMENT_TX, 0) = should_apply && is_inc_tx;          /* :110 */
+        S(ZKC_VMS_CTX_READ_ONLY, 0) = read_only; S(ZKC_VMS_CTX_WRITE_LIKE, 0) = write_like; S(ZKC_VMS_CTX_WRITE_TO_DST0, 0) = should_apply && write_like;   /* :119 */
+        const uint64_t tx = (uint64_t)st->tx_number_in_block + 1;            /* :123-126 */
+        S(ZKC_VMS_CTX_INCREMENTED_TX_NUMBER, 0) = (uint32_t)tx; S(ZKC_VMS_CTX_TX_OF, 0) = tx >> 32;
+        const uint32_t meta_hi = (c->this_shard_id & 0xFF) | (c->caller_shard_id & 0xFF) << 8 | (c->code_shard_id & 0xFF) << 16;   /* :138-159 */
+        S(ZKC_VMS_CTX_META_HIGHEST, 0) = meta_hi;
+        uint32_t r[8];
+        memset(r, 0, sizeof r);
+        r[0] = is_ergs ? ergs_left : new_sp;                                  /* :195-208 */
+        S(ZKC_VMS_CTX_LOW_U32, 0) = r[0];
+        if (is_get_u128) memcpy(r, c->context_u128_value_composite, 16);      /* :212-223 */
+        for (int i = 0; i < 4; i++) S(ZKC_VMS_CTX_RESULT_128, i) = r[i];
+        if (is_this) memcpy(r, c->this_address, 20);                          /* :235-246 */
+        for (int i = 0; i < 5; i++) S(ZKC_VMS_CTX_RESULT_160_THIS, i) = r[i];
+        if (is_caller) memcpy(r, c->caller, 20);                              /* :248-259 */
+        for (int i = 0; i < 5; i++) S(ZKC_VMS_CTX_RESULT_160_CALLER, i) = r[i];
+        if (is_code) memcpy(r, c->code_address, 20);                          /* :261-272 */
+        for (int i = 0; i < 5; i++) S(ZKC_VMS_CTX_RESULT_160_CODE, i) = r[i];
+        if (is_meta) {                                                        /* :161-180, :287-288 */
+            r[0] = st->ergs_per_pubdata_byte; r[1] = 0; r[2] = c->heap_upper_bound; r[3] = c->aux_heap_upper_bound;
+            r[4] = r[5] = r[6] = 0; r[7] = meta_hi;
+        }
+        for (int i = 0; i < 8; i++) S(ZKC_VMS_CTX_RESULT_256, i) = r[i];
+    }
+#undef BIT
+}
+
+void orc_main_vm_state_gadget_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out_all) {
+    for (size_t inst = 0; inst < n_instances; inst++) {
+        const uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit;
+        const zkc_vm_state *snaps = snapshots + inst * (limit + 1);
+        uint64_t *out = out_all + inst * (size_t)ZKC_VMS_NUM_COLS * limit;
+        for (size_t row = 0; row < limit; row++) {
+            uint32_t a[8], b[8];
+            for (int i = 0; i < 8; i++) { a[i] = (uint32_t)t[(size_t)(ZKC_VM_SRC0 + 1 + i) * limit + row]; b[i] = (uint32_t)t[(size_t)(ZKC_VM_SRC1 + 1 + i) * limit + row]; }
+            state_gadget_row(t[(size_t)ZKC_VM_PROPS * limit + row], (int)t[(size_t)ZKC_VM_SRC0 * limit + row], a, (int)t[(size_t)ZKC_VM_SRC1 * limit + row], b,
+                             (uint32_t)t[(size_t)ZKC_VM_NEW_SP * limit + row], (uint32_t)t[(size_t)ZKC_VM_DIRTY_ERGS_LEFT * limit + row], snaps + row, out, limit, row);
+        }
+    }
+}

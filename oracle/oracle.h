@@ -134,4 +134,6 @@ int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const
                             uint64_t *trace, uint64_t commitment[4], zkc_status *status);
 /* main_vm_gadgets.c: trace [n_instances][ZKC_VM_NUM_COLS][limit] -> out [n_instances][ZKC_VMG_NUM_COLS][limit] */
 void orc_main_vm_gadget_cells(const uint64_t *trace, size_t limit, size_t n_instances, uint64_t *out);
+/* the ptr / jump / context block: + snapshots [n_instances][limit + 1] -> out [n_instances][ZKC_VMS_NUM_COLS][limit] */
+void orc_main_vm_state_gadget_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out);
 #endif

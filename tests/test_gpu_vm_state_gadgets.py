@@ -1,0 +1,53 @@
+"""zkc_main_vm_state_gadget_cells (the ptr / jump / context gadget-cell block, include/zkc_b200.h ZKC_VM_STATE_GADGET_COLUMNS): CUDA vs
+the oracle (which tests/test_oracle_main_vm_gadgets.py pins on Python integers), host and device buffers, batches of instances."""
+import numpy as np
+import pytest
+
+import orc as O
+from era_zkevm_circuits_b200 import abi, isa as I
+from era_zkevm_circuits_b200.engine import ZkcError
+from test_gpu_main_vm import fresh, with_tail
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,cycles,seed,far", [(1, 1, 1, False), (1, 5000, 2, False), (3, 4097, 3, True)])
+def test_state_gadget_cells_bit_exact(engine, orc, n, cycles, seed, far):
+    import torch
+    from era_zkevm_circuits_b200 import main_vm_state_gadget_cells
+    isa, io, st = fresh(orc)
+    traces, snapshots = [], []
+    for k in range(n):
+        ops = I.random_program(isa, 1024, seed=seed + k, far_calls=far)
+        rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+        assert rc == 0
+        want = O.vm_entry_point(orc, with_tail(io, tail), isa.isa, snaps, wit, cycles, cw=cw)
+        assert want[0] == 0
+        traces.append(want[2])
+        snapshots.append(snaps)
+    trace = np.ascontiguousarray(np.stack(traces))
+    snaps = np.ascontiguousarray(np.stack(snapshots))
+    want = O.vm_state_gadget_cells(orc, trace, snaps, cycles, n)
+    assert want.shape == (n, abi.VMS_COLS["NUM_COLS"], cycles)
+    got = main_vm_state_gadget_cells(engine, trace, snaps, cycles, n)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"first differing (instance, column, row): {bad[:5].tolist()}"
+    dev = main_vm_state_gadget_cells(engine, torch.from_numpy(trace.view(np.int64)).cuda(), torch.from_numpy(snaps).cuda(), cycles, n)
+    assert np.array_equal(dev.cpu().numpy().view(np.uint64), want)
+    # single-instance form: [NUM_COLS, limit] in, [VMS NUM_COLS, limit] out
+    one = main_vm_state_gadget_cells(engine, trace[0], snaps[0], cycles)
+    assert np.array_equal(one, want[0])
+
+
+def test_state_gadget_cells_argument_checks(engine):
+    from era_zkevm_circuits_b200 import main_vm_state_gadget_cells
+    trace = np.zeros((abi.VM_COLS["NUM_COLS"], 8), dtype=np.uint64)
+    with pytest.raises(ZkcError):                                           # 8 snapshots for 8 cycles: one short
+        main_vm_state_gadget_cells(engine, trace, np.zeros((8, 1176), dtype=np.uint8), 8)
+    out = main_vm_state_gadget_cells(engine, trace, np.zeros((9, 1176), dtype=np.uint8), 8)
+    assert out.shape == (abi.VMS_COLS["NUM_COLS"], 8)
+    S = abi.VMS_COLS
+    # all-zero inputs: no opcode applies; src1 = 0 is an integer with every limb zero; the increment of tx_number 0 is 1
+    assert out[S["PTR_SRC1_IS_INTEGER"]].tolist() == [1] * 8 and out[S["PTR_ARGS_INVALID"]].tolist() == [1] * 8
+    assert out[S["PTR_SRC1_LIMB_IS_ZERO"]:S["PTR_SRC1_LIMB_IS_ZERO"] + 8].min() == 1 and out[S["CTX_INCREMENTED_TX_NUMBER"]].tolist() == [1] * 8
+    assert out[S["CTX_WRITE_LIKE"]].tolist() == [1] * 8 and out[S["CTX_RESULT_256"]:S["CTX_RESULT_256"] + 8].max() == 0

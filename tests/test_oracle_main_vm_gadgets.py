@@ -117,3 +117,120 @@ def test_gadget_cells_against_python_integers(orc):
         if t["SHIFT"]:
             assert d0 == val("SHIFT_RESULT")
     assert seen == {"ADD", "SUB", "MUL", "DIV", "SHIFT", "BINOP"}
+
+
+# ---- the second block: ptr / jump / context (ZKC_VM_STATE_GADGET_COLUMNS; oracle/main_vm_gadgets.c state_gadget_row) ------------
+S, SW = abi.VMS_COLS, abi.VMS_WIDTHS
+
+
+def vm_trace_and_snapshots(orc, cycles=4000, seed=33, far=False):
+    isa = I.Isa()
+    io = abi.VmClosedForm(); io.start_flag = 1
+    st = O.vm_initial_state(orc, io, isa.isa)
+    rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(I.random_program(isa, 1024, seed=seed, far_calls=far)), cycles, full=True)
+    assert rc == 0
+    for k in range(4):
+        io.rollback_queue_tail_for_block[k] = int(tail[k])
+    want = O.vm_entry_point(orc, io, isa.isa, snaps, wit, cycles, cw=cw)
+    assert want[0] == 0
+    return want[2], snaps
+
+
+def state_gadget_reference(trace, snaps, r):
+    """apply_ptr / apply_jump / apply_context on Python integers (256-bit operands as ONE integer, not limbs): name -> value(s)"""
+    props = int(trace[K["PROPS"], r])
+    bit = lambda n: (props >> n) & 1
+    var = lambda v: bit(16 + v)                                            # ZKC_VM_BIT_VARIANT
+    a, b = u256(trace, K["SRC0"] + 1, r), u256(trace, K["SRC1"] + 1, r)
+    a_ptr, b_ptr = int(trace[K["SRC0"], r]), int(trace[K["SRC1"], r])
+    M32 = 0xFFFFFFFF
+    out = {}
+    # ptr.rs
+    apply = bit(I.OP_PTR)
+    v_add, v_sub, v_pack, v_shrink = var(0), var(1), var(2), var(3)
+    offset = b & M32
+    out["PTR_SRC1_IS_INTEGER"] = 1 - b_ptr
+    out["PTR_ARGS_VALID"] = int(a_ptr and not b_ptr); out["PTR_ARGS_INVALID"] = 1 - out["PTR_ARGS_VALID"]
+    out["PTR_SRC1_LIMB_IS_ZERO"] = [int((b >> (32 * i)) & M32 == 0) for i in range(8)]
+    out["PTR_SRC1_32_256_IS_ZERO"] = int(b >> 32 == 0); out["PTR_SRC1_32_256_IS_NONZERO"] = int(b >> 32 != 0)
+    out["PTR_SRC1_0_128_IS_ZERO"] = int(b & ((1 << 128) - 1) == 0); out["PTR_SRC1_0_128_IS_NONZERO"] = 1 - out["PTR_SRC1_0_128_IS_ZERO"]
+    out["PTR_ARITH_VARIANT"] = v_add | v_sub
+    out["PTR_TOO_LARGE_OFFSET"] = int(b >> 32 != 0) & (v_add | v_sub)
+    out["PTR_DIRTY_PACK"] = out["PTR_SRC1_0_128_IS_NONZERO"] & v_pack
+    ptr_offset, ptr_len = a & M32, (a >> 96) & M32                        # FatPointer: offset | page | start | length
+    out["PTR_ADD_RESULT"] = (ptr_offset + offset) & M32; out["PTR_ADD_OF"] = (ptr_offset + offset) >> 32
+    out["PTR_SUB_RESULT"] = (ptr_offset - offset) & M32; out["PTR_SUB_UF"] = int(ptr_offset < offset)
+    out["PTR_SHRINK_RESULT"] = (ptr_len - offset) & M32; out["PTR_SHRINK_UF"] = int(ptr_len < offset)
+    out["PTR_ADD_PANIC"] = v_add & out["PTR_ADD_OF"]; out["PTR_SUB_PANIC"] = v_sub & out["PTR_SUB_UF"]; out["PTR_SHRINK_PANIC"] = v_shrink & out["PTR_SHRINK_UF"]
+    panic = int(any(out[k] for k in ("PTR_ARGS_INVALID", "PTR_TOO_LARGE_OFFSET", "PTR_DIRTY_PACK", "PTR_ADD_PANIC", "PTR_SUB_PANIC", "PTR_SHRINK_PANIC")))
+    out["PTR_ANY_PANIC"] = panic; out["PTR_SHOULD_PANIC"] = apply & panic; out["PTR_OK"] = 1 - panic; out["PTR_UPDATE_REGISTER"] = apply & (1 - panic)
+    out["PTR_LOW_IF_ADD"] = out["PTR_ADD_RESULT"] if v_add else ptr_offset
+    out["PTR_LOW_IF_ADD_OR_SUB"] = out["PTR_SUB_RESULT"] if v_sub else out["PTR_LOW_IF_ADD"]
+    out["PTR_96_128_IF_SHRINK"] = out["PTR_SHRINK_RESULT"] if v_shrink else ptr_len
+    hi = (b if v_pack else a) >> 128
+    out["PTR_HIGHEST_128"] = [(hi >> (32 * i)) & M32 for i in range(4)]
+    out["PTR_LOWEST32"] = ptr_offset if v_pack else out["PTR_LOW_IF_ADD_OR_SUB"]
+    out["PTR_96_128"] = ptr_len if v_pack else out["PTR_96_128_IF_SHRINK"]
+    dst = out["PTR_LOWEST32"] | (a & (((1 << 64) - 1) << 32)) | (out["PTR_96_128"] << 96) | (hi << 128)
+    out["PTR_DST0"] = [a_ptr] + [(dst >> (32 * i)) & M32 for i in range(8)]
+    # jump.rs
+    out["JUMP_DST"] = a & 0xFFFF
+    # context.rs
+    st = abi.VmState.from_buffer_copy(snaps[r].tobytes())
+    c = st.current_context
+    apply = bit(I.OP_CONTEXT)
+    is_set = var(7) | var(8) | var(9)
+    out["CTX_WRITE_TO_CONTEXT"] = apply & var(7); out["CTX_SET_PUBDATA_ERGS"] = apply & var(8); out["CTX_INCREMENT_TX"] = apply & var(9)
+    out["CTX_READ_ONLY"] = is_set; out["CTX_WRITE_LIKE"] = 1 - is_set; out["CTX_WRITE_TO_DST0"] = apply & (1 - is_set)
+    out["CTX_INCREMENTED_TX_NUMBER"] = (st.tx_number_in_block + 1) & M32; out["CTX_TX_OF"] = (st.tx_number_in_block + 1) >> 32
+    meta_hi = c.this_shard_id | c.caller_shard_id << 8 | c.code_shard_id << 16
+    out["CTX_META_HIGHEST"] = meta_hi
+    low = int(trace[K["DIRTY_ERGS_LEFT"], r]) if var(4) else int(trace[K["NEW_SP"], r])
+    out["CTX_LOW_U32"] = low
+    word = lambda limbs: sum(int(x) << (32 * i) for i, x in enumerate(limbs))
+    limbs = lambda x, n: [(x >> (32 * i)) & M32 for i in range(n)]
+    res = word(c.context_u128_value_composite) if var(6) else low
+    out["CTX_RESULT_128"] = limbs(res, 4)
+    res = word(c.this_address) if var(0) else res
+    out["CTX_RESULT_160_THIS"] = limbs(res, 5)
+    res = word(c.caller) if var(1) else res
+    out["CTX_RESULT_160_CALLER"] = limbs(res, 5)
+    res = word(c.code_address) if var(2) else res
+    out["CTX_RESULT_160_CODE"] = limbs(res, 5)
+    if var(3):
+        res = st.ergs_per_pubdata_byte | c.heap_upper_bound << 64 | c.aux_heap_upper_bound << 96 | meta_hi << 224
+    out["CTX_RESULT_256"] = limbs(res, 8)
+    return out
+
+
+def test_state_gadget_cells_against_python_integers(orc):
+    assert sum(SW.values()) == S["NUM_COLS"] == 87
+    seen_ops, seen_ctx, seen_ptr = set(), set(), 0
+    for far, seed in ((False, 33), (True, 5)):
+        trace, snaps = vm_trace_and_snapshots(orc, 3000, seed, far)
+        cycles = trace.shape[1]
+        g = O.vm_state_gadget_cells(orc, trace, snaps, cycles)
+        assert g.shape == (S["NUM_COLS"], cycles)
+        for r in range(cycles):
+            want = state_gadget_reference(trace, snaps, r)
+            assert set(want) == set(SW)
+            for name, v in want.items():
+                got = [int(x) for x in g[S[name]:S[name] + SW[name], r]]
+                assert got == (v if isinstance(v, list) else [v]), (r, name, got, v)
+            props = int(trace[K["PROPS"], r])
+            d0 = [int(x) for x in trace[K["DST0"]:K["DST0"] + 9, r]]
+            # the selected path of the DENSE trace is the gadget's own candidate
+            if (props >> I.OP_PTR) & 1:
+                seen_ops.add("PTR")
+                if want["PTR_UPDATE_REGISTER"]:
+                    seen_ptr += 1
+                    assert d0 == want["PTR_DST0"], (r, d0, want["PTR_DST0"])
+            if (props >> I.OP_CONTEXT) & 1:
+                seen_ops.add("CONTEXT")
+                seen_ctx |= {v for v in range(10) if (props >> (16 + v)) & 1}
+                if want["CTX_WRITE_TO_DST0"]:
+                    assert d0 == [0] + want["CTX_RESULT_256"], (r, d0, want["CTX_RESULT_256"])
+            if (props >> I.OP_JUMP) & 1:
+                seen_ops.add("JUMP")
+                assert int(trace[K["PC_OUT"], r]) == want["JUMP_DST"]
+    assert seen_ops == {"PTR", "CONTEXT", "JUMP"} and len(seen_ctx) >= 8 and seen_ptr > 0, (seen_ops, seen_ctx, seen_ptr)
