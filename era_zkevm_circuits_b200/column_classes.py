@@ -61,6 +61,14 @@ def _state_gadget_block():
     return np.array(cls, dtype=np.uint8)
 
 
+def _memory_sponge_block():
+    """ZKC_VM_MEMORY_SPONGE_COLUMNS: field elements (encodings, sponge states) but the SELECTED flag and the three queue lengths"""
+    cls = []
+    for name, width in abi.VMQ_WIDTHS.items():
+        cls += [B if name == "SELECTED" else U32 if name.endswith("_LENGTH_AFTER") else F] * width
+    return np.array(cls, dtype=np.uint8)
+
+
 TABLES = {
     "ram_permutation": lambda: _table([[B] * 3, MEMORY_ITEM, [F] * 8, [F] * 12, [U32], MEMORY_ITEM, [F] * 8, [F] * 12, [U32], [B] * 3, [U32],
                                        [U32] * 3, [B] * 3, [B] * 3, [B] * 10, [F] * 32, [F] * 4, [F] * 4, [U8] * 24, [F] * 2, [F], [F, F], [F] * 3,
@@ -86,6 +94,7 @@ TABLES = {
     "linear_hasher": lambda: _table([[B] * 2, LOG_ITEM, [F] * 20, [F] * 4, [U32], [B, B], [U8] * 88, [B] * 3, [U32] * 100, [B]], abi.LH_COLS["NUM_COLS"]),
     "main_vm_gadget_cells": _gadget_block,
     "main_vm_state_gadget_cells": _state_gadget_block,
+    "main_vm_memory_sponge_cells": _memory_sponge_block,
 }
 
 

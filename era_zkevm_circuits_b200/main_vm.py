@@ -208,16 +208,12 @@ def main_vm_gadget_cells(engine: Engine, trace, limit: int, n_instances: int = 1
     return out
 
 
-def main_vm_state_gadget_cells(engine: Engine, trace, snapshots, limit: int, n_instances: int = 1):
-    """The cells the ptr, jump and context gadgets allocate on every cycle whatever the opcode (include/zkc_b200.h,
-    ZKC_VM_STATE_GADGET_COLUMNS; opcodes/ptr.rs:8-183, jump.rs:3-38, context.rs:8-307), from finished DENSE traces
-    [NUM_COLS, limit] / [n, NUM_COLS, limit] and the snapshots the entry point took ([limit + 1] / [n, limit + 1] records,
-    abi.VM_STATE_DTYPE or a byte tensor on the device).  Returns [VMS_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory
-    space of `trace`."""
+def _trace_and_snapshots_block(engine: Engine, fn_name: str, n_cols: int, trace, snapshots, limit: int, n_instances: int):
+    """shared by the per-cycle blocks computed from finished DENSE traces + the snapshots the entry point took"""
     dev = on_device(trace)
     if dev != on_device(snapshots):
-        raise ZkcError(abi.ZKC_ERR_INVALID_ARGUMENT, what="main_vm_state_gadget_cells: trace and snapshots in different memory spaces")
-    shape = tuple(trace.shape[:-2]) + (abi.VMS_COLS["NUM_COLS"], limit)
+        raise ZkcError(abi.ZKC_ERR_INVALID_ARGUMENT, what=f"{fn_name}: trace and snapshots in different memory spaces")
+    shape = tuple(trace.shape[:-2]) + (n_cols, limit)
     need = (limit + 1) * n_instances * C.sizeof(abi.VmState)
     if dev:
         import torch
@@ -228,12 +224,32 @@ def main_vm_state_gadget_cells(engine: Engine, trace, snapshots, limit: int, n_i
         snapshots = np.ascontiguousarray(snapshots)
         have = snapshots.nbytes
         out = np.empty(shape, dtype=np.uint64)
-    if have < need or trace.shape[-2] != abi.VM_COLS["NUM_COLS"] or trace.shape[-1] != limit:
-        raise ZkcError(abi.ZKC_ERR_INVALID_ARGUMENT, what="main_vm_state_gadget_cells: trace / snapshots shorter than limit")
-    rc = engine.lib.zkc_main_vm_state_gadget_cells(engine.h, ptr(trace), ptr(snapshots), limit, n_instances, dev, ptr(out))
+    rows = 1
+    for d in trace.shape[:-2]:
+        rows *= int(d)
+    if have < need or trace.shape[-2] != abi.VM_COLS["NUM_COLS"] or trace.shape[-1] != limit or rows != n_instances:
+        raise ZkcError(abi.ZKC_ERR_INVALID_ARGUMENT, what=f"{fn_name}: trace / snapshots do not cover n_instances x limit cycles")
+    rc = getattr(engine.lib, fn_name)(engine.h, ptr(trace), ptr(snapshots), limit, n_instances, dev, ptr(out))
     if rc:
-        raise ZkcError(rc, what="zkc_main_vm_state_gadget_cells")
+        raise ZkcError(rc, what=fn_name)
     return out
+
+
+def main_vm_state_gadget_cells(engine: Engine, trace, snapshots, limit: int, n_instances: int = 1):
+    """The cells the ptr, jump and context gadgets allocate on every cycle whatever the opcode (include/zkc_b200.h,
+    ZKC_VM_STATE_GADGET_COLUMNS; opcodes/ptr.rs:8-183, jump.rs:3-38, context.rs:8-307), from finished DENSE traces
+    [NUM_COLS, limit] / [n, NUM_COLS, limit] and the snapshots the entry point took ([limit + 1] / [n, limit + 1] records,
+    abi.VM_STATE_DTYPE or a byte tensor on the device).  Returns [VMS_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory
+    space of `trace`."""
+    return _trace_and_snapshots_block(engine, "zkc_main_vm_state_gadget_cells", abi.VMS_COLS["NUM_COLS"], trace, snapshots, limit, n_instances)
+
+
+def main_vm_memory_sponge_cells(engine: Engine, trace, snapshots, limit: int, n_instances: int = 1):
+    """The three memory-queue relations every cycle evaluates whatever its opcode -- opcode fetch, src0 read, dst0 write
+    (main_vm/utils.rs:128-231, :387-522, cycle.rs:797-905, :937-957): initial state, permutation output, selected tail and length
+    per step (include/zkc_b200.h, ZKC_VM_MEMORY_SPONGE_COLUMNS).  Same arguments as main_vm_state_gadget_cells; returns
+    [VMQ_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory space of `trace`."""
+    return _trace_and_snapshots_block(engine, "zkc_main_vm_memory_sponge_cells", abi.VMQ_COLS["NUM_COLS"], trace, snapshots, limit, n_instances)
 
 
 # ---- transport forms over PCIe (include/zkc_b200.h, "transport forms of the main_vm call") ---------------------------------

@@ -1646,6 +1646,42 @@ enum zkc_vm_state_gadget_col {
 int zkc_main_vm_state_gadget_cells(zkc_ctx *ctx, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances,
                                    int on_device, uint64_t *gadget_trace);
 
+/* ---- the memory-queue relations every cycle evaluates, OBLIVIOUSLY -------------------------------------------------------------
+ * Three of the nine Poseidon2 relations of a cycle do not belong to an opcode gadget: the opcode fetch, the src0 read and the dst0
+ * write.  The reference builds each one on EVERY cycle whatever the access flag -- the query is encoded, absorbed with replacement
+ * into the current memory-queue tail (initial_state = encoding || tail[8..12]), the permutation computed, and the new tail / length
+ * SELECTED by the flag:
+ *   may_be_read_memory_for_code             main_vm/utils.rs:128-231   (R::compute_round_function on every cycle, :205)
+ *   may_be_read_memory_for_source_operand   main_vm/utils.rs:387-522   (initial_state :475-488, selects :496-508)
+ *   may_be_write_memory                     main_vm/cycle.rs:797-905   (initial_state :873-886, selects :894-905)
+ *   enforce_sponges                         main_vm/cycle.rs:937-957   (true_final = R(initial_state) of the candidate selected
+ *                                                                       for the slot, cycle.rs:673-721)
+ * The DENSE trace (zkc_vm_col) holds a slot's permutation output only when the relation is ENFORCED (ZKC_VM_SPONGE_ENFORCE);
+ * this block holds, for every cycle, the three initial states, R(initial_state), the selected tail and length after each step.
+ * A memory value that is not read is zero (the oracle's answer for execute = false).  SELECTED = 1 when slots 1 / 2 of
+ * enforce_sponges evaluate these two candidates, i.e. no opcode with its own sponges applies (UMA, log, near_call, far_call, ret:
+ * cycle.rs:681-721 -- then the slot's in-circuit permutation runs on the opcode's candidate and SRC0_FINAL / DST0_FINAL here are
+ * not cells of the reference; INIT / STATE_AFTER / LENGTH_AFTER are on every cycle).  The fetch's permutation is a cell on every
+ * cycle.  The remaining six slots depend on the non-selected cells of those gadgets (not produced).
+ * Inputs: SHOULD_READ_OPCODE, SUPER_PC, CODE_WORD, SRC0_PAGE / INDEX, SHOULD_READ_SRC0, SRC0_FROM_MEMORY, DST0_PAGE / INDEX,
+ * PERFORM_DST0_MEMORY_WRITE, DST0, PROPS of the DENSE trace; timestamp, code_page, memory_queue_state / length of snapshot i.
+ * X(name, width): column ZKC_VMQ_<name> .. + width - 1 of the block [ZKC_VMQ_NUM_COLS][limit]. */
+#define ZKC_VM_MEMORY_SPONGE_COLUMNS(X) \
+    X(SELECTED, 1) \
+    X(FETCH_INIT, 12) X(FETCH_FINAL, 12) X(FETCH_STATE_AFTER, 12) X(FETCH_LENGTH_AFTER, 1) \
+    X(SRC0_INIT, 12) X(SRC0_FINAL, 12) X(SRC0_STATE_AFTER, 12) X(SRC0_LENGTH_AFTER, 1) \
+    X(DST0_INIT, 12) X(DST0_FINAL, 12) X(DST0_STATE_AFTER, 12) X(DST0_LENGTH_AFTER, 1)
+enum zkc_vm_memory_sponge_col {
+#define ZKC_VMQ_X(name, width) ZKC_VMQ_##name, ZKC_VMQ_##name##_LAST = ZKC_VMQ_##name + (width)-1,
+    ZKC_VM_MEMORY_SPONGE_COLUMNS(ZKC_VMQ_X)
+#undef ZKC_VMQ_X
+    ZKC_VMQ_NUM_COLS
+};
+/* trace: DENSE traces [n_instances][ZKC_VM_NUM_COLS][limit]; snapshots: [n_instances][limit + 1] records; both host, or both
+ * device with on_device != 0; sponge_trace: out, [n_instances][ZKC_VMQ_NUM_COLS][limit] in the same memory space */
+int zkc_main_vm_memory_sponge_cells(zkc_ctx *ctx, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances,
+                                    int on_device, uint64_t *sponge_trace);
+
 /* the state main_vm_entry_point starts from when start_flag is set: initial_bootloader_state, main_vm/loading.rs:13-226 */
 int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *out);
 

@@ -324,3 +324,63 @@ void orc_main_vm_state_gadget_cells(const uint64_t *trace, const zkc_vm_state *s
         }
     }
 }
+
+/* ---- the memory-queue relations of every cycle (ZKC_VM_MEMORY_SPONGE_COLUMNS): opcode fetch, src0 read, dst0 write --------------
+ *   may_be_read_memory_for_code             /root/reference/src/main_vm/utils.rs:128-231
+ *   may_be_read_memory_for_source_operand   /root/reference/src/main_vm/utils.rs:387-522
+ *   may_be_write_memory                     /root/reference/src/main_vm/cycle.rs:797-905
+ *   enforce_sponges                         /root/reference/src/main_vm/cycle.rs:937-957
+ * Pinning: PARITY UNPINNED (Poseidon2 has no known-answer vector in the reference); checked against the second Python
+ * restatement of the permutation and against the DENSE trace's own enforced slots (tests/test_oracle_main_vm_gadgets.py). */
+static void memq_step(const uint64_t enc[8], int execute, uint64_t state[12], uint32_t *len, uint64_t *out, size_t limit, size_t row, int col_init) {
+    uint64_t s[12];
+    memcpy(s, enc, 64); memcpy(s + 8, state + 8, 32);                      /* absorb with replacement */
+    for (int i = 0; i < 12; i++) out[(size_t)(col_init + i) * limit + row] = s[i];
+    orc_poseidon2_permutation(s);
+    for (int i = 0; i < 12; i++) out[(size_t)(col_init + 12 + i) * limit + row] = s[i];
+    if (execute) { memcpy(state, s, 96); (*len)++; }                       /* Num::parallel_select / UInt32::conditionally_select */
+    for (int i = 0; i < 12; i++) out[(size_t)(col_init + 24 + i) * limit + row] = state[i];
+    out[(size_t)(col_init + 36) * limit + row] = *len;
+}
+
+void orc_main_vm_memory_sponge_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out_all) {
+    for (size_t inst = 0; inst < n_instances; inst++) {
+        const uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit;
+        const zkc_vm_state *snaps = snapshots + inst * (limit + 1);
+        uint64_t *out = out_all + inst * (size_t)ZKC_VMQ_NUM_COLS * limit;
+        for (size_t row = 0; row < limit; row++) {
+#define T(c) t[(size_t)(c) * limit + row]
+            const zkc_vm_state *st = snaps + row;
+            const uint64_t props = T(ZKC_VM_PROPS);
+            uint64_t state[12], enc[8];
+            uint32_t len = st->memory_queue_length;
+            memcpy(state, st->memory_queue_state, 96);
+            out[(size_t)ZKC_VMQ_SELECTED * limit + row] =
+                !(((props >> ZKC_VM_BIT_TYPE(ZKC_OP_UMA)) | (props >> ZKC_VM_BIT_TYPE(ZKC_OP_LOG)) | (props >> ZKC_VM_BIT_TYPE(ZKC_OP_NEAR_CALL)) |
+                   (props >> ZKC_VM_BIT_TYPE(ZKC_OP_FAR_CALL)) | (props >> ZKC_VM_BIT_TYPE(ZKC_OP_RET))) & 1);
+            zkc_memory_query q;
+            /* opcode fetch: pre_state.rs:135-171; the word read is CODE_WORD when the read happens, zero otherwise */
+            memset(&q, 0, sizeof q);
+            const int read_opcode = (int)T(ZKC_VM_SHOULD_READ_OPCODE);
+            q.timestamp = st->timestamp; q.memory_page = st->current_context.code_page; q.index = (uint32_t)T(ZKC_VM_SUPER_PC);
+            for (int i = 0; i < 8; i++) q.value[i] = read_opcode ? (uint32_t)T(ZKC_VM_CODE_WORD + i) : 0u;
+            orc_memory_query_encode(&q, enc);
+            memq_step(enc, read_opcode, state, &len, out, limit, row, ZKC_VMQ_FETCH_INIT);
+            /* src0 read: pre_state.rs:373-395, the same timestamp */
+            memset(&q, 0, sizeof q);
+            q.timestamp = st->timestamp; q.memory_page = (uint32_t)T(ZKC_VM_SRC0_PAGE); q.index = (uint32_t)T(ZKC_VM_SRC0_INDEX);
+            q.is_ptr = (uint32_t)T(ZKC_VM_SRC0_FROM_MEMORY) & 1;
+            for (int i = 0; i < 8; i++) q.value[i] = (uint32_t)T(ZKC_VM_SRC0_FROM_MEMORY + 1 + i);
+            orc_memory_query_encode(&q, enc);
+            memq_step(enc, (int)T(ZKC_VM_SHOULD_READ_SRC0), state, &len, out, limit, row, ZKC_VMQ_SRC0_INIT);
+            /* dst0 write: cycle.rs:248-284, timestamp_for_dst_write = timestamp + 3 (pre_state.rs:137-143) */
+            memset(&q, 0, sizeof q);
+            q.timestamp = st->timestamp + 3; q.memory_page = (uint32_t)T(ZKC_VM_DST0_PAGE); q.index = (uint32_t)T(ZKC_VM_DST0_INDEX);
+            q.rw_flag = 1; q.is_ptr = (uint32_t)T(ZKC_VM_DST0) & 1;
+            for (int i = 0; i < 8; i++) q.value[i] = (uint32_t)T(ZKC_VM_DST0 + 1 + i);
+            orc_memory_query_encode(&q, enc);
+            memq_step(enc, (int)T(ZKC_VM_PERFORM_DST0_MEMORY_WRITE), state, &len, out, limit, row, ZKC_VMQ_DST0_INIT);
+#undef T
+        }
+    }
+}

@@ -136,4 +136,6 @@ int orc_main_vm_entry_point(zkc_vm_closed_form *io, const zkc_vm_isa *isa, const
 void orc_main_vm_gadget_cells(const uint64_t *trace, size_t limit, size_t n_instances, uint64_t *out);
 /* the ptr / jump / context block: + snapshots [n_instances][limit + 1] -> out [n_instances][ZKC_VMS_NUM_COLS][limit] */
 void orc_main_vm_state_gadget_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out);
+/* the fetch / src0 read / dst0 write memory-queue relations of every cycle -> out [n_instances][ZKC_VMQ_NUM_COLS][limit] */
+void orc_main_vm_memory_sponge_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out);
 #endif

@@ -433,3 +433,15 @@ def vm_state_gadget_cells(lib, trace, snaps, limit, n_instances=1):
     lib.orc_main_vm_state_gadget_cells.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp]
     lib.orc_main_vm_state_gadget_cells(p(trace), p(snaps), limit, n_instances, p(out))
     return out
+
+
+def vm_memory_sponge_cells(lib, trace, snaps, limit, n_instances=1):
+    """orc_main_vm_memory_sponge_cells: DENSE trace(s) + snapshots [n?, limit + 1] -> [n?, VMQ_COLS.NUM_COLS, limit]"""
+    trace = np.ascontiguousarray(trace, dtype=np.uint64)
+    snaps = np.ascontiguousarray(snaps)
+    assert snaps.nbytes >= (limit + 1) * n_instances * C.sizeof(abi.VmState)
+    out = np.zeros(tuple(trace.shape[:-2]) + (abi.VMQ_COLS["NUM_COLS"], limit), dtype=np.uint64)
+    lib.orc_main_vm_memory_sponge_cells.restype = None
+    lib.orc_main_vm_memory_sponge_cells.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp]
+    lib.orc_main_vm_memory_sponge_cells(p(trace), p(snaps), limit, n_instances, p(out))
+    return out

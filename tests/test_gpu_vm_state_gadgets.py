@@ -51,3 +51,36 @@ def test_state_gadget_cells_argument_checks(engine):
     assert out[S["PTR_SRC1_IS_INTEGER"]].tolist() == [1] * 8 and out[S["PTR_ARGS_INVALID"]].tolist() == [1] * 8
     assert out[S["PTR_SRC1_LIMB_IS_ZERO"]:S["PTR_SRC1_LIMB_IS_ZERO"] + 8].min() == 1 and out[S["CTX_INCREMENTED_TX_NUMBER"]].tolist() == [1] * 8
     assert out[S["CTX_WRITE_LIKE"]].tolist() == [1] * 8 and out[S["CTX_RESULT_256"]:S["CTX_RESULT_256"] + 8].max() == 0
+
+
+@pytest.mark.parametrize("n,cycles,seed,far", [(1, 1, 1, False), (1, 5000, 2, False), (3, 4097, 3, True)])
+def test_memory_sponge_cells_bit_exact(engine, orc, n, cycles, seed, far):
+    """zkc_main_vm_memory_sponge_cells: the fetch / src0 read / dst0 write relations of every cycle (three chained Poseidon2
+    permutations per cycle), CUDA vs the oracle, host and device buffers, batches; and against the engine's OWN dense trace: wherever
+    a slot is enforced there, the permutation output is the same value"""
+    import torch
+    from era_zkevm_circuits_b200 import main_vm_memory_sponge_cells
+    isa, io, st = fresh(orc)
+    traces, snapshots = [], []
+    for k in range(n):
+        ops = I.random_program(isa, 1024, seed=seed + k, far_calls=far)
+        rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+        assert rc == 0
+        want = O.vm_entry_point(orc, with_tail(io, tail), isa.isa, snaps, wit, cycles, cw=cw)
+        assert want[0] == 0
+        traces.append(want[2])
+        snapshots.append(snaps)
+    trace = np.ascontiguousarray(np.stack(traces))
+    snaps = np.ascontiguousarray(np.stack(snapshots))
+    want = O.vm_memory_sponge_cells(orc, trace, snaps, cycles, n)
+    got = main_vm_memory_sponge_cells(engine, trace, snaps, cycles, n)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"first differing (instance, column, row): {bad[:5].tolist()}"
+    dev = main_vm_memory_sponge_cells(engine, torch.from_numpy(trace.view(np.int64)).cuda(), torch.from_numpy(snaps).cuda(), cycles, n)
+    assert np.array_equal(dev.cpu().numpy().view(np.uint64), want)
+    K, Q = abi.VM_COLS, abi.VMQ_COLS
+    for slot, name in enumerate(("FETCH", "SRC0", "DST0")):
+        enforced = (trace[:, K["SPONGE_ENFORCE"] + slot] != 0) & ((got[:, Q["SELECTED"]] != 0) | (slot == 0))
+        a = trace[:, K["SPONGE_FINAL"] + 12 * slot:K["SPONGE_FINAL"] + 12 * slot + 12]
+        b = got[:, Q[name + "_FINAL"]:Q[name + "_FINAL"] + 12]
+        assert np.array_equal(a.transpose(0, 2, 1)[enforced], b.transpose(0, 2, 1)[enforced]), name

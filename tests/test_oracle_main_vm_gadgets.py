@@ -234,3 +234,73 @@ def test_state_gadget_cells_against_python_integers(orc):
                 seen_ops.add("JUMP")
                 assert int(trace[K["PC_OUT"], r]) == want["JUMP_DST"]
     assert seen_ops == {"PTR", "CONTEXT", "JUMP"} and len(seen_ctx) >= 8 and seen_ptr > 0, (seen_ops, seen_ctx, seen_ptr)
+
+
+# ---- the memory-queue relations of every cycle (ZKC_VM_MEMORY_SPONGE_COLUMNS; oracle/main_vm_gadgets.c memq_step) -------------
+Q, QW = abi.VMQ_COLS, abi.VMQ_WIDTHS
+
+
+def memory_query_encoding(ts, page, index, rw, is_ptr, value):
+    """MemoryQuery::encode (base_structures/memory_query/mod.rs:103-221) from the 256-bit value as ONE integer: bytes of limbs 5-7
+    spread over the high halves of the elements that carry limbs 0-3"""
+    limb = lambda i: (value >> (32 * i)) & 0xFFFFFFFF
+    byte = lambda i, k: (limb(i) >> (8 * k)) & 0xFF
+    return [ts, page, index | rw << 32 | is_ptr << 33,
+            limb(0) | byte(5, 0) << 32 | byte(5, 1) << 40 | byte(5, 2) << 48,
+            limb(1) | byte(5, 3) << 32 | byte(6, 0) << 40 | byte(6, 1) << 48,
+            limb(2) | byte(6, 2) << 32 | byte(6, 3) << 40 | byte(7, 0) << 48,
+            limb(3) | byte(7, 1) << 32 | byte(7, 2) << 40 | byte(7, 3) << 48,
+            limb(4)]
+
+
+def test_memory_sponge_cells_against_python_and_the_dense_trace(orc):
+    import ref_poseidon2 as R
+    assert sum(QW.values()) == Q["NUM_COLS"] == 112
+    rc_ = R.constants()
+    own = (1 << I.OP_UMA) | (1 << I.OP_LOG) | (1 << I.OP_NEAR_CALL) | (1 << I.OP_FAR_CALL) | (1 << I.OP_RET)
+    seen = dict(fetch=0, fetch_skipped=0, src0=0, dst0=0, not_selected=0)
+    for far, seed, cycles in ((False, 33, 2500), (True, 5, 2500)):
+        trace, snaps = vm_trace_and_snapshots(orc, cycles, seed, far)
+        g = O.vm_memory_sponge_cells(orc, trace, snaps, cycles)
+        assert g.shape == (Q["NUM_COLS"], cycles)
+        col = lambda name, r, n=12: [int(x) for x in g[Q[name]:Q[name] + n, r]]
+        for r in range(cycles):
+            st, nxt = O.vm_state_at(snaps, r), O.vm_state_at(snaps, r + 1)
+            props = int(trace[K["PROPS"], r])
+            selected = int(props & own == 0)
+            assert int(g[Q["SELECTED"], r]) == selected
+            seen["not_selected"] += 1 - selected
+            state, length = [int(x) for x in st.memory_queue_state], st.memory_queue_length
+            steps = (
+                ("FETCH", 0, int(trace[K["SHOULD_READ_OPCODE"], r]),
+                 (st.timestamp, st.current_context.code_page, int(trace[K["SUPER_PC"], r]), 0, 0,
+                  u256(trace, K["CODE_WORD"], r) if int(trace[K["SHOULD_READ_OPCODE"], r]) else 0)),
+                ("SRC0", 1, int(trace[K["SHOULD_READ_SRC0"], r]),
+                 (st.timestamp, int(trace[K["SRC0_PAGE"], r]), int(trace[K["SRC0_INDEX"], r]), 0, int(trace[K["SRC0_FROM_MEMORY"], r]),
+                  u256(trace, K["SRC0_FROM_MEMORY"] + 1, r))),
+                ("DST0", 2, int(trace[K["PERFORM_DST0_MEMORY_WRITE"], r]),
+                 (st.timestamp + 3, int(trace[K["DST0_PAGE"], r]), int(trace[K["DST0_INDEX"], r]), 1, int(trace[K["DST0"], r]),
+                  u256(trace, K["DST0"] + 1, r))),
+            )
+            for name, slot, execute, query in steps:
+                init = memory_query_encoding(*query) + state[8:]
+                assert col(name + "_INIT", r) == init, (r, name)
+                final = col(name + "_FINAL", r)
+                # the permutation itself: the second Python restatement on a sample of rows, the DENSE trace's own slot wherever
+                # the relation is enforced there (every executed access of a cycle without an opcode that brings its own sponges)
+                if r % 40 == slot:
+                    assert R.permutation(init, rc_) == final, (r, name)
+                enforced = int(trace[K["SPONGE_ENFORCE"] + slot, r])
+                if slot == 0 or selected:
+                    assert enforced == execute, (r, name, enforced, execute)
+                    if enforced:
+                        assert [int(x) for x in trace[K["SPONGE_FINAL"] + 12 * slot:K["SPONGE_FINAL"] + 12 * slot + 12, r]] == final, (r, name)
+                if execute:
+                    state, length = final, length + 1
+                    seen[name.lower()] += 1
+                elif slot == 0:
+                    seen["fetch_skipped"] += 1
+                assert col(name + "_STATE_AFTER", r) == state and int(g[Q[name + "_LENGTH_AFTER"], r]) == length, (r, name)
+            if selected:  # no opcode touches the memory queue afterwards: this is the next cycle's queue
+                assert state == [int(x) for x in nxt.memory_queue_state] and length == nxt.memory_queue_length == int(trace[K["MEMQ_LENGTH_OUT"], r]), r
+    assert min(seen.values()) > 0, seen

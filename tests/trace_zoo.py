@@ -55,4 +55,5 @@ def oracle_traces(orc):
     r = O.vm_entry_point(orc, vio, isa.isa, snaps, wit, 2000, cw=cw); assert r[0] == 0
     out["main_vm_gadget_cells"] = O.vm_gadget_cells(orc, r[2], 2000)
     out["main_vm_state_gadget_cells"] = O.vm_state_gadget_cells(orc, r[2], snaps, 2000)
+    out["main_vm_memory_sponge_cells"] = O.vm_memory_sponge_cells(orc, r[2], snaps, 2000)
     return out
