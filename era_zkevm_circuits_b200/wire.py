@@ -10,6 +10,8 @@ default options: little-endian, fixed-width integers, u64 sequence lengths) prod
     CodeDecommitterCircuitInstanceWitness  /root/reference/src/code_unpacker_sha256/input.rs:134-140
     LogDemuxerCircuitInstanceWitness       /root/reference/src/demux_log_queue/input.rs:118-121
     LinearHasherCircuitInstanceWitness     /root/reference/src/linear_hasher/input.rs:71-80
+    VmCircuitWitness (its closed_form_input; the witness oracle W is a type the HARNESS defines, see read_vm_circuit_witness)
+                                           /root/reference/src/fsm_input_output/circuit_inputs/main_vm.rs:9-71
 
 read into the host-side witness forms of this package (closed-form struct + struct-of-arrays queue witnesses), and written
 back (test_harness-style dumps for the round-trip tests).
@@ -51,6 +53,9 @@ class Reader:
 
     def u8(self):
         return self.take(1)[0]
+
+    def u16(self):
+        return struct.unpack("<H", self.take(2))[0]
 
     def u32(self):
         return struct.unpack("<I", self.take(4))[0]
@@ -101,6 +106,7 @@ class Writer:
         self.b = bytearray()
 
     def u8(self, v): self.b.append(int(v) & 0xFF)
+    def u16(self, v): self.b += struct.pack("<H", int(v))
     def u32(self, v): self.b += struct.pack("<I", int(v))
     def u64(self, v): self.b += struct.pack("<Q", int(v))
     def boolean(self, v): self.u8(1 if v else 0)
@@ -782,3 +788,155 @@ def write_linear_hasher_witness(w_) -> bytes:
     w.b += bytes(int(b) & 0xFF for b in io.keccak256_hash)
     _write_log_queue(w, w_.queue_witness, w_.queue_prev_tails)
     return bytes(w.b)
+
+
+# ---- main_vm -----------------------------------------------------------------------------------------------------------------
+# VmLocalStateWitness: base_structures/vm_state/mod.rs:92-109 (field order = declaration order); Callstack :callstack.rs:17-21,
+# FullExecutionContext callstack.rs:45-49, ExecutionContextRecord saved_context.rs:36-59, VMRegister register/mod.rs:21-24.
+# UInt256 -> U256 (hex string), UInt160 -> Address (40 hex digits), UInt32 / UInt16 / UInt8 -> u32 / u16 / u8, Boolean -> bool.
+def _read_vm_context_record(r: Reader, c):
+    for name in ("this_address", "caller", "code_address"):
+        for i, v in enumerate(_limbs(r.h160(), 5)):
+            getattr(c, name)[i] = v
+    c.code_page, c.base_page, c.heap_upper_bound, c.aux_heap_upper_bound = r.u32(), r.u32(), r.u32(), r.u32()
+    for i, v in enumerate(r.fields(4)):
+        c.reverted_queue_head[i] = v
+    for i, v in enumerate(r.fields(4)):
+        c.reverted_queue_tail[i] = v
+    c.reverted_queue_segment_len = r.u32()
+    c.pc, c.sp, c.exception_handler_loc = r.u16(), r.u16(), r.u16()
+    c.ergs_remaining = r.u32()
+    c.is_static_execution, c.is_kernel_mode = r.boolean(), r.boolean()
+    c.this_shard_id, c.caller_shard_id, c.code_shard_id = r.u8(), r.u8(), r.u8()
+    for i in range(4):
+        c.context_u128_value_composite[i] = r.u32()
+    c.is_local_call = r.boolean()
+
+
+def _write_vm_context_record(w: Writer, c):
+    for name in ("this_address", "caller", "code_address"):
+        w.h160(_from_limbs(getattr(c, name)))
+    for v in (c.code_page, c.base_page, c.heap_upper_bound, c.aux_heap_upper_bound):
+        w.u32(v)
+    w.fields(c.reverted_queue_head); w.fields(c.reverted_queue_tail)
+    w.u32(c.reverted_queue_segment_len)
+    w.u16(c.pc); w.u16(c.sp); w.u16(c.exception_handler_loc)
+    w.u32(c.ergs_remaining)
+    w.boolean(c.is_static_execution); w.boolean(c.is_kernel_mode)
+    w.u8(c.this_shard_id); w.u8(c.caller_shard_id); w.u8(c.code_shard_id)
+    for v in c.context_u128_value_composite:
+        w.u32(v)
+    w.boolean(c.is_local_call)
+
+
+def _read_vm_state(r: Reader, st):
+    for i, v in enumerate(_limbs(r.u256(), 8)):
+        st.previous_code_word[i] = v
+    for k in range(15):
+        st.registers[k].is_pointer = r.boolean()
+        for i, v in enumerate(_limbs(r.u256(), 8)):
+            st.registers[k].value[i] = v
+    for i in range(3):
+        st.flags[i] = r.boolean()
+    st.timestamp, st.memory_page_counter, st.tx_number_in_block, st.previous_code_page = r.u32(), r.u32(), r.u32(), r.u32()
+    st.previous_super_pc = r.u16()
+    st.pending_exception = r.boolean()
+    st.ergs_per_pubdata_byte = r.u32()
+    # callstack: current_context { saved_context, log_queue_forward_tail, log_queue_forward_part_length }, depth, sponge state
+    _read_vm_context_record(r, st.current_context)
+    for i, v in enumerate(r.fields(4)):
+        st.current_context.log_queue_forward_tail[i] = v
+    st.current_context.log_queue_forward_part_length = r.u32()
+    st.context_stack_depth = r.u32()
+    for i, v in enumerate(r.fields(12)):
+        st.stack_sponge_state[i] = v
+    for i, v in enumerate(r.fields(12)):
+        st.memory_queue_state[i] = v
+    st.memory_queue_length = r.u32()
+    for i, v in enumerate(r.fields(12)):
+        st.code_decommittment_queue_state[i] = v
+    st.code_decommittment_queue_length = r.u32()
+    for i in range(4):
+        st.context_composite_u128[i] = r.u32()
+
+
+def _write_vm_state(w: Writer, st):
+    w.u256(_from_limbs(st.previous_code_word))
+    for k in range(15):
+        w.boolean(st.registers[k].is_pointer)
+        w.u256(_from_limbs(st.registers[k].value))
+    for i in range(3):
+        w.boolean(st.flags[i])
+    for v in (st.timestamp, st.memory_page_counter, st.tx_number_in_block, st.previous_code_page):
+        w.u32(v)
+    w.u16(st.previous_super_pc)
+    w.boolean(st.pending_exception)
+    w.u32(st.ergs_per_pubdata_byte)
+    _write_vm_context_record(w, st.current_context)
+    w.fields(st.current_context.log_queue_forward_tail)
+    w.u32(st.current_context.log_queue_forward_part_length)
+    w.u32(st.context_stack_depth)
+    w.fields(st.stack_sponge_state)
+    w.fields(st.memory_queue_state); w.u32(st.memory_queue_length)
+    w.fields(st.code_decommittment_queue_state); w.u32(st.code_decommittment_queue_length)
+    for v in st.context_composite_u128:
+        w.u32(v)
+
+
+def read_vm_closed_form_input(r: Reader):
+    """VmCircuitInputOutputWitness = ClosedFormInputWitness<F, VmLocalState, VmInputData, VmOutputData>
+    (fsm_input_output/circuit_inputs/main_vm.rs:9-61, fsm_input_output/mod.rs:32-48) from an open Reader -> abi.VmClosedForm"""
+    io = abi.VmClosedForm()
+    io.start_flag, io.completion_flag = r.boolean(), r.boolean()
+    # observable_input: VmInputData
+    for i, v in enumerate(r.fields(4)):
+        io.rollback_queue_tail_for_block[i] = v
+    for i, v in enumerate(r.fields(12)):
+        io.memory_queue_initial_tail[i] = v
+    io.memory_queue_initial_length = r.u32()
+    for i, v in enumerate(r.fields(12)):
+        io.decommitment_queue_initial_tail[i] = v
+    io.decommitment_queue_initial_length = r.u32()
+    io.zkporter_is_available = r.boolean()                                  # per_block_context: GlobalContext, vm_state/mod.rs:159-162
+    for i, v in enumerate(_limbs(r.u256(), 8)):
+        io.default_aa_code_hash[i] = v
+    # observable_output: VmOutputData
+    _read_queue_state(r, io.log_queue_final_state)
+    _read_queue_state(r, io.memory_queue_final_state)
+    _read_queue_state(r, io.decommitment_queue_final_state)
+    _read_vm_state(r, io.hidden_fsm_input)
+    _read_vm_state(r, io.hidden_fsm_output)
+    return io
+
+
+def write_vm_closed_form_input(w: Writer, io):
+    w.boolean(io.start_flag); w.boolean(io.completion_flag)
+    w.fields(io.rollback_queue_tail_for_block)
+    w.fields(io.memory_queue_initial_tail); w.u32(io.memory_queue_initial_length)
+    w.fields(io.decommitment_queue_initial_tail); w.u32(io.decommitment_queue_initial_length)
+    w.boolean(io.zkporter_is_available)
+    w.u256(_from_limbs(io.default_aa_code_hash))
+    _write_queue_state(w, io.log_queue_final_state)
+    _write_queue_state(w, io.memory_queue_final_state)
+    _write_queue_state(w, io.decommitment_queue_final_state)
+    _write_vm_state(w, io.hidden_fsm_input)
+    _write_vm_state(w, io.hidden_fsm_output)
+
+
+def read_vm_circuit_witness(data: bytes, read_oracle=None):
+    """bincode bytes of VmCircuitWitness<GoldilocksField, W> (circuit_inputs/main_vm.rs:64-71): `closed_form_input` followed by
+    `witness_oracle: W`.  W is whatever type the harness implements WitnessOracle with -- it is not defined in the reference crate
+    -- so its bytes are handed to `read_oracle(reader)` (which must consume them; its result is returned next to the closed form).
+    With read_oracle = None the dump must end after the closed form (a W that serialises to nothing, e.g. a unit placeholder).
+    The engine's own per-cycle form of the oracle's answers is zkc_vm_cycle_witness."""
+    r = Reader(data)
+    io = read_vm_closed_form_input(r)
+    oracle = read_oracle(r) if read_oracle is not None else None
+    r.done()
+    return io, oracle
+
+
+def write_vm_circuit_witness(io, oracle_bytes: bytes = b"") -> bytes:
+    w = Writer()
+    write_vm_closed_form_input(w, io)
+    return bytes(w.b) + bytes(oracle_bytes)

@@ -250,3 +250,59 @@ def test_log_demuxer_and_linear_hasher_dump_round_trips(orc):
     assert got.queue_witness.tobytes() == msgs.tobytes() and np.array_equal(got.queue_prev_tails, mprev)
     again = O.linear_hasher_entry_point(orc, got.closed_form_input, got.queue_witness, 210)
     assert again[0] == 0 and np.array_equal(again[3], done[3])
+
+
+def test_main_vm_closed_form_dump_round_trip_and_ingestion(orc):
+    """VmCircuitWitness.closed_form_input (circuit_inputs/main_vm.rs:9-71): byte layout of the leading fields assembled by hand, a
+    write -> read round trip of a closed form whose FSM output sits inside a far call (non-trivial context, callstack sponge, queue
+    states), the oracle W handed to a caller-supplied reader, and the ingested closed form chaining the next instance exactly like
+    the original"""
+    from era_zkevm_circuits_b200 import isa as I
+    isa = I.Isa()
+    io = abi.VmClosedForm(); io.start_flag = 1
+    io.memory_queue_initial_tail[11] = 5; io.memory_queue_initial_length = 7
+    io.zkporter_is_available = 1
+    io.default_aa_code_hash[0], io.default_aa_code_hash[7] = 0x1234, 0x0100_0000
+    st0 = O.vm_initial_state(orc, io, isa.isa)
+    cycles, first = 3000, 1700
+    rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st0, I.pack_code(I.random_program(isa, 1024, seed=3, far_calls=True)), cycles, full=True)
+    assert rc == 0
+    for k in range(4):
+        io.rollback_queue_tail_for_block[k] = int(tail[k])
+    a = O.vm_entry_point(orc, io, isa.isa, snaps[:first + 1], wit[:first], first, cw=cw)
+    assert a[0] == 0
+    done = a[1]                                                            # closed form after the first instance (FSM output filled in)
+    assert done.hidden_fsm_output.context_stack_depth >= 1 and any(done.hidden_fsm_output.stack_sponge_state)
+    dump = wire.write_vm_circuit_witness(done)
+    # start_flag, completion_flag, rollback tail (4 field elements), memory queue tail (12) + length u32
+    assert dump[:2] == bytes([1, done.completion_flag]) and dump[2:34] == b"".join(struct.pack("<Q", int(x)) for x in tail)
+    assert dump[34:34 + 96] == bytes(88) + struct.pack("<Q", 5) and dump[130:134] == struct.pack("<I", 7)
+    # decommitment tail (12) + length, then GlobalContext: bool + U256 as a hex string without leading zeros
+    o = 134 + 96 + 4
+    aa = "0x1000000" + "0" * 48 + "00001234"
+    assert dump[o:o + 1] == b"\x01" and dump[o + 1:o + 9] == struct.pack("<Q", len(aa)) and dump[o + 9:o + 9 + len(aa)] == aa.encode()
+    got, oracle = wire.read_vm_circuit_witness(dump)
+    assert oracle is None and wire.write_vm_circuit_witness(got) == dump
+    for name, _ in abi.VmState._fields_:
+        if name == "_pad":
+            continue
+        x, y = getattr(got.hidden_fsm_output, name), getattr(done.hidden_fsm_output, name)
+        assert bytes(x) == bytes(y) if hasattr(x, "_length_") or hasattr(x, "_fields_") else x == y, name
+    assert bytes(got.memory_queue_final_state) == bytes(done.memory_queue_final_state)
+    # W: whatever follows the closed form belongs to the harness' oracle type
+    tagged, oracle = wire.read_vm_circuit_witness(dump + b"\x07\x00\x00\x00", read_oracle=lambda r: r.u32())
+    assert oracle == 7 and wire.write_vm_circuit_witness(tagged) == dump
+    with pytest.raises(wire.WireError):
+        wire.read_vm_circuit_witness(dump + b"\x00")                       # trailing bytes without a reader for W
+    with pytest.raises(wire.WireError):
+        wire.read_vm_circuit_witness(dump[:-3])
+    bad = bytearray(dump); bad[0] = 2
+    with pytest.raises(wire.WireError):
+        wire.read_vm_circuit_witness(bytes(bad))
+    # ingestion: the next instance chained from the INGESTED closed form commits like the one chained from the original
+    def chained(src):
+        nxt = abi.VmClosedForm.from_buffer_copy(bytes(src)); nxt.start_flag = 0
+        nxt.hidden_fsm_input = src.hidden_fsm_output
+        return O.vm_entry_point(orc, nxt, isa.isa, snaps[first:], wit[first:], cycles - first, cw=cw)
+    want, have = chained(done), chained(got)
+    assert want[0] == have[0] == 0 and have[3].tolist() == want[3].tolist() and np.array_equal(have[2], want[2])
