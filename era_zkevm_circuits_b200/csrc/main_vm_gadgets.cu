@@ -186,9 +186,9 @@ vm_gadgets_kernel(const uint64_t *__restrict__ trace, size_t limit, size_t n_ins
 
 
 // ---- the second block (ZKC_VM_STATE_GADGET_COLUMNS): ptr, jump and context gadgets, which read the state the cycle starts from ------
-//   apply_ptr      /root/reference/src/main_vm/opcodes/ptr.rs:8-183
+//   apply_ptr      /root/reference/src/main_vm/opcodes/ptr.rs:6-183
 //   apply_jump     /root/reference/src/main_vm/opcodes/jump.rs:3-38
-//   apply_context  /root/reference/src/main_vm/opcodes/context.rs:8-307
+//   apply_context  /root/reference/src/main_vm/opcodes/context.rs:7-307
 // One thread per cycle: 21 coalesced trace columns + 27 words of its snapshot record in, 87 columns out.
 __global__ void __launch_bounds__(128)
 vm_state_gadgets_kernel(const uint64_t *__restrict__ trace, const zkc_vm_state *__restrict__ snapshots, size_t limit, size_t n_instances,

@@ -1,9 +1,9 @@
 // The memory-queue relations every main_vm cycle evaluates whatever its opcode (include/zkc_b200.h, ZKC_VM_MEMORY_SPONGE_COLUMNS):
 // opcode fetch, src0 read, dst0 write -- query encoding absorbed with replacement into the running memory-queue tail, the
 // Poseidon2 permutation of that initial state, the tail / length selected by the access flag.
-//   may_be_read_memory_for_code             /root/reference/src/main_vm/utils.rs:128-231
-//   may_be_read_memory_for_source_operand   /root/reference/src/main_vm/utils.rs:387-522
-//   may_be_write_memory                     /root/reference/src/main_vm/cycle.rs:797-905
+//   may_be_read_memory_for_code             /root/reference/src/main_vm/utils.rs:129-233
+//   may_be_read_memory_for_source_operand   /root/reference/src/main_vm/utils.rs:388-522
+//   may_be_write_memory                     /root/reference/src/main_vm/cycle.rs:799-935
 //   enforce_sponges                         /root/reference/src/main_vm/cycle.rs:937-957
 // One thread per cycle: three DEPENDENT permutations (the tail of one step is the capacity of the next), so the kernel is bound by
 // the integer pipe like every other Poseidon2 kernel of the engine (3 x ~19 k instructions per cycle); 41 trace columns + 27

@@ -237,7 +237,7 @@ def _trace_and_snapshots_block(engine: Engine, fn_name: str, n_cols: int, trace,
 
 def main_vm_state_gadget_cells(engine: Engine, trace, snapshots, limit: int, n_instances: int = 1):
     """The cells the ptr, jump and context gadgets allocate on every cycle whatever the opcode (include/zkc_b200.h,
-    ZKC_VM_STATE_GADGET_COLUMNS; opcodes/ptr.rs:8-183, jump.rs:3-38, context.rs:8-307), from finished DENSE traces
+    ZKC_VM_STATE_GADGET_COLUMNS; opcodes/ptr.rs:6-183, jump.rs:3-38, context.rs:7-307), from finished DENSE traces
     [NUM_COLS, limit] / [n, NUM_COLS, limit] and the snapshots the entry point took ([limit + 1] / [n, limit + 1] records,
     abi.VM_STATE_DTYPE or a byte tensor on the device).  Returns [VMS_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory
     space of `trace`."""
@@ -246,7 +246,7 @@ def main_vm_state_gadget_cells(engine: Engine, trace, snapshots, limit: int, n_i
 
 def main_vm_memory_sponge_cells(engine: Engine, trace, snapshots, limit: int, n_instances: int = 1):
     """The three memory-queue relations every cycle evaluates whatever its opcode -- opcode fetch, src0 read, dst0 write
-    (main_vm/utils.rs:128-231, :387-522, cycle.rs:797-905, :937-957): initial state, permutation output, selected tail and length
+    (main_vm/utils.rs:129-233, :388-522, cycle.rs:799-935, :937-957): initial state, permutation output, selected tail and length
     per step (include/zkc_b200.h, ZKC_VM_MEMORY_SPONGE_COLUMNS).  Same arguments as main_vm_state_gadget_cells; returns
     [VMQ_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory space of `trace`."""
     return _trace_and_snapshots_block(engine, "zkc_main_vm_memory_sponge_cells", abi.VMQ_COLS["NUM_COLS"], trace, snapshots, limit, n_instances)

@@ -1612,10 +1612,10 @@ int zkc_main_vm_gadget_cells(zkc_ctx *ctx, const uint64_t *trace, size_t limit, 
  * The second gadget-cell block: what apply_ptr, apply_jump and apply_context allocate on EVERY cycle whatever the opcode
  * (apply_nop allocates nothing, opcodes/nop.rs:4-24).  Unlike the arithmetic gadgets these read the VM state the cycle starts
  * from, so the call takes the per-cycle snapshots next to the finished DENSE trace:
- *   opcodes/ptr.rs:8-183      operand type / range checks of src1, the three overflowing add / sub results, the panic conditions,
+ *   opcodes/ptr.rs:6-183      operand type / range checks of src1, the three overflowing add / sub results, the panic conditions,
  *                             the selected limbs and the dst0 candidate (is_pointer of src0 + 8 limbs)
  *   opcodes/jump.rs:3-38      the UInt16 destination recomposed from the two low bytes of src0
- *   opcodes/context.rs:8-307  the three state-update flags, read_only / write_like / write_to_dst0, tx_number_in_block + 1, the
+ *   opcodes/context.rs:7-307  the three state-update flags, read_only / write_like / write_to_dst0, tx_number_in_block + 1, the
  *                             meta word's highest limb, and the widening select chain low_u32 -> 128 -> 160 (this, caller, code
  *                             address) -> 256 (meta) that ends in the dst0 candidate
  * Inputs: ZKC_VM_SRC0 / ZKC_VM_SRC1 (is_pointer + limbs, after swap and fat-pointer erasure), ZKC_VM_PROPS, ZKC_VM_NEW_SP (the
@@ -1651,9 +1651,9 @@ int zkc_main_vm_state_gadget_cells(zkc_ctx *ctx, const uint64_t *trace, const zk
  * write.  The reference builds each one on EVERY cycle whatever the access flag -- the query is encoded, absorbed with replacement
  * into the current memory-queue tail (initial_state = encoding || tail[8..12]), the permutation computed, and the new tail / length
  * SELECTED by the flag:
- *   may_be_read_memory_for_code             main_vm/utils.rs:128-231   (R::compute_round_function on every cycle, :205)
- *   may_be_read_memory_for_source_operand   main_vm/utils.rs:387-522   (initial_state :475-488, selects :496-508)
- *   may_be_write_memory                     main_vm/cycle.rs:797-905   (initial_state :873-886, selects :894-905)
+ *   may_be_read_memory_for_code             main_vm/utils.rs:129-233   (R::compute_round_function on every cycle, :212)
+ *   may_be_read_memory_for_source_operand   main_vm/utils.rs:388-522   (initial_state :479-492, selects :499-511)
+ *   may_be_write_memory                     main_vm/cycle.rs:799-935   (initial_state :871-884, selects :891-903)
  *   enforce_sponges                         main_vm/cycle.rs:937-957   (true_final = R(initial_state) of the candidate selected
  *                                                                       for the slot, cycle.rs:673-721)
  * The DENSE trace (zkc_vm_col) holds a slot's permutation output only when the relation is ENFORCED (ZKC_VM_SPONGE_ENFORCE);

@@ -221,9 +221,9 @@ void orc_main_vm_gadget_cells(const uint64_t *trace, size_t limit, size_t n_inst
 }
 
 /* ---- the second block: apply_ptr, apply_jump, apply_context (ZKC_VM_STATE_GADGET_COLUMNS) --------------------------------------
- *   apply_ptr      /root/reference/src/main_vm/opcodes/ptr.rs:8-183
+ *   apply_ptr      /root/reference/src/main_vm/opcodes/ptr.rs:6-183
  *   apply_jump     /root/reference/src/main_vm/opcodes/jump.rs:3-38
- *   apply_context  /root/reference/src/main_vm/opcodes/context.rs:8-307
+ *   apply_context  /root/reference/src/main_vm/opcodes/context.rs:7-307
  *   apply_nop      /root/reference/src/main_vm/opcodes/nop.rs:4-24 (allocates nothing)
  * Pinning: PARITY UNPINNED against the reference; the values are checked against an independent Python statement
  * (tests/test_oracle_main_vm_gadgets.py). */
@@ -236,27 +236,27 @@ static void state_gadget_row(uint64_t props, int a_ptr, const uint32_t *a, int b
         const int should_apply = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_PTR));
         const int v_add = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_ADD)), v_sub = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_SUB)),
                   v_pack = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_PACK)), v_shrink = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_PTR_SHRINK));
-        const int src1_is_integer = !b_ptr;                                   /* :50 */
-        const int args_valid = a_ptr && src1_is_integer, args_invalid = !args_valid;   /* :53-54 */
+        const int src1_is_integer = !b_ptr;                                   /* :53 */
+        const int args_valid = a_ptr && src1_is_integer, args_invalid = !args_valid;   /* :56-57 */
         int lz[8], hi_zero = 1, lo_zero = 1;
         for (int i = 0; i < 8; i++) { lz[i] = b[i] == 0; S(ZKC_VMS_PTR_SRC1_LIMB_IS_ZERO, i) = lz[i]; }
-        for (int i = 1; i < 8; i++) hi_zero &= lz[i];                         /* :61 */
-        for (int i = 0; i < 4; i++) lo_zero &= lz[i];                         /* :62 */
-        const int hi_nonzero = !hi_zero, arith = v_add || v_sub, too_large = hi_nonzero && arith;   /* :64-68 */
-        const int lo_nonzero = !lo_zero, dirty_pack = lo_nonzero && v_pack;   /* :71-73 */
-        const uint64_t sum = (uint64_t)a[0] + b[0];                           /* :76 */
+        for (int i = 1; i < 8; i++) hi_zero &= lz[i];                         /* :64 */
+        for (int i = 0; i < 4; i++) lo_zero &= lz[i];                         /* :65 */
+        const int hi_nonzero = !hi_zero, arith = v_add || v_sub, too_large = hi_nonzero && arith;   /* :67-71 */
+        const int lo_nonzero = !lo_zero, dirty_pack = lo_nonzero && v_pack;   /* :74-76 */
+        const uint64_t sum = (uint64_t)a[0] + b[0];                           /* :79 */
         const uint32_t add_r = (uint32_t)sum; const int add_of = (int)(sum >> 32), add_panic = v_add && add_of;
-        const uint32_t sub_r = a[0] - b[0]; const int sub_uf = a[0] < b[0], sub_panic = v_sub && sub_uf;          /* :79-80 */
-        const uint32_t shr_r = a[3] - b[0]; const int shr_uf = a[3] < b[0], shr_panic = v_shrink && shr_uf;       /* :82-83 */
-        const int any_panic = args_invalid || too_large || dirty_pack || add_panic || sub_panic || shr_panic;    /* :85-95 */
-        const int should_panic = should_apply && any_panic, ok = !any_panic, update = should_apply && ok;        /* :97-99 */
-        const uint32_t low_if_add = v_add ? add_r : a[0];                     /* :104-109 */
-        const uint32_t low_if_add_or_sub = v_sub ? sub_r : low_if_add;        /* :112-117 */
-        const uint32_t b96_if_shrink = v_shrink ? shr_r : a[3];               /* :120-125 */
+        const uint32_t sub_r = a[0] - b[0]; const int sub_uf = a[0] < b[0], sub_panic = v_sub && sub_uf;          /* :82-83 */
+        const uint32_t shr_r = a[3] - b[0]; const int shr_uf = a[3] < b[0], shr_panic = v_shrink && shr_uf;       /* :85-86 */
+        const int any_panic = args_invalid || too_large || dirty_pack || add_panic || sub_panic || shr_panic;    /* :88-98 */
+        const int should_panic = should_apply && any_panic, ok = !any_panic, update = should_apply && ok;        /* :100-102 */
+        const uint32_t low_if_add = v_add ? add_r : a[0];                     /* :107-112 */
+        const uint32_t low_if_add_or_sub = v_sub ? sub_r : low_if_add;        /* :115-120 */
+        const uint32_t b96_if_shrink = v_shrink ? shr_r : a[3];               /* :123-128 */
         uint32_t highest[4];
-        for (int i = 0; i < 4; i++) highest[i] = v_pack ? b[4 + i] : a[4 + i];   /* :127-142 */
-        const uint32_t lowest32 = v_pack ? a[0] : low_if_add_or_sub;          /* :144-149 */
-        const uint32_t b96 = v_pack ? a[3] : b96_if_shrink;                   /* :151-156 */
+        for (int i = 0; i < 4; i++) highest[i] = v_pack ? b[4 + i] : a[4 + i];   /* :130-145 */
+        const uint32_t lowest32 = v_pack ? a[0] : low_if_add_or_sub;          /* :147-152 */
+        const uint32_t b96 = v_pack ? a[3] : b96_if_shrink;                   /* :154-159 */
         S(ZKC_VMS_PTR_SRC1_IS_INTEGER, 0) = src1_is_integer; S(ZKC_VMS_PTR_ARGS_VALID, 0) = args_valid; S(ZKC_VMS_PTR_ARGS_INVALID, 0) = args_invalid;
         S(ZKC_VMS_PTR_SRC1_32_256_IS_ZERO, 0) = hi_zero; S(ZKC_VMS_PTR_SRC1_0_128_IS_ZERO, 0) = lo_zero; S(ZKC_VMS_PTR_SRC1_32_256_IS_NONZERO, 0) = hi_nonzero;
         S(ZKC_VMS_PTR_ARITH_VARIANT, 0) = arith; S(ZKC_VMS_PTR_TOO_LARGE_OFFSET, 0) = too_large; S(ZKC_VMS_PTR_SRC1_0_128_IS_NONZERO, 0) = lo_nonzero;
@@ -267,7 +267,7 @@ static void state_gadget_row(uint64_t props, int a_ptr, const uint32_t *a, int b
         S(ZKC_VMS_PTR_LOW_IF_ADD, 0) = low_if_add; S(ZKC_VMS_PTR_LOW_IF_ADD_OR_SUB, 0) = low_if_add_or_sub; S(ZKC_VMS_PTR_96_128_IF_SHRINK, 0) = b96_if_shrink;
         for (int i = 0; i < 4; i++) S(ZKC_VMS_PTR_HIGHEST_128, i) = highest[i];
         S(ZKC_VMS_PTR_LOWEST32, 0) = lowest32; S(ZKC_VMS_PTR_96_128, 0) = b96;
-        S(ZKC_VMS_PTR_DST0, 0) = a_ptr;                                       /* :158-173 */
+        S(ZKC_VMS_PTR_DST0, 0) = a_ptr;                                       /* :161-176 */
         S(ZKC_VMS_PTR_DST0, 1) = lowest32; S(ZKC_VMS_PTR_DST0, 2) = a[1]; S(ZKC_VMS_PTR_DST0, 3) = a[2]; S(ZKC_VMS_PTR_DST0, 4) = b96;
         for (int i = 0; i < 4; i++) S(ZKC_VMS_PTR_DST0, 5 + i) = highest[i];
     }
@@ -282,27 +282,27 @@ static void state_gadget_row(uint64_t props, int a_ptr, const uint32_t *a, int b
                   is_ergs = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_ERGS_LEFT)), is_get_u128 = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_GET_U128)),
                   is_set_u128 = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_SET_U128)),
                   is_set_ergs = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_SET_ERGS_PER_PUBDATA)), is_inc_tx = BIT(ZKC_VM_BIT_VARIANT(ZKC_VAR_CONTEXT_INC_TX_NUMBER));
-        const int read_only = is_set_u128 || is_set_ergs || is_inc_tx, write_like = !read_only;   /* :113-117 */
-        S(ZKC_VMS_CTX_WRITE_TO_CONTEXT, 0) = should_apply && is_set_u128; S(ZKC_VMS_CTX_SET_PUBDATA_ERGS, 0) = should_apply && is_set_ergs;   /* :108-109 */
-        S(ZKC_VMS_CTX_INCREMENT_TX, 0) = should_apply && is_inc_tx;          /* :110 */
-        S(ZKC_VMS_CTX_READ_ONLY, 0) = read_only; S(ZKC_VMS_CTX_WRITE_LIKE, 0) = write_like; S(ZKC_VMS_CTX_WRITE_TO_DST0, 0) = should_apply && write_like;   /* :119 */
-        const uint64_t tx = (uint64_t)st->tx_number_in_block + 1;            /* :123-126 */
+        const int read_only = is_set_u128 || is_set_ergs || is_inc_tx, write_like = !read_only;   /* :120-124 */
+        S(ZKC_VMS_CTX_WRITE_TO_CONTEXT, 0) = should_apply && is_set_u128; S(ZKC_VMS_CTX_SET_PUBDATA_ERGS, 0) = should_apply && is_set_ergs;   /* :115-116 */
+        S(ZKC_VMS_CTX_INCREMENT_TX, 0) = should_apply && is_inc_tx;          /* :117 */
+        S(ZKC_VMS_CTX_READ_ONLY, 0) = read_only; S(ZKC_VMS_CTX_WRITE_LIKE, 0) = write_like; S(ZKC_VMS_CTX_WRITE_TO_DST0, 0) = should_apply && write_like;   /* :126 */
+        const uint64_t tx = (uint64_t)st->tx_number_in_block + 1;            /* :130-133 */
         S(ZKC_VMS_CTX_INCREMENTED_TX_NUMBER, 0) = (uint32_t)tx; S(ZKC_VMS_CTX_TX_OF, 0) = tx >> 32;
-        const uint32_t meta_hi = (c->this_shard_id & 0xFF) | (c->caller_shard_id & 0xFF) << 8 | (c->code_shard_id & 0xFF) << 16;   /* :138-159 */
+        const uint32_t meta_hi = (c->this_shard_id & 0xFF) | (c->caller_shard_id & 0xFF) << 8 | (c->code_shard_id & 0xFF) << 16;   /* :145-165 */
         S(ZKC_VMS_CTX_META_HIGHEST, 0) = meta_hi;
         uint32_t r[8];
         memset(r, 0, sizeof r);
-        r[0] = is_ergs ? ergs_left : new_sp;                                  /* :195-208 */
+        r[0] = is_ergs ? ergs_left : new_sp;                                  /* :190-208 */
         S(ZKC_VMS_CTX_LOW_U32, 0) = r[0];
         if (is_get_u128) memcpy(r, c->context_u128_value_composite, 16);      /* :212-223 */
         for (int i = 0; i < 4; i++) S(ZKC_VMS_CTX_RESULT_128, i) = r[i];
-        if (is_this) memcpy(r, c->this_address, 20);                          /* :235-246 */
+        if (is_this) memcpy(r, c->this_address, 20);                          /* :235-245 */
         for (int i = 0; i < 5; i++) S(ZKC_VMS_CTX_RESULT_160_THIS, i) = r[i];
-        if (is_caller) memcpy(r, c->caller, 20);                              /* :248-259 */
+        if (is_caller) memcpy(r, c->caller, 20);                              /* :247-257 */
         for (int i = 0; i < 5; i++) S(ZKC_VMS_CTX_RESULT_160_CALLER, i) = r[i];
-        if (is_code) memcpy(r, c->code_address, 20);                          /* :261-272 */
+        if (is_code) memcpy(r, c->code_address, 20);                          /* :259-269 */
         for (int i = 0; i < 5; i++) S(ZKC_VMS_CTX_RESULT_160_CODE, i) = r[i];
-        if (is_meta) {                                                        /* :161-180, :287-288 */
+        if (is_meta) {                                                        /* :167-186, :284-285 */
             r[0] = st->ergs_per_pubdata_byte; r[1] = 0; r[2] = c->heap_upper_bound; r[3] = c->aux_heap_upper_bound;
             r[4] = r[5] = r[6] = 0; r[7] = meta_hi;
         }
@@ -326,9 +326,9 @@ void orc_main_vm_state_gadget_cells(const uint64_t *trace, const zkc_vm_state *s
 }
 
 /* ---- the memory-queue relations of every cycle (ZKC_VM_MEMORY_SPONGE_COLUMNS): opcode fetch, src0 read, dst0 write --------------
- *   may_be_read_memory_for_code             /root/reference/src/main_vm/utils.rs:128-231
- *   may_be_read_memory_for_source_operand   /root/reference/src/main_vm/utils.rs:387-522
- *   may_be_write_memory                     /root/reference/src/main_vm/cycle.rs:797-905
+ *   may_be_read_memory_for_code             /root/reference/src/main_vm/utils.rs:129-233
+ *   may_be_read_memory_for_source_operand   /root/reference/src/main_vm/utils.rs:388-522
+ *   may_be_write_memory                     /root/reference/src/main_vm/cycle.rs:799-935
  *   enforce_sponges                         /root/reference/src/main_vm/cycle.rs:937-957
  * Pinning: PARITY UNPINNED (Poseidon2 has no known-answer vector in the reference); checked against the second Python
  * restatement of the permutation and against the DENSE trace's own enforced slots (tests/test_oracle_main_vm_gadgets.py). */
@@ -359,21 +359,21 @@ void orc_main_vm_memory_sponge_cells(const uint64_t *trace, const zkc_vm_state *
                 !(((props >> ZKC_VM_BIT_TYPE(ZKC_OP_UMA)) | (props >> ZKC_VM_BIT_TYPE(ZKC_OP_LOG)) | (props >> ZKC_VM_BIT_TYPE(ZKC_OP_NEAR_CALL)) |
                    (props >> ZKC_VM_BIT_TYPE(ZKC_OP_FAR_CALL)) | (props >> ZKC_VM_BIT_TYPE(ZKC_OP_RET))) & 1);
             zkc_memory_query q;
-            /* opcode fetch: pre_state.rs:135-171; the word read is CODE_WORD when the read happens, zero otherwise */
+            /* opcode fetch: pre_state.rs:133-167; the word read is CODE_WORD when the read happens, zero otherwise */
             memset(&q, 0, sizeof q);
             const int read_opcode = (int)T(ZKC_VM_SHOULD_READ_OPCODE);
             q.timestamp = st->timestamp; q.memory_page = st->current_context.code_page; q.index = (uint32_t)T(ZKC_VM_SUPER_PC);
             for (int i = 0; i < 8; i++) q.value[i] = read_opcode ? (uint32_t)T(ZKC_VM_CODE_WORD + i) : 0u;
             orc_memory_query_encode(&q, enc);
             memq_step(enc, read_opcode, state, &len, out, limit, row, ZKC_VMQ_FETCH_INIT);
-            /* src0 read: pre_state.rs:373-395, the same timestamp */
+            /* src0 read: pre_state.rs:374-392, the same timestamp */
             memset(&q, 0, sizeof q);
             q.timestamp = st->timestamp; q.memory_page = (uint32_t)T(ZKC_VM_SRC0_PAGE); q.index = (uint32_t)T(ZKC_VM_SRC0_INDEX);
             q.is_ptr = (uint32_t)T(ZKC_VM_SRC0_FROM_MEMORY) & 1;
             for (int i = 0; i < 8; i++) q.value[i] = (uint32_t)T(ZKC_VM_SRC0_FROM_MEMORY + 1 + i);
             orc_memory_query_encode(&q, enc);
             memq_step(enc, (int)T(ZKC_VM_SHOULD_READ_SRC0), state, &len, out, limit, row, ZKC_VMQ_SRC0_INIT);
-            /* dst0 write: cycle.rs:248-284, timestamp_for_dst_write = timestamp + 3 (pre_state.rs:137-143) */
+            /* dst0 write: cycle.rs:248-284, timestamp_for_dst_write = timestamp + 3 (pre_state.rs:143-149) */
             memset(&q, 0, sizeof q);
             q.timestamp = st->timestamp + 3; q.memory_page = (uint32_t)T(ZKC_VM_DST0_PAGE); q.index = (uint32_t)T(ZKC_VM_DST0_INDEX);
             q.rw_flag = 1; q.is_ptr = (uint32_t)T(ZKC_VM_DST0) & 1;
