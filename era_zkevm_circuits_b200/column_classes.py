@@ -69,6 +69,22 @@ def _memory_sponge_block():
     return np.array(cls, dtype=np.uint8)
 
 
+def _prestate_block():
+    """ZKC_VM_PRESTATE_COLUMNS: Booleans but the UInt16 pc / indices / low halves, the UInt32 timestamps / pages / opcode halves, and the
+    VMRegister groups (is_pointer + eight UInt32 limbs)"""
+    u16 = {"PC_PLUS_ONE", "SRC0_REG_LOWEST", "DST0_REG_LOWEST", "SRC_INDEX_FOR_ABSOLUTE", "SRC_INDEX_FOR_RELATIVE", "DST_INDEX_FOR_ABSOLUTE",
+           "DST_INDEX_FOR_RELATIVE_WITH_PUSH", "DST_INDEX_FOR_RELATIVE", "DST_INDEX_SOMEWHAT_RELATIVE"}
+    u32 = {"TIMESTAMPS", "NEXT_CYCLE_TIMESTAMP", "OPCODE_SELECT_CHAIN", "DST0_REG_LOW_CHAIN", "STACK_PAGE", "HEAP_PAGE", "AUX_HEAP_PAGE"}
+    registers = {"DRAFT_SRC0_CHAIN", "SRC1_REGISTER_CHAIN", "SRC0_AFTER_USE_REG", "SRC0_AFTER_USE_IMM", "SRC0_SWAPPED", "SRC1_SWAPPED"}
+    cls = []
+    for name, width in abi.VMP_WIDTHS.items():
+        if name in registers:
+            cls += ([B] + [U32] * 8) * (width // 9)
+        else:
+            cls += [U16 if name in u16 else U32 if name in u32 else B] * width
+    return np.array(cls, dtype=np.uint8)
+
+
 TABLES = {
     "ram_permutation": lambda: _table([[B] * 3, MEMORY_ITEM, [F] * 8, [F] * 12, [U32], MEMORY_ITEM, [F] * 8, [F] * 12, [U32], [B] * 3, [U32],
                                        [U32] * 3, [B] * 3, [B] * 3, [B] * 10, [F] * 32, [F] * 4, [F] * 4, [U8] * 24, [F] * 2, [F], [F, F], [F] * 3,
@@ -95,6 +111,7 @@ TABLES = {
     "main_vm_gadget_cells": _gadget_block,
     "main_vm_state_gadget_cells": _state_gadget_block,
     "main_vm_memory_sponge_cells": _memory_sponge_block,
+    "main_vm_prestate_cells": _prestate_block,
 }
 
 

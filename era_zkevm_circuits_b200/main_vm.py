@@ -252,6 +252,15 @@ def main_vm_memory_sponge_cells(engine: Engine, trace, snapshots, limit: int, n_
     return _trace_and_snapshots_block(engine, "zkc_main_vm_memory_sponge_cells", abi.VMQ_COLS["NUM_COLS"], trace, snapshots, limit, n_instances)
 
 
+def main_vm_prestate_cells(engine: Engine, trace, snapshots, limit: int, n_instances: int = 1):
+    """The cells create_prestate allocates on the way to the values the DENSE trace names (main_vm/pre_state.rs:71-519,
+    main_vm/utils.rs:106-120, :237-386, decoded_opcode.rs:192-202): cycle control, the opcode select inside the code word, the four
+    15-bit register selector masks, the 15-step register select chains, operand locations, the src0 selects, the operand swap and the
+    pointer-erasure flags (include/zkc_b200.h, ZKC_VM_PRESTATE_COLUMNS).  Same arguments as main_vm_state_gadget_cells; returns
+    [VMP_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory space of `trace`."""
+    return _trace_and_snapshots_block(engine, "zkc_main_vm_prestate_cells", abi.VMP_COLS["NUM_COLS"], trace, snapshots, limit, n_instances)
+
+
 # ---- transport forms over PCIe (include/zkc_b200.h, "transport forms of the main_vm call") ---------------------------------
 class VmInputStreamHandle:
     """a zkc_vm_input_stream of ONE instance, in (pinned) host memory owned by the library"""

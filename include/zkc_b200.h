@@ -1682,6 +1682,51 @@ enum zkc_vm_memory_sponge_col {
 int zkc_main_vm_memory_sponge_cells(zkc_ctx *ctx, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances,
                                     int on_device, uint64_t *sponge_trace);
 
+/* ---- cells of create_prestate that are not columns of the DENSE trace -------------------------------------------------------------
+ * The DENSE trace names the RESULTS of the cycle's preamble (main_vm/pre_state.rs:71-519); this block holds the cells on the way:
+ *   pre_state.rs:88-105     execute_cycle, should_try_to_read_opcode, the pending exception taken down
+ *   pre_state.rs:107-129    pc + 1; should_read_memory (main_vm/utils.rs:106-120): page / super-pc equalities, can_skip, its negation
+ *   pre_state.rs:143-156    the four timestamps after the cycle's first, and the selected next-cycle timestamp
+ *   pre_state.rs:183-214    the three sub-pc mask bits and the three-stage select of the 64-bit opcode inside the code word
+ *                           (the last stage is the opcode BEFORE mask_into_nop / mask_into_panic)
+ *   decoded_opcode.rs:192-202  the four 15-bit register selector masks (reg_idx_into_bitspread + spread_into_bits)
+ *   pre_state.rs:303-329    the two 15-step VMRegister::conditionally_select chains that pick src0 / src1 out of the register
+ *                           file (15 x 9 cells each), the 15-step chain for the low limb of the dst0 register, both low_u16
+ *   pre_state.rs:337-343    stack / heap / aux heap page
+ *   main_vm/utils.rs:237-305   source location: absolute_mode, index_for_absolute, index_for_relative, use_stack, did_read before
+ *                           the NOP rule, not_nop
+ *   main_vm/utils.rs:307-386   destination location: index_for_absolute, index_for_relative_with_push, index_for_relative,
+ *                           did_write before the NOP rule, the push-or-relative index
+ *   pre_state.rs:403-413    src0 after the use_reg select and after the use_imm select
+ *   pre_state.rs:418-455    is_assymmetric, t0, t1 of swap_operands; both operands after the swap
+ *   pre_state.rs:457-479    not_kernel_mode, the pointer-keeping opcode class, should_erase, the two erase flags (applying them to
+ *                           the swapped operands gives ZKC_VM_SRC0 / ZKC_VM_SRC1 of the DENSE trace)
+ * Inputs: the DENSE trace (skip / pending flags, sub-pc, code word, register indices, immediates, property bits, the src0 memory
+ * value, swap flag) and snapshot i (registers, pc, sp, pages, previous code page / super-pc, timestamp, kernel mode).
+ * X(name, width): column ZKC_VMP_<name> .. + width - 1 of the block [ZKC_VMP_NUM_COLS][limit]. */
+#define ZKC_VM_PRESTATE_COLUMNS(X) \
+    X(EXECUTE_CYCLE, 1) X(SHOULD_TRY_TO_READ_OPCODE, 1) X(PENDING_EXCEPTION_TAKEN_DOWN, 1) X(PC_PLUS_ONE, 1) X(PC_PLUS_ONE_OF, 1) \
+    X(CODE_PAGES_ARE_EQUAL, 1) X(SUPER_PC_ARE_EQUAL, 1) X(CAN_SKIP_READ, 1) X(SHOULD_READ_FOR_NEW_PC, 1) \
+    X(TIMESTAMPS, 4) X(NEXT_CYCLE_TIMESTAMP, 1) X(SUBPC_BITMASK, 3) X(OPCODE_SELECT_CHAIN, 6) \
+    X(SRC0_SELECTORS, 15) X(SRC1_SELECTORS, 15) X(DST0_SELECTORS, 15) X(DST1_SELECTORS, 15) \
+    X(DRAFT_SRC0_CHAIN, 135) X(SRC1_REGISTER_CHAIN, 135) X(DST0_REG_LOW_CHAIN, 15) X(SRC0_REG_LOWEST, 1) X(DST0_REG_LOWEST, 1) \
+    X(STACK_PAGE, 1) X(HEAP_PAGE, 1) X(AUX_HEAP_PAGE, 1) \
+    X(SRC_ABSOLUTE_MODE, 1) X(SRC_INDEX_FOR_ABSOLUTE, 1) X(SRC_INDEX_FOR_RELATIVE, 1) X(SRC_USE_STACK, 1) X(SRC_DID_READ_UNMASKED, 1) X(NOT_NOP, 1) \
+    X(DST_INDEX_FOR_ABSOLUTE, 1) X(DST_INDEX_FOR_RELATIVE_WITH_PUSH, 1) X(DST_INDEX_FOR_RELATIVE, 1) X(DST_DID_WRITE_UNMASKED, 1) \
+    X(DST_INDEX_SOMEWHAT_RELATIVE, 1) \
+    X(SRC0_AFTER_USE_REG, 9) X(SRC0_AFTER_USE_IMM, 9) X(SWAP_IS_ASSYMMETRIC, 1) X(SWAP_T0, 1) X(SWAP_T1, 1) X(SRC0_SWAPPED, 9) X(SRC1_SWAPPED, 9) \
+    X(NOT_KERNEL_MODE, 1) X(KEEPS_POINTERS, 1) X(SHOULD_ERASE, 1) X(SHOULD_ERASE_SRC0, 1) X(SHOULD_ERASE_SRC1, 1)
+enum zkc_vm_prestate_col {
+#define ZKC_VMP_X(name, width) ZKC_VMP_##name, ZKC_VMP_##name##_LAST = ZKC_VMP_##name + (width)-1,
+    ZKC_VM_PRESTATE_COLUMNS(ZKC_VMP_X)
+#undef ZKC_VMP_X
+    ZKC_VMP_NUM_COLS
+};
+/* trace: DENSE traces [n_instances][ZKC_VM_NUM_COLS][limit]; snapshots: [n_instances][limit + 1] records; both host, or both
+ * device with on_device != 0; prestate_trace: out, [n_instances][ZKC_VMP_NUM_COLS][limit] in the same memory space */
+int zkc_main_vm_prestate_cells(zkc_ctx *ctx, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances,
+                               int on_device, uint64_t *prestate_trace);
+
 /* the state main_vm_entry_point starts from when start_flag is set: initial_bootloader_state, main_vm/loading.rs:13-226 */
 int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *out);
 

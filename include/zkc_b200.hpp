@@ -461,6 +461,18 @@ inline std::vector<uint64_t> main_vm_memory_sponge_cells(Engine &e, const std::v
     return out;
 }
 
+// the cells create_prestate allocates on the way to the values the DENSE trace names -- selector masks, the 15-step register select
+// chains, operand locations, src0 selects, swap, erasure flags (zkc_b200.h, ZKC_VM_PRESTATE_COLUMNS); same inputs as above (host)
+inline std::vector<uint64_t> main_vm_prestate_cells(Engine &e, const std::vector<uint64_t> &trace, const std::vector<zkc_vm_state> &snapshots,
+                                                    size_t limit) {
+    if (trace.size() < (size_t)ZKC_VM_NUM_COLS * limit || snapshots.size() < limit + 1)
+        throw Error("main_vm_prestate_cells", ZKC_ERR_INVALID_ARGUMENT, zkc_status{ZKC_ERR_INVALID_ARGUMENT, 0, -1, 0, 0});
+    std::vector<uint64_t> out((size_t)ZKC_VMP_NUM_COLS * limit);
+    const int rc = zkc_main_vm_prestate_cells(e.handle(), trace.data(), snapshots.data(), limit, 1, 0, out.data());
+    if (rc != ZKC_OK) throw Error("zkc_main_vm_prestate_cells", rc, zkc_status{rc, 0, -1, 0, 0});
+    return out;
+}
+
 // constraint evaluation of finished traces (host buffers): violating rows; st describes the first one
 inline uint64_t ram_permutation_check_trace(Engine &e, const zkc_ram_closed_form &io, const std::vector<uint64_t> &trace, size_t limit,
                                             uint32_t gates = 0, zkc_status *st = nullptr) {

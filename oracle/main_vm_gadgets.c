@@ -384,3 +384,122 @@ void orc_main_vm_memory_sponge_cells(const uint64_t *trace, const zkc_vm_state *
         }
     }
 }
+
+/* ---- cells of create_prestate that are not columns of the DENSE trace (ZKC_VM_PRESTATE_COLUMNS) ------------------------------
+ *   create_prestate                              /root/reference/src/main_vm/pre_state.rs:71-519
+ *   should_read_memory                           /root/reference/src/main_vm/utils.rs:106-120
+ *   resolve_memory_region_and_index_for_source   /root/reference/src/main_vm/utils.rs:237-305
+ *   resolve_memory_region_and_index_for_dest     /root/reference/src/main_vm/utils.rs:307-386
+ *   register selector masks                      /root/reference/src/main_vm/decoded_opcode.rs:192-202
+ * Pinning: PARITY UNPINNED against the reference; checked against an independent Python statement and against the DENSE trace's
+ * own results (tests/test_oracle_main_vm_gadgets.py). */
+#define PC(col, i) out[(size_t)((col) + (i)) * limit + row]
+static void put_reg(uint64_t *out, size_t limit, size_t row, int col, const zkc_vm_register *r) {
+    PC(col, 0) = r->is_pointer & 1;
+    for (int i = 0; i < 8; i++) PC(col, 1 + i) = r->value[i];
+}
+static uint32_t reg_mask(uint32_t idx) { return idx ? 1u << (idx - 1) : 0u; }   /* tables/integer_to_boolean_mask.rs:33-41 */
+
+void orc_main_vm_prestate_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out_all) {
+    for (size_t inst = 0; inst < n_instances; inst++) {
+        const uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit;
+        const zkc_vm_state *snaps = snapshots + inst * (limit + 1);
+        uint64_t *out = out_all + inst * (size_t)ZKC_VMP_NUM_COLS * limit;
+        for (size_t row = 0; row < limit; row++) {
+#define T(c) t[(size_t)(c) * limit + row]
+            const zkc_vm_state *st = snaps + row;
+            const zkc_vm_context *c = &st->current_context;
+            const uint64_t props = T(ZKC_VM_PROPS);
+#define BIT(n) (int)((props >> (n)) & 1)
+            /* ---- cycle control, pre_state.rs:88-156 ---- */
+            const int should_skip = (int)T(ZKC_VM_SHOULD_SKIP_CYCLE), pending = (int)T(ZKC_VM_PENDING_EXCEPTION_IN);
+            const int execute_cycle = !should_skip;                                   /* :92 */
+            PC(ZKC_VMP_EXECUTE_CYCLE, 0) = execute_cycle;
+            PC(ZKC_VMP_SHOULD_TRY_TO_READ_OPCODE, 0) = execute_cycle && !pending;      /* :98: execute_cycle.mask_negated(pending_exception) */
+            PC(ZKC_VMP_PENDING_EXCEPTION_TAKEN_DOWN, 0) = pending && !pending;         /* :103-105: masked by itself */
+            const uint32_t pc1 = c->pc + 1;                                           /* :109-111, UInt16 */
+            PC(ZKC_VMP_PC_PLUS_ONE, 0) = pc1 & 0xFFFF; PC(ZKC_VMP_PC_PLUS_ONE_OF, 0) = pc1 >> 16;
+            const uint32_t super_pc = (uint32_t)T(ZKC_VM_SUPER_PC), sub_pc = (uint32_t)T(ZKC_VM_SUB_PC);
+            const int pages_eq = st->previous_code_page == c->code_page, spc_eq = super_pc == st->previous_super_pc;   /* utils.rs:114-115 */
+            PC(ZKC_VMP_CODE_PAGES_ARE_EQUAL, 0) = pages_eq; PC(ZKC_VMP_SUPER_PC_ARE_EQUAL, 0) = spc_eq;
+            PC(ZKC_VMP_CAN_SKIP_READ, 0) = pages_eq && spc_eq; PC(ZKC_VMP_SHOULD_READ_FOR_NEW_PC, 0) = !(pages_eq && spc_eq);
+            for (int i = 0; i < 4; i++) PC(ZKC_VMP_TIMESTAMPS, i) = (uint32_t)(st->timestamp + 1 + i);   /* :144-150, increment_unchecked */
+            PC(ZKC_VMP_NEXT_CYCLE_TIMESTAMP, 0) = should_skip ? st->timestamp : (uint32_t)(st->timestamp + 4);   /* :151-156 */
+            /* ---- the opcode inside the code word, :183-214 ---- */
+            {
+                const uint32_t m = reg_mask(sub_pc);
+                uint32_t lo = (uint32_t)T(ZKC_VM_CODE_WORD + 6), hi = (uint32_t)T(ZKC_VM_CODE_WORD + 7);
+                for (int k = 0; k < 3; k++) {
+                    const int bit = (int)((m >> k) & 1);
+                    PC(ZKC_VMP_SUBPC_BITMASK, k) = bit;
+                    if (bit) { lo = (uint32_t)T(ZKC_VM_CODE_WORD + 4 - 2 * k); hi = (uint32_t)T(ZKC_VM_CODE_WORD + 5 - 2 * k); }
+                    PC(ZKC_VMP_OPCODE_SELECT_CHAIN, 2 * k) = lo; PC(ZKC_VMP_OPCODE_SELECT_CHAIN, 2 * k + 1) = hi;
+                }
+            }
+            /* ---- register selectors and the select chains, decoded_opcode.rs:192-202, pre_state.rs:303-329 ---- */
+            const uint32_t idx[4] = {(uint32_t)T(ZKC_VM_SRC0_REG), (uint32_t)T(ZKC_VM_SRC1_REG), (uint32_t)T(ZKC_VM_DST0_REG), (uint32_t)T(ZKC_VM_DST1_REG)};
+            const int sel_col[4] = {ZKC_VMP_SRC0_SELECTORS, ZKC_VMP_SRC1_SELECTORS, ZKC_VMP_DST0_SELECTORS, ZKC_VMP_DST1_SELECTORS};
+            for (int k = 0; k < 4; k++)
+                for (int r = 0; r < 15; r++) PC(sel_col[k], r) = (reg_mask(idx[k]) >> r) & 1;
+            zkc_vm_register draft_src0, src1_register;
+            memset(&draft_src0, 0, sizeof draft_src0); memset(&src1_register, 0, sizeof src1_register);
+            uint32_t dst0_low = 0;
+            for (int r = 0; r < 15; r++) {
+                if ((reg_mask(idx[0]) >> r) & 1) draft_src0 = st->registers[r];
+                if ((reg_mask(idx[1]) >> r) & 1) src1_register = st->registers[r];
+                if ((reg_mask(idx[2]) >> r) & 1) dst0_low = st->registers[r].value[0];
+                put_reg(out, limit, row, ZKC_VMP_DRAFT_SRC0_CHAIN + 9 * r, &draft_src0);
+                put_reg(out, limit, row, ZKC_VMP_SRC1_REGISTER_CHAIN + 9 * r, &src1_register);
+                PC(ZKC_VMP_DST0_REG_LOW_CHAIN, r) = dst0_low;
+            }
+            const uint32_t src0_lowest = draft_src0.value[0] & 0xFFFF, dst0_lowest = dst0_low & 0xFFFF;   /* :310, :329 */
+            PC(ZKC_VMP_SRC0_REG_LOWEST, 0) = src0_lowest; PC(ZKC_VMP_DST0_REG_LOWEST, 0) = dst0_lowest;
+            const uint32_t stack_page = c->base_page + 1;                            /* :341-343 */
+            PC(ZKC_VMP_STACK_PAGE, 0) = stack_page; PC(ZKC_VMP_HEAP_PAGE, 0) = (uint32_t)(stack_page + 1); PC(ZKC_VMP_AUX_HEAP_PAGE, 0) = (uint32_t)(stack_page + 2);
+            const int not_nop = !BIT(ZKC_VM_BIT_TYPE(ZKC_OP_NOP));
+            PC(ZKC_VMP_NOT_NOP, 0) = not_nop;
+            const uint32_t imm0 = (uint32_t)T(ZKC_VM_IMM0), imm1 = (uint32_t)T(ZKC_VM_IMM1), sp = c->sp & 0xFFFF;
+            uint32_t sp_after_src0;
+            {   /* utils.rs:237-305 */
+                const int use_code = BIT(ZKC_VM_BIT_SRC_MODE(ZKC_MODE_CODE_PAGE)), abs_ = BIT(ZKC_VM_BIT_SRC_MODE(ZKC_MODE_STACK_ABSOLUTE)),
+                          rel = BIT(ZKC_VM_BIT_SRC_MODE(ZKC_MODE_STACK_OFFSET)), pp = BIT(ZKC_VM_BIT_SRC_MODE(ZKC_MODE_STACK_PUSH_POP));
+                const uint32_t idx_abs = (src0_lowest + imm0) & 0xFFFF, idx_rel = (sp - idx_abs) & 0xFFFF;
+                const int use_stack = abs_ || rel || pp;
+                PC(ZKC_VMP_SRC_ABSOLUTE_MODE, 0) = use_code || abs_; PC(ZKC_VMP_SRC_INDEX_FOR_ABSOLUTE, 0) = idx_abs; PC(ZKC_VMP_SRC_INDEX_FOR_RELATIVE, 0) = idx_rel;
+                PC(ZKC_VMP_SRC_USE_STACK, 0) = use_stack; PC(ZKC_VMP_SRC_DID_READ_UNMASKED, 0) = use_stack || use_code;
+                sp_after_src0 = pp ? idx_rel : sp;
+            }
+            {   /* utils.rs:307-386 */
+                const int abs_ = BIT(ZKC_VM_BIT_DST_MODE(ZKC_MODE_STACK_ABSOLUTE)), rel = BIT(ZKC_VM_BIT_DST_MODE(ZKC_MODE_STACK_OFFSET)),
+                          pp = BIT(ZKC_VM_BIT_DST_MODE(ZKC_MODE_STACK_PUSH_POP));
+                const uint32_t idx_abs = (dst0_lowest + imm1) & 0xFFFF, idx_push = (sp_after_src0 + idx_abs) & 0xFFFF, idx_rel = (sp_after_src0 - idx_abs) & 0xFFFF;
+                PC(ZKC_VMP_DST_INDEX_FOR_ABSOLUTE, 0) = idx_abs; PC(ZKC_VMP_DST_INDEX_FOR_RELATIVE_WITH_PUSH, 0) = idx_push; PC(ZKC_VMP_DST_INDEX_FOR_RELATIVE, 0) = idx_rel;
+                PC(ZKC_VMP_DST_DID_WRITE_UNMASKED, 0) = abs_ || rel || pp; PC(ZKC_VMP_DST_INDEX_SOMEWHAT_RELATIVE, 0) = pp ? sp_after_src0 : idx_rel;
+            }
+            /* ---- src0 selects, swap, pointer erasure: :403-479 ---- */
+            zkc_vm_register from_mem, src0, imm_reg;
+            memset(&from_mem, 0, sizeof from_mem); memset(&imm_reg, 0, sizeof imm_reg);
+            from_mem.is_pointer = (uint32_t)T(ZKC_VM_SRC0_FROM_MEMORY) & 1;
+            for (int i = 0; i < 8; i++) from_mem.value[i] = (uint32_t)T(ZKC_VM_SRC0_FROM_MEMORY + 1 + i);
+            imm_reg.value[0] = imm0;
+            src0 = BIT(ZKC_VM_BIT_SRC_MODE(ZKC_MODE_REG_ONLY)) ? draft_src0 : from_mem;    /* :403-406 */
+            put_reg(out, limit, row, ZKC_VMP_SRC0_AFTER_USE_REG, &src0);
+            if (BIT(ZKC_VM_BIT_SRC_MODE(ZKC_MODE_IMM16))) src0 = imm_reg;                  /* :408-413 */
+            put_reg(out, limit, row, ZKC_VMP_SRC0_AFTER_USE_IMM, &src0);
+            const int is_ptr_op = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_PTR));
+            const int asym = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_SUB)) || BIT(ZKC_VM_BIT_TYPE(ZKC_OP_DIV)) || BIT(ZKC_VM_BIT_TYPE(ZKC_OP_SHIFT));   /* :421-432 */
+            const int t0 = asym && BIT(ZKC_VM_BIT_FLAG(ZKC_VM_SWAP_OPERANDS_FLAG_IDX)), t1 = is_ptr_op && BIT(ZKC_VM_BIT_FLAG(ZKC_VM_SWAP_OPERANDS_PTR_FLAG_IDX));
+            PC(ZKC_VMP_SWAP_IS_ASSYMMETRIC, 0) = asym; PC(ZKC_VMP_SWAP_T0, 0) = t0; PC(ZKC_VMP_SWAP_T1, 0) = t1;
+            const int swap = (int)T(ZKC_VM_SWAP_OPERANDS);
+            const zkc_vm_register a = swap ? src1_register : src0, b = swap ? src0 : src1_register;   /* :451-454 */
+            put_reg(out, limit, row, ZKC_VMP_SRC0_SWAPPED, &a); put_reg(out, limit, row, ZKC_VMP_SRC1_SWAPPED, &b);
+            const int not_kernel = !(c->is_kernel_mode & 1);                          /* :458 */
+            const int keeps = BIT(ZKC_VM_BIT_TYPE(ZKC_OP_RET)) || is_ptr_op || BIT(ZKC_VM_BIT_TYPE(ZKC_OP_UMA)) || BIT(ZKC_VM_BIT_TYPE(ZKC_OP_FAR_CALL));
+            PC(ZKC_VMP_NOT_KERNEL_MODE, 0) = not_kernel; PC(ZKC_VMP_KEEPS_POINTERS, 0) = keeps; PC(ZKC_VMP_SHOULD_ERASE, 0) = !keeps;   /* :459-474 */
+            PC(ZKC_VMP_SHOULD_ERASE_SRC0, 0) = (a.is_pointer & 1) && !keeps && not_kernel;   /* :475 */
+            PC(ZKC_VMP_SHOULD_ERASE_SRC1, 0) = (b.is_pointer & 1) && not_kernel;             /* :478 */
+#undef BIT
+#undef T
+        }
+    }
+}

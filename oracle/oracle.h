@@ -138,4 +138,6 @@ void orc_main_vm_gadget_cells(const uint64_t *trace, size_t limit, size_t n_inst
 void orc_main_vm_state_gadget_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out);
 /* the fetch / src0 read / dst0 write memory-queue relations of every cycle -> out [n_instances][ZKC_VMQ_NUM_COLS][limit] */
 void orc_main_vm_memory_sponge_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out);
+/* the cells of create_prestate that are not DENSE columns -> out [n_instances][ZKC_VMP_NUM_COLS][limit] */
+void orc_main_vm_prestate_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out);
 #endif

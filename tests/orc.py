@@ -435,6 +435,20 @@ def vm_state_gadget_cells(lib, trace, snaps, limit, n_instances=1):
     return out
 
 
+def vm_prestate_cells(lib, trace, snaps, limit, n_instances=1, fn=None):
+    """orc_main_vm_prestate_cells: DENSE trace(s) + snapshots [n?, limit + 1] -> [n?, VMP_COLS.NUM_COLS, limit]; `fn` = another function
+    of the same signature (the g++ build of the kernel's row statement, tests/cpp/prestate_row_host.cpp)"""
+    trace = np.ascontiguousarray(trace, dtype=np.uint64)
+    snaps = np.ascontiguousarray(snaps)
+    assert snaps.nbytes >= (limit + 1) * n_instances * C.sizeof(abi.VmState)
+    out = np.zeros(tuple(trace.shape[:-2]) + (abi.VMP_COLS["NUM_COLS"], limit), dtype=np.uint64)
+    fn = fn or lib.orc_main_vm_prestate_cells
+    fn.restype = None
+    fn.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, _vp]
+    fn(p(trace), p(snaps), limit, n_instances, p(out))
+    return out
+
+
 def vm_memory_sponge_cells(lib, trace, snaps, limit, n_instances=1):
     """orc_main_vm_memory_sponge_cells: DENSE trace(s) + snapshots [n?, limit + 1] -> [n?, VMQ_COLS.NUM_COLS, limit]"""
     trace = np.ascontiguousarray(trace, dtype=np.uint64)

@@ -84,3 +84,60 @@ def test_memory_sponge_cells_bit_exact(engine, orc, n, cycles, seed, far):
         a = trace[:, K["SPONGE_FINAL"] + 12 * slot:K["SPONGE_FINAL"] + 12 * slot + 12]
         b = got[:, Q[name + "_FINAL"]:Q[name + "_FINAL"] + 12]
         assert np.array_equal(a.transpose(0, 2, 1)[enforced], b.transpose(0, 2, 1)[enforced]), name
+
+
+@pytest.mark.parametrize("n,cycles,seed,far", [(1, 1, 1, False), (1, 5000, 2, False), (3, 4097, 3, True)])
+def test_prestate_cells_bit_exact(engine, orc, n, cycles, seed, far):
+    """zkc_main_vm_prestate_cells: the cells of create_prestate that are not DENSE columns (selector masks, the 15-step register select
+    chains, operand locations, src0 selects, swap, erasure flags), CUDA vs the oracle (pinned on Python integers and on the DENSE
+    trace's own results by tests/test_oracle_main_vm_gadgets.py), host and device buffers, batches"""
+    import torch
+    from era_zkevm_circuits_b200 import main_vm_prestate_cells
+    isa, io, st = fresh(orc)
+    traces, snapshots = [], []
+    for k in range(n):
+        ops = I.random_program(isa, 1024, seed=seed + k, far_calls=far)
+        rc, snaps, wit, status, cw, tail = O.vm_run(orc, isa.isa, st, I.pack_code(ops), cycles, full=True)
+        assert rc == 0
+        want = O.vm_entry_point(orc, with_tail(io, tail), isa.isa, snaps, wit, cycles, cw=cw)
+        assert want[0] == 0
+        traces.append(want[2])
+        snapshots.append(snaps)
+    trace = np.ascontiguousarray(np.stack(traces))
+    snaps = np.ascontiguousarray(np.stack(snapshots))
+    want = O.vm_prestate_cells(orc, trace, snaps, cycles, n)
+    assert want.shape == (n, abi.VMP_COLS["NUM_COLS"], cycles)
+    got = main_vm_prestate_cells(engine, trace, snaps, cycles, n)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"first differing (instance, column, row): {bad[:5].tolist()}"
+    dev = main_vm_prestate_cells(engine, torch.from_numpy(trace.view(np.int64)).cuda(), torch.from_numpy(snaps).cuda(), cycles, n)
+    assert np.array_equal(dev.cpu().numpy().view(np.uint64), want)
+    one = main_vm_prestate_cells(engine, trace[0], snaps[0], cycles)
+    assert np.array_equal(one, want[0])
+    # the block's last cells are the DENSE trace's operands before the erasure (base_structures/register/mod.rs:67-76)
+    K, P = abi.VM_COLS, abi.VMP_COLS
+    for src, swapped, flag in (("SRC0", "SRC0_SWAPPED", "SHOULD_ERASE_SRC0"), ("SRC1", "SRC1_SWAPPED", "SHOULD_ERASE_SRC1")):
+        keep = np.ones((1, 9, 1), dtype=np.uint64); erase = got[:, P[flag]][:, None, :]
+        keep = np.where(np.isin(np.arange(9), (0, 2, 3))[None, :, None], 1 - erase, keep)
+        assert np.array_equal(trace[:, K[src]:K[src] + 9], got[:, P[swapped]:P[swapped] + 9] * keep), src
+
+
+def test_prestate_cells_mutated_inputs_and_argument_checks(engine, orc):
+    """user mode, pointer registers, every register index, the 16- / 32-bit wraps, skipped and pending cycles, any property bits"""
+    from era_zkevm_circuits_b200 import main_vm_prestate_cells
+    from test_oracle_main_vm_gadgets import mutated_prestate_inputs
+    trace, snaps = mutated_prestate_inputs(orc, 1500, 7)
+    want = O.vm_prestate_cells(orc, trace, snaps, 1500)
+    got = main_vm_prestate_cells(engine, np.ascontiguousarray(trace), np.ascontiguousarray(snaps), 1500)
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"first differing (column, row): {bad[:5].tolist()}"
+    zero = np.zeros((abi.VM_COLS["NUM_COLS"], 8), dtype=np.uint64)
+    with pytest.raises(ZkcError):                                           # 8 snapshots for 8 cycles: one short
+        main_vm_prestate_cells(engine, zero, np.zeros((8, 1176), dtype=np.uint8), 8)
+    out = main_vm_prestate_cells(engine, zero, np.zeros((9, 1176), dtype=np.uint8), 8)
+    P = abi.VMP_COLS
+    assert out.shape == (P["NUM_COLS"], 8)
+    # all-zero inputs: the cycle executes, pc + 1 = 1, pages 1 / 2 / 3, no selector set, every chain stays zero
+    assert out[P["EXECUTE_CYCLE"]].tolist() == [1] * 8 and out[P["PC_PLUS_ONE"]].tolist() == [1] * 8 and out[P["AUX_HEAP_PAGE"]].tolist() == [3] * 8
+    assert out[P["SRC0_SELECTORS"]:P["DST1_SELECTORS"] + 15].max() == 0 and out[P["DRAFT_SRC0_CHAIN"]:P["DST0_REG_LOW_CHAIN"] + 15].max() == 0
+    assert out[P["TIMESTAMPS"]:P["TIMESTAMPS"] + 4, 0].tolist() == [1, 2, 3, 4] and out[P["CAN_SKIP_READ"]].tolist() == [1] * 8

@@ -304,3 +304,192 @@ def test_memory_sponge_cells_against_python_and_the_dense_trace(orc):
             if selected:  # no opcode touches the memory queue afterwards: this is the next cycle's queue
                 assert state == [int(x) for x in nxt.memory_queue_state] and length == nxt.memory_queue_length == int(trace[K["MEMQ_LENGTH_OUT"], r]), r
     assert min(seen.values()) > 0, seen
+
+
+# ---- the create_prestate block (ZKC_VM_PRESTATE_COLUMNS; oracle/main_vm_gadgets.c orc_main_vm_prestate_cells) ---------------------
+P, PW = abi.VMP_COLS, abi.VMP_WIDTHS
+SRC_MODE = lambda m: I.TYPE_BITS + I.VARIANT_BITS + I.FLAG_BITS + m
+DST_MODE = lambda m: I.TYPE_BITS + I.VARIANT_BITS + I.FLAG_BITS + I.SRC_BITS + m
+FLAG = lambda f: I.TYPE_BITS + I.VARIANT_BITS + f
+
+
+def prestate_reference(trace, snaps, r):
+    """create_prestate (pre_state.rs:71-519, utils.rs:106-120, :237-386) on Python integers: a register is (is_pointer, ONE 256-bit
+    integer); name -> value(s) in column order"""
+    col = lambda name, i=0: int(trace[K[name] + i, r])
+    props = col("PROPS")
+    bit = lambda n: (props >> n) & 1
+    st = abi.VmState.from_buffer_copy(snaps[r].tobytes())
+    c = st.current_context
+    M16, M32 = 0xFFFF, 0xFFFFFFFF
+    word = lambda limbs: sum(int(x) << (32 * i) for i, x in enumerate(limbs))
+    cells = lambda reg: [reg[0]] + [(reg[1] >> (32 * i)) & M32 for i in range(8)]
+    regs = [(int(x.is_pointer) & 1, word(x.value)) for x in st.registers]
+    out = {}
+    skip, pending = col("SHOULD_SKIP_CYCLE"), col("PENDING_EXCEPTION_IN")
+    out["EXECUTE_CYCLE"] = 1 - skip
+    out["SHOULD_TRY_TO_READ_OPCODE"] = int(not skip and not pending)
+    out["PENDING_EXCEPTION_TAKEN_DOWN"] = 0
+    out["PC_PLUS_ONE"], out["PC_PLUS_ONE_OF"] = (c.pc + 1) % 65536, (c.pc + 1) // 65536
+    out["CODE_PAGES_ARE_EQUAL"] = int(st.previous_code_page == c.code_page)
+    out["SUPER_PC_ARE_EQUAL"] = int(c.pc >> 2 == st.previous_super_pc)             # split_pc: super_pc = pc >> 2, sub_pc = pc & 3
+    out["CAN_SKIP_READ"] = out["CODE_PAGES_ARE_EQUAL"] & out["SUPER_PC_ARE_EQUAL"]
+    out["SHOULD_READ_FOR_NEW_PC"] = 1 - out["CAN_SKIP_READ"]
+    out["TIMESTAMPS"] = [(st.timestamp + k) & M32 for k in (1, 2, 3, 4)]
+    out["NEXT_CYCLE_TIMESTAMP"] = st.timestamp if skip else (st.timestamp + 4) & M32
+    code_word = word(col("CODE_WORD", i) for i in range(8))
+    sub_pc = c.pc & 3
+    out["SUBPC_BITMASK"] = [int(sub_pc == k) for k in (1, 2, 3)]
+    # the opcode is the sub_pc-th 64-bit lane counted from the TOP of the big-endian word; the chain holds the running selection
+    chain, sel = [], code_word >> 192
+    for k in (1, 2, 3):
+        if sub_pc == k:
+            sel = (code_word >> (192 - 64 * k)) & (2 ** 64 - 1)
+        chain += [sel & M32, sel >> 32]
+    out["OPCODE_SELECT_CHAIN"] = chain
+    idx = [col("SRC0_REG"), col("SRC1_REG"), col("DST0_REG"), col("DST1_REG")]
+    for name, i in zip(("SRC0_SELECTORS", "SRC1_SELECTORS", "DST0_SELECTORS", "DST1_SELECTORS"), idx):
+        out[name] = [int(i == k + 1) for k in range(15)]
+    pick = lambda i, k: regs[i - 1] if 1 <= i <= k + 1 else (0, 0)                  # after k + 1 steps of the chain
+    out["DRAFT_SRC0_CHAIN"] = sum((cells(pick(idx[0], k)) for k in range(15)), [])
+    out["SRC1_REGISTER_CHAIN"] = sum((cells(pick(idx[1], k)) for k in range(15)), [])
+    out["DST0_REG_LOW_CHAIN"] = [pick(idx[2], k)[1] & M32 for k in range(15)]
+    draft_src0, src1_reg = pick(idx[0], 14), pick(idx[1], 14)
+    out["SRC0_REG_LOWEST"], out["DST0_REG_LOWEST"] = draft_src0[1] & M16, pick(idx[2], 14)[1] & M16
+    out["STACK_PAGE"], out["HEAP_PAGE"], out["AUX_HEAP_PAGE"] = [(c.base_page + k) & M32 for k in (1, 2, 3)]
+    s_code, s_abs, s_rel, s_pp = (bit(SRC_MODE(m)) for m in (I.MODE_CODE, I.MODE_STACK_ABS, I.MODE_STACK_OFFSET, I.MODE_PUSH_POP))
+    src_abs = (out["SRC0_REG_LOWEST"] + col("IMM0")) & M16
+    src_rel = (c.sp - src_abs) & M16
+    out["SRC_ABSOLUTE_MODE"] = s_code | s_abs
+    out["SRC_INDEX_FOR_ABSOLUTE"], out["SRC_INDEX_FOR_RELATIVE"] = src_abs, src_rel
+    out["SRC_USE_STACK"] = s_abs | s_rel | s_pp
+    out["SRC_DID_READ_UNMASKED"] = out["SRC_USE_STACK"] | s_code
+    out["NOT_NOP"] = 1 - bit(I.OP_NOP)
+    sp1 = src_rel if s_pp else c.sp & M16
+    d_abs, d_rel, d_pp = (bit(DST_MODE(m)) for m in (I.MODE_STACK_ABS, I.MODE_STACK_OFFSET, I.MODE_PUSH_POP))
+    dst_abs = (out["DST0_REG_LOWEST"] + col("IMM1")) & M16
+    out["DST_INDEX_FOR_ABSOLUTE"] = dst_abs
+    out["DST_INDEX_FOR_RELATIVE_WITH_PUSH"], out["DST_INDEX_FOR_RELATIVE"] = (sp1 + dst_abs) & M16, (sp1 - dst_abs) & M16
+    out["DST_DID_WRITE_UNMASKED"] = d_abs | d_rel | d_pp
+    out["DST_INDEX_SOMEWHAT_RELATIVE"] = sp1 if d_pp else out["DST_INDEX_FOR_RELATIVE"]
+    from_memory = (col("SRC0_FROM_MEMORY") & 1, word(col("SRC0_FROM_MEMORY", 1 + i) for i in range(8)))
+    src0 = draft_src0 if bit(SRC_MODE(I.MODE_REG)) else from_memory
+    out["SRC0_AFTER_USE_REG"] = cells(src0)
+    src0 = (0, col("IMM0")) if bit(SRC_MODE(I.MODE_IMM16)) else src0
+    out["SRC0_AFTER_USE_IMM"] = cells(src0)
+    asym = bit(I.OP_SUB) | bit(I.OP_DIV) | bit(I.OP_SHIFT)
+    out["SWAP_IS_ASSYMMETRIC"], out["SWAP_T0"], out["SWAP_T1"] = asym, asym & bit(FLAG(1)), bit(I.OP_PTR) & bit(FLAG(0))
+    swap = out["SWAP_T0"] | out["SWAP_T1"]
+    a, b = (src1_reg, src0) if swap else (src0, src1_reg)
+    out["SRC0_SWAPPED"], out["SRC1_SWAPPED"] = cells(a), cells(b)
+    keeps = bit(I.OP_RET) | bit(I.OP_PTR) | bit(I.OP_UMA) | bit(I.OP_FAR_CALL)
+    out["NOT_KERNEL_MODE"], out["KEEPS_POINTERS"], out["SHOULD_ERASE"] = 1 - (c.is_kernel_mode & 1), keeps, 1 - keeps
+    out["SHOULD_ERASE_SRC0"] = a[0] & (1 - keeps) & out["NOT_KERNEL_MODE"]
+    out["SHOULD_ERASE_SRC1"] = b[0] & out["NOT_KERNEL_MODE"]
+    return out, swap, sp1
+
+
+def erased(cells9, flag):
+    """VMRegister::conditionally_erase_fat_pointer_data (base_structures/register/mod.rs:67-76): is_pointer and limbs 1, 2"""
+    return [0 if flag and i in (0, 2, 3) else v for i, v in enumerate(cells9)]
+
+
+def test_prestate_cells_against_python_integers_and_the_dense_trace(orc):
+    assert sum(PW.values()) == P["NUM_COLS"] == 428
+    seen = {"swap": 0, "erase0": 0, "erase1": 0, "push": 0, "pop": 0, "imm": 0, "mem": 0, "skip_read": 0, "sub_pc": set(), "masked": 0}
+    for far, seed in ((False, 33), (True, 5)):
+        trace, snaps = vm_trace_and_snapshots(orc, 3000, seed, far)
+        cycles = trace.shape[1]
+        g = O.vm_prestate_cells(orc, trace, snaps, cycles)
+        assert g.shape == (P["NUM_COLS"], cycles)
+        for r in range(cycles):
+            want, swap, sp1 = prestate_reference(trace, snaps, r)
+            assert list(want) != [] and set(want) == set(PW)
+            for name, v in want.items():
+                got = [int(x) for x in g[P[name]:P[name] + PW[name], r]]
+                assert got == (v if isinstance(v, list) else [v]), (r, name, got, v)
+            col = lambda name, i=0: int(trace[K[name] + i, r])
+            # the block's cells lead to the RESULTS the DENSE trace names
+            assert col("SWAP_OPERANDS") == swap
+            assert col("SHOULD_READ_OPCODE") == want["SHOULD_TRY_TO_READ_OPCODE"] & want["SHOULD_READ_FOR_NEW_PC"]
+            assert col("SUPER_PC") == abi.VmState.from_buffer_copy(snaps[r].tobytes()).current_context.pc >> 2
+            if not col("SHOULD_SKIP_CYCLE") and not col("PENDING_EXCEPTION_IN"):   # else mask_into_nop / mask_into_panic, :216-221
+                assert [col("OPCODE"), col("OPCODE", 1)] == want["OPCODE_SELECT_CHAIN"][4:], r
+            else:
+                seen["masked"] += 1
+            assert col("SRC0_PAGE") == (want["STACK_PAGE"] if want["SRC_USE_STACK"] else
+                                        abi.VmState.from_buffer_copy(snaps[r].tobytes()).current_context.code_page)
+            assert col("SRC0_INDEX") == (want["SRC_INDEX_FOR_ABSOLUTE"] if want["SRC_ABSOLUTE_MODE"] else want["SRC_INDEX_FOR_RELATIVE"])
+            assert col("SHOULD_READ_SRC0") == want["SRC_DID_READ_UNMASKED"] & want["NOT_NOP"]
+            assert col("SP_AFTER_SRC0") == sp1
+            props = col("PROPS")
+            d_abs, d_pp = (props >> DST_MODE(I.MODE_STACK_ABS)) & 1, (props >> DST_MODE(I.MODE_PUSH_POP)) & 1
+            assert col("DST0_PAGE") == want["STACK_PAGE"]
+            assert col("DST0_INDEX") == (want["DST_INDEX_FOR_ABSOLUTE"] if d_abs else want["DST_INDEX_SOMEWHAT_RELATIVE"])
+            assert col("DST0_PERFORMS_MEMORY_ACCESS") == want["DST_DID_WRITE_UNMASKED"] & want["NOT_NOP"]
+            assert col("NEW_SP") == (want["DST_INDEX_FOR_RELATIVE_WITH_PUSH"] if d_pp else sp1)
+            assert [col("SRC0", i) for i in range(9)] == erased(want["SRC0_SWAPPED"], want["SHOULD_ERASE_SRC0"]), r
+            assert [col("SRC1", i) for i in range(9)] == erased(want["SRC1_SWAPPED"], want["SHOULD_ERASE_SRC1"]), r
+            seen["swap"] += swap; seen["erase0"] += want["SHOULD_ERASE_SRC0"]; seen["erase1"] += want["SHOULD_ERASE_SRC1"]
+            seen["push"] += d_pp; seen["pop"] += (props >> SRC_MODE(I.MODE_PUSH_POP)) & 1
+            seen["imm"] += (props >> SRC_MODE(I.MODE_IMM16)) & 1
+            seen["mem"] += col("SHOULD_READ_SRC0"); seen["skip_read"] += want["CAN_SKIP_READ"]
+            seen["sub_pc"].add(col("SUB_PC"))
+    # every random program runs in kernel mode, to the end of its cycles and never pops a source operand: those are the mutation test's
+    assert seen["sub_pc"] == {0, 1, 2, 3} and all(v for k, v in seen.items() if k not in ("erase0", "erase1", "masked", "pop")), str(seen)
+
+
+def mutated_prestate_inputs(orc, cycles=1500, seed=7):
+    """a real trace + snapshots with the block's INPUTS redrawn at random (the block is a pure function of them): user mode, pointer
+    registers, every register index, 16-bit wrap of pc / sp / indices, 32-bit wrap of timestamp / pages, skipped and pending cycles"""
+    trace, snaps = vm_trace_and_snapshots(orc, cycles, seed, True)
+    trace, snaps = trace.copy(), snaps[:cycles + 1].copy()
+    rng = np.random.default_rng(seed)
+    st = snaps.view(abi.VM_STATE_DTYPE).reshape(-1) if hasattr(abi, "VM_STATE_DTYPE") and snaps.dtype != abi.VM_STATE_DTYPE else snaps.reshape(-1)
+    n = cycles
+    edge16 = lambda: rng.choice([0, 1, 0xFFFF, 0xFFFE], n) * (rng.random(n) < 0.3) + rng.integers(0, 1 << 16, n) * (rng.random(n) < 0.7)
+    words = np.frombuffer(st.tobytes(), dtype=np.uint32).reshape(len(st), -1).copy()
+    V = abi.VmState
+    off = lambda *path: sum(getattr(t, f).offset for t, f in path) // 4
+    C_ = type(V().current_context)
+    ctx = V.current_context.offset // 4
+    for r in range(15):
+        words[:n, V.registers.offset // 4 + 9 * r] = rng.integers(0, 2, n)
+    for f, vals in (("pc", edge16() & 0xFFFF), ("sp", edge16() & 0xFFFF), ("is_kernel_mode", rng.integers(0, 2, n)),
+                    ("base_page", np.where(rng.random(n) < 0.2, 0xFFFFFFFF - rng.integers(0, 3, n), rng.integers(0, 1 << 32, n)))):
+        words[:n, ctx + getattr(C_, f).offset // 4] = vals
+    words[:n, V.timestamp.offset // 4] = np.where(rng.random(n) < 0.2, 0xFFFFFFFF - rng.integers(0, 4, n), rng.integers(0, 1 << 32, n))
+    pc = words[:n, ctx + C_.pc.offset // 4]
+    same = rng.random(n) < 0.5
+    words[:n, V.previous_code_page.offset // 4] = np.where(same, words[:n, ctx + C_.code_page.offset // 4], rng.integers(0, 1 << 32, n))
+    words[:n, V.previous_super_pc.offset // 4] = np.where(rng.random(n) < 0.5, pc >> 2, rng.integers(0, 1 << 14, n))
+    snaps = np.frombuffer(words.tobytes(), dtype=snaps.dtype).reshape(snaps.shape)
+    trace[K["SUPER_PC"]], trace[K["SUB_PC"]] = pc >> 2, pc & 3
+    for name in ("SRC0_REG", "SRC1_REG", "DST0_REG", "DST1_REG"):
+        trace[K[name]] = rng.integers(0, 16, n)
+    trace[K["IMM0"]], trace[K["IMM1"]] = edge16() & 0xFFFF, edge16() & 0xFFFF
+    trace[K["SHOULD_SKIP_CYCLE"]], trace[K["PENDING_EXCEPTION_IN"]] = rng.random(n) < 0.2, rng.random(n) < 0.2
+    trace[K["SRC0_FROM_MEMORY"]] = rng.integers(0, 2, n)
+    for i in range(8):
+        trace[K["SRC0_FROM_MEMORY"] + 1 + i] = rng.integers(0, 1 << 32, n)
+        trace[K["CODE_WORD"] + i] = rng.integers(0, 1 << 32, n)
+    props = rng.integers(0, 1 << 38, n).astype(np.uint64)                    # any bit pattern: every cell is bitwise in the property bits
+    trace[K["PROPS"]] = props
+    pb = lambda k: (props >> np.uint64(k)) & np.uint64(1)
+    trace[K["SWAP_OPERANDS"]] = ((pb(I.OP_SUB) | pb(I.OP_DIV) | pb(I.OP_SHIFT)) & pb(FLAG(1))) | (pb(I.OP_PTR) & pb(FLAG(0)))
+    return trace, snaps
+
+
+def test_prestate_cells_on_mutated_inputs(orc):
+    trace, snaps = mutated_prestate_inputs(orc)
+    cycles = trace.shape[1]
+    g = O.vm_prestate_cells(orc, trace, snaps, cycles)
+    erase = [0, 0]
+    for r in range(cycles):
+        want, _, _ = prestate_reference(trace, snaps, r)
+        for name, v in want.items():
+            got = [int(x) for x in g[P[name]:P[name] + PW[name], r]]
+            assert got == (v if isinstance(v, list) else [v]), (r, name, got, v)
+        erase[0] += want["SHOULD_ERASE_SRC0"]; erase[1] += want["SHOULD_ERASE_SRC1"]
+    assert min(erase) > 5, erase
+    assert int(g[P["PC_PLUS_ONE_OF"]].sum()) > 0 and int((g[P["NEXT_CYCLE_TIMESTAMP"]] < 4).sum()) > 0   # both wraps happened

@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Writes include/zkc_b200_vm_variables.json: the machine-readable map from the named witness cells of one main_vm cycle to the
 place in the reference that allocates them (file:line into matter-labs/era-zkevm_circuits @ 8bf2454, src/main_vm/...), for the
-four outputs of the engine: the DENSE trace (enum zkc_vm_col) and the three oblivious blocks (ZKC_VM_GADGET_COLUMNS,
-ZKC_VM_STATE_GADGET_COLUMNS, ZKC_VM_MEMORY_SPONGE_COLUMNS).  Column numbers and widths are taken from include/zkc_b200.h (the
+five outputs of the engine: the DENSE trace (enum zkc_vm_col) and the four oblivious blocks (ZKC_VM_GADGET_COLUMNS,
+ZKC_VM_STATE_GADGET_COLUMNS, ZKC_VM_MEMORY_SPONGE_COLUMNS, ZKC_VM_PRESTATE_COLUMNS).  Column numbers and widths are taken from include/zkc_b200.h (the
 single source); this file only attaches (reference, what) to every group.  tests/test_vm_variables.py checks the result against
 the header and, when /root/reference is present, that every cited line exists.
 
@@ -170,6 +170,47 @@ MEMQ = {
     "DST0_LENGTH_AFTER": (C + ":889-896", ""),
 }
 
+D = "src/main_vm/decoded_opcode.rs"
+PRESTATE = {
+    "EXECUTE_CYCLE": (P + ":91", "should_skip_cycle.negated"),
+    "SHOULD_TRY_TO_READ_OPCODE": (P + ":98", "execute_cycle.mask_negated(pending_exception)"),
+    "PENDING_EXCEPTION_TAKEN_DOWN": (P + ":103-105", "pending_exception.mask_negated(execute_pending_exception_at_this_cycle): the flag masked by itself"),
+    "PC_PLUS_ONE": (P + ":111", "current_pc.overflowing_add(1): UInt16 result"), "PC_PLUS_ONE_OF": (P + ":111", "... its (dropped) overflow bit"),
+    "CODE_PAGES_ARE_EQUAL": (U + ":114", "should_read_memory: UInt32::equals(previous_code_page, current_code_page)"),
+    "SUPER_PC_ARE_EQUAL": (U + ":115", "UInt16::equals(super_pc, previous_super_pc)"),
+    "CAN_SKIP_READ": (U + ":117", "Boolean::multi_and"), "SHOULD_READ_FOR_NEW_PC": (U + ":119", "can_skip.negated"),
+    "TIMESTAMPS": (P + ":144-150", "four increment_unchecked of current_state.timestamp: first decommit / precompile read, second ... write, dst write, next cycle"),
+    "NEXT_CYCLE_TIMESTAMP": (P + ":151-156", "UInt32::conditionally_select(should_skip_cycle, timestamp, next_cycle_timestamp)"),
+    "SUBPC_BITMASK": (P + ":185", "subpc_spread.spread_into_bits::<3> (the spread is the VMSubPCToBitmaskTable lookup of split_pc, main_vm/utils.rs:95-104)"),
+    "OPCODE_SELECT_CHAIN": (P + ":188-206", "three <[UInt32; 2]>::conditionally_select steps over code_word.inner[6..8] / [4..6] / [2..4] / [0..2]: (low, high) after each; "
+                                            "the last pair is the opcode BEFORE mask_into_nop / mask_into_panic"),
+    "SRC0_SELECTORS": (D + ":192-193", "reg_idx_into_bitspread(src0_encoding).spread_into_bits::<REGISTERS_COUNT>: 15 Booleans"),
+    "SRC1_SELECTORS": (D + ":195-196", ""), "DST0_SELECTORS": (D + ":198-199", ""), "DST1_SELECTORS": (D + ":201-202", ""),
+    "DRAFT_SRC0_CHAIN": (P + ":303-309", "draft_src0 after each of the 15 VMRegister::conditionally_select steps: 15 x (is_pointer, 8 limbs)"),
+    "SRC1_REGISTER_CHAIN": (P + ":312-318", "src1_register after each step, likewise"),
+    "DST0_REG_LOW_CHAIN": (P + ":320-328", "current_dst0_reg_low after each of the 15 UInt32::conditionally_select steps"),
+    "SRC0_REG_LOWEST": (P + ":310", "draft_src0.value.inner[0].low_u16"), "DST0_REG_LOWEST": (P + ":329", "current_dst0_reg_low.low_u16"),
+    "STACK_PAGE": (P + ":342", "base_page.increment_unchecked"), "HEAP_PAGE": (P + ":343", "stack_page.increment_unchecked"),
+    "AUX_HEAP_PAGE": (P + ":344", "heap_page.increment_unchecked"),
+    "SRC_ABSOLUTE_MODE": (U + ":260", "resolve_memory_region_and_index_for_source: multi_or(use_code, use_stack_absolute)"),
+    "SRC_INDEX_FOR_ABSOLUTE": (U + ":261", "register_low_value.overflowing_add(imm0)"), "SRC_INDEX_FOR_RELATIVE": (U + ":262", "current_sp.overflowing_sub(index_for_absolute)"),
+    "SRC_USE_STACK": (U + ":272-279", ""), "SRC_DID_READ_UNMASKED": (U + ":280", "did_read before the NOP rule of :287"),
+    "NOT_NOP": (U + ":286", "is_nop.negated (allocated again at :353 with the same value)"),
+    "DST_INDEX_FOR_ABSOLUTE": (U + ":327", "resolve_memory_region_and_index_for_dest: register_low_value.overflowing_add(imm1)"),
+    "DST_INDEX_FOR_RELATIVE_WITH_PUSH": (U + ":328", "current_sp.overflowing_add(index_for_absolute), current_sp = new_sp_after_src0"),
+    "DST_INDEX_FOR_RELATIVE": (U + ":329", "current_sp.overflowing_sub(index_for_absolute)"),
+    "DST_DID_WRITE_UNMASKED": (U + ":340-347", "did_write before the NOP rule of :354"),
+    "DST_INDEX_SOMEWHAT_RELATIVE": (U + ":356-361", "index_with_somewhat_relative_addressing: a push writes at the current sp"),
+    "SRC0_AFTER_USE_REG": (P + ":405", "VMRegister::conditionally_select(use_reg, draft_src0, src0_register_from_mem)"),
+    "SRC0_AFTER_USE_IMM": (P + ":408-412", "VMRegister::conditionally_select(use_imm, imm_as_reg, src0)"),
+    "SWAP_IS_ASSYMMETRIC": (P + ":431", "multi_or(is_sub, is_div, is_shift)"), "SWAP_T0": (P + ":435", ""), "SWAP_T1": (P + ":443", ""),
+    "SRC0_SWAPPED": (P + ":451-452", "VMRegister::conditionally_select(swap_operands, selected_src1, selected_src0), before the erasure"),
+    "SRC1_SWAPPED": (P + ":453-454", ""),
+    "NOT_KERNEL_MODE": (P + ":458", ""), "KEEPS_POINTERS": (P + ":474-475", "multi_or(is_ret, is_ptr, is_uma, is_far_call)"), "SHOULD_ERASE": (P + ":474-475", "its negation"),
+    "SHOULD_ERASE_SRC0": (P + ":459-477", "multi_and(src0.is_pointer, should_erase, not_kernel_mode)"),
+    "SHOULD_ERASE_SRC1": (P + ":479", "multi_and(src1.is_pointer, not_kernel_mode)"),
+}
+
 
 def dense_layout():
     text = open(os.path.join(ROOT, "include", "zkc_b200.h")).read()
@@ -195,12 +236,12 @@ def build():
     x = lambda cols, widths: [(k, cols[k], widths[k]) for k in widths]
     return {
         "circuit": "main_vm: one vm_cycle (src/main_vm/cycle.rs:28-795, pre_state.rs:71-519)",
-        "trace": "column-major uint64 block[column * limit + cycle]; the four blocks are the outputs of zkc_main_vm_entry_point (DENSE), "
-                 "zkc_main_vm_gadget_cells, zkc_main_vm_state_gadget_cells, zkc_main_vm_memory_sponge_cells (include/zkc_b200.h)",
+        "trace": "column-major uint64 block[column * limit + cycle]; the five blocks are the outputs of zkc_main_vm_entry_point (DENSE), "
+                 "zkc_main_vm_gadget_cells, zkc_main_vm_state_gadget_cells, zkc_main_vm_memory_sponge_cells, zkc_main_vm_prestate_cells (include/zkc_b200.h)",
         "provenance": "values the reference's own source names, one group per allocation site; boojum is un-vendored, so which INTERNAL cells its "
                       "gadgets add (selects, range-check decompositions, Poseidon2 round cells) is not listed here: they stay host-resolved",
         "not_produced": ["non-selected cells of apply_uma / apply_log / apply_calls_and_ret", "the in-circuit permutations of slots 3..8 when not enforced",
-                         "intermediate cells of the 15-way register selects and of the state-diff select chains", "lookup / range-check decompositions"],
+                         "intermediate cells of the state-diff select chains (the 15-way register selects of create_prestate are in the prestate block)", "lookup / range-check decompositions"],
         "blocks": [
             {"block": "dense", "entry_point": "zkc_main_vm_entry_point", "enum": "zkc_vm_col", "num_columns": n_dense, "columns": block("ZKC_VM_", dense, DENSE)},
             {"block": "gadget", "entry_point": "zkc_main_vm_gadget_cells", "enum": "zkc_vm_gadget_col", "num_columns": abi.VMG_COLS["NUM_COLS"],
@@ -209,6 +250,8 @@ def build():
              "columns": block("ZKC_VMS_", x(abi.VMS_COLS, abi.VMS_WIDTHS), STATE)},
             {"block": "memory_sponge", "entry_point": "zkc_main_vm_memory_sponge_cells", "enum": "zkc_vm_memory_sponge_col", "num_columns": abi.VMQ_COLS["NUM_COLS"],
              "columns": block("ZKC_VMQ_", x(abi.VMQ_COLS, abi.VMQ_WIDTHS), MEMQ)},
+            {"block": "prestate", "entry_point": "zkc_main_vm_prestate_cells", "enum": "zkc_vm_prestate_col", "num_columns": abi.VMP_COLS["NUM_COLS"],
+             "columns": block("ZKC_VMP_", x(abi.VMP_COLS, abi.VMP_WIDTHS), PRESTATE)},
         ],
     }
 
