@@ -1117,7 +1117,9 @@ __device__ __forceinline__ uint32_t vm_cycle_dev(const zkc_vm_isa *__restrict__ 
     if constexpr (!SIM) { if (last_memq >= 0) d.chk |= (uint64_t)VM_CHK_NEXT_MEMQ << (4 * last_memq); }
     const bool dst0_update_register = dst0_reg_only || (!dst0_mem && dst0_mem_capable);
     if (dst0_update_register) d.idx0 = dst0_r;
-    if (write_dst1) d.idx1 = dst1_r;
+    // write_as_dst1 is the decoded selector bit itself (cycle.rs:330, :341-347): an encoded dst1 register is overwritten whatever the
+    // gadgets flagged -- with the zero dot product (val1 above) when none did
+    d.idx1 = dst1_r;
     d.flags[0] = set_flags ? nf0 : f0; d.flags[1] = set_flags ? nf1 : f1; d.flags[2] = set_flags ? nf2 : f2;
     d.pending = new_pending;
     if (wr) {
@@ -1582,6 +1584,7 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
                 zkc_vm_register want = reg_zero();
                 if (d.far_ret) { if (r == 0) want = d.r1_val; }
                 else want = vm_far_call_register(isa, d, r, regs.get((uint32_t)r));
+                if (d.idx1 == (uint32_t)(r + 1)) want = d.val1;  // the dst1 select comes after the specific updates / zeroing, cycle.rs:415-433
                 for (int i = 0; i < 9; i++) bad |= NXT(VW(registers) + 9 * r + i) != reg_word(want, i);
             }
         }
@@ -1625,6 +1628,7 @@ vm_cycles_kernel(VmDev *devs, const zkc_vm_isa *__restrict__ isa, VmCols cols,
                 zkc_vm_register want = reg_zero();
                 if (d.far_ret) { if (r == 0) want = d.r1_val; }
                 else want = vm_far_call_register(isa, d, r, regs.get((uint32_t)r));
+                if (d.idx1 == (uint32_t)(r + 1)) want = d.val1;  // the dst1 select comes after the specific updates / zeroing, cycle.rs:415-433
                 for (int i = 0; i < 9; i++) bad |= NXT(VW(registers) + 9 * r + i) != reg_word(want, i);
             }
         }

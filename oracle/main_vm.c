@@ -1001,7 +1001,10 @@ static uint32_t vm_cycle(const zkc_vm_isa *isa, const zkc_vm_closed_form *gc, co
         for (uint32_t r = isa->call_reserved_range[0]; r < isa->call_reserved_range[1] && r < 15; r++) s.registers[r] = zero_reg;
         if (isa->call_implicit_parameter_reg_idx < 15) s.registers[isa->call_implicit_parameter_reg_idx] = zero_reg;
     }
-    if (write_dst1 && dst1_r) s.registers[dst1_r - 1] = dst1; /* dst1 applied after dst0, cycle.rs:421-433 */
+    /* dst1 is applied after dst0 and WHATEVER the gadgets flagged: write_as_dst1 is the decoded selector bit itself (cycle.rs:330,
+     * :341-347; should_update_dst1 of :177-187 is collected and never read), so an opcode that encodes a dst1 register and has no
+     * dst1 result -- a UMA write, a read without the increment flag, a panicking UMA -- leaves (not a pointer, 0) there */
+    if (dst1_r) s.registers[dst1_r - 1] = dst1;
     ctx->ergs_remaining = ergs_candidate;
     if (reset_context_u128) memset(s.context_composite_u128, 0, 16);
     if (uma_applies) { memcpy(s.memory_queue_state, uma_memq, 96); s.memory_queue_length = uma_memq_len; }

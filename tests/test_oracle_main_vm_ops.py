@@ -76,12 +76,14 @@ def test_uma_heap_against_bytearray_model(orc):
         unaligned = off % 32 != 0
         if kind == "r":
             assert reg(after, 3) == val, (k, hex(reg(after, 3)), hex(val))
-            if inc:
-                assert reg(after, 4) == off + 32
+            # dst1 = r4 is ENCODED in every access: write_as_dst1 is the selector bit (cycle.rs:330, :341-347), so without a flagged
+            # candidate (uma.rs:944: only a read with the increment flag has one) the register takes the zero dot product
+            assert reg(after, 4) == (off + 32 if inc else 0) and after.registers[3].is_pointer == 0
             assert after_len - before_len == (2 if unaligned else 1)
         else:
             if inc:
                 assert reg(after, 3) == off + 32
+            assert reg(after, 4) == 0 and after.registers[3].is_pointer == 0
             assert after_len - before_len == (4 if unaligned else 2)
         assert trace[K["OP_AUX"] + 2, 2 * k + 1] == off % 32 and trace[K["OP_AUX"] + 1, 2 * k + 1] == off // 32
     # heap bound untouched (bootloader frame starts at 2^24), ergs: 2 per add + 6 per uma
@@ -417,3 +419,26 @@ def test_far_call_decommit_and_return(orc):
     s1 = O.vm_state_at(sn, 1)
     assert rc == 0 and s1.pending_exception == 0 and s1.current_context.is_kernel_mode == 0 and s1.code_decommittment_queue_length == 1
     assert s1.current_context.code_page == 16  # unknown code: a fresh page
+
+
+def test_encoded_dst1_register_is_written_whatever_the_gadget_flags(orc):
+    """cycle.rs:330, :341-347: write_as_dst1 = the decoded dst1 selector bit (should_update_dst1, :177-187, is never read).  An add that
+    encodes dst1 = r5 zeroes r5 (and its pointer marker); the same add masked into a NOP by a false condition decodes dst1 = 0
+    (decoded_opcode.rs:170-177) and leaves r6 alone; mul writes its high half there; dst1 wins over dst0 on the same register."""
+    isa, io, st = fresh(orc)
+    set_reg(st, 5, 0x1234 << 200, is_ptr=1); set_reg(st, 6, 77, is_ptr=1); set_reg(st, 7, 5); set_reg(st, 8, (1 << 255) + 9)
+    ops = [isa.encode(I.OP_ADD, 0, 0, src0=7, src1=7, dst0=2, dst1=5),                       # r2 = 10, r5 <- (not a pointer, 0)
+           isa.encode(I.OP_ADD, 0, 0, cond=I.COND_EQ, src0=7, src1=7, dst0=3, dst1=6),       # eq flag is clear: NOP, r3 / r6 untouched
+           isa.encode(I.OP_MUL, 0, 0, src0=8, src1=8, dst0=9, dst1=10),                      # r9 = low, r10 = high of r8 * r8
+           isa.encode(I.OP_ADD, 0, 0, src0=7, src1=7, dst0=11, dst1=11)]                     # dst0 = dst1 = r11: dst1 (zero) is applied last
+    snaps, wit, cw, tail, res = run_full(orc, isa, io, st, ops, len(ops))
+    assert res[0] == 0, (res[0], hex(res[4].failed_checks), res[4].first_bad_row)
+    s = lambda i: O.vm_state_at(snaps, i)
+    assert reg(s(1), 2) == 10 and reg(s(1), 5) == 0 and s(1).registers[4].is_pointer == 0
+    assert reg(s(2), 3) == 0 and reg(s(2), 6) == 77 and s(2).registers[5].is_pointer == 1
+    sq = ((1 << 255) + 9) ** 2
+    assert reg(s(3), 9) == sq % (1 << 256) and reg(s(3), 10) == sq >> 256
+    assert reg(s(4), 11) == 0
+    trace = res[2]
+    assert trace[K["DST1_REG"]].tolist()[:4] == [5, 0, 10, 11] and trace[K["DST1_UPDATE_REGISTER"]].tolist()[:4] == [0, 0, 1, 0]
+    assert trace[K["DST1"]:K["DST1"] + 9, 0].max() == 0
