@@ -463,18 +463,19 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
-    # ---- the FULL named witness of instance 0: the dense trace of the timed step + the four oblivious gadget-cell blocks ---------
-    # (arithmetic gadgets 724, ptr / jump / context 87, per-cycle memory sponges 112, create_prestate 428 columns per cycle).  A
+    # ---- the FULL named witness of instance 0: the dense trace of the timed step + the five oblivious gadget-cell blocks ---------
+    # (arithmetic gadgets 724, ptr / jump / context 87, per-cycle memory sponges 112, create_prestate 428, register write-back 513 columns per cycle).  A
     # secondary figure, measured after everything above and never fatal for it; 1-GPU runs only.
     full_witness = None
     if world == 1:
         try:
-            from era_zkevm_circuits_b200 import main_vm_gadget_cells, main_vm_memory_sponge_cells, main_vm_prestate_cells, main_vm_state_gadget_cells
+            from era_zkevm_circuits_b200 import main_vm_gadget_cells, main_vm_memory_sponge_cells, main_vm_prestate_cells, main_vm_state_gadget_cells, main_vm_writeback_cells
             t0_, s0_ = trace[0], d_snaps[0]
             blocks = (("vm_gadgets", main_vm_gadget_cells, abi.VMG_COLS["NUM_COLS"], lambda: main_vm_gadget_cells(eng, t0_, cycles)),
                       ("vm_state_gadgets", main_vm_state_gadget_cells, abi.VMS_COLS["NUM_COLS"], lambda: main_vm_state_gadget_cells(eng, t0_, s0_, cycles)),
                       ("vm_memory_sponges", main_vm_memory_sponge_cells, abi.VMQ_COLS["NUM_COLS"], lambda: main_vm_memory_sponge_cells(eng, t0_, s0_, cycles)),
-                      ("vm_prestate", main_vm_prestate_cells, abi.VMP_COLS["NUM_COLS"], lambda: main_vm_prestate_cells(eng, t0_, s0_, cycles)))
+                      ("vm_prestate", main_vm_prestate_cells, abi.VMP_COLS["NUM_COLS"], lambda: main_vm_prestate_cells(eng, t0_, s0_, cycles)),
+                      ("vm_writeback", main_vm_writeback_cells, abi.VMW_COLS["NUM_COLS"], lambda: main_vm_writeback_cells(eng, isa.isa, t0_, s0_, cycles)))
             per_block, total_ms = {}, 0.0
             for name, _fn, cols, call in blocks:
                 out = call(); del out                      # warm-up (first allocation of the output block)
@@ -488,11 +489,11 @@ def run_gpu(args):
                 total_ms += k_ms / k_n if k_n else 0.0
             torch.cuda.synchronize()
             cols_total = ncols + sum(b[2] for b in blocks)
-            step_ms = ms / args.steps / n + total_ms       # one instance: its share of the timed step + its four block kernels
+            step_ms = ms / args.steps / n + total_ms       # one instance: its share of the timed step + its five block kernels
             full_witness = {"columns_per_cycle": cols_total, "ms_per_instance": step_ms, "value": cycles / (step_ms * 1e-3), "unit": UNIT,
                             "kernels": per_block,
                             "note": "device-resident: the timed main_vm step (per instance) + zkc_main_vm_gadget_cells + zkc_main_vm_state_gadget_cells + "
-                                    "zkc_main_vm_memory_sponge_cells + zkc_main_vm_prestate_cells over the trace it wrote (kernel times from CUDA events inside the library)"}
+                                    "zkc_main_vm_memory_sponge_cells + zkc_main_vm_prestate_cells + zkc_main_vm_writeback_cells over the trace it wrote (kernel times from CUDA events inside the library)"}
         except Exception as ex:  # reported, never fatal for the headline numbers
             full_witness = {"error": repr(ex)[:300]}
 

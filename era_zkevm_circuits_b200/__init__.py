@@ -59,6 +59,7 @@ from .main_vm import (  # noqa: F401
     main_vm_state_gadget_cells,
     main_vm_memory_sponge_cells,
     main_vm_prestate_cells,
+    main_vm_writeback_cells,
     main_vm_entry_point,
     main_vm_entry_point_batch,
     main_vm_entry_point_columns,

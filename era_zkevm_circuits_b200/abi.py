@@ -527,6 +527,7 @@ SIGNATURES = {
     "zkc_main_vm_state_gadget_cells": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),
     "zkc_main_vm_memory_sponge_cells": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),
     "zkc_main_vm_prestate_cells": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),
+    "zkc_main_vm_writeback_cells": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp]),
     "zkc_main_vm_check_trace": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, C.c_size_t, C.c_size_t, C.c_int, _u64p, C.POINTER(Status)]),
     "zkc_main_vm_initial_state": (C.c_int, [_vp, C.POINTER(VmClosedForm), C.POINTER(VmIsa), C.POINTER(VmState)]),
     "zkc_main_vm_simulate": (C.c_int, [_vp, C.POINTER(VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp,
@@ -557,6 +558,7 @@ def _gadget_columns(macro="ZKC_VM_GADGET_COLUMNS", enum="zkc_vm_gadget_col"):
 VMG_COLS, VMG_WIDTHS = _gadget_columns()
 VMS_COLS, VMS_WIDTHS = _gadget_columns("ZKC_VM_STATE_GADGET_COLUMNS", "zkc_vm_state_gadget_col")  # ptr / jump / context block
 VMQ_COLS, VMQ_WIDTHS = _gadget_columns("ZKC_VM_MEMORY_SPONGE_COLUMNS", "zkc_vm_memory_sponge_col")  # fetch / src0 / dst0 memory-queue relations
+VMW_COLS, VMW_WIDTHS = _gadget_columns("ZKC_VM_WRITEBACK_COLUMNS", "zkc_vm_writeback_col")  # register write-back of the state diffs
 VMP_COLS, VMP_WIDTHS = _gadget_columns("ZKC_VM_PRESTATE_COLUMNS", "zkc_vm_prestate_col")  # create_prestate: selectors, select chains, locations, swap
 EVV = dict(BOOLEAN=1 << 0, QUEUE_LEN=1 << 1, ENCODING=1 << 2, ROUND_FUNCTION=1 << 3, COMPARISON=1 << 4, FLAGS=1 << 5, ENFORCE=1 << 6,
            GP_CHAIN=1 << 7, GP_ACC=1 << 8, RESULT_QUEUE=1 << 9)

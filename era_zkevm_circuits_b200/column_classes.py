@@ -85,6 +85,14 @@ def _prestate_block():
     return np.array(cls, dtype=np.uint8)
 
 
+def _writeback_block():
+    """ZKC_VM_WRITEBACK_COLUMNS: Booleans but the r2 word of a far call (0..3, a UInt32 limb) and the UInt32 limbs of the value chains"""
+    cls = []
+    for name, width in abi.VMW_WIDTHS.items():
+        cls += [U32 if name.startswith("VALUE_AFTER_") or name == "FAR_CALL_NEW_R2_LOW" else B] * width
+    return np.array(cls, dtype=np.uint8)
+
+
 TABLES = {
     "ram_permutation": lambda: _table([[B] * 3, MEMORY_ITEM, [F] * 8, [F] * 12, [U32], MEMORY_ITEM, [F] * 8, [F] * 12, [U32], [B] * 3, [U32],
                                        [U32] * 3, [B] * 3, [B] * 3, [B] * 10, [F] * 32, [F] * 4, [F] * 4, [U8] * 24, [F] * 2, [F], [F, F], [F] * 3,
@@ -112,6 +120,7 @@ TABLES = {
     "main_vm_state_gadget_cells": _state_gadget_block,
     "main_vm_memory_sponge_cells": _memory_sponge_block,
     "main_vm_prestate_cells": _prestate_block,
+    "main_vm_writeback_cells": _writeback_block,
 }
 
 

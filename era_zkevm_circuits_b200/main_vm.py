@@ -208,7 +208,7 @@ def main_vm_gadget_cells(engine: Engine, trace, limit: int, n_instances: int = 1
     return out
 
 
-def _trace_and_snapshots_block(engine: Engine, fn_name: str, n_cols: int, trace, snapshots, limit: int, n_instances: int):
+def _trace_and_snapshots_block(engine: Engine, fn_name: str, n_cols: int, trace, snapshots, limit: int, n_instances: int, isa=None):
     """shared by the per-cycle blocks computed from finished DENSE traces + the snapshots the entry point took"""
     dev = on_device(trace)
     if dev != on_device(snapshots):
@@ -229,7 +229,8 @@ def _trace_and_snapshots_block(engine: Engine, fn_name: str, n_cols: int, trace,
         rows *= int(d)
     if have < need or trace.shape[-2] != abi.VM_COLS["NUM_COLS"] or trace.shape[-1] != limit or rows != n_instances:
         raise ZkcError(abi.ZKC_ERR_INVALID_ARGUMENT, what=f"{fn_name}: trace / snapshots do not cover n_instances x limit cycles")
-    rc = getattr(engine.lib, fn_name)(engine.h, ptr(trace), ptr(snapshots), limit, n_instances, dev, ptr(out))
+    lead = (engine.h,) if isa is None else (engine.h, C.byref(isa))   # the write-back block also takes the ISA tables (host)
+    rc = getattr(engine.lib, fn_name)(*lead, ptr(trace), ptr(snapshots), limit, n_instances, dev, ptr(out))
     if rc:
         raise ZkcError(rc, what=fn_name)
     return out
@@ -259,6 +260,15 @@ def main_vm_prestate_cells(engine: Engine, trace, snapshots, limit: int, n_insta
     pointer-erasure flags (include/zkc_b200.h, ZKC_VM_PRESTATE_COLUMNS).  Same arguments as main_vm_state_gadget_cells; returns
     [VMP_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory space of `trace`."""
     return _trace_and_snapshots_block(engine, "zkc_main_vm_prestate_cells", abi.VMP_COLS["NUM_COLS"], trace, snapshots, limit, n_instances)
+
+
+def main_vm_writeback_cells(engine: Engine, isa, trace, snapshots, limit: int, n_instances: int = 1):
+    """The register write-back of the state diffs (cycle.rs:158-433): the dst0 update flags, per register write_as_dst0, the far call /
+    far return specific updates, pointer-marker removal and zero-out flags, both is_pointer dot products with their selects, and the
+    value select chain dst0 -> far call -> far return -> zero-out -> dst1 (include/zkc_b200.h, ZKC_VM_WRITEBACK_COLUMNS).  `isa`: the
+    abi.VmIsa tables (calling-convention register lists); the other arguments as main_vm_state_gadget_cells.  Returns
+    [VMW_COLS.NUM_COLS, limit] / [n, ..] uint64 in the memory space of `trace`."""
+    return _trace_and_snapshots_block(engine, "zkc_main_vm_writeback_cells", abi.VMW_COLS["NUM_COLS"], trace, snapshots, limit, n_instances, isa=isa)
 
 
 # ---- transport forms over PCIe (include/zkc_b200.h, "transport forms of the main_vm call") ---------------------------------

@@ -1727,6 +1727,43 @@ enum zkc_vm_prestate_col {
 int zkc_main_vm_prestate_cells(zkc_ctx *ctx, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances,
                                int on_device, uint64_t *prestate_trace);
 
+/* ---- the register write-back of the state diffs (cycle.rs:158-433) -----------------------------------------------------------------
+ * What vm_cycle allocates when it applies dst0 / dst1 and the far call / far return register conventions to the 15 registers:
+ *   cycle.rs:160-189   dst0_update_potentially_to_memory, can_update_dst0_as_register_only (the two multi_or over the candidates' flags)
+ *   cycle.rs:298-304   dst0_performs_reg_update, t (ZKC_VM_DST0_UPDATE_REGISTER of the DENSE trace = can_update_dst0_as_register_only | t)
+ *   cycle.rs:323-330   per register: write_as_dst0 = dst0_update_register & selector (write_as_dst1 IS the dst1 selector bit,
+ *                      ZKC_VMP_DST1_SELECTORS of the prestate block: an encoded dst1 register is written whatever the gadgets flagged)
+ *   cycle.rs:349-379   the specific updates of a far call (r1, r2: far_call.rs:1041-1043) and a far return (r1: ret.rs:444-445), the
+ *                      remove-pointer marker and the zero-out flag: multi_or over the far call's and the far return's requests
+ *                      (far_call.rs:1045-1070, ret.rs:451-462)
+ *   cycle.rs:381-421   any_ptr_update_as_dst0, the is_pointer dot product over the dst0-side candidates, is_pointer after that select,
+ *                      the dst1 dot product, is_pointer after the dst1 select (= the register's marker in the next state)
+ *   cycle.rs:423-432   the value select chain: after dst0, after the far call's update (r1, r2 only), after the far return's update
+ *                      (r1 only), after the zero-out, after dst1 (= the register's value in the next state)
+ * Inputs: the DENSE trace (property bits, dst0 / dst1 dot products, their register indices, the update / memory-access flags, the
+ * far call's ABI word in src0 and target in src1), snapshot i (registers, is_local_call, is_kernel_mode), the calling-convention
+ * register lists of the ISA tables, and snapshot i + 1 for ONE thing: the far call's / far return's new r1 when that update is
+ * applied (final_fat_ptr.into_register, far_call.rs:1008, ret.rs:441: a cell of the call / ret gadget, which this block does not
+ * re-derive; the entry point's snapshot link has verified it).  The reference allocates no zero-out select for a register no list
+ * names and no far-call step for r3..r15; the block keeps one uniform layout and passes the value through there.
+ * X(name, width): column ZKC_VMW_<name> .. + width - 1 of the block [ZKC_VMW_NUM_COLS][limit]. */
+#define ZKC_VM_WRITEBACK_COLUMNS(X) \
+    X(DST0_UPDATE_POTENTIALLY_TO_MEMORY, 1) X(CAN_UPDATE_DST0_AS_REGISTER_ONLY, 1) X(DST0_PERFORMS_REG_UPDATE, 1) X(DST0_REG_UPDATE_T, 1) \
+    X(FAR_CALL_UPDATE, 1) X(FAR_CALL_NON_SYSTEM, 1) X(FAR_CALL_CLEANUP_REGISTER, 1) X(FAR_RETURN_UPDATE, 1) X(FAR_CALL_NEW_R2_LOW, 1) \
+    X(WRITE_AS_DST0, 15) X(REMOVE_PTR_MARKER, 15) X(ZERO_OUT, 15) X(ANY_PTR_UPDATE_AS_DST0, 15) X(IS_PTR_AS_DST0, 15) X(IS_PTR_AFTER_DST0, 15) \
+    X(IS_PTR_AS_DST1, 15) X(IS_PTR_AFTER_DST1, 15) \
+    X(VALUE_AFTER_DST0, 120) X(VALUE_AFTER_FAR_CALL, 16) X(VALUE_AFTER_FAR_RETURN, 8) X(VALUE_AFTER_ZERO_OUT, 120) X(VALUE_AFTER_DST1, 120)
+enum zkc_vm_writeback_col {
+#define ZKC_VMW_X(name, width) ZKC_VMW_##name, ZKC_VMW_##name##_LAST = ZKC_VMW_##name + (width)-1,
+    ZKC_VM_WRITEBACK_COLUMNS(ZKC_VMW_X)
+#undef ZKC_VMW_X
+    ZKC_VMW_NUM_COLS
+};
+/* trace / snapshots as for zkc_main_vm_prestate_cells; isa: host pointer (its calling-convention register lists are read on the host);
+ * writeback_trace: out, [n_instances][ZKC_VMW_NUM_COLS][limit] in the memory space of trace */
+int zkc_main_vm_writeback_cells(zkc_ctx *ctx, const zkc_vm_isa *isa, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit,
+                                size_t n_instances, int on_device, uint64_t *writeback_trace);
+
 /* the state main_vm_entry_point starts from when start_flag is set: initial_bootloader_state, main_vm/loading.rs:13-226 */
 int zkc_main_vm_initial_state(zkc_ctx *ctx, const zkc_vm_closed_form *io, const zkc_vm_isa *isa, zkc_vm_state *out);
 

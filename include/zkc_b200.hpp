@@ -473,6 +473,18 @@ inline std::vector<uint64_t> main_vm_prestate_cells(Engine &e, const std::vector
     return out;
 }
 
+// the register write-back of the state diffs (cycle.rs:158-433): dst0 / dst1 update flags, the far call / far return register conventions,
+// both is_pointer dot products and the value select chain of each of the 15 registers (zkc_b200.h, ZKC_VM_WRITEBACK_COLUMNS) (host)
+inline std::vector<uint64_t> main_vm_writeback_cells(Engine &e, const zkc_vm_isa &isa, const std::vector<uint64_t> &trace,
+                                                     const std::vector<zkc_vm_state> &snapshots, size_t limit) {
+    if (trace.size() < (size_t)ZKC_VM_NUM_COLS * limit || snapshots.size() < limit + 1)
+        throw Error("main_vm_writeback_cells", ZKC_ERR_INVALID_ARGUMENT, zkc_status{ZKC_ERR_INVALID_ARGUMENT, 0, -1, 0, 0});
+    std::vector<uint64_t> out((size_t)ZKC_VMW_NUM_COLS * limit);
+    const int rc = zkc_main_vm_writeback_cells(e.handle(), &isa, trace.data(), snapshots.data(), limit, 1, 0, out.data());
+    if (rc != ZKC_OK) throw Error("zkc_main_vm_writeback_cells", rc, zkc_status{rc, 0, -1, 0, 0});
+    return out;
+}
+
 // constraint evaluation of finished traces (host buffers): violating rows; st describes the first one
 inline uint64_t ram_permutation_check_trace(Engine &e, const zkc_ram_closed_form &io, const std::vector<uint64_t> &trace, size_t limit,
                                             uint32_t gates = 0, zkc_status *st = nullptr) {

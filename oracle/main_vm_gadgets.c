@@ -503,3 +503,88 @@ void orc_main_vm_prestate_cells(const uint64_t *trace, const zkc_vm_state *snaps
         }
     }
 }
+
+/* ---- the register write-back of the state diffs (ZKC_VM_WRITEBACK_COLUMNS) ---------------------------------------------------------
+ *   dst0 / dst1 update flags, write_as_dst0      /root/reference/src/main_vm/cycle.rs:160-189, :303-330
+ *   specific updates, markers, zero-out          /root/reference/src/main_vm/cycle.rs:349-375
+ *   far call register conventions                /root/reference/src/main_vm/opcodes/call_ret_impl/far_call.rs:1041-1070
+ *   far return register conventions              /root/reference/src/main_vm/opcodes/call_ret_impl/ret.rs:442-464
+ *   is_pointer dot products and selects          /root/reference/src/main_vm/cycle.rs:377-412
+ *   value select chain                           /root/reference/src/main_vm/cycle.rs:415-433
+ * One register at a time, each step of the reference's chain as an `if`.  Pinning: PARITY UNPINNED against the reference; checked
+ * against an independent Python statement and against snapshot i + 1 (tests/test_oracle_main_vm_gadgets.py). */
+void orc_main_vm_writeback_cells(const zkc_vm_isa *isa, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances,
+                                 uint64_t *out_all) {
+    for (size_t inst = 0; inst < n_instances; inst++) {
+        const uint64_t *t = trace + inst * (size_t)ZKC_VM_NUM_COLS * limit;
+        const zkc_vm_state *snaps = snapshots + inst * (limit + 1);
+        uint64_t *out = out_all + inst * (size_t)ZKC_VMW_NUM_COLS * limit;
+        for (size_t row = 0; row < limit; row++) {
+#define T(c) t[(size_t)(c) * limit + row]
+            const zkc_vm_state *st = snaps + row, *nx = snaps + row + 1;
+            const uint64_t props = T(ZKC_VM_PROPS);
+#define TYPE(n) (int)((props >> ZKC_VM_BIT_TYPE(n)) & 1)
+            const int capable = TYPE(ZKC_OP_ADD) || TYPE(ZKC_OP_SUB) || TYPE(ZKC_OP_MUL) || TYPE(ZKC_OP_DIV) || TYPE(ZKC_OP_BINOP) ||
+                                TYPE(ZKC_OP_SHIFT) || TYPE(ZKC_OP_PTR);   /* the gadgets whose dst0 candidate may go to memory */
+            const int update_register = (int)T(ZKC_VM_DST0_UPDATE_REGISTER), memory_write = (int)T(ZKC_VM_PERFORM_DST0_MEMORY_WRITE);
+            const int memory_access = (int)T(ZKC_VM_DST0_PERFORMS_MEMORY_ACCESS);
+            const int potentially = capable && (update_register || memory_write);   /* :165: one opcode per cycle, so one flag at most */
+            const int register_only = !capable && update_register;                 /* :179 */
+            PC(ZKC_VMW_DST0_UPDATE_POTENTIALLY_TO_MEMORY, 0) = potentially; PC(ZKC_VMW_CAN_UPDATE_DST0_AS_REGISTER_ONLY, 0) = register_only;
+            PC(ZKC_VMW_DST0_PERFORMS_REG_UPDATE, 0) = !memory_access; PC(ZKC_VMW_DST0_REG_UPDATE_T, 0) = !memory_access && potentially;   /* :303-309 */
+            /* far call: execute, system_call after the kernel-target mask (far_call.rs:396-431), cleanup_register (:1045-1046), r2 (:1021-1039) */
+            const int far_call = TYPE(ZKC_OP_FAR_CALL);
+            uint32_t abi[8], target[8];
+            for (int i = 0; i < 8; i++) { abi[i] = (uint32_t)T(ZKC_VM_SRC0 + 1 + i); target[i] = (uint32_t)T(ZKC_VM_SRC1 + 1 + i); }
+            const int target_is_kernel = (target[0] >> 16) == 0 && target[1] == 0 && target[2] == 0 && target[3] == 0 && target[4] == 0;
+            const int constructor_call = ((abi[7] >> 16) & 0xFF) != 0 && (st->current_context.is_kernel_mode & 1);   /* byte 30 */
+            const int system_call = ((abi[7] >> 24) & 0xFF) != 0 && target_is_kernel;                                 /* byte 31 */
+            const int cleanup = far_call && !system_call;
+            const int far_return = TYPE(ZKC_OP_RET) && !(st->current_context.is_local_call & 1);   /* ret.rs:442, call_ret.rs:133 */
+            PC(ZKC_VMW_FAR_CALL_UPDATE, 0) = far_call; PC(ZKC_VMW_FAR_CALL_NON_SYSTEM, 0) = !system_call; PC(ZKC_VMW_FAR_CALL_CLEANUP_REGISTER, 0) = cleanup;
+            PC(ZKC_VMW_FAR_RETURN_UPDATE, 0) = far_return; PC(ZKC_VMW_FAR_CALL_NEW_R2_LOW, 0) = (uint64_t)constructor_call + 2 * (uint64_t)system_call;
+            zkc_vm_register dst0, dst1;
+            dst0.is_pointer = (uint32_t)T(ZKC_VM_DST0) & 1; dst1.is_pointer = (uint32_t)T(ZKC_VM_DST1) & 1;
+            for (int i = 0; i < 8; i++) { dst0.value[i] = (uint32_t)T(ZKC_VM_DST0 + 1 + i); dst1.value[i] = (uint32_t)T(ZKC_VM_DST1 + 1 + i); }
+            const uint32_t dst0_index = (uint32_t)T(ZKC_VM_DST0_REG), dst1_index = (uint32_t)T(ZKC_VM_DST1_REG);
+            for (uint32_t r = 0; r < ZKC_VM_REGISTERS; r++) {
+                zkc_vm_register reg = st->registers[r];
+                reg.is_pointer &= 1;
+                const int write0 = update_register && dst0_index == r + 1, write1 = dst1_index == r + 1;   /* :329-330 */
+                const int in_abi = r >= isa->call_system_abi_registers[0] && r < isa->call_system_abi_registers[1];
+                const int in_reserved = (r >= isa->call_reserved_range[0] && r < isa->call_reserved_range[1]) || r == isa->call_implicit_parameter_reg_idx;
+                const int marker = ((in_abi || in_reserved) && far_call) || (r >= 1 && far_return);        /* :357-360 */
+                const int zero_out = (in_abi && cleanup) || (in_reserved && far_call) || (r >= 1 && far_return);   /* :367-370 */
+                const int far_call_sets = far_call && r < 2, far_return_sets = far_return && r == 0;
+                zkc_vm_register new_far = {0, {0}};
+                if (far_call_sets && r == 0) new_far = nx->registers[0];          /* final_fat_ptr.into_register: hinted, see the header */
+                if (far_call_sets && r == 1) new_far.value[0] = (uint32_t)constructor_call + 2 * (uint32_t)system_call;
+                const zkc_vm_register new_ret = far_return_sets ? nx->registers[0] : new_far;   /* only read when far_return_sets */
+                const int any0 = write0 || far_call_sets || far_return_sets || marker;   /* :377 */
+                const uint32_t is_ptr_as0 = (write0 ? dst0.is_pointer : 0) + (far_call_sets ? (new_far.is_pointer & 1) : 0) +
+                                            (far_return_sets ? (new_ret.is_pointer & 1) : 0);   /* + marker * false, :380-388 */
+                PC(ZKC_VMW_WRITE_AS_DST0, r) = write0; PC(ZKC_VMW_REMOVE_PTR_MARKER, r) = marker; PC(ZKC_VMW_ZERO_OUT, r) = zero_out;
+                PC(ZKC_VMW_ANY_PTR_UPDATE_AS_DST0, r) = any0; PC(ZKC_VMW_IS_PTR_AS_DST0, r) = is_ptr_as0;
+                if (any0) reg.is_pointer = is_ptr_as0;                                          /* :389-394 */
+                PC(ZKC_VMW_IS_PTR_AFTER_DST0, r) = reg.is_pointer;
+                const uint32_t is_ptr_as1 = write1 ? dst1.is_pointer : 0;                       /* :396-404 */
+                PC(ZKC_VMW_IS_PTR_AS_DST1, r) = is_ptr_as1;
+                if (write1) reg.is_pointer = is_ptr_as1;                                        /* :405-410 */
+                PC(ZKC_VMW_IS_PTR_AFTER_DST1, r) = reg.is_pointer;
+                /* the value chain, :415-433: dst0, specific updates in push order (far call, then far return: call_ret.rs:436-449), zero-out, dst1 */
+                if (write0) memcpy(reg.value, dst0.value, 32);
+                for (int i = 0; i < 8; i++) PC(ZKC_VMW_VALUE_AFTER_DST0, 8 * r + i) = reg.value[i];
+                if (far_call_sets) memcpy(reg.value, new_far.value, 32);
+                if (r < 2) for (int i = 0; i < 8; i++) PC(ZKC_VMW_VALUE_AFTER_FAR_CALL, 8 * r + i) = reg.value[i];
+                if (far_return_sets) memcpy(reg.value, new_ret.value, 32);
+                if (r == 0) for (int i = 0; i < 8; i++) PC(ZKC_VMW_VALUE_AFTER_FAR_RETURN, i) = reg.value[i];
+                if (zero_out) memset(reg.value, 0, 32);
+                for (int i = 0; i < 8; i++) PC(ZKC_VMW_VALUE_AFTER_ZERO_OUT, 8 * r + i) = reg.value[i];
+                if (write1) memcpy(reg.value, dst1.value, 32);
+                for (int i = 0; i < 8; i++) PC(ZKC_VMW_VALUE_AFTER_DST1, 8 * r + i) = reg.value[i];
+            }
+#undef TYPE
+#undef T
+        }
+    }
+}

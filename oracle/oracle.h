@@ -140,4 +140,7 @@ void orc_main_vm_state_gadget_cells(const uint64_t *trace, const zkc_vm_state *s
 void orc_main_vm_memory_sponge_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out);
 /* the cells of create_prestate that are not DENSE columns -> out [n_instances][ZKC_VMP_NUM_COLS][limit] */
 void orc_main_vm_prestate_cells(const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances, uint64_t *out);
+/* the register write-back of the state diffs (cycle.rs:158-433) -> out [n_instances][ZKC_VMW_NUM_COLS][limit] */
+void orc_main_vm_writeback_cells(const zkc_vm_isa *isa, const uint64_t *trace, const zkc_vm_state *snapshots, size_t limit, size_t n_instances,
+                                 uint64_t *out);
 #endif

@@ -288,7 +288,7 @@ int main(int argc, char **argv) {
                             (void *)&sort_and_deduplicate_code_decommittments_entry_point, (void *)&demultiplex_storage_logs_enty_point,
                             (void *)&unpack_code_into_memory_entry_point, (void *)&keccak256_round_function_entry_point, (void *)&sha256_round_function_entry_point,
                             (void *)&main_vm_entry_point, (void *)&main_vm_initial_state, (void *)&linear_hasher_entry_point,
-                            (void *)&main_vm_gadget_cells, (void *)&main_vm_state_gadget_cells, (void *)&main_vm_memory_sponge_cells, (void *)&main_vm_prestate_cells,
+                            (void *)&main_vm_gadget_cells, (void *)&main_vm_state_gadget_cells, (void *)&main_vm_memory_sponge_cells, (void *)&main_vm_prestate_cells, (void *)&main_vm_writeback_cells,
                             (void *)&ram_permutation_check_trace, (void *)&log_sorter_check_trace,
                             (void *)&storage_validity_check_trace, (void *)&sort_decommittments_check_trace,
                             (void *)&demux_log_queue_check_trace, (void *)&sha256_round_function_check_trace,

@@ -449,6 +449,19 @@ def vm_prestate_cells(lib, trace, snaps, limit, n_instances=1, fn=None):
     return out
 
 
+def vm_writeback_cells(lib, isa, trace, snaps, limit, n_instances=1, fn=None):
+    """orc_main_vm_writeback_cells: ISA tables + DENSE trace(s) + snapshots [n?, limit + 1] -> [n?, VMW_COLS.NUM_COLS, limit]; `fn` as above"""
+    trace = np.ascontiguousarray(trace, dtype=np.uint64)
+    snaps = np.ascontiguousarray(snaps)
+    assert snaps.nbytes >= (limit + 1) * n_instances * C.sizeof(abi.VmState)
+    out = np.zeros(tuple(trace.shape[:-2]) + (abi.VMW_COLS["NUM_COLS"], limit), dtype=np.uint64)
+    fn = fn or lib.orc_main_vm_writeback_cells
+    fn.restype = None
+    fn.argtypes = [C.POINTER(abi.VmIsa), _vp, _vp, C.c_size_t, C.c_size_t, _vp]
+    fn(C.byref(isa), p(trace), p(snaps), limit, n_instances, p(out))
+    return out
+
+
 def vm_memory_sponge_cells(lib, trace, snaps, limit, n_instances=1):
     """orc_main_vm_memory_sponge_cells: DENSE trace(s) + snapshots [n?, limit + 1] -> [n?, VMQ_COLS.NUM_COLS, limit]"""
     trace = np.ascontiguousarray(trace, dtype=np.uint64)

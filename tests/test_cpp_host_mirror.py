@@ -24,7 +24,7 @@ def binary(tmp_path_factory):
 def test_compiles_links_and_refuses_without_device(binary):
     out = subprocess.run([binary, "nodevice"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "zkc_b200" in out.stdout and "24 entry points" in out.stdout
+    assert "zkc_b200" in out.stdout and "25 entry points" in out.stdout
     import torch
     if not torch.cuda.is_available():
         assert "refused without a device" in out.stdout and "NO_DEVICE" in out.stdout

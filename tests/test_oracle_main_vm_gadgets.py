@@ -493,3 +493,110 @@ def test_prestate_cells_on_mutated_inputs(orc):
         erase[0] += want["SHOULD_ERASE_SRC0"]; erase[1] += want["SHOULD_ERASE_SRC1"]
     assert min(erase) > 5, erase
     assert int(g[P["PC_PLUS_ONE_OF"]].sum()) > 0 and int((g[P["NEXT_CYCLE_TIMESTAMP"]] < 4).sum()) > 0   # both wraps happened
+
+
+# ---- the register write-back block (ZKC_VM_WRITEBACK_COLUMNS; oracle/main_vm_gadgets.c orc_main_vm_writeback_cells) -----------------
+WB, WBW = abi.VMW_COLS, abi.VMW_WIDTHS
+
+
+def writeback_reference(isa, trace, snaps, r):
+    """cycle.rs:158-433 on Python integers: a register is [is_pointer, one 256-bit integer]; each register's chain as a list of
+    (flag, candidate) pairs applied in the reference's order; name -> value(s) in column order"""
+    col = lambda name, i=0: int(trace[K[name] + i, r])
+    props = col("PROPS")
+    bit = lambda n: (props >> n) & 1
+    st = abi.VmState.from_buffer_copy(snaps[r].tobytes())
+    nx = abi.VmState.from_buffer_copy(snaps[r + 1].tobytes())
+    word = lambda limbs: sum(int(x) << (32 * i) for i, x in enumerate(limbs))
+    limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    capable = any(bit(o) for o in (I.OP_ADD, I.OP_SUB, I.OP_MUL, I.OP_DIV, I.OP_BINOP, I.OP_SHIFT, I.OP_PTR))
+    upd, memw, mem_access = col("DST0_UPDATE_REGISTER"), col("PERFORM_DST0_MEMORY_WRITE"), col("DST0_PERFORMS_MEMORY_ACCESS")
+    out = {"DST0_UPDATE_POTENTIALLY_TO_MEMORY": int(capable and (upd or memw)), "CAN_UPDATE_DST0_AS_REGISTER_ONLY": int(not capable and upd),
+           "DST0_PERFORMS_REG_UPDATE": 1 - mem_access}
+    out["DST0_REG_UPDATE_T"] = out["DST0_PERFORMS_REG_UPDATE"] & out["DST0_UPDATE_POTENTIALLY_TO_MEMORY"]
+    assert upd == out["CAN_UPDATE_DST0_AS_REGISTER_ONLY"] | out["DST0_REG_UPDATE_T"]                      # cycle.rs:310
+    abi_word, target = word(col("SRC0", 1 + i) for i in range(8)), word(col("SRC1", 1 + i) for i in range(8))
+    far_call = bit(I.OP_FAR_CALL)
+    target_is_kernel = (target & ((1 << 160) - 1)) >> 16 == 0
+    system = int((abi_word >> 248) & 0xFF != 0 and target_is_kernel)
+    constructor = int((abi_word >> 240) & 0xFF != 0 and st.current_context.is_kernel_mode & 1)
+    far_return = bit(I.OP_RET) & (1 - (st.current_context.is_local_call & 1))
+    cleanup = far_call & (1 - system)
+    out.update(FAR_CALL_UPDATE=far_call, FAR_CALL_NON_SYSTEM=1 - system, FAR_CALL_CLEANUP_REGISTER=cleanup, FAR_RETURN_UPDATE=far_return,
+               FAR_CALL_NEW_R2_LOW=constructor + 2 * system)
+    dst0 = [col("DST0") & 1, word(col("DST0", 1 + i) for i in range(8))]
+    dst1 = [col("DST1") & 1, word(col("DST1", 1 + i) for i in range(8))]
+    abi_regs = set(range(isa.call_system_abi_registers[0], isa.call_system_abi_registers[1]))
+    reserved = set(range(isa.call_reserved_range[0], isa.call_reserved_range[1])) | {isa.call_implicit_parameter_reg_idx}
+    per = {k: [] for k in WBW if WBW[k] >= 15 or k in ("VALUE_AFTER_FAR_RETURN",)}
+    for k in range(15):
+        reg = [st.registers[k].is_pointer & 1, word(st.registers[k].value)]
+        new_r1 = [nx.registers[0].is_pointer & 1, word(nx.registers[0].value)]
+        write0, write1 = int(upd and col("DST0_REG") == k + 1), int(col("DST1_REG") == k + 1)
+        ptr_side = [(write0, dst0[0])]                                   # (flag, is_pointer candidate), cycle.rs:339-362
+        val_side = [(write0, dst0[1], "VALUE_AFTER_DST0")]               # (flag, value candidate, column after the step), :343-375, :415-433
+        if k == 0:
+            ptr_side += [(far_call, new_r1[0]), (far_return, new_r1[0])]
+            val_side += [(far_call, new_r1[1], "VALUE_AFTER_FAR_CALL"), (far_return, new_r1[1], "VALUE_AFTER_FAR_RETURN")]
+        if k == 1:
+            ptr_side += [(far_call, 0)]
+            val_side += [(far_call, constructor + 2 * system, "VALUE_AFTER_FAR_CALL")]
+        marker = int((k in abi_regs | reserved and far_call) or (k >= 1 and far_return))
+        zero = int((k in abi_regs and cleanup) or (k in reserved and far_call) or (k >= 1 and far_return))
+        ptr_side.append((marker, 0))
+        val_side += [(zero, 0, "VALUE_AFTER_ZERO_OUT"), (write1, dst1[1], "VALUE_AFTER_DST1")]
+        any0, as0 = int(any(f for f, _ in ptr_side)), sum(f * v for f, v in ptr_side)
+        after0 = as0 if any0 else reg[0]
+        as1 = write1 * dst1[0]
+        for name, v in (("WRITE_AS_DST0", write0), ("REMOVE_PTR_MARKER", marker), ("ZERO_OUT", zero), ("ANY_PTR_UPDATE_AS_DST0", any0),
+                        ("IS_PTR_AS_DST0", as0), ("IS_PTR_AFTER_DST0", after0), ("IS_PTR_AS_DST1", as1), ("IS_PTR_AFTER_DST1", as1 if write1 else after0)):
+            per[name].append(v)
+        value = reg[1]
+        for flag, cand, name in val_side:
+            value = cand if flag else value
+            per[name] += limbs(value)
+    out.update(per)
+    return out
+
+
+def mutate_writeback_inputs(trace, seed):
+    """the block is a pure function of its inputs: any property bits, ABI bytes, targets, register indices, flags (in place)"""
+    rng = np.random.default_rng(seed)
+    n = trace.shape[1]
+    trace[K["PROPS"]] = rng.integers(0, 1 << 38, n).astype(np.uint64)
+    for name in ("DST0_REG", "DST1_REG"):
+        trace[K[name]] = rng.integers(0, 16, n)
+    upd, mem = rng.integers(0, 2, n), rng.integers(0, 2, n)
+    trace[K["DST0_UPDATE_REGISTER"]], trace[K["DST0_PERFORMS_MEMORY_ACCESS"]], trace[K["PERFORM_DST0_MEMORY_WRITE"]] = upd & (1 - mem), mem, mem & rng.integers(0, 2, n)
+    trace[K["SRC0"] + 8] = rng.integers(0, 1 << 32, n) * (rng.random(n) < 0.7)
+    for i in range(1, 6):
+        trace[K["SRC1"] + i] = rng.integers(0, 1 << 32, n) * (rng.random(n) < 0.3) if i > 1 else rng.integers(0, 1 << 16, n) << (16 * (rng.random(n) < 0.3))
+    trace[K["DST0"]], trace[K["DST1"]] = rng.integers(0, 2, n), rng.integers(0, 2, n)
+
+
+def test_writeback_cells_against_python_integers(orc):
+    assert sum(WBW.values()) == WB["NUM_COLS"] == 513
+    isa = I.Isa().isa
+    seen = {"far_call": 0, "far_return": 0, "dst1_zero": 0, "write0": 0, "memory": 0}
+    for far, seed, mutate in ((False, 33, False), (True, 5, False), (True, 7, True)):
+        trace, snaps = vm_trace_and_snapshots(orc, 1500, seed, far)
+        trace, snaps = trace.copy(), snaps[:1501]
+        if mutate:
+            mutate_writeback_inputs(trace, seed)
+        cycles = trace.shape[1]
+        g = O.vm_writeback_cells(orc, isa, trace, snaps, cycles)
+        for r in range(cycles):
+            try:
+                want = writeback_reference(isa, trace, snaps, r)
+            except AssertionError:
+                assert mutate          # the cycle.rs:310 identity ties the three flags together on REAL traces only
+                continue
+            assert set(want) == set(WBW)
+            for name, v in want.items():
+                got = [int(x) for x in g[WB[name]:WB[name] + WBW[name], r]]
+                assert got == (v if isinstance(v, list) else [v]), (r, name, got, v)
+            if not mutate:
+                seen["far_call"] += want["FAR_CALL_UPDATE"]; seen["far_return"] += want["FAR_RETURN_UPDATE"]; seen["write0"] += sum(want["WRITE_AS_DST0"])
+                seen["dst1_zero"] += int(int(trace[K["DST1_REG"], r]) != 0 and not int(trace[K["DST1_UPDATE_REGISTER"], r]))
+                seen["memory"] += int(trace[K["PERFORM_DST0_MEMORY_WRITE"], r])
+    assert all(seen.values()), seen

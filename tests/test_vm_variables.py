@@ -1,5 +1,5 @@
 """include/zkc_b200_vm_variables.json (tools/gen_vm_variables.py): the machine-readable map from the named witness cells of a
-main_vm cycle to the allocation site in the reference.  Checked against the header (every column of the five blocks is covered
+main_vm cycle to the allocation site in the reference.  Checked against the header (every column of the six blocks is covered
 exactly once, names / offsets / widths agree with the enums the engine compiles) and, where /root/reference is present (this
 container, not the GPU box), that every cited file:line exists and the cited lines are not blank."""
 import json
@@ -27,9 +27,10 @@ def test_blocks_cover_every_column_once_and_mirror_the_header():
     doc = load()
     want = {"dense": ("ZKC_VM_", abi.VM_COLS, None), "gadget": ("ZKC_VMG_", abi.VMG_COLS, abi.VMG_WIDTHS),
             "state_gadget": ("ZKC_VMS_", abi.VMS_COLS, abi.VMS_WIDTHS), "memory_sponge": ("ZKC_VMQ_", abi.VMQ_COLS, abi.VMQ_WIDTHS),
-            "prestate": ("ZKC_VMP_", abi.VMP_COLS, abi.VMP_WIDTHS)}
+            "prestate": ("ZKC_VMP_", abi.VMP_COLS, abi.VMP_WIDTHS),
+            "writeback": ("ZKC_VMW_", abi.VMW_COLS, abi.VMW_WIDTHS)}
     assert [b["block"] for b in doc["blocks"]] == list(want)
-    assert sum(b["num_columns"] for b in doc["blocks"]) == 276 + 724 + 87 + 112 + 428
+    assert sum(b["num_columns"] for b in doc["blocks"]) == 276 + 724 + 87 + 112 + 428 + 513
     for b in doc["blocks"]:
         prefix, cols, widths = want[b["block"]]
         assert b["num_columns"] == cols["NUM_COLS"]

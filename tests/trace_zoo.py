@@ -57,4 +57,5 @@ def oracle_traces(orc):
     out["main_vm_state_gadget_cells"] = O.vm_state_gadget_cells(orc, r[2], snaps, 2000)
     out["main_vm_memory_sponge_cells"] = O.vm_memory_sponge_cells(orc, r[2], snaps, 2000)
     out["main_vm_prestate_cells"] = O.vm_prestate_cells(orc, r[2], snaps, 2000)
+    out["main_vm_writeback_cells"] = O.vm_writeback_cells(orc, isa.isa, r[2], snaps, 2000)
     return out

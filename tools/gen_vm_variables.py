@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Writes include/zkc_b200_vm_variables.json: the machine-readable map from the named witness cells of one main_vm cycle to the
 place in the reference that allocates them (file:line into matter-labs/era-zkevm_circuits @ 8bf2454, src/main_vm/...), for the
-five outputs of the engine: the DENSE trace (enum zkc_vm_col) and the four oblivious blocks (ZKC_VM_GADGET_COLUMNS,
-ZKC_VM_STATE_GADGET_COLUMNS, ZKC_VM_MEMORY_SPONGE_COLUMNS, ZKC_VM_PRESTATE_COLUMNS).  Column numbers and widths are taken from include/zkc_b200.h (the
+six outputs of the engine: the DENSE trace (enum zkc_vm_col) and the five oblivious blocks (ZKC_VM_GADGET_COLUMNS,
+ZKC_VM_STATE_GADGET_COLUMNS, ZKC_VM_MEMORY_SPONGE_COLUMNS, ZKC_VM_PRESTATE_COLUMNS, ZKC_VM_WRITEBACK_COLUMNS).  Column numbers and widths are taken from include/zkc_b200.h (the
 single source); this file only attaches (reference, what) to every group.  tests/test_vm_variables.py checks the result against
 the header and, when /root/reference is present, that every cited line exists.
 
@@ -211,6 +211,32 @@ PRESTATE = {
     "SHOULD_ERASE_SRC1": (P + ":479", "multi_and(src1.is_pointer, not_kernel_mode)"),
 }
 
+FC, RT = O + "call_ret_impl/far_call.rs", O + "call_ret_impl/ret.rs"
+WRITEBACK = {
+    "DST0_UPDATE_POTENTIALLY_TO_MEMORY": (C + ":172", "Boolean::multi_or over the flags of the memory-capable dst0 candidates"),
+    "CAN_UPDATE_DST0_AS_REGISTER_ONLY": (C + ":189", "Boolean::multi_or over the flags of the register-only dst0 candidates"),
+    "DST0_PERFORMS_REG_UPDATE": (C + ":298", "dst0_performs_memory_access.negated"),
+    "DST0_REG_UPDATE_T": (C + ":299-302", "multi_and(dst0_performs_reg_update, dst0_update_potentially_to_memory); ZKC_VM_DST0_UPDATE_REGISTER = can_update_dst0_as_register_only | t (:304)"),
+    "FAR_CALL_UPDATE": (FC + ":1042-1043", "execute: the flag of the far call's specific updates of r1 / r2"),
+    "FAR_CALL_NON_SYSTEM": (FC + ":1045", "far_call_abi.system_call.negated (system_call after the kernel-target mask, :430-431)"),
+    "FAR_CALL_CLEANUP_REGISTER": (FC + ":1046", "multi_and(execute, non_system_call)"),
+    "FAR_RETURN_UPDATE": (RT + ":442", "update_specific_registers_on_ret = multi_and(execute, is_far_return)"),
+    "FAR_CALL_NEW_R2_LOW": (FC + ":1021-1028", "r2_low = constructor_call + 2 * system_call (Num::fma)"),
+    "WRITE_AS_DST0": (C + ":328", "per register: multi_and(dst0_update_register, dst0 selector); write_as_dst1 (:330) IS the dst1 selector, ZKC_VMP_DST1_SELECTORS"),
+    "REMOVE_PTR_MARKER": (C + ":365", "multi_or over remove_ptr_on_specific_registers[idx] (far_call.rs:1064-1067, ret.rs:461); no cell when no list names the register"),
+    "ZERO_OUT": (C + ":377", "multi_or over specific_registers_zeroing[idx] (far_call.rs:1051-1054, ret.rs:454); no cell when no list names the register"),
+    "ANY_PTR_UPDATE_AS_DST0": (C + ":381", "multi_or(write_as_dst0, the specific updates' flags, remove_ptr_marker)"),
+    "IS_PTR_AS_DST0": (C + ":390-397", "dot_product over (flag, is_pointer) of dst0, the specific updates, (marker, false)"),
+    "IS_PTR_AFTER_DST0": (C + ":399-404", "Boolean::conditionally_select(any_ptr_update_as_dst0, is_ptr_as_dst0, registers[idx].is_pointer)"),
+    "IS_PTR_AS_DST1": (C + ":408-415", "dot_product over (write_as_dst1, dst1_is_ptr)"),
+    "IS_PTR_AFTER_DST1": (C + ":416-421", "Boolean::conditionally_select(any_ptr_update_as_dst1, ...): the marker in the next state"),
+    "VALUE_AFTER_DST0": (C + ":430-431", "UInt256::conditionally_select(write_as_dst0, dst0_value, registers[idx].value): 15 x 8 limbs"),
+    "VALUE_AFTER_FAR_CALL": (C + ":430-431", "... the far call's specific update (r1 = final_fat_ptr.into_register, far_call.rs:1008; r2, :1030-1039): 2 x 8 limbs"),
+    "VALUE_AFTER_FAR_RETURN": (C + ":430-431", "... the far return's specific update of r1 (ret.rs:441-445): 8 limbs"),
+    "VALUE_AFTER_ZERO_OUT": (C + ":430-431", "... (zero_out_reg, zero_u256): 15 x 8 limbs"),
+    "VALUE_AFTER_DST1": (C + ":430-431", "... (write_as_dst1, dst1_value), the last of the chain: the value in the next state: 15 x 8 limbs"),
+}
+
 
 def dense_layout():
     text = open(os.path.join(ROOT, "include", "zkc_b200.h")).read()
@@ -236,12 +262,12 @@ def build():
     x = lambda cols, widths: [(k, cols[k], widths[k]) for k in widths]
     return {
         "circuit": "main_vm: one vm_cycle (src/main_vm/cycle.rs:28-795, pre_state.rs:71-519)",
-        "trace": "column-major uint64 block[column * limit + cycle]; the five blocks are the outputs of zkc_main_vm_entry_point (DENSE), "
-                 "zkc_main_vm_gadget_cells, zkc_main_vm_state_gadget_cells, zkc_main_vm_memory_sponge_cells, zkc_main_vm_prestate_cells (include/zkc_b200.h)",
+        "trace": "column-major uint64 block[column * limit + cycle]; the six blocks are the outputs of zkc_main_vm_entry_point (DENSE), "
+                 "zkc_main_vm_gadget_cells, zkc_main_vm_state_gadget_cells, zkc_main_vm_memory_sponge_cells, zkc_main_vm_prestate_cells, zkc_main_vm_writeback_cells (include/zkc_b200.h)",
         "provenance": "values the reference's own source names, one group per allocation site; boojum is un-vendored, so which INTERNAL cells its "
                       "gadgets add (selects, range-check decompositions, Poseidon2 round cells) is not listed here: they stay host-resolved",
         "not_produced": ["non-selected cells of apply_uma / apply_log / apply_calls_and_ret", "the in-circuit permutations of slots 3..8 when not enforced",
-                         "intermediate cells of the state-diff select chains (the 15-way register selects of create_prestate are in the prestate block)", "lookup / range-check decompositions"],
+                         "intermediate cells of the scalar state-diff select chains (pc, ergs, flags, queues; the register write-back chains are in the writeback block, the 15-way register selects of create_prestate in the prestate block)", "lookup / range-check decompositions"],
         "blocks": [
             {"block": "dense", "entry_point": "zkc_main_vm_entry_point", "enum": "zkc_vm_col", "num_columns": n_dense, "columns": block("ZKC_VM_", dense, DENSE)},
             {"block": "gadget", "entry_point": "zkc_main_vm_gadget_cells", "enum": "zkc_vm_gadget_col", "num_columns": abi.VMG_COLS["NUM_COLS"],
@@ -252,6 +278,8 @@ def build():
              "columns": block("ZKC_VMQ_", x(abi.VMQ_COLS, abi.VMQ_WIDTHS), MEMQ)},
             {"block": "prestate", "entry_point": "zkc_main_vm_prestate_cells", "enum": "zkc_vm_prestate_col", "num_columns": abi.VMP_COLS["NUM_COLS"],
              "columns": block("ZKC_VMP_", x(abi.VMP_COLS, abi.VMP_WIDTHS), PRESTATE)},
+            {"block": "writeback", "entry_point": "zkc_main_vm_writeback_cells", "enum": "zkc_vm_writeback_col", "num_columns": abi.VMW_COLS["NUM_COLS"],
+             "columns": block("ZKC_VMW_", x(abi.VMW_COLS, abi.VMW_WIDTHS), WRITEBACK)},
         ],
     }
 
