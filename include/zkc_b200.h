@@ -1334,7 +1334,8 @@ enum zkc_vm_col {
     ZKC_VM_DST1 = 79,                /* 9 */
     ZKC_VM_PERFORM_DST0_MEMORY_WRITE = 88, /* :248-254 */
     ZKC_VM_DST0_UPDATE_REGISTER = 89,      /* :312 */
-    ZKC_VM_DST1_UPDATE_REGISTER = 90,
+    ZKC_VM_DST1_UPDATE_REGISTER = 90,      /* a gadget flagged a dst1 candidate (should_update_dst1, :177-187); the register WRITE is gated by
+                                              the dst1 selector alone (:330): an encoded dst1 register takes ZKC_VM_DST1 (zero when unflagged) */
     ZKC_VM_FLAGS_OUT = 91,           /* 3 */
     ZKC_VM_PENDING_EXCEPTION_OUT = 94,
     ZKC_VM_PC_OUT = 95,

@@ -61,7 +61,7 @@ DENSE = {
     "DST1": (C + ":224-246", "dst1 = dot_product over dst_1_values"),
     "PERFORM_DST0_MEMORY_WRITE": (C + ":248-254", "dst0_performs_memory_access AND dst0_update_potentially_to_memory"),
     "DST0_UPDATE_REGISTER": (C + ":298-304", "the register-file update flag of dst0"),
-    "DST1_UPDATE_REGISTER": (C + ":185-187", "Boolean::multi_or over should_update_dst1: the register-file update flag of dst1"),
+    "DST1_UPDATE_REGISTER": (C + ":185-187", "OR of the should_update_dst1 flags the gadgets push (collected by the reference, never read): whether DST1 holds a candidate; the register WRITE is gated by the dst1 selector alone (:330), see ZKC_VMW_IS_PTR_AS_DST1 / VALUE_AFTER_DST1"),
     "FLAGS_OUT": (C + ":603-606", "new_state.flags after the candidates: overflow_or_less_than, equal, greater_than"),
     "PENDING_EXCEPTION_OUT": (C + ":615-616", "Boolean::multi_or over pending_exceptions"),
     "PC_OUT": (C + ":438-445", "new pc after new_pc_candidates"),
